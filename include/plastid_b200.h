@@ -1,0 +1,201 @@
+/*
+ * plastid_b200.h — C-ABI of libplastid_b200.so: the B200 (sm_100a) implementation of
+ * plastid's read-to-coverage hot path.
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes (device pointers
+ * unless a parameter says "host"), returns PB_OK (0) or a negative PB_E* code, and
+ * enqueues its work on `stream` (a cudaStream_t passed as void*; NULL = default
+ * stream) without synchronising unless stated.  pb_last_error() gives the text of the
+ * last failure on the calling thread.  There is no CPU fallback anywhere: without a
+ * CUDA device every compute entry point returns PB_ECUDA.
+ *
+ * Reference interfaces replaced (paths relative to the plastid source tree):
+ *   pb_map_point     FivePrimeMapFactory.__call__          plastid/genomics/map_factories.pyx:308-367
+ *                    ThreePrimeMapFactory.__call__         plastid/genomics/map_factories.pyx:407-466
+ *                    VariableFivePrimeMapFactory.__call__  plastid/genomics/map_factories.pyx:585-650
+ *                    SizeFilterFactory.__call__            plastid/genomics/map_factories.pyx:837-839
+ *                    as driven per chromosome x strand by BAMGenomeArray.get_reads_and_counts
+ *                                                          plastid/genomics/genome_array.py:760-832
+ *   pb_map_center    CenterMapFactory.__call__             plastid/genomics/map_factories.pyx:200-265
+ *   pb_map_segment   the operator call `map_fn(reads, seg)` plastid/genomics/genome_array.py:823,
+ *                    incl. StratifiedVariableFivePrimeMapFactory.__call__ map_factories.pyx:724-780
+ *   pb_length_hist   len(read.positions) bucketing         plastid/bin/psite.py:187-188,
+ *                                                          plastid/bin/phase_by_size.py:188-189
+ *   pb_region_sums   SegmentChain.get_counts / get_masked_counts + nansum / masked_length
+ *                                                          plastid/genomics/roitools.pyx:3221-3315,
+ *                                                          plastid/bin/counts_in_region.py:113-125,
+ *                                                          plastid/bin/cs.py:705-711
+ *   pb_gather_windows  the window-matrix fill loops        plastid/bin/metagene.py:895-914,
+ *                                                          plastid/bin/psite.py:153-199
+ *   pb_window_normalize  denominators / row selection / normalisation  plastid/bin/metagene.py:918-924
+ *   pb_column_profile  median | mean | sum per column      plastid/bin/metagene.py:934-953,
+ *                                                          plastid/bin/psite.py:204-234
+ *
+ * Alignment batch (SoA, sorted by (chromosome, ref_start); what pysam hands the reference
+ * as AlignedSegment.reference_start / .positions / .is_reverse):
+ *   ref_start int32[N]       0-based leftmost aligned reference position
+ *   meta      uint32[N]      bits 0-15  L = number of reference-aligned bases (CIGAR M/=/X),
+ *                                       i.e. len(read.positions) — NOT the query length
+ *                            bit  16    is_reverse
+ *                            bit  17    drop (host-evaluated filter said no)
+ *                            bits 24-31 n_blocks = number of maximal M/=/X runs (1..255)
+ *   blk_off   uint32[N+1]    offsets into blk for every read; NULL when all reads have one block
+ *   blk       int32[B][2]    {start relative to ref_start, length} of each aligned block, listed
+ *                            only for reads with n_blocks > 1
+ *   chrom_read_off int64[C+1]  reads of chromosome c are [off[c], off[c+1])
+ *
+ * Dense count planes: one vector per query strand ('+', '-', '.'), all chromosomes
+ * concatenated; chromosome c starts at bin chrom_bin_off[c] (a multiple of
+ * PB_LAYOUT_ALIGN) and has chrom_len[c] live bins; padding bins are written as 0.
+ */
+#ifndef PLASTID_B200_H
+#define PLASTID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK        0
+#define PB_EINVAL   -1   /* bad argument */
+#define PB_ECUDA    -2   /* CUDA runtime error (see pb_last_error) */
+#define PB_ENOSPACE -3   /* workspace too small */
+
+#define PB_LAYOUT_ALIGN 16384   /* chrom_bin_off[] granularity, bins */
+#define PB_LUT_SIZE     10000   /* VariableFivePrimeMapFactory LUT length, map_factories.pxd:11-12 */
+#define PB_BAD_OFFSET   (-1)
+
+/* query-strand planes (bit mask) — c_common.pxd:1-6 strand enum */
+#define PB_PLANE_PLUS  1
+#define PB_PLANE_MINUS 2
+#define PB_PLANE_ANY   4
+
+/* mapping rules */
+#define PB_RULE_FIVEPRIME  0
+#define PB_RULE_THREEPRIME 1
+#define PB_RULE_VARIABLE   2
+#define PB_RULE_CENTER     3
+#define PB_RULE_STRATIFIED 4
+
+/* indices into the uint64 stats[PB_NSTATS] vector every mapping call accumulates into */
+#define PB_STAT_DROPPED_PLUS  0   /* reads the rule could not place (do_warn paths), '+' query */
+#define PB_STAT_DROPPED_MINUS 1
+#define PB_STAT_DROPPED_ANY   2
+#define PB_STAT_DROPPED_LEN   3   /* one aligned length that was dropped (for the warning text) */
+#define PB_STAT_MAPPED_PLUS   4   /* reads whose site landed in a live bin, per plane */
+#define PB_STAT_MAPPED_MINUS  5
+#define PB_STAT_MAPPED_ANY    6
+#define PB_NSTATS             8
+
+typedef struct pb_batch {
+    int64_t         n_reads;
+    const int32_t  *ref_start;       /* device int32[n_reads] */
+    const uint32_t *meta;            /* device uint32[n_reads] */
+    const uint32_t *blk_off;         /* device uint32[n_reads+1] or NULL */
+    const int32_t  *blk;             /* device int32[B][2] or NULL */
+    const int64_t  *chrom_read_off;  /* device int64[n_chrom+1] */
+    int32_t         n_chrom;
+    int32_t         max_span;        /* >= max over reads of (reference_end - ref_start) */
+} pb_batch;
+
+typedef struct pb_layout {
+    int32_t         n_chrom;
+    int32_t         reserved;
+    const int64_t  *chrom_len;       /* device int64[n_chrom] */
+    const int64_t  *chrom_bin_off;   /* device int64[n_chrom+1], multiples of PB_LAYOUT_ALIGN */
+    int64_t         total_bins;      /* == host copy of chrom_bin_off[n_chrom] */
+} pb_layout;
+
+typedef struct pb_rule {
+    int32_t         kind;            /* PB_RULE_* */
+    int32_t         param;           /* offset (5'/3') or nibble (center) */
+    const int32_t  *lut_fw;          /* device int32[PB_LUT_SIZE]  (variable / stratified) */
+    const int32_t  *lut_rc;          /* device int32[PB_LUT_SIZE] */
+    int32_t         size_min;        /* SizeFilterFactory; 0 = no size filter */
+    int32_t         size_max;        /* -1 = no upper bound */
+    int32_t         strat_min;       /* stratified: first / last length row */
+    int32_t         strat_max;
+} pb_rule;
+
+const char *pb_version(void);
+const char *pb_last_error(void);
+int pb_device_count(void);
+
+/* Bytes of device workspace pb_map_point / pb_map_center need for this layout. */
+size_t pb_map_workspace_bytes(int64_t total_bins);
+
+/* 5' / 3' / variable-offset mapping of a whole batch into dense uint32 planes.
+ * `planes` selects which of out_plus/out_minus/out_any are produced; every bin of a selected
+ * plane is written (no prior memset needed).  stats: device uint64[PB_NSTATS], accumulated. */
+int pb_map_point(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                 uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
+                 uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Center mapping into dense float64 planes.  slot_of_len: device int16[65536] mapping aligned
+ * length L to a slot (index into inv_m) or -1 (L-2*nibble <= 0); inv_m: device double[n_slots]
+ * = 1.0/(L-2*nibble) in ascending order of map length.  Deterministic: bin = sum over slots, in
+ * slot order, of (integer coverage of that slot) * inv_m[slot]. */
+int pb_map_center(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                  const int16_t *slot_of_len, const double *inv_m, int n_slots,
+                  double *out_plus, double *out_minus, double *out_any,
+                  uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The operator itself: map reads [i0,i1) of the batch onto one segment [seg_start,seg_end) of
+ * their chromosome for query strand `strand` (PB_PLANE_*).  counts_out (caller-zeroed):
+ * int64[n] (5'/3'/variable), int64[(strat_max-strat_min+1)*n] (stratified), double[n] (center).
+ * kept_out: uint8[i1-i0] or NULL — 1 where the reference appends the read to reads_out. */
+int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
+                   int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
+                   uint64_t *stats, void *stream);
+
+/* Histogram of aligned length L over reads passing drop/size/strand filters.
+ * hist: device uint64[65536], accumulated. */
+int pb_length_hist(const pb_batch *batch, const pb_rule *rule, int strand, uint64_t *hist, void *stream);
+
+/* Masked sums over exon-block chains.  vec_dtype: 0 = uint32 planes, 1 = float64 planes.
+ * planes[3]: host array of device plane pointers ('+','-','.'); chain_plane: device uint8[n_chains]
+ * in {0,1,2}.  Blocks are in global-bin coordinates [bstart,bend).  mask_bits (or NULL): bit
+ * (mask_off[c] + j) set = j-th position of chain c (genomic order) is masked.
+ * sums: double[n_chains] over unmasked positions; live_len: int64[n_chains] unmasked length. */
+int pb_region_sums(const void *const *planes, int vec_dtype,
+                   const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                   const uint8_t *chain_plane, int64_t n_chains,
+                   const uint8_t *mask_bits, const int64_t *mask_off,
+                   double *sums, int64_t *live_len, void *stream);
+
+/* Window matrices (metagene / psite): row r = chain r laid 5'->3' (reversed when
+ * chain_reverse[r]) starting at column row_col[r] of a width-W row.  matrix: double[n*W]
+ * (NaN where no chain position), maskmat: uint8[n*W] (1 = masked or uncovered). */
+int pb_gather_windows(const void *const *planes, int vec_dtype,
+                      const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                      const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                      const int32_t *row_col, int64_t n_chains, int32_t width,
+                      const uint8_t *mask_bits, const int64_t *mask_off,
+                      double *matrix, uint8_t *maskmat, void *stream);
+
+/* metagene.py:918-924 on a window matrix (one warp per row): denom[r] = sum of unmasked cells in
+ * columns [norm_lo,norm_hi) (NaN when every cell there is masked), row_select[r] = denom >=
+ * min_counts, and (when norm_out != NULL) norm_out = matrix / denom with normmask_out = maskmat |
+ * isnan | isinf. */
+int pb_window_normalize(const double *matrix, const uint8_t *maskmat, int64_t n_rows, int32_t width,
+                        int32_t norm_lo, int32_t norm_hi, double min_counts,
+                        double *denom, uint8_t *row_select, double *norm_out, uint8_t *normmask_out,
+                        void *stream);
+
+/* metagene.py:934-953 / psite.py:213-234: per-column statistic over the unmasked cells of the
+ * selected rows.  mode 0 = median (numpy.ma.median: mean of the two middle order statistics,
+ * exact radix select), 1 = mean, 2 = sum (psite --aggregate).  n_regions[col] = number of cells
+ * used, col_sum[col] = their sum (what a multi-GPU mean all-reduces).  Columns with no usable cell
+ * give NaN (mode 0/1). */
+size_t pb_column_profile_workspace_bytes(int64_t n_rows, int32_t width);
+int pb_column_profile(const double *values, const uint8_t *valmask, const uint8_t *row_select,
+                      int64_t n_rows, int32_t width, int mode,
+                      double *profile, int64_t *n_regions, double *col_sum,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLASTID_B200_H */

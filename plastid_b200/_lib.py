@@ -1,0 +1,112 @@
+"""ctypes binding of ``libplastid_b200.so`` (C-ABI declared in ``include/plastid_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C plastid_b200/csrc``.
+There is no CPU fallback: if the library is missing, or no CUDA device is visible, every
+compute call raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplastid_b200.so")
+
+PB_OK, PB_EINVAL, PB_ECUDA, PB_ENOSPACE = 0, -1, -2, -3
+PB_LAYOUT_ALIGN = 16384
+PB_LUT_SIZE = 10000
+PB_PLANE_PLUS, PB_PLANE_MINUS, PB_PLANE_ANY = 1, 2, 4
+PB_RULE_FIVEPRIME, PB_RULE_THREEPRIME, PB_RULE_VARIABLE, PB_RULE_CENTER, PB_RULE_STRATIFIED = range(5)
+(PB_STAT_DROPPED_PLUS, PB_STAT_DROPPED_MINUS, PB_STAT_DROPPED_ANY, PB_STAT_DROPPED_LEN,
+ PB_STAT_MAPPED_PLUS, PB_STAT_MAPPED_MINUS, PB_STAT_MAPPED_ANY) = range(7)
+PB_NSTATS = 8
+
+STRAND_PLANE = {"+": PB_PLANE_PLUS, "-": PB_PLANE_MINUS, ".": PB_PLANE_ANY}
+PLANE_INDEX = {"+": 0, "-": 1, ".": 2}
+
+
+class PbBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("ref_start", C.c_void_p), ("meta", C.c_void_p),
+                ("blk_off", C.c_void_p), ("blk", C.c_void_p), ("chrom_read_off", C.c_void_p),
+                ("n_chrom", C.c_int32), ("max_span", C.c_int32)]
+
+
+class PbLayout(C.Structure):
+    _fields_ = [("n_chrom", C.c_int32), ("reserved", C.c_int32), ("chrom_len", C.c_void_p),
+                ("chrom_bin_off", C.c_void_p), ("total_bins", C.c_int64)]
+
+
+class PbRule(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("param", C.c_int32), ("lut_fw", C.c_void_p), ("lut_rc", C.c_void_p),
+                ("size_min", C.c_int32), ("size_max", C.c_int32), ("strat_min", C.c_int32),
+                ("strat_max", C.c_int32)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "pb_version": (C.c_char_p, []),
+    "pb_last_error": (C.c_char_p, []),
+    "pb_device_count": (C.c_int, []),
+    "pb_map_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "pb_map_point": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
+                               _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pb_map_center": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
+                                _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pb_map_segment": (C.c_int, [C.POINTER(PbBatch), C.c_int64, C.c_int64, C.POINTER(PbRule), C.c_int,
+                                 C.c_int64, C.c_int64, _P, _P, _P, _P]),
+    "pb_length_hist": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbRule), C.c_int, _P, _P]),
+    "pb_region_sums": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "pb_gather_windows": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32,
+                                    _P, _P, _P, _P, _P]),
+    "pb_window_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                      _P, _P, _P, _P, _P]),
+    "pb_column_profile_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "pb_column_profile": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
+}
+
+_lib = None
+
+
+class PlastidB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PlastidB200Error(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C plastid_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc):
+    if rc != PB_OK:
+        raise PlastidB200Error("libplastid_b200 error %d: %s" % (rc, lib().pb_last_error().decode()))
+
+
+def require_cuda():
+    """The product path has no CPU fallback: fail loudly without a device."""
+    import torch
+    if not torch.cuda.is_available() or lib().pb_device_count() < 1:
+        raise PlastidB200Error("plastid_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,116 @@
+// pb_common.cuh — shared device helpers for libplastid_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "plastid_b200.h"
+
+#define PB_META_L(m)    ((int)((m) & 0xFFFFu))
+#define PB_META_REV(m)  ((int)(((m) >> 16) & 1u))
+#define PB_META_DROP(m) ((int)(((m) >> 17) & 1u))
+#define PB_META_NBLK(m) ((int)((m) >> 24))
+
+void pb_set_error(const char *fmt, ...);
+
+#define PB_CUDA_CHECK(expr)                                                          \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            pb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                         __FILE__, __LINE__);                                        \
+            return PB_ECUDA;                                                         \
+        }                                                                            \
+    } while (0)
+
+// Device-side view of a batch + rule, passed by value as a kernel parameter.
+struct PbReads {
+    const int32_t  *__restrict__ ref_start;
+    const uint32_t *__restrict__ meta;
+    const uint32_t *__restrict__ blk_off;
+    const int2     *__restrict__ blk;
+    const int64_t  *__restrict__ chrom_read_off;
+    int64_t n_reads;
+    int32_t n_chrom;
+    int32_t max_span;
+};
+
+struct PbRuleDev {
+    int32_t kind, param;
+    const int32_t *__restrict__ lut_fw;
+    const int32_t *__restrict__ lut_rc;
+    int32_t size_min, size_max, strat_min, strat_max;
+};
+
+struct PbLayoutDev {
+    const int64_t *__restrict__ chrom_len;
+    const int64_t *__restrict__ chrom_bin_off;
+    int32_t n_chrom;
+};
+
+// SizeFilterFactory (map_factories.pyx:837-839) + host keep-mask.
+__device__ __forceinline__ bool pb_passes(uint32_t m, int size_min, int size_max)
+{
+    if (PB_META_DROP(m)) return false;
+    int L = PB_META_L(m);
+    if (size_min > 0 && !(L >= size_min && (L <= size_max || size_max == -1))) return false;
+    return true;
+}
+
+// Index into read.positions the rule picks when applied left-to-right ("forward": query strand
+// '+' or '.') or right-to-left ("reverse": query strand '-').  Returns -1 when the reference
+// skips the read and raises its DataWarning (map_factories.pyx:351-353, 450-452, 633-636).
+__device__ __forceinline__ int pb_rule_index(const PbRuleDev &r, int L, bool reverse_query)
+{
+    if (r.kind == PB_RULE_VARIABLE) {
+        if (L >= PB_LUT_SIZE) return -1;  // reference: out-of-bounds read; we drop
+        return reverse_query ? __ldg(r.lut_rc + L) : __ldg(r.lut_fw + L);
+    }
+    if (r.param >= L) return -1;
+    bool from_left = (r.kind == PB_RULE_FIVEPRIME) ? !reverse_query : reverse_query;
+    return from_left ? r.param : L - 1 - r.param;
+}
+
+// read.positions[idx] for a multi-block read (CIGAR expansion, pysam get_reference_positions).
+__device__ __forceinline__ int64_t pb_block_position(const PbReads &b, int64_t i, int32_t start, int idx)
+{
+    uint32_t k0 = __ldg(b.blk_off + i), k1 = __ldg(b.blk_off + i + 1);
+    for (uint32_t k = k0; k < k1; ++k) {
+        int2 bl = __ldg(b.blk + k);
+        if (idx < bl.y) return (int64_t)start + bl.x + idx;
+        idx -= bl.y;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int64_t pb_position(const PbReads &b, int64_t i, int32_t start, uint32_t m, int idx)
+{
+    if (PB_META_NBLK(m) <= 1 || b.blk_off == nullptr) return (int64_t)start + idx;
+    return pb_block_position(b, i, start, idx);
+}
+
+// first index in [lo,hi) with a[i] >= key
+__device__ __forceinline__ int64_t pb_lower_bound(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key)
+{
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if ((int64_t)__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// chromosome owning global bin g: last c with chrom_bin_off[c] <= g
+__device__ __forceinline__ int pb_chrom_of_bin(const PbLayoutDev &lay, int64_t g)
+{
+    int lo = 0, hi = lay.n_chrom;  // invariant: off[lo] <= g < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(lay.chrom_bin_off + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ unsigned long long pb_warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}

@@ -1,0 +1,341 @@
+// pb_gather.cu — gather / segmented reductions over SegmentChain exon blocks (sm_100a).
+//
+// Reference semantics restated: SegmentChain.get_counts / get_masked_counts
+// (plastid/genomics/roitools.pyx:3221-3315), the counts_in_region / cs inner loops
+// (plastid/bin/counts_in_region.py:113-125, plastid/bin/cs.py:705-711) and the metagene / psite
+// window matrices and profiles (plastid/bin/metagene.py:895-960, plastid/bin/psite.py:204-234).
+// All of this is HBM/L2-bound gather work: one warp walks one chain with coalesced 128-byte
+// reads of the dense count plane.
+#include "pb_common.cuh"
+#include <math.h>
+
+namespace {
+
+struct PbPlanes { const void *p[3]; };
+
+template <typename T> struct Acc;
+template <> struct Acc<uint32_t> { typedef unsigned long long type; };
+template <> struct Acc<double> { typedef double type; };
+
+__device__ __forceinline__ double pb_warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__device__ __forceinline__ bool pb_mask_bit(const uint8_t *__restrict__ bits, int64_t bit)
+{
+    return (__ldg(bits + (bit >> 3)) >> (bit & 7)) & 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pb_region_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                      const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
+                      int64_t n_chains, const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
+                      double *__restrict__ sums, int64_t *__restrict__ live_len)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chains) return;
+    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(chain_plane + c)]);
+    const int64_t moff = mask_bits ? __ldg(mask_off + c) : 0;
+    typename Acc<T>::type acc = 0;
+    long long live = 0;
+    int64_t j = 0;
+    for (int64_t k = __ldg(chain_off + c); k < __ldg(chain_off + c + 1); ++k) {
+        const int64_t bs = __ldg(bstart + k), be = __ldg(bend + k);
+        for (int64_t p = bs + lane; p < be; p += 32) {
+            if (mask_bits && pb_mask_bit(mask_bits, moff + j + (p - bs))) continue;
+            acc += vec[p];
+            live++;
+        }
+        j += be - bs;
+    }
+    live = (long long)pb_warp_sum((unsigned long long)live);
+    double total;
+    if (sizeof(T) == 4) total = (double)pb_warp_sum((unsigned long long)acc);
+    else total = pb_warp_sum_f64((double)acc);
+    if (lane == 0) { sums[c] = total; live_len[c] = live; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pb_gather_windows_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                         const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
+                         const uint8_t *__restrict__ chain_reverse, const int32_t *__restrict__ row_col,
+                         int64_t n_chains, int32_t width,
+                         const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
+                         double *__restrict__ matrix, uint8_t *__restrict__ maskmat)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chains) return;
+    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(chain_plane + c)]);
+    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
+    int64_t len = 0;
+    for (int64_t k = k0; k < k1; ++k) len += __ldg(bend + k) - __ldg(bstart + k);
+    const int64_t col0 = __ldg(row_col + c);
+    const bool rev = __ldg(chain_reverse + c);
+    const int64_t moff = mask_bits ? __ldg(mask_off + c) : 0;
+    double *row = matrix + c * (int64_t)width;
+    uint8_t *mrow = maskmat + c * (int64_t)width;
+    // columns no chain position reaches stay "masked NaN" (metagene.py:895-898)
+    for (int64_t col = lane; col < width; col += 32) {
+        if (col < col0 || col >= col0 + len) { row[col] = nan(""); mrow[col] = 1; }
+    }
+    int64_t j = 0;
+    for (int64_t k = k0; k < k1; ++k) {
+        const int64_t bs = __ldg(bstart + k), be = __ldg(bend + k);
+        for (int64_t p = bs + lane; p < be; p += 32) {
+            const int64_t jj = j + (p - bs);
+            const int64_t col = col0 + (rev ? (len - 1 - jj) : jj);
+            if (col >= 0 && col < width) {
+                row[col] = (double)vec[p];
+                mrow[col] = mask_bits ? (uint8_t)pb_mask_bit(mask_bits, moff + jj) : (uint8_t)0;
+            }
+        }
+        j += be - bs;
+    }
+}
+
+// one warp per row: denominator, selection, normalisation (metagene.py:918-924)
+__global__ void __launch_bounds__(256)
+pb_window_normalize_kernel(const double *__restrict__ matrix, const uint8_t *__restrict__ maskmat,
+                           int64_t n_rows, int32_t width, int32_t norm_lo, int32_t norm_hi, double min_counts,
+                           double *__restrict__ denom, uint8_t *__restrict__ row_select,
+                           double *__restrict__ norm, uint8_t *__restrict__ normmask)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const double *row = matrix + r * (int64_t)width;
+    const uint8_t *mrow = maskmat + r * (int64_t)width;
+    double acc = 0.0;
+    unsigned long long live = 0;
+    for (int col = norm_lo + lane; col < norm_hi; col += 32) {
+        if (col >= 0 && col < width && !mrow[col]) { acc += row[col]; live++; }
+    }
+    acc = pb_warp_sum_f64(acc);
+    live = pb_warp_sum(live);
+    const bool den_masked = (live == 0);  // nansum of an all-masked slice is the masked constant
+    const double d = den_masked ? nan("") : acc;
+    if (lane == 0) {
+        denom[r] = d;
+        row_select[r] = (!den_masked && acc >= min_counts) ? 1 : 0;
+    }
+    if (norm) {
+        for (int col = lane; col < width; col += 32) {
+            const double v = row[col] / d;
+            norm[r * (int64_t)width + col] = v;
+            normmask[r * (int64_t)width + col] = (mrow[col] || den_masked || isnan(v) || isinf(v)) ? 1 : 0;
+        }
+    }
+}
+
+// order-preserving map double -> uint64
+__device__ __forceinline__ unsigned long long pb_key_of(double v)
+{
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double pb_value_of(unsigned long long k)
+{
+    unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+// transpose selected, unmasked cells into per-column key lists; invalid cells become the max key
+__global__ void pb_column_keys_kernel(const double *__restrict__ norm, const uint8_t *__restrict__ normmask,
+                                      const uint8_t *__restrict__ row_select, int64_t n_rows, int32_t width,
+                                      unsigned long long *__restrict__ keys)
+{
+    __shared__ unsigned long long tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.y * 32;
+    const int c0 = blockIdx.x * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int64_t r = r0 + dy;
+        const int col = c0 + threadIdx.x;
+        unsigned long long k = ~0ull;
+        if (r < n_rows && col < width && row_select[r] && !normmask[r * (int64_t)width + col])
+            k = pb_key_of(norm[r * (int64_t)width + col]);
+        tile[dy][threadIdx.x] = k;
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int col = c0 + dy;
+        const int64_t r = r0 + threadIdx.x;
+        if (col < width && r < n_rows) keys[(int64_t)col * n_rows + r] = tile[threadIdx.x][dy];
+    }
+}
+
+// One CTA per column: count / sum of valid cells, and the two middle order statistics by
+// 8-bit-digit radix select (exact; numpy.ma.median averages the two middle values).
+__global__ void __launch_bounds__(512)
+pb_column_stats_kernel(const unsigned long long *__restrict__ keys, int64_t n_rows, int32_t width, int mode,
+                       double *__restrict__ profile, int64_t *__restrict__ n_regions, double *__restrict__ col_sum)
+{
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_cnt;
+    __shared__ double s_sum[16];
+    __shared__ unsigned long long s_prefix, s_rank;
+    const int col = blockIdx.x;
+    const unsigned long long *__restrict__ K = keys + (int64_t)col * n_rows;
+
+    // valid count + deterministic sum
+    unsigned long long cnt = 0;
+    double sum = 0.0;
+    for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        const unsigned long long k = K[r];
+        if (k != ~0ull) { cnt++; sum += pb_value_of(k); }
+    }
+    cnt = pb_warp_sum(cnt);
+    sum = pb_warp_sum_f64(sum);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt, cnt); s_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    const unsigned long long n_valid = s_cnt;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_sum[w];
+        n_regions[col] = (int64_t)n_valid;
+        col_sum[col] = t;
+        if (mode == 1) profile[col] = n_valid ? t / (double)n_valid : nan("");
+        if (mode == 2) profile[col] = t;
+    }
+    if (mode != 0) return;
+    if (n_valid == 0) { if (threadIdx.x == 0) profile[col] = nan(""); return; }
+
+    double mid[2];
+    for (int which = 0; which < 2; ++which) {
+        // ranks (0-based) of the two middle elements: (n-1)/2 and n/2
+        unsigned long long rank = which == 0 ? (n_valid - 1) / 2 : n_valid / 2;
+        unsigned long long prefix = 0;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
+            __syncthreads();
+            const unsigned long long himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+            for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+                const unsigned long long k = K[r];
+                if (k != ~0ull && (k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long run = 0;
+                int d = 0;
+                for (; d < 256; ++d) {
+                    if (run + hist[d] > rank) break;
+                    run += hist[d];
+                }
+                s_prefix = prefix | ((unsigned long long)d << shift);
+                s_rank = rank - run;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            rank = s_rank;
+            __syncthreads();
+        }
+        mid[which] = pb_value_of(prefix);
+    }
+    if (threadIdx.x == 0) profile[col] = (mid[0] + mid[1]) / 2.0;
+}
+
+}  // namespace
+
+static int check_chains(const void *const *planes, const int64_t *bstart, const int64_t *bend,
+                        const int64_t *chain_off, const uint8_t *chain_plane, int64_t n_chains,
+                        const uint8_t *mask_bits, const int64_t *mask_off, int vec_dtype)
+{
+    if (!planes || !bstart || !bend || !chain_off || !chain_plane) { pb_set_error("gather: null chain tables"); return PB_EINVAL; }
+    if (n_chains < 0) { pb_set_error("gather: negative chain count"); return PB_EINVAL; }
+    if (mask_bits && !mask_off) { pb_set_error("gather: mask_bits without mask_off"); return PB_EINVAL; }
+    if (vec_dtype != 0 && vec_dtype != 1) { pb_set_error("gather: vec_dtype must be 0 (uint32) or 1 (float64)"); return PB_EINVAL; }
+    return PB_OK;
+}
+
+extern "C" int pb_region_sums(const void *const *planes, int vec_dtype,
+                              const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                              const uint8_t *chain_plane, int64_t n_chains,
+                              const uint8_t *mask_bits, const int64_t *mask_off,
+                              double *sums, int64_t *live_len, void *stream_)
+{
+    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype);
+    if (rc) return rc;
+    if (!sums || !live_len) { pb_set_error("pb_region_sums: null outputs"); return PB_EINVAL; }
+    if (n_chains == 0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbPlanes pl{{planes[0], planes[1], planes[2]}};
+    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
+    if (vec_dtype == 0)
+        pb_region_sums_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, sums, live_len);
+    else
+        pb_region_sums_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, sums, live_len);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_gather_windows(const void *const *planes, int vec_dtype,
+                                 const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                 const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                 const int32_t *row_col, int64_t n_chains, int32_t width,
+                                 const uint8_t *mask_bits, const int64_t *mask_off,
+                                 double *matrix, uint8_t *maskmat, void *stream_)
+{
+    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype);
+    if (rc) return rc;
+    if (!chain_reverse || !row_col || !matrix || !maskmat || width <= 0) { pb_set_error("pb_gather_windows: bad arguments"); return PB_EINVAL; }
+    if (n_chains == 0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbPlanes pl{{planes[0], planes[1], planes[2]}};
+    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
+    if (vec_dtype == 0)
+        pb_gather_windows_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, row_col, n_chains, width, mask_bits, mask_off, matrix, maskmat);
+    else
+        pb_gather_windows_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, row_col, n_chains, width, mask_bits, mask_off, matrix, maskmat);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_window_normalize(const double *matrix, const uint8_t *maskmat, int64_t n_rows, int32_t width,
+                                   int32_t norm_lo, int32_t norm_hi, double min_counts,
+                                   double *denom, uint8_t *row_select, double *norm_out, uint8_t *normmask_out,
+                                   void *stream_)
+{
+    if (!matrix || !maskmat || !denom || !row_select || n_rows < 0 || width <= 0) { pb_set_error("pb_window_normalize: bad arguments"); return PB_EINVAL; }
+    if ((norm_out == nullptr) != (normmask_out == nullptr)) { pb_set_error("pb_window_normalize: norm_out and normmask_out go together"); return PB_EINVAL; }
+    if (n_rows == 0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const unsigned grid = (unsigned)((n_rows * 32 + 255) / 256);
+    pb_window_normalize_kernel<<<grid, 256, 0, stream>>>(matrix, maskmat, n_rows, width, norm_lo, norm_hi, min_counts, denom, row_select, norm_out, normmask_out);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" size_t pb_column_profile_workspace_bytes(int64_t n_rows, int32_t width)
+{
+    if (n_rows < 0 || width < 0) return 0;
+    return (size_t)n_rows * (size_t)width * sizeof(unsigned long long) + 256;
+}
+
+extern "C" int pb_column_profile(const double *values, const uint8_t *valmask, const uint8_t *row_select,
+                                 int64_t n_rows, int32_t width, int mode,
+                                 double *profile, int64_t *n_regions, double *col_sum,
+                                 void *workspace, size_t workspace_bytes, void *stream_)
+{
+    if (!values || !valmask || !row_select || !profile || !n_regions || !col_sum || n_rows < 0 || width <= 0 || mode < 0 || mode > 2) {
+        pb_set_error("pb_column_profile: bad arguments"); return PB_EINVAL;
+    }
+    if (!workspace || workspace_bytes < pb_column_profile_workspace_bytes(n_rows, width)) { pb_set_error("pb_column_profile: workspace too small"); return PB_ENOSPACE; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *keys = (unsigned long long *)workspace;
+    if (n_rows > 0) {
+        dim3 grid((unsigned)((width + 31) / 32), (unsigned)((n_rows + 31) / 32));
+        if (grid.y > 65535) { pb_set_error("pb_column_profile: more than 2,097,120 rows"); return PB_EINVAL; }
+        pb_column_keys_kernel<<<grid, dim3(32, 8), 0, stream>>>(values, valmask, row_select, n_rows, width, keys);
+    }
+    pb_column_stats_kernel<<<(unsigned)width, 512, 0, stream>>>(keys, n_rows, width, mode, profile, n_regions, col_sum);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}

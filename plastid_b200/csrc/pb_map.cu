@@ -1,0 +1,659 @@
+// pb_map.cu — alignments -> mapping rule -> dense per-strand count planes (sm_100a).
+//
+// Design ("owner computes", no global atomics, no memset pass): the concatenated genome is
+// cut into position tiles; one CTA owns one tile, keeps the tile's bins for every requested
+// query strand in shared memory, scans only the slice of the coordinate-sorted batch whose
+// reads can land in the tile (slice bounds come from pb_tile_index_kernel), applies the
+// mapping rule per read, accumulates with shared-memory integer atomics (order independent
+// => bit-exact and deterministic) and writes the finished tile once with 128-bit stores.
+// Tiles with no candidate reads (most of a human genome) skip shared memory and just store
+// zeros, so the same launch is also the memset.
+//
+// Reference semantics restated (plastid/genomics/map_factories.pyx): FivePrime :308-367,
+// ThreePrime :407-466, VariableFivePrime :585-650, Center :200-265, SizeFilter :837-839;
+// strand selection as genome_array.py:811-815.  Query strand '.' applies the FORWARD rule to
+// reads of both strands, so it is its own plane, not '+' + '-'.
+#include "pb_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kStatSlots = 64;  // stats are spread over 64 slots to keep atomics off one address
+
+// ----------------------------------------------------------------------------------------
+// tile -> candidate read slice
+// ----------------------------------------------------------------------------------------
+__global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, int64_t n_tiles,
+                                     int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    int64_t g0 = t * tile_bins;
+    int c = pb_chrom_of_bin(lay, g0);
+    int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
+    int64_t r0 = 0, r1 = 0;
+    if (c < b.n_chrom) { r0 = __ldg(b.chrom_read_off + c); r1 = __ldg(b.chrom_read_off + c + 1); }
+    // a read can only place a site in [p0, p0+T) if p0 - max_span < start < p0 + T
+    int64_t lo = pb_lower_bound(b.ref_start, r0, r1, p0 - b.max_span + 1);
+    int64_t hi = pb_lower_bound(b.ref_start, lo, r1, p0 + tile_bins);
+    tile_lo[t] = lo;
+    tile_hi[t] = hi;
+}
+
+__device__ __forceinline__ void pb_store_zero_tile(uint32_t *out, int64_t g0, int tile_bins)
+{
+    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + g0);
+    for (int j = threadIdx.x; j < tile_bins / 4; j += kThreads) dst[j] = z;
+}
+
+__device__ __forceinline__ void pb_flush_stats(const unsigned long long *local, unsigned int *s_stats,
+                                               unsigned long long *stat_slots, int64_t tile)
+{
+    // block-level reduce in shared memory, then one global atomic per non-zero counter
+#pragma unroll
+    for (int k = 0; k < PB_NSTATS; ++k) {
+        if (k == PB_STAT_DROPPED_LEN) continue;
+        unsigned long long v = pb_warp_sum(local[k]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_stats[k], (unsigned int)v);
+    }
+    unsigned int len = (unsigned int)local[PB_STAT_DROPPED_LEN];
+    len = __reduce_max_sync(0xffffffffu, len);
+    if ((threadIdx.x & 31) == 0 && len) atomicMax(&s_stats[PB_STAT_DROPPED_LEN], len);
+    __syncthreads();
+    if (threadIdx.x < PB_NSTATS) {
+        unsigned int v = s_stats[threadIdx.x];
+        if (v) {
+            unsigned long long *dst = stat_slots + (tile & (kStatSlots - 1)) * PB_NSTATS + threadIdx.x;
+            if (threadIdx.x == PB_STAT_DROPPED_LEN) atomicMax(dst, (unsigned long long)v);
+            else atomicAdd(dst, (unsigned long long)v);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// point rules: 5' / 3' / variable offset
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+pb_point_tiles_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int tile_bins, int planes,
+                      const int64_t *__restrict__ tile_lo, const int64_t *__restrict__ tile_hi,
+                      uint32_t *__restrict__ out_plus, uint32_t *__restrict__ out_minus,
+                      uint32_t *__restrict__ out_any, unsigned long long *__restrict__ stat_slots)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ unsigned int s_stats[PB_NSTATS];
+
+    const int64_t tile = blockIdx.x;
+    const int64_t g0 = tile * tile_bins;
+    const int64_t lo = __ldg(tile_lo + tile), hi = __ldg(tile_hi + tile);
+
+    if (lo >= hi) {  // nothing can land here: the launch doubles as the memset
+        if (planes & PB_PLANE_PLUS) pb_store_zero_tile(out_plus, g0, tile_bins);
+        if (planes & PB_PLANE_MINUS) pb_store_zero_tile(out_minus, g0, tile_bins);
+        if (planes & PB_PLANE_ANY) pb_store_zero_tile(out_any, g0, tile_bins);
+        return;
+    }
+
+    const int c = pb_chrom_of_bin(lay, g0);
+    const int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
+    const int64_t p1 = p0 + tile_bins;
+    const int64_t clen = __ldg(lay.chrom_len + c);
+    const int64_t plim = p1 < clen ? p1 : clen;
+
+    uint32_t *sm_plus = smem, *sm_minus = smem, *sm_any = smem;
+    {
+        int k = 0;
+        if (planes & PB_PLANE_PLUS) sm_plus = smem + (k++) * tile_bins;
+        if (planes & PB_PLANE_MINUS) sm_minus = smem + (k++) * tile_bins;
+        if (planes & PB_PLANE_ANY) sm_any = smem + (k++) * tile_bins;
+        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *s4 = reinterpret_cast<uint4 *>(smem);
+        for (int j = threadIdx.x; j < k * tile_bins / 4; j += kThreads) s4[j] = z;
+    }
+    if (threadIdx.x < PB_NSTATS) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    unsigned long long local[PB_NSTATS];
+#pragma unroll
+    for (int k = 0; k < PB_NSTATS; ++k) local[k] = 0;
+
+    const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
+               want_any = planes & PB_PLANE_ANY;
+
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+        const int32_t s = __ldg(b.ref_start + i);
+        const uint32_t m = __ldg(b.meta + i);
+        if (!pb_passes(m, r.size_min, r.size_max)) continue;
+        const int L = PB_META_L(m);
+        const bool rev = PB_META_REV(m);
+        const int idx_f = pb_rule_index(r, L, false);
+        if (idx_f < 0) {
+            // the reference skips this read and warns; count it once, in the tile owning its start
+            if (s >= p0 && s < p1) {
+                local[PB_STAT_DROPPED_ANY]++;
+                local[rev ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_PLUS]++;
+                local[PB_STAT_DROPPED_LEN] = L;
+            }
+            continue;
+        }
+        if (want_any || (!rev && want_plus)) {
+            const int64_t p = pb_position(b, i, s, m, idx_f);
+            if (p >= p0 && p < plim) {
+                const unsigned o = (unsigned)(p - p0);
+                if (want_any) { atomicAdd(&sm_any[o], 1u); local[PB_STAT_MAPPED_ANY]++; }
+                if (!rev && want_plus) { atomicAdd(&sm_plus[o], 1u); local[PB_STAT_MAPPED_PLUS]++; }
+            }
+        }
+        if (rev && want_minus) {
+            const int idx_r = pb_rule_index(r, L, true);
+            const int64_t p = pb_position(b, i, s, m, idx_r);
+            if (p >= p0 && p < plim) {
+                atomicAdd(&sm_minus[(unsigned)(p - p0)], 1u);
+                local[PB_STAT_MAPPED_MINUS]++;
+            }
+        }
+    }
+    pb_flush_stats(local, s_stats, stat_slots, tile);  // contains the __syncthreads() the stores need
+
+    {
+        int k = 0;
+        uint32_t *outs[3];
+        if (want_plus) outs[k++] = out_plus;
+        if (want_minus) outs[k++] = out_minus;
+        if (want_any) outs[k++] = out_any;
+        for (int q = 0; q < k; ++q) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(smem + q * tile_bins);
+            uint4 *dst = reinterpret_cast<uint4 *>(outs[q] + g0);
+            for (int j = threadIdx.x; j < tile_bins / 4; j += kThreads) dst[j] = src[j];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// center rule: integer difference arrays per map length, exact scan, fixed-order fp64 combine
+// ----------------------------------------------------------------------------------------
+// Shared layout: diff[plane][slot][tile_bins] int32.  Every read adds +1 at the first bin of each
+// trimmed aligned interval and -1 one past its end (clipped to the tile); an inclusive scan gives
+// the number of reads of that map length covering each bin; the bin value is
+// sum_slot cover[slot] * (1.0 / map_length[slot]) evaluated in ascending map-length order.
+template <int EPT>  // bins per thread = tile_bins / kThreads
+__global__ void __launch_bounds__(kThreads)
+pb_center_tiles_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes,
+                       const int16_t *__restrict__ slot_of_len, const double *__restrict__ inv_m,
+                       int slot0, int n_slots, int accumulate,
+                       const int64_t *__restrict__ tile_lo, const int64_t *__restrict__ tile_hi,
+                       double *__restrict__ out_plus, double *__restrict__ out_minus,
+                       double *__restrict__ out_any, unsigned long long *__restrict__ stat_slots)
+{
+    constexpr int tile_bins = EPT * kThreads;
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ unsigned int s_stats[PB_NSTATS];
+
+    const int64_t tile = blockIdx.x;
+    const int64_t g0 = tile * tile_bins;
+    const int64_t lo = __ldg(tile_lo + tile), hi = __ldg(tile_hi + tile);
+    const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
+               want_any = planes & PB_PLANE_ANY;
+    const int n_planes = (int)want_plus + (int)want_minus + (int)want_any;
+    double *outs[3];
+    {
+        int k = 0;
+        if (want_plus) outs[k++] = out_plus;
+        if (want_minus) outs[k++] = out_minus;
+        if (want_any) outs[k++] = out_any;
+    }
+
+    if (lo >= hi) {
+        if (!accumulate) {
+            for (int q = 0; q < n_planes; ++q) {
+                double2 *dst = reinterpret_cast<double2 *>(outs[q] + g0);
+                for (int j = threadIdx.x; j < tile_bins / 2; j += kThreads) dst[j] = make_double2(0.0, 0.0);
+            }
+        }
+        return;
+    }
+
+    const int c = pb_chrom_of_bin(lay, g0);
+    const int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
+    const int64_t p1 = p0 + tile_bins;
+    const int64_t clen = __ldg(lay.chrom_len + c);
+    const int64_t plim = p1 < clen ? p1 : clen;
+
+    int *diff = reinterpret_cast<int *>(smem);
+    int *warp_tot = diff + n_planes * n_slots * tile_bins;  // [n_planes*n_slots][kWarps]
+    {
+        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *s4 = reinterpret_cast<uint4 *>(smem);
+        for (int j = threadIdx.x; j < n_planes * n_slots * tile_bins / 4; j += kThreads) s4[j] = z;
+    }
+    if (threadIdx.x < PB_NSTATS) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    int *d_plus = diff, *d_minus = diff, *d_any = diff;
+    {
+        int k = 0;
+        if (want_plus) d_plus = diff + (k++) * n_slots * tile_bins;
+        if (want_minus) d_minus = diff + (k++) * n_slots * tile_bins;
+        if (want_any) d_any = diff + (k++) * n_slots * tile_bins;
+    }
+
+    unsigned long long local[PB_NSTATS];
+#pragma unroll
+    for (int k = 0; k < PB_NSTATS; ++k) local[k] = 0;
+    const int nibble = r.param;
+
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+        const int32_t s = __ldg(b.ref_start + i);
+        const uint32_t m = __ldg(b.meta + i);
+        if (!pb_passes(m, r.size_min, r.size_max)) continue;
+        const int L = PB_META_L(m);
+        const bool rev = PB_META_REV(m);
+        const bool own = (s >= p0 && s < p1);
+        const int map_len = L - 2 * nibble;
+        if (map_len < 0) {  // map_factories.pyx:246-248
+            if (own) {
+                local[PB_STAT_DROPPED_ANY]++;
+                local[rev ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_PLUS]++;
+                local[PB_STAT_DROPPED_LEN] = L;
+            }
+            continue;
+        }
+        if (map_len == 0) continue;
+        if (own) {  // every mapped read is counted once (reads_out semantics, :256)
+            local[PB_STAT_MAPPED_ANY]++;
+            local[rev ? PB_STAT_MAPPED_MINUS : PB_STAT_MAPPED_PLUS]++;
+        }
+        const int slot = (int)__ldg(slot_of_len + L) - slot0;
+        if (slot < 0 || slot >= n_slots) continue;  // handled by another pass
+        const int so = slot * tile_bins;
+        const bool do_strand = rev ? want_minus : want_plus;
+        int *d_strand = (rev ? d_minus : d_plus) + so;
+        int *d_all = d_any + so;
+
+        auto add_interval = [&](int64_t x, int64_t y) {  // aligned reference interval [x,y)
+            if (y <= p0 || x >= plim) return;
+            const unsigned ox = (unsigned)((x > p0 ? x : p0) - p0);
+            if (do_strand) atomicAdd(&d_strand[ox], 1);
+            if (want_any) atomicAdd(&d_all[ox], 1);
+            if (y < p1) {
+                const unsigned oy = (unsigned)(y - p0);
+                if (do_strand) atomicAdd(&d_strand[oy], -1);
+                if (want_any) atomicAdd(&d_all[oy], -1);
+            }
+        };
+
+        if (PB_META_NBLK(m) <= 1 || b.blk_off == nullptr) {
+            add_interval((int64_t)s + nibble, (int64_t)s + L - nibble);
+        } else {
+            const uint32_t k0 = __ldg(b.blk_off + i), k1 = __ldg(b.blk_off + i + 1);
+            int a = 0;  // aligned-base index of the block's first base
+            for (uint32_t k = k0; k < k1; ++k) {
+                const int2 bl = __ldg(b.blk + k);
+                const int ia = a > nibble ? a : nibble;
+                const int ib = (a + bl.y) < (L - nibble) ? (a + bl.y) : (L - nibble);
+                if (ia < ib) add_interval((int64_t)s + bl.x + (ia - a), (int64_t)s + bl.x + (ib - a));
+                a += bl.y;
+            }
+        }
+    }
+    pb_flush_stats(local, s_stats, stat_slots, tile);  // includes __syncthreads()
+
+    // pass 1: per-warp segment totals for every (plane, slot)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int seg = tile_bins / kWarps;  // bins per warp = EPT * 32
+    const int n_arrays = n_planes * n_slots;
+    for (int a = 0; a < n_arrays; ++a) {
+        const int *A = diff + a * tile_bins + warp * seg;
+        int t = 0;
+#pragma unroll
+        for (int ch = 0; ch < EPT; ++ch) t += A[ch * 32 + lane];
+        t = __reduce_add_sync(0xffffffffu, t);
+        if (lane == 0) warp_tot[a * kWarps + warp] = t;
+    }
+    __syncthreads();
+
+    // pass 2: scan + combine, plane by plane
+    for (int q = 0; q < n_planes; ++q) {
+        double acc[EPT];
+#pragma unroll
+        for (int ch = 0; ch < EPT; ++ch) acc[ch] = 0.0;
+        for (int sl = 0; sl < n_slots; ++sl) {
+            const int a = q * n_slots + sl;
+            const int *A = diff + a * tile_bins + warp * seg;
+            int carry = (lane < warp) ? warp_tot[a * kWarps + lane] : 0;  // kWarps <= 32
+            carry = __reduce_add_sync(0xffffffffu, carry);
+            const double w = __ldg(inv_m + slot0 + sl);
+#pragma unroll
+            for (int ch = 0; ch < EPT; ++ch) {
+                int v = A[ch * 32 + lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int u = __shfl_up_sync(0xffffffffu, v, d);
+                    if (lane >= d) v += u;
+                }
+                v += carry;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+                acc[ch] += (double)v * w;
+            }
+        }
+        double *dst = outs[q] + g0 + warp * seg;
+#pragma unroll
+        for (int ch = 0; ch < EPT; ++ch) {
+            if (accumulate) dst[ch * 32 + lane] += acc[ch];
+            else dst[ch * 32 + lane] = acc[ch];
+        }
+    }
+}
+
+__global__ void pb_stats_finish_kernel(const unsigned long long *__restrict__ slots,
+                                       unsigned long long *__restrict__ stats)
+{
+    int k = threadIdx.x;
+    if (k >= PB_NSTATS) return;
+    unsigned long long v = 0;
+    for (int s = 0; s < kStatSlots; ++s) {
+        unsigned long long x = slots[s * PB_NSTATS + k];
+        if (k == PB_STAT_DROPPED_LEN) v = x > v ? x : v; else v += x;
+    }
+    if (k == PB_STAT_DROPPED_LEN) { if (v) stats[k] = v; }
+    else stats[k] += v;
+}
+
+// ----------------------------------------------------------------------------------------
+// the operator on one segment (global atomics; small inputs)
+// ----------------------------------------------------------------------------------------
+__global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1, int strand,
+                                  int64_t seg_start, int64_t seg_end,
+                                  unsigned long long *counts_i, double *counts_f,
+                                  uint8_t *__restrict__ kept, unsigned long long *__restrict__ stats)
+{
+    const int64_t n = seg_end - seg_start;
+    const bool rq = (strand == PB_PLANE_MINUS);
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t s = __ldg(b.ref_start + i);
+        const uint32_t m = __ldg(b.meta + i);
+        uint8_t keep = 0;
+        const bool rev = PB_META_REV(m);
+        bool pass = pb_passes(m, r.size_min, r.size_max);
+        if (strand == PB_PLANE_PLUS && rev) pass = false;    // genome_array.py:811-815
+        if (strand == PB_PLANE_MINUS && !rev) pass = false;
+        if (pass) {
+            const int L = PB_META_L(m);
+            const int sidx = strand == PB_PLANE_PLUS ? PB_STAT_DROPPED_PLUS
+                           : strand == PB_PLANE_MINUS ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_ANY;
+            if (r.kind == PB_RULE_CENTER) {
+                const int nib = r.param, map_len = L - 2 * nib;
+                if (map_len < 0) {
+                    atomicAdd(&stats[sidx], 1ull);
+                    stats[PB_STAT_DROPPED_LEN] = L;
+                } else if (map_len > 0) {
+                    const double v = 1.0 / map_len;
+                    for (int k = nib; k < L - nib; ++k) {
+                        const int64_t cpos = pb_position(b, i, s, m, k) - seg_start;
+                        if (cpos >= 0 && cpos < n) atomicAdd(&counts_f[cpos], v);
+                    }
+                    keep = 1;
+                }
+            } else if (r.kind == PB_RULE_STRATIFIED) {
+                if (L >= r.strat_min && L <= r.strat_max && L < PB_LUT_SIZE) {
+                    int off = rq ? __ldg(r.lut_rc + L) : __ldg(r.lut_fw + L);
+                    if (off < 0) off += L;  // map_factories.pyx:773-774: no BAD_OFFSET test, python index -1
+                    const int64_t p = pb_position(b, i, s, m, off);
+                    if (p >= seg_start && p < seg_end) {
+                        atomicAdd(&counts_i[(int64_t)(L - r.strat_min) * n + (p - seg_start)], 1ull);
+                        keep = 1;
+                    }
+                }
+            } else {
+                const int idx = pb_rule_index(r, L, rq);
+                if (idx < 0) {
+                    atomicAdd(&stats[sidx], 1ull);
+                    stats[PB_STAT_DROPPED_LEN] = L;
+                } else {
+                    const int64_t p = pb_position(b, i, s, m, idx);
+                    if (p >= seg_start && p < seg_end) {
+                        atomicAdd(&counts_i[p - seg_start], 1ull);
+                        keep = 1;
+                    }
+                }
+            }
+        }
+        if (kept) kept[i - i0] = keep;
+    }
+}
+
+__global__ void pb_length_hist_kernel(PbReads b, PbRuleDev r, int strand, unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[1024];
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) sh[j] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = __ldg(b.meta + i);
+        if (!pb_passes(m, r.size_min, r.size_max)) continue;
+        const bool rev = PB_META_REV(m);
+        if (strand == PB_PLANE_PLUS && rev) continue;
+        if (strand == PB_PLANE_MINUS && !rev) continue;
+        const int L = PB_META_L(m);
+        if (L < 1024) atomicAdd(&sh[L], 1u); else atomicAdd(&hist[L], 1ull);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x)
+        if (sh[j]) atomicAdd(&hist[j], (unsigned long long)sh[j]);
+}
+
+PbReads to_dev(const pb_batch *b)
+{
+    PbReads d;
+    d.ref_start = b->ref_start;
+    d.meta = b->meta;
+    d.blk_off = b->blk_off;
+    d.blk = reinterpret_cast<const int2 *>(b->blk);
+    d.chrom_read_off = b->chrom_read_off;
+    d.n_reads = b->n_reads;
+    d.n_chrom = b->n_chrom;
+    d.max_span = b->max_span < 1 ? 1 : b->max_span;
+    return d;
+}
+
+PbRuleDev to_dev(const pb_rule *r)
+{
+    PbRuleDev d;
+    d.kind = r->kind; d.param = r->param;
+    d.lut_fw = r->lut_fw; d.lut_rc = r->lut_rc;
+    d.size_min = r->size_min; d.size_max = r->size_max;
+    d.strat_min = r->strat_min; d.strat_max = r->strat_max;
+    return d;
+}
+
+int check_common(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes)
+{
+    if (!batch || !layout || !rule) { pb_set_error("null batch/layout/rule"); return PB_EINVAL; }
+    if (planes <= 0 || planes > 7) { pb_set_error("planes must be a non-empty mask of PB_PLANE_*"); return PB_EINVAL; }
+    if (batch->n_reads < 0 || (batch->n_reads > 0 && (!batch->ref_start || !batch->meta))) {
+        pb_set_error("batch arrays missing"); return PB_EINVAL;
+    }
+    if (batch->n_chrom != layout->n_chrom || !batch->chrom_read_off) {
+        pb_set_error("batch/layout chromosome tables disagree"); return PB_EINVAL;
+    }
+    if (layout->total_bins <= 0 || layout->total_bins % PB_LAYOUT_ALIGN) {
+        pb_set_error("layout.total_bins must be a positive multiple of PB_LAYOUT_ALIGN"); return PB_EINVAL;
+    }
+    if ((batch->blk_off == nullptr) != (batch->blk == nullptr)) {
+        pb_set_error("blk_off and blk must both be given or both be NULL"); return PB_EINVAL;
+    }
+    return PB_OK;
+}
+
+size_t tile_index_bytes(int64_t total_bins) { return (size_t)(total_bins / 1024 + 1) * 2 * sizeof(int64_t); }
+size_t stat_slot_bytes() { return (size_t)kStatSlots * PB_NSTATS * sizeof(unsigned long long); }
+
+}  // namespace
+
+extern "C" size_t pb_map_workspace_bytes(int64_t total_bins)
+{
+    if (total_bins < 0) return 0;
+    return tile_index_bytes(total_bins) + 2 * stat_slot_bytes() + 256;
+}
+
+extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                            uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
+                            uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    int rc = check_common(batch, layout, rule, planes);
+    if (rc) return rc;
+    if (rule->kind != PB_RULE_FIVEPRIME && rule->kind != PB_RULE_THREEPRIME && rule->kind != PB_RULE_VARIABLE) {
+        pb_set_error("pb_map_point: rule kind %d is not a point rule", rule->kind); return PB_EINVAL;
+    }
+    if (rule->kind == PB_RULE_VARIABLE && (!rule->lut_fw || !rule->lut_rc)) {
+        pb_set_error("pb_map_point: variable rule needs lut_fw/lut_rc"); return PB_EINVAL;
+    }
+    if (rule->kind != PB_RULE_VARIABLE && rule->param < 0) {
+        pb_set_error("pb_map_point: offset must be >= 0"); return PB_EINVAL;
+    }
+    if (((planes & PB_PLANE_PLUS) && !out_plus) || ((planes & PB_PLANE_MINUS) && !out_minus) ||
+        ((planes & PB_PLANE_ANY) && !out_any) || !stats) {
+        pb_set_error("pb_map_point: missing output plane or stats"); return PB_EINVAL;
+    }
+    if (workspace_bytes < pb_map_workspace_bytes(layout->total_bins) || !workspace) {
+        pb_set_error("pb_map_point: workspace too small"); return PB_ENOSPACE;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int tile_bins = 8192;
+    const int64_t n_tiles = layout->total_bins / tile_bins;
+    int64_t *tile_lo = (int64_t *)workspace;
+    int64_t *tile_hi = tile_lo + (layout->total_bins / 1024 + 1);
+    unsigned long long *slots = (unsigned long long *)((char *)workspace + tile_index_bytes(layout->total_bins));
+    PbReads b = to_dev(batch);
+    PbRuleDev r = to_dev(rule);
+    PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
+
+    PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, stat_slot_bytes(), stream));
+    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, n_tiles, tile_lo, tile_hi);
+    const int n_planes = __builtin_popcount(planes);
+    const size_t smem = (size_t)n_planes * tile_bins * sizeof(uint32_t);
+    PB_CUDA_CHECK(cudaFuncSetAttribute(pb_point_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pb_point_tiles_kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>(b, r, lay, tile_bins, planes, tile_lo, tile_hi,
+                                                                         out_plus, out_minus, out_any, slots);
+    pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, (unsigned long long *)stats);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+template <int EPT>
+static int launch_center(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes,
+                         const int16_t *slot_of_len, const double *inv_m, int n_slots, int slots_per_pass,
+                         int64_t total_bins, const int64_t *tile_lo, const int64_t *tile_hi,
+                         double *out_plus, double *out_minus, double *out_any,
+                         unsigned long long *slots, cudaStream_t stream)
+{
+    constexpr int tile_bins = EPT * kThreads;
+    const int n_planes = __builtin_popcount(planes);
+    const int64_t n_tiles = total_bins / tile_bins;
+    for (int s0 = 0, pass = 0; s0 < n_slots || pass == 0; s0 += slots_per_pass, ++pass) {
+        const int ns = (n_slots - s0) < slots_per_pass ? (n_slots - s0) : slots_per_pass;
+        const int ns_eff = ns < 1 ? 1 : ns;
+        const size_t smem = ((size_t)n_planes * ns_eff * tile_bins + (size_t)n_planes * ns_eff * kWarps) * sizeof(int);
+        PB_CUDA_CHECK(cudaFuncSetAttribute(pb_center_tiles_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // stats are only accumulated by the first pass (later passes would count reads again)
+        pb_center_tiles_kernel<EPT><<<(unsigned)n_tiles, kThreads, smem, stream>>>(
+            b, r, lay, planes, slot_of_len, inv_m, s0, ns < 0 ? 0 : ns, pass > 0, tile_lo, tile_hi,
+            out_plus, out_minus, out_any, pass == 0 ? slots : slots + kStatSlots * PB_NSTATS);
+        if (n_slots == 0) break;
+    }
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                             const int16_t *slot_of_len, const double *inv_m, int n_slots,
+                             double *out_plus, double *out_minus, double *out_any,
+                             uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    int rc = check_common(batch, layout, rule, planes);
+    if (rc) return rc;
+    if (rule->kind != PB_RULE_CENTER || rule->param < 0) { pb_set_error("pb_map_center: need a center rule with nibble >= 0"); return PB_EINVAL; }
+    if (!slot_of_len || (n_slots > 0 && !inv_m) || n_slots < 0 || n_slots > 32767) { pb_set_error("pb_map_center: bad slot tables"); return PB_EINVAL; }
+    if (((planes & PB_PLANE_PLUS) && !out_plus) || ((planes & PB_PLANE_MINUS) && !out_minus) ||
+        ((planes & PB_PLANE_ANY) && !out_any) || !stats) {
+        pb_set_error("pb_map_center: missing output plane or stats"); return PB_EINVAL;
+    }
+    if (workspace_bytes < pb_map_workspace_bytes(layout->total_bins) || !workspace) {
+        pb_set_error("pb_map_center: workspace too small"); return PB_ENOSPACE;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int64_t *tile_lo = (int64_t *)workspace;
+    int64_t *tile_hi = tile_lo + (layout->total_bins / 1024 + 1);
+    unsigned long long *slots = (unsigned long long *)((char *)workspace + tile_index_bytes(layout->total_bins));
+    PbReads b = to_dev(batch);
+    PbRuleDev r = to_dev(rule);
+    PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
+    const int n_planes = __builtin_popcount(planes);
+
+    // pick the largest tile whose difference arrays fit ~96 KB (two CTAs per SM); if even the
+    // smallest tile cannot hold all slots, run several passes over slot groups.
+    const size_t budget = 96 * 1024;
+    const int ns = n_slots < 1 ? 1 : n_slots;
+    int ept = 16;
+    while (ept > 2 && (size_t)n_planes * ns * ept * kThreads * 4 > budget) ept >>= 1;
+    int per_pass = (int)(budget / ((size_t)n_planes * ept * kThreads * 4));
+    if (per_pass < 1) per_pass = 1;
+    if (per_pass > ns) per_pass = ns;
+    const int tile_bins = ept * kThreads;
+    const int64_t n_tiles = layout->total_bins / tile_bins;
+
+    PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, 2 * stat_slot_bytes(), stream));
+    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, n_tiles, tile_lo, tile_hi);
+    switch (ept) {
+    case 16: rc = launch_center<16>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
+    case 8:  rc = launch_center<8>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
+    case 4:  rc = launch_center<4>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
+    default: rc = launch_center<2>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
+    }
+    if (rc) return rc;
+    pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, (unsigned long long *)stats);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
+                              int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
+                              uint64_t *stats, void *stream_)
+{
+    if (!batch || !rule || !counts_out || !stats) { pb_set_error("pb_map_segment: null argument"); return PB_EINVAL; }
+    if (i0 < 0 || i1 < i0 || i1 > batch->n_reads) { pb_set_error("pb_map_segment: bad read range"); return PB_EINVAL; }
+    if (strand != PB_PLANE_PLUS && strand != PB_PLANE_MINUS && strand != PB_PLANE_ANY) { pb_set_error("pb_map_segment: bad strand"); return PB_EINVAL; }
+    if (seg_end < seg_start) { pb_set_error("pb_map_segment: negative-length segment"); return PB_EINVAL; }
+    if ((rule->kind == PB_RULE_VARIABLE || rule->kind == PB_RULE_STRATIFIED) && (!rule->lut_fw || !rule->lut_rc)) {
+        pb_set_error("pb_map_segment: rule needs lut_fw/lut_rc"); return PB_EINVAL;
+    }
+    if (rule->kind < 0 || rule->kind > PB_RULE_STRATIFIED) { pb_set_error("pb_map_segment: unknown rule"); return PB_EINVAL; }
+    if (i1 == i0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbReads b = to_dev(batch);
+    PbRuleDev r = to_dev(rule);
+    int64_t n = i1 - i0;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    pb_segment_kernel<<<grid, 256, 0, stream>>>(b, r, i0, i1, strand, seg_start, seg_end,
+                                                (unsigned long long *)counts_out, (double *)counts_out, kept_out,
+                                                (unsigned long long *)stats);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_length_hist(const pb_batch *batch, const pb_rule *rule, int strand, uint64_t *hist, void *stream_)
+{
+    if (!batch || !rule || !hist) { pb_set_error("pb_length_hist: null argument"); return PB_EINVAL; }
+    if (batch->n_reads == 0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbReads b = to_dev(batch);
+    PbRuleDev r = to_dev(rule);
+    unsigned grid = (unsigned)((batch->n_reads + 511) / 512);
+    if (grid > 148 * 8) grid = 148 * 8;
+    pb_length_hist_kernel<<<grid, 512, 0, stream>>>(b, r, strand, (unsigned long long *)hist);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}

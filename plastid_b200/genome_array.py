@@ -1,0 +1,611 @@
+"""Count containers: ``BAMGenomeArray``, ``GenomeArray``, ``SparseGenomeArray`` — device resident.
+
+Drop-in for the hot-path surface of ``plastid/genomics/genome_array.py``:
+``BAMGenomeArray`` :582-988 (``set_mapping``, ``add_filter``, ``get``/``__getitem__``,
+``get_reads_and_counts``, ``sum``/``set_sum``/``set_normalize``, ``to_genome_array``) and
+``GenomeArray`` :1354-1611 / ``SparseGenomeArray`` :2134-2298 (``get``/``__setitem__``/``sum``).
+
+Where the reference maps reads lazily per queried segment (one ``fetch`` + Python loop per exon),
+this container lowers the mapping rule ONCE into whole-genome count planes on the GPU
+(``pb_map_point`` / ``pb_map_center``); ``ga[seg]`` is then a slice of a plane and region tables
+are one gather launch.  Equivalence: every mapped site is one of the read's aligned positions, so
+``plane[s:e]`` equals fetch+map over ``[s,e)``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .batch import AlignmentBatch, GenomeLayout, BatchRead
+from .map_factories import (CenterMapFactory, SizeFilterFactory, StratifiedVariableFivePrimeMapFactory,
+                            _MapFactory)
+from .regions import ChainTable
+from .roitools import GenomicSegment, SegmentChain
+
+_STRANDS = ("+", "-", ".")
+
+
+# ---------------------------------------------------------------------------------------------
+# engine: batch -> planes, planes -> tables
+# ---------------------------------------------------------------------------------------------
+class CountPlanes(object):
+    """Dense per-strand count vectors on the device (uint32 for point rules, float64 for center)."""
+
+    def __init__(self, layout, dtype, device):
+        self.layout, self.dtype, self.device = layout, dtype, device
+        self.planes = {}
+        self.stats = np.zeros(_lib.PB_NSTATS, dtype=np.int64)
+
+    def alloc(self, strands):
+        import torch
+        tdtype = torch.float64 if self.dtype == "f64" else torch.int32   # int32 storage viewed as uint32
+        for s in strands:
+            if s not in self.planes:
+                self.planes[s] = torch.empty(self.layout.total_bins, dtype=tdtype, device=self.device)
+
+    def plane_ptrs(self):
+        arr = (C.c_void_p * 3)()
+        for s in _STRANDS:
+            t = self.planes.get(s)
+            arr[_lib.PLANE_INDEX[s]] = None if t is None else t.data_ptr()
+        return arr
+
+    def slice_host(self, strand, chrom, start, end):
+        base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
+        t = self.planes[strand][base + start:base + end].cpu().numpy()
+        if self.dtype == "u32":
+            return t.view(np.uint32).astype(np.int64)
+        return t
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    import torch
+    key = str(device)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), planes=None, sync_stats=True):
+    """Lower ``factory`` over a whole device batch into dense planes for the query ``strands``."""
+    import torch
+    _lib.require_cuda()
+    if not isinstance(factory, _MapFactory) or isinstance(factory, StratifiedVariableFivePrimeMapFactory):
+        raise TypeError("map_batch needs a FivePrime/ThreePrime/VariableFivePrime/Center factory")
+    dev = dbatch.device
+    is_center = isinstance(factory, CenterMapFactory)
+    if planes is None:
+        planes = CountPlanes(layout, "f64" if is_center else "u32", dev)
+    planes.alloc(strands)
+    mask = 0
+    for s in strands:
+        mask |= _lib.STRAND_PLANE[s]
+    L = _lib.lib()
+    ws_bytes = L.pb_map_workspace_bytes(layout.total_bins)
+    ws = _workspace(dev, ws_bytes)
+    stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev)
+    b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
+    outs = [_lib.ptr(planes.planes[s]) if s in strands else None for s in _STRANDS]
+    if is_center:
+        hist = torch.zeros(65536, dtype=torch.int64, device=dev)
+        _lib.check(L.pb_length_hist(C.byref(b), C.byref(rule), _lib.PB_PLANE_ANY, _lib.ptr(hist), _lib.stream_ptr()))
+        slot_of_len, inv_m = factory.slot_tables(hist.cpu().numpy())
+        d_slot = torch.from_numpy(slot_of_len).to(dev)
+        d_inv = torch.from_numpy(inv_m if len(inv_m) else np.zeros(1)).to(dev)
+        _lib.check(L.pb_map_center(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_inv),
+                                   len(inv_m), outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
+                                   _lib.stream_ptr()))
+    else:
+        _lib.check(L.pb_map_point(C.byref(b), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
+                                  _lib.ptr(stats), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+    planes.stats_dev = stats
+    if sync_stats:
+        planes.stats = stats.cpu().numpy()
+    return planes
+
+
+def region_sums(planes, table, out=None):
+    """Masked sums + unmasked lengths for every chain of ``table`` (device tensors returned)."""
+    import torch
+    _lib.require_cuda()
+    dev = planes.device
+    d = table.device(dev)
+    n = table.n_chains
+    sums = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    live = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    ptrs = planes.plane_ptrs()
+    _lib.check(_lib.lib().pb_region_sums(ptrs, 1 if planes.dtype == "f64" else 0, _lib.ptr(d["bstart"]),
+                                         _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]),
+                                         n, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]), _lib.ptr(sums),
+                                         _lib.ptr(live), _lib.stream_ptr()))
+    return sums[:n], live[:n]
+
+
+def gather_windows(planes, table, row_col, width):
+    """Window matrix (n_chains x width, NaN-filled) + mask matrix, rows laid 5'->3'."""
+    import torch
+    _lib.require_cuda()
+    dev = planes.device
+    d = table.device(dev)
+    n = table.n_chains
+    matrix = torch.empty((max(n, 1), width), dtype=torch.float64, device=dev)
+    maskmat = torch.empty((max(n, 1), width), dtype=torch.uint8, device=dev)
+    cols = torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
+    _lib.check(_lib.lib().pb_gather_windows(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
+                                            _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                            _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
+                                            n, width, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
+                                            _lib.ptr(matrix), _lib.ptr(maskmat), _lib.stream_ptr()))
+    return matrix[:n], maskmat[:n]
+
+
+def window_normalize(matrix, maskmat, norm_lo, norm_hi, min_counts, want_norm=True):
+    import torch
+    n, width = matrix.shape
+    dev = matrix.device
+    denom = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    sel = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    norm = torch.empty_like(matrix) if want_norm else None
+    nmask = torch.empty_like(maskmat) if want_norm else None
+    _lib.check(_lib.lib().pb_window_normalize(_lib.ptr(matrix), _lib.ptr(maskmat), n, width, int(norm_lo),
+                                              int(norm_hi), float(min_counts), _lib.ptr(denom), _lib.ptr(sel),
+                                              _lib.ptr(norm), _lib.ptr(nmask), _lib.stream_ptr()))
+    return denom[:n], sel[:n], norm, nmask
+
+
+def column_profile(values, valmask, row_select, mode="median"):
+    """Per-column median / mean / sum over unmasked cells of selected rows."""
+    import torch
+    n, width = values.shape
+    dev = values.device
+    L = _lib.lib()
+    ws_bytes = L.pb_column_profile_workspace_bytes(n, width)
+    ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)
+    profile = torch.empty(width, dtype=torch.float64, device=dev)
+    n_regions = torch.empty(width, dtype=torch.int64, device=dev)
+    col_sum = torch.empty(width, dtype=torch.float64, device=dev)
+    _lib.check(L.pb_column_profile(_lib.ptr(values), _lib.ptr(valmask), _lib.ptr(row_select), n, width,
+                                   {"median": 0, "mean": 1, "sum": 2}[mode], _lib.ptr(profile),
+                                   _lib.ptr(n_regions), _lib.ptr(col_sum), _lib.ptr(ws), ws_bytes,
+                                   _lib.stream_ptr()))
+    return profile, n_regions, col_sum
+
+
+def merge_batches(batches):
+    """One coordinate-sorted batch from several (the reference chains ``fetch`` over all files,
+    genome_array.py:800-809; chromosome lengths take the max over files, :667-672)."""
+    if len(batches) == 1:
+        return batches[0]
+    chroms, lens = [], {}
+    for b in batches:
+        for c, n in zip(b.chroms, b.chrom_len):
+            if c not in lens:
+                chroms.append(c)
+            lens[c] = max(lens.get(c, 0), int(n))
+    index = {c: i for i, c in enumerate(chroms)}
+    cid, start, meta, nblk_rows = [], [], [], []
+    blk_all, any_blk = [], any(b.blk is not None for b in batches)
+    for b in batches:
+        per_read_chrom = np.repeat(np.arange(len(b.chroms)), np.diff(b.chrom_read_off))
+        cid.append(np.asarray([index[c] for c in b.chroms], dtype=np.int64)[per_read_chrom])
+        start.append(b.ref_start)
+        meta.append(b.meta)
+        if any_blk:
+            if b.blk_off is None:
+                nblk_rows.append(np.zeros(len(b), dtype=np.int64))
+            else:
+                nblk_rows.append(np.diff(b.blk_off.astype(np.int64)))
+                blk_all.append(b.blk)
+    cid, start, meta = np.concatenate(cid), np.concatenate(start), np.concatenate(meta)
+    order = np.lexsort((start, cid))
+    blk_off = blk = None
+    if any_blk:
+        rows = np.concatenate(nblk_rows)
+        src_off = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(rows, out=src_off[1:])
+        blk_src = np.concatenate(blk_all) if blk_all else np.zeros((0, 2), dtype=np.int32)
+        blk_off = np.zeros(len(order) + 1, dtype=np.int64)
+        np.cumsum(rows[order], out=blk_off[1:])
+        blk = np.zeros((int(blk_off[-1]), 2), dtype=np.int32)
+        for dst in np.nonzero(rows[order])[0]:
+            src = order[dst]
+            blk[blk_off[dst]:blk_off[dst + 1]] = blk_src[src_off[src]:src_off[src + 1]]
+    counts = np.bincount(cid, minlength=len(chroms))
+    off = np.zeros(len(chroms) + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    out = AlignmentBatch(chroms, [lens[c] for c in chroms], start[order], meta[order], off, blk_off, blk,
+                         mapped=sum(b.mapped for b in batches))
+    if all(b.objects is not None for b in batches):
+        objs = [o for b in batches for o in b.objects]
+        out.objects = [objs[i] for i in order]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BAMGenomeArray
+# ---------------------------------------------------------------------------------------------
+class BAMGenomeArray(object):
+    """``BAMGenomeArray(*sources, mapping=CenterMapFactory())``.
+
+    ``sources`` are :class:`~plastid_b200.batch.AlignmentBatch` objects (what the host decoder
+    produces from a sorted BAM).  BAM paths / ``pysam.AlignmentFile`` handles are accepted when
+    ``pysam`` is importable (it is not in this image) and are decoded once into a batch.
+    """
+
+    def __init__(self, *sources, **kwargs):
+        if len(sources) == 1 and isinstance(sources[0], (list, tuple)):
+            sources = tuple(sources[0])
+        batches = []
+        for src in sources:
+            if isinstance(src, AlignmentBatch):
+                batches.append(src)
+            else:
+                from .bam_io import batch_from_bam
+                batches.append(batch_from_bam(src))
+        if not batches:
+            raise ValueError("BAMGenomeArray needs at least one alignment source")
+        self.batches = batches
+        self.batch = merge_batches(batches)
+        self.device = kwargs.get("device", "cuda")
+        self.map_fn = kwargs.get("mapping", None) or CenterMapFactory()
+        self._strands = _STRANDS
+        self._normalize = False
+        self._chr_lengths = {c: int(n) for c, n in zip(self.batch.chroms, self.batch.chrom_len)}
+        self._chroms = sorted(self._chr_lengths)
+        self.layout = GenomeLayout(self.batch.chroms, self.batch.chrom_len)
+        self._filters = {}
+        self._planes = None
+        self._dbatch = None
+        self._update()
+
+    # -- bookkeeping (genome_array.py:681-758, 930-963) ----------------------------------------
+    def reset_sum(self):
+        self._sum = sum(b.mapped for b in self.batches)
+
+    def _update(self):
+        self.reset_sum()
+        self._planes = None
+
+    def sum(self):
+        return self._sum
+
+    def set_sum(self, val):
+        self._sum = val
+
+    def set_normalize(self, value=True):
+        assert value in (True, False)
+        self._normalize = value
+
+    def add_filter(self, name, func):
+        self._filters[name] = func
+        self._planes = None
+        self._dbatch = None
+
+    def remove_filter(self, name):
+        retval = self._filters.pop(name)
+        self._planes = None
+        self._dbatch = None
+        return retval
+
+    def chroms(self):
+        return self._chroms
+
+    def lengths(self):
+        return self._chr_lengths
+
+    def strands(self):
+        return self._strands
+
+    def get_mapping(self):
+        return self.map_fn.__doc__
+
+    def set_mapping(self, mapping_function):
+        self.map_fn = mapping_function
+        self._update()
+
+    # -- lowering ------------------------------------------------------------------------------
+    def _size_filter(self):
+        """The lowered size filter: intersection of all SizeFilterFactory filters."""
+        smin, smax, have = 1, -1, False
+        for f in self._filters.values():
+            if isinstance(f, SizeFilterFactory):
+                have = True
+                smin = max(smin, f.min_)
+                if f.max_ != -1:
+                    smax = f.max_ if smax == -1 else min(smax, f.max_)
+        if not have:
+            return None
+        if smax != -1 and smax < smin:
+            smax = 0          # empty interval: nothing passes
+            sf = SizeFilterFactory.__new__(SizeFilterFactory)
+            sf.min_, sf.max_ = smin, smax
+            return sf
+        return SizeFilterFactory(smin, smax)
+
+    def _device_batch(self):
+        if self._dbatch is None:
+            hb = self.batch
+            generic = [f for f in self._filters.values() if not isinstance(f, SizeFilterFactory)]
+            if generic:      # arbitrary python predicates cannot be lowered: evaluate once on host
+                keep = np.ones(len(hb), dtype=bool)
+                for i in range(len(hb)):
+                    read = hb.read_view(i)
+                    keep[i] = all(f(read) for f in generic)
+                hb = hb.with_drop_mask(~keep)
+            self._host_batch = hb
+            self._dbatch = hb.to_device(self.device)
+        return self._dbatch
+
+    def _is_lowerable(self):
+        return isinstance(self.map_fn, _MapFactory) and not isinstance(self.map_fn, StratifiedVariableFivePrimeMapFactory)
+
+    def count_planes(self, strands=("+", "-")):
+        """Whole-genome planes for the current mapping rule and filters (computed once, cached)."""
+        if not self._is_lowerable():
+            raise TypeError("mapping function %r cannot be lowered to whole-genome planes" % (self.map_fn,))
+        need = [s for s in strands if self._planes is None or s not in self._planes.planes]
+        if need:
+            self._planes = map_batch(self._device_batch(), self.layout, self.map_fn, self._size_filter(),
+                                     strands=tuple(need), planes=self._planes)
+            st = self._planes.stats
+            if st[_lib.PB_STAT_DROPPED_ANY]:
+                self.map_fn._warn_dropped(int(st[_lib.PB_STAT_DROPPED_ANY]), int(st[_lib.PB_STAT_DROPPED_LEN]))
+        return self._planes
+
+    # -- queries -------------------------------------------------------------------------------
+    def _read_range(self, chrom, start, end):
+        hb = self._host_batch if self._dbatch is not None else self.batch
+        c = self.layout.index[chrom]
+        r0, r1 = int(hb.chrom_read_off[c]), int(hb.chrom_read_off[c + 1])
+        starts = hb.ref_start[r0:r1]
+        lo = r0 + int(np.searchsorted(starts, start - hb.max_span + 1, side="left"))
+        hi = r0 + int(np.searchsorted(starts, end, side="left"))
+        return lo, max(hi, lo)
+
+    def get_reads_and_counts(self, roi, roi_order=True):
+        chrom, strand, start, end = roi.chrom, roi.strand, roi.start, roi.end
+        if chrom not in self._chr_lengths:
+            shape = [1] + getattr(self.map_fn, "shape", [])
+            return [], np.zeros(shape)
+        if not isinstance(self.map_fn, _MapFactory):
+            raise TypeError("only plastid_b200 map factories can be evaluated on the GPU")
+        dbatch = self._device_batch()
+        lo, hi = self._read_range(chrom, start, end)
+        qs = strand if strand in ("+", "-") else "."
+        if hi > lo:
+            counts, kept = self.map_fn.map_segment(dbatch, lo, hi, start, end, qs, self._size_filter())
+            reads = [self._host_batch.read_view(lo + int(i)) for i in np.nonzero(kept)[0]]
+        else:
+            counts = np.zeros(self.map_fn._leading_shape() + [end - start], dtype=self.map_fn.count_dtype)
+            reads = []
+        if self._normalize is True:
+            counts = counts / float(self.sum()) * 1e6
+        if roi_order == True and strand == "-":
+            counts = counts[..., ::-1]
+        return reads, counts
+
+    def get_reads(self, roi):
+        reads, _ = self.get_reads_and_counts(roi)
+        return reads
+
+    def get(self, roi, roi_order=True):
+        if isinstance(roi, SegmentChain):
+            return roi.get_counts(self)
+        if roi.chrom not in self._chr_lengths or not self._is_lowerable():
+            return self.get_reads_and_counts(roi, roi_order=roi_order)[1]
+        qs = roi.strand if roi.strand in ("+", "-") else "."
+        planes = self.count_planes(("+", "-") if qs != "." else (".",))
+        counts = planes.slice_host(qs, roi.chrom, roi.start, roi.end)
+        if self._normalize is True:
+            counts = counts / float(self.sum()) * 1e6
+        if roi_order == True and roi.strand == "-":
+            counts = counts[..., ::-1]
+        return counts
+
+    def __getitem__(self, roi):
+        return self.get(roi, roi_order=True)
+
+    # -- bulk entry points used by the scripts --------------------------------------------------
+    def chain_table(self, chains, use_masks=True):
+        return ChainTable.from_chains(chains, self.layout, use_masks=use_masks)
+
+    def count_chains(self, chains, use_masks=True):
+        """(sums float64[n], unmasked lengths int64[n]) for a list of chains in one launch —
+        what ``numpy.nansum(chain.get_masked_counts(ga))`` and ``chain.masked_length`` give."""
+        table = chains if isinstance(chains, ChainTable) else self.chain_table(chains, use_masks)
+        need = sorted(set(_STRANDS[p] for p in np.unique(table.chain_plane)), key=_STRANDS.index) or ["+"]
+        planes = self.count_planes(tuple(need))
+        sums, live = region_sums(planes, table)
+        sums, live = sums.cpu().numpy(), live.cpu().numpy()
+        if self._normalize is True:
+            sums = sums / float(self.sum()) * 1e6
+        return sums, live
+
+    def to_genome_array(self, array_type=None):
+        """genome_array.py:965-988 — including its quirk of dropping each chromosome's last base."""
+        import torch
+        if array_type is None:
+            array_type = GenomeArray
+        ga = array_type(chr_lengths=self.lengths(), strands=self.strands(), device=self.device)
+        planes = self.count_planes(_STRANDS)
+        for chrom in self.chroms():
+            base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
+            n = self._chr_lengths[chrom] - 1
+            for strand in _STRANDS:
+                src = planes.planes[strand][base:base + n]
+                if planes.dtype == "u32":
+                    vals = (src.to(torch.int64) & 0xFFFFFFFF).to(torch.float64)
+                else:
+                    vals = src.clone()
+                if self._normalize is True:
+                    vals = vals / float(self.sum()) * 1e6
+                ga._set_device(chrom, strand, 0, vals)     # `ga[seg] = self[seg]`; both in 5'->3' order
+        return ga
+
+
+# ---------------------------------------------------------------------------------------------
+# GenomeArray / SparseGenomeArray (mutable float64 planes)
+# ---------------------------------------------------------------------------------------------
+class GenomeArray(object):
+    """``GenomeArray(chr_lengths=None, strands=None, min_chr_size=MIN_CHR_SIZE)`` with float64
+    device planes (genome_array.py:1354-1611).  Chromosomes seen first in ``__setitem__`` are
+    created on demand; reads outside the known range return zeros."""
+    MIN_CHR_SIZE = 10 * 1000 * 1000
+
+    def __init__(self, chr_lengths=None, strands=None, min_chr_size=None, device="cuda"):
+        self.device = device
+        self._strands = tuple(strands) if strands is not None else ("+", "-")
+        self.min_chr_size = self.MIN_CHR_SIZE if min_chr_size is None else min_chr_size
+        self._chr_lengths = dict(chr_lengths or {})
+        self._chroms = {}
+        self._sum = None
+        self._normalize = False
+        for chrom, n in self._chr_lengths.items():
+            self._alloc(chrom, n)
+
+    def _alloc(self, chrom, n):
+        import torch
+        _lib.require_cuda()
+        self._chroms[chrom] = {s: torch.zeros(int(n), dtype=torch.float64, device=self.device)
+                               for s in self._strands}
+        self._chr_lengths[chrom] = int(n)
+
+    def _grow(self, chrom, n):
+        import torch
+        for s, t in self._chroms[chrom].items():
+            new = torch.zeros(int(n), dtype=torch.float64, device=self.device)
+            new[:t.numel()] = t
+            self._chroms[chrom][s] = new
+        self._chr_lengths[chrom] = int(n)
+
+    def chroms(self):
+        return list(self._chroms.keys())
+
+    def strands(self):
+        return self._strands
+
+    def lengths(self):
+        return {c: self._chr_lengths[c] for c in self._chroms}
+
+    def reset_sum(self):
+        self._sum = None
+
+    def set_sum(self, val):
+        self._sum = val
+
+    def sum(self):
+        if self._sum is None:
+            total = 0.0
+            for planes in self._chroms.values():
+                for t in planes.values():
+                    total += float(t.sum().item())
+            self._sum = total
+        return self._sum
+
+    def set_normalize(self, value=True):
+        assert value in (True, False)
+        self._normalize = value
+
+    def _set_device(self, chrom, strand, start, vals):
+        if chrom not in self._chroms:
+            self._alloc(chrom, max(self.min_chr_size, start + vals.numel()))
+        elif start + vals.numel() > self._chr_lengths[chrom]:
+            self._grow(chrom, start + vals.numel() + 10000)
+        self._chroms[chrom][strand][start:start + vals.numel()] = vals
+        self._sum = None
+
+    def __setitem__(self, seg, val):
+        import torch
+        self._sum = None
+        if isinstance(seg, SegmentChain):
+            if isinstance(val, np.ndarray):
+                if seg.strand == "-":
+                    val = val[::-1]
+                x = 0
+                for sub in seg:
+                    n = len(sub)
+                    self._set_device(sub.chrom, sub.strand, sub.start,
+                                     torch.from_numpy(np.ascontiguousarray(val[x:x + n], dtype=np.float64)).to(self.device))
+                    x += n
+            else:
+                for sub in seg:
+                    self[sub] = val
+            return
+        if seg.strand not in self._strands:
+            raise KeyError("strand %r not in array" % seg.strand)
+        n = len(seg)
+        if isinstance(val, np.ndarray):
+            if seg.strand == "-":
+                val = val[::-1]
+            vals = torch.from_numpy(np.ascontiguousarray(val, dtype=np.float64)).to(self.device)
+        else:
+            vals = torch.full((n,), float(val), dtype=torch.float64, device=self.device)
+        self._set_device(seg.chrom, seg.strand, seg.start, vals)
+
+    def plane(self, chrom, strand):
+        return self._chroms[chrom][strand]
+
+    def get(self, roi, roi_order=True):
+        if isinstance(roi, SegmentChain):
+            return roi.get_counts(self)
+        n = len(roi)
+        if roi.chrom not in self._chroms or roi.strand not in self._strands:
+            vals = np.zeros(n, dtype=np.float64)
+        else:
+            t = self._chroms[roi.chrom][roi.strand]
+            vals = np.zeros(n, dtype=np.float64)
+            a, b = max(roi.start, 0), min(roi.end, t.numel())
+            if a < b:
+                vals[a - roi.start:b - roi.start] = t[a:b].cpu().numpy()
+        if self._normalize is True:
+            vals = 1e6 * vals / self.sum()
+        if roi_order == True and roi.strand == "-":
+            vals = vals[::-1]
+        return vals
+
+    def __getitem__(self, roi):
+        return self.get(roi, roi_order=True)
+
+    def count_chains(self, chains, use_masks=True):
+        """Bulk masked sums over chains (same contract as ``BAMGenomeArray.count_chains``)."""
+        import torch
+        chroms = sorted(self._chroms)
+        layout = GenomeLayout(chroms, [self._chr_lengths[c] for c in chroms])
+        planes = CountPlanes(layout, "f64", self.device)
+        planes.alloc(self._strands)
+        for s in self._strands:
+            planes.planes[s].zero_()
+            for chrom in chroms:
+                base = int(layout.chrom_bin_off[layout.index[chrom]])
+                t = self._chroms[chrom][s]
+                planes.planes[s][base:base + t.numel()] = t
+        table = ChainTable.from_chains(chains, layout, use_masks=use_masks, unstranded="." in self._strands
+                                       and "+" not in self._strands)
+        sums, live = region_sums(planes, table)
+        sums, live = sums.cpu().numpy(), live.cpu().numpy()
+        if self._normalize is True:
+            sums = 1e6 * sums / self.sum()
+        return sums, live
+
+
+class SparseGenomeArray(GenomeArray):
+    """Same API as :class:`GenomeArray`; chromosome planes are allocated on first write
+    (genome_array.py:2134-2298 uses scipy DOK matrices to save host RAM; 180 GB of HBM make dense
+    planes per touched chromosome the cheaper representation here)."""
+
+    def __init__(self, chr_lengths=None, strands=None, min_chr_size=None, device="cuda"):
+        GenomeArray.__init__(self, None, strands, min_chr_size, device)
+        self._declared = dict(chr_lengths or {})
+
+    def _alloc(self, chrom, n):
+        GenomeArray._alloc(self, chrom, max(n, self._declared.get(chrom, 0)))
+
+    def lengths(self):
+        out = dict(self._declared)
+        out.update(GenomeArray.lengths(self))
+        return out

@@ -1,0 +1,79 @@
+"""Lowering of ``SegmentChain`` collections to the flat block / mask tables the gather kernels read
+(``pb_region_sums`` / ``pb_gather_windows`` in ``include/plastid_b200.h``)."""
+import numpy as np
+
+from . import _lib
+
+
+class ChainTable(object):
+    """Flat tables for a list of chains: blocks in global-bin coordinates, per-chain plane index and
+    orientation, optional mask bits (bit j of chain c = j-th chain position in genomic order)."""
+
+    def __init__(self, layout, bstart, bend, chain_off, chain_plane, chain_reverse, chain_len,
+                 mask_bits=None, mask_off=None, known=None):
+        self.layout = layout
+        self.bstart = np.ascontiguousarray(bstart, dtype=np.int64)
+        self.bend = np.ascontiguousarray(bend, dtype=np.int64)
+        self.chain_off = np.ascontiguousarray(chain_off, dtype=np.int64)
+        self.chain_plane = np.ascontiguousarray(chain_plane, dtype=np.uint8)
+        self.chain_reverse = np.ascontiguousarray(chain_reverse, dtype=np.uint8)
+        self.chain_len = np.ascontiguousarray(chain_len, dtype=np.int64)
+        self.mask_bits = None if mask_bits is None else np.ascontiguousarray(mask_bits, dtype=np.uint8)
+        self.mask_off = None if mask_off is None else np.ascontiguousarray(mask_off, dtype=np.int64)
+        self.known = np.ones(len(self.chain_len), dtype=bool) if known is None else np.asarray(known, dtype=bool)
+        self._dev = {}
+
+    @property
+    def n_chains(self):
+        return len(self.chain_len)
+
+    @classmethod
+    def from_chains(cls, chains, layout, use_masks=True, unstranded=False):
+        """Chains on chromosomes missing from ``layout`` get zero blocks (the reference returns a
+        zero vector for them, genome_array.py:795-798) and ``known`` False."""
+        bstart, bend, chain_off = [], [], [0]
+        plane, reverse, length, known = [], [], [], []
+        mask_off, bits = [], []
+        nbits = 0
+        any_mask = False
+        for ch in chains:
+            ok = len(ch) > 0 and ch.chrom in layout.index
+            known.append(ok or len(ch) == 0)
+            strand = "." if unstranded or ch.strand not in ("+", "-") else ch.strand
+            plane.append(_lib.PLANE_INDEX[strand])
+            reverse.append(1 if ch.strand == "-" else 0)
+            if ok:
+                base = int(layout.chrom_bin_off[layout.index[ch.chrom]])
+                for seg in ch:
+                    bstart.append(base + seg.start)
+                    bend.append(base + seg.end)
+                length.append(ch.length)
+            else:
+                length.append(0)
+            chain_off.append(len(bstart))
+            mask_off.append(nbits)
+            if ok and use_masks and getattr(ch, "_mask_intervals", None):
+                any_mask = True
+                bits.append(ch.position_mask())
+            else:
+                bits.append(np.zeros(length[-1], dtype=np.uint8))
+            nbits += length[-1]
+        mask_bits = None
+        if any_mask:
+            flat = np.concatenate(bits) if bits else np.zeros(0, dtype=np.uint8)
+            mask_bits = np.packbits(flat, bitorder="little")
+            if len(mask_bits) == 0:
+                mask_bits = np.zeros(1, dtype=np.uint8)
+        return cls(layout, bstart, bend, chain_off, plane, reverse, length,
+                   mask_bits, mask_off if any_mask else None, known)
+
+    def device(self, device):
+        import torch
+        key = str(device)
+        if key not in self._dev:
+            def up(a):
+                return None if a is None else torch.from_numpy(a).to(device)
+            self._dev[key] = dict(bstart=up(self.bstart), bend=up(self.bend), chain_off=up(self.chain_off),
+                                  chain_plane=up(self.chain_plane), chain_reverse=up(self.chain_reverse),
+                                  mask_bits=up(self.mask_bits), mask_off=up(self.mask_off))
+        return self._dev[key]

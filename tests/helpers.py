@@ -1,0 +1,69 @@
+"""Shared test helpers: the reference's own test fixtures, transcribed, plus oracle glue."""
+import numpy as np
+
+from oracle import pyoracle as po
+
+
+def kat_reads():
+    """test_map_factories.py:19-28: per strand, 15 reads starting at 0 with '<L>M', L = 25..39."""
+    return {s: [po.Read(0, [(po.CMATCH, L)], s == "-") for L in range(25, 40)] for s in ("+", "-")}
+
+
+def kat_expected():
+    """test_map_factories.py:29-49 closed-form expectations."""
+    mn, mx = 25, 40
+    exp = {}
+    for mapping in ("fiveprime", "threeprime", "center"):
+        for param in (0, 10):
+            for strand in ("+", "-"):
+                exp[(mapping, param, strand)] = np.zeros(2000)
+    exp[("fiveprime", 0, "+")][0] = mx - mn
+    exp[("fiveprime", 10, "+")][10] = mx - mn
+    exp[("fiveprime", 0, "-")][mn - 1:mx - 1] = 1
+    exp[("fiveprime", 10, "-")][mn - 11:mx - 11] = 1
+    exp[("threeprime", 0, "-")][0] = mx - mn
+    exp[("threeprime", 10, "-")][10] = mx - mn
+    exp[("threeprime", 0, "+")][mn - 1:mx - 1] = 1
+    exp[("threeprime", 10, "+")][mn - 11:mx - 11] = 1
+    for L in range(mn, mx):
+        exp[("center", 0, "+")][:L] += 1.0 / L
+        exp[("center", 0, "-")][:L] += 1.0 / L
+        exp[("center", 10, "+")][10:L - 10] += 1.0 / (L - 20)
+        exp[("center", 10, "-")][10:L - 10] += 1.0 / (L - 20)
+    return exp
+
+
+def random_cigar_reads(rng, n, chrom_len, max_start=None):
+    """Reads with every CIGAR op (M I D N S H P = X), for oracle cross-checks."""
+    reads = []
+    for _ in range(n):
+        ops = []
+        if rng.random() < 0.2:
+            ops.append((po.CHARD_CLIP, int(rng.integers(1, 5))))
+        if rng.random() < 0.3:
+            ops.append((po.CSOFT_CLIP, int(rng.integers(1, 6))))
+        nseg = int(rng.integers(1, 5))
+        for k in range(nseg):
+            ops.append((int(rng.choice([po.CMATCH, po.CEQUAL, po.CDIFF])), int(rng.integers(1, 30))))
+            if k < nseg - 1:
+                mid = int(rng.choice([po.CINS, po.CDEL, po.CREF_SKIP, po.CPAD, po.CMATCH]))
+                ops.append((mid, int(rng.integers(1, 40 if mid != po.CREF_SKIP else 400))))
+        if rng.random() < 0.3:
+            ops.append((po.CSOFT_CLIP, int(rng.integers(1, 6))))
+        span = sum(n_ for op, n_ in ops if op in (po.CMATCH, po.CEQUAL, po.CDIFF, po.CDEL, po.CREF_SKIP))
+        hi = (max_start if max_start is not None else chrom_len - span - 1)
+        start = int(rng.integers(0, max(hi, 1)))
+        reads.append(po.Read(start, ops, bool(rng.integers(0, 2))))
+    return reads
+
+
+def oracle_planes(hb, kind, strand, **kw):
+    """Concatenated whole-genome vector (one per chromosome) from the C oracle."""
+    from oracle import coracle
+    out = []
+    dropped = 0
+    for c in range(len(hb.chroms)):
+        vec, _kept, d, _l = coracle.genome_vector(hb, c, strand, **kw)
+        out.append(vec)
+        dropped += d
+    return out, dropped

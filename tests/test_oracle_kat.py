@@ -1,0 +1,151 @@
+"""Pins the oracles against the reference's own known-answer tests (no GPU).
+
+Transcribed from plastid/test/unit/genomics/test_map_factories.py:17-200 and
+plastid/test/unit/util/scriptlib/test_argparsers.py:69-130; the C oracle is cross-checked against
+the Python restatement on random CIGARs, and the CIGAR consume table against the table printed from
+the reference's vendored htslib header (tests/golden/cigar_consume_table.txt, made by
+`make -C oracle ref`)."""
+import io
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from oracle import coracle
+from plastid_b200.batch import pack_reads, cigar_to_blocks
+from helpers import kat_reads, kat_expected, random_cigar_reads
+
+SEG = {s: po.Seg("mock", 0, 2000, s) for s in ("+", "-")}
+FACTORY = {"fiveprime": po.FivePrimeMap, "threeprime": po.ThreePrimeMap, "center": po.CenterMap}
+
+
+@pytest.mark.parametrize("mapping", ["fiveprime", "threeprime", "center"])
+@pytest.mark.parametrize("param", [0, 10])
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_kat_fiveprime_threeprime_center(mapping, param, strand):
+    reads = kat_reads()[strand]
+    kept, counts = FACTORY[mapping](param)(reads, SEG[strand])
+    assert kept == reads
+    assert (counts == kat_expected()[(mapping, param, strand)]).all()      # exact, as the reference test
+
+
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_kat_variable(strand):
+    reads = kat_reads()[strand]
+    fancy = {L: L // 2 for L in range(25, 40)}
+    expected = np.zeros(2000)
+    for r in reads:
+        idx = fancy[len(r.positions)]
+        expected[r.positions[idx] if strand == "+" else r.positions[-idx - 1]] += 1
+    for dict_, exp in (({"default": 0}, kat_expected()[("fiveprime", 0, strand)]), (fancy, expected)):
+        _, counts = po.VariableFivePrimeMap(dict_)(reads, SEG[strand])
+        assert (counts == exp).all()
+        text = "\n".join("%s\t%s" % kv for kv in dict_.items())
+        _, counts = po.VariableFivePrimeMap(po.parse_offset_file(io.StringIO(text)))(reads, SEG[strand])
+        assert (counts == exp).all()
+
+
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_kat_unmappable(strand):
+    reads = kat_reads()[strand]
+    lens = [len(r.positions) for r in reads]
+    cases = {
+        "fiveprime": (po.FivePrimeMap(30), sum(L > 30 for L in lens)),
+        "threeprime": (po.ThreePrimeMap(30), sum(L > 30 for L in lens)),
+        "center": (po.CenterMap(15), sum(L > 30 for L in lens)),
+        "variable": (po.VariableFivePrimeMap({25: 10, "default": 28}), sum(L > 28 or L == 25 for L in lens)),
+    }
+    for name, (fn, n_exp) in cases.items():
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            kept, counts = fn(reads, SEG[strand])
+        assert len(kept) == n_exp, name
+        assert abs(counts.sum() - n_exp) < 1e-9, name
+        assert any(issubclass(x.category, po.DataWarning) for x in w), name
+
+
+def test_offset_file_parser():
+    lines = ["26\t12", "27\t12", "28\t13", "29\t13", "30\t14", "31\t13", "default\t13"]
+    exp = {26: 12, 27: 12, 28: 13, 29: 13, 30: 14, 31: 13, "default": 13}
+    assert po.parse_offset_file(io.StringIO("\n".join(lines))) == exp
+    assert po.parse_offset_file(io.StringIO("length\tp_offset\n" + "\n".join(lines))) == exp
+    assert po.parse_offset_file(io.StringIO(lines[-1])) == {"default": 13}
+    with pytest.raises(po.MalformedFileError):
+        po.parse_offset_file(io.StringIO("\n".join(lines + lines)))
+    with pytest.raises(po.MalformedFileError):
+        po.parse_offset_file(io.StringIO("25\t12\n28\t15\t52\n"))
+    with pytest.raises(po.MalformedFileError):
+        po.parse_offset_file(io.StringIO("25\t12\n27\n"))
+    with pytest.raises(po.MalformedFileError):
+        po.parse_offset_file(io.StringIO("25\t12\nabc\t13\n"))
+    with pytest.raises(po.MalformedFileError):
+        po.parse_offset_file(io.StringIO("25\t12\n26\t1.5\n"))
+
+
+def test_cigar_table_matches_reference_header():
+    path = os.path.join(os.path.dirname(__file__), "golden", "cigar_consume_table.txt")
+    table = {}
+    for line in open(path):
+        ch, op, q, r = line.split("\t")
+        table[int(op)] = (int(q), int(r))
+    for op in range(10):
+        pos = po.positions_from_cigar(100, [(op, 7)])
+        end = po.Read(100, [(op, 7)], False).reference_end
+        q, r = table[op]
+        assert (len(pos) == 7) == (q == 1 and r == 1)          # only ops consuming both emit positions
+        assert (end == 107) == (r == 1)
+        blocks, span = cigar_to_blocks([(op, 7)])
+        assert (span == 7) == (r == 1) and (len(blocks) == 1) == (q == 1 and r == 1)
+
+
+def test_c_oracle_matches_python_oracle_on_random_cigars():
+    rng = np.random.default_rng(7)
+    reads = random_cigar_reads(rng, 400, 6000, max_start=3000)
+    hb = pack_reads({"c": reads}, {"c": 6000})
+    luts = po.build_offset_luts({L: L // 3 for L in range(10, 60)} | {"default": 2})
+    for strand in ("+", "-", "."):
+        seg = po.Seg("c", 500, 3500, strand)
+        sel = [r for r in hb.objects if strand == "." or r.is_reverse == (strand == "-")]
+        for name, pyfn, kw in (
+                ("fiveprime", po.FivePrimeMap(11), dict(rule="fiveprime", offset=11)),
+                ("threeprime", po.ThreePrimeMap(4), dict(rule="threeprime", offset=4)),
+                ("variable", po.VariableFivePrimeMap({L: L // 3 for L in range(10, 60)} | {"default": 2}),
+                 dict(rule="variable", luts=luts))):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                kept_py, exp = pyfn(sel, seg)
+            got, kept, _d, _l = coracle.map_point(hb, 0, len(hb), kw["rule"], kw.get("offset", 0), kw.get("luts"),
+                                                  None, strand, seg.start, seg.end, want_kept=True)
+            assert (got == exp).all(), (name, strand)
+            assert [hb.objects[i] for i in np.nonzero(kept)[0]] == kept_py, (name, strand)
+        for nib in (0, 5, 12):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                kept_py, exp = po.CenterMap(nib)(sel, seg)
+            got, kept, _d, _l = coracle.map_center(hb, 0, len(hb), nib, None, strand, seg.start, seg.end, True)
+            assert (got == exp).all(), (nib, strand)            # same order of fp64 adds => bit equal
+            assert [hb.objects[i] for i in np.nonzero(kept)[0]] == kept_py
+        strat = po.StratifiedVariableFivePrimeMap({20: 3, 21: 20, "default": 30}, 18, 40)
+        kept_py, exp = strat(sel, seg)
+        got, kept = coracle.map_stratified(hb, 0, len(hb), (strat.fw, strat.rc), 18, 40, None, strand,
+                                           seg.start, seg.end, True)
+        assert (got == exp).all(), strand
+        assert [hb.objects[i] for i in np.nonzero(kept)[0]] == kept_py
+
+
+def test_size_filter_and_strand_filter_in_c_oracle():
+    rng = np.random.default_rng(3)
+    reads = random_cigar_reads(rng, 300, 5000, max_start=2500)
+    hb = pack_reads({"c": reads}, {"c": 5000})
+    store = po.ReadStore({"c": 5000}, {"c": hb.objects})
+    ga = po.OracleBAMGenomeArray(store, mapping=po.FivePrimeMap(3))
+    ga.add_filter("size", po.SizeFilter(20, 45))
+    for strand in ("+", "-", "."):
+        seg = po.Seg("c", 100, 2900, strand)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            exp = ga.get(seg, roi_order=False)
+        got, _, _, _ = coracle.map_point(hb, 0, len(hb), "fiveprime", 3, None, (20, 45), strand, 100, 2900)
+        assert (got == exp).all()
