@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the read-to-coverage hot path (BASELINE.json metric: mapped reads/sec + region
+counts/sec, % of the HBM roofline, reference CPU path timed beside it).
+
+Workload (BASELINE.json configs[1], the metric's quoted configuration): VariableFivePrimeMapFactory
+with per-read-length P-site offsets + size filter 25-100 over 200 M synthetic 25-35 nt ribo-seq reads
+on a human-scale genome (hg38 chromosome lengths, 3.09 Gb) into dense '+' and '-' count vectors,
+followed by masked-free region counts over 60 k CDS-like SegmentChains.  One "step" = that whole
+pass over one batch.  At N > 1 every rank owns one such read shard (read-range sharding, weak
+scaling) and the per-region count tables are summed with one NCCL all-reduce.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mapped_reads_per_sec"
+UNIT = "reads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=200_000_000, help="reads per GPU")
+    ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of hg38 chromosome lengths")
+    ap.add_argument("--regions", type=int, default=60_000)
+    ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_world(args, rank, device):
+    import torch
+    import plastid_b200 as pb
+    from plastid_b200 import synth
+    chroms, lens = synth.human_like_genome(args.genome_scale)
+    ann = synth.make_annotation(chroms, lens, args.regions, seed=0, exons=(1, 3), exon_len=(150, 600),
+                                intron_len=(100, 3000))
+    layout = pb.GenomeLayout(chroms, lens)
+    table = synth.annotation_table(ann, layout)
+    dbatch = synth.riboseq_reads(ann, args.reads, seed=100 + rank, device=device, frac_in=0.85)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return chroms, lens, ann, layout, table, dbatch
+
+
+def cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, threads):
+    """The oracle's restatement of the reference path on `chrom_ids`: per chromosome x strand the
+    per-read loop of VariableFivePrimeMapFactory.__call__ over the whole chromosome segment, then the
+    SegmentChain sums of the regions on those chromosomes.  Returns (seconds, reads, regions)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import coracle
+    luts = (fac.forward_offsets, fac.reverse_offsets)
+    coracle.lib()
+
+    def one(c):
+        n_reg = 0
+        for pidx, strand in enumerate(("+", "-")):
+            vec = coracle.genome_vector(hb, c, strand, rule="variable", luts=luts, size_filter=(25, 100))[0]
+            base = int(layout.chrom_bin_off[c])
+            sel = np.nonzero((table.chain_plane == pidx) & (table.bstart[table.chain_off[:-1]] >= base)
+                             & (table.bstart[table.chain_off[:-1]] < int(layout.chrom_bin_off[c + 1])))[0]
+            if len(sel):
+                offs = [0]
+                bs, be = [], []
+                for i in sel:
+                    a, b = table.chain_off[i], table.chain_off[i + 1]
+                    bs.append(table.bstart[a:b] - base)
+                    be.append(table.bend[a:b] - base)
+                    offs.append(offs[-1] + b - a)
+                coracle.region_sums(vec.astype(np.uint32), np.concatenate(bs), np.concatenate(be), offs)
+            n_reg += len(sel)
+        return int(hb.chrom_read_off[c + 1] - hb.chrom_read_off[c]), n_reg
+
+    t0 = time.perf_counter()
+    if threads > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(one, chrom_ids))
+    else:
+        res = [one(c) for c in chrom_ids]
+    dt = time.perf_counter() - t0
+    return dt, sum(r[0] for r in res), sum(r[1] for r in res)
+
+
+def host_sample(dbatch, chroms, lens, chrom_ids):
+    """Host copy of the reads of the chosen chromosomes only (bounded CPU sample)."""
+    from plastid_b200.batch import AlignmentBatch
+    off = dbatch.chrom_read_off.cpu().numpy()
+    new_off = np.zeros(len(chroms) + 1, dtype=np.int64)
+    starts, metas = [], []
+    for c in range(len(chroms)):
+        if c in chrom_ids:
+            a, b = int(off[c]), int(off[c + 1])
+            starts.append(dbatch.ref_start[a:b].cpu().numpy())
+            metas.append(dbatch.meta[a:b].cpu().numpy().view(np.uint32))
+            new_off[c + 1] = new_off[c] + (b - a)
+        else:
+            new_off[c + 1] = new_off[c]
+    return AlignmentBatch(chroms, lens, np.concatenate(starts), np.concatenate(metas), new_off,
+                          max_span=dbatch.max_span)
+
+
+def main():
+    args = parse_args()
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = "cuda:%d" % local_rank
+    if world > 1 and args.impl != "reference":
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    import plastid_b200 as pb
+    from plastid_b200 import synth, _lib
+    from plastid_b200.genome_array import map_batch, region_sums, CountPlanes
+
+    chroms, lens, ann, layout, table, dbatch = build_world(args, rank, device)
+    fac = pb.VariableFivePrimeMapFactory(synth.RIBO_OFFSETS)
+    sf = pb.SizeFilterFactory(25, 100)
+    n_reads = dbatch.n_reads
+    workload = ("C2: VariableFivePrimeMapFactory(p-site offsets)+size filter 25-100, %d synthetic 25-35 nt "
+                "ribo-seq reads/GPU, hg38-scale genome x%.3g (%d bins, '+' and '-' planes), %d region counts"
+                % (n_reads, args.genome_scale, layout.total_bins, ann.n_tx))
+    config = {"workload": workload, "reads_per_gpu": n_reads, "genome_bins": int(layout.total_bins),
+              "regions": ann.n_tx, "sharding": "read-range per GPU; NCCL all-reduce of region tables" if world > 1
+              else "single GPU", "l2": "inputs (%.2f GB) and outputs (%.1f GB) larger than the 126 MB L2"
+              % (8 * n_reads / 1e9, 8 * layout.total_bins / 1e9)}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        threads = os.cpu_count() or 1
+        order = np.argsort(-np.asarray(lens))
+        chrom_ids = sorted(int(c) for c in order[:max(1, min(threads, 8))])
+        hb = host_sample(dbatch, chroms, lens, set(chrom_ids))
+        del dbatch
+        torch.cuda.empty_cache()
+        times = []
+        for it in range(args.warmup + args.steps):
+            dt, nr, nreg = cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, threads)
+            if it >= args.warmup:
+                times.append(dt)
+        ms = 1000.0 * float(np.mean(times))
+        val = nr / (ms / 1000.0)
+        sample = "chromosomes %s (%d reads, %d regions) of the workload per step" % (
+            ",".join(chroms[c] for c in chrom_ids), nr, nreg)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "oracle port of map_factories.pyx/roitools.pyx loops (the Cython reference cannot be "
+                        "built here: pysam absent); chromosome-parallel over %d host threads" % threads}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ device-resident steps
+    planes = CountPlanes(layout, "u32", device)
+    planes.alloc(("+", "-"))
+    table.device(device)
+    L = _lib.lib()
+
+    def step():
+        map_batch(dbatch, layout, fac, sf, strands=("+", "-"), planes=planes, sync_stats=False)
+        sums, live = region_sums(planes, table)
+        if world > 1:
+            dist.all_reduce(sums)
+        return sums, live
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs ~1 s to come up: start before the warm-up
+    for _ in range(max(args.warmup, 3)):
+        step()
+    fence()
+    L.pb_enable_kernel_timing(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        sums, live = step()
+    ev1.record()
+    fence()
+    total_ms = ev0.elapsed_time(ev1)
+    kms, kn = C.c_float(0), C.c_int(0)
+    _lib.check(L.pb_tiles_kernel_ms_total(C.byref(kms), C.byref(kn)))
+    L.pb_enable_kernel_timing(0)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n_reads * world / (ms_per_step / 1000.0)
+    region_rate = ann.n_tx * world / (ms_per_step / 1000.0)
+
+    # ------------------------------------------------------------------ end-to-end (host buffers)
+    h_start = torch.empty(n_reads, dtype=torch.int32).pin_memory()
+    h_meta = torch.empty(n_reads, dtype=torch.int32).pin_memory()
+    h_start.copy_(dbatch.ref_start)
+    h_meta.copy_(dbatch.meta)
+    h_sums = torch.empty(ann.n_tx, dtype=torch.float64).pin_memory()
+    h_live = torch.empty(ann.n_tx, dtype=torch.int64).pin_memory()
+    h2d = h_start.numel() * 4 + h_meta.numel() * 4
+    d2h = h_sums.numel() * 8 + h_live.numel() * 8
+
+    def e2e_step():
+        dbatch.ref_start.copy_(h_start, non_blocking=True)
+        dbatch.meta.copy_(h_meta, non_blocking=True)
+        s, l = step()
+        h_sums.copy_(s, non_blocking=True)
+        h_live.copy_(l, non_blocking=True)
+        torch.cuda.synchronize()          # the caller holds the table before the next batch starts
+
+    for _ in range(2):
+        e2e_step()
+    fence()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    fence()
+    e2e_ms = max(ev0.elapsed_time(ev1), 1000.0 * (time.perf_counter() - t0)) / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_reads * world / (float(t.item()) / 1000.0)
+    clocks = sampler.stop()              # samples cover warm-up, the timed steps and the e2e steps
+    table_checksum = float(h_sums.sum().item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ roofline of the tiles kernel
+    peak, peak_src = peaks()
+    alg_bytes = 8.0 * n_reads + 4.0 * layout.total_bins * 2          # SoA in once + every bin out once
+    k_ms = kms.value / max(kn.value, 1)
+    achieved = alg_bytes / (k_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "pb_point_tiles_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "launches_timed": kn.value,
+                "kernel_share_of_step": k_ms / ms_per_step}
+
+    # ------------------------------------------------------------------ cpu_baseline (rank 0, N=1)
+    cpu = None
+    if world == 1:
+        order = np.argsort(-np.asarray(lens))
+        chrom_ids = sorted(int(c) for c in order[:args.cpu_sample_chroms])
+        hb = host_sample(dbatch, chroms, lens, set(chrom_ids))
+        dt, nr, nreg = cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, 1)
+        cpu = {"value": nr / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%s: %d reads + %d region sums in %.2f s (oracle C port, one thread)"
+                         % (",".join(chroms[c] for c in chrom_ids), nr, nreg, dt)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+            "region_counts_per_sec": region_rate,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t.item()), "steps": e2e_steps},
+            "gpu_launches": 4 * args.steps, "kernels_per_step": ["pb_tile_index_kernel", "pb_point_tiles_kernel",
+                                                                  "pb_stats_finish_kernel", "pb_region_sums_kernel"],
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -142,13 +142,23 @@ int pb_map_center(const pb_batch *batch, const pb_layout *layout, const pb_rule 
                   double *out_plus, double *out_minus, double *out_any,
                   uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Measurement hook (bench.py roofline): while enabled, pb_map_point / pb_map_center bracket their
+ * tiles kernel with CUDA events on the launch stream (up to 256 launches since the last enable);
+ * pb_tiles_kernel_ms_total waits for them and returns the summed device time and launch count. */
+void pb_enable_kernel_timing(int on);
+int pb_tiles_kernel_ms_total(float *ms_total, int *n_launches);
+
 /* The operator itself: map reads [i0,i1) of the batch onto one segment [seg_start,seg_end) of
- * their chromosome for query strand `strand` (PB_PLANE_*).  counts_out (caller-zeroed):
- * int64[n] (5'/3'/variable), int64[(strat_max-strat_min+1)*n] (stratified), double[n] (center).
- * kept_out: uint8[i1-i0] or NULL — 1 where the reference appends the read to reads_out. */
+ * their chromosome for query strand `strand` (PB_PLANE_*), which sets the direction the rule is
+ * applied in (map_factories.pyx:345-346, 444-445, 625-626).  filter_strand != 0 additionally drops
+ * reads of the other strand first, as BAMGenomeArray.get_reads_and_counts does before calling the
+ * rule (genome_array.py:811-815); a bare `map_fn(reads, seg)` call passes 0.  counts_out
+ * (caller-zeroed): int64[n] (5'/3'/variable), int64[(strat_max-strat_min+1)*n] (stratified),
+ * double[n] (center).  kept_out: uint8[i1-i0] or NULL — 1 where the reference appends the read to
+ * reads_out. */
 int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
-                   int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
-                   uint64_t *stats, void *stream);
+                   int filter_strand, int64_t seg_start, int64_t seg_end, void *counts_out,
+                   uint8_t *kept_out, uint64_t *stats, void *stream);
 
 /* Histogram of aligned length L over reads passing drop/size/strand filters.
  * hist: device uint64[65536], accumulated. */

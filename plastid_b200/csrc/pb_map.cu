@@ -363,7 +363,7 @@ __global__ void pb_stats_finish_kernel(const unsigned long long *__restrict__ sl
 // ----------------------------------------------------------------------------------------
 // the operator on one segment (global atomics; small inputs)
 // ----------------------------------------------------------------------------------------
-__global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1, int strand,
+__global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1, int strand, int filter_strand,
                                   int64_t seg_start, int64_t seg_end,
                                   unsigned long long *counts_i, double *counts_f,
                                   uint8_t *__restrict__ kept, unsigned long long *__restrict__ stats)
@@ -377,8 +377,8 @@ __global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1
         uint8_t keep = 0;
         const bool rev = PB_META_REV(m);
         bool pass = pb_passes(m, r.size_min, r.size_max);
-        if (strand == PB_PLANE_PLUS && rev) pass = false;    // genome_array.py:811-815
-        if (strand == PB_PLANE_MINUS && !rev) pass = false;
+        if (filter_strand && strand == PB_PLANE_PLUS && rev) pass = false;    // genome_array.py:811-815
+        if (filter_strand && strand == PB_PLANE_MINUS && !rev) pass = false;
         if (pass) {
             const int L = PB_META_L(m);
             const int sidx = strand == PB_PLANE_PLUS ? PB_STAT_DROPPED_PLUS
@@ -487,6 +487,30 @@ int check_common(const pb_batch *batch, const pb_layout *layout, const pb_rule *
     return PB_OK;
 }
 
+// optional device timing of the dominant (tiles) kernel, for bench.py's roofline line: a ring of
+// CUDA event pairs recorded on the launch stream, summed by pb_tiles_kernel_ms_total().
+constexpr int kTimingRing = 256;
+bool g_timing = false;
+cudaEvent_t g_ev[kTimingRing][2];
+int g_ev_created = 0, g_ev_count = 0;
+
+void timing_begin(cudaStream_t stream)
+{
+    if (!g_timing || g_ev_count >= kTimingRing) return;
+    if (g_ev_count >= g_ev_created) {
+        cudaEventCreate(&g_ev[g_ev_created][0]);
+        cudaEventCreate(&g_ev[g_ev_created][1]);
+        g_ev_created++;
+    }
+    cudaEventRecord(g_ev[g_ev_count][0], stream);
+}
+void timing_end(cudaStream_t stream)
+{
+    if (!g_timing || g_ev_count >= kTimingRing) return;
+    cudaEventRecord(g_ev[g_ev_count][1], stream);
+    g_ev_count++;
+}
+
 size_t tile_index_bytes(int64_t total_bins) { return (size_t)(total_bins / 1024 + 1) * 2 * sizeof(int64_t); }
 size_t stat_slot_bytes() { return (size_t)kStatSlots * PB_NSTATS * sizeof(unsigned long long); }
 
@@ -535,8 +559,10 @@ extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, cons
     const int n_planes = __builtin_popcount(planes);
     const size_t smem = (size_t)n_planes * tile_bins * sizeof(uint32_t);
     PB_CUDA_CHECK(cudaFuncSetAttribute(pb_point_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    timing_begin(stream);
     pb_point_tiles_kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>(b, r, lay, tile_bins, planes, tile_lo, tile_hi,
                                                                          out_plus, out_minus, out_any, slots);
+    timing_end(stream);
     pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, (unsigned long long *)stats);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
@@ -606,20 +632,39 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
 
     PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, 2 * stat_slot_bytes(), stream));
     pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, n_tiles, tile_lo, tile_hi);
+    timing_begin(stream);
     switch (ept) {
     case 16: rc = launch_center<16>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
     case 8:  rc = launch_center<8>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
     case 4:  rc = launch_center<4>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
     default: rc = launch_center<2>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
     }
+    timing_end(stream);
     if (rc) return rc;
     pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, (unsigned long long *)stats);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
 
+extern "C" void pb_enable_kernel_timing(int on) { g_timing = on != 0; g_ev_count = 0; }
+
+extern "C" int pb_tiles_kernel_ms_total(float *ms_total, int *n_launches)
+{
+    if (!ms_total || !n_launches) { pb_set_error("pb_tiles_kernel_ms_total: null"); return PB_EINVAL; }
+    float total = 0.f;
+    for (int i = 0; i < g_ev_count; ++i) {
+        float ms = 0.f;
+        PB_CUDA_CHECK(cudaEventSynchronize(g_ev[i][1]));
+        PB_CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]));
+        total += ms;
+    }
+    *ms_total = total;
+    *n_launches = g_ev_count;
+    return PB_OK;
+}
+
 extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
-                              int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
+                              int filter_strand, int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
                               uint64_t *stats, void *stream_)
 {
     if (!batch || !rule || !counts_out || !stats) { pb_set_error("pb_map_segment: null argument"); return PB_EINVAL; }
@@ -637,7 +682,7 @@ extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, con
     int64_t n = i1 - i0;
     unsigned grid = (unsigned)((n + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    pb_segment_kernel<<<grid, 256, 0, stream>>>(b, r, i0, i1, strand, seg_start, seg_end,
+    pb_segment_kernel<<<grid, 256, 0, stream>>>(b, r, i0, i1, strand, filter_strand, seg_start, seg_end,
                                                 (unsigned long long *)counts_out, (double *)counts_out, kept_out,
                                                 (unsigned long long *)stats);
     PB_CUDA_CHECK(cudaGetLastError());

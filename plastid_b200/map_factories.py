@@ -84,7 +84,8 @@ class _MapFactory(object):
     def _warn_dropped(self, n_dropped, a_length):
         raise NotImplementedError
 
-    def map_segment(self, dbatch, i0, i1, seg_start, seg_end, strand, size_filter=None, want_kept=True):
+    def map_segment(self, dbatch, i0, i1, seg_start, seg_end, strand, size_filter=None, want_kept=True,
+                    filter_strand=True):
         """Run the operator on reads ``[i0,i1)`` of a device batch; returns (counts ndarray, kept
         ndarray of bool or None)."""
         import torch
@@ -99,7 +100,7 @@ class _MapFactory(object):
         rule = self.pb_rule(dev, size_filter)
         b = dbatch.c_struct()
         _lib.check(_lib.lib().pb_map_segment(C.byref(b), i0, i1, C.byref(rule), _lib.STRAND_PLANE[strand],
-                                             int(seg_start), int(seg_end), _lib.ptr(counts), _lib.ptr(kept),
+                                             int(bool(filter_strand)), int(seg_start), int(seg_end), _lib.ptr(counts), _lib.ptr(kept),
                                              _lib.ptr(stats), _lib.stream_ptr()))
         st = stats.cpu().numpy()
         dropped = int(st[{"+": 0, "-": 1, ".": 2}[strand]])
@@ -118,7 +119,7 @@ class _MapFactory(object):
         hb = pack_reads({"_": reads}, {"_": max(end, 1)}, keep_objects=True)
         if len(hb) == 0:
             return [], np.zeros(self._leading_shape() + [max(end - start, 0)], dtype=self.count_dtype)
-        counts, kept = self.map_segment(hb.to_device("cuda"), 0, len(hb), start, end, strand)
+        counts, kept = self.map_segment(hb.to_device("cuda"), 0, len(hb), start, end, strand, filter_strand=False)
         # pack_reads sorts by start; reads_out keeps the caller's order like the reference loop
         kept_ids = set(id(hb.objects[i]) for i in np.nonzero(kept)[0])
         reads_out = [r for r in reads if id(r) in kept_ids]

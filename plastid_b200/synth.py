@@ -221,3 +221,16 @@ def device_batch_to_host(db, chroms, chrom_len, mapped=None):
     return AlignmentBatch(chroms, np.asarray(chrom_len), h(db.ref_start, None), h(db.meta, np.uint32),
                           h(db.chrom_read_off, None), h(db.blk_off, np.uint32), h(db.blk, None),
                           max_span=db.max_span, mapped=mapped)
+
+
+def annotation_table(annotation, layout):
+    """Vectorised :class:`~plastid_b200.regions.ChainTable` for every transcript of a synthetic
+    annotation (no masks) — same tables ``ChainTable.from_chains(annotation.chains(), layout)`` builds."""
+    from .regions import ChainTable
+    ex_tx = np.repeat(np.arange(annotation.n_tx), np.diff(annotation.tx_off))
+    base = layout.chrom_bin_off[np.asarray([layout.index[c] for c in annotation.chroms])][annotation.tx_chrom]
+    bstart = base[ex_tx] + annotation.ex_start
+    bend = base[ex_tx] + annotation.ex_end
+    length = np.add.reduceat(annotation.ex_end - annotation.ex_start, annotation.tx_off[:-1])
+    return ChainTable(layout, bstart, bend, annotation.tx_off, annotation.tx_strand.astype(np.uint8),
+                      annotation.tx_strand.astype(np.uint8), length)

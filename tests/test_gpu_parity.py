@@ -1,0 +1,389 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracles, bit-exact for integer rules,
+rel <= 1e-6 (north_star; observed ~1e-15) for CenterMapFactory's fractional weights."""
+import io
+import warnings
+
+import numpy as np
+import pytest
+
+import plastid_b200 as pb
+from plastid_b200 import synth, _lib
+from plastid_b200.genome_array import map_batch, region_sums, gather_windows, window_normalize, column_profile
+from plastid_b200.regions import ChainTable
+from oracle import pyoracle as po
+from oracle import coracle
+from helpers import kat_reads, kat_expected, random_cigar_reads
+
+pytestmark = pytest.mark.gpu
+
+CENTER_RTOL = 1e-6      # north_star tolerance for fractional weights
+
+
+def plane_chrom(planes, layout, strand, c):
+    base = int(layout.chrom_bin_off[c])
+    t = planes.planes[strand][base:base + int(layout.chrom_len[c])].cpu().numpy()
+    return t.view(np.uint32).astype(np.int64) if planes.dtype == "u32" else t
+
+
+def padding_is_zero(planes, layout, strand):
+    t = planes.planes[strand].cpu().numpy()
+    t = t.view(np.uint32) if planes.dtype == "u32" else t
+    for c in range(len(layout.chroms)):
+        a = int(layout.chrom_bin_off[c]) + int(layout.chrom_len[c])
+        if np.any(t[a:int(layout.chrom_bin_off[c + 1])] != 0):
+            return False
+    return True
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own known answers, through the drop-in factories
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mapping", ["fiveprime", "threeprime", "center"])
+@pytest.mark.parametrize("param", [0, 10])
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_kat_factories(cuda_device, mapping, param, strand):
+    fac = {"fiveprime": pb.FivePrimeMapFactory, "threeprime": pb.ThreePrimeMapFactory,
+           "center": pb.CenterMapFactory}[mapping](param)
+    reads = kat_reads()[strand]
+    reads_out, counts = fac(reads, pb.GenomicSegment("mock", 0, 2000, strand))
+    assert reads_out == reads
+    exp = kat_expected()[(mapping, param, strand)]
+    if mapping == "center":
+        np.testing.assert_allclose(counts, exp, rtol=CENTER_RTOL, atol=0)
+        assert counts.dtype == np.float64
+    else:
+        assert (counts == exp).all() and counts.dtype == np.int64
+
+
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_kat_variable_and_from_file(cuda_device, strand):
+    reads = kat_reads()[strand]
+    seg = pb.GenomicSegment("mock", 0, 2000, strand)
+    fancy = {L: L // 2 for L in range(25, 40)}
+    expected = np.zeros(2000)
+    for r in reads:
+        idx = fancy[len(r.positions)]
+        expected[r.positions[idx] if strand == "+" else r.positions[-idx - 1]] += 1
+    for dict_, exp in (({"default": 0}, kat_expected()[("fiveprime", 0, strand)]), (fancy, expected)):
+        _, counts = pb.VariableFivePrimeMapFactory(dict_)(reads, seg)
+        assert (counts == exp).all()
+        fh = io.StringIO("\n".join("%s\t%s" % kv for kv in dict_.items()))
+        _, counts = pb.VariableFivePrimeMapFactory.from_file(fh)(reads, seg)
+        assert (counts == exp).all()
+
+
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_kat_unmappable(cuda_device, strand):
+    reads = kat_reads()[strand]
+    seg = pb.GenomicSegment("mock", 0, 2000, strand)
+    lens = [len(r.positions) for r in reads]
+    cases = {"fiveprime": (pb.FivePrimeMapFactory(30), sum(L > 30 for L in lens)),
+             "threeprime": (pb.ThreePrimeMapFactory(30), sum(L > 30 for L in lens)),
+             "center": (pb.CenterMapFactory(15), sum(L > 30 for L in lens)),
+             "variable": (pb.VariableFivePrimeMapFactory({25: 10, "default": 28}),
+                          sum(L > 28 or L == 25 for L in lens))}
+    for name, (fn, n_exp) in cases.items():
+        pb.map_factories._warned.clear()
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            reads_out, counts = fn(reads, seg)
+        assert len(reads_out) == n_exp, name
+        assert abs(counts.sum() - n_exp) < 1e-9, name
+        assert any(issubclass(x.category, pb.DataWarning) for x in w), name
+
+
+# ---------------------------------------------------------------------------------------------
+# operator on random CIGARs vs the Python oracle (every op, spliced, stratified quirk)
+# ---------------------------------------------------------------------------------------------
+def test_segment_operator_random_cigars(cuda_device):
+    rng = np.random.default_rng(11)
+    reads = random_cigar_reads(rng, 500, 8000, max_start=4000)
+    offs = {L: L // 3 for L in range(10, 60)}
+    offs["default"] = 2
+    for strand in ("+", "-", "."):
+        seg_o = po.Seg("c", 700, 4200, strand)
+        seg = pb.GenomicSegment("c", 700, 4200, strand)
+        pairs = [(po.FivePrimeMap(11), pb.FivePrimeMapFactory(11)), (po.ThreePrimeMap(4), pb.ThreePrimeMapFactory(4)),
+                 (po.VariableFivePrimeMap(offs), pb.VariableFivePrimeMapFactory(offs)),
+                 (po.StratifiedVariableFivePrimeMap({20: 3, 21: 20, "default": 30}, 18, 40),
+                  pb.StratifiedVariableFivePrimeMapFactory({20: 3, 21: 20, "default": 30}, 18, 40)),
+                 (po.CenterMap(0), pb.CenterMapFactory(0)), (po.CenterMap(7), pb.CenterMapFactory(7))]
+        for ofn, gfn in pairs:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                kept_o, exp = ofn(reads, seg_o)
+                kept_g, got = gfn(reads, seg)
+            assert kept_g == kept_o, (type(gfn).__name__, strand)
+            assert got.shape == exp.shape
+            if isinstance(gfn, pb.CenterMapFactory):
+                np.testing.assert_allclose(got, exp, rtol=CENTER_RTOL, atol=1e-300)
+                assert ((got == 0) == (exp == 0)).all()
+            else:
+                assert (got == exp).all(), (type(gfn).__name__, strand)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-genome planes vs the C oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def small_world(cuda_device):
+    chroms, lens = synth.yeast_like_genome(total=1_200_000, n_chrom=5)
+    lens[2] = 16384 * 3                  # a chromosome ending exactly on the layout alignment
+    lens[3] = 100_001
+    ann = synth.make_annotation(chroms, lens, 200, seed=5, exons=(1, 3), exon_len=(200, 600), intron_len=(50, 400))
+    dbatch = synth.riboseq_reads(ann, 400_000, seed=9, device=cuda_device, lengths=range(18, 41))
+    hb = synth.device_batch_to_host(dbatch, chroms, lens)
+    hb.check_sorted()
+    layout = pb.GenomeLayout(chroms, lens)
+    return dict(chroms=chroms, lens=lens, ann=ann, dbatch=dbatch, hb=hb, layout=layout)
+
+
+POINT_CASES = [("fiveprime", pb.FivePrimeMapFactory(14), dict(rule="fiveprime", offset=14)),
+               ("fiveprime0", pb.FivePrimeMapFactory(0), dict(rule="fiveprime", offset=0)),
+               ("fiveprime30", pb.FivePrimeMapFactory(30), dict(rule="fiveprime", offset=30)),
+               ("threeprime", pb.ThreePrimeMapFactory(15), dict(rule="threeprime", offset=15)),
+               ("threeprime0", pb.ThreePrimeMapFactory(0), dict(rule="threeprime", offset=0))]
+
+
+@pytest.mark.parametrize("name,factory,okw", POINT_CASES, ids=[c[0] for c in POINT_CASES])
+@pytest.mark.parametrize("size_filter", [None, (25, 35)])
+def test_point_planes_bit_exact(small_world, name, factory, okw, size_filter):
+    w = small_world
+    sf = None if size_filter is None else pb.SizeFilterFactory(*size_filter)
+    planes = map_batch(w["dbatch"], w["layout"], factory, sf, strands=("+", "-", "."))
+    total = {"+": 0, "-": 0, ".": 0}
+    dropped = {}
+    for strand in ("+", "-", "."):
+        dropped[strand] = 0
+        for c in range(len(w["chroms"])):
+            exp, _, d, _ = coracle.genome_vector(w["hb"], c, strand, size_filter=size_filter, **okw)
+            got = plane_chrom(planes, w["layout"], strand, c)
+            assert (got == exp).all(), (name, strand, c)
+            total[strand] += int(exp.sum())
+            dropped[strand] += d
+        assert padding_is_zero(planes, w["layout"], strand)
+    st = planes.stats
+    assert [int(st[_lib.PB_STAT_MAPPED_PLUS]), int(st[_lib.PB_STAT_MAPPED_MINUS]), int(st[_lib.PB_STAT_MAPPED_ANY])] \
+        == [total["+"], total["-"], total["."]]
+    assert [int(st[0]), int(st[1]), int(st[2])] == [dropped["+"], dropped["-"], dropped["."]]
+
+
+def test_variable_planes_bit_exact(small_world):
+    w = small_world
+    offs = dict(synth.RIBO_OFFSETS)
+    offs[20] = 25            # offset >= length with default: entry skipped, falls back to the default fill
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fac = pb.VariableFivePrimeMapFactory(offs)
+        luts = po.build_offset_luts(offs)
+    assert (fac.forward_offsets == luts[0]).all() and (fac.reverse_offsets == luts[1]).all()
+    planes = map_batch(w["dbatch"], w["layout"], fac, None, strands=("+", "-", "."))
+    n_dropped = 0
+    for strand in ("+", "-", "."):
+        for c in range(len(w["chroms"])):
+            exp, _, d, _ = coracle.genome_vector(w["hb"], c, strand, rule="variable", luts=luts)
+            assert (plane_chrom(planes, w["layout"], strand, c) == exp).all(), (strand, c)
+            n_dropped += d if strand == "." else 0
+    assert n_dropped > 0 and int(planes.stats[_lib.PB_STAT_DROPPED_ANY]) == n_dropped   # lengths <= 14 have no offset
+
+
+@pytest.mark.parametrize("nibble", [0, 12, 20])
+def test_center_planes(small_world, nibble):
+    w = small_world
+    planes = map_batch(w["dbatch"], w["layout"], pb.CenterMapFactory(nibble), None, strands=("+", "-", "."))
+    for strand in ("+", "-", "."):
+        for c in range(len(w["chroms"])):
+            exp, _, _, _ = coracle.genome_vector(w["hb"], c, strand, nibble=nibble)
+            got = plane_chrom(planes, w["layout"], strand, c)
+            np.testing.assert_allclose(got, exp, rtol=CENTER_RTOL, atol=0)
+            assert ((got == 0) == (exp == 0)).all()
+        assert padding_is_zero(planes, w["layout"], strand)
+    # each mapped read contributes exactly 1.0 in total
+    tot = sum(float(planes.planes["."].sum().item()) for _ in [0])
+    assert abs(tot - int(planes.stats[_lib.PB_STAT_MAPPED_ANY])) < 1e-6 * max(tot, 1)
+
+
+def test_spliced_reads_planes(cuda_device):
+    chroms, lens = ["a", "b", "c"], np.array([400_000, 16384, 250_000])
+    dbatch = synth.rnaseq_reads(chroms, lens, 150_000, seed=4, device=cuda_device, intron=(100, 30000))
+    hb = synth.device_batch_to_host(dbatch, chroms, lens)
+    hb.check_sorted()
+    assert hb.blk is not None and hb.max_span > 10_000
+    layout = pb.GenomeLayout(chroms, lens)
+    for fac, okw in ((pb.FivePrimeMapFactory(70), dict(rule="fiveprime", offset=70)),
+                     (pb.ThreePrimeMapFactory(3), dict(rule="threeprime", offset=3))):
+        planes = map_batch(dbatch, layout, fac, None, strands=("+", "-", "."))
+        for strand in ("+", "-", "."):
+            for c in range(3):
+                exp, _, _, _ = coracle.genome_vector(hb, c, strand, **okw)
+                assert (plane_chrom(planes, layout, strand, c) == exp).all(), (okw, strand, c)
+    planes = map_batch(dbatch, layout, pb.CenterMapFactory(12), None, strands=("+", "-"))
+    for strand in ("+", "-"):
+        for c in range(3):
+            exp, _, _, _ = coracle.genome_vector(hb, c, strand, nibble=12)
+            got = plane_chrom(planes, layout, strand, c)
+            np.testing.assert_allclose(got, exp, rtol=CENTER_RTOL, atol=0)
+            assert ((got == 0) == (exp == 0)).all()
+
+
+def test_empty_and_tiny_batches(cuda_device):
+    import torch
+    chroms, lens = ["x", "y"], np.array([1000, 50])
+    layout = pb.GenomeLayout(chroms, lens)
+    empty = pb.batch_from_arrays(chroms, lens, [], [], [], [])
+    for fac in (pb.FivePrimeMapFactory(0), pb.CenterMapFactory(0)):
+        planes = map_batch(empty.to_device(cuda_device), layout, fac, None, strands=("+", "-", "."))
+        for s in ("+", "-", "."):
+            assert float(planes.planes[s].double().abs().sum().item()) == 0.0
+    one = pb.batch_from_arrays(chroms, lens, [1, 0, 0], [49, 999, 0], [1, 1, 30], [0, 1, 0])
+    planes = map_batch(one.to_device(cuda_device), layout, pb.FivePrimeMapFactory(0), None, strands=("+", "-", "."))
+    got = plane_chrom(planes, layout, ".", 0)
+    assert got[0] == 1 and got[999] == 1 and got.sum() == 2
+    assert plane_chrom(planes, layout, "-", 0)[999] == 1 and plane_chrom(planes, layout, "+", 1)[49] == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# containers and reductions
+# ---------------------------------------------------------------------------------------------
+def test_bam_genome_array_matches_reference_semantics(cuda_device):
+    rng = np.random.default_rng(21)
+    lens = {"chrA": 5000, "chrB": 3000}
+    reads = {"chrA": random_cigar_reads(rng, 700, 5000, max_start=4000),
+             "chrB": random_cigar_reads(rng, 300, 3000, max_start=2000)}
+    hb = pb.pack_reads(reads, lens)
+    store = po.ReadStore(lens, reads)
+    for ofn, gfn in ((po.FivePrimeMap(5), pb.FivePrimeMapFactory(5)), (po.CenterMap(3), pb.CenterMapFactory(3)),
+                     (po.ThreePrimeMap(0), pb.ThreePrimeMapFactory(0))):
+        oga = po.OracleBAMGenomeArray(store, mapping=ofn)
+        ga = pb.BAMGenomeArray(hb, mapping=gfn, device=cuda_device)
+        oga.add_filter("size", po.SizeFilter(15, 80))
+        ga.add_filter("size", pb.SizeFilterFactory(15, 80))
+        assert ga.sum() == oga.sum() and ga.chroms() == oga.chroms()
+        for strand in ("+", "-", "."):
+            for chrom, a, b in (("chrA", 0, 5000), ("chrA", 1234, 2345), ("chrB", 2900, 3000), ("chrZ", 5, 10)):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    exp = oga[po.Seg(chrom, a, b, strand)]
+                    got = ga[pb.GenomicSegment(chrom, a, b, strand)]
+                assert got.shape == exp.shape
+                np.testing.assert_allclose(got, exp, rtol=CENTER_RTOL, atol=0)
+                if not isinstance(gfn, pb.CenterMapFactory):
+                    assert (got == exp).all()
+        # get_reads_and_counts returns the reads the reference returns
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r_exp, c_exp = oga.get_reads_and_counts(po.Seg("chrA", 1000, 1500, "+"))
+            r_got, c_got = ga.get_reads_and_counts(pb.GenomicSegment("chrA", 1000, 1500, "+"))
+        assert r_got == r_exp
+        np.testing.assert_allclose(c_got, c_exp, rtol=CENTER_RTOL, atol=0)
+        # normalisation (genome_array.py:826-827)
+        ga.set_normalize(True)
+        oga.set_normalize(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np.testing.assert_allclose(ga[pb.GenomicSegment("chrA", 0, 5000, "-")],
+                                       oga[po.Seg("chrA", 0, 5000, "-")], rtol=1e-12)
+        # generic python filter is honoured (host keep-mask)
+        ga.set_normalize(False)
+        oga.set_normalize(False)
+        ga.add_filter("odd", lambda r: r.reference_start % 2 == 1)
+        oga.add_filter("odd", lambda r: r.reference_start % 2 == 1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np.testing.assert_allclose(ga[pb.GenomicSegment("chrA", 0, 5000, ".")],
+                                       oga[po.Seg("chrA", 0, 5000, ".")], rtol=CENTER_RTOL)
+
+
+def test_segmentchain_counts_and_masks(small_world, cuda_device):
+    w = small_world
+    ga = pb.BAMGenomeArray(w["hb"], mapping=pb.FivePrimeMapFactory(14), device=cuda_device)
+    ga.add_filter("size", pb.SizeFilterFactory(25, 100))
+    chains = w["ann"].chains()
+    masks = synth.make_masks(w["ann"], frac=0.2, seed=2)
+    for ch, m in zip(chains, masks):
+        ch.add_masks(*m)
+    sums, live = ga.count_chains(chains)
+    # oracle: per chromosome/strand vectors + python chain walk
+    vecs = {}
+    for c, chrom in enumerate(w["chroms"]):
+        for strand in ("+", "-"):
+            vecs[(chrom, strand)] = coracle.genome_vector(w["hb"], c, strand, rule="fiveprime", offset=14,
+                                                          size_filter=(25, 100))[0]
+    for i in list(range(0, len(chains), 7)) + [len(chains) - 1]:
+        ch = chains[i]
+        pos = np.asarray(ch.get_position_list())
+        keep = ch.position_mask() == 0
+        exp = vecs[(ch.chrom, ch.strand)][pos][keep].sum()
+        assert sums[i] == exp and live[i] == keep.sum() == ch.masked_length, i
+        # the per-chain object path gives the same masked vector, 5'->3'
+        mc = ch.get_masked_counts(ga)
+        ref = vecs[(ch.chrom, ch.strand)][pos].astype(float)
+        refm = ~keep
+        if ch.strand == "-":
+            ref, refm = ref[::-1], refm[::-1]
+        assert (mc.data == ref).all() and (mc.mask == refm).all()
+    # C oracle for the whole table, unmasked
+    table = ChainTable.from_chains(chains, ga.layout, use_masks=False)
+    s2, l2 = ga.count_chains(table)
+    for strand, pidx in (("+", 0), ("-", 1)):
+        sel = np.nonzero(table.chain_plane == pidx)[0]
+        big = np.zeros(ga.layout.total_bins, dtype=np.uint32)
+        for c, chrom in enumerate(w["chroms"]):
+            base = int(ga.layout.chrom_bin_off[c])
+            big[base:base + int(w["lens"][c])] = vecs[(chrom, strand)]
+        for i in sel[::11]:
+            a, b = table.chain_off[i], table.chain_off[i + 1]
+            es, el = coracle.region_sums(big, table.bstart[a:b], table.bend[a:b], [0, b - a])
+            assert s2[i] == es[0] and l2[i] == el[0]
+
+
+def test_window_matrix_and_profiles(small_world, cuda_device):
+    import torch
+    w = small_world
+    ga = pb.BAMGenomeArray(w["hb"], mapping=pb.FivePrimeMapFactory(12), device=cuda_device)
+    chains = w["ann"].chains()
+    width, flank = 120, 30
+    wins, cols = [], []
+    rng = np.random.default_rng(0)
+    for ch in chains:
+        n = min(ch.length, int(rng.integers(40, width - 10)))
+        win = ch.get_subchain(0, n)
+        if rng.random() < 0.3:
+            a = win.get_genomic_coordinate(int(rng.integers(0, n)))[1]
+            win.add_masks(pb.GenomicSegment(win.chrom, a, a + 25, win.strand))
+        wins.append(win)
+        cols.append(int(rng.integers(0, width - n + 1)))
+    planes = ga.count_planes(("+", "-"))
+    table = ChainTable.from_chains(wins, ga.layout)
+    mat, mmask = gather_windows(planes, table, cols, width)
+    # oracle: metagene.py:895-914
+    exp = np.ma.MaskedArray(np.tile(np.nan, (len(wins), width)), mask=np.tile(True, (len(wins), width)))
+    for i, (win, col) in enumerate(zip(wins, cols)):
+        mvec = win.get_masked_counts(ga)
+        exp.data[i, col:col + win.length] = mvec.data
+        exp.mask[i, col:col + win.length] = mvec.mask
+    got = mat.cpu().numpy()
+    gm = mmask.cpu().numpy().astype(bool)
+    assert (gm == exp.mask).all()
+    assert (got[~gm] == exp.data[~gm]).all() and np.isnan(got[np.isnan(exp.data)]).all()
+    # metagene.py:918-953
+    ns, ne, min_counts = flank, flank + 40, 8
+    denom = np.nansum(exp[:, ns:ne], axis=1)
+    row_select = denom >= min_counts
+    norm = (exp.T.astype(float) / denom).T
+    norm = np.ma.MaskedArray(norm, mask=exp.mask)
+    with np.errstate(all="ignore"):
+        norm.mask[np.isnan(norm)] = True
+        norm.mask[np.isinf(norm)] = True
+    d, sel, nmat, nmask = window_normalize(mat, mmask, ns, ne, min_counts)
+    sel_h = sel.cpu().numpy().astype(bool)
+    rs = np.ma.filled(row_select, False).astype(bool)
+    assert (sel_h == rs).all()
+    assert (nmask.cpu().numpy().astype(bool)[rs] == np.ma.getmaskarray(norm)[rs]).all()
+    for mode, fn in (("median", np.ma.median), ("mean", np.ma.mean)):
+        prof, nreg, csum = column_profile(nmat, nmask, sel, mode)
+        e = fn(norm[rs], axis=0)
+        np.testing.assert_allclose(prof.cpu().numpy(), np.ma.filled(e, np.nan), rtol=1e-12, equal_nan=True)
+        assert (nreg.cpu().numpy() == (~np.ma.getmaskarray(norm))[rs].sum(0)).all()
+    prof, nreg, csum = column_profile(mat, mmask, torch.ones_like(sel), "sum")
+    np.testing.assert_allclose(prof.cpu().numpy(), np.ma.filled(exp.sum(0), 0.0), rtol=1e-12)
