@@ -24,28 +24,36 @@ constexpr int kStatSlots = 64;  // stats are spread over 64 slots to keep atomic
 // ----------------------------------------------------------------------------------------
 // tile -> candidate read slice
 // ----------------------------------------------------------------------------------------
+struct __align__(16) PbTile {
+    long long lo;   // first candidate read
+    long long p0;   // chromosome coordinate of the tile's first bin
+    int n;          // number of candidate reads [lo, lo+n)
+    int live;       // bins of the tile that lie inside the chromosome (0..tile_bins)
+    int chrom;
+    int pad;
+};
+
 __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, int64_t n_tiles,
-                                     int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi)
+                                     PbTile *__restrict__ tiles)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     int64_t g0 = t * tile_bins;
     int c = pb_chrom_of_bin(lay, g0);
     int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
+    int64_t clen = __ldg(lay.chrom_len + c);
     int64_t r0 = 0, r1 = 0;
     if (c < b.n_chrom) { r0 = __ldg(b.chrom_read_off + c); r1 = __ldg(b.chrom_read_off + c + 1); }
     // a read can only place a site in [p0, p0+T) if p0 - max_span < start < p0 + T
     int64_t lo = pb_lower_bound(b.ref_start, r0, r1, p0 - b.max_span + 1);
     int64_t hi = pb_lower_bound(b.ref_start, lo, r1, p0 + tile_bins);
-    tile_lo[t] = lo;
-    tile_hi[t] = hi;
-}
-
-__device__ __forceinline__ void pb_store_zero_tile(uint32_t *out, int64_t g0, int tile_bins)
-{
-    uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    uint4 *dst = reinterpret_cast<uint4 *>(out + g0);
-    for (int j = threadIdx.x; j < tile_bins / 4; j += kThreads) dst[j] = z;
+    int64_t live = clen - p0;
+    live = live < 0 ? 0 : (live > tile_bins ? tile_bins : live);
+    PbTile d;
+    d.lo = lo; d.p0 = p0;
+    d.n = (live > 0 && hi - lo < 0x7fffffff) ? (int)(hi - lo) : (live > 0 ? 0x7fffffff : 0);
+    d.live = (int)live; d.chrom = c; d.pad = 0;
+    tiles[t] = d;
 }
 
 __device__ __forceinline__ void pb_flush_stats(const unsigned long long *local, unsigned int *s_stats,
@@ -73,101 +81,152 @@ __device__ __forceinline__ void pb_flush_stats(const unsigned long long *local, 
 }
 
 // ----------------------------------------------------------------------------------------
-// point rules: 5' / 3' / variable offset
+// point rules: 5' / 3' / variable offset — persistent CTAs, dynamic tile queue, TMA bulk stores
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-pb_point_tiles_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int tile_bins, int planes,
-                      const int64_t *__restrict__ tile_lo, const int64_t *__restrict__ tile_hi,
+__device__ __forceinline__ void pb_fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void pb_bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pb_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void pb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+constexpr int kPThreads = 256;     // threads per persistent CTA
+constexpr int kPTileBins = 4096;   // bins per tile: 16 KB per plane in shared memory
+constexpr int kPUnroll = 4;        // independent read loads in flight per thread
+
+// Invariant: at the top of every loop iteration the shared tile buffer is all zero and visible to
+// the async proxy.  Empty tiles are therefore one bulk store of the buffer as it is; tiles with
+// reads accumulate into it, store it, wait until the TMA engine has READ it (not until the write
+// has landed), and re-zero it.  The SM never touches the output bytes itself.
+__global__ void __launch_bounds__(kPThreads)
+pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restrict__ tiles, int64_t n_tiles,
+                      unsigned long long *__restrict__ tile_counter,
                       uint32_t *__restrict__ out_plus, uint32_t *__restrict__ out_minus,
                       uint32_t *__restrict__ out_any, unsigned long long *__restrict__ stat_slots)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ unsigned int s_stats[PB_NSTATS];
-
-    const int64_t tile = blockIdx.x;
-    const int64_t g0 = tile * tile_bins;
-    const int64_t lo = __ldg(tile_lo + tile), hi = __ldg(tile_hi + tile);
-
-    if (lo >= hi) {  // nothing can land here: the launch doubles as the memset
-        if (planes & PB_PLANE_PLUS) pb_store_zero_tile(out_plus, g0, tile_bins);
-        if (planes & PB_PLANE_MINUS) pb_store_zero_tile(out_minus, g0, tile_bins);
-        if (planes & PB_PLANE_ANY) pb_store_zero_tile(out_any, g0, tile_bins);
-        return;
-    }
-
-    const int c = pb_chrom_of_bin(lay, g0);
-    const int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
-    const int64_t p1 = p0 + tile_bins;
-    const int64_t clen = __ldg(lay.chrom_len + c);
-    const int64_t plim = p1 < clen ? p1 : clen;
-
-    uint32_t *sm_plus = smem, *sm_minus = smem, *sm_any = smem;
-    {
-        int k = 0;
-        if (planes & PB_PLANE_PLUS) sm_plus = smem + (k++) * tile_bins;
-        if (planes & PB_PLANE_MINUS) sm_minus = smem + (k++) * tile_bins;
-        if (planes & PB_PLANE_ANY) sm_any = smem + (k++) * tile_bins;
-        uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        uint4 *s4 = reinterpret_cast<uint4 *>(smem);
-        for (int j = threadIdx.x; j < k * tile_bins / 4; j += kThreads) s4[j] = z;
-    }
-    if (threadIdx.x < PB_NSTATS) s_stats[threadIdx.x] = 0;
-    __syncthreads();
-
-    unsigned long long local[PB_NSTATS];
-#pragma unroll
-    for (int k = 0; k < PB_NSTATS; ++k) local[k] = 0;
+    extern __shared__ __align__(128) uint32_t smem[];
+    __shared__ long long s_next[2];
 
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
                want_any = planes & PB_PLANE_ANY;
-
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
-        const int32_t s = __ldg(b.ref_start + i);
-        const uint32_t m = __ldg(b.meta + i);
-        if (!pb_passes(m, r.size_min, r.size_max)) continue;
-        const int L = PB_META_L(m);
-        const bool rev = PB_META_REV(m);
-        const int idx_f = pb_rule_index(r, L, false);
-        if (idx_f < 0) {
-            // the reference skips this read and warns; count it once, in the tile owning its start
-            if (s >= p0 && s < p1) {
-                local[PB_STAT_DROPPED_ANY]++;
-                local[rev ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_PLUS]++;
-                local[PB_STAT_DROPPED_LEN] = L;
-            }
-            continue;
-        }
-        if (want_any || (!rev && want_plus)) {
-            const int64_t p = pb_position(b, i, s, m, idx_f);
-            if (p >= p0 && p < plim) {
-                const unsigned o = (unsigned)(p - p0);
-                if (want_any) { atomicAdd(&sm_any[o], 1u); local[PB_STAT_MAPPED_ANY]++; }
-                if (!rev && want_plus) { atomicAdd(&sm_plus[o], 1u); local[PB_STAT_MAPPED_PLUS]++; }
-            }
-        }
-        if (rev && want_minus) {
-            const int idx_r = pb_rule_index(r, L, true);
-            const int64_t p = pb_position(b, i, s, m, idx_r);
-            if (p >= p0 && p < plim) {
-                atomicAdd(&sm_minus[(unsigned)(p - p0)], 1u);
-                local[PB_STAT_MAPPED_MINUS]++;
-            }
-        }
-    }
-    pb_flush_stats(local, s_stats, stat_slots, tile);  // contains the __syncthreads() the stores need
-
+    const int n_planes = (int)want_plus + (int)want_minus + (int)want_any;
+    uint32_t *sm_plus = smem, *sm_minus = smem, *sm_any = smem;
     {
         int k = 0;
-        uint32_t *outs[3];
-        if (want_plus) outs[k++] = out_plus;
-        if (want_minus) outs[k++] = out_minus;
-        if (want_any) outs[k++] = out_any;
-        for (int q = 0; q < k; ++q) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(smem + q * tile_bins);
-            uint4 *dst = reinterpret_cast<uint4 *>(outs[q] + g0);
-            for (int j = threadIdx.x; j < tile_bins / 4; j += kThreads) dst[j] = src[j];
+        if (want_plus) sm_plus = smem + (k++) * kPTileBins;
+        if (want_minus) sm_minus = smem + (k++) * kPTileBins;
+        if (want_any) sm_any = smem + (k++) * kPTileBins;
+    }
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 *smem4 = reinterpret_cast<uint4 *>(smem);
+    for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
+    if (threadIdx.x == 0) s_next[0] = (long long)atomicAdd(tile_counter, 1ull);
+    pb_fence_proxy_async();
+    __syncthreads();
+
+    unsigned long long drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;
+    unsigned int drop_len = 0;
+
+    for (int it = 0;; ++it) {
+        const long long tile = s_next[it & 1];
+        if (tile >= n_tiles) break;
+        if (threadIdx.x == 0) s_next[(it + 1) & 1] = (long long)atomicAdd(tile_counter, 1ull);
+        const PbTile d = tiles[tile];
+        const int64_t g0 = tile * kPTileBins;
+
+        if (d.n > 0) {
+            if (threadIdx.x == 0) pb_bulk_wait_read0();   // earlier stores of the zero buffer have read it
+            __syncthreads();
+            const int64_t p0 = d.p0, plim = d.p0 + d.live, p1 = d.p0 + kPTileBins;
+            const int64_t hi = d.lo + d.n;
+            for (int64_t base = d.lo + threadIdx.x; base < hi; base += (int64_t)kPUnroll * kPThreads) {
+                int32_t sv[kPUnroll];
+                uint32_t mv[kPUnroll];
+#pragma unroll
+                for (int u = 0; u < kPUnroll; ++u) {
+                    const int64_t i = base + (int64_t)u * kPThreads;
+                    const bool ok = i < hi;
+                    sv[u] = ok ? __ldg(b.ref_start + i) : 0;
+                    mv[u] = ok ? __ldg(b.meta + i) : (1u << 17);   // drop bit: skipped below
+                }
+#pragma unroll
+                for (int u = 0; u < kPUnroll; ++u) {
+                    const int32_t s = sv[u];
+                    const uint32_t m = mv[u];
+                    if (!pb_passes(m, r.size_min, r.size_max)) continue;
+                    const int64_t i = base + (int64_t)u * kPThreads;
+                    const int L = PB_META_L(m);
+                    const bool rev = PB_META_REV(m);
+                    const int idx_f = pb_rule_index(r, L, false);
+                    if (idx_f < 0) {
+                        // the reference skips this read and warns; count it once, in the tile owning its start
+                        if (s >= p0 && s < p1) {
+                            drop_a++;
+                            if (rev) drop_m++; else drop_p++;
+                            drop_len = L;
+                        }
+                        continue;
+                    }
+                    if (want_any || (!rev && want_plus)) {
+                        const int64_t p = pb_position(b, i, s, m, idx_f);
+                        if (p >= p0 && p < plim) {
+                            const unsigned o = (unsigned)(p - p0);
+                            if (want_any) { atomicAdd(&sm_any[o], 1u); map_a++; }
+                            if (!rev && want_plus) { atomicAdd(&sm_plus[o], 1u); map_p++; }
+                        }
+                    }
+                    if (rev && want_minus) {
+                        const int idx_r = pb_rule_index(r, L, true);
+                        const int64_t p = pb_position(b, i, s, m, idx_r);
+                        if (p >= p0 && p < plim) {
+                            atomicAdd(&sm_minus[(unsigned)(p - p0)], 1u);
+                            map_m++;
+                        }
+                    }
+                }
+            }
+            pb_fence_proxy_async();
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            int k = 0;
+            if (want_plus) pb_bulk_store(out_plus + g0, smem + (k++) * kPTileBins, kPTileBins * 4);
+            if (want_minus) pb_bulk_store(out_minus + g0, smem + (k++) * kPTileBins, kPTileBins * 4);
+            if (want_any) pb_bulk_store(out_any + g0, smem + (k++) * kPTileBins, kPTileBins * 4);
+            pb_bulk_commit();
+            if (d.n > 0) pb_bulk_wait_read0();
+        }
+        __syncthreads();
+        if (d.n > 0) {
+            for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
+            pb_fence_proxy_async();
+            __syncthreads();
         }
     }
+
+    // per-CTA statistics: warp reduce -> shared -> one global atomic per counter
+    {
+        unsigned long long v[6] = {drop_p, drop_m, drop_a, map_p, map_m, map_a};
+        const int idx[6] = {PB_STAT_DROPPED_PLUS, PB_STAT_DROPPED_MINUS, PB_STAT_DROPPED_ANY,
+                            PB_STAT_MAPPED_PLUS, PB_STAT_MAPPED_MINUS, PB_STAT_MAPPED_ANY};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const unsigned long long t = pb_warp_sum(v[k]);
+            if ((threadIdx.x & 31) == 0 && t)
+                atomicAdd(stat_slots + (blockIdx.x & (kStatSlots - 1)) * PB_NSTATS + idx[k], t);
+        }
+        const unsigned int len = __reduce_max_sync(0xffffffffu, drop_len);
+        if ((threadIdx.x & 31) == 0 && len)
+            atomicMax(stat_slots + (blockIdx.x & (kStatSlots - 1)) * PB_NSTATS + PB_STAT_DROPPED_LEN,
+                      (unsigned long long)len);
+    }
+    if (threadIdx.x == 0) pb_bulk_wait_all();
 }
 
 // ----------------------------------------------------------------------------------------
@@ -182,17 +241,18 @@ __global__ void __launch_bounds__(kThreads)
 pb_center_tiles_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes,
                        const int16_t *__restrict__ slot_of_len, const double *__restrict__ inv_m,
                        int slot0, int n_slots, int accumulate,
-                       const int64_t *__restrict__ tile_lo, const int64_t *__restrict__ tile_hi,
+                       const PbTile *__restrict__ tiles,
                        double *__restrict__ out_plus, double *__restrict__ out_minus,
                        double *__restrict__ out_any, unsigned long long *__restrict__ stat_slots)
 {
     constexpr int tile_bins = EPT * kThreads;
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ __align__(128) uint32_t smem[];
     __shared__ unsigned int s_stats[PB_NSTATS];
 
     const int64_t tile = blockIdx.x;
     const int64_t g0 = tile * tile_bins;
-    const int64_t lo = __ldg(tile_lo + tile), hi = __ldg(tile_hi + tile);
+    const PbTile d = tiles[tile];
+    const int64_t lo = d.lo, hi = d.lo + d.n;
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
                want_any = planes & PB_PLANE_ANY;
     const int n_planes = (int)want_plus + (int)want_minus + (int)want_any;
@@ -214,11 +274,9 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes,
         return;
     }
 
-    const int c = pb_chrom_of_bin(lay, g0);
-    const int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
+    const int64_t p0 = d.p0;
     const int64_t p1 = p0 + tile_bins;
-    const int64_t clen = __ldg(lay.chrom_len + c);
-    const int64_t plim = p1 < clen ? p1 : clen;
+    const int64_t plim = p0 + d.live;
 
     int *diff = reinterpret_cast<int *>(smem);
     int *warp_tot = diff + n_planes * n_slots * tile_bins;  // [n_planes*n_slots][kWarps]
@@ -511,7 +569,7 @@ void timing_end(cudaStream_t stream)
     g_ev_count++;
 }
 
-size_t tile_index_bytes(int64_t total_bins) { return (size_t)(total_bins / 1024 + 1) * 2 * sizeof(int64_t); }
+size_t tile_index_bytes(int64_t total_bins) { return (size_t)(total_bins / 1024 + 1) * sizeof(PbTile); }
 size_t stat_slot_bytes() { return (size_t)kStatSlots * PB_NSTATS * sizeof(unsigned long long); }
 
 }  // namespace
@@ -519,7 +577,7 @@ size_t stat_slot_bytes() { return (size_t)kStatSlots * PB_NSTATS * sizeof(unsign
 extern "C" size_t pb_map_workspace_bytes(int64_t total_bins)
 {
     if (total_bins < 0) return 0;
-    return tile_index_bytes(total_bins) + 2 * stat_slot_bytes() + 256;
+    return tile_index_bytes(total_bins) + 2 * stat_slot_bytes() + 256;  // + tile counter
 }
 
 extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
@@ -545,23 +603,33 @@ extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, cons
         pb_set_error("pb_map_point: workspace too small"); return PB_ENOSPACE;
     }
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int tile_bins = 8192;
-    const int64_t n_tiles = layout->total_bins / tile_bins;
-    int64_t *tile_lo = (int64_t *)workspace;
-    int64_t *tile_hi = tile_lo + (layout->total_bins / 1024 + 1);
+    const int64_t n_tiles = layout->total_bins / kPTileBins;
+    PbTile *tiles = (PbTile *)workspace;
     unsigned long long *slots = (unsigned long long *)((char *)workspace + tile_index_bytes(layout->total_bins));
+    unsigned long long *tile_counter = slots + 2 * kStatSlots * PB_NSTATS;
     PbReads b = to_dev(batch);
     PbRuleDev r = to_dev(rule);
     PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
 
-    PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, stat_slot_bytes(), stream));
-    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, n_tiles, tile_lo, tile_hi);
+    PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, 2 * stat_slot_bytes() + 64, stream));
+    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, kPTileBins, n_tiles, tiles);
     const int n_planes = __builtin_popcount(planes);
-    const size_t smem = (size_t)n_planes * tile_bins * sizeof(uint32_t);
+    const size_t smem = (size_t)n_planes * kPTileBins * sizeof(uint32_t);
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        PB_CUDA_CHECK(cudaGetDevice(&dev));
+        PB_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
     PB_CUDA_CHECK(cudaFuncSetAttribute(pb_point_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_point_tiles_kernel, kPThreads, smem));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)sm_count * occ;     // persistent: one resident wave, tiles come from a queue
+    if (grid > n_tiles) grid = n_tiles;
     timing_begin(stream);
-    pb_point_tiles_kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>(b, r, lay, tile_bins, planes, tile_lo, tile_hi,
-                                                                         out_plus, out_minus, out_any, slots);
+    pb_point_tiles_kernel<<<(unsigned)grid, kPThreads, smem, stream>>>(b, r, planes, tiles, n_tiles, tile_counter,
+                                                                      out_plus, out_minus, out_any, slots);
     timing_end(stream);
     pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, (unsigned long long *)stats);
     PB_CUDA_CHECK(cudaGetLastError());
@@ -571,7 +639,7 @@ extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, cons
 template <int EPT>
 static int launch_center(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes,
                          const int16_t *slot_of_len, const double *inv_m, int n_slots, int slots_per_pass,
-                         int64_t total_bins, const int64_t *tile_lo, const int64_t *tile_hi,
+                         int64_t total_bins, const PbTile *tiles,
                          double *out_plus, double *out_minus, double *out_any,
                          unsigned long long *slots, cudaStream_t stream)
 {
@@ -585,7 +653,7 @@ static int launch_center(const PbReads &b, const PbRuleDev &r, const PbLayoutDev
         PB_CUDA_CHECK(cudaFuncSetAttribute(pb_center_tiles_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // stats are only accumulated by the first pass (later passes would count reads again)
         pb_center_tiles_kernel<EPT><<<(unsigned)n_tiles, kThreads, smem, stream>>>(
-            b, r, lay, planes, slot_of_len, inv_m, s0, ns < 0 ? 0 : ns, pass > 0, tile_lo, tile_hi,
+            b, r, lay, planes, slot_of_len, inv_m, s0, ns < 0 ? 0 : ns, pass > 0, tiles,
             out_plus, out_minus, out_any, pass == 0 ? slots : slots + kStatSlots * PB_NSTATS);
         if (n_slots == 0) break;
     }
@@ -610,8 +678,7 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
         pb_set_error("pb_map_center: workspace too small"); return PB_ENOSPACE;
     }
     cudaStream_t stream = (cudaStream_t)stream_;
-    int64_t *tile_lo = (int64_t *)workspace;
-    int64_t *tile_hi = tile_lo + (layout->total_bins / 1024 + 1);
+    PbTile *tiles = (PbTile *)workspace;
     unsigned long long *slots = (unsigned long long *)((char *)workspace + tile_index_bytes(layout->total_bins));
     PbReads b = to_dev(batch);
     PbRuleDev r = to_dev(rule);
@@ -631,13 +698,13 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     const int64_t n_tiles = layout->total_bins / tile_bins;
 
     PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, 2 * stat_slot_bytes(), stream));
-    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, n_tiles, tile_lo, tile_hi);
+    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, n_tiles, tiles);
     timing_begin(stream);
     switch (ept) {
-    case 16: rc = launch_center<16>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
-    case 8:  rc = launch_center<8>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
-    case 4:  rc = launch_center<4>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
-    default: rc = launch_center<2>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tile_lo, tile_hi, out_plus, out_minus, out_any, slots, stream); break;
+    case 16: rc = launch_center<16>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tiles, out_plus, out_minus, out_any, slots, stream); break;
+    case 8:  rc = launch_center<8>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tiles, out_plus, out_minus, out_any, slots, stream); break;
+    case 4:  rc = launch_center<4>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tiles, out_plus, out_minus, out_any, slots, stream); break;
+    default: rc = launch_center<2>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tiles, out_plus, out_minus, out_any, slots, stream); break;
     }
     timing_end(stream);
     if (rc) return rc;

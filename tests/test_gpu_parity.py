@@ -168,23 +168,28 @@ def test_point_planes_bit_exact(small_world, name, factory, okw, size_filter):
     assert [int(st[0]), int(st[1]), int(st[2])] == [dropped["+"], dropped["-"], dropped["."]]
 
 
-def test_variable_planes_bit_exact(small_world):
+@pytest.mark.parametrize("with_default", [True, False])
+def test_variable_planes_bit_exact(small_world, with_default):
     w = small_world
     offs = dict(synth.RIBO_OFFSETS)
-    offs[20] = 25            # offset >= length with default: entry skipped, falls back to the default fill
+    if with_default:
+        offs[20] = 25        # offset >= length with default: entry skipped, falls back to the default fill
+    else:
+        del offs["default"]  # lengths outside 25..35 have no offset: dropped + DataWarning
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         fac = pb.VariableFivePrimeMapFactory(offs)
         luts = po.build_offset_luts(offs)
     assert (fac.forward_offsets == luts[0]).all() and (fac.reverse_offsets == luts[1]).all()
     planes = map_batch(w["dbatch"], w["layout"], fac, None, strands=("+", "-", "."))
-    n_dropped = 0
+    n_dropped = {"+": 0, "-": 0, ".": 0}
     for strand in ("+", "-", "."):
         for c in range(len(w["chroms"])):
             exp, _, d, _ = coracle.genome_vector(w["hb"], c, strand, rule="variable", luts=luts)
             assert (plane_chrom(planes, w["layout"], strand, c) == exp).all(), (strand, c)
-            n_dropped += d if strand == "." else 0
-    assert n_dropped > 0 and int(planes.stats[_lib.PB_STAT_DROPPED_ANY]) == n_dropped   # lengths <= 14 have no offset
+            n_dropped[strand] += d
+    assert (n_dropped["."] > 0) == (not with_default)
+    assert [int(x) for x in planes.stats[:3]] == [n_dropped["+"], n_dropped["-"], n_dropped["."]]
 
 
 @pytest.mark.parametrize("nibble", [0, 12, 20])
