@@ -30,6 +30,7 @@
  *   pb_window_normalize  denominators / row selection / normalisation  plastid/bin/metagene.py:918-924
  *   pb_column_profile  median | mean | sum per column      plastid/bin/metagene.py:934-953,
  *                                                          plastid/bin/psite.py:204-234
+ *   pb_phase_sums    sub-codon phase accumulation          plastid/bin/phase_by_size.py:165-235
  *
  * Alignment batch (SoA, sorted by (chromosome, ref_start); what pysam hands the reference
  * as AlignedSegment.reference_start / .positions / .is_reverse):
@@ -150,14 +151,18 @@ int pb_tiles_kernel_ms_total(float *ms_total, int *n_launches);
 
 /* The operator itself: map reads [i0,i1) of the batch onto one segment [seg_start,seg_end) of
  * their chromosome for query strand `strand` (PB_PLANE_*), which sets the direction the rule is
- * applied in (map_factories.pyx:345-346, 444-445, 625-626).  filter_strand != 0 additionally drops
- * reads of the other strand first, as BAMGenomeArray.get_reads_and_counts does before calling the
- * rule (genome_array.py:811-815); a bare `map_fn(reads, seg)` call passes 0.  counts_out
- * (caller-zeroed): int64[n] (5'/3'/variable), int64[(strat_max-strat_min+1)*n] (stratified),
- * double[n] (center).  kept_out: uint8[i1-i0] or NULL — 1 where the reference appends the read to
- * reads_out. */
+ * applied in (map_factories.pyx:345-346, 444-445, 625-626).  flags:
+ *   PB_SEG_FILTER_STRAND  drop reads of the other strand first, as BAMGenomeArray.get_reads_and_counts
+ *                         does before calling the rule (genome_array.py:811-815);
+ *   PB_SEG_FETCH_OVERLAP  drop reads whose reference span does not overlap the segment, i.e. those
+ *                         pysam's fetch(chrom, start, end) would not have returned (genome_array.py:800-809).
+ * A bare `map_fn(reads, seg)` call passes 0.  counts_out (caller-zeroed): int64[n] (5'/3'/variable),
+ * int64[(strat_max-strat_min+1)*n] (stratified), double[n] (center).  kept_out: uint8[i1-i0] or NULL
+ * — 1 where the reference appends the read to reads_out. */
+#define PB_SEG_FILTER_STRAND 1
+#define PB_SEG_FETCH_OVERLAP 2
 int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
-                   int filter_strand, int64_t seg_start, int64_t seg_end, void *counts_out,
+                   int flags, int64_t seg_start, int64_t seg_end, void *counts_out,
                    uint8_t *kept_out, uint64_t *stats, void *stream);
 
 /* Histogram of aligned length L over reads passing drop/size/strand filters.
@@ -204,6 +209,14 @@ int pb_column_profile(const double *values, const uint8_t *valmask, const uint8_
                       int64_t n_rows, int32_t width, int mode,
                       double *profile, int64_t *n_regions, double *col_sum,
                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* phase_by_size.py:197-214: per chain, counts laid 5'->3' are cut into codons (a trailing partial
+ * codon is ignored), the python slice [codon_front:codon_back] of codons is kept, and counts are
+ * summed per sub-codon phase.  out: double[n_chains*3]. */
+int pb_phase_sums(const void *const *planes, int vec_dtype,
+                  const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                  const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
+                  int32_t codon_front, int32_t codon_back, double *out, void *stream);
 
 #ifdef __cplusplus
 }

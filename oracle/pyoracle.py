@@ -295,18 +295,28 @@ class SizeFilter(object):
 # BAMGenomeArray semantics over an in-memory read store (genome_array.py:626-988)
 # ---------------------------------------------------------------------------
 class ReadStore(object):
-    """In-memory stand-in for an indexed BAM: ``fetch`` returns, in coordinate
-    order (stable for ties), reads whose reference span overlaps ``[start,end)``
-    (pysam ``AlignmentFile.fetch`` [3rd-party])."""
+    """In-memory stand-in for an indexed BAM: ``fetch`` returns, in coordinate order (stable for
+    ties), reads whose reference span overlaps ``[start,end)`` (pysam ``AlignmentFile.fetch``
+    [3rd-party]).  A bisect on the sorted starts only narrows the scan; the overlap test decides."""
 
     def __init__(self, chrom_lengths, reads_by_chrom):
+        import bisect
+        self._bisect = bisect
         self.lengths = dict(chrom_lengths)
         self.references = list(chrom_lengths)
         self.reads = {c: sorted(r, key=lambda x: x.reference_start) for c, r in reads_by_chrom.items()}
+        self.starts = {c: [r.reference_start for r in v] for c, v in self.reads.items()}
+        self.max_span = {c: max([r.reference_end - r.reference_start for r in v] + [1]) for c, v in self.reads.items()}
         self.mapped = sum(len(v) for v in self.reads.values())
 
     def fetch(self, reference, start, end):
-        for r in self.reads.get(reference, ()):
+        reads = self.reads.get(reference, ())
+        if not reads:
+            return
+        starts = self.starts[reference]
+        lo = self._bisect.bisect_left(starts, start - self.max_span[reference])
+        hi = self._bisect.bisect_left(starts, end)
+        for r in reads[lo:hi]:
             if r.reference_start < end and r.reference_end > start:
                 yield r
 

@@ -1,0 +1,94 @@
+"""``counts_in_region``: masked counts, counts per nucleotide and RPKM per region
+(plastid/bin/counts_in_region.py:63-131), all regions in one gather launch."""
+import argparse
+import sys
+
+import numpy as np
+
+from . import _cli
+
+
+def format_row(name, region, counts, length, normconst):
+    """counts_in_region.py:120-124: rpnt = counts/length, rpkm = rpnt * 1e9/sum; '%.8e' x3, '%d'."""
+    rpnt = np.nan if length == 0 else float(counts) / length
+    rpkm = np.nan if length == 0 else rpnt * normconst
+    return [name, region, "%.8e" % counts, "%.8e" % rpnt, "%.8e" % rpkm, "%d" % length]
+
+
+def count_regions(ga, chains, masks=None):
+    """Rows of the output table for ``chains`` (SegmentChains; ``masks[i]`` = mask segments of
+    chain i, added with ``add_masks`` exactly as counts_in_region.py:115-116 does).
+
+    Returns ``(ga_sum, rows)``; every row is ``[name, region, counts, rpnt, rpkm, length]`` already
+    formatted (``%.8e`` x3, ``%d``) as the reference writes it."""
+    ga_sum = ga.sum()
+    normconst = 1000.0 * 1e6 / ga_sum
+    if masks is not None:
+        for ch, m in zip(chains, masks):
+            if m:
+                ch.add_masks(*m)
+    sums, live = ga.count_chains(chains)
+    rows = []
+    for ch, counts, length in zip(chains, sums, live):
+        if length == 0 and ch.length > 0:
+            counts = np.nan            # nansum of a fully masked vector formats as 'nan' 
+        rows.append(format_row(ch.get_name(), str(ch), counts, length, normconst))
+    return ga_sum, rows
+
+
+def write_table(fout, ga_sum, rows):
+    fout.write("## total_dataset_counts: %s\n" % ga_sum)
+    fout.write("region_name\tregion\tcounts\tcounts_per_nucleotide\trpkm\tlength\n")
+    for row in rows:
+        fout.write("%s\n" % "\t".join(row))
+
+
+def main(argv=sys.argv[1:]):
+    parser = argparse.ArgumentParser(description=__doc__)
+    _cli.add_alignment_args(parser)
+    parser.add_argument("--annotation_files", nargs="+", required=True, help="BED files of regions")
+    parser.add_argument("--mask_annotation_files", nargs="*", default=[], help="BED files of masked regions")
+    parser.add_argument("outfile")
+    args = parser.parse_args(argv)
+    ga = _cli.genome_array_from_args(args)
+    chains = []
+    for fn in args.annotation_files:
+        chains.extend(_cli.read_bed(fn))
+    masks = None
+    if args.mask_annotation_files:
+        mask_chains = []
+        for fn in args.mask_annotation_files:
+            mask_chains.extend(_cli.read_bed(fn))
+        masks = overlapping_masks(chains, mask_chains)
+    ga_sum, rows = count_regions(ga, chains, masks)
+    with open(args.outfile, "w") as fout:
+        write_table(fout, ga_sum, rows)
+
+
+def overlapping_masks(chains, mask_chains):
+    """Mask segments overlapping each chain on its chromosome and strand — what
+    ``GenomeHash.get_overlapping_features`` (plastid/genomics/genome_hash.py:259-436) returns to
+    counts_in_region.py:114; unstranded ('.') masks apply to both strands."""
+    by_key = {}
+    for mc in mask_chains:
+        for seg in mc:
+            by_key.setdefault(seg.chrom, []).append(seg)
+    for segs in by_key.values():
+        segs.sort(key=lambda s: s.start)
+    out = []
+    from ..roitools import GenomicSegment
+    for ch in chains:
+        hits = []
+        if len(ch):
+            lo, hi = ch.spanning_segment.start, ch.spanning_segment.end
+            for seg in by_key.get(ch.chrom, ()):
+                if seg.start >= hi:
+                    break
+                if seg.end > lo and seg.strand in (ch.strand, "."):
+                    hits.append(GenomicSegment(seg.chrom, seg.start, seg.end, ch.strand))
+        out.append(hits)
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,74 @@
+"""``phase_by_size``: sub-codon phasing of read 5' ends (or any point rule) per read length
+(plastid/bin/phase_by_size.py:165-235)."""
+import argparse
+import sys
+
+import numpy as np
+
+from . import _cli
+from ..genome_array import map_batch, phase_sums
+from ..map_factories import SizeFilterFactory, CenterMapFactory
+from ..regions import ChainTable
+from ..roitools import SegmentChain
+from .psite import _length_filter
+
+
+def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
+    """Phase sums per read length over the CDS chains: ``{length: float64[3]}``.
+
+    ``back_buffer`` is the python slice stop the reference uses (``-1`` with an ROI file,
+    ``-codon_buffer`` with an annotation; note ``-0`` selects nothing there, and here).  Point
+    rules only: with CenterMapFactory the reference re-maps reads of earlier exons against later
+    ones (phase_by_size.py:186-194) — a quirk this path does not reproduce."""
+    if isinstance(ga.map_fn, CenterMapFactory):
+        raise TypeError("phase_by_size on the GPU path supports point mapping rules only")
+    back_buffer = -codon_buffer if back_buffer is None else back_buffer
+    chains = [c for c in cds_chains if len(c) > 0]
+    table = ChainTable.from_chains(chains, ga.layout, use_masks=False)
+    need = tuple(sorted(set("+-."[p] for p in np.unique(table.chain_plane))) or ["+"])
+    dbatch = ga._device_batch()
+    planes = None
+    out = {}
+    for k in read_lengths:
+        sf = _length_filter(ga, k)
+        if sf is None:
+            out[k] = np.zeros(3)
+            continue
+        planes = map_batch(dbatch, ga.layout, ga.map_fn, sf, strands=need, planes=planes, sync_stats=False)
+        out[k] = phase_sums(planes, table, codon_buffer, back_buffer).sum(dim=0).cpu().numpy()
+    return out
+
+
+def phase_table(sums):
+    lengths = sorted(sums)
+    counted = np.array([sums[k].sum() for k in lengths])
+    with np.errstate(all="ignore"):
+        frac = counted.astype(float) / counted.sum()
+        phases = np.array([sums[k].astype(float) / sums[k].astype(float).sum() for k in lengths])
+    return lengths, counted, frac, phases
+
+
+def main(argv=sys.argv[1:]):
+    parser = argparse.ArgumentParser(description=__doc__)
+    _cli.add_alignment_args(parser)
+    parser.add_argument("roi_file", help="ROI file from `metagene generate` (CDS start windows)")
+    parser.add_argument("outbase")
+    parser.add_argument("--codon_buffer", type=int, default=5)
+    args = parser.parse_args(argv)
+    ga = _cli.genome_array_from_args(args)
+    roi = _cli.read_pl_table(args.roi_file)
+    cds = []
+    for region, offset, zero_point in zip(roi["region"], roi["alignment_offset"], roi["zero_point"]):
+        chain = SegmentChain.from_str(region)                              # roi_row_to_cds, :58-77
+        cds_start = int(zero_point) - int(round(float(offset)))
+        cds.append(chain.get_subchain(cds_start, chain.length))
+    sums = do_phase(ga, cds, list(range(args.min_length, args.max_length + 1)), args.codon_buffer, -1)
+    lengths, counted, frac, phases = phase_table(sums)
+    with open("%s_phasing.txt" % args.outbase, "w") as fout:
+        fout.write("read_length\treads_counted\tfraction_reads_counted\tphase0\tphase1\tphase2\n")
+        for i, k in enumerate(lengths):
+            fout.write("%d\t%d\t%.6f\t%.6f\t%.6f\t%.6f\n" % (k, counted[i], frac[i], phases[i][0], phases[i][1], phases[i][2]))
+
+
+if __name__ == "__main__":
+    main()

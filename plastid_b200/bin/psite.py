@@ -1,0 +1,121 @@
+"""``psite``: per-read-length 5' metagene around start codons -> P-site offset per length
+(plastid/bin/psite.py:90-238, 462-552)."""
+import argparse
+import sys
+import warnings
+
+import numpy as np
+
+from . import _cli
+from .metagene import rois_from_table, _NORM_START_DEFAULT, _NORM_END_DEFAULT
+from ..genome_array import map_batch, gather_windows, window_normalize, column_profile
+from ..map_factories import FivePrimeMapFactory, SizeFilterFactory
+from ..regions import ChainTable
+
+
+def _length_filter(ga, k):
+    """Size filter passing exactly length k, intersected with the array's own size filter."""
+    sf = ga._size_filter()
+    if sf is not None and not (sf.min_ <= k and (sf.max_ == -1 or k <= sf.max_)):
+        return None
+    return SizeFilterFactory(k, k)
+
+
+def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_len=25, max_len=35,
+             aggregate=False, keep=False):
+    """Per read length k in [min_len, max_len]: window matrix of counts of k-mers under ``ga.map_fn``
+    (psite.main forces FivePrimeMapFactory(0), psite.py:357-359), then the same normalise / median
+    (or ``--aggregate`` nansum) as ``metagene count``.  One map+gather pass per length, reusing one
+    set of count planes."""
+    wins, cols, window_size, flank = rois_from_table(roi_table)
+    norm_start = _NORM_START_DEFAULT if norm_start is None else norm_start
+    norm_end = _NORM_END_DEFAULT if norm_end is None else norm_end
+    table = ChainTable.from_chains(wins, ga.layout)
+    need = tuple(sorted(set("+-."[p] for p in np.unique(table.chain_plane))) or ["+"])
+    dbatch = ga._device_batch()
+    planes = None
+    out = {"x": np.arange(-flank, window_size - flank), "profiles": {}, "regions_counted": {}, "raw": {}}
+    for k in range(min_len, max_len + 1):
+        sf = _length_filter(ga, k)
+        if sf is None:
+            sf = SizeFilterFactory.__new__(SizeFilterFactory)
+            sf.min_, sf.max_ = 1, 0                      # nothing passes
+        planes = map_batch(dbatch, ga.layout, ga.map_fn, sf, strands=need, planes=planes, sync_stats=False)
+        mat, mmask = gather_windows(planes, table, cols, window_size)
+        denom, sel, norm, nmask = window_normalize(mat, mmask, norm_start, norm_end, min_counts)
+        if aggregate:
+            profile, n_regions, _ = column_profile(mat, mmask, sel, "sum")
+            _p, n_regions, _ = column_profile(norm, nmask, sel, "mean")     # regions_counted uses the norm mask
+        else:
+            profile, n_regions, _ = column_profile(norm, nmask, sel, "median")
+        prof = profile.cpu().numpy()
+        if sel.sum().item() == 0 and not aggregate:
+            prof = np.zeros(window_size)
+        out["profiles"][k] = prof
+        out["regions_counted"][k] = n_regions.cpu().numpy()
+        if keep:
+            out["raw"][k] = np.ma.MaskedArray(mat.cpu().numpy(), mask=mmask.cpu().numpy().astype(bool))
+    return out
+
+
+def pick_offsets(x, profiles, default=13, constrain=None, require_upstream=False):
+    """psite.py:462-521: offset per length = -x[argmax(profile)] over the allowed columns."""
+    x = np.asarray(x)
+    if constrain is not None:
+        mask = np.tile(True, len(x))
+        zp = (x == 0).argmax()
+        l, r = constrain
+        mindist, maxdist = min(l, r), max(l, r)
+        mask[zp - maxdist:zp - mindist + 1] = False
+    elif require_upstream:
+        mask = x >= 0
+    else:
+        mask = np.tile(False, len(x))
+    offsets = {}
+    for k, y in profiles.items():
+        ymask = np.ma.MaskedArray(np.asarray(y, dtype=float), mask=mask)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if (~mask).sum() == np.isnan(ymask).sum() or np.nanmax(ymask) == 0:
+                offsets[k] = default
+            else:
+                offsets[k] = -x[np.ma.argmax(ymask)]
+    return offsets
+
+
+def write_offsets(fout, offsets, default):
+    fout.write("length\tp_offset\n")
+    for k in offsets:
+        fout.write("%s\t%s\n" % (k, offsets[k]))
+    fout.write("default\t%s" % default)
+
+
+def main(argv=sys.argv[1:]):
+    parser = argparse.ArgumentParser(description=__doc__)
+    _cli.add_alignment_args(parser)
+    parser.add_argument("roi_file")
+    parser.add_argument("outbase")
+    parser.add_argument("--normalize_over", type=int, nargs=2, default=None)
+    parser.add_argument("--min_counts", type=int, default=10)
+    parser.add_argument("--aggregate", action="store_true")
+    parser.add_argument("--default", type=int, default=13)
+    parser.add_argument("--require_upstream", action="store_true")
+    parser.add_argument("--constrain", type=int, nargs=2, default=None)
+    args = parser.parse_args(argv)
+    ga = _cli.genome_array_from_args(args)
+    ga.set_mapping(FivePrimeMapFactory(0))                       # psite.py:357-359
+    for name in list(ga._filters):                               # psite.py:380-383
+        ga.remove_filter(name)
+    roi = _cli.read_pl_table(args.roi_file)
+    ns = ne = None
+    if args.normalize_over is not None:
+        flank = int(roi["zero_point"][0])
+        ns, ne = args.normalize_over[0] + flank, args.normalize_over[1] + flank
+    out = do_count(ga, roi, ns, ne, args.min_counts, args.min_length, args.max_length, args.aggregate)
+    offsets = pick_offsets(out["x"], out["profiles"], args.default, args.constrain, args.require_upstream)
+    with open("%s_p_offsets.txt" % args.outbase, "w") as fout:
+        write_offsets(fout, offsets, args.default)
+
+
+if __name__ == "__main__":
+    main()

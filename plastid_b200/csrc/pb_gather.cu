@@ -100,6 +100,55 @@ pb_gather_windows_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, co
     }
 }
 
+// phase_by_size.py:197-214: counts laid 5'->3', cut into codons, `[front:back]` codon slice, summed
+// per sub-codon phase.  One warp per chain; out[c*3 + phase].
+template <typename T>
+__global__ void __launch_bounds__(256)
+pb_phase_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                     const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
+                     const uint8_t *__restrict__ chain_reverse, int64_t n_chains, int32_t front, int32_t back,
+                     double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chains) return;
+    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(chain_plane + c)]);
+    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
+    int64_t len = 0;
+    for (int64_t k = k0; k < k1; ++k) len += __ldg(bend + k) - __ldg(bstart + k);
+    const int64_t ncod = len / 3;                       // a trailing partial codon is ignored (:203-212)
+    int64_t cod_lo = front < 0 ? ncod + front : front;  // python slice semantics for [front:back]
+    int64_t cod_hi = back < 0 ? ncod + back : back;
+    cod_lo = cod_lo < 0 ? 0 : (cod_lo > ncod ? ncod : cod_lo);
+    cod_hi = cod_hi < 0 ? 0 : (cod_hi > ncod ? ncod : cod_hi);
+    const bool rev = __ldg(chain_reverse + c);
+    typename Acc<T>::type acc0 = 0, acc1 = 0, acc2 = 0;
+    int64_t j = 0;
+    for (int64_t k = k0; k < k1; ++k) {
+        const int64_t bs = __ldg(bstart + k), be = __ldg(bend + k);
+        for (int64_t p = bs + lane; p < be; p += 32) {
+            const int64_t jj = j + (p - bs);
+            const int64_t t = rev ? (len - 1 - jj) : jj;  // 5'->3' index
+            const int64_t cod = t / 3;
+            if (cod >= cod_lo && cod < cod_hi) {
+                const int ph = (int)(t - cod * 3);
+                const T v = vec[p];
+                if (ph == 0) acc0 += v; else if (ph == 1) acc1 += v; else acc2 += v;
+            }
+        }
+        j += be - bs;
+    }
+    double r0, r1, r2;
+    if (sizeof(T) == 4) {
+        r0 = (double)pb_warp_sum((unsigned long long)acc0);
+        r1 = (double)pb_warp_sum((unsigned long long)acc1);
+        r2 = (double)pb_warp_sum((unsigned long long)acc2);
+    } else {
+        r0 = pb_warp_sum_f64((double)acc0); r1 = pb_warp_sum_f64((double)acc1); r2 = pb_warp_sum_f64((double)acc2);
+    }
+    if (lane == 0) { out[c * 3] = r0; out[c * 3 + 1] = r1; out[c * 3 + 2] = r2; }
+}
+
 // one warp per row: denominator, selection, normalisation (metagene.py:918-924)
 __global__ void __launch_bounds__(256)
 pb_window_normalize_kernel(const double *__restrict__ matrix, const uint8_t *__restrict__ maskmat,
@@ -336,6 +385,26 @@ extern "C" int pb_column_profile(const double *values, const uint8_t *valmask, c
         pb_column_keys_kernel<<<grid, dim3(32, 8), 0, stream>>>(values, valmask, row_select, n_rows, width, keys);
     }
     pb_column_stats_kernel<<<(unsigned)width, 512, 0, stream>>>(keys, n_rows, width, mode, profile, n_regions, col_sum);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,
+                             const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                             const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
+                             int32_t codon_front, int32_t codon_back, double *out, void *stream_)
+{
+    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, nullptr, nullptr, vec_dtype);
+    if (rc) return rc;
+    if (!chain_reverse || !out) { pb_set_error("pb_phase_sums: bad arguments"); return PB_EINVAL; }
+    if (n_chains == 0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbPlanes pl{{planes[0], planes[1], planes[2]}};
+    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
+    if (vec_dtype == 0)
+        pb_phase_sums_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, out);
+    else
+        pb_phase_sums_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, out);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

@@ -421,7 +421,7 @@ __global__ void pb_stats_finish_kernel(const unsigned long long *__restrict__ sl
 // ----------------------------------------------------------------------------------------
 // the operator on one segment (global atomics; small inputs)
 // ----------------------------------------------------------------------------------------
-__global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1, int strand, int filter_strand,
+__global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1, int strand, int flags,
                                   int64_t seg_start, int64_t seg_end,
                                   unsigned long long *counts_i, double *counts_f,
                                   uint8_t *__restrict__ kept, unsigned long long *__restrict__ stats)
@@ -435,8 +435,17 @@ __global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1
         uint8_t keep = 0;
         const bool rev = PB_META_REV(m);
         bool pass = pb_passes(m, r.size_min, r.size_max);
-        if (filter_strand && strand == PB_PLANE_PLUS && rev) pass = false;    // genome_array.py:811-815
-        if (filter_strand && strand == PB_PLANE_MINUS && !rev) pass = false;
+        if ((flags & PB_SEG_FILTER_STRAND) && strand == PB_PLANE_PLUS && rev) pass = false;    // genome_array.py:811-815
+        if ((flags & PB_SEG_FILTER_STRAND) && strand == PB_PLANE_MINUS && !rev) pass = false;
+        if (pass && (flags & PB_SEG_FETCH_OVERLAP)) {
+            // AlignmentFile.fetch(chrom, start, end): only reads whose reference span overlaps the segment
+            int64_t span = PB_META_L(m);
+            if (PB_META_NBLK(m) > 1 && b.blk_off != nullptr) {
+                const int2 last = __ldg(b.blk + (__ldg(b.blk_off + i + 1) - 1));
+                span = (int64_t)last.x + last.y;
+            }
+            if (!((int64_t)s < seg_end && (int64_t)s + span > seg_start)) pass = false;
+        }
         if (pass) {
             const int L = PB_META_L(m);
             const int sidx = strand == PB_PLANE_PLUS ? PB_STAT_DROPPED_PLUS
@@ -731,7 +740,7 @@ extern "C" int pb_tiles_kernel_ms_total(float *ms_total, int *n_launches)
 }
 
 extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
-                              int filter_strand, int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
+                              int flags, int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
                               uint64_t *stats, void *stream_)
 {
     if (!batch || !rule || !counts_out || !stats) { pb_set_error("pb_map_segment: null argument"); return PB_EINVAL; }
@@ -749,7 +758,7 @@ extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, con
     int64_t n = i1 - i0;
     unsigned grid = (unsigned)((n + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    pb_segment_kernel<<<grid, 256, 0, stream>>>(b, r, i0, i1, strand, filter_strand, seg_start, seg_end,
+    pb_segment_kernel<<<grid, 256, 0, stream>>>(b, r, i0, i1, strand, flags, seg_start, seg_end,
                                                 (unsigned long long *)counts_out, (double *)counts_out, kept_out,
                                                 (unsigned long long *)stats);
     PB_CUDA_CHECK(cudaGetLastError());

@@ -144,6 +144,21 @@ def gather_windows(planes, table, row_col, width):
     return matrix[:n], maskmat[:n]
 
 
+def phase_sums(planes, table, codon_front, codon_back):
+    """Per-chain sub-codon phase sums (n_chains x 3, device tensor)."""
+    import torch
+    _lib.require_cuda()
+    dev = planes.device
+    d = table.device(dev)
+    n = table.n_chains
+    out = torch.zeros((max(n, 1), 3), dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().pb_phase_sums(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
+                                        _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                        _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), n,
+                                        int(codon_front), int(codon_back), _lib.ptr(out), _lib.stream_ptr()))
+    return out[:n]
+
+
 def window_normalize(matrix, maskmat, norm_lo, norm_hi, min_counts, want_norm=True):
     import torch
     n, width = matrix.shape

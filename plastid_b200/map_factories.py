@@ -85,7 +85,7 @@ class _MapFactory(object):
         raise NotImplementedError
 
     def map_segment(self, dbatch, i0, i1, seg_start, seg_end, strand, size_filter=None, want_kept=True,
-                    filter_strand=True):
+                    flags=3):
         """Run the operator on reads ``[i0,i1)`` of a device batch; returns (counts ndarray, kept
         ndarray of bool or None)."""
         import torch
@@ -100,7 +100,7 @@ class _MapFactory(object):
         rule = self.pb_rule(dev, size_filter)
         b = dbatch.c_struct()
         _lib.check(_lib.lib().pb_map_segment(C.byref(b), i0, i1, C.byref(rule), _lib.STRAND_PLANE[strand],
-                                             int(bool(filter_strand)), int(seg_start), int(seg_end), _lib.ptr(counts), _lib.ptr(kept),
+                                             int(flags), int(seg_start), int(seg_end), _lib.ptr(counts), _lib.ptr(kept),
                                              _lib.ptr(stats), _lib.stream_ptr()))
         st = stats.cpu().numpy()
         dropped = int(st[{"+": 0, "-": 1, ".": 2}[strand]])
@@ -113,13 +113,14 @@ class _MapFactory(object):
     def __call__(self, reads, seg):
         if reads is None or seg is None:
             raise TypeError("reads and seg may not be None")
+        _lib.require_cuda()
         reads = list(reads)
         start, end, strand = _seg_fields(seg)
         strand = strand if strand in ("+", "-") else "."
         hb = pack_reads({"_": reads}, {"_": max(end, 1)}, keep_objects=True)
         if len(hb) == 0:
             return [], np.zeros(self._leading_shape() + [max(end - start, 0)], dtype=self.count_dtype)
-        counts, kept = self.map_segment(hb.to_device("cuda"), 0, len(hb), start, end, strand, filter_strand=False)
+        counts, kept = self.map_segment(hb.to_device("cuda"), 0, len(hb), start, end, strand, flags=0)
         # pack_reads sorts by start; reads_out keeps the caller's order like the reference loop
         kept_ids = set(id(hb.objects[i]) for i in np.nonzero(kept)[0])
         reads_out = [r for r in reads if id(r) in kept_ids]

@@ -208,6 +208,9 @@ class SegmentChain(object):
             return []
         return [GenomicSegment(self.chrom, a, b, self.strand) for a, b in self._mask_intervals]
 
+    def get_masks(self):
+        return self.mask_segments
+
     def add_masks(self, *mask_segments):
         if len(mask_segments) == 0:
             return

@@ -1,0 +1,164 @@
+"""GPU parity of the script-level counting loops (counts_in_region, cs count, metagene count, psite,
+phase_by_size) against the oracle's statement-by-statement restatements of the reference scripts."""
+import warnings
+
+import numpy as np
+import pytest
+
+import plastid_b200 as pb
+from plastid_b200 import synth
+from plastid_b200.bin import counts_in_region, cs, metagene, psite, phase_by_size
+from oracle import pyoracle as po
+from oracle import scripts as osc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def world(cuda_device):
+    chroms, lens = synth.yeast_like_genome(total=700_000, n_chrom=4)
+    ann = synth.make_annotation(chroms, lens, 120, seed=8, exons=(1, 3), exon_len=(150, 500), intron_len=(40, 300))
+    hb = synth.device_batch_to_host(synth.riboseq_reads(ann, 60_000, seed=4, device="cpu", lengths=range(22, 38)),
+                                    chroms, lens)
+    reads = {c: [] for c in chroms}
+    for i in range(len(hb)):
+        c = int(np.searchsorted(hb.chrom_read_off, i, side="right")) - 1
+        reads[chroms[c]].append(po.Read(int(hb.ref_start[i]), [(0, int(hb.meta[i] & 0xFFFF))], bool((hb.meta[i] >> 16) & 1)))
+    store = po.ReadStore(dict(zip(chroms, [int(x) for x in lens])), reads)
+    hb2 = pb.pack_reads(reads, dict(zip(chroms, [int(x) for x in lens])))
+    return dict(chroms=chroms, lens=lens, ann=ann, store=store, hb=hb2, dev=cuda_device)
+
+
+def make_gas(w, ofn, gfn, size=(25, 100)):
+    oga = po.OracleBAMGenomeArray(w["store"], mapping=ofn)
+    ga = pb.BAMGenomeArray(w["hb"], mapping=gfn, device=w["dev"])
+    if size is not None:
+        oga.add_filter("size", po.SizeFilter(*size))
+        ga.add_filter("size", pb.SizeFilterFactory(*size))
+    return oga, ga
+
+
+def test_counts_in_region(world):
+    w = world
+    oga, ga = make_gas(w, po.FivePrimeMap(14), pb.FivePrimeMapFactory(14))
+    chains = w["ann"].chains()
+    masks = synth.make_masks(w["ann"], frac=0.25, seed=3)
+    masks[5] = [pb.GenomicSegment(chains[5].chrom, chains[5].spanning_segment.start - 10,
+                                  chains[5].spanning_segment.end + 10, chains[5].strand)]      # fully masked
+    chains.append(pb.SegmentChain(pb.GenomicSegment("chrUnknown", 10, 500, "+"), ID="nowhere"))
+    masks.append([])
+    ochains = []
+    for ch in chains:
+        oc = po.Chain(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in ch])
+        oc.name = ch.get_name()
+        ochains.append(oc)
+    omasks = [[po.Seg(m.chrom, m.start, m.end, m.strand) for m in ms] for ms in masks]
+    exp = osc.counts_in_region_rows(oga, ochains, omasks)
+    ga_sum, got = counts_in_region.count_regions(ga, chains, masks)
+    assert ga_sum == oga.sum()
+    assert got == exp
+    assert got[5][2] == "nan" and got[5][5] == "0"
+
+
+def test_cs_count(world):
+    w = world
+    oga, ga = make_gas(w, po.ThreePrimeMap(0), pb.ThreePrimeMapFactory(0))
+    chains = w["ann"].chains()
+    pos = {"region": [], "exon": [], "utr5": [], "cds": [], "utr3": []}
+    for ch in chains[:60]:
+        n = ch.length
+        a, b = n // 5, n - n // 4
+        pos["region"].append(ch.get_name())
+        pos["exon"].append(str(ch))
+        pos["utr5"].append(str(ch.get_subchain(0, a)))
+        pos["cds"].append(str(ch.get_subchain(a, b)))
+        pos["utr3"].append(str(ch.get_subchain(b, n)) if len(pos["region"]) % 7 else "na")
+    exp = osc.cs_count(oga, pos)
+    order, got = cs.do_count(ga, pos)
+    assert order[0] == "region" and len(order) == 13
+    for col in order:
+        for e, g in zip(exp[col], got[col]):
+            if isinstance(e, float) and np.isnan(e):
+                assert np.isnan(g), col
+            elif col.endswith("_rpkm"):
+                assert g == pytest.approx(e, rel=1e-14), col
+            else:
+                assert g == e, col
+
+
+def roi_rows(w, flank=50, down=100, mask_every=4):
+    rows = {"region": [], "masked": [], "alignment_offset": [], "window_size": [], "zero_point": []}
+    for i, ch in enumerate(w["ann"].chains()):
+        start = min(ch.length // 3, 200)
+        lo, hi = max(0, start - flank), min(ch.length, start + down)
+        win = ch.get_subchain(lo, hi)
+        rows["region"].append(str(win))
+        if i % mask_every == 0:
+            g = win.get_genomic_coordinate(min(60, win.length - 1))[1]
+            rows["masked"].append("%s:%d-%d(%s)" % (win.chrom, g, g + 12, win.strand))
+        else:
+            rows["masked"].append("na")
+        rows["alignment_offset"].append(flank - (start - lo))
+        rows["window_size"].append(flank + down)
+        rows["zero_point"].append(flank)
+    return rows
+
+
+def as_oracle_rows(rows):
+    return [dict(region=r, masked=m, alignment_offset=o)
+            for r, m, o in zip(rows["region"], rows["masked"], rows["alignment_offset"])]
+
+
+@pytest.mark.parametrize("use_mean", [False, True])
+def test_metagene_count(world, use_mean):
+    w = world
+    oga, ga = make_gas(w, po.FivePrimeMap(12), pb.FivePrimeMapFactory(12))
+    rows = roi_rows(w)
+    counts, norm, profile, num_genes, row_select = osc.metagene_count(oga, as_oracle_rows(rows), 150, 70, 100, 3, use_mean)
+    out = metagene.do_count(ga, rows, 70, 100, 3, use_mean, keep=True)
+    assert (np.ma.getmaskarray(out["counts"]) == np.ma.getmaskarray(counts)).all()
+    assert (out["counts"].compressed() == counts.compressed()).all()
+    rs = np.ma.filled(row_select, False).astype(bool)
+    assert (out["row_select"] == rs).all() and rs.sum() > 10
+    assert (np.ma.getmaskarray(out["norm_counts"])[rs] == np.ma.getmaskarray(norm)[rs]).all()
+    np.testing.assert_allclose(out["norm_counts"][rs].compressed(), norm[rs].compressed(), rtol=1e-15)
+    np.testing.assert_allclose(out["metagene_average"], np.ma.filled(profile, np.nan), rtol=1e-12, equal_nan=True)
+    assert (out["regions_counted"] == num_genes).all()
+    assert (out["x"] == np.arange(-50, 100)).all()
+
+
+@pytest.mark.parametrize("aggregate", [False, True])
+def test_psite(world, aggregate):
+    w = world
+    oga, ga = make_gas(w, po.FivePrimeMap(0), pb.FivePrimeMapFactory(0), size=None)     # psite.py:357-383
+    rows = roi_rows(w)
+    raw, profiles, regions = osc.psite_count(oga, as_oracle_rows(rows), 150, 70, 100, 2, 26, 33, aggregate)
+    out = psite.do_count(ga, rows, 70, 100, 2, 26, 33, aggregate, keep=True)
+    for k in range(26, 34):
+        assert (np.ma.getmaskarray(out["raw"][k]) == np.ma.getmaskarray(raw[k])).all(), k
+        assert (out["raw"][k].compressed() == raw[k].compressed()).all(), k
+        np.testing.assert_allclose(out["profiles"][k], np.ma.filled(profiles[k], np.nan), rtol=1e-12, equal_nan=True)
+        assert (out["regions_counted"][k] == regions[k]).all(), k
+    x = np.arange(-50, 100)
+    for kw in (dict(), dict(require_upstream=True), dict(constrain=(5, 25))):
+        assert psite.pick_offsets(x, out["profiles"], 13, **kw) == osc.psite_pick_offsets(x, profiles, 13, **kw)
+
+
+@pytest.mark.parametrize("back", [-1, -5, 0])
+def test_phase_by_size(world, back):
+    w = world
+    offs = dict(synth.RIBO_OFFSETS)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oga, ga = make_gas(w, po.VariableFivePrimeMap(offs), pb.VariableFivePrimeMapFactory(offs))
+    chains = w["ann"].chains()
+    cds = [ch.get_subchain(ch.length // 6, ch.length - ch.length // 8) for ch in chains[:80]]
+    ocds = [po.Chain(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in ch]) for ch in cds]
+    lengths = list(range(24, 36))
+    exp = osc.phase_by_size(oga, ocds, lengths, 5, back)
+    got = phase_by_size.do_phase(ga, cds, lengths, 5, back)
+    for k in lengths:
+        assert (got[k] == exp[k]).all(), k
+    if back != 0:
+        assert sum(v.sum() for v in got.values()) > 1000
+        assert got[24].sum() == 0          # below the 25-100 size filter

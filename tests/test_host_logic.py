@@ -1,0 +1,286 @@
+"""Host-side logic and the C-ABI surface (no GPU, no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import plastid_b200 as pb
+from plastid_b200 import _lib, synth
+from plastid_b200.batch import cigar_to_blocks, pack_reads, batch_from_arrays
+from plastid_b200.genome_array import merge_batches
+from plastid_b200.regions import ChainTable
+from oracle import pyoracle as po
+from helpers import random_cigar_reads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------- C-ABI surface
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "plastid_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 14
+    handle = C.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(handle, name), "libplastid_b200.so does not export %s" % name
+    assert sorted(_lib.exported_symbols()) == names       # the ctypes table binds exactly the header
+
+
+def test_abi_struct_layouts_match_header():
+    assert C.sizeof(_lib.PbBatch) == 56 and C.sizeof(_lib.PbLayout) == 32 and C.sizeof(_lib.PbRule) == 40
+    assert _lib.lib().pb_version().startswith(b"plastid_b200")
+
+
+def test_argument_errors_are_reported_without_a_device():
+    L = _lib.lib()
+    assert L.pb_map_point(None, None, None, 3, None, None, None, None, None, 0, None) == _lib.PB_EINVAL
+    assert b"null" in L.pb_last_error()
+    assert L.pb_region_sums(None, 0, None, None, None, None, 0, None, None, None, None, None) == _lib.PB_EINVAL
+    assert L.pb_map_workspace_bytes(16384 * 4) > 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(_lib.PlastidB200Error):
+        _lib.require_cuda()
+    reads = [po.Read(0, [(0, 30)], False)]
+    with pytest.raises(_lib.PlastidB200Error):
+        pb.FivePrimeMapFactory(0)(reads, pb.GenomicSegment("c", 0, 100, "+"))
+    with pytest.raises(_lib.PlastidB200Error):
+        pb.GenomeArray({"c": 100})
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _dirs, files in os.walk(os.path.join(ROOT, "plastid_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|oracle[./]|liboracle", text, flags=re.M), \
+                    "%s reaches into oracle/" % fn
+
+
+# ------------------------------------------------------------------------------- packing
+def test_cigar_to_blocks():
+    M, I, D, N, S, H, P, EQ, X = range(9)
+    assert cigar_to_blocks([(M, 30)]) == ([(0, 30)], 30)
+    assert cigar_to_blocks([(S, 3), (M, 10), (I, 2), (M, 10), (S, 4)]) == ([(0, 20)], 20)
+    assert cigar_to_blocks([(M, 10), (D, 2), (M, 10)]) == ([(0, 10), (12, 10)], 22)
+    assert cigar_to_blocks([(EQ, 5), (X, 1), (EQ, 4), (N, 100), (M, 7), (H, 9)]) == ([(0, 10), (110, 7)], 117)
+    assert cigar_to_blocks([(M, 5), (P, 3), (M, 5)]) == ([(0, 10)], 10)
+    assert cigar_to_blocks([(S, 30)]) == ([], 0)
+
+
+def test_pack_reads_matches_oracle_positions():
+    rng = np.random.default_rng(5)
+    reads = {"a": random_cigar_reads(rng, 200, 5000, 3000), "b": random_cigar_reads(rng, 50, 2000, 1000)}
+    hb = pack_reads(reads, {"a": 5000, "b": 2000})
+    hb.check_sorted()
+    assert len(hb) == 250 and list(hb.chrom_read_off) == [0, 200, 250]
+    for i, r in enumerate(hb.objects):
+        assert hb.positions_of(i) == r.positions
+        assert hb.read_view(i) is r
+        assert bool(hb.is_reverse[i]) == r.is_reverse and int(hb.aligned_len[i]) == len(r.positions)
+    assert hb.max_span >= max(r.reference_end - r.positions[0] for r in hb.objects if r.positions)
+    # a read whose CIGAR starts with a deletion: positions start after it
+    odd = pack_reads({"a": [po.Read(100, [(2, 5), (0, 10)], False), po.Read(102, [(0, 4)], True)]}, {"a": 1000})
+    assert list(odd.ref_start) == [102, 105] and odd.positions_of(1) == list(range(105, 115))
+    with pytest.raises(ValueError):
+        pack_reads({"a": [po.Read(0, [(0, 70000)], False)]}, {"a": 100000})
+    with pytest.raises(ValueError):
+        pack_reads({"a": [po.Read(0, [(0, 1), (3, 1)] * 300, False)]}, {"a": 100000})
+
+
+def test_batch_from_arrays_and_merge():
+    chroms, lens = ["x", "y"], [1000, 500]
+    b1 = batch_from_arrays(chroms, lens, [1, 0, 0], [49, 999, 0], [1, 1, 30], [0, 1, 0])
+    assert list(b1.ref_start) == [0, 999, 49] and list(b1.chrom_read_off) == [0, 2, 3]
+    assert list(b1.aligned_len) == [30, 1, 1] and list(b1.is_reverse) == [False, True, False]
+    nb = [1, 2]
+    blk = [[0, 10], [0, 5], [50, 5]]
+    b2 = batch_from_arrays(["y", "z"], [700, 50], [0, 0], [20, 5], [10, 10], [0, 1], blocks=(nb, blk))
+    assert b2.blk is not None and b2.positions_of(0) == list(range(5, 10)) + list(range(55, 60))
+    m = merge_batches([b1, b2])
+    assert m.chroms == ["x", "y", "z"] and list(m.chrom_len) == [1000, 700, 50]
+    assert list(m.chrom_read_off) == [0, 2, 5, 5] and m.mapped == 5
+    assert list(m.ref_start) == [0, 999, 5, 20, 49]
+    assert m.positions_of(2) == list(range(5, 10)) + list(range(55, 60)) and m.positions_of(3) == list(range(20, 30))
+    d = m.with_drop_mask(np.array([0, 1, 0, 0, 1], dtype=bool))
+    assert list((d.meta >> 17) & 1) == [0, 1, 0, 0, 1] and list(d.aligned_len) == list(m.aligned_len)
+    empty = batch_from_arrays(chroms, lens, [], [], [], [])
+    assert len(empty) == 0 and list(empty.chrom_read_off) == [0, 0, 0] and empty.max_span == 1
+
+
+def test_genome_layout():
+    lay = pb.GenomeLayout(["a", "b", "c"], [100, 16384, 16385])
+    assert list(lay.chrom_bin_off) == [0, 16384, 32768, 65536] and lay.total_bins == 65536
+    assert lay.bin_of("c", 7) == 32775
+    with pytest.raises(ValueError):
+        pb.GenomeLayout([], [])
+
+
+# ------------------------------------------------------------------------------- factories (host side)
+def test_factory_constructors_and_luts():
+    with pytest.raises(ValueError):
+        pb.FivePrimeMapFactory(-1)
+    with pytest.raises(ValueError):
+        pb.ThreePrimeMapFactory(-3)
+    with pytest.raises(ValueError):
+        pb.CenterMapFactory(-1)
+    with pytest.raises(ValueError):
+        pb.SizeFilterFactory(0, 10)
+    with pytest.raises(ValueError):
+        pb.SizeFilterFactory(30, 20)
+    with pytest.raises(ValueError):
+        pb.StratifiedVariableFivePrimeMapFactory({"default": 3}, 30, 30)
+    f = pb.FivePrimeMapFactory(3)
+    f.offset = 9
+    assert f.offset == 9
+    c = pb.CenterMapFactory(2)
+    c.nibble = 5
+    assert c.nibble == 5
+    s = pb.StratifiedVariableFivePrimeMapFactory({"default": 3}, 26, 30)
+    assert s.shape == [5] and list(s.row_keys) == [26, 27, 28, 29, 30]
+    import warnings
+    for d in ({"default": 0}, {25: 10, "default": 28}, {L: L // 2 for L in range(25, 40)}, dict(synth.RIBO_OFFSETS),
+              {20: 25, 30: 40, "default": 27}, None):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fac = pb.VariableFivePrimeMapFactory(d)
+            fw, rc = po.build_offset_luts(d)
+        assert (fac.forward_offsets == fw).all() and (fac.reverse_offsets == rc).all()
+    with pytest.raises(UnboundLocalError):
+        pb.VariableFivePrimeMapFactory({20: 25})
+    sf = pb.SizeFilterFactory(25, 30)
+    assert [sf(po.Read(0, [(0, L)], False)) for L in (24, 25, 30, 31)] == [False, True, True, False]
+    assert pb.SizeFilterFactory(25)(po.Read(0, [(0, 4000)], False))
+    slot, inv = pb.CenterMapFactory(12).slot_tables(np.bincount([24, 25, 25, 30, 100], minlength=65536))
+    assert list(inv) == [1.0, 1.0 / 6, 1.0 / 76] and slot[24] == -1 and list(slot[[25, 30, 100]]) == [0, 1, 2]
+
+
+def test_offset_file_errors():
+    import io
+    good = "25\t12\n26\t13\ndefault\t14\n"
+    fac = pb.VariableFivePrimeMapFactory.from_file(io.StringIO("# comment\n" + good))
+    assert fac.forward_offsets[25] == 12 and fac.forward_offsets[40] == 14
+    for bad in (good + good, "25\t12\t7\n", "25\n", "abc\t3\n", "25\t1.5\n"):
+        with pytest.raises(pb.MalformedFileError):
+            pb.VariableFivePrimeMapFactory.from_file(io.StringIO(bad))
+
+
+# ------------------------------------------------------------------------------- SegmentChain
+def test_segmentchain_layout_and_strings():
+    ch = pb.SegmentChain(pb.GenomicSegment("chrA", 250, 300, "-"), pb.GenomicSegment("chrA", 100, 150, "-"),
+                         pb.GenomicSegment("chrA", 150, 170, "-"), pb.GenomicSegment("chrA", 160, 180, "-"))
+    assert str(ch) == "chrA:100-180^250-300(-)" and ch.length == 130 and len(ch) == 2
+    assert str(pb.SegmentChain.from_str(str(ch))) == str(ch)
+    assert str(pb.SegmentChain()) == "na" and len(pb.SegmentChain.from_str("na")) == 0
+    o = po.Chain(po.Seg("chrA", 250, 300, "-"), po.Seg("chrA", 100, 150, "-"), po.Seg("chrA", 150, 170, "-"),
+                 po.Seg("chrA", 160, 180, "-"))
+    assert str(o) == str(ch) and o.position_list == ch.get_position_list()
+    with pytest.raises(ValueError):
+        pb.SegmentChain(pb.GenomicSegment("chrA", 0, 5, "+"), pb.GenomicSegment("chrB", 10, 15, "+"))
+    with pytest.raises(ValueError):
+        pb.SegmentChain(pb.GenomicSegment("chrA", 0, 5, "+"), pb.GenomicSegment("chrA", 10, 15, "-"))
+    # coordinates (roitools.pyx:2957-3106)
+    assert ch.get_genomic_coordinate(0) == ("chrA", 299, "-") and ch.get_genomic_coordinate(129) == ("chrA", 100, "-")
+    assert ch.get_genomic_coordinate(50) == ("chrA", 179, "-")
+    assert ch.get_genomic_coordinate(0, stranded=False) == ("chrA", 100, "-")
+    assert ch.get_segmentchain_coordinate("chrA", 299, "-") == 0
+    with pytest.raises(KeyError):
+        ch.get_segmentchain_coordinate("chrA", 200, "-")
+    with pytest.raises(IndexError):
+        ch.get_genomic_coordinate(130)
+    sub = ch.get_subchain(40, 60)
+    assert str(sub) == "chrA:170-180^250-260(-)"
+    assert str(pb.GenomicSegment.from_str("chrX:5-99(+)")) == "chrX:5-99(+)"
+
+
+def test_add_masks_known_answers():
+    """plastid/test/unit/genomics/test_roitools.py:976-1035 and :1382-1417, transcribed."""
+    for strand, opp in (("+", "-"), ("-", "+")):
+        for cls, seg in ((pb.SegmentChain, pb.GenomicSegment), (po.Chain, po.Seg)):
+            ivc = cls(seg("chrA", 100, 150, strand), seg("chrA", 250, 300, strand))
+            mask_a, mask_b, mask_c = seg("chrA", 125, 150, strand), seg("chrA", 275, 300, strand), seg("chrA", 275, 350, strand)
+
+            def masks():
+                if cls is pb.SegmentChain:
+                    return [(m.start, m.end) for m in ivc.get_masks()]
+                pm = ivc.position_mask or [0] * ivc.length
+                cov = [p for p, m in zip(ivc.position_list, pm) if m]
+                out = []
+                for p in cov:
+                    if out and out[-1][1] == p:
+                        out[-1][1] = p + 1
+                    else:
+                        out.append([p, p + 1])
+                return [tuple(x) for x in out]
+
+            with pytest.raises(ValueError):
+                ivc.add_masks(seg("chrA", 125, 150, opp))
+            with pytest.raises(ValueError):
+                ivc.add_masks(seg("chrB", 125, 150, strand), seg("chrB", 275, 300, strand))
+            assert masks() == []
+            ivc.add_masks(seg("chrA", 155, 245, strand))          # intron mask: nothing
+            assert masks() == [] and ivc.masked_length == 100
+            ivc.add_masks(mask_a)
+            assert masks() == [(125, 150)]
+            ivc.add_masks(mask_a)
+            assert masks() == [(125, 150)]
+            ivc.add_masks(mask_b)
+            assert masks() == [(125, 150), (275, 300)] and ivc.masked_length == 50
+            ivc = cls(seg("chrA", 100, 150, strand), seg("chrA", 250, 300, strand))
+            ivc.add_masks(mask_a, mask_c)                          # trimmed to the chain
+            assert masks() == [(125, 150), (275, 300)]
+    ivc1 = pb.SegmentChain(pb.GenomicSegment("chrA", 100, 150, "+"), pb.GenomicSegment("chrA", 150, 200, "+"),
+                           pb.GenomicSegment("chrA", 250, 350, "+"))
+    assert (ivc1.length, ivc1.masked_length) == (200, 200)
+    ivc1.add_masks(pb.GenomicSegment("chrA", 400, 500, "+"))
+    assert ivc1.masked_length == 200
+    ivc1.add_masks(pb.GenomicSegment("chrA", 50, 125, "+"))
+    assert (ivc1.length, ivc1.masked_length) == (200, 175)
+    assert ivc1.position_mask().sum() == 25 and ivc1.position_mask()[:25].all()
+
+
+def test_chain_table_lowering():
+    chroms, lens = ["a", "b"], [50000, 20000]
+    lay = pb.GenomeLayout(chroms, lens)
+    c1 = pb.SegmentChain(pb.GenomicSegment("a", 10, 20, "+"), pb.GenomicSegment("a", 30, 35, "+"))
+    c2 = pb.SegmentChain(pb.GenomicSegment("b", 5, 9, "-"))
+    c3 = pb.SegmentChain(pb.GenomicSegment("zz", 5, 9, "+"))
+    c4 = pb.SegmentChain()
+    c1.add_masks(pb.GenomicSegment("a", 18, 32, "+"))
+    t = ChainTable.from_chains([c1, c2, c3, c4], lay)
+    assert list(t.chain_off) == [0, 2, 3, 3, 3] and list(t.bstart) == [10, 30, 65536 + 5]
+    assert list(t.chain_plane) == [0, 1, 0, 2] and list(t.chain_reverse) == [0, 1, 0, 0]
+    assert list(t.chain_len) == [15, 4, 0, 0] and list(t.known) == [True, True, False, True]
+    bits = np.unpackbits(t.mask_bits, bitorder="little")
+    assert list(bits[:15]) == [0] * 8 + [1, 1] + [1, 1] + [0, 0, 0] and list(t.mask_off) == [0, 15, 19, 19]
+    ann = synth.make_annotation(chroms, lens, 12, seed=3, exons=(1, 3), exon_len=(50, 200), intron_len=(20, 300))
+    t1, t2 = synth.annotation_table(ann, lay), ChainTable.from_chains(ann.chains(), lay)
+    for f in ("bstart", "bend", "chain_off", "chain_plane", "chain_reverse", "chain_len"):
+        assert (getattr(t1, f) == getattr(t2, f)).all()
+
+
+def test_synthetic_generators_are_seeded_and_sorted():
+    chroms, lens = synth.yeast_like_genome(600_000, 4)
+    ann = synth.make_annotation(chroms, lens, 60, seed=1, exons=(1, 2), exon_len=(200, 600), intron_len=(50, 400))
+    a = synth.device_batch_to_host(synth.riboseq_reads(ann, 20000, seed=3, device="cpu"), chroms, lens)
+    b = synth.device_batch_to_host(synth.riboseq_reads(ann, 20000, seed=3, device="cpu"), chroms, lens)
+    a.check_sorted()
+    assert (a.ref_start == b.ref_start).all() and (a.meta == b.meta).all()
+    assert a.aligned_len.min() >= 25 and a.aligned_len.max() <= 35
+    assert ((a.ref_start + a.aligned_len) <= np.repeat(lens, np.diff(a.chrom_read_off))).all() and a.ref_start.min() >= 0
+    r = synth.device_batch_to_host(synth.rnaseq_reads(chroms, lens, 5000, seed=2, device="cpu"), chroms, lens)
+    r.check_sorted()
+    nb = (r.meta >> 24).astype(int)
+    assert set(np.unique(nb)) == {1, 2, 3} and (np.diff(r.blk_off.astype(int)) == np.where(nb > 1, nb, 0)).all()
+    assert all(len(r.positions_of(i)) == 100 for i in range(0, 5000, 97))

@@ -149,3 +149,38 @@ def test_size_filter_and_strand_filter_in_c_oracle():
             exp = ga.get(seg, roi_order=False)
         got, _, _, _ = coracle.map_point(hb, 0, len(hb), "fiveprime", 3, None, (20, 45), strand, 100, 2900)
         assert (got == exp).all()
+
+
+DOC_ROWS = """ORFL1W_(RL1)    merlin:1316-2398(+)     1.14000000e+02  1.05360444e-01          2.10520051e+02  1082
+ORFL2C          merlin:2401-2772(-)     1.00000000e+01  2.69541779e-02          5.38569762e+01  371
+ORFL3C          merlin:2834-3064(-)     1.50000000e+01  6.52173913e-02          1.30310466e+02  230
+ORFL4C          merlin:2929-3201(-)     1.40000000e+01  5.14705882e-02          1.02843064e+02  272
+ORFL5C          merlin:4074-4307(-)     2.30000000e+01  9.87124464e-02          1.97236729e+02  233
+ORFL6C          merlin:4078-4488(-)     6.10000000e+01  1.48780488e-01          2.97277373e+02  410
+ORFL7C          merlin:4335-4739(-)     6.20000000e+01  1.53465347e-01          3.06638160e+02  404"""
+
+
+def test_counts_in_region_rows_printed_in_the_reference_docs():
+    """docs/source/examples/gene_expression.rst:75-83 (total_dataset_counts: 500477): the oracle's
+    and the product's row arithmetic + formatting reproduce every printed value."""
+    from oracle import scripts as osc
+    from plastid_b200.bin.counts_in_region import format_row
+    for line in DOC_ROWS.split("\n"):
+        name, region, counts, rpnt, rpkm, length = line.split()
+        exp = [name, region, counts, rpnt, rpkm, length]
+        assert osc.format_counts_row(name, region, float(counts), int(length), 500477) == exp
+        assert format_row(name, region, float(counts), int(length), 1000.0 * 1e6 / 500477) == exp
+        chain = po.Chain.from_str(region)
+        assert chain.length == int(length) and str(chain) == region
+
+
+def test_offsets_table_from_reference_docs():
+    """docs/source/examples/p_site.rst:143-151 style table round-trips through both parsers."""
+    import plastid_b200 as pb
+    text = "length\tp_offset\n29\t12\n30\t12\n31\t13\n32\t14\n33\t14\n34\t14\n35\t14\ndefault\t14"
+    exp = {29: 12, 30: 12, 31: 13, 32: 14, 33: 14, 34: 14, 35: 14, "default": 14}
+    assert po.parse_offset_file(io.StringIO(text)) == exp
+    fac = pb.VariableFivePrimeMapFactory.from_file(io.StringIO(text))
+    fw, rc = po.build_offset_luts(exp)
+    assert (fac.forward_offsets == fw).all() and (fac.reverse_offsets == rc).all()
+    assert fw[28] == 14 and fw[14] == -1 and rc[30] == 17
