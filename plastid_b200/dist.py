@@ -1,0 +1,161 @@
+"""Multi-GPU sharding of the counting path (one process per GPU, ``torch.distributed``).
+
+The reference is single-process; counts at a position depend only on the reads
+mapped there and region / window values only on their own positions, so the path shards with no
+count-vector collective:
+
+* **read-range sharding** (``shard_reads``): every rank maps a contiguous slice of the
+  coordinate-sorted batch over the whole layout; region sums, phase sums and mean-profile
+  numerators are linear in the reads, so the small result tables are summed with one all-reduce
+  (``allreduce_sum``).  This is the weak-scaling mode ``bench.py`` runs.
+* **chromosome sharding** (``assign_chromosomes`` / ``shard_chromosomes``): every rank owns whole
+  chromosomes (longest-processing-time assignment by read count) and only the regions on them; the
+  per-region tables are gathered (``gather_rows``).  Exact medians need the normalised window rows
+  of all ranks (``gather_matrix``) — a median is not all-reducible.
+
+NCCL is used on GPUs, gloo in the CPU tests; all messages are small (<= a few hundred MB).
+"""
+import numpy as np
+
+from .batch import AlignmentBatch
+
+
+def is_distributed():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
+def world():
+    import torch.distributed as dist
+    if not is_distributed():
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+# ------------------------------------------------------------------------------- planning (host)
+def read_range(n_reads, rank, world_size):
+    """Contiguous, balanced slice [a, b) of the read index space for ``rank``."""
+    base, extra = divmod(int(n_reads), int(world_size))
+    a = rank * base + min(rank, extra)
+    return a, a + base + (1 if rank < extra else 0)
+
+
+def shard_reads(hb, rank, world_size):
+    """Read-range shard of a host batch (same chromosomes and layout; ``mapped`` stays the global
+    count so RPKM normalisation is unchanged)."""
+    a, b = read_range(len(hb), rank, world_size)
+    off = np.clip(hb.chrom_read_off, a, b) - a
+    blk_off = blk = None
+    if hb.blk_off is not None:
+        k0, k1 = int(hb.blk_off[a]), int(hb.blk_off[b])
+        blk_off = hb.blk_off[a:b + 1].astype(np.int64) - k0
+        blk = hb.blk[k0:k1]
+    out = AlignmentBatch(hb.chroms, hb.chrom_len, hb.ref_start[a:b], hb.meta[a:b], off, blk_off, blk,
+                         max_span=hb.max_span, mapped=hb.mapped)
+    if hb.objects is not None:
+        out.objects = hb.objects[a:b]
+    return out
+
+
+def assign_chromosomes(hb, world_size):
+    """Longest-processing-time assignment of chromosomes to ranks by read count (ties: length).
+    Returns a list of sorted chromosome-index lists, one per rank."""
+    n_reads = np.diff(hb.chrom_read_off)
+    order = sorted(range(len(hb.chroms)), key=lambda c: (-int(n_reads[c]), -int(hb.chrom_len[c]), c))
+    load = [0] * world_size
+    owned = [[] for _ in range(world_size)]
+    for c in order:
+        r = min(range(world_size), key=lambda j: (load[j], j))
+        owned[r].append(c)
+        load[r] += int(n_reads[c]) + 1
+    return [sorted(x) for x in owned]
+
+
+def shard_chromosomes(hb, chrom_ids):
+    """Batch restricted to ``chrom_ids`` (their reads, their chromosomes only)."""
+    chrom_ids = list(chrom_ids)
+    starts, metas, off = [], [], [0]
+    blk_rows, blks = [], []
+    for c in chrom_ids:
+        a, b = int(hb.chrom_read_off[c]), int(hb.chrom_read_off[c + 1])
+        starts.append(hb.ref_start[a:b])
+        metas.append(hb.meta[a:b])
+        off.append(off[-1] + b - a)
+        if hb.blk_off is not None:
+            k0, k1 = int(hb.blk_off[a]), int(hb.blk_off[b])
+            blk_rows.append(np.diff(hb.blk_off[a:b + 1].astype(np.int64)))
+            blks.append(hb.blk[k0:k1])
+    blk_off = blk = None
+    if hb.blk_off is not None and chrom_ids:
+        rows = np.concatenate(blk_rows)
+        blk_off = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(rows, out=blk_off[1:])
+        blk = np.concatenate(blks) if blks else np.zeros((0, 2), dtype=np.int32)
+        if len(blk) == 0:
+            blk_off = blk = None
+    cat = (lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt))
+    return AlignmentBatch([hb.chroms[c] for c in chrom_ids], hb.chrom_len[chrom_ids], cat(starts, np.int32),
+                          cat(metas, np.uint32), off, blk_off, blk, max_span=hb.max_span, mapped=hb.mapped)
+
+
+def owner_of_chains(chains, hb, owned):
+    """Rank owning each chain under a chromosome assignment (-1: chromosome unknown -> rank 0)."""
+    rank_of = {}
+    for r, ids in enumerate(owned):
+        for c in ids:
+            rank_of[hb.chroms[c]] = r
+    return np.asarray([rank_of.get(ch.chrom, 0) if len(ch) else 0 for ch in chains], dtype=np.int64)
+
+
+# ------------------------------------------------------------------------------- collectives
+def allreduce_sum(t):
+    """In-place sum over ranks of a (small) tensor: region tables, phase sums, profile numerators."""
+    import torch.distributed as dist
+    if is_distributed() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def gather_rows(local_values, owner, rank=None):
+    """Assemble a per-region table from per-rank pieces: rank r computed the rows with
+    ``owner == r`` (in order); every rank gets the full table."""
+    import torch
+    import torch.distributed as dist
+    owner = np.asarray(owner)
+    if not is_distributed() or dist.get_world_size() == 1:
+        return local_values
+    rank = dist.get_rank() if rank is None else rank
+    ws = dist.get_world_size()
+    shape = (len(owner),) + tuple(local_values.shape[1:])
+    full = torch.zeros(shape, dtype=local_values.dtype, device=local_values.device)
+    idx = torch.from_numpy(np.nonzero(owner == rank)[0]).to(local_values.device)
+    full[idx] = local_values
+    dist.all_reduce(full, op=dist.ReduceOp.SUM)      # rows are disjoint across ranks: sum == gather
+    return full
+
+
+def gather_matrix(local_rows):
+    """Concatenate row blocks of all ranks (rank order) on every rank — the exchange an exact
+    multi-GPU median needs.  Row counts may differ between ranks."""
+    import torch
+    import torch.distributed as dist
+    if not is_distributed() or dist.get_world_size() == 1:
+        return local_rows
+    ws = dist.get_world_size()
+    n = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=local_rows.device)
+    counts = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    width = tuple(local_rows.shape[1:])
+    pad = torch.zeros((max(counts),) + width, dtype=local_rows.dtype, device=local_rows.device)
+    pad[:local_rows.shape[0]] = local_rows
+    parts = [torch.zeros_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def mean_profile(col_sum, n_regions):
+    """Multi-GPU ``--use_mean`` metagene profile: all-reduce numerators and counts, then divide."""
+    allreduce_sum(col_sum)
+    allreduce_sum(n_regions)
+    return col_sum / n_regions.to(col_sum.dtype)

@@ -437,6 +437,7 @@ class BAMGenomeArray(object):
         planes = self.count_planes(tuple(need))
         sums, live = region_sums(planes, table)
         sums, live = sums.cpu().numpy(), live.cpu().numpy()
+        live[~table.known] = table.unknown_live[~table.known]
         if self._normalize is True:
             sums = sums / float(self.sum()) * 1e6
         return sums, live

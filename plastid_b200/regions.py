@@ -21,6 +21,9 @@ class ChainTable(object):
         self.mask_bits = None if mask_bits is None else np.ascontiguousarray(mask_bits, dtype=np.uint8)
         self.mask_off = None if mask_off is None else np.ascontiguousarray(mask_off, dtype=np.int64)
         self.known = np.ones(len(self.chain_len), dtype=bool) if known is None else np.asarray(known, dtype=bool)
+        # unmasked length of chains on chromosomes the layout does not know (they count 0 over their
+        # full length: ga.get returns a broadcastable zero vector, genome_array.py:795-798)
+        self.unknown_live = np.zeros(len(self.chain_len), dtype=np.int64)
         self._dev = {}
 
     @property
@@ -64,8 +67,12 @@ class ChainTable(object):
             mask_bits = np.packbits(flat, bitorder="little")
             if len(mask_bits) == 0:
                 mask_bits = np.zeros(1, dtype=np.uint8)
-        return cls(layout, bstart, bend, chain_off, plane, reverse, length,
-                   mask_bits, mask_off if any_mask else None, known)
+        out = cls(layout, bstart, bend, chain_off, plane, reverse, length,
+                  mask_bits, mask_off if any_mask else None, known)
+        for i, ch in enumerate(chains):
+            if not out.known[i]:
+                out.unknown_live[i] = ch.masked_length if use_masks else ch.length
+        return out
 
     def device(self, device):
         import torch

@@ -1,0 +1,131 @@
+"""World-size-2 gloo tests of the multi-GPU host logic (sharding plans + collectives) on CPU.  The
+per-rank compute is stood in by the C oracle (checker), so the test pins that read-range sharding +
+all-reduce and chromosome sharding + gather both reproduce the unsharded tables exactly."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _world():
+    import plastid_b200 as pb
+    from plastid_b200 import synth
+    chroms, lens = synth.yeast_like_genome(total=500_000, n_chrom=5)
+    ann = synth.make_annotation(chroms, lens, 80, seed=2, exons=(1, 3), exon_len=(150, 500), intron_len=(40, 300))
+    hb = synth.device_batch_to_host(synth.riboseq_reads(ann, 40_000, seed=6, device="cpu"), chroms, lens)
+    spliced = synth.device_batch_to_host(synth.rnaseq_reads(chroms, lens, 8_000, seed=3, device="cpu",
+                                                            intron=(50, 2000)), chroms, lens)
+    return chroms, lens, ann, hb, spliced
+
+
+def _region_table(hb, chains, offset=14):
+    """Unmasked 5' region sums of `chains` over batch `hb` with the C oracle."""
+    from oracle import coracle
+    vec = {}
+    out = np.zeros(len(chains))
+    for i, ch in enumerate(chains):
+        if ch.chrom not in hb.chroms:
+            continue
+        c = hb.chroms.index(ch.chrom)
+        key = (c, ch.strand)
+        if key not in vec:
+            vec[key] = coracle.genome_vector(hb, c, ch.strand, rule="fiveprime", offset=offset, size_filter=(25, 100))[0]
+        out[i] = sum(vec[key][s.start:s.end].sum() for s in ch)
+    return out
+
+
+def _worker(rank, world_size, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from plastid_b200 import dist as pd
+        chroms, lens, ann, hb, spliced = _world()
+        chains = ann.chains()
+        full = _region_table(hb, chains)
+
+        # read-range sharding: every rank a slice of the reads, tables all-reduced
+        for batch in (hb, spliced):
+            shard = pd.shard_reads(batch, rank, world_size)
+            shard.check_sorted()
+            assert shard.mapped == batch.mapped
+            n = torch.tensor([len(shard)], dtype=torch.int64)
+            pd.allreduce_sum(n)
+            assert int(n.item()) == len(batch)
+            if batch.blk is not None:
+                for i in range(0, len(shard), 501):
+                    a, _b = pd.read_range(len(batch), rank, world_size)
+                    assert shard.positions_of(i) == batch.positions_of(a + i)
+        local = torch.from_numpy(_region_table(pd.shard_reads(hb, rank, world_size), chains))
+        pd.allreduce_sum(local)
+        assert (local.numpy() == full).all()
+
+        # chromosome sharding: disjoint ownership, tables gathered
+        owned = pd.assign_chromosomes(hb, world_size)
+        assert sorted(c for ids in owned for c in ids) == list(range(len(chroms)))
+        loads = [sum(int(np.diff(hb.chrom_read_off)[c]) for c in ids) for ids in owned]
+        assert max(loads) <= 0.75 * len(hb)
+        mine = pd.shard_chromosomes(hb, owned[rank])
+        mine.check_sorted()
+        owner = pd.owner_of_chains(chains, hb, owned)
+        my_chains = [ch for ch, o in zip(chains, owner) if o == rank]
+        gathered = pd.gather_rows(torch.from_numpy(_region_table(mine, my_chains)), owner)
+        assert (gathered.numpy() == full).all()
+
+        # profiles: mean by all-reduce, median needs the gathered rows
+        rng = np.random.default_rng(5)
+        mat = rng.random((37, 20))
+        mask = rng.random((37, 20)) < 0.2
+        rows = np.array_split(np.arange(37), world_size)[rank]
+        col_sum = torch.from_numpy(np.where(mask[rows], 0.0, mat[rows]).sum(0))
+        cnt = torch.from_numpy((~mask[rows]).sum(0))
+        prof = pd.mean_profile(col_sum, cnt)
+        np.testing.assert_allclose(prof.numpy(), np.ma.MaskedArray(mat, mask=mask).mean(0).filled(np.nan), rtol=1e-12)
+        allrows = pd.gather_matrix(torch.from_numpy(np.where(mask[rows], np.nan, mat[rows])))
+        assert allrows.shape == (37, 20)
+        med = np.nanmedian(allrows.numpy(), axis=0)
+        np.testing.assert_allclose(med, np.ma.median(np.ma.MaskedArray(mat, mask=mask), axis=0).filled(np.nan), rtol=1e-12)
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    port = _free_port()
+    with mp.Manager() as manager:
+        results = manager.dict()
+        mp.spawn(_worker, args=(2, port, results), nprocs=2, join=True)
+        assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def test_sharding_plans_single_process():
+    from plastid_b200 import dist as pd
+    chroms, lens, ann, hb, spliced = _world()
+    assert [pd.read_range(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    total = 0
+    for r in range(3):
+        s = pd.shard_reads(spliced, r, 3)
+        total += len(s)
+        assert s.chrom_read_off[-1] == len(s) and (np.diff(s.chrom_read_off) >= 0).all()
+    assert total == len(spliced)
+    owned = pd.assign_chromosomes(hb, 8)          # more ranks than chromosomes: some ranks idle
+    assert sum(len(x) for x in owned) == len(chroms) and sum(1 for x in owned if not x) == 3
+    empty = pd.shard_chromosomes(hb, [])
+    assert len(empty) == 0 and empty.chroms == []
+    assert pd.world() == (0, 1)
