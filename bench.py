@@ -39,6 +39,10 @@ def parse_args():
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of hg38 chromosome lengths")
     ap.add_argument("--regions", type=int, default=60_000)
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"],
+                    help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
+                         "are side measurements (c1 counts_in_region yeast-scale, c3 CenterMapFactory(12) on "
+                         "spliced 100-nt reads, c5 ThreePrimeMapFactory 500 M reads)")
     return ap.parse_args()
 
 
@@ -97,33 +101,58 @@ def peaks():
 
 
 def build_world(args, rank, device):
+    """Synthetic genome, annotation, device-resident read batch and mapping rule of the workload."""
     import torch
     import plastid_b200 as pb
     from plastid_b200 import synth
-    chroms, lens = synth.human_like_genome(args.genome_scale)
-    ann = synth.make_annotation(chroms, lens, args.regions, seed=0, exons=(1, 3), exon_len=(150, 600),
-                                intron_len=(100, 3000))
+    wl = args.workload
+    if wl == "c1":
+        chroms, lens = synth.yeast_like_genome()
+        n_reads = 2_000_000 if args.reads == 200_000_000 else args.reads
+        ann = synth.make_annotation(chroms, lens, 6000, seed=0, exons=(1, 2), exon_len=(300, 700), intron_len=(80, 200))
+        fac, sf, oracle_kw = pb.FivePrimeMapFactory(14), pb.SizeFilterFactory(25, 100), dict(rule="fiveprime", offset=14)
+        name = "C1: counts_in_region, FivePrimeMapFactory(14)+size filter 25-100, yeast-scale 12 Mb genome"
+    else:
+        chroms, lens = synth.human_like_genome(args.genome_scale)
+        n_tx = args.regions if wl != "c5" else 20000
+        ann = synth.make_annotation(chroms, lens, n_tx, seed=0, exons=(1, 3), exon_len=(150, 600), intron_len=(100, 3000))
+        if wl == "c2":
+            n_reads = args.reads
+            fac, sf = pb.VariableFivePrimeMapFactory(synth.RIBO_OFFSETS), pb.SizeFilterFactory(25, 100)
+            oracle_kw = dict(rule="variable", luts=(fac.forward_offsets, fac.reverse_offsets))
+            name = "C2: VariableFivePrimeMapFactory(p-site offsets)+size filter 25-100"
+        elif wl == "c3":
+            n_reads = 100_000_000 if args.reads == 200_000_000 else args.reads
+            fac, sf, oracle_kw = pb.CenterMapFactory(12), None, dict(nibble=12)
+            name = "C3: CenterMapFactory(nibble=12), 100-nt reads, 30% one N gap, 3% two"
+        else:
+            n_reads = 500_000_000 if args.reads == 200_000_000 else args.reads
+            fac, sf, oracle_kw = pb.ThreePrimeMapFactory(0), pb.SizeFilterFactory(25, 100), dict(rule="threeprime", offset=0)
+            name = "C5: cs count, ThreePrimeMapFactory(0)+size filter 25-100"
     layout = pb.GenomeLayout(chroms, lens)
     table = synth.annotation_table(ann, layout)
-    dbatch = synth.riboseq_reads(ann, args.reads, seed=100 + rank, device=device, frac_in=0.85)
+    if wl == "c3":
+        dbatch = synth.rnaseq_reads(chroms, lens, n_reads, seed=100 + rank, device=device)
+    else:
+        dbatch = synth.riboseq_reads(ann, n_reads, seed=100 + rank, device=device, frac_in=0.85 if wl != "c1" else 0.9)
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
-    return chroms, lens, ann, layout, table, dbatch
+    return dict(chroms=chroms, lens=lens, ann=ann, layout=layout, table=table, dbatch=dbatch, fac=fac, sf=sf,
+                oracle_kw=oracle_kw, name=name, center=(wl == "c3"))
 
 
-def cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, threads):
+def cpu_reference_pass(hb, lens, table, layout, oracle_kw, size_filter, chrom_ids, threads):
     """The oracle's restatement of the reference path on `chrom_ids`: per chromosome x strand the
     per-read loop of VariableFivePrimeMapFactory.__call__ over the whole chromosome segment, then the
     SegmentChain sums of the regions on those chromosomes.  Returns (seconds, reads, regions)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import coracle
-    luts = (fac.forward_offsets, fac.reverse_offsets)
     coracle.lib()
 
     def one(c):
         n_reg = 0
         for pidx, strand in enumerate(("+", "-")):
-            vec = coracle.genome_vector(hb, c, strand, rule="variable", luts=luts, size_filter=(25, 100))[0]
+            vec = coracle.genome_vector(hb, c, strand, size_filter=size_filter, **oracle_kw)[0]
             base = int(layout.chrom_bin_off[c])
             sel = np.nonzero((table.chain_plane == pidx) & (table.bstart[table.chain_off[:-1]] >= base)
                              & (table.bstart[table.chain_off[:-1]] < int(layout.chrom_bin_off[c + 1])))[0]
@@ -135,7 +164,8 @@ def cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, threads):
                     bs.append(table.bstart[a:b] - base)
                     be.append(table.bend[a:b] - base)
                     offs.append(offs[-1] + b - a)
-                coracle.region_sums(vec.astype(np.uint32), np.concatenate(bs), np.concatenate(be), offs)
+                coracle.region_sums(vec if vec.dtype == np.float64 else vec.astype(np.uint32),
+                                    np.concatenate(bs), np.concatenate(be), offs)
             n_reg += len(sel)
         return int(hb.chrom_read_off[c + 1] - hb.chrom_read_off[c]), n_reg
 
@@ -151,20 +181,34 @@ def cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, threads):
 
 def host_sample(dbatch, chroms, lens, chrom_ids):
     """Host copy of the reads of the chosen chromosomes only (bounded CPU sample)."""
-    from plastid_b200.batch import AlignmentBatch
-    off = dbatch.chrom_read_off.cpu().numpy()
-    new_off = np.zeros(len(chroms) + 1, dtype=np.int64)
-    starts, metas = [], []
-    for c in range(len(chroms)):
-        if c in chrom_ids:
+    from plastid_b200 import dist as pdist
+    from plastid_b200.synth import device_batch_to_host
+    if len(chrom_ids) == len(chroms) or dbatch.blk_off is not None:
+        hb = device_batch_to_host(dbatch, chroms, lens)
+        if len(chrom_ids) == len(chroms):
+            return hb
+        sub = pdist.shard_chromosomes(hb, sorted(chrom_ids))
+    else:
+        from plastid_b200.batch import AlignmentBatch
+        off = dbatch.chrom_read_off.cpu().numpy()
+        starts, metas, new_off = [], [], [0]
+        for c in sorted(chrom_ids):
             a, b = int(off[c]), int(off[c + 1])
             starts.append(dbatch.ref_start[a:b].cpu().numpy())
             metas.append(dbatch.meta[a:b].cpu().numpy().view(np.uint32))
-            new_off[c + 1] = new_off[c] + (b - a)
-        else:
-            new_off[c + 1] = new_off[c]
-    return AlignmentBatch(chroms, lens, np.concatenate(starts), np.concatenate(metas), new_off,
-                          max_span=dbatch.max_span)
+            new_off.append(new_off[-1] + b - a)
+        sub = AlignmentBatch([chroms[c] for c in sorted(chrom_ids)], np.asarray(lens)[sorted(chrom_ids)],
+                             np.concatenate(starts), np.concatenate(metas), new_off, max_span=dbatch.max_span)
+    # re-expand to the full chromosome list so chromosome indices keep their meaning
+    full_off = np.zeros(len(chroms) + 1, dtype=np.int64)
+    pos = 0
+    for c in range(len(chroms)):
+        if c in chrom_ids:
+            j = sorted(chrom_ids).index(c)
+            pos += int(sub.chrom_read_off[j + 1] - sub.chrom_read_off[j])
+        full_off[c + 1] = pos
+    from plastid_b200.batch import AlignmentBatch
+    return AlignmentBatch(chroms, lens, sub.ref_start, sub.meta, full_off, sub.blk_off, sub.blk, max_span=sub.max_span)
 
 
 def main():
@@ -187,38 +231,38 @@ def main():
     from plastid_b200 import synth, _lib
     from plastid_b200.genome_array import map_batch, region_sums, CountPlanes
 
-    chroms, lens, ann, layout, table, dbatch = build_world(args, rank, device)
-    fac = pb.VariableFivePrimeMapFactory(synth.RIBO_OFFSETS)
-    sf = pb.SizeFilterFactory(25, 100)
+    W = build_world(args, rank, device)
+    chroms, lens, ann, layout, table, dbatch = W["chroms"], W["lens"], W["ann"], W["layout"], W["table"], W["dbatch"]
+    fac, sf, is_center = W["fac"], W["sf"], W["center"]
+    sf_tuple = None if sf is None else (sf.min_, sf.max_)
     n_reads = dbatch.n_reads
-    workload = ("C2: VariableFivePrimeMapFactory(p-site offsets)+size filter 25-100, %d synthetic 25-35 nt "
-                "ribo-seq reads/GPU, hg38-scale genome x%.3g (%d bins, '+' and '-' planes), %d region counts"
-                % (n_reads, args.genome_scale, layout.total_bins, ann.n_tx))
+    workload = ("%s, %d synthetic reads/GPU, %d chromosomes (%d bins, '+' and '-' planes), %d region counts"
+                % (W["name"], n_reads, len(chroms), layout.total_bins, ann.n_tx))
     config = {"workload": workload, "reads_per_gpu": n_reads, "genome_bins": int(layout.total_bins),
               "regions": ann.n_tx, "sharding": "read-range per GPU; NCCL all-reduce of region tables" if world > 1
               else "single GPU", "l2": "inputs (%.2f GB) and outputs (%.1f GB) larger than the 126 MB L2"
-              % (8 * n_reads / 1e9, 8 * layout.total_bins / 1e9)}
+              % (8 * n_reads / 1e9, (16 if is_center else 8) * layout.total_bins / 1e9)}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         threads = os.cpu_count() or 1
-        order = np.argsort(-np.asarray(lens))
-        chrom_ids = sorted(int(c) for c in order[:max(1, min(threads, 8))])
+        # every chromosome of the workload, longest first, one chromosome per task over all host threads
+        chrom_ids = [int(c) for c in np.argsort(-np.asarray(lens))]
         hb = host_sample(dbatch, chroms, lens, set(chrom_ids))
         del dbatch
         torch.cuda.empty_cache()
         times = []
         for it in range(args.warmup + args.steps):
-            dt, nr, nreg = cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, threads)
+            dt, nr, nreg = cpu_reference_pass(hb, lens, table, layout, W["oracle_kw"], sf_tuple, chrom_ids, threads)
             if it >= args.warmup:
                 times.append(dt)
         ms = 1000.0 * float(np.mean(times))
         val = nr / (ms / 1000.0)
-        sample = "chromosomes %s (%d reads, %d regions) of the workload per step" % (
-            ",".join(chroms[c] for c in chrom_ids), nr, nreg)
+        sample = "the whole workload per step: %d chromosomes, %d reads, %d regions" % (len(chrom_ids), nr, nreg)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is_center else "int64", "data": "synthetic",
+                "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "oracle port of map_factories.pyx/roitools.pyx loops (the Cython reference cannot be "
@@ -227,7 +271,7 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ device-resident steps
-    planes = CountPlanes(layout, "u32", device)
+    planes = CountPlanes(layout, "f64" if is_center else "u32", device)
     planes.alloc(("+", "-"))
     table.device(device)
     L = _lib.lib()
@@ -275,11 +319,21 @@ def main():
     h_sums = torch.empty(ann.n_tx, dtype=torch.float64).pin_memory()
     h_live = torch.empty(ann.n_tx, dtype=torch.int64).pin_memory()
     h2d = h_start.numel() * 4 + h_meta.numel() * 4
+    h_blk_off = h_blk = None
+    if dbatch.blk_off is not None:
+        h_blk_off = torch.empty_like(dbatch.blk_off, device="cpu").pin_memory()
+        h_blk = torch.empty_like(dbatch.blk, device="cpu").pin_memory()
+        h_blk_off.copy_(dbatch.blk_off)
+        h_blk.copy_(dbatch.blk)
+        h2d += h_blk_off.numel() * 4 + h_blk.numel() * 4
     d2h = h_sums.numel() * 8 + h_live.numel() * 8
 
     def e2e_step():
         dbatch.ref_start.copy_(h_start, non_blocking=True)
         dbatch.meta.copy_(h_meta, non_blocking=True)
+        if h_blk is not None:
+            dbatch.blk_off.copy_(h_blk_off, non_blocking=True)
+            dbatch.blk.copy_(h_blk, non_blocking=True)
         s, l = step()
         h_sums.copy_(s, non_blocking=True)
         h_live.copy_(l, non_blocking=True)
@@ -310,10 +364,13 @@ def main():
 
     # ------------------------------------------------------------------ roofline of the tiles kernel
     peak, peak_src = peaks()
-    alg_bytes = 8.0 * n_reads + 4.0 * layout.total_bins * 2          # SoA in once + every bin out once
+    n_blk = 0 if dbatch.blk is None else dbatch.blk.shape[0]
+    # SoA in once (+ block table for spliced reads) + every bin of both planes out once
+    alg_bytes = 8.0 * n_reads + (4.0 * (n_reads + 1) + 8.0 * n_blk if n_blk else 0.0) \
+        + (8.0 if is_center else 4.0) * layout.total_bins * 2
     k_ms = kms.value / max(kn.value, 1)
     achieved = alg_bytes / (k_ms / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pb_point_tiles_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "pb_center_tiles_kernel" if is_center else "pb_point_tiles_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "launches_timed": kn.value,
                 "kernel_share_of_step": k_ms / ms_per_step}
@@ -324,19 +381,22 @@ def main():
         order = np.argsort(-np.asarray(lens))
         chrom_ids = sorted(int(c) for c in order[:args.cpu_sample_chroms])
         hb = host_sample(dbatch, chroms, lens, set(chrom_ids))
-        dt, nr, nreg = cpu_reference_pass(hb, lens, table, layout, fac, chrom_ids, 1)
+        dt, nr, nreg = cpu_reference_pass(hb, lens, table, layout, W["oracle_kw"], sf_tuple, chrom_ids, 1)
         cpu = {"value": nr / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "%s: %d reads + %d region sums in %.2f s (oracle C port, one thread)"
                          % (",".join(chroms[c] for c in chrom_ids), nr, nreg, dt)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is_center else "u32", "data": "synthetic",
+            "config": config,
             "region_counts_per_sec": region_rate,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t.item()), "steps": e2e_steps},
-            "gpu_launches": 4 * args.steps, "kernels_per_step": ["pb_tile_index_kernel", "pb_point_tiles_kernel",
-                                                                  "pb_stats_finish_kernel", "pb_region_sums_kernel"],
+            "gpu_launches": (5 if is_center else 4) * args.steps,
+            "kernels_per_step": (["pb_length_hist_kernel", "pb_tile_index_kernel", "pb_center_tiles_kernel"] if is_center
+                                 else ["pb_tile_index_kernel", "pb_point_tiles_kernel"])
+            + ["pb_stats_finish_kernel", "pb_region_sums_kernel"],
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}
     print(json.dumps(line))
     if world > 1:

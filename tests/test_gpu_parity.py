@@ -392,3 +392,60 @@ def test_window_matrix_and_profiles(small_world, cuda_device):
         assert (nreg.cpu().numpy() == (~np.ma.getmaskarray(norm))[rs].sum(0)).all()
     prof, nreg, csum = column_profile(mat, mmask, torch.ones_like(sel), "sum")
     np.testing.assert_allclose(prof.cpu().numpy(), np.ma.filled(exp.sum(0), 0.0), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# GenomeArray / SparseGenomeArray: the reference's own known answers (test_roitools.py:1274-1379)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cls", [pb.GenomeArray, pb.SparseGenomeArray])
+def test_genome_array_masked_counts_known_answers(cuda_device, cls):
+    for strand in ("+", "-"):
+        ga = cls({"chrA": 2000}, device=cuda_device)
+        ga[pb.GenomicSegment("chrA", 100, 200, strand)] = 1
+        ga[pb.GenomicSegment("chrA", 250, 350, strand)] = 5
+        chain = pb.SegmentChain(pb.GenomicSegment("chrA", 100, 150, strand), pb.GenomicSegment("chrA", 150, 200, strand),
+                                pb.GenomicSegment("chrA", 250, 350, strand))
+        unmasked = np.zeros(chain.length)
+        if strand == "+":
+            unmasked[:100], unmasked[100:200] = 1, 5
+        else:
+            unmasked[-100:], unmasked[-200:-100] = 1, 5
+        assert (chain.get_masked_counts(ga) == unmasked).all()
+        chain.add_masks(pb.GenomicSegment("chrA", 400, 500, strand))
+        assert (chain.get_masked_counts(ga) == unmasked).all()
+        chain.add_masks(pb.GenomicSegment("chrA", 50, 125, strand))
+        mask = np.tile(False, chain.length)
+        if strand == "+":
+            mask[:25] = True
+        else:
+            mask[-25:] = True
+        found = chain.get_masked_counts(ga)
+        assert (found.mask == mask).all() and (found.data == unmasked).all()
+        assert ga.sum() == 600.0
+        sums, live = ga.count_chains([chain])
+        assert sums[0] == 575.0 and live[0] == 175
+    ga = cls({"chrA": 2000}, device=cuda_device)
+    ga[pb.GenomicSegment("chrA", 100, 200, "+")] = 1
+    ga[pb.GenomicSegment("chrA", 250, 350, "+")] = 1
+    ivc = pb.SegmentChain(pb.GenomicSegment("chrA", 100, 150, "+"), pb.GenomicSegment("chrA", 150, 200, "+"),
+                          pb.GenomicSegment("chrA", 250, 350, "+"))
+    assert sum(ivc.get_counts(ga)) == 200 and ivc.get_masked_counts(ga).sum() == 200
+    ivc.add_masks(pb.GenomicSegment("chrA", 50, 125, "+"))
+    assert ivc.get_masked_counts(ga).sum() == 175 and sum(ivc.get_counts(ga)) == 200
+    # vectors are set 5'->3' and read back the same way; chains set exon by exon (genome_array.py:1561-1575)
+    vec = np.arange(30, dtype=float)
+    rc = pb.SegmentChain(pb.GenomicSegment("chrA", 500, 510, "-"), pb.GenomicSegment("chrA", 600, 620, "-"))
+    ga2 = cls({"chrA": 2000}, strands=("+", "-"), device=cuda_device)
+    ga2[rc] = vec
+    assert (ga2[rc] == vec).all() and (ga2[pb.GenomicSegment("chrA", 600, 620, "-")] == vec[:20]).all()
+    assert (ga2.get(pb.GenomicSegment("chrA", 500, 510, "-"), roi_order=False) == vec[20:][::-1]).all()
+    assert (ga2[pb.GenomicSegment("chrB", 0, 7, "+")] == 0).all()
+
+
+def test_to_genome_array_drops_last_base_like_the_reference(cuda_device):
+    hb = pb.batch_from_arrays(["c"], [100], [0, 0, 0], [0, 50, 99], [1, 1, 1], [0, 0, 1])
+    ga = pb.BAMGenomeArray(hb, mapping=pb.FivePrimeMapFactory(0), device=cuda_device)
+    dense = ga.to_genome_array()
+    assert dense.sum() == 4.0            # '+': 0,50   '-': (99 dropped)   '.': 0,50 (99 dropped) -- genome_array.py:985
+    assert dense[pb.GenomicSegment("c", 0, 100, "+")].sum() == 2 and dense[pb.GenomicSegment("c", 0, 100, "-")].sum() == 0
+    assert ga[pb.GenomicSegment("c", 0, 100, "-")].sum() == 1
