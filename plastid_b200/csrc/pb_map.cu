@@ -96,6 +96,17 @@ __device__ __forceinline__ void pb_bulk_commit() { asm volatile("cp.async.bulk.c
 __device__ __forceinline__ void pb_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void pb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+constexpr unsigned kNoKey = 0xffffffffu;
+
+// Measured (profiles/NOTES_r01.md): grouping lanes by target word with match.any before the shared
+// atomic is SLOWER than the plain atomic on both C2 (4.43 -> 5.01 ms) and C5 (8.83 -> 11.33 ms):
+// shared atomics cost ~2 cycles per active lane whether or not addresses collide, and MATCH.ANY
+// costs more than it saves.  So: one plain shared atomic per mapped read.
+__device__ __forceinline__ void pb_smem_inc(uint32_t *smem, unsigned key)
+{
+    if (key != kNoKey) atomicAdd(&smem[key], 1u);
+}
+
 constexpr int kPThreads = 256;     // threads per persistent CTA
 constexpr int kPTileBins = 4096;   // bins per tile: 16 KB per plane in shared memory
 constexpr int kPUnroll = 4;        // independent read loads in flight per thread
@@ -145,12 +156,14 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
             __syncthreads();
             const int64_t p0 = d.p0, plim = d.p0 + d.live, p1 = d.p0 + kPTileBins;
             const int64_t hi = d.lo + d.n;
-            for (int64_t base = d.lo + threadIdx.x; base < hi; base += (int64_t)kPUnroll * kPThreads) {
+            const unsigned plus_base = (unsigned)(sm_plus - smem), minus_base = (unsigned)(sm_minus - smem),
+                           any_base = (unsigned)(sm_any - smem);
+            for (int64_t base = d.lo; base < hi; base += (int64_t)kPUnroll * kPThreads) {
                 int32_t sv[kPUnroll];
                 uint32_t mv[kPUnroll];
 #pragma unroll
                 for (int u = 0; u < kPUnroll; ++u) {
-                    const int64_t i = base + (int64_t)u * kPThreads;
+                    const int64_t i = base + (int64_t)u * kPThreads + threadIdx.x;
                     const bool ok = i < hi;
                     sv[u] = ok ? __ldg(b.ref_start + i) : 0;
                     mv[u] = ok ? __ldg(b.meta + i) : (1u << 17);   // drop bit: skipped below
@@ -159,36 +172,40 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
                 for (int u = 0; u < kPUnroll; ++u) {
                     const int32_t s = sv[u];
                     const uint32_t m = mv[u];
-                    if (!pb_passes(m, r.size_min, r.size_max)) continue;
-                    const int64_t i = base + (int64_t)u * kPThreads;
+                    const int64_t i = base + (int64_t)u * kPThreads + threadIdx.x;
                     const int L = PB_META_L(m);
                     const bool rev = PB_META_REV(m);
-                    const int idx_f = pb_rule_index(r, L, false);
-                    if (idx_f < 0) {
-                        // the reference skips this read and warns; count it once, in the tile owning its start
-                        if (s >= p0 && s < p1) {
-                            drop_a++;
-                            if (rev) drop_m++; else drop_p++;
-                            drop_len = L;
+                    unsigned key_strand = kNoKey, key_any = kNoKey;   // word index into smem, or none
+                    if (pb_passes(m, r.size_min, r.size_max)) {
+                        const int idx_f = pb_rule_index(r, L, false);
+                        if (idx_f < 0) {
+                            // the reference skips this read and warns; count it once, in the tile owning its start
+                            if (s >= p0 && s < p1) {
+                                drop_a++;
+                                if (rev) drop_m++; else drop_p++;
+                                drop_len = L;
+                            }
+                        } else {
+                            if (want_any || (!rev && want_plus)) {
+                                const int64_t p = pb_position(b, i, s, m, idx_f);
+                                if (p >= p0 && p < plim) {
+                                    const unsigned o = (unsigned)(p - p0);
+                                    if (want_any) { key_any = any_base + o; map_a++; }
+                                    if (!rev && want_plus) { key_strand = plus_base + o; map_p++; }
+                                }
+                            }
+                            if (rev && want_minus) {
+                                const int idx_r = pb_rule_index(r, L, true);
+                                const int64_t p = pb_position(b, i, s, m, idx_r);
+                                if (p >= p0 && p < plim) {
+                                    key_strand = minus_base + (unsigned)(p - p0);
+                                    map_m++;
+                                }
+                            }
                         }
-                        continue;
                     }
-                    if (want_any || (!rev && want_plus)) {
-                        const int64_t p = pb_position(b, i, s, m, idx_f);
-                        if (p >= p0 && p < plim) {
-                            const unsigned o = (unsigned)(p - p0);
-                            if (want_any) { atomicAdd(&sm_any[o], 1u); map_a++; }
-                            if (!rev && want_plus) { atomicAdd(&sm_plus[o], 1u); map_p++; }
-                        }
-                    }
-                    if (rev && want_minus) {
-                        const int idx_r = pb_rule_index(r, L, true);
-                        const int64_t p = pb_position(b, i, s, m, idx_r);
-                        if (p >= p0 && p < plim) {
-                            atomicAdd(&sm_minus[(unsigned)(p - p0)], 1u);
-                            map_m++;
-                        }
-                    }
+                    pb_smem_inc(smem, key_strand);
+                    pb_smem_inc(smem, key_any);
                 }
             }
             pb_fence_proxy_async();
