@@ -127,12 +127,31 @@ int pb_device_count(void);
 /* Bytes of device workspace pb_map_point / pb_map_center need for this layout. */
 size_t pb_map_workspace_bytes(int64_t total_bins);
 
+/* wire16: compact 4-byte-per-read transfer format of an unspliced batch (every read one block,
+ * L < 16384), what the host decoder hands over PCIe.  start_lo uint16[N] = ref_start & 0xFFFF;
+ * meta16 uint16[N] = L | is_reverse<<14 | drop<<15; the chromosome axis is cut into 65536-position
+ * segments, seg_off int64[n_seg+1] = first read of each segment, seg_base int32[n_seg] = chromosome
+ * coordinate of its first position (all device pointers).  Expands into ref_start / meta of the
+ * SoA batch above, for reads [read_begin, read_end) (a streamed upload expands chunk by chunk). */
+int pb_unpack_wire16(const uint16_t *start_lo, const uint16_t *meta16, const int64_t *seg_off,
+                     const int32_t *seg_base, int64_t n_seg, int64_t read_begin, int64_t read_end,
+                     int32_t *ref_start_out, uint32_t *meta_out, void *stream);
+
 /* 5' / 3' / variable-offset mapping of a whole batch into dense uint32 planes.
  * `planes` selects which of out_plus/out_minus/out_any are produced; every bin of a selected
  * plane is written (no prior memset needed).  stats: device uint64[PB_NSTATS], accumulated. */
 int pb_map_point(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
                  uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
                  uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The same over the bins [bin_begin, bin_end) only (both multiples of PB_LAYOUT_ALIGN), reading no
+ * read at or beyond read_limit: lets a host->device upload of a sorted batch be overlapped with
+ * mapping — once the reads up to a position have landed, the planes up to that position can be
+ * produced.  stats accumulate over the calls. */
+int pb_map_point_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                       uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
+                       uint64_t *stats, void *workspace, size_t workspace_bytes,
+                       int64_t bin_begin, int64_t bin_end, int64_t read_limit, void *stream);
 
 /* Center mapping into dense float64 planes.  slot_of_len: device int16[65536] mapping aligned
  * length L to a slot (index into inv_m) or -1 (L-2*nibble <= 0); inv_m: device double[n_slots]

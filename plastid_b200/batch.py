@@ -168,6 +168,124 @@ class AlignmentBatch(object):
         return BatchRead(self, i)
 
 
+class Wire16Batch(object):
+    """Compact 4-byte-per-read host format of an unspliced batch (``pb_unpack_wire16`` in
+    ``include/plastid_b200.h``): what crosses PCIe instead of the 8-byte SoA."""
+    SEG_BITS = 16
+
+    def __init__(self, chroms, chrom_len, chrom_read_off, start_lo, meta16, seg_off, seg_base, max_span, mapped):
+        self.chroms, self.chrom_len = list(chroms), np.asarray(chrom_len, dtype=np.int64)
+        self.chrom_read_off = np.ascontiguousarray(chrom_read_off, dtype=np.int64)
+        self.start_lo = np.ascontiguousarray(start_lo, dtype=np.uint16)
+        self.meta16 = np.ascontiguousarray(meta16, dtype=np.uint16)
+        self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        self.seg_base = np.ascontiguousarray(seg_base, dtype=np.int32)
+        self.max_span, self.mapped = int(max_span), int(mapped)
+
+    def __len__(self):
+        return len(self.start_lo)
+
+    @property
+    def nbytes(self):
+        return self.start_lo.nbytes + self.meta16.nbytes + self.seg_off.nbytes + self.seg_base.nbytes \
+            + self.chrom_read_off.nbytes
+
+    @classmethod
+    def from_batch(cls, hb):
+        if hb.blk is not None:
+            raise ValueError("wire16 carries single-block reads only")
+        L = hb.meta & 0xFFFF
+        if len(L) and int(L.max()) >= (1 << 14):
+            raise ValueError("wire16 needs aligned lengths < 16384")
+        meta16 = (L | (((hb.meta >> 16) & 1) << 14) | (((hb.meta >> 17) & 1) << 15)).astype(np.uint16)
+        n_seg_chrom = np.maximum((hb.chrom_len + 65535) >> 16, 1)
+        seg_first = np.zeros(len(hb.chroms) + 1, dtype=np.int64)
+        np.cumsum(n_seg_chrom, out=seg_first[1:])
+        chrom_of_read = np.repeat(np.arange(len(hb.chroms)), np.diff(hb.chrom_read_off))
+        seg_of_read = seg_first[chrom_of_read] + (hb.ref_start.astype(np.int64) >> 16)
+        n_seg = int(seg_first[-1])
+        seg_off = np.zeros(n_seg + 1, dtype=np.int64)
+        np.cumsum(np.bincount(seg_of_read, minlength=n_seg), out=seg_off[1:])
+        seg_base = np.concatenate([np.arange(n, dtype=np.int64) << 16 for n in n_seg_chrom]).astype(np.int32)
+        return cls(hb.chroms, hb.chrom_len, hb.chrom_read_off, (hb.ref_start & 0xFFFF).astype(np.uint16), meta16,
+                   seg_off, seg_base, hb.max_span, hb.mapped)
+
+    def pinned(self):
+        import torch
+        def pin(a, view=None):
+            return torch.from_numpy(a.view(view) if view is not None else a).pin_memory()
+        return dict(start_lo=pin(self.start_lo, np.int16), meta16=pin(self.meta16, np.int16),
+                    seg_off=pin(self.seg_off), seg_base=pin(self.seg_base), chrom_read_off=pin(self.chrom_read_off))
+
+
+class Wire16Receiver(object):
+    """Device-side landing buffers for wire16 transfers + the expanded :class:`DeviceBatch`."""
+
+    def __init__(self, wire, device):
+        import torch
+        n, n_seg = len(wire), len(wire.seg_base)
+        self.n_seg = n_seg
+        self.start_lo = torch.empty(n, dtype=torch.int16, device=device)
+        self.meta16 = torch.empty(n, dtype=torch.int16, device=device)
+        self.seg_off = torch.empty(n_seg + 1, dtype=torch.int64, device=device)
+        self.seg_base = torch.empty(n_seg, dtype=torch.int32, device=device)
+        self.batch = DeviceBatch(n, len(wire.chroms), wire.max_span, torch.empty(n, dtype=torch.int32, device=device),
+                                 torch.empty(n, dtype=torch.int32, device=device),
+                                 torch.empty(len(wire.chroms) + 1, dtype=torch.int64, device=device))
+
+    def receive(self, pinned):
+        """Enqueue H2D copies of one wire16 batch and its expansion; returns the DeviceBatch."""
+        from . import _lib
+        self.start_lo.copy_(pinned["start_lo"], non_blocking=True)
+        self.meta16.copy_(pinned["meta16"], non_blocking=True)
+        self._receive_tables(pinned)
+        self._unpack(0, self.batch.n_reads)
+        return self.batch
+
+    def _receive_tables(self, pinned):
+        self.seg_off.copy_(pinned["seg_off"], non_blocking=True)
+        self.seg_base.copy_(pinned["seg_base"], non_blocking=True)
+        self.batch.chrom_read_off.copy_(pinned["chrom_read_off"], non_blocking=True)
+
+    def _unpack(self, a, b):
+        from . import _lib
+        _lib.check(_lib.lib().pb_unpack_wire16(_lib.ptr(self.start_lo), _lib.ptr(self.meta16), _lib.ptr(self.seg_off),
+                                               _lib.ptr(self.seg_base), self.n_seg, int(a), int(b),
+                                               _lib.ptr(self.batch.ref_start), _lib.ptr(self.batch.meta),
+                                               _lib.stream_ptr()))
+
+    @staticmethod
+    def plan_chunks(wire, layout, n_chunks):
+        """Cut the sorted batch at 65536-position segment boundaries into ``n_chunks`` pieces of about
+        equal read count: ``[(read_a, read_b, bin_a, bin_b), ...]`` covering all reads and all bins."""
+        n_seg = len(wire.seg_base)
+        n_seg_chrom = np.maximum((wire.chrom_len + 65535) >> 16, 1)
+        seg_first = np.zeros(len(wire.chroms) + 1, dtype=np.int64)
+        np.cumsum(n_seg_chrom, out=seg_first[1:])
+        targets = (np.arange(1, n_chunks) * len(wire)) // max(n_chunks, 1)
+        cuts = sorted(set(int(x) for x in np.searchsorted(wire.seg_off[:-1], targets, side="left")) - {0, n_seg})
+        seg_cuts = [0] + cuts + [n_seg]
+        out = []
+        for s0, s1 in zip(seg_cuts[:-1], seg_cuts[1:]):
+            def bin_of(s):
+                if s >= n_seg:
+                    return layout.total_bins
+                c = int(np.searchsorted(seg_first, s, side="right")) - 1
+                return int(layout.chrom_bin_off[c]) + ((s - int(seg_first[c])) << 16)
+            out.append((int(wire.seg_off[s0]), int(wire.seg_off[s1]), bin_of(s0), bin_of(s1)))
+        return out
+
+    def receive_chunk(self, pinned, a, b, copy_stream):
+        """H2D of reads [a,b) on ``copy_stream``; returns the event the compute stream must wait for."""
+        import torch
+        with torch.cuda.stream(copy_stream):
+            self.start_lo[a:b].copy_(pinned["start_lo"][a:b], non_blocking=True)
+            self.meta16[a:b].copy_(pinned["meta16"][a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+
 class BatchRead(object):
     """Duck-typed stand-in for ``pysam.AlignedSegment`` built from one batch row."""
     __slots__ = ("batch", "index")

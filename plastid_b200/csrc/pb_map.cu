@@ -33,17 +33,21 @@ struct __align__(16) PbTile {
     int pad;
 };
 
-__global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, int64_t n_tiles,
-                                     PbTile *__restrict__ tiles)
+__global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, int64_t tile_begin, int64_t tile_end,
+                                     int64_t read_limit, PbTile *__restrict__ tiles)
 {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
+    int64_t t = tile_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tile_end) return;
     int64_t g0 = t * tile_bins;
     int c = pb_chrom_of_bin(lay, g0);
     int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
     int64_t clen = __ldg(lay.chrom_len + c);
     int64_t r0 = 0, r1 = 0;
     if (c < b.n_chrom) { r0 = __ldg(b.chrom_read_off + c); r1 = __ldg(b.chrom_read_off + c + 1); }
+    // streaming uploads: reads at or beyond read_limit have not arrived yet (and, being sorted, start
+    // beyond every tile of the range being mapped)
+    if (r1 > read_limit) r1 = read_limit;
+    if (r0 > r1) r0 = r1;
     // a read can only place a site in [p0, p0+T) if p0 - max_span < start < p0 + T
     int64_t lo = pb_lower_bound(b.ref_start, r0, r1, p0 - b.max_span + 1);
     int64_t hi = pb_lower_bound(b.ref_start, lo, r1, p0 + tile_bins);
@@ -116,8 +120,8 @@ constexpr int kPUnroll = 4;        // independent read loads in flight per threa
 // reads accumulate into it, store it, wait until the TMA engine has READ it (not until the write
 // has landed), and re-zero it.  The SM never touches the output bytes itself.
 __global__ void __launch_bounds__(kPThreads)
-pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restrict__ tiles, int64_t n_tiles,
-                      unsigned long long *__restrict__ tile_counter,
+pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restrict__ tiles, int64_t tile_begin,
+                      int64_t n_tiles, unsigned long long *__restrict__ tile_counter,
                       uint32_t *__restrict__ out_plus, uint32_t *__restrict__ out_minus,
                       uint32_t *__restrict__ out_any, unsigned long long *__restrict__ stat_slots)
 {
@@ -137,7 +141,7 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     uint4 *smem4 = reinterpret_cast<uint4 *>(smem);
     for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
-    if (threadIdx.x == 0) s_next[0] = (long long)atomicAdd(tile_counter, 1ull);
+    if (threadIdx.x == 0) s_next[0] = tile_begin + (long long)atomicAdd(tile_counter, 1ull);
     pb_fence_proxy_async();
     __syncthreads();
 
@@ -147,7 +151,7 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
     for (int it = 0;; ++it) {
         const long long tile = s_next[it & 1];
         if (tile >= n_tiles) break;
-        if (threadIdx.x == 0) s_next[(it + 1) & 1] = (long long)atomicAdd(tile_counter, 1ull);
+        if (threadIdx.x == 0) s_next[(it + 1) & 1] = tile_begin + (long long)atomicAdd(tile_counter, 1ull);
         const PbTile d = tiles[tile];
         const int64_t g0 = tile * kPTileBins;
 
@@ -528,6 +532,45 @@ __global__ void pb_length_hist_kernel(PbReads b, PbRuleDev r, int strand, unsign
         if (sh[j]) atomicAdd(&hist[j], (unsigned long long)sh[j]);
 }
 
+// ----------------------------------------------------------------------------------------
+// wire16: compact host format of an unspliced batch (4 B per read) -> the SoA the kernels stream
+// ----------------------------------------------------------------------------------------
+// Reads are sorted, so within one 65536-position segment of a chromosome the start needs 16 bits;
+// seg_off[s] is the first read of segment s, seg_base[s] the chromosome coordinate of its first
+// position.  One warp expands 1024 consecutive reads: one binary search for the chunk's segment,
+// then every lane walks forward (segments are crossed rarely).
+__global__ void __launch_bounds__(256)
+pb_unpack_wire16_kernel(const uint16_t *__restrict__ start_lo, const uint16_t *__restrict__ meta16,
+                        const int64_t *__restrict__ seg_off, const int32_t *__restrict__ seg_base,
+                        int64_t n_seg, int64_t read_begin, int64_t n_reads, int32_t *__restrict__ ref_start,
+                        uint32_t *__restrict__ meta)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t chunk0 = read_begin + warp * 1024;
+    if (chunk0 >= n_reads) return;
+    int64_t lo = 0, hi = n_seg;       // last segment with seg_off[s] <= chunk0
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(seg_off + mid) <= chunk0) lo = mid; else hi = mid;
+    }
+    int64_t seg = lo;
+    int64_t seg_end = __ldg(seg_off + seg + 1);
+    int32_t base = __ldg(seg_base + seg);
+    const int64_t chunk1 = chunk0 + 1024 < n_reads ? chunk0 + 1024 : n_reads;
+    for (int64_t i = chunk0 + lane; i < chunk1; i += 32) {
+        while (i >= seg_end) {        // empty segments are skipped too
+            ++seg;
+            seg_end = __ldg(seg_off + seg + 1);
+            base = __ldg(seg_base + seg);
+        }
+        const uint32_t m = __ldg(meta16 + i);
+        ref_start[i] = base + (int32_t)__ldg(start_lo + i);
+        // L (14 bits) | reverse | drop  ->  L | reverse<<16 | drop<<17 | n_blocks(=1)<<24
+        meta[i] = (m & 0x3fffu) | (((m >> 14) & 1u) << 16) | (((m >> 15) & 1u) << 17) | (1u << 24);
+    }
+}
+
 PbReads to_dev(const pb_batch *b)
 {
     PbReads d;
@@ -606,9 +649,10 @@ extern "C" size_t pb_map_workspace_bytes(int64_t total_bins)
     return tile_index_bytes(total_bins) + 2 * stat_slot_bytes() + 256;  // + tile counter
 }
 
-extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
-                            uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
-                            uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                                  uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
+                                  uint64_t *stats, void *workspace, size_t workspace_bytes,
+                                  int64_t bin_begin, int64_t bin_end, int64_t read_limit, void *stream_)
 {
     int rc = check_common(batch, layout, rule, planes);
     if (rc) return rc;
@@ -628,8 +672,14 @@ extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, cons
     if (workspace_bytes < pb_map_workspace_bytes(layout->total_bins) || !workspace) {
         pb_set_error("pb_map_point: workspace too small"); return PB_ENOSPACE;
     }
+    if (bin_begin < 0 || bin_end > layout->total_bins || bin_begin > bin_end || bin_begin % PB_LAYOUT_ALIGN ||
+        bin_end % PB_LAYOUT_ALIGN) {
+        pb_set_error("pb_map_point_range: bin range must be PB_LAYOUT_ALIGN-aligned and inside the layout"); return PB_EINVAL;
+    }
+    if (read_limit < 0 || read_limit > batch->n_reads) read_limit = batch->n_reads;
+    if (bin_begin == bin_end) return PB_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int64_t n_tiles = layout->total_bins / kPTileBins;
+    const int64_t tile_begin = bin_begin / kPTileBins, n_tiles = bin_end / kPTileBins;   // n_tiles = end of range
     PbTile *tiles = (PbTile *)workspace;
     unsigned long long *slots = (unsigned long long *)((char *)workspace + tile_index_bytes(layout->total_bins));
     unsigned long long *tile_counter = slots + 2 * kStatSlots * PB_NSTATS;
@@ -638,7 +688,8 @@ extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, cons
     PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
 
     PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, 2 * stat_slot_bytes() + 64, stream));
-    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, kPTileBins, n_tiles, tiles);
+    pb_tile_index_kernel<<<(unsigned)((n_tiles - tile_begin + 255) / 256), 256, 0, stream>>>(b, lay, kPTileBins, tile_begin,
+                                                                                              n_tiles, read_limit, tiles);
     const int n_planes = __builtin_popcount(planes);
     const size_t smem = (size_t)n_planes * kPTileBins * sizeof(uint32_t);
     static int sm_count = 0;
@@ -652,14 +703,23 @@ extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, cons
     PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_point_tiles_kernel, kPThreads, smem));
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)sm_count * occ;     // persistent: one resident wave, tiles come from a queue
-    if (grid > n_tiles) grid = n_tiles;
+    if (grid > n_tiles - tile_begin) grid = n_tiles - tile_begin;
     timing_begin(stream);
-    pb_point_tiles_kernel<<<(unsigned)grid, kPThreads, smem, stream>>>(b, r, planes, tiles, n_tiles, tile_counter,
+    pb_point_tiles_kernel<<<(unsigned)grid, kPThreads, smem, stream>>>(b, r, planes, tiles, tile_begin, n_tiles, tile_counter,
                                                                       out_plus, out_minus, out_any, slots);
     timing_end(stream);
     pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, (unsigned long long *)stats);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
+}
+
+extern "C" int pb_map_point(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                            uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
+                            uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    if (!layout || !batch) { pb_set_error("null batch/layout/rule"); return PB_EINVAL; }
+    return pb_map_point_range(batch, layout, rule, planes, out_plus, out_minus, out_any, stats, workspace,
+                              workspace_bytes, 0, layout->total_bins, batch->n_reads, stream_);
 }
 
 template <int EPT>
@@ -724,7 +784,7 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     const int64_t n_tiles = layout->total_bins / tile_bins;
 
     PB_CUDA_CHECK(cudaMemsetAsync(slots, 0, 2 * stat_slot_bytes(), stream));
-    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, n_tiles, tiles);
+    pb_tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, 0, n_tiles, batch->n_reads, tiles);
     timing_begin(stream);
     switch (ept) {
     case 16: rc = launch_center<16>(b, r, lay, planes, slot_of_len, inv_m, n_slots, per_pass, layout->total_bins, tiles, out_plus, out_minus, out_any, slots, stream); break;
@@ -792,6 +852,24 @@ extern "C" int pb_length_hist(const pb_batch *batch, const pb_rule *rule, int st
     unsigned grid = (unsigned)((batch->n_reads + 511) / 512);
     if (grid > 148 * 8) grid = 148 * 8;
     pb_length_hist_kernel<<<grid, 512, 0, stream>>>(b, r, strand, (unsigned long long *)hist);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_unpack_wire16(const uint16_t *start_lo, const uint16_t *meta16, const int64_t *seg_off,
+                                const int32_t *seg_base, int64_t n_seg, int64_t read_begin, int64_t read_end,
+                                int32_t *ref_start_out, uint32_t *meta_out, void *stream_)
+{
+    if (read_begin < 0 || read_end < read_begin || n_seg < 0) { pb_set_error("pb_unpack_wire16: bad range"); return PB_EINVAL; }
+    if (read_end == read_begin) return PB_OK;
+    const int64_t n_reads = read_end;
+    if (!start_lo || !meta16 || !seg_off || !seg_base || !ref_start_out || !meta_out || n_seg < 1) {
+        pb_set_error("pb_unpack_wire16: null argument"); return PB_EINVAL;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t warps = (read_end - read_begin + 1023) / 1024;
+    const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+    pb_unpack_wire16_kernel<<<grid, 256, 0, stream>>>(start_lo, meta16, seg_off, seg_base, n_seg, read_begin, n_reads, ref_start_out, meta_out);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

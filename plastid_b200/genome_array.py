@@ -109,6 +109,44 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     return planes
 
 
+def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=None, strands=("+", "-"),
+                        planes=None, copy_stream=None):
+    """Upload a pinned wire16 batch chunk by chunk on ``copy_stream`` and map each chunk's bin range
+    (``pb_map_point_range``) on the current stream as soon as its reads have landed, so the PCIe
+    transfer and the mapping overlap.  Point rules only.  Returns the planes (stats on device)."""
+    import torch
+    _lib.require_cuda()
+    if not isinstance(factory, _MapFactory) or isinstance(factory, (StratifiedVariableFivePrimeMapFactory, CenterMapFactory)):
+        raise TypeError("streamed mapping supports FivePrime/ThreePrime/VariableFivePrime factories")
+    dbatch = receiver.batch
+    dev = dbatch.device
+    if planes is None:
+        planes = CountPlanes(layout, "u32", dev)
+    planes.alloc(strands)
+    mask = 0
+    for s in strands:
+        mask |= _lib.STRAND_PLANE[s]
+    L = _lib.lib()
+    ws_bytes = L.pb_map_workspace_bytes(layout.total_bins)
+    ws = _workspace(dev, ws_bytes)
+    stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev)
+    copy_stream = copy_stream or torch.cuda.Stream(device=dev)
+    compute = torch.cuda.current_stream()
+    copy_stream.wait_stream(compute)          # landing buffers may still be read by earlier work
+    with torch.cuda.stream(copy_stream):
+        receiver._receive_tables(pinned)
+    events = [receiver.receive_chunk(pinned, a, b, copy_stream) for a, b, _x, _y in chunks]
+    b_c, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
+    outs = [_lib.ptr(planes.planes[s]) if s in strands else None for s in _STRANDS]
+    for (a, b, bin_a, bin_b), ev in zip(chunks, events):
+        compute.wait_event(ev)
+        receiver._unpack(a, b)
+        _lib.check(L.pb_map_point_range(C.byref(b_c), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
+                                        _lib.ptr(stats), _lib.ptr(ws), ws_bytes, bin_a, bin_b, b, _lib.stream_ptr()))
+    planes.stats_dev = stats
+    return planes
+
+
 def region_sums(planes, table, out=None):
     """Masked sums + unmasked lengths for every chain of ``table`` (device tensors returned)."""
     import torch

@@ -449,3 +449,43 @@ def test_to_genome_array_drops_last_base_like_the_reference(cuda_device):
     assert dense.sum() == 4.0            # '+': 0,50   '-': (99 dropped)   '.': 0,50 (99 dropped) -- genome_array.py:985
     assert dense[pb.GenomicSegment("c", 0, 100, "+")].sum() == 2 and dense[pb.GenomicSegment("c", 0, 100, "-")].sum() == 0
     assert ga[pb.GenomicSegment("c", 0, 100, "-")].sum() == 1
+
+
+def test_wire16_unpack_on_device(small_world, cuda_device):
+    from plastid_b200.batch import Wire16Batch, Wire16Receiver
+    hb = small_world["hb"]
+    wire = Wire16Batch.from_batch(hb)
+    rx = Wire16Receiver(wire, cuda_device)
+    db = rx.receive(wire.pinned())
+    assert (db.ref_start.cpu().numpy() == hb.ref_start).all()
+    assert (db.meta.cpu().numpy().view(np.uint32) == hb.meta).all()
+    assert (db.chrom_read_off.cpu().numpy() == hb.chrom_read_off).all()
+    planes = map_batch(db, small_world["layout"], pb.FivePrimeMapFactory(14), None, strands=("+",))
+    exp = coracle.genome_vector(hb, 0, "+", rule="fiveprime", offset=14)[0]
+    assert (plane_chrom(planes, small_world["layout"], "+", 0) == exp).all()
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3, 8])
+def test_streamed_upload_matches_whole_batch(small_world, cuda_device, n_chunks):
+    """wire16 chunks uploaded on a copy stream + pb_map_point_range per chunk == one whole launch."""
+    import torch
+    from plastid_b200.batch import Wire16Batch, Wire16Receiver
+    from plastid_b200.genome_array import map_wire16_streamed
+    w = small_world
+    wire = Wire16Batch.from_batch(w["hb"])
+    rx = Wire16Receiver(wire, cuda_device)
+    rx.batch.ref_start.fill_(-7)                  # poison: nothing may be read before it has landed
+    rx.batch.meta.fill_(0)
+    chunks = Wire16Receiver.plan_chunks(wire, w["layout"], n_chunks)
+    assert chunks[0][0] == 0 and chunks[-1][1] == len(wire) and chunks[-1][3] == w["layout"].total_bins
+    fac = pb.VariableFivePrimeMapFactory(synth.RIBO_OFFSETS)
+    planes = map_wire16_streamed(rx, wire.pinned(), chunks, w["layout"], fac, pb.SizeFilterFactory(20, 38),
+                                 ("+", "-", "."))
+    torch.cuda.synchronize()
+    ref = map_batch(w["dbatch"], w["layout"], fac, pb.SizeFilterFactory(20, 38), strands=("+", "-", "."))
+    for s in ("+", "-", "."):
+        assert torch.equal(planes.planes[s], ref.planes[s])
+    assert (planes.stats_dev.cpu().numpy() == ref.stats).all()
+    exp = coracle.genome_vector(w["hb"], 1, "-", rule="variable", luts=(fac.forward_offsets, fac.reverse_offsets),
+                                size_filter=(20, 38))[0]
+    assert (plane_chrom(planes, w["layout"], "-", 1) == exp).all()

@@ -284,3 +284,40 @@ def test_synthetic_generators_are_seeded_and_sorted():
     nb = (r.meta >> 24).astype(int)
     assert set(np.unique(nb)) == {1, 2, 3} and (np.diff(r.blk_off.astype(int)) == np.where(nb > 1, nb, 0)).all()
     assert all(len(r.positions_of(i)) == 100 for i in range(0, 5000, 97))
+
+
+def test_wire16_host_format_round_trip():
+    from plastid_b200.batch import Wire16Batch
+    chroms, lens = ["a", "b", "c"], np.array([200_000, 65536, 70_000])
+    ann = synth.make_annotation(chroms, lens, 30, seed=1, exons=(1, 2), exon_len=(200, 600), intron_len=(50, 400))
+    hb = synth.device_batch_to_host(synth.riboseq_reads(ann, 30000, seed=3, device="cpu"), chroms, lens)
+    hb = hb.with_drop_mask(np.arange(len(hb)) % 17 == 0)
+    w = Wire16Batch.from_batch(hb)
+    assert w.nbytes < 0.55 * (hb.ref_start.nbytes + hb.meta.nbytes)
+    assert len(w.seg_base) == 4 + 1 + 2 and list(w.seg_base) == [0, 65536, 131072, 196608, 0, 0, 65536]
+    seg = np.searchsorted(w.seg_off, np.arange(len(w)), side="right") - 1
+    assert (w.seg_base[seg].astype(np.int64) + w.start_lo == hb.ref_start).all()
+    m = w.meta16.astype(np.uint32)
+    meta = (m & 0x3FFF) | (((m >> 14) & 1) << 16) | (((m >> 15) & 1) << 17) | (1 << 24)
+    assert (meta == hb.meta).all()
+    spliced = synth.device_batch_to_host(synth.rnaseq_reads(chroms, lens, 2000, seed=2, device="cpu"), chroms, lens)
+    with pytest.raises(ValueError):
+        Wire16Batch.from_batch(spliced)
+
+
+def test_wire16_chunk_plan_covers_reads_and_bins():
+    from plastid_b200.batch import Wire16Batch, Wire16Receiver
+    chroms, lens = synth.human_like_genome(0.004)
+    ann = synth.make_annotation(chroms, lens, 300, seed=1, exons=(1, 2), exon_len=(200, 600), intron_len=(50, 400))
+    hb = synth.device_batch_to_host(synth.riboseq_reads(ann, 50000, seed=3, device="cpu"), chroms, lens)
+    wire, lay = Wire16Batch.from_batch(hb), pb.GenomeLayout(chroms, lens)
+    for k in (1, 2, 8, 64):
+        plan = Wire16Receiver.plan_chunks(wire, lay, k)
+        assert 1 <= len(plan) <= k and plan[0][0] == 0 and plan[0][2] == 0
+        assert plan[-1][1] == len(wire) and plan[-1][3] == lay.total_bins
+        for (a, b, x, y), (a2, b2, x2, y2) in zip(plan[:-1], plan[1:]):
+            assert b == a2 and y == x2 and x % _lib.PB_LAYOUT_ALIGN == 0 and a <= b and x < y
+        for a, b, x, y in plan:
+            c = np.searchsorted(hb.chrom_read_off, np.arange(a, b), side="right") - 1
+            g = lay.chrom_bin_off[c] + hb.ref_start[a:b]
+            assert (g >= x).all() and (g < y).all()
