@@ -99,6 +99,9 @@ typedef struct pb_batch {
     const int64_t  *chrom_read_off;  /* device int64[n_chrom+1] */
     int32_t         n_chrom;
     int32_t         max_span;        /* >= max over reads of (reference_end - ref_start) */
+    int64_t         n_blk;           /* rows of blk (0 when blk is NULL) */
+    int32_t         max_block_len;   /* >= longest aligned block (= longest L when blk is NULL) */
+    int32_t         reserved;
 } pb_batch;
 
 typedef struct pb_layout {
@@ -124,8 +127,9 @@ const char *pb_version(void);
 const char *pb_last_error(void);
 int pb_device_count(void);
 
-/* Bytes of device workspace pb_map_point / pb_map_center need for this layout. */
-size_t pb_map_workspace_bytes(int64_t total_bins);
+/* Bytes of device workspace pb_map_point / pb_map_center need for this layout and a batch with
+ * n_blk block rows (0 for unspliced batches). */
+size_t pb_map_workspace_bytes(int64_t total_bins, int64_t n_blk);
 
 /* wire16: compact 4-byte-per-read transfer format of an unspliced batch (every read one block,
  * L < 16384), what the host decoder hands over PCIe.  start_lo uint16[N] = ref_start & 0xFFFF;

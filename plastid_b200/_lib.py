@@ -26,7 +26,8 @@ PLANE_INDEX = {"+": 0, "-": 1, ".": 2}
 class PbBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("ref_start", C.c_void_p), ("meta", C.c_void_p),
                 ("blk_off", C.c_void_p), ("blk", C.c_void_p), ("chrom_read_off", C.c_void_p),
-                ("n_chrom", C.c_int32), ("max_span", C.c_int32)]
+                ("n_chrom", C.c_int32), ("max_span", C.c_int32), ("n_blk", C.c_int64),
+                ("max_block_len", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PbLayout(C.Structure):
@@ -45,7 +46,7 @@ _SIGNATURES = {
     "pb_version": (C.c_char_p, []),
     "pb_last_error": (C.c_char_p, []),
     "pb_device_count": (C.c_int, []),
-    "pb_map_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "pb_map_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "pb_unpack_wire16": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "pb_map_point_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
                                      _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, C.c_int64, C.c_int64, _P]),

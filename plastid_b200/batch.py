@@ -93,6 +93,7 @@ class AlignmentBatch(object):
         if max_span is None:
             max_span = self.compute_max_span()
         self.max_span = int(max_span)
+        self.max_block_len = self.compute_max_block_len()
         self.mapped = n if mapped is None else int(mapped)   # what `bamfile.mapped` reports
         self.objects = None      # optional list of the original read objects, batch order
         self._dev = {}
@@ -115,6 +116,13 @@ class AlignmentBatch(object):
         if self.blk is not None and len(self.blk):
             span = max(span, int((self.blk[:, 0] + self.blk[:, 1]).max()))
         return max(span, 1)
+
+    def compute_max_block_len(self):
+        """Longest aligned block: the halo of the tile candidate window (single-block reads: L)."""
+        if len(self.ref_start) == 0:
+            return 1
+        out = int((self.meta & 0xFFFF).max())      # >= every block of every read
+        return max(out, 1)
 
     def check_sorted(self):
         for c in range(len(self.chroms)):
@@ -321,10 +329,14 @@ class BatchRead(object):
 class DeviceBatch(object):
     """Device-resident mirror of an :class:`AlignmentBatch` (torch tensors used as buffers only)."""
 
-    def __init__(self, n_reads, n_chrom, max_span, ref_start, meta, chrom_read_off, blk_off=None, blk=None):
+    def __init__(self, n_reads, n_chrom, max_span, ref_start, meta, chrom_read_off, blk_off=None, blk=None,
+                 max_block_len=None):
         self.n_reads, self.n_chrom, self.max_span = int(n_reads), int(n_chrom), int(max_span)
         self.ref_start, self.meta, self.chrom_read_off = ref_start, meta, chrom_read_off
         self.blk_off, self.blk = blk_off, blk
+        self.n_blk = 0 if blk is None else int(blk.shape[0])
+        # without better knowledge the reference span bounds every block
+        self.max_block_len = int(max_span if max_block_len is None else max_block_len)
 
     @classmethod
     def from_host(cls, hb, device, non_blocking=False):
@@ -336,7 +348,7 @@ class DeviceBatch(object):
             t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a)
             return t.to(device, non_blocking=non_blocking)
         return cls(len(hb), len(hb.chroms), hb.max_span, up(hb.ref_start), up(hb.meta),
-                   up(hb.chrom_read_off), up(hb.blk_off), up(hb.blk))
+                   up(hb.chrom_read_off), up(hb.blk_off), up(hb.blk), hb.max_block_len)
 
     @property
     def device(self):
@@ -346,7 +358,8 @@ class DeviceBatch(object):
         return _lib.PbBatch(self.n_reads, self.ref_start.data_ptr(), self.meta.data_ptr(),
                             None if self.blk_off is None else self.blk_off.data_ptr(),
                             None if self.blk is None else self.blk.data_ptr(),
-                            self.chrom_read_off.data_ptr(), self.n_chrom, self.max_span)
+                            self.chrom_read_off.data_ptr(), self.n_chrom, self.max_span, self.n_blk,
+                            self.max_block_len, 0)
 
 
 def pack_reads(reads_by_chrom, chrom_lengths, keep_objects=True, mapped=None):

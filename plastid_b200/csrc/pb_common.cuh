@@ -29,8 +29,10 @@ struct PbReads {
     const int2     *__restrict__ blk;
     const int64_t  *__restrict__ chrom_read_off;
     int64_t n_reads;
+    int64_t n_blk;          // entries of blk (0 when every read is one block)
     int32_t n_chrom;
     int32_t max_span;
+    int32_t max_block_len;  // longest aligned block in the batch: halo of the tile candidate window
 };
 
 struct PbRuleDev {

@@ -1,0 +1,196 @@
+// pb_misc.cu — the per-segment operator, the aligned-length histogram and the wire16 expansion.
+#include "pb_tiles.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------------------
+// the operator on one segment (global atomics; small inputs)
+// ----------------------------------------------------------------------------------------
+__global__ void pb_segment_kernel(PbReads b, PbRuleDev r, int64_t i0, int64_t i1, int strand, int flags,
+                                  int64_t seg_start, int64_t seg_end,
+                                  unsigned long long *counts_i, double *counts_f,
+                                  uint8_t *__restrict__ kept, unsigned long long *__restrict__ stats)
+{
+    const int64_t n = seg_end - seg_start;
+    const bool rq = (strand == PB_PLANE_MINUS);
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t s = __ldg(b.ref_start + i);
+        const uint32_t m = __ldg(b.meta + i);
+        uint8_t keep = 0;
+        const bool rev = PB_META_REV(m);
+        bool pass = pb_passes(m, r.size_min, r.size_max);
+        if ((flags & PB_SEG_FILTER_STRAND) && strand == PB_PLANE_PLUS && rev) pass = false;    // genome_array.py:811-815
+        if ((flags & PB_SEG_FILTER_STRAND) && strand == PB_PLANE_MINUS && !rev) pass = false;
+        if (pass && (flags & PB_SEG_FETCH_OVERLAP)) {
+            // AlignmentFile.fetch(chrom, start, end): only reads whose reference span overlaps the segment
+            int64_t span = PB_META_L(m);
+            if (PB_META_NBLK(m) > 1 && b.blk_off != nullptr) {
+                const int2 last = __ldg(b.blk + (__ldg(b.blk_off + i + 1) - 1));
+                span = (int64_t)last.x + last.y;
+            }
+            if (!((int64_t)s < seg_end && (int64_t)s + span > seg_start)) pass = false;
+        }
+        if (pass) {
+            const int L = PB_META_L(m);
+            const int sidx = strand == PB_PLANE_PLUS ? PB_STAT_DROPPED_PLUS
+                           : strand == PB_PLANE_MINUS ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_ANY;
+            if (r.kind == PB_RULE_CENTER) {
+                const int nib = r.param, map_len = L - 2 * nib;
+                if (map_len < 0) {
+                    atomicAdd(&stats[sidx], 1ull);
+                    stats[PB_STAT_DROPPED_LEN] = L;
+                } else if (map_len > 0) {
+                    const double v = 1.0 / map_len;
+                    for (int k = nib; k < L - nib; ++k) {
+                        const int64_t cpos = pb_position(b, i, s, m, k) - seg_start;
+                        if (cpos >= 0 && cpos < n) atomicAdd(&counts_f[cpos], v);
+                    }
+                    keep = 1;
+                }
+            } else if (r.kind == PB_RULE_STRATIFIED) {
+                if (L >= r.strat_min && L <= r.strat_max && L < PB_LUT_SIZE) {
+                    int off = rq ? __ldg(r.lut_rc + L) : __ldg(r.lut_fw + L);
+                    if (off < 0) off += L;  // map_factories.pyx:773-774: no BAD_OFFSET test, python index -1
+                    const int64_t p = pb_position(b, i, s, m, off);
+                    if (p >= seg_start && p < seg_end) {
+                        atomicAdd(&counts_i[(int64_t)(L - r.strat_min) * n + (p - seg_start)], 1ull);
+                        keep = 1;
+                    }
+                }
+            } else {
+                const int idx = pb_rule_index(r, L, rq);
+                if (idx < 0) {
+                    atomicAdd(&stats[sidx], 1ull);
+                    stats[PB_STAT_DROPPED_LEN] = L;
+                } else {
+                    const int64_t p = pb_position(b, i, s, m, idx);
+                    if (p >= seg_start && p < seg_end) {
+                        atomicAdd(&counts_i[p - seg_start], 1ull);
+                        keep = 1;
+                    }
+                }
+            }
+        }
+        if (kept) kept[i - i0] = keep;
+    }
+}
+
+__global__ void pb_length_hist_kernel(PbReads b, PbRuleDev r, int strand, unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[1024];
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) sh[j] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = __ldg(b.meta + i);
+        if (!pb_passes(m, r.size_min, r.size_max)) continue;
+        const bool rev = PB_META_REV(m);
+        if (strand == PB_PLANE_PLUS && rev) continue;
+        if (strand == PB_PLANE_MINUS && !rev) continue;
+        const int L = PB_META_L(m);
+        if (L < 1024) atomicAdd(&sh[L], 1u); else atomicAdd(&hist[L], 1ull);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x)
+        if (sh[j]) atomicAdd(&hist[j], (unsigned long long)sh[j]);
+}
+
+// ----------------------------------------------------------------------------------------
+// wire16: compact host format of an unspliced batch (4 B per read) -> the SoA the kernels stream
+// ----------------------------------------------------------------------------------------
+// Reads are sorted, so within one 65536-position segment of a chromosome the start needs 16 bits;
+// seg_off[s] is the first read of segment s, seg_base[s] the chromosome coordinate of its first
+// position.  One warp expands 1024 consecutive reads: one binary search for the chunk's segment,
+// then every lane walks forward (segments are crossed rarely).
+__global__ void __launch_bounds__(256)
+pb_unpack_wire16_kernel(const uint16_t *__restrict__ start_lo, const uint16_t *__restrict__ meta16,
+                        const int64_t *__restrict__ seg_off, const int32_t *__restrict__ seg_base,
+                        int64_t n_seg, int64_t read_begin, int64_t n_reads, int32_t *__restrict__ ref_start,
+                        uint32_t *__restrict__ meta)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t chunk0 = read_begin + warp * 1024;
+    if (chunk0 >= n_reads) return;
+    int64_t lo = 0, hi = n_seg;       // last segment with seg_off[s] <= chunk0
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(seg_off + mid) <= chunk0) lo = mid; else hi = mid;
+    }
+    int64_t seg = lo;
+    int64_t seg_end = __ldg(seg_off + seg + 1);
+    int32_t base = __ldg(seg_base + seg);
+    const int64_t chunk1 = chunk0 + 1024 < n_reads ? chunk0 + 1024 : n_reads;
+    for (int64_t i = chunk0 + lane; i < chunk1; i += 32) {
+        while (i >= seg_end) {        // empty segments are skipped too
+            ++seg;
+            seg_end = __ldg(seg_off + seg + 1);
+            base = __ldg(seg_base + seg);
+        }
+        const uint32_t m = __ldg(meta16 + i);
+        ref_start[i] = base + (int32_t)__ldg(start_lo + i);
+        // L (14 bits) | reverse | drop  ->  L | reverse<<16 | drop<<17 | n_blocks(=1)<<24
+        meta[i] = (m & 0x3fffu) | (((m >> 14) & 1u) << 16) | (((m >> 15) & 1u) << 17) | (1u << 24);
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
+                              int flags, int64_t seg_start, int64_t seg_end, void *counts_out, uint8_t *kept_out,
+                              uint64_t *stats, void *stream_)
+{
+    if (!batch || !rule || !counts_out || !stats) { pb_set_error("pb_map_segment: null argument"); return PB_EINVAL; }
+    if (i0 < 0 || i1 < i0 || i1 > batch->n_reads) { pb_set_error("pb_map_segment: bad read range"); return PB_EINVAL; }
+    if (strand != PB_PLANE_PLUS && strand != PB_PLANE_MINUS && strand != PB_PLANE_ANY) { pb_set_error("pb_map_segment: bad strand"); return PB_EINVAL; }
+    if (seg_end < seg_start) { pb_set_error("pb_map_segment: negative-length segment"); return PB_EINVAL; }
+    if ((rule->kind == PB_RULE_VARIABLE || rule->kind == PB_RULE_STRATIFIED) && (!rule->lut_fw || !rule->lut_rc)) {
+        pb_set_error("pb_map_segment: rule needs lut_fw/lut_rc"); return PB_EINVAL;
+    }
+    if (rule->kind < 0 || rule->kind > PB_RULE_STRATIFIED) { pb_set_error("pb_map_segment: unknown rule"); return PB_EINVAL; }
+    if (i1 == i0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbReads b = pb_to_dev(batch);
+    PbRuleDev r = pb_to_dev(rule);
+    int64_t n = i1 - i0;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    pb_segment_kernel<<<grid, 256, 0, stream>>>(b, r, i0, i1, strand, flags, seg_start, seg_end,
+                                                (unsigned long long *)counts_out, (double *)counts_out, kept_out,
+                                                (unsigned long long *)stats);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_length_hist(const pb_batch *batch, const pb_rule *rule, int strand, uint64_t *hist, void *stream_)
+{
+    if (!batch || !rule || !hist) { pb_set_error("pb_length_hist: null argument"); return PB_EINVAL; }
+    if (batch->n_reads == 0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbReads b = pb_to_dev(batch);
+    PbRuleDev r = pb_to_dev(rule);
+    unsigned grid = (unsigned)((batch->n_reads + 511) / 512);
+    if (grid > 148 * 8) grid = 148 * 8;
+    pb_length_hist_kernel<<<grid, 512, 0, stream>>>(b, r, strand, (unsigned long long *)hist);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_unpack_wire16(const uint16_t *start_lo, const uint16_t *meta16, const int64_t *seg_off,
+                                const int32_t *seg_base, int64_t n_seg, int64_t read_begin, int64_t read_end,
+                                int32_t *ref_start_out, uint32_t *meta_out, void *stream_)
+{
+    if (read_begin < 0 || read_end < read_begin || n_seg < 0) { pb_set_error("pb_unpack_wire16: bad range"); return PB_EINVAL; }
+    if (read_end == read_begin) return PB_OK;
+    const int64_t n_reads = read_end;
+    if (!start_lo || !meta16 || !seg_off || !seg_base || !ref_start_out || !meta_out || n_seg < 1) {
+        pb_set_error("pb_unpack_wire16: null argument"); return PB_EINVAL;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t warps = (read_end - read_begin + 1023) / 1024;
+    const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+    pb_unpack_wire16_kernel<<<grid, 256, 0, stream>>>(start_lo, meta16, seg_off, seg_base, n_seg, read_begin, n_reads, ref_start_out, meta_out);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}

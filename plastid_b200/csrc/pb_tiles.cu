@@ -1,0 +1,406 @@
+// pb_tiles.cu — kernels shared by the point and center mapping paths: tile candidate index,
+// binning of multi-block (spliced) reads by tile, statistics, workspace and timing plumbing.
+#include "pb_tiles.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------------------
+// tile -> candidate read slice
+// ----------------------------------------------------------------------------------------
+__global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, int64_t tile_begin, int64_t tile_end,
+                                     int64_t read_limit, PbTile *__restrict__ tiles)
+{
+    int64_t t = tile_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tile_end) return;
+    int64_t g0 = t * tile_bins;
+    int c = pb_chrom_of_bin(lay, g0);
+    int64_t p0 = g0 - __ldg(lay.chrom_bin_off + c);
+    int64_t clen = __ldg(lay.chrom_len + c);
+    int64_t r0 = 0, r1 = 0;
+    if (c < b.n_chrom) { r0 = __ldg(b.chrom_read_off + c); r1 = __ldg(b.chrom_read_off + c + 1); }
+    // streaming uploads: reads at or beyond read_limit have not arrived yet (and, being sorted, start
+    // beyond every tile of the range being mapped)
+    if (r1 > read_limit) r1 = read_limit;
+    if (r0 > r1) r0 = r1;
+    // a single-block read [s, s+L) can only touch [p0, p0+T) if p0 - max_block_len < s < p0 + T;
+    // multi-block reads reach their tiles through the binned records instead
+    int64_t lo = pb_lower_bound(b.ref_start, r0, r1, p0 - b.max_block_len + 1);
+    int64_t hi = pb_lower_bound(b.ref_start, lo, r1, p0 + tile_bins);
+    int64_t live = clen - p0;
+    live = live < 0 ? 0 : (live > tile_bins ? tile_bins : live);
+    PbTile d;
+    d.lo = lo; d.p0 = p0;
+    d.n = (live > 0 && hi - lo < 0x7fffffff) ? (int)(hi - lo) : (live > 0 ? 0x7fffffff : 0);
+    d.live = (int)live; d.chrom = c; d.pad = 0;
+    tiles[t] = d;
+}
+
+// ----------------------------------------------------------------------------------------
+// K1: CIGAR blocks of multi-block reads -> per-tile record buckets (counting sort by tile)
+// ----------------------------------------------------------------------------------------
+template <bool CENTER>
+__global__ void __launch_bounds__(256)
+pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t *__restrict__ slot_of_len,
+              int tile_bins, int fill, uint32_t *__restrict__ rec_cursor, const uint32_t *__restrict__ rec_off,
+              PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
+{
+    unsigned long long drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;
+    unsigned int drop_len = 0;
+    const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
+               want_any = planes & PB_PLANE_ANY;
+    constexpr int kU = 4;   // independent meta loads in flight per thread
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < b.n_reads; i0 += stride * kU) {
+      uint32_t mv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) mv[u] = i0 + u * stride < b.n_reads ? __ldg(b.meta + i0 + u * stride) : 0u;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = i0 + u * stride;
+        const uint32_t m = mv[u];
+        if (PB_META_NBLK(m) <= 1) continue;      // also skips the out-of-range filler (n_blocks 0)
+        if (!pb_passes(m, r.size_min, r.size_max)) continue;
+        int c = 0;
+        {   // chromosome of read i: last c with chrom_read_off[c] <= i
+            int lo = 0, hi = b.n_chrom;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(b.chrom_read_off + mid) <= i) lo = mid; else hi = mid;
+            }
+            c = lo;
+        }
+        const int64_t base = __ldg(lay.chrom_bin_off + c), clen = __ldg(lay.chrom_len + c);
+        const int32_t s = __ldg(b.ref_start + i);
+        const int L = PB_META_L(m);
+        const bool rev = PB_META_REV(m);
+        auto emit = [&](int64_t x, int64_t y, uint32_t tag) {
+            if (x < 0 || x >= clen) return;
+            if (y > clen) y = clen;
+            const int64_t tile = (base + x) / tile_bins;
+            const uint32_t k = atomicAdd(&rec_cursor[tile], 1u);
+            if (fill) {
+                PbRec rec;
+                rec.x = (int32_t)x; rec.y = (int32_t)y; rec.tag = tag; rec.pad = 0;
+                recs[__ldg(rec_off + tile) + k] = rec;
+            }
+        };
+        if (CENTER) {
+            const int nibble = r.param, map_len = L - 2 * nibble;
+            if (map_len < 0) {                                   // map_factories.pyx:246-248
+                drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L;
+                continue;
+            }
+            if (map_len == 0) continue;
+            map_a++; if (rev) map_m++; else map_p++;           // reads_out semantics (:256)
+            const int slot = (int)__ldg(slot_of_len + L);
+            if (slot < 0) continue;
+            const uint32_t tag = (uint32_t)slot | ((uint32_t)rev << 16);
+            const uint32_t k0 = __ldg(b.blk_off + i), k1 = __ldg(b.blk_off + i + 1);
+            int a = 0;  // aligned-base index of the block's first base
+            for (uint32_t k = k0; k < k1; ++k) {
+                const int2 bl = __ldg(b.blk + k);
+                const int ia = a > nibble ? a : nibble;
+                const int ib = (a + bl.y) < (L - nibble) ? (a + bl.y) : (L - nibble);
+                if (ia < ib) emit((int64_t)s + bl.x + (ia - a), (int64_t)s + bl.x + (ib - a), tag);
+                a += bl.y;
+            }
+        } else {
+            const int idx_f = pb_rule_index(r, L, false);
+            if (idx_f < 0) {                                     // the reference skips the read and warns
+                drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L;
+                continue;
+            }
+            int64_t p_f = -1, p_r = -1;
+            uint32_t tag_f = 0, tag_r = 0;
+            if (want_any || (!rev && want_plus)) {
+                p_f = pb_block_position(b, i, s, idx_f);
+                if (p_f >= 0 && p_f < clen) {
+                    if (want_any) { tag_f |= PB_PLANE_ANY; map_a++; }
+                    if (!rev && want_plus) { tag_f |= PB_PLANE_PLUS; map_p++; }
+                }
+            }
+            if (rev && want_minus) {
+                p_r = pb_block_position(b, i, s, pb_rule_index(r, L, true));
+                if (p_r >= 0 && p_r < clen) { tag_r = PB_PLANE_MINUS; map_m++; }
+            }
+            if (tag_f && tag_r && p_f == p_r) { tag_f |= tag_r; tag_r = 0; }
+            if (tag_f) emit(p_f, p_f + 1, tag_f);
+            if (tag_r) emit(p_r, p_r + 1, tag_r);
+        }
+      }
+    }
+    if (!fill) pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
+}
+
+// exclusive scan of the per-tile record counts in three small launches (4096 counts per CTA, scan
+// of the CTA totals, add-back); zeroes the counts so the fill pass can reuse them as cursors.
+constexpr int kScanThreads = 1024, kScanPer = 4, kScanChunk = kScanThreads * kScanPer;
+
+__device__ __forceinline__ uint32_t pb_block_exclusive_scan(uint32_t v, uint32_t *s_warp, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += u;
+        }
+        s_warp[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t before = warp ? s_warp[warp - 1] : 0;
+    if (total) *total = s_warp[31];
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+pb_scan_chunks_kernel(uint32_t *__restrict__ cursor, uint32_t *__restrict__ off, uint32_t *__restrict__ part, int64_t n)
+{
+    __shared__ uint32_t s_warp[32];
+    const int64_t j0 = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanPer;
+    uint32_t c[kScanPer], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) { c[k] = j0 + k < n ? cursor[j0 + k] : 0; sum += c[k]; }
+    uint32_t total = 0;
+    uint32_t run = pb_block_exclusive_scan(sum, s_warp, &total);
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        if (j0 + k < n) { off[j0 + k] = run; cursor[j0 + k] = 0; }
+        run += c[k];
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) pb_scan_top_kernel(uint32_t *__restrict__ part, int64_t nb)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += kScanThreads) {
+        const int64_t j = base + threadIdx.x;
+        const uint32_t v = j < nb ? part[j] : 0;
+        uint32_t total = 0;
+        const uint32_t ex = pb_block_exclusive_scan(v, s_warp, &total);
+        const uint32_t carry = s_carry;
+        if (j < nb) part[j] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[nb] = s_carry;   // grand total
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+pb_scan_add_kernel(uint32_t *__restrict__ off, const uint32_t *__restrict__ part, int64_t n, int64_t nb)
+{
+    const uint32_t add = part[blockIdx.x];
+    const int64_t j0 = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanPer;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k)
+        if (j0 + k < n) off[j0 + k] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) off[n] = part[nb];
+}
+
+__global__ void pb_stats_finish_kernel(const unsigned long long *__restrict__ slots,
+                                       unsigned long long *__restrict__ stats)
+{
+    int k = threadIdx.x;
+    if (k >= PB_NSTATS) return;
+    unsigned long long v = 0;
+    for (int s = 0; s < kStatSlots; ++s) {
+        unsigned long long x = slots[s * PB_NSTATS + k];
+        if (k == PB_STAT_DROPPED_LEN) v = x > v ? x : v; else v += x;
+    }
+    if (k == PB_STAT_DROPPED_LEN) { if (v) stats[k] = v; }
+    else stats[k] += v;
+}
+
+// optional device timing of the dominant (tiles) kernel, for bench.py's roofline line: a ring of
+// CUDA event pairs recorded on the launch stream, summed by pb_tiles_kernel_ms_total().
+constexpr int kTimingRing = 256;
+bool g_timing = false;
+cudaEvent_t g_ev[kTimingRing][2];
+int g_ev_created = 0, g_ev_count = 0;
+
+}  // namespace
+
+void pb_timing_begin(cudaStream_t stream)
+{
+    if (!g_timing || g_ev_count >= kTimingRing) return;
+    if (g_ev_count >= g_ev_created) {
+        cudaEventCreate(&g_ev[g_ev_created][0]);
+        cudaEventCreate(&g_ev[g_ev_created][1]);
+        g_ev_created++;
+    }
+    cudaEventRecord(g_ev[g_ev_count][0], stream);
+}
+
+void pb_timing_end(cudaStream_t stream)
+{
+    if (!g_timing || g_ev_count >= kTimingRing) return;
+    cudaEventRecord(g_ev[g_ev_count][1], stream);
+    g_ev_count++;
+}
+
+extern "C" void pb_enable_kernel_timing(int on) { g_timing = on != 0; g_ev_count = 0; }
+
+extern "C" int pb_tiles_kernel_ms_total(float *ms_total, int *n_launches)
+{
+    if (!ms_total || !n_launches) { pb_set_error("pb_tiles_kernel_ms_total: null"); return PB_EINVAL; }
+    float total = 0.f;
+    for (int i = 0; i < g_ev_count; ++i) {
+        float ms = 0.f;
+        PB_CUDA_CHECK(cudaEventSynchronize(g_ev[i][1]));
+        PB_CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]));
+        total += ms;
+    }
+    *ms_total = total;
+    *n_launches = g_ev_count;
+    return PB_OK;
+}
+
+size_t pb_ws_tile_bytes(int64_t total_bins) { return (size_t)(total_bins / 1024 + 1) * sizeof(PbTile); }
+size_t pb_ws_stat_bytes() { return (size_t)kStatSlots * PB_NSTATS * sizeof(unsigned long long); }
+static size_t ws_part_bytes(int64_t total_bins) { return (((size_t)(total_bins / 1024 / 4096 + 4) * sizeof(uint32_t)) + 255) & ~(size_t)255; }
+static size_t ws_idx_bytes(int64_t total_bins) { return (((size_t)(total_bins / 1024 + 2) * sizeof(uint32_t)) + 255) & ~(size_t)255; }
+
+extern "C" size_t pb_map_workspace_bytes(int64_t total_bins, int64_t n_blk)
+{
+    if (total_bins < 0 || n_blk < 0) return 0;
+    size_t bytes = pb_ws_tile_bytes(total_bins) + 2 * pb_ws_stat_bytes() + 256;
+    if (n_blk > 0) bytes += 2 * ws_idx_bytes(total_bins) + ws_part_bytes(total_bins) + (size_t)n_blk * sizeof(PbRec);
+    return bytes + 256;
+}
+
+int pb_carve_workspace(void *base, size_t bytes, int64_t total_bins, int64_t n_blk, PbWorkspace *ws)
+{
+    if (!base || bytes < pb_map_workspace_bytes(total_bins, n_blk)) { pb_set_error("workspace too small"); return PB_ENOSPACE; }
+    if (n_blk >= 0xffffffffll) { pb_set_error("more than 2^32-1 block rows in one batch"); return PB_EINVAL; }
+    char *p = (char *)base;
+    ws->tiles = (PbTile *)p;                     p += pb_ws_tile_bytes(total_bins);
+    ws->slots = (unsigned long long *)p;         p += 2 * pb_ws_stat_bytes();
+    ws->tile_counter = (unsigned long long *)p;  p += 256;
+    ws->rec_off = ws->rec_cursor = ws->scan_part = nullptr;
+    ws->recs = nullptr;
+    if (n_blk > 0) {
+        ws->rec_off = (uint32_t *)p;             p += ws_idx_bytes(total_bins);
+        ws->rec_cursor = (uint32_t *)p;          p += ws_idx_bytes(total_bins);
+        ws->scan_part = (uint32_t *)p;           p += ws_part_bytes(total_bins);
+        ws->recs = (PbRec *)p;
+    }
+    return PB_OK;
+}
+
+PbReads pb_to_dev(const pb_batch *b)
+{
+    PbReads d;
+    d.ref_start = b->ref_start;
+    d.meta = b->meta;
+    d.blk_off = b->blk_off;
+    d.blk = reinterpret_cast<const int2 *>(b->blk);
+    d.chrom_read_off = b->chrom_read_off;
+    d.n_reads = b->n_reads;
+    d.n_blk = b->blk ? b->n_blk : 0;
+    d.n_chrom = b->n_chrom;
+    d.max_span = b->max_span < 1 ? 1 : b->max_span;
+    d.max_block_len = b->max_block_len < 1 ? d.max_span : b->max_block_len;
+    return d;
+}
+
+PbRuleDev pb_to_dev(const pb_rule *r)
+{
+    PbRuleDev d;
+    d.kind = r->kind; d.param = r->param;
+    d.lut_fw = r->lut_fw; d.lut_rc = r->lut_rc;
+    d.size_min = r->size_min; d.size_max = r->size_max;
+    d.strat_min = r->strat_min; d.strat_max = r->strat_max;
+    return d;
+}
+
+int pb_check_common(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes)
+{
+    if (!batch || !layout || !rule) { pb_set_error("null batch/layout/rule"); return PB_EINVAL; }
+    if (planes <= 0 || planes > 7) { pb_set_error("planes must be a non-empty mask of PB_PLANE_*"); return PB_EINVAL; }
+    if (batch->n_reads < 0 || (batch->n_reads > 0 && (!batch->ref_start || !batch->meta))) {
+        pb_set_error("batch arrays missing"); return PB_EINVAL;
+    }
+    if (batch->n_chrom != layout->n_chrom || !batch->chrom_read_off) {
+        pb_set_error("batch/layout chromosome tables disagree"); return PB_EINVAL;
+    }
+    if (layout->total_bins <= 0 || layout->total_bins % PB_LAYOUT_ALIGN) {
+        pb_set_error("layout.total_bins must be a positive multiple of PB_LAYOUT_ALIGN"); return PB_EINVAL;
+    }
+    if ((batch->blk_off == nullptr) != (batch->blk == nullptr)) {
+        pb_set_error("blk_off and blk must both be given or both be NULL"); return PB_EINVAL;
+    }
+    if (batch->blk && batch->n_blk < 0) { pb_set_error("negative n_blk"); return PB_EINVAL; }
+    return PB_OK;
+}
+
+int pb_sm_count(int *out)
+{
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        PB_CUDA_CHECK(cudaGetDevice(&dev));
+        PB_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    *out = sm_count;
+    return PB_OK;
+}
+
+int pb_launch_tile_index(const PbReads &b, const PbLayoutDev &lay, int tile_bins, int64_t tile_begin, int64_t tile_end,
+                         int64_t read_limit, PbTile *tiles, cudaStream_t stream)
+{
+    if (tile_end <= tile_begin) return PB_OK;
+    pb_tile_index_kernel<<<(unsigned)((tile_end - tile_begin + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, tile_begin,
+                                                                                             tile_end, read_limit, tiles);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes, int center,
+                      const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, const PbWorkspace &ws,
+                      cudaStream_t stream)
+{
+    if (!b.blk_off || b.n_blk <= 0 || b.n_reads == 0) return PB_OK;
+    int sms = 0;
+    int rc = pb_sm_count(&sms);
+    if (rc) return rc;
+    int64_t want = (b.n_reads + 255) / 256;
+    unsigned grid = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+    PB_CUDA_CHECK(cudaMemsetAsync(ws.rec_cursor, 0, (size_t)(n_tiles + 1) * sizeof(uint32_t), stream));
+    for (int fill = 0; fill < 2; ++fill) {
+        if (center)
+            pb_bin_kernel<true><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_bins, fill, ws.rec_cursor,
+                                                          ws.rec_off, ws.recs, ws.slots);
+        else
+            pb_bin_kernel<false><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_bins, fill, ws.rec_cursor,
+                                                           ws.rec_off, ws.recs, ws.slots);
+        if (!fill) {
+            const int64_t nb = (n_tiles + kScanChunk - 1) / kScanChunk;
+            pb_scan_chunks_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(ws.rec_cursor, ws.rec_off, ws.scan_part, n_tiles);
+            pb_scan_top_kernel<<<1, kScanThreads, 0, stream>>>(ws.scan_part, nb);
+            pb_scan_add_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(ws.rec_off, ws.scan_part, n_tiles, nb);
+        }
+    }
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_launch_stats_finish(const unsigned long long *slots, unsigned long long *stats, cudaStream_t stream)
+{
+    pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, stats);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}

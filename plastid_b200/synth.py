@@ -167,6 +167,7 @@ def _finish(chroms, chrom_len, chrom, start, L, rev, device, blocks=None):
     off[1:] = torch.cumsum(counts, 0)
     blk_off = blk = None
     max_span = int(L.max().item()) if L.numel() else 1
+    max_block_len = max_span
     if blocks is not None:
         nb, rel, ln = blocks            # nb[N], rel[N,K], ln[N,K] (K = max blocks; unused entries 0)
         nb_s, rel_s, ln_s = nb[order], rel[order], ln[order]
@@ -178,7 +179,8 @@ def _finish(chroms, chrom_len, chrom, start, L, rev, device, blocks=None):
         blk = torch.stack([rel_s[valid], ln_s[valid]], dim=1).to(torch.int32).contiguous()
         max_span = max(max_span, int((rel + ln).max().item()))
         blk_off = blk_off.to(torch.int32)
-    return DeviceBatch(len(order), len(chroms), max_span, start_s.contiguous(), meta.contiguous(), off, blk_off, blk)
+    return DeviceBatch(len(order), len(chroms), max_span, start_s.contiguous(), meta.contiguous(), off, blk_off, blk,
+                       max_block_len)
 
 
 def rnaseq_reads(chroms, chrom_len, n_reads, seed=0, device="cpu", read_len=100, one_gap=0.30, two_gaps=0.03,
