@@ -127,9 +127,9 @@ const char *pb_version(void);
 const char *pb_last_error(void);
 int pb_device_count(void);
 
-/* Bytes of device workspace pb_map_point / pb_map_center need for this layout and a batch with
- * n_blk block rows (0 for unspliced batches). */
-size_t pb_map_workspace_bytes(int64_t total_bins, int64_t n_blk);
+/* Bytes of device workspace pb_map_point / pb_map_center need for this layout and a batch of
+ * n_reads reads with n_blk block rows (0 for unspliced batches). */
+size_t pb_map_workspace_bytes(int64_t total_bins, int64_t n_blk, int64_t n_reads);
 
 /* wire16: compact 4-byte-per-read transfer format of an unspliced batch (every read one block,
  * L < 16384), what the host decoder hands over PCIe.  start_lo uint16[N] = ref_start & 0xFFFF;

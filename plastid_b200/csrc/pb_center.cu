@@ -291,7 +291,7 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     PbRuleDev r = pb_to_dev(rule);
     PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
     PbWorkspace ws;
-    rc = pb_carve_workspace(workspace, workspace_bytes, layout->total_bins, b.n_blk, &ws);
+    rc = pb_carve_workspace(workspace, workspace_bytes, layout->total_bins, b.n_blk, b.n_reads, &ws);
     if (rc) return rc;
     const int n_planes = __builtin_popcount(planes);
 
@@ -311,7 +311,7 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     const int lookback = (b.max_block_len + tile_bins - 1) / tile_bins;
 
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
-    rc = pb_launch_tile_index(b, lay, tile_bins, 0, n_tiles, batch->n_reads, ws.tiles, stream);
+    rc = pb_launch_tile_index(b, lay, tile_bins, 0, n_tiles, batch->n_reads, 0, ws, stream);
     if (rc) return rc;
     rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, ws, stream);
     if (rc) return rc;

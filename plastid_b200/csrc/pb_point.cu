@@ -32,6 +32,86 @@ __device__ __forceinline__ void pb_smem_inc(uint32_t *smem, unsigned key)
 constexpr int kPThreads = 256;     // threads per persistent CTA
 constexpr int kPTileBins = 4096;   // bins per tile: 16 KB per plane in shared memory
 constexpr int kPUnroll = 4;        // independent read loads in flight per thread
+constexpr int kPSplit = 32768;     // candidate reads one tile job scans; the rest become overflow jobs
+
+struct PbCounters {
+    unsigned long long drop_p, drop_m, drop_a, map_p, map_m, map_a;
+    unsigned int drop_len;
+};
+
+struct PbPlaneBases {
+    unsigned plus, minus, any;     // word offsets of the planes inside the shared tile buffer
+    bool want_plus, want_minus, want_any;
+};
+
+// Apply the rule to the single-block reads [lo, hi) of the sorted batch and add their sites that fall
+// into the tile [p0, plim) to the shared tile buffer.  Trip count is CTA-uniform.
+__device__ __forceinline__ void pb_scan_reads(const PbReads &b, const PbRuleDev &r, bool skip_multi, int64_t lo,
+                                              int64_t hi, int64_t p0, int64_t plim, int64_t p1, uint32_t *smem,
+                                              const PbPlaneBases &pl, PbCounters &c)
+{
+    for (int64_t base = lo; base < hi; base += (int64_t)kPUnroll * kPThreads) {
+        int32_t sv[kPUnroll];
+        uint32_t mv[kPUnroll];
+#pragma unroll
+        for (int u = 0; u < kPUnroll; ++u) {
+            const int64_t i = base + (int64_t)u * kPThreads + threadIdx.x;
+            const bool ok = i < hi;
+            sv[u] = ok ? __ldg(b.ref_start + i) : 0;
+            mv[u] = ok ? __ldg(b.meta + i) : (1u << 17);   // drop bit: skipped below
+        }
+#pragma unroll
+        for (int u = 0; u < kPUnroll; ++u) {
+            const int32_t s = sv[u];
+            const uint32_t m = mv[u];
+            const int L = PB_META_L(m);
+            const bool rev = PB_META_REV(m);
+            unsigned key_strand = kNoKey, key_any = kNoKey;   // word index into smem, or none
+            // multi-block reads were mapped by pb_bin_kernel and arrive through the tile's bucket
+            if (pb_passes(m, r.size_min, r.size_max) && !(skip_multi && PB_META_NBLK(m) > 1)) {
+                const int idx_f = pb_rule_index(r, L, false);
+                if (idx_f < 0) {
+                    // the reference skips this read and warns; count it once, in the tile owning its start
+                    if (s >= p0 && s < p1) {
+                        c.drop_a++;
+                        if (rev) c.drop_m++; else c.drop_p++;
+                        c.drop_len = L;
+                    }
+                } else {
+                    if (pl.want_any || (!rev && pl.want_plus)) {
+                        const int64_t p = (int64_t)s + idx_f;
+                        if (p >= p0 && p < plim) {
+                            const unsigned o = (unsigned)(p - p0);
+                            if (pl.want_any) { key_any = pl.any + o; c.map_a++; }
+                            if (!rev && pl.want_plus) { key_strand = pl.plus + o; c.map_p++; }
+                        }
+                    }
+                    if (rev && pl.want_minus) {
+                        const int64_t p = (int64_t)s + pb_rule_index(r, L, true);
+                        if (p >= p0 && p < plim) {
+                            key_strand = pl.minus + (unsigned)(p - p0);
+                            c.map_m++;
+                        }
+                    }
+                }
+            }
+            pb_smem_inc(smem, key_strand);
+            pb_smem_inc(smem, key_any);
+        }
+    }
+}
+
+__device__ __forceinline__ PbPlaneBases pb_plane_bases(int planes)
+{
+    PbPlaneBases pl;
+    pl.want_plus = planes & PB_PLANE_PLUS; pl.want_minus = planes & PB_PLANE_MINUS; pl.want_any = planes & PB_PLANE_ANY;
+    unsigned k = 0;
+    pl.plus = pl.minus = pl.any = 0;
+    if (pl.want_plus) pl.plus = (k++) * kPTileBins;
+    if (pl.want_minus) pl.minus = (k++) * kPTileBins;
+    if (pl.want_any) pl.any = (k++) * kPTileBins;
+    return pl;
+}
 
 // Invariant: at the top of every loop iteration the shared tile buffer is all zero and visible to
 // the async proxy.  Empty tiles are therefore one bulk store of the buffer as it is; tiles with
@@ -47,16 +127,8 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ long long s_q[3];
 
-    const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
-               want_any = planes & PB_PLANE_ANY;
-    const int n_planes = (int)want_plus + (int)want_minus + (int)want_any;
-    uint32_t *sm_plus = smem, *sm_minus = smem, *sm_any = smem;
-    {
-        int k = 0;
-        if (want_plus) sm_plus = smem + (k++) * kPTileBins;
-        if (want_minus) sm_minus = smem + (k++) * kPTileBins;
-        if (want_any) sm_any = smem + (k++) * kPTileBins;
-    }
+    const PbPlaneBases pl = pb_plane_bases(planes);
+    const int n_planes = (int)pl.want_plus + (int)pl.want_minus + (int)pl.want_any;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     uint4 *smem4 = reinterpret_cast<uint4 *>(smem);
     for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
@@ -67,8 +139,7 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
     pb_fence_proxy_async();
     __syncthreads();
 
-    unsigned long long drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;
-    unsigned int drop_len = 0;
+    PbCounters c = {0, 0, 0, 0, 0, 0, 0};
 
     // Look-ahead tile queue: the CTA always knows its current and its next tile.  Thread 0 claims the
     // tile for iteration k+2 at the top of iteration k and only publishes it at the end, so the atomic's
@@ -91,75 +162,24 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
         if (has_work) {
             if (threadIdx.x == 0) pb_bulk_wait_read0();   // earlier stores of the zero buffer have read it
             __syncthreads();
-            const int64_t p0 = d.p0, plim = d.p0 + d.live, p1 = d.p0 + kPTileBins;
-            const int64_t hi = d.lo + d.n;
-            const unsigned plus_base = (unsigned)(sm_plus - smem), minus_base = (unsigned)(sm_minus - smem),
-                           any_base = (unsigned)(sm_any - smem);
-            for (int64_t base = d.lo; base < hi; base += (int64_t)kPUnroll * kPThreads) {
-                int32_t sv[kPUnroll];
-                uint32_t mv[kPUnroll];
-#pragma unroll
-                for (int u = 0; u < kPUnroll; ++u) {
-                    const int64_t i = base + (int64_t)u * kPThreads + threadIdx.x;
-                    const bool ok = i < hi;
-                    sv[u] = ok ? __ldg(b.ref_start + i) : 0;
-                    mv[u] = ok ? __ldg(b.meta + i) : (1u << 17);   // drop bit: skipped below
-                }
-#pragma unroll
-                for (int u = 0; u < kPUnroll; ++u) {
-                    const int32_t s = sv[u];
-                    const uint32_t m = mv[u];
-                    const int L = PB_META_L(m);
-                    const bool rev = PB_META_REV(m);
-                    unsigned key_strand = kNoKey, key_any = kNoKey;   // word index into smem, or none
-                    // multi-block reads were mapped by pb_bin_kernel and arrive through the bucket below
-                    if (pb_passes(m, r.size_min, r.size_max) && !(rec_off && PB_META_NBLK(m) > 1)) {
-                        const int idx_f = pb_rule_index(r, L, false);
-                        if (idx_f < 0) {
-                            // the reference skips this read and warns; count it once, in the tile owning its start
-                            if (s >= p0 && s < p1) {
-                                drop_a++;
-                                if (rev) drop_m++; else drop_p++;
-                                drop_len = L;
-                            }
-                        } else {
-                            if (want_any || (!rev && want_plus)) {
-                                const int64_t p = (int64_t)s + idx_f;
-                                if (p >= p0 && p < plim) {
-                                    const unsigned o = (unsigned)(p - p0);
-                                    if (want_any) { key_any = any_base + o; map_a++; }
-                                    if (!rev && want_plus) { key_strand = plus_base + o; map_p++; }
-                                }
-                            }
-                            if (rev && want_minus) {
-                                const int64_t p = (int64_t)s + pb_rule_index(r, L, true);
-                                if (p >= p0 && p < plim) {
-                                    key_strand = minus_base + (unsigned)(p - p0);
-                                    map_m++;
-                                }
-                            }
-                        }
-                    }
-                    pb_smem_inc(smem, key_strand);
-                    pb_smem_inc(smem, key_any);
-                }
-            }
+            const int64_t p0 = d.p0;
+            pb_scan_reads(b, r, rec_off != nullptr, d.lo, d.lo + d.n, p0, p0 + d.live, p0 + kPTileBins, smem, pl, c);
             if (tile_nxt < n_tiles) pb_prefetch_reads_l2(b, d_nxt);
             for (uint32_t j = rec_lo + threadIdx.x; j < rec_hi; j += kPThreads) {
                 const PbRec rec = recs[j];      // site already bounds-checked and counted by pb_bin_kernel
                 const unsigned o = (unsigned)((int64_t)rec.x - p0);
-                if (rec.tag & PB_PLANE_PLUS) atomicAdd(&sm_plus[o], 1u);
-                if (rec.tag & PB_PLANE_MINUS) atomicAdd(&sm_minus[o], 1u);
-                if (rec.tag & PB_PLANE_ANY) atomicAdd(&sm_any[o], 1u);
+                if (rec.tag & PB_PLANE_PLUS) atomicAdd(&smem[pl.plus + o], 1u);
+                if (rec.tag & PB_PLANE_MINUS) atomicAdd(&smem[pl.minus + o], 1u);
+                if (rec.tag & PB_PLANE_ANY) atomicAdd(&smem[pl.any + o], 1u);
             }
             pb_fence_proxy_async();
             __syncthreads();
         }
         if (threadIdx.x == 0) {
             int q = 0;
-            if (want_plus) pb_bulk_store(out_plus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
-            if (want_minus) pb_bulk_store(out_minus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
-            if (want_any) pb_bulk_store(out_any + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
+            if (pl.want_plus) pb_bulk_store(out_plus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
+            if (pl.want_minus) pb_bulk_store(out_minus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
+            if (pl.want_any) pb_bulk_store(out_any + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
             pb_bulk_commit();
             if (has_work) pb_bulk_wait_read0();
             s_q[(k + 2) % 3] = claimed;
@@ -177,7 +197,55 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
         tile_nxt = tile_nn; d_nxt = d_nn;
     }
 
-    pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
+    pb_flush_cta_stats(c.drop_p, c.drop_m, c.drop_a, c.drop_len, c.map_p, c.map_m, c.map_a, stat_slots);
+    if (threadIdx.x == 0) pb_bulk_wait_all();
+}
+
+// Overflow jobs: the candidate reads of a tile beyond the first kPSplit (pile-ups on highly expressed
+// genes put millions of reads into one tile, and one CTA walking them alone would set the kernel's
+// duration).  Runs after the tiles kernel on the same stream, so every plane already holds its tile;
+// each job accumulates its slice in shared memory and ADDS it with a TMA bulk reduction
+// (cp.reduce.async.bulk ... .add.u32, SASS UBLKRED) — integer adds commute, so the result stays
+// bit-exact and deterministic.
+__global__ void __launch_bounds__(kPThreads)
+pb_point_overflow_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restrict__ tiles, int skip_multi,
+                         const PbJob *__restrict__ jobs, const unsigned long long *__restrict__ n_jobs_p,
+                         unsigned long long *__restrict__ job_counter,
+                         uint32_t *__restrict__ out_plus, uint32_t *__restrict__ out_minus,
+                         uint32_t *__restrict__ out_any, unsigned long long *__restrict__ stat_slots)
+{
+    extern __shared__ __align__(128) uint32_t smem[];
+    __shared__ long long s_job;
+    const long long n_jobs = (long long)*n_jobs_p;
+    if (n_jobs == 0) return;
+    const PbPlaneBases pl = pb_plane_bases(planes);
+    const int n_planes = (int)pl.want_plus + (int)pl.want_minus + (int)pl.want_any;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 *smem4 = reinterpret_cast<uint4 *>(smem);
+    PbCounters c = {0, 0, 0, 0, 0, 0, 0};
+    for (;;) {
+        if (threadIdx.x == 0) s_job = (long long)atomicAdd(job_counter, 1ull);
+        for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
+        __syncthreads();
+        const long long job = s_job;
+        if (job >= n_jobs) break;
+        const PbJob jb = jobs[job];
+        const PbTile d = tiles[jb.tile];
+        pb_scan_reads(b, r, skip_multi != 0, jb.lo, jb.lo + jb.n, d.p0, d.p0 + d.live, d.p0 + kPTileBins, smem, pl, c);
+        pb_fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int64_t g0 = jb.tile * kPTileBins;
+            int q = 0;
+            if (pl.want_plus) pb_bulk_add_u32(out_plus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
+            if (pl.want_minus) pb_bulk_add_u32(out_minus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
+            if (pl.want_any) pb_bulk_add_u32(out_any + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
+            pb_bulk_commit();
+            pb_bulk_wait_read0();
+        }
+        __syncthreads();
+    }
+    pb_flush_cta_stats(c.drop_p, c.drop_m, c.drop_a, c.drop_len, c.map_p, c.map_m, c.map_a, stat_slots);
     if (threadIdx.x == 0) pb_bulk_wait_all();
 }
 
@@ -215,7 +283,7 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
     PbRuleDev r = pb_to_dev(rule);
     PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
     PbWorkspace ws;
-    rc = pb_carve_workspace(workspace, workspace_bytes, layout->total_bins, b.n_blk, &ws);
+    rc = pb_carve_workspace(workspace, workspace_bytes, layout->total_bins, b.n_blk, b.n_reads, &ws);
     if (rc) return rc;
     if (b.n_blk > 0 && (tile_begin != 0 || n_tiles != layout->total_bins / kPTileBins)) {
         // binning needs every read resident; streamed uploads are unspliced by format (wire16)
@@ -224,7 +292,7 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
     }
 
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
-    rc = pb_launch_tile_index(b, lay, kPTileBins, tile_begin, n_tiles, read_limit, ws.tiles, stream);
+    rc = pb_launch_tile_index(b, lay, kPTileBins, tile_begin, n_tiles, read_limit, kPSplit, ws, stream);
     if (rc) return rc;
     // multi-block (spliced) reads: map them once and bin their sites by tile
     rc = pb_launch_binning(b, r, lay, planes, 0, nullptr, kPTileBins, layout->total_bins / kPTileBins, ws, stream);
@@ -244,6 +312,14 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
     pb_point_tiles_kernel<<<(unsigned)grid, kPThreads, smem, stream>>>(b, r, planes, ws.tiles, tile_begin, n_tiles,
                                                                       ws.tile_counter, ws.rec_off, ws.recs,
                                                                       out_plus, out_minus, out_any, ws.slots);
+    // slices of pile-up tiles beyond kPSplit reads: added on top of the stored tiles (exits at once
+    // when the tile index found none)
+    PB_CUDA_CHECK(cudaFuncSetAttribute(pb_point_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_point_overflow_kernel, kPThreads, smem));
+    if (occ < 1) occ = 1;
+    pb_point_overflow_kernel<<<(unsigned)(sm_count * occ), kPThreads, smem, stream>>>(
+        b, r, planes, ws.tiles, b.n_blk > 0, ws.jobs, ws.tile_counter + 1, ws.tile_counter + 2,
+        out_plus, out_minus, out_any, ws.slots);
     pb_timing_end(stream);
     PB_CUDA_CHECK(cudaGetLastError());
     return pb_launch_stats_finish(ws.slots, (unsigned long long *)stats, stream);

@@ -8,7 +8,9 @@ namespace {
 // tile -> candidate read slice
 // ----------------------------------------------------------------------------------------
 __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, int64_t tile_begin, int64_t tile_end,
-                                     int64_t read_limit, PbTile *__restrict__ tiles)
+                                     int64_t read_limit, int split, PbTile *__restrict__ tiles,
+                                     PbJob *__restrict__ jobs, int64_t job_capacity,
+                                     unsigned long long *__restrict__ n_jobs)
 {
     int64_t t = tile_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= tile_end) return;
@@ -32,6 +34,22 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
     d.lo = lo; d.p0 = p0;
     d.n = (live > 0 && hi - lo < 0x7fffffff) ? (int)(hi - lo) : (live > 0 ? 0x7fffffff : 0);
     d.live = (int)live; d.chrom = c; d.pad = 0;
+    if (split > 0 && d.n > split) {
+        // pile-up: the tile job keeps the first `split` candidates, the rest become overflow jobs
+        const long long rest = (long long)d.n - split;
+        const long long nj = (rest + split - 1) / split;
+        const long long at = (long long)atomicAdd(n_jobs, (unsigned long long)nj);
+        for (long long j = 0; j < nj; ++j) {
+            if (at + j >= job_capacity) break;      // cannot happen: capacity covers sum(n) / split
+            PbJob jb;
+            jb.lo = lo + split + j * split;
+            jb.tile = t;
+            jb.n = (int)(rest - j * split < split ? rest - j * split : split);
+            jb.pad[0] = jb.pad[1] = jb.pad[2] = 0;
+            jobs[at + j] = jb;
+        }
+        d.n = split;
+    }
     tiles[t] = d;
 }
 
@@ -274,22 +292,29 @@ size_t pb_ws_stat_bytes() { return (size_t)kStatSlots * PB_NSTATS * sizeof(unsig
 static size_t ws_part_bytes(int64_t total_bins) { return (((size_t)(total_bins / 1024 / 4096 + 4) * sizeof(uint32_t)) + 255) & ~(size_t)255; }
 static size_t ws_idx_bytes(int64_t total_bins) { return (((size_t)(total_bins / 1024 + 2) * sizeof(uint32_t)) + 255) & ~(size_t)255; }
 
-extern "C" size_t pb_map_workspace_bytes(int64_t total_bins, int64_t n_blk)
+// every candidate read appears in at most two tiles' windows, so sum(n)/split + one per tile bounds
+// the overflow jobs; split is never below 4096 reads
+static int64_t ws_job_capacity(int64_t total_bins, int64_t n_reads) { return 2 * n_reads / 4096 + 1024; }
+
+extern "C" size_t pb_map_workspace_bytes(int64_t total_bins, int64_t n_blk, int64_t n_reads)
 {
-    if (total_bins < 0 || n_blk < 0) return 0;
+    if (total_bins < 0 || n_blk < 0 || n_reads < 0) return 0;
     size_t bytes = pb_ws_tile_bytes(total_bins) + 2 * pb_ws_stat_bytes() + 256;
+    bytes += (size_t)ws_job_capacity(total_bins, n_reads) * sizeof(PbJob);
     if (n_blk > 0) bytes += 2 * ws_idx_bytes(total_bins) + ws_part_bytes(total_bins) + (size_t)n_blk * sizeof(PbRec);
     return bytes + 256;
 }
 
-int pb_carve_workspace(void *base, size_t bytes, int64_t total_bins, int64_t n_blk, PbWorkspace *ws)
+int pb_carve_workspace(void *base, size_t bytes, int64_t total_bins, int64_t n_blk, int64_t n_reads, PbWorkspace *ws)
 {
-    if (!base || bytes < pb_map_workspace_bytes(total_bins, n_blk)) { pb_set_error("workspace too small"); return PB_ENOSPACE; }
+    if (!base || bytes < pb_map_workspace_bytes(total_bins, n_blk, n_reads)) { pb_set_error("workspace too small"); return PB_ENOSPACE; }
     if (n_blk >= 0xffffffffll) { pb_set_error("more than 2^32-1 block rows in one batch"); return PB_EINVAL; }
     char *p = (char *)base;
     ws->tiles = (PbTile *)p;                     p += pb_ws_tile_bytes(total_bins);
     ws->slots = (unsigned long long *)p;         p += 2 * pb_ws_stat_bytes();
     ws->tile_counter = (unsigned long long *)p;  p += 256;
+    ws->job_capacity = ws_job_capacity(total_bins, n_reads);
+    ws->jobs = (PbJob *)p;                       p += (size_t)ws->job_capacity * sizeof(PbJob);
     ws->rec_off = ws->rec_cursor = ws->scan_part = nullptr;
     ws->recs = nullptr;
     if (n_blk > 0) {
@@ -360,11 +385,12 @@ int pb_sm_count(int *out)
 }
 
 int pb_launch_tile_index(const PbReads &b, const PbLayoutDev &lay, int tile_bins, int64_t tile_begin, int64_t tile_end,
-                         int64_t read_limit, PbTile *tiles, cudaStream_t stream)
+                         int64_t read_limit, int split, const PbWorkspace &ws, cudaStream_t stream)
 {
     if (tile_end <= tile_begin) return PB_OK;
-    pb_tile_index_kernel<<<(unsigned)((tile_end - tile_begin + 255) / 256), 256, 0, stream>>>(b, lay, tile_bins, tile_begin,
-                                                                                             tile_end, read_limit, tiles);
+    if (split > 0 && split < 4096) split = 4096;
+    pb_tile_index_kernel<<<(unsigned)((tile_end - tile_begin + 255) / 256), 256, 0, stream>>>(
+        b, lay, tile_bins, tile_begin, tile_end, read_limit, split, ws.tiles, ws.jobs, ws.job_capacity, ws.tile_counter + 1);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

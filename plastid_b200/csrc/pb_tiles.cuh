@@ -24,10 +24,20 @@ struct __align__(16) PbRec {
     uint32_t pad;
 };
 
+// Overflow job of the point kernel: candidate reads [lo, lo+n) of `tile` beyond the tile job's share.
+struct __align__(16) PbJob {
+    long long lo;
+    long long tile;
+    int n;
+    int pad[3];
+};
+
 struct PbWorkspace {
     PbTile *tiles;                  // [total_bins/1024 + 1]
     unsigned long long *slots;      // [2][kStatSlots][PB_NSTATS] (second copy: scratch for repeat passes)
-    unsigned long long *tile_counter;
+    unsigned long long *tile_counter;  // [0] tile queue, [1] number of overflow jobs, [2] overflow queue
+    PbJob *jobs;                    // [job_capacity]
+    int64_t job_capacity;
     uint32_t *rec_off;              // [n_tiles + 1] exclusive offsets of the per-tile record buckets
     uint32_t *rec_cursor;           // [n_tiles + 1] counts, then fill cursors
     uint32_t *scan_part;            // per-4096-tile partial sums of the offset scan
@@ -36,15 +46,17 @@ struct PbWorkspace {
 
 size_t pb_ws_tile_bytes(int64_t total_bins);
 size_t pb_ws_stat_bytes();
-int pb_carve_workspace(void *base, size_t bytes, int64_t total_bins, int64_t n_blk, PbWorkspace *ws);
+int pb_carve_workspace(void *base, size_t bytes, int64_t total_bins, int64_t n_blk, int64_t n_reads, PbWorkspace *ws);
 
 PbReads pb_to_dev(const pb_batch *b);
 PbRuleDev pb_to_dev(const pb_rule *r);
 int pb_check_common(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes);
 int pb_sm_count(int *out);
 
+// split > 0: a tile keeps at most `split` candidate reads; the rest are appended to ws.jobs in slices
+// of `split` reads (ws.tile_counter[1] counts them).
 int pb_launch_tile_index(const PbReads &b, const PbLayoutDev &lay, int tile_bins, int64_t tile_begin, int64_t tile_end,
-                         int64_t read_limit, PbTile *tiles, cudaStream_t stream);
+                         int64_t read_limit, int split, const PbWorkspace &ws, cudaStream_t stream);
 // Bin the contributions of multi-block reads by tile (no-op when the batch has none): count,
 // exclusive scan, fill.  center = 0: point-rule sites; center = 1: trimmed aligned intervals.
 int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes, int center,
@@ -68,6 +80,12 @@ __device__ __forceinline__ void pb_bulk_store(void *gdst, const void *ssrc, uint
 __device__ __forceinline__ void pb_bulk_add_f64(void *gdst, const void *ssrc, uint32_t bytes)
 {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+// global[dst] += shared[src] elementwise in uint32 (SASS UBLKRED.ADD)
+__device__ __forceinline__ void pb_bulk_add_u32(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], %2;"
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void pb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

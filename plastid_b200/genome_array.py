@@ -86,7 +86,7 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     for s in strands:
         mask |= _lib.STRAND_PLANE[s]
     L = _lib.lib()
-    ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, dbatch.n_blk)
+    ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, dbatch.n_blk, dbatch.n_reads)
     ws = _workspace(dev, ws_bytes)
     stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev)
     b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
@@ -127,7 +127,7 @@ def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=N
     for s in strands:
         mask |= _lib.STRAND_PLANE[s]
     L = _lib.lib()
-    ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, 0)
+    ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, 0, dbatch.n_reads)
     ws = _workspace(dev, ws_bytes)
     stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev)
     copy_stream = copy_stream or torch.cuda.Stream(device=dev)

@@ -489,3 +489,30 @@ def test_streamed_upload_matches_whole_batch(small_world, cuda_device, n_chunks)
     exp = coracle.genome_vector(w["hb"], 1, "-", rule="variable", luts=(fac.forward_offsets, fac.reverse_offsets),
                                 size_filter=(20, 38))[0]
     assert (plane_chrom(planes, w["layout"], "-", 1) == exp).all()
+
+
+def test_pileup_tile_is_split_into_overflow_jobs(cuda_device):
+    """> 32768 candidate reads in one 4096-bin tile: the tile job keeps the first slice, the rest are
+    added by pb_point_overflow_kernel with TMA bulk reductions — still bit-exact, stats included."""
+    rng = np.random.default_rng(3)
+    chroms, lens = ["a", "b"], np.array([30_000, 9_000])
+    n_hot, n_bg = 150_000, 20_000
+    start = np.concatenate([rng.integers(5000, 5300, n_hot), rng.integers(0, 29_900, n_bg), rng.integers(0, 8_900, 5000)])
+    cid = np.concatenate([np.zeros(n_hot + n_bg, dtype=int), np.ones(5000, dtype=int)])
+    L = rng.integers(20, 41, len(start))
+    rev = rng.integers(0, 2, len(start))
+    hb = pb.batch_from_arrays(chroms, lens, cid, start, L, rev)
+    layout = pb.GenomeLayout(chroms, lens)
+    offs = {k: k // 2 for k in range(24, 41)}            # lengths 20..23 have no offset: dropped
+    fac = pb.VariableFivePrimeMapFactory(offs)
+    planes = map_batch(hb.to_device(cuda_device), layout, fac, None, strands=("+", "-", "."))
+    luts = (fac.forward_offsets, fac.reverse_offsets)
+    dropped = {}
+    for strand in ("+", "-", "."):
+        dropped[strand] = 0
+        for c in range(2):
+            exp, _, d, _ = coracle.genome_vector(hb, c, strand, rule="variable", luts=luts)
+            assert (plane_chrom(planes, layout, strand, c) == exp).all(), (strand, c)
+            dropped[strand] += d
+    assert [int(x) for x in planes.stats[:3]] == [dropped["+"], dropped["-"], dropped["."]] and dropped["."] > 1000
+    assert int(planes.stats[_lib.PB_STAT_MAPPED_ANY]) == len(hb) - dropped["."]

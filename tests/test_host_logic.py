@@ -43,8 +43,8 @@ def test_argument_errors_are_reported_without_a_device():
     assert L.pb_map_point(None, None, None, 3, None, None, None, None, None, 0, None) == _lib.PB_EINVAL
     assert b"null" in L.pb_last_error()
     assert L.pb_region_sums(None, 0, None, None, None, None, 0, None, None, None, None, None) == _lib.PB_EINVAL
-    assert L.pb_map_workspace_bytes(16384 * 4, 0) > 0
-    assert L.pb_map_workspace_bytes(16384 * 4, 1000) >= L.pb_map_workspace_bytes(16384 * 4, 0) + 16000
+    assert L.pb_map_workspace_bytes(16384 * 4, 0, 100) > 0
+    assert L.pb_map_workspace_bytes(16384 * 4, 1000, 100) >= L.pb_map_workspace_bytes(16384 * 4, 0, 100) + 16000
 
 
 def test_no_cpu_fallback():
