@@ -36,7 +36,7 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
     constexpr int T = EPT * kCThreads;
     constexpr int seg = T / kCWarps;  // bins per warp in the scan = EPT * 32
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ long long s_q[3];
+    __shared__ PbSlot s_ring[4];
 
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
                want_any = planes & PB_PLANE_ANY;
@@ -45,7 +45,7 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
     double *stage = reinterpret_cast<double *>(smem_raw);           // [n_planes][T] fp64 staging
     double *zbuf = stage + (size_t)n_planes * T;                    // [kZeroBins] zeros, never written
     int *diff = reinterpret_cast<int *>(zbuf + kZeroBins);          // [n_arrays][T]
-    int *warp_tot = diff + (size_t)n_arrays * T;                    // [n_arrays][kCWarps]
+    int *warp_tot = diff + (size_t)n_arrays * T;                    // [2][n_arrays][kCWarps] (double-buffered by tile parity)
     double *outs[3];
     int *d_plus = diff, *d_minus = diff, *d_any = diff;
     {
@@ -57,13 +57,11 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
     {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         uint4 *s4 = reinterpret_cast<uint4 *>(smem_raw);
-        const int n16 = ((n_planes * T + kZeroBins) * 8 + n_arrays * T * 4) / 16;
+        const int n16 = ((n_planes * T + kZeroBins) * 8 + n_arrays * T * 4 + 2 * n_arrays * kCWarps * 4) / 16;
         for (int j = threadIdx.x; j < n16; j += kCThreads) s4[j] = z;
     }
-    if (threadIdx.x == 0) {
-        s_q[0] = (long long)atomicAdd(tile_counter, 1ull);
-        s_q[1] = (long long)atomicAdd(tile_counter, 1ull);
-    }
+    PbQueueRegs q;
+    if (threadIdx.x == 0) pb_queue_init(s_ring, q, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
     pb_fence_proxy_async();
     __syncthreads();
 
@@ -72,35 +70,15 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
     const int nibble = r.param;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // Look-ahead tile queue (see pb_point.cu): current and next tile are always known; the tile for
-    // iteration k+2 is claimed at the top of iteration k and published at its end, so the atomic, the
-    // next descriptor / bucket bounds and the L2 prefetch of the next tile's reads overlap with the
-    // current tile.
-    auto load_tile = [&](long long t, PbTile &dd, uint32_t &rl, uint32_t &rh) {
-        dd = PbTile{0, 0, 0, 0, 0, 0};
-        rl = rh = 0;
-        if (t >= n_tiles) return;
-        dd = tiles[t];
-        if (rec_off) {
-            rl = __ldg(rec_off + (t > lookback ? t - lookback : 0));
-            rh = __ldg(rec_off + t + 1);
-        }
-    };
-    long long tile = s_q[0], tile_nxt = s_q[1];
-    PbTile d, d_nxt;
-    uint32_t rec_lo, rec_hi, rl_nxt, rh_nxt;
-    load_tile(tile, d, rec_lo, rec_hi);
-    load_tile(tile_nxt, d_nxt, rl_nxt, rh_nxt);
-    for (int k = 0; tile < n_tiles; ++k) {
-        long long claimed = 0;
-        if (threadIdx.x == 0) claimed = (long long)atomicAdd(tile_counter, 1ull);
+    int parity = 0;   // which copy of the segment sums the current tile-with-work uses
+    for (int k = 0;; ++k) {
+        if (threadIdx.x == 0) pb_queue_step(s_ring, q, k, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
+        const PbSlot &cur = s_ring[k & 3];
+        const long long tile = cur.tile;
+        if (tile >= n_tiles) break;
+        const PbTile d = cur.d;
+        const uint32_t rec_lo = cur.rec_lo, rec_hi = cur.rec_hi;
         const int64_t g0 = tile * T;
-        if (rec_off) {
-            // an interval starting up to `lookback` tiles earlier can reach this tile, but only from the
-            // same chromosome (rare: the first tiles of a chromosome)
-            const long long first = tile - d.p0 / T;
-            if (tile - lookback < first) rec_lo = __ldg(rec_off + first);
-        }
         const bool has_work = d.n > 0 || rec_hi > rec_lo;
         if (!has_work) {
             if (threadIdx.x == 0) {
@@ -109,24 +87,26 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
                         for (int z = 0; z < T; z += kZeroBins) pb_bulk_store(outs[q] + g0 + z, zbuf, kZeroBins * 8);
                     pb_bulk_commit();
                 }
-                s_q[(k + 2) % 3] = claimed;
             }
             __syncthreads();
         } else {
 
         const int64_t p0 = d.p0, p1 = d.p0 + T, plim = d.p0 + d.live;
-        auto add_interval = [&](int64_t x, int64_t y, int so, bool rev) {  // aligned reference interval [x,y)
+        // Difference update of one aligned reference interval [x,y) of map-length slot `sl`.  The sum
+        // of each warp segment (what the scan needs as carry-in) is kept up to date with a second
+        // shared atomic instead of re-reading every difference word before the scan.
+        int *tot = warp_tot + parity * n_arrays * kCWarps;
+        auto add_interval = [&](int64_t x, int64_t y, int sl, bool rev) {
             if (y <= p0 || x >= plim) return;
             const bool do_strand = rev ? want_minus : want_plus;
-            int *d_strand = (rev ? d_minus : d_plus) + so;
-            int *d_all = d_any + so;
+            const int a_strand = ((rev ? d_minus : d_plus) - diff) / T + sl, a_all = (d_any - diff) / T + sl;
             const unsigned ox = (unsigned)((x > p0 ? x : p0) - p0);
-            if (do_strand) atomicAdd(&d_strand[ox], 1);
-            if (want_any) atomicAdd(&d_all[ox], 1);
+            if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + ox], 1); atomicAdd(&tot[a_strand * kCWarps + ox / seg], 1); }
+            if (want_any) { atomicAdd(&diff[(size_t)a_all * T + ox], 1); atomicAdd(&tot[a_all * kCWarps + ox / seg], 1); }
             if (y < p1) {
                 const unsigned oy = (unsigned)(y - p0);
-                if (do_strand) atomicAdd(&d_strand[oy], -1);
-                if (want_any) atomicAdd(&d_all[oy], -1);
+                if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + oy], -1); atomicAdd(&tot[a_strand * kCWarps + oy / seg], -1); }
+                if (want_any) { atomicAdd(&diff[(size_t)a_all * T + oy], -1); atomicAdd(&tot[a_all * kCWarps + oy / seg], -1); }
             }
         };
 
@@ -160,33 +140,25 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
                 if (own) { map_a++; if (rev) map_m++; else map_p++; }   // reads_out semantics (:256)
                 const int slot = (int)__ldg(slot_of_len + L) - slot0;
                 if (slot < 0 || slot >= n_slots) continue;         // another pass handles this map length
-                add_interval((int64_t)s + nibble, (int64_t)s + L - nibble, slot * T, rev);
+                add_interval((int64_t)s + nibble, (int64_t)s + L - nibble, slot, rev);
             }
         }
-        if (tile_nxt < n_tiles) pb_prefetch_reads_l2(b, d_nxt);
+        if (s_ring[(k + 1) & 3].tile < n_tiles) pb_prefetch_tile_l2(b, recs, s_ring[(k + 1) & 3]);
         // trimmed aligned intervals of multi-block reads (already filtered and counted by pb_bin_kernel)
         for (uint32_t j = rec_lo + threadIdx.x; j < rec_hi; j += kCThreads) {
             const PbRec rec = recs[j];
             const int slot = (int)(rec.tag & 0xffffu) - slot0;
             if (slot < 0 || slot >= n_slots) continue;
-            add_interval(rec.x, rec.y, slot * T, (rec.tag >> 16) & 1u);
+            add_interval(rec.x, rec.y, slot, (rec.tag >> 16) & 1u);
         }
         __syncthreads();
-
-        // pass 1: per-warp segment totals for every (plane, slot) difference array
-        for (int a = 0; a < n_arrays; ++a) {
-            const int *A = diff + (size_t)a * T + warp * seg;
-            int t = 0;
-#pragma unroll
-            for (int ch = 0; ch < EPT; ++ch) t += A[ch * 32 + lane];
-            t = __reduce_add_sync(0xffffffffu, t);
-            if (lane == 0) warp_tot[a * kCWarps + warp] = t;
-        }
 
         // the previous tile's bulk copies must have read the staging buffers before they are rewritten
-        // (they were issued a whole read-scan ago); the barrier also publishes warp_tot
+        // (they were issued a whole read-scan ago); the barrier also publishes the difference arrays
         if (threadIdx.x == 0) pb_bulk_wait_read0();
         __syncthreads();
+        // the other parity's segment sums were last used by the previous tile: clear them for the next
+        for (int j = threadIdx.x; j < n_arrays * kCWarps; j += kCThreads) warp_tot[(parity ^ 1) * n_arrays * kCWarps + j] = 0;
 
         // pass 2: exact scan + fixed-order combine into the staging buffers; every thread zeroes the
         // difference words it consumed, so the arrays are clean for the next tile without another pass
@@ -197,7 +169,7 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
             for (int sl = 0; sl < n_slots; ++sl) {
                 const int a = q * n_slots + sl;
                 int *A = diff + (size_t)a * T + warp * seg;
-                int carry = (lane < warp) ? warp_tot[a * kCWarps + lane] : 0;
+                int carry = (lane < warp) ? tot[a * kCWarps + lane] : 0;
                 carry = __reduce_add_sync(0xffffffffu, carry);
                 const double w = __ldg(inv_m + slot0 + sl);
 #pragma unroll
@@ -218,7 +190,6 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
 #pragma unroll
             for (int ch = 0; ch < EPT; ++ch) buf[ch * 32 + lane] = acc[ch];
         }
-        if (threadIdx.x == 0) s_q[(k + 2) % 3] = claimed;
         pb_fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -228,11 +199,8 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
             }
             pb_bulk_commit();
         }
+        parity ^= 1;
         }   // has_work
-        const long long tile_nn = s_q[(k + 2) % 3];
-        tile = tile_nxt; d = d_nxt; rec_lo = rl_nxt; rec_hi = rh_nxt;
-        tile_nxt = tile_nn;
-        load_tile(tile_nn, d_nxt, rl_nxt, rh_nxt);
     }
     if (stat_slots) pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
     if (threadIdx.x == 0) pb_bulk_wait_all();
@@ -253,7 +221,7 @@ int launch_center(const PbReads &b, const PbRuleDev &r, int planes, const int16_
         int ns = n_slots - s0 < per_pass ? n_slots - s0 : per_pass;
         if (ns < 0) ns = 0;
         const size_t smem = ((size_t)n_planes * T + kZeroBins) * 8 + (size_t)n_planes * ns * T * 4 +
-                            (size_t)n_planes * ns * kCWarps * 4 + 16;
+                            (size_t)2 * n_planes * ns * kCWarps * 4 + 16;
         PB_CUDA_CHECK(cudaFuncSetAttribute(pb_center_tiles_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_center_tiles_kernel<EPT>, kCThreads, smem));

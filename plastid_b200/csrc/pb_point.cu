@@ -147,6 +147,15 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
     // with the current tile — the chain of dependent DRAM round trips per tile is what bounds a CTA.
     // (Claiming runs of consecutive tiles instead was measured slower on skewed data: hot tiles are
     // neighbours, and a run lands on one CTA.)
+#ifdef PB_POINT_SIMPLE_QUEUE
+    for (int k = 0;; ++k) {
+        const long long tile = s_q[k & 1];
+        if (tile >= n_tiles) break;
+        if (threadIdx.x == 0) s_q[(k + 1) & 1] = tile_begin + (long long)atomicAdd(tile_counter, 1ull);
+        const PbTile d = tiles[tile];
+        const long long tile_nxt = n_tiles;
+        const PbTile d_nxt = {0, 0, 0, 0, 0, 0};
+#else
     long long tile = s_q[0], tile_nxt = s_q[1];
     PbTile d = {0, 0, 0, 0, 0, 0}, d_nxt = {0, 0, 0, 0, 0, 0};
     if (tile < n_tiles) d = tiles[tile];
@@ -154,6 +163,7 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
     for (int k = 0; tile < n_tiles; ++k) {
         long long claimed = 0;
         if (threadIdx.x == 0) claimed = tile_begin + (long long)atomicAdd(tile_counter, 1ull);
+#endif
         const int64_t g0 = tile * kPTileBins;
         uint32_t rec_lo = 0, rec_hi = 0;       // this tile's bucket of binned multi-block sites
         if (rec_off) { rec_lo = __ldg(rec_off + tile); rec_hi = __ldg(rec_off + tile + 1); }
@@ -182,19 +192,25 @@ pb_point_tiles_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__restri
             if (pl.want_any) pb_bulk_store(out_any + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
             pb_bulk_commit();
             if (has_work) pb_bulk_wait_read0();
+#ifndef PB_POINT_SIMPLE_QUEUE
             s_q[(k + 2) % 3] = claimed;
+#endif
         }
         __syncthreads();
+#ifndef PB_POINT_SIMPLE_QUEUE
         const long long tile_nn = s_q[(k + 2) % 3];
         PbTile d_nn = {0, 0, 0, 0, 0, 0};
         if (tile_nn < n_tiles) d_nn = tiles[tile_nn];     // in flight while the buffer is re-zeroed
+#endif
         if (has_work) {
             for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
             pb_fence_proxy_async();
             __syncthreads();
         }
+#ifndef PB_POINT_SIMPLE_QUEUE
         tile = tile_nxt; d = d_nxt;
         tile_nxt = tile_nn; d_nxt = d_nn;
+#endif
     }
 
     pb_flush_cta_stats(c.drop_p, c.drop_m, c.drop_a, c.drop_len, c.map_p, c.map_m, c.map_a, stat_slots);

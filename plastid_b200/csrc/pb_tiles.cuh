@@ -94,6 +94,83 @@ __device__ __forceinline__ void pb_bulk_wait_read1() { asm volatile("cp.async.bu
 __device__ __forceinline__ void pb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 
+// ---- look-ahead tile queue of the persistent mapping kernels -----------------------------------
+// A CTA always has its current and its next tile (descriptor + record-bucket bounds) in shared
+// memory.  Thread 0 runs a three-stage pipeline, one stage per loop iteration, so that nothing it
+// consumes was requested less than a whole tile ago: claim a tile from the global counter -> load its
+// descriptor -> publish it in the 4-entry ring two iterations before it becomes current.  The chain
+// of dependent round trips (atomic, descriptor, reads) is what would otherwise bound a CTA.
+// (Claiming runs of consecutive tiles instead was measured slower on skewed data: hot tiles are
+// neighbours, and a run lands on one CTA.)  Used by the center kernel; the point kernel keeps its
+// register-held two-deep look-ahead, which measured faster there (profiles/NOTES_r01.md).
+struct __align__(16) PbSlot {
+    PbTile d;
+    long long tile;
+    uint32_t rec_lo, rec_hi;
+    long long pad;
+};
+
+struct PbQueueRegs {      // meaningful in thread 0 only
+    PbTile d;
+    long long tile_loaded, tile_claimed;
+    uint32_t rl, rh;
+};
+
+__device__ __forceinline__ void pb_queue_load(const PbTile *__restrict__ tiles, const uint32_t *__restrict__ rec_off,
+                                              long long lookback, long long n_tiles, long long t, PbTile &d,
+                                              uint32_t &rl, uint32_t &rh)
+{
+    d = PbTile{0, 0, 0, 0, 0, 0};
+    rl = rh = 0;
+    if (t >= n_tiles) return;
+    d = tiles[t];
+    if (rec_off) {
+        rl = __ldg(rec_off + (t > lookback ? t - lookback : 0));
+        rh = __ldg(rec_off + t + 1);
+    }
+}
+
+__device__ __forceinline__ void pb_queue_publish(PbSlot &slot, const PbQueueRegs &q, const uint32_t *__restrict__ rec_off,
+                                                 long long lookback, int tile_bins)
+{
+    slot.d = q.d;
+    slot.tile = q.tile_loaded;
+    uint32_t rl = q.rl;
+    if (rec_off && lookback > 0) {
+        // records may only be taken from earlier tiles of the same chromosome (rare: its first tiles)
+        const long long first = q.tile_loaded - q.d.p0 / tile_bins;
+        if (q.tile_loaded - lookback < first) rl = __ldg(rec_off + first);
+    }
+    slot.rec_lo = rl;
+    slot.rec_hi = q.rh;
+}
+
+// thread 0, before the first barrier: claim four tiles, publish the first two, keep two in flight
+__device__ __forceinline__ void pb_queue_init(PbSlot *ring, PbQueueRegs &q, const PbTile *__restrict__ tiles,
+                                              const uint32_t *__restrict__ rec_off, long long lookback,
+                                              long long tile_begin, long long n_tiles, int tile_bins,
+                                              unsigned long long *__restrict__ counter)
+{
+    for (int i = 0; i < 3; ++i) {
+        q.tile_loaded = tile_begin + (long long)atomicAdd(counter, 1ull);
+        pb_queue_load(tiles, rec_off, lookback, n_tiles, q.tile_loaded, q.d, q.rl, q.rh);
+        if (i < 2) pb_queue_publish(ring[i], q, rec_off, lookback, tile_bins);
+    }
+    q.tile_claimed = tile_begin + (long long)atomicAdd(counter, 1ull);
+}
+
+// thread 0, top of iteration k: publish the tile for iteration k+2, load the next descriptor, claim
+__device__ __forceinline__ void pb_queue_step(PbSlot *ring, PbQueueRegs &q, int k, const PbTile *__restrict__ tiles,
+                                              const uint32_t *__restrict__ rec_off, long long lookback,
+                                              long long tile_begin, long long n_tiles, int tile_bins,
+                                              unsigned long long *__restrict__ counter)
+{
+    pb_queue_publish(ring[(k + 2) & 3], q, rec_off, lookback, tile_bins);
+    q.tile_loaded = q.tile_claimed;
+    pb_queue_load(tiles, rec_off, lookback, n_tiles, q.tile_loaded, q.d, q.rl, q.rh);
+    q.tile_claimed = tile_begin + (long long)atomicAdd(counter, 1ull);
+}
+
 // Pull the cache lines holding the candidate reads of a tile into L2 (no register destination).
 __device__ __forceinline__ void pb_prefetch_reads_l2(const PbReads &b, const PbTile &d)
 {
@@ -101,6 +178,21 @@ __device__ __forceinline__ void pb_prefetch_reads_l2(const PbReads &b, const PbT
     for (long long j = (d.lo & ~31ll) + (long long)threadIdx.x * 32; j < end; j += (long long)blockDim.x * 32) {
         asm volatile("prefetch.global.L2 [%0];" :: "l"(b.ref_start + j));
         asm volatile("prefetch.global.L2 [%0];" :: "l"(b.meta + j));
+    }
+}
+
+// Pull the cache lines holding the candidate reads (and binned records) of a tile into L2.
+__device__ __forceinline__ void pb_prefetch_tile_l2(const PbReads &b, const PbRec *__restrict__ recs, const PbSlot &s)
+{
+    const long long end = s.d.lo + s.d.n;
+    for (long long j = (s.d.lo & ~31ll) + (long long)threadIdx.x * 32; j < end; j += (long long)blockDim.x * 32) {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(b.ref_start + j));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(b.meta + j));
+    }
+    if (recs) {   // 8 records per 128-byte line
+        for (long long j = (long long)(s.rec_lo & ~7u) + (long long)threadIdx.x * 8; j < (long long)s.rec_hi;
+             j += (long long)blockDim.x * 8)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(recs + j));
     }
 }
 
