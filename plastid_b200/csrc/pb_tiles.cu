@@ -57,9 +57,9 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
 // K1: CIGAR blocks of multi-block reads -> per-tile record buckets (counting sort by tile)
 // ----------------------------------------------------------------------------------------
 template <bool CENTER>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)   // latency-bound gather chains: favour resident threads over registers
 pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t *__restrict__ slot_of_len,
-              int tile_bins, int fill, uint32_t *__restrict__ rec_cursor, const uint32_t *__restrict__ rec_off,
+              int tile_shift, int fill, uint32_t *__restrict__ rec_cursor, const uint32_t *__restrict__ rec_off,
               PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
 {
     unsigned long long drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;
@@ -94,8 +94,16 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
         auto emit = [&](int64_t x, int64_t y, uint32_t tag) {
             if (x < 0 || x >= clen) return;
             if (y > clen) y = clen;
-            const int64_t tile = (base + x) / tile_bins;
-            const uint32_t k = atomicAdd(&rec_cursor[tile], 1u);
+            const int64_t tile = (base + x) >> tile_shift;       // tile sizes are powers of two
+            // reads are coordinate-sorted, so the lanes that are here together mostly target the same
+            // tile: one atomic per group of lanes instead of one per record
+            const unsigned lane = threadIdx.x & 31;
+            const unsigned act = __activemask();
+            const unsigned peers = __match_any_sync(act, (unsigned long long)tile);
+            const int leader = __ffs(peers) - 1;
+            uint32_t k = 0;
+            if ((int)lane == leader) k = atomicAdd(&rec_cursor[tile], (uint32_t)__popc(peers));
+            k = __shfl_sync(peers, k, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
             if (fill) {
                 PbRec rec;
                 rec.x = (int32_t)x; rec.y = (int32_t)y; rec.tag = tag; rec.pad = 0;
@@ -404,14 +412,17 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
     int rc = pb_sm_count(&sms);
     if (rc) return rc;
     int64_t want = (b.n_reads + 255) / 256;
-    unsigned grid = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+    unsigned grid = (unsigned)(want < (int64_t)sms * 32 ? want : (int64_t)sms * 32);
     PB_CUDA_CHECK(cudaMemsetAsync(ws.rec_cursor, 0, (size_t)(n_tiles + 1) * sizeof(uint32_t), stream));
+    int tile_shift = 0;
+    while ((1 << tile_shift) < tile_bins) ++tile_shift;
+    if ((1 << tile_shift) != tile_bins) { pb_set_error("tile size must be a power of two"); return PB_EINVAL; }
     for (int fill = 0; fill < 2; ++fill) {
         if (center)
-            pb_bin_kernel<true><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_bins, fill, ws.rec_cursor,
+            pb_bin_kernel<true><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, fill, ws.rec_cursor,
                                                           ws.rec_off, ws.recs, ws.slots);
         else
-            pb_bin_kernel<false><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_bins, fill, ws.rec_cursor,
+            pb_bin_kernel<false><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, fill, ws.rec_cursor,
                                                            ws.rec_off, ws.recs, ws.slots);
         if (!fill) {
             const int64_t nb = (n_tiles + kScanChunk - 1) / kScanChunk;
