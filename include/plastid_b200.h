@@ -67,6 +67,7 @@ extern "C" {
 #define PB_LAYOUT_ALIGN 16384   /* chrom_bin_off[] granularity, bins */
 #define PB_LUT_SIZE     10000   /* VariableFivePrimeMapFactory LUT length, map_factories.pxd:11-12 */
 #define PB_BAD_OFFSET   (-1)
+#define PB_MAX_BLOCKS   255     /* aligned blocks per read (meta bits 24-31) */
 
 /* query-strand planes (bit mask) — c_common.pxd:1-6 strand enum */
 #define PB_PLANE_PLUS  1
@@ -122,6 +123,30 @@ typedef struct pb_rule {
     int32_t         strat_min;       /* stratified: first / last length row */
     int32_t         strat_max;
 } pb_rule;
+
+/* ---- host side: BAM -> SoA batch (no CUDA involved) -----------------------------------------------
+ * Streams a coordinate-sorted BAM once (BGZF inflate on `n_threads` host threads, 0 = all), keeps
+ * every mapped record as one batch row (CIGAR M/=/X runs merged into aligned blocks) and skips
+ * records without reference / with the unmapped flag.  Replaces pysam's AlignmentFile / fetch /
+ * AlignedSegment.positions on the way into the path (plastid/genomics/genome_array.py:660-690,
+ * 800-809).  pb_bam_n_mapped is what `bamfile.mapped` reports (genome_array.py:690).  pb_bam_copy
+ * writes the decoded arrays into caller-owned HOST buffers (e.g. pinned): ref_start int32[n_reads],
+ * meta uint32[n_reads], chrom_read_off int64[n_ref+1], and — when pb_bam_n_blk > 0 — blk_off
+ * uint32[n_reads+1] and blk int32[n_blk][2]. */
+typedef struct pb_bam pb_bam;
+int pb_bam_open(const char *path, pb_bam **out);
+int pb_bam_decode(pb_bam *h, int n_threads);
+int pb_bam_n_ref(const pb_bam *h);
+const char *pb_bam_ref_name(const pb_bam *h, int i);
+int64_t pb_bam_ref_len(const pb_bam *h, int i);
+int64_t pb_bam_n_reads(const pb_bam *h);
+int64_t pb_bam_n_blk(const pb_bam *h);
+int64_t pb_bam_n_mapped(const pb_bam *h);
+int64_t pb_bam_n_skipped(const pb_bam *h);
+int32_t pb_bam_max_span(const pb_bam *h);
+int pb_bam_copy(const pb_bam *h, int32_t *ref_start, uint32_t *meta, uint32_t *blk_off, int32_t *blk,
+                int64_t *chrom_read_off);
+void pb_bam_close(pb_bam *h);
 
 const char *pb_version(void);
 const char *pb_last_error(void);

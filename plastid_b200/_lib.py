@@ -46,6 +46,18 @@ _SIGNATURES = {
     "pb_version": (C.c_char_p, []),
     "pb_last_error": (C.c_char_p, []),
     "pb_device_count": (C.c_int, []),
+    "pb_bam_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "pb_bam_decode": (C.c_int, [_P, C.c_int]),
+    "pb_bam_n_ref": (C.c_int, [_P]),
+    "pb_bam_ref_name": (C.c_char_p, [_P, C.c_int]),
+    "pb_bam_ref_len": (C.c_int64, [_P, C.c_int]),
+    "pb_bam_n_reads": (C.c_int64, [_P]),
+    "pb_bam_n_blk": (C.c_int64, [_P]),
+    "pb_bam_n_mapped": (C.c_int64, [_P]),
+    "pb_bam_n_skipped": (C.c_int64, [_P]),
+    "pb_bam_max_span": (C.c_int32, [_P]),
+    "pb_bam_copy": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "pb_bam_close": (None, [_P]),
     "pb_map_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "pb_unpack_wire16": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "pb_map_point_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,

@@ -1,32 +1,67 @@
-"""BAM -> SoA batch on the host.
+"""BAM <-> SoA batch on the host.
 
-The reference leaves BAM decoding to pysam (``plastid/genomics/genome_array.py:660, 800-809``).
-pysam is a third-party dependency that is absent from this image; when it is importable a sorted
-BAM is decoded once, whole, into an :class:`~plastid_b200.batch.AlignmentBatch` (no per-region
-``fetch``).  Like the reference, no flag other than is_reverse is interpreted: secondary,
-duplicate and QC-fail alignments are counted; unmapped records (no reference id / no CIGAR) have
-no positions and are skipped, as ``fetch`` never returns them.
+The reference leaves BAM decoding to pysam (``plastid/genomics/genome_array.py:660, 800-809``),
+a third-party dependency.  Here a sorted BAM is decoded ONCE, whole, by the library's own
+multithreaded BGZF/BAM reader (``pb_bam_*`` in ``include/plastid_b200.h``, zlib underneath) into an
+:class:`~plastid_b200.batch.AlignmentBatch` — no per-region ``fetch``, no index needed.  Like the
+reference, no flag other than is_reverse is interpreted: secondary, duplicate and QC-fail
+alignments are counted; records without a reference or flagged unmapped have no positions and are
+skipped.  Open ``pysam.AlignmentFile`` handles are accepted too when pysam is installed.
+
+``write_bam`` is a small pure-Python BAM writer (tests, synthetic data); it is not on the path.
 """
+import ctypes as C
+import struct
+import zlib
+
 import numpy as np
 
+from . import _lib
 from .batch import AlignmentBatch, cigar_to_blocks, MAX_ALIGNED_LEN, MAX_BLOCKS
 
 
-def batch_from_bam(source):
+def batch_from_bam(source, threads=0, pinned=False):
+    """Decode a coordinate-sorted BAM (path, or an open pysam file) into an AlignmentBatch."""
+    if not isinstance(source, (str, bytes)):
+        return _batch_from_pysam(source)
+    L = _lib.lib()
+    handle = C.c_void_p()
+    path = source.encode() if isinstance(source, str) else source
+    _lib.check(L.pb_bam_open(path, C.byref(handle)))
     try:
-        import pysam
-    except ImportError:
-        raise ImportError("decoding BAM files needs pysam, which is not installed here; "
-                          "build an AlignmentBatch with plastid_b200.batch.pack_reads / batch_from_arrays instead")
-    bam = pysam.AlignmentFile(source, "rb") if isinstance(source, str) else source
+        _lib.check(L.pb_bam_decode(handle, int(threads)))
+        n_ref = L.pb_bam_n_ref(handle)
+        chroms = [L.pb_bam_ref_name(handle, i).decode() for i in range(n_ref)]
+        lens = [L.pb_bam_ref_len(handle, i) for i in range(n_ref)]
+        n, n_blk = L.pb_bam_n_reads(handle), L.pb_bam_n_blk(handle)
+
+        def buf(count, dtype):
+            if pinned:
+                import torch
+                tdt = {np.int32: torch.int32, np.uint32: torch.int32, np.int64: torch.int64}[dtype]
+                return torch.empty(max(count, 1), dtype=tdt).pin_memory().numpy().view(dtype)[:count]
+            return np.empty(count, dtype=dtype)
+        start, meta = buf(n, np.int32), buf(n, np.uint32)
+        off = np.empty(n_ref + 1, dtype=np.int64)
+        blk_off = blk = None
+        if n_blk:
+            blk_off, blk = buf(n + 1, np.uint32), buf(2 * n_blk, np.int32)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        _lib.check(L.pb_bam_copy(handle, p(start), p(meta), p(blk_off), p(blk), p(off)))
+        return AlignmentBatch(chroms, lens, start, meta, off, blk_off, None if blk is None else blk.reshape(-1, 2),
+                              max_span=L.pb_bam_max_span(handle), mapped=L.pb_bam_n_mapped(handle))
+    finally:
+        L.pb_bam_close(handle)
+
+
+def _batch_from_pysam(bam):
     chroms, lengths = list(bam.references), list(bam.lengths)
     per_chrom = [[] for _ in chroms]
     for read in bam.fetch(until_eof=True):
         if read.is_unmapped or read.reference_id < 0 or not read.cigartuples:
             continue
         per_chrom[read.reference_id].append(read)
-    starts, metas, blk_off, blks = [], [], [0], []
-    off = [0]
+    starts, metas, blk_off, blks, off = [], [], [0], [], [0]
     multi = False
     for reads in per_chrom:
         recs = []
@@ -54,3 +89,46 @@ def batch_from_bam(source):
         kw = dict(blk_off=np.asarray(blk_off, dtype=np.uint32), blk=np.asarray(blks, dtype=np.int32).reshape(-1, 2))
     return AlignmentBatch(chroms, lengths, np.asarray(starts, dtype=np.int32), np.asarray(metas, dtype=np.uint32),
                           off, mapped=bam.mapped, **kw)
+
+
+# ------------------------------------------------------------------------------- writer (tests)
+def _bgzf_block(data, level=6):
+    comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+    body = comp.compress(data) + comp.flush()
+    bsize = len(body) + 25
+    header = struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, ord("B"), ord("C"), 2, bsize)
+    return header + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data))
+
+
+def write_bam(path, chrom_lengths, records, block_bytes=60000):
+    """Write a BAM file.  ``chrom_lengths``: ordered ``{name: length}``; ``records``: iterable of
+    ``(chrom_index or -1, pos, flag, cigartuples)`` already in coordinate order."""
+    chroms = list(chrom_lengths)
+    text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (c, chrom_lengths[c]) for c in chroms)
+    out = [b"BAM\x01", struct.pack("<i", len(text)), text.encode(), struct.pack("<i", len(chroms))]
+    for c in chroms:
+        name = c.encode() + b"\0"
+        out.append(struct.pack("<i", len(name)) + name + struct.pack("<i", chrom_lengths[c]))
+    for i, (tid, pos, flag, cigar) in enumerate(records):
+        name = ("r%d" % i).encode() + b"\0"
+        qlen = sum(n for op, n in cigar if op in (0, 1, 4, 7, 8))
+        span = sum(n for op, n in cigar if op in (0, 2, 3, 7, 8))
+        end = pos + max(span, 1)
+        bin_ = _reg2bin(max(pos, 0), max(end, 1))
+        core = struct.pack("<iiBBHHHiiii", tid, pos, len(name), 60, bin_, len(cigar), flag, qlen, -1, -1, 0)
+        body = core + name + b"".join(struct.pack("<I", (n << 4) | op) for op, n in cigar)
+        body += b"\x11" * ((qlen + 1) // 2) + b"\xff" * qlen
+        out.append(struct.pack("<i", len(body)) + body)
+    data = b"".join(out)
+    with open(path, "wb") as fh:
+        for a in range(0, len(data), block_bytes):
+            fh.write(_bgzf_block(data[a:a + block_bytes]))
+        fh.write(_bgzf_block(b""))          # EOF marker
+
+
+def _reg2bin(beg, end):
+    end -= 1
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return base + (beg >> shift)
+    return 0

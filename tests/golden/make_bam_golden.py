@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/htslib_*.{bam,dump.txt}: a seeded SAM with every CIGAR op, unmapped and
+placed-unmapped records, converted to BAM and dumped back by the REFERENCE's vendored htslib 1.3
+(oracle/_ref/ref_bam_tool, built by `make -C oracle ref`; needs /root/reference).  The committed
+outputs pin plastid_b200/csrc/pb_bam.cpp against the reference's own BAM writer/reader."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import random_cigar_reads          # noqa: E402
+
+TOOL = os.path.join(ROOT, "oracle", "_ref", "ref_bam_tool")
+OPS = "MIDNSHP=X"
+
+
+def main():
+    rng = np.random.default_rng(2024)
+    lens = {"chrA": 60000, "chrB": 25000, "chrEmpty": 500, "chrC": 9000}
+    lines = ["@HD\tVN:1.4\tSO:coordinate"] + ["@SQ\tSN:%s\tLN:%d" % kv for kv in lens.items()]
+    n = 0
+    for chrom, count in (("chrA", 1500), ("chrB", 600), ("chrC", 200)):
+        reads = sorted(random_cigar_reads(rng, count, lens[chrom], lens[chrom] - 2000), key=lambda r: r.reference_start)
+        for r in reads:
+            qlen = sum(k for op, k in r.cigartuples if op in (0, 1, 4, 7, 8))
+            cigar = "".join("%d%s" % (k, OPS[op]) for op, k in r.cigartuples)
+            flag = (16 if r.is_reverse else 0) | (256 if n % 37 == 0 else 0) | (1024 if n % 53 == 0 else 0)
+            lines.append("r%d\t%d\t%s\t%d\t60\t%s\t*\t0\t0\t%s\t*" % (n, flag, chrom, r.reference_start + 1, cigar, "A" * qlen))
+            if n % 101 == 0:      # an unmapped mate placed at the same coordinate
+                lines.append("u%d\t4\t%s\t%d\t0\t*\t*\t0\t0\tACGT\t*" % (n, chrom, r.reference_start + 1))
+            n += 1
+    for k in range(5):
+        lines.append("x%d\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t*" % k)
+    sam = os.path.join(HERE, "_tmp.sam")
+    with open(sam, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    bam = os.path.join(HERE, "htslib_allops.bam")
+    subprocess.check_call([TOOL, "sam2bam", sam, bam])
+    with open(os.path.join(HERE, "htslib_allops.dump.txt"), "w") as fh:
+        subprocess.check_call([TOOL, "dump", bam], stdout=fh)
+    os.remove(sam)
+    print("wrote", bam, os.path.getsize(bam), "bytes")
+
+
+if __name__ == "__main__":
+    main()

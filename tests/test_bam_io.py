@@ -1,0 +1,111 @@
+"""Host BAM decoder (pb_bam_*, no GPU): against the reference's vendored htslib through committed
+fixtures (tests/golden/htslib_allops.*, made by tests/golden/make_bam_golden.py with
+oracle/_ref/ref_bam_tool), against the packer on random CIGARs, and on malformed input."""
+import os
+
+import numpy as np
+import pytest
+
+import plastid_b200 as pb
+from plastid_b200 import _lib, bam_io
+from plastid_b200.batch import cigar_to_blocks, pack_reads
+from oracle import pyoracle as po
+from helpers import random_cigar_reads
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def parse_dump(path):
+    refs, recs = [], []
+    for line in open(path):
+        f = line.split()
+        if f[0] == "@":
+            refs.append((f[1], int(f[2])))
+            continue
+        tid, pos, flag, n_cigar = (int(x) for x in f[:4])
+        cigar = [tuple(int(v) for v in c.split(":")) for c in f[4].split(",")] if n_cigar else []
+        recs.append((tid, pos, flag, cigar, int(f[-1])))
+    return refs, recs
+
+
+def test_decoder_matches_reference_htslib_dump():
+    refs, recs = parse_dump(os.path.join(GOLD, "htslib_allops.dump.txt"))
+    hb = bam_io.batch_from_bam(os.path.join(GOLD, "htslib_allops.bam"), threads=3)
+    assert hb.chroms == [r[0] for r in refs] and list(hb.chrom_len) == [r[1] for r in refs]
+    mapped = [r for r in recs if r[0] >= 0 and not (r[2] & 4) and r[3]]
+    assert len(hb) == len(mapped) == hb.mapped and len(recs) - len(mapped) == 5 + sum(1 for r in recs if r[0] >= 0 and r[2] & 4)
+    assert list(np.diff(hb.chrom_read_off)) == [sum(1 for r in mapped if r[0] == t) for t in range(len(refs))]
+    hb.check_sorted()
+    # rows are in file order within a chromosome (stable); compare field by field with htslib's view
+    i = 0
+    for tid, pos, flag, cigar, endpos in mapped:
+        blocks, span = cigar_to_blocks(cigar)
+        shift = blocks[0][0] if blocks else 0
+        assert int(hb.ref_start[i]) == pos + shift
+        m = int(hb.meta[i])
+        assert (m & 0xFFFF) == sum(n for _a, n in blocks) and ((m >> 16) & 1) == ((flag >> 4) & 1) and (m >> 24) == len(blocks)
+        assert hb.positions_of(i) == po.positions_from_cigar(pos, cigar)
+        assert pos + span == endpos                    # htslib's bam_endpos == our reference span
+        i += 1
+    assert hb.max_span == max(cigar_to_blocks(c)[1] - (cigar_to_blocks(c)[0][0][0]) for _t, _p, _f, c, _e in mapped)
+
+
+@pytest.mark.parametrize("window", [None, "70000"])
+def test_decoder_matches_packer_on_random_cigars(tmp_path, monkeypatch, window):
+    if window:
+        monkeypatch.setenv("PB_BAM_WINDOW", window)
+    rng = np.random.default_rng(9)
+    lens = {"chrA": 300_000, "chrB": 40_000, "chrNone": 1000}
+    reads = {"chrA": random_cigar_reads(rng, 30_000, 300_000, 290_000), "chrB": random_cigar_reads(rng, 4000, 40_000, 30_000)}
+    recs = []
+    for ci, c in enumerate(lens):
+        for k, r in enumerate(sorted(reads.get(c, []), key=lambda x: x.reference_start)):
+            recs.append((ci, r.reference_start, 16 if r.is_reverse else 0, r.cigartuples))
+            if k % 500 == 0:
+                recs.append((ci, r.reference_start, 4, []))
+    recs.append((-1, -1, 4, []))
+    path = str(tmp_path / "t.bam")
+    bam_io.write_bam(path, lens, recs, block_bytes=20_000 if window else 60_000)
+    assert os.path.getsize(path) > (3 * 70_000 if window else 0)
+    hb = bam_io.batch_from_bam(path, threads=4)
+    ref = pack_reads(reads, lens)
+    assert hb.chroms == ref.chroms and hb.mapped == len(ref) == len(hb)
+    for f in ("ref_start", "meta", "chrom_read_off", "blk_off", "blk"):
+        assert (getattr(hb, f) == getattr(ref, f)).all(), f
+    assert hb.max_span == ref.max_span and hb.max_block_len == ref.max_block_len
+    single = bam_io.batch_from_bam(path, threads=1)
+    assert (single.ref_start == hb.ref_start).all() and (single.blk == hb.blk).all()
+
+
+def test_unspliced_file_has_no_block_table(tmp_path):
+    lens = {"c": 5000}
+    recs = [(0, p, (p % 2) * 16, [(4, 2), (0, 20 + p % 7), (1, 3), (0, 5)]) for p in range(0, 4000, 3)]
+    path = str(tmp_path / "u.bam")
+    bam_io.write_bam(path, lens, recs)
+    hb = bam_io.batch_from_bam(path)
+    assert hb.blk is None and hb.blk_off is None and len(hb) == len(recs)
+    assert list(hb.aligned_len[:3]) == [25 + 0, 25 + 3, 25 + 6] and hb.mapped == len(recs)
+
+
+def test_malformed_input_is_reported(tmp_path):
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(b"this is not a bam file at all" * 10)
+    with pytest.raises(_lib.PlastidB200Error, match="BGZF"):
+        bam_io.batch_from_bam(str(bad))
+    with pytest.raises(_lib.PlastidB200Error, match="cannot open"):
+        bam_io.batch_from_bam(str(tmp_path / "missing.bam"))
+    good = tmp_path / "g.bam"
+    bam_io.write_bam(str(good), {"c": 1000}, [(0, 5, 0, [(0, 30)])] * 50)
+    data = good.read_bytes()
+    trunc = tmp_path / "trunc.bam"
+    trunc.write_bytes(data[:len(data) // 2])
+    with pytest.raises(_lib.PlastidB200Error):
+        bam_io.batch_from_bam(str(trunc))
+    unsorted = tmp_path / "unsorted.bam"
+    bam_io.write_bam(str(unsorted), {"a": 1000, "b": 1000}, [(1, 5, 0, [(0, 30)]), (0, 5, 0, [(0, 30)])])
+    with pytest.raises(_lib.PlastidB200Error, match="sorted"):
+        bam_io.batch_from_bam(str(unsorted))
+    empty = tmp_path / "empty.bam"
+    bam_io.write_bam(str(empty), {"a": 1000}, [])
+    hb = bam_io.batch_from_bam(str(empty))
+    assert len(hb) == 0 and hb.chroms == ["a"] and hb.mapped == 0

@@ -516,3 +516,27 @@ def test_pileup_tile_is_split_into_overflow_jobs(cuda_device):
             dropped[strand] += d
     assert [int(x) for x in planes.stats[:3]] == [dropped["+"], dropped["-"], dropped["."]] and dropped["."] > 1000
     assert int(planes.stats[_lib.PB_STAT_MAPPED_ANY]) == len(hb) - dropped["."]
+
+
+def test_bam_genome_array_from_bam_file(tmp_path, cuda_device):
+    """BAMGenomeArray("x.bam"): decoded by the library's own BGZF/BAM reader, no pysam."""
+    from plastid_b200 import bam_io
+    rng = np.random.default_rng(8)
+    lens = {"chrA": 9000, "chrB": 4000}
+    reads = {"chrA": random_cigar_reads(rng, 1500, 9000, 7000), "chrB": random_cigar_reads(rng, 500, 4000, 3000)}
+    recs = []
+    for ci, c in enumerate(lens):
+        for r in sorted(reads[c], key=lambda x: x.reference_start):
+            recs.append((ci, r.reference_start, 16 if r.is_reverse else 0, r.cigartuples))
+    path = str(tmp_path / "x.bam")
+    bam_io.write_bam(path, lens, recs)
+    ga = pb.BAMGenomeArray(path, mapping=pb.ThreePrimeMapFactory(2), device=cuda_device)
+    oga = po.OracleBAMGenomeArray(po.ReadStore(lens, reads), mapping=po.ThreePrimeMap(2))
+    assert ga.sum() == oga.sum() == 2000 and ga.chroms() == ["chrA", "chrB"] and ga.lengths() == lens
+    for strand in ("+", "-", "."):
+        for chrom, a, b in (("chrA", 0, 9000), ("chrB", 100, 3900)):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                exp = oga[po.Seg(chrom, a, b, strand)]
+                got = ga[pb.GenomicSegment(chrom, a, b, strand)]
+            assert (got == exp).all(), (strand, chrom)
