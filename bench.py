@@ -39,10 +39,11 @@ def parse_args():
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of hg38 chromosome lengths")
     ap.add_argument("--regions", type=int, default=60_000)
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
                          "are side measurements (c1 counts_in_region yeast-scale, c3 CenterMapFactory(12) on "
-                         "spliced 100-nt reads, c5 ThreePrimeMapFactory 500 M reads)")
+                         "spliced 100-nt reads, c4 metagene count over 60 k windows of the c2 planes, "
+                         "c5 ThreePrimeMapFactory 500 M reads)")
     return ap.parse_args()
 
 
@@ -106,6 +107,8 @@ def build_world(args, rank, device):
     import plastid_b200 as pb
     from plastid_b200 import synth
     wl = args.workload
+    if wl == "c4":
+        wl = "c2"           # same reads, genome and mapping rule; the timed step is the metagene pass
     if wl == "c1":
         chroms, lens = synth.yeast_like_genome()
         n_reads = 2_000_000 if args.reads == 200_000_000 else args.reads
@@ -211,6 +214,71 @@ def host_sample(dbatch, chroms, lens, chrom_ids):
     return AlignmentBatch(chroms, lens, sub.ref_start, sub.meta, full_off, sub.blk_off, sub.blk, max_span=sub.max_span)
 
 
+def run_c4(args, W, device, rank, world, dist):
+    """BASELINE config 4: metagene count over 60 k windows (-50/+300 nt, 5 % masked) of the C2 count
+    planes: gather the window matrix, (N > 1: all-reduce it, counts are linear in the read shards),
+    normalise, exact per-column median.  One step = that pass; the mapping itself is not timed."""
+    import torch
+    from plastid_b200 import synth
+    from plastid_b200.genome_array import map_batch, gather_windows, window_normalize, column_profile
+    layout, ann, dbatch = W["layout"], W["ann"], W["dbatch"]
+    planes = map_batch(dbatch, layout, W["fac"], W["sf"], strands=("+", "-"))
+    table, cols = synth.window_table(ann, layout, width=350)
+    table.device(device)
+    width, n = 350, table.n_chains
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    gather_ms = []
+
+    def step(timed=False):
+        if timed:
+            ev[2].record()
+        mat, mmask = gather_windows(planes, table, cols, width)
+        if timed:
+            ev[3].record()
+        if world > 1:
+            mat = torch.nan_to_num(mat, nan=0.0)
+            dist.all_reduce(mat)
+        denom, sel, norm, nmask = window_normalize(mat, mmask, 70, 100, 10)
+        prof, nreg, csum = column_profile(norm, nmask, sel, "median")
+        return prof, nreg
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(args.steps):
+        prof, nreg = step(timed=True)
+        torch.cuda.synchronize()
+        gather_ms.append(ev[2].elapsed_time(ev[3]))
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms = float(t.item())
+    positions = int(table.chain_len.sum())
+    alg = 4.0 * positions + positions / 8.0 + 16.0 * len(table.bstart) + 9.0 * n * width
+    g_ms = float(np.mean(gather_ms))
+    peak, peak_src = peaks()
+    line = {"metric": "metagene_windows_per_sec", "value": n / (ms / 1000.0), "unit": "windows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: metagene count, %d windows x %d nt over the C2 planes, 5%% masked, "
+                                   "norm window [20,50) from the landmark, min_counts 10, exact median profile" % (n, width),
+                       "reads_per_gpu": dbatch.n_reads, "windows": n, "width": width},
+            "roofline": {"bound": "hbm", "kernel": "pb_gather_windows_kernel", "achieved": alg / (g_ms / 1000.0) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (g_ms / 1000.0) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": g_ms,
+                         "kernel_share_of_step": g_ms / ms},
+            "profile_checksum": float(torch.nan_to_num(prof).sum().item()), "regions_counted_max": int(nreg.max().item())}
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
     import torch
@@ -242,6 +310,12 @@ def main():
               "regions": ann.n_tx, "sharding": "read-range per GPU; NCCL all-reduce of region tables" if world > 1
               else "single GPU", "l2": "inputs (%.2f GB) and outputs (%.1f GB) larger than the 126 MB L2"
               % (8 * n_reads / 1e9, (16 if is_center else 8) * layout.total_bins / 1e9)}
+
+    if args.workload == "c4" and args.impl != "reference":
+        run_c4(args, W, device, rank, world, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -390,8 +464,16 @@ def main():
         + (8.0 if is_center else 4.0) * layout.total_bins * 2
     k_ms = kms.value / max(kn.value, 1)
     achieved = alg_bytes / (k_ms / 1000.0) / 1e9
+    kernel_name = "pb_center_tiles_kernel" if is_center else "pb_point_tiles_kernel"
+    traffic = None                    # DRAM bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tpath) and args.genome_scale == 1.0:
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("%s:%s" % (kernel_name, args.workload))
+        if traffic is not None and abs(n_reads - {"c2": 200_000_000, "c3": 100_000_000}.get(args.workload, -1)) > 0:
+            traffic = None            # captured at the default size only
     roofline = {"bound": "hbm", "kernel": "pb_center_tiles_kernel" if is_center else "pb_point_tiles_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "launches_timed": kn.value,
                 "kernel_share_of_step": k_ms / ms_per_step}
 
@@ -406,6 +488,13 @@ def main():
                "sample": "%s: %d reads + %d region sums in %.2f s (oracle C port, one thread)"
                          % (",".join(chroms[c] for c in chrom_ids), nr, nreg, dt)}
 
+    binning = ["pb_bin_kernel(count)", "pb_scan_chunks_kernel", "pb_scan_top_kernel", "pb_scan_add_kernel",
+               "pb_bin_kernel(fill)"] if dbatch.blk_off is not None else []
+    if is_center:
+        kernels_per_step = ["pb_length_hist_kernel", "pb_tile_index_kernel"] + binning + ["pb_center_tiles_kernel"]
+    else:
+        kernels_per_step = ["pb_tile_index_kernel"] + binning + ["pb_point_tiles_kernel", "pb_point_overflow_kernel"]
+    kernels_per_step += ["pb_stats_finish_kernel", "pb_region_sums_kernel"]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is_center else "u32", "data": "synthetic",
@@ -415,10 +504,7 @@ def main():
                     "ms_per_step": float(t.item()), "steps": e2e_steps,
                     "host_format": "wire16 (4 B/read), 8-chunk upload overlapped with pb_map_point_range"
                     if use_wire16 else "SoA (8 B/read + blocks)"},
-            "gpu_launches": (5 if is_center else 4) * args.steps,
-            "kernels_per_step": (["pb_length_hist_kernel", "pb_tile_index_kernel", "pb_center_tiles_kernel"] if is_center
-                                 else ["pb_tile_index_kernel", "pb_point_tiles_kernel"])
-            + ["pb_stats_finish_kernel", "pb_region_sums_kernel"],
+            "gpu_launches": len(kernels_per_step) * args.steps, "kernels_per_step": kernels_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}
     print(json.dumps(line))
     if world > 1:

@@ -99,6 +99,17 @@ __device__ __forceinline__ int64_t pb_lower_bound(const int32_t *__restrict__ a,
     return lo;
 }
 
+// lower_bound when the answer is expected a short way past `lo` (candidate slices are a few hundred
+// reads): gallop 1,2,4,... from lo — probes that stay within a couple of cache lines — then bisect
+__device__ __forceinline__ int64_t pb_lower_bound_near(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key)
+{
+    if (lo >= hi || (int64_t)__ldg(a + lo) >= key) return lo;
+    int64_t step = 1, prev = lo;      // invariant: a[prev] < key
+    while (prev + step < hi && (int64_t)__ldg(a + prev + step) < key) { prev += step; step <<= 1; }
+    const int64_t top = prev + step < hi ? prev + step : hi;
+    return pb_lower_bound(a, prev + 1, top, key);
+}
+
 // chromosome owning global bin g: last c with chrom_bin_off[c] <= g
 __device__ __forceinline__ int pb_chrom_of_bin(const PbLayoutDev &lay, int64_t g)
 {

@@ -46,10 +46,18 @@ pb_region_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const
     int64_t j = 0;
     for (int64_t k = __ldg(chain_off + c); k < __ldg(chain_off + c + 1); ++k) {
         const int64_t bs = __ldg(bstart + k), be = __ldg(bend + k);
-        for (int64_t p = bs + lane; p < be; p += 32) {
-            if (mask_bits && pb_mask_bit(mask_bits, moff + j + (p - bs))) continue;
-            acc += vec[p];
-            live++;
+        // four independent 128-byte rows in flight per warp (the loop is latency-, not bandwidth-bound)
+        for (int64_t p = bs + lane; p < be; p += 128) {
+            T v[4];
+            bool use[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t q = p + 32 * u;
+                use[u] = q < be && !(mask_bits && pb_mask_bit(mask_bits, moff + j + (q - bs)));
+                v[u] = use[u] ? vec[q] : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc += v[u]; live += use[u]; }
         }
         j += be - bs;
     }

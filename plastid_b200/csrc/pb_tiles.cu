@@ -27,7 +27,7 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
     // a single-block read [s, s+L) can only touch [p0, p0+T) if p0 - max_block_len < s < p0 + T;
     // multi-block reads reach their tiles through the binned records instead
     int64_t lo = pb_lower_bound(b.ref_start, r0, r1, p0 - b.max_block_len + 1);
-    int64_t hi = pb_lower_bound(b.ref_start, lo, r1, p0 + tile_bins);
+    int64_t hi = pb_lower_bound_near(b.ref_start, lo, r1, p0 + tile_bins);
     int64_t live = clen - p0;
     live = live < 0 ? 0 : (live > tile_bins ? tile_bins : live);
     PbTile d;

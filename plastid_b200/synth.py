@@ -236,3 +236,47 @@ def annotation_table(annotation, layout):
     length = np.add.reduceat(annotation.ex_end - annotation.ex_start, annotation.tx_off[:-1])
     return ChainTable(layout, bstart, bend, annotation.tx_off, annotation.tx_strand.astype(np.uint8),
                       annotation.tx_strand.astype(np.uint8), length)
+
+
+def window_table(annotation, layout, width=350, mask_frac=0.05, mask_block=20, seed=7):
+    """Metagene-style windows (BASELINE config 4): for every transcript the first ``width`` positions
+    of the chain in 5'->3' order (shorter chains give shorter windows, right-aligned like an upstream
+    flank that runs off the transcript), about ``mask_frac`` of positions masked in ``mask_block``-nt
+    runs.  Returns (ChainTable, row_col int32[n])."""
+    from .regions import ChainTable
+    rng = np.random.default_rng(seed)
+    bstart, bend, chain_off, plane, length, row_col = [], [], [0], [], [], []
+    base_of = layout.chrom_bin_off[np.asarray([layout.index[c] for c in annotation.chroms])]
+    bits = []
+    for t in range(annotation.n_tx):
+        a, b = int(annotation.tx_off[t]), int(annotation.tx_off[t + 1])
+        ex = [(int(annotation.ex_start[k]), int(annotation.ex_end[k])) for k in range(a, b)]
+        rev = bool(annotation.tx_strand[t])
+        need, segs = width, []
+        for s, e in (reversed(ex) if rev else ex):            # walk 5'->3'
+            take = min(need, e - s)
+            segs.append((e - take, e) if rev else (s, s + take))
+            need -= take
+            if need == 0:
+                break
+        segs.sort()
+        base = int(base_of[int(annotation.tx_chrom[t])])
+        for s, e in segs:
+            bstart.append(base + s)
+            bend.append(base + e)
+        n = width - need
+        chain_off.append(len(bstart))
+        plane.append(1 if rev else 0)
+        length.append(n)
+        row_col.append(width - n)
+        m = np.zeros(n, dtype=np.uint8)
+        for _ in range(rng.binomial(max(n // mask_block, 1), mask_frac)):
+            p = int(rng.integers(0, max(n - mask_block, 1)))
+            m[p:p + mask_block] = 1
+        bits.append(m)
+    mask_off = np.zeros(len(length), dtype=np.int64)
+    np.cumsum(length[:-1], out=mask_off[1:])
+    flat = np.concatenate(bits) if bits else np.zeros(0, dtype=np.uint8)
+    table = ChainTable(layout, bstart, bend, chain_off, plane, plane, length,
+                       np.packbits(flat, bitorder="little"), mask_off)
+    return table, np.asarray(row_col, dtype=np.int32)
