@@ -176,11 +176,13 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
                 for (int ch = 0; ch < EPT; ++ch) {
                     int v = A[ch * 32 + lane];
                     A[ch * 32 + lane] = 0;
+                    // Kogge-Stone step = shuffle + add predicated on the shuffle's own in-range flag
+                    // (two instructions instead of shuffle + compare + select + add)
 #pragma unroll
-                    for (int dd = 1; dd < 32; dd <<= 1) {
-                        const int u = __shfl_up_sync(0xffffffffu, v, dd);
-                        if (lane >= dd) v += u;
-                    }
+                    for (int dd = 1; dd < 32; dd <<= 1)
+                        asm volatile("{ .reg .s32 t; .reg .pred p;\n\t"
+                                     "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+                                     "@p add.s32 %0, %0, t; }" : "+r"(v) : "r"(dd));
                     v += carry;
                     carry = __shfl_sync(0xffffffffu, v, 31);
                     acc[ch] += (double)v * w;
