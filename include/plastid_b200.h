@@ -31,6 +31,8 @@
  *   pb_column_profile  median | mean | sum per column      plastid/bin/metagene.py:934-953,
  *                                                          plastid/bin/psite.py:204-234
  *   pb_phase_sums    sub-codon phase accumulation          plastid/bin/phase_by_size.py:165-235
+ *   pb_stratified_windows  per-read-length window matrices plastid/bin/psite.py:176-199,
+ *                                                          plastid/bin/phase_by_size.py:186-194
  *
  * Alignment batch (SoA, sorted by (chromosome, ref_start); what pysam hands the reference
  * as AlignedSegment.reference_start / .positions / .is_reverse):
@@ -257,6 +259,22 @@ int pb_column_profile(const double *values, const uint8_t *valmask, const uint8_
                       int64_t n_rows, int32_t width, int mode,
                       double *profile, int64_t *n_regions, double *col_sum,
                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* psite.py:176-199 / phase_by_size.py:186-194 in one launch: for every window chain and every aligned
+ * length in [min_len, max_len], the counts of the reads the point rule maps into the window, laid
+ * 5'->3' from column row_col[c] of a width-W row (strand-matched like get_reads_and_counts; the rule
+ * runs right-to-left for '-' windows).  out: uint32[(max_len-min_len+1)][n_chains][width];
+ * maskmat: uint8[n_chains][width], 1 = masked or outside the chain (shared by all lengths).
+ * phase_mode != 0 (phase_by_size.py:197-214): width is 3, columns are sub-codon phases of the codons
+ * in the python slice [codon_front:codon_back] of the chain; row_col and maskmat are unused. */
+int pb_stratified_windows(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                          int min_len, int max_len,
+                          const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                          const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                          const int32_t *row_col, int64_t n_chains, int32_t width,
+                          int phase_mode, int32_t codon_front, int32_t codon_back,
+                          const uint8_t *mask_bits, const int64_t *mask_off,
+                          uint32_t *out, uint8_t *maskmat, void *stream);
 
 /* phase_by_size.py:197-214: per chain, counts laid 5'->3' are cut into codons (a trailing partial
  * codon is ignored), the python slice [codon_front:codon_back] of codons is kept, and counts are

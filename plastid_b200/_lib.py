@@ -77,6 +77,9 @@ _SIGNATURES = {
     "pb_window_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                       _P, _P, _P, _P, _P]),
     "pb_column_profile_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "pb_stratified_windows": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int, C.c_int,
+                                        _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_int32,
+                                        _P, _P, _P, _P, _P]),
     "pb_phase_sums": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "pb_column_profile": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
 }

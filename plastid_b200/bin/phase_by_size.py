@@ -6,11 +6,12 @@ import sys
 import numpy as np
 
 from . import _cli
-from ..genome_array import map_batch, phase_sums
-from ..map_factories import SizeFilterFactory, CenterMapFactory
+import torch
+
+from ..genome_array import stratified_windows
+from ..map_factories import CenterMapFactory
 from ..regions import ChainTable
 from ..roitools import SegmentChain
-from .psite import _length_filter
 
 
 def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
@@ -24,19 +25,16 @@ def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
         raise TypeError("phase_by_size on the GPU path supports point mapping rules only")
     back_buffer = -codon_buffer if back_buffer is None else back_buffer
     chains = [c for c in cds_chains if len(c) > 0]
+    read_lengths = list(read_lengths)
+    if not read_lengths:
+        return {}
     table = ChainTable.from_chains(chains, ga.layout, use_masks=False)
-    need = tuple(sorted(set("+-."[p] for p in np.unique(table.chain_plane))) or ["+"])
-    dbatch = ga._device_batch()
-    planes = None
-    out = {}
-    for k in read_lengths:
-        sf = _length_filter(ga, k)
-        if sf is None:
-            out[k] = np.zeros(3)
-            continue
-        planes = map_batch(dbatch, ga.layout, ga.map_fn, sf, strands=need, planes=planes, sync_stats=False)
-        out[k] = phase_sums(planes, table, codon_buffer, back_buffer).sum(dim=0).cpu().numpy()
-    return out
+    lo, hi = min(read_lengths), max(read_lengths)
+    # all lengths and all chains in one launch: [n_len, n_chains, 3] -> sum over chains
+    strat, _ = stratified_windows(ga._device_batch(), ga.layout, ga.map_fn, ga._size_filter(), table, None, 3,
+                                  lo, hi, phase=(codon_buffer, back_buffer))
+    sums = strat.to(torch.float64).sum(dim=1).cpu().numpy()
+    return {k: sums[k - lo] for k in read_lengths}
 
 
 def phase_table(sums):

@@ -8,43 +8,41 @@ import numpy as np
 
 from . import _cli
 from .metagene import rois_from_table, _NORM_START_DEFAULT, _NORM_END_DEFAULT
-from ..genome_array import map_batch, gather_windows, window_normalize, column_profile
-from ..map_factories import FivePrimeMapFactory, SizeFilterFactory
+from ..genome_array import stratified_windows, window_normalize, column_profile
+from ..map_factories import (FivePrimeMapFactory, SizeFilterFactory, CenterMapFactory,
+                             StratifiedVariableFivePrimeMapFactory, _MapFactory)
 from ..regions import ChainTable
-
-
-def _length_filter(ga, k):
-    """Size filter passing exactly length k, intersected with the array's own size filter."""
-    sf = ga._size_filter()
-    if sf is not None and not (sf.min_ <= k and (sf.max_ == -1 or k <= sf.max_)):
-        return None
-    return SizeFilterFactory(k, k)
 
 
 def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_len=25, max_len=35,
              aggregate=False, keep=False):
     """Per read length k in [min_len, max_len]: window matrix of counts of k-mers under ``ga.map_fn``
     (psite.main forces FivePrimeMapFactory(0), psite.py:357-359), then the same normalise / median
-    (or ``--aggregate`` nansum) as ``metagene count``.  One map+gather pass per length, reusing one
-    set of count planes."""
+    (or ``--aggregate`` nansum) as ``metagene count``.  All lengths are counted in ONE launch
+    (``pb_stratified_windows``) straight from the sorted batch; no per-length genome vectors exist."""
+    import torch
     wins, cols, window_size, flank = rois_from_table(roi_table)
     norm_start = _NORM_START_DEFAULT if norm_start is None else norm_start
     norm_end = _NORM_END_DEFAULT if norm_end is None else norm_end
+    if isinstance(ga.map_fn, (CenterMapFactory, StratifiedVariableFivePrimeMapFactory)) or not isinstance(ga.map_fn, _MapFactory):
+        raise TypeError("psite on the GPU path needs a point mapping rule (5'/3'/variable)")
     table = ChainTable.from_chains(wins, ga.layout)
-    need = tuple(sorted(set("+-."[p] for p in np.unique(table.chain_plane))) or ["+"])
     dbatch = ga._device_batch()
-    planes = None
+    strat, maskmat = stratified_windows(dbatch, ga.layout, ga.map_fn, ga._size_filter(), table, cols, window_size,
+                                        min_len, max_len)
+    dev = strat.device
+    colidx = torch.arange(window_size, device=dev)[None, :]
+    c0 = torch.as_tensor(np.asarray(cols), device=dev)[:, None]
+    clen = torch.from_numpy(table.chain_len).to(dev)[:, None]
+    uncovered = (colidx < c0) | (colidx >= c0 + clen)
     out = {"x": np.arange(-flank, window_size - flank), "profiles": {}, "regions_counted": {}, "raw": {}}
     for k in range(min_len, max_len + 1):
-        sf = _length_filter(ga, k)
-        if sf is None:
-            sf = SizeFilterFactory.__new__(SizeFilterFactory)
-            sf.min_, sf.max_ = 1, 0                      # nothing passes
-        planes = map_batch(dbatch, ga.layout, ga.map_fn, sf, strands=need, planes=planes, sync_stats=False)
-        mat, mmask = gather_windows(planes, table, cols, window_size)
-        denom, sel, norm, nmask = window_normalize(mat, mmask, norm_start, norm_end, min_counts)
+        mat = strat[k - min_len].to(torch.float64)
+        mat[uncovered] = float("nan")                    # cells no chain position reaches (psite.py:153-157)
+        mat = mat.contiguous()
+        denom, sel, norm, nmask = window_normalize(mat, maskmat, norm_start, norm_end, min_counts)
         if aggregate:
-            profile, n_regions, _ = column_profile(mat, mmask, sel, "sum")
+            profile, n_regions, _ = column_profile(mat, maskmat, sel, "sum")
             _p, n_regions, _ = column_profile(norm, nmask, sel, "mean")     # regions_counted uses the norm mask
         else:
             profile, n_regions, _ = column_profile(norm, nmask, sel, "median")
@@ -54,7 +52,7 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
         out["profiles"][k] = prof
         out["regions_counted"][k] = n_regions.cpu().numpy()
         if keep:
-            out["raw"][k] = np.ma.MaskedArray(mat.cpu().numpy(), mask=mmask.cpu().numpy().astype(bool))
+            out["raw"][k] = np.ma.MaskedArray(mat.cpu().numpy(), mask=maskmat.cpu().numpy().astype(bool))
     return out
 
 

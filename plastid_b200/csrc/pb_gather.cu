@@ -6,7 +6,7 @@
 // window matrices and profiles (plastid/bin/metagene.py:895-960, plastid/bin/psite.py:204-234).
 // All of this is HBM/L2-bound gather work: one warp walks one chain with coalesced 128-byte
 // reads of the dense count plane.
-#include "pb_common.cuh"
+#include "pb_tiles.cuh"
 #include <math.h>
 
 namespace {
@@ -413,6 +413,128 @@ extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,
         pb_phase_sums_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, out);
     else
         pb_phase_sums_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, out);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// psite / phase_by_size inner loops in one launch: per-read-length window matrices
+// ----------------------------------------------------------------------------------------
+// Reference (plastid/bin/psite.py:176-199, plastid/bin/phase_by_size.py:186-194): per window and
+// exon, fetch the reads the mapping rule keeps there, bucket them by aligned length, map every
+// bucket, lay the vectors 5'->3'.  Here one CTA owns one window: the reads that can map into each
+// of its blocks are a contiguous slice of the coordinate-sorted batch (two binary searches), the rule
+// is applied per read and the (length, column) cell is incremented in a shared-memory histogram.
+namespace {
+
+__global__ void __launch_bounds__(128)
+pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_len, int n_len,
+                             const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                             const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
+                             const uint8_t *__restrict__ chain_reverse, const int32_t *__restrict__ row_col,
+                             int64_t n_chains, int32_t width, int phase_mode, int32_t codon_front, int32_t codon_back,
+                             const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
+                             uint32_t *__restrict__ out, uint8_t *__restrict__ maskmat)
+{
+    extern __shared__ uint32_t hist[];   // [n_len][width]  (phase mode: width == 3 sub-codon phases)
+    const int64_t c = blockIdx.x;
+    for (int j = threadIdx.x; j < n_len * width; j += blockDim.x) hist[j] = 0;
+    __syncthreads();
+    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
+    int64_t len = 0;
+    for (int64_t k = k0; k < k1; ++k) len += __ldg(bend + k) - __ldg(bstart + k);
+    const int plane = __ldg(chain_plane + c);            // 0 '+', 1 '-', 2 '.'
+    const bool rev_out = __ldg(chain_reverse + c);
+    const bool rq = plane == 1;                          // rule direction follows the window's strand
+    const int64_t col0 = phase_mode ? 0 : __ldg(row_col + c);
+    // phase mode (phase_by_size.py:197-214): codons [codon_front:codon_back] (python slice) of the chain
+    const int64_t ncod = len / 3;
+    int64_t cod_lo = codon_front < 0 ? ncod + codon_front : codon_front, cod_hi = codon_back < 0 ? ncod + codon_back : codon_back;
+    cod_lo = cod_lo < 0 ? 0 : (cod_lo > ncod ? ncod : cod_lo);
+    cod_hi = cod_hi < 0 ? 0 : (cod_hi > ncod ? ncod : cod_hi);
+    int64_t j0 = 0;
+    for (int64_t k = k0; k < k1; ++k) {
+        const int64_t gs = __ldg(bstart + k), ge = __ldg(bend + k);
+        const int ch = pb_chrom_of_bin(lay, gs);
+        const int64_t base = __ldg(lay.chrom_bin_off + ch);
+        const int64_t bs = gs - base, be = ge - base;    // chromosome coordinates of the block
+        int64_t r0 = 0, r1 = 0;
+        if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
+        const int64_t lo = pb_lower_bound(b.ref_start, r0, r1, bs - b.max_span + 1);
+        const int64_t hi = pb_lower_bound_near(b.ref_start, lo, r1, be);
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const uint32_t m = __ldg(b.meta + i);
+            if (!pb_passes(m, r.size_min, r.size_max)) continue;
+            const bool rev = PB_META_REV(m);
+            if ((plane == 0 && rev) || (plane == 1 && !rev)) continue;    // genome_array.py:811-815
+            const int L = PB_META_L(m);
+            if (L < min_len || L >= min_len + n_len) continue;           // psite.py:187: len(positions) in read_dict
+            const int idx = pb_rule_index(r, L, rq);
+            if (idx < 0) continue;
+            const int64_t p = pb_position(b, i, __ldg(b.ref_start + i), m, idx);
+            if (p < bs || p >= be) continue;
+            const int64_t jj = j0 + (p - bs);
+            int64_t col = col0 + (rev_out ? (len - 1 - jj) : jj);
+            if (phase_mode) {
+                const int64_t cod = col / 3;
+                col = (cod >= cod_lo && cod < cod_hi) ? col - cod * 3 : -1;
+            }
+            if (col >= 0 && col < width) atomicAdd(&hist[(L - min_len) * width + (int)col], 1u);
+        }
+        j0 += be - bs;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_len * width; j += blockDim.x) {
+        const int row = j / width, col = j - row * width;
+        out[((int64_t)row * n_chains + c) * width + col] = hist[j];
+    }
+    // the validity mask every length shares (get_masked_counts(ga).mask, psite.py:166)
+    if (phase_mode || !maskmat) return;
+    const int64_t moff = mask_bits ? __ldg(mask_off + c) : 0;
+    for (int col = threadIdx.x; col < width; col += blockDim.x) {
+        uint8_t mk = 1;
+        const int64_t t = col - col0;                    // 5'->3' index along the chain
+        if (t >= 0 && t < len) {
+            const int64_t jj = rev_out ? (len - 1 - t) : t;
+            mk = mask_bits ? (uint8_t)pb_mask_bit(mask_bits, moff + jj) : (uint8_t)0;
+        }
+        maskmat[c * (int64_t)width + col] = mk;
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_stratified_windows(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                                     int min_len, int max_len,
+                                     const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                     const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                     const int32_t *row_col, int64_t n_chains, int32_t width,
+                                     int phase_mode, int32_t codon_front, int32_t codon_back,
+                                     const uint8_t *mask_bits, const int64_t *mask_off,
+                                     uint32_t *out, uint8_t *maskmat, void *stream_)
+{
+    if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !chain_reverse || !out ||
+        (!phase_mode && (!row_col || !maskmat))) { pb_set_error("pb_stratified_windows: null argument"); return PB_EINVAL; }
+    if (phase_mode) width = 3;
+    if (rule->kind != PB_RULE_FIVEPRIME && rule->kind != PB_RULE_THREEPRIME && rule->kind != PB_RULE_VARIABLE) {
+        pb_set_error("pb_stratified_windows: needs a point rule"); return PB_EINVAL;
+    }
+    if (rule->kind == PB_RULE_VARIABLE && (!rule->lut_fw || !rule->lut_rc)) { pb_set_error("pb_stratified_windows: variable rule needs LUTs"); return PB_EINVAL; }
+    if (max_len < min_len || min_len < 0 || width <= 0 || n_chains < 0) { pb_set_error("pb_stratified_windows: bad sizes"); return PB_EINVAL; }
+    if (mask_bits && !mask_off) { pb_set_error("pb_stratified_windows: mask_bits without mask_off"); return PB_EINVAL; }
+    const int n_len = max_len - min_len + 1;
+    const size_t smem = (size_t)n_len * width * sizeof(uint32_t);
+    if (smem > 200 * 1024) { pb_set_error("pb_stratified_windows: %d lengths x %d columns do not fit in shared memory", n_len, width); return PB_EINVAL; }
+    if (n_chains == 0) return PB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbReads b = pb_to_dev(batch);
+    PbRuleDev r = pb_to_dev(rule);
+    PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
+    PB_CUDA_CHECK(cudaFuncSetAttribute(pb_stratified_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pb_stratified_windows_kernel<<<(unsigned)n_chains, 128, smem, stream>>>(b, r, lay, min_len, n_len, bstart, bend, chain_off,
+                                                                           chain_plane, chain_reverse, row_col, n_chains, width,
+                                                                           phase_mode, codon_front, codon_back,
+                                                                           mask_bits, mask_off, out, maskmat);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

@@ -182,6 +182,32 @@ def gather_windows(planes, table, row_col, width):
     return matrix[:n], maskmat[:n]
 
 
+def stratified_windows(dbatch, layout, factory, size_filter, table, row_col, width, min_len, max_len, phase=None):
+    """Per-read-length window matrices in one launch: (int32[n_len, n_chains, width], uint8 mask
+    [n_chains, width]) — the inner loops of psite.py:176-199 / phase_by_size.py:186-194.
+    ``phase=(codon_front, codon_back)``: per-length sub-codon phase counts instead (width 3)."""
+    import torch
+    _lib.require_cuda()
+    dev = dbatch.device
+    d = table.device(dev)
+    n = table.n_chains
+    n_len = max_len - min_len + 1
+    if phase is not None:
+        width, row_col = 3, np.zeros(n, dtype=np.int32)
+    out = torch.zeros((n_len, max(n, 1), width), dtype=torch.int32, device=dev)
+    maskmat = torch.empty((max(n, 1), width), dtype=torch.uint8, device=dev)
+    cols = torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
+    b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
+    _lib.check(_lib.lib().pb_stratified_windows(C.byref(b), C.byref(lay), C.byref(rule), int(min_len), int(max_len),
+                                                _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                                _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
+                                                n, width, int(phase is not None), int(phase[0]) if phase else 0,
+                                                int(phase[1]) if phase else 0, _lib.ptr(d["mask_bits"]),
+                                                _lib.ptr(d["mask_off"]), _lib.ptr(out), _lib.ptr(maskmat),
+                                                _lib.stream_ptr()))
+    return out[:, :n], maskmat[:n]
+
+
 def phase_sums(planes, table, codon_front, codon_back):
     """Per-chain sub-codon phase sums (n_chains x 3, device tensor)."""
     import torch

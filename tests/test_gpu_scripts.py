@@ -162,3 +162,18 @@ def test_phase_by_size(world, back):
     if back != 0:
         assert sum(v.sum() for v in got.values()) > 1000
         assert got[24].sum() == 0          # below the 25-100 size filter
+
+
+def test_phase_sums_on_planes_agree_with_single_launch_path(world):
+    """pb_phase_sums over per-length count planes (one map pass per length) == pb_stratified_windows."""
+    from plastid_b200.genome_array import map_batch, phase_sums
+    from plastid_b200.regions import ChainTable
+    w = world
+    oga, ga = make_gas(w, po.FivePrimeMap(3), pb.FivePrimeMapFactory(3))
+    cds = [ch.get_subchain(ch.length // 6, ch.length - ch.length // 8) for ch in w["ann"].chains()[:80]]
+    got = phase_by_size.do_phase(ga, cds, [27, 28, 31], 5, -1)
+    table = ChainTable.from_chains(cds, ga.layout, use_masks=False)
+    for k in (27, 28, 31):
+        planes = map_batch(ga._device_batch(), ga.layout, ga.map_fn, pb.SizeFilterFactory(k, k), strands=("+", "-"))
+        exp = phase_sums(planes, table, 5, -1).sum(dim=0).cpu().numpy()
+        assert (got[k] == exp).all() and exp.sum() > 0
