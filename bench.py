@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of hg38 chromosome lengths")
     ap.add_argument("--regions", type=int, default=60_000)
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5", "peaks"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
                          "are side measurements (c1 counts_in_region yeast-scale, c3 CenterMapFactory(12) on "
                          "spliced 100-nt reads, c2p the psite pass over 60 k start windows x 11 read lengths of the c2 reads, "
@@ -215,6 +215,37 @@ def host_sample(dbatch, chroms, lens, chrom_ids):
     return AlignmentBatch(chroms, lens, sub.ref_start, sub.meta, full_off, sub.blk_off, sub.blk, max_span=sub.max_span)
 
 
+def run_peaks(args, device):
+    """the L2 atomic peak next to hbm_gbs — 2^30 `red.global.add.u32` updates, (i) uniformly
+    random over 24.8 GB of bins, (ii) coordinate-sorted with +-64 nt jitter over a 3.1 G-bin plane.  One JSON
+    line; also written to gpurun_out/atomic_peaks.json (committed copy: profiles/atomic_peaks_r01.json)."""
+    import torch
+    from plastid_b200 import _lib
+    L = _lib.lib()
+    n_upd = 1 << 30
+    out = {"metric": "atomic_updates_per_sec", "unit": "updates/s", "n_updates": n_upd, "op": "red.global.add.u32"}
+    for name, mode, n_bins, jitter in (("uniform_24.8GB", 0, 6_200_000_000, 0), ("sorted_jitter64_3.1Gbins", 1, 3_100_000_000, 64)):
+        bins = torch.zeros(n_bins, dtype=torch.int32, device=device)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for it in range(5):
+            ev0.record()
+            _lib.check(L.pb_atomic_probe(_lib.ptr(bins), n_bins, n_upd, mode, jitter, _lib.stream_ptr()))
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            best = ms if best is None or (it > 0 and ms < best) else best
+        total = int(bins.to(torch.int64).sum().item()) if n_bins <= 3_100_000_000 else None
+        out[name] = {"ms": best, "updates_per_sec": n_upd / (best / 1000.0), "n_bins": n_bins, "jitter": jitter,
+                     "updates_landed_check": total}
+        del bins
+        torch.cuda.empty_cache()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "atomic_peaks.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    print(json.dumps(out))
+
+
 def run_c4(args, W, device, rank, world, dist):
     """BASELINE config 4: metagene count over 60 k windows (-50/+300 nt, 5 % masked) of the C2 count
     planes: gather the window matrix, (N > 1: all-reduce it, counts are linear in the read shards),
@@ -360,6 +391,10 @@ def main():
     from plastid_b200 import synth, _lib
     from plastid_b200.genome_array import map_batch, region_sums, CountPlanes
 
+    if args.workload == "peaks":
+        if rank == 0:
+            run_peaks(args, device)
+        return 0
     W = build_world(args, rank, device)
     chroms, lens, ann, layout, table, dbatch = W["chroms"], W["lens"], W["ann"], W["layout"], W["table"], W["dbatch"]
     fac, sf, is_center = W["fac"], W["sf"], W["center"]

@@ -284,6 +284,12 @@ int pb_phase_sums(const void *const *planes, int vec_dtype,
                   const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
                   int32_t codon_front, int32_t codon_back, double *out, void *stream);
 
+/* Roofline probe (the atomic peak a scatter-add design would be bound by; no
+ * reference counterpart, not on the product path): n_updates `red.global.add.u32` into
+ * bins[0..n_bins) — mode 0 uniformly random targets, mode 1 sorted targets with +-jitter.
+ * bench.py --workload peaks times it with CUDA events. */
+int pb_atomic_probe(uint32_t *bins, int64_t n_bins, int64_t n_updates, int mode, int jitter, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@
 // block, not the longest intron); finished tiles are staged as fp64 in shared memory and leave the
 // SM as TMA bulk stores (or bulk fp64 reductions when map lengths need more than one pass).
 #include "pb_tiles.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -23,41 +24,71 @@ constexpr int kCWarps = kCThreads / 32;
 constexpr int kCUnroll = 4;
 constexpr int kZeroBins = 256;   // 2 KB of fp64 zeros: tiles nothing lands in are stored from here
 
-template <int EPT>  // bins per thread; tile = EPT * 256 bins
-__global__ void __launch_bounds__(kCThreads)
-pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
+// exact int -> double for 0 <= x < 2^32 with one DADD instead of an I2F: 2^52 + x is representable
+__device__ __forceinline__ double pb_u32_to_f64(int x)
+{
+    return __hiloint2double(0x43300000, x) - 4503599627370496.0;
+}
+
+// One barrier per tile: the difference arrays are double-buffered by iteration parity, every warp
+// scans and writes out its own chunks of the tile, so a warp that is done moves on to the next tile
+// while slower warps still scan.  A thread owns 4 CONSECUTIVE bins of a 128-bin chunk (one LDS.128,
+// a 3-add serial scan, one 5-step warp scan per chunk); the running sum entering a chunk comes from
+// per-chunk totals kept with a second shared atomic, so chunks are independent of each other.
+// The first candidate read and binned record of every thread for tile k+1 are loaded into
+// registers before the barrier of tile k and applied after its scan (software pipeline: their
+// latency is covered by the scan instead of being waited for at the barrier).
+//
+// DIRECT: the finished bins leave the registers as 256-bit global stores (STG.E.256; a warp writes
+// 1 KB contiguous per instruction) — no fp64 staging buffer, so the shared-memory pipe carries only
+// the difference arrays.  The staged variant (TMA bulk store / bulk fp64 reduction) remains for the
+// accumulating passes of batches with more map lengths than fit, and for planes not 32-byte aligned.
+//
+// PLANES / ONE_SLOT: compile-time copies of the plane mask and of "this pass has exactly one map
+// length" for the common cases ('+' and '-' planes, all reads trimmed to one length), so the plane
+// and slot loops unroll and their address arithmetic folds; PLANES = 0 / ONE_SLOT = false is the
+// generic kernel.
+template <int EPT, bool DIRECT, int PLANES, bool ONE_SLOT>  // EPT bins per thread (4, 8 or 16); tile = EPT * 256 bins
+__global__ void __launch_bounds__(kCThreads, DIRECT ? 4 : 3)
+pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
                        const int16_t *__restrict__ slot_of_len, const double *__restrict__ inv_m,
-                       int slot0, int n_slots, int accumulate, int lookback,
+                       int slot0, int n_slots_rt, int accumulate, int lookback,
                        const PbTile *__restrict__ tiles, int64_t n_tiles, unsigned long long *__restrict__ tile_counter,
                        const uint32_t *__restrict__ rec_off, const PbRec *__restrict__ recs,
                        double *__restrict__ out_plus, double *__restrict__ out_minus, double *__restrict__ out_any,
                        unsigned long long *__restrict__ stat_slots)
 {
+    const int planes = PLANES ? PLANES : planes_rt;
+    const int n_slots = ONE_SLOT ? 1 : n_slots_rt;
     constexpr int T = EPT * kCThreads;
-    constexpr int seg = T / kCWarps;  // bins per warp in the scan = EPT * 32
+    constexpr int kChunk = 128;                 // bins per scan unit: 32 lanes x 4 consecutive bins
+    constexpr int nChunks = T / kChunk;         // <= 32: one warp reduction yields a chunk's carry-in
+    constexpr int kPerWarp = nChunks / kCWarps; // chunks scanned by each warp (contiguous)
+    static_assert(EPT % 4 == 0 && nChunks <= 32, "tile = 1024, 2048 or 4096 bins");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ PbSlot s_ring[4];
 
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
                want_any = planes & PB_PLANE_ANY;
-    const int n_planes = (int)want_plus + (int)want_minus + (int)want_any;
+    const int n_planes = PLANES ? ((PLANES & 1) + ((PLANES >> 1) & 1) + ((PLANES >> 2) & 1))
+                                : (int)want_plus + (int)want_minus + (int)want_any;
     const int n_arrays = n_planes * n_slots;
-    double *stage = reinterpret_cast<double *>(smem_raw);           // [n_planes][T] fp64 staging
-    double *zbuf = stage + (size_t)n_planes * T;                    // [kZeroBins] zeros, never written
-    int *diff = reinterpret_cast<int *>(zbuf + kZeroBins);          // [n_arrays][T]
-    int *warp_tot = diff + (size_t)n_arrays * T;                    // [2][n_arrays][kCWarps] (double-buffered by tile parity)
+    double *stage = reinterpret_cast<double *>(smem_raw);           // [n_planes][T] fp64 staging (staged variant)
+    double *zbuf = stage + (DIRECT ? 0 : (size_t)n_planes * T);     // [kZeroBins] zeros, never written
+    int *diff_all = reinterpret_cast<int *>(zbuf + kZeroBins);      // [2][n_arrays][T] by iteration parity
+    int *tot_all = diff_all + (size_t)2 * n_arrays * T;             // [3][n_arrays][nChunks] by iteration mod 3
     double *outs[3];
-    int *d_plus = diff, *d_minus = diff, *d_any = diff;
+    int a_plus = 0, a_minus = 0, a_any = 0;                         // first array (slot 0) of each plane
     {
         int k = 0;
-        if (want_plus) { outs[k] = out_plus; d_plus = diff + (size_t)(k++) * n_slots * T; }
-        if (want_minus) { outs[k] = out_minus; d_minus = diff + (size_t)(k++) * n_slots * T; }
-        if (want_any) { outs[k] = out_any; d_any = diff + (size_t)(k++) * n_slots * T; }
+        if (want_plus) { outs[k] = out_plus; a_plus = (k++) * n_slots; }
+        if (want_minus) { outs[k] = out_minus; a_minus = (k++) * n_slots; }
+        if (want_any) { outs[k] = out_any; a_any = (k++) * n_slots; }
     }
     {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         uint4 *s4 = reinterpret_cast<uint4 *>(smem_raw);
-        const int n16 = ((n_planes * T + kZeroBins) * 8 + n_arrays * T * 4 + 2 * n_arrays * kCWarps * 4) / 16;
+        const int n16 = (((DIRECT ? 0 : n_planes * T) + kZeroBins) * 8 + 2 * n_arrays * T * 4 + 3 * n_arrays * nChunks * 4 + 15) / 16;
         for (int j = threadIdx.x; j < n16; j += kCThreads) s4[j] = z;
     }
     PbQueueRegs q;
@@ -65,13 +96,31 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
     pb_fence_proxy_async();
     __syncthreads();
 
-    unsigned long long drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;
+    unsigned int drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;   // per thread: < 2^32
     unsigned int drop_len = 0;
     const int nibble = r.param;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double w_one = (ONE_SLOT && n_slots_rt > 0) ? __ldg(inv_m + slot0) : 0.0;
 
-    int parity = 0;   // which copy of the segment sums the current tile-with-work uses
-    for (int k = 0;; ++k) {
+    // register stage of the software pipeline: this thread's first candidate read and first binned
+    // record of the tile that becomes current in the next iteration (drop bit / empty interval = none)
+    int32_t pre_s = 0;
+    uint32_t pre_m = 1u << 17;
+    PbRec pre_rec = PbRec{0, 0, 0u, 0u};
+    auto preload = [&](const PbSlot &nx) {
+        pre_m = 1u << 17;
+        pre_rec.x = pre_rec.y = 0;
+        if (nx.tile >= n_tiles) return;
+        if ((int)threadIdx.x < nx.d.n) {
+            pre_s = __ldg(b.ref_start + nx.d.lo + threadIdx.x);
+            pre_m = __ldg(b.meta + nx.d.lo + threadIdx.x);
+        }
+        if (nx.rec_lo + threadIdx.x < nx.rec_hi) pre_rec = recs[nx.rec_lo + threadIdx.x];
+    };
+    preload(s_ring[0]);
+
+    int k3 = 0;       // k mod 3
+    for (int k = 0;; ++k, k3 = (k3 == 2 ? 0 : k3 + 1)) {
         if (threadIdx.x == 0) pb_queue_step(s_ring, q, k, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
         const PbSlot &cur = s_ring[k & 3];
         const long long tile = cur.tile;
@@ -80,164 +129,222 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes,
         const uint32_t rec_lo = cur.rec_lo, rec_hi = cur.rec_hi;
         const int64_t g0 = tile * T;
         const bool has_work = d.n > 0 || rec_hi > rec_lo;
-        if (!has_work) {
-            if (threadIdx.x == 0) {
-                if (!accumulate) {
-                    for (int q = 0; q < n_planes; ++q)
-                        for (int z = 0; z < T; z += kZeroBins) pb_bulk_store(outs[q] + g0 + z, zbuf, kZeroBins * 8);
-                    pb_bulk_commit();
+        int *diff = diff_all + (size_t)(k & 1) * n_arrays * T;
+        int *tot = tot_all + k3 * n_arrays * nChunks;
+        int *tot_next2 = tot_all + (k3 == 0 ? 2 : k3 - 1) * n_arrays * nChunks;   // (k + 2) mod 3
+
+        if (has_work) {
+            const int64_t p0 = d.p0, p1 = d.p0 + T, plim = d.p0 + d.live;
+            // Difference update of one aligned reference interval [x,y) of map-length slot `sl`; the
+            // total of the 128-bin chunk is kept up to date alongside (the scan's carry-in).
+            auto add_interval = [&](int64_t x, int64_t y, int sl, bool rev) {
+                if (y <= p0 || x >= plim) return;
+                const bool do_strand = rev ? want_minus : want_plus;
+                const int a_strand = (rev ? a_minus : a_plus) + sl, a_all = a_any + sl;
+                const unsigned ox = (unsigned)((x > p0 ? x : p0) - p0);
+                if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + ox], 1); atomicAdd(&tot[a_strand * nChunks + ox / kChunk], 1); }
+                if (want_any) { atomicAdd(&diff[(size_t)a_all * T + ox], 1); atomicAdd(&tot[a_all * nChunks + ox / kChunk], 1); }
+                if (y < p1) {
+                    const unsigned oy = (unsigned)(y - p0);
+                    if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + oy], -1); atomicAdd(&tot[a_strand * nChunks + oy / kChunk], -1); }
+                    if (want_any) { atomicAdd(&diff[(size_t)a_all * T + oy], -1); atomicAdd(&tot[a_all * nChunks + oy / kChunk], -1); }
                 }
-            }
-            __syncthreads();
-        } else {
-
-        const int64_t p0 = d.p0, p1 = d.p0 + T, plim = d.p0 + d.live;
-        // Difference update of one aligned reference interval [x,y) of map-length slot `sl`.  The sum
-        // of each warp segment (what the scan needs as carry-in) is kept up to date with a second
-        // shared atomic instead of re-reading every difference word before the scan.
-        int *tot = warp_tot + parity * n_arrays * kCWarps;
-        auto add_interval = [&](int64_t x, int64_t y, int sl, bool rev) {
-            if (y <= p0 || x >= plim) return;
-            const bool do_strand = rev ? want_minus : want_plus;
-            const int a_strand = ((rev ? d_minus : d_plus) - diff) / T + sl, a_all = (d_any - diff) / T + sl;
-            const unsigned ox = (unsigned)((x > p0 ? x : p0) - p0);
-            if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + ox], 1); atomicAdd(&tot[a_strand * kCWarps + ox / seg], 1); }
-            if (want_any) { atomicAdd(&diff[(size_t)a_all * T + ox], 1); atomicAdd(&tot[a_all * kCWarps + ox / seg], 1); }
-            if (y < p1) {
-                const unsigned oy = (unsigned)(y - p0);
-                if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + oy], -1); atomicAdd(&tot[a_strand * kCWarps + oy / seg], -1); }
-                if (want_any) { atomicAdd(&diff[(size_t)a_all * T + oy], -1); atomicAdd(&tot[a_all * kCWarps + oy / seg], -1); }
-            }
-        };
-
-        // single-block reads of the candidate slice
-        const int64_t hi = d.lo + d.n;
-        for (int64_t base = d.lo; base < hi; base += (int64_t)kCUnroll * kCThreads) {
-            int32_t sv[kCUnroll];
-            uint32_t mv[kCUnroll];
-#pragma unroll
-            for (int u = 0; u < kCUnroll; ++u) {
-                const int64_t i = base + (int64_t)u * kCThreads + threadIdx.x;
-                const bool ok = i < hi;
-                sv[u] = ok ? __ldg(b.ref_start + i) : 0;
-                mv[u] = ok ? __ldg(b.meta + i) : (1u << 17);
-            }
-#pragma unroll
-            for (int u = 0; u < kCUnroll; ++u) {
-                const int32_t s = sv[u];
-                const uint32_t m = mv[u];
-                if (!pb_passes(m, r.size_min, r.size_max)) continue;
-                if (rec_off && PB_META_NBLK(m) > 1) continue;      // arrives through the bucket
+            };
+            auto one_read = [&](int32_t s, uint32_t m) {
+                if (!pb_passes(m, r.size_min, r.size_max)) return;
+                if (rec_off && PB_META_NBLK(m) > 1) return;        // arrives through the bucket
                 const int L = PB_META_L(m);
                 const bool rev = PB_META_REV(m);
                 const bool own = (s >= p0 && s < p1);
                 const int map_len = L - 2 * nibble;
                 if (map_len < 0) {                                 // map_factories.pyx:246-248
                     if (own) { drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L; }
-                    continue;
+                    return;
                 }
-                if (map_len == 0) continue;
+                if (map_len == 0) return;
                 if (own) { map_a++; if (rev) map_m++; else map_p++; }   // reads_out semantics (:256)
                 const int slot = (int)__ldg(slot_of_len + L) - slot0;
-                if (slot < 0 || slot >= n_slots) continue;         // another pass handles this map length
+                if (slot < 0 || slot >= n_slots) return;           // another pass handles this map length
                 add_interval((int64_t)s + nibble, (int64_t)s + L - nibble, slot, rev);
+            };
+            auto one_rec = [&](const PbRec &rec) {
+                const int slot = (int)(rec.tag & 0xffffu) - slot0;
+                if (slot < 0 || slot >= n_slots) return;
+                add_interval(rec.x, rec.y, slot, (rec.tag >> 16) & 1u);
+            };
+
+            // the first 256 candidate reads / binned records were loaded a tile ago
+            one_read(pre_s, pre_m);
+            if (pre_rec.y > pre_rec.x) one_rec(pre_rec);
+            // dense tiles: the rest of the candidate slice, kCUnroll independent loads per thread
+            const int64_t hi = d.lo + d.n;
+            for (int64_t base = d.lo + kCThreads; base < hi; base += (int64_t)kCUnroll * kCThreads) {
+                int32_t sv[kCUnroll];
+                uint32_t mv[kCUnroll];
+#pragma unroll
+                for (int u = 0; u < kCUnroll; ++u) {
+                    const int64_t i = base + (int64_t)u * kCThreads + threadIdx.x;
+                    const bool ok = i < hi;
+                    sv[u] = ok ? __ldg(b.ref_start + i) : 0;
+                    mv[u] = ok ? __ldg(b.meta + i) : (1u << 17);
+                }
+#pragma unroll
+                for (int u = 0; u < kCUnroll; ++u) one_read(sv[u], mv[u]);
             }
+            // trimmed aligned intervals of multi-block reads (already filtered and counted by pb_bin_kernel)
+            for (uint32_t j = rec_lo + kCThreads + threadIdx.x; j < rec_hi; j += kCThreads) one_rec(recs[j]);
+            // this warp's previous bulk copies must have read its staging segment before it is rewritten
+            if (!DIRECT && lane == 0) pb_bulk_wait_read0();
+        } else if (threadIdx.x == 0 && !accumulate) {
+            for (int qq = 0; qq < n_planes; ++qq)
+                for (int z = 0; z < T; z += kZeroBins) pb_bulk_store(outs[qq] + g0 + z, zbuf, kZeroBins * 8);
+            pb_bulk_commit();
         }
-        if (s_ring[(k + 1) & 3].tile < n_tiles) pb_prefetch_tile_l2(b, recs, s_ring[(k + 1) & 3]);
-        // trimmed aligned intervals of multi-block reads (already filtered and counted by pb_bin_kernel)
-        for (uint32_t j = rec_lo + threadIdx.x; j < rec_hi; j += kCThreads) {
-            const PbRec rec = recs[j];
-            const int slot = (int)(rec.tag & 0xffffu) - slot0;
-            if (slot < 0 || slot >= n_slots) continue;
-            add_interval(rec.x, rec.y, slot, (rec.tag >> 16) & 1u);
-        }
-        __syncthreads();
+        preload(s_ring[(k + 1) & 3]);     // consumed after this tile's scan
+        __syncthreads();   // the only barrier of the iteration: publishes the difference arrays
+        // chunk totals of iteration k+2 (= k-1 mod 3, consumed before this barrier) are cleared here:
+        // they are not touched again before the next barrier
+        for (int j = threadIdx.x; j < n_arrays * nChunks; j += kCThreads) tot_next2[j] = 0;
+        // the tile after next was published before the barrier: pull its reads and records into L2
+        if (s_ring[(k + 2) & 3].tile < n_tiles) pb_prefetch_tile_l2(b, recs, s_ring[(k + 2) & 3]);
+        if (!has_work) continue;
 
-        // the previous tile's bulk copies must have read the staging buffers before they are rewritten
-        // (they were issued a whole read-scan ago); the barrier also publishes the difference arrays
-        if (threadIdx.x == 0) pb_bulk_wait_read0();
-        __syncthreads();
-        // the other parity's segment sums were last used by the previous tile: clear them for the next
-        for (int j = threadIdx.x; j < n_arrays * kCWarps; j += kCThreads) warp_tot[(parity ^ 1) * n_arrays * kCWarps + j] = 0;
-
-        // pass 2: exact scan + fixed-order combine into the staging buffers; every thread zeroes the
-        // difference words it consumed, so the arrays are clean for the next tile without another pass
-        for (int q = 0; q < n_planes; ++q) {
-            double acc[EPT];
+        // exact scan of this warp's chunks + fixed-order combine over the slots; the difference
+        // words are zeroed as they are consumed
+#pragma unroll 1
+        for (int cc = 0; cc < kPerWarp; ++cc) {
+            const int c = warp * kPerWarp + cc;
 #pragma unroll
-            for (int ch = 0; ch < EPT; ++ch) acc[ch] = 0.0;
-            for (int sl = 0; sl < n_slots; ++sl) {
-                const int a = q * n_slots + sl;
-                int *A = diff + (size_t)a * T + warp * seg;
-                int carry = (lane < warp) ? tot[a * kCWarps + lane] : 0;
-                carry = __reduce_add_sync(0xffffffffu, carry);
-                const double w = __ldg(inv_m + slot0 + sl);
-#pragma unroll
-                for (int ch = 0; ch < EPT; ++ch) {
-                    int v = A[ch * 32 + lane];
-                    A[ch * 32 + lane] = 0;
+            for (int qq = 0; qq < (PLANES ? n_planes : 3); ++qq) {
+                if (!PLANES && qq >= n_planes) break;
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 1
+                for (int sl = 0; sl < n_slots; ++sl) {
+                    const int a = qq * n_slots + sl;
+                    int4 *A = reinterpret_cast<int4 *>(diff + (size_t)a * T + c * kChunk);
+                    int carry = (lane < c) ? tot[a * nChunks + lane] : 0;
+                    const int4 v = A[lane];
+                    A[lane] = make_int4(0, 0, 0, 0);
+                    carry = __reduce_add_sync(0xffffffffu, carry);
+                    const double w = ONE_SLOT ? w_one : __ldg(inv_m + slot0 + sl);
+                    const int s1 = v.x, s2 = s1 + v.y, s3 = s2 + v.z, s4 = s3 + v.w;
+                    int incl = s4;
                     // Kogge-Stone step = shuffle + add predicated on the shuffle's own in-range flag
-                    // (two instructions instead of shuffle + compare + select + add)
 #pragma unroll
                     for (int dd = 1; dd < 32; dd <<= 1)
                         asm volatile("{ .reg .s32 t; .reg .pred p;\n\t"
                                      "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
-                                     "@p add.s32 %0, %0, t; }" : "+r"(v) : "r"(dd));
-                    v += carry;
-                    carry = __shfl_sync(0xffffffffu, v, 31);
-                    acc[ch] += (double)v * w;
+                                     "@p add.s32 %0, %0, t; }" : "+r"(incl) : "r"(dd));
+                    const int before = incl - s4 + carry;     // coverage entering this thread's 4 bins
+                    acc0 += pb_u32_to_f64(before + s1) * w;
+                    acc1 += pb_u32_to_f64(before + s2) * w;
+                    acc2 += pb_u32_to_f64(before + s3) * w;
+                    acc3 += pb_u32_to_f64(before + s4) * w;
+                }
+                if (DIRECT) {
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                                 :: "l"(outs[qq] + g0 + c * kChunk + lane * 4), "d"(acc0), "d"(acc1), "d"(acc2), "d"(acc3)
+                                 : "memory");
+                } else {
+                    // a lane's 32 bytes go out as two 16-byte stores; lanes 4-7 of every eight store their
+                    // halves in the opposite order, which keeps each quarter-warp on 32 distinct banks
+                    double2 *buf = reinterpret_cast<double2 *>(stage + (size_t)qq * T + c * kChunk);
+                    const int flip = (lane >> 2) & 1;
+                    const double2 lo2 = make_double2(acc0, acc1), hi2 = make_double2(acc2, acc3);
+                    buf[lane * 2 + flip] = flip ? hi2 : lo2;
+                    buf[lane * 2 + (flip ^ 1)] = flip ? lo2 : hi2;
                 }
             }
-            double *buf = stage + (size_t)q * T + warp * seg;
-#pragma unroll
-            for (int ch = 0; ch < EPT; ++ch) buf[ch * 32 + lane] = acc[ch];
         }
-        pb_fence_proxy_async();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int q = 0; q < n_planes; ++q) {
-                if (accumulate) pb_bulk_add_f64(outs[q] + g0, stage + (size_t)q * T, T * 8);
-                else pb_bulk_store(outs[q] + g0, stage + (size_t)q * T, T * 8);
+        if (!DIRECT) {
+            pb_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                constexpr int seg = kPerWarp * kChunk;
+                for (int qq = 0; qq < n_planes; ++qq) {
+                    double *dst = outs[qq] + g0 + warp * seg;
+                    const double *src = stage + (size_t)qq * T + warp * seg;
+                    if (accumulate) pb_bulk_add_f64(dst, src, seg * 8);
+                    else pb_bulk_store(dst, src, seg * 8);
+                }
+                pb_bulk_commit();
             }
-            pb_bulk_commit();
         }
-        parity ^= 1;
-        }   // has_work
     }
     if (stat_slots) pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
-    if (threadIdx.x == 0) pb_bulk_wait_all();
+    if (lane == 0) pb_bulk_wait_all();   // staged tiles (every warp) and zero tiles (thread 0)
+}
+
+// staging + zero block + double-buffered difference arrays + three rotating copies of the segment sums
+size_t pb_center_smem_bytes(int n_planes, int n_slots, int tile_bins, bool direct)
+{
+    return ((direct ? 0 : (size_t)n_planes * tile_bins) + kZeroBins) * 8 + (size_t)2 * n_planes * n_slots * tile_bins * 4 +
+           (size_t)3 * n_planes * n_slots * (tile_bins / 128) * 4 + 16;
+}
+
+template <int EPT, bool DIRECT, int PLANES, bool ONE_SLOT>
+int launch_center_kernel(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
+                         int s0, int ns, int pass, int lookback, int64_t n_tiles, int sm_count, const PbWorkspace &ws,
+                         double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+{
+    constexpr int T = EPT * kCThreads;
+    const int n_planes = __builtin_popcount(planes);
+    const size_t smem = pb_center_smem_bytes(n_planes, ns, T, DIRECT);
+    auto kern = pb_center_tiles_kernel<EPT, DIRECT, PLANES, ONE_SLOT>;
+    PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCThreads, smem));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)sm_count * occ;
+    if (grid > n_tiles) grid = n_tiles;
+    PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 64, stream));
+    // statistics are accumulated by the first pass only (later passes see the same reads again)
+    kern<<<(unsigned)grid, kCThreads, smem, stream>>>(
+        b, r, planes, slot_of_len, inv_m, s0, ns, pass > 0, lookback, ws.tiles, n_tiles, ws.tile_counter,
+        ws.rec_off, ws.recs, out_plus, out_minus, out_any, pass == 0 ? ws.slots : nullptr);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+// specialised instantiations exist for the direct-store kernel on 2048-bin tiles with one map length
+// and the plane sets the host layer asks for ('+','-' | '.' | all three); everything else is generic
+template <int EPT, bool DIRECT>
+int launch_center_pass(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
+                       int s0, int ns, int pass, int lookback, int64_t n_tiles, int sm_count, const PbWorkspace &ws,
+                       double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+{
+#define PB_CENTER_ARGS b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, n_tiles, sm_count, ws, out_plus, out_minus, out_any, stream
+    if (EPT == 8 && DIRECT && ns == 1 && !getenv("PB_CENTER_GENERIC")) {
+        if (planes == (PB_PLANE_PLUS | PB_PLANE_MINUS)) return launch_center_kernel<8, true, PB_PLANE_PLUS | PB_PLANE_MINUS, true>(PB_CENTER_ARGS);
+        if (planes == PB_PLANE_ANY) return launch_center_kernel<8, true, PB_PLANE_ANY, true>(PB_CENTER_ARGS);
+        if (planes == 7) return launch_center_kernel<8, true, 7, true>(PB_CENTER_ARGS);
+    }
+    return launch_center_kernel<EPT, DIRECT, 0, false>(PB_CENTER_ARGS);
+#undef PB_CENTER_ARGS
 }
 
 template <int EPT>
 int launch_center(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
-                  int n_slots, int per_pass, int lookback, int64_t total_bins, const PbWorkspace &ws,
+                  int n_slots, int per_pass, int lookback, int64_t total_bins, bool direct_ok, const PbWorkspace &ws,
                   double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
 {
-    constexpr int T = EPT * kCThreads;
-    const int n_planes = __builtin_popcount(planes);
-    const int64_t n_tiles = total_bins / T;
+    const int64_t n_tiles = total_bins / (EPT * kCThreads);
     int sm_count = 0;
     int rc = pb_sm_count(&sm_count);
     if (rc) return rc;
     for (int s0 = 0, pass = 0; s0 < n_slots || pass == 0; s0 += per_pass, ++pass) {
         int ns = n_slots - s0 < per_pass ? n_slots - s0 : per_pass;
         if (ns < 0) ns = 0;
-        const size_t smem = ((size_t)n_planes * T + kZeroBins) * 8 + (size_t)n_planes * ns * T * 4 +
-                            (size_t)2 * n_planes * ns * kCWarps * 4 + 16;
-        PB_CUDA_CHECK(cudaFuncSetAttribute(pb_center_tiles_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_center_tiles_kernel<EPT>, kCThreads, smem));
-        if (occ < 1) occ = 1;
-        int64_t grid = (int64_t)sm_count * occ;
-        if (grid > n_tiles) grid = n_tiles;
-        PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 64, stream));
-        // statistics are accumulated by the first pass only (later passes see the same reads again)
-        pb_center_tiles_kernel<EPT><<<(unsigned)grid, kCThreads, smem, stream>>>(
-            b, r, planes, slot_of_len, inv_m, s0, ns, pass > 0, lookback, ws.tiles, n_tiles, ws.tile_counter,
-            ws.rec_off, ws.recs, out_plus, out_minus, out_any, pass == 0 ? ws.slots : nullptr);
+        // the first pass stores every bin (direct 256-bit stores when allowed); later passes add to them
+        if (pass == 0 && direct_ok)
+            rc = launch_center_pass<EPT, true>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, n_tiles, sm_count,
+                                               ws, out_plus, out_minus, out_any, stream);
+        else
+            rc = launch_center_pass<EPT, false>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, n_tiles, sm_count,
+                                                ws, out_plus, out_minus, out_any, stream);
+        if (rc) return rc;
         if (n_slots == 0) break;
     }
-    PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
 
@@ -265,17 +372,23 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     if (rc) return rc;
     const int n_planes = __builtin_popcount(planes);
 
-    // 2048-bin tiles when all difference arrays fit next to the staging buffers in ~72 KB (three or
-    // four CTAs per SM); otherwise 1024-bin tiles, and several accumulating passes over groups of map lengths
-    // if even those cannot hold every slot at once.
+    // 2048-bin tiles when everything fits in ~75 KB (three CTAs per SM); otherwise 1024-bin tiles, and
+    // several accumulating passes over groups of map lengths if even those cannot hold every slot.
     const int ns = n_slots < 1 ? 1 : n_slots;
     int ept = 8, per_pass = ns;
-    if (((size_t)n_planes * 2048 + kZeroBins) * 8 + (size_t)n_planes * ns * 2048 * 4 > 72 * 1024) {
+    if (pb_center_smem_bytes(n_planes, ns, 2048, false) > 75 * 1024) {
         ept = 4;
-        per_pass = (int)((200 * 1024 - ((size_t)n_planes * 1024 + kZeroBins) * 8) / ((size_t)n_planes * 1024 * 4));
-        if (per_pass > ns) per_pass = ns;
-        if (per_pass < 1) per_pass = 1;
+        while (per_pass > 1 && pb_center_smem_bytes(n_planes, per_pass, 1024, false) > 200 * 1024) --per_pass;
     }
+    // 256-bit global stores need 32-byte aligned planes (chromosome offsets are multiples of 16384 bins)
+    bool direct_ok = true;
+    for (double *p : {out_plus, out_minus, out_any})
+        if (p && ((uintptr_t)p & 31)) direct_ok = false;
+    if (const char *e = getenv("PB_CENTER_EPT")) {       // measurement overrides (profiles/NOTES)
+        const int v = atoi(e);
+        if ((v == 4 || v == 8 || v == 16) && pb_center_smem_bytes(n_planes, per_pass, v * kCThreads, false) <= 200 * 1024) ept = v;
+    }
+    if (const char *e = getenv("PB_CENTER_DIRECT")) direct_ok = direct_ok && atoi(e) != 0;
     const int tile_bins = ept * kCThreads;
     const int64_t n_tiles = layout->total_bins / tile_bins;
     const int lookback = (b.max_block_len + tile_bins - 1) / tile_bins;
@@ -286,11 +399,14 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, ws, stream);
     if (rc) return rc;
     pb_timing_begin(stream);
-    if (ept == 8)
-        rc = launch_center<8>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, ws,
+    if (ept == 16)
+        rc = launch_center<16>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, direct_ok, ws,
+                               out_plus, out_minus, out_any, stream);
+    else if (ept == 8)
+        rc = launch_center<8>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, direct_ok, ws,
                               out_plus, out_minus, out_any, stream);
     else
-        rc = launch_center<4>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, ws,
+        rc = launch_center<4>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, direct_ok, ws,
                               out_plus, out_minus, out_any, stream);
     pb_timing_end(stream);
     if (rc) return rc;
