@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=200_000_000, help="reads per GPU")
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of hg38 chromosome lengths")
     ap.add_argument("--regions", type=int, default=60_000)
+    ap.add_argument("--e2e-format", default="delta8", choices=["delta8", "wire16"],
+                    help="host transfer format of the end-to-end leg (unspliced batches)")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="upload chunks overlapped with mapping in the e2e leg")
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5", "peaks"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
@@ -92,6 +95,28 @@ class ClockSampler(object):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU before any pinned host buffer is
+    allocated, so that the e2e upload reads host memory of the GPU's own NUMA node (first touch).
+    Returns a short description for the JSON line; silently a no-op where NVML or affinity is missing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + bit for w, word in enumerate(words) for bit in range(64) if (word >> bit) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to GPU %d" % (len(cpus), idx)
+    except Exception as exc:      # measurement nicety only
+        return "unbound (%s)" % type(exc).__name__
+    return "unbound"
 
 
 def peaks():
@@ -384,6 +409,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
+    numa = bind_to_gpu_numa_node(local_rank) if args.impl != "reference" else "all host threads"
     if world > 1 and args.impl != "reference":
         dist.init_process_group("nccl", device_id=torch.device(device))
 
@@ -403,7 +429,7 @@ def main():
     workload = ("%s, %d synthetic reads/GPU, %d chromosomes (%d bins, '+' and '-' planes), %d region counts"
                 % (W["name"], n_reads, len(chroms), layout.total_bins, ann.n_tx))
     config = {"workload": workload, "reads_per_gpu": n_reads, "genome_bins": int(layout.total_bins),
-              "regions": ann.n_tx, "sharding": "read-range per GPU; NCCL all-reduce of region tables" if world > 1
+              "regions": ann.n_tx, "host_affinity": numa, "sharding": "read-range per GPU; NCCL all-reduce of region tables" if world > 1
               else "single GPU", "l2": "inputs (%.2f GB) and outputs (%.1f GB) larger than the 126 MB L2"
               % (8 * n_reads / 1e9, (16 if is_center else 8) * layout.total_bins / 1e9)}
 
@@ -490,22 +516,23 @@ def main():
     # The caller holds the batch in pinned host memory in the transfer format the host decoder
     # emits: wire16 (4 B/read) for unspliced batches, the plain SoA otherwise.  Every step copies it
     # to the device, expands it, runs the same kernels and reads the region table back.
-    from plastid_b200.batch import Wire16Batch, Wire16Receiver
+    from plastid_b200.batch import Wire16Batch, Wire16Receiver, Delta8Batch, Delta8Receiver
     h_sums = torch.empty(ann.n_tx, dtype=torch.float64).pin_memory()
     h_live = torch.empty(ann.n_tx, dtype=torch.int64).pin_memory()
     d2h = h_sums.numel() * 8 + h_live.numel() * 8
     use_wire16 = dbatch.blk_off is None
     if use_wire16:
-        wire = Wire16Batch.from_batch(synth.device_batch_to_host(dbatch, chroms, lens))
+        WireBatch, WireReceiver = (Delta8Batch, Delta8Receiver) if args.e2e_format == "delta8" else (Wire16Batch, Wire16Receiver)
+        wire = WireBatch.from_batch(synth.device_batch_to_host(dbatch, chroms, lens))
         pinned = wire.pinned()
-        receiver = Wire16Receiver(wire, device)
+        receiver = WireReceiver(wire, device)
         h2d = wire.nbytes
-        chunks = Wire16Receiver.plan_chunks(wire, layout, 8)
+        chunks = WireReceiver.plan_chunks(wire, layout, args.e2e_chunks)
         copy_stream = torch.cuda.Stream(device=device)
         from plastid_b200.genome_array import map_wire16_streamed
 
         def e2e_step():
-            # upload in 8 chunks on a copy stream; each chunk's bins are mapped as soon as it has landed
+            # upload in chunks on a copy stream; each chunk's bins are mapped as soon as it has landed
             map_wire16_streamed(receiver, pinned, chunks, layout, fac, sf, ("+", "-"), planes, copy_stream)
             s, l = region_sums(planes, table)
             if world > 1:
@@ -603,7 +630,8 @@ def main():
             "region_counts_per_sec": region_rate,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t.item()), "steps": e2e_steps,
-                    "host_format": "wire16 (4 B/read), 8-chunk upload overlapped with pb_map_point_range"
+                    "host_format": ("%s (%.2f B/read), %d-chunk upload overlapped with pb_map_point_range"
+                                    % (args.e2e_format, h2d / max(n_reads, 1), len(chunks)))
                     if use_wire16 else "SoA (8 B/read + blocks)"},
             "gpu_launches": len(kernels_per_step) * args.steps, "kernels_per_step": kernels_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}

@@ -168,6 +168,19 @@ int pb_unpack_wire16(const uint16_t *start_lo, const uint16_t *meta16, const int
                      const int32_t *seg_base, int64_t n_seg, int64_t read_begin, int64_t read_end,
                      int32_t *ref_start_out, uint32_t *meta_out, void *stream);
 
+/* delta8: 2-byte-per-read transfer format of a sorted unspliced batch.  Reads are grouped in blocks of
+ * 128 consecutive reads.  dstart uint8[N128] = start - start of the previous read (0 for the first read of
+ * a block, whose start is blk_base int32[n_blk]); code uint8[N128] = index into dict uint32[256] of
+ * full meta words (N128 = N rounded up to 128).  dstart == 255 marks an exception (delta >= 255, a
+ * chromosome change, a meta word outside the dictionary): its start and meta word are exc_start /
+ * exc_meta at ordinal blk_exc_off[B] + (exceptions before it within block B); blk_exc_off
+ * uint32[n_blk+1].  Expands reads [read_begin, read_end) (read_begin a multiple of 128) into
+ * ref_start / meta of the SoA batch; every read before read_end must be < n_reads. */
+int pb_unpack_delta8(const uint8_t *dstart, const uint8_t *code, const int32_t *blk_base,
+                     const uint32_t *blk_exc_off, const int32_t *exc_start, const uint32_t *exc_meta,
+                     const uint32_t *dict, int64_t n_reads, int64_t read_begin, int64_t read_end,
+                     int32_t *ref_start_out, uint32_t *meta_out, void *stream);
+
 /* 5' / 3' / variable-offset mapping of a whole batch into dense uint32 planes.
  * `planes` selects which of out_plus/out_minus/out_any are produced; every bin of a selected
  * plane is written (no prior memset needed).  stats: device uint64[PB_NSTATS], accumulated. */

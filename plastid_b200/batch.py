@@ -294,6 +294,181 @@ class Wire16Receiver(object):
         return ev
 
 
+class Delta8Batch(object):
+    """2-byte-per-read host format of a sorted unspliced batch (``pb_unpack_delta8`` in
+    ``include/plastid_b200.h``): one byte of start delta + one byte of meta-dictionary index per
+    read, blocks of 128 reads with an absolute base, an exception list for everything that does not
+    fit (delta >= 255, chromosome changes, rare meta words)."""
+    BLOCK = 128
+
+    def __init__(self, chroms, chrom_len, chrom_read_off, n_reads, dstart, code, blk_base, blk_exc_off,
+                 exc_start, exc_meta, meta_dict, read_bin16k, max_span, mapped):
+        self.chroms, self.chrom_len = list(chroms), np.asarray(chrom_len, dtype=np.int64)
+        self.chrom_read_off = np.ascontiguousarray(chrom_read_off, dtype=np.int64)
+        self.n_reads = int(n_reads)
+        self.dstart = np.ascontiguousarray(dstart, dtype=np.uint8)
+        self.code = np.ascontiguousarray(code, dtype=np.uint8)
+        self.blk_base = np.ascontiguousarray(blk_base, dtype=np.int32)
+        self.blk_exc_off = np.ascontiguousarray(blk_exc_off, dtype=np.uint32)
+        self.exc_start = np.ascontiguousarray(exc_start, dtype=np.int32)
+        self.exc_meta = np.ascontiguousarray(exc_meta, dtype=np.uint32)
+        self.meta_dict = np.ascontiguousarray(meta_dict, dtype=np.uint32)
+        # chromosome index and start of the first read of every block (chunk planning only; stays on the host)
+        self.blk_chrom, self.blk_first_start = read_bin16k
+        self.max_span, self.mapped = int(max_span), int(mapped)
+
+    def __len__(self):
+        return self.n_reads
+
+    @property
+    def nbytes(self):
+        """Bytes that cross PCIe per batch."""
+        return (self.dstart.nbytes + self.code.nbytes + self.blk_base.nbytes + self.blk_exc_off.nbytes
+                + self.exc_start.nbytes + self.exc_meta.nbytes + self.meta_dict.nbytes + self.chrom_read_off.nbytes)
+
+    @classmethod
+    def from_batch(cls, hb):
+        if hb.blk is not None:
+            raise ValueError("delta8 carries single-block reads only")
+        n, K = len(hb), cls.BLOCK
+        n_blk = (n + K - 1) // K
+        start = hb.ref_start.astype(np.int64)
+        meta = hb.meta.astype(np.uint32)
+        chrom_of_read = np.repeat(np.arange(len(hb.chroms), dtype=np.int32), np.diff(hb.chrom_read_off))
+        delta = np.zeros(n, dtype=np.int64)
+        if n > 1:
+            delta[1:] = start[1:] - start[:-1]
+        first_of_chrom = np.zeros(n, dtype=bool)
+        if n:
+            first_of_chrom[0] = True
+            first_of_chrom[1:] = chrom_of_read[1:] != chrom_of_read[:-1]
+        first_of_blk = np.zeros(n, dtype=bool)
+        first_of_blk[::K] = True
+        delta[first_of_blk] = 0
+        # dictionary: the 255 most frequent meta words (index 255 is never used as a code)
+        words, counts = np.unique(meta, return_counts=True)
+        order = np.argsort(-counts, kind="stable")[:255]
+        dict_words = np.sort(words[order])
+        pos = np.searchsorted(dict_words, meta)
+        pos_c = np.minimum(pos, max(len(dict_words) - 1, 0))
+        in_dict = (dict_words[pos_c] == meta) if len(dict_words) else np.zeros(n, dtype=bool)
+        exc = (delta >= 255) | (delta < 0) | (first_of_chrom & ~first_of_blk) | ~in_dict
+        dstart = np.zeros(n_blk * K, dtype=np.uint8)
+        code = np.zeros(n_blk * K, dtype=np.uint8)
+        dstart[:n] = np.where(exc, 255, np.clip(delta, 0, 254)).astype(np.uint8)
+        code[:n] = np.where(in_dict, pos_c, 0).astype(np.uint8)
+        meta_dict = np.zeros(256, dtype=np.uint32)
+        meta_dict[:len(dict_words)] = dict_words
+        exc_per_blk = np.add.reduceat(exc.astype(np.int64), np.arange(0, n, K)) if n else np.zeros(0, dtype=np.int64)
+        blk_exc_off = np.zeros(n_blk + 1, dtype=np.int64)
+        np.cumsum(exc_per_blk, out=blk_exc_off[1:])
+        if blk_exc_off[-1] >= (1 << 32):
+            raise ValueError("delta8: too many exceptions")
+        return cls(hb.chroms, hb.chrom_len, hb.chrom_read_off, n, dstart, code, hb.ref_start[::K],
+                   blk_exc_off, hb.ref_start[exc], meta[exc], meta_dict,
+                   (chrom_of_read[::K].copy(), hb.ref_start[::K].astype(np.int64)), hb.max_span, hb.mapped)
+
+    def pinned(self):
+        import torch
+
+        def pin(a, view=None):
+            a = a.view(view) if view is not None else a
+            return torch.from_numpy(a if len(a) else np.zeros(1, dtype=a.dtype)).pin_memory()
+        return dict(dstart=pin(self.dstart), code=pin(self.code), blk_base=pin(self.blk_base),
+                    blk_exc_off=pin(self.blk_exc_off, np.int32), exc_start=pin(self.exc_start),
+                    exc_meta=pin(self.exc_meta, np.int32), meta_dict=pin(self.meta_dict, np.int32),
+                    chrom_read_off=pin(self.chrom_read_off))
+
+
+class Delta8Receiver(object):
+    """Device-side landing buffers for delta8 transfers + the expanded :class:`DeviceBatch`; same
+    interface as :class:`Wire16Receiver` (``plan_chunks`` / ``receive_chunk`` / ``_unpack``)."""
+
+    def __init__(self, wire, device):
+        import torch
+        n, K = len(wire), Delta8Batch.BLOCK
+        self.wire = wire
+        n_blk = len(wire.blk_base)
+        self.dstart = torch.empty(n_blk * K, dtype=torch.uint8, device=device)
+        self.code = torch.empty(n_blk * K, dtype=torch.uint8, device=device)
+        self.blk_base = torch.empty(max(n_blk, 1), dtype=torch.int32, device=device)
+        self.blk_exc_off = torch.empty(n_blk + 1, dtype=torch.int32, device=device)
+        self.exc_start = torch.empty(max(len(wire.exc_start), 1), dtype=torch.int32, device=device)
+        self.exc_meta = torch.empty(max(len(wire.exc_meta), 1), dtype=torch.int32, device=device)
+        self.meta_dict = torch.empty(256, dtype=torch.int32, device=device)
+        self.batch = DeviceBatch(n, len(wire.chroms), wire.max_span, torch.empty(n, dtype=torch.int32, device=device),
+                                 torch.empty(n, dtype=torch.int32, device=device),
+                                 torch.empty(len(wire.chroms) + 1, dtype=torch.int64, device=device))
+
+    def receive(self, pinned):
+        """Enqueue the H2D copies of one whole batch and its expansion; returns the DeviceBatch."""
+        self._receive_tables(pinned)
+        n = self.batch.n_reads
+        self._copy_range(pinned, 0, n)
+        self._unpack(0, n)
+        return self.batch
+
+    def _receive_tables(self, pinned):
+        self.meta_dict.copy_(pinned["meta_dict"], non_blocking=True)
+        self.batch.chrom_read_off.copy_(pinned["chrom_read_off"], non_blocking=True)
+
+    def _copy_range(self, pinned, a, b):
+        """Everything reads [a,b) need (a a multiple of 128): both byte streams, block tables, exceptions."""
+        K = Delta8Batch.BLOCK
+        if b <= a:
+            return
+        b0, b1 = a // K, (b + K - 1) // K
+        self.dstart[b0 * K:b1 * K].copy_(pinned["dstart"][b0 * K:b1 * K], non_blocking=True)
+        self.code[b0 * K:b1 * K].copy_(pinned["code"][b0 * K:b1 * K], non_blocking=True)
+        self.blk_base[b0:b1].copy_(pinned["blk_base"][b0:b1], non_blocking=True)
+        self.blk_exc_off[b0:b1 + 1].copy_(pinned["blk_exc_off"][b0:b1 + 1], non_blocking=True)
+        e0, e1 = int(self.wire.blk_exc_off[b0]), int(self.wire.blk_exc_off[b1])
+        if e1 > e0:
+            self.exc_start[e0:e1].copy_(pinned["exc_start"][e0:e1], non_blocking=True)
+            self.exc_meta[e0:e1].copy_(pinned["exc_meta"][e0:e1], non_blocking=True)
+
+    def _unpack(self, a, b):
+        from . import _lib
+        _lib.check(_lib.lib().pb_unpack_delta8(_lib.ptr(self.dstart), _lib.ptr(self.code), _lib.ptr(self.blk_base),
+                                               _lib.ptr(self.blk_exc_off), _lib.ptr(self.exc_start),
+                                               _lib.ptr(self.exc_meta), _lib.ptr(self.meta_dict),
+                                               self.batch.n_reads, int(a), int(b),
+                                               _lib.ptr(self.batch.ref_start), _lib.ptr(self.batch.meta),
+                                               _lib.stream_ptr()))
+
+    @staticmethod
+    def plan_chunks(wire, layout, n_chunks):
+        """Cut the sorted batch at block (128-read) boundaries into ``n_chunks`` pieces of about equal
+        read count: ``[(read_a, read_b, bin_a, bin_b), ...]``.  bin_b is the global bin of read_b's
+        start rounded down to the layout granularity: every read at or beyond read_b starts at or
+        beyond it, so bins below bin_b are final once reads [0, read_b) have landed.  Ranges that
+        would be empty are merged into the next chunk."""
+        from . import _lib
+        K, n = Delta8Batch.BLOCK, len(wire)
+        n_blk = len(wire.blk_base)
+        cuts = sorted(set(int((j * n_blk) // n_chunks) for j in range(1, n_chunks)) - {0, n_blk})
+        out, read_a, bin_a = [], 0, 0
+        for cb in cuts:
+            c = int(wire.blk_chrom[cb])
+            g = int(layout.chrom_bin_off[c]) + int(wire.blk_first_start[cb])
+            bin_b = (g // _lib.PB_LAYOUT_ALIGN) * _lib.PB_LAYOUT_ALIGN
+            if bin_b <= bin_a:
+                continue
+            out.append((read_a, cb * K, bin_a, bin_b))
+            read_a, bin_a = cb * K, bin_b
+        out.append((read_a, n, bin_a, int(layout.total_bins)))
+        return out
+
+    def receive_chunk(self, pinned, a, b, copy_stream):
+        """H2D of reads [a,b) on ``copy_stream``; returns the event the compute stream must wait for."""
+        import torch
+        with torch.cuda.stream(copy_stream):
+            self._copy_range(pinned, a, b)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+
 class BatchRead(object):
     """Duck-typed stand-in for ``pysam.AlignedSegment`` built from one batch row."""
     __slots__ = ("batch", "index")

@@ -135,6 +135,83 @@ pb_unpack_wire16_kernel(const uint16_t *__restrict__ start_lo, const uint16_t *_
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// delta8: 2-byte-per-read host format of a sorted unspliced batch -> the SoA
+// ----------------------------------------------------------------------------------------
+// Reads are coordinate-sorted, so consecutive starts differ by little: per read one byte of start
+// delta and one byte indexing a 255-entry dictionary of meta words.  Reads are grouped in blocks of
+// 128; blk_base[B] is the start of the block's first read.  dstart == 255 marks an exception (delta
+// >= 255, first read of a chromosome, meta word not in the dictionary): start and meta come from
+// exc_start / exc_meta at ordinal blk_exc_off[B] + (exceptions before it in the block).
+// One warp expands one block, 4 consecutive reads per lane: ballots give the exception ordinals, a
+// segmented warp scan (exceptions reset the running start) the absolute starts; 16-byte stores.
+__global__ void __launch_bounds__(256)
+pb_unpack_delta8_kernel(const uint32_t *__restrict__ dstart4, const uint32_t *__restrict__ code4,
+                        const int32_t *__restrict__ blk_base, const uint32_t *__restrict__ blk_exc_off,
+                        const int32_t *__restrict__ exc_start, const uint32_t *__restrict__ exc_meta,
+                        const uint32_t *__restrict__ dict, int64_t n_reads, int64_t blk_begin, int64_t blk_end,
+                        int32_t *__restrict__ ref_start, uint32_t *__restrict__ meta)
+{
+    __shared__ uint32_t s_dict[256];
+    s_dict[threadIdx.x] = __ldg(dict + threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t B = blk_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (B >= blk_end) return;
+    const int64_t i0 = B * 128 + lane * 4;
+    const uint32_t d4 = __ldg(dstart4 + B * 32 + lane), c4 = __ldg(code4 + B * 32 + lane);
+    uint32_t d[4], ord[4];
+    bool ex[4];
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t before = __ldg(blk_exc_off + B), own = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        d[j] = (d4 >> (8 * j)) & 0xffu;
+        ex[j] = d[j] == 255u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) before += __popc(__ballot_sync(0xffffffffu, ex[j]) & lt);
+    int32_t es[4];
+    uint32_t m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ord[j] = before + own;
+        own += ex[j];
+        es[j] = ex[j] ? __ldg(exc_start + ord[j]) : 0;
+        m[j] = ex[j] ? __ldg(exc_meta + ord[j]) : s_dict[(c4 >> (8 * j)) & 0xffu];
+    }
+    // lane summary (f = saw an absolute start, v = running start or sum of deltas)
+    bool f = false;
+    int32_t v = 0;
+    if (lane == 0) { f = true; v = __ldg(blk_base + B); d[0] = ex[0] ? d[0] : 0u; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (ex[j]) { f = true; v = es[j]; } else v += (int32_t)d[j];
+    }
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const int32_t pv = __shfl_up_sync(0xffffffffu, v, dd);
+        const bool pf = __shfl_up_sync(0xffffffffu, (int)f, dd) != 0;
+        if (lane >= dd && !f) { v += pv; f = pf; }
+    }
+    int32_t cur = __shfl_up_sync(0xffffffffu, v, 1);   // inclusive result of the lane before = carry-in
+    if (lane == 0) cur = __ldg(blk_base + B);
+    int32_t out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (ex[j]) cur = es[j]; else cur += (int32_t)d[j];
+        out[j] = cur;
+    }
+    if (i0 + 4 <= n_reads) {
+        *reinterpret_cast<int4 *>(ref_start + i0) = make_int4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<uint4 *>(meta + i0) = make_uint4(m[0], m[1], m[2], m[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < n_reads) { ref_start[i0 + j] = out[j]; meta[i0 + j] = m[j]; }
+    }
+}
+
 }  // namespace
 
 extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
@@ -191,6 +268,30 @@ extern "C" int pb_unpack_wire16(const uint16_t *start_lo, const uint16_t *meta16
     const int64_t warps = (read_end - read_begin + 1023) / 1024;
     const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
     pb_unpack_wire16_kernel<<<grid, 256, 0, stream>>>(start_lo, meta16, seg_off, seg_base, n_seg, read_begin, n_reads, ref_start_out, meta_out);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_unpack_delta8(const uint8_t *dstart, const uint8_t *code, const int32_t *blk_base,
+                                const uint32_t *blk_exc_off, const int32_t *exc_start, const uint32_t *exc_meta,
+                                const uint32_t *dict, int64_t n_reads, int64_t read_begin, int64_t read_end,
+                                int32_t *ref_start_out, uint32_t *meta_out, void *stream)
+{
+    if (!dstart || !code || !blk_base || !blk_exc_off || !dict || !ref_start_out || !meta_out) {
+        pb_set_error("pb_unpack_delta8: null argument"); return PB_EINVAL;
+    }
+    if (read_begin < 0 || read_end < read_begin || read_end > n_reads || (read_begin & 127)) {
+        pb_set_error("pb_unpack_delta8: bad read range (begin must be a multiple of 128)"); return PB_EINVAL;
+    }
+    if ((((uintptr_t)dstart | (uintptr_t)code) & 3) || (((uintptr_t)ref_start_out | (uintptr_t)meta_out) & 15)) {
+        pb_set_error("pb_unpack_delta8: streams must be 4-byte aligned, outputs 16-byte aligned"); return PB_EINVAL;
+    }
+    if (read_end == read_begin) return PB_OK;
+    const int64_t b0 = read_begin >> 7, b1 = (read_end + 127) >> 7;
+    const int64_t grid = (b1 - b0 + 7) / 8;   // 8 warps = 8 blocks of 128 reads per CTA
+    pb_unpack_delta8_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint32_t *)dstart, (const uint32_t *)code, blk_base, blk_exc_off, exc_start, exc_meta, dict,
+        read_end, b0, b1, ref_start_out, meta_out);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

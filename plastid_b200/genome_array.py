@@ -111,7 +111,7 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
 
 def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=None, strands=("+", "-"),
                         planes=None, copy_stream=None):
-    """Upload a pinned wire16 batch chunk by chunk on ``copy_stream`` and map each chunk's bin range
+    """Upload a pinned wire16 / delta8 batch (``Wire16Receiver`` / ``Delta8Receiver``) chunk by chunk on ``copy_stream`` and map each chunk's bin range
     (``pb_map_point_range``) on the current stream as soon as its reads have landed, so the PCIe
     transfer and the mapping overlap.  Point rules only.  Returns the planes (stats on device)."""
     import torch

@@ -67,3 +67,23 @@ def oracle_planes(hb, kind, strand, **kw):
         out.append(vec)
         dropped += d
     return out, dropped
+
+
+def delta8_decode(w):
+    """Plain-numpy statement of the delta8 format (include/plastid_b200.h, pb_unpack_delta8): test
+    checker for the host encoder, independent of the device kernel."""
+    n, K = w.n_reads, 128
+    start = np.zeros(n, dtype=np.int64)
+    meta = np.zeros(n, dtype=np.uint32)
+    for B in range(len(w.blk_base)):
+        cur, e = int(w.blk_base[B]), int(w.blk_exc_off[B])
+        for i in range(B * K, min((B + 1) * K, n)):
+            if w.dstart[i] == 255:
+                cur, meta[i] = int(w.exc_start[e]), w.exc_meta[e]
+                e += 1
+            else:
+                cur += int(w.dstart[i]) if i > B * K else 0
+                meta[i] = w.meta_dict[w.code[i]]
+            start[i] = cur
+        assert e == int(w.blk_exc_off[B + 1])
+    return start, meta

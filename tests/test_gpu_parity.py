@@ -491,6 +491,43 @@ def test_streamed_upload_matches_whole_batch(small_world, cuda_device, n_chunks)
     assert (plane_chrom(planes, w["layout"], "-", 1) == exp).all()
 
 
+def test_delta8_unpack_on_device(cuda_device):
+    """2-byte transfer format: device expansion == the batch it was packed from, incl. exceptions
+    (large gaps, chromosome changes inside a block, > 255 distinct meta words) and a ragged tail."""
+    from plastid_b200.batch import Delta8Batch, Delta8Receiver
+    from test_host_logic import _delta8_world
+    for n_reads, rare in ((30000, True), (30001, False), (127, False), (3, False)):
+        chroms, lens, hb = _delta8_world(n_reads, rare)
+        wire = Delta8Batch.from_batch(hb)
+        rx = Delta8Receiver(wire, cuda_device)
+        rx.batch.ref_start.fill_(-7)
+        db = rx.receive(wire.pinned())
+        assert (db.ref_start.cpu().numpy() == hb.ref_start).all()
+        assert (db.meta.cpu().numpy().view(np.uint32) == hb.meta).all()
+        assert (db.chrom_read_off.cpu().numpy() == hb.chrom_read_off).all()
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3, 8])
+def test_delta8_streamed_upload_matches_whole_batch(small_world, cuda_device, n_chunks):
+    import torch
+    from plastid_b200.batch import Delta8Batch, Delta8Receiver
+    from plastid_b200.genome_array import map_wire16_streamed
+    w = small_world
+    wire = Delta8Batch.from_batch(w["hb"])
+    rx = Delta8Receiver(wire, cuda_device)
+    rx.batch.ref_start.fill_(-7)                  # poison: nothing may be read before it has landed
+    rx.batch.meta.fill_(0)
+    chunks = Delta8Receiver.plan_chunks(wire, w["layout"], n_chunks)
+    fac = pb.VariableFivePrimeMapFactory(synth.RIBO_OFFSETS)
+    planes = map_wire16_streamed(rx, wire.pinned(), chunks, w["layout"], fac, pb.SizeFilterFactory(20, 38),
+                                 ("+", "-", "."))
+    torch.cuda.synchronize()
+    ref = map_batch(w["dbatch"], w["layout"], fac, pb.SizeFilterFactory(20, 38), strands=("+", "-", "."))
+    for s in ("+", "-", "."):
+        assert torch.equal(planes.planes[s], ref.planes[s])
+    assert (planes.stats_dev.cpu().numpy() == ref.stats).all()
+
+
 def test_pileup_tile_is_split_into_overflow_jobs(cuda_device):
     """> 32768 candidate reads in one 4096-bin tile: the tile job keeps the first slice, the rest are
     added by pb_point_overflow_kernel with TMA bulk reductions — still bit-exact, stats included."""

@@ -306,6 +306,66 @@ def test_wire16_host_format_round_trip():
         Wire16Batch.from_batch(spliced)
 
 
+def _delta8_world(n_reads=30000, rare_meta=True):
+    chroms, lens = ["a", "b", "c", "d"], np.array([200_000, 65536, 70_000, 3_000_000])
+    ann = synth.make_annotation(chroms, lens, 40, seed=1, exons=(1, 2), exon_len=(200, 600), intron_len=(50, 400))
+    hb = synth.device_batch_to_host(synth.riboseq_reads(ann, n_reads, seed=3, device="cpu"), chroms, lens)
+    hb = hb.with_drop_mask(np.arange(len(hb)) % 17 == 0)
+    if rare_meta:      # > 255 distinct meta words: the rare ones must travel as exceptions
+        meta = hb.meta.copy()
+        odd = np.arange(len(hb)) % 29 == 0
+        meta[odd] = (meta[odd] & ~np.uint32(0xFFFF)) | (300 + (np.arange(odd.sum()) % 700)).astype(np.uint32)
+        from plastid_b200.batch import AlignmentBatch
+        hb = AlignmentBatch(hb.chroms, hb.chrom_len, hb.ref_start, meta, hb.chrom_read_off, max_span=2000)
+    return chroms, lens, hb
+
+
+def test_delta8_host_format_round_trip():
+    from plastid_b200.batch import Delta8Batch
+    from helpers import delta8_decode
+    chroms, lens, hb = _delta8_world()
+    w = Delta8Batch.from_batch(hb)
+    assert len(w.dstart) % 128 == 0 and len(w.dstart) == len(w.code) >= len(hb)
+    assert len(np.unique(hb.meta)) > 255 and len(w.exc_start) == int(w.blk_exc_off[-1]) > 0
+    start, meta = delta8_decode(w)
+    assert (start == hb.ref_start).all() and (meta == hb.meta).all()
+    # the common case is 2 bytes per read + block tables; exceptions stay a small share
+    _c, _l, plain = _delta8_world(rare_meta=False)
+    wp = Delta8Batch.from_batch(plain)
+    assert wp.nbytes < 0.36 * (plain.ref_start.nbytes + plain.meta.nbytes)
+    s2, m2 = delta8_decode(wp)
+    assert (s2 == plain.ref_start).all() and (m2 == plain.meta).all()
+    # degenerate batches: empty, one read, exactly one block
+    for n in (0, 1, 128, 129):
+        sub = pb.batch_from_arrays(["a", "b"], [1000, 1000], [0] * (n // 2) + [1] * (n - n // 2),
+                                   sorted(range(n // 2)) + sorted(range(n - n // 2)), [30] * n, [i % 2 for i in range(n)])
+        ws = Delta8Batch.from_batch(sub)
+        s3, m3 = delta8_decode(ws)
+        assert (s3 == sub.ref_start).all() and (m3 == sub.meta).all()
+    spliced = synth.device_batch_to_host(synth.rnaseq_reads(chroms, lens, 2000, seed=2, device="cpu"), chroms, lens)
+    with pytest.raises(ValueError):
+        Delta8Batch.from_batch(spliced)
+
+
+def test_delta8_chunk_plan_covers_reads_and_bins():
+    from plastid_b200.batch import Delta8Batch, Delta8Receiver
+    chroms, lens = synth.human_like_genome(0.004)
+    ann = synth.make_annotation(chroms, lens, 300, seed=1, exons=(1, 2), exon_len=(200, 600), intron_len=(50, 400))
+    hb = synth.device_batch_to_host(synth.riboseq_reads(ann, 50000, seed=3, device="cpu"), chroms, lens)
+    wire, lay = Delta8Batch.from_batch(hb), pb.GenomeLayout(chroms, lens)
+    c_of = np.searchsorted(hb.chrom_read_off, np.arange(len(hb)), side="right") - 1
+    g = lay.chrom_bin_off[c_of] + hb.ref_start
+    for k in (1, 2, 8, 64):
+        plan = Delta8Receiver.plan_chunks(wire, lay, k)
+        assert 1 <= len(plan) <= k and plan[0][0] == 0 and plan[0][2] == 0
+        assert plan[-1][1] == len(wire) and plan[-1][3] == lay.total_bins
+        for (a, b, x, y), (a2, b2, x2, y2) in zip(plan[:-1], plan[1:]):
+            assert b == a2 and y == x2 and x % _lib.PB_LAYOUT_ALIGN == 0 and a % 128 == 0 and a < b and x < y
+        for a, b, x, y in plan:
+            # bins below y are final once reads [0, b) have landed: nothing later starts below y
+            assert (g[b:] >= y).all()
+
+
 def test_wire16_chunk_plan_covers_reads_and_bins():
     from plastid_b200.batch import Wire16Batch, Wire16Receiver
     chroms, lens = synth.human_like_genome(0.004)
