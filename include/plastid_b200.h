@@ -30,6 +30,10 @@
  *   pb_window_normalize  denominators / row selection / normalisation  plastid/bin/metagene.py:918-924
  *   pb_column_profile  median | mean | sum per column      plastid/bin/metagene.py:934-953,
  *                                                          plastid/bin/psite.py:204-234
+ *   pb_mask_chains   GenomeHash.get_overlapping_features + SegmentChain.add_masks for all regions
+ *                                                          plastid/genomics/genome_hash.py:259-436,
+ *                                                          plastid/genomics/roitools.pyx:2213-2301
+ *   pb_export_runs   BAMGenomeArray.to_variable_step / to_bedgraph  plastid/genomics/genome_array.py:990-1111
  *   pb_phase_sums    sub-codon phase accumulation          plastid/bin/phase_by_size.py:165-235
  *   pb_stratified_windows  per-read-length window matrices plastid/bin/psite.py:176-199,
  *                                                          plastid/bin/phase_by_size.py:186-194
@@ -243,6 +247,20 @@ int pb_region_sums(const void *const *planes, int vec_dtype,
                    const uint8_t *mask_bits, const int64_t *mask_off,
                    double *sums, int64_t *live_len, void *stream);
 
+/* Mask pipeline: mask bits of every chain from one interval set, replacing the per-region
+ * GenomeHash.get_overlapping_features + SegmentChain.add_masks of counts_in_region.py:114-115
+ * (plastid/genomics/genome_hash.py:259-436, plastid/genomics/roitools.pyx:2213-2301).
+ * mask_start/mask_end int64[M]: mask intervals in global-bin coordinates, merged and sorted within each
+ * strand class; class k ('+','-','.' = 0,1,2, the chain_plane numbering) owns
+ * [mask_class_off[k], mask_class_off[k+1]) (int64[4]).  For every chain c, bit (mask_off[c] + j) of
+ * mask_bits is OR-ed with "the j-th chain position (genomic order) lies in a mask interval of the chain's
+ * class".  mask_bits: caller-initialised (zeros, or bits from add_masks), 4-byte aligned, padded to a
+ * multiple of 4 bytes; the layout pb_region_sums / pb_gather_windows / pb_stratified_windows read. */
+int pb_mask_chains(const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                   const uint8_t *chain_plane, int64_t n_chains,
+                   const int64_t *mask_start, const int64_t *mask_end, const int64_t *mask_class_off,
+                   const int64_t *mask_off, uint8_t *mask_bits, void *stream);
+
 /* Window matrices (metagene / psite): row r = chain r laid 5'->3' (reversed when
  * chain_reverse[r]) starting at column row_col[r] of a width-W row.  matrix: double[n*W]
  * (NaN where no chain position), maskmat: uint8[n*W] (1 = masked or uncovered). */
@@ -296,6 +314,18 @@ int pb_phase_sums(const void *const *planes, int vec_dtype,
                   const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
                   const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
                   int32_t codon_front, int32_t codon_back, double *out, void *stream);
+
+/* Track export: BAMGenomeArray.to_variable_step / to_bedgraph (plastid/genomics/genome_array.py:990-1111)
+ * as a stream compaction of one chromosome's count vector vec[0..n_bins) (vec_dtype 0 = uint32, 1 =
+ * float64).  mode 0 (variableStep): one record per non-zero bin — out_start = 0-based position, out_val
+ * its value.  mode 1 (bedGraph): one record per run of equal positive values, runs cut at multiples of
+ * `window` like the reference's window loop — out_start/out_end = [start, end), out_val the value.
+ * Records come out in ascending position.  *n_out (device) receives the number of records; they are
+ * written only when it is <= capacity, so a call with capacity 0 just counts. */
+size_t pb_export_workspace_bytes(int64_t n_bins);
+int pb_export_runs(const void *vec, int vec_dtype, int64_t n_bins, int64_t window, int mode,
+                   int64_t capacity, int64_t *out_start, int64_t *out_end, double *out_val,
+                   int64_t *n_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Roofline probe (the atomic peak a scatter-add design would be bound by; no
  * reference counterpart, not on the product path): n_updates `red.global.add.u32` into

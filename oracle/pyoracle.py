@@ -394,6 +394,47 @@ class OracleBAMGenomeArray(object):
             return roi.get_counts(self)
         return self.get_reads_and_counts(roi, roi_order=roi_order)[1]
 
+    def to_variable_step(self, fh, trackname, strand, window_size=100000, **kwargs):   # :990-1037
+        assert strand in self.strands()
+        fh.write("track type=wiggle_0 name=%s" % trackname)
+        for k, v in sorted(kwargs.items(), key=lambda x: x[0]):
+            fh.write(" %s=%s" % (k, v))
+        fh.write("\n")
+        for chrom in sorted(self.chroms()):
+            my_size = self.lengths()[chrom]
+            fh.write("variableStep chrom=%s span=1\n" % chrom)
+            for my_start in range(0, my_size, window_size):
+                my_end = min(my_start + window_size, my_size)
+                my_counts = self.get(Seg(chrom, my_start, my_end, strand), roi_order=False)
+                if my_counts.sum() > 0:
+                    for idx in my_counts.nonzero()[0]:
+                        fh.write("%s\t%s\n" % (my_start + idx + 1, my_counts[idx]))
+
+    def to_bedgraph(self, fh, trackname, strand, window_size=100000, **kwargs):        # :1039-1111
+        assert strand in self.strands()
+        assert window_size > 0
+        fh.write("track type=bedGraph name=%s" % trackname)
+        for k, v in sorted(kwargs.items(), key=lambda x: x[0]):
+            fh.write(" %s=%s" % (k, v))
+        fh.write("\n")
+        for chrom in sorted(self.chroms()):
+            my_size = self.lengths()[chrom]
+            for my_start in range(0, my_size, window_size):
+                my_end = min(my_start + window_size, my_size)
+                my_counts = self.get(Seg(chrom, my_start, my_end, strand), roi_order=False)
+                if my_counts.sum() > 0:
+                    genomic_start_x = my_start
+                    last_val = my_counts[0]
+                    for x, val in enumerate(my_counts[1:]):
+                        if val != last_val:
+                            genomic_end_x = 1 + x + my_start
+                            if last_val > 0:
+                                fh.write("%s\t%s\t%s\t%s\n" % (chrom, genomic_start_x, genomic_end_x, last_val))
+                            last_val = val
+                            genomic_start_x = genomic_end_x
+                    if last_val > 0:
+                        fh.write("%s\t%s\t%s\t%s\n" % (chrom, genomic_start_x, my_end, last_val))
+
     def __getitem__(self, roi):
         return self.get(roi, roi_order=True)
 
@@ -484,3 +525,54 @@ class Chain(object):
             mask = np.empty_like(counts)
             mask[..., :] = m
         return np.ma.MaskedArray(counts, mask=mask.astype(bool), copy=copy)
+
+
+# ---------------------------------------------------------------------------
+# GenomeHash overlap query (genome_hash.py:81, 236-436) + SegmentChain.overlaps (roitools.pyx:1811-1876)
+# ---------------------------------------------------------------------------
+_STRAND_BITS = {"+": 1, "-": 2, ".": 3}                             # c_common.pxd:1-6
+
+
+def chains_overlap(a, b):
+    """SegmentChain.overlaps: same chromosome, strand bits intersect (roitools.pyx:1873), and two
+    neighbours of the merged sorted segment list overlap (c_unstranded_overlaps :1811-1836)."""
+    if a.chrom != b.chrom or not (_STRAND_BITS[a.strand] & _STRAND_BITS[b.strand]):
+        return False
+    segs = sorted(a.segments + b.segments, key=lambda s: (s.start, s.end))
+    return any(r.start < l.end for l, r in zip(segs[:-1], segs[1:]))
+
+
+class GenomeHash(object):
+    """``GenomeHash(features, binsize=20000)`` restated: features are binned by chromosome, strand
+    and ``start // binsize .. end // binsize`` of each segment; only '+' and '-' tables exist
+    (:236-257), so a '.' feature raises KeyError exactly like the reference."""
+
+    def __init__(self, features, binsize=20000):
+        self.binsize = binsize
+        self.features = list(features)
+        self._hash = {}
+        for fid, f in enumerate(self.features):
+            if f.chrom not in self._hash:
+                self._hash[f.chrom] = {"+": {}, "-": {}}
+            for b in self._bins(f):
+                try:
+                    self._hash[f.chrom][f.strand][b].append(fid)
+                except KeyError:
+                    self._hash[f.chrom][f.strand][b] = [fid]        # KeyError again for '.'
+
+    def _bins(self, chain):                                         # :259-291
+        bins = []
+        for seg in chain.segments:
+            bins.extend(range(seg.start // self.binsize, seg.end // self.binsize + 1))
+        return list(set(bins))
+
+    def get_overlapping_features(self, roi, stranded=True):         # :300-436, stranded query only
+        assert stranded is True
+        try:
+            nearby = self._hash[roi.chrom][roi.strand]
+        except KeyError:
+            nearby = {}
+        ids = set()
+        for b in self._bins(roi):
+            ids.update(nearby.get(b, ()))
+        return [self.features[i] for i in sorted(ids) if chains_overlap(roi, self.features[i])]

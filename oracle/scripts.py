@@ -17,13 +17,17 @@ import numpy as np
 from .pyoracle import Chain, Seg
 
 
-def counts_in_region_rows(ga, chains, masks=None):
-    """plastid/bin/counts_in_region.py:107-125 -> list of output rows (lists of str)."""
+def counts_in_region_rows(ga, chains, masks=None, crossmap=None):
+    """plastid/bin/counts_in_region.py:107-125 -> list of output rows (lists of str).  ``crossmap``:
+    an :class:`oracle.pyoracle.GenomeHash` of mask features, queried per region like :114-115."""
     ga_sum = ga.sum()
     normconst = 1000.0 * 1e6 / ga_sum                                         # :108
     rows = []
     for n, ivc in enumerate(chains):
         name = ivc.name if hasattr(ivc, "name") else str(ivc)
+        if crossmap is not None:
+            hits = crossmap.get_overlapping_features(ivc)                      # :114
+            ivc.add_masks(*[seg for f in hits for seg in f.segments])          # :115
         if masks is not None and masks[n]:
             ivc.add_masks(*masks[n])                                           # :115-116
         with warnings.catch_warnings():

@@ -15,9 +15,11 @@ def format_row(name, region, counts, length, normconst):
     return [name, region, "%.8e" % counts, "%.8e" % rpnt, "%.8e" % rpkm, "%d" % length]
 
 
-def count_regions(ga, chains, masks=None):
+def count_regions(ga, chains, masks=None, mask_features=None):
     """Rows of the output table for ``chains`` (SegmentChains; ``masks[i]`` = mask segments of
     chain i, added with ``add_masks`` exactly as counts_in_region.py:115-116 does).
+    ``mask_features``: the mask annotation itself (SegmentChains) — the overlap query and the
+    masking of every region then run on the device (``plastid_b200.masks``), no per-region work.
 
     Returns ``(ga_sum, rows)``; every row is ``[name, region, counts, rpnt, rpkm, length]`` already
     formatted (``%.8e`` x3, ``%d``) as the reference writes it."""
@@ -27,7 +29,13 @@ def count_regions(ga, chains, masks=None):
         for ch, m in zip(chains, masks):
             if m:
                 ch.add_masks(*m)
-    sums, live = ga.count_chains(chains)
+    if mask_features is not None:
+        from ..masks import MaskIndex, apply_mask_index
+        table = ga.chain_table(chains)
+        apply_mask_index(table, MaskIndex(mask_features, ga.layout), ga.device)
+        sums, live = ga.count_chains(table)
+    else:
+        sums, live = ga.count_chains(chains)
     rows = []
     for ch, counts, length in zip(chains, sums, live):
         if length == 0 and ch.length > 0:
@@ -54,24 +62,27 @@ def main(argv=sys.argv[1:]):
     chains = []
     for fn in args.annotation_files:
         chains.extend(_cli.read_bed(fn))
-    masks = None
+    mask_chains = None
     if args.mask_annotation_files:
         mask_chains = []
         for fn in args.mask_annotation_files:
             mask_chains.extend(_cli.read_bed(fn))
-        masks = overlapping_masks(chains, mask_chains)
-    ga_sum, rows = count_regions(ga, chains, masks)
+    ga_sum, rows = count_regions(ga, chains, mask_features=mask_chains)
     with open(args.outfile, "w") as fout:
         write_table(fout, ga_sum, rows)
 
 
 def overlapping_masks(chains, mask_chains):
-    """Mask segments overlapping each chain on its chromosome and strand — what
-    ``GenomeHash.get_overlapping_features`` (plastid/genomics/genome_hash.py:259-436) returns to
-    counts_in_region.py:114; unstranded ('.') masks apply to both strands."""
+    """Host statement of the same query, per chain: the segments of the mask features on the chain's
+    chromosome and strand that reach into its span — what ``GenomeHash.get_overlapping_features``
+    (plastid/genomics/genome_hash.py:259-436) hands to ``add_masks`` at counts_in_region.py:114-115.
+    The hash keeps '+' and '-' tables only (genome_hash.py:236-257): a '.' mask feature is a KeyError
+    there and here."""
     by_key = {}
     for mc in mask_chains:
         for seg in mc:
+            if seg.strand not in ("+", "-"):
+                raise KeyError(seg.strand)
             by_key.setdefault(seg.chrom, []).append(seg)
     for segs in by_key.values():
         segs.sort(key=lambda s: s.start)
@@ -84,7 +95,7 @@ def overlapping_masks(chains, mask_chains):
             for seg in by_key.get(ch.chrom, ()):
                 if seg.start >= hi:
                     break
-                if seg.end > lo and seg.strand in (ch.strand, "."):
+                if seg.end > lo and seg.strand == ch.strand:
                     hits.append(GenomicSegment(seg.chrom, seg.start, seg.end, ch.strand))
         out.append(hits)
     return out

@@ -299,6 +299,62 @@ pb_column_stats_kernel(const unsigned long long *__restrict__ keys, int64_t n_ro
     if (threadIdx.x == 0) profile[col] = (mid[0] + mid[1]) / 2.0;
 }
 
+// ----------------------------------------------------------------------------------------
+// mask pipeline: per-chain mask bits from a sorted interval set, all chains in one launch
+// ----------------------------------------------------------------------------------------
+// Replaces, for a whole region list at once, GenomeHash.get_overlapping_features + SegmentChain.add_masks
+// (genome_hash.py:259-436, roitools.pyx:2213-2301): the masked positions of a chain are (union of the
+// mask features on its chromosome and strand) ∩ (chain positions).  Mask intervals arrive merged and
+// sorted per strand class in global-bin coordinates, so interval ends are sorted too: one binary
+// search per exon block finds the first interval that can overlap it.  One warp per chain, lanes over
+// blocks; bits are OR-ed in (a chain's bit range is not word aligned, neighbours share words).
+__global__ void pb_mask_chains_kernel(const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                                      const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
+                                      int64_t n_chains, const int64_t *__restrict__ mstart, const int64_t *__restrict__ mend,
+                                      const int64_t *__restrict__ mclass_off, const int64_t *__restrict__ mask_off,
+                                      unsigned int *__restrict__ mask_words)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chains) return;
+    const int cls = chain_plane[c];
+    const int64_t m0 = __ldg(mclass_off + cls), m1 = __ldg(mclass_off + cls + 1);
+    if (m0 == m1) return;
+    const int64_t b0 = __ldg(chain_off + c), b1 = __ldg(chain_off + c + 1);
+    int64_t chain_pos = __ldg(mask_off + c);       // bit index of the chain position the batch starts at
+    for (int64_t j0 = b0; j0 < b1; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const int64_t bs = j < b1 ? __ldg(bstart + j) : 0, be = j < b1 ? __ldg(bend + j) : 0;
+        long long incl = be - bs;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const int64_t bit0 = chain_pos + (incl - (be - bs));
+        chain_pos += __shfl_sync(0xffffffffu, incl, 31);
+        if (be <= bs) continue;
+        int64_t lo = m0, hi = m1;                   // first interval with mend > bs
+        while (lo < hi) {
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(mend + mid) <= bs) lo = mid + 1; else hi = mid;
+        }
+        for (int64_t k = lo; k < m1; ++k) {
+            const int64_t ms = __ldg(mstart + k);
+            if (ms >= be) break;
+            const int64_t me = __ldg(mend + k);
+            const int64_t a = bit0 + ((ms > bs ? ms : bs) - bs), b = bit0 + ((me < be ? me : be) - bs);   // bits [a, b)
+            const int64_t w0 = a >> 5, w1 = (b - 1) >> 5;
+            for (int64_t w = w0; w <= w1; ++w) {
+                unsigned int m = 0xffffffffu;
+                if (w == w0) m &= 0xffffffffu << (a & 31);
+                if (w == w1) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+                atomicOr(mask_words + w, m);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 static int check_chains(const void *const *planes, const int64_t *bstart, const int64_t *bend,
@@ -535,6 +591,25 @@ extern "C" int pb_stratified_windows(const pb_batch *batch, const pb_layout *lay
                                                                            chain_plane, chain_reverse, row_col, n_chains, width,
                                                                            phase_mode, codon_front, codon_back,
                                                                            mask_bits, mask_off, out, maskmat);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_mask_chains(const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                              const uint8_t *chain_plane, int64_t n_chains,
+                              const int64_t *mask_start, const int64_t *mask_end, const int64_t *mask_class_off,
+                              const int64_t *mask_off, uint8_t *mask_bits, void *stream_)
+{
+    if (!bstart || !bend || !chain_off || !chain_plane || !mask_start || !mask_end || !mask_class_off || !mask_off ||
+        !mask_bits || n_chains < 0) {
+        pb_set_error("pb_mask_chains: null argument"); return PB_EINVAL;
+    }
+    if ((uintptr_t)mask_bits & 3) { pb_set_error("pb_mask_chains: mask_bits must be 4-byte aligned"); return PB_EINVAL; }
+    if (n_chains == 0) return PB_OK;
+    const int64_t grid = (n_chains * 32 + 255) / 256;
+    pb_mask_chains_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream_>>>(
+        bstart, bend, chain_off, chain_plane, n_chains, mask_start, mask_end, mask_class_off, mask_off,
+        reinterpret_cast<unsigned int *>(mask_bits));
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

@@ -435,6 +435,20 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
     return PB_OK;
 }
 
+int64_t pb_scan_part_entries(int64_t n) { return (n + kScanChunk - 1) / kScanChunk + 1; }
+
+// off[0..n] = exclusive prefix sums of counts[0..n) (off[n] = total); counts are zeroed on the way
+int pb_launch_exclusive_scan_u32(uint32_t *counts, uint32_t *off, uint32_t *part, int64_t n, cudaStream_t stream)
+{
+    const int64_t nb = (n + kScanChunk - 1) / kScanChunk;
+    if (nb == 0) { PB_CUDA_CHECK(cudaMemsetAsync(off, 0, sizeof(uint32_t), stream)); return PB_OK; }
+    pb_scan_chunks_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(counts, off, part, n);
+    pb_scan_top_kernel<<<1, kScanThreads, 0, stream>>>(part, nb);
+    pb_scan_add_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(off, part, n, nb);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
 int pb_launch_stats_finish(const unsigned long long *slots, unsigned long long *stats, cudaStream_t stream)
 {
     pb_stats_finish_kernel<<<1, 32, 0, stream>>>(slots, stats);

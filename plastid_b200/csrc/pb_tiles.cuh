@@ -63,6 +63,9 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
                       const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, const PbWorkspace &ws,
                       cudaStream_t stream);
 int pb_launch_stats_finish(const unsigned long long *slots, unsigned long long *stats, cudaStream_t stream);
+// exclusive prefix sums of uint32 counts (three small launches); part needs pb_scan_part_entries(n) words
+int64_t pb_scan_part_entries(int64_t n);
+int pb_launch_exclusive_scan_u32(uint32_t *counts, uint32_t *off, uint32_t *part, int64_t n, cudaStream_t stream);
 void pb_timing_begin(cudaStream_t stream);
 void pb_timing_end(cudaStream_t stream);
 

@@ -506,6 +506,71 @@ class BAMGenomeArray(object):
             sums = sums / float(self.sum()) * 1e6
         return sums, live
 
+    # -- track export (genome_array.py:990-1111): run-length / non-zero compaction on the device ----
+    def _export_records(self, chrom, strand, mode, window_size):
+        """(start, end, value) arrays of one chromosome strand from ``pb_export_runs``."""
+        import torch
+        planes = self.count_planes((strand,))
+        dev = planes.device
+        base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
+        n = self._chr_lengths[chrom]
+        vec = planes.planes[strand][base:base + n]
+        L = _lib.lib()
+        ws_bytes = L.pb_export_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        dtype = 1 if planes.dtype == "f64" else 0
+
+        def call(cap, st, en, va):
+            _lib.check(L.pb_export_runs(_lib.ptr(vec), dtype, n, int(window_size), mode, cap, _lib.ptr(st), _lib.ptr(en),
+                                        _lib.ptr(va), _lib.ptr(n_out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+            return int(n_out.item())
+        total = call(0, None, None, None)            # counting pass
+        st = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+        en = torch.empty(max(total, 1), dtype=torch.int64, device=dev) if mode == 1 else None
+        va = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+        if total:
+            call(total, st, en, va)
+        vals = va[:total].cpu().numpy()
+        if planes.dtype == "u32":
+            vals = vals.astype(np.int64)             # the reference's point rules count in int
+        if self._normalize is True:
+            vals = vals / float(self.sum()) * 1e6
+        return st[:total].cpu().numpy(), (en[:total].cpu().numpy() if mode == 1 else None), vals
+
+    @staticmethod
+    def _write_track_header(fh, kind, trackname, kwargs):
+        fh.write("track type=%s name=%s" % (kind, trackname))
+        for k, v in sorted(kwargs.items(), key=lambda x: x[0]):
+            fh.write(" %s=%s" % (k, v))
+        fh.write("\n")
+
+    def to_variable_step(self, fh, trackname, strand, window_size=100000, printer=None, **kwargs):
+        """genome_array.py:990-1037: every non-zero position as ``1-based position<TAB>value``."""
+        assert strand in self.strands()
+        if not self._is_lowerable():
+            raise TypeError("track export needs a mapping rule that lowers to whole-genome planes")
+        self._write_track_header(fh, "wiggle_0", trackname, kwargs)
+        for chrom in sorted(self.chroms()):
+            if printer is not None:
+                printer.write("Writing chromosome %s..." % chrom)
+            fh.write("variableStep chrom=%s span=1\n" % chrom)
+            pos, _e, vals = self._export_records(chrom, strand, 0, window_size)
+            fh.write("".join("%s\t%s\n" % (p + 1, v) for p, v in zip(pos.tolist(), vals)))
+
+    def to_bedgraph(self, fh, trackname, strand, window_size=100000, printer=None, **kwargs):
+        """genome_array.py:1039-1111: runs of equal positive values, cut at ``window_size`` boundaries."""
+        assert strand in self.strands()
+        assert window_size > 0
+        if not self._is_lowerable():
+            raise TypeError("track export needs a mapping rule that lowers to whole-genome planes")
+        self._write_track_header(fh, "bedGraph", trackname, kwargs)
+        for chrom in sorted(self.chroms()):
+            if printer is not None:
+                printer.write("Writing chromosome %s..." % chrom)
+            st, en, vals = self._export_records(chrom, strand, 1, window_size)
+            fh.write("".join("%s\t%s\t%s\t%s\n" % (chrom, a, b, v) for a, b, v in zip(st.tolist(), en.tolist(), vals)))
+
     def to_genome_array(self, array_type=None):
         """genome_array.py:965-988 — including its quirk of dropping each chromosome's last base."""
         import torch

@@ -60,6 +60,55 @@ def test_counts_in_region(world):
     assert got[5][2] == "nan" and got[5][5] == "0"
 
 
+def _mask_features(w, rng, n=150):
+    """Mask annotation as a crossmap would give it: one- and two-segment features on both strands,
+    some inside transcripts, some spanning exon boundaries, some far from any region, a few duplicated."""
+    chains = w["ann"].chains()
+    feats = []
+    for k in range(n):
+        ch = chains[int(rng.integers(len(chains)))]
+        span = ch.spanning_segment
+        a = int(rng.integers(max(span.start - 300, 0), span.end + 100))
+        segs = [pb.GenomicSegment(ch.chrom, a, a + int(rng.integers(1, 400)), ch.strand if k % 5 else "+-"[k % 2])]
+        if k % 3 == 0:
+            b = segs[0].end + int(rng.integers(1, 2000))
+            segs.append(pb.GenomicSegment(ch.chrom, b, b + int(rng.integers(1, 300)), segs[0].strand))
+        feats.append(pb.SegmentChain(*segs, ID="mask%d" % k))
+    feats.append(pb.SegmentChain(pb.GenomicSegment("chrUnknown", 0, 1000, "+"), ID="elsewhere"))
+    return feats + feats[:7]
+
+
+def test_counts_in_region_with_device_mask_pipeline(world):
+    """Mask annotation -> pb_mask_chains == per-region GenomeHash.get_overlapping_features + add_masks."""
+    w = world
+    oga, ga = make_gas(w, po.FivePrimeMap(14), pb.FivePrimeMapFactory(14))
+    chains = w["ann"].chains()
+    chains.append(pb.SegmentChain(pb.GenomicSegment("chrUnknown", 10, 500, "+"), ID="nowhere"))
+    chains.append(pb.SegmentChain(pb.GenomicSegment(chains[0].chrom, 10, 500, "."), ID="unstranded"))
+    feats = _mask_features(w, np.random.default_rng(11))
+    # one region also carries a mask of its own from add_masks: both must apply
+    own = pb.GenomicSegment(chains[3].chrom, chains[3].spanning_segment.start, chains[3].spanning_segment.start + 40, chains[3].strand)
+    chains[3].add_masks(own)
+    ochains = []
+    for ch in chains:
+        oc = po.Chain(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in ch])
+        oc.name = ch.get_name()
+        ochains.append(oc)
+    ochains[3].add_masks(po.Seg(own.chrom, own.start, own.end, own.strand))
+    ofeats = [po.Chain(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in f]) for f in feats]
+    exp = osc.counts_in_region_rows(oga, ochains, crossmap=po.GenomeHash(ofeats))
+    ga_sum, got = counts_in_region.count_regions(ga, chains, mask_features=feats)
+    assert got == exp
+    assert sum(int(r[5]) for r in got) < sum(ch.length for ch in chains)       # something was masked
+    # the host statement of the query (per-chain add_masks) gives the same table
+    chains2 = w["ann"].chains() + chains[-2:]
+    chains2[3].add_masks(own)
+    _s, got2 = counts_in_region.count_regions(ga, chains2, masks=counts_in_region.overlapping_masks(chains2, feats))
+    assert got2 == exp
+    with pytest.raises(KeyError):
+        counts_in_region.count_regions(ga, chains[:2], mask_features=[pb.SegmentChain(pb.GenomicSegment(chains[0].chrom, 1, 9, "."))])
+
+
 def test_cs_count(world):
     w = world
     oga, ga = make_gas(w, po.ThreePrimeMap(0), pb.ThreePrimeMapFactory(0))
@@ -177,3 +226,51 @@ def test_phase_sums_on_planes_agree_with_single_launch_path(world):
         planes = map_batch(ga._device_batch(), ga.layout, ga.map_fn, pb.SizeFilterFactory(k, k), strands=("+", "-"))
         exp = phase_sums(planes, table, 5, -1).sum(dim=0).cpu().numpy()
         assert (got[k] == exp).all() and exp.sum() > 0
+
+
+@pytest.mark.parametrize("window", [100000, 1000, 7])
+def test_track_export_matches_reference_loops(world, window):
+    """to_variable_step / to_bedgraph (genome_array.py:990-1111): identical files, incl. runs cut at
+    window boundaries, both strands and the merged '.' strand, raw and normalised."""
+    import io
+    w = world
+    oga, ga = make_gas(w, po.FivePrimeMap(14), pb.FivePrimeMapFactory(14))
+    for strand in ("+", "-", "."):
+        for norm in (False, True):
+            oga.set_normalize(norm)
+            ga.set_normalize(norm)
+            a, b = io.StringIO(), io.StringIO()
+            oga.to_bedgraph(a, "trk", strand, window_size=window, color="0,0,255", alwaysZero="on")
+            ga.to_bedgraph(b, "trk", strand, window_size=window, color="0,0,255", alwaysZero="on")
+            assert a.getvalue() == b.getvalue() and a.getvalue().count("\n") > 100
+            a, b = io.StringIO(), io.StringIO()
+            oga.to_variable_step(a, "trk", strand, window_size=window)
+            ga.to_variable_step(b, "trk", strand, window_size=window)
+            assert a.getvalue() == b.getvalue()
+    oga.set_normalize(False)
+    ga.set_normalize(False)
+
+
+def test_track_export_center_rule_within_tolerance(world):
+    import io
+    w = world
+    oga, ga = make_gas(w, po.CenterMap(12), pb.CenterMapFactory(12))
+    a, b = io.StringIO(), io.StringIO()
+    oga.to_variable_step(a, "trk", "+", window_size=5000)
+    ga.to_variable_step(b, "trk", "+", window_size=5000)
+    la, lb = a.getvalue().splitlines(), b.getvalue().splitlines()
+    assert len(la) == len(lb) > 100
+    for x, y in zip(la, lb):
+        if "\t" not in x:
+            assert x == y
+            continue
+        (px, vx), (py, vy) = x.split("\t"), y.split("\t")
+        assert px == py and abs(float(vx) - float(vy)) <= 1e-6 * abs(float(vx))      # north-star tolerance
+    # bedGraph of fractional coverage: same run boundaries wherever the values are exactly representable
+    a, b = io.StringIO(), io.StringIO()
+    oga.to_bedgraph(a, "trk", "-", window_size=100000)
+    ga.to_bedgraph(b, "trk", "-", window_size=100000)
+    ra = [l.split("\t") for l in a.getvalue().splitlines()[1:]]
+    rb = [l.split("\t") for l in b.getvalue().splitlines()[1:]]
+    cov = lambda rows: sum((int(r[2]) - int(r[1])) * float(r[3]) for r in rows)
+    assert abs(cov(ra) - cov(rb)) <= 1e-6 * cov(ra) and rb[0][:2] == ra[0][:2]

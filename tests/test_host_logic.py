@@ -382,3 +382,41 @@ def test_wire16_chunk_plan_covers_reads_and_bins():
             c = np.searchsorted(hb.chrom_read_off, np.arange(a, b), side="right") - 1
             g = lay.chrom_bin_off[c] + hb.ref_start[a:b]
             assert (g >= x).all() and (g < y).all()
+
+
+def test_mask_index_merges_per_strand_in_global_bins():
+    from plastid_b200.masks import MaskIndex
+    lay = pb.GenomeLayout(["a", "b"], [50_000, 20_000])
+    seg = pb.GenomicSegment
+    feats = [pb.SegmentChain(seg("b", 10, 20, "+"), seg("b", 100, 120, "+")), pb.SegmentChain(seg("a", 5, 15, "-")),
+             pb.SegmentChain(seg("b", 15, 30, "+")), pb.SegmentChain(seg("a", 15, 18, "-")),      # touching: merged
+             pb.SegmentChain(seg("zz", 1, 2, "+")), pb.SegmentChain(seg("a", 40, 50, "+"))]
+    mi = MaskIndex(feats, lay)
+    base_b = int(lay.chrom_bin_off[1])
+    assert list(mi.class_off) == [0, 3, 4, 4]
+    assert list(zip(mi.mask_start, mi.mask_end)) == [(40, 50), (base_b + 10, base_b + 30), (base_b + 100, base_b + 120), (5, 18)]
+    with pytest.raises(KeyError):
+        MaskIndex([pb.SegmentChain(seg("a", 1, 2, "."))], lay)
+    assert len(MaskIndex([], lay)) == 0
+
+
+def test_oracle_genome_hash_overlap_query():
+    """genome_hash.py:259-436 restated: bins by chromosome and strand, true position overlap, all
+    segments of a hit feature are returned (and masked only where they meet the region)."""
+    from oracle import pyoracle as po
+    S = po.Seg
+    roi = po.Chain(S("c", 100, 200, "+"), S("c", 300, 400, "+"))
+    feats = [po.Chain(S("c", 150, 160, "+")),                       # inside exon 1
+             po.Chain(S("c", 200, 300, "+")),                       # intron only: no shared position
+             po.Chain(S("c", 390, 30000, "+"), S("c", 50, 60, "+")),  # second exon + a far segment
+             po.Chain(S("c", 150, 160, "-")),                       # other strand
+             po.Chain(S("d", 150, 160, "+")),                       # other chromosome
+             po.Chain(S("c", 45000, 45010, "+"))]                   # same hash neighbourhood rules, no overlap
+    gh = po.GenomeHash(feats)
+    hits = gh.get_overlapping_features(roi)
+    assert hits == [feats[0], feats[2]]
+    roi.add_masks(*[s for f in hits for s in f.segments])
+    assert roi.masked_length == 200 - 10 - 10 and sum(roi.position_mask[50:60]) == 10 and sum(roi.position_mask[190:]) == 10
+    assert gh.get_overlapping_features(po.Chain(S("c", 100, 200, "."))) == []
+    with pytest.raises(KeyError):
+        po.GenomeHash([po.Chain(S("c", 1, 5, "."))])
