@@ -31,6 +31,12 @@ def count_regions(ga, chains, masks=None, mask_features=None):
                 ch.add_masks(*m)
     if mask_features is not None:
         from ..masks import MaskIndex, apply_mask_index
+        # regions on chromosomes the alignments do not know count zero over their unmasked length
+        # (genome_array.py:795-798): their masks never reach the device, so they are applied here
+        unknown = [ch for ch in chains if len(ch) and ch.chrom not in ga.layout.index]
+        for ch, m in zip(unknown, overlapping_masks(unknown, mask_features)):
+            if m:
+                ch.add_masks(*m)
         table = ga.chain_table(chains)
         apply_mask_index(table, MaskIndex(mask_features, ga.layout), ga.device)
         sums, live = ga.count_chains(table)
