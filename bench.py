@@ -240,6 +240,46 @@ def host_sample(dbatch, chroms, lens, chrom_ids):
     return AlignmentBatch(chroms, lens, sub.ref_start, sub.meta, full_off, sub.blk_off, sub.blk, max_span=sub.max_span)
 
 
+def python_loop_estimate(hb, chrom_id, workload, n_sample=100_000):
+    """"Reference as shipped" estimate: the per-read Python/Cython loop of the mapping rule
+    restated in pure Python (oracle/pyoracle.py), timed on the first `n_sample` reads of one chromosome,
+    read objects prebuilt (BAM decoding excluded).  One host core."""
+    from oracle import pyoracle as po
+    from plastid_b200 import synth
+    a = int(hb.chrom_read_off[chrom_id])
+    b = min(int(hb.chrom_read_off[chrom_id + 1]), a + n_sample)
+    if b <= a:
+        return None
+    if hb.blk_off is None:
+        reads = [po.Read(int(s), [(po.CMATCH, int(m & 0xFFFF))], bool((m >> 16) & 1))
+                 for s, m in zip(hb.ref_start[a:b].tolist(), hb.meta[a:b].tolist())]
+    else:
+        reads = []
+        for i in range(a, b):
+            pos = hb.positions_of(i)
+            ops, prev = [], None
+            for p in pos:       # rebuild a CIGAR of M runs and N gaps from the aligned positions
+                if prev is not None and p != prev + 1:
+                    ops.append((po.CREF_SKIP, p - prev - 1))
+                if ops and ops[-1][0] == po.CMATCH and (prev is None or p == prev + 1):
+                    ops[-1] = (po.CMATCH, ops[-1][1] + 1)
+                else:
+                    ops.append((po.CMATCH, 1))
+                prev = p
+            reads.append(po.Read(int(hb.ref_start[i]), ops, bool((hb.meta[i] >> 16) & 1)))
+    fn = {"c1": lambda: po.FivePrimeMap(14), "c2": lambda: po.VariableFivePrimeMap(dict(synth.RIBO_OFFSETS)),
+          "c3": lambda: po.CenterMap(12), "c5": lambda: po.ThreePrimeMap(0)}[workload]()
+    seg_end = max(r.reference_end for r in reads) + 1
+    t0 = time.perf_counter()
+    for strand in ("+", "-"):      # get_reads_and_counts: strand filter, then the rule (genome_array.py:811-823)
+        mine = [r for r in reads if r.is_reverse is (strand == "-")]
+        fn(mine, po.Seg(hb.chroms[chrom_id], int(reads[0].reference_start), seg_end, strand))
+    dt = time.perf_counter() - t0
+    return {"value": len(reads) / dt, "unit": UNIT, "cores": 1,
+            "sample": "%d reads of %s through the pure-Python restatement of the rule's per-read loop in %.2f s"
+                      % (len(reads), hb.chroms[chrom_id], dt)}
+
+
 def run_peaks(args, device):
     """the L2 atomic peak next to hbm_gbs — 2^30 `red.global.add.u32` updates, (i) uniformly
     random over 24.8 GB of bins, (ii) coordinate-sorted with +-64 nt jitter over a 3.1 G-bin plane.  One JSON
@@ -615,6 +655,10 @@ def main():
         cpu = {"value": nr / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "%s: %d reads + %d region sums in %.2f s (oracle C port, one thread)"
                          % (",".join(chroms[c] for c in chrom_ids), nr, nreg, dt)}
+        try:
+            cpu["python_loop"] = python_loop_estimate(hb, chrom_ids[0], args.workload)
+        except Exception as exc:      # an estimate beside the baseline, never a reason to lose the line
+            cpu["python_loop"] = {"error": repr(exc)}
 
     binning = ["pb_bin_kernel(count)", "pb_scan_chunks_kernel", "pb_scan_top_kernel", "pb_scan_add_kernel",
                "pb_bin_kernel(fill)"] if dbatch.blk_off is not None else []

@@ -66,29 +66,33 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
     unsigned int drop_len = 0;
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
                want_any = planes & PB_PLANE_ANY;
-    constexpr int kU = 4;   // independent meta loads in flight per thread
+    constexpr int kU = 4;   // independent reads in flight per thread
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // a thread's read indices only grow: the chromosome of the previous read is the place to start from
+    int c = 0;
+    int64_t c_end = __ldg(b.chrom_read_off + 1);
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < b.n_reads; i0 += stride * kU) {
-      uint32_t mv[kU];
+      // everything a multi-block read needs before its block gather is fetched up front, for all kU
+      // reads at once (streaming loads): the dependent chain is then gather -> cursor atomic -> store
+      uint32_t mv[kU], kv[kU];
+      int32_t sv[kU];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) mv[u] = i0 + u * stride < b.n_reads ? __ldg(b.meta + i0 + u * stride) : 0u;
+      for (int u = 0; u < kU; ++u) {
+          const int64_t i = i0 + u * stride;
+          const bool ok = i < b.n_reads;
+          mv[u] = ok ? __ldg(b.meta + i) : 0u;
+          sv[u] = ok ? __ldg(b.ref_start + i) : 0;
+          kv[u] = ok ? __ldg(b.blk_off + i) : 0u;
+      }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t i = i0 + u * stride;
         const uint32_t m = mv[u];
         if (PB_META_NBLK(m) <= 1) continue;      // also skips the out-of-range filler (n_blocks 0)
         if (!pb_passes(m, r.size_min, r.size_max)) continue;
-        int c = 0;
-        {   // chromosome of read i: last c with chrom_read_off[c] <= i
-            int lo = 0, hi = b.n_chrom;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(b.chrom_read_off + mid) <= i) lo = mid; else hi = mid;
-            }
-            c = lo;
-        }
+        while (i >= c_end && c + 1 < b.n_chrom) { ++c; c_end = __ldg(b.chrom_read_off + c + 1); }
         const int64_t base = __ldg(lay.chrom_bin_off + c), clen = __ldg(lay.chrom_len + c);
-        const int32_t s = __ldg(b.ref_start + i);
+        const int32_t s = sv[u];
         const int L = PB_META_L(m);
         const bool rev = PB_META_REV(m);
         auto emit = [&](int64_t x, int64_t y, uint32_t tag) {
@@ -121,7 +125,7 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
             const int slot = (int)__ldg(slot_of_len + L);
             if (slot < 0) continue;
             const uint32_t tag = (uint32_t)slot | ((uint32_t)rev << 16);
-            const uint32_t k0 = __ldg(b.blk_off + i), k1 = __ldg(b.blk_off + i + 1);
+            const uint32_t k0 = kv[u], k1 = k0 + (uint32_t)PB_META_NBLK(m);   // blk lists multi-block reads only
             int a = 0;  // aligned-base index of the block's first base
             for (uint32_t k = k0; k < k1; ++k) {
                 const int2 bl = __ldg(b.blk + k);

@@ -13,6 +13,13 @@ count-vector collective:
   per-region tables are gathered (``gather_rows``).  Exact medians need the normalised window rows
   of all ranks (``gather_matrix``) — a median is not all-reducible.
 
+* **position-range sharding** (``position_cuts`` / ``shard_positions`` / ``clip_table``):
+  the concatenated genome is cut into contiguous bin ranges balanced by read count; a rank holds
+  the planes of its range only (1/N of the memory), receives the reads that start inside it plus a
+  halo of ``max_span`` before it (those are sent to both neighbours, each counts only sites inside
+  its own range), and sums the parts of every region that fall into its range; the partial region
+  tables are summed with one all-reduce.  No count-vector collective here either.
+
 NCCL is used on GPUs, gloo in the CPU tests; all messages are small (<= a few hundred MB).
 """
 import numpy as np
@@ -54,6 +61,105 @@ def shard_reads(hb, rank, world_size):
                          max_span=hb.max_span, mapped=hb.mapped)
     if hb.objects is not None:
         out.objects = hb.objects[a:b]
+    return out
+
+
+def position_cuts(hb, layout, world_size):
+    """Global-bin cut points ``int64[world_size + 1]`` (multiples of PB_LAYOUT_ALIGN, first 0, last
+    ``layout.total_bins``) splitting the reads into ``world_size`` contiguous position ranges of about
+    equal read count."""
+    from . import _lib
+    A = _lib.PB_LAYOUT_ALIGN
+    n = len(hb)
+    cuts = [0]
+    for r in range(1, world_size):
+        i = (r * n) // world_size
+        if i >= n:
+            g = int(layout.total_bins)
+        else:
+            c = int(np.searchsorted(hb.chrom_read_off, i, side="right")) - 1
+            g = int(layout.chrom_bin_off[c]) + int(hb.ref_start[i])
+        cuts.append(max((g // A) * A, cuts[-1]))
+    cuts.append(int(layout.total_bins))
+    return np.asarray(cuts, dtype=np.int64)
+
+
+def shard_positions(hb, layout, rank, world_size, cuts=None):
+    """Position-range shard: ``(sub_batch, bin_lo, bin_hi)``.  ``sub_batch`` holds, per chromosome,
+    the reads starting in ``[lo - hb.max_span, hi)`` of the part of the chromosome inside the rank's
+    range — every read that can put a site into ``[bin_lo, bin_hi)`` — with the same chromosomes
+    and layout as ``hb`` (coordinates stay global)."""
+    cuts = position_cuts(hb, layout, world_size) if cuts is None else cuts
+    g_lo, g_hi = int(cuts[rank]), int(cuts[rank + 1])
+    keep = []
+    off = [0]
+    for c in range(len(hb.chroms)):
+        base = int(layout.chrom_bin_off[c])
+        a, b = int(hb.chrom_read_off[c]), int(hb.chrom_read_off[c + 1])
+        lo, hi = g_lo - base, g_hi - base           # range in this chromosome's coordinates
+        if hi <= 0 or lo >= int(hb.chrom_len[c]) or b <= a or g_hi <= g_lo:
+            off.append(off[-1])
+            continue
+        i0 = a + int(np.searchsorted(hb.ref_start[a:b], lo - hb.max_span, side="left"))
+        i1 = a + int(np.searchsorted(hb.ref_start[a:b], hi, side="left"))
+        keep.append((i0, i1))
+        off.append(off[-1] + max(i1 - i0, 0))
+    idx = np.concatenate([np.arange(i0, i1) for i0, i1 in keep]) if keep else np.zeros(0, dtype=np.int64)
+    blk_off = blk = None
+    if hb.blk_off is not None and len(idx):
+        rows = (hb.blk_off[idx + 1].astype(np.int64) - hb.blk_off[idx].astype(np.int64))
+        blk_off = np.zeros(len(idx) + 1, dtype=np.int64)
+        np.cumsum(rows, out=blk_off[1:])
+        parts = [hb.blk[int(hb.blk_off[i0]):int(hb.blk_off[i1])] for i0, i1 in keep]
+        blk = np.concatenate(parts) if parts else np.zeros((0, 2), dtype=np.int32)
+        if len(blk) == 0:
+            blk_off = blk = None
+    sub = AlignmentBatch(hb.chroms, hb.chrom_len, hb.ref_start[idx], hb.meta[idx], off, blk_off, blk,
+                         max_span=hb.max_span, mapped=hb.mapped)
+    return sub, g_lo, g_hi
+
+
+def clip_table(table, bin_lo, bin_hi):
+    """The part of every chain of a :class:`~plastid_b200.regions.ChainTable` inside the global bins
+    ``[bin_lo, bin_hi)``: blocks clipped (or dropped), mask bits re-based to the clipped chain
+    positions.  Region sums and unmasked lengths over clipped tables of all ranks add up to those of
+    the whole table, so one all-reduce finishes a position-sharded region table."""
+    from .regions import ChainTable
+    bstart, bend, chain_off, length = [], [], [0], []
+    bits_out, mask_off = [], []
+    nbits = 0
+    old_bits = None
+    if table.mask_bits is not None:
+        old_bits = np.unpackbits(table.mask_bits, bitorder="little")
+    for c in range(table.n_chains):
+        pos = 0                                   # chain position of the current block's first base
+        n_c = 0
+        pieces = []
+        for j in range(int(table.chain_off[c]), int(table.chain_off[c + 1])):
+            bs, be = int(table.bstart[j]), int(table.bend[j])
+            lo, hi = max(bs, bin_lo), min(be, bin_hi)
+            if lo < hi:
+                bstart.append(lo)
+                bend.append(hi)
+                if old_bits is not None:
+                    m0 = int(table.mask_off[c]) + pos + (lo - bs)
+                    pieces.append(old_bits[m0:m0 + (hi - lo)])
+                n_c += hi - lo
+            pos += be - bs
+        chain_off.append(len(bstart))
+        length.append(n_c)
+        mask_off.append(nbits)
+        if old_bits is not None:
+            bits_out.append(np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.uint8))
+        nbits += n_c
+    mask_bits = None
+    if old_bits is not None:
+        flat = np.concatenate(bits_out) if bits_out else np.zeros(0, dtype=np.uint8)
+        mask_bits = np.packbits(flat, bitorder="little")
+        if len(mask_bits) == 0:
+            mask_bits = np.zeros(1, dtype=np.uint8)
+    out = ChainTable(table.layout, bstart, bend, chain_off, table.chain_plane, table.chain_reverse, length,
+                     mask_bits, mask_off if old_bits is not None else None, table.known)
     return out
 
 

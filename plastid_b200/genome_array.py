@@ -31,8 +31,14 @@ _STRANDS = ("+", "-", ".")
 class CountPlanes(object):
     """Dense per-strand count vectors on the device (uint32 for point rules, float64 for center)."""
 
-    def __init__(self, layout, dtype, device):
+    def __init__(self, layout, dtype, device, bin_range=None):
+        """``bin_range=(lo, hi)`` (multiples of PB_LAYOUT_ALIGN): a position-sharded rank holds only
+        the bins [lo, hi) of every plane; kernels still address global bins, so they are handed the
+        address bin 0 would have (``plane_ptr``) and are only ever asked for bins of the range."""
         self.layout, self.dtype, self.device = layout, dtype, device
+        self.bin_lo, self.bin_hi = (0, int(layout.total_bins)) if bin_range is None else (int(bin_range[0]), int(bin_range[1]))
+        if self.bin_lo % _lib.PB_LAYOUT_ALIGN or self.bin_hi % _lib.PB_LAYOUT_ALIGN or not 0 <= self.bin_lo <= self.bin_hi <= layout.total_bins:
+            raise ValueError("bin_range must be multiples of %d inside the layout" % _lib.PB_LAYOUT_ALIGN)
         self.planes = {}
         self.stats = np.zeros(_lib.PB_NSTATS, dtype=np.int64)
 
@@ -41,18 +47,31 @@ class CountPlanes(object):
         tdtype = torch.float64 if self.dtype == "f64" else torch.int32   # int32 storage viewed as uint32
         for s in strands:
             if s not in self.planes:
-                self.planes[s] = torch.empty(self.layout.total_bins, dtype=tdtype, device=self.device)
+                self.planes[s] = torch.empty(max(self.bin_hi - self.bin_lo, 1), dtype=tdtype, device=self.device)
+
+    def plane_ptr(self, strand):
+        """Address of global bin 0 of a plane (below the allocation for a range-only plane)."""
+        t = self.planes.get(strand)
+        if t is None:
+            return None
+        return C.c_void_p(t.data_ptr() - self.bin_lo * t.element_size())
 
     def plane_ptrs(self):
         arr = (C.c_void_p * 3)()
         for s in _STRANDS:
-            t = self.planes.get(s)
-            arr[_lib.PLANE_INDEX[s]] = None if t is None else t.data_ptr()
+            p = self.plane_ptr(s)
+            arr[_lib.PLANE_INDEX[s]] = None if p is None else p.value
         return arr
+
+    def bins(self, strand, g0, g1):
+        """Device view of global bins [g0, g1) of a plane (must lie inside this rank's range)."""
+        if g0 < self.bin_lo or g1 > self.bin_hi:
+            raise IndexError("bins [%d, %d) are outside this rank's range [%d, %d)" % (g0, g1, self.bin_lo, self.bin_hi))
+        return self.planes[strand][g0 - self.bin_lo:g1 - self.bin_lo]
 
     def slice_host(self, strand, chrom, start, end):
         base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
-        t = self.planes[strand][base + start:base + end].cpu().numpy()
+        t = self.bins(strand, base + start, base + end).cpu().numpy()
         if self.dtype == "u32":
             return t.view(np.uint32).astype(np.int64)
         return t
@@ -71,8 +90,11 @@ def _workspace(device, nbytes):
     return ws
 
 
-def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), planes=None, sync_stats=True):
-    """Lower ``factory`` over a whole device batch into dense planes for the query ``strands``."""
+def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), planes=None, sync_stats=True,
+              bin_range=None):
+    """Lower ``factory`` over a whole device batch into dense planes for the query ``strands``.
+    ``bin_range=(lo, hi)``: produce only the global bins [lo, hi) (position sharding,
+    ``plastid_b200.dist.shard_positions``; point rules) into range-only planes."""
     import torch
     _lib.require_cuda()
     if not isinstance(factory, _MapFactory) or isinstance(factory, StratifiedVariableFivePrimeMapFactory):
@@ -80,7 +102,12 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     dev = dbatch.device
     is_center = isinstance(factory, CenterMapFactory)
     if planes is None:
-        planes = CountPlanes(layout, "f64" if is_center else "u32", dev)
+        planes = CountPlanes(layout, "f64" if is_center else "u32", dev, bin_range)
+    ranged = (planes.bin_lo, planes.bin_hi) != (0, int(layout.total_bins))
+    if bin_range is not None and (planes.bin_lo, planes.bin_hi) != tuple(int(x) for x in bin_range):
+        raise ValueError("planes were allocated for another bin range")
+    if ranged and is_center:
+        raise ValueError("position-range mapping is implemented for the point rules (pb_map_point_range)")
     planes.alloc(strands)
     mask = 0
     for s in strands:
@@ -90,8 +117,12 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     ws = _workspace(dev, ws_bytes)
     stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev)
     b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
-    outs = [_lib.ptr(planes.planes[s]) if s in strands else None for s in _STRANDS]
-    if is_center:
+    outs = [planes.plane_ptr(s) if s in strands else None for s in _STRANDS]
+    if ranged:
+        _lib.check(L.pb_map_point_range(C.byref(b), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
+                                        _lib.ptr(stats), _lib.ptr(ws), ws_bytes, planes.bin_lo, planes.bin_hi,
+                                        dbatch.n_reads, _lib.stream_ptr()))
+    elif is_center:
         hist = torch.zeros(65536, dtype=torch.int64, device=dev)
         _lib.check(L.pb_length_hist(C.byref(b), C.byref(rule), _lib.PB_PLANE_ANY, _lib.ptr(hist), _lib.stream_ptr()))
         slot_of_len, inv_m = factory.slot_tables(hist.cpu().numpy())
@@ -137,7 +168,7 @@ def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=N
         receiver._receive_tables(pinned)
     events = [receiver.receive_chunk(pinned, a, b, copy_stream) for a, b, _x, _y in chunks]
     b_c, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
-    outs = [_lib.ptr(planes.planes[s]) if s in strands else None for s in _STRANDS]
+    outs = [planes.plane_ptr(s) if s in strands else None for s in _STRANDS]
     for (a, b, bin_a, bin_b), ev in zip(chunks, events):
         compute.wait_event(ev)
         receiver._unpack(a, b)
@@ -514,7 +545,7 @@ class BAMGenomeArray(object):
         dev = planes.device
         base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
         n = self._chr_lengths[chrom]
-        vec = planes.planes[strand][base:base + n]
+        vec = planes.bins(strand, base, base + n)
         L = _lib.lib()
         ws_bytes = L.pb_export_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -582,7 +613,7 @@ class BAMGenomeArray(object):
             base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
             n = self._chr_lengths[chrom] - 1
             for strand in _STRANDS:
-                src = planes.planes[strand][base:base + n]
+                src = planes.bins(strand, base, base + n)
                 if planes.dtype == "u32":
                     vals = (src.to(torch.int64) & 0xFFFFFFFF).to(torch.float64)
                 else:

@@ -76,6 +76,43 @@ def _worker(rank, world_size, port, results):
         pd.allreduce_sum(local)
         assert (local.numpy() == full).all()
 
+        # position-range sharding: range-only vectors from the reads of the range + halo, region
+        # tables clipped to the range and all-reduced
+        import plastid_b200 as pb
+        from plastid_b200.regions import ChainTable
+        from oracle import coracle
+        lay = pb.GenomeLayout(chroms, lens)
+        table = ChainTable.from_chains(chains, lay, use_masks=False)
+        for batch in (hb, spliced):
+            cuts = pd.position_cuts(batch, lay, world_size)
+            sub, lo, hi = pd.shard_positions(batch, lay, rank, world_size, cuts)
+            sub.check_sorted()
+            clipped = pd.clip_table(table, lo, hi)
+            part = np.zeros(len(chains))
+            whole = np.zeros(len(chains))
+            vec_sub, vec_all = {}, {}
+            for i, ch in enumerate(chains):
+                c = chroms.index(ch.chrom)
+                key = (c, ch.strand)
+                if key not in vec_sub:
+                    kw = dict(rule="fiveprime", offset=14, size_filter=(25, 100))
+                    vec_sub[key] = coracle.genome_vector(sub, c, ch.strand, **kw)[0]
+                    vec_all[key] = coracle.genome_vector(batch, c, ch.strand, **kw)[0]
+                    base = int(lay.chrom_bin_off[c])
+                    a, b = max(lo - base, 0), min(hi - base, int(lens[c]))
+                    if a < b:      # inside the rank's range the shard reproduces the whole-batch vector
+                        assert (vec_sub[key][a:b] == vec_all[key][a:b]).all()
+                base = int(lay.chrom_bin_off[c])
+                for j in range(int(clipped.chain_off[i]), int(clipped.chain_off[i + 1])):
+                    part[i] += vec_sub[key][int(clipped.bstart[j]) - base:int(clipped.bend[j]) - base].sum()
+                whole[i] = sum(vec_all[key][s.start:s.end].sum() for s in ch)
+            t = torch.from_numpy(part)
+            pd.allreduce_sum(t)
+            assert (t.numpy() == whole).all()
+            ln = torch.from_numpy(clipped.chain_len.copy())
+            pd.allreduce_sum(ln)
+            assert (ln.numpy() == table.chain_len).all()
+
         # chromosome sharding: disjoint ownership, tables gathered
         owned = pd.assign_chromosomes(hb, world_size)
         assert sorted(c for ids in owned for c in ids) == list(range(len(chroms)))
@@ -126,6 +163,33 @@ def test_sharding_plans_single_process():
     assert total == len(spliced)
     owned = pd.assign_chromosomes(hb, 8)          # more ranks than chromosomes: some ranks idle
     assert sum(len(x) for x in owned) == len(chroms) and sum(1 for x in owned if not x) == 3
+    import plastid_b200 as pb
+    from plastid_b200.regions import ChainTable
+    lay = pb.GenomeLayout(chroms, lens)
+    for W in (1, 3, 8):
+        cuts = pd.position_cuts(hb, lay, W)
+        assert len(cuts) == W + 1 and cuts[0] == 0 and cuts[-1] == lay.total_bins and (cuts % 16384 == 0).all()
+        covered = 0
+        for r in range(W):
+            sub, lo, hi = pd.shard_positions(spliced, lay, r, W, cuts)
+            sub.check_sorted()
+            c_of = np.searchsorted(sub.chrom_read_off, np.arange(len(sub)), side="right") - 1
+            g = lay.chrom_bin_off[c_of] + sub.ref_start
+            assert (g < hi).all() and (g >= lo - spliced.max_span).all()
+            covered += int(((g >= lo) & (g < hi)).sum())
+        assert covered == len(spliced)            # every read is "owned" by exactly one rank
+    chains = ann.chains()
+    masks = synth_masks = __import__("plastid_b200").synth.make_masks(ann, frac=0.3, seed=1)
+    for ch, m in zip(chains, masks):
+        if m:
+            ch.add_masks(*m)
+    table = ChainTable.from_chains(chains, lay)
+    cuts = pd.position_cuts(hb, lay, 4)
+    parts = [pd.clip_table(table, int(cuts[r]), int(cuts[r + 1])) for r in range(4)]
+    assert (sum(p.chain_len for p in parts) == table.chain_len).all()
+    bits = np.unpackbits(table.mask_bits, bitorder="little")
+    n_masked = sum(int(np.unpackbits(p.mask_bits, bitorder="little")[:int(p.chain_len.sum())].sum()) for p in parts)
+    assert n_masked == int(bits[:int(table.chain_len.sum())].sum()) > 0
     empty = pd.shard_chromosomes(hb, [])
     assert len(empty) == 0 and empty.chroms == []
     assert pd.world() == (0, 1)

@@ -528,6 +528,54 @@ def test_delta8_streamed_upload_matches_whole_batch(small_world, cuda_device, n_
     assert (planes.stats_dev.cpu().numpy() == ref.stats).all()
 
 
+@pytest.mark.parametrize("world_size", [2, 3, 7])
+@pytest.mark.parametrize("spliced", [False, True])
+def test_position_range_sharding_matches_whole_batch(small_world, cuda_device, world_size, spliced):
+    """every rank maps only its bin range from the reads starting in it + a halo, into
+    range-only planes; clipped region tables of all ranks add up to the whole table (one all-reduce)."""
+    import torch
+    from plastid_b200 import dist as pd
+    from plastid_b200.batch import DeviceBatch
+    from plastid_b200.genome_array import region_sums
+    from plastid_b200.regions import ChainTable
+    w = small_world
+    if spliced:
+        hb = synth.device_batch_to_host(synth.rnaseq_reads(w["chroms"], w["lens"], 60_000, seed=4, device="cpu",
+                                                           intron=(50, 3000)), w["chroms"], w["lens"])
+        fac, sf = pb.ThreePrimeMapFactory(3), None
+    else:
+        hb, fac, sf = w["hb"], pb.VariableFivePrimeMapFactory(synth.RIBO_OFFSETS), pb.SizeFilterFactory(20, 38)
+    lay = w["layout"]
+    chains = w["ann"].chains()
+    masks = synth.make_masks(w["ann"], frac=0.3, seed=2)
+    for ch, m in zip(chains, masks):
+        if m:
+            ch.add_masks(*m)
+    table = ChainTable.from_chains(chains, lay)
+    whole = map_batch(DeviceBatch.from_host(hb, cuda_device), lay, fac, sf, strands=("+", "-"))
+    ref_sums, ref_live = region_sums(whole, table)
+    cuts = pd.position_cuts(hb, lay, world_size)
+    assert cuts[0] == 0 and cuts[-1] == lay.total_bins and (np.diff(cuts) >= 0).all() and (cuts % 16384 == 0).all()
+    sums = torch.zeros_like(ref_sums)
+    live = torch.zeros_like(ref_live)
+    mapped = np.zeros(_lib.PB_NSTATS, dtype=np.int64)
+    for rank in range(world_size):
+        sub, lo, hi = pd.shard_positions(hb, lay, rank, world_size, cuts)
+        if hi == lo:
+            continue
+        planes = map_batch(DeviceBatch.from_host(sub, cuda_device), lay, fac, sf, strands=("+", "-"), bin_range=(lo, hi))
+        for s in ("+", "-"):
+            assert planes.planes[s].numel() == hi - lo
+            assert torch.equal(planes.planes[s], whole.planes[s][lo:hi])
+        s_r, l_r = region_sums(planes, pd.clip_table(table, lo, hi))
+        sums += s_r
+        live += l_r
+        mapped += planes.stats
+    assert torch.equal(sums, ref_sums) and torch.equal(live, ref_live)
+    for k in (_lib.PB_STAT_MAPPED_PLUS, _lib.PB_STAT_MAPPED_MINUS, _lib.PB_STAT_DROPPED_PLUS, _lib.PB_STAT_DROPPED_MINUS):
+        assert mapped[k] == whole.stats[k]        # halo reads are not counted twice
+
+
 def test_pileup_tile_is_split_into_overflow_jobs(cuda_device):
     """> 32768 candidate reads in one 4096-bin tile: the tile job keeps the first slice, the rest are
     added by pb_point_overflow_kernel with TMA bulk reductions — still bit-exact, stats included."""
