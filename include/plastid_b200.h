@@ -195,7 +195,11 @@ int pb_map_point(const pb_batch *batch, const pb_layout *layout, const pb_rule *
 /* The same over the bins [bin_begin, bin_end) only (both multiples of PB_LAYOUT_ALIGN), reading no
  * read at or beyond read_limit: lets a host->device upload of a sorted batch be overlapped with
  * mapping — once the reads up to a position have landed, the planes up to that position can be
- * produced.  stats accumulate over the calls. */
+ * produced — and lets a position-sharded rank produce its own bin range from the reads
+ * that start in it plus a halo.  Only bins of the range are written, so a plane pointer may be the
+ * address bin 0 WOULD have for a buffer holding just [bin_begin, bin_end).  Statistics count the
+ * reads / sites of the range only (they add up over disjoint ranges).  Batches with multi-block reads
+ * need read_limit == n_reads. */
 int pb_map_point_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
                        uint32_t *out_plus, uint32_t *out_minus, uint32_t *out_any,
                        uint64_t *stats, void *workspace, size_t workspace_bytes,

@@ -396,7 +396,7 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
     rc = pb_launch_tile_index(b, lay, tile_bins, 0, n_tiles, batch->n_reads, 0, ws, stream);
     if (rc) return rc;
-    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, ws, stream);
+    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, 0, n_tiles, ws, stream);
     if (rc) return rc;
     pb_timing_begin(stream);
     if (ept == 16)

@@ -301,9 +301,9 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
     PbWorkspace ws;
     rc = pb_carve_workspace(workspace, workspace_bytes, layout->total_bins, b.n_blk, b.n_reads, &ws);
     if (rc) return rc;
-    if (b.n_blk > 0 && (tile_begin != 0 || n_tiles != layout->total_bins / kPTileBins)) {
-        // binning needs every read resident; streamed uploads are unspliced by format (wire16)
-        pb_set_error("pb_map_point_range: batches with multi-block reads must be mapped over the whole layout");
+    if (b.n_blk > 0 && read_limit != batch->n_reads) {
+        // binning walks every read of the batch; streamed uploads are unspliced by format (wire16 / delta8)
+        pb_set_error("pb_map_point_range: batches with multi-block reads need every read resident (read_limit == n_reads)");
         return PB_EINVAL;
     }
 
@@ -311,7 +311,8 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
     rc = pb_launch_tile_index(b, lay, kPTileBins, tile_begin, n_tiles, read_limit, kPSplit, ws, stream);
     if (rc) return rc;
     // multi-block (spliced) reads: map them once and bin their sites by tile
-    rc = pb_launch_binning(b, r, lay, planes, 0, nullptr, kPTileBins, layout->total_bins / kPTileBins, ws, stream);
+    rc = pb_launch_binning(b, r, lay, planes, 0, nullptr, kPTileBins, layout->total_bins / kPTileBins, tile_begin, n_tiles,
+                           ws, stream);
     if (rc) return rc;
     const int n_planes = __builtin_popcount(planes);
     const size_t smem = (size_t)n_planes * kPTileBins * sizeof(uint32_t);

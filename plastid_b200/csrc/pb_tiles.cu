@@ -59,9 +59,11 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
 template <bool CENTER>
 __global__ void __launch_bounds__(256, 8)   // latency-bound gather chains: favour resident threads over registers
 pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t *__restrict__ slot_of_len,
-              int tile_shift, int fill, uint32_t *__restrict__ rec_cursor, const uint32_t *__restrict__ rec_off,
-              PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
+              int tile_shift, int64_t tile_lo, int64_t tile_hi, int fill, uint32_t *__restrict__ rec_cursor,
+              const uint32_t *__restrict__ rec_off, PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
 {
+    // [tile_lo, tile_hi): the tiles this launch produces (position-sharded ranks map a bin range only);
+    // records and statistics outside it belong to another rank
     unsigned long long drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;
     unsigned int drop_len = 0;
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
@@ -95,10 +97,16 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
         const int32_t s = sv[u];
         const int L = PB_META_L(m);
         const bool rev = PB_META_REV(m);
+        auto in_range = [&](int64_t x) {
+            const int64_t t = (base + x) >> tile_shift;
+            return t >= tile_lo && t < tile_hi;
+        };
+        const bool own = in_range(s);                            // the read's start lies in this launch's tiles
         auto emit = [&](int64_t x, int64_t y, uint32_t tag) {
             if (x < 0 || x >= clen) return;
             if (y > clen) y = clen;
             const int64_t tile = (base + x) >> tile_shift;       // tile sizes are powers of two
+            if (tile < tile_lo || tile >= tile_hi) return;
             // reads are coordinate-sorted, so the lanes that are here together mostly target the same
             // tile: one atomic per group of lanes instead of one per record
             const unsigned lane = threadIdx.x & 31;
@@ -117,11 +125,11 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
         if (CENTER) {
             const int nibble = r.param, map_len = L - 2 * nibble;
             if (map_len < 0) {                                   // map_factories.pyx:246-248
-                drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L;
+                if (own) { drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L; }
                 continue;
             }
             if (map_len == 0) continue;
-            map_a++; if (rev) map_m++; else map_p++;           // reads_out semantics (:256)
+            if (own) { map_a++; if (rev) map_m++; else map_p++; }   // reads_out semantics (:256)
             const int slot = (int)__ldg(slot_of_len + L);
             if (slot < 0) continue;
             const uint32_t tag = (uint32_t)slot | ((uint32_t)rev << 16);
@@ -137,21 +145,21 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
         } else {
             const int idx_f = pb_rule_index(r, L, false);
             if (idx_f < 0) {                                     // the reference skips the read and warns
-                drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L;
+                if (own) { drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L; }
                 continue;
             }
             int64_t p_f = -1, p_r = -1;
             uint32_t tag_f = 0, tag_r = 0;
             if (want_any || (!rev && want_plus)) {
                 p_f = pb_block_position(b, i, s, idx_f);
-                if (p_f >= 0 && p_f < clen) {
+                if (p_f >= 0 && p_f < clen && in_range(p_f)) {
                     if (want_any) { tag_f |= PB_PLANE_ANY; map_a++; }
                     if (!rev && want_plus) { tag_f |= PB_PLANE_PLUS; map_p++; }
                 }
             }
             if (rev && want_minus) {
                 p_r = pb_block_position(b, i, s, pb_rule_index(r, L, true));
-                if (p_r >= 0 && p_r < clen) { tag_r = PB_PLANE_MINUS; map_m++; }
+                if (p_r >= 0 && p_r < clen && in_range(p_r)) { tag_r = PB_PLANE_MINUS; map_m++; }
             }
             if (tag_f && tag_r && p_f == p_r) { tag_f |= tag_r; tag_r = 0; }
             if (tag_f) emit(p_f, p_f + 1, tag_f);
@@ -408,8 +416,8 @@ int pb_launch_tile_index(const PbReads &b, const PbLayoutDev &lay, int tile_bins
 }
 
 int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes, int center,
-                      const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, const PbWorkspace &ws,
-                      cudaStream_t stream)
+                      const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, int64_t tile_lo, int64_t tile_hi,
+                      const PbWorkspace &ws, cudaStream_t stream)
 {
     if (!b.blk_off || b.n_blk <= 0 || b.n_reads == 0) return PB_OK;
     int sms = 0;
@@ -423,10 +431,10 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
     if ((1 << tile_shift) != tile_bins) { pb_set_error("tile size must be a power of two"); return PB_EINVAL; }
     for (int fill = 0; fill < 2; ++fill) {
         if (center)
-            pb_bin_kernel<true><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, fill, ws.rec_cursor,
+            pb_bin_kernel<true><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, fill, ws.rec_cursor,
                                                           ws.rec_off, ws.recs, ws.slots);
         else
-            pb_bin_kernel<false><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, fill, ws.rec_cursor,
+            pb_bin_kernel<false><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, fill, ws.rec_cursor,
                                                            ws.rec_off, ws.recs, ws.slots);
         if (!fill) {
             const int64_t nb = (n_tiles + kScanChunk - 1) / kScanChunk;

@@ -59,9 +59,10 @@ int pb_launch_tile_index(const PbReads &b, const PbLayoutDev &lay, int tile_bins
                          int64_t read_limit, int split, const PbWorkspace &ws, cudaStream_t stream);
 // Bin the contributions of multi-block reads by tile (no-op when the batch has none): count,
 // exclusive scan, fill.  center = 0: point-rule sites; center = 1: trimmed aligned intervals.
+// Only records (and statistics) of tiles [tile_lo, tile_hi) are produced.
 int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes, int center,
-                      const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, const PbWorkspace &ws,
-                      cudaStream_t stream);
+                      const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, int64_t tile_lo, int64_t tile_hi,
+                      const PbWorkspace &ws, cudaStream_t stream);
 int pb_launch_stats_finish(const unsigned long long *slots, unsigned long long *stats, cudaStream_t stream);
 // exclusive prefix sums of uint32 counts (three small launches); part needs pb_scan_part_entries(n) words
 int64_t pb_scan_part_entries(int64_t n);
