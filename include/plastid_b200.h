@@ -294,6 +294,13 @@ int pb_column_profile(const double *values, const uint8_t *valmask, const uint8_
                       int64_t n_rows, int32_t width, int mode,
                       double *profile, int64_t *n_regions, double *col_sum,
                       void *workspace, size_t workspace_bytes, void *stream);
+/* The same for n_batch equally shaped matrices stacked row-wise (psite.py:176-234: one matrix per read
+ * length): values/valmask [n_batch][n_rows][width], row_select [n_batch][n_rows]; profile, n_regions,
+ * col_sum [n_batch][width]; workspace n_batch x pb_column_profile_workspace_bytes(n_rows, width). */
+int pb_column_profile_batched(const double *values, const uint8_t *valmask, const uint8_t *row_select,
+                              int32_t n_batch, int64_t n_rows, int32_t width, int mode,
+                              double *profile, int64_t *n_regions, double *col_sum,
+                              void *workspace, size_t workspace_bytes, void *stream);
 
 /* psite.py:176-199 / phase_by_size.py:186-194 in one launch: for every window chain and every aligned
  * length in [min_len, max_len], the counts of the reads the point rule maps into the window, laid

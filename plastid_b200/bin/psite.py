@@ -31,28 +31,35 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
     strat, maskmat = stratified_windows(dbatch, ga.layout, ga.map_fn, ga._size_filter(), table, cols, window_size,
                                         min_len, max_len)
     dev = strat.device
+    n_len, n = max_len - min_len + 1, table.n_chains
     colidx = torch.arange(window_size, device=dev)[None, :]
     c0 = torch.as_tensor(np.asarray(cols), device=dev)[:, None]
     clen = torch.from_numpy(table.chain_len).to(dev)[:, None]
     uncovered = (colidx < c0) | (colidx >= c0 + clen)
     out = {"x": np.arange(-flank, window_size - flank), "profiles": {}, "regions_counted": {}, "raw": {}}
-    for k in range(min_len, max_len + 1):
-        mat = strat[k - min_len].to(torch.float64)
-        mat[uncovered] = float("nan")                    # cells no chain position reaches (psite.py:153-157)
-        mat = mat.contiguous()
-        denom, sel, norm, nmask = window_normalize(mat, maskmat, norm_start, norm_end, min_counts)
-        if aggregate:
-            profile, n_regions, _ = column_profile(mat, maskmat, sel, "sum")
-            _p, n_regions, _ = column_profile(norm, nmask, sel, "mean")     # regions_counted uses the norm mask
-        else:
-            profile, n_regions, _ = column_profile(norm, nmask, sel, "median")
-        prof = profile.cpu().numpy()
-        if sel.sum().item() == 0 and not aggregate:
+    # all read lengths at once: the matrices are stacked row-wise, normalised in one launch and reduced
+    # per (length, column) in one launch
+    mat = strat.to(torch.float64)                                    # [n_len, n, W]
+    mat.masked_fill_(uncovered[None, :, :], float("nan"))            # cells no chain position reaches (psite.py:153-157)
+    mat = mat.view(n_len * n, window_size)
+    mask_all = maskmat.repeat(n_len, 1)                              # the position mask is shared by all lengths
+    denom, sel, norm, nmask = window_normalize(mat, mask_all, norm_start, norm_end, min_counts)
+    if aggregate:
+        profile, _n, _ = column_profile(mat, mask_all, sel, "sum", n_batch=n_len)
+        _p, n_regions, _ = column_profile(norm, nmask, sel, "mean", n_batch=n_len)     # regions_counted uses the norm mask
+    else:
+        profile, n_regions, _ = column_profile(norm, nmask, sel, "median", n_batch=n_len)
+    profile = profile.view(n_len, window_size).cpu().numpy()
+    n_regions = n_regions.view(n_len, window_size).cpu().numpy()
+    any_sel = sel.view(n_len, n).any(dim=1).cpu().numpy()
+    for j, k in enumerate(range(min_len, max_len + 1)):
+        prof = profile[j]
+        if not any_sel[j] and not aggregate:
             prof = np.zeros(window_size)
         out["profiles"][k] = prof
-        out["regions_counted"][k] = n_regions.cpu().numpy()
+        out["regions_counted"][k] = n_regions[j]
         if keep:
-            out["raw"][k] = np.ma.MaskedArray(mat.cpu().numpy(), mask=maskmat.cpu().numpy().astype(bool))
+            out["raw"][k] = np.ma.MaskedArray(mat[j * n:(j + 1) * n].cpu().numpy(), mask=maskmat.cpu().numpy().astype(bool))
     return out
 
 

@@ -363,6 +363,10 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
         ((planes & PB_PLANE_ANY) && !out_any) || !stats) {
         pb_set_error("pb_map_center: missing output plane or stats"); return PB_EINVAL;
     }
+    if ((((uintptr_t)out_plus | (uintptr_t)out_minus | (uintptr_t)out_any) & 15) ||
+        ((uintptr_t)workspace & 15)) {      // TMA bulk stores / reductions move 16-byte units
+        pb_set_error("pb_map_center: planes and workspace must be 16-byte aligned"); return PB_EINVAL;
+    }
     cudaStream_t stream = (cudaStream_t)stream_;
     PbReads b = pb_to_dev(batch);
     PbRuleDev r = pb_to_dev(rule);

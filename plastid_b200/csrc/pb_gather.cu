@@ -209,6 +209,11 @@ __global__ void pb_column_keys_kernel(const double *__restrict__ norm, const uin
                                       unsigned long long *__restrict__ keys)
 {
     __shared__ unsigned long long tile[32][33];
+    // blockIdx.z = matrix of a batch (psite: one per read length); each has its own rows, select flags, keys
+    norm += (int64_t)blockIdx.z * n_rows * width;
+    normmask += (int64_t)blockIdx.z * n_rows * width;
+    row_select += (int64_t)blockIdx.z * n_rows;
+    keys += (int64_t)blockIdx.z * n_rows * width;
     const int64_t r0 = (int64_t)blockIdx.y * 32;
     const int c0 = blockIdx.x * 32;
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
@@ -265,38 +270,57 @@ pb_column_stats_kernel(const unsigned long long *__restrict__ keys, int64_t n_ro
     if (mode != 0) return;
     if (n_valid == 0) { if (threadIdx.x == 0) profile[col] = nan(""); return; }
 
-    double mid[2];
-    for (int which = 0; which < 2; ++which) {
-        // ranks (0-based) of the two middle elements: (n-1)/2 and n/2
-        unsigned long long rank = which == 0 ? (n_valid - 1) / 2 : n_valid / 2;
-        unsigned long long prefix = 0;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
-            __syncthreads();
-            const unsigned long long himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-            for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
-                const unsigned long long k = K[r];
-                if (k != ~0ull && (k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long run = 0;
-                int d = 0;
-                for (; d < 256; ++d) {
-                    if (run + hist[d] > rank) break;
-                    run += hist[d];
-                }
-                s_prefix = prefix | ((unsigned long long)d << shift);
-                s_rank = rank - run;
-            }
-            __syncthreads();
-            prefix = s_prefix;
-            rank = s_rank;
-            __syncthreads();
+    // lower middle element (0-based rank (n-1)/2) by radix select, 8 bits per pass
+    unsigned long long rank = (n_valid - 1) / 2;
+    unsigned long long prefix = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
+        __syncthreads();
+        const unsigned long long himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+            const unsigned long long k = K[r];
+            if (k != ~0ull && (k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
         }
-        mid[which] = pb_value_of(prefix);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long run = 0;
+            int d = 0;
+            for (; d < 256; ++d) {
+                if (run + hist[d] > rank) break;
+                run += hist[d];
+            }
+            s_prefix = prefix | ((unsigned long long)d << shift);
+            s_rank = rank - run;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        rank = s_rank;
+        __syncthreads();
     }
-    if (threadIdx.x == 0) profile[col] = (mid[0] + mid[1]) / 2.0;
+    const unsigned long long key0 = prefix;
+    // upper middle element (rank n/2): the same key when n is odd or key0 repeats far enough, else the
+    // smallest key above it — one more pass instead of a second select
+    unsigned long long key1 = key0;
+    if ((n_valid & 1ull) == 0) {
+        unsigned long long le = 0, succ = ~0ull;
+        for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+            const unsigned long long k = K[r];
+            if (k == ~0ull) continue;
+            if (k <= key0) le++; else if (k < succ) succ = k;
+        }
+        le = pb_warp_sum(le);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, succ, d);
+            succ = o < succ ? o : succ;
+        }
+        if (threadIdx.x == 0) { s_cnt = 0; s_prefix = ~0ull; }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt, le); atomicMin(&s_prefix, succ); }
+        __syncthreads();
+        if (s_cnt <= n_valid / 2) key1 = s_prefix;       // fewer than n/2 + 1 keys are <= key0
+    }
+    if (threadIdx.x == 0) profile[col] = (pb_value_of(key0) + pb_value_of(key1)) / 2.0;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -432,25 +456,38 @@ extern "C" size_t pb_column_profile_workspace_bytes(int64_t n_rows, int32_t widt
     return (size_t)n_rows * (size_t)width * sizeof(unsigned long long) + 256;
 }
 
+extern "C" int pb_column_profile_batched(const double *values, const uint8_t *valmask, const uint8_t *row_select,
+                                         int32_t n_batch, int64_t n_rows, int32_t width, int mode,
+                                         double *profile, int64_t *n_regions, double *col_sum,
+                                         void *workspace, size_t workspace_bytes, void *stream_)
+{
+    if (!values || !valmask || !row_select || !profile || !n_regions || !col_sum || n_rows < 0 || width <= 0 ||
+        mode < 0 || mode > 2 || n_batch < 1 || n_batch > 65535) {
+        pb_set_error("pb_column_profile: bad arguments"); return PB_EINVAL;
+    }
+    if (!workspace || workspace_bytes < (size_t)n_batch * pb_column_profile_workspace_bytes(n_rows, width)) {
+        pb_set_error("pb_column_profile: workspace too small"); return PB_ENOSPACE;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *keys = (unsigned long long *)workspace;
+    if (n_rows > 0) {
+        dim3 grid((unsigned)((width + 31) / 32), (unsigned)((n_rows + 31) / 32), (unsigned)n_batch);
+        if (grid.y > 65535) { pb_set_error("pb_column_profile: more than 2,097,120 rows"); return PB_EINVAL; }
+        pb_column_keys_kernel<<<grid, dim3(32, 8), 0, stream>>>(values, valmask, row_select, n_rows, width, keys);
+    }
+    // one CTA per column of every matrix: column b*width + c reads keys[(b*width + c) * n_rows ...]
+    pb_column_stats_kernel<<<(unsigned)(n_batch * width), 512, 0, stream>>>(keys, n_rows, width, mode, profile, n_regions, col_sum);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
 extern "C" int pb_column_profile(const double *values, const uint8_t *valmask, const uint8_t *row_select,
                                  int64_t n_rows, int32_t width, int mode,
                                  double *profile, int64_t *n_regions, double *col_sum,
                                  void *workspace, size_t workspace_bytes, void *stream_)
 {
-    if (!values || !valmask || !row_select || !profile || !n_regions || !col_sum || n_rows < 0 || width <= 0 || mode < 0 || mode > 2) {
-        pb_set_error("pb_column_profile: bad arguments"); return PB_EINVAL;
-    }
-    if (!workspace || workspace_bytes < pb_column_profile_workspace_bytes(n_rows, width)) { pb_set_error("pb_column_profile: workspace too small"); return PB_ENOSPACE; }
-    cudaStream_t stream = (cudaStream_t)stream_;
-    unsigned long long *keys = (unsigned long long *)workspace;
-    if (n_rows > 0) {
-        dim3 grid((unsigned)((width + 31) / 32), (unsigned)((n_rows + 31) / 32));
-        if (grid.y > 65535) { pb_set_error("pb_column_profile: more than 2,097,120 rows"); return PB_EINVAL; }
-        pb_column_keys_kernel<<<grid, dim3(32, 8), 0, stream>>>(values, valmask, row_select, n_rows, width, keys);
-    }
-    pb_column_stats_kernel<<<(unsigned)width, 512, 0, stream>>>(keys, n_rows, width, mode, profile, n_regions, col_sum);
-    PB_CUDA_CHECK(cudaGetLastError());
-    return PB_OK;
+    return pb_column_profile_batched(values, valmask, row_select, 1, n_rows, width, mode, profile, n_regions, col_sum,
+                                     workspace, workspace_bytes, stream_);
 }
 
 extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,

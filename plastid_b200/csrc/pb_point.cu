@@ -287,6 +287,10 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
         ((planes & PB_PLANE_ANY) && !out_any) || !stats) {
         pb_set_error("pb_map_point: missing output plane or stats"); return PB_EINVAL;
     }
+    if ((((uintptr_t)out_plus | (uintptr_t)out_minus | (uintptr_t)out_any) & 15) ||
+        ((uintptr_t)workspace & 15)) {      // TMA bulk stores move 16-byte units
+        pb_set_error("pb_map_point: planes and workspace must be 16-byte aligned"); return PB_EINVAL;
+    }
     if (bin_begin < 0 || bin_end > layout->total_bins || bin_begin > bin_end || bin_begin % PB_LAYOUT_ALIGN ||
         bin_end % PB_LAYOUT_ALIGN) {
         pb_set_error("pb_map_point_range: bin range must be PB_LAYOUT_ALIGN-aligned and inside the layout"); return PB_EINVAL;

@@ -268,22 +268,42 @@ def window_normalize(matrix, maskmat, norm_lo, norm_hi, min_counts, want_norm=Tr
     return denom[:n], sel[:n], norm, nmask
 
 
-def column_profile(values, valmask, row_select, mode="median"):
-    """Per-column median / mean / sum over unmasked cells of selected rows."""
+def column_profile(values, valmask, row_select, mode="median", n_batch=1):
+    """Per-column median / mean / sum over unmasked cells of selected rows.  ``n_batch`` > 1: ``values``
+    stacks that many equally shaped matrices row-wise (psite: one per read length); the results come
+    back as ``[n_batch, width]`` from one launch."""
     import torch
-    n, width = values.shape
+    n_all, width = values.shape
+    if n_all % n_batch:
+        raise ValueError("rows must divide evenly over the batch")
+    n = n_all // n_batch
     dev = values.device
     L = _lib.lib()
-    ws_bytes = L.pb_column_profile_workspace_bytes(n, width)
-    ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)
-    profile = torch.empty(width, dtype=torch.float64, device=dev)
-    n_regions = torch.empty(width, dtype=torch.int64, device=dev)
-    col_sum = torch.empty(width, dtype=torch.float64, device=dev)
-    _lib.check(L.pb_column_profile(_lib.ptr(values), _lib.ptr(valmask), _lib.ptr(row_select), n, width,
-                                   {"median": 0, "mean": 1, "sum": 2}[mode], _lib.ptr(profile),
-                                   _lib.ptr(n_regions), _lib.ptr(col_sum), _lib.ptr(ws), ws_bytes,
-                                   _lib.stream_ptr()))
-    return profile, n_regions, col_sum
+    ws_bytes = n_batch * L.pb_column_profile_workspace_bytes(n, width)
+    ws = _scratch(dev, int(ws_bytes))
+    profile = torch.empty(n_batch * width, dtype=torch.float64, device=dev)
+    n_regions = torch.empty(n_batch * width, dtype=torch.int64, device=dev)
+    col_sum = torch.empty(n_batch * width, dtype=torch.float64, device=dev)
+    _lib.check(L.pb_column_profile_batched(_lib.ptr(values), _lib.ptr(valmask), _lib.ptr(row_select), n_batch, n, width,
+                                           {"median": 0, "mean": 1, "sum": 2}[mode], _lib.ptr(profile),
+                                           _lib.ptr(n_regions), _lib.ptr(col_sum), _lib.ptr(ws), ws_bytes,
+                                           _lib.stream_ptr()))
+    if n_batch == 1:
+        return profile, n_regions, col_sum
+    return profile.view(n_batch, width), n_regions.view(n_batch, width), col_sum.view(n_batch, width)
+
+
+_scratch_bufs = {}
+
+
+def _scratch(device, nbytes):
+    """Reusable device scratch (radix-select keys): grown, never shrunk, one per device."""
+    import torch
+    key = str(device)
+    buf = _scratch_bufs.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _scratch_bufs[key] = buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+    return buf
 
 
 def merge_batches(batches):
