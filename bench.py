@@ -551,6 +551,22 @@ def main():
     value = n_reads * world / (ms_per_step / 1000.0)
     region_rate = ann.n_tx * world / (ms_per_step / 1000.0)
 
+    # ------------------------------------------------------------------ launch-bound workloads: CUDA graph replay
+    graph_ms = None
+    if args.workload == "c1" and world == 1:
+        from plastid_b200.genome_array import GraphedCount
+        gc_ = GraphedCount(dbatch, layout, fac, sf, table, strands=("+", "-"))
+        for _ in range(3):
+            gc_.replay()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps * 10):
+            g_sums, g_live = gc_.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        graph_ms = ev0.elapsed_time(ev1) / (args.steps * 10)
+        assert torch.equal(g_sums, sums) and torch.equal(g_live, live), "graph replay differs from the eager pass"
+
     # ------------------------------------------------------------------ end-to-end (host buffers)
     # The caller holds the batch in pinned host memory in the transfer format the host decoder
     # emits: wire16 (4 B/read) for unspliced batches, the plain SoA otherwise.  Every step copies it
@@ -566,7 +582,8 @@ def main():
         pinned = wire.pinned()
         receiver = WireReceiver(wire, device)
         h2d = wire.nbytes
-        chunks = WireReceiver.plan_chunks(wire, layout, args.e2e_chunks)
+        # small batches are launch-bound: fewer, larger chunks (about 8 M reads each at least)
+        chunks = WireReceiver.plan_chunks(wire, layout, max(1, min(args.e2e_chunks, n_reads // 8_000_000)))
         copy_stream = torch.cuda.Stream(device=device)
         from plastid_b200.genome_array import map_wire16_streamed
 
@@ -678,6 +695,10 @@ def main():
                     if use_wire16 else "SoA (8 B/read + blocks)"},
             "gpu_launches": len(kernels_per_step) * args.steps, "kernels_per_step": kernels_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}
+    if graph_ms is not None:
+        # the same pass replayed as one CUDA graph launch (launch-latency bound workload)
+        line["cuda_graph"] = {"ms_per_step": graph_ms, "value": n_reads / (graph_ms / 1000.0), "unit": UNIT,
+                              "region_counts_per_sec": ann.n_tx / (graph_ms / 1000.0), "replays_timed": args.steps * 10}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

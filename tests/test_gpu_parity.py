@@ -576,6 +576,25 @@ def test_position_range_sharding_matches_whole_batch(small_world, cuda_device, w
         assert mapped[k] == whole.stats[k]        # halo reads are not counted twice
 
 
+def test_cuda_graph_replay_matches_eager_pass(small_world, cuda_device):
+    import torch
+    from plastid_b200.genome_array import GraphedCount
+    w = small_world
+    fac, sf = pb.VariableFivePrimeMapFactory(synth.RIBO_OFFSETS), pb.SizeFilterFactory(20, 38)
+    table = ChainTable.from_chains(w["ann"].chains(), w["layout"])
+    eager = map_batch(w["dbatch"], w["layout"], fac, sf, strands=("+", "-"))
+    e_sums, e_live = region_sums(eager, table)
+    g = GraphedCount(w["dbatch"], w["layout"], fac, sf, table)
+    for _ in range(3):
+        g.planes.planes["+"].fill_(-1)            # every bin is rewritten by each replay
+        sums, live = g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(sums, e_sums) and torch.equal(live, e_live)
+        assert torch.equal(g.planes.planes["+"], eager.planes["+"]) and torch.equal(g.planes.planes["-"], eager.planes["-"])
+    with pytest.raises(TypeError):
+        GraphedCount(w["dbatch"], w["layout"], pb.CenterMapFactory(12), None, table)
+
+
 def test_pileup_tile_is_split_into_overflow_jobs(cuda_device):
     """> 32768 candidate reads in one 4096-bin tile: the tile job keeps the first slice, the rest are
     added by pb_point_overflow_kernel with TMA bulk reductions — still bit-exact, stats included."""
