@@ -214,6 +214,18 @@ int pb_map_center(const pb_batch *batch, const pb_layout *layout, const pb_rule 
                   double *out_plus, double *out_minus, double *out_any,
                   uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Center mapping of a batch with MANY distinct map lengths (the reference's default CenterMapFactory() on
+ * 25-35 nt ribo-seq reads has a dozen) in one pass: every read adds the integer weight
+ * w_fix[slot] = round(2^shift / m) to one 64-bit difference array per plane; bin = total * 2^-shift.
+ * Deterministic (integer accumulation), exact zeros; relative error against sum(1/m) is at most
+ * m * 2^-(shift+1) per map length — the caller picks shift <= 62 - log2(sum over reads of 1/m) so that no
+ * total overflows and keeps that error far below the 1e-6 tolerance (plastid_b200.genome_array.map_batch
+ * requires <= 1e-9, else it uses pb_map_center).  Planes must be 32-byte aligned. */
+int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                        const int16_t *slot_of_len, const int64_t *w_fix, int n_slots, int shift,
+                        double *out_plus, double *out_minus, double *out_any,
+                        uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Measurement hook (bench.py roofline): while enabled, pb_map_point / pb_map_center bracket their
  * tiles kernel with CUDA events on the launch stream (up to 256 launches since the last enable);
  * pb_tiles_kernel_ms_total waits for them and returns the summed device time and launch count. */

@@ -15,6 +15,7 @@
 // block, not the longest intron); finished tiles are staged as fp64 in shared memory and leave the
 // SM as TMA bulk stores (or bulk fp64 reductions when map lengths need more than one pass).
 #include "pb_tiles.cuh"
+#include <math.h>
 #include <stdlib.h>
 
 namespace {
@@ -275,6 +276,265 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
     if (lane == 0) pb_bulk_wait_all();   // staged tiles (every warp) and zero tiles (thread 0)
 }
 
+// ----------------------------------------------------------------------------------------
+// many map lengths at once: 64-bit fixed-point weights
+// ----------------------------------------------------------------------------------------
+// With S distinct map lengths the exact kernel above needs S integer difference arrays per plane;
+// ribo-seq reads (25-35 nt, the reference's default CenterMapFactory()) have a dozen, which does not
+// fit next to a useful tile and forced many accumulating passes (13x slower than one length).  Here
+// every read adds the INTEGER weight W_m = round(2^shift / m) to ONE 64-bit difference array per
+// plane: integer accumulation commutes (deterministic, exact zeros), the prefix scan is exact, and
+// bin = total * 2^-shift.  The host picks `shift` from the length histogram so that no total can
+// overflow 63 bits and checks that m * 2^-(shift+1) — the relative error against sum(1/m) — stays far
+// below the north star's 1e-6 (map_batch falls back to the exact multi-pass kernel otherwise).
+// Same skeleton as the exact kernel: one barrier per tile, double-buffered arrays, 4 consecutive bins
+// per thread, register-prefetched reads, 256-bit direct stores.  64-bit shared atomics are CAS loops on
+// sm_100 (ATOMS.CAST.SPIN.64): fine for the ~100 reads of an ordinary tile.
+// Run-aggregated 64-bit add, called by all 32 lanes: consecutive lanes with the same key (reads are
+// coordinate-sorted, so equal targets come in runs) are summed with a segmented warp scan and the last
+// lane of every run issues ONE atomic.  64-bit shared atomics are CAS loops; in a pile-up tile, where
+// hundreds of reads share a start, this removes the same-address contention.  key < 0 = nothing to add.
+__device__ __forceinline__ void pb_run_add_u64(unsigned long long *arr, int key, unsigned long long w)
+{
+    const int lane = threadIdx.x & 31;
+    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    bool head = (lane == 0) || (key != kprev);
+    const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+    const bool tail = (lane == 31) || (knext != key);
+    unsigned long long v = w;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, v, dd);
+        const bool hup = __shfl_up_sync(0xffffffffu, (int)head, dd) != 0;
+        if (lane >= dd && !head) { v += up; head = hup; }
+    }
+    if (tail && key >= 0 && v != 0ull) atomicAdd(arr + key, v);
+}
+
+constexpr int kCDenseReads = 2048;   // candidate reads per tile from which the aggregated path is used
+
+template <int PLANES>
+__global__ void __launch_bounds__(kCThreads, 3)
+pb_center_fixed_kernel(PbReads b, PbRuleDev r, int planes_rt,
+                       const int16_t *__restrict__ slot_of_len, const long long *__restrict__ w_fix, double scale,
+                       int lookback, const PbTile *__restrict__ tiles, int64_t n_tiles,
+                       unsigned long long *__restrict__ tile_counter,
+                       const uint32_t *__restrict__ rec_off, const PbRec *__restrict__ recs,
+                       double *__restrict__ out_plus, double *__restrict__ out_minus, double *__restrict__ out_any,
+                       unsigned long long *__restrict__ stat_slots)
+{
+    typedef unsigned long long u64;
+    constexpr int EPT = 8, T = EPT * kCThreads, kChunk = 128, nChunks = T / kChunk, kPerWarp = nChunks / kCWarps;
+    const int planes = PLANES ? PLANES : planes_rt;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ PbSlot s_ring[4];
+    const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
+               want_any = planes & PB_PLANE_ANY;
+    const int n_planes = PLANES ? ((PLANES & 1) + ((PLANES >> 1) & 1) + ((PLANES >> 2) & 1))
+                                : (int)want_plus + (int)want_minus + (int)want_any;
+    double *zbuf = reinterpret_cast<double *>(smem_raw);            // [kZeroBins] zeros, never written
+    u64 *diff_all = reinterpret_cast<u64 *>(zbuf + kZeroBins);      // [2][n_planes][T] by iteration parity
+    u64 *tot_all = diff_all + (size_t)2 * n_planes * T;             // [3][n_planes][nChunks] by iteration mod 3
+    double *outs[3];
+    int a_plus = 0, a_minus = 0, a_any = 0;
+    {
+        int k = 0;
+        if (want_plus) { outs[k] = out_plus; a_plus = k++; }
+        if (want_minus) { outs[k] = out_minus; a_minus = k++; }
+        if (want_any) { outs[k] = out_any; a_any = k++; }
+    }
+    {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *s4 = reinterpret_cast<uint4 *>(smem_raw);
+        const int n16 = (kZeroBins * 8 + 2 * n_planes * T * 8 + 3 * n_planes * nChunks * 8 + 15) / 16;
+        for (int j = threadIdx.x; j < n16; j += kCThreads) s4[j] = z;
+    }
+    PbQueueRegs q;
+    if (threadIdx.x == 0) pb_queue_init(s_ring, q, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
+    pb_fence_proxy_async();
+    __syncthreads();
+
+    unsigned int drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0, drop_len = 0;
+    const int nibble = r.param;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int32_t pre_s = 0;
+    uint32_t pre_m = 1u << 17;
+    PbRec pre_rec = PbRec{0, 0, 0u, 0u};
+    auto preload = [&](const PbSlot &nx) {
+        pre_m = 1u << 17;
+        pre_rec.x = pre_rec.y = 0;
+        if (nx.tile >= n_tiles) return;
+        if ((int)threadIdx.x < nx.d.n) {
+            pre_s = __ldg(b.ref_start + nx.d.lo + threadIdx.x);
+            pre_m = __ldg(b.meta + nx.d.lo + threadIdx.x);
+        }
+        if (nx.rec_lo + threadIdx.x < nx.rec_hi) pre_rec = recs[nx.rec_lo + threadIdx.x];
+    };
+    preload(s_ring[0]);
+
+    int k3 = 0;
+    for (int k = 0;; ++k, k3 = (k3 == 2 ? 0 : k3 + 1)) {
+        if (threadIdx.x == 0) pb_queue_step(s_ring, q, k, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
+        const PbSlot &cur = s_ring[k & 3];
+        const long long tile = cur.tile;
+        if (tile >= n_tiles) break;
+        const PbTile d = cur.d;
+        const uint32_t rec_lo = cur.rec_lo, rec_hi = cur.rec_hi;
+        const int64_t g0 = tile * T;
+        const bool has_work = d.n > 0 || rec_hi > rec_lo;
+        u64 *diff = diff_all + (size_t)(k & 1) * n_planes * T;
+        u64 *tot = tot_all + k3 * n_planes * nChunks;
+        u64 *tot_next2 = tot_all + (k3 == 0 ? 2 : k3 - 1) * n_planes * nChunks;
+
+        if (has_work) {
+            const int64_t p0 = d.p0, p1 = d.p0 + T, plim = d.p0 + d.live;
+            auto add_interval = [&](int64_t x, int64_t y, u64 w, bool rev) {
+                if (y <= p0 || x >= plim) return;
+                const bool do_strand = rev ? want_minus : want_plus;
+                const int a_strand = rev ? a_minus : a_plus;
+                const unsigned ox = (unsigned)((x > p0 ? x : p0) - p0);
+                if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + ox], w); atomicAdd(&tot[a_strand * nChunks + ox / kChunk], w); }
+                if (want_any) { atomicAdd(&diff[(size_t)a_any * T + ox], w); atomicAdd(&tot[a_any * nChunks + ox / kChunk], w); }
+                if (y < p1) {
+                    const unsigned oy = (unsigned)(y - p0);
+                    const u64 nw = 0ull - w;                       // two's complement: adds -w
+                    if (do_strand) { atomicAdd(&diff[(size_t)a_strand * T + oy], nw); atomicAdd(&tot[a_strand * nChunks + oy / kChunk], nw); }
+                    if (want_any) { atomicAdd(&diff[(size_t)a_any * T + oy], nw); atomicAdd(&tot[a_any * nChunks + oy / kChunk], nw); }
+                }
+            };
+            // decode one read into its trimmed interval and weight (statistics on the way)
+            auto decode = [&](int32_t s, uint32_t m, int64_t &x, int64_t &y, u64 &w, bool &rev) -> bool {
+                if (!pb_passes(m, r.size_min, r.size_max)) return false;
+                if (rec_off && PB_META_NBLK(m) > 1) return false;  // arrives through the bucket
+                const int L = PB_META_L(m);
+                rev = PB_META_REV(m);
+                const bool own = (s >= p0 && s < p1);
+                const int map_len = L - 2 * nibble;
+                if (map_len < 0) {                                 // map_factories.pyx:246-248
+                    if (own) { drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L; }
+                    return false;
+                }
+                if (map_len == 0) return false;
+                if (own) { map_a++; if (rev) map_m++; else map_p++; }   // reads_out semantics (:256)
+                const int slot = (int)__ldg(slot_of_len + L);
+                if (slot < 0) return false;
+                x = (int64_t)s + nibble;
+                y = (int64_t)s + L - nibble;
+                w = (u64)__ldg(w_fix + slot);
+                return true;
+            };
+            // pile-up tiles: all lanes take part, equal targets are summed in the warp first
+            auto agg_interval = [&](bool valid, int64_t x, int64_t y, u64 w, bool rev) {
+                const bool in = valid && !(y <= p0 || x >= plim);
+                const bool has_y = in && y < p1;
+                const int kx = in ? (int)((x > p0 ? x : p0) - p0) : -1, ky = has_y ? (int)(y - p0) : -1;
+                const int cx = in ? kx / kChunk : -1, cy = has_y ? ky / kChunk : -1;
+                const u64 nw = 0ull - w;
+                if (want_plus) {
+                    const u64 wx = (in && !rev) ? w : 0ull, wy = (has_y && !rev) ? nw : 0ull;
+                    pb_run_add_u64(diff + (size_t)a_plus * T, kx, wx);  pb_run_add_u64(tot + a_plus * nChunks, cx, wx);
+                    pb_run_add_u64(diff + (size_t)a_plus * T, ky, wy);  pb_run_add_u64(tot + a_plus * nChunks, cy, wy);
+                }
+                if (want_minus) {
+                    const u64 wx = (in && rev) ? w : 0ull, wy = (has_y && rev) ? nw : 0ull;
+                    pb_run_add_u64(diff + (size_t)a_minus * T, kx, wx); pb_run_add_u64(tot + a_minus * nChunks, cx, wx);
+                    pb_run_add_u64(diff + (size_t)a_minus * T, ky, wy); pb_run_add_u64(tot + a_minus * nChunks, cy, wy);
+                }
+                if (want_any) {
+                    const u64 wx = in ? w : 0ull, wy = has_y ? nw : 0ull;
+                    pb_run_add_u64(diff + (size_t)a_any * T, kx, wx);   pb_run_add_u64(tot + a_any * nChunks, cx, wx);
+                    pb_run_add_u64(diff + (size_t)a_any * T, ky, wy);   pb_run_add_u64(tot + a_any * nChunks, cy, wy);
+                }
+            };
+            const bool dense = d.n >= kCDenseReads || (rec_hi - rec_lo) >= (uint32_t)kCDenseReads;   // CTA-uniform
+            auto one_read = [&](int32_t s, uint32_t m) {
+                int64_t x = 0, y = 0;
+                u64 w = 0;
+                bool rev = false;
+                const bool valid = decode(s, m, x, y, w, rev);
+                if (dense) agg_interval(valid, x, y, w, rev);
+                else if (valid) add_interval(x, y, w, rev);
+            };
+            auto one_rec = [&](bool have, const PbRec &rec) {
+                const u64 w = have ? (u64)__ldg(w_fix + (rec.tag & 0xffffu)) : 0ull;
+                const bool rev = (rec.tag >> 16) & 1u;
+                if (dense) agg_interval(have, rec.x, rec.y, w, rev);
+                else if (have) add_interval(rec.x, rec.y, w, rev);
+            };
+            one_read(pre_s, pre_m);
+            one_rec(pre_rec.y > pre_rec.x, pre_rec);
+            const int64_t hi = d.lo + d.n;
+            for (int64_t base = d.lo + kCThreads; base < hi; base += (int64_t)kCUnroll * kCThreads) {
+                int32_t sv[kCUnroll];
+                uint32_t mv[kCUnroll];
+#pragma unroll
+                for (int u = 0; u < kCUnroll; ++u) {
+                    const int64_t i = base + (int64_t)u * kCThreads + threadIdx.x;
+                    const bool ok = i < hi;
+                    sv[u] = ok ? __ldg(b.ref_start + i) : 0;
+                    mv[u] = ok ? __ldg(b.meta + i) : (1u << 17);
+                }
+#pragma unroll
+                for (int u = 0; u < kCUnroll; ++u) one_read(sv[u], mv[u]);
+            }
+            for (uint32_t j0 = rec_lo + kCThreads; j0 < rec_hi; j0 += kCThreads) {     // warp-uniform trip count
+                const uint32_t j = j0 + threadIdx.x;
+                PbRec rec = PbRec{0, 0, 0u, 0u};
+                if (j < rec_hi) rec = recs[j];
+                one_rec(j < rec_hi, rec);
+            }
+        } else if (threadIdx.x == 0) {
+            for (int qq = 0; qq < n_planes; ++qq)
+                for (int z = 0; z < T; z += kZeroBins) pb_bulk_store(outs[qq] + g0 + z, zbuf, kZeroBins * 8);
+            pb_bulk_commit();
+        }
+        preload(s_ring[(k + 1) & 3]);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_planes * nChunks; j += kCThreads) tot_next2[j] = 0;
+        if (s_ring[(k + 2) & 3].tile < n_tiles) pb_prefetch_tile_l2(b, recs, s_ring[(k + 2) & 3]);
+        if (!has_work) continue;
+
+#pragma unroll
+        for (int qq = 0; qq < (PLANES ? n_planes : 3); ++qq) {
+            if (!PLANES && qq >= n_planes) break;
+            // carry-in of every chunk of this plane: exclusive scan of the 16 chunk totals across lanes
+            long long tsum = lane < nChunks ? (long long)tot[qq * nChunks + lane] : 0ll;
+            const long long town = tsum;
+#pragma unroll
+            for (int dd = 1; dd < nChunks; dd <<= 1) {
+                const long long up = __shfl_up_sync(0xffffffffu, tsum, dd);
+                if (lane >= dd) tsum += up;
+            }
+            const long long tex = tsum - town;
+#pragma unroll
+            for (int cc = 0; cc < kPerWarp; ++cc) {
+                const int c = warp * kPerWarp + cc;
+                const long long carry = __shfl_sync(0xffffffffu, tex, c);
+                ulonglong2 *A = reinterpret_cast<ulonglong2 *>(diff + (size_t)qq * T + c * kChunk + lane * 4);
+                const ulonglong2 v01 = A[0], v23 = A[1];
+                A[0] = make_ulonglong2(0ull, 0ull);
+                A[1] = make_ulonglong2(0ull, 0ull);
+                const long long s1 = (long long)v01.x, s2 = s1 + (long long)v01.y, s3 = s2 + (long long)v23.x,
+                                s4 = s3 + (long long)v23.y;
+                long long incl = s4;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const long long up = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if (lane >= dd) incl += up;
+                }
+                const long long before = incl - s4 + carry;
+                const double o0 = (double)(before + s1) * scale, o1 = (double)(before + s2) * scale,
+                             o2 = (double)(before + s3) * scale, o3 = (double)(before + s4) * scale;
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                             :: "l"(outs[qq] + g0 + c * kChunk + lane * 4), "d"(o0), "d"(o1), "d"(o2), "d"(o3) : "memory");
+            }
+        }
+    }
+    if (stat_slots) pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
+    if (threadIdx.x == 0) pb_bulk_wait_all();
+}
+
 // staging + zero block + double-buffered difference arrays + three rotating copies of the segment sums
 size_t pb_center_smem_bytes(int n_planes, int n_slots, int tile_bins, bool direct)
 {
@@ -412,6 +672,84 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     else
         rc = launch_center<4>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, direct_ok, ws,
                               out_plus, out_minus, out_any, stream);
+    pb_timing_end(stream);
+    if (rc) return rc;
+    return pb_launch_stats_finish(ws.slots, (unsigned long long *)stats, stream);
+}
+
+namespace {
+size_t pb_center_fixed_smem(int n_planes)
+{
+    constexpr int T = 8 * kCThreads;
+    return (size_t)kZeroBins * 8 + (size_t)2 * n_planes * T * 8 + (size_t)3 * n_planes * (T / 128) * 8 + 16;
+}
+
+template <int PLANES>
+int launch_center_fixed(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const long long *w_fix,
+                        double scale, int lookback, int64_t n_tiles, const PbWorkspace &ws,
+                        double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+{
+    const size_t smem = pb_center_fixed_smem(__builtin_popcount(planes));
+    auto kern = pb_center_fixed_kernel<PLANES>;
+    PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, sm_count = 0;
+    PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCThreads, smem));
+    if (occ < 1) occ = 1;
+    int rc = pb_sm_count(&sm_count);
+    if (rc) return rc;
+    int64_t grid = (int64_t)sm_count * occ;
+    if (grid > n_tiles) grid = n_tiles;
+    PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 64, stream));
+    kern<<<(unsigned)grid, kCThreads, smem, stream>>>(b, r, planes, slot_of_len, w_fix, scale, lookback, ws.tiles, n_tiles,
+                                                      ws.tile_counter, ws.rec_off, ws.recs, out_plus, out_minus, out_any, ws.slots);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+}  // namespace
+
+extern "C" int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                                   const int16_t *slot_of_len, const int64_t *w_fix, int n_slots, int shift,
+                                   double *out_plus, double *out_minus, double *out_any,
+                                   uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    int rc = pb_check_common(batch, layout, rule, planes);
+    if (rc) return rc;
+    if (rule->kind != PB_RULE_CENTER || rule->param < 0) { pb_set_error("pb_map_center_fixed: need a center rule with nibble >= 0"); return PB_EINVAL; }
+    if (!slot_of_len || !w_fix || n_slots < 1 || n_slots > 32767 || shift < 1 || shift > 62) {
+        pb_set_error("pb_map_center_fixed: bad weight tables"); return PB_EINVAL;
+    }
+    if (((planes & PB_PLANE_PLUS) && !out_plus) || ((planes & PB_PLANE_MINUS) && !out_minus) ||
+        ((planes & PB_PLANE_ANY) && !out_any) || !stats) {
+        pb_set_error("pb_map_center_fixed: missing output plane or stats"); return PB_EINVAL;
+    }
+    if ((((uintptr_t)out_plus | (uintptr_t)out_minus | (uintptr_t)out_any) & 31) || ((uintptr_t)workspace & 15)) {
+        pb_set_error("pb_map_center_fixed: planes must be 32-byte aligned (256-bit stores), workspace 16-byte"); return PB_EINVAL;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PbReads b = pb_to_dev(batch);
+    PbRuleDev r = pb_to_dev(rule);
+    PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
+    PbWorkspace ws;
+    rc = pb_carve_workspace(workspace, workspace_bytes, layout->total_bins, b.n_blk, b.n_reads, &ws);
+    if (rc) return rc;
+    const int tile_bins = 8 * kCThreads;
+    const int64_t n_tiles = layout->total_bins / tile_bins;
+    const int lookback = (b.max_block_len + tile_bins - 1) / tile_bins;
+    const double scale = ldexp(1.0, -shift);
+
+    PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
+    rc = pb_launch_tile_index(b, lay, tile_bins, 0, n_tiles, batch->n_reads, 0, ws, stream);
+    if (rc) return rc;
+    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, 0, n_tiles, ws, stream);
+    if (rc) return rc;
+    pb_timing_begin(stream);
+    const long long *w = reinterpret_cast<const long long *>(w_fix);
+    if (planes == (PB_PLANE_PLUS | PB_PLANE_MINUS))
+        rc = launch_center_fixed<PB_PLANE_PLUS | PB_PLANE_MINUS>(b, r, planes, slot_of_len, w, scale, lookback, n_tiles, ws, out_plus, out_minus, out_any, stream);
+    else if (planes == 7)
+        rc = launch_center_fixed<7>(b, r, planes, slot_of_len, w, scale, lookback, n_tiles, ws, out_plus, out_minus, out_any, stream);
+    else
+        rc = launch_center_fixed<0>(b, r, planes, slot_of_len, w, scale, lookback, n_tiles, ws, out_plus, out_minus, out_any, stream);
     pb_timing_end(stream);
     if (rc) return rc;
     return pb_launch_stats_finish(ws.slots, (unsigned long long *)stats, stream);

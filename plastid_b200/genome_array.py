@@ -12,6 +12,7 @@ are one gather launch.  Equivalence: every mapped site is one of the read's alig
 ``plane[s:e]`` equals fetch+map over ``[s,e)``.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -125,12 +126,23 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     elif is_center:
         hist = torch.zeros(65536, dtype=torch.int64, device=dev)
         _lib.check(L.pb_length_hist(C.byref(b), C.byref(rule), _lib.PB_PLANE_ANY, _lib.ptr(hist), _lib.stream_ptr()))
-        slot_of_len, inv_m = factory.slot_tables(hist.cpu().numpy())
-        d_slot = torch.from_numpy(slot_of_len).to(dev)
-        d_inv = torch.from_numpy(inv_m if len(inv_m) else np.zeros(1)).to(dev)
-        _lib.check(L.pb_map_center(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_inv),
-                                   len(inv_m), outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
-                                   _lib.stream_ptr()))
+        h_hist = hist.cpu().numpy()
+        fixed = factory.fixed_point_tables(h_hist)
+        aligned = all(planes.planes[s].data_ptr() % 32 == 0 for s in strands)
+        if fixed is not None and aligned and not os.environ.get("PB_CENTER_EXACT"):
+            # many map lengths: one pass with 64-bit fixed-point weights (rel. error <= 1e-9, see the header)
+            slot_of_len, w_fix, shift = fixed
+            d_slot, d_w = torch.from_numpy(slot_of_len).to(dev), torch.from_numpy(w_fix).to(dev)
+            _lib.check(L.pb_map_center_fixed(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_w),
+                                             len(w_fix), shift, outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws),
+                                             ws_bytes, _lib.stream_ptr()))
+        else:
+            slot_of_len, inv_m = factory.slot_tables(h_hist)
+            d_slot = torch.from_numpy(slot_of_len).to(dev)
+            d_inv = torch.from_numpy(inv_m if len(inv_m) else np.zeros(1)).to(dev)
+            _lib.check(L.pb_map_center(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_inv),
+                                       len(inv_m), outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
+                                       _lib.stream_ptr()))
     else:
         _lib.check(L.pb_map_point(C.byref(b), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
                                   _lib.ptr(stats), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))

@@ -166,6 +166,30 @@ class CenterMapFactory(_MapFactory):
         return slot_of_len, inv_m
 
 
+    FIXED_MAX_REL_ERR = 1e-9       # three orders below the north star's 1e-6
+
+    def fixed_point_tables(self, length_hist):
+        """Integer weights for ``pb_map_center_fixed``: ``(slot_of_len, w_fix int64[S], shift)`` or ``None``
+        when one map length suffices (the exact kernel is used) or the weights cannot be made precise
+        enough.  ``shift`` is the largest power of two for which the sum over ALL reads of
+        ``round(2^shift / m)`` stays below 2^62 (no bin total can overflow); the relative error of a
+        weight against ``1/m`` is at most ``m * 2^-(shift+1)``."""
+        hist = np.asarray(length_hist, dtype=np.float64)
+        lengths = np.nonzero(hist)[0]
+        lengths = lengths[lengths - 2 * self._nibble > 0]
+        if len(lengths) < 2:
+            return None
+        m = (lengths - 2 * self._nibble).astype(np.int64)
+        bound = float((hist[lengths] / m).sum()) + 1.0          # sum over reads of 1/m
+        shift = min(52, int(np.floor(61.0 - np.log2(bound))))
+        if shift < 1 or float(m.max()) * 2.0 ** -(shift + 1) > self.FIXED_MAX_REL_ERR:
+            return None
+        slot_of_len = np.full(65536, -1, dtype=np.int16)
+        slot_of_len[lengths] = np.arange(len(lengths), dtype=np.int16)
+        w_fix = np.asarray([((1 << shift) + int(mm) // 2) // int(mm) for mm in m], dtype=np.int64)
+        return slot_of_len, w_fix, shift
+
+
 class FivePrimeMapFactory(_MapFactory):
     """``FivePrimeMapFactory(offset=0)`` — map_factories.pyx:278-374."""
     kind = _lib.PB_RULE_FIVEPRIME

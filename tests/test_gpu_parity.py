@@ -622,6 +622,45 @@ def test_pileup_tile_is_split_into_overflow_jobs(cuda_device):
     assert int(planes.stats[_lib.PB_STAT_MAPPED_ANY]) == len(hb) - dropped["."]
 
 
+@pytest.mark.parametrize("exact", [False, True])
+def test_center_many_lengths_and_pileup_tiles(cuda_device, monkeypatch, exact):
+    """Center rule on reads of 21 different lengths: the one-pass 64-bit fixed-point kernel (sparse tiles:
+    plain shared atomics; pile-up tiles: run-aggregated adds) and, forced by PB_CENTER_EXACT, the exact
+    multi-pass kernel — both within the north star's 1e-6 of the oracle with the same zero pattern,
+    statistics included; repeated launches are bit-identical (integer accumulation)."""
+    import torch
+    if exact:
+        monkeypatch.setenv("PB_CENTER_EXACT", "1")
+    rng = np.random.default_rng(5)
+    chroms, lens = ["a", "b"], np.array([60_000, 9_000])
+    n_hot, n_bg = 60_000, 20_000
+    start = np.concatenate([rng.integers(5000, 5200, n_hot), rng.integers(0, 59_900, n_bg), rng.integers(0, 8_900, 5000)])
+    cid = np.concatenate([np.zeros(n_hot + n_bg, dtype=int), np.ones(5000, dtype=int)])
+    L = rng.integers(20, 41, len(start))
+    rev = rng.integers(0, 2, len(start))
+    hb = pb.batch_from_arrays(chroms, lens, cid, start, L, rev)
+    layout = pb.GenomeLayout(chroms, lens)
+    fac = pb.CenterMapFactory(11)                      # L = 20, 21 are shorter than 2*nibble: dropped; L = 22: m = 0
+    db = hb.to_device(cuda_device)
+    planes = map_batch(db, layout, fac, None, strands=("+", "-", "."))
+    first = {s: planes.planes[s].clone() for s in ("+", "-", ".")}
+    dropped = {}
+    for strand in ("+", "-", "."):
+        dropped[strand] = 0
+        for c in range(2):
+            exp, _, d, _ = coracle.genome_vector(hb, c, strand, nibble=11)
+            got = plane_chrom(planes, layout, strand, c)
+            assert ((got == 0) == (exp == 0)).all(), (strand, c)
+            np.testing.assert_allclose(got, exp, rtol=CENTER_RTOL, atol=0)
+            if not exact:
+                np.testing.assert_allclose(got, exp, rtol=1e-9, atol=0)     # the bound map_batch demands of the weights
+            dropped[strand] += d
+    assert [int(x) for x in planes.stats[:3]] == [dropped["+"], dropped["-"], dropped["."]] and dropped["."] > 1000
+    again = map_batch(db, layout, fac, None, strands=("+", "-", "."))
+    for s in ("+", "-", "."):
+        assert torch.equal(again.planes[s], first[s])
+
+
 def test_bam_genome_array_from_bam_file(tmp_path, cuda_device):
     """BAMGenomeArray("x.bam"): decoded by the library's own BGZF/BAM reader, no pysam."""
     from plastid_b200 import bam_io
