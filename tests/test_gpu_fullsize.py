@@ -98,3 +98,52 @@ def test_oracle_checked_sample_at_full_size(c2):
         got = planes.planes[strand][base:base + int(c2["lens"][c])].cpu().numpy().view(np.uint32)
         assert (got == exp).all()
         assert not planes.planes[strand][base + int(c2["lens"][c]):int(layout.chrom_bin_off[c + 1])].any()
+
+
+def test_center_rule_at_full_size(cuda_device):
+    """BASELINE config 3 at full size (100 M spliced 100-nt reads, CenterMapFactory(12), fp64 planes):
+    conservation (every read that lies inside its chromosome adds exactly 1 in total), bit-identical
+    repeats, padding stays zero, and chr21 against the C oracle within the north star's tolerance."""
+    chroms, lens = synth.human_like_genome(1.0)
+    layout = pb.GenomeLayout(chroms, lens)
+    db = synth.rnaseq_reads(chroms, lens, 100_000_000, seed=100, device=cuda_device)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    fac = pb.CenterMapFactory(12)
+    planes = map_batch(db, layout, fac, None, strands=("+", "-"))
+    st = planes.stats
+    n_rev = int((((db.meta >> 16) & 1) == 1).sum().item())
+    assert int(st[_lib.PB_STAT_DROPPED_ANY]) == 0
+    assert int(st[_lib.PB_STAT_MAPPED_MINUS]) == n_rev and int(st[_lib.PB_STAT_MAPPED_PLUS]) == db.n_reads - n_rev
+    tot = {s: float(planes.planes[s].sum().item()) for s in "+-"}
+    assert abs(tot["+"] - (db.n_reads - n_rev)) <= 1e-6 * db.n_reads and abs(tot["-"] - n_rev) <= 1e-6 * db.n_reads
+    first = planes.planes["-"].clone()
+    again = map_batch(db, layout, fac, None, strands=("+", "-"), planes=planes)
+    assert torch.equal(again.planes["-"], first)
+    del first
+    hb = synth.device_batch_to_host(db, chroms, lens)
+    c = chroms.index("chr21")
+    sub = pdist.shard_chromosomes(hb, [c])
+    base = int(layout.chrom_bin_off[c])
+    for strand in "+-":
+        exp = coracle.genome_vector(sub, 0, strand, nibble=12)[0]
+        got = planes.planes[strand][base:base + int(lens[c])].cpu().numpy()
+        assert ((got == 0) == (exp == 0)).all()
+        np.testing.assert_allclose(got, exp, rtol=1e-6, atol=0)
+        assert not planes.planes[strand][base + int(lens[c]):int(layout.chrom_bin_off[c + 1])].any()
+
+
+def test_delta8_transfer_format_at_scale(c2, cuda_device):
+    """50 M reads of the C2 batch through the 2-byte transfer format: the device expansion returns the
+    batch bit for bit, at under 2.3 bytes per read."""
+    from plastid_b200.batch import AlignmentBatch, Delta8Batch, Delta8Receiver
+    db = c2["dbatch"]
+    n = 50_000_000
+    off = torch.clamp(db.chrom_read_off, 0, n).cpu().numpy()
+    hb = AlignmentBatch(c2["chroms"], c2["lens"], db.ref_start[:n].cpu().numpy(), db.meta[:n].cpu().numpy().view(np.uint32),
+                        off, max_span=db.max_span)
+    wire = Delta8Batch.from_batch(hb)
+    assert wire.nbytes < 2.3 * n
+    rx = Delta8Receiver(wire, cuda_device)
+    out = rx.receive(wire.pinned())
+    assert torch.equal(out.ref_start, db.ref_start[:n]) and torch.equal(out.meta, db.meta[:n])
