@@ -87,3 +87,53 @@ def delta8_decode(w):
             start[i] = cur
         assert e == int(w.blk_exc_off[B + 1])
     return start, meta
+
+
+def genome_array_recipe(seed=0, n_regions=24, reads_per_region=150, read_length=30, chrom_len=60_000):
+    """The reference's own golden-vector recipe (plastid/test/unit/genomics/test_genome_array.py:1832-1866),
+    with our seed and synthetic regions instead of its BED file: per region (1-3 exons, either strand)
+    ``reads_per_region`` reads of ``read_length`` nt are placed at random TRANSCRIPT offsets; the expected
+    count vectors are written down directly in transcript coordinates — 5'/3' ends at offset 0 and 15,
+    every position 1/30 (center 0) and the inner six positions 1/6 (center 12) — without any CIGAR
+    walking.  Reads that span an exon junction are spliced (one N gap per junction).
+
+    Returns ``(reads, vectors)``: ``reads`` = list of oracle Read objects (coordinate-sorted),
+    ``vectors[(rule, param, strand)]`` = float64[chrom_len]."""
+    rng = np.random.default_rng(seed)
+    vectors = {(rule, par, st): np.zeros(chrom_len) for rule, pars in (("fiveprime", (0, 15)), ("threeprime", (0, 15)),
+                                                                      ("center", (0, 12)))
+               for par in pars for st in "+-"}
+    reads = []
+    cursor = 500
+    for r in range(n_regions):
+        n_ex = int(rng.integers(1, 4))
+        exons = []
+        for _ in range(n_ex):
+            ln = int(rng.integers(40, 400))
+            exons.append((cursor, cursor + ln))
+            cursor += ln + int(rng.integers(30, 900))
+        cursor += 300
+        strand = "+-"[r % 2]
+        genomic = np.concatenate([np.arange(a, b) for a, b in exons])          # ascending genomic positions
+        tx = genomic if strand == "+" else genomic[::-1]                       # transcript order, 5' -> 3'
+        for loc in rng.integers(0, len(tx) - read_length + 1, size=reads_per_region):
+            for offset in (0, 15):                                             # test_genome_array.py:1851-1855
+                vectors[("fiveprime", offset, strand)][tx[loc + offset]] += 1
+                vectors[("threeprime", offset, strand)][tx[loc + read_length - offset - 1]] += 1
+            pos = np.sort(tx[loc:loc + read_length])                           # :1858 get_subchain(...).get_position_list()
+            for p_ in pos:
+                vectors[("center", 0, strand)][p_] += 1.0 / len(pos)           # :1860-1861
+            for p_ in pos[12:-12]:
+                vectors[("center", 12, strand)][p_] += 1.0 / (len(pos) - 24)   # :1862-1866
+            ops, run, prev = [], 0, None
+            for p_ in pos.tolist():                                            # the alignment a spliced aligner reports
+                if prev is not None and p_ != prev + 1:
+                    ops += [(po.CMATCH, run), (po.CREF_SKIP, p_ - prev - 1)]
+                    run = 0
+                run += 1
+                prev = p_
+            ops.append((po.CMATCH, run))
+            reads.append(po.Read(int(pos[0]), ops, strand == "-"))
+    reads.sort(key=lambda x: x.reference_start)
+    assert cursor < chrom_len
+    return reads, vectors

@@ -661,6 +661,31 @@ def test_center_many_lengths_and_pileup_tiles(cuda_device, monkeypatch, exact):
         assert torch.equal(again.planes[s], first[s])
 
 
+def test_gpu_reproduces_the_reference_golden_vector_recipe(cuda_device):
+    """The CUDA path against count vectors built by the reference's own recipe
+    (test_genome_array.py:1832-1866; tests/helpers.py:genome_array_recipe): 5'/3' at offsets 0 and 15 bit
+    for bit, center 0/12 within the reference's 1e-8, spliced reads included — whole-genome planes
+    and the per-segment operator."""
+    from helpers import genome_array_recipe
+    reads, vectors = genome_array_recipe(seed=11)
+    n = len(next(iter(vectors.values())))
+    hb = pb.pack_reads({"chrA": reads}, {"chrA": n})
+    assert hb.blk is not None
+    layout = pb.GenomeLayout(["chrA"], [n])
+    db = hb.to_device(cuda_device)
+    facs = {"fiveprime": pb.FivePrimeMapFactory, "threeprime": pb.ThreePrimeMapFactory, "center": pb.CenterMapFactory}
+    for (rule, par, strand), exp in vectors.items():
+        planes = map_batch(db, layout, facs[rule](par), None, strands=(strand,))
+        got = plane_chrom(planes, layout, strand, 0)
+        ga = pb.BAMGenomeArray(hb, mapping=facs[rule](par), device=cuda_device)
+        seg = ga.get(pb.GenomicSegment("chrA", 100, n - 100, strand), roi_order=False)
+        if rule == "center":
+            np.testing.assert_allclose(got, exp, rtol=0, atol=1e-8)
+            np.testing.assert_allclose(seg, exp[100:n - 100], rtol=0, atol=1e-8)
+        else:
+            assert (got == exp).all() and (seg == exp[100:n - 100]).all(), (rule, par, strand)
+
+
 def test_bam_genome_array_from_bam_file(tmp_path, cuda_device):
     """BAMGenomeArray("x.bam"): decoded by the library's own BGZF/BAM reader, no pysam."""
     from plastid_b200 import bam_io

@@ -184,3 +184,21 @@ def test_offsets_table_from_reference_docs():
     fw, rc = po.build_offset_luts(exp)
     assert (fac.forward_offsets == fw).all() and (fac.reverse_offsets == rc).all()
     assert fw[28] == 14 and fw[14] == -1 and rc[30] == 17
+
+
+def test_oracle_reproduces_the_reference_golden_vector_recipe():
+    """count vectors built by the recipe of test_genome_array.py:1832-1866 — written in
+    transcript coordinates, no CIGAR involved — against the oracle's map factories on the same reads,
+    including reads spliced over one or two exon junctions."""
+    from helpers import genome_array_recipe
+    reads, vectors = genome_array_recipe(seed=7)
+    assert sum(1 for r in reads if len(r.cigartuples) > 1) > 100          # spliced reads are in play
+    n = len(next(iter(vectors.values())))
+    rules = {"fiveprime": po.FivePrimeMap, "threeprime": po.ThreePrimeMap, "center": po.CenterMap}
+    for (rule, par, strand), exp in vectors.items():
+        mine = [r for r in reads if r.is_reverse is (strand == "-")]      # genome_array.py:811-815
+        _kept, got = rules[rule](par)(mine, po.Seg("chrA", 0, n, strand))
+        if rule == "center":
+            np.testing.assert_allclose(got, exp, rtol=0, atol=1e-8)        # the reference's own tolerance (test_genome_array.py:254)
+        else:
+            assert (got == exp).all(), (rule, par, strand)
