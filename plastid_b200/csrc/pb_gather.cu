@@ -234,28 +234,54 @@ __global__ void pb_column_keys_kernel(const double *__restrict__ norm, const uin
 
 // One CTA per column: count / sum of valid cells, and the two middle order statistics by
 // 8-bit-digit radix select (exact; numpy.ma.median averages the two middle values).
+// Three passes read the whole column: (1) count, sum and the histogram of the top digit, (2) the
+// second digit, (3) the third digit while the keys that match the 16 selected bits are COMPACTED
+// into `cand`; the remaining five digits and the successor search only walk the candidates (a few
+// percent of the column for normalised counts, whose top 16 bits — sign, exponent, 4 mantissa bits —
+// already separate most values).
+__device__ __forceinline__ void pb_select_digit(const unsigned int *hist, unsigned long long rank, int shift,
+                                                unsigned long long prefix, unsigned long long *s_prefix,
+                                                unsigned long long *s_rank)
+{
+    unsigned long long run = 0;
+    int d = 0;
+    for (; d < 256; ++d) {
+        if (run + hist[d] > rank) break;
+        run += hist[d];
+    }
+    *s_prefix = prefix | ((unsigned long long)d << shift);
+    *s_rank = rank - run;
+}
+
 __global__ void __launch_bounds__(512)
-pb_column_stats_kernel(const unsigned long long *__restrict__ keys, int64_t n_rows, int32_t width, int mode,
+pb_column_stats_kernel(const unsigned long long *__restrict__ keys, unsigned long long *__restrict__ cand_all,
+                       int64_t n_rows, int32_t width, int mode,
                        double *__restrict__ profile, int64_t *__restrict__ n_regions, double *__restrict__ col_sum)
 {
     __shared__ unsigned int hist[256];
-    __shared__ unsigned long long s_cnt;
+    __shared__ unsigned long long s_cnt, s_prefix, s_rank, s_succ;
+    __shared__ unsigned int s_m;
     __shared__ double s_sum[16];
-    __shared__ unsigned long long s_prefix, s_rank;
     const int col = blockIdx.x;
     const unsigned long long *__restrict__ K = keys + (int64_t)col * n_rows;
+    unsigned long long *__restrict__ cand = cand_all + (int64_t)col * n_rows;
 
-    // valid count + deterministic sum
+    // pass 1: valid count + deterministic sum + histogram of the top digit
+    for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
+    if (threadIdx.x == 0) { s_cnt = 0; s_m = 0; s_succ = ~0ull; }
+    __syncthreads();
     unsigned long long cnt = 0;
     double sum = 0.0;
     for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
         const unsigned long long k = K[r];
-        if (k != ~0ull) { cnt++; sum += pb_value_of(k); }
+        if (k != ~0ull) {
+            cnt++;
+            sum += pb_value_of(k);
+            if (mode == 0) atomicAdd(&hist[k >> 56], 1u);
+        }
     }
     cnt = pb_warp_sum(cnt);
     sum = pb_warp_sum_f64(sum);
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt, cnt); s_sum[threadIdx.x >> 5] = sum; }
     __syncthreads();
     const unsigned long long n_valid = s_cnt;
@@ -270,42 +296,73 @@ pb_column_stats_kernel(const unsigned long long *__restrict__ keys, int64_t n_ro
     if (mode != 0) return;
     if (n_valid == 0) { if (threadIdx.x == 0) profile[col] = nan(""); return; }
 
-    // lower middle element (0-based rank (n-1)/2) by radix select, 8 bits per pass
-    unsigned long long rank = (n_valid - 1) / 2;
-    unsigned long long prefix = 0;
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    // lower middle element: 0-based rank (n-1)/2
+    const unsigned long long rank0 = (n_valid - 1) / 2;
+    if (threadIdx.x == 0) pb_select_digit(hist, rank0, 56, 0ull, &s_prefix, &s_rank);
+    __syncthreads();
+    unsigned long long prefix = s_prefix, rank = s_rank;
+    __syncthreads();
+    // pass 2: second digit among the keys that share the top digit
+    for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        const unsigned long long k = K[r];
+        if (k != ~0ull && (k >> 56) == (prefix >> 56)) atomicAdd(&hist[(k >> 48) & 0xff], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) pb_select_digit(hist, rank, 48, prefix, &s_prefix, &s_rank);
+    __syncthreads();
+    prefix = s_prefix; rank = s_rank;
+    __syncthreads();
+    // keys below the selected 16-bit bucket: what the residual rank no longer counts
+    const unsigned long long below = rank0 - rank;
+    // pass 3: third digit + compaction of the bucket + smallest key above the bucket
+    for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
+    __syncthreads();
+    unsigned long long succ_out = ~0ull;
+    for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        const unsigned long long k = K[r];
+        if (k == ~0ull) continue;
+        if ((k >> 48) == (prefix >> 48)) {
+            atomicAdd(&hist[(k >> 40) & 0xff], 1u);
+            cand[atomicAdd(&s_m, 1u)] = k;
+        } else if ((k >> 48) > (prefix >> 48) && k < succ_out) succ_out = k;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, succ_out, d);
+        succ_out = o < succ_out ? o : succ_out;
+    }
+    if ((threadIdx.x & 31) == 0 && succ_out != ~0ull) atomicMin(&s_succ, succ_out);
+    __syncthreads();       // also publishes cand[] (written and read by this CTA only)
+    const unsigned int m = s_m;
+    if (threadIdx.x == 0) pb_select_digit(hist, rank, 40, prefix, &s_prefix, &s_rank);
+    __syncthreads();
+    prefix = s_prefix; rank = s_rank;
+    __syncthreads();
+    // remaining five digits over the candidates only
+    for (int shift = 32; shift >= 0; shift -= 8) {
         for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
         __syncthreads();
-        const unsigned long long himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-        for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
-            const unsigned long long k = K[r];
-            if (k != ~0ull && (k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
+        const unsigned long long himask = ~0ull << (shift + 8);
+        for (unsigned int r = threadIdx.x; r < m; r += blockDim.x) {
+            const unsigned long long k = cand[r];
+            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long run = 0;
-            int d = 0;
-            for (; d < 256; ++d) {
-                if (run + hist[d] > rank) break;
-                run += hist[d];
-            }
-            s_prefix = prefix | ((unsigned long long)d << shift);
-            s_rank = rank - run;
-        }
+        if (threadIdx.x == 0) pb_select_digit(hist, rank, shift, prefix, &s_prefix, &s_rank);
         __syncthreads();
-        prefix = s_prefix;
-        rank = s_rank;
+        prefix = s_prefix; rank = s_rank;
         __syncthreads();
     }
     const unsigned long long key0 = prefix;
     // upper middle element (rank n/2): the same key when n is odd or key0 repeats far enough, else the
-    // smallest key above it — one more pass instead of a second select
+    // smallest key above it (among the candidates, or the smallest key above the bucket)
     unsigned long long key1 = key0;
     if ((n_valid & 1ull) == 0) {
         unsigned long long le = 0, succ = ~0ull;
-        for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
-            const unsigned long long k = K[r];
-            if (k == ~0ull) continue;
+        for (unsigned int r = threadIdx.x; r < m; r += blockDim.x) {
+            const unsigned long long k = cand[r];
             if (k <= key0) le++; else if (k < succ) succ = k;
         }
         le = pb_warp_sum(le);
@@ -314,11 +371,11 @@ pb_column_stats_kernel(const unsigned long long *__restrict__ keys, int64_t n_ro
             const unsigned long long o = __shfl_xor_sync(0xffffffffu, succ, d);
             succ = o < succ ? o : succ;
         }
-        if (threadIdx.x == 0) { s_cnt = 0; s_prefix = ~0ull; }
+        if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt, le); atomicMin(&s_prefix, succ); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt, le); if (succ != ~0ull) atomicMin(&s_succ, succ); }
         __syncthreads();
-        if (s_cnt <= n_valid / 2) key1 = s_prefix;       // fewer than n/2 + 1 keys are <= key0
+        if (below + s_cnt <= n_valid / 2) key1 = s_succ;      // fewer than n/2 + 1 keys are <= key0
     }
     if (threadIdx.x == 0) profile[col] = (pb_value_of(key0) + pb_value_of(key1)) / 2.0;
 }
@@ -453,7 +510,7 @@ extern "C" int pb_window_normalize(const double *matrix, const uint8_t *maskmat,
 extern "C" size_t pb_column_profile_workspace_bytes(int64_t n_rows, int32_t width)
 {
     if (n_rows < 0 || width < 0) return 0;
-    return (size_t)n_rows * (size_t)width * sizeof(unsigned long long) + 256;
+    return 2 * (size_t)n_rows * (size_t)width * sizeof(unsigned long long) + 256;   // keys + select candidates
 }
 
 extern "C" int pb_column_profile_batched(const double *values, const uint8_t *valmask, const uint8_t *row_select,
@@ -476,7 +533,8 @@ extern "C" int pb_column_profile_batched(const double *values, const uint8_t *va
         pb_column_keys_kernel<<<grid, dim3(32, 8), 0, stream>>>(values, valmask, row_select, n_rows, width, keys);
     }
     // one CTA per column of every matrix: column b*width + c reads keys[(b*width + c) * n_rows ...]
-    pb_column_stats_kernel<<<(unsigned)(n_batch * width), 512, 0, stream>>>(keys, n_rows, width, mode, profile, n_regions, col_sum);
+    unsigned long long *cand = keys + (size_t)n_batch * (size_t)n_rows * (size_t)width;
+    pb_column_stats_kernel<<<(unsigned)(n_batch * width), 512, 0, stream>>>(keys, cand, n_rows, width, mode, profile, n_regions, col_sum);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
