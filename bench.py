@@ -383,7 +383,7 @@ def run_c2p(args, W, device, rank, world, dist):
     import torch
     import plastid_b200 as pb
     from plastid_b200 import synth
-    from plastid_b200.genome_array import stratified_windows, window_normalize, column_profile
+    from plastid_b200.genome_array import stratified_windows, count_profiles
     layout, ann, dbatch = W["layout"], W["ann"], W["dbatch"]
     table, cols = synth.window_table(ann, layout, width=350)
     table.device(device)
@@ -400,11 +400,8 @@ def run_c2p(args, W, device, rank, world, dist):
             ev[3].record()
         if world > 1:
             dist.all_reduce(strat)
-        # all read lengths stacked row-wise: one normalise launch, one (length, column) median launch
-        n_len = hi - lo + 1
-        mat = strat.to(torch.float64).view(n_len * n, width)
-        denom, sel, norm, nmask = window_normalize(mat, maskmat.repeat(n_len, 1), 70, 100, 10)
-        return column_profile(norm, nmask, sel, "median", n_batch=n_len)[0]
+        # normalisation fused with key extraction, then one (length, column) median launch
+        return count_profiles(strat, maskmat, 70, 100, 10, "median")[0]
 
     for _ in range(max(args.warmup, 3)):
         step()

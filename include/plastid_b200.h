@@ -314,6 +314,19 @@ int pb_column_profile_batched(const double *values, const uint8_t *valmask, cons
                               double *profile, int64_t *n_regions, double *col_sum,
                               void *workspace, size_t workspace_bytes, void *stream);
 
+/* psite.py:200-234 on integer count matrices (the output of pb_stratified_windows) in two launches:
+ * normalisation (denominator over [norm_lo, norm_hi), unmasked cells only; rows with denominator >=
+ * min_counts are selected; nan / inf quotients are masked) fused with the key extraction, then the
+ * per-(matrix, column) median (mode 0) or mean (mode 1) of the normalised cells.  counts
+ * uint32[n_batch][n_rows][width]; maskmat uint8[n_rows][width] when mask_shared (one position mask for
+ * all matrices) else [n_batch][n_rows][width]; row_select uint8[n_batch][n_rows] (output); profile,
+ * n_regions, col_sum [n_batch][width]; workspace n_batch x pb_column_profile_workspace_bytes. */
+int pb_count_profiles_u32(const uint32_t *counts, const uint8_t *maskmat, int mask_shared,
+                          int32_t n_batch, int64_t n_rows, int32_t width,
+                          int32_t norm_lo, int32_t norm_hi, double min_counts, int mode,
+                          uint8_t *row_select, double *profile, int64_t *n_regions, double *col_sum,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
 /* psite.py:176-199 / phase_by_size.py:186-194 in one launch: for every window chain and every aligned
  * length in [min_len, max_len], the counts of the reads the point rule maps into the window, laid
  * 5'->3' from column row_col[c] of a width-W row (strand-matched like get_reads_and_counts; the rule

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "pb_export_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "pb_export_runs": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pb_atomic_probe": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
+    "pb_count_profiles_u32": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int,
+                                        _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pb_column_profile_batched": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "pb_column_profile": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
 }

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _cli
 from .metagene import rois_from_table, _NORM_START_DEFAULT, _NORM_END_DEFAULT
-from ..genome_array import stratified_windows, window_normalize, column_profile
+from ..genome_array import stratified_windows, window_normalize, column_profile, count_profiles
 from ..map_factories import (FivePrimeMapFactory, SizeFilterFactory, CenterMapFactory,
                              StratifiedVariableFivePrimeMapFactory, _MapFactory)
 from ..regions import ChainTable
@@ -37,6 +37,16 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
     clen = torch.from_numpy(table.chain_len).to(dev)[:, None]
     uncovered = (colidx < c0) | (colidx >= c0 + clen)
     out = {"x": np.arange(-flank, window_size - flank), "profiles": {}, "regions_counted": {}, "raw": {}}
+    if not aggregate and not keep:
+        # the default path: normalisation fused with the key extraction, medians per (length, column) —
+        # no float64 / normalised / mask matrices are materialised
+        profile, n_regions, sel = count_profiles(strat, maskmat, norm_start, norm_end, min_counts, "median")
+        profile, n_regions = profile.cpu().numpy(), n_regions.cpu().numpy()
+        any_sel = sel.any(dim=1).cpu().numpy()
+        for j, k in enumerate(range(min_len, max_len + 1)):
+            out["profiles"][k] = profile[j] if any_sel[j] else np.zeros(window_size)
+            out["regions_counted"][k] = n_regions[j]
+        return out
     # all read lengths at once: the matrices are stacked row-wise, normalised in one launch and reduced
     # per (length, column) in one launch
     mat = strat.to(torch.float64)                                    # [n_len, n, W]

@@ -232,6 +232,66 @@ __global__ void pb_column_keys_kernel(const double *__restrict__ norm, const uin
     }
 }
 
+// psite.py:200-234 for integer count matrices in one pass over the counts: per row the denominator over
+// the normalisation window (unmasked cells only; all masked => masked row), the row's selection flag,
+// and — instead of materialising float64, normalised and mask matrices — the order-preserving keys of
+// the normalised cells written straight into the per-column key lists the median select reads.
+// Integer counts sum exactly in fp64, so the denominator does not depend on summation order; the
+// quotient is the same IEEE division `matrix / denom` the separate kernels perform.
+// grid = (ceil(n_rows / 32), n_batch); the position mask may be shared by all matrices of the batch.
+__global__ void __launch_bounds__(256)
+pb_norm_keys_u32_kernel(const uint32_t *__restrict__ counts, const uint8_t *__restrict__ maskmat, int mask_shared,
+                        int64_t n_rows, int32_t width, int32_t norm_lo, int32_t norm_hi, double min_counts,
+                        uint8_t *__restrict__ row_select, unsigned long long *__restrict__ keys)
+{
+    __shared__ double s_den[32];
+    __shared__ unsigned char s_sel[32];
+    __shared__ unsigned long long tile[32][33];
+    const int64_t mat = (int64_t)blockIdx.y * n_rows * width;
+    counts += mat;
+    keys += mat;
+    if (!mask_shared) maskmat += mat;
+    row_select += (int64_t)blockIdx.y * n_rows;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rr = warp * 4; rr < warp * 4 + 4; ++rr) {
+        const int64_t r = r0 + rr;
+        double acc = 0.0;
+        int live = 0;
+        if (r < n_rows)
+            for (int col = norm_lo + lane; col < norm_hi && col < width; col += 32)
+                if (col >= 0 && !maskmat[r * width + col]) { acc += (double)counts[r * width + col]; live++; }
+        acc = pb_warp_sum_f64(acc);
+        live = __reduce_add_sync(0xffffffffu, live);
+        if (lane == 0) {
+            const bool den_masked = (live == 0);       // nansum of an all-masked slice is the masked constant
+            s_den[rr] = den_masked ? nan("") : acc;
+            s_sel[rr] = (!den_masked && acc >= min_counts) ? 1 : 0;
+            if (r < n_rows) row_select[r] = s_sel[rr];
+        }
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < width; c0 += 32) {
+        for (int dy = warp; dy < 32; dy += 8) {
+            const int64_t r = r0 + dy;
+            const int col = c0 + lane;
+            unsigned long long k = ~0ull;
+            if (r < n_rows && col < width && s_sel[dy] && !maskmat[r * width + col]) {
+                const double v = (double)counts[r * width + col] / s_den[dy];
+                if (!(isnan(v) || isinf(v))) k = pb_key_of(v);                 // metagene.py:923-924
+            }
+            tile[dy][lane] = k;
+        }
+        __syncthreads();
+        for (int dy = warp; dy < 32; dy += 8) {
+            const int col = c0 + dy;
+            const int64_t r = r0 + lane;
+            if (col < width && r < n_rows) keys[(int64_t)col * n_rows + r] = tile[lane][dy];
+        }
+        __syncthreads();
+    }
+}
+
 // One CTA per column: count / sum of valid cells, and the two middle order statistics by
 // 8-bit-digit radix select (exact; numpy.ma.median averages the two middle values).
 // Three passes read the whole column: (1) count, sum and the histogram of the top digit, (2) the
@@ -534,6 +594,32 @@ extern "C" int pb_column_profile_batched(const double *values, const uint8_t *va
     }
     // one CTA per column of every matrix: column b*width + c reads keys[(b*width + c) * n_rows ...]
     unsigned long long *cand = keys + (size_t)n_batch * (size_t)n_rows * (size_t)width;
+    pb_column_stats_kernel<<<(unsigned)(n_batch * width), 512, 0, stream>>>(keys, cand, n_rows, width, mode, profile, n_regions, col_sum);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_count_profiles_u32(const uint32_t *counts, const uint8_t *maskmat, int mask_shared,
+                                     int32_t n_batch, int64_t n_rows, int32_t width,
+                                     int32_t norm_lo, int32_t norm_hi, double min_counts, int mode,
+                                     uint8_t *row_select, double *profile, int64_t *n_regions, double *col_sum,
+                                     void *workspace, size_t workspace_bytes, void *stream_)
+{
+    if (!counts || !maskmat || !row_select || !profile || !n_regions || !col_sum || n_rows < 0 || width <= 0 ||
+        (mode != 0 && mode != 1) || n_batch < 1 || n_batch > 65535) {
+        pb_set_error("pb_count_profiles_u32: bad arguments"); return PB_EINVAL;
+    }
+    if (!workspace || workspace_bytes < (size_t)n_batch * pb_column_profile_workspace_bytes(n_rows, width)) {
+        pb_set_error("pb_count_profiles_u32: workspace too small"); return PB_ENOSPACE;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *keys = (unsigned long long *)workspace;
+    unsigned long long *cand = keys + (size_t)n_batch * (size_t)n_rows * (size_t)width;
+    if (n_rows > 0) {
+        dim3 grid((unsigned)((n_rows + 31) / 32), (unsigned)n_batch);
+        pb_norm_keys_u32_kernel<<<grid, 256, 0, stream>>>(counts, maskmat, mask_shared, n_rows, width, norm_lo, norm_hi,
+                                                          min_counts, row_select, keys);
+    }
     pb_column_stats_kernel<<<(unsigned)(n_batch * width), 512, 0, stream>>>(keys, cand, n_rows, width, mode, profile, n_regions, col_sum);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;

@@ -332,6 +332,29 @@ def column_profile(values, valmask, row_select, mode="median", n_batch=1):
     return profile.view(n_batch, width), n_regions.view(n_batch, width), col_sum.view(n_batch, width)
 
 
+def count_profiles(strat, maskmat, norm_lo, norm_hi, min_counts, mode="median"):
+    """Normalise + per-column median / mean of the integer window matrices ``strat``
+    (uint32 ``[n_batch, n_rows, width]``, e.g. from :func:`stratified_windows`) without materialising
+    float64 / normalised / mask matrices: ``(profile [n_batch, width], n_regions, row_select [n_batch, n_rows])``.
+    ``maskmat`` ``[n_rows, width]`` is the position mask shared by all matrices."""
+    import torch
+    strat = strat.contiguous()
+    maskmat = maskmat.contiguous()
+    n_batch, n, width = strat.shape
+    dev = strat.device
+    L = _lib.lib()
+    ws_bytes = n_batch * L.pb_column_profile_workspace_bytes(n, width)
+    ws = _scratch(dev, int(ws_bytes))
+    sel = torch.empty(n_batch * max(n, 1), dtype=torch.uint8, device=dev)
+    profile = torch.empty(n_batch * width, dtype=torch.float64, device=dev)
+    n_regions = torch.empty(n_batch * width, dtype=torch.int64, device=dev)
+    col_sum = torch.empty(n_batch * width, dtype=torch.float64, device=dev)
+    _lib.check(L.pb_count_profiles_u32(_lib.ptr(strat), _lib.ptr(maskmat), 1, n_batch, n, width, int(norm_lo), int(norm_hi),
+                                       float(min_counts), {"median": 0, "mean": 1}[mode], _lib.ptr(sel), _lib.ptr(profile),
+                                       _lib.ptr(n_regions), _lib.ptr(col_sum), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+    return profile.view(n_batch, width), n_regions.view(n_batch, width), sel[:n_batch * n].view(n_batch, n)
+
+
 _scratch_bufs = {}
 
 
