@@ -110,6 +110,22 @@ __device__ __forceinline__ int64_t pb_lower_bound_near(const int32_t *__restrict
     return pb_lower_bound(a, prev + 1, top, key);
 }
 
+// lower_bound by a whole warp (all 32 lanes call with the same arguments): every step probes 32
+// evenly spaced elements at once, so a range of n needs log32(n) dependent round trips instead of log2(n)
+__device__ __forceinline__ int64_t pb_lower_bound_warp(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key)
+{
+    const int lane = threadIdx.x & 31;
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo) / 32;
+        const int64_t p = lo + (int64_t)(lane + 1) * step - 1;           // <= hi - 1
+        const int n = __popc(__ballot_sync(0xffffffffu, (int64_t)__ldg(a + p) < key));   // sorted: a prefix of lanes
+        if (n < 32) hi = lo + (int64_t)(n + 1) * step - 1;               // a[that probe] >= key
+        lo += (int64_t)n * step;                                         // a[lo - 1] < key
+    }
+    const int64_t p = lo + lane;
+    return lo + __popc(__ballot_sync(0xffffffffu, p < hi && (int64_t)__ldg(a + p) < key));
+}
+
 // chromosome owning global bin g: last c with chrom_bin_off[c] <= g
 __device__ __forceinline__ int pb_chrom_of_bin(const PbLayoutDev &lay, int64_t g)
 {

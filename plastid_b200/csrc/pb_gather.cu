@@ -697,26 +697,40 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
         const int64_t bs = gs - base, be = ge - base;    // chromosome coordinates of the block
         int64_t r0 = 0, r1 = 0;
         if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
-        const int64_t lo = pb_lower_bound(b.ref_start, r0, r1, bs - b.max_span + 1);
-        const int64_t hi = pb_lower_bound_near(b.ref_start, lo, r1, be);
-        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            const uint32_t m = __ldg(b.meta + i);
-            if (!pb_passes(m, r.size_min, r.size_max)) continue;
-            const bool rev = PB_META_REV(m);
-            if ((plane == 0 && rev) || (plane == 1 && !rev)) continue;    // genome_array.py:811-815
-            const int L = PB_META_L(m);
-            if (L < min_len || L >= min_len + n_len) continue;           // psite.py:187: len(positions) in read_dict
-            const int idx = pb_rule_index(r, L, rq);
-            if (idx < 0) continue;
-            const int64_t p = pb_position(b, i, __ldg(b.ref_start + i), m, idx);
-            if (p < bs || p >= be) continue;
-            const int64_t jj = j0 + (p - bs);
-            int64_t col = col0 + (rev_out ? (len - 1 - jj) : jj);
-            if (phase_mode) {
-                const int64_t cod = col / 3;
-                col = (cod >= cod_lo && cod < cod_hi) ? col - cod * 3 : -1;
+        // every warp runs the same two 32-ary searches (same addresses: L1 hits after the first warp)
+        const int64_t lo = pb_lower_bound_warp(b.ref_start, r0, r1, bs - b.max_span + 1);
+        const int64_t hi = pb_lower_bound_warp(b.ref_start, lo, r1, be);
+        constexpr int kU = 4;       // independent reads in flight per thread
+        for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)kU * blockDim.x) {
+            uint32_t mv[kU];
+            int32_t sv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                mv[u] = i < hi ? __ldg(b.meta + i) : (1u << 17);
+                sv[u] = i < hi ? __ldg(b.ref_start + i) : 0;
             }
-            if (col >= 0 && col < width) atomicAdd(&hist[(L - min_len) * width + (int)col], 1u);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                const uint32_t m = mv[u];
+                if (!pb_passes(m, r.size_min, r.size_max)) continue;
+                const bool rev = PB_META_REV(m);
+                if ((plane == 0 && rev) || (plane == 1 && !rev)) continue;    // genome_array.py:811-815
+                const int L = PB_META_L(m);
+                if (L < min_len || L >= min_len + n_len) continue;           // psite.py:187: len(positions) in read_dict
+                const int idx = pb_rule_index(r, L, rq);
+                if (idx < 0) continue;
+                const int64_t p = pb_position(b, i, sv[u], m, idx);
+                if (p < bs || p >= be) continue;
+                const int64_t jj = j0 + (p - bs);
+                int64_t col = col0 + (rev_out ? (len - 1 - jj) : jj);
+                if (phase_mode) {
+                    const int64_t cod = col / 3;
+                    col = (cod >= cod_lo && cod < cod_hi) ? col - cod * 3 : -1;
+                }
+                if (col >= 0 && col < width) atomicAdd(&hist[(L - min_len) * width + (int)col], 1u);
+            }
         }
         j0 += be - bs;
     }

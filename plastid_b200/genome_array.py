@@ -264,7 +264,8 @@ def stratified_windows(dbatch, layout, factory, size_filter, table, row_col, wid
     n_len = max_len - min_len + 1
     if phase is not None:
         width, row_col = 3, np.zeros(n, dtype=np.int32)
-    out = torch.zeros((n_len, max(n, 1), width), dtype=torch.int32, device=dev)
+    alloc = torch.empty if n else torch.zeros          # the kernel writes every cell of every chain
+    out = alloc((n_len, max(n, 1), width), dtype=torch.int32, device=dev)
     maskmat = torch.empty((max(n, 1), width), dtype=torch.uint8, device=dev)
     cols = torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
     b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
