@@ -38,9 +38,9 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=200_000_000, help="reads per GPU")
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of hg38 chromosome lengths")
     ap.add_argument("--regions", type=int, default=60_000)
-    ap.add_argument("--e2e-format", default="delta8", choices=["delta8", "wire16"],
+    ap.add_argument("--e2e-format", default="delta3", choices=["delta3", "delta8", "wire16"],
                     help="host transfer format of the end-to-end leg (unspliced batches)")
-    ap.add_argument("--e2e-chunks", type=int, default=16, help="upload chunks overlapped with mapping in the e2e leg")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="upload chunks overlapped with mapping in the e2e leg")
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5", "peaks"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
@@ -568,13 +568,14 @@ def main():
     # The caller holds the batch in pinned host memory in the transfer format the host decoder
     # emits: wire16 (4 B/read) for unspliced batches, the plain SoA otherwise.  Every step copies it
     # to the device, expands it, runs the same kernels and reads the region table back.
-    from plastid_b200.batch import Wire16Batch, Wire16Receiver, Delta8Batch, Delta8Receiver
+    from plastid_b200.batch import Wire16Batch, Wire16Receiver, Delta8Batch, Delta8Receiver, Delta3Batch, Delta3Receiver
     h_sums = torch.empty(ann.n_tx, dtype=torch.float64).pin_memory()
     h_live = torch.empty(ann.n_tx, dtype=torch.int64).pin_memory()
     d2h = h_sums.numel() * 8 + h_live.numel() * 8
     use_wire16 = dbatch.blk_off is None
     if use_wire16:
-        WireBatch, WireReceiver = (Delta8Batch, Delta8Receiver) if args.e2e_format == "delta8" else (Wire16Batch, Wire16Receiver)
+        WireBatch, WireReceiver = {"delta3": (Delta3Batch, Delta3Receiver), "delta8": (Delta8Batch, Delta8Receiver),
+                                   "wire16": (Wire16Batch, Wire16Receiver)}[args.e2e_format]
         wire = WireBatch.from_batch(synth.device_batch_to_host(dbatch, chroms, lens))
         pinned = wire.pinned()
         receiver = WireReceiver(wire, device)

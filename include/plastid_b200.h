@@ -185,6 +185,19 @@ int pb_unpack_delta8(const uint8_t *dstart, const uint8_t *code, const int32_t *
                      const uint32_t *dict, int64_t n_reads, int64_t read_begin, int64_t read_end,
                      int32_t *ref_start_out, uint32_t *meta_out, void *stream);
 
+/* delta3: 1-byte-per-read transfer format of a sorted unspliced batch (the upload is PCIe-bound: bytes
+ * are time).  packed uint8[N128]: bits 0-2 = start delta 0..6 from the previous read (0 for the first read
+ * of a 128-read block, whose start is blk_base[B]), 7 = the delta is 7 + the next byte of the `wide`
+ * stream, whose value 255 marks an exception (chromosome change, delta > 261, rare meta word) resolved
+ * from exc_start / exc_meta; bits 3-7 = index into dict uint32[32] of meta words (31 only with
+ * exceptions).  blk_wide_off / blk_exc_off uint32[n_blk+1]: ordinals of each block's first wide byte /
+ * exception.  Same contract as pb_unpack_delta8 otherwise. */
+int pb_unpack_delta3(const uint8_t *packed, const uint8_t *wide, const int32_t *blk_base,
+                     const uint32_t *blk_wide_off, const uint32_t *blk_exc_off,
+                     const int32_t *exc_start, const uint32_t *exc_meta, const uint32_t *dict,
+                     int64_t n_reads, int64_t read_begin, int64_t read_end,
+                     int32_t *ref_start_out, uint32_t *meta_out, void *stream);
+
 /* 5' / 3' / variable-offset mapping of a whole batch into dense uint32 planes.
  * `planes` selects which of out_plus/out_minus/out_any are produced; every bin of a selected
  * plane is written (no prior memset needed).  stats: device uint64[PB_NSTATS], accumulated. */

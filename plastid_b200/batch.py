@@ -469,6 +469,139 @@ class Delta8Receiver(object):
         return ev
 
 
+class Delta3Batch(object):
+    """1-byte-per-read host format of a sorted unspliced batch (``pb_unpack_delta3`` in
+    ``include/plastid_b200.h``): 3 bits of start delta + 5 bits of meta-dictionary index per read, a
+    byte stream for deltas of 7..261, an exception list for the rest; blocks of 128 reads."""
+    BLOCK = 128
+
+    def __init__(self, chroms, chrom_len, chrom_read_off, n_reads, packed, wide, blk_base, blk_wide_off, blk_exc_off,
+                 exc_start, exc_meta, meta_dict, blk_first, max_span, mapped):
+        self.chroms, self.chrom_len = list(chroms), np.asarray(chrom_len, dtype=np.int64)
+        self.chrom_read_off = np.ascontiguousarray(chrom_read_off, dtype=np.int64)
+        self.n_reads = int(n_reads)
+        self.packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self.wide = np.ascontiguousarray(wide, dtype=np.uint8)
+        self.blk_base = np.ascontiguousarray(blk_base, dtype=np.int32)
+        self.blk_wide_off = np.ascontiguousarray(blk_wide_off, dtype=np.uint32)
+        self.blk_exc_off = np.ascontiguousarray(blk_exc_off, dtype=np.uint32)
+        self.exc_start = np.ascontiguousarray(exc_start, dtype=np.int32)
+        self.exc_meta = np.ascontiguousarray(exc_meta, dtype=np.uint32)
+        self.meta_dict = np.ascontiguousarray(meta_dict, dtype=np.uint32)
+        self.blk_chrom, self.blk_first_start = blk_first      # chunk planning only; stays on the host
+        self.max_span, self.mapped = int(max_span), int(mapped)
+
+    def __len__(self):
+        return self.n_reads
+
+    @property
+    def nbytes(self):
+        """Bytes that cross PCIe per batch."""
+        return (self.packed.nbytes + self.wide.nbytes + self.blk_base.nbytes + self.blk_wide_off.nbytes
+                + self.blk_exc_off.nbytes + self.exc_start.nbytes + self.exc_meta.nbytes + self.meta_dict.nbytes
+                + self.chrom_read_off.nbytes)
+
+    @classmethod
+    def from_batch(cls, hb):
+        if hb.blk is not None:
+            raise ValueError("delta3 carries single-block reads only")
+        n, K = len(hb), cls.BLOCK
+        n_blk = (n + K - 1) // K
+        start = hb.ref_start.astype(np.int64)
+        meta = hb.meta.astype(np.uint32)
+        chrom_of_read = np.repeat(np.arange(len(hb.chroms), dtype=np.int32), np.diff(hb.chrom_read_off))
+        delta = np.zeros(n, dtype=np.int64)
+        if n > 1:
+            delta[1:] = start[1:] - start[:-1]
+        first_of_chrom = np.zeros(n, dtype=bool)
+        if n:
+            first_of_chrom[0] = True
+            first_of_chrom[1:] = chrom_of_read[1:] != chrom_of_read[:-1]
+        first_of_blk = np.zeros(n, dtype=bool)
+        first_of_blk[::K] = True
+        delta[first_of_blk] = 0
+        words, counts = np.unique(meta, return_counts=True)
+        dict_words = np.sort(words[np.argsort(-counts, kind="stable")[:31]])
+        pos = np.minimum(np.searchsorted(dict_words, meta), max(len(dict_words) - 1, 0))
+        in_dict = (dict_words[pos] == meta) if len(dict_words) else np.zeros(n, dtype=bool)
+        exc = (delta > 7 + 254) | (delta < 0) | (first_of_chrom & ~first_of_blk) | ~in_dict
+        widef = exc | (delta >= 7)
+        packed = np.zeros(n_blk * K, dtype=np.uint8)
+        packed[:n] = (np.where(widef, 7, delta) | (np.where(exc, 31, pos) << 3)).astype(np.uint8)
+        wide = np.where(exc, 255, delta - 7)[widef].astype(np.uint8)
+        meta_dict = np.zeros(32, dtype=np.uint32)
+        meta_dict[:len(dict_words)] = dict_words
+
+        def block_offsets(flags):
+            per = np.add.reduceat(flags.astype(np.int64), np.arange(0, n, K)) if n else np.zeros(0, dtype=np.int64)
+            off = np.zeros(n_blk + 1, dtype=np.int64)
+            np.cumsum(per, out=off[1:])
+            if off[-1] >= (1 << 32):
+                raise ValueError("delta3: too many escapes")
+            return off
+        return cls(hb.chroms, hb.chrom_len, hb.chrom_read_off, n, packed, wide, hb.ref_start[::K], block_offsets(widef),
+                   block_offsets(exc), hb.ref_start[exc], meta[exc], meta_dict,
+                   (chrom_of_read[::K].copy(), hb.ref_start[::K].astype(np.int64)), hb.max_span, hb.mapped)
+
+    def pinned(self):
+        import torch
+
+        def pin(a, view=None):
+            a = a.view(view) if view is not None else a
+            return torch.from_numpy(a if len(a) else np.zeros(1, dtype=a.dtype)).pin_memory()
+        return dict(packed=pin(self.packed), wide=pin(self.wide), blk_base=pin(self.blk_base),
+                    blk_wide_off=pin(self.blk_wide_off, np.int32), blk_exc_off=pin(self.blk_exc_off, np.int32),
+                    exc_start=pin(self.exc_start), exc_meta=pin(self.exc_meta, np.int32),
+                    meta_dict=pin(self.meta_dict, np.int32), chrom_read_off=pin(self.chrom_read_off))
+
+
+class Delta3Receiver(Delta8Receiver):
+    """Device-side landing buffers for delta3 transfers (same interface as :class:`Delta8Receiver`)."""
+
+    def __init__(self, wire, device):
+        import torch
+        n, K = len(wire), Delta3Batch.BLOCK
+        self.wire = wire
+        n_blk = len(wire.blk_base)
+        self.packed = torch.empty(n_blk * K, dtype=torch.uint8, device=device)
+        self.wide = torch.empty(max(len(wire.wide), 1), dtype=torch.uint8, device=device)
+        self.blk_base = torch.empty(max(n_blk, 1), dtype=torch.int32, device=device)
+        self.blk_wide_off = torch.empty(n_blk + 1, dtype=torch.int32, device=device)
+        self.blk_exc_off = torch.empty(n_blk + 1, dtype=torch.int32, device=device)
+        self.exc_start = torch.empty(max(len(wire.exc_start), 1), dtype=torch.int32, device=device)
+        self.exc_meta = torch.empty(max(len(wire.exc_meta), 1), dtype=torch.int32, device=device)
+        self.meta_dict = torch.empty(32, dtype=torch.int32, device=device)
+        self.batch = DeviceBatch(n, len(wire.chroms), wire.max_span, torch.empty(n, dtype=torch.int32, device=device),
+                                 torch.empty(n, dtype=torch.int32, device=device),
+                                 torch.empty(len(wire.chroms) + 1, dtype=torch.int64, device=device))
+
+    def _copy_range(self, pinned, a, b):
+        K = Delta3Batch.BLOCK
+        if b <= a:
+            return
+        b0, b1 = a // K, (b + K - 1) // K
+        self.packed[b0 * K:b1 * K].copy_(pinned["packed"][b0 * K:b1 * K], non_blocking=True)
+        self.blk_base[b0:b1].copy_(pinned["blk_base"][b0:b1], non_blocking=True)
+        self.blk_wide_off[b0:b1 + 1].copy_(pinned["blk_wide_off"][b0:b1 + 1], non_blocking=True)
+        self.blk_exc_off[b0:b1 + 1].copy_(pinned["blk_exc_off"][b0:b1 + 1], non_blocking=True)
+        w0, w1 = int(self.wire.blk_wide_off[b0]), int(self.wire.blk_wide_off[b1])
+        if w1 > w0:
+            self.wide[w0:w1].copy_(pinned["wide"][w0:w1], non_blocking=True)
+        e0, e1 = int(self.wire.blk_exc_off[b0]), int(self.wire.blk_exc_off[b1])
+        if e1 > e0:
+            self.exc_start[e0:e1].copy_(pinned["exc_start"][e0:e1], non_blocking=True)
+            self.exc_meta[e0:e1].copy_(pinned["exc_meta"][e0:e1], non_blocking=True)
+
+    def _unpack(self, a, b):
+        from . import _lib
+        _lib.check(_lib.lib().pb_unpack_delta3(_lib.ptr(self.packed), _lib.ptr(self.wide), _lib.ptr(self.blk_base),
+                                               _lib.ptr(self.blk_wide_off), _lib.ptr(self.blk_exc_off),
+                                               _lib.ptr(self.exc_start), _lib.ptr(self.exc_meta), _lib.ptr(self.meta_dict),
+                                               self.batch.n_reads, int(a), int(b),
+                                               _lib.ptr(self.batch.ref_start), _lib.ptr(self.batch.meta),
+                                               _lib.stream_ptr()))
+
+
 class BatchRead(object):
     """Duck-typed stand-in for ``pysam.AlignedSegment`` built from one batch row."""
     __slots__ = ("batch", "index")

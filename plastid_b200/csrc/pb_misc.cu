@@ -212,6 +212,95 @@ pb_unpack_delta8_kernel(const uint32_t *__restrict__ dstart4, const uint32_t *__
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// delta3: 1-byte-per-read host format (3-bit start delta + 5-bit meta-dictionary index) -> the SoA
+// ----------------------------------------------------------------------------------------
+// The transfer is PCIe-bound, so bytes are time.  Per read one byte: bits 0-2 = start delta 0..6, 7 = the
+// delta is 7 + the next byte of the `wide` stream (wide byte 255 = exception: absolute start and meta
+// word from exc_start / exc_meta); bits 3-7 = index into a 31-entry dictionary of meta words (31 is only
+// written for exceptions).  Blocks of 128 reads carry an absolute base and the ordinals of their first
+// wide byte and first exception.  One warp per block, 4 consecutive reads per lane: two rounds of
+// ballots (wide ordinals, then exception ordinals), a segmented warp scan, 16-byte stores.
+__global__ void __launch_bounds__(256)
+pb_unpack_delta3_kernel(const uint32_t *__restrict__ packed4, const uint8_t *__restrict__ wide,
+                        const int32_t *__restrict__ blk_base, const uint32_t *__restrict__ blk_wide_off,
+                        const uint32_t *__restrict__ blk_exc_off, const int32_t *__restrict__ exc_start,
+                        const uint32_t *__restrict__ exc_meta, const uint32_t *__restrict__ dict,
+                        int64_t n_reads, int64_t blk_begin, int64_t blk_end,
+                        int32_t *__restrict__ ref_start, uint32_t *__restrict__ meta)
+{
+    __shared__ uint32_t s_dict[32];
+    if (threadIdx.x < 32) s_dict[threadIdx.x] = __ldg(dict + threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t B = blk_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (B >= blk_end) return;
+    const int64_t i0 = B * 128 + lane * 4;
+    const uint32_t p4 = __ldg(packed4 + B * 32 + lane);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t d[4], code[4];
+    bool wd[4], ex[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t byte = (p4 >> (8 * j)) & 0xffu;
+        d[j] = byte & 7u;
+        code[j] = byte >> 3;
+        wd[j] = d[j] == 7u;
+    }
+    uint32_t wbefore = __ldg(blk_wide_off + B), own = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wbefore += __popc(__ballot_sync(0xffffffffu, wd[j]) & lt);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t wv = wd[j] ? (uint32_t)__ldg(wide + wbefore + own) : 0u;
+        own += wd[j];
+        ex[j] = wd[j] && wv == 255u;
+        if (wd[j]) d[j] = 7u + wv;
+    }
+    uint32_t ebefore = __ldg(blk_exc_off + B);
+    own = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ebefore += __popc(__ballot_sync(0xffffffffu, ex[j]) & lt);
+    int32_t es[4];
+    uint32_t m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t e = ebefore + own;
+        own += ex[j];
+        es[j] = ex[j] ? __ldg(exc_start + e) : 0;
+        m[j] = ex[j] ? __ldg(exc_meta + e) : s_dict[code[j]];
+    }
+    bool f = false;
+    int32_t v = 0;
+    if (lane == 0) { f = true; v = __ldg(blk_base + B); d[0] = ex[0] ? d[0] : 0u; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (ex[j]) { f = true; v = es[j]; } else v += (int32_t)d[j];
+    }
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const int32_t pv = __shfl_up_sync(0xffffffffu, v, dd);
+        const bool pf = __shfl_up_sync(0xffffffffu, (int)f, dd) != 0;
+        if (lane >= dd && !f) { v += pv; f = pf; }
+    }
+    int32_t cur = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) cur = __ldg(blk_base + B);
+    int32_t out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (ex[j]) cur = es[j]; else cur += (int32_t)d[j];
+        out[j] = cur;
+    }
+    if (i0 + 4 <= n_reads) {
+        *reinterpret_cast<int4 *>(ref_start + i0) = make_int4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<uint4 *>(meta + i0) = make_uint4(m[0], m[1], m[2], m[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < n_reads) { ref_start[i0 + j] = out[j]; meta[i0 + j] = m[j]; }
+    }
+}
+
 }  // namespace
 
 extern "C" int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule *rule, int strand,
@@ -291,6 +380,31 @@ extern "C" int pb_unpack_delta8(const uint8_t *dstart, const uint8_t *code, cons
     const int64_t grid = (b1 - b0 + 7) / 8;   // 8 warps = 8 blocks of 128 reads per CTA
     pb_unpack_delta8_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
         (const uint32_t *)dstart, (const uint32_t *)code, blk_base, blk_exc_off, exc_start, exc_meta, dict,
+        read_end, b0, b1, ref_start_out, meta_out);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_unpack_delta3(const uint8_t *packed, const uint8_t *wide, const int32_t *blk_base,
+                                const uint32_t *blk_wide_off, const uint32_t *blk_exc_off,
+                                const int32_t *exc_start, const uint32_t *exc_meta, const uint32_t *dict,
+                                int64_t n_reads, int64_t read_begin, int64_t read_end,
+                                int32_t *ref_start_out, uint32_t *meta_out, void *stream)
+{
+    if (!packed || !wide || !blk_base || !blk_wide_off || !blk_exc_off || !dict || !ref_start_out || !meta_out) {
+        pb_set_error("pb_unpack_delta3: null argument"); return PB_EINVAL;
+    }
+    if (read_begin < 0 || read_end < read_begin || read_end > n_reads || (read_begin & 127)) {
+        pb_set_error("pb_unpack_delta3: bad read range (begin must be a multiple of 128)"); return PB_EINVAL;
+    }
+    if (((uintptr_t)packed & 3) || (((uintptr_t)ref_start_out | (uintptr_t)meta_out) & 15)) {
+        pb_set_error("pb_unpack_delta3: packed stream must be 4-byte aligned, outputs 16-byte aligned"); return PB_EINVAL;
+    }
+    if (read_end == read_begin) return PB_OK;
+    const int64_t b0 = read_begin >> 7, b1 = (read_end + 127) >> 7;
+    const int64_t grid = (b1 - b0 + 7) / 8;
+    pb_unpack_delta3_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint32_t *)packed, wide, blk_base, blk_wide_off, blk_exc_off, exc_start, exc_meta, dict,
         read_end, b0, b1, ref_start_out, meta_out);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;

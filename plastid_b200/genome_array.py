@@ -81,9 +81,9 @@ class CountPlanes(object):
 _workspaces = {}
 
 
-def _workspace(device, nbytes):
+def _workspace(device, nbytes, slot=0):
     import torch
-    key = str(device)
+    key = (str(device), slot)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
@@ -171,23 +171,56 @@ def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=N
         mask |= _lib.STRAND_PLANE[s]
     L = _lib.lib()
     ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, 0, dbatch.n_reads)
-    ws = _workspace(dev, ws_bytes)
-    stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev)
+    # Two compute lanes (streams) take the chunks alternately, each with its own workspace and statistics:
+    # the tail of one chunk's persistent kernel overlaps the expansion and the first tiles of the next.
+    n_lanes = 2 if len(chunks) > 1 else 1
+    ws = [_workspace(dev, ws_bytes, slot=j) for j in range(n_lanes)]
+    stats = [torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev) for _ in range(n_lanes)]
     copy_stream = copy_stream or torch.cuda.Stream(device=dev)
     compute = torch.cuda.current_stream()
+    lanes = [compute] + [_side_stream(dev, j) for j in range(1, n_lanes)]
     copy_stream.wait_stream(compute)          # landing buffers may still be read by earlier work
+    for ln in lanes[1:]:
+        ln.wait_stream(compute)
     with torch.cuda.stream(copy_stream):
         receiver._receive_tables(pinned)
     events = [receiver.receive_chunk(pinned, a, b, copy_stream) for a, b, _x, _y in chunks]
     b_c, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
     outs = [planes.plane_ptr(s) if s in strands else None for s in _STRANDS]
-    for (a, b, bin_a, bin_b), ev in zip(chunks, events):
-        compute.wait_event(ev)
-        receiver._unpack(a, b)
-        _lib.check(L.pb_map_point_range(C.byref(b_c), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
-                                        _lib.ptr(stats), _lib.ptr(ws), ws_bytes, bin_a, bin_b, b, _lib.stream_ptr()))
-    planes.stats_dev = stats
+    unpacked = None                           # event: the previous chunk's reads are expanded (halo of this chunk)
+    for k, ((a, b, bin_a, bin_b), ev) in enumerate(zip(chunks, events)):
+        ln = lanes[k % n_lanes]
+        with torch.cuda.stream(ln):
+            ln.wait_event(ev)
+            receiver._unpack(a, b)
+            done = torch.cuda.Event()
+            done.record(ln)
+            if unpacked is not None:
+                ln.wait_event(unpacked)
+            unpacked = done
+            _lib.check(L.pb_map_point_range(C.byref(b_c), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
+                                            _lib.ptr(stats[k % n_lanes]), _lib.ptr(ws[k % n_lanes]), ws_bytes, bin_a, bin_b, b,
+                                            _lib.stream_ptr()))
+    for ln in lanes[1:]:
+        compute.wait_stream(ln)
+    total = stats[0]
+    for st in stats[1:]:
+        dropped_len = torch.maximum(total[_lib.PB_STAT_DROPPED_LEN], st[_lib.PB_STAT_DROPPED_LEN])
+        total = total + st
+        total[_lib.PB_STAT_DROPPED_LEN] = dropped_len
+    planes.stats_dev = total
     return planes
+
+
+_side_streams = {}
+
+
+def _side_stream(device, j):
+    import torch
+    key = (str(device), j)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 def region_sums(planes, table, out=None):

@@ -137,3 +137,29 @@ def genome_array_recipe(seed=0, n_regions=24, reads_per_region=150, read_length=
     reads.sort(key=lambda x: x.reference_start)
     assert cursor < chrom_len
     return reads, vectors
+
+
+def delta3_decode(w):
+    """Plain-numpy statement of the delta3 format (include/plastid_b200.h, pb_unpack_delta3)."""
+    n, K = w.n_reads, 128
+    start = np.zeros(n, dtype=np.int64)
+    meta = np.zeros(n, dtype=np.uint32)
+    for B in range(len(w.blk_base)):
+        cur, wi, e = int(w.blk_base[B]), int(w.blk_wide_off[B]), int(w.blk_exc_off[B])
+        for i in range(B * K, min((B + 1) * K, n)):
+            d, code = int(w.packed[i]) & 7, int(w.packed[i]) >> 3
+            is_exc = False
+            if d == 7:
+                wv = int(w.wide[wi])
+                wi += 1
+                is_exc = wv == 255
+                d = 7 + wv
+            if is_exc:
+                cur, meta[i] = int(w.exc_start[e]), w.exc_meta[e]
+                e += 1
+            else:
+                cur += d if i > B * K else 0
+                meta[i] = w.meta_dict[code]
+            start[i] = cur
+        assert wi == int(w.blk_wide_off[B + 1]) and e == int(w.blk_exc_off[B + 1])
+    return start, meta

@@ -507,11 +507,30 @@ def test_delta8_unpack_on_device(cuda_device):
         assert (db.chrom_read_off.cpu().numpy() == hb.chrom_read_off).all()
 
 
+def test_delta3_unpack_on_device(cuda_device):
+    """1-byte transfer format: device expansion == the batch it was packed from (wide deltas,
+    exceptions, chromosome changes inside a block, > 31 distinct meta words, ragged tail)."""
+    from plastid_b200.batch import Delta3Batch, Delta3Receiver
+    from test_host_logic import _delta8_world
+    for n_reads, rare in ((30000, True), (30001, False), (127, False), (3, False)):
+        chroms, lens, hb = _delta8_world(n_reads, rare)
+        wire = Delta3Batch.from_batch(hb)
+        rx = Delta3Receiver(wire, cuda_device)
+        rx.batch.ref_start.fill_(-7)
+        db = rx.receive(wire.pinned())
+        assert (db.ref_start.cpu().numpy() == hb.ref_start).all()
+        assert (db.meta.cpu().numpy().view(np.uint32) == hb.meta).all()
+        assert (db.chrom_read_off.cpu().numpy() == hb.chrom_read_off).all()
+
+
+@pytest.mark.parametrize("fmt", ["delta8", "delta3"])
 @pytest.mark.parametrize("n_chunks", [1, 3, 8])
-def test_delta8_streamed_upload_matches_whole_batch(small_world, cuda_device, n_chunks):
+def test_delta8_streamed_upload_matches_whole_batch(small_world, cuda_device, n_chunks, fmt):
     import torch
-    from plastid_b200.batch import Delta8Batch, Delta8Receiver
+    from plastid_b200 import batch as pbatch
     from plastid_b200.genome_array import map_wire16_streamed
+    Delta8Batch, Delta8Receiver = ((pbatch.Delta8Batch, pbatch.Delta8Receiver) if fmt == "delta8"
+                                   else (pbatch.Delta3Batch, pbatch.Delta3Receiver))
     w = small_world
     wire = Delta8Batch.from_batch(w["hb"])
     rx = Delta8Receiver(wire, cuda_device)

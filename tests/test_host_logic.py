@@ -347,6 +347,31 @@ def test_delta8_host_format_round_trip():
         Delta8Batch.from_batch(spliced)
 
 
+def test_delta3_host_format_round_trip():
+    from plastid_b200.batch import Delta3Batch, Delta3Receiver
+    from helpers import delta3_decode
+    chroms, lens, hb = _delta8_world()                  # > 31 distinct meta words: rare ones become exceptions
+    w = Delta3Batch.from_batch(hb)
+    assert len(w.packed) % 128 == 0 and int(w.blk_exc_off[-1]) == len(w.exc_start) > 0 and int(w.blk_wide_off[-1]) == len(w.wide)
+    start, meta = delta3_decode(w)
+    assert (start == hb.ref_start).all() and (meta == hb.meta).all()
+    _c, _l, plain = _delta8_world(rare_meta=False)
+    wp = Delta3Batch.from_batch(plain)
+    assert wp.nbytes < 0.25 * (plain.ref_start.nbytes + plain.meta.nbytes)       # < 2 bytes per read even on a sparse batch
+    s2, m2 = delta3_decode(wp)
+    assert (s2 == plain.ref_start).all() and (m2 == plain.meta).all()
+    for n in (0, 1, 128, 129):
+        sub = pb.batch_from_arrays(["a", "b"], [100000, 1000], [0] * (n // 2) + [1] * (n - n // 2),
+                                   sorted(x * 97 % 5000 for x in range(n // 2)) + sorted(range(n - n // 2)), [30] * n,
+                                   [i % 2 for i in range(n)])
+        ws = Delta3Batch.from_batch(sub)
+        s3, m3 = delta3_decode(ws)
+        assert (s3 == sub.ref_start).all() and (m3 == sub.meta).all()
+    lay = pb.GenomeLayout(chroms, lens)
+    plan = Delta3Receiver.plan_chunks(w, lay, 8)
+    assert plan[0][0] == 0 and plan[-1][1] == len(w) and plan[-1][3] == lay.total_bins
+
+
 def test_delta8_chunk_plan_covers_reads_and_bins():
     from plastid_b200.batch import Delta8Batch, Delta8Receiver
     chroms, lens = synth.human_like_genome(0.004)
