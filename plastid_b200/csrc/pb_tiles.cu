@@ -1,6 +1,7 @@
 // pb_tiles.cu — kernels shared by the point and center mapping paths: tile candidate index,
 // binning of multi-block (spliced) reads by tile, statistics, workspace and timing plumbing.
 #include "pb_tiles.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -56,8 +57,8 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
 // ----------------------------------------------------------------------------------------
 // K1: CIGAR blocks of multi-block reads -> per-tile record buckets (counting sort by tile)
 // ----------------------------------------------------------------------------------------
-template <bool CENTER>
-__global__ void __launch_bounds__(256, 8)   // latency-bound gather chains: favour resident threads over registers
+template <bool CENTER, int OCC>
+__global__ void __launch_bounds__(256, OCC)   // latency-bound gather chains: resident threads vs registers (OCC CTAs/SM)
 pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t *__restrict__ slot_of_len,
               int tile_shift, int64_t tile_lo, int64_t tile_hi, int fill, uint32_t *__restrict__ rec_cursor,
               const uint32_t *__restrict__ rec_off, PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
@@ -429,13 +430,16 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
     int tile_shift = 0;
     while ((1 << tile_shift) < tile_bins) ++tile_shift;
     if ((1 << tile_shift) != tile_bins) { pb_set_error("tile size must be a power of two"); return PB_EINVAL; }
+    int occ_sel = 8;
+    if (const char *e = getenv("PB_BIN_OCC")) occ_sel = atoi(e);        // measurement override (profiles/NOTES)
     for (int fill = 0; fill < 2; ++fill) {
-        if (center)
-            pb_bin_kernel<true><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, fill, ws.rec_cursor,
-                                                          ws.rec_off, ws.recs, ws.slots);
-        else
-            pb_bin_kernel<false><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, fill, ws.rec_cursor,
-                                                           ws.rec_off, ws.recs, ws.slots);
+#define PB_BIN_LAUNCH(C_, O_) pb_bin_kernel<C_, O_><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, fill, ws.rec_cursor, ws.rec_off, ws.recs, ws.slots)
+        if (center) {
+            if (occ_sel == 4) PB_BIN_LAUNCH(true, 4); else if (occ_sel == 6) PB_BIN_LAUNCH(true, 6); else PB_BIN_LAUNCH(true, 8);
+        } else {
+            if (occ_sel == 4) PB_BIN_LAUNCH(false, 4); else if (occ_sel == 6) PB_BIN_LAUNCH(false, 6); else PB_BIN_LAUNCH(false, 8);
+        }
+#undef PB_BIN_LAUNCH
         if (!fill) {
             const int64_t nb = (n_tiles + kScanChunk - 1) / kScanChunk;
             pb_scan_chunks_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(ws.rec_cursor, ws.rec_off, ws.scan_part, n_tiles);
