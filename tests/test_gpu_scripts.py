@@ -286,3 +286,54 @@ def test_track_export_center_rule_within_tolerance(world):
     rb = [l.split("\t") for l in b.getvalue().splitlines()[1:]]
     cov = lambda rows: sum((int(r[2]) - int(r[1])) * float(r[3]) for r in rows)
     assert abs(cov(ra) - cov(rb)) <= 1e-6 * cov(ra) and rb[0][:2] == ra[0][:2]
+
+
+def test_make_wiggle_and_counts_in_region_command_lines(world, tmp_path):
+    """The script entry points end to end: batch file -> tracks / region table on disk, against the
+    oracle's restatements of the reference programs (make_wiggle.py:172-209, counts_in_region.py:107-125)."""
+    import io
+    from plastid_b200.bin import _cli, make_wiggle
+    w = world
+    batch = str(tmp_path / "reads.npz")
+    _cli.save_batch(batch, w["hb"])
+    out = str(tmp_path / "trk")
+    make_wiggle.main(["--count_files", batch, "--fiveprime", "--offset", "14", "--device", w["dev"], "-o", out,
+                      "--color", "#0000FF", "--window_size", "5000"])
+    oga, _ga = make_gas(w, po.FivePrimeMap(14), pb.FivePrimeMapFactory(14))
+    for suffix, strand in (("fw", "+"), ("rc", "-")):
+        exp = io.StringIO()
+        oga.to_bedgraph(exp, "%s_%s" % (out, suffix), strand, window_size=5000, color="0,0,255")
+        assert open("%s_%s.wig" % (out, suffix)).read() == exp.getvalue()
+    make_wiggle.main(["--count_files", batch, "--threeprime", "--device", w["dev"], "-o", out, "-t", "mytrack",
+                      "--output_format", "variable_step"])
+    oga3, _ = make_gas(w, po.ThreePrimeMap(0), pb.ThreePrimeMapFactory(0))
+    exp = io.StringIO()
+    oga3.to_variable_step(exp, "mytrack_rc", "-", color="0,0,0")
+    assert open(out + "_rc.wig").read() == exp.getvalue()
+    # counts_in_region from BED files, with a mask annotation
+    chains = w["ann"].chains()[:40]
+    bed, mbed, table = str(tmp_path / "a.bed"), str(tmp_path / "m.bed"), str(tmp_path / "out.txt")
+    with open(bed, "w") as fh:
+        for ch in chains:
+            sp = ch.spanning_segment
+            sizes = ",".join(str(len(s)) for s in ch)
+            starts = ",".join(str(s.start - sp.start) for s in ch)
+            fh.write("\t".join([ch.chrom, str(sp.start), str(sp.end), ch.get_name(), "0", ch.strand, str(sp.start), str(sp.end),
+                                 "0,0,0", str(len(ch)), sizes, starts]) + "\n")
+    feats = _mask_features(w, np.random.default_rng(4), n=60)[:-8]
+    with open(mbed, "w") as fh:
+        for f in feats:
+            for s in f:
+                fh.write("\t".join([s.chrom, str(s.start), str(s.end), f.get_name(), "0", s.strand]) + "\n")
+    counts_in_region.main(["--annotation_files", bed, "--mask_annotation_files", mbed, "--count_files", batch,
+                           "--fiveprime", "--offset", "14", "--device", w["dev"], table])
+    ochains = []
+    for ch in chains:
+        oc = po.Chain(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in ch])
+        oc.name = ch.get_name()
+        ochains.append(oc)
+    ofeats = [po.Chain(po.Seg(s.chrom, s.start, s.end, s.strand)) for f in feats for s in f]
+    exp_rows = osc.counts_in_region_rows(oga, ochains, crossmap=po.GenomeHash(ofeats))
+    lines = open(table).read().splitlines()
+    assert lines[0] == "## total_dataset_counts: %s" % oga.sum()
+    assert [l.split("\t") for l in lines[2:]] == exp_rows
