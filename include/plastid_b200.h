@@ -198,6 +198,17 @@ int pb_unpack_delta3(const uint8_t *packed, const uint8_t *wide, const int32_t *
                      int64_t n_reads, int64_t read_begin, int64_t read_end,
                      int32_t *ref_start_out, uint32_t *meta_out, void *stream);
 
+/* Host side (no CUDA): pack a sorted unspliced SoA batch (HOST arrays) into the delta3 streams above, on
+ * n_threads host threads (0 = all).  Caller-owned HOST buffers sized for the worst case: packed
+ * uint8[n_blk*128], wide uint8[n_reads], blk_base int32[n_blk], blk_wide_off / blk_exc_off uint32[n_blk+1],
+ * exc_start int32[n_reads], exc_meta uint32[n_reads], dict32 uint32[32] (n_blk = ceil(n_reads / 128));
+ * *n_wide_out / *n_exc_out receive how many wide bytes / exceptions were written. */
+int pb_pack_delta3(const int32_t *ref_start, const uint32_t *meta, const int64_t *chrom_read_off,
+                   int32_t n_chrom, int64_t n_reads, int n_threads,
+                   uint8_t *packed, uint8_t *wide, int32_t *blk_base, uint32_t *blk_wide_off,
+                   uint32_t *blk_exc_off, int32_t *exc_start, uint32_t *exc_meta, uint32_t *dict32,
+                   int64_t *n_wide_out, int64_t *n_exc_out);
+
 /* 5' / 3' / variable-offset mapping of a whole batch into dense uint32 planes.
  * `planes` selects which of out_plus/out_minus/out_any are produced; every bin of a selected
  * plane is written (no prior memset needed).  stats: device uint64[PB_NSTATS], accumulated. */

@@ -502,11 +502,38 @@ class Delta3Batch(object):
                 + self.chrom_read_off.nbytes)
 
     @classmethod
-    def from_batch(cls, hb):
+    def from_batch(cls, hb, native=True, threads=0):
+        """``native``: encode with the library's multithreaded host encoder (``pb_pack_delta3``, no CUDA
+        involved); ``False`` = the numpy statement of the format below (tests compare the two)."""
         if hb.blk is not None:
             raise ValueError("delta3 carries single-block reads only")
         n, K = len(hb), cls.BLOCK
         n_blk = (n + K - 1) // K
+        if native:
+            import ctypes as C
+            from . import _lib
+            start32 = np.ascontiguousarray(hb.ref_start, dtype=np.int32)
+            meta32 = np.ascontiguousarray(hb.meta, dtype=np.uint32)
+            off = np.ascontiguousarray(hb.chrom_read_off, dtype=np.int64)
+            packed = np.empty(n_blk * K, dtype=np.uint8)
+            wide = np.empty(max(n, 1), dtype=np.uint8)
+            blk_base = np.empty(max(n_blk, 1), dtype=np.int32)
+            blk_wide_off = np.empty(n_blk + 1, dtype=np.uint32)
+            blk_exc_off = np.empty(n_blk + 1, dtype=np.uint32)
+            exc_start = np.empty(max(n, 1), dtype=np.int32)
+            exc_meta = np.empty(max(n, 1), dtype=np.uint32)
+            meta_dict = np.empty(32, dtype=np.uint32)
+            n_wide, n_exc = C.c_int64(0), C.c_int64(0)
+
+            def p(a):
+                return C.c_void_p(a.ctypes.data)
+            _lib.check(_lib.lib().pb_pack_delta3(p(start32), p(meta32), p(off), len(hb.chroms), n, int(threads), p(packed),
+                                                 p(wide), p(blk_base), p(blk_wide_off), p(blk_exc_off), p(exc_start),
+                                                 p(exc_meta), p(meta_dict), C.byref(n_wide), C.byref(n_exc)))
+            chrom_of_blk = (np.searchsorted(off, np.arange(0, n, K), side="right") - 1).astype(np.int32)
+            return cls(hb.chroms, hb.chrom_len, hb.chrom_read_off, n, packed, wide[:n_wide.value].copy(), blk_base[:n_blk],
+                       blk_wide_off, blk_exc_off, exc_start[:n_exc.value].copy(), exc_meta[:n_exc.value].copy(), meta_dict,
+                       (chrom_of_blk, start32[::K].astype(np.int64)), hb.max_span, hb.mapped)
         start = hb.ref_start.astype(np.int64)
         meta = hb.meta.astype(np.uint32)
         chrom_of_read = np.repeat(np.arange(len(hb.chroms), dtype=np.int32), np.diff(hb.chrom_read_off))

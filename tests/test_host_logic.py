@@ -370,6 +370,17 @@ def test_delta3_host_format_round_trip():
     lay = pb.GenomeLayout(chroms, lens)
     plan = Delta3Receiver.plan_chunks(w, lay, 8)
     assert plan[0][0] == 0 and plan[-1][1] == len(w) and plan[-1][3] == lay.total_bins
+    # the library's multithreaded host encoder writes the same streams as the numpy statement of the format
+    fields = ("packed", "wide", "blk_base", "blk_wide_off", "blk_exc_off", "exc_start", "exc_meta", "meta_dict",
+              "blk_chrom", "blk_first_start")
+    empty_chrom = pb.batch_from_arrays(["a", "e", "b"], [100000, 50, 1000], [0] * 300 + [2] * 200,
+                                       sorted(x * 97 % 5000 for x in range(300)) + sorted(range(200)), [30] * 500, [0] * 500)
+    for batch in (hb, plain, empty_chrom, pb.batch_from_arrays(["a"], [10], [], [], [], [])):
+        for threads in (1, 3):
+            nat, ref = Delta3Batch.from_batch(batch, native=True, threads=threads), Delta3Batch.from_batch(batch, native=False)
+            for f in fields:
+                assert np.array_equal(getattr(nat, f), getattr(ref, f)), f
+            assert nat.nbytes == ref.nbytes
 
 
 def test_delta8_chunk_plan_covers_reads_and_bins():
