@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--e2e-format", default="delta3", choices=["delta3", "delta8", "wire16"],
                     help="host transfer format of the end-to-end leg (unspliced batches)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="upload chunks overlapped with mapping in the e2e leg")
+    ap.add_argument("--sharding", default="reads", choices=["reads", "positions"],
+                    help="multi-GPU mode: 'reads' (default, weak scaling: every GPU maps its own batch over the whole genome) "
+                         "or 'positions' (strong scaling of ONE batch: every GPU owns a contiguous bin range, SURVEY 8e)")
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5", "peaks"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
@@ -163,7 +166,8 @@ def build_world(args, rank, device):
     if wl == "c3":
         dbatch = synth.rnaseq_reads(chroms, lens, n_reads, seed=100 + rank, device=device)
     else:
-        dbatch = synth.riboseq_reads(ann, n_reads, seed=100 + rank, device=device, frac_in=0.85 if wl != "c1" else 0.9)
+        seed = 100 if getattr(args, "sharding", "reads") == "positions" else 100 + rank     # positions: ONE batch, all ranks
+        dbatch = synth.riboseq_reads(ann, n_reads, seed=seed, device=device, frac_in=0.85 if wl != "c1" else 0.9)
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     return dict(chroms=chroms, lens=lens, ann=ann, layout=layout, table=table, dbatch=dbatch, fac=fac, sf=sf,
@@ -309,6 +313,67 @@ def run_peaks(args, device):
     with open(os.path.join(ROOT, "gpurun_out", "atomic_peaks.json"), "w") as fh:
         json.dump(out, fh, indent=1)
     print(json.dumps(out))
+
+
+def run_position_sharded(args, W, device, rank, world, dist):
+    """Strong scaling of one C2 batch by position ranges: every rank builds the SAME batch,
+    keeps the reads that start in its bin range (+ halo), allocates range-only planes, maps its range
+    with pb_map_point_range and sums the clipped region table; one all-reduce per step."""
+    import torch
+    from plastid_b200 import dist as pdist
+    from plastid_b200.genome_array import map_batch, region_sums, CountPlanes
+    layout, table, fac, sf, dbatch = W["layout"], W["table"], W["fac"], W["sf"], W["dbatch"]
+    n_total = dbatch.n_reads
+    sub, lo, hi, cuts = pdist.shard_positions_device(dbatch, layout, rank, world)
+    del dbatch
+    W["dbatch"] = None
+    torch.cuda.empty_cache()
+    clipped = pdist.clip_table(table, lo, hi)
+    clipped.device(device)
+    planes = CountPlanes(layout, "u32", device, bin_range=(lo, hi))
+    planes.alloc(("+", "-"))
+
+    def step():
+        map_batch(sub, layout, fac, sf, strands=("+", "-"), planes=planes, sync_stats=False, bin_range=(lo, hi))
+        sums, live = region_sums(planes, clipped)
+        if world > 1:
+            dist.all_reduce(sums)
+        return sums
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        sums = step()
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=device)
+    share = torch.tensor([float(sub.n_reads), float(hi - lo)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(share) for _ in range(world)]
+        dist.all_gather(gathered, share)
+    else:
+        gathered = [share]
+    if rank != 0:
+        return
+    ms = float(t.item())
+    line = {"metric": METRIC, "value": n_total / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "%s, ONE batch of %d synthetic reads over %d bins sharded by position range over %d GPUs "
+                                   "(range-only planes, halo reads, clipped region tables all-reduced)"
+                                   % (W["name"], n_total, layout.total_bins, world),
+                       "reads_per_rank_incl_halo": [int(g[0].item()) for g in gathered],
+                       "bins_per_rank": [int(g[1].item()) for g in gathered]},
+            "region_counts_per_sec": W["ann"].n_tx / (ms / 1000.0), "table_checksum": float(sums.sum().item())}
+    print(json.dumps(line))
 
 
 def run_c4(args, W, device, rank, world, dist):
@@ -469,6 +534,13 @@ def main():
               else "single GPU", "l2": "inputs (%.2f GB) and outputs (%.1f GB) larger than the 126 MB L2"
               % (8 * n_reads / 1e9, (16 if is_center else 8) * layout.total_bins / 1e9)}
 
+    if args.sharding == "positions" and args.impl != "reference":
+        if args.workload != "c2":
+            raise SystemExit("--sharding positions is implemented for the c2 workload")
+        run_position_sharded(args, W, device, rank, world, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     if args.workload == "c2p" and args.impl != "reference":
         run_c2p(args, W, device, rank, world, dist)
         if world > 1:

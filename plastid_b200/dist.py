@@ -119,6 +119,53 @@ def shard_positions(hb, layout, rank, world_size, cuts=None):
     return sub, g_lo, g_hi
 
 
+def shard_positions_device(dbatch, layout, rank, world_size):
+    """:func:`shard_positions` for a batch that already lives on the device (unspliced batches): the
+    same cuts (global bin of read ``r * n // world``, rounded down to the layout granularity), the
+    rank's reads + halo gathered per chromosome with searches on the device.
+    Returns ``(sub_batch, bin_lo, bin_hi, cuts)``."""
+    import torch
+    from . import _lib
+    from .batch import DeviceBatch
+    if dbatch.blk_off is not None:
+        raise ValueError("shard_positions_device handles unspliced batches; shard spliced batches on the host")
+    A, n = _lib.PB_LAYOUT_ALIGN, dbatch.n_reads
+    off = dbatch.chrom_read_off.cpu().numpy()
+    cuts = [0]
+    for r in range(1, world_size):
+        i = (r * n) // world_size
+        if i >= n:
+            g = int(layout.total_bins)
+        else:
+            c = int(np.searchsorted(off, i, side="right")) - 1
+            g = int(layout.chrom_bin_off[c]) + int(dbatch.ref_start[i].item())
+        cuts.append(max((g // A) * A, cuts[-1]))
+    cuts.append(int(layout.total_bins))
+    g_lo, g_hi = cuts[rank], cuts[rank + 1]
+    pieces, new_off = [], [0]
+    for c in range(dbatch.n_chrom):
+        base = int(layout.chrom_bin_off[c])
+        a, b = int(off[c]), int(off[c + 1])
+        lo, hi = g_lo - base, g_hi - base
+        if hi <= 0 or lo >= int(layout.chrom_len[c]) or b <= a or g_hi <= g_lo:
+            new_off.append(new_off[-1])
+            continue
+        seg = dbatch.ref_start[a:b]
+        clen = int(layout.chrom_len[c])              # keep the search keys inside int32
+        keys = torch.tensor([max(lo - dbatch.max_span, -clen - 1), min(hi, clen)], dtype=seg.dtype, device=seg.device)
+        i0, i1 = (a + int(x) for x in torch.searchsorted(seg, keys, right=False).tolist())
+        pieces.append((i0, i1))
+        new_off.append(new_off[-1] + max(i1 - i0, 0))
+    if pieces:
+        starts = torch.cat([dbatch.ref_start[i0:i1] for i0, i1 in pieces])
+        metas = torch.cat([dbatch.meta[i0:i1] for i0, i1 in pieces])
+    else:
+        starts, metas = dbatch.ref_start[:0].clone(), dbatch.meta[:0].clone()
+    sub = DeviceBatch(int(starts.numel()), dbatch.n_chrom, dbatch.max_span, starts, metas,
+                      torch.tensor(new_off, dtype=torch.int64, device=starts.device), None, None, dbatch.max_block_len)
+    return sub, g_lo, g_hi, np.asarray(cuts, dtype=np.int64)
+
+
 def clip_table(table, bin_lo, bin_hi):
     """The part of every chain of a :class:`~plastid_b200.regions.ChainTable` inside the global bins
     ``[bin_lo, bin_hi)``: blocks clipped (or dropped), mask bits re-based to the clipped chain

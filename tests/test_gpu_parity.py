@@ -591,6 +591,13 @@ def test_position_range_sharding_matches_whole_batch(small_world, cuda_device, w
         live += l_r
         mapped += planes.stats
     assert torch.equal(sums, ref_sums) and torch.equal(live, ref_live)
+    if not spliced:      # the device-side sharder picks the same cuts and the same reads
+        dfull = DeviceBatch.from_host(hb, cuda_device)
+        for rank in range(world_size):
+            sub, lo, hi = pd.shard_positions(hb, lay, rank, world_size, cuts)
+            dsub, dlo, dhi, dcuts = pd.shard_positions_device(dfull, lay, rank, world_size)
+            assert (dlo, dhi) == (lo, hi) and (dcuts == cuts).all() and dsub.n_reads == len(sub)
+            assert (dsub.ref_start.cpu().numpy() == sub.ref_start).all() and (dsub.chrom_read_off.cpu().numpy() == sub.chrom_read_off).all()
     for k in (_lib.PB_STAT_MAPPED_PLUS, _lib.PB_STAT_MAPPED_MINUS, _lib.PB_STAT_DROPPED_PLUS, _lib.PB_STAT_DROPPED_MINUS):
         assert mapped[k] == whole.stats[k]        # halo reads are not counted twice
 
