@@ -37,6 +37,9 @@
  *   pb_phase_sums    sub-codon phase accumulation          plastid/bin/phase_by_size.py:165-235
  *   pb_stratified_windows  per-read-length window matrices plastid/bin/psite.py:176-199,
  *                                                          plastid/bin/phase_by_size.py:186-194
+ *   pb_landmark_windows  window_landmark / window_cds_start / window_cds_stop
+ *                                                          plastid/bin/metagene.py:180-340
+ *   pb_spanning_windows  maximal_spanning_window per gene  plastid/bin/metagene.py:343-502, 702-735
  *
  * Alignment batch (SoA, sorted by (chromosome, ref_start); what pysam hands the reference
  * as AlignedSegment.reference_start / .positions / .is_reverse):
@@ -386,6 +389,50 @@ size_t pb_export_workspace_bytes(int64_t n_bins);
 int pb_export_runs(const void *vec, int vec_dtype, int64_t n_bins, int64_t window, int mode,
                    int64_t capacity, int64_t *out_start, int64_t *out_end, double *out_val,
                    int64_t *n_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* `metagene generate` geometry.  Transcript table: blocks [tx_bstart, tx_bend) ascending per
+ * transcript, in ONE coordinate system shared by all chromosomes (global bins: chrom_bin_off[c] + position),
+ * so that equal coordinates mean equal genomic positions; tx_bcum = chain coordinate of each block's first
+ * base in genomic order (exclusive running sum of block lengths within the transcript); transcript t owns
+ * blocks [tx_off[t], tx_off[t+1]); tx_reverse[t] = 1 for '-' strand transcripts.
+ *
+ * pb_landmark_windows: window_landmark(region, flank_up, flank_down, landmark=tx_landmark[t]) with
+ * ref_delta = 0 (plastid/bin/metagene.py:180-239; window_cds_start / window_cds_stop :241-340 pass
+ * cds_start / cds_end - 3), one thread per transcript.  tx_landmark[t] < 0 = no landmark (non-coding).
+ * win_out int64[n_tx][4] = {w_start, w_end, w_off, ref_pos}: the window covers transcript coordinates
+ * [w_start, w_end) and is placed at column w_off of a (flank_up + flank_down)-wide row; ref_pos = genomic
+ * coordinate of the landmark.  flags_out uint8[n_tx]: PB_WIN_HAS_REF, PB_WIN_INDEX_ERROR (landmark beyond
+ * the transcript: the reference catches IndexError and ignores the region, :457-461). */
+#define PB_WIN_HAS_REF     1
+#define PB_WIN_INDEX_ERROR 2
+int pb_landmark_windows(const int64_t *tx_bstart, const int64_t *tx_bend, const int64_t *tx_bcum,
+                        const int64_t *tx_off, const uint8_t *tx_reverse, const int64_t *tx_landmark,
+                        int64_t n_tx, int32_t flank_up, int32_t flank_down,
+                        int64_t *win_out, uint8_t *flags_out, void *stream);
+
+/* pb_spanning_windows: maximal_spanning_window (plastid/bin/metagene.py:343-502) for every group of
+ * transcripts (group_regions_make_windows :702-735 calls it once per gene) in one launch, one warp per
+ * group.  Group g = transcripts grp_tx[grp_off[g] .. grp_off[g+1]) (indices into the transcript table, in
+ * the order the reference would iterate them: the LAST one decides the offset quirk of :495-499);
+ * win / flags as written by pb_landmark_windows (or filled by the host from a custom window function:
+ * blocks = the window's own blocks, w_start = 0, w_end = its length).  A column of the
+ * (flank_up + flank_down)-wide alignment is kept when every transcript of the group has the same genomic
+ * position there.  Outputs per group: status (PB_SPAN_NONE: landmarks differ / a transcript has none / no
+ * shared column; PB_SPAN_WINDOW; PB_SPAN_REF_OUTSIDE: the reference would raise KeyError at :498),
+ * offset = alignment_offset, n_pos = window length, n_blk = its number of blocks, refpos = the shared
+ * landmark coordinate.  Call once with out_off == NULL (count), exclusive-scan n_blk into out_off, and call
+ * again with out_off / out_bstart / out_bend to write the blocks of group g, ascending, at out_off[g]
+ * (the second call reads n_blk and leaves the per-group outputs untouched). */
+#define PB_SPAN_NONE        0
+#define PB_SPAN_WINDOW      1
+#define PB_SPAN_REF_OUTSIDE 2
+int pb_spanning_windows(const int64_t *tx_bstart, const int64_t *tx_bend, const int64_t *tx_bcum,
+                        const int64_t *tx_off, const uint8_t *tx_reverse,
+                        const int64_t *win, const uint8_t *flags,
+                        const int64_t *grp_off, const int64_t *grp_tx, int64_t n_grp,
+                        int32_t flank_up, int32_t flank_down,
+                        uint8_t *status, int32_t *offset, int32_t *n_pos, int32_t *n_blk, int64_t *refpos,
+                        const int64_t *out_off, int64_t *out_bstart, int64_t *out_bend, void *stream);
 
 /* Roofline probe (the atomic peak a scatter-add design would be bound by; no
  * reference counterpart, not on the product path): n_updates `red.global.add.u32` into

@@ -8,8 +8,9 @@ tensors as device buffers.  There is no CPU fallback.
 from .map_factories import (CenterMapFactory, FivePrimeMapFactory, ThreePrimeMapFactory,
                             VariableFivePrimeMapFactory, StratifiedVariableFivePrimeMapFactory,
                             SizeFilterFactory, DataWarning, MalformedFileError)
-from .roitools import GenomicSegment, SegmentChain
+from .roitools import GenomicSegment, SegmentChain, Transcript, positions_to_segments
 from .batch import AlignmentBatch, GenomeLayout, pack_reads, batch_from_arrays
 from .genome_array import BAMGenomeArray, GenomeArray, SparseGenomeArray
+from .masks import GenomeHash
 
 __version__ = "0.1.0"

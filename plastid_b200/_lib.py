@@ -18,6 +18,8 @@ PB_RULE_FIVEPRIME, PB_RULE_THREEPRIME, PB_RULE_VARIABLE, PB_RULE_CENTER, PB_RULE
 (PB_STAT_DROPPED_PLUS, PB_STAT_DROPPED_MINUS, PB_STAT_DROPPED_ANY, PB_STAT_DROPPED_LEN,
  PB_STAT_MAPPED_PLUS, PB_STAT_MAPPED_MINUS, PB_STAT_MAPPED_ANY) = range(7)
 PB_NSTATS = 8
+PB_WIN_HAS_REF, PB_WIN_INDEX_ERROR = 1, 2
+PB_SPAN_NONE, PB_SPAN_WINDOW, PB_SPAN_REF_OUTSIDE = 0, 1, 2
 
 STRAND_PLANE = {"+": PB_PLANE_PLUS, "-": PB_PLANE_MINUS, ".": PB_PLANE_ANY}
 PLANE_INDEX = {"+": 0, "-": 1, ".": 2}
@@ -90,6 +92,9 @@ _SIGNATURES = {
     "pb_mask_chains": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "pb_export_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "pb_export_runs": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pb_landmark_windows": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
+    "pb_spanning_windows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32,
+                                      _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pb_atomic_probe": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
     "pb_count_profiles_u32": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int,
                                         _P, _P, _P, _P, _P, C.c_size_t, _P]),

@@ -8,7 +8,7 @@ from ..batch import AlignmentBatch
 from ..genome_array import BAMGenomeArray
 from ..map_factories import (CenterMapFactory, FivePrimeMapFactory, ThreePrimeMapFactory,
                              VariableFivePrimeMapFactory, SizeFilterFactory)
-from ..roitools import GenomicSegment, SegmentChain
+from ..roitools import GenomicSegment, SegmentChain, Transcript
 
 
 def add_alignment_args(parser):
@@ -63,8 +63,11 @@ def genome_array_from_args(args):
     return ga
 
 
-def read_bed(path):
-    """BED3-BED12 -> list of SegmentChain (thin stand-in for plastid/readers/bed.py)."""
+def read_bed(path, as_transcripts=False):
+    """BED3-BED12(+) -> list of SegmentChain (thin stand-in for plastid/readers/bed.py).  With
+    ``as_transcripts`` every line becomes a :class:`Transcript` whose coding region is
+    thickStart..thickEnd (none when they are equal, like ``Transcript.from_bed``); a 13th column, when
+    present, is taken as ``gene_id``."""
     chains = []
     with open(path) as fh:
         for line in fh:
@@ -80,7 +83,15 @@ def read_bed(path):
                 segs = [GenomicSegment(chrom, start + a, start + a + n, strand) for a, n in zip(starts, sizes)]
             else:
                 segs = [GenomicSegment(chrom, start, end, strand)]
-            chains.append(SegmentChain(*segs, ID=name))
+            if as_transcripts:
+                attr = dict(ID=name)
+                if len(f) > 7 and int(f[6]) < int(f[7]):
+                    attr.update(cds_genome_start=int(f[6]), cds_genome_end=int(f[7]))
+                if len(f) > 12 and f[12]:
+                    attr["gene_id"] = f[12]
+                chains.append(Transcript(*segs, **attr))
+            else:
+                chains.append(SegmentChain(*segs, ID=name))
     return chains
 
 

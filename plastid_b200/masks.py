@@ -57,6 +57,72 @@ class MaskIndex(object):
         return self._dev[key]
 
 
+class GenomeHash(object):
+    """``GenomeHash(features)``: the mask container the reference's programs pass around
+    (plastid/genomics/genome_hash.py:81-436).  Queries for many regions at once go through
+    :meth:`mask_index` + :func:`apply_mask_index` (one launch); ``get_overlapping_features`` /
+    ``hash[roi]`` answer for one region on the host with the reference's semantics: same chromosome,
+    same strand, at least one shared position.  Like the reference's ``_make_hash`` (:236-257) only '+'
+    and '-' features are accepted (a '.' feature raises ``KeyError``)."""
+
+    def __init__(self, features=None, binsize=20000, do_copy=True):
+        self.binsize = binsize
+        self.features = list(features or [])
+        for f in self.features:
+            if len(f) and f.strand not in ("+", "-"):
+                raise KeyError(f.strand)
+        self._index = {}
+
+    def __len__(self):
+        return len(self.features)
+
+    def mask_index(self, layout):
+        key = id(layout)
+        if key not in self._index:
+            self._index[key] = (layout, MaskIndex(self.features, layout))
+        return self._index[key][1]
+
+    def get_overlapping_features(self, roi, stranded=True):
+        out = []
+        for f in self.features:
+            if len(f) == 0 or len(roi) == 0 or f.chrom != roi.chrom:
+                continue
+            if stranded and f.strand != roi.strand:
+                continue
+            if any(a.start < b.end and b.start < a.end for a in f for b in roi):
+                out.append(f)
+        return out
+
+    __getitem__ = get_overlapping_features
+
+
+def mask_intervals_of_chains(table, bits):
+    """Decode the mask bits of every chain of ``table`` (device tensor written by
+    :func:`apply_mask_index`) into per-chain lists of masked ``(start, end)`` intervals in chromosome
+    coordinates — what ``SegmentChain.get_masks`` reports after the reference's ``add_masks``."""
+    flat = np.unpackbits(bits.cpu().numpy(), bitorder="little")
+    out, off = [], 0
+    for c in range(table.n_chains):
+        ivs = []
+        k0, k1 = int(table.chain_off[c]), int(table.chain_off[c + 1])
+        if k1 > k0:
+            base = int(table.layout.chrom_bin_off[np.searchsorted(table.layout.chrom_bin_off, table.bstart[k0], side="right") - 1])
+            for k in range(k0, k1):
+                n = int(table.bend[k] - table.bstart[k])
+                m = flat[off:off + n]
+                off += n
+                if m.any():
+                    edge = np.flatnonzero(np.diff(np.concatenate(([0], m, [0]))))
+                    start = int(table.bstart[k]) - base
+                    for a, b in zip(edge[0::2], edge[1::2]):
+                        if ivs and ivs[-1][1] == start + int(a):
+                            ivs[-1] = (ivs[-1][0], start + int(b))
+                        else:
+                            ivs.append((start + int(a), start + int(b)))
+        out.append(ivs)
+    return out
+
+
 def apply_mask_index(table, index, device):
     """OR the masks of ``index`` into the mask bits of every chain of ``table`` (a
     :class:`~plastid_b200.regions.ChainTable`) on ``device``; masks the chains already carry from

@@ -85,6 +85,17 @@ def _intersect_intervals(xs, ys):
     return out
 
 
+def positions_to_segments(chrom, strand, positions):
+    """Set of positions -> sorted list of maximal runs (``roitools.pyx`` ``positions_to_segments``)."""
+    pos = np.unique(np.fromiter(positions, dtype=np.int64))
+    if len(pos) == 0:
+        return []
+    cut = np.flatnonzero(np.diff(pos) != 1)
+    starts = np.concatenate(([pos[0]], pos[cut + 1]))
+    ends = np.concatenate((pos[cut], [pos[-1]])) + 1
+    return [GenomicSegment(chrom, int(a), int(b), strand) for a, b in zip(starts, ends)]
+
+
 class SegmentChain(object):
     """``SegmentChain(*segments, **attr)``: sorted, merged exon blocks on one chromosome strand."""
 
@@ -154,6 +165,20 @@ class SegmentChain(object):
             segs.append(GenomicSegment(chrom, int(a), int(b), strand))
         return SegmentChain(*segs)
 
+    def as_bed(self, thickstart=None, thickend=None):
+        """BED12 line (roitools.pyx:2660-2806 with its defaults: score 0, colour 0,0,0,
+        ``thickstart`` / ``thickend`` from ``attr`` else the chain's start); "" for an empty chain."""
+        if len(self) == 0:
+            return ""
+        span = self.spanning_segment
+        thickstart = self.attr.get("thickstart", span.start) if thickstart is None else thickstart
+        thickend = self.attr.get("thickend", span.start) if thickend is None else thickend
+        fields = [span.chrom, span.start, span.end, self.get_name(), 0, span.strand, thickstart, thickend,
+                  self.attr.get("color", "0,0,0"), len(self),
+                  ",".join(str(len(x)) for x in self) + ",",
+                  ",".join(str(x.start - span.start) for x in self) + ","]
+        return "\t".join(str(x) for x in fields) + "\n"
+
     def get_position_list(self):
         out = []
         for s in self._segments:
@@ -184,12 +209,18 @@ class SegmentChain(object):
         raise KeyError("Position %s:%s(%s) is not in SegmentChain %s" % (chrom, genomic_x, strand, self))
 
     def get_subchain(self, start, end, stranded=True, **extra_attr):
+        """roitools.pyx:3121-3218: a python slice ``[start:end]`` of the position hash (so bounds outside
+        the chain clamp instead of raising); ``ID`` becomes ``<name>_subchain``."""
         if start is None or end is None:
             raise TypeError("start and end may not be None")
-        if start < 0 or end > self.length or end < start:
-            raise IndexError("get_subchain: bounds %s-%s outside chain of length %s" % (start, end, self.length))
+        attr = dict(self.attr)
+        attr.update(extra_attr)
+        attr["ID"] = "%s_subchain" % self.get_name()
+        if start == end:
+            return SegmentChain(**attr)
         if stranded and self.strand == "-":
             start, end = self.length - end, self.length - start
+        start, end, _ = slice(start, end).indices(self.length)
         segs = []
         for k, s in enumerate(self._segments):
             a = max(start, int(self._cum[k]))
@@ -197,8 +228,6 @@ class SegmentChain(object):
             if a < b:
                 off = int(self._cum[k])
                 segs.append(GenomicSegment(self.chrom, s.start + a - off, s.start + b - off, self.strand))
-        attr = dict(self.attr)
-        attr.update(extra_attr)
         return SegmentChain(*segs, **attr)
 
     # -- masks -------------------------------------------------------------------------------
@@ -273,3 +302,58 @@ class SegmentChain(object):
             mask = np.empty_like(counts)
             mask[..., :] = m
         return np.ma.MaskedArray(counts, mask=mask.astype(bool), copy=copy)
+
+
+class Transcript(SegmentChain):
+    """``Transcript(*segments, cds_genome_start=None, cds_genome_end=None, **attr)``: a chain with a
+    coding region (roitools.pyx:3565-3913).  ``cds_start`` / ``cds_end`` are transcript coordinates
+    derived like ``_update_cds`` (:3883-3913), including its end-of-exon handling."""
+
+    def __init__(self, *segments, **attr):
+        SegmentChain.__init__(self, *segments, **attr)
+        if "type" not in self.attr:
+            self.attr["type"] = "mRNA"
+        self.cds_genome_start = attr.get("cds_genome_start", None)
+        self.cds_genome_end = attr.get("cds_genome_end", None)
+        self.cds_start = self.cds_end = None
+        if self.cds_genome_start is not None and self.cds_genome_end is not None:
+            self._update_cds()
+        else:
+            self.cds_genome_start = self.cds_genome_end = None
+
+    def _update_cds(self):
+        gs, ge = int(self.cds_genome_start), int(self.cds_genome_end)
+        coord = lambda x: self.get_segmentchain_coordinate(self.chrom, x, self.strand)   # noqa: E731
+        if self.strand != "-":
+            self.cds_start = coord(gs)
+            try:
+                self.cds_end = coord(ge)
+            except KeyError:                      # half-open end coincides with an exon end (:3900-3905)
+                self.cds_end = 1 + coord(ge - 1)
+        else:
+            self.cds_start = coord(ge - 1)
+            self.cds_end = 1 + coord(gs)
+
+    def get_gene(self):
+        """``gene_id``, else ``Parent``, else ``gene_<name>`` (roitools.pyx:2154-2173)."""
+        gene = self.attr.get("gene_id", self.attr.get("Parent", "gene_%s" % self.get_name()))
+        if isinstance(gene, list):
+            gene = ",".join(sorted(gene))
+        return gene
+
+    def _sub(self, start, end, suffix, **extra_attr):
+        if self.cds_genome_start is None or self.cds_genome_end is None:
+            return SegmentChain()
+        sub = SegmentChain.get_subchain(self, start, end)
+        sub.attr = dict(gene_id=self.get_gene(), transcript_id=self.get_name(), ID="%s_%s" % (self.get_name(), suffix))
+        sub.attr.update(extra_attr)
+        return sub
+
+    def get_cds(self, **extra_attr):              # roitools.pyx:4005-4046
+        return self._sub(self.cds_start, self.cds_end, "CDS", **extra_attr)
+
+    def get_utr5(self, **extra_attr):             # :4048-4087
+        return self._sub(0, self.cds_start, "5UTR", type="5UTR", **extra_attr)
+
+    def get_utr3(self, **extra_attr):             # :4089-4130
+        return self._sub(self.cds_end, self.length, "3UTR", type="3UTR", **extra_attr)

@@ -163,3 +163,111 @@ def delta3_decode(w):
             start[i] = cur
         assert wi == int(w.blk_wide_off[B + 1]) and e == int(w.blk_exc_off[B + 1])
     return start, meta
+
+
+# ---------------------------------------------------------------------------------------------
+# metagene generate golden data (tests/golden/metagene_generate.json, from the reference's
+# plastid/test/unit/bin/test_metagene.py via tests/golden/make_metagene_generate_golden.py)
+# ---------------------------------------------------------------------------------------------
+def metagene_generate_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metagene_generate.json")) as fh:
+        return json.load(fh)
+
+
+def gff3_transcript_records(text):
+    """Minimal GFF3 transcript assembly for the golden GFF: what ``GFF3_TranscriptAssembler``
+    (plastid/readers/gff.py:1440-1560) yields for it — segments = exon + CDS features of a parent
+    transcript (1-based inclusive -> 0-based half-open), ``cds_genome_start/end`` = first CDS start /
+    last CDS end, ``gene_id`` = the mRNA's sorted, comma-joined ``Parent``.  Returns a dict
+    name -> dict(chrom, strand, segments, cds_genome_start, cds_genome_end, gene_id)."""
+    tx_parent, exons, cds = {}, {}, {}
+    for line in text.splitlines():
+        if not line.strip() or line.startswith("#"):
+            continue
+        f = line.split("\t")
+        chrom, ftype, start, end, strand = f[0], f[2].strip(), int(f[3]) - 1, int(f[4]), f[6].strip()
+        attr = dict(kv.split("=", 1) for kv in f[8].strip().split(";") if "=" in kv)
+        if ftype == "mRNA":
+            tx_parent[attr["ID"]] = ",".join(sorted(attr.get("Parent", attr["ID"]).split(",")))
+        elif ftype in ("exon", "CDS"):
+            for parent in attr["Parent"].split(","):
+                (exons if ftype == "exon" else cds).setdefault(parent, []).append((chrom, start, end, strand))
+    out = {}
+    for name in sorted(set(exons) | set(cds)):
+        feats = exons.get(name, []) + cds.get(name, [])
+        rec = dict(chrom=feats[0][0], strand=feats[0][3], segments=[(s, e) for _, s, e, _ in feats],
+                   cds_genome_start=None, cds_genome_end=None, gene_id=tx_parent.get(name, name))
+        if name in cds:
+            ordered = sorted(cds[name], key=lambda x: (x[1], x[2]))
+            rec["cds_genome_start"], rec["cds_genome_end"] = ordered[0][1], ordered[-1][2]
+        out[name] = rec
+    return out
+
+
+def random_gene_models(rng, n_genes, chroms=("chrA", "chrB"), spacing=6000):
+    """Seeded multi-isoform gene models for the maximal-spanning-window tests: per gene 1-4 transcripts
+    derived from one exon chain by the variations the reference's own cases cover (shared start codon
+    with different 5' UTRs, alternative start, skipped / shifted downstream exons, non-coding isoform,
+    CDS start at a splice junction or at the transcript's first base).  Returns records shaped like
+    :func:`gff3_transcript_records` (name -> dict), in a deterministic order."""
+    out = {}
+    for g in range(n_genes):
+        chrom = chroms[g % len(chroms)]
+        strand = "+-"[int(rng.integers(0, 2))]
+        pos = 1000 + (g // len(chroms)) * spacing + int(rng.integers(0, 500))
+        n_ex = int(rng.integers(1, 6))
+        exons = []
+        for _ in range(n_ex):
+            ln = int(rng.integers(20, 400))
+            exons.append((pos, pos + ln))
+            pos += ln + int(rng.integers(30, 300))
+        total = sum(e - s for s, e in exons)
+
+        def genomic(chain, x):                       # unstranded chain coordinate -> genomic position
+            for s, e in chain:
+                if x < e - s:
+                    return s + x
+                x -= e - s
+            raise IndexError(x)
+
+        # coding region in unstranded chain coordinates [a, b)
+        a = int(rng.integers(0, max(total // 2, 1)))
+        b = int(rng.integers(min(a + 3, total), total + 1))
+        if rng.random() < 0.15:
+            a = 0
+        if rng.random() < 0.15 and n_ex > 1:
+            a = exons[0][1] - exons[0][0]            # first base of the second exon
+            b = max(b, min(a + 3, total))
+        if b <= a:
+            b = min(a + 3, total)
+        cds = (genomic(exons, a), genomic(exons, b - 1) + 1) if b > a else None
+        n_iso = int(rng.integers(1, 5))
+        for k in range(n_iso):
+            segs = list(exons)
+            this_cds = cds
+            kind = int(rng.integers(0, 7)) if k else 0
+            if kind == 1:                            # longer / shorter first exon (left end moves)
+                s, e = segs[0]
+                segs[0] = (max(s + int(rng.integers(-200, 15)), 0), e)
+            elif kind == 2:                          # last exon's right end moves
+                s, e = segs[-1]
+                segs[-1] = (s, e + int(rng.integers(-15, 200)))
+            elif kind == 3 and len(segs) > 2:        # skip an internal exon
+                del segs[int(rng.integers(1, len(segs) - 1))]
+            elif kind == 4:                          # non-coding isoform
+                this_cds = None
+            elif kind == 5 and cds is not None:      # alternative start / stop
+                this_cds = (cds[0] + 3, cds[1]) if cds[1] - cds[0] > 6 else cds
+            elif kind == 6:                          # extra upstream exon
+                segs = [(max(segs[0][0] - 400, 0), max(segs[0][0] - 300, 1))] + segs
+            segs = [(s, e) for s, e in segs if e > s]
+            covered = set(p for s, e in segs for p in range(s, e))
+            if this_cds is not None and not (this_cds[0] in covered and this_cds[1] - 1 in covered):
+                this_cds = None                      # the assembler would reject it; keep it non-coding
+            out["g%04d.t%d" % (g, k)] = dict(chrom=chrom, strand=strand, segments=segs,
+                                             cds_genome_start=None if this_cds is None else this_cds[0],
+                                             cds_genome_end=None if this_cds is None else this_cds[1],
+                                             gene_id="g%04d" % g)
+    return out

@@ -337,3 +337,135 @@ def test_make_wiggle_and_counts_in_region_command_lines(world, tmp_path):
     lines = open(table).read().splitlines()
     assert lines[0] == "## total_dataset_counts: %s" % oga.sum()
     assert [l.split("\t") for l in lines[2:]] == exp_rows
+
+
+# ---------------------------------------------------------------------------------------------
+# metagene generate: pb_landmark_windows + pb_spanning_windows + pb_mask_chains
+# ---------------------------------------------------------------------------------------------
+def _transcripts(records, product=True):
+    from oracle import generate as og
+    out = []
+    for name, r in records.items():
+        kw = dict(ID=name, gene_id=r["gene_id"], cds_genome_start=r["cds_genome_start"], cds_genome_end=r["cds_genome_end"])
+        if product:
+            out.append(pb.Transcript(*[pb.GenomicSegment(r["chrom"], s, e, r["strand"]) for s, e in r["segments"]], **kw))
+        else:
+            out.append(og.Tx(*[po.Seg(r["chrom"], s, e, r["strand"]) for s, e in r["segments"]], **kw))
+    return out
+
+
+def _check_reference_rows(rows, result_groups, up):
+    result_groups = sorted(result_groups, key=lambda x: x[0])
+    rows = sorted(rows, key=lambda r: r["region"])
+    c = 0
+    for n, group in enumerate(result_groups):
+        if group[1] is None or group[2] is None:
+            c += 1
+            continue
+        row = rows[n - c]
+        assert str(pb.SegmentChain.from_str(group[0])) == row["region"]
+        assert group[1] == row["alignment_offset"] and group[2] == row["zero_point"] == up
+        if len(group) == 4:
+            assert group[3] == row["masked"]
+    assert len(result_groups) - c == len(rows)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_metagene_generate_reproduces_the_reference_tables(cuda_device, masked):
+    """plastid/test/unit/bin/test_metagene.py:292-326 through the device path, incl. a custom window
+    function (evaluated per region on the host, solved on the device)."""
+    from helpers import metagene_generate_golden, gff3_transcript_records
+    gold = metagene_generate_golden()
+    txs = {t.get_name(): t for t in _transcripts(gff3_transcript_records(gold["transcripts_gff"]))}
+    mask_hash = pb.GenomeHash([pb.SegmentChain.from_str(m) for m in gold["masks"]] if masked else [])
+    results = gold["do_generate_max_window_results_masked" if masked else "do_generate_max_window_results"]
+    custom = lambda region, up, down: metagene.window_cds_start(region, up, down)       # noqa: E731
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for up, down in gold["flanks"]:
+            for name, group in gold["do_generate_max_window"].items():
+                for func in (metagene.window_cds_start, custom):
+                    df = metagene.group_regions_make_windows([txs[t] for t in group], mask_hash, up, down, func,
+                                                             device=cuda_device)
+                    _check_reference_rows(df.to_dict("records"), [results["%s_%s_%s" % (name, up, down)]], up)
+        for name, group in gold["do_generate_multi_gene"].items():
+            df = metagene.group_regions_make_windows([txs[t] for t in group], mask_hash, 50, 100,
+                                                     metagene.window_cds_start, device=cuda_device)
+            _check_reference_rows(df.to_dict("records"), gold["do_generate_multi_gene_results"]["%s_50_100" % name], 50)
+        # single-gene entry point
+        roi, offset = metagene.maximal_spanning_window([txs[t] for t in gold["do_generate_max_window"]["3_same_start_plus"]],
+                                                       mask_hash, 50, 100, device=cuda_device)
+        assert str(roi) == "2L:7985664-7985768^7985833-7985839(+)" and offset == 40
+        assert roi.attr["thickstart"] == 7985674 and roi.masked_length == roi.length - (50 if masked else 0)
+        roi, offset = metagene.maximal_spanning_window([txs[t] for t in gold["do_generate_max_window"]["3_diff_start_plus"]],
+                                                       mask_hash, 50, 100, device=cuda_device)
+        assert len(roi) == 0 and np.isnan(offset)
+
+
+@pytest.mark.parametrize("landmark", ["cds_start", "cds_stop"])
+def test_metagene_generate_random_gene_models_match_oracle(cuda_device, landmark):
+    from helpers import random_gene_models
+    from oracle import generate as og
+    rng = np.random.default_rng(11)
+    recs = random_gene_models(rng, 400)
+    txs, otxs = _transcripts(recs), _transcripts(recs, product=False)
+    masks = []
+    for r in list(recs.values())[::3]:                               # masks placed on the genes themselves
+        if r["cds_genome_start"] is not None:
+            edge = r["cds_genome_start"] if (landmark == "cds_start") == (r["strand"] == "+") else r["cds_genome_end"]
+            s = max(edge + int(rng.integers(-60, 60)), 0)
+            masks.append((r["chrom"], s, s + int(rng.integers(1, 40)), r["strand"] if rng.random() < 0.8 else "+"))
+    mh = pb.GenomeHash([pb.SegmentChain(pb.GenomicSegment(*m)) for m in masks])
+    omh = po.GenomeHash([po.Chain(po.Seg(*m)) for m in masks])
+    ofunc = og.window_cds_start if landmark == "cds_start" else og.window_cds_stop
+    n_masked = n_spliced = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for up, down in ((50, 100), (0, 30), (100, 0), (20, 400), (3, 3), (33, 31)):
+            df = metagene.do_generate(txs, mh, landmark, up, down, device=cuda_device)
+            exp = og.group_regions_make_windows(otxs, omh, up, down, ofunc)
+            got = df.to_dict("records")
+            assert len(got) == len(exp) and len(exp) > 200
+            for a, b in zip(got, exp):
+                for k in ("region_id", "region", "masked", "alignment_offset", "zero_point", "region_length",
+                          "threeprime_offset", "window_size"):
+                    assert a[k] == b[k], (k, a, b)
+                n_masked += a["masked"] != "na"
+                n_spliced += "^" in a["region"]
+    assert n_masked > 50 and n_spliced > 200
+
+
+def test_metagene_generate_then_count(world, tmp_path):
+    """generate -> ROI file -> count, as the two sub-programs are chained (metagene.py:1269-1330)."""
+    w = world
+    ann = w["ann"]
+    txs = []
+    for t, ch in enumerate(ann.chains()):
+        a = ch.get_genomic_coordinate(ch.length // 5)[1]
+        b = ch.get_genomic_coordinate(ch.length - ch.length // 5)[1]
+        lo, hi = (a, b + 1) if ch.strand == "+" else (b, a + 1)
+        txs.append(pb.Transcript(*ch.segments, ID=ch.get_name(), gene_id="gene%d" % t, cds_genome_start=lo, cds_genome_end=hi))
+    bed = tmp_path / "tx.bed"
+    with open(bed, "w") as fh:
+        for tx in txs:
+            line = tx.as_bed(thickstart=tx.cds_genome_start, thickend=tx.cds_genome_end).rstrip("\n")
+            fh.write(line + "\t" + tx.attr["gene_id"] + "\n")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        metagene.main(["generate", "--annotation_files", str(bed), "--upstream", "30", "--downstream", "120",
+                       str(tmp_path / "mg")])
+    from plastid_b200.bin import _cli
+    roi = _cli.read_pl_table(str(tmp_path / "mg_rois.txt"))
+    assert len(roi["region"]) == len(txs) and set(roi["zero_point"]) == {"30"}
+    from oracle import generate as og
+    otxs = [og.Tx(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in tx], ID=tx.get_name(), gene_id=tx.attr["gene_id"],
+                  cds_genome_start=tx.cds_genome_start, cds_genome_end=tx.cds_genome_end) for tx in txs]
+    exp = og.group_regions_make_windows(otxs, po.GenomeHash([]), 30, 120, og.window_cds_start)
+    assert [r["region"] for r in exp] == roi["region"]
+    assert [str(r["alignment_offset"]) for r in exp] == roi["alignment_offset"]
+    oga, ga = make_gas(w, po.FivePrimeMap(12), pb.FivePrimeMapFactory(12))
+    out = metagene.do_count(ga, roi, 40, 90, min_counts=5)
+    counts, norm, profile, num_genes, row_select = osc.metagene_count(oga, exp, 150, 40, 90, 5)
+    assert np.ma.filled(row_select, False).sum() > 10
+    np.testing.assert_allclose(out["metagene_average"], np.ma.filled(profile, np.nan), rtol=1e-12, equal_nan=True)
+    assert (out["regions_counted"] == num_genes).all()

@@ -456,3 +456,97 @@ def test_oracle_genome_hash_overlap_query():
     assert gh.get_overlapping_features(po.Chain(S("c", 100, 200, "."))) == []
     with pytest.raises(KeyError):
         po.GenomeHash([po.Chain(S("c", 1, 5, "."))])
+
+
+# ---------------------------------------------------------------------------------------------
+# metagene generate: host objects (Transcript, window functions, GenomeHash, lowering)
+# ---------------------------------------------------------------------------------------------
+def _golden_transcripts():
+    from helpers import metagene_generate_golden, gff3_transcript_records
+    gold = metagene_generate_golden()
+    txs = {}
+    for name, r in gff3_transcript_records(gold["transcripts_gff"]).items():
+        segs = [pb.GenomicSegment(r["chrom"], s, e, r["strand"]) for s, e in r["segments"]]
+        txs[name] = pb.Transcript(*segs, ID=name, gene_id=r["gene_id"], cds_genome_start=r["cds_genome_start"],
+                                  cds_genome_end=r["cds_genome_end"])
+    return gold, txs
+
+
+@pytest.mark.parametrize("which", ["cds_start", "cds_stop", "cds_stop_with_delta"])
+def test_window_functions_match_reference_tables(which):
+    """plastid/test/unit/bin/test_metagene.py:118-176 (data in tests/golden/metagene_generate.json)."""
+    from plastid_b200.bin import metagene as mg
+    gold, txs = _golden_transcripts()
+    func = mg.window_cds_start if which == "cds_start" else mg.window_cds_stop
+    for up, down in gold["flanks"]:
+        for txid in gold["cds_start_queries" if which == "cds_start" else "cds_stop_queries"]:
+            known = gold[which + "_results"]["%s_%s_%s" % (txid, up, down)]
+            roi, offset, ref = func(txs[txid], up, down, ref_delta=3 if which.endswith("delta") else 0)
+            assert str(roi) == str(pb.SegmentChain.from_str(known[0]))
+            if known[1] is None or known[2] is None:
+                assert np.isnan(offset) and np.isnan(ref)
+            else:
+                assert offset == known[1] and tuple(ref) == tuple(known[2])
+
+
+def test_transcript_cds_coordinates_and_subregions():
+    """Transcript._update_cds (roitools.pyx:3883-3913), get_cds / get_utr5 / get_utr3 (:4005-4130)."""
+    for strand in "+-":
+        tx = pb.Transcript(pb.GenomicSegment("chrA", 100, 200, strand), pb.GenomicSegment("chrA", 300, 400, strand),
+                           ID="tx", cds_genome_start=150, cds_genome_end=350)
+        assert (tx.cds_start, tx.cds_end) == (50, 150)
+        assert tx.get_cds().length == 100 and tx.get_utr5().length == 50 and tx.get_utr3().length == 50
+        assert str(tx.get_cds()) == "chrA:150-200^300-350(%s)" % strand
+        assert str(tx.get_utr5()) == ("chrA:100-150(+)" if strand == "+" else "chrA:350-400(-)")
+        assert tx.get_gene() == "gene_tx" and tx.get_cds().get_name() == "tx_CDS"
+    # half-open CDS end on an exon end (the KeyError branch of _update_cds)
+    tx = pb.Transcript(pb.GenomicSegment("chrA", 100, 200, "+"), pb.GenomicSegment("chrA", 300, 400, "+"),
+                       cds_genome_start=120, cds_genome_end=200)
+    assert (tx.cds_start, tx.cds_end) == (20, 100)
+    nc = pb.Transcript(pb.GenomicSegment("chrA", 100, 200, "+"), ID="nc")
+    assert nc.cds_start is None and len(nc.get_cds()) == 0 and len(nc.get_utr3()) == 0
+    assert pb.Transcript(pb.GenomicSegment("c", 1, 5, "+"), Parent=["g2", "g1"]).get_gene() == "g1,g2"
+    # get_subchain slices like the reference's position hash: out-of-range bounds clamp
+    ch = pb.SegmentChain(pb.GenomicSegment("chrA", 100, 150, "+"), ID="x")
+    assert str(ch.get_subchain(40, 80)) == "chrA:140-150(+)" and len(ch.get_subchain(60, 80)) == 0
+    assert ch.get_subchain(0, 10).get_name() == "x_subchain"
+    assert [str(s) for s in pb.positions_to_segments("c", "+", {5, 3, 4, 9, 10, 20})] == ["c:3-6(+)", "c:9-11(+)", "c:20-21(+)"]
+    bed = pb.SegmentChain(pb.GenomicSegment("c", 10, 20, "-"), pb.GenomicSegment("c", 30, 45, "-"), ID="w", thickstart=12,
+                          thickend=13).as_bed()
+    assert bed == "c\t10\t45\tw\t0\t-\t12\t13\t0,0,0\t2\t10,15,\t0,20,\n"
+
+
+def test_genome_hash_and_transcript_table_lowering():
+    from plastid_b200.windows import TranscriptTable, layout_for_features
+    from plastid_b200.masks import mask_intervals_of_chains
+    from plastid_b200.regions import ChainTable
+    import torch
+    gold, txs = _golden_transcripts()
+    masks = [pb.SegmentChain.from_str(m) for m in gold["masks"]]
+    gh = pb.GenomeHash(masks)
+    roi = pb.SegmentChain.from_str("2L:7985674-7985768^7985833-7985839(+)")
+    assert [str(m) for m in gh[roi]] == ["2L:7985694-7985744(+)"]
+    assert gh.get_overlapping_features(pb.SegmentChain.from_str("2L:7985674-7985768(-)")) == []
+    with pytest.raises(KeyError):
+        pb.GenomeHash([pb.SegmentChain.from_str("2L:5-10(.)")])
+    names = ["FBtr0079531", "FBtr0081950", "FBtr0081950_no_cds"]
+    layout = layout_for_features([txs[n] for n in names], masks)
+    assert layout.chroms == ["2L", "3R", "4"]
+    table = TranscriptTable.from_transcripts([txs[n] for n in names], layout,
+                                             [txs[n].cds_start for n in names])
+    assert table.n_tx == 3 and list(table.reverse) == [0, 1, 1] and list(table.landmark[:2]) == [txs[names[0]].cds_start, txs[names[1]].cds_start]
+    assert table.landmark[2] == -1
+    for t, n in enumerate(names):                                  # bcum restarts per transcript
+        k0, k1 = int(table.tx_off[t]), int(table.tx_off[t + 1])
+        lens = table.bend[k0:k1] - table.bstart[k0:k1]
+        assert list(table.bcum[k0:k1]) == list(np.cumsum(lens) - lens) and lens.sum() == txs[n].length
+    with pytest.raises(ValueError):
+        TranscriptTable.from_transcripts([pb.SegmentChain(pb.GenomicSegment("2L", 5, 9, "."))], layout, [None])
+    # mask bits -> intervals, in the layout pb_mask_chains writes (bit mask_off[c] + j, genomic order)
+    chains = [roi, pb.SegmentChain.from_str("3R:4519776-4519894(-)")]
+    ctable = ChainTable.from_chains(chains, layout)
+    flat = np.zeros(((roi.length + chains[1].length + 31) // 32) * 32 + 32, dtype=np.uint8)
+    flat[20:70] = 1                                                # 2L:7985694-7985744
+    flat[roi.length + 103:roi.length + 115] = 1                    # 3R:4519879-4519891
+    bits = torch.from_numpy(np.packbits(flat, bitorder="little"))
+    assert mask_intervals_of_chains(ctable, bits) == [[(7985694, 7985744)], [(4519879, 4519891)]]

@@ -202,3 +202,92 @@ def test_oracle_reproduces_the_reference_golden_vector_recipe():
             np.testing.assert_allclose(got, exp, rtol=0, atol=1e-8)        # the reference's own tolerance (test_genome_array.py:254)
         else:
             assert (got == exp).all(), (rule, par, strand)
+
+
+# ---------------------------------------------------------------------------------------------
+# metagene generate geometry: oracle/generate.py against the reference's own tables
+# (plastid/test/unit/bin/test_metagene.py:118-326, data transcribed to tests/golden/metagene_generate.json)
+# ---------------------------------------------------------------------------------------------
+from oracle import generate as og                              # noqa: E402
+from helpers import metagene_generate_golden, gff3_transcript_records   # noqa: E402
+
+
+def _oracle_transcripts(gold):
+    out = {}
+    for name, rec in gff3_transcript_records(gold["transcripts_gff"]).items():
+        segs = [po.Seg(rec["chrom"], s, e, rec["strand"]) for s, e in rec["segments"]]
+        out[name] = og.Tx(*segs, ID=name, gene_id=rec["gene_id"], cds_genome_start=rec["cds_genome_start"],
+                          cds_genome_end=rec["cds_genome_end"])
+    return out
+
+
+def _check_window(result, known):
+    roi, offset, ref_point = result
+    known_roi, known_offset, known_ref = known
+    assert str(roi) == str(po.Chain.from_str(known_roi))
+    if known_offset is None or known_ref is None:                # nan in the reference's tables
+        assert np.isnan(offset) and ref_point is np.nan
+    else:
+        assert offset == known_offset and tuple(ref_point) == tuple(known_ref)
+
+
+@pytest.mark.parametrize("which", ["cds_start", "cds_stop", "cds_stop_with_delta"])
+def test_oracle_window_functions_match_reference_tables(which):
+    gold = metagene_generate_golden()
+    txs = _oracle_transcripts(gold)
+    func = og.window_cds_start if which == "cds_start" else og.window_cds_stop
+    queries = gold["cds_start_queries" if which == "cds_start" else "cds_stop_queries"]
+    n = 0
+    for up, down in gold["flanks"]:
+        for txid in queries:
+            known = gold[which + "_results"]["%s_%s_%s" % (txid, up, down)]
+            _check_window(func(txs[txid], up, down, ref_delta=3 if which.endswith("delta") else 0), known)
+            n += 1
+    assert n == 40
+
+
+def test_oracle_window_landmark_properties():
+    """test_metagene.py:179-216 (check_window_landmark) on the same two spliced chains."""
+    for strand in "+-":
+        chain = po.Chain(po.Seg("chrA", 50, 350, strand), po.Seg("chrA", 500, 900, strand))
+        for landmark in range(0, 700, 50):
+            roi, offset, ref = og.window_landmark(chain, 50, 100, landmark=landmark)
+            assert ref == og.get_genomic_coordinate(chain, landmark)
+            assert ref[1] in roi.position_list
+            if landmark + 100 <= roi.length:
+                assert offset + roi.length == 150
+            else:
+                assert offset + roi.length <= 150
+            assert og.get_segmentchain_coordinate(roi, ref[1]) + offset == 50
+
+
+def _check_maximal_windows(rows, result_groups, up):
+    result_groups = sorted(result_groups, key=lambda x: x[0])
+    rows = sorted(rows, key=lambda r: r["region"])
+    c = 0
+    for n, group in enumerate(result_groups):
+        if group[1] is None or group[2] is None:
+            c += 1
+            continue
+        row = rows[n - c]
+        assert str(po.Chain.from_str(group[0])) == row["region"]
+        assert group[1] == row["alignment_offset"] and group[2] == row["zero_point"] == up
+        if len(group) == 4:
+            assert group[3] == row["masked"]
+    assert len(result_groups) - c == len(rows)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_oracle_maximal_spanning_windows_match_reference_tables(masked):
+    gold = metagene_generate_golden()
+    txs = _oracle_transcripts(gold)
+    mask_hash = po.GenomeHash([po.Chain.from_str(m) for m in gold["masks"]] if masked else [])
+    results = gold["do_generate_max_window_results_masked" if masked else "do_generate_max_window_results"]
+    for up, down in gold["flanks"]:
+        for name, group in gold["do_generate_max_window"].items():
+            rows = og.group_regions_make_windows([txs[t] for t in group], mask_hash, up, down, og.window_cds_start)
+            _check_maximal_windows(rows, [results["%s_%s_%s" % (name, up, down)]], up)
+    if not masked:
+        for name, group in gold["do_generate_multi_gene"].items():
+            rows = og.group_regions_make_windows([txs[t] for t in group], mask_hash, 50, 100, og.window_cds_start)
+            _check_maximal_windows(rows, gold["do_generate_multi_gene_results"]["%s_50_100" % name], 50)
