@@ -423,6 +423,27 @@ def run_c4(args, W, device, rank, world, dist):
     if rank != 0:
         return
     ms = float(t.item())
+    # `metagene generate` geometry at the same scale: landmark windows of 3 isoforms per gene and
+    # the maximal spanning window of every gene (count + fill launches), tables resident on the device
+    from plastid_b200.windows import landmark_windows, spanning_windows
+    iso_table, grp_off, grp_tx = synth.isoform_table(ann, layout, n_iso=3)
+    iso_table.device(device)
+    gen_ms = []
+    for i in range(3 + args.steps):
+        torch.cuda.synchronize()
+        ev[2].record()
+        win, flags = landmark_windows(iso_table, 50, 300, device)
+        ev[3].record()
+        t0 = time.perf_counter()
+        res = spanning_windows(iso_table, win, flags, grp_off, grp_tx, 50, 300, device)
+        wall = (time.perf_counter() - t0) * 1e3
+        if i >= 3:
+            gen_ms.append((ev[2].elapsed_time(ev[3]), wall))
+    generate = {"genes": int(len(grp_off) - 1), "transcripts": int(iso_table.n_tx), "window": 350,
+                "landmark_kernel_ms": float(np.mean([a for a, _ in gen_ms])),
+                "spanning_windows_wall_ms": float(np.mean([b for _, b in gen_ms])),
+                "windows_found": int((res["status"] == 1).sum()), "window_blocks": int(res["n_blk"].sum()),
+                "note": "wall time of count + scan + fill launches incl. the device->host copy of the result tables"}
     positions = int(table.chain_len.sum())
     alg = 4.0 * positions + positions / 8.0 + 16.0 * len(table.bstart) + 9.0 * n * width
     g_ms = float(np.mean(gather_ms))
@@ -437,6 +458,7 @@ def run_c4(args, W, device, rank, world, dist):
                          "peak": peak, "unit": "GB/s", "frac": alg / (g_ms / 1000.0) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": g_ms,
                          "kernel_share_of_step": g_ms / ms},
+            "generate": generate,
             "profile_checksum": float(torch.nan_to_num(prof).sum().item()), "regions_counted_max": int(nreg.max().item())}
     print(json.dumps(line))
 

@@ -280,3 +280,49 @@ def window_table(annotation, layout, width=350, mask_frac=0.05, mask_block=20, s
     table = ChainTable(layout, bstart, bend, chain_off, plane, plane, length,
                        np.packbits(flat, bitorder="little"), mask_off)
     return table, np.asarray(row_col, dtype=np.int32)
+
+
+def isoform_table(annotation, layout, n_iso=3, seed=9, max_shift=150, max_landmark=300):
+    """``metagene generate`` input at annotation scale: every transcript of ``annotation`` becomes a gene
+    with ``n_iso`` isoforms (as is; 5'-most genomic exon extended to the left; 3'-most genomic exon
+    extended to the right; further isoforms repeat these with new extents) that share one landmark
+    position.  Returns (TranscriptTable, grp_off, grp_tx): gene t = isoforms ``grp_tx[grp_off[t]:grp_off[t+1]]``."""
+    from .windows import TranscriptTable
+    rng = np.random.default_rng(seed)
+    n = annotation.n_tx
+    tx_off = np.asarray(annotation.tx_off, dtype=np.int64)
+    counts = np.diff(tx_off)
+    base = layout.chrom_bin_off[np.asarray([layout.index[c] for c in annotation.chroms])][np.asarray(annotation.tx_chrom)]
+    ex_s = np.asarray(annotation.ex_start, dtype=np.int64) + np.repeat(base, counts)
+    ex_e = np.asarray(annotation.ex_end, dtype=np.int64) + np.repeat(base, counts)
+    rev = np.asarray(annotation.tx_strand, dtype=np.uint8)
+    length = np.add.reduceat(ex_e - ex_s, tx_off[:-1])
+    lm0 = np.minimum(rng.integers(0, max_landmark, n), length - 1)
+    bs, be, rv, lm, ch = [], [], [], [], []
+    for k in range(n_iso):
+        s, e = ex_s.copy(), ex_e.copy()
+        five = np.zeros(n, dtype=np.int64)
+        if k % 3 == 1:
+            d = rng.integers(1, max_shift, n)
+            s[tx_off[:-1]] -= d
+            five = np.where(rev == 0, d, 0)
+        elif k % 3 == 2:
+            d = rng.integers(1, max_shift, n)
+            e[tx_off[1:] - 1] += d
+            five = np.where(rev == 1, d, 0)
+        bs.append(s)
+        be.append(e)
+        rv.append(rev)
+        lm.append(lm0 + five)
+        ch.append(np.asarray(annotation.tx_chrom))
+    table = TranscriptTable(layout, np.concatenate(bs), np.concatenate(be), _stack_offsets(tx_off, n_iso),
+                            np.concatenate(rv), np.concatenate(lm), np.concatenate(ch))
+    grp_off = np.arange(n + 1, dtype=np.int64) * n_iso
+    grp_tx = (np.arange(n, dtype=np.int64)[:, None] + np.arange(n_iso, dtype=np.int64)[None, :] * n).reshape(-1)
+    return table, grp_off, grp_tx
+
+
+def _stack_offsets(tx_off, copies):
+    """Offsets of ``copies`` concatenated copies of a block table with offsets ``tx_off``."""
+    total = int(tx_off[-1])
+    return np.concatenate([[0]] + [tx_off[1:] + k * total for k in range(copies)]).astype(np.int64)
