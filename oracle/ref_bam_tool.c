@@ -6,10 +6,23 @@
  *
  *   ref_bam_tool sam2bam in.sam out.bam
  *   ref_bam_tool dump in.bam          -> "tid pos flag n_cigar op:len,op:len,..." per record
+ *   ref_bam_tool positions in.bam     -> "qname tid pos" for every reference position a read has an ALIGNED
+ *                                        base at, as seen by htslib's own pileup engine (bam_plp_auto:
+ *                                        the read is in the column and neither is_del nor is_refskip).
+ *                                        Per read this is pysam's AlignedSegment.positions
+ *                                        (= get_reference_positions()), the a1 row of SURVEY 8(a).
  */
 #include <stdio.h>
 #include <string.h>
 #include "htslib/sam.h"
+
+typedef struct { samFile *in; bam_hdr_t *h; } plp_src;
+
+static int plp_read(void *data, bam1_t *b)
+{
+    plp_src *s = (plp_src *)data;
+    return sam_read1(s->in, s->h, b);
+}
 
 int main(int argc, char **argv)
 {
@@ -42,6 +55,24 @@ int main(int argc, char **argv)
         sam_close(in);
         return 0;
     }
-    fprintf(stderr, "usage: ref_bam_tool sam2bam in.sam out.bam | dump in.bam\n");
+    if (argc >= 3 && !strcmp(argv[1], "positions")) {
+        plp_src src;
+        src.in = sam_open(argv[2], "r");
+        if (!src.in) return 2;
+        src.h = sam_hdr_read(src.in);
+        bam_plp_t it = bam_plp_init(plp_read, &src);
+        bam_plp_set_maxcnt(it, 1 << 30);
+        int tid, pos, n;
+        const bam_pileup1_t *col;
+        while ((col = bam_plp_auto(it, &tid, &pos, &n)) != 0)
+            for (int k = 0; k < n; ++k)
+                if (!col[k].is_del && !col[k].is_refskip)
+                    printf("%s %d %d\n", bam_get_qname(col[k].b), tid, pos);
+        if (n < 0) return 5;
+        bam_plp_destroy(it);
+        sam_close(src.in);
+        return 0;
+    }
+    fprintf(stderr, "usage: ref_bam_tool sam2bam in.sam out.bam | dump in.bam | positions in.bam\n");
     return 1;
 }

@@ -45,7 +45,37 @@ def main():
         subprocess.check_call([TOOL, "dump", bam], stdout=fh)
     os.remove(sam)
     print("wrote", bam, os.path.getsize(bam), "bytes")
+    write_positions(bam)
+
+
+def write_positions(bam):
+    """htslib_allops.positions.txt: per read, the reference positions carrying one of its aligned bases
+    according to the reference's vendored htslib PILEUP engine (`ref_bam_tool positions`), folded into
+    runs: ``qname tid start-end,start-end,...`` (half-open).  Pins AlignedSegment.positions (SURVEY 8a
+    row a1) for every CIGAR op against code of the reference tree itself."""
+    out = subprocess.check_output([TOOL, "positions", bam]).decode().split("\n")
+    per, order = {}, []
+    for line in out:
+        if not line:
+            continue
+        name, tid, pos = line.split()
+        if name not in per:
+            per[name] = (int(tid), [])
+            order.append(name)
+        per[name][1].append(int(pos))
+    with open(os.path.join(HERE, "htslib_allops.positions.txt"), "w") as fh:
+        for name in sorted(order, key=lambda q: int(q[1:])):
+            tid, pos = per[name]
+            pos = np.asarray(sorted(pos))
+            cut = np.flatnonzero(np.diff(pos) != 1)
+            starts = np.concatenate(([pos[0]], pos[cut + 1]))
+            ends = np.concatenate((pos[cut], [pos[-1]])) + 1
+            fh.write("%s %d %s\n" % (name, tid, ",".join("%d-%d" % ab for ab in zip(starts, ends))))
+    print("wrote htslib_allops.positions.txt:", len(order), "reads")
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "positions":      # only the pileup-derived positions of the committed BAM
+        write_positions(os.path.join(HERE, "htslib_allops.bam"))
+    else:
+        main()

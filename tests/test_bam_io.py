@@ -109,3 +109,32 @@ def test_malformed_input_is_reported(tmp_path):
     bam_io.write_bam(str(empty), {"a": 1000}, [])
     hb = bam_io.batch_from_bam(str(empty))
     assert len(hb) == 0 and hb.chroms == ["a"] and hb.mapped == 0
+
+
+def test_positions_match_reference_htslib_pileup():
+    """SURVEY 8(a) row a1 for EVERY CIGAR op: the reference's vendored htslib pileup engine
+    (kent/src/htslib/sam.c bam_plp_auto via oracle/_ref/ref_bam_tool positions; committed output
+    tests/golden/htslib_allops.positions.txt) reports, per read, the reference positions that carry an
+    aligned base.  The oracle's CIGAR walk, the host packer and the BAM decoder must give the same
+    positions for all 2300 reads (M, I, D, N, S, H, P, =, X all occur)."""
+    refs, recs = parse_dump(os.path.join(GOLD, "htslib_allops.dump.txt"))
+    mapped = [r for r in recs if r[0] >= 0 and not (r[2] & 4) and r[3]]
+    gold = {}
+    for line in open(os.path.join(GOLD, "htslib_allops.positions.txt")):
+        name, tid, runs = line.split()
+        pos = []
+        for run in runs.split(","):
+            a, b = run.split("-")
+            pos.extend(range(int(a), int(b)))
+        gold[int(name[1:])] = (int(tid), pos)
+    assert sorted(gold) == list(range(len(mapped)))             # reads are named r<n> in file order
+    hb = bam_io.batch_from_bam(os.path.join(GOLD, "htslib_allops.bam"), threads=2)
+    ops_seen = set()
+    for i, (tid, pos, flag, cigar, endpos) in enumerate(mapped):
+        ops_seen.update(op for op, _n in cigar)
+        assert gold[i][0] == tid
+        assert po.positions_from_cigar(pos, cigar) == gold[i][1]          # oracle == reference htslib
+        blocks, _span = cigar_to_blocks(cigar)
+        assert [pos + a + k for a, n in blocks for k in range(n)] == gold[i][1]   # host packer
+        assert hb.positions_of(i) == gold[i][1]                                   # BAM decoder
+    assert ops_seen == set(range(9))

@@ -734,3 +734,58 @@ def test_bam_genome_array_from_bam_file(tmp_path, cuda_device):
                 exp = oga[po.Seg(chrom, a, b, strand)]
                 got = ga[pb.GenomicSegment(chrom, a, b, strand)]
             assert (got == exp).all(), (strand, chrom)
+
+
+def test_golden_bam_count_vectors_from_reference_htslib_positions(cuda_device):
+    """End of the chain for non-M CIGARs without the oracle in between: the committed golden BAM (every
+    CIGAR op; written and piled up by the reference's vendored htslib, tests/golden/htslib_allops.*) is
+    decoded and mapped on the device; the expected vectors are built directly from the pileup-derived
+    ``positions`` of each read with the rules' definitions (map_factories.pyx:345-353, 444-452, 246-254)."""
+    import os
+    gold_dir = os.path.join(os.path.dirname(__file__), "golden")
+    lens, flags = [], []
+    for line in open(os.path.join(gold_dir, "htslib_allops.dump.txt")):
+        f = line.split()
+        if f[0] == "@":
+            lens.append((f[1], int(f[2])))
+        elif int(f[0]) >= 0 and not (int(f[2]) & 4) and int(f[3]):
+            flags.append(int(f[2]))
+    reads = []
+    for line in open(os.path.join(gold_dir, "htslib_allops.positions.txt")):
+        name, tid, runs = line.split()
+        pos = [p for run in runs.split(",") for p in range(int(run.split("-")[0]), int(run.split("-")[1]))]
+        reads.append((int(tid), pos, bool(flags[int(name[1:])] & 16)))
+    assert len(reads) == len(flags) == 2300
+
+    def expected(rule, param, strand):
+        out = {c: np.zeros(n, dtype=np.float64) for c, n in lens}
+        for tid, pos, is_rev in reads:
+            if strand != "." and is_rev != (strand == "-"):
+                continue
+            vec, L = out[lens[tid][0]], len(pos)
+            if rule == "center":
+                m = L - 2 * param
+                if m > 0:
+                    for p in pos[param:L - param]:
+                        vec[p] += 1.0 / m
+            elif param < L:
+                from_left = (rule == "fiveprime") == (strand != "-")
+                vec[pos[param] if from_left else pos[L - 1 - param]] += 1
+        return out
+
+    path = os.path.join(gold_dir, "htslib_allops.bam")
+    for rule, param, factory in (("fiveprime", 0, pb.FivePrimeMapFactory(0)), ("fiveprime", 7, pb.FivePrimeMapFactory(7)),
+                                 ("threeprime", 3, pb.ThreePrimeMapFactory(3)), ("center", 5, pb.CenterMapFactory(5))):
+        ga = pb.BAMGenomeArray(path, mapping=factory, device=cuda_device)
+        for strand in ("+", "-", "."):
+            exp = expected(rule, param, strand)
+            for chrom, n in lens:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    got = ga.get(pb.GenomicSegment(chrom, 0, n, strand), roi_order=False)
+                if rule == "center":
+                    assert ((got == 0) == (exp[chrom] == 0)).all()
+                    np.testing.assert_allclose(got, exp[chrom], rtol=1e-6, atol=0)      # north-star tolerance
+                else:
+                    assert (got == exp[chrom]).all(), (rule, param, strand, chrom)
+                assert exp[chrom].sum() > 0 or chrom == "chrEmpty"
