@@ -40,6 +40,8 @@
  *   pb_landmark_windows  window_landmark / window_cds_start / window_cds_stop
  *                                                          plastid/bin/metagene.py:180-340
  *   pb_spanning_windows  maximal_spanning_window per gene  plastid/bin/metagene.py:343-502, 702-735
+ *   pb_chain_union / pb_chain_binary  position-set pooling / masking of `cs generate`
+ *                                                          plastid/bin/cs.py:242-496
  *
  * Alignment batch (SoA, sorted by (chromosome, ref_start); what pysam hands the reference
  * as AlignedSegment.reference_start / .positions / .is_reverse):
@@ -433,6 +435,29 @@ int pb_spanning_windows(const int64_t *tx_bstart, const int64_t *tx_bend, const 
                         int32_t flank_up, int32_t flank_down,
                         uint8_t *status, int32_t *offset, int32_t *n_pos, int32_t *n_blk, int64_t *refpos,
                         const int64_t *out_off, int64_t *out_bstart, int64_t *out_bend, void *stream);
+
+/* `cs generate` position-set arithmetic (plastid/bin/cs.py:242-496 process_partial_group pools,
+ * intersects and subtracts python sets of genomic positions per merged gene).  A chain table is
+ * {bstart, bend, chain_off}: chain c owns blocks [chain_off[c], chain_off[c+1]), sorted, disjoint and
+ * non-touching, in one coordinate system for all chromosomes (global bins).  Both operations are
+ * count / fill pairs like pb_spanning_windows: call with out_off == NULL to get n_blk[i], exclusive-scan it
+ * into out_off, call again to write the blocks of output chain i at out_off[i].  Outputs are again sorted,
+ * disjoint and non-touching.
+ *
+ * pb_chain_union: output chain g = union of the chains members[grp_off[g] .. grp_off[g+1]) (touching
+ * blocks merge, as positions_to_segments does); one warp per group, lanes over members.
+ * pb_chain_binary: output chain i = A[a_idx[i]] AND B[b_idx[i]] (op PB_CHAIN_AND) or A[a_idx[i]] minus
+ * B[b_idx[i]] (op PB_CHAIN_SUB); b_idx[i] < 0 = empty B. */
+#define PB_CHAIN_AND 0
+#define PB_CHAIN_SUB 1
+int pb_chain_union(const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                   const int64_t *grp_off, const int64_t *members, int64_t n_grp,
+                   int32_t *n_blk, const int64_t *out_off, int64_t *out_bstart, int64_t *out_bend, void *stream);
+int pb_chain_binary(int op,
+                    const int64_t *a_bstart, const int64_t *a_bend, const int64_t *a_off, const int64_t *a_idx,
+                    const int64_t *b_bstart, const int64_t *b_bend, const int64_t *b_off, const int64_t *b_idx,
+                    int64_t n_out, int32_t *n_blk, const int64_t *out_off, int64_t *out_bstart, int64_t *out_bend,
+                    void *stream);
 
 /* Roofline probe (the atomic peak a scatter-add design would be bound by; no
  * reference counterpart, not on the product path): n_updates `red.global.add.u32` into

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY — CPU restatement of the geometry of ``metagene generate``.
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the geometry of ``metagene generate`` and of the
+position-set arithmetic of ``cs generate`` (second half of this file).
 
 Follows, line by line, plastid v0.6.1:
 
@@ -18,7 +19,7 @@ import warnings
 
 import numpy as np
 
-from .pyoracle import Chain, Seg, DataWarning
+from .pyoracle import Chain, Seg, DataWarning, GenomeHash
 
 nan = np.nan
 
@@ -234,3 +235,130 @@ def group_regions_make_windows(source, mask_hash, flank_upstream, flank_downstre
                          "threeprime_offset": window_size - offset - window.length})
     rows.sort(key=lambda r: r["region_id"])
     return rows
+
+
+# ---------------------------------------------------------------------------
+# cs generate: plastid/bin/cs.py:190-496 (merge_genes, process_partial_group), with python position sets
+# exactly as the reference; plastid/util/services/sets.py:16-120 merge_sets = connected components of sets
+# sharing a member.  PARITY UNPINNED: the reference holds no in-tree known answers for `cs generate`
+# (test_cs.py compares against files of its external data bundle), so this restatement is the anchor.
+# ---------------------------------------------------------------------------
+import itertools
+
+
+def tx_subchain(tx, start, end):
+    return get_subchain(tx, start, end)
+
+
+def tx_cds(tx):                                                      # roitools.pyx:4005-4046
+    return tx_subchain(tx, tx.cds_start, tx.cds_end) if tx.cds_genome_start is not None else Chain()
+
+
+def tx_utr5(tx):                                                     # :4048-4087
+    return tx_subchain(tx, 0, tx.cds_start) if tx.cds_genome_start is not None else Chain()
+
+
+def tx_utr3(tx):                                                     # :4089-4130
+    return tx_subchain(tx, tx.cds_end, tx.length) if tx.cds_genome_start is not None else Chain()
+
+
+def merge_sets(list_of_sets):
+    """sets.py:16-120: merge sets that share a member until none do."""
+    groups = []
+    for s in {frozenset(x) for x in list_of_sets}:
+        s = set(s)
+        keep = []
+        for g in groups:
+            if g & s:
+                s |= g
+            else:
+                keep.append(g)
+        keep.append(s)
+        groups = keep
+    return groups
+
+
+def merge_genes(tx_ivcs):                                            # cs.py:190-239
+    dout = {}
+    exondicts = {"+": {}, "-": {}}
+    for txid in tx_ivcs.keys():
+        chain = tx_ivcs[txid]
+        gene = chain.get_gene()
+        for iv in chain.segments:
+            exondicts[chain.strand].setdefault(chain.chrom, {}).setdefault((iv.start, iv.end), []).append(gene)
+    for strand in exondicts:
+        for chrom in exondicts[strand]:
+            for group in merge_sets([set(v) for v in exondicts[strand][chrom].values()]):
+                merged_name = ",".join(sorted(group))
+                for gene in group:
+                    dout[gene] = merged_name
+    return dout
+
+
+def _chain_of(chrom, strand, positions):
+    return Chain(*positions_to_segments(chrom, strand, positions))
+
+
+def cs_process_partial_group(transcripts, mask_hash):
+    """cs.py:242-496 -> (gene rows, transcript rows, merged_genes); rows are dicts of chain strings
+    sorted by ``region`` (the ``*_bed`` columns are left out)."""
+    keycombos = list(itertools.permutations(("utr5", "cds", "utr3"), 2))
+    merged_genes = merge_genes(transcripts)
+    merged_gene_tx = {}
+    for txid in transcripts:
+        merged_gene_tx.setdefault(merged_genes[transcripts[txid].get_gene()], []).append(txid)
+
+    gene_rows, tx_rows = [], []
+    raw = []
+    for gene_id, my_txids in merged_gene_tx.items():                 # :313-348
+        positions = []
+        for txid in my_txids:
+            positions.extend(transcripts[txid].position_list)
+        first = transcripts[my_txids[0]]
+        raw.append(_chain_of(first.chrom, first.strand, set(positions)))
+    gene_hash = GenomeHash(raw)                                      # :352
+
+    for (gene_id, my_txids), gene_ivc_raw in zip(merged_gene_tx.items(), raw):      # :354-470
+        chrom, strand = gene_ivc_raw.chrom, gene_ivc_raw.strand
+        masked_positions = []
+        raw_positions = set(gene_ivc_raw.position_list)
+        nearby = [x for x in gene_hash.get_overlapping_features(gene_ivc_raw) if set(x.position_list) != raw_positions]
+        for gene in nearby:
+            masked_positions.extend(gene.position_list)
+        for mask in mask_hash.get_overlapping_features(gene_ivc_raw):
+            masked_positions.extend(mask.position_list)
+        masked_positions = set(masked_positions)
+        total_mask = _chain_of(chrom, strand, raw_positions & masked_positions)
+        post_mask = _chain_of(chrom, strand, raw_positions - masked_positions)
+        masked_positions = set(total_mask.position_list)
+        tmp_positions = {"utr5": set(), "cds": set(), "utr3": set()}
+        txids = sorted(my_txids)
+        for txid in txids:
+            tx = transcripts[txid]
+            tmp_positions["utr5"] |= set(tx_utr5(tx).position_list)
+            tmp_positions["cds"] |= set(tx_cds(tx).position_list)
+            tmp_positions["utr3"] |= set(tx_utr3(tx).position_list)
+        for txid in txids:
+            tx = transcripts[txid]
+            tpos = {"utr5": set(tx_utr5(tx).position_list), "cds": set(tx_cds(tx).position_list),
+                    "utr3": set(tx_utr3(tx).position_list)}
+            for key1, key2 in keycombos:
+                tpos[key1] -= tmp_positions[key2]
+                tpos[key1] -= masked_positions
+            row = {"region": txid, "exon": str(_chain_of(chrom, strand, set(tx.position_list) - masked_positions)),
+                   "masked": str(total_mask), "exon_unmasked": str(tx), "transcript_ids": txid}
+            for k, v in tpos.items():
+                row[k] = str(_chain_of(chrom, strand, v))
+            tx_rows.append(row)
+        tmp2 = {k: set(v) for k, v in tmp_positions.items()}
+        for k1, k2 in keycombos:
+            tmp_positions[k1] -= tmp2[k2]
+            tmp_positions[k1] -= masked_positions
+        row = {"region": gene_id, "transcript_ids": ",".join(sorted(my_txids)), "exon_unmasked": str(gene_ivc_raw),
+               "masked": str(total_mask), "exon": str(post_mask)}
+        for k in tmp_positions:
+            row[k] = str(_chain_of(chrom, strand, tmp_positions[k]))
+        gene_rows.append(row)
+    gene_rows.sort(key=lambda r: r["region"])
+    tx_rows.sort(key=lambda r: r["region"])
+    return gene_rows, tx_rows, merged_genes

@@ -20,6 +20,7 @@ PB_RULE_FIVEPRIME, PB_RULE_THREEPRIME, PB_RULE_VARIABLE, PB_RULE_CENTER, PB_RULE
 PB_NSTATS = 8
 PB_WIN_HAS_REF, PB_WIN_INDEX_ERROR = 1, 2
 PB_SPAN_NONE, PB_SPAN_WINDOW, PB_SPAN_REF_OUTSIDE = 0, 1, 2
+PB_CHAIN_AND, PB_CHAIN_SUB = 0, 1
 
 STRAND_PLANE = {"+": PB_PLANE_PLUS, "-": PB_PLANE_MINUS, ".": PB_PLANE_ANY}
 PLANE_INDEX = {"+": 0, "-": 1, ".": 2}
@@ -95,6 +96,8 @@ _SIGNATURES = {
     "pb_landmark_windows": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
     "pb_spanning_windows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pb_chain_union": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "pb_chain_binary": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "pb_atomic_probe": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
     "pb_count_profiles_u32": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int,
                                         _P, _P, _P, _P, _P, C.c_size_t, _P]),

@@ -271,3 +271,58 @@ def random_gene_models(rng, n_genes, chroms=("chrA", "chrB"), spacing=6000):
                                              cds_genome_end=None if this_cds is None else this_cds[1],
                                              gene_id="g%04d" % g)
     return out
+
+
+def add_shared_exon_genes(records, rng):
+    """Extends :func:`random_gene_models` records with the cases ``cs generate`` merges or masks on:
+    a second gene id owning a copy of another gene's transcript (shared exons -> merged gene, also a
+    chain of three genes merged transitively), and two genes with identical position sets but no common
+    exon (not merged, and not masked against each other, cs.py:364-366)."""
+    out = dict(records)
+    names = list(records)
+    for i, name in enumerate(names[::7]):
+        r = records[name]
+        copy = dict(r, gene_id=r["gene_id"] + "m", segments=list(r["segments"]))
+        if (i % 2 and copy["cds_genome_start"] is not None and copy["cds_genome_end"] - copy["cds_genome_start"] > 9
+                and any(s <= copy["cds_genome_start"] + 3 < e for s, e in copy["segments"])):
+            copy["cds_genome_start"] += 3
+        out[name + ".m"] = copy
+        if i % 3 == 0:                                               # third gene sharing only the LAST exon with the copy
+            s, e = r["segments"][-1]
+            out[name + ".mm"] = dict(chrom=r["chrom"], strand=r["strand"], segments=[(s, e), (e + 50, e + 90)],
+                                     cds_genome_start=None, cds_genome_end=None, gene_id=r["gene_id"] + "mm")
+    far = 10_000_000
+    out["twin.a1"] = dict(chrom="chrA", strand="+", segments=[(far, far + 10)], cds_genome_start=None, cds_genome_end=None, gene_id="twinA")
+    out["twin.a2"] = dict(chrom="chrA", strand="+", segments=[(far + 10, far + 20)], cds_genome_start=None, cds_genome_end=None, gene_id="twinA")
+    out["twin.b"] = dict(chrom="chrA", strand="+", segments=[(far, far + 20)], cds_genome_start=far + 3, cds_genome_end=far + 12, gene_id="twinB")
+    out["twin.c"] = dict(chrom="chrA", strand="+", segments=[(far + 15, far + 40)], cds_genome_start=None, cds_genome_end=None, gene_id="twinC")
+    return out
+
+
+def cs_generate_hand_case():
+    """A hand-derived known answer for ``cs generate`` (the reference ships none in-tree): gene A with two
+    coding isoforms, a non-coding gene B overlapping A's 3' end, one mask.  Derivation (cs.py:313-470):
+    A's positions 100-200^300-450; B covers 380-450 of them and the mask 120-130 -> masked; pooled
+    utr5 = 100-180, cds = 150-200^300-350, utr3 = 350-450; every class loses the other classes' pooled
+    positions and the masked ones."""
+    records = {
+        "A1": dict(chrom="c", strand="+", segments=[(100, 200), (300, 400)], cds_genome_start=150, cds_genome_end=350, gene_id="A"),
+        "A2": dict(chrom="c", strand="+", segments=[(100, 200), (300, 450)], cds_genome_start=180, cds_genome_end=350, gene_id="A"),
+        "B1": dict(chrom="c", strand="+", segments=[(380, 500)], cds_genome_start=None, cds_genome_end=None, gene_id="B"),
+    }
+    masks = [("c", 120, 130, "+")]
+    genes = {
+        "A": dict(transcript_ids="A1,A2", exon_unmasked="c:100-200^300-450(+)", masked="c:120-130^380-450(+)",
+                  exon="c:100-120^130-200^300-380(+)", utr5="c:100-120^130-150(+)", cds="c:180-200^300-350(+)",
+                  utr3="c:350-380(+)"),
+        "B": dict(transcript_ids="B1", exon_unmasked="c:380-500(+)", masked="c:380-450(+)", exon="c:450-500(+)",
+                  utr5="na", cds="na", utr3="na"),
+    }
+    transcripts = {
+        "A1": dict(exon="c:100-120^130-200^300-380(+)", utr5="c:100-120^130-150(+)", cds="c:180-200^300-350(+)",
+                   utr3="c:350-380(+)", masked="c:120-130^380-450(+)", exon_unmasked="c:100-200^300-400(+)"),
+        "A2": dict(exon="c:100-120^130-200^300-380(+)", utr5="c:100-120^130-150(+)", cds="c:180-200^300-350(+)",
+                   utr3="c:350-380(+)", masked="c:120-130^380-450(+)", exon_unmasked="c:100-200^300-450(+)"),
+        "B1": dict(exon="c:450-500(+)", utr5="na", cds="na", utr3="na", masked="c:380-450(+)", exon_unmasked="c:380-500(+)"),
+    }
+    return records, masks, genes, transcripts

@@ -469,3 +469,131 @@ def test_metagene_generate_then_count(world, tmp_path):
     assert np.ma.filled(row_select, False).sum() > 10
     np.testing.assert_allclose(out["metagene_average"], np.ma.filled(profile, np.nan), rtol=1e-12, equal_nan=True)
     assert (out["regions_counted"] == num_genes).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# cs generate: pb_chain_union / pb_chain_binary
+# ---------------------------------------------------------------------------------------------
+def _random_chains(rng, n, span=4000):
+    chains = []
+    for _ in range(n):
+        k = int(rng.integers(0, 9))
+        cuts = np.sort(rng.choice(span, size=2 * k, replace=False)) if k else np.zeros(0, dtype=np.int64)
+        blocks = [(int(a), int(b)) for a, b in zip(cuts[0::2], cuts[1::2]) if b > a]
+        merged = []
+        for a, b in blocks:                                          # normalise: non-touching
+            if merged and a <= merged[-1][1]:
+                merged[-1] = (merged[-1][0], max(b, merged[-1][1]))
+            else:
+                merged.append((a, b))
+        chains.append(merged)
+    return chains
+
+
+def _to_set(device, chains):
+    from plastid_b200.chains import ChainSet
+    off = np.zeros(len(chains) + 1, dtype=np.int64)
+    np.cumsum([len(c) for c in chains], out=off[1:])
+    flat = [b for c in chains for b in c]
+    return ChainSet.from_numpy([a for a, _ in flat], [b for _, b in flat], off, device)
+
+
+def _positions(chain):
+    return set(p for a, b in chain for p in range(a, b))
+
+
+def _runs(positions):
+    out = []
+    for p in sorted(positions):
+        if out and out[-1][1] == p:
+            out[-1][1] = p + 1
+        else:
+            out.append([p, p + 1])
+    return [tuple(x) for x in out]
+
+
+def test_chain_set_algebra_matches_python_sets(cuda_device):
+    from plastid_b200.chains import chain_union, chain_binary
+    rng = np.random.default_rng(31)
+    a_chains, b_chains = _random_chains(rng, 300), _random_chains(rng, 200)
+    A, B = _to_set(cuda_device, a_chains), _to_set(cuda_device, b_chains)
+    a_idx = rng.integers(0, 300, 500)
+    b_idx = rng.integers(-1, 200, 500)
+    for op in ("and", "sub"):
+        bs, be, off = chain_binary(op, A, a_idx, B, b_idx).numpy()
+        for i in range(500):
+            pa = _positions(a_chains[a_idx[i]])
+            pb_ = _positions(b_chains[b_idx[i]]) if b_idx[i] >= 0 else set()
+            exp = _runs(pa & pb_ if op == "and" else pa - pb_)
+            assert list(zip(bs[off[i]:off[i + 1]], be[off[i]:off[i + 1]])) == exp, (op, i)
+    sizes = rng.integers(0, 70, 150)                                  # groups of 0..69 members (more than a warp)
+    grp_off = np.zeros(151, dtype=np.int64)
+    np.cumsum(sizes, out=grp_off[1:])
+    members = rng.integers(0, 300, int(grp_off[-1]))
+    bs, be, off = chain_union(A, grp_off, members).numpy()
+    for g in range(150):
+        exp = _runs(set().union(*[_positions(a_chains[m]) for m in members[grp_off[g]:grp_off[g + 1]]]))
+        assert list(zip(bs[off[g]:off[g + 1]], be[off[g]:off[g + 1]])) == exp, g
+    # touching blocks of different members merge; empty inputs give empty chains
+    T = _to_set(cuda_device, [[(0, 10)], [(10, 20)], [], [(25, 30)]])
+    bs, be, off = chain_union(T, [0, 4, 4, 5], [0, 1, 2, 3, 2]).numpy()
+    assert list(zip(bs, be)) == [(0, 20), (25, 30)] and list(off) == [0, 2, 2, 2]
+
+
+@pytest.mark.parametrize("seed,spacing", [(3, 1500), (4, 700), (5, 400)])
+def test_cs_generate_matches_oracle(cuda_device, seed, spacing):
+    from helpers import random_gene_models, add_shared_exon_genes
+    from oracle import generate as og
+    rng = np.random.default_rng(seed)
+    recs = add_shared_exon_genes(random_gene_models(rng, 150, spacing=spacing), rng)
+    txs = {t.get_name(): t for t in _transcripts(recs)}
+    otxs = {t.get_name(): t for t in _transcripts(recs, product=False)}
+    masks = []
+    for i in range(80):
+        s = int(rng.integers(0, 75 * spacing))
+        masks.append(("chrA" if i % 2 else "chrB", s, s + int(rng.integers(5, 300)), "+-"[i % 3 == 0]))
+    mh = pb.GenomeHash([pb.SegmentChain(pb.GenomicSegment(*m)) for m in masks])
+    omh = po.GenomeHash([po.Chain(po.Seg(*m)) for m in masks])
+    gene_df, tx_df, merged = cs.process_partial_group(txs, mh, device=cuda_device)
+    exp_genes, exp_txs, exp_merged = og.cs_process_partial_group(otxs, omh)
+    assert merged == exp_merged and len(set(merged.values())) < len(merged)
+    got_genes, got_txs = gene_df.to_dict("records"), tx_df.to_dict("records")
+    assert len(got_genes) == len(exp_genes) and len(got_txs) == len(exp_txs)
+    for got, exp in ((got_genes, exp_genes), (got_txs, exp_txs)):
+        for a, b in zip(got, exp):
+            for k in b:
+                assert a[k] == b[k], (k, a, b)
+    assert sum(r["masked"] != "na" for r in got_genes) > 20
+    twins = {r["region"]: r for r in got_genes if r["region"].startswith("twin")}
+    assert twins["twinA"]["masked"] == twins["twinB"]["masked"] == "chrA:10000015-10000020(+)"   # by twinC only
+
+
+def test_cs_generate_hand_case_and_command_line(world, tmp_path):
+    from helpers import cs_generate_hand_case
+    records, masks, genes, transcripts = cs_generate_hand_case()
+    txs = _transcripts(records)
+    gene_df, tx_df, merged = cs.do_generate(txs, pb.GenomeHash([pb.SegmentChain(pb.GenomicSegment(*m)) for m in masks]),
+                                            device=world["dev"])
+    assert {r["region"]: {k: r[k] for k in genes[r["region"]]} for r in gene_df.to_dict("records")} == genes
+    assert {r["region"]: {k: r[k] for k in transcripts[r["region"]]} for r in tx_df.to_dict("records")} == transcripts
+    assert gene_df["exon_bed"].iloc[0] == "c\t100\t380\tA\t0\t+\t100\t100\t0,0,0\t3\t20,70,80,\t0,30,200,\n"
+    # generate -> positions file -> count on the synthetic world's annotation
+    w = world
+    bed = tmp_path / "tx.bed"
+    with open(bed, "w") as fh:
+        for t, ch in enumerate(w["ann"].chains()):
+            a = ch.get_genomic_coordinate(ch.length // 5)[1]
+            b = ch.get_genomic_coordinate(ch.length - ch.length // 5)[1]
+            lo, hi = (a, b + 1) if ch.strand == "+" else (b, a + 1)
+            fh.write(ch.as_bed(thickstart=lo, thickend=hi).rstrip("\n") + "\tgene%d\n" % t)
+    cs.main(["generate", "--annotation_files", str(bed), str(tmp_path / "cs")])
+    from plastid_b200.bin import _cli
+    pos = _cli.read_pl_table(str(tmp_path / "cs_gene.positions"))
+    assert len(pos["region"]) == len(w["ann"].chains())
+    assert len(open(str(tmp_path / "cs_merged.txt")).read().splitlines()) == len(pos["region"])
+    oga, ga = make_gas(w, po.ThreePrimeMap(0), pb.ThreePrimeMapFactory(0))
+    order, cols = cs.do_count(ga, pos)
+    ref = osc.cs_count(oga, pos)
+    for k in ("exon_reads", "cds_reads", "utr5_length", "utr3_rpkm"):
+        np.testing.assert_allclose(np.asarray(cols[k], dtype=float), np.asarray(ref[k], dtype=float), rtol=1e-12, equal_nan=True)
+    assert sum(cols["cds_reads"]) > 0

@@ -291,3 +291,32 @@ def test_oracle_maximal_spanning_windows_match_reference_tables(masked):
         for name, group in gold["do_generate_multi_gene"].items():
             rows = og.group_regions_make_windows([txs[t] for t in group], mask_hash, 50, 100, og.window_cds_start)
             _check_maximal_windows(rows, gold["do_generate_multi_gene_results"]["%s_50_100" % name], 50)
+
+
+def test_oracle_cs_generate_hand_derived_case():
+    """``cs generate`` has no in-tree known answers in the reference (parity unpinned): the oracle is
+    held to a hand-derived case instead (tests/helpers.py:cs_generate_hand_case)."""
+    from helpers import cs_generate_hand_case
+    records, masks, genes, transcripts = cs_generate_hand_case()
+    txs = {n: og.Tx(*[po.Seg(r["chrom"], s, e, r["strand"]) for s, e in r["segments"]], ID=n, gene_id=r["gene_id"],
+                    cds_genome_start=r["cds_genome_start"], cds_genome_end=r["cds_genome_end"]) for n, r in records.items()}
+    g_rows, t_rows, merged = og.cs_process_partial_group(txs, po.GenomeHash([po.Chain(po.Seg(*m)) for m in masks]))
+    assert merged == {"A": "A", "B": "B"}
+    assert {r["region"]: {k: r[k] for k in genes[r["region"]]} for r in g_rows} == genes
+    assert {r["region"]: {k: r[k] for k in transcripts[r["region"]]} for r in t_rows} == transcripts
+
+
+def test_merge_genes_host_matches_oracle():
+    """plastid_b200.bin.cs.merge_genes (union-find) against the restated merge_sets loop (cs.py:190-239)."""
+    from helpers import random_gene_models, add_shared_exon_genes
+    import plastid_b200 as pb
+    from plastid_b200.bin import cs
+    rng = np.random.default_rng(21)
+    recs = add_shared_exon_genes(random_gene_models(rng, 120, spacing=900), rng)
+    otx = {n: og.Tx(*[po.Seg(r["chrom"], s, e, r["strand"]) for s, e in r["segments"]], ID=n, gene_id=r["gene_id"])
+           for n, r in recs.items()}
+    ptx = {n: pb.Transcript(*[pb.GenomicSegment(r["chrom"], s, e, r["strand"]) for s, e in r["segments"]], ID=n,
+                            gene_id=r["gene_id"]) for n, r in recs.items()}
+    exp = og.merge_genes(otx)
+    assert cs.merge_genes(ptx) == exp
+    assert len(set(exp.values())) < len(exp) and any(v.count(",") == 2 for v in exp.values())   # pairs and a chain of three
