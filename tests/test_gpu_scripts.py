@@ -586,7 +586,7 @@ def test_cs_generate_hand_case_and_command_line(world, tmp_path):
             b = ch.get_genomic_coordinate(ch.length - ch.length // 5)[1]
             lo, hi = (a, b + 1) if ch.strand == "+" else (b, a + 1)
             fh.write(ch.as_bed(thickstart=lo, thickend=hi).rstrip("\n") + "\tgene%d\n" % t)
-    cs.main(["generate", "--annotation_files", str(bed), str(tmp_path / "cs")])
+    cs.main(["generate", str(tmp_path / "cs"), "--annotation_files", str(bed)])
     from plastid_b200.bin import _cli
     pos = _cli.read_pl_table(str(tmp_path / "cs_gene.positions"))
     assert len(pos["region"]) == len(w["ann"].chains())
