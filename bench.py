@@ -41,6 +41,11 @@ def parse_args():
     ap.add_argument("--e2e-format", default="delta3", choices=["delta3", "delta8", "wire16"],
                     help="host transfer format of the end-to-end leg (unspliced batches)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="upload chunks overlapped with mapping in the e2e leg")
+    ap.add_argument("--e2e-weights", default="1,1,1,1,1,1,1,1",
+                    help="relative read counts of the upload chunks of the e2e leg (delta3 / delta8), comma-separated")
+    ap.add_argument("--e2e-sweep", default=None,
+                    help="measurement aid: further chunk schedules (';'-separated weight lists) timed after the e2e leg, "
+                         "one JSON line each on stderr")
     ap.add_argument("--sharding", default="reads", choices=["reads", "positions"],
                     help="multi-GPU mode: 'reads' (default, weak scaling: every GPU maps its own batch over the whole genome) "
                          "or 'positions' (strong scaling of ONE batch: every GPU owns a contiguous bin range, SURVEY 8e)")
@@ -675,7 +680,12 @@ def main():
         receiver = WireReceiver(wire, device)
         h2d = wire.nbytes
         # small batches are launch-bound: fewer, larger chunks (about 8 M reads each at least)
-        chunks = WireReceiver.plan_chunks(wire, layout, max(1, min(args.e2e_chunks, n_reads // 8_000_000)))
+        n_chunks = max(1, min(args.e2e_chunks, n_reads // 8_000_000))
+        weights = [float(x) for x in args.e2e_weights.split(",")]
+        if args.e2e_format == "wire16" or n_chunks < args.e2e_chunks or len(weights) < 2:
+            chunks = WireReceiver.plan_chunks(wire, layout, n_chunks)
+        else:
+            chunks = WireReceiver.plan_chunks(wire, layout, len(weights), weights)
         copy_stream = torch.cuda.Stream(device=device)
         from plastid_b200.genome_array import map_wire16_streamed
 
@@ -724,6 +734,18 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n_reads * world / (float(t.item()) / 1000.0)
+    if args.e2e_sweep and use_wire16 and args.e2e_format != "wire16" and world == 1:
+        for sched in args.e2e_sweep.split(";"):
+            chunks = WireReceiver.plan_chunks(wire, layout, 0, [float(x) for x in sched.split(",")])
+            for _ in range(2):
+                e2e_step()
+            fence()
+            t1 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            fence()
+            sys.stderr.write(json.dumps({"e2e_schedule": sched, "chunks": len(chunks),
+                                         "ms_per_step": 1000.0 * (time.perf_counter() - t1) / e2e_steps}) + "\n")
     clocks = sampler.stop()              # samples cover warm-up, the timed steps and the e2e steps
     table_checksum = float(h_sums.sum().item())
 

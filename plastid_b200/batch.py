@@ -437,16 +437,26 @@ class Delta8Receiver(object):
                                                _lib.stream_ptr()))
 
     @staticmethod
-    def plan_chunks(wire, layout, n_chunks):
+    def plan_chunks(wire, layout, n_chunks, weights=None):
         """Cut the sorted batch at block (128-read) boundaries into ``n_chunks`` pieces of about equal
-        read count: ``[(read_a, read_b, bin_a, bin_b), ...]``.  bin_b is the global bin of read_b's
+        read count — or, with ``weights`` (one positive number per chunk), of read counts in those
+        proportions: ``[(read_a, read_b, bin_a, bin_b), ...]``.  bin_b is the global bin of read_b's
         start rounded down to the layout granularity: every read at or beyond read_b starts at or
         beyond it, so bins below bin_b are final once reads [0, read_b) have landed.  Ranges that
-        would be empty are merged into the next chunk."""
+        would be empty are merged into the next chunk.  (When the upload is the slower side, the step ends
+        one chunk-mapping after the last byte lands: a small LAST chunk shortens that tail; when mapping
+        is the slower side a small FIRST chunk starts it earlier.)"""
         from . import _lib
         K, n = Delta8Batch.BLOCK, len(wire)
         n_blk = len(wire.blk_base)
-        cuts = sorted(set(int((j * n_blk) // n_chunks) for j in range(1, n_chunks)) - {0, n_blk})
+        if weights is not None:
+            w = np.asarray(weights, dtype=np.float64)
+            if len(w) < 1 or (w <= 0).any():
+                raise ValueError("plan_chunks: weights must be positive")
+            frac = np.cumsum(w)[:-1] / w.sum()
+            cuts = sorted(set(int(f * n_blk) for f in frac) - {0, n_blk})
+        else:
+            cuts = sorted(set(int((j * n_blk) // n_chunks) for j in range(1, n_chunks)) - {0, n_blk})
         out, read_a, bin_a = [], 0, 0
         for cb in cuts:
             c = int(wire.blk_chrom[cb])

@@ -69,33 +69,49 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
     unsigned int drop_len = 0;
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
                want_any = planes & PB_PLANE_ANY;
-    constexpr int kU = 4;   // independent reads in flight per thread
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // a thread's read indices only grow: the chromosome of the previous read is the place to start from
+    // A warp takes 128 consecutive reads per round.  Only the multi-block ones (a third of the C3 batch)
+    // have work to do, so the warp first compacts them into a dense shared-memory list (ballot + prefix
+    // popcount) and then walks that list with all lanes busy: ncu showed the uncompacted loop issue-bound at
+    // 11 of 32 lanes active per instruction.
+    constexpr int kU = 4;   // 32-read groups per round (independent loads in flight per thread)
+    __shared__ uint4 dense[8][kU * 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // a lane's read indices only grow: the chromosome of the previous read is the place to start from
     int c = 0;
     int64_t c_end = __ldg(b.chrom_read_off + 1);
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < b.n_reads; i0 += stride * kU) {
-      // everything a multi-block read needs before its block gather is fetched up front, for all kU
-      // reads at once (streaming loads): the dependent chain is then gather -> cursor atomic -> store
+    for (int64_t q = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); q * (kU * 32) < b.n_reads; q += n_warps) {
+      const int64_t r0 = q * (kU * 32);
       uint32_t mv[kU], kv[kU];
       int32_t sv[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-          const int64_t i = i0 + u * stride;
+          const int64_t i = r0 + u * 32 + lane;
           const bool ok = i < b.n_reads;
           mv[u] = ok ? __ldg(b.meta + i) : 0u;
           sv[u] = ok ? __ldg(b.ref_start + i) : 0;
           kv[u] = ok ? __ldg(b.blk_off + i) : 0u;
       }
+      int n_dense = 0;
+      __syncwarp();                                // the previous round's list has been consumed
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const int64_t i = i0 + u * stride;
-        const uint32_t m = mv[u];
-        if (PB_META_NBLK(m) <= 1) continue;      // also skips the out-of-range filler (n_blocks 0)
-        if (!pb_passes(m, r.size_min, r.size_max)) continue;
+          // n_blocks 0 is the out-of-range filler
+          const bool work = PB_META_NBLK(mv[u]) > 1 && pb_passes(mv[u], r.size_min, r.size_max);
+          const unsigned bal = __ballot_sync(0xffffffffu, work);
+          if (work) dense[wid][n_dense + __popc(bal & ((1u << lane) - 1u))] =
+              make_uint4(mv[u], (uint32_t)sv[u], kv[u], (uint32_t)(u * 32 + lane));
+          n_dense += __popc(bal);
+      }
+      __syncwarp();
+      for (int j = lane; j < n_dense; j += 32) {
+        const uint4 e = dense[wid][j];
+        const int64_t i = r0 + e.w;
+        const uint32_t m = e.x;
+        const uint32_t k_first = e.z;
         while (i >= c_end && c + 1 < b.n_chrom) { ++c; c_end = __ldg(b.chrom_read_off + c + 1); }
         const int64_t base = __ldg(lay.chrom_bin_off + c), clen = __ldg(lay.chrom_len + c);
-        const int32_t s = sv[u];
+        const int32_t s = (int32_t)e.y;
         const int L = PB_META_L(m);
         const bool rev = PB_META_REV(m);
         auto in_range = [&](int64_t x) {
@@ -134,7 +150,7 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
             const int slot = (int)__ldg(slot_of_len + L);
             if (slot < 0) continue;
             const uint32_t tag = (uint32_t)slot | ((uint32_t)rev << 16);
-            const uint32_t k0 = kv[u], k1 = k0 + (uint32_t)PB_META_NBLK(m);   // blk lists multi-block reads only
+            const uint32_t k0 = k_first, k1 = k0 + (uint32_t)PB_META_NBLK(m);   // blk lists multi-block reads only
             int a = 0;  // aligned-base index of the block's first base
             for (uint32_t k = k0; k < k1; ++k) {
                 const int2 bl = __ldg(b.blk + k);
