@@ -698,6 +698,25 @@ def main():
             h_sums.copy_(s, non_blocking=True)
             h_live.copy_(l, non_blocking=True)
             torch.cuda.synchronize()      # the caller holds the table before the next batch starts
+    elif args.e2e_format == "delta3":
+        # batches with multi-block reads: delta3 streams for (ref_start, meta) + one 4-byte block word per aligned
+        # block; blk_off is rebuilt on the device (pb_unpack_blocks).  The Center / binned path needs the whole
+        # batch before it can start, so the upload is not chunked.
+        from plastid_b200.batch import Delta3SplicedBatch, Delta3SplicedReceiver
+        swire = Delta3SplicedBatch.from_batch(synth.device_batch_to_host(dbatch, chroms, lens))
+        spinned = swire.pinned()
+        sreceiver = Delta3SplicedReceiver(swire, device)
+        h2d = swire.nbytes
+        resident = dbatch
+
+        def e2e_step():
+            nonlocal dbatch
+            dbatch = sreceiver.receive(spinned)
+            s, l = step()
+            dbatch = resident
+            h_sums.copy_(s, non_blocking=True)
+            h_live.copy_(l, non_blocking=True)
+            torch.cuda.synchronize()
     else:
         h_start = torch.empty(n_reads, dtype=torch.int32).pin_memory()
         h_meta = torch.empty(n_reads, dtype=torch.int32).pin_memory()
@@ -806,7 +825,8 @@ def main():
                     "ms_per_step": float(t.item()), "steps": e2e_steps,
                     "host_format": ("%s (%.2f B/read), %d-chunk upload overlapped with pb_map_point_range"
                                     % (args.e2e_format, h2d / max(n_reads, 1), len(chunks)))
-                    if use_wire16 else "SoA (8 B/read + blocks)"},
+                    if use_wire16 else ("delta3 + block words (%.2f B/read), whole batch uploaded before the binned path starts"
+                                        % (h2d / max(n_reads, 1)) if args.e2e_format == "delta3" else "SoA (8 B/read + blocks)")},
             "gpu_launches": len(kernels_per_step) * args.steps, "kernels_per_step": kernels_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}
     if graph_ms is not None:

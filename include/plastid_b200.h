@@ -203,6 +203,19 @@ int pb_unpack_delta3(const uint8_t *packed, const uint8_t *wide, const int32_t *
                      int64_t n_reads, int64_t read_begin, int64_t read_end,
                      int32_t *ref_start_out, uint32_t *meta_out, void *stream);
 
+/* Block words: the aligned-block table of a spliced batch in 4 bytes per block, the companion of delta3 for
+ * batches with multi-block reads (delta3 carries ref_start / meta of every read; meta bits 24-31 say how many
+ * blocks a read has).  bwords uint32[n_rows], one word per block of every multi-block read in read order:
+ * bits 0-11 = block length (1..4095), bits 12-31 = gap between the end of the read's previous block (0 for
+ * its first block) and this block's start (0..1048574); 0xFFFFFFFF = the block does not fit and is listed as
+ * {gap, len} in bexc int32[n_exc][2] under its row number bexc_row uint32[n_exc] (ascending).  Rebuilds
+ * blk_off uint32[n_reads+1] (exclusive scan of the block counts of multi-block reads) and
+ * blk int32[n_rows][2] = {start relative to ref_start, length} of the SoA batch. */
+size_t pb_unpack_blocks_workspace_bytes(int64_t n_reads);
+int pb_unpack_blocks(const uint32_t *meta, int64_t n_reads, const uint32_t *bwords, int64_t n_rows,
+                     const uint32_t *bexc_row, const int32_t *bexc, int64_t n_exc,
+                     uint32_t *blk_off_out, int32_t *blk_out, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Host side (no CUDA): pack a sorted unspliced SoA batch (HOST arrays) into the delta3 streams above, on
  * n_threads host threads (0 = all).  Caller-owned HOST buffers sized for the worst case: packed
  * uint8[n_blk*128], wide uint8[n_reads], blk_base int32[n_blk], blk_wide_off / blk_exc_off uint32[n_blk+1],

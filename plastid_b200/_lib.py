@@ -67,6 +67,8 @@ _SIGNATURES = {
     "pb_pack_delta3": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pb_unpack_delta3": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
+    "pb_unpack_blocks_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "pb_unpack_blocks": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     "pb_map_point_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
                                      _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, C.c_int64, C.c_int64, _P]),
     "pb_map_point": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,

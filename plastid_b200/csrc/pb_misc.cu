@@ -409,3 +409,85 @@ extern "C" int pb_unpack_delta3(const uint8_t *packed, const uint8_t *wide, cons
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
+
+// ----------------------------------------------------------------------------------------
+// block words: the aligned-block table of a spliced batch in 4 bytes per block (PCIe transfer format)
+// ----------------------------------------------------------------------------------------
+namespace {
+
+__global__ void pb_block_counts_kernel(const uint32_t *__restrict__ meta, int64_t n, uint32_t *__restrict__ counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nb = PB_META_NBLK(__ldg(meta + i));
+    counts[i] = nb > 1 ? (uint32_t)nb : 0u;           // the block table lists multi-block reads only
+}
+
+__global__ void pb_unpack_blocks_kernel(const uint32_t *__restrict__ meta, int64_t n,
+                                        const uint32_t *__restrict__ bwords, int64_t n_rows,
+                                        const uint32_t *__restrict__ bexc_row, const int32_t *__restrict__ bexc,
+                                        int64_t n_exc, const uint32_t *__restrict__ blk_off, int2 *__restrict__ blk)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nb = PB_META_NBLK(__ldg(meta + i));
+    if (nb <= 1) return;
+    const uint32_t k0 = __ldg(blk_off + i);
+    int32_t pos = 0;                                  // end of the previous block, relative to ref_start
+    for (int j = 0; j < nb; ++j) {
+        const int64_t k = (int64_t)k0 + j;
+        if (k >= n_rows) return;                      // inconsistent input: never write past the table
+        const uint32_t w = __ldg(bwords + k);
+        int32_t gap, len;
+        if (w == 0xFFFFFFFFu) {                       // does not fit 20 + 12 bits: listed by row
+            int64_t lo = 0, hi = n_exc;
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)__ldg(bexc_row + mid) < k) lo = mid + 1; else hi = mid; }
+            if (lo >= n_exc) return;
+            gap = __ldg(bexc + 2 * lo);
+            len = __ldg(bexc + 2 * lo + 1);
+        } else {
+            len = (int32_t)(w & 0xFFFu);
+            gap = (int32_t)(w >> 12);
+        }
+        blk[k] = make_int2(pos + gap, len);
+        pos += gap + len;
+    }
+}
+
+}  // namespace
+
+extern "C" size_t pb_unpack_blocks_workspace_bytes(int64_t n_reads)
+{
+    if (n_reads < 0) return 0;
+    return (size_t)(n_reads + pb_scan_part_entries(n_reads) + 16) * sizeof(uint32_t);
+}
+
+extern "C" int pb_unpack_blocks(const uint32_t *meta, int64_t n_reads, const uint32_t *bwords, int64_t n_rows,
+                                const uint32_t *bexc_row, const int32_t *bexc, int64_t n_exc,
+                                uint32_t *blk_off_out, int32_t *blk_out, void *workspace, size_t workspace_bytes,
+                                void *stream)
+{
+    if (!meta || !blk_off_out || !workspace || n_reads < 0 || n_rows < 0 || n_exc < 0 ||
+        (n_rows > 0 && (!bwords || !blk_out)) || (n_exc > 0 && (!bexc_row || !bexc))) {
+        pb_set_error("pb_unpack_blocks: null argument or negative size"); return PB_EINVAL;
+    }
+    if (workspace_bytes < pb_unpack_blocks_workspace_bytes(n_reads)) {
+        pb_set_error("pb_unpack_blocks: workspace too small"); return PB_ENOSPACE;
+    }
+    if (n_reads >= ((int64_t)1 << 32) || n_rows >= ((int64_t)1 << 32)) {
+        pb_set_error("pb_unpack_blocks: block offsets are 32-bit"); return PB_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_reads == 0) { PB_CUDA_CHECK(cudaMemsetAsync(blk_off_out, 0, sizeof(uint32_t), st)); return PB_OK; }
+    uint32_t *counts = (uint32_t *)workspace;
+    uint32_t *part = counts + n_reads;
+    const unsigned grid = (unsigned)((n_reads + 255) / 256);
+    pb_block_counts_kernel<<<grid, 256, 0, st>>>(meta, n_reads, counts);
+    int rc = pb_launch_exclusive_scan_u32(counts, blk_off_out, part, n_reads, st);
+    if (rc != PB_OK) return rc;
+    if (n_rows > 0)
+        pb_unpack_blocks_kernel<<<grid, 256, 0, st>>>(meta, n_reads, bwords, n_rows, bexc_row, bexc, n_exc, blk_off_out,
+                                                      (int2 *)blk_out);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}

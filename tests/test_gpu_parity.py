@@ -789,3 +789,36 @@ def test_golden_bam_count_vectors_from_reference_htslib_positions(cuda_device):
                 else:
                     assert (got == exp[chrom]).all(), (rule, param, strand, chrom)
                 assert exp[chrom].sum() > 0 or chrom == "chrEmpty"
+
+
+def test_spliced_transfer_format_round_trip(cuda_device):
+    """delta3 + block words (pb_unpack_delta3, pb_unpack_blocks): the device batch rebuilt from the
+    4-byte-per-block transfer format equals the SoA batch, incl. exception rows, and maps identically."""
+    import torch
+    from plastid_b200.batch import Delta3SplicedBatch, Delta3SplicedReceiver, DeviceBatch
+    rng = np.random.default_rng(13)
+    lens = {"chrA": 3_000_000, "chrB": 50_000}
+    reads = {"chrA": random_cigar_reads(rng, 20_000, 3_000_000, 900_000), "chrB": random_cigar_reads(rng, 3000, 50_000, 40_000)}
+    reads["chrA"].append(po.Read(1000, [(0, 30), (3, 1_500_000), (0, 20)], False))
+    reads["chrA"].append(po.Read(2000, [(0, 5000), (3, 70), (0, 4095), (2, 1), (0, 4096)], True))
+    hb = pb.pack_reads(reads, lens, keep_objects=False)
+    wire = Delta3SplicedBatch.from_batch(hb)
+    assert len(wire.bexc_row) >= 2
+    rx = Delta3SplicedReceiver(wire, cuda_device)
+    pinned = wire.pinned()
+    for _ in range(2):                                              # buffers are reusable
+        db = rx.receive(pinned)
+        torch.cuda.synchronize()
+        assert (db.ref_start.cpu().numpy() == hb.ref_start).all()
+        assert (db.meta.cpu().numpy().view(np.uint32) == hb.meta).all()
+        assert (db.chrom_read_off.cpu().numpy() == hb.chrom_read_off).all()
+        assert (db.blk_off.cpu().numpy().view(np.uint32) == hb.blk_off).all()
+        assert (db.blk.cpu().numpy() == hb.blk).all()
+        assert db.n_blk == len(hb.blk) and db.max_block_len == hb.max_block_len
+    layout = pb.GenomeLayout(list(lens), list(lens.values()))
+    ref = DeviceBatch.from_host(hb, cuda_device)
+    for fac in (pb.FivePrimeMapFactory(3), pb.CenterMapFactory(2)):
+        a = map_batch(db, layout, fac, None, strands=("+", "-"))
+        b = map_batch(ref, layout, fac, None, strands=("+", "-"))
+        for strand in ("+", "-"):
+            assert torch.equal(a.planes[strand], b.planes[strand])

@@ -44,6 +44,14 @@ def test_argument_errors_are_reported_without_a_device():
     assert b"null" in L.pb_last_error()
     assert L.pb_region_sums(None, 0, None, None, None, None, 0, None, None, None, None, None) == _lib.PB_EINVAL
     assert L.pb_map_workspace_bytes(16384 * 4, 0, 100) > 0
+    # the annotation-side entry points validate before touching the device too
+    assert L.pb_landmark_windows(None, None, None, None, None, None, 5, 50, 50, None, None, None) == _lib.PB_EINVAL
+    assert L.pb_landmark_windows(None, None, None, None, None, None, 0, 50, 50, None, None, None) == _lib.PB_OK
+    assert L.pb_spanning_windows(None, None, None, None, None, None, None, None, None, 3, 50, -1,
+                                 None, None, None, None, None, None, None, None, None) == _lib.PB_EINVAL
+    assert L.pb_chain_union(None, None, None, None, None, 2, None, None, None, None, None) == _lib.PB_EINVAL
+    assert L.pb_chain_binary(7, None, None, None, None, None, None, None, None, 1, None, None, None, None, None) == _lib.PB_EINVAL
+    assert b"pb_chain_binary" in L.pb_last_error()
     assert L.pb_map_workspace_bytes(16384 * 4, 1000, 100) >= L.pb_map_workspace_bytes(16384 * 4, 0, 100) + 16000
 
 
@@ -550,3 +558,34 @@ def test_genome_hash_and_transcript_table_lowering():
     flat[roi.length + 103:roi.length + 115] = 1                    # 3R:4519879-4519891
     bits = torch.from_numpy(np.packbits(flat, bitorder="little"))
     assert mask_intervals_of_chains(ctable, bits) == [[(7985694, 7985744)], [(4519879, 4519891)]]
+
+
+def test_block_words_encode_the_block_table():
+    """Delta3SplicedBatch: 4-byte block words (12-bit length, 20-bit gap, exception rows) decode back to
+    the SoA block table (host statement of what pb_unpack_blocks does on the device)."""
+    from plastid_b200.batch import Delta3SplicedBatch
+    rng = np.random.default_rng(12)
+    reads = random_cigar_reads(rng, 2000, 400_000, 300_000)
+    reads.append(po.Read(1000, [(0, 30), (3, 2_000_000), (0, 20)], False))          # intron beyond 20 bits
+    reads.append(po.Read(2000, [(0, 5000), (3, 70), (0, 4095), (2, 1), (0, 4096)], True))   # lengths around 12 bits
+    hb = pack_reads({"chrA": reads}, {"chrA": 5_000_000}, keep_objects=False)
+    wire = Delta3SplicedBatch.from_batch(hb)
+    assert len(wire.bwords) == len(hb.blk) and 2 <= len(wire.bexc_row) <= 4
+    assert wire.nbytes == wire.base.nbytes + 4 * len(hb.blk) + 12 * len(wire.bexc_row)
+    exc = dict(zip(wire.bexc_row.tolist(), wire.bexc.tolist()))
+    k, out = 0, []
+    for i in range(len(hb)):
+        nb = int(hb.meta[i] >> 24)
+        if nb <= 1:
+            continue
+        pos = 0
+        for _ in range(nb):
+            word = int(wire.bwords[k])
+            gap, ln = exc[k] if word == 0xFFFFFFFF else (word >> 12, word & 0xFFF)
+            out.append((pos + gap, ln))
+            pos += gap + ln
+            k += 1
+    assert out == [tuple(x) for x in hb.blk.tolist()]
+    # a batch without multi-block reads ships no block words
+    plain = pack_reads({"chrA": [po.Read(5, [(0, 30)], False), po.Read(9, [(0, 28)], True)]}, {"chrA": 1000}, keep_objects=False)
+    assert len(Delta3SplicedBatch.from_batch(plain).bwords) == 0
