@@ -589,3 +589,33 @@ def test_block_words_encode_the_block_table():
     # a batch without multi-block reads ships no block words
     plain = pack_reads({"chrA": [po.Read(5, [(0, 30)], False), po.Read(9, [(0, 28)], True)]}, {"chrA": 1000}, keep_objects=False)
     assert len(Delta3SplicedBatch.from_batch(plain).bwords) == 0
+
+
+def test_phase_table_reproduces_the_rows_printed_in_the_reference_docs():
+    """docs/source/examples/phasing.rst:194-205 prints a `phase_by_size` table (SRR609197): with the
+    per-length phase counts that table implies, `phase_table` reproduces every printed
+    ``fraction_reads_counted`` and ``phase0..2`` value in the reference's ``%.6f`` format
+    (phase_by_size.py:220-232, 243-251)."""
+    from plastid_b200.bin.phase_by_size import phase_table
+    doc = """25 6511 0.009640 0.326832 0.327599 0.345569
+             26 9952 0.014735 0.385953 0.295217 0.318830
+             27 17636 0.026111 0.320934 0.282717 0.396348
+             28 42976 0.063629 0.251792 0.381794 0.366414
+             29 93754 0.138809 0.309309 0.370971 0.319720
+             30 148400 0.219716 0.318733 0.367635 0.313632
+             31 155684 0.230501 0.336624 0.421713 0.241663
+             32 118565 0.175543 0.445578 0.374141 0.180281
+             33 58761 0.087000 0.511121 0.299076 0.189803
+             34 18818 0.027861 0.508237 0.276597 0.215166
+             35 4360 0.006455 0.514450 0.236468 0.249083"""
+    rows = [line.split() for line in doc.splitlines()]
+    sums = {}
+    for length, reads, _frac, p0, p1, p2 in rows:
+        counts = np.array([round(float(p) * int(reads)) for p in (p0, p1, p2)], dtype=np.float64)
+        assert counts.sum() == int(reads)                      # the printed fractions imply integer counts
+        sums[int(length)] = counts
+    lengths, counted, frac, phases = phase_table(sums)
+    for i, (length, reads, f, p0, p1, p2) in enumerate(rows):
+        assert lengths[i] == int(length) and counted[i] == int(reads)
+        assert "%.6f" % frac[i] == f
+        assert ["%.6f" % x for x in phases[i]] == [p0, p1, p2]
