@@ -77,6 +77,12 @@ def process_partial_group(transcripts, mask_hash=None, printer=None, device="cud
     for t, tx in zip(txids, txs):
         merged_gene_tx.setdefault(merged_genes[tx.get_gene()], []).append(t)
     gene_ids = list(merged_gene_tx)
+    for gene_id, members in merged_gene_tx.items():
+        where = {(transcripts[t].chrom, transcripts[t].strand) for t in members}
+        if len(where) > 1:
+            # the reference notes "Skipping gene ..." but goes on to pool the positions of both places as if
+            # they were one chromosome strand (cs.py:324-343); refuse instead of writing nonsense
+            raise ValueError("gene %s has transcripts on several chromosomes or strands: %s" % (gene_id, sorted(where)))
     gene_index = {g: i for i, g in enumerate(gene_ids)}
     gene_of_tx = np.asarray([gene_index[merged_genes[tx.get_gene()]] for tx in txs], dtype=np.int64)
     n_tx, n_gene = len(txs), len(gene_ids)

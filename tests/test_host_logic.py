@@ -619,3 +619,11 @@ def test_phase_table_reproduces_the_rows_printed_in_the_reference_docs():
         assert lengths[i] == int(length) and counted[i] == int(reads)
         assert "%.6f" % frac[i] == f
         assert ["%.6f" % x for x in phases[i]] == [p0, p1, p2]
+
+
+def test_cs_generate_refuses_genes_on_several_chromosomes():
+    from plastid_b200.bin import cs
+    tx = {"a": pb.Transcript(pb.GenomicSegment("c1", 1, 5, "+"), ID="a", gene_id="g"),
+          "b": pb.Transcript(pb.GenomicSegment("c2", 1, 5, "+"), ID="b", gene_id="g")}
+    with pytest.raises(ValueError):
+        cs.process_partial_group(tx, None, device="cpu")      # raised before any device work
