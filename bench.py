@@ -539,6 +539,8 @@ def main():
     device = "cuda:%d" % local_rank
     numa = bind_to_gpu_numa_node(local_rank) if args.impl != "reference" else "all host threads"
     if world > 1 and args.impl != "reference":
+        # NCCL writes its version banner / debug lines to stdout by default: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     import plastid_b200 as pb
