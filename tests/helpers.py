@@ -326,3 +326,27 @@ def cs_generate_hand_case():
         "B1": dict(exon="c:450-500(+)", utr5="na", cds="na", utr3="na", masked="c:380-450(+)", exon_unmasked="c:380-500(+)"),
     }
     return records, masks, genes, transcripts
+
+
+def merge_segments_known_answers():
+    """plastid/test/unit/genomics/test_roitools.py:356-398 (test_merge_segments), transcribed:
+    list of (input intervals, expected merged intervals) on one chromosome strand."""
+    seg = [(0, 100), (50, 200), (250, 300), (300, 330), (500, 550), (525, 575), (570, 590), (575, 580)]
+    s01, s23, s456 = (0, 200), (250, 330), (500, 590)
+    pick = lambda *idx: [seg[i] for i in idx]                           # noqa: E731
+    return [(pick(0, 1), [s01]), (pick(1, 0), [s01]),                   # two overlapping
+            (pick(0, 2), [seg[0], seg[2]]), (pick(2, 0), [seg[0], seg[2]]),   # two non-overlapping
+            (pick(2, 3), [s23]), (pick(3, 2), [s23]),                   # two adjacent
+            (pick(0, 1, 2, 3, 4), [s01, s23, seg[4]]), (pick(4, 1, 3, 2, 0), [s01, s23, seg[4]]),
+            (pick(4, 5, 6), [s456]), (pick(4, 6, 5), [s456]),           # three overlapping
+            (pick(6, 7), [seg[6]]), (pick(7, 6), [seg[6]]),             # one internal
+            (pick(4, 5, 7, 6), [s456]), (pick(7, 4, 6, 5), [s456]),
+            (pick(0), [seg[0]]), (pick(0, 0, 0), [seg[0]]), ([], [])]
+
+
+def positions_to_segments_known_answers():
+    """plastid/test/unit/genomics/test_roitools.py:212-268 (test_positions_to_segments), transcribed:
+    list of (positions, expected intervals)."""
+    return [([], []), (list(range(100)), [(0, 100)]),
+            (list(range(100)) + list(range(150, 200)), [(0, 100), (150, 200)]),
+            (list(range(100)) + list(range(150, 200)) + list(range(195, 205)), [(0, 100), (150, 205)])]

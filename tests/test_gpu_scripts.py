@@ -534,6 +534,16 @@ def test_chain_set_algebra_matches_python_sets(cuda_device):
     for g in range(150):
         exp = _runs(set().union(*[_positions(a_chains[m]) for m in members[grp_off[g]:grp_off[g + 1]]]))
         assert list(zip(bs[off[g]:off[g + 1]], be[off[g]:off[g + 1]])) == exp, g
+    # the reference's own merge_segments known answers (test_roitools.py:356-398): union of one-block chains
+    from helpers import merge_segments_known_answers
+    kat = merge_segments_known_answers()
+    singles = [[seg] for segs, _ in kat for seg in segs]
+    S = _to_set(cuda_device, singles)
+    k_off = np.zeros(len(kat) + 1, dtype=np.int64)
+    np.cumsum([len(segs) for segs, _ in kat], out=k_off[1:])
+    bs, be, off = chain_union(S, k_off, np.arange(len(singles), dtype=np.int64)).numpy()
+    for g, (_segs, expected) in enumerate(kat):
+        assert list(zip(bs[off[g]:off[g + 1]], be[off[g]:off[g + 1]])) == expected, g
     # touching blocks of different members merge; empty inputs give empty chains
     T = _to_set(cuda_device, [[(0, 10)], [(10, 20)], [], [(25, 30)]])
     bs, be, off = chain_union(T, [0, 4, 4, 5], [0, 1, 2, 3, 2]).numpy()

@@ -627,3 +627,61 @@ def test_cs_generate_refuses_genes_on_several_chromosomes():
           "b": pb.Transcript(pb.GenomicSegment("c2", 1, 5, "+"), ID="b", gene_id="g")}
     with pytest.raises(ValueError):
         cs.process_partial_group(tx, None, device="cpu")      # raised before any device work
+
+
+def test_merge_and_positions_to_segments_reference_known_answers():
+    """test_roitools.py:212-268 and :356-398 for the host objects and the oracle's restatements."""
+    from helpers import merge_segments_known_answers, positions_to_segments_known_answers
+    from oracle import generate as og
+    for strand in "+-.":
+        for positions, expected in positions_to_segments_known_answers():
+            got = pb.positions_to_segments("chrA", strand, positions)
+            assert [(s.chrom, s.start, s.end, s.strand) for s in got] == [("chrA", a, b, strand) for a, b in expected]
+            got = og.positions_to_segments("chrA", strand, positions)
+            assert [(s.chrom, s.start, s.end, s.strand) for s in got] == [("chrA", a, b, strand) for a, b in expected]
+    for segs, expected in merge_segments_known_answers():
+        chain = pb.SegmentChain(*[pb.GenomicSegment("chrA", a, b, "+") for a, b in segs])
+        assert [(s.start, s.end) for s in chain] == expected
+        ochain = po.Chain(*[po.Seg("chrA", a, b, "+") for a, b in segs])
+        assert [(s.start, s.end) for s in ochain.segments] == expected
+
+
+def test_segmentchain_coordinate_known_answers_from_the_reference_tests():
+    """test_roitools.py:1120-1273 (get_segmentchain_coordinate, get_genomic_coordinate, get_subchain —
+    incl. the sub-range 2..27 of a 10-nt chain, which clamps like a python slice), transcribed; run
+    against the host SegmentChain and the oracle's restatement."""
+    from oracle import generate as og
+    for strand in "+-":
+        ivc = pb.SegmentChain(*[pb.GenomicSegment("chrA", a, b, strand) for a, b in ((20, 40), (60, 70), (80, 90))])
+        och = po.Chain(*[po.Seg("chrA", a, b, strand) for a, b in ((20, 40), (60, 70), (80, 90))])
+        c = 0
+        for iv in ivc:
+            for x in range(iv.start, iv.end):
+                expected = c if strand == "+" else ivc.length - 1 - c
+                assert ivc.get_segmentchain_coordinate("chrA", x, strand, stranded=True) == expected
+                assert ivc.get_segmentchain_coordinate("chrA", x, strand, stranded=False) == c
+                assert og.get_segmentchain_coordinate(och, x, stranded=True) == expected
+                assert og.get_segmentchain_coordinate(och, x, stranded=False) == c
+                c += 1
+    blocks = ((2, 3), (15, 19), (20, 24), (29, 30))
+    ivca = pb.SegmentChain(*[pb.GenomicSegment("chrA", a, b, "+") for a, b in blocks])
+    nvca = pb.SegmentChain(*[pb.GenomicSegment("chrA", a, b, "-") for a, b in blocks])
+    oca = po.Chain(*[po.Seg("chrA", a, b, "+") for a, b in blocks])
+    ocn = po.Chain(*[po.Seg("chrA", a, b, "-") for a, b in blocks])
+    assert ivca.get_genomic_coordinate(0)[1] == 2 and ivca.get_genomic_coordinate(ivca.length - 1)[1] == 29
+    assert ivca.get_genomic_coordinate(0, stranded=False)[1] == 2
+    assert nvca.get_genomic_coordinate(0)[1] == 29 and nvca.get_genomic_coordinate(nvca.length - 1)[1] == 2
+    assert nvca.get_genomic_coordinate(0, stranded=False)[1] == 2 and nvca.get_genomic_coordinate(9, stranded=False)[1] == 29
+    for ivc, och in ((ivca, oca), (nvca, ocn)):
+        positions = set(ivc.get_genomic_coordinate(i)[1] for i in range(ivc.length))
+        assert [(s.start, s.end) for s in pb.positions_to_segments(ivc.chrom, ivc.strand, positions)] == list(blocks)
+        for i in range(ivc.length):
+            for stranded in (True, False):
+                x = ivc.get_genomic_coordinate(i, stranded=stranded)[1]
+                assert ivc.get_segmentchain_coordinate(ivc.chrom, x, ivc.strand, stranded=stranded) == i
+                assert og.get_genomic_coordinate(och, i, stranded=stranded)[1] == x
+    assert str(ivca.get_subchain(0, ivca.length)) == str(ivca) and str(nvca.get_subchain(0, nvca.length)) == str(nvca)
+    assert ivca.get_subchain(2, 27).get_position_set() == {16, 17, 18, 20, 21, 22, 23, 29}
+    assert nvca.get_subchain(2, 27).get_position_set() == {2, 15, 16, 17, 18, 20, 21, 22}
+    assert set(og.get_subchain(oca, 2, 27).position_list) == {16, 17, 18, 20, 21, 22, 23, 29}
+    assert set(og.get_subchain(ocn, 2, 27).position_list) == {2, 15, 16, 17, 18, 20, 21, 22}
