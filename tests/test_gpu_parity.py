@@ -822,3 +822,66 @@ def test_spliced_transfer_format_round_trip(cuda_device):
         b = map_batch(ref, layout, fac, None, strands=("+", "-"))
         for strand in ("+", "-"):
             assert torch.equal(a.planes[strand], b.planes[strand])
+
+
+def test_genome_array_setitem_known_answers_from_the_reference_tests(cuda_device):
+    """plastid/test/unit/genomics/test_genome_array.py:811-898 (scalar / vector ``__setitem__`` over
+    segments and chains, both strands, incl. a chain running past the declared chromosome end) and the
+    auto-grow / ``+=`` part of ``test_setters_and_getters`` (:1146-1160), for GenomeArray and
+    SparseGenomeArray."""
+    rng = np.random.default_rng(17)
+    for cls in (pb.GenomeArray, pb.SparseGenomeArray):
+        ga = cls({"chrA": 2000}, device=cuda_device)
+        segplus, segminus = pb.GenomicSegment("chrA", 50, 100, "+"), pb.GenomicSegment("chrA", 50, 100, "-")
+        ga[segplus] = 52
+        ga[segminus] = 342
+        assert (ga.get(segplus, roi_order=False) == 52).all() and (ga.get(segminus, roi_order=False) == 342).all()
+        assert ga.sum() == 52 * len(segplus) + 342 * len(segminus)
+
+        ga = cls({"chrA": 2000}, device=cuda_device)
+        r1, r2 = rng.integers(0, 242, 50), rng.integers(0, 242, 50)
+        ga[segplus] = r1
+        ga[segminus] = r2
+        assert (ga.get(segplus, roi_order=False) == r1).all()
+        assert (ga.get(segminus, roi_order=False) == r2[::-1]).all() and (ga[segminus] == r2).all()
+        assert ga.sum() == r1.sum() + r2.sum()
+
+        blocks = ((50, 100), (150, 732), (1800, 2500))
+        pluschain = pb.SegmentChain(*[pb.GenomicSegment("chrA", a, b, "+") for a, b in blocks])
+        minuschain = pb.SegmentChain(*[pb.GenomicSegment("chrA", a, b, "-") for a, b in blocks])
+        ga = cls({"chrA": 2000}, device=cuda_device)
+        ga[pluschain] = 31
+        ga[minuschain] = 424
+        for seg in pluschain:
+            assert (ga.get(seg, roi_order=False) == 31).all()
+        for seg in minuschain:
+            assert (ga.get(seg, roi_order=False) == 424).all()
+        assert ga.sum() == 31 * pluschain.length + 424 * minuschain.length
+
+        ga = cls({"chrA": 2000}, device=cuda_device)
+        plusvec, minusvec = rng.integers(0, 250, pluschain.length), rng.integers(0, 250, minuschain.length)
+        ga[pluschain] = plusvec
+        ga[minuschain] = minusvec
+        x = 0
+        for seg in pluschain:
+            sub = ga.get(seg, roi_order=False)
+            assert (sub == plusvec[x:x + len(sub)]).all()
+            x += len(sub)
+        x = 0
+        for seg in minuschain:
+            sub = ga.get(seg, roi_order=False)[::-1]
+            assert (sub == minusvec[len(minusvec) - x - len(sub):len(minusvec) - x]).all()
+            x += len(sub)
+        assert ga.sum() == plusvec.sum() + minusvec.sum()
+        assert (pluschain.get_counts(ga) == plusvec).all() and (minuschain.get_counts(ga) == minusvec).all()
+
+        gnd = cls({"chrA": 1000, "chrB": 10000}, device=cuda_device)
+        iv1, iv2 = pb.GenomicSegment("chrA", 10000, 11000, "+"), pb.GenomicSegment("chrA", 10500, 11000, "+")
+        iv3 = pb.GenomicSegment("chrA", 500000 + 10500, 500000 + 11000, "+")
+        iv4 = pb.GenomicSegment("chrB", 500000 + 10500, 500000 + 11000, "+")
+        gnd[iv1] = 1
+        assert sum(gnd[iv1]) == 1000
+        gnd[iv2] += 1
+        assert sum(gnd[iv1]) == 1500 and sum(gnd[iv2]) == 1000 and gnd.lengths()["chrA"] > 1000
+        gnd[iv3] += 1
+        assert sum(gnd[iv3]) == 500 and sum(gnd[iv4]) == 0
