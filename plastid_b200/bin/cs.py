@@ -31,6 +31,8 @@ def merge_genes(tx_ivcs):
 
     owner, scope = {}, {}
     for txid, chain in tx_ivcs.items():
+        if chain.strand not in ("+", "-"):
+            raise KeyError(chain.strand)           # the reference keeps '+' and '-' exon tables only (cs.py:203)
         gene = chain.get_gene()
         parent.setdefault(gene, gene)
         for iv in chain:
