@@ -268,6 +268,22 @@ int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layout, const pb
                         double *out_plus, double *out_minus, double *out_any,
                         uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* pb_map_center / pb_map_center_fixed over the bins [bin_begin, bin_end) only (multiples of PB_LAYOUT_ALIGN):
+ * the Center rule for one rank of a position-sharded genome.  Same contract as
+ * pb_map_point_range for plane pointers (the address bin 0 WOULD have) and statistics (reads are counted by
+ * the range holding their start, so ranges add up); every read of the batch must be resident.  A bin's
+ * value depends only on the reads covering it, so ranges reproduce the whole-genome planes bit for bit. */
+int pb_map_center_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                        const int16_t *slot_of_len, const double *inv_m, int n_slots,
+                        double *out_plus, double *out_minus, double *out_any,
+                        uint64_t *stats, void *workspace, size_t workspace_bytes,
+                        int64_t bin_begin, int64_t bin_end, void *stream);
+int pb_map_center_fixed_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                              const int16_t *slot_of_len, const int64_t *w_fix, int n_slots, int shift,
+                              double *out_plus, double *out_minus, double *out_any,
+                              uint64_t *stats, void *workspace, size_t workspace_bytes,
+                              int64_t bin_begin, int64_t bin_end, void *stream);
+
 /* Measurement hook (bench.py roofline): while enabled, pb_map_point / pb_map_center bracket their
  * tiles kernel with CUDA events on the launch stream (up to 256 launches since the last enable);
  * pb_tiles_kernel_ms_total waits for them and returns the summed device time and launch count. */

@@ -54,11 +54,13 @@ __global__ void __launch_bounds__(kCThreads, DIRECT ? 4 : 3)
 pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
                        const int16_t *__restrict__ slot_of_len, const double *__restrict__ inv_m,
                        int slot0, int n_slots_rt, int accumulate, int lookback,
-                       const PbTile *__restrict__ tiles, int64_t n_tiles, unsigned long long *__restrict__ tile_counter,
+                       const PbTile *__restrict__ tiles, int64_t tile_begin, int64_t n_tiles,
+                       unsigned long long *__restrict__ tile_counter,
                        const uint32_t *__restrict__ rec_off, const PbRec *__restrict__ recs,
                        double *__restrict__ out_plus, double *__restrict__ out_minus, double *__restrict__ out_any,
                        unsigned long long *__restrict__ stat_slots)
 {
+    // tiles [tile_begin, n_tiles) are produced (n_tiles = end of the range; whole genome: 0 .. total tiles)
     const int planes = PLANES ? PLANES : planes_rt;
     const int n_slots = ONE_SLOT ? 1 : n_slots_rt;
     constexpr int T = EPT * kCThreads;
@@ -93,7 +95,7 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
         for (int j = threadIdx.x; j < n16; j += kCThreads) s4[j] = z;
     }
     PbQueueRegs q;
-    if (threadIdx.x == 0) pb_queue_init(s_ring, q, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
+    if (threadIdx.x == 0) pb_queue_init(s_ring, q, tiles, rec_off, lookback, tile_begin, n_tiles, T, tile_counter);
     pb_fence_proxy_async();
     __syncthreads();
 
@@ -122,7 +124,7 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
 
     int k3 = 0;       // k mod 3
     for (int k = 0;; ++k, k3 = (k3 == 2 ? 0 : k3 + 1)) {
-        if (threadIdx.x == 0) pb_queue_step(s_ring, q, k, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
+        if (threadIdx.x == 0) pb_queue_step(s_ring, q, k, tiles, rec_off, lookback, tile_begin, n_tiles, T, tile_counter);
         const PbSlot &cur = s_ring[k & 3];
         const long long tile = cur.tile;
         if (tile >= n_tiles) break;
@@ -317,7 +319,7 @@ template <int PLANES>
 __global__ void __launch_bounds__(kCThreads, 3)
 pb_center_fixed_kernel(PbReads b, PbRuleDev r, int planes_rt,
                        const int16_t *__restrict__ slot_of_len, const long long *__restrict__ w_fix, double scale,
-                       int lookback, const PbTile *__restrict__ tiles, int64_t n_tiles,
+                       int lookback, const PbTile *__restrict__ tiles, int64_t tile_begin, int64_t n_tiles,
                        unsigned long long *__restrict__ tile_counter,
                        const uint32_t *__restrict__ rec_off, const PbRec *__restrict__ recs,
                        double *__restrict__ out_plus, double *__restrict__ out_minus, double *__restrict__ out_any,
@@ -350,7 +352,7 @@ pb_center_fixed_kernel(PbReads b, PbRuleDev r, int planes_rt,
         for (int j = threadIdx.x; j < n16; j += kCThreads) s4[j] = z;
     }
     PbQueueRegs q;
-    if (threadIdx.x == 0) pb_queue_init(s_ring, q, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
+    if (threadIdx.x == 0) pb_queue_init(s_ring, q, tiles, rec_off, lookback, tile_begin, n_tiles, T, tile_counter);
     pb_fence_proxy_async();
     __syncthreads();
 
@@ -375,7 +377,7 @@ pb_center_fixed_kernel(PbReads b, PbRuleDev r, int planes_rt,
 
     int k3 = 0;
     for (int k = 0;; ++k, k3 = (k3 == 2 ? 0 : k3 + 1)) {
-        if (threadIdx.x == 0) pb_queue_step(s_ring, q, k, tiles, rec_off, lookback, 0, n_tiles, T, tile_counter);
+        if (threadIdx.x == 0) pb_queue_step(s_ring, q, k, tiles, rec_off, lookback, tile_begin, n_tiles, T, tile_counter);
         const PbSlot &cur = s_ring[k & 3];
         const long long tile = cur.tile;
         if (tile >= n_tiles) break;
@@ -544,8 +546,8 @@ size_t pb_center_smem_bytes(int n_planes, int n_slots, int tile_bins, bool direc
 
 template <int EPT, bool DIRECT, int PLANES, bool ONE_SLOT>
 int launch_center_kernel(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
-                         int s0, int ns, int pass, int lookback, int64_t n_tiles, int sm_count, const PbWorkspace &ws,
-                         double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+                         int s0, int ns, int pass, int lookback, int64_t tile_begin, int64_t n_tiles, int sm_count,
+                         const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
 {
     constexpr int T = EPT * kCThreads;
     const int n_planes = __builtin_popcount(planes);
@@ -556,11 +558,11 @@ int launch_center_kernel(const PbReads &b, const PbRuleDev &r, int planes, const
     PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCThreads, smem));
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)sm_count * occ;
-    if (grid > n_tiles) grid = n_tiles;
+    if (grid > n_tiles - tile_begin) grid = n_tiles - tile_begin;
     PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 64, stream));
     // statistics are accumulated by the first pass only (later passes see the same reads again)
     kern<<<(unsigned)grid, kCThreads, smem, stream>>>(
-        b, r, planes, slot_of_len, inv_m, s0, ns, pass > 0, lookback, ws.tiles, n_tiles, ws.tile_counter,
+        b, r, planes, slot_of_len, inv_m, s0, ns, pass > 0, lookback, ws.tiles, tile_begin, n_tiles, ws.tile_counter,
         ws.rec_off, ws.recs, out_plus, out_minus, out_any, pass == 0 ? ws.slots : nullptr);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
@@ -570,10 +572,10 @@ int launch_center_kernel(const PbReads &b, const PbRuleDev &r, int planes, const
 // and the plane sets the host layer asks for ('+','-' | '.' | all three); everything else is generic
 template <int EPT, bool DIRECT>
 int launch_center_pass(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
-                       int s0, int ns, int pass, int lookback, int64_t n_tiles, int sm_count, const PbWorkspace &ws,
-                       double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+                       int s0, int ns, int pass, int lookback, int64_t tile_begin, int64_t n_tiles, int sm_count,
+                       const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
 {
-#define PB_CENTER_ARGS b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, n_tiles, sm_count, ws, out_plus, out_minus, out_any, stream
+#define PB_CENTER_ARGS b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, tile_begin, n_tiles, sm_count, ws, out_plus, out_minus, out_any, stream
     if (EPT == 8 && DIRECT && ns == 1 && !getenv("PB_CENTER_GENERIC")) {
         if (planes == (PB_PLANE_PLUS | PB_PLANE_MINUS)) return launch_center_kernel<8, true, PB_PLANE_PLUS | PB_PLANE_MINUS, true>(PB_CENTER_ARGS);
         if (planes == PB_PLANE_ANY) return launch_center_kernel<8, true, PB_PLANE_ANY, true>(PB_CENTER_ARGS);
@@ -585,10 +587,10 @@ int launch_center_pass(const PbReads &b, const PbRuleDev &r, int planes, const i
 
 template <int EPT>
 int launch_center(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
-                  int n_slots, int per_pass, int lookback, int64_t total_bins, bool direct_ok, const PbWorkspace &ws,
-                  double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+                  int n_slots, int per_pass, int lookback, int64_t bin_begin, int64_t bin_end, bool direct_ok,
+                  const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
 {
-    const int64_t n_tiles = total_bins / (EPT * kCThreads);
+    const int64_t tile_begin = bin_begin / (EPT * kCThreads), n_tiles = bin_end / (EPT * kCThreads);   // n_tiles = end
     int sm_count = 0;
     int rc = pb_sm_count(&sm_count);
     if (rc) return rc;
@@ -597,11 +599,11 @@ int launch_center(const PbReads &b, const PbRuleDev &r, int planes, const int16_
         if (ns < 0) ns = 0;
         // the first pass stores every bin (direct 256-bit stores when allowed); later passes add to them
         if (pass == 0 && direct_ok)
-            rc = launch_center_pass<EPT, true>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, n_tiles, sm_count,
-                                               ws, out_plus, out_minus, out_any, stream);
+            rc = launch_center_pass<EPT, true>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, tile_begin, n_tiles,
+                                               sm_count, ws, out_plus, out_minus, out_any, stream);
         else
-            rc = launch_center_pass<EPT, false>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, n_tiles, sm_count,
-                                                ws, out_plus, out_minus, out_any, stream);
+            rc = launch_center_pass<EPT, false>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, tile_begin, n_tiles,
+                                                sm_count, ws, out_plus, out_minus, out_any, stream);
         if (rc) return rc;
         if (n_slots == 0) break;
     }
@@ -610,13 +612,30 @@ int launch_center(const PbReads &b, const PbRuleDev &r, int planes, const int16_
 
 }  // namespace
 
-extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
-                             const int16_t *slot_of_len, const double *inv_m, int n_slots,
-                             double *out_plus, double *out_minus, double *out_any,
-                             uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+namespace {
+// [bin_begin, bin_end) must be multiples of PB_LAYOUT_ALIGN inside the layout (0 .. total_bins = everything)
+int pb_check_bin_range(const pb_layout *layout, int64_t bin_begin, int64_t bin_end, const char *who)
+{
+    if (bin_begin < 0 || bin_end > layout->total_bins || bin_begin > bin_end || bin_begin % PB_LAYOUT_ALIGN ||
+        bin_end % PB_LAYOUT_ALIGN) {
+        pb_set_error("%s: bin range must lie in the layout on multiples of PB_LAYOUT_ALIGN", who);
+        return PB_EINVAL;
+    }
+    return PB_OK;
+}
+}  // namespace
+
+extern "C" int pb_map_center_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                                   const int16_t *slot_of_len, const double *inv_m, int n_slots,
+                                   double *out_plus, double *out_minus, double *out_any,
+                                   uint64_t *stats, void *workspace, size_t workspace_bytes,
+                                   int64_t bin_begin, int64_t bin_end, void *stream_)
 {
     int rc = pb_check_common(batch, layout, rule, planes);
     if (rc) return rc;
+    rc = pb_check_bin_range(layout, bin_begin, bin_end, "pb_map_center_range");
+    if (rc) return rc;
+    if (bin_begin == bin_end) return PB_OK;
     if (rule->kind != PB_RULE_CENTER || rule->param < 0) { pb_set_error("pb_map_center: need a center rule with nibble >= 0"); return PB_EINVAL; }
     if (!slot_of_len || (n_slots > 0 && !inv_m) || n_slots < 0 || n_slots > 32767) { pb_set_error("pb_map_center: bad slot tables"); return PB_EINVAL; }
     if (((planes & PB_PLANE_PLUS) && !out_plus) || ((planes & PB_PLANE_MINUS) && !out_minus) ||
@@ -655,26 +674,37 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
     if (const char *e = getenv("PB_CENTER_DIRECT")) direct_ok = direct_ok && atoi(e) != 0;
     const int tile_bins = ept * kCThreads;
     const int64_t n_tiles = layout->total_bins / tile_bins;
+    const int64_t tile_lo = bin_begin / tile_bins, tile_hi = bin_end / tile_bins;   // PB_LAYOUT_ALIGN is a multiple of every tile size
     const int lookback = (b.max_block_len + tile_bins - 1) / tile_bins;
 
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
-    rc = pb_launch_tile_index(b, lay, tile_bins, 0, n_tiles, batch->n_reads, 0, ws, stream);
+    rc = pb_launch_tile_index(b, lay, tile_bins, tile_lo, tile_hi, batch->n_reads, 0, ws, stream);
     if (rc) return rc;
-    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, 0, n_tiles, ws, stream);
+    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, tile_lo, tile_hi, ws, stream);
     if (rc) return rc;
     pb_timing_begin(stream);
     if (ept == 16)
-        rc = launch_center<16>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, direct_ok, ws,
+        rc = launch_center<16>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, bin_begin, bin_end, direct_ok, ws,
                                out_plus, out_minus, out_any, stream);
     else if (ept == 8)
-        rc = launch_center<8>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, direct_ok, ws,
+        rc = launch_center<8>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, bin_begin, bin_end, direct_ok, ws,
                               out_plus, out_minus, out_any, stream);
     else
-        rc = launch_center<4>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, layout->total_bins, direct_ok, ws,
+        rc = launch_center<4>(b, r, planes, slot_of_len, inv_m, n_slots, per_pass, lookback, bin_begin, bin_end, direct_ok, ws,
                               out_plus, out_minus, out_any, stream);
     pb_timing_end(stream);
     if (rc) return rc;
     return pb_launch_stats_finish(ws.slots, (unsigned long long *)stats, stream);
+}
+
+extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                             const int16_t *slot_of_len, const double *inv_m, int n_slots,
+                             double *out_plus, double *out_minus, double *out_any,
+                             uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    if (!layout) { pb_set_error("pb_map_center: null argument"); return PB_EINVAL; }
+    return pb_map_center_range(batch, layout, rule, planes, slot_of_len, inv_m, n_slots, out_plus, out_minus, out_any,
+                               stats, workspace, workspace_bytes, 0, layout->total_bins, stream_);
 }
 
 namespace {
@@ -686,7 +716,7 @@ size_t pb_center_fixed_smem(int n_planes)
 
 template <int PLANES>
 int launch_center_fixed(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const long long *w_fix,
-                        double scale, int lookback, int64_t n_tiles, const PbWorkspace &ws,
+                        double scale, int lookback, int64_t tile_begin, int64_t n_tiles, const PbWorkspace &ws,
                         double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
 {
     const size_t smem = pb_center_fixed_smem(__builtin_popcount(planes));
@@ -698,22 +728,26 @@ int launch_center_fixed(const PbReads &b, const PbRuleDev &r, int planes, const 
     int rc = pb_sm_count(&sm_count);
     if (rc) return rc;
     int64_t grid = (int64_t)sm_count * occ;
-    if (grid > n_tiles) grid = n_tiles;
+    if (grid > n_tiles - tile_begin) grid = n_tiles - tile_begin;
     PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 64, stream));
-    kern<<<(unsigned)grid, kCThreads, smem, stream>>>(b, r, planes, slot_of_len, w_fix, scale, lookback, ws.tiles, n_tiles,
+    kern<<<(unsigned)grid, kCThreads, smem, stream>>>(b, r, planes, slot_of_len, w_fix, scale, lookback, ws.tiles, tile_begin, n_tiles,
                                                       ws.tile_counter, ws.rec_off, ws.recs, out_plus, out_minus, out_any, ws.slots);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
 }  // namespace
 
-extern "C" int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+extern "C" int pb_map_center_fixed_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
                                    const int16_t *slot_of_len, const int64_t *w_fix, int n_slots, int shift,
                                    double *out_plus, double *out_minus, double *out_any,
-                                   uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+                                   uint64_t *stats, void *workspace, size_t workspace_bytes,
+                                   int64_t bin_begin, int64_t bin_end, void *stream_)
 {
     int rc = pb_check_common(batch, layout, rule, planes);
     if (rc) return rc;
+    rc = pb_check_bin_range(layout, bin_begin, bin_end, "pb_map_center_fixed_range");
+    if (rc) return rc;
+    if (bin_begin == bin_end) return PB_OK;
     if (rule->kind != PB_RULE_CENTER || rule->param < 0) { pb_set_error("pb_map_center_fixed: need a center rule with nibble >= 0"); return PB_EINVAL; }
     if (!slot_of_len || !w_fix || n_slots < 1 || n_slots > 32767 || shift < 1 || shift > 62) {
         pb_set_error("pb_map_center_fixed: bad weight tables"); return PB_EINVAL;
@@ -734,23 +768,34 @@ extern "C" int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layou
     if (rc) return rc;
     const int tile_bins = 8 * kCThreads;
     const int64_t n_tiles = layout->total_bins / tile_bins;
+    const int64_t tile_lo = bin_begin / tile_bins, tile_hi = bin_end / tile_bins;
     const int lookback = (b.max_block_len + tile_bins - 1) / tile_bins;
     const double scale = ldexp(1.0, -shift);
 
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
-    rc = pb_launch_tile_index(b, lay, tile_bins, 0, n_tiles, batch->n_reads, 0, ws, stream);
+    rc = pb_launch_tile_index(b, lay, tile_bins, tile_lo, tile_hi, batch->n_reads, 0, ws, stream);
     if (rc) return rc;
-    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, 0, n_tiles, ws, stream);
+    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, tile_lo, tile_hi, ws, stream);
     if (rc) return rc;
     pb_timing_begin(stream);
     const long long *w = reinterpret_cast<const long long *>(w_fix);
     if (planes == (PB_PLANE_PLUS | PB_PLANE_MINUS))
-        rc = launch_center_fixed<PB_PLANE_PLUS | PB_PLANE_MINUS>(b, r, planes, slot_of_len, w, scale, lookback, n_tiles, ws, out_plus, out_minus, out_any, stream);
+        rc = launch_center_fixed<PB_PLANE_PLUS | PB_PLANE_MINUS>(b, r, planes, slot_of_len, w, scale, lookback, tile_lo, tile_hi, ws, out_plus, out_minus, out_any, stream);
     else if (planes == 7)
-        rc = launch_center_fixed<7>(b, r, planes, slot_of_len, w, scale, lookback, n_tiles, ws, out_plus, out_minus, out_any, stream);
+        rc = launch_center_fixed<7>(b, r, planes, slot_of_len, w, scale, lookback, tile_lo, tile_hi, ws, out_plus, out_minus, out_any, stream);
     else
-        rc = launch_center_fixed<0>(b, r, planes, slot_of_len, w, scale, lookback, n_tiles, ws, out_plus, out_minus, out_any, stream);
+        rc = launch_center_fixed<0>(b, r, planes, slot_of_len, w, scale, lookback, tile_lo, tile_hi, ws, out_plus, out_minus, out_any, stream);
     pb_timing_end(stream);
     if (rc) return rc;
     return pb_launch_stats_finish(ws.slots, (unsigned long long *)stats, stream);
+}
+
+extern "C" int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
+                                   const int16_t *slot_of_len, const int64_t *w_fix, int n_slots, int shift,
+                                   double *out_plus, double *out_minus, double *out_any,
+                                   uint64_t *stats, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    if (!layout) { pb_set_error("pb_map_center_fixed: null argument"); return PB_EINVAL; }
+    return pb_map_center_fixed_range(batch, layout, rule, planes, slot_of_len, w_fix, n_slots, shift, out_plus, out_minus,
+                                     out_any, stats, workspace, workspace_bytes, 0, layout->total_bins, stream_);
 }

@@ -60,11 +60,12 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
 template <bool CENTER, int OCC>
 __global__ void __launch_bounds__(256, OCC)   // latency-bound gather chains: resident threads vs registers (OCC CTAs/SM)
 pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t *__restrict__ slot_of_len,
-              int tile_shift, int64_t tile_lo, int64_t tile_hi, int fill, uint32_t *__restrict__ rec_cursor,
+              int tile_shift, int64_t tile_lo, int64_t tile_hi, int64_t tile_rec_lo, int fill, uint32_t *__restrict__ rec_cursor,
               const uint32_t *__restrict__ rec_off, PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
 {
     // [tile_lo, tile_hi): the tiles this launch produces (position-sharded ranks map a bin range only);
-    // records and statistics outside it belong to another rank
+    // records and statistics outside it belong to another rank.  Center intervals reach into later tiles, so
+    // their records are kept from tile_rec_lo = tile_lo - lookback on (the tiles kernel looks that far back).
     unsigned long long drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0;
     unsigned int drop_len = 0;
     const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS,
@@ -123,7 +124,7 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
             if (x < 0 || x >= clen) return;
             if (y > clen) y = clen;
             const int64_t tile = (base + x) >> tile_shift;       // tile sizes are powers of two
-            if (tile < tile_lo || tile >= tile_hi) return;
+            if (tile < tile_rec_lo || tile >= tile_hi) return;
             // reads are coordinate-sorted, so the lanes that are here together mostly target the same
             // tile: one atomic per group of lanes instead of one per record
             const unsigned lane = threadIdx.x & 31;
@@ -446,10 +447,15 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
     int tile_shift = 0;
     while ((1 << tile_shift) < tile_bins) ++tile_shift;
     if ((1 << tile_shift) != tile_bins) { pb_set_error("tile size must be a power of two"); return PB_EINVAL; }
+    int64_t tile_rec_lo = tile_lo;
+    if (center) {
+        const int64_t lookback = ((int64_t)b.max_block_len + tile_bins - 1) / tile_bins;
+        tile_rec_lo = tile_lo > lookback ? tile_lo - lookback : 0;
+    }
     int occ_sel = 8;
     if (const char *e = getenv("PB_BIN_OCC")) occ_sel = atoi(e);        // measurement override (profiles/NOTES)
     for (int fill = 0; fill < 2; ++fill) {
-#define PB_BIN_LAUNCH(C_, O_) pb_bin_kernel<C_, O_><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, fill, ws.rec_cursor, ws.rec_off, ws.recs, ws.slots)
+#define PB_BIN_LAUNCH(C_, O_) pb_bin_kernel<C_, O_><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, tile_rec_lo, fill, ws.rec_cursor, ws.rec_off, ws.recs, ws.slots)
         if (center) {
             if (occ_sel == 4) PB_BIN_LAUNCH(true, 4); else if (occ_sel == 6) PB_BIN_LAUNCH(true, 6); else PB_BIN_LAUNCH(true, 8);
         } else {

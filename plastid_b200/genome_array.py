@@ -92,10 +92,14 @@ def _workspace(device, nbytes, slot=0):
 
 
 def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), planes=None, sync_stats=True,
-              bin_range=None):
+              bin_range=None, length_hist=None):
     """Lower ``factory`` over a whole device batch into dense planes for the query ``strands``.
     ``bin_range=(lo, hi)``: produce only the global bins [lo, hi) (position sharding,
-    ``plastid_b200.dist.shard_positions``; point rules) into range-only planes."""
+    ``plastid_b200.dist.shard_positions``) into range-only planes.
+    ``length_hist`` (Center rule; int64[65536], reads per aligned length after the filters): the histogram
+    the slot / fixed-point tables are derived from.  Default: measured on ``dbatch`` (one device->host
+    round trip).  Ranks of a position-sharded run pass the histogram of the WHOLE batch (all-reduced), so
+    that every rank uses the same tables and the planes match the unsharded ones bit for bit."""
     import torch
     _lib.require_cuda()
     if not isinstance(factory, _MapFactory) or isinstance(factory, StratifiedVariableFivePrimeMapFactory):
@@ -107,8 +111,6 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     ranged = (planes.bin_lo, planes.bin_hi) != (0, int(layout.total_bins))
     if bin_range is not None and (planes.bin_lo, planes.bin_hi) != tuple(int(x) for x in bin_range):
         raise ValueError("planes were allocated for another bin range")
-    if ranged and is_center:
-        raise ValueError("position-range mapping is implemented for the point rules (pb_map_point_range)")
     planes.alloc(strands)
     mask = 0
     for s in strands:
@@ -119,30 +121,34 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev)
     b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
     outs = [planes.plane_ptr(s) if s in strands else None for s in _STRANDS]
-    if ranged:
+    if ranged and not is_center:
         _lib.check(L.pb_map_point_range(C.byref(b), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
                                         _lib.ptr(stats), _lib.ptr(ws), ws_bytes, planes.bin_lo, planes.bin_hi,
                                         dbatch.n_reads, _lib.stream_ptr()))
     elif is_center:
-        hist = torch.zeros(65536, dtype=torch.int64, device=dev)
-        _lib.check(L.pb_length_hist(C.byref(b), C.byref(rule), _lib.PB_PLANE_ANY, _lib.ptr(hist), _lib.stream_ptr()))
-        h_hist = hist.cpu().numpy()
+        if length_hist is None:
+            h_hist = length_histogram(dbatch, factory, size_filter)
+        else:
+            h_hist = np.ascontiguousarray(length_hist, dtype=np.int64)
+            if h_hist.shape != (65536,):
+                raise ValueError("length_hist must have 65536 entries")
         fixed = factory.fixed_point_tables(h_hist)
         aligned = all(planes.planes[s].data_ptr() % 32 == 0 for s in strands)
         if fixed is not None and aligned and not os.environ.get("PB_CENTER_EXACT"):
             # many map lengths: one pass with 64-bit fixed-point weights (rel. error <= 1e-9, see the header)
             slot_of_len, w_fix, shift = fixed
             d_slot, d_w = torch.from_numpy(slot_of_len).to(dev), torch.from_numpy(w_fix).to(dev)
-            _lib.check(L.pb_map_center_fixed(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_w),
-                                             len(w_fix), shift, outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws),
-                                             ws_bytes, _lib.stream_ptr()))
+            _lib.check(L.pb_map_center_fixed_range(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot),
+                                                   _lib.ptr(d_w), len(w_fix), shift, outs[0], outs[1], outs[2],
+                                                   _lib.ptr(stats), _lib.ptr(ws), ws_bytes, planes.bin_lo, planes.bin_hi,
+                                                   _lib.stream_ptr()))
         else:
             slot_of_len, inv_m = factory.slot_tables(h_hist)
             d_slot = torch.from_numpy(slot_of_len).to(dev)
             d_inv = torch.from_numpy(inv_m if len(inv_m) else np.zeros(1)).to(dev)
-            _lib.check(L.pb_map_center(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_inv),
-                                       len(inv_m), outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
-                                       _lib.stream_ptr()))
+            _lib.check(L.pb_map_center_range(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_inv),
+                                             len(inv_m), outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
+                                             planes.bin_lo, planes.bin_hi, _lib.stream_ptr()))
     else:
         _lib.check(L.pb_map_point(C.byref(b), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
                                   _lib.ptr(stats), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
@@ -210,6 +216,16 @@ def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=N
         total[_lib.PB_STAT_DROPPED_LEN] = dropped_len
     planes.stats_dev = total
     return planes
+
+
+def length_histogram(dbatch, factory, size_filter=None):
+    """Reads per aligned length (int64[65536]) after the drop bit and the size filter (``pb_length_hist``)."""
+    import torch
+    _lib.require_cuda()
+    hist = torch.zeros(65536, dtype=torch.int64, device=dbatch.device)
+    b, rule = dbatch.c_struct(), factory.pb_rule(dbatch.device, size_filter)
+    _lib.check(_lib.lib().pb_length_hist(C.byref(b), C.byref(rule), _lib.PB_PLANE_ANY, _lib.ptr(hist), _lib.stream_ptr()))
+    return hist.cpu().numpy()
 
 
 _side_streams = {}

@@ -885,3 +885,44 @@ def test_genome_array_setitem_known_answers_from_the_reference_tests(cuda_device
         assert sum(gnd[iv1]) == 1500 and sum(gnd[iv2]) == 1000 and gnd.lengths()["chrA"] > 1000
         gnd[iv3] += 1
         assert sum(gnd[iv3]) == 500 and sum(gnd[iv4]) == 0
+
+
+@pytest.mark.parametrize("world_size", [2, 5])
+@pytest.mark.parametrize("kind", ["spliced_one_length", "ribo_many_lengths", "ribo_exact"])
+def test_position_range_sharding_center_rule(small_world, cuda_device, world_size, kind, monkeypatch):
+    """SURVEY 8e for the Center rule (pb_map_center_range / pb_map_center_fixed_range): range-only fp64
+    planes of every rank equal the whole-genome planes bit for bit — intervals that start before a range
+    and reach into it come through the bin kernel's look-back records and the halo reads — and the
+    statistics add up.  Ranks derive their slot / fixed-point tables from the histogram of the whole batch."""
+    import torch
+    from plastid_b200 import dist as pd
+    from plastid_b200.batch import DeviceBatch
+    from plastid_b200.genome_array import length_histogram
+    w = small_world
+    lay = w["layout"]
+    if kind == "spliced_one_length":
+        hb = synth.device_batch_to_host(synth.rnaseq_reads(w["chroms"], w["lens"], 60_000, seed=4, device="cpu",
+                                                           intron=(50, 3000)), w["chroms"], w["lens"])
+        fac = pb.CenterMapFactory(12)
+    else:
+        hb, fac = w["hb"], pb.CenterMapFactory(3 if kind == "ribo_exact" else 0)
+        if kind == "ribo_exact":
+            monkeypatch.setenv("PB_CENTER_EXACT", "1")
+    dfull = DeviceBatch.from_host(hb, cuda_device)
+    hist = length_histogram(dfull, fac)
+    whole = map_batch(dfull, lay, fac, None, strands=("+", "-"), length_hist=hist)
+    assert float(whole.planes["+"].sum().item()) > 0
+    cuts = pd.position_cuts(hb, lay, world_size)
+    mapped = np.zeros(_lib.PB_NSTATS, dtype=np.int64)
+    for rank in range(world_size):
+        sub, lo, hi = pd.shard_positions(hb, lay, rank, world_size, cuts)
+        if hi == lo:
+            continue
+        planes = map_batch(DeviceBatch.from_host(sub, cuda_device), lay, fac, None, strands=("+", "-"), bin_range=(lo, hi),
+                           length_hist=hist)
+        for s in ("+", "-"):
+            assert planes.planes[s].numel() == hi - lo
+            assert torch.equal(planes.planes[s], whole.planes[s][lo:hi]), (kind, rank, s)
+        mapped += planes.stats
+    for k in (_lib.PB_STAT_MAPPED_PLUS, _lib.PB_STAT_MAPPED_MINUS, _lib.PB_STAT_DROPPED_PLUS, _lib.PB_STAT_DROPPED_MINUS):
+        assert mapped[k] == whole.stats[k]
