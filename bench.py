@@ -29,6 +29,28 @@ METRIC = "mapped_reads_per_sec"
 UNIT = "reads/s"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL (its version banner), torchrun children and other
+    libraries write to file descriptor 1 behind Python's back, so descriptor 1 is pointed at stderr for the
+    whole run and the JSON line alone is written to the original stdout (``emit``)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,10 +190,10 @@ def build_world(args, rank, device):
             name = "C5: cs count, ThreePrimeMapFactory(0)+size filter 25-100"
     layout = pb.GenomeLayout(chroms, lens)
     table = synth.annotation_table(ann, layout)
+    seed = 100 if getattr(args, "sharding", "reads") == "positions" else 100 + rank     # positions: ONE batch, all ranks
     if wl == "c3":
-        dbatch = synth.rnaseq_reads(chroms, lens, n_reads, seed=100 + rank, device=device)
+        dbatch = synth.rnaseq_reads(chroms, lens, n_reads, seed=seed, device=device)
     else:
-        seed = 100 if getattr(args, "sharding", "reads") == "positions" else 100 + rank     # positions: ONE batch, all ranks
         dbatch = synth.riboseq_reads(ann, n_reads, seed=seed, device=device, frac_in=0.85 if wl != "c1" else 0.9)
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
@@ -317,7 +339,7 @@ def run_peaks(args, device):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "atomic_peaks.json"), "w") as fh:
         json.dump(out, fh, indent=1)
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 def run_position_sharded(args, W, device, rank, world, dist):
@@ -326,20 +348,34 @@ def run_position_sharded(args, W, device, rank, world, dist):
     with pb_map_point_range and sums the clipped region table; one all-reduce per step."""
     import torch
     from plastid_b200 import dist as pdist
-    from plastid_b200.genome_array import map_batch, region_sums, CountPlanes
+    from plastid_b200 import synth
+    from plastid_b200.batch import DeviceBatch
+    from plastid_b200.genome_array import map_batch, region_sums, CountPlanes, length_histogram
+    from plastid_b200.map_factories import CenterMapFactory
     layout, table, fac, sf, dbatch = W["layout"], W["table"], W["fac"], W["sf"], W["dbatch"]
     n_total = dbatch.n_reads
-    sub, lo, hi, cuts = pdist.shard_positions_device(dbatch, layout, rank, world)
+    is_center = isinstance(fac, CenterMapFactory)
+    # Center rule: every rank derives its slot tables from the histogram of the WHOLE batch (in a real run: one
+    # 512 KB all-reduce), so that the sharded planes equal the unsharded ones bit for bit
+    hist = length_histogram(dbatch, fac, sf) if is_center else None
+    if dbatch.blk_off is None:
+        sub, lo, hi, cuts = pdist.shard_positions_device(dbatch, layout, rank, world)
+    else:                                       # spliced batches are sharded on the host (set-up, not timed)
+        hb = synth.device_batch_to_host(dbatch, W["chroms"], W["lens"])
+        h_sub, lo, hi = pdist.shard_positions(hb, layout, rank, world)
+        sub = DeviceBatch.from_host(h_sub, device)
+        del hb, h_sub
     del dbatch
     W["dbatch"] = None
     torch.cuda.empty_cache()
     clipped = pdist.clip_table(table, lo, hi)
     clipped.device(device)
-    planes = CountPlanes(layout, "u32", device, bin_range=(lo, hi))
+    planes = CountPlanes(layout, "f64" if is_center else "u32", device, bin_range=(lo, hi))
     planes.alloc(("+", "-"))
 
     def step():
-        map_batch(sub, layout, fac, sf, strands=("+", "-"), planes=planes, sync_stats=False, bin_range=(lo, hi))
+        map_batch(sub, layout, fac, sf, strands=("+", "-"), planes=planes, sync_stats=False, bin_range=(lo, hi),
+                  length_hist=hist)
         sums, live = region_sums(planes, clipped)
         if world > 1:
             dist.all_reduce(sums)
@@ -371,14 +407,14 @@ def run_position_sharded(args, W, device, rank, world, dist):
     ms = float(t.item())
     line = {"metric": METRIC, "value": n_total / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if is_center else "u32", "data": "synthetic",
             "config": {"workload": "%s, ONE batch of %d synthetic reads over %d bins sharded by position range over %d GPUs "
                                    "(range-only planes, halo reads, clipped region tables all-reduced)"
                                    % (W["name"], n_total, layout.total_bins, world),
                        "reads_per_rank_incl_halo": [int(g[0].item()) for g in gathered],
                        "bins_per_rank": [int(g[1].item()) for g in gathered]},
             "region_counts_per_sec": W["ann"].n_tx / (ms / 1000.0), "table_checksum": float(sums.sum().item())}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def run_c4(args, W, device, rank, world, dist):
@@ -465,7 +501,7 @@ def run_c4(args, W, device, rank, world, dist):
                          "kernel_share_of_step": g_ms / ms},
             "generate": generate,
             "profile_checksum": float(torch.nan_to_num(prof).sum().item()), "regions_counted_max": int(nreg.max().item())}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def run_c2p(args, W, device, rank, world, dist):
@@ -521,11 +557,12 @@ def run_c2p(args, W, device, rank, world, dist):
                                    "median profiles" % (dbatch.n_reads, n, width, lo, hi)},
             "stratified_kernel_ms": float(np.mean(k_ms)), "kernel_share_of_step": float(np.mean(k_ms)) / ms,
             "profile_checksum": float(torch.nan_to_num(profs).sum().item())}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -539,8 +576,6 @@ def main():
     device = "cuda:%d" % local_rank
     numa = bind_to_gpu_numa_node(local_rank) if args.impl != "reference" else "all host threads"
     if world > 1 and args.impl != "reference":
-        # NCCL writes its version banner / debug lines to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     import plastid_b200 as pb
@@ -564,8 +599,8 @@ def main():
               % (8 * n_reads / 1e9, (16 if is_center else 8) * layout.total_bins / 1e9)}
 
     if args.sharding == "positions" and args.impl != "reference":
-        if args.workload != "c2":
-            raise SystemExit("--sharding positions is implemented for the c2 workload")
+        if args.workload not in ("c2", "c3", "c5"):
+            raise SystemExit("--sharding positions is implemented for the mapping workloads c2, c3 and c5")
         run_position_sharded(args, W, device, rank, world, dist)
         if world > 1:
             dist.destroy_process_group()
@@ -605,7 +640,7 @@ def main():
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "oracle port of map_factories.pyx/roitools.pyx loops (the Cython reference cannot be "
                         "built here: pysam absent); chromosome-parallel over %d host threads" % threads}
-        print(json.dumps(line))
+        emit(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ device-resident steps
@@ -835,7 +870,7 @@ def main():
         # the same pass replayed as one CUDA graph launch (launch-latency bound workload)
         line["cuda_graph"] = {"ms_per_step": graph_ms, "value": n_reads / (graph_ms / 1000.0), "unit": UNIT,
                               "region_counts_per_sec": ann.n_tx / (graph_ms / 1000.0), "replays_timed": args.steps * 10}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
