@@ -681,6 +681,7 @@ class Delta3SplicedBatch(object):
 
     def __init__(self, base, bwords, bexc_row, bexc, max_block_len):
         self.base = base                                   # Delta3Batch of (ref_start, meta)
+        self.length_hist = None                            # set by from_batch: reads per aligned length
         self.bwords = np.ascontiguousarray(bwords, dtype=np.uint32)
         self.bexc_row = np.ascontiguousarray(bexc_row, dtype=np.uint32)
         self.bexc = np.ascontiguousarray(bexc, dtype=np.int32).reshape(-1, 2)
@@ -698,8 +699,11 @@ class Delta3SplicedBatch(object):
         plain = AlignmentBatch(hb.chroms, hb.chrom_len, hb.ref_start, hb.meta, hb.chrom_read_off, None, None,
                                hb.max_span, hb.mapped)
         base = Delta3Batch.from_batch(plain, native=native, threads=threads)
+        hist = meta_length_hist(hb.meta)
         if hb.blk is None or len(hb.blk) == 0:
-            return cls(base, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros((0, 2), np.int32), hb.max_block_len)
+            out = cls(base, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros((0, 2), np.int32), hb.max_block_len)
+            out.length_hist = hist
+            return out
         rel, ln = hb.blk[:, 0].astype(np.int64), hb.blk[:, 1].astype(np.int64)
         n_rows = len(rel)
         if n_rows >= (1 << 32):
@@ -714,8 +718,10 @@ class Delta3SplicedBatch(object):
         fits = (ln >= 1) & (ln < 4096) & (gap >= 0) & (gap < (1 << 20) - 1)
         words = np.where(fits, ln | (gap << 12), 0xFFFFFFFF).astype(np.uint32)
         rows = np.flatnonzero(~fits)
-        return cls(base, words, rows.astype(np.uint32), np.stack([gap[rows], ln[rows]], axis=1).astype(np.int32),
-                   hb.max_block_len)
+        out = cls(base, words, rows.astype(np.uint32), np.stack([gap[rows], ln[rows]], axis=1).astype(np.int32),
+                  hb.max_block_len)
+        out.length_hist = hist
+        return out
 
     def pinned(self):
         import torch
@@ -746,7 +752,7 @@ class Delta3SplicedReceiver(object):
         self.batch = DeviceBatch(n, ib.n_chrom, ib.max_span, ib.ref_start, ib.meta, ib.chrom_read_off,
                                  torch.empty(n + 1, dtype=torch.int32, device=device),
                                  torch.empty((max(rows, 1), 2), dtype=torch.int32, device=device)[:rows],
-                                 wire.max_block_len)
+                                 wire.max_block_len, wire.length_hist)
 
     def receive(self, pinned):
         """Enqueue the H2D copies of one whole batch and its expansion on the current stream."""
@@ -766,17 +772,28 @@ class Delta3SplicedReceiver(object):
         return self.batch
 
 
+def meta_length_hist(meta):
+    """Reads per aligned length (int64[65536]) of a host ``meta`` array; reads with the drop bit are left out."""
+    m = np.asarray(meta).view(np.uint32) if np.asarray(meta).dtype != np.uint32 else np.asarray(meta)
+    keep = (m >> 17) & 1 == 0
+    return np.bincount((m[keep] & 0xFFFF).astype(np.int64), minlength=65536).astype(np.int64)
+
+
 class DeviceBatch(object):
     """Device-resident mirror of an :class:`AlignmentBatch` (torch tensors used as buffers only)."""
 
     def __init__(self, n_reads, n_chrom, max_span, ref_start, meta, chrom_read_off, blk_off=None, blk=None,
-                 max_block_len=None):
+                 max_block_len=None, length_hist=None):
         self.n_reads, self.n_chrom, self.max_span = int(n_reads), int(n_chrom), int(max_span)
         self.ref_start, self.meta, self.chrom_read_off = ref_start, meta, chrom_read_off
         self.blk_off, self.blk = blk_off, blk
         self.n_blk = 0 if blk is None else int(blk.shape[0])
         # without better knowledge the reference span bounds every block
         self.max_block_len = int(max_span if max_block_len is None else max_block_len)
+        # batch-level metadata like max_span: reads per aligned length (int64[65536], drop bit honoured), known
+        # to whoever produced the batch (decoder, transfer-format receiver); None = measure on the device.
+        # The Center rule derives its table of map lengths from it.
+        self.length_hist = None if length_hist is None else np.ascontiguousarray(length_hist, dtype=np.int64)
 
     @classmethod
     def from_host(cls, hb, device, non_blocking=False):
@@ -788,7 +805,7 @@ class DeviceBatch(object):
             t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a)
             return t.to(device, non_blocking=non_blocking)
         return cls(len(hb), len(hb.chroms), hb.max_span, up(hb.ref_start), up(hb.meta),
-                   up(hb.chrom_read_off), up(hb.blk_off), up(hb.blk), hb.max_block_len)
+                   up(hb.chrom_read_off), up(hb.blk_off), up(hb.blk), hb.max_block_len, meta_length_hist(hb.meta))
 
     @property
     def device(self):

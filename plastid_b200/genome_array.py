@@ -97,8 +97,8 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     ``bin_range=(lo, hi)``: produce only the global bins [lo, hi) (position sharding,
     ``plastid_b200.dist.shard_positions``) into range-only planes.
     ``length_hist`` (Center rule; int64[65536], reads per aligned length after the filters): the histogram
-    the slot / fixed-point tables are derived from.  Default: measured on ``dbatch`` (one device->host
-    round trip).  Ranks of a position-sharded run pass the histogram of the WHOLE batch (all-reduced), so
+    the slot / fixed-point tables are derived from.  Default: ``dbatch.length_hist`` when the batch
+    carries it, else measured on the device (``pb_length_hist`` + one device->host round trip).  Ranks of a position-sharded run pass the histogram of the WHOLE batch (all-reduced), so
     that every rank uses the same tables and the planes match the unsharded ones bit for bit."""
     import torch
     _lib.require_cuda()
@@ -126,7 +126,16 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
                                         _lib.ptr(stats), _lib.ptr(ws), ws_bytes, planes.bin_lo, planes.bin_hi,
                                         dbatch.n_reads, _lib.stream_ptr()))
     elif is_center:
-        if length_hist is None:
+        if length_hist is None and getattr(dbatch, "length_hist", None) is not None and not os.environ.get("PB_MEASURE_HIST"):
+            # the batch came with its histogram (decoder / receiver metadata): apply the size filter to it
+            h_hist = dbatch.length_hist.copy()
+            if size_filter is not None:
+                lens_ = np.arange(65536)
+                keep = lens_ >= size_filter.min_
+                if size_filter.max_ != -1:
+                    keep &= lens_ <= size_filter.max_
+                h_hist[~keep] = 0
+        elif length_hist is None:
             h_hist = length_histogram(dbatch, factory, size_filter)
         else:
             h_hist = np.ascontiguousarray(length_hist, dtype=np.int64)

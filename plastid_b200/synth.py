@@ -179,8 +179,10 @@ def _finish(chroms, chrom_len, chrom, start, L, rev, device, blocks=None):
         blk = torch.stack([rel_s[valid], ln_s[valid]], dim=1).to(torch.int32).contiguous()
         max_span = max(max_span, int((rel + ln).max().item()))
         blk_off = blk_off.to(torch.int32)
+    # batch metadata a decoder knows for free: reads per aligned length
+    hist = torch.bincount(L.to(torch.int64), minlength=65536).cpu().numpy() if L.numel() else np.zeros(65536, dtype=np.int64)
     return DeviceBatch(len(order), len(chroms), max_span, start_s.contiguous(), meta.contiguous(), off, blk_off, blk,
-                       max_block_len)
+                       max_block_len, hist)
 
 
 def rnaseq_reads(chroms, chrom_len, n_reads, seed=0, device="cpu", read_len=100, one_gap=0.30, two_gaps=0.03,

@@ -926,3 +926,24 @@ def test_position_range_sharding_center_rule(small_world, cuda_device, world_siz
         mapped += planes.stats
     for k in (_lib.PB_STAT_MAPPED_PLUS, _lib.PB_STAT_MAPPED_MINUS, _lib.PB_STAT_DROPPED_PLUS, _lib.PB_STAT_DROPPED_MINUS):
         assert mapped[k] == whole.stats[k]
+
+
+def test_center_tables_from_batch_metadata_equal_device_histogram(small_world, cuda_device):
+    """A batch that carries its length histogram (decoder / receiver metadata) skips the device
+    histogram + host round trip of the Center rule; the planes are identical, with and without a size
+    filter and with host-evaluated drop bits."""
+    import torch
+    from plastid_b200.batch import DeviceBatch
+    w = small_world
+    hb = w["hb"]
+    d_meta = DeviceBatch.from_host(hb, cuda_device)
+    assert d_meta.length_hist is not None and d_meta.length_hist.sum() == len(hb)
+    for sf in (None, pb.SizeFilterFactory(24, 33), pb.SizeFilterFactory(30, -1)):
+        for fac in (pb.CenterMapFactory(0), pb.CenterMapFactory(11)):
+            with_meta = map_batch(d_meta, w["layout"], fac, sf, strands=("+", "-"))
+            d_plain = DeviceBatch.from_host(hb, cuda_device)
+            d_plain.length_hist = None
+            measured = map_batch(d_plain, w["layout"], fac, sf, strands=("+", "-"))
+            for s in ("+", "-"):
+                assert torch.equal(with_meta.planes[s], measured.planes[s])
+            assert (with_meta.stats == measured.stats).all()
