@@ -307,6 +307,21 @@ def gather_matrix(local_rows):
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
 
 
+def global_length_hist(sub, layout, bin_lo, bin_hi):
+    """Center rule under position-range sharding: the aligned-length histogram of the WHOLE batch, from
+    which every rank derives the same slot / fixed-point tables (``map_batch(..., length_hist=...)``) so
+    that the sharded planes equal the unsharded ones bit for bit.  Every rank counts the reads of ``sub``
+    (its shard incl. halo, from :func:`shard_positions`) that START in its own range — each read of the
+    batch is owned by exactly one rank — and the 65536 counters are all-reduced (512 KB)."""
+    import torch
+    from .batch import meta_length_hist
+    c_of = np.searchsorted(sub.chrom_read_off, np.arange(len(sub)), side="right") - 1
+    g = layout.chrom_bin_off[c_of] + sub.ref_start.astype(np.int64)
+    owned = (g >= bin_lo) & (g < bin_hi)
+    hist = torch.from_numpy(meta_length_hist(sub.meta[owned]))
+    return allreduce_sum(hist).numpy()
+
+
 def mean_profile(col_sum, n_regions):
     """Multi-GPU ``--use_mean`` metagene profile: all-reduce numerators and counts, then divide."""
     allreduce_sum(col_sum)

@@ -138,6 +138,12 @@ def _worker(rank, world_size, port, results):
         assert allrows.shape == (37, 20)
         med = np.nanmedian(allrows.numpy(), axis=0)
         np.testing.assert_allclose(med, np.ma.median(np.ma.MaskedArray(mat, mask=mask), axis=0).filled(np.nan), rtol=1e-12)
+        # Center rule under position sharding: every rank ends up with the histogram of the whole batch
+        from plastid_b200.batch import meta_length_hist
+        lay = pb.GenomeLayout(chroms, lens)
+        for batch in (hb, spliced):
+            sub, lo, hi = pd.shard_positions(batch, lay, rank, world_size)
+            assert (pd.global_length_hist(sub, lay, lo, hi) == meta_length_hist(batch.meta)).all()
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
