@@ -746,11 +746,22 @@ def main():
         h2d = swire.nbytes
         resident = dbatch
 
+        s_chunks = Delta3SplicedReceiver.plan_chunks(swire, layout, max(1, min(args.e2e_chunks, n_reads // 8_000_000)))
+        s_copy = torch.cuda.Stream(device=device)
+        from plastid_b200.genome_array import map_center_streamed
+
         def e2e_step():
             nonlocal dbatch
-            dbatch = sreceiver.receive(spinned)
-            s, l = step()
-            dbatch = resident
+            if is_center:
+                # chunked upload; every chunk's final bin range is mapped (pb_map_center_range) while later chunks land
+                map_center_streamed(sreceiver, spinned, s_chunks, layout, fac, sf, ("+", "-"), planes, s_copy)
+                s, l = region_sums(planes, table)
+                if world > 1:
+                    dist.all_reduce(s)
+            else:
+                dbatch = sreceiver.receive(spinned)
+                s, l = step()
+                dbatch = resident
             h_sums.copy_(s, non_blocking=True)
             h_live.copy_(l, non_blocking=True)
             torch.cuda.synchronize()
@@ -862,8 +873,10 @@ def main():
                     "ms_per_step": float(t.item()), "steps": e2e_steps,
                     "host_format": ("%s (%.2f B/read), %d-chunk upload overlapped with pb_map_point_range"
                                     % (args.e2e_format, h2d / max(n_reads, 1), len(chunks)))
-                    if use_wire16 else ("delta3 + block words (%.2f B/read), whole batch uploaded before the binned path starts"
-                                        % (h2d / max(n_reads, 1)) if args.e2e_format == "delta3" else "SoA (8 B/read + blocks)")},
+                    if use_wire16 else (("delta3 + block words (%.2f B/read), %s" % (
+                        h2d / max(n_reads, 1), ("%d-chunk upload overlapped with pb_map_center_range" % len(s_chunks)) if is_center
+                        else "whole batch uploaded before the binned path starts"))
+                        if args.e2e_format == "delta3" else "SoA (8 B/read + blocks)")},
             "gpu_launches": len(kernels_per_step) * args.steps, "kernels_per_step": kernels_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}
     if graph_ms is not None:

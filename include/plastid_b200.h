@@ -215,6 +215,14 @@ size_t pb_unpack_blocks_workspace_bytes(int64_t n_reads);
 int pb_unpack_blocks(const uint32_t *meta, int64_t n_reads, const uint32_t *bwords, int64_t n_rows,
                      const uint32_t *bexc_row, const int32_t *bexc, int64_t n_exc,
                      uint32_t *blk_off_out, int32_t *blk_out, void *workspace, size_t workspace_bytes, void *stream);
+/* The same for the reads [read_begin, read_end) of a batch that is still being uploaded: row_base = number of
+ * block rows of the reads before read_begin (the sender knows it); writes blk_off[read_begin .. read_end] and
+ * the rows of these reads.  Workspace: pb_unpack_blocks_workspace_bytes(read_end - read_begin). */
+int pb_unpack_blocks_range(const uint32_t *meta, int64_t n_reads, int64_t read_begin, int64_t read_end,
+                           int64_t row_base, const uint32_t *bwords, int64_t n_rows,
+                           const uint32_t *bexc_row, const int32_t *bexc, int64_t n_exc,
+                           uint32_t *blk_off_out, int32_t *blk_out, void *workspace, size_t workspace_bytes,
+                           void *stream);
 
 /* Host side (no CUDA): pack a sorted unspliced SoA batch (HOST arrays) into the delta3 streams above, on
  * n_threads host threads (0 = all).  Caller-owned HOST buffers sized for the worst case: packed
@@ -271,18 +279,21 @@ int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layout, const pb
 /* pb_map_center / pb_map_center_fixed over the bins [bin_begin, bin_end) only (multiples of PB_LAYOUT_ALIGN):
  * the Center rule for one rank of a position-sharded genome.  Same contract as
  * pb_map_point_range for plane pointers (the address bin 0 WOULD have) and statistics (reads are counted by
- * the range holding their start, so ranges add up); every read of the batch must be resident.  A bin's
- * value depends only on the reads covering it, so ranges reproduce the whole-genome planes bit for bit. */
+ * the range holding their start, so ranges add up).  A bin's value depends only on the reads covering it, so
+ * ranges reproduce the whole-genome planes bit for bit.  Only the reads [read_begin, read_limit) are looked at
+ * (0 and -1 = all): a streamed upload of a sorted batch maps the bins below the start of read `read_limit`
+ * from the reads that have landed, and may skip the reads before read_begin when it knows that they end
+ * before bin_begin (their reference span, introns included, lies below it). */
 int pb_map_center_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
                         const int16_t *slot_of_len, const double *inv_m, int n_slots,
                         double *out_plus, double *out_minus, double *out_any,
                         uint64_t *stats, void *workspace, size_t workspace_bytes,
-                        int64_t bin_begin, int64_t bin_end, void *stream);
+                        int64_t bin_begin, int64_t bin_end, int64_t read_begin, int64_t read_limit, void *stream);
 int pb_map_center_fixed_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule, int planes,
                               const int16_t *slot_of_len, const int64_t *w_fix, int n_slots, int shift,
                               double *out_plus, double *out_minus, double *out_any,
                               uint64_t *stats, void *workspace, size_t workspace_bytes,
-                              int64_t bin_begin, int64_t bin_end, void *stream);
+                              int64_t bin_begin, int64_t bin_end, int64_t read_begin, int64_t read_limit, void *stream);
 
 /* Measurement hook (bench.py roofline): while enabled, pb_map_point / pb_map_center bracket their
  * tiles kernel with CUDA events on the launch stream (up to 256 launches since the last enable);

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "pb_unpack_delta3": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "pb_unpack_blocks_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "pb_unpack_blocks": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
+    "pb_unpack_blocks_range": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64,
+                                         _P, _P, _P, C.c_size_t, _P]),
     "pb_map_point_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
                                      _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, C.c_int64, C.c_int64, _P]),
     "pb_map_point": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
@@ -78,9 +80,11 @@ _SIGNATURES = {
     "pb_map_center_fixed": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
                                       _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pb_map_center_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
-                                      _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, C.c_int64, _P]),
+                                      _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, C.c_int64, C.c_int64,
+                                      C.c_int64, _P]),
     "pb_map_center_fixed_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int,
-                                            _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, C.c_int64, _P]),
+                                            _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, C.c_int64, C.c_int64,
+                                            C.c_int64, C.c_int64, _P]),
     "pb_enable_kernel_timing": (None, [C.c_int]),
     "pb_tiles_kernel_ms_total": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "pb_map_segment": (C.c_int, [C.POINTER(PbBatch), C.c_int64, C.c_int64, C.POINTER(PbRule), C.c_int, C.c_int,

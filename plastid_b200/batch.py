@@ -682,6 +682,7 @@ class Delta3SplicedBatch(object):
     def __init__(self, base, bwords, bexc_row, bexc, max_block_len):
         self.base = base                                   # Delta3Batch of (ref_start, meta)
         self.length_hist = None                            # set by from_batch: reads per aligned length
+        self.row_of_read = None                            # host only (chunk planning): block rows before each read
         self.bwords = np.ascontiguousarray(bwords, dtype=np.uint32)
         self.bexc_row = np.ascontiguousarray(bexc_row, dtype=np.uint32)
         self.bexc = np.ascontiguousarray(bexc, dtype=np.int32).reshape(-1, 2)
@@ -703,6 +704,7 @@ class Delta3SplicedBatch(object):
         if hb.blk is None or len(hb.blk) == 0:
             out = cls(base, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros((0, 2), np.int32), hb.max_block_len)
             out.length_hist = hist
+            out.row_of_read = np.zeros(len(hb) + 1, dtype=np.int64)
             return out
         rel, ln = hb.blk[:, 0].astype(np.int64), hb.blk[:, 1].astype(np.int64)
         n_rows = len(rel)
@@ -721,6 +723,7 @@ class Delta3SplicedBatch(object):
         out = cls(base, words, rows.astype(np.uint32), np.stack([gap[rows], ln[rows]], axis=1).astype(np.int32),
                   hb.max_block_len)
         out.length_hist = hist
+        out.row_of_read = hb.blk_off.astype(np.int64)
         return out
 
     def pinned(self):
@@ -756,20 +759,64 @@ class Delta3SplicedReceiver(object):
 
     def receive(self, pinned):
         """Enqueue the H2D copies of one whole batch and its expansion on the current stream."""
-        n, rows, n_exc = self.batch.n_reads, len(self.wire.bwords), len(self.wire.bexc_row)
+        n = self.batch.n_reads
+        self.receive_tables(pinned)
+        self._copy_chunk(pinned, 0, n)
+        self.unpack_chunk(0, n)
+        return self.batch
+
+    # ---- chunked interface (map_center_streamed): same roles as Delta8Receiver's -----------------------------
+    @staticmethod
+    def plan_chunks(wire, layout, n_chunks, weights=None):
+        """``[(read_a, read_b, bin_a, bin_b), ...]`` like :meth:`Delta8Receiver.plan_chunks`: bins below bin_b
+        are final once reads [0, read_b) have landed (aligned positions never lie before a read's start)."""
+        return Delta3Receiver.plan_chunks(wire.base, layout, n_chunks, weights)
+
+    def receive_tables(self, pinned):
+        """Dictionary, chromosome offsets and the (rare) block exceptions: needed by every chunk."""
+        n_exc = len(self.wire.bexc_row)
         self.inner._receive_tables(pinned)
-        self.inner._copy_range(pinned, 0, n)
-        if rows:
-            self.bwords[:rows].copy_(pinned["bwords"][:rows], non_blocking=True)
         if n_exc:
             self.bexc_row[:n_exc].copy_(pinned["bexc_row"][:n_exc], non_blocking=True)
             self.bexc[:2 * n_exc].copy_(pinned["bexc"][:2 * n_exc], non_blocking=True)
-        self.inner._unpack(0, n)
-        _lib.check(_lib.lib().pb_unpack_blocks(_lib.ptr(self.batch.meta), n, _lib.ptr(self.bwords), rows,
-                                               _lib.ptr(self.bexc_row), _lib.ptr(self.bexc), n_exc,
-                                               _lib.ptr(self.batch.blk_off), _lib.ptr(self.batch.blk) if rows else None,
-                                               _lib.ptr(self.ws), self.ws_bytes, _lib.stream_ptr()))
-        return self.batch
+
+    def _copy_chunk(self, pinned, a, b):
+        self.inner._copy_range(pinned, a, b)
+        r0, r1 = int(self.wire.row_of_read[a]), int(self.wire.row_of_read[b])
+        if r1 > r0:
+            self.bwords[r0:r1].copy_(pinned["bwords"][r0:r1], non_blocking=True)
+
+    def receive_chunk(self, pinned, a, b, copy_stream):
+        """H2D of reads [a,b) and their block words on ``copy_stream``; returns the event to wait for."""
+        import torch
+        with torch.cuda.stream(copy_stream):
+            self._copy_chunk(pinned, a, b)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def unpack_chunk(self, a, b):
+        """Expand reads [a,b) (a a multiple of 128) on the current stream: start / meta, then blk_off / blk."""
+        rows, n_exc = len(self.wire.bwords), len(self.wire.bexc_row)
+        self.inner._unpack(a, b)
+        _lib.check(_lib.lib().pb_unpack_blocks_range(_lib.ptr(self.batch.meta), self.batch.n_reads, int(a), int(b),
+                                                     int(self.wire.row_of_read[a]), _lib.ptr(self.bwords), rows,
+                                                     _lib.ptr(self.bexc_row), _lib.ptr(self.bexc), n_exc,
+                                                     _lib.ptr(self.batch.blk_off), _lib.ptr(self.batch.blk) if rows else None,
+                                                     _lib.ptr(self.ws), self.ws_bytes, _lib.stream_ptr()))
+
+    def first_read_reaching(self, bin_a, layout):
+        """Index of a read at or before the first read that can put a base at or beyond global bin ``bin_a``:
+        reads are sorted, a read spans at most ``max_span`` positions, and the wire keeps the first start of
+        every 128-read block — the answer is the start of the block before the first block whose first read
+        starts within ``max_span`` of ``bin_a``."""
+        base = self.wire.base
+        cached = getattr(self, "_block_first_bin", None)
+        if cached is None or cached[0] is not layout:          # 0.8 M entries for 100 M reads: build once
+            cached = (layout, layout.chrom_bin_off[base.blk_chrom] + base.blk_first_start)      # ascending
+            self._block_first_bin = cached
+        j = int(np.searchsorted(cached[1], int(bin_a) - int(base.max_span), side="left"))
+        return max(j - 1, 0) * Delta3Batch.BLOCK
 
 
 def meta_length_hist(meta):

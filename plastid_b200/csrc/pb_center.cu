@@ -629,13 +629,16 @@ extern "C" int pb_map_center_range(const pb_batch *batch, const pb_layout *layou
                                    const int16_t *slot_of_len, const double *inv_m, int n_slots,
                                    double *out_plus, double *out_minus, double *out_any,
                                    uint64_t *stats, void *workspace, size_t workspace_bytes,
-                                   int64_t bin_begin, int64_t bin_end, void *stream_)
+                                   int64_t bin_begin, int64_t bin_end, int64_t read_begin, int64_t read_limit,
+                                   void *stream_)
 {
     int rc = pb_check_common(batch, layout, rule, planes);
     if (rc) return rc;
     rc = pb_check_bin_range(layout, bin_begin, bin_end, "pb_map_center_range");
     if (rc) return rc;
     if (bin_begin == bin_end) return PB_OK;
+    if (read_begin < 0) read_begin = 0;
+    if (read_limit < 0 || read_limit > batch->n_reads) read_limit = batch->n_reads;
     if (rule->kind != PB_RULE_CENTER || rule->param < 0) { pb_set_error("pb_map_center: need a center rule with nibble >= 0"); return PB_EINVAL; }
     if (!slot_of_len || (n_slots > 0 && !inv_m) || n_slots < 0 || n_slots > 32767) { pb_set_error("pb_map_center: bad slot tables"); return PB_EINVAL; }
     if (((planes & PB_PLANE_PLUS) && !out_plus) || ((planes & PB_PLANE_MINUS) && !out_minus) ||
@@ -678,9 +681,9 @@ extern "C" int pb_map_center_range(const pb_batch *batch, const pb_layout *layou
     const int lookback = (b.max_block_len + tile_bins - 1) / tile_bins;
 
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
-    rc = pb_launch_tile_index(b, lay, tile_bins, tile_lo, tile_hi, batch->n_reads, 0, ws, stream);
+    rc = pb_launch_tile_index(b, lay, tile_bins, tile_lo, tile_hi, read_limit, 0, ws, stream);
     if (rc) return rc;
-    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, tile_lo, tile_hi, ws, stream);
+    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, tile_lo, tile_hi, read_begin, read_limit, ws, stream);
     if (rc) return rc;
     pb_timing_begin(stream);
     if (ept == 16)
@@ -704,7 +707,7 @@ extern "C" int pb_map_center(const pb_batch *batch, const pb_layout *layout, con
 {
     if (!layout) { pb_set_error("pb_map_center: null argument"); return PB_EINVAL; }
     return pb_map_center_range(batch, layout, rule, planes, slot_of_len, inv_m, n_slots, out_plus, out_minus, out_any,
-                               stats, workspace, workspace_bytes, 0, layout->total_bins, stream_);
+                               stats, workspace, workspace_bytes, 0, layout->total_bins, 0, -1, stream_);
 }
 
 namespace {
@@ -741,13 +744,16 @@ extern "C" int pb_map_center_fixed_range(const pb_batch *batch, const pb_layout 
                                    const int16_t *slot_of_len, const int64_t *w_fix, int n_slots, int shift,
                                    double *out_plus, double *out_minus, double *out_any,
                                    uint64_t *stats, void *workspace, size_t workspace_bytes,
-                                   int64_t bin_begin, int64_t bin_end, void *stream_)
+                                   int64_t bin_begin, int64_t bin_end, int64_t read_begin, int64_t read_limit,
+                                   void *stream_)
 {
     int rc = pb_check_common(batch, layout, rule, planes);
     if (rc) return rc;
     rc = pb_check_bin_range(layout, bin_begin, bin_end, "pb_map_center_fixed_range");
     if (rc) return rc;
     if (bin_begin == bin_end) return PB_OK;
+    if (read_begin < 0) read_begin = 0;
+    if (read_limit < 0 || read_limit > batch->n_reads) read_limit = batch->n_reads;
     if (rule->kind != PB_RULE_CENTER || rule->param < 0) { pb_set_error("pb_map_center_fixed: need a center rule with nibble >= 0"); return PB_EINVAL; }
     if (!slot_of_len || !w_fix || n_slots < 1 || n_slots > 32767 || shift < 1 || shift > 62) {
         pb_set_error("pb_map_center_fixed: bad weight tables"); return PB_EINVAL;
@@ -773,9 +779,9 @@ extern "C" int pb_map_center_fixed_range(const pb_batch *batch, const pb_layout 
     const double scale = ldexp(1.0, -shift);
 
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
-    rc = pb_launch_tile_index(b, lay, tile_bins, tile_lo, tile_hi, batch->n_reads, 0, ws, stream);
+    rc = pb_launch_tile_index(b, lay, tile_bins, tile_lo, tile_hi, read_limit, 0, ws, stream);
     if (rc) return rc;
-    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, tile_lo, tile_hi, ws, stream);
+    rc = pb_launch_binning(b, r, lay, planes, 1, slot_of_len, tile_bins, n_tiles, tile_lo, tile_hi, read_begin, read_limit, ws, stream);
     if (rc) return rc;
     pb_timing_begin(stream);
     const long long *w = reinterpret_cast<const long long *>(w_fix);
@@ -797,5 +803,5 @@ extern "C" int pb_map_center_fixed(const pb_batch *batch, const pb_layout *layou
 {
     if (!layout) { pb_set_error("pb_map_center_fixed: null argument"); return PB_EINVAL; }
     return pb_map_center_fixed_range(batch, layout, rule, planes, slot_of_len, w_fix, n_slots, shift, out_plus, out_minus,
-                                     out_any, stats, workspace, workspace_bytes, 0, layout->total_bins, stream_);
+                                     out_any, stats, workspace, workspace_bytes, 0, layout->total_bins, 0, -1, stream_);
 }

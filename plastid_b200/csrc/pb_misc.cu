@@ -423,6 +423,12 @@ __global__ void pb_block_counts_kernel(const uint32_t *__restrict__ meta, int64_
     counts[i] = nb > 1 ? (uint32_t)nb : 0u;           // the block table lists multi-block reads only
 }
 
+__global__ void pb_add_u32_kernel(uint32_t *__restrict__ v, int64_t n, uint32_t add)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += add;
+}
+
 __global__ void pb_unpack_blocks_kernel(const uint32_t *__restrict__ meta, int64_t n,
                                         const uint32_t *__restrict__ bwords, int64_t n_rows,
                                         const uint32_t *__restrict__ bexc_row, const int32_t *__restrict__ bexc,
@@ -462,32 +468,52 @@ extern "C" size_t pb_unpack_blocks_workspace_bytes(int64_t n_reads)
     return (size_t)(n_reads + pb_scan_part_entries(n_reads) + 16) * sizeof(uint32_t);
 }
 
-extern "C" int pb_unpack_blocks(const uint32_t *meta, int64_t n_reads, const uint32_t *bwords, int64_t n_rows,
-                                const uint32_t *bexc_row, const int32_t *bexc, int64_t n_exc,
-                                uint32_t *blk_off_out, int32_t *blk_out, void *workspace, size_t workspace_bytes,
-                                void *stream)
+extern "C" int pb_unpack_blocks_range(const uint32_t *meta, int64_t n_reads, int64_t read_begin, int64_t read_end,
+                                      int64_t row_base, const uint32_t *bwords, int64_t n_rows,
+                                      const uint32_t *bexc_row, const int32_t *bexc, int64_t n_exc,
+                                      uint32_t *blk_off_out, int32_t *blk_out, void *workspace, size_t workspace_bytes,
+                                      void *stream)
 {
     if (!meta || !blk_off_out || !workspace || n_reads < 0 || n_rows < 0 || n_exc < 0 ||
         (n_rows > 0 && (!bwords || !blk_out)) || (n_exc > 0 && (!bexc_row || !bexc))) {
         pb_set_error("pb_unpack_blocks: null argument or negative size"); return PB_EINVAL;
     }
-    if (workspace_bytes < pb_unpack_blocks_workspace_bytes(n_reads)) {
+    if (read_begin < 0 || read_end < read_begin || read_end > n_reads || row_base < 0 || row_base > n_rows) {
+        pb_set_error("pb_unpack_blocks: bad read range or row base"); return PB_EINVAL;
+    }
+    const int64_t n = read_end - read_begin;
+    if (workspace_bytes < pb_unpack_blocks_workspace_bytes(n)) {
         pb_set_error("pb_unpack_blocks: workspace too small"); return PB_ENOSPACE;
     }
     if (n_reads >= ((int64_t)1 << 32) || n_rows >= ((int64_t)1 << 32)) {
         pb_set_error("pb_unpack_blocks: block offsets are 32-bit"); return PB_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_reads == 0) { PB_CUDA_CHECK(cudaMemsetAsync(blk_off_out, 0, sizeof(uint32_t), st)); return PB_OK; }
+    if (n == 0) {
+        if (read_begin == 0) PB_CUDA_CHECK(cudaMemsetAsync(blk_off_out, 0, sizeof(uint32_t), st));
+        return PB_OK;
+    }
+    // blk_off[read_begin .. read_end] = row_base + exclusive scan of the block counts of these reads
     uint32_t *counts = (uint32_t *)workspace;
-    uint32_t *part = counts + n_reads;
-    const unsigned grid = (unsigned)((n_reads + 255) / 256);
-    pb_block_counts_kernel<<<grid, 256, 0, st>>>(meta, n_reads, counts);
-    int rc = pb_launch_exclusive_scan_u32(counts, blk_off_out, part, n_reads, st);
+    uint32_t *part = counts + n;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    pb_block_counts_kernel<<<grid, 256, 0, st>>>(meta + read_begin, n, counts);
+    int rc = pb_launch_exclusive_scan_u32(counts, blk_off_out + read_begin, part, n, st);
     if (rc != PB_OK) return rc;
+    if (row_base > 0)
+        pb_add_u32_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(blk_off_out + read_begin, n + 1, (uint32_t)row_base);
     if (n_rows > 0)
-        pb_unpack_blocks_kernel<<<grid, 256, 0, st>>>(meta, n_reads, bwords, n_rows, bexc_row, bexc, n_exc, blk_off_out,
-                                                      (int2 *)blk_out);
+        pb_unpack_blocks_kernel<<<grid, 256, 0, st>>>(meta + read_begin, n, bwords, n_rows, bexc_row, bexc, n_exc,
+                                                      blk_off_out + read_begin, (int2 *)blk_out);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
+}
+
+extern "C" int pb_unpack_blocks(const uint32_t *meta, int64_t n_reads, const uint32_t *bwords, int64_t n_rows,
+                                const uint32_t *bexc_row, const int32_t *bexc, int64_t n_exc,
+                                uint32_t *blk_off_out, int32_t *blk_out, void *workspace, size_t workspace_bytes,
+                                void *stream)
+{
+    return pb_unpack_blocks_range(meta, n_reads, 0, n_reads, 0, bwords, n_rows, bexc_row, bexc, n_exc, blk_off_out,
+                                  blk_out, workspace, workspace_bytes, stream);
 }

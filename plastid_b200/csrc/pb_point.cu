@@ -316,7 +316,7 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
     if (rc) return rc;
     // multi-block (spliced) reads: map them once and bin their sites by tile
     rc = pb_launch_binning(b, r, lay, planes, 0, nullptr, kPTileBins, layout->total_bins / kPTileBins, tile_begin, n_tiles,
-                           ws, stream);
+                           0, b.n_reads, ws, stream);
     if (rc) return rc;
     const int n_planes = __builtin_popcount(planes);
     const size_t smem = (size_t)n_planes * kPTileBins * sizeof(uint32_t);

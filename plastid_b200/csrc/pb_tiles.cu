@@ -60,7 +60,8 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
 template <bool CENTER, int OCC>
 __global__ void __launch_bounds__(256, OCC)   // latency-bound gather chains: resident threads vs registers (OCC CTAs/SM)
 pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t *__restrict__ slot_of_len,
-              int tile_shift, int64_t tile_lo, int64_t tile_hi, int64_t tile_rec_lo, int fill, uint32_t *__restrict__ rec_cursor,
+              int tile_shift, int64_t tile_lo, int64_t tile_hi, int64_t tile_rec_lo, int64_t read_begin, int fill,
+              uint32_t *__restrict__ rec_cursor,
               const uint32_t *__restrict__ rec_off, PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
 {
     // [tile_lo, tile_hi): the tiles this launch produces (position-sharded ranks map a bin range only);
@@ -81,14 +82,17 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
     // a lane's read indices only grow: the chromosome of the previous read is the place to start from
     int c = 0;
     int64_t c_end = __ldg(b.chrom_read_off + 1);
-    for (int64_t q = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); q * (kU * 32) < b.n_reads; q += n_warps) {
+    // reads [read_begin, b.n_reads) are looked at (a streamed upload maps a bin range from the reads that can
+    // reach it: those before read_begin end before the range, those from b.n_reads on have not arrived)
+    for (int64_t q = read_begin / (kU * 32) + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+         q * (kU * 32) < b.n_reads; q += n_warps) {
       const int64_t r0 = q * (kU * 32);
       uint32_t mv[kU], kv[kU];
       int32_t sv[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
           const int64_t i = r0 + u * 32 + lane;
-          const bool ok = i < b.n_reads;
+          const bool ok = i >= read_begin && i < b.n_reads;
           mv[u] = ok ? __ldg(b.meta + i) : 0u;
           sv[u] = ok ? __ldg(b.ref_start + i) : 0;
           kv[u] = ok ? __ldg(b.blk_off + i) : 0u;
@@ -435,13 +439,18 @@ int pb_launch_tile_index(const PbReads &b, const PbLayoutDev &lay, int tile_bins
 
 int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes, int center,
                       const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, int64_t tile_lo, int64_t tile_hi,
-                      const PbWorkspace &ws, cudaStream_t stream)
+                      int64_t read_begin, int64_t read_limit, const PbWorkspace &ws, cudaStream_t stream)
 {
     if (!b.blk_off || b.n_blk <= 0 || b.n_reads == 0) return PB_OK;
+    if (read_begin < 0) read_begin = 0;
+    if (read_limit < 0 || read_limit > b.n_reads) read_limit = b.n_reads;
+    PbReads bw = b;                       // the kernel's loop bound: reads from read_limit on have not arrived
+    bw.n_reads = read_limit;
     int sms = 0;
     int rc = pb_sm_count(&sms);
     if (rc) return rc;
-    int64_t want = (b.n_reads + 255) / 256;
+    int64_t want = (read_limit - read_begin + 255) / 256;
+    if (want < 1) want = 1;
     unsigned grid = (unsigned)(want < (int64_t)sms * 32 ? want : (int64_t)sms * 32);
     PB_CUDA_CHECK(cudaMemsetAsync(ws.rec_cursor, 0, (size_t)(n_tiles + 1) * sizeof(uint32_t), stream));
     int tile_shift = 0;
@@ -455,7 +464,7 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
     int occ_sel = 8;
     if (const char *e = getenv("PB_BIN_OCC")) occ_sel = atoi(e);        // measurement override (profiles/NOTES)
     for (int fill = 0; fill < 2; ++fill) {
-#define PB_BIN_LAUNCH(C_, O_) pb_bin_kernel<C_, O_><<<grid, 256, 0, stream>>>(b, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, tile_rec_lo, fill, ws.rec_cursor, ws.rec_off, ws.recs, ws.slots)
+#define PB_BIN_LAUNCH(C_, O_) pb_bin_kernel<C_, O_><<<grid, 256, 0, stream>>>(bw, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, tile_rec_lo, read_begin, fill, ws.rec_cursor, ws.rec_off, ws.recs, ws.slots)
         if (center) {
             if (occ_sel == 4) PB_BIN_LAUNCH(true, 4); else if (occ_sel == 6) PB_BIN_LAUNCH(true, 6); else PB_BIN_LAUNCH(true, 8);
         } else {

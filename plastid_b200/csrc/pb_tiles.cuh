@@ -62,7 +62,7 @@ int pb_launch_tile_index(const PbReads &b, const PbLayoutDev &lay, int tile_bins
 // Only records (and statistics) of tiles [tile_lo, tile_hi) are produced.
 int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &lay, int planes, int center,
                       const int16_t *slot_of_len, int tile_bins, int64_t n_tiles, int64_t tile_lo, int64_t tile_hi,
-                      const PbWorkspace &ws, cudaStream_t stream);
+                      int64_t read_begin, int64_t read_limit, const PbWorkspace &ws, cudaStream_t stream);
 int pb_launch_stats_finish(const unsigned long long *slots, unsigned long long *stats, cudaStream_t stream);
 // exclusive prefix sums of uint32 counts (three small launches); part needs pb_scan_part_entries(n) words
 int64_t pb_scan_part_entries(int64_t n);

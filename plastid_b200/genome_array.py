@@ -128,36 +128,15 @@ def map_batch(dbatch, layout, factory, size_filter=None, strands=("+", "-"), pla
     elif is_center:
         if length_hist is None and getattr(dbatch, "length_hist", None) is not None and not os.environ.get("PB_MEASURE_HIST"):
             # the batch came with its histogram (decoder / receiver metadata): apply the size filter to it
-            h_hist = dbatch.length_hist.copy()
-            if size_filter is not None:
-                lens_ = np.arange(65536)
-                keep = lens_ >= size_filter.min_
-                if size_filter.max_ != -1:
-                    keep &= lens_ <= size_filter.max_
-                h_hist[~keep] = 0
+            h_hist = _filtered_hist(dbatch.length_hist, size_filter)
         elif length_hist is None:
             h_hist = length_histogram(dbatch, factory, size_filter)
         else:
             h_hist = np.ascontiguousarray(length_hist, dtype=np.int64)
             if h_hist.shape != (65536,):
                 raise ValueError("length_hist must have 65536 entries")
-        fixed = factory.fixed_point_tables(h_hist)
-        aligned = all(planes.planes[s].data_ptr() % 32 == 0 for s in strands)
-        if fixed is not None and aligned and not os.environ.get("PB_CENTER_EXACT"):
-            # many map lengths: one pass with 64-bit fixed-point weights (rel. error <= 1e-9, see the header)
-            slot_of_len, w_fix, shift = fixed
-            d_slot, d_w = torch.from_numpy(slot_of_len).to(dev), torch.from_numpy(w_fix).to(dev)
-            _lib.check(L.pb_map_center_fixed_range(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot),
-                                                   _lib.ptr(d_w), len(w_fix), shift, outs[0], outs[1], outs[2],
-                                                   _lib.ptr(stats), _lib.ptr(ws), ws_bytes, planes.bin_lo, planes.bin_hi,
-                                                   _lib.stream_ptr()))
-        else:
-            slot_of_len, inv_m = factory.slot_tables(h_hist)
-            d_slot = torch.from_numpy(slot_of_len).to(dev)
-            d_inv = torch.from_numpy(inv_m if len(inv_m) else np.zeros(1)).to(dev)
-            _lib.check(L.pb_map_center_range(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_inv),
-                                             len(inv_m), outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
-                                             planes.bin_lo, planes.bin_hi, _lib.stream_ptr()))
+        launch = _center_launcher(factory, h_hist, planes, strands, dev)
+        launch(b, lay, rule, mask, outs, stats, ws, ws_bytes, planes.bin_lo, planes.bin_hi, 0, -1)
     else:
         _lib.check(L.pb_map_point(C.byref(b), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
                                   _lib.ptr(stats), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
@@ -216,6 +195,112 @@ def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=N
             _lib.check(L.pb_map_point_range(C.byref(b_c), C.byref(lay), C.byref(rule), mask, outs[0], outs[1], outs[2],
                                             _lib.ptr(stats[k % n_lanes]), _lib.ptr(ws[k % n_lanes]), ws_bytes, bin_a, bin_b, b,
                                             _lib.stream_ptr()))
+    for ln in lanes[1:]:
+        compute.wait_stream(ln)
+    total = stats[0]
+    for st in stats[1:]:
+        dropped_len = torch.maximum(total[_lib.PB_STAT_DROPPED_LEN], st[_lib.PB_STAT_DROPPED_LEN])
+        total = total + st
+        total[_lib.PB_STAT_DROPPED_LEN] = dropped_len
+    planes.stats_dev = total
+    return planes
+
+
+def _center_launcher(factory, h_hist, planes, strands, dev):
+    """Slot / fixed-point tables of the Center rule for a batch with length histogram ``h_hist`` (uploaded
+    once) -> ``launch(batch, layout, rule, mask, outs, stats, ws, ws_bytes, bin_lo, bin_hi, read_begin,
+    read_limit)`` enqueueing ``pb_map_center_range`` / ``pb_map_center_fixed_range`` on the current stream."""
+    import torch
+    L = _lib.lib()
+    fixed = factory.fixed_point_tables(h_hist)
+    aligned = all(planes.planes[s].data_ptr() % 32 == 0 for s in strands)
+    if fixed is not None and aligned and not os.environ.get("PB_CENTER_EXACT"):
+        # many map lengths: one pass with 64-bit fixed-point weights (rel. error <= 1e-9, see the header)
+        slot_of_len, w_fix, shift = fixed
+        d_slot, d_w = torch.from_numpy(slot_of_len).to(dev), torch.from_numpy(w_fix).to(dev)
+
+        def launch(b, lay, rule, mask, outs, stats, ws, ws_bytes, bin_lo, bin_hi, read_begin, read_limit):
+            _lib.check(L.pb_map_center_fixed_range(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot),
+                                                   _lib.ptr(d_w), len(w_fix), shift, outs[0], outs[1], outs[2],
+                                                   _lib.ptr(stats), _lib.ptr(ws), ws_bytes, int(bin_lo), int(bin_hi),
+                                                   int(read_begin), int(read_limit), _lib.stream_ptr()))
+    else:
+        slot_of_len, inv_m = factory.slot_tables(h_hist)
+        d_slot = torch.from_numpy(slot_of_len).to(dev)
+        d_inv = torch.from_numpy(inv_m if len(inv_m) else np.zeros(1)).to(dev)
+
+        def launch(b, lay, rule, mask, outs, stats, ws, ws_bytes, bin_lo, bin_hi, read_begin, read_limit):
+            _lib.check(L.pb_map_center_range(C.byref(b), C.byref(lay), C.byref(rule), mask, _lib.ptr(d_slot), _lib.ptr(d_inv),
+                                             len(inv_m), outs[0], outs[1], outs[2], _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
+                                             int(bin_lo), int(bin_hi), int(read_begin), int(read_limit), _lib.stream_ptr()))
+    return launch
+
+
+def _filtered_hist(hist, size_filter):
+    """Batch-metadata histogram with the size filter applied (what ``pb_length_hist`` would measure)."""
+    h = np.ascontiguousarray(hist, dtype=np.int64).copy()
+    if size_filter is not None:
+        lens_ = np.arange(65536)
+        keep = lens_ >= size_filter.min_
+        if size_filter.max_ != -1:
+            keep &= lens_ <= size_filter.max_
+        h[~keep] = 0
+    return h
+
+
+def map_center_streamed(receiver, pinned, chunks, layout, factory, size_filter=None, strands=("+", "-"),
+                        planes=None, copy_stream=None):
+    """Center rule over a batch WITH multi-block reads that is still being uploaded
+    (``Delta3SplicedReceiver``): chunk by chunk on ``copy_stream``; as soon as a chunk's reads and block
+    words have landed and are expanded, the bins below the next chunk's first read are final and are
+    produced with ``pb_map_center_range`` from the reads that can reach them (read window = from one
+    128-read block before the first read within ``max_span`` of the range).  Two compute lanes take the
+    chunks alternately.  Same result, bit for bit, as :func:`map_batch` on the whole batch."""
+    import torch
+    _lib.require_cuda()
+    if not isinstance(factory, CenterMapFactory):
+        raise TypeError("map_center_streamed is the Center rule's streamed path")
+    dbatch = receiver.batch
+    if dbatch.length_hist is None:
+        raise ValueError("the transfer format must carry the batch's length histogram")
+    dev = dbatch.device
+    if planes is None:
+        planes = CountPlanes(layout, "f64", dev)
+    planes.alloc(strands)
+    mask = 0
+    for s in strands:
+        mask |= _lib.STRAND_PLANE[s]
+    launch = _center_launcher(factory, _filtered_hist(dbatch.length_hist, size_filter), planes, strands, dev)
+    L = _lib.lib()
+    ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, dbatch.n_blk, dbatch.n_reads)
+    n_lanes = 2 if len(chunks) > 1 else 1
+    ws = [_workspace(dev, ws_bytes, slot=j) for j in range(n_lanes)]
+    stats = [torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev) for _ in range(n_lanes)]
+    copy_stream = copy_stream or torch.cuda.Stream(device=dev)
+    compute = torch.cuda.current_stream()
+    lanes = [compute] + [_side_stream(dev, j) for j in range(1, n_lanes)]
+    copy_stream.wait_stream(compute)
+    for ln in lanes[1:]:
+        ln.wait_stream(compute)
+    with torch.cuda.stream(copy_stream):
+        receiver.receive_tables(pinned)
+    events = [receiver.receive_chunk(pinned, a, b, copy_stream) for a, b, _x, _y in chunks]
+    b_c, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
+    outs = [planes.plane_ptr(s) if s in strands else None for s in _STRANDS]
+    unpacked = None
+    for k, ((a, b, bin_a, bin_b), ev) in enumerate(zip(chunks, events)):
+        ln = lanes[k % n_lanes]
+        with torch.cuda.stream(ln):
+            ln.wait_event(ev)
+            if unpacked is not None:
+                # expansions run one after the other (they share the receiver's scan workspace), and the read
+                # window of this chunk reaches back into the previous one
+                ln.wait_event(unpacked)
+            receiver.unpack_chunk(a, b)
+            unpacked = torch.cuda.Event()
+            unpacked.record(ln)
+            launch(b_c, lay, rule, mask, outs, stats[k % n_lanes], ws[k % n_lanes], ws_bytes, bin_a, bin_b,
+                   receiver.first_read_reaching(bin_a, layout), b)
     for ln in lanes[1:]:
         compute.wait_stream(ln)
     total = stats[0]

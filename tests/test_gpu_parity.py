@@ -947,3 +947,59 @@ def test_center_tables_from_batch_metadata_equal_device_histogram(small_world, c
             for s in ("+", "-"):
                 assert torch.equal(with_meta.planes[s], measured.planes[s])
             assert (with_meta.stats == measured.stats).all()
+
+
+def test_center_streamed_upload_many_chunks_repeated(cuda_device):
+    """The same at a size where chunks of both compute lanes are in flight together: 2 M spliced reads, 12
+    and 24 chunks, repeated — every repeat must reproduce the whole-batch planes bit for bit."""
+    import torch
+    from plastid_b200.batch import Delta3SplicedBatch, Delta3SplicedReceiver, DeviceBatch
+    from plastid_b200.genome_array import map_center_streamed
+    chroms, lens = synth.human_like_genome(0.02)
+    lay = pb.GenomeLayout(chroms, lens)
+    dbatch = synth.rnaseq_reads(chroms, lens, 2_000_000, seed=21, device=cuda_device)
+    hb = synth.device_batch_to_host(dbatch, chroms, lens)
+    fac = pb.CenterMapFactory(12)
+    whole = map_batch(dbatch, lay, fac, None, strands=("+", "-"))
+    wire = Delta3SplicedBatch.from_batch(hb)
+    rx = Delta3SplicedReceiver(wire, cuda_device)
+    pinned = wire.pinned()
+    planes = None
+    for n_chunks in (12, 24):
+        chunks = Delta3SplicedReceiver.plan_chunks(wire, lay, n_chunks)
+        assert len(chunks) == n_chunks
+        for rep in range(4):
+            planes = map_center_streamed(rx, pinned, chunks, lay, fac, None, ("+", "-"), planes)
+            torch.cuda.synchronize()
+            for s in ("+", "-"):
+                assert torch.equal(planes.planes[s], whole.planes[s]), (n_chunks, rep, s)
+            assert (planes.stats_dev.cpu().numpy()[:7] == whole.stats[:7]).all()
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3, 7])
+def test_center_streamed_upload_matches_whole_batch(small_world, cuda_device, n_chunks):
+    """map_center_streamed: a spliced batch uploaded chunk by chunk (delta3 + block words), every chunk's
+    final bin range produced with pb_map_center_range from a read window — planes, statistics and the
+    rebuilt block table equal the whole-batch path bit for bit."""
+    import torch
+    from plastid_b200.batch import Delta3SplicedBatch, Delta3SplicedReceiver, DeviceBatch
+    from plastid_b200.genome_array import map_center_streamed
+    w = small_world
+    lay = w["layout"]
+    hb = synth.device_batch_to_host(synth.rnaseq_reads(w["chroms"], w["lens"], 80_000, seed=6, device="cpu",
+                                                       intron=(50, 4000)), w["chroms"], w["lens"])
+    fac = pb.CenterMapFactory(12)
+    whole = map_batch(DeviceBatch.from_host(hb, cuda_device), lay, fac, None, strands=("+", "-"))
+    wire = Delta3SplicedBatch.from_batch(hb)
+    rx = Delta3SplicedReceiver(wire, cuda_device)
+    pinned = wire.pinned()
+    chunks = Delta3SplicedReceiver.plan_chunks(wire, lay, n_chunks)
+    assert len(chunks) >= min(n_chunks, 2) - 1 and chunks[0][0] == 0 and chunks[-1][1] == len(hb) and chunks[-1][3] == lay.total_bins
+    for _ in range(2):                                              # buffers and planes are reusable
+        planes = map_center_streamed(rx, pinned, chunks, lay, fac, None, ("+", "-"))
+        torch.cuda.synchronize()
+        for s in ("+", "-"):
+            assert torch.equal(planes.planes[s], whole.planes[s]), (n_chunks, s)
+        assert (planes.stats_dev.cpu().numpy()[:7] == whole.stats[:7]).all()
+        assert (rx.batch.blk_off.cpu().numpy().view(np.uint32) == hb.blk_off).all()
+        assert (rx.batch.blk.cpu().numpy() == hb.blk).all()
