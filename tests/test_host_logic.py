@@ -685,3 +685,33 @@ def test_segmentchain_coordinate_known_answers_from_the_reference_tests():
     assert nvca.get_subchain(2, 27).get_position_set() == {2, 15, 16, 17, 18, 20, 21, 22}
     assert set(og.get_subchain(oca, 2, 27).position_list) == {16, 17, 18, 20, 21, 22, 23, 29}
     assert set(og.get_subchain(ocn, 2, 27).position_list) == {2, 15, 16, 17, 18, 20, 21, 22}
+
+
+def test_spliced_chunk_plan_and_read_windows():
+    """Host side of map_center_streamed: the chunk plan of a spliced batch (bins below bin_b are final once
+    reads [0, read_b) have landed) and the read window of every chunk (no read before it can reach the
+    chunk's first bin), checked against the reads themselves."""
+    from plastid_b200.batch import Delta3SplicedBatch, Delta3SplicedReceiver
+    chroms, lens = synth.human_like_genome(0.005)
+    hb = synth.device_batch_to_host(synth.rnaseq_reads(chroms, lens, 300_000, seed=100, device="cpu"), chroms, lens)
+    wire = Delta3SplicedBatch.from_batch(hb)
+    lay = pb.GenomeLayout(chroms, lens)
+    assert wire.length_hist.sum() == len(hb) and (wire.row_of_read == hb.blk_off).all()
+    c_of = np.searchsorted(hb.chrom_read_off, np.arange(len(hb)), side="right") - 1
+    g = lay.chrom_bin_off[c_of] + hb.ref_start                      # global bin of every read's start
+
+    class Stub(object):                                             # first_read_reaching needs only .wire
+        pass
+    rx = Stub()
+    rx.wire = wire
+    for n in (1, 5, 12):
+        chunks = Delta3SplicedReceiver.plan_chunks(wire, lay, n)
+        assert chunks[0][0] == 0 and chunks[0][2] == 0 and chunks[-1][1] == len(hb) and chunks[-1][3] == lay.total_bins
+        for (a, b, bin_a, bin_b), nxt in zip(chunks, chunks[1:] + [None]):
+            assert a % 128 == 0 and bin_a % 16384 == 0 and bin_a < bin_b and a < b
+            if nxt is not None:
+                assert nxt[0] == b and nxt[2] == bin_b and g[b:].min() >= bin_b      # later reads start beyond bin_b
+            i0 = Delta3SplicedReceiver.first_read_reaching(rx, bin_a, lay)
+            reaching = np.flatnonzero(g + hb.max_span > bin_a)
+            assert i0 % 128 == 0 and (len(reaching) == 0 or i0 <= reaching[0])
+            assert i0 <= a
