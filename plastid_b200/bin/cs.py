@@ -29,7 +29,7 @@ def merge_genes(tx_ivcs):
             x = parent[x]
         return x
 
-    owner, scope = {}, {}
+    owner = {}
     for txid, chain in tx_ivcs.items():
         if chain.strand not in ("+", "-"):
             raise KeyError(chain.strand)           # the reference keeps '+' and '-' exon tables only (cs.py:203)
@@ -37,7 +37,6 @@ def merge_genes(tx_ivcs):
         parent.setdefault(gene, gene)
         for iv in chain:
             key = (chain.strand, chain.chrom, iv.start, iv.end)
-            scope.setdefault((chain.strand, chain.chrom), set()).add(gene)
             if key in owner:
                 a, b = find(owner[key]), find(gene)
                 if a != b:
@@ -75,7 +74,7 @@ def process_partial_group(transcripts, mask_hash=None, printer=None, device="cud
     txids = list(transcripts)
     txs = [transcripts[t] for t in txids]
     merged_genes = merge_genes(transcripts)
-    merged_gene_tx, gene_of_tx = {}, []
+    merged_gene_tx = {}
     for t, tx in zip(txids, txs):
         merged_gene_tx.setdefault(merged_genes[tx.get_gene()], []).append(t)
     gene_ids = list(merged_gene_tx)
