@@ -715,3 +715,26 @@ def test_spliced_chunk_plan_and_read_windows():
             reaching = np.flatnonzero(g + hb.max_span > bin_a)
             assert i0 % 128 == 0 and (len(reaching) == 0 or i0 <= reaching[0])
             assert i0 <= a
+
+
+def test_mask_accessors_known_answers_from_the_reference_tests():
+    """test_roitools.py:1037-1095 (get_masks, get_masks_as_segmentchain, reset_masks), transcribed."""
+    for strand in ("+", "-"):
+        def chain():
+            return pb.SegmentChain(pb.GenomicSegment("chrA", 100, 150, strand), pb.GenomicSegment("chrA", 250, 300, strand))
+        mask_a, mask_b = pb.GenomicSegment("chrA", 125, 150, strand), pb.GenomicSegment("chrA", 275, 300, strand)
+        ch = chain()
+        assert ch.get_masks() == []
+        assert len(ch.get_masks_as_segmentchain()) == 0 and isinstance(ch.get_masks_as_segmentchain(), pb.SegmentChain)
+        ch.add_masks(mask_a)
+        assert ch.get_masks() == [mask_a]
+        assert str(ch.get_masks_as_segmentchain()) == str(pb.SegmentChain(mask_a))
+        ch.reset_masks()
+        assert ch.get_masks() == []
+        ch.add_masks(mask_a, mask_b)
+        assert ch.get_masks() == [mask_a, mask_b]
+        assert str(ch.get_masks_as_segmentchain()) == str(pb.SegmentChain(mask_a, mask_b))
+        pre_length = ch.length
+        assert ch.masked_length == pre_length - len(mask_a) - len(mask_b)
+        ch.reset_masks()
+        assert ch.get_masks() == [] and ch.masked_length == pre_length
