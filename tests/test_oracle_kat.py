@@ -320,3 +320,27 @@ def test_merge_genes_host_matches_oracle():
     exp = og.merge_genes(otx)
     assert cs.merge_genes(ptx) == exp
     assert len(set(exp.values())) < len(exp) and any(v.count(",") == 2 for v in exp.values())   # pairs and a chain of three
+
+
+def test_merge_sets_known_answers_from_the_reference_tests():
+    """plastid/test/unit/util/services/test_sets.py:14-83, transcribed: the grouping step of `cs generate`
+    (merge_genes: genes sharing an exon are merged transitively).  Checked for the oracle's merge_sets and,
+    with every set turned into an exon shared by its member genes, for the product's union-find merge_genes."""
+    import plastid_b200 as pb
+    from plastid_b200.bin import cs
+    a = ["h", "abm", "c", "c", "bj", "i", "ko", "n", "go", "ik", "ei", "a", "dh", "l", "gjk", "f", "b", "gn", "dmp", "in"]
+    b = ["gm", "o", "ag", "f", "h", "h", "o", "bl", "e", "p", "j", "p", "k", "cf", "bc", "b", "ik", "g", "jm", "bn", "i",
+         "do", "bl", "a", "ap"]
+    exp_a = ["c", "f", "l", "abdeghijkmnop"]
+    exp_b = ["h", "e", "ik", "do", "bcfln", "agjmp"]
+    tform = lambda groups: frozenset(frozenset(g) for g in groups)          # noqa: E731
+    for sets, expected in ((a, exp_a), (b, exp_b)):
+        assert tform(og.merge_sets([set(s) for s in sets])) == tform(expected)
+        txs = {}
+        for k, members in enumerate(sets):
+            for gene in members:                                    # exon k belongs to a transcript of every member gene
+                name = "%s.%d" % (gene, k)
+                txs[name] = pb.Transcript(pb.GenomicSegment("chrA", 1000 * k, 1000 * k + 100, "+"), ID=name, gene_id=gene)
+        merged = cs.merge_genes(txs)
+        assert tform(v.split(",") for v in merged.values()) == tform(expected)
+        assert all(merged[g] == ",".join(sorted(merged[g].split(","))) for g in merged)
