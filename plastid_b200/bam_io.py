@@ -100,9 +100,11 @@ def _bgzf_block(data, level=6):
     return header + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data))
 
 
-def write_bam(path, chrom_lengths, records, block_bytes=60000):
+def write_bam(path, chrom_lengths, records, block_bytes=60000, record_aligned=False):
     """Write a BAM file.  ``chrom_lengths``: ordered ``{name: length}``; ``records``: iterable of
-    ``(chrom_index or -1, pos, flag, cigartuples)`` already in coordinate order."""
+    ``(chrom_index or -1, pos, flag, cigartuples)`` already in coordinate order.  ``record_aligned``:
+    start a new BGZF member rather than split a record across two, as htslib's writer does
+    (``bgzf_flush_try``); otherwise members are cut every ``block_bytes`` bytes wherever that falls."""
     chroms = list(chrom_lengths)
     text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (c, chrom_lengths[c]) for c in chroms)
     out = [b"BAM\x01", struct.pack("<i", len(text)), text.encode(), struct.pack("<i", len(chroms))]
@@ -119,10 +121,29 @@ def write_bam(path, chrom_lengths, records, block_bytes=60000):
         body = core + name + b"".join(struct.pack("<I", (n << 4) | op) for op, n in cigar)
         body += b"\x11" * ((qlen + 1) // 2) + b"\xff" * qlen
         out.append(struct.pack("<i", len(body)) + body)
-    data = b"".join(out)
+    n_head = 4 + len(chroms)
     with open(path, "wb") as fh:
-        for a in range(0, len(data), block_bytes):
-            fh.write(_bgzf_block(data[a:a + block_bytes]))
+        if record_aligned:
+            head = b"".join(out[:n_head])
+            for a in range(0, len(head), block_bytes):
+                fh.write(_bgzf_block(head[a:a + block_bytes]))
+            pending, size = [], 0
+            for rec in out[n_head:]:
+                if pending and size + len(rec) > block_bytes:
+                    fh.write(_bgzf_block(b"".join(pending)))
+                    pending, size = [], 0
+                if len(rec) > block_bytes:              # a record larger than a member has to span several
+                    for a in range(0, len(rec), block_bytes):
+                        fh.write(_bgzf_block(rec[a:a + block_bytes]))
+                    continue
+                pending.append(rec)
+                size += len(rec)
+            if pending:
+                fh.write(_bgzf_block(b"".join(pending)))
+        else:
+            data = b"".join(out)
+            for a in range(0, len(data), block_bytes):
+                fh.write(_bgzf_block(data[a:a + block_bytes]))
         fh.write(_bgzf_block(b""))          # EOF marker
 
 

@@ -171,11 +171,13 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
         const long v = atol(w);
         if (v >= (1 << 16)) kWindow = (size_t)v;
     }
+    size_t kWalkMin = (size_t)4 << 20;                 // plain bytes below which the record walk stays serial
+    if (const char *w = getenv("PB_BAM_WALK_MIN")) kWalkMin = (size_t)std::max(0l, atol(w));
     std::vector<uint8_t> comp(kWindow + (1 << 16));
     RawBuf plain;
     size_t comp_have = 0, carry = 0;
     bool eof = false, header_done = false;
-    int32_t last_tid = -1, last_pos = -1;
+    int32_t last_tid = -1;
     std::vector<uint32_t> nlisted_all;
     std::vector<int32_t> tid_all;
     int rc = PB_OK;
@@ -266,44 +268,106 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
             header_done = true;
             cur = p;
         }
-        // record boundaries in this window
-        std::vector<std::pair<size_t, uint32_t>> recs;
-        while (cur + 4 <= have) {
-            const uint32_t bs = rd32(plain.data() + cur);
-            if (cur + 4 + bs > have) break;
-            recs.emplace_back(cur + 4, bs);
-            cur += 4 + (size_t)bs;
+        // record boundaries in this window.  A record's size is only known from its own header, so the walk is a
+        // dependent chain of 4-byte loads; it is run speculatively in parallel: the window is cut at BGZF member
+        // boundaries (htslib starts a new member rather than splitting a record, so a member boundary is almost always
+        // a record boundary), every thread walks from its guess to the next cut, and a chain is accepted only when
+        // the walk before it arrives exactly at its first byte — otherwise that stretch is walked again serially
+        // from the true position.  Only the first record of every 65536 is noted; the conversion threads walk
+        // their own chunk again.
+        const size_t chunk = 1 << 16;
+        struct Chain { size_t begin = 0, limit = 0, end = 0; std::vector<std::pair<size_t, size_t>> chunks; };
+        auto walk = [&](Chain &c) {            // records starting in [begin, limit); 'end' = first byte not consumed
+            size_t at = c.begin, n_here = 0;
+            c.chunks.clear();
+            while (at < c.limit && at + 4 <= have) {
+                const uint32_t bs = rd32(plain.data() + at);
+                if (at + 4 + bs > have) break;
+                if ((n_here & (chunk - 1)) == 0) c.chunks.emplace_back(at, 0);
+                ++n_here;
+                c.chunks.back().second++;
+                at += 4 + (size_t)bs;
+            }
+            c.end = at;
+        };
+        std::vector<Chain> chains;
+        {
+            const size_t n_parts = (n_threads > 1 && have - cur >= kWalkMin) ? (size_t)n_threads : 1;
+            std::vector<size_t> cuts{cur};
+            for (size_t k = 1; k < n_parts; ++k) {
+                const size_t g = blocks[k * blocks.size() / n_parts].dst;
+                if (g > cuts.back()) cuts.push_back(g);
+            }
+            chains.resize(cuts.size());
+            for (size_t k = 0; k < cuts.size(); ++k) {
+                chains[k].begin = cuts[k];
+                chains[k].limit = k + 1 < cuts.size() ? cuts[k + 1] : have;
+            }
+            parallel_for(n_threads, chains.size(), [&](size_t k) { walk(chains[k]); });
+        }
+        std::vector<std::pair<size_t, size_t>> chunk_first;    // (first byte, records) per conversion chunk
+        size_t n_recs = 0;
+        for (size_t k = 0; k < chains.size(); ++k) {
+            Chain &c = chains[k];
+            if (c.begin != cur) {                                // guess missed: walk this stretch from the true position
+                if (cur >= c.limit) continue;                    // (a record reaching past the whole stretch)
+                c.begin = cur;
+                walk(c);
+            }
+            chunk_first.insert(chunk_first.end(), c.chunks.begin(), c.chunks.end());
+            for (const auto &ch : c.chunks) n_recs += ch.second;
+            cur = c.end;
+            if (cur < c.limit) break;                            // stopped at an incomplete record: the window ends here
         }
         t_walk += now() - ta; ta = now();
-        // convert in parallel, chunk by chunk, then append in order
-        const size_t chunk = 1 << 16;
-        const size_t n_chunks = (recs.size() + chunk - 1) / chunk;
+        // convert in parallel, chunk by chunk
+        const size_t n_chunks = chunk_first.size();
         std::vector<Decoded> parts(n_chunks);
         parallel_for(n_threads, n_chunks, [&](size_t ci) {
             Decoded &d = parts[ci];
-            const size_t a = ci * chunk, e = std::min(recs.size(), a + chunk);
-            d.start.reserve(e - a); d.meta.reserve(e - a); d.nlisted.reserve(e - a); d.tid.reserve(e - a);
-            for (size_t i = a; i < e && d.err.empty(); ++i) convert_record(plain.data() + recs[i].first, recs[i].second, d);
+            const size_t n_here = chunk_first[ci].second;
+            d.start.reserve(n_here); d.meta.reserve(n_here); d.nlisted.reserve(n_here); d.tid.reserve(n_here);
+            size_t at = chunk_first[ci].first;
+            for (size_t i = 0; i < n_here && d.err.empty(); ++i) {
+                const uint32_t bs = rd32(plain.data() + at);
+                convert_record(plain.data() + at + 4, bs, d);
+                at += 4 + (size_t)bs;
+            }
+            // coordinate order is a precondition (samtools sort): reference ids never decrease.  (A leading
+            // deletion can move a START past its successor; that is tolerated here and repaired below.)
+            for (size_t i = 1; i < d.tid.size() && d.err.empty(); ++i)
+                if (d.tid[i] < d.tid[i - 1]) d.err = "BAM file is not coordinate-sorted";
         });
         t_conv += now() - ta; ta = now();
-        for (Decoded &d : parts) {
+        // append in order: sizes -> offsets -> parallel copies into the grown arrays
+        std::vector<size_t> at_read(n_chunks + 1, h->start.size()), at_blk(n_chunks + 1, h->blk.size());
+        for (size_t ci = 0; ci < n_chunks && rc == PB_OK; ++ci) {
+            Decoded &d = parts[ci];
             if (!d.err.empty()) { err = d.err; rc = PB_EINVAL; break; }
-            for (size_t i = 0; i < d.start.size(); ++i) {     // coordinate order is a precondition (samtools sort)
-                if (d.tid[i] < last_tid || (d.tid[i] == last_tid && d.start[i] < last_pos)) {
-                    // a leading deletion can move a start past its successor; tolerate, fix below
-                    if (d.tid[i] < last_tid) { err = "BAM file is not coordinate-sorted"; rc = PB_EINVAL; break; }
-                }
-                last_tid = d.tid[i]; last_pos = d.start[i];
+            if (!d.tid.empty()) {
+                if (d.tid.front() < last_tid) { err = "BAM file is not coordinate-sorted"; rc = PB_EINVAL; break; }
+                last_tid = d.tid.back();
             }
-            if (rc) break;
-            h->start.insert(h->start.end(), d.start.begin(), d.start.end());
-            h->meta.insert(h->meta.end(), d.meta.begin(), d.meta.end());
-            h->blk.insert(h->blk.end(), d.blk.begin(), d.blk.end());
-            nlisted_all.insert(nlisted_all.end(), d.nlisted.begin(), d.nlisted.end());
-            tid_all.insert(tid_all.end(), d.tid.begin(), d.tid.end());
+            at_read[ci + 1] = at_read[ci] + d.start.size();
+            at_blk[ci + 1] = at_blk[ci] + d.blk.size();
             h->mapped += d.mapped; h->skipped += d.skipped;
             h->max_span = std::max(h->max_span, d.max_span);
         }
+        if (rc) break;
+        h->start.resize(at_read[n_chunks]); h->meta.resize(at_read[n_chunks]);
+        nlisted_all.resize(at_read[n_chunks]); tid_all.resize(at_read[n_chunks]);
+        h->blk.resize(at_blk[n_chunks]);
+        parallel_for(n_threads, n_chunks, [&](size_t ci) {
+            const Decoded &d = parts[ci];
+            const size_t n_here = d.start.size();
+            if (n_here) {
+                memcpy(h->start.data() + at_read[ci], d.start.data(), n_here * sizeof(int32_t));
+                memcpy(h->meta.data() + at_read[ci], d.meta.data(), n_here * sizeof(uint32_t));
+                memcpy(nlisted_all.data() + at_read[ci], d.nlisted.data(), n_here * sizeof(uint32_t));
+                memcpy(tid_all.data() + at_read[ci], d.tid.data(), n_here * sizeof(int32_t));
+            }
+            if (!d.blk.empty()) memcpy(h->blk.data() + at_blk[ci], d.blk.data(), d.blk.size() * sizeof(int32_t));
+        });
         carry = have - cur;
         memmove(plain.data(), plain.data() + cur, carry);
         plain.resize(carry);

@@ -50,10 +50,14 @@ def test_decoder_matches_reference_htslib_dump():
     assert hb.max_span == max(cigar_to_blocks(c)[1] - (cigar_to_blocks(c)[0][0][0]) for _t, _p, _f, c, _e in mapped)
 
 
-@pytest.mark.parametrize("window", [None, "70000"])
-def test_decoder_matches_packer_on_random_cigars(tmp_path, monkeypatch, window):
+@pytest.mark.parametrize("window,aligned", [(None, False), ("70000", False), (None, True), ("70000", True)])
+def test_decoder_matches_packer_on_random_cigars(tmp_path, monkeypatch, window, aligned):
+    """Windows of 70 kB exercise the carry-over of partial members / records; PB_BAM_WALK_MIN=0 switches the
+    speculative parallel record walk on for small inputs: with record-aligned members (htslib's layout) every
+    guess is a record boundary, with members cut anywhere every guess misses and is walked again."""
     if window:
         monkeypatch.setenv("PB_BAM_WINDOW", window)
+    monkeypatch.setenv("PB_BAM_WALK_MIN", "0")
     rng = np.random.default_rng(9)
     lens = {"chrA": 300_000, "chrB": 40_000, "chrNone": 1000}
     reads = {"chrA": random_cigar_reads(rng, 30_000, 300_000, 290_000), "chrB": random_cigar_reads(rng, 4000, 40_000, 30_000)}
@@ -65,7 +69,7 @@ def test_decoder_matches_packer_on_random_cigars(tmp_path, monkeypatch, window):
                 recs.append((ci, r.reference_start, 4, []))
     recs.append((-1, -1, 4, []))
     path = str(tmp_path / "t.bam")
-    bam_io.write_bam(path, lens, recs, block_bytes=20_000 if window else 60_000)
+    bam_io.write_bam(path, lens, recs, block_bytes=20_000 if window else 60_000, record_aligned=aligned)
     assert os.path.getsize(path) > (3 * 70_000 if window else 0)
     hb = bam_io.batch_from_bam(path, threads=4)
     ref = pack_reads(reads, lens)
@@ -75,6 +79,27 @@ def test_decoder_matches_packer_on_random_cigars(tmp_path, monkeypatch, window):
     assert hb.max_span == ref.max_span and hb.max_block_len == ref.max_block_len
     single = bam_io.batch_from_bam(path, threads=1)
     assert (single.ref_start == hb.ref_start).all() and (single.blk == hb.blk).all()
+
+
+def test_parallel_record_walk_with_records_spanning_members(tmp_path, monkeypatch):
+    """Record-aligned members of 2 kB with a 3000-nt read now and then: the long records span several members, so
+    some of the walk's guesses are record boundaries and some fall inside a record; the result has to be the
+    serial walk's either way."""
+    monkeypatch.setenv("PB_BAM_WALK_MIN", "0")
+    rng = np.random.default_rng(4)
+    pos = np.sort(rng.integers(0, 900_000, 6000))
+    recs = [(0, int(p), int(rng.integers(0, 2)) * 16,
+             [(0, 3000)] if i % 97 == 5 else [(0, 12), (3, int(rng.integers(50, 900))), (0, 18)] if i % 5 == 0 else [(0, int(rng.integers(25, 36)))])
+            for i, p in enumerate(pos)]
+    path = str(tmp_path / "long.bam")
+    bam_io.write_bam(path, {"c": 1_000_000}, recs, block_bytes=2000, record_aligned=True)
+    one = bam_io.batch_from_bam(path, threads=1)
+    assert len(one) == len(recs) and int(one.aligned_len.max()) == 3000
+    assert [int(x) for x in one.ref_start[:50]] == [r[1] for r in recs[:50]]
+    for threads in (2, 5, 8):
+        many = bam_io.batch_from_bam(path, threads=threads)
+        for f in ("ref_start", "meta", "chrom_read_off", "blk_off", "blk"):
+            assert (getattr(many, f) == getattr(one, f)).all(), (threads, f)
 
 
 def test_unspliced_file_has_no_block_table(tmp_path):
