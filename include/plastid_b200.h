@@ -159,6 +159,13 @@ int pb_bam_copy(const pb_bam *h, int32_t *ref_start, uint32_t *meta, uint32_t *b
                 int64_t *chrom_read_off);
 void pb_bam_close(pb_bam *h);
 
+/* The decoder's own raw-DEFLATE (RFC 1951) inflater, one BGZF member at a time: `in_len` compressed bytes
+ * -> exactly `out_len` bytes (the member's ISIZE).  0 on success, -1 on malformed / truncated data or a
+ * size mismatch; never writes outside [out, out + out_len).  Stands where htslib's bgzf.c calls zlib's
+ * inflate() underneath pysam (kent/src/htslib/bgzf.c:292-316, `inflate_block`).  PB_BAM_ZLIB=1 in the environment
+ * makes pb_bam_decode use zlib instead (A/B and cross-checks). */
+int pb_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
+
 const char *pb_version(void);
 const char *pb_last_error(void);
 int pb_device_count(void);

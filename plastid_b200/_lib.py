@@ -61,6 +61,7 @@ _SIGNATURES = {
     "pb_bam_max_span": (C.c_int32, [_P]),
     "pb_bam_copy": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "pb_bam_close": (None, [_P]),
+    "pb_inflate_raw": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t]),
     "pb_map_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "pb_unpack_wire16": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "pb_unpack_delta8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),

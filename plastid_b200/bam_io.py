@@ -100,11 +100,13 @@ def _bgzf_block(data, level=6):
     return header + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data))
 
 
-def write_bam(path, chrom_lengths, records, block_bytes=60000, record_aligned=False):
+def write_bam(path, chrom_lengths, records, block_bytes=60000, record_aligned=False, payload_rng=None):
     """Write a BAM file.  ``chrom_lengths``: ordered ``{name: length}``; ``records``: iterable of
     ``(chrom_index or -1, pos, flag, cigartuples)`` already in coordinate order.  ``record_aligned``:
     start a new BGZF member rather than split a record across two, as htslib's writer does
-    (``bgzf_flush_try``); otherwise members are cut every ``block_bytes`` bytes wherever that falls."""
+    (``bgzf_flush_try``); otherwise members are cut every ``block_bytes`` bytes wherever that falls.
+    ``payload_rng``: a numpy Generator draws bases and (skewed) qualities so that the file compresses like
+    sequencing data (about 3-4x); without it both are constant bytes."""
     chroms = list(chrom_lengths)
     text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (c, chrom_lengths[c]) for c in chroms)
     out = [b"BAM\x01", struct.pack("<i", len(text)), text.encode(), struct.pack("<i", len(chroms))]
@@ -119,7 +121,12 @@ def write_bam(path, chrom_lengths, records, block_bytes=60000, record_aligned=Fa
         bin_ = _reg2bin(max(pos, 0), max(end, 1))
         core = struct.pack("<iiBBHHHiiii", tid, pos, len(name), 60, bin_, len(cigar), flag, qlen, -1, -1, 0)
         body = core + name + b"".join(struct.pack("<I", (n << 4) | op) for op, n in cigar)
-        body += b"\x11" * ((qlen + 1) // 2) + b"\xff" * qlen
+        if payload_rng is None:
+            body += b"\x11" * ((qlen + 1) // 2) + b"\xff" * qlen
+        else:
+            seq = (1 << payload_rng.integers(0, 4, (qlen + 1) // 2)) * 16 + (1 << payload_rng.integers(0, 4, (qlen + 1) // 2))
+            qual = 40 - np.minimum(payload_rng.geometric(0.35, qlen), 38)
+            body += seq.astype(np.uint8).tobytes() + qual.astype(np.uint8).tobytes()
         out.append(struct.pack("<i", len(body)) + body)
     n_head = 4 + len(chroms)
     with open(path, "wb") as fh:

@@ -184,6 +184,7 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
     std::string err;
 
     const bool dbg = getenv("PB_BAM_DEBUG") != nullptr;
+    const bool use_zlib = getenv("PB_BAM_ZLIB") != nullptr;       // A/B and cross-checks; default: pb_inflate_raw
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_read = 0, t_inflate = 0, t_walk = 0, t_conv = 0, t_app = 0, t0 = now();
     while (rc == PB_OK && !(eof && comp_have == 0)) {
@@ -227,6 +228,10 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
         parallel_for(n_threads, blocks.size(), [&](size_t i) {
             const Block &b = blocks[i];
             if (b.usize == 0) return;
+            if (!use_zlib) {
+                if (pb_inflate_raw(comp.data() + b.src, b.csize, plain.data() + b.dst, b.usize) != 0) bad = 1;
+                return;
+            }
             z_stream zs;
             memset(&zs, 0, sizeof(zs));
             if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }

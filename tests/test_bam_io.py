@@ -1,6 +1,7 @@
 """Host BAM decoder (pb_bam_*, no GPU): against the reference's vendored htslib through committed
 fixtures (tests/golden/htslib_allops.*, made by tests/golden/make_bam_golden.py with
 oracle/_ref/ref_bam_tool), against the packer on random CIGARs, and on malformed input."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -100,6 +101,91 @@ def test_parallel_record_walk_with_records_spanning_members(tmp_path, monkeypatc
         many = bam_io.batch_from_bam(path, threads=threads)
         for f in ("ref_start", "meta", "chrom_read_off", "blk_off", "blk"):
             assert (getattr(many, f) == getattr(one, f)).all(), (threads, f)
+
+
+def _pb_inflate(comp, n):
+    """pb_inflate_raw into a buffer with 64 guard bytes behind it, which have to survive."""
+    out = (C.c_uint8 * (n + 64))()
+    C.memset(C.byref(out, n), 0xA5, 64)
+    rc = _lib.lib().pb_inflate_raw(comp, len(comp), out, n)
+    raw = bytes(out)
+    assert raw[n:] == b"\xa5" * 64, "pb_inflate_raw wrote past the end of its output"
+    return rc, raw[:n]
+
+
+def _deflate_payload(rng, kind, n):
+    if kind == 0:                                                # incompressible: stored blocks
+        return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    if kind == 1:                                                # four symbols: short codes, literal pairs
+        return rng.integers(0, 4, n, dtype=np.uint8).tobytes()
+    if kind == 2:                                                # one byte: distance-1 runs of 258
+        return bytes(n)
+    if kind == 3:                                                # period 50: far matches, chained
+        return (rng.integers(0, 256, 50, dtype=np.uint8).tobytes() * (n // 50 + 1))[:n]
+    if kind == 4:                                                # short periods: distances 1..7
+        period = int(rng.integers(1, 8))
+        return (rng.integers(0, 256, period, dtype=np.uint8).tobytes() * (n // period + 1))[:n]
+    if kind == 5:                                                # halving frequencies: code lengths up to 15 (sub-tables)
+        return np.minimum(rng.geometric(0.5, n) + rng.integers(0, 2, n) * 40, 255).astype(np.uint8).tobytes()
+    if kind == 6:                                                # skewed qualities + random bases, like a BAM record
+        q = 40 - np.minimum(rng.geometric(0.35, n), 38)
+        noisy = rng.random(n) < 0.3
+        q[noisy] = rng.integers(0, 256, int(noisy.sum()))
+        return q.astype(np.uint8).tobytes()
+    words = [rng.integers(97, 123, int(rng.integers(2, 12)), dtype=np.uint8).tobytes() for _ in range(2000)]
+    return b" ".join(words[int(i)] for i in rng.integers(0, 2000, n // 4 + 4))[:n]      # text: all of it mixed
+
+
+def test_inflater_matches_zlib_on_every_block_shape():
+    """pb_inflate_raw against zlib: stored / fixed / dynamic blocks, all levels and strategies, several blocks per
+    stream (sync and full flushes), sizes around the fast loop's 320-byte margin and at a BGZF member's maximum;
+    wrong sizes, truncated and corrupted input are refused without a write outside the output."""
+    import zlib
+    rng = np.random.default_rng(11)
+    sizes = [0, 1, 2, 7, 100, 319, 320, 321, 1000, 5000, 65280]
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    for it in range(600):
+        n = int(sizes[it % len(sizes)]) if it % 3 else int(rng.integers(0, 65281))
+        data = _deflate_payload(rng, it % 8, n)
+        co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, -15, int(rng.integers(1, 10)), int(rng.choice(strategies)))
+        if n > 10 and rng.random() < 0.3:
+            k = int(rng.integers(1, n))
+            comp = co.compress(data[:k]) + co.flush(zlib.Z_SYNC_FLUSH if rng.random() < 0.5 else zlib.Z_FULL_FLUSH) \
+                + co.compress(data[k:]) + co.flush()
+        else:
+            comp = co.compress(data) + co.flush()
+        rc, out = _pb_inflate(comp, n)
+        assert rc == 0 and out == data, (it, n)
+        if n:
+            assert _pb_inflate(comp, n - 1)[0] == -1 and _pb_inflate(comp, n + 1)[0] == -1
+            assert _pb_inflate(comp[:int(rng.integers(0, len(comp) - 1))], n)[0] == -1
+        if len(comp) > 4:
+            bad = bytearray(comp)
+            for _ in range(3):
+                bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+            rc, out = _pb_inflate(bytes(bad), n)
+            assert rc == -1 or zlib.decompress(bytes(bad), -15) == out       # accepted only if zlib reads the same
+
+
+def test_inflater_refuses_malformed_headers():
+    # block type 3; stored block with a bad complement; dynamic header with HLIT = 31 (288 codes)
+    assert _pb_inflate(bytes([0b111]), 0)[0] == -1
+    assert _pb_inflate(bytes([0b001, 5, 0, 0, 0]) + b"hello", 5)[0] == -1
+    assert _pb_inflate(bytes([0b001, 5, 0, 0xFA, 0xFF]) + b"hello", 5) == (0, b"hello")
+    assert _pb_inflate(bytes([0b11111101, 0xFF, 0xFF, 0xFF]), 10)[0] == -1
+    assert _pb_inflate(b"", 0)[0] == -1 and _pb_inflate(bytes([0b011, 0]), 0) == (0, b"")      # empty fixed block
+
+
+def test_decoder_same_arrays_with_zlib(tmp_path, monkeypatch):
+    rng = np.random.default_rng(2)
+    pos = np.sort(rng.integers(0, 90_000, 20_000))
+    recs = [(0, int(p), int(rng.integers(0, 2)) * 16, [(0, int(rng.integers(20, 40)))]) for p in pos]
+    path = str(tmp_path / "p.bam")
+    bam_io.write_bam(path, {"c": 100_000}, recs, record_aligned=True, payload_rng=rng)
+    own = bam_io.batch_from_bam(path, threads=3)
+    monkeypatch.setenv("PB_BAM_ZLIB", "1")
+    ref = bam_io.batch_from_bam(path, threads=3)
+    assert len(own) == len(recs) and (own.ref_start == ref.ref_start).all() and (own.meta == ref.meta).all()
 
 
 def test_unspliced_file_has_no_block_table(tmp_path):
