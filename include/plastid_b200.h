@@ -140,7 +140,8 @@ typedef struct pb_rule {
  * every mapped record as one batch row (CIGAR M/=/X runs merged into aligned blocks) and skips
  * records without reference / with the unmapped flag.  Replaces pysam's AlignmentFile / fetch /
  * AlignedSegment.positions on the way into the path (plastid/genomics/genome_array.py:660-690,
- * 800-809).  pb_bam_n_mapped is what `bamfile.mapped` reports (genome_array.py:690).  pb_bam_copy
+ * 800-809).  Every member's CRC32 is verified (PB_BAM_NOCRC=1 skips it; the reference's vendored htslib 1.3 never
+ * checks it on read, kent/src/htslib/bgzf.c:292-316).  pb_bam_n_mapped is what `bamfile.mapped` reports (genome_array.py:690).  pb_bam_copy
  * writes the decoded arrays into caller-owned HOST buffers (e.g. pinned): ref_start int32[n_reads],
  * meta uint32[n_reads], chrom_read_off int64[n_ref+1], and — when pb_bam_n_blk > 0 — blk_off
  * uint32[n_reads+1] and blk int32[n_blk][2]. */

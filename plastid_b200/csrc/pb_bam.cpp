@@ -31,7 +31,7 @@ void pb_set_error(const char *fmt, ...);
 
 namespace {
 
-struct Block { size_t src, csize, dst, usize; };   // one BGZF member inside the current window
+struct Block { size_t src, csize, dst, usize; uint32_t crc; };   // one BGZF member inside the current window
 
 struct Decoded {            // per-chunk output of the record conversion
     std::vector<int32_t> start;
@@ -184,6 +184,7 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
     std::string err;
 
     const bool dbg = getenv("PB_BAM_DEBUG") != nullptr;
+    const bool check_crc = getenv("PB_BAM_NOCRC") == nullptr;      // every member's CRC32 is verified (zlib's crc32)
     const bool use_zlib = getenv("PB_BAM_ZLIB") != nullptr;       // A/B and cross-checks; default: pb_inflate_raw
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_read = 0, t_inflate = 0, t_walk = 0, t_conv = 0, t_app = 0, t0 = now();
@@ -212,7 +213,7 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
             if (!bsize) { err = "BGZF member without a BC subfield"; rc = PB_EINVAL; break; }
             if (off + bsize > comp_have) break;               // incomplete member: wait for more input
             const uint32_t isize = rd32(p + bsize - 4);
-            blocks.push_back({off + 12 + xlen, bsize - xlen - 20, udst, isize});
+            blocks.push_back({off + 12 + xlen, bsize - xlen - 20, udst, isize, rd32(p + bsize - 8)});
             udst += isize;
             off += bsize;
         }
@@ -230,6 +231,7 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
             if (b.usize == 0) return;
             if (!use_zlib) {
                 if (pb_inflate_raw(comp.data() + b.src, b.csize, plain.data() + b.dst, b.usize) != 0) bad = 1;
+                else if (check_crc && (uint32_t)crc32(crc32(0L, Z_NULL, 0), plain.data() + b.dst, (uInt)b.usize) != b.crc) bad = 2;
                 return;
             }
             z_stream zs;
@@ -239,9 +241,10 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
             zs.next_out = plain.data() + b.dst; zs.avail_out = (uInt)b.usize;
             const int zr = inflate(&zs, Z_FINISH);
             if (zr != Z_STREAM_END || zs.total_out != b.usize) bad = 1;
+            else if (check_crc && (uint32_t)crc32(crc32(0L, Z_NULL, 0), plain.data() + b.dst, (uInt)b.usize) != b.crc) bad = 2;
             inflateEnd(&zs);
         });
-        if (bad) { err = "corrupt BGZF member (inflate failed)"; rc = PB_EINVAL; break; }
+        if (bad) { err = bad == 2 ? "corrupt BGZF member (CRC32 mismatch)" : "corrupt BGZF member (inflate failed)"; rc = PB_EINVAL; break; }
         memmove(comp.data(), comp.data() + off, comp_have - off);
         comp_have -= off;
 

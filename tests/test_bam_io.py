@@ -212,6 +212,20 @@ def test_malformed_input_is_reported(tmp_path):
     trunc.write_bytes(data[:len(data) // 2])
     with pytest.raises(_lib.PlastidB200Error):
         bam_io.batch_from_bam(str(trunc))
+    # one flipped bit in the first member's CRC32 field (the member ends 8 bytes before the next one's magic)
+    first_len = int.from_bytes(data[16:18], "little") + 1
+    flipped = bytearray(data)
+    flipped[first_len - 8] ^= 0x10
+    crc = tmp_path / "crc.bam"
+    crc.write_bytes(bytes(flipped))
+    with pytest.raises(_lib.PlastidB200Error, match="CRC32"):
+        bam_io.batch_from_bam(str(crc))
+    # and one in its payload: either the inflater or the CRC refuses it
+    flipped = bytearray(data)
+    flipped[first_len - 12] ^= 0x04
+    crc.write_bytes(bytes(flipped))
+    with pytest.raises(_lib.PlastidB200Error, match="corrupt BGZF"):
+        bam_io.batch_from_bam(str(crc))
     unsorted = tmp_path / "unsorted.bam"
     bam_io.write_bam(str(unsorted), {"a": 1000, "b": 1000}, [(1, 5, 0, [(0, 30)]), (0, 5, 0, [(0, 30)])])
     with pytest.raises(_lib.PlastidB200Error, match="sorted"):
