@@ -14,7 +14,7 @@ import warnings
 
 import numpy as np
 
-from .pyoracle import Chain, Seg
+from .pyoracle import Chain
 
 
 def counts_in_region_rows(ga, chains, masks=None, crossmap=None):

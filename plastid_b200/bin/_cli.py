@@ -1,7 +1,5 @@
 """Small shared helpers for the script entry points: alignment / annotation / table I/O and the
 mapping-rule flags of ``plastid/util/scriptlib/argparsers.py:337-503`` (same names and defaults)."""
-import argparse
-
 import numpy as np
 
 from ..batch import AlignmentBatch

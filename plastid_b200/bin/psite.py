@@ -9,7 +9,7 @@ import numpy as np
 from . import _cli
 from .metagene import rois_from_table, _NORM_START_DEFAULT, _NORM_END_DEFAULT
 from ..genome_array import stratified_windows, window_normalize, column_profile, count_profiles
-from ..map_factories import (FivePrimeMapFactory, SizeFilterFactory, CenterMapFactory,
+from ..map_factories import (FivePrimeMapFactory, CenterMapFactory,
                              StratifiedVariableFivePrimeMapFactory, _MapFactory)
 from ..regions import ChainTable
 

@@ -278,7 +278,6 @@ def gather_rows(local_values, owner, rank=None):
     if not is_distributed() or dist.get_world_size() == 1:
         return local_values
     rank = dist.get_rank() if rank is None else rank
-    ws = dist.get_world_size()
     shape = (len(owner),) + tuple(local_values.shape[1:])
     full = torch.zeros(shape, dtype=local_values.dtype, device=local_values.device)
     idx = torch.from_numpy(np.nonzero(owner == rank)[0]).to(local_values.device)

@@ -17,11 +17,11 @@ import os
 import numpy as np
 
 from . import _lib
-from .batch import AlignmentBatch, GenomeLayout, BatchRead
+from .batch import AlignmentBatch, GenomeLayout
 from .map_factories import (CenterMapFactory, SizeFilterFactory, StratifiedVariableFivePrimeMapFactory,
                             _MapFactory)
 from .regions import ChainTable
-from .roitools import GenomicSegment, SegmentChain
+from .roitools import SegmentChain
 
 _STRANDS = ("+", "-", ".")
 

@@ -14,7 +14,7 @@ import warnings
 import numpy as np
 
 from . import _lib
-from .batch import pack_reads, AlignmentBatch
+from .batch import pack_reads
 
 LUT_SIZE = _lib.PB_LUT_SIZE
 _BAD_OFFSET = -1

@@ -7,7 +7,7 @@ product's compute path.
 import numpy as np
 import torch
 
-from .batch import AlignmentBatch, DeviceBatch, GenomeLayout
+from .batch import AlignmentBatch, DeviceBatch
 from .roitools import GenomicSegment, SegmentChain
 
 # hg38 primary assembly chromosome lengths (chr1..22, X, Y): 3.09 Gb

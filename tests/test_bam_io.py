@@ -7,7 +7,6 @@ import os
 import numpy as np
 import pytest
 
-import plastid_b200 as pb
 from plastid_b200 import _lib, bam_io
 from plastid_b200.batch import cigar_to_blocks, pack_reads
 from oracle import pyoracle as po
