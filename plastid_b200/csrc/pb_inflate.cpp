@@ -24,14 +24,18 @@ enum { T_INVALID = 0, T_LITERAL = 1, T_LENGTH = 2, T_END = 3, T_SUB = 4 };
 #endif
 enum { LIT_BITS = PB_LIT_BITS, OFF_BITS = 8, PRE_BITS = 7, LIT_TABLE = 2400, OFF_TABLE = 512, PRE_TABLE = 128 };
 
-// table entry: bits 0-7 stream bits to consume (the shift count as it is), 8-11 extra bits (or sub-table index
-// bits; literals: how many, 1 or 2), 12-15 type, 16-31 value (literal, or two: first | second << 8; base length /
-// distance; sub-table start)
+// table entry: bits 0-7 stream bits to consume (the shift count as it is; for lengths and distances the code AND
+// its extra bits, so that one shift per symbol is all the bit buffer's dependency chain sees), 8-11 extra bits (or
+// sub-table index bits; literals: how many, 1 or 2), 12-15 type, 16-31 value (literal, or two: first | second << 8;
+// base length / distance; sub-table start)
 inline u32 entry(u32 type, u32 extra, u32 value) { return (extra << 8) | (type << 12) | (value << 16); }
 inline u32 e_type(u32 e) { return (e >> 12) & 15; }
 inline u32 e_bits(u32 e) { return e & 63; }
 inline u32 e_extra(u32 e) { return (e >> 8) & 15; }
 inline u32 e_value(u32 e) { return e >> 16; }
+// the extra bits of a length / distance entry, out of the bit buffer as it was before the entry's bits were dropped
+inline u32 e_extra_value(u64 saved, u32 e) { return (u32)(saved >> (e_bits(e) - e_extra(e))) & ((1u << e_extra(e)) - 1); }
+inline u32 with_bits(u32 e, u32 code_bits) { return e | (code_bits + (e_type(e) == T_LENGTH ? e_extra(e) : 0)); }
 
 const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -90,6 +94,9 @@ bool build_table(u32 *table, u32 table_cap, u32 tbits, const uint8_t *lens, u32 
     u32 count[16] = {0};
     for (u32 s = 0; s < n; ++s) count[lens[s]]++;
     const u32 tsize = 1u << tbits;
+#ifdef PB_INFLATE_POISON        // tests: whatever an earlier block left in the table must not matter
+    for (u32 i = 0; i < table_cap; ++i) table[i] = entry(T_LITERAL, 1, 0x5A) | (1 + i % 3);
+#endif
     if (count[0] == n) {                                    // no codes at all: fine for distances (literals only)
         memset(table, 0, tsize * sizeof(u32));
         return kind == K_OFFSET;
@@ -120,14 +127,14 @@ bool build_table(u32 *table, u32 table_cap, u32 tbits, const uint8_t *lens, u32 
             uint8_t &m = sub_max[r & (tsize - 1)];
             if (len > m) m = (uint8_t)len;
         } else {
-            const u32 e = symbol_entry(kind, s) | len;
+            const u32 e = with_bits(symbol_entry(kind, s), len);
             for (u32 i = r; i < tsize; i += 1u << len) table[i] = e;
         }
     }
-#ifndef PB_INFLATE_NO_PAIRS
-    if (kind == K_LITLEN) pair_literals(table, tbits);
-#endif
-    if (!need_sub) return true;
+    if (!need_sub) {
+        if (kind == K_LITLEN) pair_literals(table, tbits);
+        return true;
+    }
     u32 next_free = tsize;
     for (u32 p = 0; p < tsize; ++p) {
         if (!sub_max[p]) continue;
@@ -137,11 +144,12 @@ bool build_table(u32 *table, u32 table_cap, u32 tbits, const uint8_t *lens, u32 
         table[p] = entry(T_SUB, sbits, next_free) | tbits;
         next_free += 1u << sbits;
     }
+    if (kind == K_LITLEN) pair_literals(table, tbits);      // only now is every primary entry this code's own
     for (u32 s = 0; s < n; ++s) {
         const u32 len = lens[s];
         if (len <= tbits) continue;
         const u32 r = rev[s], sub = table[r & (tsize - 1)];
-        const u32 e = symbol_entry(kind, s) | (len - tbits);
+        const u32 e = with_bits(symbol_entry(kind, s), len - tbits);
         u32 *t = table + e_value(sub);
         for (u32 i = r >> tbits; i < (1u << e_extra(sub)); i += 1u << (len - tbits)) t[i] = e;
     }
@@ -198,14 +206,16 @@ struct Stream {
     u32 take(u32 n) { const u32 v = peek(n); drop(n); return v; }
 };
 
-// one table lookup, sub-table included; consumes the codeword, returns the entry
-inline u32 decode(Stream &s, const u32 *table, u32 tbits)
+// one table lookup, sub-table included; consumes the entry's bits (code + extra bits), returns the entry and the
+// bit buffer the extra bits can be read from (e_extra_value)
+inline u32 decode(Stream &s, const u32 *table, u32 tbits, u64 &saved)
 {
     u32 e = table[s.peek(tbits)];
     if (e_type(e) == T_SUB) {
         s.drop(tbits);
         e = table[e_value(e) + s.peek(e_extra(e))];
     }
+    saved = s.bitbuf;
     s.drop(e_bits(e));
     return e;
 }
@@ -228,7 +238,8 @@ bool read_dynamic_header(Stream &stream, Tables &t)
     const u32 total = hlit + hdist;
     while (i < total) {
         if (s.bitcnt < 14) s.refill();                // 7 code bits + 7 extra bits at most
-        const u32 e = decode(s, pre, PRE_BITS);
+        u64 saved;
+        const u32 e = decode(s, pre, PRE_BITS, saved);
         if (e_type(e) != T_LITERAL) return false;
         const u32 sym = e_value(e);
         if (sym < 16) { lens[i++] = (uint8_t)sym; continue; }
@@ -266,11 +277,13 @@ int inflate_block(Stream &stream, const Tables &t, uint8_t *out_begin, uint8_t *
     if ((size_t)(s.in_end - s.in_next) >= FAST_IN_MARGIN && (size_t)(out_end - out) >= FAST_OUT_MARGIN) {
         s.refill_fast();
         u32 e = t.lit[s.peek(LIT_BITS)];
+        u64 saved;
         for (;;) {
             // here: at least 56 valid bits, `e` = primary entry of the next symbol (nothing consumed for it yet)
 #define PB_RESOLVE(e)                                                                                   \
             do {                                                                                        \
                 if (e_type(e) == T_SUB) { s.drop(LIT_BITS); e = t.lit[e_value(e) + s.peek(e_extra(e))]; } \
+                saved = s.bitbuf;                                                                       \
                 s.drop(e_bits(e));                                                                      \
             } while (0)
             PB_RESOLVE(e);
@@ -295,11 +308,13 @@ int inflate_block(Stream &stream, const Tables &t, uint8_t *out_begin, uint8_t *
             }
 #undef PB_RESOLVE
             if (e_type(e) != T_LENGTH) PB_RETURN(e_type(e) == T_END ? 0 : -1);
-            const u32 length = e_value(e) + s.take(e_extra(e));       // at least 11 bits are left, 5 needed
-            s.refill_fast();
-            e = decode(s, t.off, OFF_BITS);
+            // a length first thing after a refill leaves 56 - 20 bits, enough for any distance (15 + 13); after
+            // literals (15 + 15 + 20 bits at most, out of 56) the buffer is topped up first
+            const u32 length = e_value(e) + e_extra_value(saved, e);
+            if (s.bitcnt < 28) s.refill_fast();
+            e = decode(s, t.off, OFF_BITS, saved);
             if (e_type(e) != T_LENGTH) PB_RETURN(-1);
-            const u32 offset = e_value(e) + s.take(e_extra(e));
+            const u32 offset = e_value(e) + e_extra_value(saved, e);
             if (offset > (size_t)(out - out_begin)) PB_RETURN(-1);
             const uint8_t *src = out - offset;
             uint8_t *dst = out;
@@ -327,7 +342,8 @@ int inflate_block(Stream &stream, const Tables &t, uint8_t *out_begin, uint8_t *
     // careful loop: every read and write checked
     for (;;) {
         s.refill();
-        u32 e = decode(s, t.lit, LIT_BITS);
+        u64 saved;
+        u32 e = decode(s, t.lit, LIT_BITS, saved);
         if (e_type(e) == T_LITERAL) {
             if ((size_t)(out_end - out) < e_extra(e)) PB_RETURN(-1);
             *out++ = (uint8_t)e_value(e);
@@ -337,11 +353,11 @@ int inflate_block(Stream &stream, const Tables &t, uint8_t *out_begin, uint8_t *
         if (e_type(e) != T_LENGTH) {
             PB_RETURN(e_type(e) == T_END ? 0 : -1);
         }
-        const u32 length = e_value(e) + s.take(e_extra(e));
+        const u32 length = e_value(e) + e_extra_value(saved, e);
         s.refill();
-        e = decode(s, t.off, OFF_BITS);
+        e = decode(s, t.off, OFF_BITS, saved);
         if (e_type(e) != T_LENGTH) PB_RETURN(-1);
-        const u32 offset = e_value(e) + s.take(e_extra(e));
+        const u32 offset = e_value(e) + e_extra_value(saved, e);
         if (offset > (size_t)(out - out_begin) || length > (size_t)(out_end - out)) PB_RETURN(-1);
         const uint8_t *src = out - offset;
         for (u32 k = 0; k < length; ++k) out[k] = src[k];

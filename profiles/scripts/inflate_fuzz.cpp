@@ -1,7 +1,9 @@
 // Sanitizer fuzz of pb_inflate_raw against zlib (host only).  From the repo root:
-//   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=undefined -Iinclude \
-//       profiles/scripts/inflate_fuzz.cpp plastid_b200/csrc/pb_inflate.cpp -o /tmp/inflate_fuzz -lz && /tmp/inflate_fuzz
-// 6000 streams (all levels / strategies / flush kinds, exact-size heap buffers) + 36000 truncated or corrupted ones.
+//   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=undefined -DPB_INFLATE_POISON -Iinclude \
+//       profiles/scripts/inflate_fuzz.cpp plastid_b200/csrc/pb_inflate.cpp -o /tmp/inflate_fuzz -lz && /tmp/inflate_fuzz [streams]
+// 6000 streams by default (all levels / strategies / flush kinds, exact-size heap buffers) + 6 truncated or corrupted
+// variants of each.  PB_INFLATE_POISON fills the decode tables with plausible-looking stale entries before every
+// build: nothing a previous block left behind may leak into the next one (tests/test_bam_io.py runs this too).
 #include <zlib.h>
 #include <cstdio>
 #include <cstdint>
@@ -10,10 +12,11 @@
 #include <random>
 #include <vector>
 extern "C" int pb_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
-int main() {
+int main(int argc, char **argv) {
+    const int n_iter = argc > 1 ? atoi(argv[1]) : 6000;
     std::mt19937_64 rng(7);
     size_t ok = 0, rejected = 0, accepted_bad = 0;
-    for (int it = 0; it < 6000; ++it) {
+    for (int it = 0; it < n_iter; ++it) {
         size_t n = (it % 5 == 0) ? rng() % 65281 : (size_t[]){0, 1, 3, 100, 319, 320, 321, 4000, 65280}[rng() % 9];
         std::vector<uint8_t> data(n);
         int kind = rng() % 7;

@@ -175,6 +175,20 @@ def test_inflater_refuses_malformed_headers():
     assert _pb_inflate(b"", 0)[0] == -1 and _pb_inflate(bytes([0b011, 0]), 0) == (0, b"")      # empty fixed block
 
 
+def test_inflater_fuzz_with_poisoned_tables(tmp_path):
+    """The C++ fuzz driver (profiles/scripts/inflate_fuzz.cpp) built with PB_INFLATE_POISON: decode tables are filled
+    with stale-looking entries before every build, so an entry a code does not define itself cannot go unnoticed
+    (this is what caught literal pairing reading a previous block's entries)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "inflate_fuzz")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DPB_INFLATE_POISON", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "profiles", "scripts", "inflate_fuzz.cpp"),
+                           os.path.join(root, "plastid_b200", "csrc", "pb_inflate.cpp"), "-o", exe, "-lz"])
+    out = subprocess.run([exe, "1200"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("ok 1200"), out.stdout + out.stderr
+
+
 def test_decoder_same_arrays_with_zlib(tmp_path, monkeypatch):
     rng = np.random.default_rng(2)
     pos = np.sort(rng.integers(0, 90_000, 20_000))
