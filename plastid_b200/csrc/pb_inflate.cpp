@@ -75,12 +75,16 @@ inline u32 symbol_entry(Kind kind, u32 sym)
 // that symbol is a literal too, the entry carries both (value = first | second << 8, bits = both codes).
 void pair_literals(u32 *table, u32 tbits)
 {
-    // descending and in place: entry i looks at entry i >> (its code length), which lies below i and is still single
+    // descending and in place: entry i looks at entry i >> (its code length), which lies below i and is still single;
+    // written without a branch (the pattern of literal / non-literal entries is not predictable)
     for (u32 i = (1u << tbits) - 1; i > 0; --i) {
         const u32 a = table[i];
         const u32 la = e_bits(a), b = table[i >> la];
-        const bool both = ((a & b) >> 12 & 15) == T_LITERAL && ((a | b) >> 12 & 15) == T_LITERAL && la + e_bits(b) <= tbits;
-        if (both) table[i] = entry(T_LITERAL, 2, e_value(a) | (e_value(b) << 8)) | (la + e_bits(b));
+        const u32 lit = (u32)T_LITERAL << 12;
+        const u32 not_both = (((a ^ lit) | (b ^ lit)) & 0xF000u) | ((tbits - la - e_bits(b)) >> 31);   // 0 = pair them
+        const u32 keep = 0u - (u32)(not_both != 0);
+        const u32 pair = entry(T_LITERAL, 2, e_value(a) | ((b >> 8) & 0xFF00)) | (la + e_bits(b));
+        table[i] = (a & keep) | (pair & ~keep);
     }
     const u32 a = table[0];                               // index 0 pairs with itself
     if (e_type(a) == T_LITERAL && e_extra(a) == 1 && 2 * e_bits(a) <= tbits)
@@ -113,10 +117,10 @@ bool build_table(u32 *table, u32 table_cap, u32 tbits, const uint8_t *lens, u32 
     u32 next_code[16], code = 0;
     count[0] = 0;
     for (u32 len = 1; len <= 15; ++len) { code = (code + count[len - 1]) << 1; next_code[len] = code; }
-    uint16_t rev[320];
-    uint8_t sub_max[1 << LIT_BITS];
-    const bool need_sub = max_len > tbits;
-    if (need_sub) memset(sub_max, 0, tsize);
+    uint16_t rev[320], long_syms[320];
+    uint8_t sub_max[1 << LIT_BITS];                       // per primary index: longest code below it, bit 7 = allocated
+    u32 n_long = 0;
+    if (max_len > tbits) memset(sub_max, 0, tsize);
     for (u32 s = 0; s < n; ++s) {
         const u32 len = lens[s];
         if (!len) continue;
@@ -124,6 +128,7 @@ bool build_table(u32 *table, u32 table_cap, u32 tbits, const uint8_t *lens, u32 
         const u32 r = (((u32)kRev8[c & 255] << 8) | kRev8[c >> 8]) >> (16 - len);
         rev[s] = (uint16_t)r;
         if (len > tbits) {
+            long_syms[n_long++] = (uint16_t)s;
             uint8_t &m = sub_max[r & (tsize - 1)];
             if (len > m) m = (uint8_t)len;
         } else {
@@ -131,23 +136,19 @@ bool build_table(u32 *table, u32 table_cap, u32 tbits, const uint8_t *lens, u32 
             for (u32 i = r; i < tsize; i += 1u << len) table[i] = e;
         }
     }
-    if (!need_sub) {
-        if (kind == K_LITLEN) pair_literals(table, tbits);
-        return true;
-    }
     u32 next_free = tsize;
-    for (u32 p = 0; p < tsize; ++p) {
-        if (!sub_max[p]) continue;
+    for (u32 k = 0; k < n_long; ++k) {                    // one sub-table per primary index that long codes share
+        const u32 p = rev[long_syms[k]] & (tsize - 1);
+        if (sub_max[p] & 0x80) continue;
         const u32 sbits = sub_max[p] - tbits;
+        sub_max[p] |= 0x80;
         if (next_free + (1u << sbits) > table_cap) return false;
-        if (left > 0) memset(table + next_free, 0, sizeof(u32) << sbits);
         table[p] = entry(T_SUB, sbits, next_free) | tbits;
         next_free += 1u << sbits;
     }
-    if (kind == K_LITLEN) pair_literals(table, tbits);      // only now is every primary entry this code's own
-    for (u32 s = 0; s < n; ++s) {
-        const u32 len = lens[s];
-        if (len <= tbits) continue;
+    if (kind == K_LITLEN) pair_literals(table, tbits);    // only now is every primary entry this code's own
+    for (u32 k = 0; k < n_long; ++k) {
+        const u32 s = long_syms[k], len = lens[s];
         const u32 r = rev[s], sub = table[r & (tsize - 1)];
         const u32 e = with_bits(symbol_entry(kind, s), len - tbits);
         u32 *t = table + e_value(sub);
