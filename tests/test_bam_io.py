@@ -201,6 +201,46 @@ def test_decoder_same_arrays_with_zlib(tmp_path, monkeypatch):
     assert len(own) == len(recs) and (own.ref_start == ref.ref_start).all() and (own.meta == ref.meta).all()
 
 
+class _FakePysamRead(object):
+    """The attributes of pysam.AlignedSegment the adaptor reads (genome_array.py:800-815, map_factories.pyx:243)."""
+
+    def __init__(self, tid, read, unmapped=False):
+        self.reference_id, self.reference_start = tid, read.reference_start
+        self.cigartuples, self.is_reverse, self.is_unmapped = (None if unmapped else read.cigartuples), read.is_reverse, unmapped
+
+
+class _FakePysamFile(object):
+    def __init__(self, lens, reads_by_chrom):
+        self.references, self.lengths = tuple(lens), tuple(lens.values())
+        self._reads = []
+        for tid, c in enumerate(lens):
+            for k, r in enumerate(reads_by_chrom.get(c, [])):          # file order: unsorted on purpose
+                self._reads.append(_FakePysamRead(tid, r))
+                if k % 100 == 0:
+                    self._reads.append(_FakePysamRead(tid, r, unmapped=True))
+        self._reads.append(_FakePysamRead(-1, reads_by_chrom["chrA"][0]))
+        self.mapped = sum(len(v) for v in reads_by_chrom.values())
+
+    def fetch(self, until_eof=False):
+        assert until_eof
+        return iter(self._reads)
+
+
+def test_open_pysam_handles_are_accepted_like_paths():
+    """`BAMGenomeArray(pysam.AlignmentFile(...))` users: anything that is not a path goes through the pysam adaptor
+    (pysam itself is not installed here, so a stand-in with the same attributes): same batch as the packer's."""
+    rng = np.random.default_rng(21)
+    lens = {"chrA": 50_000, "chrB": 9000, "chrEmpty": 100}
+    reads = {"chrA": random_cigar_reads(rng, 3000, 50_000, 45_000), "chrB": random_cigar_reads(rng, 500, 9000, 6000)}
+    hb = bam_io.batch_from_bam(_FakePysamFile(lens, reads))
+    ref = pack_reads(reads, lens)
+    assert hb.chroms == ref.chroms and len(hb) == len(ref) and hb.mapped == ref.mapped
+    for f in ("ref_start", "meta", "chrom_read_off", "blk_off", "blk"):
+        assert (getattr(hb, f) == getattr(ref, f)).all(), f
+    assert hb.max_span == ref.max_span
+    hb.check_sorted()
+
+
 def test_unspliced_file_has_no_block_table(tmp_path):
     lens = {"c": 5000}
     recs = [(0, p, (p % 2) * 16, [(4, 2), (0, 20 + p % 7), (1, 3), (0, 5)]) for p in range(0, 4000, 3)]
