@@ -334,6 +334,11 @@ class Transcript(SegmentChain):
             self.cds_start = coord(ge - 1)
             self.cds_end = 1 + coord(gs)
 
+    def as_bed(self, thickstart=None, thickend=None):
+        """BED12 line with the coding region in the thickStart / thickEnd columns (roitools.pyx:4385-4455)."""
+        return SegmentChain.as_bed(self, thickstart=self.cds_genome_start if thickstart is None else thickstart,
+                                   thickend=self.cds_genome_end if thickend is None else thickend)
+
     def get_gene(self):
         """``gene_id``, else ``Parent``, else ``gene_<name>`` (roitools.pyx:2154-2173)."""
         gene = self.attr.get("gene_id", self.attr.get("Parent", "gene_%s" % self.get_name()))

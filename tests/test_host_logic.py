@@ -738,3 +738,142 @@ def test_mask_accessors_known_answers_from_the_reference_tests():
         assert ch.masked_length == pre_length - len(mask_a) - len(mask_b)
         ch.reset_masks()
         assert ch.get_masks() == [] and ch.masked_length == pre_length
+
+
+class _HostGenomeArray(object):
+    """The smallest valid `ga` of the reference's contract: anything with ``get(seg, roi_order)``
+    (`roitools.pyx:3259-3268` calls exactly ``ga.get(seg, roi_order=False)``).  Optional leading axis."""
+
+    def __init__(self, length, rows=None):
+        shape = (length,) if rows is None else (rows, length)
+        self.data = {s: np.zeros(shape) for s in "+-"}
+
+    def set(self, seg, val):
+        self.data[seg.strand][..., seg.start:seg.end] = val
+
+    def get(self, seg, roi_order=True):
+        out = self.data[seg.strand][..., seg.start:seg.end].copy()
+        return out[..., ::-1] if (roi_order and seg.strand == "-") else out
+
+
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_get_counts_and_masked_counts_over_any_ga_object(strand):
+    """test_roitools.py:1274-1337 (get_masked_counts plus / minus) and :1340-1417 (counts 200 -> 175 under a mask)
+    through the generic per-exon path of SegmentChain.get_counts — a host object stands in for the genome array."""
+    S = pb.GenomicSegment
+    ga = _HostGenomeArray(2000)
+    ga.set(S("chrA", 100, 200, strand), 1)
+    ga.set(S("chrA", 250, 350, strand), 5)
+    chain = pb.SegmentChain(S("chrA", 100, 150, strand), S("chrA", 150, 200, strand), S("chrA", 250, 350, strand))
+    unmasked = np.zeros(chain.length)
+    if strand == "+":
+        unmasked[:100], unmasked[100:200] = 1, 5
+    else:
+        unmasked[-100:], unmasked[-200:-100] = 1, 5
+    assert (chain.get_counts(ga) == unmasked).all() and chain.get_counts(ga).dtype == np.float64
+    assert (chain.get_counts(ga, stranded=False) == (unmasked if strand == "+" else unmasked[::-1])).all()
+    assert (chain.get_masked_counts(ga) == unmasked).all()
+    chain.add_masks(S("chrA", 400, 500, strand))
+    assert (chain.get_masked_counts(ga) == unmasked).all() and chain.masked_length == 200
+    chain.add_masks(S("chrA", 50, 125, strand))
+    mask = np.tile(False, chain.length)
+    if strand == "+":
+        mask[:25] = True
+    else:
+        mask[-25:] = True
+    found = chain.get_masked_counts(ga)
+    assert (found.mask == mask).all() and (found.data == unmasked).all()
+    assert found.sum() == 575 and chain.get_counts(ga).sum() == 600 and chain.masked_length == 175
+    # `stranded` is ignored by get_masked_counts, like the reference (roitools.pyx:3301)
+    assert (chain.get_masked_counts(ga, stranded=False).data == unmasked).all()
+    # leading (stratification) axes are kept, the mask is broadcast over them (roitools.pyx:3259-3268, 3308-3313)
+    ga2 = _HostGenomeArray(2000, rows=3)
+    for r in range(3):
+        ga2.data[strand][r, 100:200] = r + 1
+    found2 = chain.get_masked_counts(ga2)
+    assert found2.shape == (3, 200) and (found2.mask == mask[None, :]).all()
+    assert list(found2.sum(axis=1)) == [75.0, 150.0, 225.0]
+
+
+def test_empty_chain_counts_warn_and_return_an_empty_vector():
+    chain = pb.SegmentChain()
+    with pytest.warns(pb.DataWarning, match="zero-length"):
+        out = chain.get_counts(_HostGenomeArray(10))
+    assert out.shape == (0,) and out.dtype == np.float64
+
+
+def test_genomic_segment_ordering_and_hashing():
+    S = pb.GenomicSegment
+    a, b, c = S("chrA", 10, 20, "+"), S("chrA", 10, 20, "+"), S("chrA", 10, 25, "-")
+    assert a == b and not (a != b) and hash(a) == hash(b) and a != c and len({a, b, c}) == 2
+    segs = [S("chrB", 0, 5, "+"), S("chrA", 50, 60, "-"), S("chrA", 50, 60, "+"), S("chrA", 5, 100, "+")]
+    assert [str(s) for s in sorted(segs)] == ["chrA:5-100(+)", "chrA:50-60(+)", "chrA:50-60(-)", "chrB:0-5(+)"]
+    assert repr(a).endswith("chrA:10-20(+)>") or "chrA:10-20(+)" in repr(a)
+    assert S.from_str("chrA:10-20(+)") == a
+
+
+def test_center_fixed_point_weights_bound_their_error():
+    """CenterMapFactory.fixed_point_tables: integer weights round(2^shift / m) whose relative error against 1/m
+    is at most m * 2^-(shift+1), with a shift that keeps the sum over all reads below 2^62."""
+    fac = pb.CenterMapFactory(nibble=3)
+    hist = np.zeros(65536, dtype=np.int64)
+    assert fac.fixed_point_tables(hist) is None
+    hist[30] = 10**8
+    assert fac.fixed_point_tables(hist) is None              # one map length: the exact kernel
+    hist[25:36] = 10**7
+    hist[6] = 5                                                # L - 2*nibble == 0: no slot
+    hist[4] = 7                                                # negative map length: no slot
+    slot_of_len, w_fix, shift = fac.fixed_point_tables(hist)
+    lengths = np.arange(25, 36)
+    assert (slot_of_len[lengths] == np.arange(11)).all() and slot_of_len[6] == -1 and slot_of_len[4] == -1
+    assert (slot_of_len >= 0).sum() == 11 and 1 <= shift <= 52
+    m = lengths - 6
+    rel = np.abs(w_fix.astype(np.float64) / 2.0 ** shift - 1.0 / m) * m
+    assert (rel <= m * 2.0 ** -(shift + 1) + 1e-18).all() and rel.max() < fac.FIXED_MAX_REL_ERR
+    total = sum(int(hist[L]) * int(w) for L, w in zip(lengths, w_fix))
+    assert total < 2 ** 62
+    s2, inv_m = fac.slot_tables(hist)
+    assert (s2 == slot_of_len).all() and np.array_equal(inv_m, 1.0 / m)
+    # so many reads that no shift keeps 1e-9: refused, the caller falls back to exact passes
+    hist[:] = 0
+    hist[2000:2003] = 2 ** 40
+    assert pb.CenterMapFactory(0).fixed_point_tables(hist) is None
+
+
+def test_script_table_io_round_trips(tmp_path):
+    """bin/_cli.py: alignment batches as .npz, BED3-12(+gene_id) as chains / transcripts, plastid's tab tables."""
+    from plastid_b200.bin import _cli
+    rng = np.random.default_rng(5)
+    lens = {"chrA": 30_000, "chrB": 4000}
+    for reads in ({"chrA": random_cigar_reads(rng, 300, 30_000, 25_000), "chrB": random_cigar_reads(rng, 40, 4000, 2000)},
+                  {"chrA": [po.Read(int(p), [(0, 30)], bool(p % 2)) for p in range(0, 900, 7)]}):
+        hb = pack_reads(reads, lens)
+        path = str(tmp_path / "b.npz")
+        _cli.save_batch(path, hb)
+        back = _cli.load_batch(path)
+        assert back.chroms == hb.chroms and back.mapped == hb.mapped and back.max_span == hb.max_span
+        for f in ("ref_start", "meta", "chrom_read_off", "chrom_len"):
+            assert (getattr(back, f) == getattr(hb, f)).all(), f
+        assert (back.blk is None) == (hb.blk is None) and (hb.blk is None or ((back.blk == hb.blk).all() and (back.blk_off == hb.blk_off).all()))
+    bed = tmp_path / "a.bed"
+    bed.write_text("track name=x\n# comment\n"
+                   "chrA\t100\t400\ttxA\t0\t+\t150\t350\t0\t2\t100,100,\t0,200,\tgeneA\n"
+                   "chrA\t1000\t1100\ttxB\t0\t-\t1000\t1000\t0\t1\t100,\t0,\n"
+                   "chrB\t5\t50\n")
+    chains = _cli.read_bed(str(bed))
+    assert [str(c) for c in chains] == ["chrA:100-200^300-400(+)", "chrA:1000-1100(-)", "chrB:5-50(.)"]
+    assert [c.get_name() for c in chains] == ["txA", "txB", "chrB:5-50"]
+    txs = _cli.read_bed(str(bed), as_transcripts=True)
+    assert txs[0].cds_genome_start == 150 and txs[0].cds_genome_end == 350 and txs[0].get_gene() == "geneA"
+    assert str(txs[0].get_cds()) == "chrA:150-200^300-350(+)" and txs[1].cds_genome_start is None
+    assert txs[0].as_bed().rstrip("\n").split("\t") == ["chrA", "100", "400", "txA", "0", "+", "150", "350", "0,0,0", "2", "100,100,", "0,200,"]
+    assert txs[1].as_bed().split("\t")[6:8] == ["1000", "1000"]           # no coding region: thick columns = chain start
+    again = tmp_path / "again.bed"
+    again.write_text("".join(t.as_bed() for t in txs))
+    assert [(str(t), t.cds_genome_start, t.cds_genome_end) for t in _cli.read_bed(str(again), as_transcripts=True)] == \
+        [(str(t), t.cds_genome_start, t.cds_genome_end) for t in txs]
+    tab = tmp_path / "t.txt"
+    tab.write_text("## note\nregion_name\tregion\tcounts\n#x\ntxA\tchrA:100-200^300-400(+)\t5\ntxB\tchrA:1000-1100(-)\t7\n")
+    cols = _cli.read_pl_table(str(tab))
+    assert cols == {"region_name": ["txA", "txB"], "region": ["chrA:100-200^300-400(+)", "chrA:1000-1100(-)"], "counts": ["5", "7"]}
+    assert [str(pb.SegmentChain.from_str(r)) for r in cols["region"]] == cols["region"]
