@@ -877,3 +877,88 @@ def test_script_table_io_round_trips(tmp_path):
     cols = _cli.read_pl_table(str(tab))
     assert cols == {"region_name": ["txA", "txB"], "region": ["chrA:100-200^300-400(+)", "chrA:1000-1100(-)"], "counts": ["5", "7"]}
     assert [str(pb.SegmentChain.from_str(r)) for r in cols["region"]] == cols["region"]
+
+
+class _HostCountingArray(object):
+    """Stand-in for the device genome array in the script loops: ``sum()``, ``get(seg, roi_order)`` answered by the
+    oracle's BAMGenomeArray, ``count_chains`` = masked sum + unmasked length per chain through the PRODUCT's chain
+    objects (add_masks / get_masked_counts / masked_length) — so the host side of count_regions can be held against
+    the oracle's restatement of the script without a GPU."""
+
+    def __init__(self, oga):
+        self.oga = oga
+
+    def sum(self):
+        return self.oga.sum()
+
+    def get(self, seg, roi_order=True):
+        return self.oga.get(po.Seg(seg.chrom, seg.start, seg.end, seg.strand), roi_order=roi_order)
+
+    def count_chains(self, chains):
+        sums = [float(np.nansum(ch.get_masked_counts(self).filled(0.0))) if ch.length else 0.0 for ch in chains]
+        return np.asarray(sums), np.asarray([ch.masked_length for ch in chains])
+
+
+def test_counts_in_region_host_side_against_the_oracle_script(tmp_path):
+    from oracle import scripts as osc
+    from plastid_b200.bin import counts_in_region
+    chroms, lens = synth.yeast_like_genome(total=120_000, n_chrom=3)
+    ann = synth.make_annotation(chroms, lens, 30, seed=8, exons=(1, 3), exon_len=(150, 400), intron_len=(40, 300))
+    hb = synth.device_batch_to_host(synth.riboseq_reads(ann, 6000, seed=4, device="cpu", lengths=range(24, 36)), chroms, lens)
+    reads = {c: [] for c in chroms}
+    for i in range(len(hb)):
+        c = int(np.searchsorted(hb.chrom_read_off, i, side="right")) - 1
+        reads[chroms[c]].append(po.Read(int(hb.ref_start[i]), [(0, int(hb.meta[i] & 0xFFFF))], bool((hb.meta[i] >> 16) & 1)))
+    oga = po.OracleBAMGenomeArray(po.ReadStore(dict(zip(chroms, [int(x) for x in lens])), reads), mapping=po.FivePrimeMap(14))
+    oga.add_filter("size", po.SizeFilter(25, 100))
+    ga = _HostCountingArray(oga)
+
+    def both_kinds():
+        chains = ann.chains()
+        chains.append(pb.SegmentChain(pb.GenomicSegment("chrUnknown", 10, 500, "+"), ID="nowhere"))
+        ochains = []
+        for ch in chains:
+            oc = po.Chain(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in ch])
+            oc.name = ch.get_name()
+            ochains.append(oc)
+        return chains, ochains
+
+    # masks handed over per region (counts_in_region.py:115-116), one region fully masked
+    chains, ochains = both_kinds()
+    masks = synth.make_masks(ann, frac=0.25, seed=3) + [[]]
+    span = chains[5].spanning_segment
+    masks[5] = [pb.GenomicSegment(span.chrom, span.start - 10, span.end + 10, span.strand)]
+    omasks = [[po.Seg(m.chrom, m.start, m.end, m.strand) for m in ms] for ms in masks]
+    exp = osc.counts_in_region_rows(oga, ochains, omasks)
+    ga_sum, got = counts_in_region.count_regions(ga, chains, masks)
+    assert ga_sum == oga.sum() and got == exp
+    assert got[5][2] == "nan" and got[5][3] == "nan" and got[5][5] == "0" and got[-1][2] == "0.00000000e+00"
+    assert sum(float(r[2]) for r in got if r[2] != "nan") > 0
+    out = tmp_path / "counts.txt"
+    with open(out, "w") as fh:
+        counts_in_region.write_table(fh, ga_sum, got)
+    text = out.read_text().split("\n")
+    assert text[0] == "## total_dataset_counts: %s" % oga.sum()
+    assert text[1].split("\t") == ["region_name", "region", "counts", "counts_per_nucleotide", "rpkm", "length"]
+    assert [line.split("\t") for line in text[2:-1]] == exp
+
+    # masks found by the overlap query of a mask annotation (counts_in_region.py:114-115 through GenomeHash)
+    chains, ochains = both_kinds()
+    rng = np.random.default_rng(11)
+    feats = []
+    for k in range(60):
+        ch = chains[int(rng.integers(len(chains) - 1))]
+        sp = ch.spanning_segment
+        a = int(rng.integers(max(sp.start - 300, 0), sp.end + 100))
+        segs = [pb.GenomicSegment(ch.chrom, a, a + int(rng.integers(1, 400)), ch.strand if k % 5 else "+-"[k % 2])]
+        if k % 3 == 0:
+            b = segs[0].end + int(rng.integers(1, 2000))
+            segs.append(pb.GenomicSegment(ch.chrom, b, b + int(rng.integers(1, 300)), segs[0].strand))
+        feats.append(pb.SegmentChain(*segs, ID="mask%d" % k))
+    feats += feats[:5]
+    ofeats = [po.Chain(*[po.Seg(s.chrom, s.start, s.end, s.strand) for s in f]) for f in feats]
+    exp = osc.counts_in_region_rows(oga, ochains, crossmap=po.GenomeHash(ofeats))
+    _sum, got = counts_in_region.count_regions(ga, chains, masks=counts_in_region.overlapping_masks(chains, feats))
+    assert got == exp and sum(int(r[5]) for r in got) < sum(ch.length for ch in chains)
+    with pytest.raises(KeyError):
+        counts_in_region.overlapping_masks(chains[:2], [pb.SegmentChain(pb.GenomicSegment(chains[0].chrom, 1, 9, "."))])
