@@ -962,3 +962,35 @@ def test_counts_in_region_host_side_against_the_oracle_script(tmp_path):
     assert got == exp and sum(int(r[5]) for r in got) < sum(ch.length for ch in chains)
     with pytest.raises(KeyError):
         counts_in_region.overlapping_masks(chains[:2], [pb.SegmentChain(pb.GenomicSegment(chains[0].chrom, 1, 9, "."))])
+
+
+def test_psite_offset_choice_and_offset_file_round_trip(tmp_path):
+    """psite.py:462-521 by hand: the offset of a read length is the distance from the profile's highest allowed
+    column to the landmark; all-NaN or all-zero profiles take the default; --constrain / --require_upstream limit
+    the columns.  The table psite writes is what VariableFivePrimeMapFactory.from_file reads (p_site.rst:128-151)."""
+    from plastid_b200.bin import psite
+    from oracle import scripts as osc
+    x = np.arange(-50, 100)
+    profiles = {}
+    for k, peak in ((28, -12), (29, -13), (30, -13), (31, 5), (32, None), (33, "zero")):
+        y = np.full(len(x), np.nan) if peak is None else np.zeros(len(x))
+        if isinstance(peak, int):
+            y[:] = 0.1
+            y[x == peak] = 3.0
+            y[x == -30] = 2.0                                   # a lower, farther peak
+        profiles[k] = y
+    free = psite.pick_offsets(x, profiles, default=13)
+    assert free == {28: 12, 29: 13, 30: 13, 31: -5, 32: 13, 33: 13}
+    assert psite.pick_offsets(x, profiles, default=13, require_upstream=True)[31] == 30        # columns x < 0 only
+    tight = psite.pick_offsets(x, profiles, default=14, constrain=(25, 35))                    # 25..35 nt upstream
+    assert tight == {28: 30, 29: 30, 30: 30, 31: 30, 32: 14, 33: 14}
+    for kw in (dict(), dict(require_upstream=True), dict(constrain=(35, 25)), dict(constrain=(0, 20))):
+        assert psite.pick_offsets(x, profiles, 13, **kw) == osc.psite_pick_offsets(x, profiles, 13, **kw)
+    path = tmp_path / "p_offsets.txt"
+    with open(path, "w") as fh:
+        psite.write_offsets(fh, {k: v for k, v in free.items() if v >= 0}, 13)
+    assert path.read_text().split("\n")[0] == "length\tp_offset" and path.read_text().endswith("default\t13")
+    fac = pb.VariableFivePrimeMapFactory.from_file(str(path))
+    fw, rc = po.build_offset_luts({28: 12, 29: 13, 30: 13, 32: 13, 33: 13, "default": 13})
+    assert (fac.forward_offsets == fw).all() and (fac.reverse_offsets == rc).all()
+    assert fac.forward_offsets[28] == 12 and fac.forward_offsets[31] == 13 and fac.forward_offsets[13] == -1
