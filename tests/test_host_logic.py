@@ -894,14 +894,15 @@ class _HostCountingArray(object):
     def get(self, seg, roi_order=True):
         return self.oga.get(po.Seg(seg.chrom, seg.start, seg.end, seg.strand), roi_order=roi_order)
 
-    def count_chains(self, chains):
+    def count_chains(self, chains, use_masks=True):
+        if not use_masks:
+            return (np.asarray([float(ch.get_counts(self).sum()) if ch.length else 0.0 for ch in chains]),
+                    np.asarray([ch.length for ch in chains]))
         sums = [float(np.nansum(ch.get_masked_counts(self).filled(0.0))) if ch.length else 0.0 for ch in chains]
         return np.asarray(sums), np.asarray([ch.masked_length for ch in chains])
 
 
-def test_counts_in_region_host_side_against_the_oracle_script(tmp_path):
-    from oracle import scripts as osc
-    from plastid_b200.bin import counts_in_region
+def _host_world(mapping):
     chroms, lens = synth.yeast_like_genome(total=120_000, n_chrom=3)
     ann = synth.make_annotation(chroms, lens, 30, seed=8, exons=(1, 3), exon_len=(150, 400), intron_len=(40, 300))
     hb = synth.device_batch_to_host(synth.riboseq_reads(ann, 6000, seed=4, device="cpu", lengths=range(24, 36)), chroms, lens)
@@ -909,8 +910,15 @@ def test_counts_in_region_host_side_against_the_oracle_script(tmp_path):
     for i in range(len(hb)):
         c = int(np.searchsorted(hb.chrom_read_off, i, side="right")) - 1
         reads[chroms[c]].append(po.Read(int(hb.ref_start[i]), [(0, int(hb.meta[i] & 0xFFFF))], bool((hb.meta[i] >> 16) & 1)))
-    oga = po.OracleBAMGenomeArray(po.ReadStore(dict(zip(chroms, [int(x) for x in lens])), reads), mapping=po.FivePrimeMap(14))
+    oga = po.OracleBAMGenomeArray(po.ReadStore(dict(zip(chroms, [int(x) for x in lens])), reads), mapping=mapping)
     oga.add_filter("size", po.SizeFilter(25, 100))
+    return ann, oga
+
+
+def test_counts_in_region_host_side_against_the_oracle_script(tmp_path):
+    from oracle import scripts as osc
+    from plastid_b200.bin import counts_in_region
+    ann, oga = _host_world(po.FivePrimeMap(14))
     ga = _HostCountingArray(oga)
 
     def both_kinds():
@@ -994,3 +1002,39 @@ def test_psite_offset_choice_and_offset_file_round_trip(tmp_path):
     fw, rc = po.build_offset_luts({28: 12, 29: 13, 30: 13, 32: 13, 33: 13, "default": 13})
     assert (fac.forward_offsets == fw).all() and (fac.reverse_offsets == rc).all()
     assert fac.forward_offsets[28] == 12 and fac.forward_offsets[31] == 13 and fac.forward_offsets[13] == -1
+
+
+def test_cs_count_host_side_against_the_oracle_script(tmp_path):
+    """cs.py:682-714 (`cs count`): per gene and per class reads / length / RPKM, nan where a class is empty,
+    formatted with %.8f — the product's do_count + write_table over a host stand-in vs the oracle's loop."""
+    import warnings
+    from oracle import scripts as osc
+    from plastid_b200.bin import cs
+    ann, oga = _host_world(po.ThreePrimeMap(0))
+    ga = _HostCountingArray(oga)
+    pos = {"region": [], "exon": [], "utr5": [], "cds": [], "utr3": []}
+    for i, ch in enumerate(ann.chains()):
+        n = ch.length
+        a, b = n // 5, n - n // 4
+        pos["region"].append(ch.get_name())
+        pos["exon"].append(str(ch))
+        pos["utr5"].append(str(ch.get_subchain(0, a)) if i % 7 else "na")          # an empty class now and then
+        pos["cds"].append(str(ch.get_subchain(a, b)))
+        pos["utr3"].append(str(ch.get_subchain(b, n)))
+    exp = osc.cs_count(oga, pos)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        order, cols = cs.do_count(ga, pos)
+    assert order[0] == "region" and len(order) == 13 and cols["region"] == exp["region"]
+    for key in order[1:]:
+        got, want = np.asarray(cols[key], dtype=float), np.asarray(exp[key], dtype=float)
+        assert np.array_equal(got, want, equal_nan=True), key
+    assert np.isnan(cols["utr5_rpkm"][0]) and cols["utr5_length"][0] == 0 and cols["utr5_reads"][0] == 0
+    assert sum(cols["exon_reads"]) > 0
+    out = tmp_path / "cs.txt"
+    with open(out, "w") as fh:
+        cs.write_table(fh, order, cols)
+    lines = out.read_text().rstrip("\n").split("\n")
+    assert lines[0].split("\t") == order and len(lines) == 1 + len(pos["region"])
+    first = dict(zip(order, lines[1].split("\t")))
+    assert first["utr5_rpkm"] == "nan" and first["utr5_reads"] == "0" and first["exon_rpkm"] == "%.8f" % exp["exon_rpkm"][0]
