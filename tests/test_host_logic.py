@@ -1038,3 +1038,29 @@ def test_cs_count_host_side_against_the_oracle_script(tmp_path):
     assert lines[0].split("\t") == order and len(lines) == 1 + len(pos["region"])
     first = dict(zip(order, lines[1].split("\t")))
     assert first["utr5_rpkm"] == "nan" and first["utr5_reads"] == "0" and first["exon_rpkm"] == "%.8f" % exp["exon_rpkm"][0]
+
+
+def test_mapping_rule_plugin_descriptors(tmp_path):
+    """The `plastid.mapping_rules` entry-point contract (argparsers.py:505-534, docs/source/devinfo/entrypoints.rst):
+    a dict with name / bamfunc / help whose bamfunc is called as functools.partial(bamfunc, args=args)()
+    (argparsers.py:695-696) and has to hand back a mapping rule."""
+    import argparse
+    import functools
+    from plastid_b200 import plugins
+    path = tmp_path / "p_offsets.txt"
+    path.write_text("length\tp_offset\n28\t12\n29\t13\ndefault\t13")
+    args = argparse.Namespace(offset=14, nibble=12)
+    made = {}
+    for desc in (plugins.fiveprime, plugins.threeprime, plugins.center, plugins.fiveprime_variable):
+        assert set(desc) >= {"name", "bamfunc", "help"} and desc["name"].startswith("b200_") and desc["help"]
+        if desc is plugins.fiveprime_variable:
+            args = argparse.Namespace(offset=str(path), nibble=0)
+        made[desc["name"]] = functools.partial(desc["bamfunc"], args=args)()
+    assert isinstance(made["b200_fiveprime"], pb.FivePrimeMapFactory) and made["b200_fiveprime"].offset == 14
+    assert type(made["b200_threeprime"]) is pb.ThreePrimeMapFactory and made["b200_threeprime"].offset == 14
+    assert isinstance(made["b200_center"], pb.CenterMapFactory) and made["b200_center"].nibble == 12
+    var = made["b200_fiveprime_variable"]
+    assert isinstance(var, pb.VariableFivePrimeMapFactory) and var.forward_offsets[28] == 12 and var.forward_offsets[40] == 13
+    assert plugins.device_option["name"] == "device" and plugins.device_option["default"] == "cuda"
+    for rule in made.values():
+        assert callable(rule)                                   # fn(reads, seg) -> (reads_out, counts)
