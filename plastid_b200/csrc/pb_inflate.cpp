@@ -75,6 +75,9 @@ inline u32 symbol_entry(Kind kind, u32 sym)
 // that symbol is a literal too, the entry carries both (value = first | second << 8, bits = both codes).
 void pair_literals(u32 *table, u32 tbits)
 {
+#ifdef PB_INFLATE_NO_PAIRS      // A/B only
+    return;
+#endif
     // descending and in place: entry i looks at entry i >> (its code length), which lies below i and is still single;
     // written without a branch (the pattern of literal / non-literal entries is not predictable)
     for (u32 i = (1u << tbits) - 1; i > 0; --i) {
