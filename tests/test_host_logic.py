@@ -1064,3 +1064,24 @@ def test_mapping_rule_plugin_descriptors(tmp_path):
     assert plugins.device_option["name"] == "device" and plugins.device_option["default"] == "cuda"
     for rule in made.values():
         assert callable(rule)                                   # fn(reads, seg) -> (reads_out, counts)
+
+
+def test_batch_rows_viewed_as_read_objects():
+    """`reads_out` of a batch decoded from a file holds BatchRead views (no pysam objects exist there): the
+    attributes a mapping rule or a user filter reads (map_factories.pyx:243,345; genome_array.py:811-818)."""
+    rng = np.random.default_rng(3)
+    lens = {"chrA": 20_000}
+    reads = {"chrA": random_cigar_reads(rng, 200, 20_000, 15_000)}
+    packed = pack_reads(reads, lens, keep_objects=False)
+    assert packed.objects is None
+    ordered = sorted(reads["chrA"], key=lambda r: r.positions[0])
+    for i in (0, 1, 57, 199):
+        view = packed.read_view(i)
+        want = po.positions_from_cigar(ordered[i].reference_start, ordered[i].cigartuples)
+        assert view.positions == want == view.get_reference_positions()
+        assert view.reference_start == want[0] and view.is_reverse == ordered[i].is_reverse
+        assert view == packed.read_view(i) and hash(view) == hash(packed.read_view(i)) and view != packed.read_view(i + 1 if i < 199 else 0)
+        assert ("#%d" % i) in repr(view)
+    assert len({packed.read_view(i) for i in range(200)} | {packed.read_view(0)}) == 200
+    kept = pack_reads(reads, lens)                              # the packer's own objects when they are kept
+    assert kept.read_view(0) is kept.objects[0] and kept.read_view(0).positions == packed.read_view(0).positions
