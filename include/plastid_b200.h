@@ -34,6 +34,7 @@
  *                                                          plastid/genomics/genome_hash.py:259-436,
  *                                                          plastid/genomics/roitools.pyx:2213-2301
  *   pb_export_runs   BAMGenomeArray.to_variable_step / to_bedgraph  plastid/genomics/genome_array.py:990-1111
+ *   pb_format_track  the per-line text writes of the same two methods (host)  :1030-1037, 1096-1111
  *   pb_phase_sums    sub-codon phase accumulation          plastid/bin/phase_by_size.py:165-235
  *   pb_stratified_windows  per-read-length window matrices plastid/bin/psite.py:176-199,
  *                                                          plastid/bin/phase_by_size.py:186-194
@@ -439,6 +440,17 @@ size_t pb_export_workspace_bytes(int64_t n_bins);
 int pb_export_runs(const void *vec, int vec_dtype, int64_t n_bins, int64_t window, int mode,
                    int64_t capacity, int64_t *out_start, int64_t *out_end, double *out_val,
                    int64_t *n_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The text of those records (host side, no CUDA), formatted like the reference's per-line Python writes:
+ * kind 0 (variableStep) `"%s\t%s\n" % (start + 1, value)` (plastid/genomics/genome_array.py:1030-1037), kind 1
+ * (bedGraph) `"%s\t%s\t%s\t%s\n" % (chrom, start, end, value)` (:1096-1111).  `values` is int64[n] or — when
+ * values_are_float — float64[n], printed as str() of a numpy.float64 prints them (shortest round-trip digits,
+ * fixed notation for 1e-4 <= |x| < 1e16 with ".0" on integers, else exponent form with two exponent digits at least).
+ * HOST pointers.  `out` has to hold pb_format_track_bound(kind, chrom, n) bytes; returns the bytes written
+ * (no terminator), -1 on bad arguments.  n_threads 0 = all. */
+int64_t pb_format_track_bound(int kind, const char *chrom, int64_t n);
+int64_t pb_format_track(int kind, const char *chrom, const int64_t *start, const int64_t *end, const void *values,
+                        int values_are_float, int64_t n, char *out, int64_t cap, int n_threads);
 
 /* `metagene generate` geometry.  Transcript table: blocks [tx_bstart, tx_bend) ascending per
  * transcript, in ONE coordinate system shared by all chromosomes (global bins: chrom_bin_off[c] + position),

@@ -62,6 +62,8 @@ _SIGNATURES = {
     "pb_bam_copy": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "pb_bam_close": (None, [_P]),
     "pb_inflate_raw": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t]),
+    "pb_format_track_bound": (C.c_int64, [C.c_int, C.c_char_p, C.c_int64]),
+    "pb_format_track": (C.c_int64, [C.c_int, C.c_char_p, _P, _P, _P, C.c_int, C.c_int64, _P, C.c_int64, C.c_int]),
     "pb_map_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "pb_unpack_wire16": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "pb_unpack_delta8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),

@@ -796,6 +796,27 @@ class BAMGenomeArray(object):
         return st[:total].cpu().numpy(), (en[:total].cpu().numpy() if mode == 1 else None), vals
 
     @staticmethod
+    def _write_records(fh, kind, chrom, st, en, vals, chunk=1 << 20):
+        """Lines of one chromosome (``pb_format_track``: the reference's per-line ``fh.write("%s\\t%s\\n" % ...)``,
+        genome_array.py:1030-1037, 1096-1111, as one native pass per 1 M records)."""
+        L = _lib.lib()
+        is_float = vals.dtype.kind == "f"
+        vals = np.ascontiguousarray(vals, dtype=np.float64 if is_float else np.int64)
+        st = np.ascontiguousarray(st, dtype=np.int64)
+        en = None if en is None else np.ascontiguousarray(en, dtype=np.int64)
+        name = chrom.encode()
+        p = lambda a, lo: None if a is None else C.c_void_p(a.ctypes.data + lo * a.itemsize)   # noqa: E731
+        cap = L.pb_format_track_bound(kind, name, min(chunk, len(st)))
+        buf = np.empty(cap, dtype=np.uint8)
+        for lo in range(0, len(st), chunk):
+            n = min(chunk, len(st) - lo)
+            got = L.pb_format_track(kind, name, p(st, lo), p(en, lo), p(vals, lo), int(is_float), n,
+                                    buf.ctypes.data_as(C.c_void_p), cap, 0)
+            if got < 0:
+                raise _lib.PlastidB200Error(L.pb_last_error().decode())
+            fh.write(buf[:got].tobytes().decode("ascii"))
+
+    @staticmethod
     def _write_track_header(fh, kind, trackname, kwargs):
         fh.write("track type=%s name=%s" % (kind, trackname))
         for k, v in sorted(kwargs.items(), key=lambda x: x[0]):
@@ -813,7 +834,7 @@ class BAMGenomeArray(object):
                 printer.write("Writing chromosome %s..." % chrom)
             fh.write("variableStep chrom=%s span=1\n" % chrom)
             pos, _e, vals = self._export_records(chrom, strand, 0, window_size)
-            fh.write("".join("%s\t%s\n" % (p + 1, v) for p, v in zip(pos.tolist(), vals)))
+            self._write_records(fh, 0, chrom, pos, None, vals)
 
     def to_bedgraph(self, fh, trackname, strand, window_size=100000, printer=None, **kwargs):
         """genome_array.py:1039-1111: runs of equal positive values, cut at ``window_size`` boundaries."""
@@ -826,7 +847,7 @@ class BAMGenomeArray(object):
             if printer is not None:
                 printer.write("Writing chromosome %s..." % chrom)
             st, en, vals = self._export_records(chrom, strand, 1, window_size)
-            fh.write("".join("%s\t%s\t%s\t%s\n" % (chrom, a, b, v) for a, b, v in zip(st.tolist(), en.tolist(), vals)))
+            self._write_records(fh, 1, chrom, st, en, vals)
 
     def to_genome_array(self, array_type=None):
         """genome_array.py:965-988 — including its quirk of dropping each chromosome's last base."""

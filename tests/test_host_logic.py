@@ -1085,3 +1085,79 @@ def test_batch_rows_viewed_as_read_objects():
     assert len({packed.read_view(i) for i in range(200)} | {packed.read_view(0)}) == 200
     kept = pack_reads(reads, lens)                              # the packer's own objects when they are kept
     assert kept.read_view(0) is kept.objects[0] and kept.read_view(0).positions == packed.read_view(0).positions
+
+
+def _python_track_lines(kind, chrom, st, en, vals):
+    """The reference's own per-line writes (genome_array.py:1030-1037, 1096-1111) on numpy scalars."""
+    if kind == 0:
+        return "".join("%s\t%s\n" % (p + 1, v) for p, v in zip(st.tolist(), vals))
+    return "".join("%s\t%s\t%s\t%s\n" % (chrom, a, b, v) for a, b, v in zip(st.tolist(), en.tolist(), vals))
+
+
+def test_track_text_is_formatted_like_python_does():
+    """pb_format_track (what to_variable_step / to_bedgraph write with) against Python's `%s` of numpy scalars:
+    integer counts, normalised counts, Center-rule fractions, and the corners of float repr (exponent thresholds at
+    1e-4 and 1e16, subnormals, 17-digit values, integers-valued floats, nan / inf / signed zero)."""
+    import io
+    rng = np.random.default_rng(13)
+    n = 50_000
+    st = np.sort(rng.integers(0, 2_000_000_000, n)).astype(np.int64)
+    en = st + rng.integers(1, 5000, n)
+    corner = np.array([1e-4, 9.999e-5, 1e-5, 1.5e-7, 1e16, 9999999999999998.0, 1.2345678901234567e16, 123456789.125, 0.1 + 0.2, 1 / 3.0,
+                       5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 1e22, 1e23, 100000.0, 5.0, 0.5, 1e15, 123456.0,
+                       0.0001234, 12.0 / 76, 1e6 / 3e8, 0.0, -0.0, -2.5, float("nan"), float("inf"), float("-inf"), 1e100, 4.35, 0.3])
+    families = [
+        rng.integers(1, 100_000, n).astype(np.int64),                                     # raw counts
+        np.array([0, 1, 9, 10, 99, 2**31, 2**40, 2**62, -7], dtype=np.int64),             # integer corners
+        rng.integers(1, 5000, n) / 500477.0 * 1e6,                                         # normalised counts
+        rng.integers(1, 4000, n) / 76.0,                                                   # Center fractions, one map length
+        (rng.integers(1, 300, n) / rng.integers(1, 40, n)) + (rng.integers(0, 50, n) / 13.0),
+        rng.random(n) * 10.0 ** rng.integers(-12, 20, n),                                 # every magnitude
+        corner,
+        np.ldexp(rng.random(n), rng.integers(-1070, 1020, n)),                            # down to subnormals
+    ]
+    for vals in families:
+        m = len(vals)
+        for kind, chrom in ((0, "chrI"), (1, "chrI"), (1, "a_rather_long_contig_name|with.odd-chars")):
+            fh = io.StringIO()
+            pb.BAMGenomeArray._write_records(fh, kind, chrom, st[:m], en[:m] if kind else None, vals, chunk=7001)
+            assert fh.getvalue() == _python_track_lines(kind, chrom, st[:m], en[:m], vals), (kind, vals.dtype)
+    fh = io.StringIO()
+    pb.BAMGenomeArray._write_records(fh, 1, "c", st[:0], en[:0], families[0][:0])
+    assert fh.getvalue() == ""
+    big = np.arange(300_000, dtype=np.int64)                                               # several threads, one chunk
+    fh = io.StringIO()
+    pb.BAMGenomeArray._write_records(fh, 0, "c", big, None, big % 977 / 7.0)
+    assert fh.getvalue() == _python_track_lines(0, "c", big, None, big % 977 / 7.0)
+    L = _lib.lib()
+    assert L.pb_format_track(2, b"c", None, None, None, 0, 0, None, 0, 1) == -1
+    one = np.zeros(1, dtype=np.int64)
+    p = one.ctypes.data_as(C.c_void_p)
+    assert L.pb_format_track(0, None, p, None, p, 0, 1, p, 8, 1) == -1 and b"bound" in L.pb_last_error()
+
+
+def test_track_writers_around_the_formatter(monkeypatch):
+    """to_variable_step / to_bedgraph with the device compaction replaced by given records: header line, track
+    keywords in sorted order, chromosomes in sorted order, `variableStep` lines, one formatted line per record
+    (genome_array.py:990-1111)."""
+    import io
+    records = {"chrB": (np.array([4, 9, 10], dtype=np.int64), np.array([6, 10, 40], dtype=np.int64), np.array([2, 1, 7], dtype=np.int64)),
+               "chrA": (np.array([0, 99], dtype=np.int64), np.array([3, 100], dtype=np.int64), np.array([0.5, 1e-05])),
+               "chrC": (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))}
+    ga = object.__new__(pb.BAMGenomeArray)
+    monkeypatch.setattr(pb.BAMGenomeArray, "strands", lambda self: ("+", "-", "."))
+    monkeypatch.setattr(pb.BAMGenomeArray, "chroms", lambda self: ["chrB", "chrC", "chrA"])
+    monkeypatch.setattr(pb.BAMGenomeArray, "_is_lowerable", lambda self: True)
+    monkeypatch.setattr(pb.BAMGenomeArray, "_export_records",
+                        lambda self, chrom, strand, mode, window: (records[chrom][0], records[chrom][1] if mode == 1 else None, records[chrom][2]))
+    fh = io.StringIO()
+    ga.to_variable_step(fh, "tr", "+", color="0,0,255", autoScale="on")
+    assert fh.getvalue() == ("track type=wiggle_0 name=tr autoScale=on color=0,0,255\n"
+                             "variableStep chrom=chrA span=1\n1\t0.5\n100\t1e-05\n"
+                             "variableStep chrom=chrB span=1\n5\t2\n10\t1\n11\t7\n"
+                             "variableStep chrom=chrC span=1\n")
+    fh = io.StringIO()
+    ga.to_bedgraph(fh, "tr", "-")
+    assert fh.getvalue() == ("track type=bedGraph name=tr\n"
+                             "chrA\t0\t3\t0.5\nchrA\t99\t100\t1e-05\n"
+                             "chrB\t4\t6\t2\nchrB\t9\t10\t1\nchrB\t10\t40\t7\n")
