@@ -936,13 +936,11 @@ def batch_from_arrays(chroms, chrom_len, chrom_id, ref_start, aligned_len, is_re
         listed = np.where(nb_in[order] > 1, nb_in[order], 0)
         blk_off = np.zeros(len(order) + 1, dtype=np.int64)
         np.cumsum(listed, out=blk_off[1:])
-        blk = np.zeros((int(blk_off[-1]), 2), dtype=np.int32)
-        multi = np.nonzero(listed)[0]
-        for dst_i in multi:                     # spliced reads only
-            src = order[dst_i]
-            blk[blk_off[dst_i]:blk_off[dst_i + 1]] = blk_in[in_off[src]:in_off[src + 1]]
-        if len(multi) == 0:
+        if blk_off[-1] == 0:
             blk_off = blk = None
+        else:                                   # rows of the multi-block reads only, one gather for all of them
+            take = np.repeat(in_off[:-1][order] - blk_off[:-1], listed) + np.arange(int(blk_off[-1]), dtype=np.int64)
+            blk = np.ascontiguousarray(blk_in[take], dtype=np.int32).reshape(-1, 2)
     meta = (aligned_len[order].astype(np.uint32)
             | (np.asarray(is_reverse, dtype=np.uint32)[order] << 16)
             | (nblk[order].astype(np.uint32) << 24))

@@ -538,7 +538,9 @@ def merge_batches(batches):
                 nblk_rows.append(np.diff(b.blk_off.astype(np.int64)))
                 blk_all.append(b.blk)
     cid, start, meta = np.concatenate(cid), np.concatenate(start), np.concatenate(meta)
-    order = np.lexsort((start, cid))
+    # every input is sorted already: a stable sort of one combined key only has to merge a few runs (ties keep
+    # the order of the files, as the reference's chained fetch does)
+    order = np.argsort((cid << 32) + start.astype(np.int64), kind="stable")
     blk_off = blk = None
     if any_blk:
         rows = np.concatenate(nblk_rows)
@@ -547,10 +549,9 @@ def merge_batches(batches):
         blk_src = np.concatenate(blk_all) if blk_all else np.zeros((0, 2), dtype=np.int32)
         blk_off = np.zeros(len(order) + 1, dtype=np.int64)
         np.cumsum(rows[order], out=blk_off[1:])
-        blk = np.zeros((int(blk_off[-1]), 2), dtype=np.int32)
-        for dst in np.nonzero(rows[order])[0]:
-            src = order[dst]
-            blk[blk_off[dst]:blk_off[dst + 1]] = blk_src[src_off[src]:src_off[src + 1]]
+        # row k of destination read d comes from row src_off[order[d]] + k: one gather for all reads
+        take = np.repeat(src_off[:-1][order] - blk_off[:-1], rows[order]) + np.arange(int(blk_off[-1]), dtype=np.int64)
+        blk = np.ascontiguousarray(blk_src[take], dtype=np.int32).reshape(-1, 2)
     counts = np.bincount(cid, minlength=len(chroms))
     off = np.zeros(len(chroms) + 1, dtype=np.int64)
     np.cumsum(counts, out=off[1:])

@@ -1161,3 +1161,50 @@ def test_track_writers_around_the_formatter(monkeypatch):
     assert fh.getvalue() == ("track type=bedGraph name=tr\n"
                              "chrA\t0\t3\t0.5\nchrA\t99\t100\t1e-05\n"
                              "chrB\t4\t6\t2\nchrB\t9\t10\t1\nchrB\t10\t40\t7\n")
+
+
+def _spliced_arrays(rng, n, n_chrom, with_blocks=True):
+    cid = rng.integers(0, n_chrom, n)
+    start = rng.integers(0, 3000, n)                        # many ties: the merge has to be stable
+    nb = rng.choice([1, 1, 1, 2, 3, 5], n) if with_blocks else np.ones(n, dtype=np.int64)
+    rows, L = [], np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        at = 0
+        for _k in range(int(nb[i])):
+            ln = int(rng.integers(1, 40))
+            rows.append((at, ln))
+            L[i] += ln
+            at += ln + int(rng.integers(1, 500))
+    return cid, start, L, rng.integers(0, 2, n), nb, np.asarray(rows, dtype=np.int32)
+
+
+def test_batches_from_arrays_and_merges_keep_every_read_and_block():
+    """batch_from_arrays / merge_batches on random spliced reads (vectorised block gathers) against a plain
+    per-read statement: stable order by (chromosome, start), every read's blocks behind it, file order for ties
+    (the reference chains `fetch` over the files in the order given, genome_array.py:800-809)."""
+    rng = np.random.default_rng(17)
+    chroms, lens = ["a", "b", "c"], [10**6] * 3
+    parts, flat = [], []
+    for f, (n, with_blocks) in enumerate(((700, True), (300, False), (500, True), (0, True))):
+        cid, start, L, rev, nb, rows = _spliced_arrays(rng, n, 3, with_blocks)
+        b = batch_from_arrays(chroms, lens, cid, start, L, rev, blocks=(nb, rows) if with_blocks else None)
+        b.check_sorted()
+        at = np.concatenate([[0], np.cumsum(nb)])
+        reads = [(int(cid[i]), int(start[i]), int(L[i]), bool(rev[i]), [tuple(r) for r in rows[at[i]:at[i + 1]].tolist()]) for i in range(n)]
+        want = sorted(reads, key=lambda r: (r[0], r[1]))                      # sorted() is stable
+        assert len(b) == n
+        for i, (c, s, ln, rv, blks) in enumerate(want):
+            assert int(b.ref_start[i]) == s and int(b.aligned_len[i]) == ln and bool(b.is_reverse[i]) == rv
+            assert b.positions_of(i) == [s + a + k for a, m in blks for k in range(m)]
+        assert list(np.diff(b.chrom_read_off)) == [sum(1 for r in reads if r[0] == c) for c in range(3)]
+        parts.append(b)
+        flat.extend((r, f) for r in want)
+    m = merge_batches(parts)
+    m.check_sorted()
+    want = sorted(flat, key=lambda x: (x[0][0], x[0][1]))                      # ties: first file first
+    assert len(m) == len(want) == 1500 and m.mapped == 1500
+    for i, ((c, s, ln, rv, blks), _f) in enumerate(want):
+        assert int(m.ref_start[i]) == s and int(m.aligned_len[i]) == ln and bool(m.is_reverse[i]) == rv
+        assert m.positions_of(i) == [s + a + k for a, mm in blks for k in range(mm)]
+    assert (m.meta >> 24).tolist() == [len(r[0][4]) for r in want]
+    assert merge_batches(parts[1:2]).blk is None and merge_batches([parts[1], parts[1]]).blk is None
