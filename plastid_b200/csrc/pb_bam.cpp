@@ -11,6 +11,9 @@
 // records count); records without a reference or with the unmapped flag have no positions and are
 // skipped.  File format: SAM/BAM specification v1 §4 (BGZF §4.1, BAM §4.2); cross-checked against
 // the reference's vendored htslib 1.3 through tests/golden/*.bam (see oracle/Makefile).
+// Not resolved: CIGARs of more than 65535 operations kept in a CG:B,I tag behind a "<l>S<n>N" placeholder (SAM spec
+// 4.2.2, long reads) — the record then has no aligned block and maps nowhere, as with the reference's htslib 1.3,
+// which predates the tag.
 #include <zlib.h>
 
 #include <algorithm>
