@@ -392,22 +392,28 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
     if (rc) { pb_set_error("pb_bam_decode(%s): %s", h->path.c_str(), err.c_str()); return rc; }
 
     const size_t n = h->start.size(), n_ref = h->ref_name.size();
+    // reference ids never decrease (checked above), so the per-chromosome offsets are n_ref binary searches
     h->chrom_read_off.assign(n_ref + 1, 0);
-    for (size_t i = 0; i < n; ++i) {
-        if ((size_t)tid_all[i] >= n_ref) { pb_set_error("pb_bam_decode: record refers to reference %d of %zu", tid_all[i], n_ref); return PB_EINVAL; }
-        h->chrom_read_off[tid_all[i] + 1]++;
+    if (n && (size_t)tid_all.back() >= n_ref) {
+        pb_set_error("pb_bam_decode: record refers to reference %d of %zu", tid_all.back(), n_ref);
+        return PB_EINVAL;
     }
-    for (size_t c = 0; c < n_ref; ++c) h->chrom_read_off[c + 1] += h->chrom_read_off[c];
+    for (size_t c = 0; c <= n_ref; ++c)
+        h->chrom_read_off[c] = std::lower_bound(tid_all.begin(), tid_all.end(), (int32_t)c) - tid_all.begin();
     // starts must be non-decreasing per chromosome; a (rare) leading-deletion shift is repaired by a
     // stable sort of that chromosome's rows
     bool any_multi = !h->blk.empty();
-    std::vector<uint64_t> blk_start(n + 1, 0);
-    for (size_t i = 0; i < n; ++i) blk_start[i + 1] = blk_start[i] + nlisted_all[i];
-    bool sorted = true;
-    for (size_t c = 0; c < n_ref && sorted; ++c)
-        for (int64_t i = h->chrom_read_off[c] + 1; i < h->chrom_read_off[c + 1]; ++i)
-            if (h->start[i] < h->start[i - 1]) { sorted = false; break; }
+    std::atomic<int> unsorted{0};
+    const size_t piece = (size_t)1 << 20;
+    parallel_for(n_threads, (n + piece - 1) / piece, [&](size_t k) {
+        const size_t a = std::max<size_t>(k * piece, 1), e = std::min(n, (k + 1) * piece);
+        for (size_t i = a; i < e; ++i)
+            if (h->start[i] < h->start[i - 1] && tid_all[i] == tid_all[i - 1]) { unsorted = 1; return; }
+    });
+    const bool sorted = unsorted == 0;
     if (!sorted) {
+        std::vector<uint64_t> blk_start(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) blk_start[i + 1] = blk_start[i] + nlisted_all[i];
         std::vector<size_t> order(n);
         for (size_t i = 0; i < n; ++i) order[i] = i;
         for (size_t c = 0; c < n_ref; ++c)

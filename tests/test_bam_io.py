@@ -316,3 +316,38 @@ def test_positions_match_reference_htslib_pileup():
         assert [pos + a + k for a, n in blocks for k in range(n)] == gold[i][1]   # host packer
         assert hb.positions_of(i) == gold[i][1]                                   # BAM decoder
     assert ops_seen == set(range(9))
+
+
+def test_leading_deletions_reorder_rows_and_their_blocks(tmp_path, monkeypatch):
+    """A leading D / N moves a read's first aligned position past the file's POS, possibly past its successors:
+    rows (and the block rows of spliced reads among them) are put back in start order, per chromosome, stably."""
+    monkeypatch.setenv("PB_BAM_WALK_MIN", "0")
+    rng = np.random.default_rng(6)
+    lens = {"chrA": 100_000, "chrB": 50_000}
+    reads, recs = {"chrA": [], "chrB": []}, []
+    for ci, c in enumerate(lens):
+        for pos in np.sort(rng.integers(0, 40_000, 4000)).tolist():
+            kind = int(rng.integers(0, 6))
+            if kind == 0:
+                cigar = [(2, int(rng.integers(1, 300))), (0, 25)]                             # leading deletion
+            elif kind == 1:
+                cigar = [(4, 3), (3, int(rng.integers(1, 200))), (0, 10), (3, 700), (0, 12)]    # clip, leading skip, spliced
+            elif kind == 2:
+                cigar = [(0, 14), (3, int(rng.integers(50, 900))), (0, 16), (2, 4), (0, 5)]
+            else:
+                cigar = [(0, int(rng.integers(20, 40)))]
+            rev = bool(rng.integers(0, 2))
+            reads[c].append(po.Read(pos, cigar, rev))
+            recs.append((ci, pos, 16 if rev else 0, cigar))
+    path = str(tmp_path / "lead.bam")
+    bam_io.write_bam(path, lens, recs, block_bytes=30_000, record_aligned=True)
+    ref = pack_reads(reads, lens)
+    for threads in (1, 4):
+        hb = bam_io.batch_from_bam(path, threads=threads)
+        hb.check_sorted()
+        assert len(hb) == len(ref) == 8000
+        for f in ("ref_start", "meta", "chrom_read_off", "blk_off", "blk"):
+            assert (getattr(hb, f) == getattr(ref, f)).all(), (threads, f)
+    assert (np.diff(hb.ref_start[:4000]) >= 0).all() and int(hb.ref_start[0]) >= 0
+    starts_in_file = np.array([r[1] for r in recs[:4000]])
+    assert not np.array_equal(np.sort(hb.ref_start[:4000]), starts_in_file)                    # something did move
