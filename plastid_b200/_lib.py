@@ -166,3 +166,21 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_threads(requested=0):
+    """Worker threads for the host-side passes (BAM decode, transfer-format packing, track text): ``requested`` when
+    positive, else the CPUs this process may run on (its affinity mask, not the machine's core count — a rank bound to
+    its GPU's NUMA node must not start a thread per core of the whole box), shared out among the ranks of the node
+    when torchrun started several and nobody narrowed the mask."""
+    if requested and int(requested) > 0:
+        return int(requested)
+    import os
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        allowed = os.cpu_count() or 1
+    ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    if ranks > 1 and allowed == (os.cpu_count() or allowed):
+        allowed = max(1, allowed // ranks)
+    return max(1, allowed)

@@ -29,7 +29,7 @@ def batch_from_bam(source, threads=0, pinned=False):
     path = source.encode() if isinstance(source, str) else source
     _lib.check(L.pb_bam_open(path, C.byref(handle)))
     try:
-        _lib.check(L.pb_bam_decode(handle, int(threads)))
+        _lib.check(L.pb_bam_decode(handle, _lib.host_threads(threads)))
         n_ref = L.pb_bam_n_ref(handle)
         chroms = [L.pb_bam_ref_name(handle, i).decode() for i in range(n_ref)]
         lens = [L.pb_bam_ref_len(handle, i) for i in range(n_ref)]

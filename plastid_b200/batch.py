@@ -537,7 +537,7 @@ class Delta3Batch(object):
 
             def p(a):
                 return C.c_void_p(a.ctypes.data)
-            _lib.check(_lib.lib().pb_pack_delta3(p(start32), p(meta32), p(off), len(hb.chroms), n, int(threads), p(packed),
+            _lib.check(_lib.lib().pb_pack_delta3(p(start32), p(meta32), p(off), len(hb.chroms), n, _lib.host_threads(threads), p(packed),
                                                  p(wide), p(blk_base), p(blk_wide_off), p(blk_exc_off), p(exc_start),
                                                  p(exc_meta), p(meta_dict), C.byref(n_wide), C.byref(n_exc)))
             chrom_of_blk = (np.searchsorted(off, np.arange(0, n, K), side="right") - 1).astype(np.int32)

@@ -812,7 +812,7 @@ class BAMGenomeArray(object):
         for lo in range(0, len(st), chunk):
             n = min(chunk, len(st) - lo)
             got = L.pb_format_track(kind, name, p(st, lo), p(en, lo), p(vals, lo), int(is_float), n,
-                                    buf.ctypes.data_as(C.c_void_p), cap, 0)
+                                    buf.ctypes.data_as(C.c_void_p), cap, _lib.host_threads())
             if got < 0:
                 raise _lib.PlastidB200Error(L.pb_last_error().decode())
             fh.write(buf[:got].tobytes().decode("ascii"))

@@ -1208,3 +1208,21 @@ def test_batches_from_arrays_and_merges_keep_every_read_and_block():
         assert m.positions_of(i) == [s + a + k for a, mm in blks for k in range(mm)]
     assert (m.meta >> 24).tolist() == [len(r[0][4]) for r in want]
     assert merge_batches(parts[1:2]).blk is None and merge_batches([parts[1], parts[1]]).blk is None
+
+
+def test_host_thread_count_follows_affinity_and_ranks(monkeypatch):
+    import os
+    assert _lib.host_threads(3) == 3
+    allowed = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    assert _lib.host_threads() == _lib.host_threads(0) == allowed
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    if allowed == os.cpu_count():
+        assert _lib.host_threads() == max(1, allowed // 8)
+    if hasattr(os, "sched_setaffinity") and allowed > 1:
+        before = os.sched_getaffinity(0)
+        try:
+            os.sched_setaffinity(0, set(sorted(before)[:1]))
+            assert _lib.host_threads() == 1                    # a narrowed mask is taken as it is, ranks or not
+        finally:
+            os.sched_setaffinity(0, before)
