@@ -14,6 +14,8 @@
 // Not resolved: CIGARs of more than 65535 operations kept in a CG:B,I tag behind a "<l>S<n>N" placeholder (SAM spec
 // 4.2.2, long reads) — the record then has no aligned block and maps nowhere, as with the reference's htslib 1.3,
 // which predates the tag.
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -176,7 +178,23 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
     }
     size_t kWalkMin = (size_t)4 << 20;                 // plain bytes below which the record walk stays serial
     if (const char *w = getenv("PB_BAM_WALK_MIN")) kWalkMin = (size_t)std::max(0l, atol(w));
-    std::vector<uint8_t> comp(kWindow + (1 << 16));
+    // input: the file mapped read-only where that works (members are inflated straight out of the page cache by the
+    // worker threads, the kernel reads ahead), else read() into a window buffer (pipes; PB_BAM_NOMMAP=1 for tests)
+    const uint8_t *map = nullptr;
+    size_t map_size = 0, map_pos = 0;
+    {
+        struct stat st;
+        if (!getenv("PB_BAM_NOMMAP") && fstat(fileno(fh), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(fh), 0);
+            if (m != MAP_FAILED) {
+                map = (const uint8_t *)m;
+                map_size = (size_t)st.st_size;
+                madvise(m, map_size, MADV_SEQUENTIAL);
+            }
+        }
+    }
+    std::vector<uint8_t> comp(map ? 0 : kWindow + (1 << 16));
+    const uint8_t *cbase = comp.data();
     RawBuf plain;
     size_t comp_have = 0, carry = 0;
     bool eof = false, header_done = false;
@@ -193,7 +211,11 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
     double t_read = 0, t_inflate = 0, t_walk = 0, t_conv = 0, t_app = 0, t0 = now();
     while (rc == PB_OK && !(eof && comp_have == 0)) {
         double ta = now();
-        if (!eof && comp_have < kWindow) {
+        if (map) {
+            cbase = map + map_pos;
+            comp_have = std::min(kWindow, map_size - map_pos);
+            eof = map_pos + comp_have == map_size;
+        } else if (!eof && comp_have < kWindow) {
             const size_t got = fread(comp.data() + comp_have, 1, kWindow - comp_have, fh);
             comp_have += got;
             if (got == 0) eof = true;
@@ -202,7 +224,7 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
         std::vector<Block> blocks;
         size_t off = 0, udst = carry;
         while (off + 18 <= comp_have) {
-            const uint8_t *p = comp.data() + off;
+            const uint8_t *p = cbase + off;
             if (p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) { err = "not a BGZF file (bad member header)"; rc = PB_EINVAL; break; }
             const uint32_t xlen = rd16(p + 10);
             if (off + 12 + xlen > comp_have) break;
@@ -233,14 +255,14 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
             const Block &b = blocks[i];
             if (b.usize == 0) return;
             if (!use_zlib) {
-                if (pb_inflate_raw(comp.data() + b.src, b.csize, plain.data() + b.dst, b.usize) != 0) bad = 1;
+                if (pb_inflate_raw(cbase + b.src, b.csize, plain.data() + b.dst, b.usize) != 0) bad = 1;
                 else if (check_crc && (uint32_t)crc32(crc32(0L, Z_NULL, 0), plain.data() + b.dst, (uInt)b.usize) != b.crc) bad = 2;
                 return;
             }
             z_stream zs;
             memset(&zs, 0, sizeof(zs));
             if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-            zs.next_in = comp.data() + b.src; zs.avail_in = (uInt)b.csize;
+            zs.next_in = (Bytef *)(cbase + b.src); zs.avail_in = (uInt)b.csize;
             zs.next_out = plain.data() + b.dst; zs.avail_out = (uInt)b.usize;
             const int zr = inflate(&zs, Z_FINISH);
             if (zr != Z_STREAM_END || zs.total_out != b.usize) bad = 1;
@@ -248,7 +270,8 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
             inflateEnd(&zs);
         });
         if (bad) { err = bad == 2 ? "corrupt BGZF member (CRC32 mismatch)" : "corrupt BGZF member (inflate failed)"; rc = PB_EINVAL; break; }
-        memmove(comp.data(), comp.data() + off, comp_have - off);
+        if (map) map_pos += off;
+        else memmove(comp.data(), comp.data() + off, comp_have - off);
         comp_have -= off;
 
         t_inflate += now() - ta; ta = now();
@@ -384,6 +407,7 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
         plain.resize(carry);
         t_app += now() - ta;
     }
+    if (map) munmap((void *)map, map_size);
     fclose(fh);
     if (dbg) fprintf(stderr, "pb_bam_decode: read %.3f inflate %.3f walk %.3f convert %.3f append %.3f total %.3f s\n",
                      t_read, t_inflate, t_walk, t_conv, t_app, now() - t0);

@@ -199,6 +199,12 @@ def test_decoder_same_arrays_with_zlib(tmp_path, monkeypatch):
     monkeypatch.setenv("PB_BAM_ZLIB", "1")
     ref = bam_io.batch_from_bam(path, threads=3)
     assert len(own) == len(recs) and (own.ref_start == ref.ref_start).all() and (own.meta == ref.meta).all()
+    # and through read() into a window buffer instead of the mapped file (what a pipe gets), in small windows
+    monkeypatch.delenv("PB_BAM_ZLIB")
+    monkeypatch.setenv("PB_BAM_NOMMAP", "1")
+    monkeypatch.setenv("PB_BAM_WINDOW", "70000")
+    buffered = bam_io.batch_from_bam(path, threads=3)
+    assert (buffered.ref_start == own.ref_start).all() and (buffered.meta == own.meta).all() and buffered.mapped == own.mapped
 
 
 class _FakePysamRead(object):
