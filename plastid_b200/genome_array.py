@@ -815,7 +815,7 @@ class BAMGenomeArray(object):
                                     buf.ctypes.data_as(C.c_void_p), cap, _lib.host_threads())
             if got < 0:
                 raise _lib.PlastidB200Error(L.pb_last_error().decode())
-            fh.write(buf[:got].tobytes().decode("ascii"))
+            fh.write(buf[:got].tobytes().decode("utf-8"))
 
     @staticmethod
     def _write_track_header(fh, kind, trackname, kwargs):
