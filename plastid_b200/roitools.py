@@ -119,12 +119,14 @@ class SegmentChain(object):
             self._segments = []
             self.chrom = self.strand = None
             self.spanning_segment = None
-        self.length = sum(len(s) for s in self._segments)
-        self.masked_length = self.length
         # cumulative chain coordinate of each block's first base (genomic order)
-        self._cum = np.zeros(len(self._segments) + 1, dtype=np.int64)
-        if self._segments:
-            np.cumsum([len(s) for s in self._segments], out=self._cum[1:])
+        cum, total = [0], 0
+        for s in self._segments:
+            total += s.end - s.start
+            cum.append(total)
+        self.length = total
+        self.masked_length = total
+        self._cum = np.array(cum, dtype=np.int64)
 
     # -- container protocol ------------------------------------------------------------------
     def __len__(self):
