@@ -1226,3 +1226,29 @@ def test_host_thread_count_follows_affinity_and_ranks(monkeypatch):
             assert _lib.host_threads() == 1                    # a narrowed mask is taken as it is, ranks or not
         finally:
             os.sched_setaffinity(0, before)
+
+
+@pytest.mark.parametrize("prog", ["counts_in_region", "cs", "metagene", "psite", "phase_by_size", "make_wiggle"])
+def test_script_command_lines_parse_without_a_device(prog, capsys):
+    """Every sub-program builds its parser and prints its usage without touching CUDA; the reference's mapping flags
+    (argparsers.py:337-503: --fiveprime --threeprime --center --fiveprime_variable --offset --nibble --min_length
+    --max_length --sum) are there wherever alignments are read."""
+    import importlib
+    mod = importlib.import_module("plastid_b200.bin.%s" % prog)
+    with pytest.raises(SystemExit) as e:
+        mod.main(["--help"])
+    assert e.value.code == 0
+    usage = capsys.readouterr().out
+    sub = {"cs": "count", "metagene": "count"}.get(prog)
+    if sub is not None:
+        assert "generate" in usage and "count" in usage
+        with pytest.raises(SystemExit) as e:
+            mod.main([sub, "--help"])
+        assert e.value.code == 0
+        usage = capsys.readouterr().out
+    for flag in ("--count_files", "--fiveprime", "--threeprime", "--center", "--fiveprime_variable", "--offset", "--nibble",
+                 "--min_length", "--max_length", "--sum"):
+        assert flag in usage, (prog, flag)
+    with pytest.raises(SystemExit) as e:                      # required arguments missing: argparse's exit status 2
+        mod.main([sub] if sub else [])
+    assert e.value.code == 2
