@@ -43,6 +43,10 @@
  *   pb_spanning_windows  maximal_spanning_window per gene  plastid/bin/metagene.py:343-502, 702-735
  *   pb_chain_union / pb_chain_binary  position-set pooling / masking of `cs generate`
  *                                                          plastid/bin/cs.py:242-496
+ *   pb_bam_*         (host) pysam.AlignmentFile open / references / lengths / mapped / fetch and
+ *                    AlignedSegment.positions / is_reverse  plastid/genomics/genome_array.py:660-690, 800-815
+ *   pb_inflate_raw   (host) zlib's inflate() per BGZF member underneath pysam's htslib
+ *                                                          kent/src/htslib/bgzf.c:292-316
  *
  * Alignment batch (SoA, sorted by (chromosome, ref_start); what pysam hands the reference
  * as AlignedSegment.reference_start / .positions / .is_reverse):
