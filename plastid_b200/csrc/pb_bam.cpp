@@ -215,6 +215,10 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
             cbase = map + map_pos;
             comp_have = std::min(kWindow, map_size - map_pos);
             eof = map_pos + comp_have == map_size;
+            if (!eof) {                                    // the window after this one: start reading it now
+                const size_t next = (map_pos + comp_have) & ~(size_t)4095;
+                madvise((void *)(map + next), std::min(kWindow, map_size - next), MADV_WILLNEED);
+            }
         } else if (!eof && comp_have < kWindow) {
             const size_t got = fread(comp.data() + comp_have, 1, kWindow - comp_have, fh);
             comp_have += got;
