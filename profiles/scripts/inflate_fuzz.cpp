@@ -2,7 +2,8 @@
 //   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=undefined -DPB_INFLATE_POISON -Iinclude \
 //       profiles/scripts/inflate_fuzz.cpp plastid_b200/csrc/pb_inflate.cpp -o /tmp/inflate_fuzz -lz && /tmp/inflate_fuzz [streams]
 // 6000 streams by default (all levels / strategies / flush kinds, exact-size heap buffers) + 6 truncated or corrupted
-// variants of each.  PB_INFLATE_POISON fills the decode tables with plausible-looking stale entries before every
+// variants of each, every one of them also read by zlib: both have to accept the same streams with the same bytes.
+// PB_INFLATE_POISON fills the decode tables with plausible-looking stale entries before every
 // build: nothing a previous block left behind may leak into the next one (tests/test_bam_io.py runs this too).
 #include <zlib.h>
 #include <cstdio>
@@ -15,7 +16,7 @@ extern "C" int pb_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, si
 int main(int argc, char **argv) {
     const int n_iter = argc > 1 ? atoi(argv[1]) : 6000;
     std::mt19937_64 rng(7);
-    size_t ok = 0, rejected = 0, accepted_bad = 0;
+    size_t ok = 0, rejected = 0, accepted_bad = 0, diffs = 0;
     for (int it = 0; it < n_iter; ++it) {
         size_t n = (it % 5 == 0) ? rng() % 65281 : (size_t[]){0, 1, 3, 100, 319, 320, 321, 4000, 65280}[rng() % 9];
         std::vector<uint8_t> data(n);
@@ -52,9 +53,21 @@ int main(int argc, char **argv) {
             size_t n2 = (c == 4 && n) ? n - 1 - rng() % n : n;
             int rc = pb_inflate_raw(bad, l2, out, n2);
             if (rc == 0) ++accepted_bad; else ++rejected;
+            {   // differential: zlib reads the same damaged stream; both have to agree on acceptance and on the bytes
+                std::vector<uint8_t> zout(n2 + 16);
+                z_stream zi; memset(&zi, 0, sizeof zi); inflateInit2(&zi, -15);
+                zi.next_in = bad; zi.avail_in = l2; zi.next_out = zout.data(); zi.avail_out = n2 + 16;
+                int zr = inflate(&zi, Z_FINISH);
+                bool zok = zr == Z_STREAM_END && zi.total_out == n2;
+                inflateEnd(&zi);
+                if (zok != (rc == 0) || (zok && n2 && memcmp(zout.data(), out, n2))) {
+                    printf("DIFF it=%d c=%d n2=%zu l2=%zu pb=%d zlib=%d total_out=%lu\n", it, c, n2, l2, rc, zr, zi.total_out); ++diffs;
+                }
+            }
             free(bad);
         }
         free(in); free(out);
     }
-    printf("ok %zu, corrupted: rejected %zu, accepted %zu\n", ok, rejected, accepted_bad);
+    printf("ok %zu, corrupted: rejected %zu, accepted %zu, disagreements with zlib %zu\n", ok, rejected, accepted_bad, diffs);
+    if (diffs) return 5;
 }

@@ -187,6 +187,7 @@ def test_inflater_fuzz_with_poisoned_tables(tmp_path):
                            os.path.join(root, "plastid_b200", "csrc", "pb_inflate.cpp"), "-o", exe, "-lz"])
     out = subprocess.run([exe, "1200"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.startswith("ok 1200"), out.stdout + out.stderr
+    assert "disagreements with zlib 0" in out.stdout          # damaged streams: accepted exactly when zlib accepts them
 
 
 def test_decoder_same_arrays_with_zlib(tmp_path, monkeypatch):
