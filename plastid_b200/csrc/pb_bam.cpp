@@ -209,6 +209,7 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
     const bool use_zlib = getenv("PB_BAM_ZLIB") != nullptr;       // A/B and cross-checks; default: pb_inflate_raw
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_read = 0, t_inflate = 0, t_walk = 0, t_conv = 0, t_app = 0, t0 = now();
+    size_t n_chains_all = 0, n_chains_rewalked = 0;        // speculative record walk: stretches / stretches walked twice
     while (rc == PB_OK && !(eof && comp_have == 0)) {
         double ta = now();
         if (map) {
@@ -347,7 +348,9 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
         size_t n_recs = 0;
         for (size_t k = 0; k < chains.size(); ++k) {
             Chain &c = chains[k];
+            ++n_chains_all;
             if (c.begin != cur) {                                // guess missed: walk this stretch from the true position
+                ++n_chains_rewalked;
                 if (cur >= c.limit) continue;                    // (a record reaching past the whole stretch)
                 c.begin = cur;
                 walk(c);
@@ -413,8 +416,9 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
     }
     if (map) munmap((void *)map, map_size);
     fclose(fh);
-    if (dbg) fprintf(stderr, "pb_bam_decode: read %.3f inflate %.3f walk %.3f convert %.3f append %.3f total %.3f s\n",
-                     t_read, t_inflate, t_walk, t_conv, t_app, now() - t0);
+    if (dbg) fprintf(stderr, "pb_bam_decode: read %.3f inflate %.3f walk %.3f convert %.3f append %.3f total %.3f s; "
+                             "record walk: %zu stretches, %zu walked again\n",
+                     t_read, t_inflate, t_walk, t_conv, t_app, now() - t0, n_chains_all, n_chains_rewalked);
     if (rc == PB_OK && !header_done) { err = "empty or truncated BAM file"; rc = PB_EINVAL; }
     if (rc == PB_OK && carry != 0) { err = "truncated BAM record at end of file"; rc = PB_EINVAL; }
     if (rc) { pb_set_error("pb_bam_decode(%s): %s", h->path.c_str(), err.c_str()); return rc; }

@@ -358,3 +358,50 @@ def test_leading_deletions_reorder_rows_and_their_blocks(tmp_path, monkeypatch):
     assert (np.diff(hb.ref_start[:4000]) >= 0).all() and int(hb.ref_start[0]) >= 0
     starts_in_file = np.array([r[1] for r in recs[:4000]])
     assert not np.array_equal(np.sort(hb.ref_start[:4000]), starts_in_file)                    # something did move
+
+
+def test_speculative_walk_holds_on_a_file_written_by_the_reference_htslib(tmp_path):
+    """The record walk guesses that BGZF members start at record boundaries.  That is how htslib writes (bgzf_flush_try
+    before a record that does not fit): a 60 k-record BAM written by the reference's vendored htslib 1.3
+    (oracle/_ref/ref_bam_tool sam2bam; only where /root/reference was there to build it) is walked without a single
+    stretch done twice, and decodes to what htslib's own dump of it says."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_bam_tool")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/ref_bam_tool not built (needs the reference tree)")
+    rng = np.random.default_rng(77)
+    lens = {"chrA": 900_000, "chrB": 300_000}
+    lines = ["@HD\tVN:1.4\tSO:coordinate"] + ["@SQ\tSN:%s\tLN:%d" % kv for kv in lens.items()]
+    n = 0
+    for chrom, count in (("chrA", 45_000), ("chrB", 15_000)):
+        for pos in np.sort(rng.integers(0, lens[chrom] - 2000, count)).tolist():
+            L = int(rng.integers(25, 76))
+            cigar = "%dM" % L if n % 4 else "%dM%dN%dM" % (L // 2, int(rng.integers(50, 900)), L - L // 2)
+            seq = "".join("ACGT"[k] for k in rng.integers(0, 4, L))
+            qual = "".join(chr(33 + int(q)) for q in 40 - np.minimum(rng.geometric(0.35, L), 38))
+            lines.append("read%07d\t%d\t%s\t%d\t60\t%s\t*\t0\t0\t%s\t%s\tNM:i:%d" % (n, 16 * (n % 2), chrom, pos + 1, cigar, seq, qual, n % 3))
+            n += 1
+    sam, bam = str(tmp_path / "h.sam"), str(tmp_path / "h.bam")
+    with open(sam, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    subprocess.check_call([tool, "sam2bam", sam, bam])
+    assert os.path.getsize(bam) > 20 * 65536 // 4                                   # dozens of members
+    code = ("import sys; sys.path.insert(0, %r); from plastid_b200.bam_io import batch_from_bam; "
+            "b = batch_from_bam(%r, threads=6); print(len(b), b.mapped)" % (os.path.dirname(os.path.dirname(tool)), bam))
+    env = dict(os.environ, PB_BAM_DEBUG="1", PB_BAM_WALK_MIN="0")
+    run = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.split() == ["60000", "60000"], run.stderr
+    walk = run.stderr.split("record walk:")[1].split()
+    assert int(walk[0]) >= 4 and int(walk[2]) == 0, run.stderr                      # several stretches, none walked again
+    hb = bam_io.batch_from_bam(bam, threads=6)
+    dump = subprocess.check_output([tool, "dump", bam]).decode().splitlines()
+    recs = [d.split() for d in dump if not d.startswith("@")]
+    assert len(recs) == len(hb) == 60_000
+    for i in (0, 1, 2, 29_999, 45_000, 59_999):
+        tid, pos, flag = int(recs[i][0]), int(recs[i][1]), int(recs[i][2])
+        cig = [tuple(int(v) for v in c.split(":")) for c in recs[i][4].split(",")]
+        assert int(hb.ref_start[i]) == pos and bool((int(hb.meta[i]) >> 16) & 1) == bool(flag & 16)
+        assert hb.positions_of(i) == po.positions_from_cigar(pos, cig)
+    starts = np.array([int(r[1]) for r in recs])
+    assert (hb.ref_start == starts).all()
