@@ -60,17 +60,10 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=200_000_000, help="reads per GPU")
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of hg38 chromosome lengths")
     ap.add_argument("--regions", type=int, default=60_000)
-    ap.add_argument("--e2e-format", default="delta3", choices=["delta3", "delta8", "wire16"],
-                    help="host transfer format of the end-to-end leg (unspliced batches)")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="upload chunks overlapped with mapping in the e2e leg")
-    ap.add_argument("--e2e-weights", default="1,1,1,1,1,1,1,1",
-                    help="relative read counts of the upload chunks of the e2e leg (delta3 / delta8), comma-separated")
-    ap.add_argument("--e2e-sweep", default=None,
-                    help="measurement aid: further chunk schedules (';'-separated weight lists) timed after the e2e leg, "
-                         "one JSON line each on stderr")
-    ap.add_argument("--sharding", default="reads", choices=["reads", "positions"],
-                    help="multi-GPU mode: 'reads' (default, weak scaling: every GPU maps its own batch over the whole genome) "
-                         "or 'positions' (strong scaling of ONE batch: every GPU owns a contiguous bin range, SURVEY 8e)")
+    ap.add_argument("--sharding", default="positions", choices=["positions", "chromosomes", "reads"],
+                    help="multi-GPU mode: 'positions' (default; strong scaling of ONE batch: every GPU owns a contiguous bin "
+                         "range balanced by read count, SURVEY 8e), 'chromosomes' (the same with cuts on chromosome boundaries, "
+                         "BASELINE config 5) or 'reads' (weak scaling: every GPU maps its own batch over the whole genome)")
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5", "peaks"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
@@ -127,10 +120,11 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def bind_to_gpu_numa_node(local_rank):
-    """Pin this rank to the CPU cores NVML reports as local to its GPU before any pinned host buffer is
-    allocated, so that the e2e upload reads host memory of the GPU's own NUMA node (first touch).
-    Returns a short description for the JSON line; silently a no-op where NVML or affinity is missing."""
+def bind_to_gpu_numa_node(local_rank, world=1):
+    """Pin this rank to CPU cores NVML reports as local to its GPU before any pinned host buffer is allocated, so that
+    the e2e upload reads host memory of the GPU's own NUMA node (first touch).  Several ranks whose GPUs share one
+    node (all eight do on this pool's boxes) take DISJOINT slices of its cores, so that their encoder / copy threads
+    do not pile onto the same ones.  Returns a short description; silently a no-op where NVML or affinity is missing."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -142,8 +136,12 @@ def bind_to_gpu_numa_node(local_rank):
         cpus = {64 * w + bit for w, word in enumerate(words) for bit in range(64) if (word >> bit) & 1}
         cpus &= os.sched_getaffinity(0)
         if cpus:
-            os.sched_setaffinity(0, cpus)
-            return "%d cpus local to GPU %d" % (len(cpus), idx)
+            mine = sorted(cpus)
+            if world > 1 and len(mine) >= world:
+                per = len(mine) // world
+                mine = mine[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, set(mine))
+            return "%d cpus (%d-%d) local to GPU %d" % (len(mine), mine[0], mine[-1], idx)
     except Exception as exc:      # measurement nicety only
         return "unbound (%s)" % type(exc).__name__
     return "unbound"
@@ -190,7 +188,7 @@ def build_world(args, rank, device):
             name = "C5: cs count, ThreePrimeMapFactory(0)+size filter 25-100"
     layout = pb.GenomeLayout(chroms, lens)
     table = synth.annotation_table(ann, layout)
-    seed = 100 if getattr(args, "sharding", "reads") == "positions" else 100 + rank     # positions: ONE batch, all ranks
+    seed = 100 + rank if getattr(args, "sharding", "positions") == "reads" else 100     # position sharding: ONE batch on all ranks
     if wl == "c3":
         dbatch = synth.rnaseq_reads(chroms, lens, n_reads, seed=seed, device=device)
     else:
@@ -342,81 +340,6 @@ def run_peaks(args, device):
     emit(json.dumps(out))
 
 
-def run_position_sharded(args, W, device, rank, world, dist):
-    """Strong scaling of one C2 batch by position ranges: every rank builds the SAME batch,
-    keeps the reads that start in its bin range (+ halo), allocates range-only planes, maps its range
-    with pb_map_point_range and sums the clipped region table; one all-reduce per step."""
-    import torch
-    from plastid_b200 import dist as pdist
-    from plastid_b200 import synth
-    from plastid_b200.batch import DeviceBatch
-    from plastid_b200.genome_array import map_batch, region_sums, CountPlanes, length_histogram
-    from plastid_b200.map_factories import CenterMapFactory
-    layout, table, fac, sf, dbatch = W["layout"], W["table"], W["fac"], W["sf"], W["dbatch"]
-    n_total = dbatch.n_reads
-    is_center = isinstance(fac, CenterMapFactory)
-    # Center rule: every rank derives its slot tables from the histogram of the WHOLE batch (in a real run: one
-    # 512 KB all-reduce), so that the sharded planes equal the unsharded ones bit for bit
-    hist = length_histogram(dbatch, fac, sf) if is_center else None
-    if dbatch.blk_off is None:
-        sub, lo, hi, cuts = pdist.shard_positions_device(dbatch, layout, rank, world)
-    else:                                       # spliced batches are sharded on the host (set-up, not timed)
-        hb = synth.device_batch_to_host(dbatch, W["chroms"], W["lens"])
-        h_sub, lo, hi = pdist.shard_positions(hb, layout, rank, world)
-        sub = DeviceBatch.from_host(h_sub, device)
-        del hb, h_sub
-    del dbatch
-    W["dbatch"] = None
-    torch.cuda.empty_cache()
-    clipped = pdist.clip_table(table, lo, hi)
-    clipped.device(device)
-    planes = CountPlanes(layout, "f64" if is_center else "u32", device, bin_range=(lo, hi))
-    planes.alloc(("+", "-"))
-
-    def step():
-        map_batch(sub, layout, fac, sf, strands=("+", "-"), planes=planes, sync_stats=False, bin_range=(lo, hi),
-                  length_hist=hist)
-        sums, live = region_sums(planes, clipped)
-        if world > 1:
-            dist.all_reduce(sums)
-        return sums
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        sums = step()
-    ev1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=device)
-    share = torch.tensor([float(sub.n_reads), float(hi - lo)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(share) for _ in range(world)]
-        dist.all_gather(gathered, share)
-    else:
-        gathered = [share]
-    if rank != 0:
-        return
-    ms = float(t.item())
-    line = {"metric": METRIC, "value": n_total / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64" if is_center else "u32", "data": "synthetic",
-            "config": {"workload": "%s, ONE batch of %d synthetic reads over %d bins sharded by position range over %d GPUs "
-                                   "(range-only planes, halo reads, clipped region tables all-reduced)"
-                                   % (W["name"], n_total, layout.total_bins, world),
-                       "reads_per_rank_incl_halo": [int(g[0].item()) for g in gathered],
-                       "bins_per_rank": [int(g[1].item()) for g in gathered]},
-            "region_counts_per_sec": W["ann"].n_tx / (ms / 1000.0), "table_checksum": float(sums.sum().item())}
-    emit(json.dumps(line))
-
-
 def run_c4(args, W, device, rank, world, dist):
     """BASELINE config 4: metagene count over 60 k windows (-50/+300 nt, 5 % masked) of the C2 count
     planes: gather the window matrix, (N > 1: all-reduce it, counts are linear in the read shards),
@@ -424,8 +347,14 @@ def run_c4(args, W, device, rank, world, dist):
     import torch
     from plastid_b200 import synth
     from plastid_b200.genome_array import map_batch, gather_windows, window_normalize, column_profile
-    layout, ann, dbatch = W["layout"], W["ann"], W["dbatch"]
-    planes = map_batch(dbatch, layout, W["fac"], W["sf"], strands=("+", "-"))
+    from plastid_b200.genome_array import CountPlanes
+    layout, ann = W["layout"], W["ann"]
+    # N > 1: ONE batch sharded by position range — every rank maps the planes of its own range, fills the window cells
+    # of its own positions, and the count matrix (60 k x 350 float64 = 168 MB) is completed with one all-reduce
+    dbatch, lo, hi, n_total = shard_world(args, W, device, rank, world)
+    ranged = (lo, hi) != (0, int(layout.total_bins))
+    planes = CountPlanes(layout, "u32", device, (lo, hi) if ranged else None)
+    map_batch(dbatch, layout, W["fac"], W["sf"], strands=("+", "-"), planes=planes, bin_range=(lo, hi) if ranged else None)
     table, cols = synth.window_table(ann, layout, width=350)
     table.device(device)
     width, n = 350, table.n_chains
@@ -439,8 +368,7 @@ def run_c4(args, W, device, rank, world, dist):
         if timed:
             ev[3].record()
         if world > 1:
-            mat = torch.nan_to_num(mat, nan=0.0)
-            dist.all_reduce(mat)
+            dist.all_reduce(mat)         # cells of other ranks' positions are 0, cells without a position NaN everywhere
         denom, sel, norm, nmask = window_normalize(mat, mmask, 70, 100, 10)
         prof, nreg, csum = column_profile(norm, nmask, sel, "median")
         return prof, nreg
@@ -491,10 +419,11 @@ def run_c4(args, W, device, rank, world, dist):
     peak, peak_src = peaks()
     line = {"metric": "metagene_windows_per_sec", "value": n / (ms / 1000.0), "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if args.sharding == "reads" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C4: metagene count, %d windows x %d nt over the C2 planes, 5%% masked, "
                                    "norm window [20,50) from the landmark, min_counts 10, exact median profile" % (n, width),
-                       "reads_per_gpu": dbatch.n_reads, "windows": n, "width": width},
+                       "reads": n_total, "windows": n, "width": width},
+            "sharding": "single GPU" if world == 1 else args.sharding,
             "roofline": {"bound": "hbm", "kernel": "pb_gather_windows_kernel", "achieved": alg / (g_ms / 1000.0) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg / (g_ms / 1000.0) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": g_ms,
@@ -512,7 +441,8 @@ def run_c2p(args, W, device, rank, world, dist):
     import plastid_b200 as pb
     from plastid_b200 import synth
     from plastid_b200.genome_array import stratified_windows, count_profiles
-    layout, ann, dbatch = W["layout"], W["ann"], W["dbatch"]
+    layout, ann = W["layout"], W["ann"]
+    dbatch, b_lo, b_hi, n_total = shard_world(args, W, device, rank, world)     # N > 1: sites are counted by the rank owning them
     table, cols = synth.window_table(ann, layout, width=350)
     table.device(device)
     fac = pb.FivePrimeMapFactory(0)
@@ -523,7 +453,7 @@ def run_c2p(args, W, device, rank, world, dist):
     def step(timed=False):
         if timed:
             ev[2].record()
-        strat, maskmat = stratified_windows(dbatch, layout, fac, None, table, cols, width, lo, hi)
+        strat, maskmat = stratified_windows(dbatch, layout, fac, None, table, cols, width, lo, hi, bin_range=(b_lo, b_hi))
         if timed:
             ev[3].record()
         if world > 1:
@@ -552,12 +482,60 @@ def run_c2p(args, W, device, rank, world, dist):
     ms = float(t.item())
     line = {"metric": "psite_window_profiles_per_sec", "value": n * (hi - lo + 1) / (ms / 1000.0), "unit": "window-lengths/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "C2 psite pass: FivePrimeMapFactory(0), %d reads/GPU, %d windows x %d nt x lengths %d-%d, "
-                                   "median profiles" % (dbatch.n_reads, n, width, lo, hi)},
+            "higher_is_better": True, "scaling": "weak" if args.sharding == "reads" else "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "C2 psite pass: FivePrimeMapFactory(0), %d reads, %d windows x %d nt x lengths %d-%d, "
+                                   "median profiles" % (n_total, n, width, lo, hi)},
+            "sharding": "single GPU" if world == 1 else args.sharding,
             "stratified_kernel_ms": float(np.mean(k_ms)), "kernel_share_of_step": float(np.mean(k_ms)) / ms,
             "profile_checksum": float(torch.nan_to_num(profs).sum().item())}
     emit(json.dumps(line))
+
+
+def shard_world(args, W, device, rank, world):
+    """The reads and bin range of this rank.  ``positions`` (default at N > 1; strong scaling): every rank
+    built the SAME batch, keeps the reads that start in its bin range plus a halo, and owns the planes of that range
+    only (``chromosomes``: cuts on chromosome boundaries, BASELINE config 5).  ``reads`` (weak scaling): every rank has
+    its own batch and maps it over the whole genome."""
+    import torch
+    from plastid_b200 import dist as pdist
+    from plastid_b200 import synth
+    from plastid_b200.batch import DeviceBatch
+    layout, dbatch = W["layout"], W["dbatch"]
+    total = int(layout.total_bins)
+    if world == 1 or args.sharding == "reads":
+        return dbatch, 0, total, dbatch.n_reads * world
+    n_total = dbatch.n_reads
+    if dbatch.blk_off is None and args.sharding == "positions":
+        sub, lo, hi, _cuts = pdist.shard_positions_device(dbatch, layout, rank, world)
+    else:                                       # spliced batches / chromosome cuts are sharded on the host (set-up)
+        hb = synth.device_batch_to_host(dbatch, W["chroms"], W["lens"])
+        h_sub, lo, hi = pdist.shard_positions(hb, layout, rank, world,
+                                              snap="chromosomes" if args.sharding == "chromosomes" else "bins")
+        sub = DeviceBatch.from_host(h_sub, device)
+        del hb, h_sub
+    W["dbatch"] = None
+    del dbatch
+    torch.cuda.empty_cache()
+    return sub, int(lo), int(hi), n_total
+
+
+def _owned_reads(hb, layout, lo, hi):
+    """Mask of the reads of a host shard that START in the rank's own bins (halo reads belong to the neighbour)."""
+    c_of = np.searchsorted(hb.chrom_read_off, np.arange(len(hb)), side="right") - 1
+    g = layout.chrom_bin_off[c_of] + hb.ref_start.astype(np.int64)
+    return (g >= lo) & (g < hi)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def main():
@@ -574,13 +552,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
-    numa = bind_to_gpu_numa_node(local_rank) if args.impl != "reference" else "all host threads"
+    numa = bind_to_gpu_numa_node(local_rank, world) if args.impl != "reference" else "all host threads"
     if world > 1 and args.impl != "reference":
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     import plastid_b200 as pb
     from plastid_b200 import synth, _lib
-    from plastid_b200.genome_array import map_batch, region_sums, CountPlanes
+    from plastid_b200.genome_array import map_batch, region_sums, chain_counts, CountPlanes, length_histogram
+    from plastid_b200.map_factories import CenterMapFactory
 
     if args.workload == "peaks":
         if rank == 0:
@@ -590,21 +569,14 @@ def main():
     chroms, lens, ann, layout, table, dbatch = W["chroms"], W["lens"], W["ann"], W["layout"], W["table"], W["dbatch"]
     fac, sf, is_center = W["fac"], W["sf"], W["center"]
     sf_tuple = None if sf is None else (sf.min_, sf.max_)
-    n_reads = dbatch.n_reads
-    workload = ("%s, %d synthetic reads/GPU, %d chromosomes (%d bins, '+' and '-' planes), %d region counts"
-                % (W["name"], n_reads, len(chroms), layout.total_bins, ann.n_tx))
-    config = {"workload": workload, "reads_per_gpu": n_reads, "genome_bins": int(layout.total_bins),
-              "regions": ann.n_tx, "host_affinity": numa, "sharding": "read-range per GPU; NCCL all-reduce of region tables" if world > 1
-              else "single GPU", "l2": "inputs (%.2f GB) and outputs (%.1f GB) larger than the 126 MB L2"
-              % (8 * n_reads / 1e9, (16 if is_center else 8) * layout.total_bins / 1e9)}
+    n_batch_reads = dbatch.n_reads
+    # `config` names the workload and nothing that differs between the two arms (the driver compares it)
+    workload = ("%s, %d synthetic reads, %d chromosomes (%d bins, '+' and '-' planes), %d region counts"
+                % (W["name"], n_batch_reads, len(chroms), layout.total_bins, ann.n_tx))
+    config = {"workload": workload, "reads": n_batch_reads, "genome_bins": int(layout.total_bins), "regions": ann.n_tx,
+              "l2": "inputs (%.2f GB) and outputs (%.1f GB) larger than the 126 MB L2"
+                    % (8 * n_batch_reads / 1e9, (16 if is_center else 8) * layout.total_bins / 1e9)}
 
-    if args.sharding == "positions" and args.impl != "reference":
-        if args.workload not in ("c2", "c3", "c5"):
-            raise SystemExit("--sharding positions is implemented for the mapping workloads c2, c3 and c5")
-        run_position_sharded(args, W, device, rank, world, dist)
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
     if args.workload == "c2p" and args.impl != "reference":
         run_c2p(args, W, device, rank, world, dist)
         if world > 1:
@@ -634,26 +606,53 @@ def main():
         sample = "the whole workload per step: %d chromosomes, %d reads, %d regions" % (len(chrom_ids), nr, nreg)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is_center else "int64", "data": "synthetic",
-                "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "scaling": "strong" if args.sharding != "reads" else "weak", "vs_baseline": None,
+                "dtype": "f64" if is_center else "int64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                 "cpu_model": cpu_model()},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "oracle port of map_factories.pyx/roitools.pyx loops (the Cython reference cannot be "
-                        "built here: pysam absent); chromosome-parallel over %d host threads" % threads}
+                "host": {"affinity": numa, "cpu_model": cpu_model(), "threads": threads},
+                "note": "oracle port of map_factories.pyx/roitools.pyx loops (the Cython reference needs pysam, absent from "
+                        "the GPU box); chromosome-parallel over %d host threads; region sums read the int64 vectors the "
+                        "rules return" % threads}
         emit(json.dumps(line))
         return 0
 
-    # ------------------------------------------------------------------ device-resident steps
-    planes = CountPlanes(layout, "f64" if is_center else "u32", device)
+    # ------------------------------------------------------------------ this rank's share
+    sub, lo, hi, n_total = shard_world(args, W, device, rank, world)
+    ranged = (lo, hi) != (0, int(layout.total_bins))
+    dbatch = None
+    # Center rule: every rank derives its slot tables from the histogram of the WHOLE batch (in a real run: one
+    # 512 KB all-reduce, BAMGenomeArray does it), so that sharded planes equal unsharded ones bit for bit
+    hist = None
+    if is_center and ranged:
+        from plastid_b200.genome_array import _filtered_hist
+        c_of = torch.bucketize(torch.arange(sub.n_reads, device=device), sub.chrom_read_off[1:], right=True)
+        g = torch.from_numpy(layout.chrom_bin_off).to(device)[c_of] + sub.ref_start.to(torch.int64)
+        keep = (g >= lo) & (g < hi) & (((sub.meta >> 17) & 1) == 0)       # reads are counted by the rank owning their start
+        hist_t = torch.bincount((sub.meta[keep] & 0xFFFF).to(torch.int64), minlength=65536)
+        dist.all_reduce(hist_t)
+        hist = _filtered_hist(hist_t.cpu().numpy(), sf)
+        del c_of, g, keep, hist_t
+    planes = CountPlanes(layout, "f64" if is_center else "u32", device, (lo, hi) if ranged else None)
     planes.alloc(("+", "-"))
     table.device(device)
     L = _lib.lib()
 
-    def step():
-        map_batch(dbatch, layout, fac, sf, strands=("+", "-"), planes=planes, sync_stats=False)
+    def step(events=None):
+        if events is not None:
+            events[0].record()
+        map_batch(sub, layout, fac, sf, strands=("+", "-"), planes=planes, sync_stats=False,
+                  bin_range=(lo, hi) if ranged else None, length_hist=hist)
+        if events is not None:
+            events[1].record()
         sums, live = region_sums(planes, table)
+        if events is not None:
+            events[2].record()
         if world > 1:
             dist.all_reduce(sums)
+        if events is not None:
+            events[3].record()
         return sums, live
 
     def fence():
@@ -663,35 +662,68 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()                      # nvidia-smi needs ~1 s to come up: start before the warm-up
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
         step()
     fence()
     L.pb_enable_kernel_timing(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        sums, live = step()
-    ev1.record()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        sums, live = step(evs[k])
     fence()
-    total_ms = ev0.elapsed_time(ev1)
+    total_ms = evs[0][0].elapsed_time(evs[-1][3])
     kms, kn = C.c_float(0), C.c_int(0)
     _lib.check(L.pb_tiles_kernel_ms_total(C.byref(kms), C.byref(kn)))
     L.pb_enable_kernel_timing(0)
+    step_ms = [evs[k][0].elapsed_time(evs[k + 1][0]) for k in range(args.steps - 1)] + [evs[-1][0].elapsed_time(evs[-1][3])]
+    map_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    sums_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    coll_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
     t = torch.tensor([total_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    value = n_reads * world / (ms_per_step / 1000.0)
-    region_rate = ann.n_tx * world / (ms_per_step / 1000.0)
+    value = n_total / (ms_per_step / 1000.0)
+    region_rate = ann.n_tx * (world if args.sharding == "reads" else 1) / (ms_per_step / 1000.0)
+    table_checksum_dev = float(sums.sum().item())
+
+    # per-rank diagnostics: who holds what, where the step goes (a slow rank or a slow collective shows here)
+    k_ms = kms.value / max(kn.value, 1)
+    mine = torch.tensor([float(sub.n_reads), float(hi - lo), k_ms, map_ms, sums_ms, coll_ms, float(np.median(step_ms)),
+                         float(np.max(step_ms))], dtype=torch.float64, device=device)
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
+    names = ["reads_incl_halo", "bins", "tiles_kernel_ms", "map_ms", "region_sums_ms", "allreduce_wait_ms", "step_ms_median",
+             "step_ms_max"]
+    ranks_info = {n: [round(float(p[i].item()), 4) if i >= 2 else int(p[i].item()) for p in per_rank] for i, n in enumerate(names)}
+
+    # a longer timed region for N > 1 (the K contract steps above stay the headline): a stall of one rank cannot
+    # hide in, or dominate, a 100-step mean
+    extended = None
+    if world > 1:
+        n_ext = max(100, args.steps)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fence()
+        ev0.record()
+        for _ in range(n_ext):
+            step()
+        ev1.record()
+        fence()
+        te = torch.tensor([ev0.elapsed_time(ev1) / n_ext], dtype=torch.float64, device=device)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        extended = {"steps": n_ext, "ms_per_step": float(te.item()), "value": n_total / (float(te.item()) / 1000.0)}
 
     # ------------------------------------------------------------------ launch-bound workloads: CUDA graph replay
     graph_ms = None
     if args.workload == "c1" and world == 1:
         from plastid_b200.genome_array import GraphedCount
-        gc_ = GraphedCount(dbatch, layout, fac, sf, table, strands=("+", "-"))
+        gc_ = GraphedCount(sub, layout, fac, sf, table, strands=("+", "-"))
         for _ in range(3):
             gc_.replay()
         torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps * 10):
             g_sums, g_live = gc_.replay()
@@ -699,189 +731,205 @@ def main():
         torch.cuda.synchronize()
         graph_ms = ev0.elapsed_time(ev1) / (args.steps * 10)
         assert torch.equal(g_sums, sums) and torch.equal(g_live, live), "graph replay differs from the eager pass"
+        del gc_
 
-    # ------------------------------------------------------------------ end-to-end (host buffers)
-    # The caller holds the batch in pinned host memory in the transfer format the host decoder
-    # emits: wire16 (4 B/read) for unspliced batches, the plain SoA otherwise.  Every step copies it
-    # to the device, expands it, runs the same kernels and reads the region table back.
-    from plastid_b200.batch import Wire16Batch, Wire16Receiver, Delta8Batch, Delta8Receiver, Delta3Batch, Delta3Receiver
-    h_sums = torch.empty(ann.n_tx, dtype=torch.float64).pin_memory()
-    h_live = torch.empty(ann.n_tx, dtype=torch.int64).pin_memory()
-    d2h = h_sums.numel() * 8 + h_live.numel() * 8
-    use_wire16 = dbatch.blk_off is None
-    if use_wire16:
-        WireBatch, WireReceiver = {"delta3": (Delta3Batch, Delta3Receiver), "delta8": (Delta8Batch, Delta8Receiver),
-                                   "wire16": (Wire16Batch, Wire16Receiver)}[args.e2e_format]
-        wire = WireBatch.from_batch(synth.device_batch_to_host(dbatch, chroms, lens))
-        pinned = wire.pinned()
-        receiver = WireReceiver(wire, device)
-        h2d = wire.nbytes
-        # small batches are launch-bound: fewer, larger chunks (about 8 M reads each at least)
-        n_chunks = max(1, min(args.e2e_chunks, n_reads // 8_000_000))
-        weights = [float(x) for x in args.e2e_weights.split(",")]
-        if args.e2e_format == "wire16" or n_chunks < args.e2e_chunks or len(weights) < 2:
-            chunks = WireReceiver.plan_chunks(wire, layout, n_chunks)
-        else:
-            chunks = WireReceiver.plan_chunks(wire, layout, len(weights), weights)
-        copy_stream = torch.cuda.Stream(device=device)
-        from plastid_b200.genome_array import map_wire16_streamed
-
-        def e2e_step():
-            # upload in chunks on a copy stream; each chunk's bins are mapped as soon as it has landed
-            map_wire16_streamed(receiver, pinned, chunks, layout, fac, sf, ("+", "-"), planes, copy_stream)
-            s, l = region_sums(planes, table)
+    # ------------------------------------------------------------------ table-only: plane-free region counts
+    # counts_in_region / cs count need the region table, not the count vectors: pb_chain_counts maps every read's
+    # site straight onto the chains.  Reported beside the dense figure (SURVEY 8d "touched-only"), never instead of it.
+    table_only = None
+    if not is_center:
+        ref_sums = sums.clone()
+        for _ in range(3):
+            d_sums, d_live = chain_counts(sub, layout, fac, sf, table, (lo, hi))
             if world > 1:
-                dist.all_reduce(s)
-            h_sums.copy_(s, non_blocking=True)
-            h_live.copy_(l, non_blocking=True)
-            torch.cuda.synchronize()      # the caller holds the table before the next batch starts
-    elif args.e2e_format == "delta3":
-        # batches with multi-block reads: delta3 streams for (ref_start, meta) + one 4-byte block word per aligned
-        # block; blk_off is rebuilt on the device (pb_unpack_blocks).  The Center / binned path needs the whole
-        # batch before it can start, so the upload is not chunked.
-        from plastid_b200.batch import Delta3SplicedBatch, Delta3SplicedReceiver
-        swire = Delta3SplicedBatch.from_batch(synth.device_batch_to_host(dbatch, chroms, lens))
-        spinned = swire.pinned()
-        sreceiver = Delta3SplicedReceiver(swire, device)
-        h2d = swire.nbytes
-        resident = dbatch
+                dist.all_reduce(d_sums)
+        fence()
+        n_to = max(args.steps, 10)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n_to):
+            d_sums, d_live = chain_counts(sub, layout, fac, sf, table, (lo, hi))
+            if world > 1:
+                dist.all_reduce(d_sums)
+        ev1.record()
+        fence()
+        tt = torch.tensor([ev0.elapsed_time(ev1) / n_to], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        to_ms = float(tt.item())
+        n_blocks = len(table.bstart)
+        # compulsory traffic: every read once (8 B) + the chain tables + the result table
+        to_alg = 8.0 * sub.n_reads + 16.0 * n_blocks + 8.0 * (ann.n_tx + 1) + ann.n_tx + 16.0 * ann.n_tx
+        table_only = {"kernel": "pb_chain_counts_kernel", "ms_per_step": to_ms, "value": n_total / (to_ms / 1000.0), "unit": UNIT,
+                      "region_counts_per_sec": ann.n_tx / (to_ms / 1000.0), "steps": n_to,
+                      "identical_to_plane_path": bool(torch.equal(d_sums, ref_sums) and torch.equal(d_live, live)),
+                      "algorithmic_bytes_per_launch": to_alg, "plane_bytes_not_written": 4.0 * (hi - lo) * 2,
+                      "speedup_vs_planes": ms_per_step / to_ms}
 
-        s_chunks = Delta3SplicedReceiver.plan_chunks(swire, layout, max(1, min(args.e2e_chunks, n_reads // 8_000_000)))
-        s_copy = torch.cuda.Stream(device=device)
-        from plastid_b200.genome_array import map_center_streamed
+    # ------------------------------------------------------------------ end-to-end through the product API
+    # Host buffers = the AlignmentBatch the decoder hands out (bam_io.batch_from_bam packs the transfer format while
+    # decoding: delta3 streams + block words, in pinned memory).  Every step constructs a BAMGenomeArray on it and
+    # asks for the planes and the region table: upload (chunked, overlapped with mapping), expansion, mapping, region
+    # sums, the all-reduce at N > 1 and the device->host copy of the table are all inside the clock.
+    del planes
+    torch.cuda.empty_cache()
+    hb = synth.device_batch_to_host(sub, chroms, lens, mapped=n_total)
+    t_pack = time.perf_counter()
+    hb.pack()
+    hb.transfer_pinned()
+    pack_s = time.perf_counter() - t_pack
+    h2d = hb.transfer.nbytes
+    d2h = ann.n_tx * 16 + _lib.PB_NSTATS * 8
 
-        def e2e_step():
-            nonlocal dbatch
-            if is_center:
-                # chunked upload; every chunk's final bin range is mapped (pb_map_center_range) while later chunks land
-                map_center_streamed(sreceiver, spinned, s_chunks, layout, fac, sf, ("+", "-"), planes, s_copy)
-                s, l = region_sums(planes, table)
-                if world > 1:
-                    dist.all_reduce(s)
-            else:
-                dbatch = sreceiver.receive(spinned)
-                s, l = step()
-                dbatch = resident
-            h_sums.copy_(s, non_blocking=True)
-            h_live.copy_(l, non_blocking=True)
-            torch.cuda.synchronize()
-    else:
-        h_start = torch.empty(n_reads, dtype=torch.int32).pin_memory()
-        h_meta = torch.empty(n_reads, dtype=torch.int32).pin_memory()
-        h_start.copy_(dbatch.ref_start)
-        h_meta.copy_(dbatch.meta)
-        h_blk_off = torch.empty_like(dbatch.blk_off, device="cpu").pin_memory()
-        h_blk = torch.empty_like(dbatch.blk, device="cpu").pin_memory()
-        h_blk_off.copy_(dbatch.blk_off)
-        h_blk.copy_(dbatch.blk)
-        h2d = (h_start.numel() + h_meta.numel() + h_blk_off.numel() + h_blk.numel()) * 4
+    raw_hist = None
+    if is_center and ranged:                 # the whole batch's histogram, known to whoever decoded and sharded it
+        from plastid_b200.batch import meta_length_hist
+        raw_hist = torch.from_numpy(meta_length_hist(hb.meta[_owned_reads(hb, layout, lo, hi)])).to(device)
+        dist.all_reduce(raw_hist)
+        raw_hist = raw_hist.cpu().numpy()
 
-        def e2e_step():
-            dbatch.ref_start.copy_(h_start, non_blocking=True)
-            dbatch.meta.copy_(h_meta, non_blocking=True)
-            dbatch.blk_off.copy_(h_blk_off, non_blocking=True)
-            dbatch.blk.copy_(h_blk, non_blocking=True)
-            s, l = step()
-            h_sums.copy_(s, non_blocking=True)
-            h_live.copy_(l, non_blocking=True)
-            torch.cuda.synchronize()
+    def api_step(batch, use_planes=True):
+        ga = pb.BAMGenomeArray(batch, mapping=fac, device=device, shard=None, bin_range=(lo, hi) if ranged else None,
+                               length_hist=raw_hist)
+        if sf is not None:
+            ga.add_filter("size", sf)
+        if use_planes:
+            ga.count_planes(("+", "-"))
+        return ga.count_chains(table, planes=use_planes)
 
-    for _ in range(2):
-        e2e_step()
-    fence()
+    def timed(fn, n_steps, n_warm=2):
+        for _ in range(n_warm):
+            out = fn()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            out = fn()
+        fence()
+        ms = 1000.0 * (time.perf_counter() - t0) / n_steps
+        tm = torch.tensor([ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item()), out
+
     e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    ev1.record()
-    fence()
-    e2e_ms = max(ev0.elapsed_time(ev1), 1000.0 * (time.perf_counter() - t0)) / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_reads * world / (float(t.item()) / 1000.0)
-    if args.e2e_sweep and use_wire16 and args.e2e_format != "wire16" and world == 1:
-        for sched in args.e2e_sweep.split(";"):
-            chunks = WireReceiver.plan_chunks(wire, layout, 0, [float(x) for x in sched.split(",")])
-            for _ in range(2):
-                e2e_step()
-            fence()
-            t1 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step()
-            fence()
-            sys.stderr.write(json.dumps({"e2e_schedule": sched, "chunks": len(chunks),
-                                         "ms_per_step": 1000.0 * (time.perf_counter() - t1) / e2e_steps}) + "\n")
+    e2e_ms, (h_sums, h_live) = timed(lambda: api_step(hb), e2e_steps)
+    e2e_value = n_total / (e2e_ms / 1000.0)
+    api_checksum = float(np.sum(h_sums))
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+           "steps": e2e_steps, "api": "BAMGenomeArray(batch).count_planes(('+','-')); .count_chains(table)",
+           "host_format": "%s (%.2f B/read): what bam_io.batch_from_bam emits; uploaded in chunks, expanded on the device, "
+                          "each chunk's bin range mapped while the next is on the wire"
+                          % (type(hb.transfer).__name__, h2d / max(len(hb), 1)),
+           "table_equals_device_resident_leg": bool(abs(api_checksum - table_checksum_dev) == 0.0),
+           "pack_seconds_outside_clock": round(pack_s, 3),
+           "pack_note": "the transfer format is written once per batch by the decoder (host, %d threads here); a plain SoA "
+                        "batch is timed below with nothing outside the clock" % _lib.host_threads()}
+    if table_only is not None:
+        to_ms_e2e, (t_sums, _tl) = timed(lambda: api_step(hb, use_planes=False), e2e_steps)
+        e2e["table_only"] = {"value": n_total / (to_ms_e2e / 1000.0), "ms_per_step": to_ms_e2e,
+                             "api": "BAMGenomeArray(batch).count_chains(table)  (no planes: pb_chain_counts)",
+                             "table_equals_plane_path": bool(np.array_equal(t_sums, h_sums))}
+    # the same call on a plain SoA batch (8 B/read in pageable numpy arrays, no transfer format): every host
+    # transform and the whole upload inside the clock
+    from plastid_b200.batch import AlignmentBatch
+    plain = AlignmentBatch(hb.chroms, hb.chrom_len, hb.ref_start, hb.meta, hb.chrom_read_off, hb.blk_off, hb.blk,
+                           max_span=hb.max_span, mapped=hb.mapped)
+    soa_steps = 3
+
+    def soa_step():
+        plain._dev.clear()                       # a fresh batch every step: no cached device copy
+        return api_step(plain)
+    soa_ms, (s_sums, _sl) = timed(soa_step, soa_steps, n_warm=1)
+    soa_bytes = 8 * len(hb) + (0 if hb.blk is None else 4 * (len(hb) + 1) + 8 * len(hb.blk))
+    e2e["soa_input"] = {"value": n_total / (soa_ms / 1000.0), "ms_per_step": soa_ms, "h2d_bytes_per_step": soa_bytes,
+                        "steps": soa_steps, "host_format": "plain SoA in pageable numpy arrays, nothing precomputed",
+                        "table_equals_packed_path": bool(np.array_equal(s_sums, h_sums))}
     clocks = sampler.stop()              # samples cover warm-up, the timed steps and the e2e steps
-    table_checksum = float(h_sums.sum().item())
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ------------------------------------------------------------------ roofline of the tiles kernel
+    # ------------------------------------------------------------------ rooflines
     peak, peak_src = peaks()
-    n_blk = 0 if dbatch.blk is None else dbatch.blk.shape[0]
-    # SoA in once (+ block table for spliced reads) + every bin of both planes out once
-    alg_bytes = 8.0 * n_reads + (4.0 * (n_reads + 1) + 8.0 * n_blk if n_blk else 0.0) \
-        + (8.0 if is_center else 4.0) * layout.total_bins * 2
-    k_ms = kms.value / max(kn.value, 1)
+    n_blk = 0 if sub.blk is None else sub.blk.shape[0]
+    # tiles kernel: SoA in once (+ block table for spliced reads) + every bin of both planes out once — per rank
+    alg_bytes = 8.0 * sub.n_reads + (4.0 * (sub.n_reads + 1) + 8.0 * n_blk if n_blk else 0.0) \
+        + (8.0 if is_center else 4.0) * (hi - lo) * 2
     achieved = alg_bytes / (k_ms / 1000.0) / 1e9
     kernel_name = "pb_center_tiles_kernel" if is_center else "pb_point_tiles_kernel"
     traffic = None                    # DRAM bytes per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath) and args.genome_scale == 1.0:
+    if os.path.exists(tpath) and args.genome_scale == 1.0 and world == 1:
         with open(tpath) as fh:
             traffic = json.load(fh).get("%s:%s" % (kernel_name, args.workload))
-        if traffic is not None and abs(n_reads - {"c2": 200_000_000, "c3": 100_000_000}.get(args.workload, -1)) > 0:
+        if traffic is not None and abs(n_batch_reads - {"c2": 200_000_000, "c3": 100_000_000}.get(args.workload, -1)) > 0:
             traffic = None            # captured at the default size only
-    roofline = {"bound": "hbm", "kernel": "pb_center_tiles_kernel" if is_center else "pb_point_tiles_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "launches_timed": kn.value,
                 "kernel_share_of_step": k_ms / ms_per_step}
+    # region sums: every chain position of this rank's bins read once (4 or 8 B) + tables + results
+    own = np.clip(np.minimum(table.bend, hi) - np.maximum(table.bstart, lo), 0, None).sum()
+    g_alg = (8.0 if is_center else 4.0) * float(own) + 16.0 * len(table.bstart) + 8.0 * (ann.n_tx + 1) + ann.n_tx + 16.0 * ann.n_tx
+    g_traffic = None
+    gpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if os.path.exists(gpath) and args.genome_scale == 1.0 and world == 1:
+        with open(gpath) as fh:
+            g_traffic = json.load(fh).get("pb_region_sums_kernel:%s" % args.workload)
+    roofline_gather = {"bound": "hbm", "kernel": "pb_region_sums_kernel", "achieved": g_alg / (sums_ms / 1000.0) / 1e9, "peak": peak,
+                       "unit": "GB/s", "frac": g_alg / (sums_ms / 1000.0) / 1e9 / peak, "traffic": g_traffic,
+                       "algorithmic_bytes_per_launch": g_alg, "kernel_ms": sums_ms, "positions": int(own), "chains": ann.n_tx,
+                       "note": "CUDA events around the launch inside the timed steps"}
+    if table_only is not None:
+        table_only["roofline"] = {"bound": "hbm", "achieved": table_only["algorithmic_bytes_per_launch"] / (table_only["ms_per_step"] / 1000.0) / 1e9,
+                                  "peak": peak, "unit": "GB/s",
+                                  "frac": table_only["algorithmic_bytes_per_launch"] / (table_only["ms_per_step"] / 1000.0) / 1e9 / peak,
+                                  "note": "touched-only figure of SURVEY 8(d): reads in + chain tables, no planes"}
 
     # ------------------------------------------------------------------ cpu_baseline (rank 0, N=1)
     cpu = None
     if world == 1:
         order = np.argsort(-np.asarray(lens))
         chrom_ids = sorted(int(c) for c in order[:args.cpu_sample_chroms])
-        hb = host_sample(dbatch, chroms, lens, set(chrom_ids))
-        dt, nr, nreg = cpu_reference_pass(hb, lens, table, layout, W["oracle_kw"], sf_tuple, chrom_ids, 1)
-        cpu = {"value": nr / dt, "unit": UNIT, "cores": 1, "kind": "port",
+        hs = host_sample(sub, chroms, lens, set(chrom_ids))
+        dt, nr, nreg = cpu_reference_pass(hs, lens, table, layout, W["oracle_kw"], sf_tuple, chrom_ids, 1)
+        cpu = {"value": nr / dt, "unit": UNIT, "cores": 1, "kind": "port", "cpu_model": cpu_model(),
                "sample": "%s: %d reads + %d region sums in %.2f s (oracle C port, one thread)"
                          % (",".join(chroms[c] for c in chrom_ids), nr, nreg, dt)}
         try:
-            cpu["python_loop"] = python_loop_estimate(hb, chrom_ids[0], args.workload)
+            cpu["python_loop"] = python_loop_estimate(hs, chrom_ids[0], args.workload)
         except Exception as exc:      # an estimate beside the baseline, never a reason to lose the line
             cpu["python_loop"] = {"error": repr(exc)}
 
     binning = ["pb_bin_kernel(count)", "pb_scan_chunks_kernel", "pb_scan_top_kernel", "pb_scan_add_kernel",
-               "pb_bin_kernel(fill)"] if dbatch.blk_off is not None else []
+               "pb_bin_kernel(fill)"] if sub.blk_off is not None else []
     if is_center:
-        kernels_per_step = ["pb_length_hist_kernel", "pb_tile_index_kernel"] + binning + ["pb_center_tiles_kernel"]
+        kernels_per_step = ["pb_tile_index_kernel"] + binning + ["pb_center_tiles_kernel"]
     else:
         kernels_per_step = ["pb_tile_index_kernel"] + binning + ["pb_point_tiles_kernel", "pb_point_overflow_kernel"]
     kernels_per_step += ["pb_stats_finish_kernel", "pb_region_sums_kernel"]
+    sharding_text = {"reads": "read-range: every GPU maps its own batch over the whole genome (weak scaling)",
+                     "positions": "ONE batch sharded by position range: range-only planes, halo reads, region tables all-reduced "
+                                  "(strong scaling, SURVEY 8e)",
+                     "chromosomes": "ONE batch sharded by runs of whole chromosomes (strong scaling, BASELINE config 5)"}[args.sharding]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is_center else "u32", "data": "synthetic",
-            "config": config,
+            "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if args.sharding == "reads" else "strong", "vs_baseline": None,
+            "dtype": "f64" if is_center else "u32", "data": "synthetic", "config": config,
             "region_counts_per_sec": region_rate,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(t.item()), "steps": e2e_steps,
-                    "host_format": ("%s (%.2f B/read), %d-chunk upload overlapped with pb_map_point_range"
-                                    % (args.e2e_format, h2d / max(n_reads, 1), len(chunks)))
-                    if use_wire16 else (("delta3 + block words (%.2f B/read), %s" % (
-                        h2d / max(n_reads, 1), ("%d-chunk upload overlapped with pb_map_center_range" % len(s_chunks)) if is_center
-                        else "whole batch uploaded before the binned path starts"))
-                        if args.e2e_format == "delta3" else "SoA (8 B/read + blocks)")},
-            "gpu_launches": len(kernels_per_step) * args.steps, "kernels_per_step": kernels_per_step,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "table_checksum": table_checksum}
+            "sharding": "single GPU" if world == 1 else sharding_text, "per_rank": ranks_info,
+            "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(np.max(step_ms)),
+            "host": {"affinity": numa, "cpu_model": cpu_model(), "host_threads": _lib.host_threads()},
+            "e2e": e2e, "gpu_launches": len(kernels_per_step) * args.steps, "kernels_per_step": kernels_per_step,
+            "roofline": roofline, "roofline_gather": roofline_gather, "table_only": table_only, "cpu_baseline": cpu,
+            "clocks": clocks, "table_checksum": api_checksum}
+    if extended is not None:
+        line["extended"] = extended
     if graph_ms is not None:
         # the same pass replayed as one CUDA graph launch (launch-latency bound workload)
-        line["cuda_graph"] = {"ms_per_step": graph_ms, "value": n_reads / (graph_ms / 1000.0), "unit": UNIT,
+        line["cuda_graph"] = {"ms_per_step": graph_ms, "value": n_total / (graph_ms / 1000.0), "unit": UNIT,
                               "region_counts_per_sec": ann.n_tx / (graph_ms / 1000.0), "replays_timed": args.steps * 10}
     emit(json.dumps(line))
     if world > 1:

@@ -344,6 +344,34 @@ int pb_region_sums(const void *const *planes, int vec_dtype,
                    const uint8_t *chain_plane, int64_t n_chains,
                    const uint8_t *mask_bits, const int64_t *mask_off,
                    double *sums, int64_t *live_len, void *stream);
+/* The same for one rank of a position-sharded genome: only positions whose global bin lies in
+ * [bin_begin, bin_end) are read and summed — the others count zero but keep their place in the chain — so
+ * the sums of all ranks add up to the whole table (one all-reduce); live_len is geometry and comes out whole
+ * on every rank.  Plane pointers are the address bin 0 WOULD have (see pb_map_point_range), 16-byte aligned;
+ * mask_bits 4-byte aligned and padded to whole 32-bit words.  Blocks lying wholly outside the layout (the
+ * part of a region beyond its chromosome's end, lowered to coordinates >= total_bins) count zero the same
+ * way: the reference returns zeros there (fetch yields no reads). */
+int pb_region_sums_range(const void *const *planes, int vec_dtype,
+                         const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                         const uint8_t *chain_plane, int64_t n_chains,
+                         const uint8_t *mask_bits, const int64_t *mask_off,
+                         int64_t bin_begin, int64_t bin_end,
+                         double *sums, int64_t *live_len, void *stream);
+
+/* Plane-free region counts of a point rule (5' / 3' / variable): sums[c] = number of reads whose mapped site
+ * lies on an unmasked position of chain c (strand-matched like BAMGenomeArray.get_reads_and_counts,
+ * plastid/genomics/genome_array.py:811-815; rule direction from the chain's strand), live_len[c] = unmasked
+ * length — exactly what pb_region_sums returns over the planes pb_map_point would write, without writing them
+ * (table-only programs: plastid/bin/counts_in_region.py:107-125, plastid/bin/cs.py:688-714).  One CTA per
+ * chain walks the contiguous slice of the sorted batch that can reach each block.  Sites outside
+ * [bin_begin, bin_end) count zero (position sharding).  stats (or NULL): PB_STAT_DROPPED_* / _LEN are raised
+ * when a read near a chain could not be placed by the rule (the reference's DataWarning paths). */
+int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                    const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                    const uint8_t *chain_plane, int64_t n_chains,
+                    const uint8_t *mask_bits, const int64_t *mask_off,
+                    int64_t bin_begin, int64_t bin_end,
+                    double *sums, int64_t *live_len, uint64_t *stats, void *stream);
 
 /* Mask pipeline: mask bits of every chain from one interval set, replacing the per-region
  * GenomeHash.get_overlapping_features + SegmentChain.add_masks of counts_in_region.py:114-115
@@ -368,6 +396,27 @@ int pb_gather_windows(const void *const *planes, int vec_dtype,
                       const int32_t *row_col, int64_t n_chains, int32_t width,
                       const uint8_t *mask_bits, const int64_t *mask_off,
                       double *matrix, uint8_t *maskmat, void *stream);
+/* Position-sharded form: cells whose position lies outside [bin_begin, bin_end) are written as 0 (not NaN), so
+ * that the matrices of all ranks add up; NaN cells (no chain position) and maskmat are identical on every rank. */
+int pb_gather_windows_range(const void *const *planes, int vec_dtype,
+                            const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                            const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                            const int32_t *row_col, int64_t n_chains, int32_t width,
+                            const uint8_t *mask_bits, const int64_t *mask_off,
+                            int64_t bin_begin, int64_t bin_end,
+                            double *matrix, uint8_t *maskmat, void *stream);
+
+/* Count vectors of many chains at once, ragged: chain c laid 5'->3' (reversed when chain_reverse[c]) into cells
+ * [row_off[c], row_off[c] + length of c) of `values` (double) and `masked` (uint8, 1 = masked position) —
+ * SegmentChain.get_masked_counts for every region of plastid/bin/get_count_vectors.py:92-104 in one launch.
+ * Same range semantics as pb_gather_windows_range (cells of other ranks' positions are 0). */
+int pb_gather_chains_range(const void *const *planes, int vec_dtype,
+                           const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                           const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                           const int64_t *row_off, int64_t n_chains,
+                           const uint8_t *mask_bits, const int64_t *mask_off,
+                           int64_t bin_begin, int64_t bin_end,
+                           double *values, uint8_t *masked, void *stream);
 
 /* metagene.py:918-924 on a window matrix (one warp per row): denom[r] = sum of unmasked cells in
  * columns [norm_lo,norm_hi) (NaN when every cell there is masked), row_select[r] = denom >=
@@ -424,6 +473,17 @@ int pb_stratified_windows(const pb_batch *batch, const pb_layout *layout, const 
                           int phase_mode, int32_t codon_front, int32_t codon_back,
                           const uint8_t *mask_bits, const int64_t *mask_off,
                           uint32_t *out, uint8_t *maskmat, void *stream);
+/* Position-sharded form: only sites whose global bin lies in [bin_begin, bin_end) are counted (a rank's batch
+ * holds its own reads plus a halo; each site is owned by exactly one rank), so the matrices of all ranks add up. */
+int pb_stratified_windows_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                                int min_len, int max_len,
+                                const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                const int32_t *row_col, int64_t n_chains, int32_t width,
+                                int phase_mode, int32_t codon_front, int32_t codon_back,
+                                const uint8_t *mask_bits, const int64_t *mask_off,
+                                int64_t bin_begin, int64_t bin_end,
+                                uint32_t *out, uint8_t *maskmat, void *stream);
 
 /* phase_by_size.py:197-214: per chain, counts laid 5'->3' are cut into codons (a trailing partial
  * codon is ignored), the python slice [codon_front:codon_back] of codons is kept, and counts are
@@ -432,6 +492,11 @@ int pb_phase_sums(const void *const *planes, int vec_dtype,
                   const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
                   const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
                   int32_t codon_front, int32_t codon_back, double *out, void *stream);
+int pb_phase_sums_range(const void *const *planes, int vec_dtype,
+                        const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                        const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
+                        int32_t codon_front, int32_t codon_back, int64_t bin_begin, int64_t bin_end,
+                        double *out, void *stream);
 
 /* Track export: BAMGenomeArray.to_variable_step / to_bedgraph (plastid/genomics/genome_array.py:990-1111)
  * as a stream compaction of one chromosome's count vector vec[0..n_bins) (vec_dtype 0 = uint32, 1 =

@@ -95,9 +95,11 @@ def region_sums(vec, bstart, bend, chain_off, mask_bits=None, mask_off=None):
     n = len(chain_off) - 1
     sums = np.zeros(n, dtype=np.float64)
     live = np.zeros(n, dtype=np.int64)
-    fn = lib().or_region_sums_f64 if vec.dtype == np.float64 else lib().or_region_sums_u32
-    if vec.dtype not in (np.float64, np.uint32):
-        raise TypeError("vector must be uint32 or float64")
+    fns = {np.dtype(np.float64): "or_region_sums_f64", np.dtype(np.uint32): "or_region_sums_u32",
+           np.dtype(np.int64): "or_region_sums_i64"}
+    if vec.dtype not in fns:
+        raise TypeError("vector must be uint32, int64 or float64")
+    fn = getattr(lib(), fns[vec.dtype])
     fn(_p(vec), _p(bstart), _p(bend), _p(chain_off), C.c_int64(n), _p(mask_bits),
        _p(None if mask_off is None else np.ascontiguousarray(mask_off, dtype=np.int64)), _p(sums), _p(live))
     return sums, live

@@ -222,3 +222,29 @@ int or_region_sums_f64(const double *vec, const int64_t *bstart, const int64_t *
     }
     return 0;
 }
+
+/* The same over the int64 vector the reference's point rules return (map_factories.pyx:334: numpy.zeros(..., dtype=int)),
+ * so that a caller holding such a vector does not have to narrow it first. */
+int or_region_sums_i64(const int64_t *vec, const int64_t *bstart, const int64_t *bend,
+                       const int64_t *chain_off, int64_t n_chains,
+                       const uint8_t *mask_bits, const int64_t *mask_off,
+                       double *sums, int64_t *masked_len)
+{
+    for (int64_t c = 0; c < n_chains; ++c) {
+        double acc = 0.0;
+        int64_t j = 0, keep = 0;
+        for (int64_t k = chain_off[c]; k < chain_off[c + 1]; ++k) {
+            for (int64_t p = bstart[k]; p < bend[k]; ++p, ++j) {
+                int masked = 0;
+                if (mask_bits) {
+                    int64_t bit = mask_off[c] + j;
+                    masked = (mask_bits[bit >> 3] >> (bit & 7)) & 1;
+                }
+                if (!masked) { acc += (double)vec[p]; keep++; }
+            }
+        }
+        sums[c] = acc;
+        masked_len[c] = keep;
+    }
+    return 0;
+}

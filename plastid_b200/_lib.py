@@ -94,6 +94,18 @@ _SIGNATURES = {
                                  C.c_int64, C.c_int64, _P, _P, _P, _P]),
     "pb_length_hist": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbRule), C.c_int, _P, _P]),
     "pb_region_sums": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "pb_region_sums_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "pb_chain_counts": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), _P, _P, _P, _P, C.c_int64, _P, _P,
+                                  C.c_int64, C.c_int64, _P, _P, _P, _P]),
+    "pb_gather_windows_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32,
+                                          _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "pb_gather_chains_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64,
+                                         _P, _P, _P]),
+    "pb_stratified_windows_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int, C.c_int,
+                                              _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_int32,
+                                              _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "pb_phase_sums_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32,
+                                      C.c_int64, C.c_int64, _P, _P]),
     "pb_gather_windows": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32,
                                     _P, _P, _P, _P, _P]),
     "pb_window_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,

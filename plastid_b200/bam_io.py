@@ -20,10 +20,13 @@ from . import _lib
 from .batch import AlignmentBatch, cigar_to_blocks, MAX_ALIGNED_LEN, MAX_BLOCKS
 
 
-def batch_from_bam(source, threads=0, pinned=False):
-    """Decode a coordinate-sorted BAM (path, or an open pysam file) into an AlignmentBatch."""
+def batch_from_bam(source, threads=0, pinned=False, pack=True):
+    """Decode a coordinate-sorted BAM (path, or an open pysam file) into an AlignmentBatch.  ``pack``: also emit
+    the batch's transfer format (``AlignmentBatch.pack``: delta3 streams + block words) — the form
+    ``BAMGenomeArray`` uploads — while the decoder's threads are at hand."""
     if not isinstance(source, (str, bytes)):
-        return _batch_from_pysam(source)
+        out = _batch_from_pysam(source)
+        return out.pack(threads) if pack else out
     L = _lib.lib()
     handle = C.c_void_p()
     path = source.encode() if isinstance(source, str) else source
@@ -48,8 +51,9 @@ def batch_from_bam(source, threads=0, pinned=False):
             blk_off, blk = buf(n + 1, np.uint32), buf(2 * n_blk, np.int32)
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         _lib.check(L.pb_bam_copy(handle, p(start), p(meta), p(blk_off), p(blk), p(off)))
-        return AlignmentBatch(chroms, lens, start, meta, off, blk_off, None if blk is None else blk.reshape(-1, 2),
-                              max_span=L.pb_bam_max_span(handle), mapped=L.pb_bam_n_mapped(handle))
+        out = AlignmentBatch(chroms, lens, start, meta, off, blk_off, None if blk is None else blk.reshape(-1, 2),
+                             max_span=L.pb_bam_max_span(handle), mapped=L.pb_bam_n_mapped(handle))
+        return out.pack(threads) if pack else out
     finally:
         L.pb_bam_close(handle)
 

@@ -97,6 +97,10 @@ class AlignmentBatch(object):
         self.mapped = n if mapped is None else int(mapped)   # what `bamfile.mapped` reports
         self.objects = None      # optional list of the original read objects, batch order
         self._dev = {}
+        # the batch in the form that crosses PCIe (delta3 streams, plus block words for spliced batches), written
+        # once by whoever produced the batch — the BAM decoder does (bam_io.batch_from_bam) — see pack()
+        self.transfer = None
+        self._transfer_pinned = None
 
     def __len__(self):
         return len(self.ref_start)
@@ -137,6 +141,26 @@ class AlignmentBatch(object):
                              self.blk_off, self.blk, self.max_span, self.mapped)
         out.objects = self.objects
         return out
+
+    def pack(self, threads=0):
+        """Attach the transfer format of this batch (:class:`Delta3Batch`, or :class:`Delta3SplicedBatch` when it has
+        multi-block reads): 1-1.3 bytes per read instead of the SoA's 8, 4 bytes per aligned block instead of 12.
+        Encoded by the library's multithreaded host encoder (``pb_pack_delta3``); done once per batch — the decoder
+        calls it — after which :class:`~plastid_b200.genome_array.BAMGenomeArray` ships this form to the device
+        and expands it there.  Returns ``self``."""
+        if self.transfer is None:
+            cls = Delta3Batch if self.blk is None else Delta3SplicedBatch
+            self.transfer = cls.from_batch(self, threads=threads)
+            self._transfer_pinned = None
+        return self
+
+    def transfer_pinned(self):
+        """The transfer format in page-locked host memory (dict of tensors), built on first use."""
+        if self.transfer is None:
+            raise ValueError("batch has no transfer format: call pack() first")
+        if self._transfer_pinned is None:
+            self._transfer_pinned = self.transfer.pinned()
+        return self._transfer_pinned
 
     def pinned(self):
         """Pinned host tensors (for timed H2D copies)."""

@@ -58,24 +58,23 @@ def write_table(fout, ga_sum, rows):
 
 
 def main(argv=sys.argv[1:]):
+    """Same command line as plastid/bin/counts_in_region.py:63-131 (``--normalize`` is disabled there, :60).
+    Under ``torchrun`` every rank counts the positions of its own genome range; rank 0 writes the table."""
     parser = argparse.ArgumentParser(description=__doc__)
-    _cli.add_alignment_args(parser)
-    parser.add_argument("--annotation_files", nargs="+", required=True, help="BED files of regions")
-    parser.add_argument("--mask_annotation_files", nargs="*", default=[], help="BED files of masked regions")
-    parser.add_argument("outfile")
+    _cli.add_base_args(parser)
+    _cli.add_alignment_args(parser, disabled=("normalize",))
+    _cli.add_annotation_args(parser)
+    _cli.add_mask_args(parser)
+    parser.add_argument("outfile", type=str, help="Output filename")
     args = parser.parse_args(argv)
-    ga = _cli.genome_array_from_args(args)
-    chains = []
-    for fn in args.annotation_files:
-        chains.extend(_cli.read_bed(fn))
-    mask_chains = None
-    if args.mask_annotation_files:
-        mask_chains = []
-        for fn in args.mask_annotation_files:
-            mask_chains.extend(_cli.read_bed(fn))
+    ga = _cli.genome_array_from_args(args, disabled=("normalize",))
+    chains = _cli.chains_from_args(args)
+    mask_chains = _cli.chains_from_args(args, prefix="mask_") if args.mask_annotation_files else None
     ga_sum, rows = count_regions(ga, chains, mask_features=mask_chains)
-    with open(args.outfile, "w") as fout:
-        write_table(fout, ga_sum, rows)
+    if _cli.is_writer():
+        with open(args.outfile, "w") as fout:
+            write_table(fout, ga_sum, rows)
+    _cli.finish_distributed()
 
 
 def overlapping_masks(chains, mask_chains):

@@ -286,36 +286,44 @@ def _fmt(v):
 
 
 def write_table(fout, order, cols):
+    """The reference writes a pandas table with ``float_format="%.8f"`` (cs.py:716-727): a column holding any float
+    is a float column, and its integer zeros (``sum([])`` of an empty chain) print as ``0.00000000`` too."""
     fout.write("\t".join(order) + "\n")
+    is_float = {c: any(isinstance(v, (float, np.floating)) for v in cols[c]) for c in order}
     for i in range(len(cols["region"])):
-        fout.write("\t".join(_fmt(cols[c][i]) for c in order) + "\n")
+        fout.write("\t".join(_fmt(float(cols[c][i]) if is_float[c] else cols[c][i]) for c in order) + "\n")
 
 
 def main(argv=sys.argv[1:]):
+    """``cs generate OUTBASE --annotation_files ...`` / ``cs count POSITION_FILE OUTBASE --count_files ...``
+    (plastid/bin/cs.py:1259-1380).  ``count`` under ``torchrun``: every rank counts its own genome range."""
     parser = argparse.ArgumentParser(description=__doc__)
     sub = parser.add_subparsers(dest="program")
     gp = sub.add_parser("generate")
-    gp.add_argument("--annotation_files", nargs="+", required=True,
-                    help="BED12 + gene_id column; thickStart/thickEnd give the coding region")
-    gp.add_argument("--mask_annotation_files", nargs="+", default=[])
+    _cli.add_base_args(gp)
+    _cli.add_annotation_args(gp)
+    _cli.add_mask_args(gp)
     gp.add_argument("--device", default="cuda")
     gp.add_argument("outbase")
     cp = sub.add_parser("count")
-    _cli.add_alignment_args(cp)
+    _cli.add_base_args(cp)
+    _cli.add_alignment_args(cp, disabled=("normalize",))
     cp.add_argument("position_file")
     cp.add_argument("outbase")
     args = parser.parse_args(argv)
     if args.program == "generate":
-        transcripts = [tx for path in args.annotation_files for tx in _cli.read_bed(path, as_transcripts=True)]
-        masks = [m for path in args.mask_annotation_files for m in _cli.read_bed(path)]
+        transcripts = _cli.chains_from_args(args, as_transcripts=True)
+        masks = _cli.chains_from_args(args, prefix="mask_")
         do_generate(transcripts, GenomeHash(masks), args.outbase, args.device)
         return
     if args.program != "count":
         parser.error("the `generate` and `count` sub-programs are on the GPU path")
-    ga = _cli.genome_array_from_args(args)
+    ga = _cli.genome_array_from_args(args, disabled=("normalize",))
     order, cols = do_count(ga, _cli.read_pl_table(args.position_file))
-    with open("%s.txt" % args.outbase, "w") as fout:
-        write_table(fout, order, cols)
+    if _cli.is_writer():
+        with open("%s.txt" % args.outbase, "w") as fout:
+            write_table(fout, order, cols)
+    _cli.finish_distributed()
 
 
 if __name__ == "__main__":

@@ -30,19 +30,20 @@ def write_tracks(ga, outbase, track_name=None, color=None, output_format="bedgra
 
 
 def main(argv=sys.argv[1:]):
+    """``make_wiggle -o OUTBASE --count_files ... [--output_format bedgraph|variable_step] [--normalize]`` with the
+    reference's flags (plastid/bin/make_wiggle.py:99-209)."""
     parser = argparse.ArgumentParser(description=__doc__)
+    _cli.add_base_args(parser)
     _cli.add_alignment_args(parser)
     parser.add_argument("-o", "--out", dest="outbase", required=True, metavar="FILENAME", help="Base name for output files")
     parser.add_argument("--window_size", default=100000, type=int, metavar="N")
     parser.add_argument("--color", default=None, help="RGB hex string '#NNNNNN'")
     parser.add_argument("-t", "--track_name", dest="track_name", default=None)
     parser.add_argument("--output_format", choices=("bedgraph", "variable_step"), default="bedgraph")
-    parser.add_argument("--normalize", action="store_true", help="export reads per million instead of raw counts")
     args = parser.parse_args(argv)
     ga = _cli.genome_array_from_args(args)
-    if args.normalize:
-        ga.set_normalize(True)
     write_tracks(ga, args.outbase, args.track_name, args.color, args.output_format, args.window_size)
+    _cli.finish_distributed()
 
 
 if __name__ == "__main__":

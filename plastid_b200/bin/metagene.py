@@ -26,21 +26,23 @@ _NORM_START_DEFAULT, _NORM_END_DEFAULT = 20, 50      # metagene.py:770-771
 # generate: window functions (host objects, same signatures and return values as the reference)
 # ---------------------------------------------------------------------------------------------
 def window_landmark(region, flank_upstream=50, flank_downstream=50, ref_delta=0, landmark=0):
-    """plastid/bin/metagene.py:180-239 -> (window SegmentChain, alignment offset, (chrom, pos, strand))."""
-    if landmark + ref_delta >= flank_upstream:
-        fiveprime_offset = 0
-        my_start = landmark + ref_delta - flank_upstream
+    """Window of ``flank_upstream + flank_downstream`` transcript positions around ``landmark + ref_delta`` ->
+    ``(window SegmentChain, alignment offset, (chrom, position, strand) of the zero point)``; same contract as
+    plastid/bin/metagene.py:180-239.  Host-object form of what ``pb_landmark_windows`` computes for a whole
+    transcript table: the window is the transcript-coordinate interval ``[zero - up, zero + down)`` clipped to the
+    region, and the offset is the number of leading window columns the region cannot fill."""
+    zero = landmark + ref_delta
+    lo, hi = max(zero - flank_upstream, 0), min(zero + flank_downstream, region.length)
+    # columns missing on the 5' side; the reference measures the shortfall from `landmark` alone (its ref_delta
+    # quirk, :223), and so does pb_landmark_windows
+    offset = flank_upstream - landmark if zero < flank_upstream else 0
+    window = region.get_subchain(lo, hi)
+    if zero == region.length:                  # zero point one past the 3' end: not a transcript position
+        span = region.spanning_segment
+        zero_point = (span.chrom, span.end if span.strand == "+" else span.start - 1, span.strand)
     else:
-        fiveprime_offset = flank_upstream - landmark            # as the reference: without ref_delta
-        my_start = 0
-    my_end = min(region.length, landmark + ref_delta + flank_downstream)
-    roi = region.get_subchain(my_start, my_end)
-    span = region.spanning_segment
-    if landmark + ref_delta == region.length:
-        ref_point = (span.chrom, span.end, span.strand) if span.strand == "+" else (span.chrom, span.start - 1, span.strand)
-    else:
-        ref_point = region.get_genomic_coordinate(landmark + ref_delta)
-    return roi, fiveprime_offset, ref_point
+        zero_point = region.get_genomic_coordinate(zero)
+    return window, offset, zero_point
 
 
 def window_cds_start(transcript, flank_upstream, flank_downstream, ref_delta=0):
@@ -238,6 +240,7 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, use_m
     need = sorted(set("+-."[p] for p in np.unique(table.chain_plane))) or ["+"]
     planes = ga.count_planes(tuple(need))
     mat, mmask = gather_windows(planes, table, cols, window_size)
+    ga._allreduce(mat)           # multi-GPU: every rank filled the cells of its own positions (others 0, NaN where no position)
     if ga._normalize is True:
         mat = mat / float(ga.sum()) * 1e6
     denom, sel, norm, nmask = window_normalize(mat, mmask, norm_start, norm_end, min_counts)
@@ -254,6 +257,23 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, use_m
     return out
 
 
+def keep_matrices(out):
+    """The three ``--keep`` matrices as the reference's ``numpy.savetxt`` calls write them (metagene.py:926-932).
+    ``savetxt`` stores the DATA of a masked array, and numpy.ma's division leaves the numerator in every cell it
+    masks (masked numerator, masked or zero denominator): so the raw file keeps the counts of masked positions, the
+    normalised file holds quotients only where the division was defined, and the mask file flags every other cell
+    (``MaskedArray(x, mask=m)`` keeps the mask ``x`` already has)."""
+    counts = out["counts"]
+    raw = np.ma.getdata(counts).astype(np.float64)
+    cmask = np.ma.getmaskarray(counts)
+    den = np.asarray(out["denominator"], dtype=np.float64)[:, None]
+    with np.errstate(all="ignore"):
+        quotient = raw / den
+    defined = ~cmask & ~np.isnan(den) & (den != 0) & np.isfinite(quotient)
+    norm = np.where(defined, quotient, raw)
+    return raw, norm, ~defined | np.isnan(norm) | np.isinf(norm)
+
+
 def write_profile(fout, out):
     fout.write("x\tmetagene_average\tregions_counted\n")
     for x, y, n in zip(out["x"], out["metagene_average"], out["regions_counted"]):
@@ -261,12 +281,15 @@ def write_profile(fout, out):
 
 
 def main(argv=sys.argv[1:]):
+    """``metagene generate OUTBASE ...`` / ``metagene count ROI_FILE OUTBASE ...`` with the reference's flags
+    (plastid/bin/metagene.py:1118-1340).  ``count`` under ``torchrun``: every rank gathers the window cells of its own
+    genome range, the count matrix is all-reduced, rank 0 writes."""
     parser = argparse.ArgumentParser(description=__doc__)
     sub = parser.add_subparsers(dest="program")
     gp = sub.add_parser("generate")
-    gp.add_argument("--annotation_files", nargs="+", required=True,
-                    help="BED12(+gene_id) transcripts; thickStart/thickEnd give the coding region")
-    gp.add_argument("--mask_annotation_files", nargs="+", default=[], help="BED regions to mask")
+    _cli.add_base_args(gp)
+    _cli.add_annotation_args(gp)
+    _cli.add_mask_args(gp)
     gp.add_argument("--landmark", choices=("cds_start", "cds_stop"), default="cds_start")
     gp.add_argument("--upstream", type=int, default=50)
     gp.add_argument("--downstream", type=int, default=50)
@@ -274,17 +297,20 @@ def main(argv=sys.argv[1:]):
     gp.add_argument("--device", default="cuda")
     gp.add_argument("outbase")
     cp = sub.add_parser("count")
+    _cli.add_base_args(cp)
     _cli.add_alignment_args(cp)
     cp.add_argument("roi_file")
     cp.add_argument("outbase")
-    cp.add_argument("--normalize_over", type=int, nargs=2, default=None)
-    cp.add_argument("--min_counts", type=int, default=10)
-    cp.add_argument("--use_mean", action="store_true")
-    cp.add_argument("--keep", action="store_true")
+    cp.add_argument("--min_counts", type=int, default=10, metavar="N")
+    cp.add_argument("--normalize_over", type=int, nargs=2, default=None, metavar="N")
+    cp.add_argument("--norm_region", type=int, nargs=2, default=None, metavar="N", help="Deprecated. Use --normalize_over")
+    cp.add_argument("--landmark", type=str, default=None, help="Name of landmark at zero point, optional.")
+    cp.add_argument("--use_mean", action="store_true", default=False)
+    cp.add_argument("--keep", action="store_true", default=False)
     args = parser.parse_args(argv)
     if args.program == "generate":
-        transcripts = [tx for path in args.annotation_files for tx in _cli.read_bed(path, as_transcripts=True)]
-        masks = [m for path in args.mask_annotation_files for m in _cli.read_bed(path)]
+        transcripts = _cli.chains_from_args(args, as_transcripts=True)
+        masks = _cli.chains_from_args(args, prefix="mask_")
         roi_table = do_generate(transcripts, GenomeHash(masks), args.landmark, args.upstream, args.downstream,
                                 args.group_by, args.device)
         roi_table.to_csv("%s_rois.txt" % args.outbase, sep="\t", header=True, index=False, na_rep="nan",
@@ -297,17 +323,29 @@ def main(argv=sys.argv[1:]):
         parser.error("the `generate` and `count` sub-programs are on the GPU path")
     ga = _cli.genome_array_from_args(args)
     roi = _cli.read_pl_table(args.roi_file)
-    ns = ne = None
-    if args.normalize_over is not None:
-        flank = int(roi["zero_point"][0])
-        ns, ne = args.normalize_over[0] + flank, args.normalize_over[1] + flank
+    ns, ne = norm_region_from_args(roi, args)
     out = do_count(ga, roi, ns, ne, args.min_counts, args.use_mean, args.keep)
-    with open("%s_metagene_profile.txt" % args.outbase, "w") as fout:
-        write_profile(fout, out)
-    if args.keep:
-        np.savetxt("%s_rawcounts.txt.gz" % args.outbase, out["counts"].filled(np.nan), delimiter="\t", fmt="%.8f")
-        np.savetxt("%s_normcounts.txt.gz" % args.outbase, out["norm_counts"].filled(np.nan), delimiter="\t")
-        np.savetxt("%s_mask.txt.gz" % args.outbase, np.ma.getmaskarray(out["norm_counts"]), delimiter="\t")
+    if _cli.is_writer():
+        with open("%s_metagene_profile.txt" % args.outbase, "w") as fout:
+            write_profile(fout, out)
+        if args.keep:
+            raw, norm, mask = keep_matrices(out)
+            np.savetxt("%s_rawcounts.txt.gz" % args.outbase, raw, delimiter="\t", fmt="%.8f")
+            np.savetxt("%s_normcounts.txt.gz" % args.outbase, norm, delimiter="\t")
+            np.savetxt("%s_mask.txt.gz" % args.outbase, mask, delimiter="\t")
+    _cli.finish_distributed()
+
+
+def norm_region_from_args(roi_table, args):
+    """plastid/bin/metagene.py:776-818 (``_get_norm_region``): ``--normalize_over`` counts from the landmark,
+    the deprecated ``--norm_region`` and the default (20, 50) from the window's first column."""
+    flank = int(roi_table["zero_point"][0])
+    if args.normalize_over is not None:
+        return args.normalize_over[0] + flank, args.normalize_over[1] + flank
+    if getattr(args, "norm_region", None) is not None:
+        warnings.warn("`--norm_region` is deprecated. Use `--normalize_over` instead.", DataWarning)
+        return tuple(args.norm_region)
+    return _NORM_START_DEFAULT, _NORM_END_DEFAULT
 
 
 if __name__ == "__main__":

@@ -32,8 +32,9 @@ def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
     lo, hi = min(read_lengths), max(read_lengths)
     # all lengths and all chains in one launch: [n_len, n_chains, 3] -> sum over chains
     strat, _ = stratified_windows(ga._device_batch(), ga.layout, ga.map_fn, ga._size_filter(), table, None, 3,
-                                  lo, hi, phase=(codon_buffer, back_buffer))
-    sums = strat.to(torch.float64).sum(dim=1).cpu().numpy()
+                                  lo, hi, phase=(codon_buffer, back_buffer), bin_range=ga.bin_range)
+    # multi-GPU: an 11 x 3 table per rank (the sites of its own genome range), completed with one all-reduce
+    sums = ga._allreduce(strat.to(torch.float64).sum(dim=1)).cpu().numpy()
     return {k: sums[k - lo] for k in read_lengths}
 
 
@@ -47,25 +48,42 @@ def phase_table(sums):
 
 
 def main(argv=sys.argv[1:]):
+    """``phase_by_size [ROI_FILE] OUTBASE --count_files ... [--annotation_files ...]`` with the reference's flags
+    (plastid/bin/phase_by_size.py:79-262): regions from an ROI file of ``metagene generate`` (CDS part of every
+    window, last codon dropped) or the coding regions of an annotation (``codon_buffer`` codons dropped at both ends)."""
     parser = argparse.ArgumentParser(description=__doc__)
-    _cli.add_alignment_args(parser)
-    parser.add_argument("roi_file", help="ROI file from `metagene generate` (CDS start windows)")
+    _cli.add_base_args(parser)
+    _cli.add_alignment_args(parser, disabled=("normalize",))
+    _cli.add_annotation_args(parser)
+    parser.add_argument("roi_file", type=str, nargs="?", default=None,
+                        help="ROI file from `metagene generate` (CDS start windows); else give --annotation_files")
     parser.add_argument("outbase")
     parser.add_argument("--codon_buffer", type=int, default=5)
     args = parser.parse_args(argv)
-    ga = _cli.genome_array_from_args(args)
-    roi = _cli.read_pl_table(args.roi_file)
-    cds = []
-    for region, offset, zero_point in zip(roi["region"], roi["alignment_offset"], roi["zero_point"]):
-        chain = SegmentChain.from_str(region)                              # roi_row_to_cds, :58-77
-        cds_start = int(zero_point) - int(round(float(offset)))
-        cds.append(chain.get_subchain(cds_start, chain.length))
-    sums = do_phase(ga, cds, list(range(args.min_length, args.max_length + 1)), args.codon_buffer, -1)
+    ga = _cli.genome_array_from_args(args, disabled=("normalize",))
+    if args.roi_file is not None:
+        roi = _cli.read_pl_table(args.roi_file)
+        cds = []
+        for region, offset, zero_point in zip(roi["region"], roi["alignment_offset"], roi["zero_point"]):
+            chain = SegmentChain.from_str(region)                              # roi_row_to_cds, :58-77
+            cds_start = int(zero_point) - int(round(float(offset)))
+            cds.append(chain.get_subchain(cds_start, chain.length))
+        back_buffer = -1
+    else:
+        if len(args.annotation_files) == 0:
+            sys.stderr.write("Either an ROI file or at least annotation file must be given.\n")
+            sys.exit(1)
+        cds = [tx.get_cds() for tx in _cli.chains_from_args(args, as_transcripts=True)]
+        back_buffer = -args.codon_buffer
+    sums = do_phase(ga, cds, list(range(args.min_length, args.max_length + 1)), args.codon_buffer, back_buffer)
     lengths, counted, frac, phases = phase_table(sums)
-    with open("%s_phasing.txt" % args.outbase, "w") as fout:
-        fout.write("read_length\treads_counted\tfraction_reads_counted\tphase0\tphase1\tphase2\n")
-        for i, k in enumerate(lengths):
-            fout.write("%d\t%d\t%.6f\t%.6f\t%.6f\t%.6f\n" % (k, counted[i], frac[i], phases[i][0], phases[i][1], phases[i][2]))
+    if _cli.is_writer():
+        with open("%s_phasing.txt" % args.outbase, "w") as fout:
+            fout.write("read_length\treads_counted\tfraction_reads_counted\tphase0\tphase1\tphase2\n")
+            for i, k in enumerate(lengths):
+                fout.write("%d\t%d\t%s\n" % (k, counted[i], "\t".join("nan" if np.isnan(v) else "%.6f" % v
+                                                                      for v in [frac[i]] + list(phases[i]))))
+    _cli.finish_distributed()
 
 
 if __name__ == "__main__":

@@ -29,14 +29,15 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
     table = ChainTable.from_chains(wins, ga.layout)
     dbatch = ga._device_batch()
     strat, maskmat = stratified_windows(dbatch, ga.layout, ga.map_fn, ga._size_filter(), table, cols, window_size,
-                                        min_len, max_len)
+                                        min_len, max_len, bin_range=ga.bin_range)
+    ga._allreduce(strat)         # multi-GPU: every rank counted the sites of its own genome range
     dev = strat.device
     n_len, n = max_len - min_len + 1, table.n_chains
     colidx = torch.arange(window_size, device=dev)[None, :]
     c0 = torch.as_tensor(np.asarray(cols), device=dev)[:, None]
     clen = torch.from_numpy(table.chain_len).to(dev)[:, None]
     uncovered = (colidx < c0) | (colidx >= c0 + clen)
-    out = {"x": np.arange(-flank, window_size - flank), "profiles": {}, "regions_counted": {}, "raw": {}}
+    out = {"x": np.arange(-flank, window_size - flank), "profiles": {}, "regions_counted": {}, "raw": {}, "denominator": {}}
     if not aggregate and not keep:
         # the default path: normalisation fused with the key extraction, medians per (length, column) —
         # no float64 / normalised / mask matrices are materialised
@@ -70,6 +71,7 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
         out["regions_counted"][k] = n_regions[j]
         if keep:
             out["raw"][k] = np.ma.MaskedArray(mat[j * n:(j + 1) * n].cpu().numpy(), mask=maskmat.cpu().numpy().astype(bool))
+            out["denominator"][k] = denom[j * n:(j + 1) * n].cpu().numpy()
     return out
 
 
@@ -105,31 +107,55 @@ def write_offsets(fout, offsets, default):
     fout.write("default\t%s" % default)
 
 
+def write_profiles(fout, out):
+    """``OUTBASE_metagene_profiles.txt`` (psite.py:401-411): x, then one ``N-mers`` column per read length, as pandas
+    writes floats (``na_rep='nan'``)."""
+    lengths = list(out["profiles"])
+    fout.write("\t".join(["x"] + ["%s-mers" % k for k in lengths]) + "\n")
+    cols = [np.ma.filled(np.ma.asarray(out["profiles"][k], dtype=float), np.nan) for k in lengths]
+    for i, x in enumerate(out["x"]):
+        fout.write("\t".join([str(int(x))] + ["nan" if np.isnan(c[i]) else repr(float(c[i])) for c in cols]) + "\n")
+
+
 def main(argv=sys.argv[1:]):
+    """``psite ROI_FILE OUTBASE --count_files ...`` with the reference's flags (plastid/bin/psite.py:241-351; no mapping
+    flags: reads are mapped at their 5' ends, :357-359).  Under ``torchrun`` every rank counts the sites of its own
+    genome range; the per-length window matrices are all-reduced and rank 0 writes."""
     parser = argparse.ArgumentParser(description=__doc__)
-    _cli.add_alignment_args(parser)
+    _cli.add_base_args(parser)
+    _cli.add_alignment_args(parser, disabled=("normalize",))
+    parser.add_argument("--min_counts", type=int, default=10, metavar="N")
+    parser.add_argument("--normalize_over", type=int, nargs=2, default=None, metavar="N")
+    parser.add_argument("--norm_region", type=int, nargs=2, default=None, metavar="N", help="Deprecated. Use --normalize_over")
+    parser.add_argument("--require_upstream", action="store_true", default=False)
+    parser.add_argument("--constrain", type=int, nargs=2, default=None, metavar="X")
+    parser.add_argument("--aggregate", action="store_true", default=False)
+    parser.add_argument("--keep", action="store_true", default=False)
+    parser.add_argument("--default", type=int, default=13)
     parser.add_argument("roi_file")
     parser.add_argument("outbase")
-    parser.add_argument("--normalize_over", type=int, nargs=2, default=None)
-    parser.add_argument("--min_counts", type=int, default=10)
-    parser.add_argument("--aggregate", action="store_true")
-    parser.add_argument("--default", type=int, default=13)
-    parser.add_argument("--require_upstream", action="store_true")
-    parser.add_argument("--constrain", type=int, nargs=2, default=None)
     args = parser.parse_args(argv)
-    ga = _cli.genome_array_from_args(args)
-    ga.set_mapping(FivePrimeMapFactory(0))                       # psite.py:357-359
+    args.mapping, args.offset = "fiveprime", 0                   # psite.py:357-359
+    ga = _cli.genome_array_from_args(args, disabled=("normalize",))
     for name in list(ga._filters):                               # psite.py:380-383
         ga.remove_filter(name)
     roi = _cli.read_pl_table(args.roi_file)
-    ns = ne = None
-    if args.normalize_over is not None:
-        flank = int(roi["zero_point"][0])
-        ns, ne = args.normalize_over[0] + flank, args.normalize_over[1] + flank
-    out = do_count(ga, roi, ns, ne, args.min_counts, args.min_length, args.max_length, args.aggregate)
+    from .metagene import norm_region_from_args, keep_matrices
+    ns, ne = norm_region_from_args(roi, args)
+    out = do_count(ga, roi, ns, ne, args.min_counts, args.min_length, args.max_length, args.aggregate, keep=args.keep)
     offsets = pick_offsets(out["x"], out["profiles"], args.default, args.constrain, args.require_upstream)
-    with open("%s_p_offsets.txt" % args.outbase, "w") as fout:
-        write_offsets(fout, offsets, args.default)
+    if _cli.is_writer():
+        with open("%s_metagene_profiles.txt" % args.outbase, "w") as fout:
+            write_profiles(fout, out)
+        if args.keep:
+            for k in out["raw"]:
+                raw, norm, mask = keep_matrices(dict(counts=out["raw"][k], denominator=out["denominator"][k]))
+                np.savetxt("%s_%s_rawcounts.txt.gz" % (args.outbase, k), raw, delimiter="\t")
+                np.savetxt("%s_%s_normcounts.txt.gz" % (args.outbase, k), norm, delimiter="\t")
+                np.savetxt("%s_%s_mask.txt.gz" % (args.outbase, k), mask, delimiter="\t")
+        with open("%s_p_offsets.txt" % args.outbase, "w") as fout:
+            write_offsets(fout, offsets, args.default)
+    _cli.finish_distributed()
 
 
 if __name__ == "__main__":

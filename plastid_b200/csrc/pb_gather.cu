@@ -29,85 +29,6 @@ __device__ __forceinline__ bool pb_mask_bit(const uint8_t *__restrict__ bits, in
     return (__ldg(bits + (bit >> 3)) >> (bit & 7)) & 1;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-pb_region_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
-                      const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
-                      int64_t n_chains, const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
-                      double *__restrict__ sums, int64_t *__restrict__ live_len)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_chains) return;
-    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(chain_plane + c)]);
-    const int64_t moff = mask_bits ? __ldg(mask_off + c) : 0;
-    typename Acc<T>::type acc = 0;
-    long long live = 0;
-    int64_t j = 0;
-    for (int64_t k = __ldg(chain_off + c); k < __ldg(chain_off + c + 1); ++k) {
-        const int64_t bs = __ldg(bstart + k), be = __ldg(bend + k);
-        // four independent 128-byte rows in flight per warp (the loop is latency-, not bandwidth-bound)
-        for (int64_t p = bs + lane; p < be; p += 128) {
-            T v[4];
-            bool use[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t q = p + 32 * u;
-                use[u] = q < be && !(mask_bits && pb_mask_bit(mask_bits, moff + j + (q - bs)));
-                v[u] = use[u] ? vec[q] : T(0);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { acc += v[u]; live += use[u]; }
-        }
-        j += be - bs;
-    }
-    live = (long long)pb_warp_sum((unsigned long long)live);
-    double total;
-    if (sizeof(T) == 4) total = (double)pb_warp_sum((unsigned long long)acc);
-    else total = pb_warp_sum_f64((double)acc);
-    if (lane == 0) { sums[c] = total; live_len[c] = live; }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-pb_gather_windows_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
-                         const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
-                         const uint8_t *__restrict__ chain_reverse, const int32_t *__restrict__ row_col,
-                         int64_t n_chains, int32_t width,
-                         const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
-                         double *__restrict__ matrix, uint8_t *__restrict__ maskmat)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_chains) return;
-    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(chain_plane + c)]);
-    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
-    int64_t len = 0;
-    for (int64_t k = k0; k < k1; ++k) len += __ldg(bend + k) - __ldg(bstart + k);
-    const int64_t col0 = __ldg(row_col + c);
-    const bool rev = __ldg(chain_reverse + c);
-    const int64_t moff = mask_bits ? __ldg(mask_off + c) : 0;
-    double *row = matrix + c * (int64_t)width;
-    uint8_t *mrow = maskmat + c * (int64_t)width;
-    // columns no chain position reaches stay "masked NaN" (metagene.py:895-898)
-    for (int64_t col = lane; col < width; col += 32) {
-        if (col < col0 || col >= col0 + len) { row[col] = nan(""); mrow[col] = 1; }
-    }
-    int64_t j = 0;
-    for (int64_t k = k0; k < k1; ++k) {
-        const int64_t bs = __ldg(bstart + k), be = __ldg(bend + k);
-        for (int64_t p = bs + lane; p < be; p += 32) {
-            const int64_t jj = j + (p - bs);
-            const int64_t col = col0 + (rev ? (len - 1 - jj) : jj);
-            if (col >= 0 && col < width) {
-                row[col] = (double)vec[p];
-                mrow[col] = mask_bits ? (uint8_t)pb_mask_bit(mask_bits, moff + jj) : (uint8_t)0;
-            }
-        }
-        j += be - bs;
-    }
-}
-
 // phase_by_size.py:197-214: counts laid 5'->3', cut into codons, `[front:back]` codon slice, summed
 // per sub-codon phase.  One warp per chain; out[c*3 + phase].
 template <typename T>
@@ -115,7 +36,7 @@ __global__ void __launch_bounds__(256)
 pb_phase_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
                      const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
                      const uint8_t *__restrict__ chain_reverse, int64_t n_chains, int32_t front, int32_t back,
-                     double *__restrict__ out)
+                     long long lo, long long hi, double *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -138,7 +59,7 @@ pb_phase_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const 
             const int64_t jj = j + (p - bs);
             const int64_t t = rev ? (len - 1 - jj) : jj;  // 5'->3' index
             const int64_t cod = t / 3;
-            if (cod >= cod_lo && cod < cod_hi) {
+            if (cod >= cod_lo && cod < cod_hi && p >= lo && p < hi) {     // positions of other ranks count zero
                 const int ph = (int)(t - cod * 3);
                 const T v = vec[p];
                 if (ph == 0) acc0 += v; else if (ph == 1) acc1 += v; else acc2 += v;
@@ -509,49 +430,6 @@ static int check_chains(const void *const *planes, const int64_t *bstart, const 
     return PB_OK;
 }
 
-extern "C" int pb_region_sums(const void *const *planes, int vec_dtype,
-                              const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                              const uint8_t *chain_plane, int64_t n_chains,
-                              const uint8_t *mask_bits, const int64_t *mask_off,
-                              double *sums, int64_t *live_len, void *stream_)
-{
-    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype);
-    if (rc) return rc;
-    if (!sums || !live_len) { pb_set_error("pb_region_sums: null outputs"); return PB_EINVAL; }
-    if (n_chains == 0) return PB_OK;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    PbPlanes pl{{planes[0], planes[1], planes[2]}};
-    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
-    if (vec_dtype == 0)
-        pb_region_sums_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, sums, live_len);
-    else
-        pb_region_sums_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, sums, live_len);
-    PB_CUDA_CHECK(cudaGetLastError());
-    return PB_OK;
-}
-
-extern "C" int pb_gather_windows(const void *const *planes, int vec_dtype,
-                                 const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                                 const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                                 const int32_t *row_col, int64_t n_chains, int32_t width,
-                                 const uint8_t *mask_bits, const int64_t *mask_off,
-                                 double *matrix, uint8_t *maskmat, void *stream_)
-{
-    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype);
-    if (rc) return rc;
-    if (!chain_reverse || !row_col || !matrix || !maskmat || width <= 0) { pb_set_error("pb_gather_windows: bad arguments"); return PB_EINVAL; }
-    if (n_chains == 0) return PB_OK;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    PbPlanes pl{{planes[0], planes[1], planes[2]}};
-    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
-    if (vec_dtype == 0)
-        pb_gather_windows_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, row_col, n_chains, width, mask_bits, mask_off, matrix, maskmat);
-    else
-        pb_gather_windows_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, row_col, n_chains, width, mask_bits, mask_off, matrix, maskmat);
-    PB_CUDA_CHECK(cudaGetLastError());
-    return PB_OK;
-}
-
 extern "C" int pb_window_normalize(const double *matrix, const uint8_t *maskmat, int64_t n_rows, int32_t width,
                                    int32_t norm_lo, int32_t norm_hi, double min_counts,
                                    double *denom, uint8_t *row_select, double *norm_out, uint8_t *normmask_out,
@@ -634,10 +512,11 @@ extern "C" int pb_column_profile(const double *values, const uint8_t *valmask, c
                                      workspace, workspace_bytes, stream_);
 }
 
-extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,
-                             const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                             const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
-                             int32_t codon_front, int32_t codon_back, double *out, void *stream_)
+extern "C" int pb_phase_sums_range(const void *const *planes, int vec_dtype,
+                                   const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                   const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
+                                   int32_t codon_front, int32_t codon_back, int64_t bin_begin, int64_t bin_end,
+                                   double *out, void *stream_)
 {
     int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, nullptr, nullptr, vec_dtype);
     if (rc) return rc;
@@ -647,11 +526,20 @@ extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,
     PbPlanes pl{{planes[0], planes[1], planes[2]}};
     const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
     if (vec_dtype == 0)
-        pb_phase_sums_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, out);
+        pb_phase_sums_kernel<uint32_t><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, bin_begin, bin_end, out);
     else
-        pb_phase_sums_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, out);
+        pb_phase_sums_kernel<double><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains, codon_front, codon_back, bin_begin, bin_end, out);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
+}
+
+extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,
+                             const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                             const uint8_t *chain_plane, const uint8_t *chain_reverse, int64_t n_chains,
+                             int32_t codon_front, int32_t codon_back, double *out, void *stream_)
+{
+    return pb_phase_sums_range(planes, vec_dtype, bstart, bend, chain_off, chain_plane, chain_reverse, n_chains,
+                               codon_front, codon_back, 0, INT64_MAX, out, stream_);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -671,6 +559,7 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
                              const uint8_t *__restrict__ chain_reverse, const int32_t *__restrict__ row_col,
                              int64_t n_chains, int32_t width, int phase_mode, int32_t codon_front, int32_t codon_back,
                              const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
+                             long long lo_bin, long long hi_bin,
                              uint32_t *__restrict__ out, uint8_t *__restrict__ maskmat)
 {
     extern __shared__ uint32_t hist[];   // [n_len][width]  (phase mode: width == 3 sub-codon phases)
@@ -723,6 +612,7 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
                 if (idx < 0) continue;
                 const int64_t p = pb_position(b, i, sv[u], m, idx);
                 if (p < bs || p >= be) continue;
+                if (base + p < lo_bin || base + p >= hi_bin) continue;        // the site belongs to another rank
                 const int64_t jj = j0 + (p - bs);
                 int64_t col = col0 + (rev_out ? (len - 1 - jj) : jj);
                 if (phase_mode) {
@@ -755,14 +645,15 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
 
 }  // namespace
 
-extern "C" int pb_stratified_windows(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
-                                     int min_len, int max_len,
-                                     const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                                     const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                                     const int32_t *row_col, int64_t n_chains, int32_t width,
-                                     int phase_mode, int32_t codon_front, int32_t codon_back,
-                                     const uint8_t *mask_bits, const int64_t *mask_off,
-                                     uint32_t *out, uint8_t *maskmat, void *stream_)
+extern "C" int pb_stratified_windows_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                                           int min_len, int max_len,
+                                           const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                           const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                           const int32_t *row_col, int64_t n_chains, int32_t width,
+                                           int phase_mode, int32_t codon_front, int32_t codon_back,
+                                           const uint8_t *mask_bits, const int64_t *mask_off,
+                                           int64_t bin_begin, int64_t bin_end,
+                                           uint32_t *out, uint8_t *maskmat, void *stream_)
 {
     if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !chain_reverse || !out ||
         (!phase_mode && (!row_col || !maskmat))) { pb_set_error("pb_stratified_windows: null argument"); return PB_EINVAL; }
@@ -785,9 +676,23 @@ extern "C" int pb_stratified_windows(const pb_batch *batch, const pb_layout *lay
     pb_stratified_windows_kernel<<<(unsigned)n_chains, 128, smem, stream>>>(b, r, lay, min_len, n_len, bstart, bend, chain_off,
                                                                            chain_plane, chain_reverse, row_col, n_chains, width,
                                                                            phase_mode, codon_front, codon_back,
-                                                                           mask_bits, mask_off, out, maskmat);
+                                                                           mask_bits, mask_off, bin_begin, bin_end, out, maskmat);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
+}
+
+extern "C" int pb_stratified_windows(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                                     int min_len, int max_len,
+                                     const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                     const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                     const int32_t *row_col, int64_t n_chains, int32_t width,
+                                     int phase_mode, int32_t codon_front, int32_t codon_back,
+                                     const uint8_t *mask_bits, const int64_t *mask_off,
+                                     uint32_t *out, uint8_t *maskmat, void *stream_)
+{
+    return pb_stratified_windows_range(batch, layout, rule, min_len, max_len, bstart, bend, chain_off, chain_plane,
+                                       chain_reverse, row_col, n_chains, width, phase_mode, codon_front, codon_back,
+                                       mask_bits, mask_off, 0, INT64_MAX, out, maskmat, stream_);
 }
 
 extern "C" int pb_mask_chains(const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,

@@ -64,13 +64,25 @@ def shard_reads(hb, rank, world_size):
     return out
 
 
-def position_cuts(hb, layout, world_size):
+def position_cuts(hb, layout, world_size, snap="bins"):
     """Global-bin cut points ``int64[world_size + 1]`` (multiples of PB_LAYOUT_ALIGN, first 0, last
     ``layout.total_bins``) splitting the reads into ``world_size`` contiguous position ranges of about
-    equal read count."""
+    equal read count.  ``snap="chromosomes"``: cuts fall on chromosome boundaries only (BASELINE config 5,
+    "sharded by chromosome": every rank owns a run of whole chromosomes) — the boundary whose cumulative read
+    count is nearest each target."""
     from . import _lib
     A = _lib.PB_LAYOUT_ALIGN
     n = len(hb)
+    if snap == "chromosomes":
+        cum = np.asarray(hb.chrom_read_off, dtype=np.int64)          # reads before chromosome c
+        cuts = [0]
+        for r in range(1, world_size):
+            c = int(np.argmin(np.abs(cum - (r * n) // world_size)))
+            cuts.append(max(int(layout.chrom_bin_off[c]), cuts[-1]))
+        cuts.append(int(layout.total_bins))
+        return np.asarray(cuts, dtype=np.int64)
+    if snap != "bins":
+        raise ValueError("snap must be 'bins' or 'chromosomes'")
     cuts = [0]
     for r in range(1, world_size):
         i = (r * n) // world_size
@@ -84,12 +96,12 @@ def position_cuts(hb, layout, world_size):
     return np.asarray(cuts, dtype=np.int64)
 
 
-def shard_positions(hb, layout, rank, world_size, cuts=None):
+def shard_positions(hb, layout, rank, world_size, cuts=None, snap="bins"):
     """Position-range shard: ``(sub_batch, bin_lo, bin_hi)``.  ``sub_batch`` holds, per chromosome,
     the reads starting in ``[lo - hb.max_span, hi)`` of the part of the chromosome inside the rank's
     range — every read that can put a site into ``[bin_lo, bin_hi)`` — with the same chromosomes
     and layout as ``hb`` (coordinates stay global)."""
-    cuts = position_cuts(hb, layout, world_size) if cuts is None else cuts
+    cuts = position_cuts(hb, layout, world_size, snap) if cuts is None else cuts
     g_lo, g_hi = int(cuts[rank]), int(cuts[rank + 1])
     keep = []
     off = [0]

@@ -249,13 +249,15 @@ def _filtered_hist(hist, size_filter):
 
 
 def map_center_streamed(receiver, pinned, chunks, layout, factory, size_filter=None, strands=("+", "-"),
-                        planes=None, copy_stream=None):
+                        planes=None, copy_stream=None, length_hist=None):
     """Center rule over a batch WITH multi-block reads that is still being uploaded
     (``Delta3SplicedReceiver``): chunk by chunk on ``copy_stream``; as soon as a chunk's reads and block
     words have landed and are expanded, the bins below the next chunk's first read are final and are
     produced with ``pb_map_center_range`` from the reads that can reach them (read window = from one
     128-read block before the first read within ``max_span`` of the range).  Two compute lanes take the
-    chunks alternately.  Same result, bit for bit, as :func:`map_batch` on the whole batch."""
+    chunks alternately.  Same result, bit for bit, as :func:`map_batch` on the whole batch.
+    ``length_hist``: histogram to derive the slot tables from (already filtered; a position-sharded rank passes the
+    whole batch's); default: the receiver batch's own."""
     import torch
     _lib.require_cuda()
     if not isinstance(factory, CenterMapFactory):
@@ -270,7 +272,8 @@ def map_center_streamed(receiver, pinned, chunks, layout, factory, size_filter=N
     mask = 0
     for s in strands:
         mask |= _lib.STRAND_PLANE[s]
-    launch = _center_launcher(factory, _filtered_hist(dbatch.length_hist, size_filter), planes, strands, dev)
+    hist = _filtered_hist(dbatch.length_hist, size_filter) if length_hist is None else np.ascontiguousarray(length_hist, dtype=np.int64)
+    launch = _center_launcher(factory, hist, planes, strands, dev)
     L = _lib.lib()
     ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, dbatch.n_blk, dbatch.n_reads)
     n_lanes = 2 if len(chunks) > 1 else 1
@@ -343,10 +346,35 @@ def region_sums(planes, table, out=None):
     sums = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
     live = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     ptrs = planes.plane_ptrs()
-    _lib.check(_lib.lib().pb_region_sums(ptrs, 1 if planes.dtype == "f64" else 0, _lib.ptr(d["bstart"]),
-                                         _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]),
-                                         n, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]), _lib.ptr(sums),
-                                         _lib.ptr(live), _lib.stream_ptr()))
+    # positions outside this rank's bins (position sharding; parts of a region beyond its chromosome) count zero
+    _lib.check(_lib.lib().pb_region_sums_range(ptrs, 1 if planes.dtype == "f64" else 0, _lib.ptr(d["bstart"]),
+                                               _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]),
+                                               n, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
+                                               planes.bin_lo, planes.bin_hi, _lib.ptr(sums), _lib.ptr(live),
+                                               _lib.stream_ptr()))
+    return sums[:n], live[:n]
+
+
+def chain_counts(dbatch, layout, factory, size_filter, table, bin_range=None, stats=None):
+    """Plane-free region counts of a point rule (``pb_chain_counts``): ``(sums float64[n], unmasked lengths
+    int64[n])`` straight from the sorted device batch — what :func:`region_sums` gives over the planes
+    :func:`map_batch` would write, without the 4 bytes per genome position of the planes.  ``bin_range``: the
+    global bins this rank owns (sites elsewhere count zero).  ``stats``: device int64[PB_NSTATS] or None."""
+    import torch
+    _lib.require_cuda()
+    if not isinstance(factory, _MapFactory) or isinstance(factory, (StratifiedVariableFivePrimeMapFactory, CenterMapFactory)):
+        raise TypeError("chain_counts needs a FivePrime/ThreePrime/VariableFivePrime factory")
+    dev = dbatch.device
+    d = table.device(dev)
+    n = table.n_chains
+    sums = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    live = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    lo, hi = (0, int(layout.total_bins)) if bin_range is None else (int(bin_range[0]), int(bin_range[1]))
+    b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
+    _lib.check(_lib.lib().pb_chain_counts(C.byref(b), C.byref(lay), C.byref(rule), _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]),
+                                          _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]), n, _lib.ptr(d["mask_bits"]),
+                                          _lib.ptr(d["mask_off"]), lo, hi, _lib.ptr(sums), _lib.ptr(live), _lib.ptr(stats),
+                                          _lib.stream_ptr()))
     return sums[:n], live[:n]
 
 
@@ -387,18 +415,43 @@ def gather_windows(planes, table, row_col, width):
     matrix = torch.empty((max(n, 1), width), dtype=torch.float64, device=dev)
     maskmat = torch.empty((max(n, 1), width), dtype=torch.uint8, device=dev)
     cols = torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
-    _lib.check(_lib.lib().pb_gather_windows(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
-                                            _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
-                                            _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
-                                            n, width, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
-                                            _lib.ptr(matrix), _lib.ptr(maskmat), _lib.stream_ptr()))
+    _lib.check(_lib.lib().pb_gather_windows_range(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
+                                                  _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                                  _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
+                                                  n, width, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
+                                                  planes.bin_lo, planes.bin_hi,
+                                                  _lib.ptr(matrix), _lib.ptr(maskmat), _lib.stream_ptr()))
     return matrix[:n], maskmat[:n]
 
 
-def stratified_windows(dbatch, layout, factory, size_filter, table, row_col, width, min_len, max_len, phase=None):
+def gather_chains(planes, table):
+    """Count vectors of every chain of ``table`` in one launch, ragged: ``(values float64[total], masked uint8[total],
+    row_off int64[n + 1])`` — chain ``c`` owns cells ``[row_off[c], row_off[c + 1])``, laid 5'->3'."""
+    import torch
+    _lib.require_cuda()
+    dev = planes.device
+    d = table.device(dev)
+    n = table.n_chains
+    row_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(table.chain_len, out=row_off[1:])
+    total = int(row_off[-1])
+    values = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+    masked = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    d_off = torch.from_numpy(row_off).to(dev)
+    _lib.check(_lib.lib().pb_gather_chains_range(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
+                                                 _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                                 _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(d_off), n,
+                                                 _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]), planes.bin_lo, planes.bin_hi,
+                                                 _lib.ptr(values), _lib.ptr(masked), _lib.stream_ptr()))
+    return values[:total], masked[:total], row_off
+
+
+def stratified_windows(dbatch, layout, factory, size_filter, table, row_col, width, min_len, max_len, phase=None,
+                       bin_range=None):
     """Per-read-length window matrices in one launch: (int32[n_len, n_chains, width], uint8 mask
     [n_chains, width]) — the inner loops of psite.py:176-199 / phase_by_size.py:186-194.
-    ``phase=(codon_front, codon_back)``: per-length sub-codon phase counts instead (width 3)."""
+    ``phase=(codon_front, codon_back)``: per-length sub-codon phase counts instead (width 3).
+    ``bin_range``: the global bins this rank owns — sites elsewhere are not counted (position sharding)."""
     import torch
     _lib.require_cuda()
     dev = dbatch.device
@@ -412,13 +465,14 @@ def stratified_windows(dbatch, layout, factory, size_filter, table, row_col, wid
     maskmat = torch.empty((max(n, 1), width), dtype=torch.uint8, device=dev)
     cols = torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
     b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
-    _lib.check(_lib.lib().pb_stratified_windows(C.byref(b), C.byref(lay), C.byref(rule), int(min_len), int(max_len),
-                                                _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
-                                                _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
-                                                n, width, int(phase is not None), int(phase[0]) if phase else 0,
-                                                int(phase[1]) if phase else 0, _lib.ptr(d["mask_bits"]),
-                                                _lib.ptr(d["mask_off"]), _lib.ptr(out), _lib.ptr(maskmat),
-                                                _lib.stream_ptr()))
+    lo, hi = (0, int(layout.total_bins)) if bin_range is None else (int(bin_range[0]), int(bin_range[1]))
+    _lib.check(_lib.lib().pb_stratified_windows_range(C.byref(b), C.byref(lay), C.byref(rule), int(min_len), int(max_len),
+                                                      _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                                      _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
+                                                      n, width, int(phase is not None), int(phase[0]) if phase else 0,
+                                                      int(phase[1]) if phase else 0, _lib.ptr(d["mask_bits"]),
+                                                      _lib.ptr(d["mask_off"]), lo, hi, _lib.ptr(out), _lib.ptr(maskmat),
+                                                      _lib.stream_ptr()))
     return out[:, :n], maskmat[:n]
 
 
@@ -430,10 +484,11 @@ def phase_sums(planes, table, codon_front, codon_back):
     d = table.device(dev)
     n = table.n_chains
     out = torch.zeros((max(n, 1), 3), dtype=torch.float64, device=dev)
-    _lib.check(_lib.lib().pb_phase_sums(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
-                                        _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
-                                        _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), n,
-                                        int(codon_front), int(codon_back), _lib.ptr(out), _lib.stream_ptr()))
+    _lib.check(_lib.lib().pb_phase_sums_range(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
+                                              _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                              _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), n,
+                                              int(codon_front), int(codon_back), planes.bin_lo, planes.bin_hi,
+                                              _lib.ptr(out), _lib.stream_ptr()))
     return out[:n]
 
 
@@ -563,15 +618,40 @@ def merge_batches(batches):
     return out
 
 
+def _resolve_shard(shard):
+    """``"auto"``: (rank, world) of the initialised ``torch.distributed`` process group, else (0, 1);
+    ``None``: never shard; ``(rank, world)``: as given (no collective is issued unless a group is initialised)."""
+    if shard is None:
+        return 0, 1
+    if shard == "auto":
+        from . import dist as pdist
+        return pdist.world()
+    rank, world = shard
+    if not 0 <= int(rank) < int(world):
+        raise ValueError("shard=(rank, world) needs 0 <= rank < world")
+    return int(rank), int(world)
+
+
 # ---------------------------------------------------------------------------------------------
 # BAMGenomeArray
 # ---------------------------------------------------------------------------------------------
 class BAMGenomeArray(object):
     """``BAMGenomeArray(*sources, mapping=CenterMapFactory())``.
 
-    ``sources`` are :class:`~plastid_b200.batch.AlignmentBatch` objects (what the host decoder
-    produces from a sorted BAM).  BAM paths / ``pysam.AlignmentFile`` handles are accepted when
-    ``pysam`` is importable (it is not in this image) and are decoded once into a batch.
+    ``sources`` are sorted BAM paths (decoded once, whole, by the library's own BGZF/BAM decoder — no index, no
+    pysam needed), open ``pysam.AlignmentFile`` handles, or :class:`~plastid_b200.batch.AlignmentBatch` objects.
+
+    How the alignments reach the device: a batch that carries its transfer format (``AlignmentBatch.pack`` — the
+    decoder emits it) is uploaded in that form (1-1.3 bytes per read, 4 per aligned block) chunk by chunk on a copy
+    stream and expanded on the device; whole-genome planes are mapped range by range while later chunks are still
+    landing (``map_wire16_streamed`` / ``map_center_streamed``).  A plain SoA batch is uploaded as it is.
+
+    More than one GPU (``torch.distributed`` initialised, one process per GPU; or ``shard=(rank, world)``): every
+    rank owns a contiguous range of the concatenated genome (cuts balanced by read count; ``sharding="chromosomes"``
+    puts them on chromosome boundaries), keeps the reads that can map into it (its own plus a halo of ``max_span``)
+    and the planes of that range only.  Region tables, window matrices and ``ga[seg]`` vectors are completed with
+    one all-reduce (every position is owned by exactly one rank); no count vector ever crosses NVLink.
+    ``bin_range=(lo, hi)``: the sources are already this rank's shard of such a partition.
     """
 
     def __init__(self, *sources, **kwargs):
@@ -588,6 +668,8 @@ class BAMGenomeArray(object):
             raise ValueError("BAMGenomeArray needs at least one alignment source")
         self.batches = batches
         self.batch = merge_batches(batches)
+        if len(batches) > 1 and all(b.transfer is not None for b in batches):
+            self.batch.pack()
         self.device = kwargs.get("device", "cuda")
         self.map_fn = kwargs.get("mapping", None) or CenterMapFactory()
         self._strands = _STRANDS
@@ -598,6 +680,30 @@ class BAMGenomeArray(object):
         self._filters = {}
         self._planes = None
         self._dbatch = None
+        self._full_dbatch = None
+        self._receiver = None
+        # Center rule on a sharded array: the aligned-length histogram of the WHOLE batch (every rank derives the same
+        # slot tables from it); known here when this object shards the sources itself, handed in with pre-sharded ones
+        self._global_hist = kwargs.get("length_hist")
+        # -- position-range ownership ------------------------------------------------------------
+        self._rank, self._world = _resolve_shard(kwargs.get("shard", "auto"))
+        self._collective = self._world > 1
+        self._local = self.batch                      # the reads this rank maps
+        self._bin_range = (0, int(self.layout.total_bins))
+        if kwargs.get("bin_range") is not None:       # pre-sharded sources
+            self._bin_range = (int(kwargs["bin_range"][0]), int(kwargs["bin_range"][1]))
+            from . import dist as pdist
+            self._collective = pdist.is_distributed() and pdist.world()[1] > 1
+        elif self._world > 1:
+            from . import dist as pdist
+            snap = {"positions": "bins", "chromosomes": "chromosomes"}[kwargs.get("sharding", "positions")]
+            sub, lo, hi = pdist.shard_positions(self.batch, self.layout, self._rank, self._world, snap=snap)
+            if self.batch.transfer is not None:
+                sub.pack()
+            self._local, self._bin_range = sub, (lo, hi)
+            if self._global_hist is None:
+                from .batch import meta_length_hist
+                self._global_hist = meta_length_hist(self.batch.meta)     # every rank decoded the whole file
         self._update()
 
     # -- bookkeeping (genome_array.py:681-758, 930-963) ----------------------------------------
@@ -621,12 +727,14 @@ class BAMGenomeArray(object):
     def add_filter(self, name, func):
         self._filters[name] = func
         self._planes = None
-        self._dbatch = None
+        if not isinstance(func, SizeFilterFactory):      # size filters are lowered into the kernels; others re-flag reads
+            self._dbatch = self._full_dbatch = self._receiver = None
 
     def remove_filter(self, name):
         retval = self._filters.pop(name)
         self._planes = None
-        self._dbatch = None
+        if not isinstance(retval, SizeFilterFactory):
+            self._dbatch = self._full_dbatch = self._receiver = None
         return retval
 
     def chroms(self):
@@ -644,6 +752,15 @@ class BAMGenomeArray(object):
     def set_mapping(self, mapping_function):
         self.map_fn = mapping_function
         self._update()
+
+    @property
+    def bin_range(self):
+        """Global bins ``(lo, hi)`` this rank owns (the whole layout on one GPU)."""
+        return self._bin_range
+
+    @property
+    def is_sharded(self):
+        return self._bin_range != (0, int(self.layout.total_bins))
 
     # -- lowering ------------------------------------------------------------------------------
     def _size_filter(self):
@@ -664,39 +781,151 @@ class BAMGenomeArray(object):
             return sf
         return SizeFilterFactory(smin, smax)
 
+    def _filtered(self, hb):
+        """``hb`` with the verdicts of the generic (non-size) filters in the drop bit.  Filters that are not
+        SizeFilterFactory objects are arbitrary python predicates over reads (genome_array.py:819-820): they cannot
+        be lowered and are evaluated once per read on the host."""
+        generic = [f for f in self._filters.values() if not isinstance(f, SizeFilterFactory)]
+        if not generic:
+            return hb
+        keep = np.ones(len(hb), dtype=bool)
+        for i in range(len(hb)):
+            read = hb.read_view(i)
+            keep[i] = all(f(read) for f in generic)
+        out = hb.with_drop_mask(~keep)
+        if hb.transfer is not None:
+            out.pack()
+        return out
+
+    def _make_receiver(self, hb):
+        from .batch import Delta3Receiver, Delta3SplicedBatch, Delta3SplicedReceiver
+        cls = Delta3SplicedReceiver if isinstance(hb.transfer, Delta3SplicedBatch) else Delta3Receiver
+        return cls(hb.transfer, self.device)
+
     def _device_batch(self):
+        """This rank's reads on the device (uploaded once): the transfer format when the batch carries it — expanded
+        on the device — else the SoA."""
         if self._dbatch is None:
-            hb = self.batch
-            generic = [f for f in self._filters.values() if not isinstance(f, SizeFilterFactory)]
-            if generic:      # arbitrary python predicates cannot be lowered: evaluate once on host
-                keep = np.ones(len(hb), dtype=bool)
-                for i in range(len(hb)):
-                    read = hb.read_view(i)
-                    keep[i] = all(f(read) for f in generic)
-                hb = hb.with_drop_mask(~keep)
-            self._host_batch = hb
-            self._dbatch = hb.to_device(self.device)
+            hb = self._host_batch = self._filtered(self._local)
+            if hb.transfer is not None and len(hb):
+                self._receiver = self._make_receiver(hb)
+                self._dbatch = self._receiver.receive(hb.transfer_pinned())
+                if self._dbatch.length_hist is None:
+                    from .batch import meta_length_hist
+                    self._dbatch.length_hist = meta_length_hist(hb.meta)
+            else:
+                self._dbatch = hb.to_device(self.device)
         return self._dbatch
+
+    def _whole_device_batch(self):
+        """Every read of the sources on this device: what the per-segment operator (``get_reads_and_counts``) reads.
+        The same object as :meth:`_device_batch` unless the array is sharded."""
+        if not self.is_sharded:
+            self._whole_host = None
+            return self._device_batch()
+        if self._full_dbatch is None:
+            self._whole_host = self._filtered(self.batch)
+            self._full_dbatch = self._whole_host.to_device(self.device)
+        return self._full_dbatch
 
     def _is_lowerable(self):
         return isinstance(self.map_fn, _MapFactory) and not isinstance(self.map_fn, StratifiedVariableFivePrimeMapFactory)
 
+    def _center_hist(self):
+        """Aligned-length histogram the Center rule derives its tables from: of the WHOLE batch on every rank
+        (one 512 KB all-reduce), so that sharded planes equal unsharded ones bit for bit."""
+        if not self.is_sharded:
+            return None
+        from .batch import meta_length_hist
+        generic = any(not isinstance(f, SizeFilterFactory) for f in self._filters.values())
+        if self._global_hist is not None and not generic:
+            h = self._global_hist
+        elif self._collective:                      # python filters re-flag reads: count what is left, rank by rank
+            from . import dist as pdist
+            h = pdist.global_length_hist(self._host_batch, self.layout, *self._bin_range)
+        else:
+            h = meta_length_hist(self._host_batch.meta)
+        return _filtered_hist(h, self._size_filter())
+
     def count_planes(self, strands=("+", "-")):
-        """Whole-genome planes for the current mapping rule and filters (computed once, cached)."""
+        """Planes of this rank's bin range for the current mapping rule and filters (computed once, cached)."""
         if not self._is_lowerable():
             raise TypeError("mapping function %r cannot be lowered to whole-genome planes" % (self.map_fn,))
-        need = [s for s in strands if self._planes is None or s not in self._planes.planes]
-        if need:
-            self._planes = map_batch(self._device_batch(), self.layout, self.map_fn, self._size_filter(),
-                                     strands=tuple(need), planes=self._planes)
-            st = self._planes.stats
-            if st[_lib.PB_STAT_DROPPED_ANY]:
-                self.map_fn._warn_dropped(int(st[_lib.PB_STAT_DROPPED_ANY]), int(st[_lib.PB_STAT_DROPPED_LEN]))
+        need = tuple(s for s in strands if self._planes is None or s not in self._planes.planes)
+        if not need:
+            return self._planes
+        is_center = isinstance(self.map_fn, CenterMapFactory)
+        if self._planes is None:
+            self._planes = CountPlanes(self.layout, "f64" if is_center else "u32", self.device,
+                                       self._bin_range if self.is_sharded else None)
+        sf = self._size_filter()
+        if self._bin_range[0] == self._bin_range[1]:          # a rank that owns no bins (more ranks than chromosomes)
+            import torch
+            self._planes.alloc(need)
+            self._planes.stats_dev = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=self.device)
+            self._planes.stats = np.zeros(_lib.PB_NSTATS, dtype=np.int64)
+            return self._planes
+        if self._dbatch is None:
+            hb = self._host_batch = self._filtered(self._local)
+            spliced = hb.blk is not None
+            # point rules stream unspliced batches, the Center rule streams spliced ones (the cases the range kernels
+            # can start on before every read has landed); the other two combinations upload whole, then map
+            if hb.transfer is not None and len(hb) and is_center == spliced:
+                # the upload is the long pole: ship the transfer format in chunks on a copy stream and map every
+                # chunk's bin range while the next chunks are still on the wire
+                self._receiver = self._make_receiver(hb)
+                chunks = self._plan_chunks(hb)
+                if is_center:
+                    map_center_streamed(self._receiver, hb.transfer_pinned(), chunks, self.layout, self.map_fn, sf, need,
+                                        self._planes, length_hist=self._center_hist())
+                else:
+                    map_wire16_streamed(self._receiver, hb.transfer_pinned(), chunks, self.layout, self.map_fn, sf, need,
+                                        self._planes)
+                self._dbatch = self._receiver.batch
+                if self._dbatch.length_hist is None:
+                    from .batch import meta_length_hist
+                    self._dbatch.length_hist = meta_length_hist(hb.meta)
+                self._finish_stats()
+                return self._planes
+        dbatch = self._device_batch()
+        map_batch(dbatch, self.layout, self.map_fn, sf, strands=need, planes=self._planes, sync_stats=False,
+                  bin_range=self._bin_range if self.is_sharded else None,
+                  length_hist=self._center_hist() if is_center else None)
+        self._finish_stats()
         return self._planes
 
+    def _plan_chunks(self, hb):
+        """Upload chunks ``[(read_a, read_b, bin_a, bin_b)]`` clipped to this rank's bins: about 8 M reads each, at
+        most 8 (small batches are launch-bound: fewer, larger chunks)."""
+        n_chunks = max(1, min(8, len(hb) // 8_000_000))
+        chunks = type(self._receiver).plan_chunks(hb.transfer, self.layout, n_chunks)
+        lo, hi = self._bin_range
+        out = []
+        for a, b, bin_a, bin_b in chunks:
+            bin_a, bin_b = max(bin_a, lo), min(bin_b, hi)
+            if bin_b > bin_a or not out:
+                out.append((a, b, bin_a, max(bin_b, bin_a)))
+            else:                                   # nothing to map yet: the reads ride along with the next chunk
+                pa, pb_, pbin_a, pbin_b = out[-1]
+                out[-1] = (pa, b, pbin_a, pbin_b)
+        a, b, bin_a, bin_b = out[-1]
+        out[-1] = (a, len(hb), bin_a, hi)
+        return out
+
+    def _finish_stats(self):
+        st = self._planes.stats = self._planes.stats_dev.cpu().numpy()
+        if st[_lib.PB_STAT_DROPPED_ANY]:
+            self.map_fn._warn_dropped(int(st[_lib.PB_STAT_DROPPED_ANY]), int(st[_lib.PB_STAT_DROPPED_LEN]))
+
+    def _allreduce(self, t):
+        """Complete a table of which every rank holds the part of its own positions."""
+        if self._collective:
+            from . import dist as pdist
+            pdist.allreduce_sum(t)
+        return t
+
     # -- queries -------------------------------------------------------------------------------
-    def _read_range(self, chrom, start, end):
-        hb = self._host_batch if self._dbatch is not None else self.batch
+    def _read_range(self, hb, chrom, start, end):
         c = self.layout.index[chrom]
         r0, r1 = int(hb.chrom_read_off[c]), int(hb.chrom_read_off[c + 1])
         starts = hb.ref_start[r0:r1]
@@ -711,12 +940,13 @@ class BAMGenomeArray(object):
             return [], np.zeros(shape)
         if not isinstance(self.map_fn, _MapFactory):
             raise TypeError("only plastid_b200 map factories can be evaluated on the GPU")
-        dbatch = self._device_batch()
-        lo, hi = self._read_range(chrom, start, end)
+        dbatch = self._whole_device_batch()
+        hb = self._whole_host if self.is_sharded else self._host_batch
+        lo, hi = self._read_range(hb, chrom, start, end)
         qs = strand if strand in ("+", "-") else "."
         if hi > lo:
             counts, kept = self.map_fn.map_segment(dbatch, lo, hi, start, end, qs, self._size_filter())
-            reads = [self._host_batch.read_view(lo + int(i)) for i in np.nonzero(kept)[0]]
+            reads = [hb.read_view(lo + int(i)) for i in np.nonzero(kept)[0]]
         else:
             counts = np.zeros(self.map_fn._leading_shape() + [end - start], dtype=self.map_fn.count_dtype)
             reads = []
@@ -737,27 +967,87 @@ class BAMGenomeArray(object):
             return self.get_reads_and_counts(roi, roi_order=roi_order)[1]
         qs = roi.strand if roi.strand in ("+", "-") else "."
         planes = self.count_planes(("+", "-") if qs != "." else (".",))
-        counts = planes.slice_host(qs, roi.chrom, roi.start, roi.end)
+        counts = self._plane_slice(planes, qs, roi.chrom, roi.start, roi.end)
         if self._normalize is True:
             counts = counts / float(self.sum()) * 1e6
         if roi_order == True and roi.strand == "-":
             counts = counts[..., ::-1]
         return counts
 
+    def _plane_slice(self, planes, strand, chrom, start, end):
+        """``plane[start:end]`` of one chromosome as a fresh host vector: positions outside the chromosome are zero
+        (the reference's fetch finds no reads there), positions of other ranks arrive through an all-reduce."""
+        import torch
+        n = max(end - start, 0)
+        ci = self.layout.index[chrom]
+        base, clen = int(self.layout.chrom_bin_off[ci]), int(self.layout.chrom_len[ci])
+        a, b = min(max(start, 0), clen), max(min(end, clen), 0)           # inside the chromosome
+        g0, g1 = max(base + a, planes.bin_lo), min(base + b, planes.bin_hi)   # inside this rank's bins
+        whole = g0 == base + start and g1 == base + end
+        if whole and not self._collective:
+            t = planes.bins(strand, g0, g1)
+        else:
+            t = torch.zeros(n, dtype=planes.planes[strand].dtype, device=planes.device)
+            if g1 > g0:
+                t[g0 - base - start:g1 - base - start] = planes.bins(strand, g0, g1)
+            if self._collective:
+                t = t.to(torch.int64) & 0xFFFFFFFF if planes.dtype == "u32" else t
+                self._allreduce(t)
+        out = t.cpu().numpy()
+        if planes.dtype == "u32":
+            return (out.view(np.uint32) if out.dtype == np.int32 else out).astype(np.int64)
+        return out
+
     def __getitem__(self, roi):
         return self.get(roi, roi_order=True)
+
+    def _chrom_vector(self, planes, strand, chrom, n=None):
+        """Device vector of the first ``n`` bins (default: all) of one chromosome strand, complete on every rank: a
+        view of the plane on one GPU; on a sharded array the owned part in a zero vector, completed by an all-reduce
+        (what whole-chromosome consumers — track export, ``to_genome_array`` — read)."""
+        import torch
+        ci = self.layout.index[chrom]
+        base = int(self.layout.chrom_bin_off[ci])
+        n = int(self.layout.chrom_len[ci]) if n is None else int(n)
+        if not self.is_sharded:
+            return planes.bins(strand, base, base + n)
+        vec = torch.zeros(max(n, 1), dtype=planes.planes[strand].dtype, device=planes.device)[:n]
+        g0, g1 = max(base, planes.bin_lo), min(base + n, planes.bin_hi)
+        if g1 > g0:
+            vec[g0 - base:g1 - base] = planes.bins(strand, g0, g1)
+        return self._allreduce(vec)            # int32 storage of uint32 counts: x + 0 + ... + 0 is exact in two's complement
 
     # -- bulk entry points used by the scripts --------------------------------------------------
     def chain_table(self, chains, use_masks=True):
         return ChainTable.from_chains(chains, self.layout, use_masks=use_masks)
 
-    def count_chains(self, chains, use_masks=True):
+    def count_chains(self, chains, use_masks=True, planes=None):
         """(sums float64[n], unmasked lengths int64[n]) for a list of chains in one launch —
-        what ``numpy.nansum(chain.get_masked_counts(ga))`` and ``chain.masked_length`` give."""
+        what ``numpy.nansum(chain.get_masked_counts(ga))`` and ``chain.masked_length`` give.
+
+        ``planes``: ``True`` sums over the count planes (building them if need be), ``False`` counts straight from
+        the sorted reads without planes (``pb_chain_counts``: point rules; table-only programs never pay for
+        4 bytes per genome position), ``None`` (default) takes the planes when they exist already and the
+        plane-free path otherwise."""
         table = chains if isinstance(chains, ChainTable) else self.chain_table(chains, use_masks)
-        need = sorted(set(_STRANDS[p] for p in np.unique(table.chain_plane)), key=_STRANDS.index) or ["+"]
-        planes = self.count_planes(tuple(need))
-        sums, live = region_sums(planes, table)
+        need = tuple(sorted(set(_STRANDS[p] for p in np.unique(table.chain_plane)), key=_STRANDS.index)) or ("+",)
+        direct_ok = self._is_lowerable() and not isinstance(self.map_fn, CenterMapFactory)
+        have = self._planes is not None and all(s in self._planes.planes for s in need)
+        if planes is None:
+            planes = have or not direct_ok
+        if planes is False and not direct_ok:
+            raise TypeError("plane-free counting needs a FivePrime/ThreePrime/VariableFivePrime mapping rule")
+        if planes:
+            sums, live = region_sums(self.count_planes(need), table)
+        else:
+            import torch
+            stats = torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=self.device)
+            sums, live = chain_counts(self._device_batch(), self.layout, self.map_fn, self._size_filter(), table,
+                                      self._bin_range, stats)
+            st = stats.cpu().numpy()
+            if st[:3].any():
+                self.map_fn._warn_dropped(int(st[:3].sum()), int(st[_lib.PB_STAT_DROPPED_LEN]))
+        sums = self._allreduce(sums)
         sums, live = sums.cpu().numpy(), live.cpu().numpy()
         live[~table.known] = table.unknown_live[~table.known]
         if self._normalize is True:
@@ -770,9 +1060,8 @@ class BAMGenomeArray(object):
         import torch
         planes = self.count_planes((strand,))
         dev = planes.device
-        base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
         n = self._chr_lengths[chrom]
-        vec = planes.bins(strand, base, base + n)
+        vec = self._chrom_vector(planes, strand, chrom)
         L = _lib.lib()
         ws_bytes = L.pb_export_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -858,10 +1147,9 @@ class BAMGenomeArray(object):
         ga = array_type(chr_lengths=self.lengths(), strands=self.strands(), device=self.device)
         planes = self.count_planes(_STRANDS)
         for chrom in self.chroms():
-            base = int(self.layout.chrom_bin_off[self.layout.index[chrom]])
             n = self._chr_lengths[chrom] - 1
             for strand in _STRANDS:
-                src = planes.bins(strand, base, base + n)
+                src = self._chrom_vector(planes, strand, chrom, n)
                 if planes.dtype == "u32":
                     vals = (src.to(torch.int64) & 0xFFFFFFFF).to(torch.float64)
                 else:

@@ -106,12 +106,13 @@ def mask_intervals_of_chains(table, bits):
         ivs = []
         k0, k1 = int(table.chain_off[c]), int(table.chain_off[c + 1])
         if k1 > k0:
-            base = int(table.layout.chrom_bin_off[np.searchsorted(table.layout.chrom_bin_off, table.bstart[k0], side="right") - 1])
+            real = [k for k in range(k0, k1) if table.bstart[k] < int(table.layout.total_bins)]    # not beyond the chromosome
+            base = int(table.layout.chrom_bin_off[np.searchsorted(table.layout.chrom_bin_off, table.bstart[real[0]], side="right") - 1]) if real else 0
             for k in range(k0, k1):
                 n = int(table.bend[k] - table.bstart[k])
                 m = flat[off:off + n]
                 off += n
-                if m.any():
+                if m.any() and table.bstart[k] < int(table.layout.total_bins):
                     edge = np.flatnonzero(np.diff(np.concatenate(([0], m, [0]))))
                     start = int(table.bstart[k]) - base
                     for a, b in zip(edge[0::2], edge[1::2]):

@@ -4,6 +4,30 @@ import numpy as np
 
 from . import _lib
 
+# Positions of a region that lie outside its chromosome (an annotation longer than the BAM header says, a window
+# flank, a negative start) are lowered to blocks in this coordinate range, beyond every layout: the gather kernels
+# clip every block to the bin range they are given, so these positions count zero — the reference returns zeros
+# there, `fetch` yields no reads (genome_array.py:800-809) — while keeping their place in the chain (length, mask
+# bits and window columns are unchanged).
+VIRTUAL_BIN = 1 << 60
+
+
+def lower_segment(start, end, base, chrom_len):
+    """Blocks ``[(bstart, bend), ...]`` in genomic order for the chromosome positions ``[start, end)`` of a chromosome
+    whose bin 0 is global bin ``base``: the part inside ``[0, chrom_len)`` in global bins, the parts outside as
+    virtual blocks of the same lengths."""
+    out = []
+    left = min(end, 0)
+    if start < left:
+        out.append((VIRTUAL_BIN, VIRTUAL_BIN + (left - start)))
+    a, b = max(start, 0), min(end, chrom_len)
+    if a < b:
+        out.append((base + a, base + b))
+    right = max(start, chrom_len, 0)
+    if right < end:
+        out.append((VIRTUAL_BIN + right, VIRTUAL_BIN + end))
+    return out
+
 
 class ChainTable(object):
     """Flat tables for a list of chains: blocks in global-bin coordinates, per-chain plane index and
@@ -46,10 +70,12 @@ class ChainTable(object):
             plane.append(_lib.PLANE_INDEX[strand])
             reverse.append(1 if ch.strand == "-" else 0)
             if ok:
-                base = int(layout.chrom_bin_off[layout.index[ch.chrom]])
+                ci = layout.index[ch.chrom]
+                base, clen = int(layout.chrom_bin_off[ci]), int(layout.chrom_len[ci])
                 for seg in ch:
-                    bstart.append(base + seg.start)
-                    bend.append(base + seg.end)
+                    for piece in lower_segment(seg.start, seg.end, base, clen):
+                        bstart.append(piece[0])
+                        bend.append(piece[1])
                 length.append(ch.length)
             else:
                 length.append(0)
@@ -80,7 +106,10 @@ class ChainTable(object):
         if key not in self._dev:
             def up(a):
                 return None if a is None else torch.from_numpy(a).to(device)
+            bits = self.mask_bits
+            if bits is not None and len(bits) % 4:          # the kernels read the bit array as whole 32-bit words
+                bits = np.concatenate([bits, np.zeros(4 - len(bits) % 4, dtype=np.uint8)])
             self._dev[key] = dict(bstart=up(self.bstart), bend=up(self.bend), chain_off=up(self.chain_off),
                                   chain_plane=up(self.chain_plane), chain_reverse=up(self.chain_reverse),
-                                  mask_bits=up(self.mask_bits), mask_off=up(self.mask_off))
+                                  mask_bits=up(bits), mask_off=up(self.mask_off))
         return self._dev[key]
