@@ -334,6 +334,22 @@ def run_peaks(args, device):
                      "updates_landed_check": total}
         del bins
         torch.cuda.empty_cache()
+    # gather pattern: scattered segments of the size of an exon block / window out of a 12.4 GB plane
+    plane = torch.zeros(3_088_465_920, dtype=torch.int32, device=device)
+    out["gather_segments"] = {}
+    for chunk, n_chunks in ((256, 480_000), (768, 120_000), (1536, 120_000), (4096, 60_000)):
+        res = torch.empty(n_chunks, dtype=torch.int32, device=device)
+        best = None
+        for it in range(6):
+            ev0.record()
+            _lib.check(L.pb_gather_probe(_lib.ptr(plane), plane.numel(), chunk, n_chunks, _lib.ptr(res), _lib.stream_ptr()))
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            best = ms if best is None or (it > 0 and ms < best) else best
+        nbytes = 4.0 * chunk * n_chunks
+        out["gather_segments"]["%d_bins_x_%d" % (chunk, n_chunks)] = {"ms": best, "bytes": nbytes, "GBps": nbytes / (best / 1000.0) / 1e9}
+    del plane
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "atomic_peaks.json"), "w") as fh:
         json.dump(out, fh, indent=1)
@@ -357,6 +373,7 @@ def run_c4(args, W, device, rank, world, dist):
     map_batch(dbatch, layout, W["fac"], W["sf"], strands=("+", "-"), planes=planes, bin_range=(lo, hi) if ranged else None)
     table, cols = synth.window_table(ann, layout, width=350)
     table.device(device)
+    cols = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).to(device)       # the ROI table's offsets, resident
     width, n = 350, table.n_chains
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     gather_ms = []
@@ -686,6 +703,7 @@ def main():
     value = n_total / (ms_per_step / 1000.0)
     region_rate = ann.n_tx * (world if args.sharding == "reads" else 1) / (ms_per_step / 1000.0)
     table_checksum_dev = float(sums.sum().item())
+    resident_table = sums.cpu().numpy().copy()
 
     # per-rank diagnostics: who holds what, where the step goes (a slow rank or a slow collective shows here)
     k_ms = kms.value / max(kn.value, 1)
@@ -820,7 +838,7 @@ def main():
            "host_format": "%s (%.2f B/read): what bam_io.batch_from_bam emits; uploaded in chunks, expanded on the device, "
                           "each chunk's bin range mapped while the next is on the wire"
                           % (type(hb.transfer).__name__, h2d / max(len(hb), 1)),
-           "table_equals_device_resident_leg": bool(abs(api_checksum - table_checksum_dev) == 0.0),
+           "table_equals_device_resident_leg": bool(np.array_equal(h_sums, resident_table)),
            "pack_seconds_outside_clock": round(pack_s, 3),
            "pack_note": "the transfer format is written once per batch by the decoder (host, %d threads here); a plain SoA "
                         "batch is timed below with nothing outside the clock" % _lib.host_threads()}

@@ -335,43 +335,50 @@ int pb_map_segment(const pb_batch *batch, int64_t i0, int64_t i1, const pb_rule 
 int pb_length_hist(const pb_batch *batch, const pb_rule *rule, int strand, uint64_t *hist, void *stream);
 
 /* Masked sums over exon-block chains.  vec_dtype: 0 = uint32 planes, 1 = float64 planes.
- * planes[3]: host array of device plane pointers ('+','-','.'); chain_plane: device uint8[n_chains]
- * in {0,1,2}.  Blocks are in global-bin coordinates [bstart,bend).  mask_bits (or NULL): bit
- * (mask_off[c] + j) set = j-th position of chain c (genomic order) is masked.
- * sums: double[n_chains] over unmasked positions; live_len: int64[n_chains] unmasked length. */
+ * planes[3]: host array of device plane pointers ('+','-','.'), each the address bin 0 WOULD have (see
+ * pb_map_point_range), 16-byte aligned; chain_plane: device uint8[n_chains] in {0,1,2}.  Blocks are in global-bin
+ * coordinates [bstart,bend), chain c owns blocks [chain_off[c], chain_off[c+1]); block_chain int32[B] = chain of
+ * every block, block_pos int64[B] = chain position (genomic order) of its first base, block_plane uint8[B] =
+ * chain_plane of its chain (so that a block's data loads depend on one round trip only).  mask_bits (or NULL): bit
+ * (mask_off[c] + j) set = j-th position of chain c (genomic order) is masked; 4-byte aligned, padded to whole
+ * 32-bit words.  sums: double[n_chains] over unmasked positions; live_len: int64[n_chains] unmasked length.
+ *
+ * [bin_begin, bin_end): the global bins the calling rank owns (position sharding; 0 .. total_bins on one
+ * GPU).  Only positions inside are read and summed — the others count zero but keep their place in the chain — so
+ * the sums of all ranks add up to the whole table (one all-reduce); live_len is geometry and comes out whole on
+ * every rank.  Blocks lying wholly outside the layout (the part of a region beyond its chromosome's end, lowered
+ * to coordinates >= total_bins) count zero the same way: the reference returns zeros there (fetch yields no reads).
+ * Two launches: one warp per BLOCK writes a partial sum into the workspace (n_blocks doubles), one warp per chain adds
+ * them in a fixed order (deterministic for float64 planes too). */
+size_t pb_region_sums_workspace_bytes(int64_t n_blocks);
 int pb_region_sums(const void *const *planes, int vec_dtype,
                    const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                   const uint8_t *chain_plane, int64_t n_chains,
-                   const uint8_t *mask_bits, const int64_t *mask_off,
-                   double *sums, int64_t *live_len, void *stream);
-/* The same for one rank of a position-sharded genome: only positions whose global bin lies in
- * [bin_begin, bin_end) are read and summed — the others count zero but keep their place in the chain — so
- * the sums of all ranks add up to the whole table (one all-reduce); live_len is geometry and comes out whole
- * on every rank.  Plane pointers are the address bin 0 WOULD have (see pb_map_point_range), 16-byte aligned;
- * mask_bits 4-byte aligned and padded to whole 32-bit words.  Blocks lying wholly outside the layout (the
- * part of a region beyond its chromosome's end, lowered to coordinates >= total_bins) count zero the same
- * way: the reference returns zeros there (fetch yields no reads). */
-int pb_region_sums_range(const void *const *planes, int vec_dtype,
-                         const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                         const uint8_t *chain_plane, int64_t n_chains,
-                         const uint8_t *mask_bits, const int64_t *mask_off,
-                         int64_t bin_begin, int64_t bin_end,
-                         double *sums, int64_t *live_len, void *stream);
+                   const uint8_t *chain_plane, const int32_t *block_chain, const int64_t *block_pos,
+                   const uint8_t *block_plane,
+                   int64_t n_chains, int64_t n_blocks, const uint8_t *mask_bits, const int64_t *mask_off,
+                   int64_t bin_begin, int64_t bin_end,
+                   double *sums, int64_t *live_len, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Plane-free region counts of a point rule (5' / 3' / variable): sums[c] = number of reads whose mapped site
  * lies on an unmasked position of chain c (strand-matched like BAMGenomeArray.get_reads_and_counts,
  * plastid/genomics/genome_array.py:811-815; rule direction from the chain's strand), live_len[c] = unmasked
  * length — exactly what pb_region_sums returns over the planes pb_map_point would write, without writing them
- * (table-only programs: plastid/bin/counts_in_region.py:107-125, plastid/bin/cs.py:688-714).  One CTA per
- * chain walks the contiguous slice of the sorted batch that can reach each block.  Sites outside
- * [bin_begin, bin_end) count zero (position sharding).  stats (or NULL): PB_STAT_DROPPED_* / _LEN are raised
- * when a read near a chain could not be placed by the rule (the reference's DataWarning paths). */
+ * (table-only programs: plastid/bin/counts_in_region.py:107-125, plastid/bin/cs.py:688-714).  The reads that can
+ * reach a block are a contiguous slice of the sorted batch; the work is cut into 2048-read items over all blocks
+ * (expression is skewed: a few chains hold millions of reads) and taken by persistent warps.  Sites outside
+ * [bin_begin, bin_end) count zero (position sharding).  n_blocks = rows of bstart / bend / block_chain / block_pos.
+ * stats (or NULL): PB_STAT_DROPPED_* / _LEN are raised when a read near a chain could not be placed by the rule
+ * (the reference's DataWarning paths).  Workspace: pb_chain_counts_workspace_bytes.  batch->ref_start and batch->meta
+ * must be 16-byte aligned and allocated in whole 16-byte units (reads are loaded four at a time). */
+size_t pb_chain_counts_workspace_bytes(int64_t total_bins, int64_t n_blocks, int64_t n_chains);
 int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
                     const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                    const uint8_t *chain_plane, int64_t n_chains,
+                    const uint8_t *chain_plane, const int32_t *block_chain, const int64_t *block_pos,
+                    int64_t n_chains, int64_t n_blocks,
                     const uint8_t *mask_bits, const int64_t *mask_off,
                     int64_t bin_begin, int64_t bin_end,
-                    double *sums, int64_t *live_len, uint64_t *stats, void *stream);
+                    double *sums, int64_t *live_len, uint64_t *stats,
+                    void *workspace, size_t workspace_bytes, void *stream);
 
 /* Mask pipeline: mask bits of every chain from one interval set, replacing the per-region
  * GenomeHash.get_overlapping_features + SegmentChain.add_masks of counts_in_region.py:114-115
@@ -389,34 +396,33 @@ int pb_mask_chains(const int64_t *bstart, const int64_t *bend, const int64_t *ch
 
 /* Window matrices (metagene / psite): row r = chain r laid 5'->3' (reversed when
  * chain_reverse[r]) starting at column row_col[r] of a width-W row.  matrix: double[n*W]
- * (NaN where no chain position), maskmat: uint8[n*W] (1 = masked or uncovered). */
+ * (NaN where no chain position), maskmat: uint8[n*W] (1 = masked or uncovered).  block_chain / block_pos as for
+ * pb_region_sums, chain_len int64[n_chains] = positions per chain.  Cells whose position lies outside
+ * [bin_begin, bin_end) are written as 0 (not NaN), so that the matrices of all ranks of a position-sharded genome add
+ * up; NaN cells (no chain position) and maskmat are identical on every rank.  One warp per exon block. */
 int pb_gather_windows(const void *const *planes, int vec_dtype,
                       const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
                       const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                      const int32_t *row_col, int64_t n_chains, int32_t width,
+                      const int32_t *block_chain, const int64_t *block_pos, const uint8_t *block_plane,
+                      const int64_t *chain_len,
+                      const int32_t *row_col, int64_t n_chains, int64_t n_blocks, int32_t width,
                       const uint8_t *mask_bits, const int64_t *mask_off,
+                      int64_t bin_begin, int64_t bin_end,
                       double *matrix, uint8_t *maskmat, void *stream);
-/* Position-sharded form: cells whose position lies outside [bin_begin, bin_end) are written as 0 (not NaN), so
- * that the matrices of all ranks add up; NaN cells (no chain position) and maskmat are identical on every rank. */
-int pb_gather_windows_range(const void *const *planes, int vec_dtype,
-                            const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                            const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                            const int32_t *row_col, int64_t n_chains, int32_t width,
-                            const uint8_t *mask_bits, const int64_t *mask_off,
-                            int64_t bin_begin, int64_t bin_end,
-                            double *matrix, uint8_t *maskmat, void *stream);
 
 /* Count vectors of many chains at once, ragged: chain c laid 5'->3' (reversed when chain_reverse[c]) into cells
  * [row_off[c], row_off[c] + length of c) of `values` (double) and `masked` (uint8, 1 = masked position) —
  * SegmentChain.get_masked_counts for every region of plastid/bin/get_count_vectors.py:92-104 in one launch.
- * Same range semantics as pb_gather_windows_range (cells of other ranks' positions are 0). */
-int pb_gather_chains_range(const void *const *planes, int vec_dtype,
-                           const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                           const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                           const int64_t *row_off, int64_t n_chains,
-                           const uint8_t *mask_bits, const int64_t *mask_off,
-                           int64_t bin_begin, int64_t bin_end,
-                           double *values, uint8_t *masked, void *stream);
+ * Same range semantics as pb_gather_windows (cells of other ranks' positions are 0). */
+int pb_gather_chains(const void *const *planes, int vec_dtype,
+                     const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                     const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                     const int32_t *block_chain, const int64_t *block_pos, const uint8_t *block_plane,
+                     const int64_t *chain_len,
+                     const int64_t *row_off, int64_t n_chains, int64_t n_blocks,
+                     const uint8_t *mask_bits, const int64_t *mask_off,
+                     int64_t bin_begin, int64_t bin_end,
+                     double *values, uint8_t *masked, void *stream);
 
 /* metagene.py:918-924 on a window matrix (one warp per row): denom[r] = sum of unmasked cells in
  * columns [norm_lo,norm_hi) (NaN when every cell there is masked), row_select[r] = denom >=
@@ -593,6 +599,13 @@ int pb_chain_binary(int op,
  * bins[0..n_bins) — mode 0 uniformly random targets, mode 1 sorted targets with +-jitter.
  * bench.py --workload peaks times it with CUDA events. */
 int pb_atomic_probe(uint32_t *bins, int64_t n_bins, int64_t n_updates, int mode, int jitter, void *stream);
+
+/* Roofline probe for the region kernels (no reference counterpart, not on the product path): n_chunks warps each
+ * read `chunk_bins` consecutive uint32 bins (a multiple of 4) from a pseudo-random 16-byte aligned place in
+ * vec[0..n_bins) with 16-byte loads and write one word to out[n_chunks].  The bytes per second this launch achieves
+ * are what HBM delivers for scattered kilobyte-sized segments — the access pattern of pb_region_sums /
+ * pb_gather_windows over tens of thousands of exon blocks in a 12-25 GB plane. */
+int pb_gather_probe(const uint32_t *vec, int64_t n_bins, int chunk_bins, int64_t n_chunks, uint32_t *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -93,21 +93,21 @@ _SIGNATURES = {
     "pb_map_segment": (C.c_int, [C.POINTER(PbBatch), C.c_int64, C.c_int64, C.POINTER(PbRule), C.c_int, C.c_int,
                                  C.c_int64, C.c_int64, _P, _P, _P, _P]),
     "pb_length_hist": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbRule), C.c_int, _P, _P]),
-    "pb_region_sums": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
-    "pb_region_sums_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
-    "pb_chain_counts": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), _P, _P, _P, _P, C.c_int64, _P, _P,
-                                  C.c_int64, C.c_int64, _P, _P, _P, _P]),
-    "pb_gather_windows_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32,
-                                          _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
-    "pb_gather_chains_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64,
-                                         _P, _P, _P]),
+    "pb_region_sums_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "pb_region_sums": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int64,
+                                 _P, _P, _P, C.c_size_t, _P]),
+    "pb_gather_windows": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32,
+                                    _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "pb_gather_chains": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64,
+                                   _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "pb_chain_counts_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "pb_chain_counts": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), _P, _P, _P, _P, _P, _P, C.c_int64,
+                                  C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
     "pb_stratified_windows_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int, C.c_int,
                                               _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_int32,
                                               _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "pb_phase_sums_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_int64, C.c_int64, _P, _P]),
-    "pb_gather_windows": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32,
-                                    _P, _P, _P, _P, _P]),
     "pb_window_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                       _P, _P, _P, _P, _P]),
     "pb_column_profile_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
@@ -124,6 +124,7 @@ _SIGNATURES = {
     "pb_chain_union": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "pb_chain_binary": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "pb_atomic_probe": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
+    "pb_gather_probe": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, _P, _P]),
     "pb_count_profiles_u32": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int,
                                         _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pb_column_profile_batched": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
@@ -168,6 +169,15 @@ def require_cuda():
     import torch
     if not torch.cuda.is_available() or lib().pb_device_count() < 1:
         raise PlastidB200Error("plastid_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def device_key(device):
+    """Canonical name of a torch device ("cuda" and "cuda:0" name the same GPU): cache key of per-device tables."""
+    import torch
+    dv = torch.device(device)
+    if dv.type == "cuda" and dv.index is None and torch.cuda.is_available():
+        dv = torch.device("cuda", torch.cuda.current_device())
+    return str(dv)
 
 
 def ptr(t):

@@ -60,7 +60,7 @@ class GenomeLayout(object):
 
     def device_tables(self, device):
         import torch
-        key = str(device)
+        key = _lib.device_key(device)
         if key not in self._dev:
             self._dev[key] = (torch.from_numpy(self.chrom_len).to(device),
                               torch.from_numpy(self.chrom_bin_off).to(device))
@@ -151,6 +151,10 @@ class AlignmentBatch(object):
         if self.transfer is None:
             cls = Delta3Batch if self.blk is None else Delta3SplicedBatch
             self.transfer = cls.from_batch(self, threads=threads)
+            if getattr(self.transfer, "length_hist", None) is None:
+                # batch metadata like max_span: reads per aligned length, known to whoever produced the batch (the
+                # Center rule derives its tables from it without a pass over the reads)
+                self.transfer.length_hist = meta_length_hist(self.meta)
             self._transfer_pinned = None
         return self
 
@@ -176,7 +180,7 @@ class AlignmentBatch(object):
         return out
 
     def to_device(self, device="cuda"):
-        key = str(device)
+        key = _lib.device_key(device)
         if key not in self._dev:
             self._dev[key] = DeviceBatch.from_host(self, device)
         return self._dev[key]
@@ -524,6 +528,7 @@ class Delta3Batch(object):
         self.meta_dict = np.ascontiguousarray(meta_dict, dtype=np.uint32)
         self.blk_chrom, self.blk_first_start = blk_first      # chunk planning only; stays on the host
         self.max_span, self.mapped = int(max_span), int(mapped)
+        self.length_hist = None                               # batch metadata, set by AlignmentBatch.pack
 
     def __len__(self):
         return self.n_reads
@@ -634,7 +639,8 @@ class Delta3Receiver(Delta8Receiver):
         self.meta_dict = torch.empty(32, dtype=torch.int32, device=device)
         self.batch = DeviceBatch(n, len(wire.chroms), wire.max_span, torch.empty(n, dtype=torch.int32, device=device),
                                  torch.empty(n, dtype=torch.int32, device=device),
-                                 torch.empty(len(wire.chroms) + 1, dtype=torch.int64, device=device))
+                                 torch.empty(len(wire.chroms) + 1, dtype=torch.int64, device=device),
+                                 length_hist=getattr(wire, "length_hist", None))
 
     def _copy_range(self, pinned, a, b):
         K = Delta3Batch.BLOCK
@@ -876,7 +882,8 @@ class DeviceBatch(object):
             t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a)
             return t.to(device, non_blocking=non_blocking)
         return cls(len(hb), len(hb.chroms), hb.max_span, up(hb.ref_start), up(hb.meta),
-                   up(hb.chrom_read_off), up(hb.blk_off), up(hb.blk), hb.max_block_len, meta_length_hist(hb.meta))
+                   up(hb.chrom_read_off), up(hb.blk_off), up(hb.blk), hb.max_block_len,
+                   None if hb.transfer is None else getattr(hb.transfer, "length_hist", None))
 
     @property
     def device(self):

@@ -28,13 +28,21 @@ def init_distributed(device="cuda"):
     import torch
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # PB_DIST_BACKEND=gloo + PB_DIST_ONE_DEVICE=1: several ranks on ONE GPU, tables all-reduced through gloo — how the
+    # single-GPU test box exercises the multi-rank code path (NCCL refuses two ranks on one device)
+    backend = os.environ.get("PB_DIST_BACKEND")
     if str(device).startswith("cuda") and torch.cuda.is_available():
+        if os.environ.get("PB_DIST_ONE_DEVICE"):
+            local = 0
         torch.cuda.set_device(local)
         device = "cuda:%d" % local
         if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device(device))
+            if (backend or "nccl") == "nccl":
+                dist.init_process_group("nccl", device_id=torch.device(device))
+            else:
+                dist.init_process_group(backend)
     elif not dist.is_initialized():
-        dist.init_process_group("gloo")
+        dist.init_process_group(backend or "gloo")
     return device
 
 

@@ -248,9 +248,9 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, use_m
     out = {"x": np.arange(-flank, window_size - flank), "metagene_average": profile.cpu().numpy(),
            "regions_counted": n_regions.cpu().numpy(), "row_select": sel.cpu().numpy().astype(bool),
            "denominator": denom.cpu().numpy()}
-    if sel.sum().item() == 0:
-        # numpy.ma.median of an empty selection raises; the reference falls back to zeros (:940-944)
-        out["metagene_average"] = np.zeros(window_size)
+    # no row reaches min_counts: numpy.ma.median / mean of the empty selection is an all-masked vector, written as
+    # nan (observed with the reference run under numpy 2.3; its zeros fallback, :940-944, needs an exception that numpy
+    # no longer raises) — which is what the column kernel returns for columns without a usable cell
     if keep:
         out["counts"] = np.ma.MaskedArray(mat.cpu().numpy(), mask=mmask.cpu().numpy().astype(bool))
         out["norm_counts"] = np.ma.MaskedArray(norm.cpu().numpy(), mask=nmask.cpu().numpy().astype(bool))

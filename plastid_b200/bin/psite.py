@@ -45,7 +45,7 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
         profile, n_regions = profile.cpu().numpy(), n_regions.cpu().numpy()
         any_sel = sel.any(dim=1).cpu().numpy()
         for j, k in enumerate(range(min_len, max_len + 1)):
-            out["profiles"][k] = profile[j] if any_sel[j] else np.zeros(window_size)
+            out["profiles"][k] = profile[j]          # no selected row: all nan, like numpy.ma.median of an empty selection
             out["regions_counted"][k] = n_regions[j]
         return out
     # all read lengths at once: the matrices are stacked row-wise, normalised in one launch and reduced
@@ -56,7 +56,9 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
     mask_all = maskmat.repeat(n_len, 1)                              # the position mask is shared by all lengths
     denom, sel, norm, nmask = window_normalize(mat, mask_all, norm_start, norm_end, min_counts)
     if aggregate:
-        profile, _n, _ = column_profile(mat, mask_all, sel, "sum", n_batch=n_len)
+        profile, n_used, _ = column_profile(mat, mask_all, sel, "sum", n_batch=n_len)
+        # numpy.nansum over a masked matrix (psite.py:226): a column whose selected cells are all masked is masked itself
+        profile = profile.masked_fill(n_used == 0, float("nan"))
         _p, n_regions, _ = column_profile(norm, nmask, sel, "mean", n_batch=n_len)     # regions_counted uses the norm mask
     else:
         profile, n_regions, _ = column_profile(norm, nmask, sel, "median", n_batch=n_len)
@@ -64,10 +66,7 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, min_l
     n_regions = n_regions.view(n_len, window_size).cpu().numpy()
     any_sel = sel.view(n_len, n).any(dim=1).cpu().numpy()
     for j, k in enumerate(range(min_len, max_len + 1)):
-        prof = profile[j]
-        if not any_sel[j] and not aggregate:
-            prof = np.zeros(window_size)
-        out["profiles"][k] = prof
+        out["profiles"][k] = profile[j]
         out["regions_counted"][k] = n_regions[j]
         if keep:
             out["raw"][k] = np.ma.MaskedArray(mat[j * n:(j + 1) * n].cpu().numpy(), mask=maskmat.cpu().numpy().astype(bool))

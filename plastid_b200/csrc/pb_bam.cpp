@@ -14,6 +14,8 @@
 // Not resolved: CIGARs of more than 65535 operations kept in a CG:B,I tag behind a "<l>S<n>N" placeholder (SAM spec
 // 4.2.2, long reads) — the record then has no aligned block and maps nowhere, as with the reference's htslib 1.3,
 // which predates the tag.
+#include <climits>
+#include <cstdint>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <zlib.h>
@@ -60,14 +62,23 @@ bool convert_record(const uint8_t *rec, uint32_t size, Decoded &out)
     const int32_t tid = (int32_t)rd32(rec), pos = (int32_t)rd32(rec + 4);
     const uint32_t l_read_name = rec[8];
     const uint32_t n_cigar = rd16(rec + 12), flag = rd16(rec + 14);
-    if (tid < 0 || (flag & 0x4) || n_cigar == 0) { out.skipped++; return true; }
+    if (tid < 0 || (flag & 0x4)) { out.skipped++; return true; }
+    // `bamfile.mapped` (genome_array.py:690) is the index statistic: every placed record without the unmapped flag,
+    // whatever its CIGAR (htslib hts_idx_push counts by flag) — counted here before records without positions are skipped
+    out.mapped++;
+    if (n_cigar == 0) { out.skipped++; return true; }
     if (32 + l_read_name + 4ull * n_cigar > size) { out.err = "BAM record shorter than its CIGAR"; return false; }
     const uint8_t *cig = rec + 32 + l_read_name;
+    if (pos < 0) { out.err = "mapped BAM record with a negative position"; return false; }
     int32_t ref = 0, blocks[2 * PB_MAX_BLOCKS];
     int nb = 0;
-    int64_t L = 0;
+    int64_t L = 0, span64 = 0;
     for (uint32_t k = 0; k < n_cigar; ++k) {
         const uint32_t c = rd32(cig + 4 * k), op = c & 0xf, len = c >> 4;
+        if (op == 0 || op == 7 || op == 8 || op == 2 || op == 3) {
+            span64 += len;                                   // reference bases consumed so far
+            if ((int64_t)pos + span64 > INT32_MAX) { out.err = "alignment reaching beyond 2^31 reference positions"; return false; }
+        }
         if (op == 0 || op == 7 || op == 8) {
             if (len == 0) continue;
             if (nb && blocks[2 * nb - 2] + blocks[2 * nb - 1] == ref) blocks[2 * nb - 1] += (int32_t)len;
@@ -81,13 +92,15 @@ bool convert_record(const uint8_t *rec, uint32_t size, Decoded &out)
         }
     }
     if (L > 0xFFFF) { out.err = "alignment with more than 65535 aligned bases"; return false; }
+    // no aligned base at all (a CIGAR of S / I / H / P only): len(read.positions) == 0 — no rule can place it and a
+    // batch row without blocks would read as filler; counted with the records that carry no positions
+    if (L == 0) { out.skipped++; return true; }
     int32_t start = pos;
     if (nb && blocks[0] != 0) {            // leading D/N: positions start after it
         const int32_t shift = blocks[0];
         start += shift;
         for (int j = 0; j < nb; ++j) blocks[2 * j] -= shift;
     }
-    out.mapped++;
     out.tid.push_back(tid);
     out.start.push_back(start);
     out.meta.push_back((uint32_t)L | ((flag & 0x10) ? (1u << 16) : 0u) | ((uint32_t)nb << 24));
@@ -241,8 +254,12 @@ extern "C" int pb_bam_decode(pb_bam *h, int n_threads)
                 x += 4 + slen;
             }
             if (!bsize) { err = "BGZF member without a BC subfield"; rc = PB_EINVAL; break; }
+            // BSIZE covers the 12-byte header, the extra field and the 8-byte trailer at least: anything smaller would
+            // put the CRC / ISIZE words before the member and make the compressed size wrap
+            if (bsize < 12 + xlen + 8) { err = "corrupt BGZF member header (BSIZE smaller than the header it sits in)"; rc = PB_EINVAL; break; }
             if (off + bsize > comp_have) break;               // incomplete member: wait for more input
             const uint32_t isize = rd32(p + bsize - 4);
+            if (isize > 65536) { err = "corrupt BGZF member header (ISIZE above the 64 KiB the format allows)"; rc = PB_EINVAL; break; }
             blocks.push_back({off + 12 + xlen, bsize - xlen - 20, udst, isize, rd32(p + bsize - 8)});
             udst += isize;
             off += bsize;

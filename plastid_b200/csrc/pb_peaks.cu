@@ -51,3 +51,45 @@ extern "C" int pb_atomic_probe(uint32_t *bins, int64_t n_bins, int64_t n_updates
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
+
+// ---- gather probe: the access pattern of the region kernels with nothing else in the way -------------------------
+// n_chunks warps-worth of work: chunk j is `chunk_bins` consecutive uint32 bins starting at a pseudo-random, 4-aligned
+// bin of [0, n_bins); a warp reads its chunk with 16-byte loads (four in flight per lane), folds it into one word and
+// writes that word.  What this launch achieves in bytes per second is the rate HBM delivers for scattered
+// kilobyte-sized segments — the denominator the region sums and window gathers can be held to
+// (bench.py --workload peaks; no reference counterpart, not on the product path).
+namespace {
+
+__global__ void __launch_bounds__(256)
+pb_gather_probe_kernel(const uint4 *__restrict__ vec, int64_t n_groups, int chunk_groups, int64_t n_chunks,
+                       uint32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_chunks) return;
+    const int64_t g0 = (int64_t)(pb_mix64((uint64_t)j + 0x51ed270b0f4cull) % (uint64_t)(n_groups - chunk_groups));
+    uint32_t acc = 0;
+    for (int u0 = lane; u0 < chunk_groups; u0 += 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) v[x] = u0 + 32 * x < chunk_groups ? __ldg(vec + g0 + u0 + 32 * x) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc += v[x].x + v[x].y + v[x].z + v[x].w;
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if (lane == 0) out[j] = acc;
+}
+
+}  // namespace
+
+extern "C" int pb_gather_probe(const uint32_t *vec, int64_t n_bins, int chunk_bins, int64_t n_chunks, uint32_t *out, void *stream)
+{
+    if (!vec || !out || chunk_bins < 4 || (chunk_bins & 3) || n_bins <= chunk_bins || n_chunks <= 0 || ((uintptr_t)vec & 15)) {
+        pb_set_error("pb_gather_probe: bad argument");
+        return PB_EINVAL;
+    }
+    pb_gather_probe_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(vec), n_bins / 4, chunk_bins / 4, n_chunks, out);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}

@@ -81,254 +81,384 @@ template <> __device__ __forceinline__ void add_group<double>(double &acc, const
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// masked sums: one warp per chain, 16-byte groups flattened over the lanes
+// masked sums: one warp per exon BLOCK (16-byte loads, four in flight per lane), then one warp per chain
 // ------------------------------------------------------------------------------------------------------------
+// History (profiles/NOTES_r02.md): one warp per chain walking block after block ran at 0.23 of the HBM rate (every
+// warp waiting on one 128-byte row at a time); flattening a chain's — then four chains' — units over the lanes of one
+// warp kept more bytes in flight but spent ~120 warp instructions per 32 loads on block look-ups and 64-bit shuffles
+// (ncu: issue slots 49 % busy, 28 % of the warps resident at 76 registers): 0.31-0.34.  The probe pb_gather_probe shows
+// what the memory system gives for this access pattern when nothing else is in the way: 4.4-6.3 TB/s for scattered
+// 1-6 KB segments.  So the block is the unit of work: its warp does what the probe does (plus head / tail trimming
+// and mask bits), writes ONE partial sum, and a second tiny launch adds the partial sums of every chain in a fixed
+// order (deterministic for float64 planes too).  block_chain / block_pos come from the host table.
 template <typename T, bool MASK>
 __global__ void __launch_bounds__(256)
-pb_region_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
-                      const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane, int64_t n_chains,
-                      const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
-                      long long lo, long long hi, double *__restrict__ sums, int64_t *__restrict__ live_len)
+pb_block_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                     const int32_t *__restrict__ block_chain, const int64_t *__restrict__ block_pos,
+                     const uint8_t *__restrict__ block_plane, int64_t n_blocks,
+                     const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
+                     long long lo, long long hi, double *__restrict__ block_sum)
 {
     constexpr int V = VecOf<T>::V, U = 4;
     typedef typename VecOf<T>::L L;
     const int lane = threadIdx.x & 31;
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_chains) return;
-    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(chain_plane + c)]);
-    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
-    const long long moff = MASK ? __ldg(mask_off + c) : 0;
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_blocks) return;
+    const long long bs = __ldg(bstart + k), be = __ldg(bend + k);
+    const long long cs = bs > lo ? bs : lo, ce = be < hi ? be : hi;          // the part this rank owns
+    if (cs >= ce) { if (lane == 0) block_sum[k] = 0.0; return; }
+    // the plane of a block comes from the host table: the data loads depend on ONE round trip (bounds + plane), not
+    // on block -> chain -> plane
+    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(block_plane + k)]);
+    const long long g0 = cs & ~(long long)(V - 1);
+    const int head = (int)(cs - g0), span = (int)(ce - g0);                  // owned elements: [head, span) relative to g0
+    const int n_groups = (span + V - 1) / V;
+    const L *__restrict__ src = reinterpret_cast<const L *>(vec + g0);
+    const long long mbase = MASK ? __ldg(mask_off + __ldg(block_chain + k)) + __ldg(block_pos + k) + (g0 - bs) : 0;   // mask bit of element g0
     typename VecOf<T>::Acc acc = 0;
-    long long jbase = 0;                     // chain position of the batch's first block
-    for (int64_t kb = k0; kb < k1; kb += 32) {
-        const int nb = (int)(k1 - kb < 32 ? k1 - kb : 32);
-        long long bs = 0, be = 0;
-        if (lane < nb) { bs = __ldg(bstart + kb + lane); be = __ldg(bend + kb + lane); }
-        const long long cs = bs > lo ? bs : lo, ce = be < hi ? be : hi;      // the part this rank owns
-        const long long g0 = cs & ~(long long)(V - 1);
-        const int units = cs < ce ? (int)((ce - g0 + V - 1) / V) : 0;
-        int incl_u = units;
-        long long incl_len = be - bs;
+    for (int u0 = lane; u0 < n_groups; u0 += 32 * U) {
+        L v[U];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int up_u = __shfl_up_sync(kFull, incl_u, d);
-            const long long up_l = __shfl_up_sync(kFull, incl_len, d);
-            if (lane >= d) { incl_u += up_u; incl_len += up_l; }
-        }
-        const int pre_u = incl_u - units;
-        const int total_u = __shfl_sync(kFull, incl_u, 31);
-        const int head = (int)(cs - g0);                                   // elements of the first group before cs
-        const int span = (int)(ce - g0);                                   // end of the owned part, relative to g0
-        const long long mbase = moff + jbase + (incl_len - (be - bs)) + (g0 - bs);   // mask bit of element g0
-        jbase += shfl_ll(incl_len, 31);
-        for (int u0 = 0; u0 < total_u; u0 += 32 * U) {
-            int uu[U], blk[U];
+        for (int x = 0; x < U; ++x) if (u0 + 32 * x < n_groups) v[x] = __ldg(src + u0 + 32 * x);
 #pragma unroll
-            for (int x = 0; x < U; ++x) { uu[x] = u0 + x * 32 + lane; blk[x] = 0; }
-            for (int i = 1; i < nb; ++i) {
-                const int s = __shfl_sync(kFull, pre_u, i);
-#pragma unroll
-                for (int x = 0; x < U; ++x) blk[x] += (uu[x] >= s);
-            }
-            L v[U];
-            int rel[U], hd[U], sp[U];
-            long long mb[U];
-            bool ok[U];
-#pragma unroll
-            for (int x = 0; x < U; ++x) {
-                const long long g = shfl_ll(g0, blk[x]);
-                const int pre = __shfl_sync(kFull, pre_u, blk[x]);
-                hd[x] = __shfl_sync(kFull, head, blk[x]);
-                sp[x] = __shfl_sync(kFull, span, blk[x]);
-                if (MASK) mb[x] = shfl_ll(mbase, blk[x]);
-                ok[x] = uu[x] < total_u;
-                rel[x] = (uu[x] - pre) * V;                                // first element of the group, relative to g0
-                if (ok[x]) v[x] = __ldg(reinterpret_cast<const L *>(vec + g + rel[x]));
-            }
-#pragma unroll
-            for (int x = 0; x < U; ++x) {
-                if (!ok[x]) continue;
-                const int e_lo = hd[x] > rel[x] ? hd[x] - rel[x] : 0;
-                const int e_hi = sp[x] - rel[x] < V ? sp[x] - rel[x] : V;
-                uint32_t m = ((1u << e_hi) - 1u) & ~((1u << e_lo) - 1u);
-                if (MASK) m &= ~(mask_bits_at(mask_words, mb[x] + rel[x] + e_lo, e_hi - e_lo) << e_lo);
-                add_group<T>(acc, v[x], m);
-            }
+        for (int x = 0; x < U; ++x) {
+            const int u = u0 + 32 * x;
+            if (u >= n_groups) break;
+            const int rel = u * V;
+            const int e_lo = head > rel ? head - rel : 0;
+            const int e_hi = span - rel < V ? span - rel : V;
+            uint32_t m = ((1u << e_hi) - 1u) & ~((1u << e_lo) - 1u);
+            if (MASK) m &= ~(mask_bits_at(mask_words, mbase + rel + e_lo, e_hi - e_lo) << e_lo);
+            add_group<T>(acc, v[x], m);
         }
     }
-    long long live = jbase;
-    if (MASK) live -= warp_popcount_bits(mask_words, moff, jbase, lane);
     double total;
-    if (sizeof(T) == 4) total = (double)pb_warp_sum((unsigned long long)acc);
+    if (sizeof(T) == 4) total = (double)pb_warp_sum((unsigned long long)acc);   // exact: counts stay far below 2^53
     else total = warp_sum_f64((double)acc);
-    if (lane == 0) { sums[c] = total; live_len[c] = live; }
+    if (lane == 0) block_sum[k] = total;
+}
+
+// one THREAD per chain (chains have a handful of blocks): partial sums of its blocks in block order, its length, its
+// masked positions
+__global__ void __launch_bounds__(256)
+pb_chain_totals_kernel(const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                       const int64_t *__restrict__ chain_off, int64_t n_chains,
+                       const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
+                       const double *__restrict__ block_sum, const unsigned long long *__restrict__ counts,
+                       double *__restrict__ sums, int64_t *__restrict__ live_len)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
+    long long len = 0;
+    double acc = 0.0;
+    for (int64_t k = k0; k < k1; ++k) {
+        len += __ldg(bend + k) - __ldg(bstart + k);
+        if (block_sum) acc += block_sum[k];
+    }
+    long long live = len;
+    if (mask_words && len > 0) {
+        const long long b0 = __ldg(mask_off + c);
+        const long long wa = b0 >> 5, wb = (b0 + len - 1) >> 5;
+        long long cnt = 0;
+        for (long long w = wa; w <= wb; ++w) {
+            uint32_t x = __ldg(mask_words + w);
+            if (w == wa) x &= kFull << (b0 & 31);
+            if (w == wb) x &= kFull >> (31 - ((b0 + len - 1) & 31));
+            cnt += __popc(x);
+        }
+        live -= cnt;
+    }
+    sums[c] = counts ? (double)counts[c] : acc;
+    live_len[c] = live;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// window matrices: one warp per chain, chain positions flattened over the lanes, one store per cell
+// window matrices: one warp per exon block writes the cells of its positions; one warp per chain fills the rest
 // ------------------------------------------------------------------------------------------------------------
+// Window rows (row_off == NULL): row c of a width-wide matrix, chain c laid 5'->3' from column row_col[c].  Ragged rows
+// (pb_gather_chains): chain c owns cells [row_off[c], row_off[c] + its length) of a flat vector.
 template <typename T, bool MASK>
 __global__ void __launch_bounds__(256)
-pb_gather_windows_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
-                         const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
-                         const uint8_t *__restrict__ chain_reverse, const int32_t *__restrict__ row_col,
-                         const int64_t *__restrict__ row_off, int64_t n_chains, int32_t width_,
-                         const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
-                         long long lo, long long hi, double *__restrict__ matrix, uint8_t *__restrict__ maskmat)
+pb_window_blocks_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                        const int32_t *__restrict__ block_chain, const int64_t *__restrict__ block_pos,
+                        const uint8_t *__restrict__ block_plane, const uint8_t *__restrict__ chain_reverse,
+                        const int64_t *__restrict__ chain_len, const int32_t *__restrict__ row_col,
+                        const int64_t *__restrict__ row_off, int64_t n_blocks, int32_t width_,
+                        const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
+                        long long lo, long long hi, double *__restrict__ matrix, uint8_t *__restrict__ maskmat)
 {
     constexpr int U = 4;
     const int lane = threadIdx.x & 31;
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_chains) return;
-    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(chain_plane + c)]);
-    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_blocks) return;
+    const long long bs = __ldg(bstart + k), be = __ldg(bend + k);
+    const int n = (int)(be - bs);
+    const int c = __ldg(block_chain + k);
+    const T *__restrict__ vec = static_cast<const T *>(planes.p[__ldg(block_plane + k)]);
+    const long long len = __ldg(chain_len + c), pos0 = __ldg(block_pos + k);
     const bool rev = __ldg(chain_reverse + c);
-    const long long moff = MASK ? __ldg(mask_off + c) : 0;
-    long long len = 0;
-    for (int64_t k = k0 + lane; k < k1; k += 32) len += __ldg(bend + k) - __ldg(bstart + k);
-    len = (long long)pb_warp_sum((unsigned long long)len);
-    // window rows (row_off == NULL): row c of a width-wide matrix, the chain laid from column row_col[c];
-    // ragged rows: chain c owns cells [row_off[c], row_off[c] + its length) of a flat vector
     const long long col0 = row_off ? 0 : __ldg(row_col + c);
     const long long width = row_off ? len : width_;
     const int64_t cell0 = row_off ? __ldg(row_off + c) : c * (int64_t)width_;
     double *__restrict__ row = matrix + cell0;
     uint8_t *__restrict__ mrow = maskmat + cell0;
-    // columns no chain position reaches stay "masked NaN" (metagene.py:895-898)
-    for (long long col = lane; col < width; col += 32)
-        if (col < col0 || col >= col0 + len) { row[col] = nan(""); mrow[col] = 1; }
-    long long jbase = 0;
-    for (int64_t kb = k0; kb < k1; kb += 32) {
-        const int nb = (int)(k1 - kb < 32 ? k1 - kb : 32);
-        long long bs = 0, be = 0;
-        if (lane < nb) { bs = __ldg(bstart + kb + lane); be = __ldg(bend + kb + lane); }
-        const int n_i = (int)(be - bs);
-        int incl = n_i;
+    const long long mbase = MASK ? __ldg(mask_off + c) + pos0 : 0;
+    // column of the block's first position and the direction columns run in
+    const long long cfirst = col0 + (rev ? len - 1 - pos0 : pos0);
+    const int dir = rev ? -1 : 1;
+    for (int i0 = lane; i0 < n; i0 += 32 * U) {
+        T v[U];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int up = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += up;
+        for (int x = 0; x < U; ++x) {
+            const int i = i0 + 32 * x;
+            const long long p = bs + i;
+            v[x] = T(0);
+            if (i < n && p >= lo && p < hi) v[x] = __ldg(vec + p);          // positions of other ranks count zero
         }
-        const int pre = incl - n_i;
-        const int total = __shfl_sync(kFull, incl, 31);
-        for (int t0 = 0; t0 < total; t0 += 32 * U) {
-            int tt[U], blk[U];
 #pragma unroll
-            for (int x = 0; x < U; ++x) { tt[x] = t0 + x * 32 + lane; blk[x] = 0; }
-            for (int i = 1; i < nb; ++i) {
-                const int s = __shfl_sync(kFull, pre, i);
-#pragma unroll
-                for (int x = 0; x < U; ++x) blk[x] += (tt[x] >= s);
-            }
-            T v[U];
-            bool ok[U];
-#pragma unroll
-            for (int x = 0; x < U; ++x) {
-                const long long b0 = shfl_ll(bs, blk[x]);
-                const int p0 = __shfl_sync(kFull, pre, blk[x]);
-                ok[x] = tt[x] < total;
-                const long long p = b0 + (tt[x] - p0);
-                v[x] = T(0);
-                if (ok[x] && p >= lo && p < hi) v[x] = __ldg(vec + p);
-            }
-#pragma unroll
-            for (int x = 0; x < U; ++x) {
-                if (!ok[x]) continue;
-                const long long jj = jbase + tt[x];
-                const long long col = col0 + (rev ? (len - 1 - jj) : jj);
-                if (col >= 0 && col < width) {
-                    row[col] = (double)v[x];
-                    mrow[col] = MASK ? (uint8_t)mask_bits_at(mask_words, moff + jj, 1) : (uint8_t)0;
-                }
+        for (int x = 0; x < U; ++x) {
+            const int i = i0 + 32 * x;
+            if (i >= n) break;
+            const long long col = cfirst + dir * (long long)i;
+            if (col >= 0 && col < width) {
+                row[col] = (double)v[x];
+                mrow[col] = MASK ? (uint8_t)mask_bits_at(mask_words, mbase + i, 1) : (uint8_t)0;
             }
         }
-        jbase += total;
     }
 }
 
+// columns no chain position reaches stay "masked NaN" (metagene.py:895-898)
+__global__ void __launch_bounds__(256)
+pb_window_fill_kernel(const int64_t *__restrict__ chain_len, const int32_t *__restrict__ row_col, int64_t n_chains,
+                      int32_t width, double *__restrict__ matrix, uint8_t *__restrict__ maskmat)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chains) return;
+    const long long col0 = __ldg(row_col + c), len = __ldg(chain_len + c);
+    double *__restrict__ row = matrix + c * (int64_t)width;
+    uint8_t *__restrict__ mrow = maskmat + c * (int64_t)width;
+    const long long a = col0 < 0 ? 0 : (col0 < width ? col0 : width);                 // covered columns: [a, b)
+    const long long b = col0 + len < 0 ? 0 : (col0 + len < width ? col0 + len : width);
+    for (long long col = lane; col < a; col += 32) { row[col] = nan(""); mrow[col] = 1; }
+    for (long long col = (b > a ? b : a) + lane; col < width; col += 32) { row[col] = nan(""); mrow[col] = 1; }
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// plane-free region counts of a point rule: one CTA per chain walks the reads that can map into each of its
-// blocks (a contiguous slice of the coordinate-sorted batch) — no count vectors are materialised.
+// plane-free region counts of a point rule: no count vectors are materialised.
 // Equals pb_region_sums over the planes pb_map_point would write (same strand pre-filter per query strand,
 // genome_array.py:811-815; same rule direction; same masks).
+//
+// The reads that can map into a block are a contiguous slice of the coordinate-sorted batch.  Expression is skewed —
+// a few chains hold millions of reads — so the work is cut by READS, not by chains:
+//   1. pb_read_index_kernel   first read at or beyond every 16384-bin boundary of the layout (a few hundred KB, L2)
+//   2. pb_chain_slices_kernel one warp per block: its read slice (two short searches inside the index cell) and the
+//                             number of 2048-read work items it needs
+//   3. exclusive scan of the item counts
+//   4. pb_chain_items_kernel  persistent warps take items round-robin: look the block up (32-ary search of the
+//                             offsets), count the sites of the item's reads that land on unmasked positions of the
+//                             block inside this rank's bins, one 64-bit atomic per item
+//   5. pb_chain_totals_kernel one warp per chain: the count as float64, the unmasked length
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-pb_chain_counts_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
-                       const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
-                       const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane, int64_t n_chains,
-                       const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
-                       long long lo, long long hi, long long total_bins,
-                       double *__restrict__ sums, int64_t *__restrict__ live_len, unsigned long long *__restrict__ stats)
+constexpr int kItemReads = 2048;
+constexpr int kIndexShift = 14;          // PB_LAYOUT_ALIGN = 1 << 14: an index cell never spans two chromosomes
+
+__global__ void pb_read_index_kernel(PbReads b, PbLayoutDev lay, long long n_cells, long long *__restrict__ index)
 {
-    __shared__ unsigned long long s_count;
-    __shared__ unsigned int s_drop, s_drop_len;
-    const int64_t c = blockIdx.x;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_cells) return;
+    if (g == n_cells) { index[g] = b.n_reads; return; }
+    const long long bin = g << kIndexShift;
+    const int ch = pb_chrom_of_bin(lay, bin);
+    long long r0 = b.n_reads, r1 = b.n_reads;
+    if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
+    index[g] = pb_lower_bound(b.ref_start, r0, r1, bin - __ldg(lay.chrom_bin_off + ch));
+}
+
+// first read of chromosome ch (reads [r0, r1)) starting at or beyond chromosome position p, through the index
+__device__ __forceinline__ long long pb_indexed_lower_bound(const PbReads &b, const long long *__restrict__ index,
+                                                            long long base, long long padded_end, long long r0, long long r1,
+                                                            long long p)
+{
+    if (p <= 0) return r0;
+    if (base + p >= padded_end) return r1;
+    const long long g = (base + p) >> kIndexShift;
+    long long a = __ldg(index + g), e = __ldg(index + g + 1);
+    a = a < r0 ? r0 : a;
+    e = e > r1 ? r1 : e;
+    return pb_lower_bound_warp(b.ref_start, a, e, p);
+}
+
+__global__ void __launch_bounds__(256)
+pb_chain_slices_kernel(PbReads b, PbLayoutDev lay, const long long *__restrict__ index,
+                       const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend, int64_t n_blocks,
+                       long long lo, long long hi, long long total_bins,
+                       long long *__restrict__ slice_first, uint32_t *__restrict__ items)
+{
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { s_count = 0; s_drop = 0; s_drop_len = 0; }
-    __syncthreads();
-    const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
-    const int plane = __ldg(chain_plane + c);            // 0 '+', 1 '-', 2 '.'
-    const bool rq = plane == 1;                          // rule direction follows the chain's strand
-    const long long moff = mask_words ? __ldg(mask_off + c) : 0;
-    unsigned long long count = 0;
-    unsigned int drop = 0, drop_len = 0;
-    long long j0 = 0;
-    for (int64_t k = k0; k < k1; ++k) {
-        const long long gs = __ldg(bstart + k), ge = __ldg(bend + k);
-        const long long cs = gs > lo ? gs : lo, ce = ge < hi ? ge : hi;      // owned part, global bins
-        if (cs < ce && gs >= 0 && gs < total_bins) {
-            const int ch = pb_chrom_of_bin(lay, gs);
-            const long long base = __ldg(lay.chrom_bin_off + ch);
-            const long long ps = cs - base, pe = ce - base;                  // chromosome coordinates
-            int64_t r0 = 0, r1 = 0;
-            if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
-            const int64_t first = pb_lower_bound_warp(b.ref_start, r0, r1, ps - b.max_span + 1);
-            const int64_t last = pb_lower_bound_warp(b.ref_start, first, r1, pe);
-            constexpr int kU = 4;
-            for (int64_t i0 = first + threadIdx.x; i0 < last; i0 += (int64_t)kU * blockDim.x) {
-                uint32_t mv[kU];
-                int32_t sv[kU];
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_blocks) return;
+    const long long gs = __ldg(bstart + k), ge = __ldg(bend + k);
+    const long long cs = gs > lo ? gs : lo, ce = ge < hi ? ge : hi;
+    long long first = 0, last = 0;
+    if (cs < ce && gs >= 0 && gs < total_bins) {
+        const int ch = pb_chrom_of_bin(lay, gs);
+        const long long base = __ldg(lay.chrom_bin_off + ch), padded_end = __ldg(lay.chrom_bin_off + ch + 1);
+        long long r0 = 0, r1 = 0;
+        if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
+        first = pb_indexed_lower_bound(b, index, base, padded_end, r0, r1, cs - base - b.max_span + 1);
+        last = pb_indexed_lower_bound(b, index, base, padded_end, r0, r1, ce - base);
+        if (last < first) last = first;
+    }
+    if (lane == 0) {
+        slice_first[2 * k] = first;
+        slice_first[2 * k + 1] = last;
+        items[k] = (uint32_t)((last - first + kItemReads - 1) / kItemReads);
+    }
+}
+
+// last k with off[k] <= item (off ascending, off[0] = 0, off[n] = total > item), by a whole warp
+__device__ __forceinline__ long long pb_block_of_item(const uint32_t *__restrict__ off, long long n, uint32_t item)
+{
+    const int lane = threadIdx.x & 31;
+    long long lo = 0, hi = n;                 // invariant: off[lo] <= item < off[hi]
+    while (hi - lo > 32) {
+        const long long step = (hi - lo) / 32;
+        const long long p = lo + (long long)(lane + 1) * step;           // <= hi
+        const bool le = p < hi && __ldg(off + p) <= item;
+        const int cnt = __popc(__ballot_sync(kFull, le));                 // probes are ascending: a prefix of lanes
+        if (cnt < 32) hi = lo + (long long)(cnt + 1) * step < hi ? lo + (long long)(cnt + 1) * step : hi;
+        lo += (long long)cnt * step;
+    }
+    const long long p = lo + 1 + lane;
+    return lo + __popc(__ballot_sync(kFull, p < hi && __ldg(off + p) <= item));
+}
+
+// Sites of the reads [first, first + n) that land on unmasked positions [ps, ps + width) of one block; everything the
+// item fixes (rule direction, strand class, size window, LUT) is resolved before the loop, positions are 32-bit
+// chromosome coordinates, and the range test is one unsigned compare.  A lane takes FOUR consecutive reads per
+// 16-byte load of each array (the item is walked from the 4-aligned read at or before `first`), two such loads of
+// each array in flight.  MODE 0: idx = param, 1: idx = L - 1 - param, 2: LUT.
+template <int MODE, bool BLOCKS>
+__device__ __forceinline__ unsigned int pb_count_item(const PbReads &b, long long first, int n, int lane,
+                                                      int param, const int32_t *__restrict__ lut,
+                                                      unsigned size_lo, unsigned size_span, unsigned strand_care, unsigned strand_want,
+                                                      int ps, unsigned width, const uint32_t *__restrict__ mask_words, long long mbit,
+                                                      unsigned int &drop_len)
+{
+    const long long a0 = first & ~3ll;                         // 16-byte aligned start
+    const int skip = (int)(first - a0), end = skip + n;        // reads [skip, end) of the aligned run are the item's
+    const uint4 *__restrict__ meta4 = reinterpret_cast<const uint4 *>(b.meta + a0);
+    const int4 *__restrict__ start4 = reinterpret_cast<const int4 *>(b.ref_start + a0);
+    const int n_quads = (end + 3) >> 2;
+    unsigned int count = 0;
+    constexpr int kU = 2;
+    for (int q0 = lane; q0 < n_quads; q0 += 32 * kU) {
+        uint4 mq[kU];
+        int4 sq[kU];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int64_t i = i0 + (int64_t)u * blockDim.x;
-                    mv[u] = i < last ? __ldg(b.meta + i) : (1u << 17);
-                    sv[u] = i < last ? __ldg(b.ref_start + i) : 0;
-                }
+        for (int u = 0; u < kU; ++u) {
+            const int q = q0 + 32 * u;
+            // the last quad may reach past the batch's last read by up to 3 elements: the arrays of a batch are
+            // allocated in whole 16-byte units by every producer (torch allocations are 512-byte granular)
+            if (q < n_quads) { mq[u] = __ldg(meta4 + q); sq[u] = __ldg(start4 + q); }
+            else { mq[u] = make_uint4(1u << 17, 1u << 17, 1u << 17, 1u << 17); sq[u] = make_int4(0, 0, 0, 0); }
+        }
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const uint32_t m = mv[u];
-                    if (!pb_passes(m, r.size_min, r.size_max)) continue;
-                    const bool rev = PB_META_REV(m);
-                    if ((plane == 0 && rev) || (plane == 1 && !rev)) continue;
-                    const int L = PB_META_L(m);
-                    const int idx = pb_rule_index(r, L, rq);
-                    if (idx < 0) { drop = 1; drop_len = L; continue; }
-                    const long long p = pb_position(b, i0 + (int64_t)u * blockDim.x, sv[u], m, idx);
-                    if (p < ps || p >= pe) continue;
-                    if (mask_words && mask_bits_at(mask_words, moff + j0 + (base + p - gs), 1)) continue;
-                    count++;
-                }
+        for (int u = 0; u < kU; ++u) {
+            const uint32_t mm[4] = {mq[u].x, mq[u].y, mq[u].z, mq[u].w};
+            const int32_t ss[4] = {sq[u].x, sq[u].y, sq[u].z, sq[u].w};
+            const int j0 = (q0 + 32 * u) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                if (j < skip || j >= end) continue;
+                const uint32_t m = mm[e];
+                const unsigned L = m & 0xFFFFu;
+                // drop bit, size window, strand class in three tests
+                if ((m & (1u << 17)) || (L - size_lo) > size_span || ((((m >> 16) & 1u) ^ strand_want) & strand_care)) continue;
+                int idx;
+                if (MODE == 2) idx = L < (unsigned)PB_LUT_SIZE ? __ldg(lut + L) : -1;
+                else idx = (unsigned)param < L ? (MODE == 0 ? param : (int)L - 1 - param) : -1;
+                if (idx < 0) { drop_len = L; continue; }
+                int p;
+                if (BLOCKS && (m >> 24) > 1) {
+                    const long long pp = pb_block_position(b, a0 + j, ss[e], idx);
+                    if (pp < 0) continue;
+                    p = (int)pp;
+                } else p = ss[e] + idx;
+                if ((unsigned)(p - ps) >= width) continue;
+                if (mask_words && mask_bits_at(mask_words, mbit + p, 1)) continue;
+                count++;
             }
         }
-        j0 += ge - gs;
     }
-    count = pb_warp_sum(count);
-    drop = __reduce_or_sync(kFull, drop);
-    drop_len = __reduce_max_sync(kFull, drop_len);
-    if (lane == 0) {
-        if (count) atomicAdd(&s_count, count);
-        if (drop) { atomicOr(&s_drop, 1u); atomicMax(&s_drop_len, drop_len); }
+    return count;
+}
+
+__global__ void __launch_bounds__(256)
+pb_chain_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
+                      const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                      const int32_t *__restrict__ block_chain, const int64_t *__restrict__ block_pos,
+                      const uint8_t *__restrict__ chain_plane, int64_t n_blocks,
+                      const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
+                      long long lo, long long hi, const long long *__restrict__ slice_first,
+                      const uint32_t *__restrict__ item_off, unsigned long long *__restrict__ counts,
+                      unsigned long long *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t total = __ldg(item_off + n_blocks);
+    // SizeFilterFactory as one unsigned window test: (L - size_lo) <= size_span
+    const unsigned size_lo = r.size_min > 0 ? (unsigned)r.size_min : 0u;
+    const unsigned size_span = r.size_min > 0 && r.size_max != -1 ? (r.size_max >= r.size_min ? (unsigned)(r.size_max - r.size_min) : 0u) : 0xFFFFu;
+    const bool size_empty = r.size_min > 0 && r.size_max != -1 && r.size_max < r.size_min;
+    const bool has_blocks = b.blk_off != nullptr;
+    unsigned int drop_len = 0;
+    int drop_plane = 0;
+    for (long long item = warp; item < (long long)total; item += n_warps) {
+        const long long k = pb_block_of_item(item_off, n_blocks, (uint32_t)item);
+        const long long gs = __ldg(bstart + k), ge = __ldg(bend + k);
+        const long long cs = gs > lo ? gs : lo, ce = ge < hi ? ge : hi;
+        const int c = __ldg(block_chain + k);
+        const int plane = __ldg(chain_plane + c);            // 0 '+', 1 '-', 2 '.'
+        const bool rq = plane == 1;                          // rule direction follows the chain's strand
+        const int ch = pb_chrom_of_bin(lay, gs);
+        const long long base = __ldg(lay.chrom_bin_off + ch);
+        const int ps = (int)(cs - base);
+        const unsigned width = (unsigned)(ce - cs);
+        const long long mbit = mask_words ? __ldg(mask_off + c) + __ldg(block_pos + k) - (gs - base) : 0;   // + p = mask bit
+        const long long first = __ldg(slice_first + 2 * k) + (item - (long long)__ldg(item_off + k)) * kItemReads;
+        const long long slice_end = __ldg(slice_first + 2 * k + 1);
+        const int n = (int)(slice_end - first < kItemReads ? slice_end - first : kItemReads);
+        const unsigned strand_care = plane == 2 ? 0u : 1u, strand_want = plane == 1 ? 1u : 0u;
+        unsigned int count = 0, dl = 0;
+        if (!size_empty) {
+            if (r.kind == PB_RULE_VARIABLE) {
+                const int32_t *lut = rq ? r.lut_rc : r.lut_fw;
+                count = has_blocks ? pb_count_item<2, true>(b, first, n, lane, 0, lut, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl)
+                                   : pb_count_item<2, false>(b, first, n, lane, 0, lut, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl);
+            } else if (((r.kind == PB_RULE_FIVEPRIME) ? !rq : rq)) {        // offset counted from the left end
+                count = has_blocks ? pb_count_item<0, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl)
+                                   : pb_count_item<0, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl);
+            } else {
+                count = has_blocks ? pb_count_item<1, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl)
+                                   : pb_count_item<1, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl);
+            }
+        }
+        if (dl) { drop_len = dl; drop_plane = plane; }
+        count = __reduce_add_sync(kFull, count);
+        if (lane == 0 && count) atomicAdd(counts + c, (unsigned long long)count);
     }
-    __syncthreads();
-    long long live = j0;
-    if (threadIdx.x < 32 && mask_words) live -= warp_popcount_bits(mask_words, moff, j0, lane);
-    if (threadIdx.x == 0) {
-        sums[c] = (double)s_count;
-        live_len[c] = live;
-        if (s_drop && stats) {
-            const int which = plane == 0 ? PB_STAT_DROPPED_PLUS : (plane == 1 ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_ANY);
+    if (stats && __any_sync(kFull, drop_len != 0)) {
+        const unsigned int len = __reduce_max_sync(kFull, drop_len);
+        if (drop_len == len) {                                // flags, not counts: which strand class saw a drop
+            const int which = drop_plane == 0 ? PB_STAT_DROPPED_PLUS : (drop_plane == 1 ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_ANY);
             atomicAdd(stats + which, 1ull);
-            atomicMax(stats + PB_STAT_DROPPED_LEN, (unsigned long long)s_drop_len);
+            atomicMax(stats + PB_STAT_DROPPED_LEN, (unsigned long long)len);
         }
     }
 }
@@ -348,85 +478,61 @@ int check_chains(const void *const *planes, const int64_t *bstart, const int64_t
 
 }  // namespace
 
-extern "C" int pb_region_sums_range(const void *const *planes, int vec_dtype,
-                                    const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                                    const uint8_t *chain_plane, int64_t n_chains,
-                                    const uint8_t *mask_bits, const int64_t *mask_off,
-                                    int64_t bin_begin, int64_t bin_end,
-                                    double *sums, int64_t *live_len, void *stream_)
+extern "C" size_t pb_region_sums_workspace_bytes(int64_t n_blocks)
 {
-    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype, bin_begin, bin_end);
-    if (rc) return rc;
-    if (!sums || !live_len) { pb_set_error("pb_region_sums: null outputs"); return PB_EINVAL; }
-    for (int i = 0; i < 3; ++i)
-        if ((uintptr_t)planes[i] & 15) { pb_set_error("pb_region_sums: planes must be 16-byte aligned"); return PB_EINVAL; }
-    if (n_chains == 0) return PB_OK;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    PbPlanes pl{{planes[0], planes[1], planes[2]}};
-    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
-    const uint32_t *mw = reinterpret_cast<const uint32_t *>(mask_bits);
-#define PB_LAUNCH_SUMS(T, M) pb_region_sums_kernel<T, M><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, n_chains, mw, mask_off, bin_begin, bin_end, sums, live_len)
-    if (vec_dtype == 0) { if (mw) PB_LAUNCH_SUMS(uint32_t, true); else PB_LAUNCH_SUMS(uint32_t, false); }
-    else { if (mw) PB_LAUNCH_SUMS(double, true); else PB_LAUNCH_SUMS(double, false); }
-#undef PB_LAUNCH_SUMS
-    PB_CUDA_CHECK(cudaGetLastError());
-    return PB_OK;
+    return n_blocks < 0 ? 0 : (size_t)n_blocks * sizeof(double) + 16;
 }
 
 extern "C" int pb_region_sums(const void *const *planes, int vec_dtype,
                               const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                              const uint8_t *chain_plane, int64_t n_chains,
-                              const uint8_t *mask_bits, const int64_t *mask_off,
-                              double *sums, int64_t *live_len, void *stream_)
-{
-    return pb_region_sums_range(planes, vec_dtype, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off,
-                                0, INT64_MAX, sums, live_len, stream_);
-}
-
-extern "C" int pb_gather_windows_range(const void *const *planes, int vec_dtype,
-                                       const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                                       const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                                       const int32_t *row_col, int64_t n_chains, int32_t width,
-                                       const uint8_t *mask_bits, const int64_t *mask_off,
-                                       int64_t bin_begin, int64_t bin_end,
-                                       double *matrix, uint8_t *maskmat, void *stream_)
+                              const uint8_t *chain_plane, const int32_t *block_chain, const int64_t *block_pos,
+                              const uint8_t *block_plane,
+                              int64_t n_chains, int64_t n_blocks, const uint8_t *mask_bits, const int64_t *mask_off,
+                              int64_t bin_begin, int64_t bin_end,
+                              double *sums, int64_t *live_len, void *workspace, size_t workspace_bytes, void *stream_)
 {
     int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype, bin_begin, bin_end);
     if (rc) return rc;
-    if (!chain_reverse || !row_col || !matrix || !maskmat || width <= 0) { pb_set_error("pb_gather_windows: bad arguments"); return PB_EINVAL; }
+    if (!sums || !live_len || !block_chain || !block_pos || !block_plane || n_blocks < 0) { pb_set_error("pb_region_sums: null outputs or block tables"); return PB_EINVAL; }
+    for (int i = 0; i < 3; ++i)
+        if ((uintptr_t)planes[i] & 15) { pb_set_error("pb_region_sums: planes must be 16-byte aligned"); return PB_EINVAL; }
+    if (!workspace || workspace_bytes < pb_region_sums_workspace_bytes(n_blocks)) { pb_set_error("pb_region_sums: workspace too small"); return PB_ENOSPACE; }
     if (n_chains == 0) return PB_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     PbPlanes pl{{planes[0], planes[1], planes[2]}};
-    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
+    double *block_sum = (double *)workspace;
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mask_bits);
-#define PB_LAUNCH_WIN(T, M) pb_gather_windows_kernel<T, M><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, row_col, nullptr, n_chains, width, mw, mask_off, bin_begin, bin_end, matrix, maskmat)
-    if (vec_dtype == 0) { if (mw) PB_LAUNCH_WIN(uint32_t, true); else PB_LAUNCH_WIN(uint32_t, false); }
-    else { if (mw) PB_LAUNCH_WIN(double, true); else PB_LAUNCH_WIN(double, false); }
-#undef PB_LAUNCH_WIN
+    if (n_blocks > 0) {
+        const unsigned grid = (unsigned)((n_blocks * 32 + 255) / 256);
+#define PB_LAUNCH_SUMS(T, M) pb_block_sums_kernel<T, M><<<grid, 256, 0, stream>>>(pl, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end, block_sum)
+        if (vec_dtype == 0) { if (mw) PB_LAUNCH_SUMS(uint32_t, true); else PB_LAUNCH_SUMS(uint32_t, false); }
+        else { if (mw) PB_LAUNCH_SUMS(double, true); else PB_LAUNCH_SUMS(double, false); }
+#undef PB_LAUNCH_SUMS
+    }
+    pb_chain_totals_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, stream>>>(
+        bstart, bend, chain_off, n_chains, mw, mask_off, block_sum, nullptr, sums, live_len);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
 
-extern "C" int pb_gather_chains_range(const void *const *planes, int vec_dtype,
-                                      const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                                      const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                                      const int64_t *row_off, int64_t n_chains,
-                                      const uint8_t *mask_bits, const int64_t *mask_off,
-                                      int64_t bin_begin, int64_t bin_end,
-                                      double *values, uint8_t *masked, void *stream_)
+static int launch_windows(const void *const *planes, int vec_dtype,
+                          const int64_t *bstart, const int64_t *bend, const int32_t *block_chain, const int64_t *block_pos,
+                          const uint8_t *block_plane, const uint8_t *chain_reverse, const int64_t *chain_len,
+                          const int32_t *row_col, const int64_t *row_off, int64_t n_chains, int64_t n_blocks, int32_t width,
+                          const uint8_t *mask_bits, const int64_t *mask_off, int64_t bin_begin, int64_t bin_end,
+                          double *matrix, uint8_t *maskmat, cudaStream_t stream)
 {
-    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype, bin_begin, bin_end);
-    if (rc) return rc;
-    if (!chain_reverse || !row_off || !values || !masked) { pb_set_error("pb_gather_chains: bad arguments"); return PB_EINVAL; }
-    if (n_chains == 0) return PB_OK;
-    cudaStream_t stream = (cudaStream_t)stream_;
     PbPlanes pl{{planes[0], planes[1], planes[2]}};
-    const unsigned grid = (unsigned)((n_chains * 32 + 255) / 256);
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mask_bits);
-#define PB_LAUNCH_FLAT(T, M) pb_gather_windows_kernel<T, M><<<grid, 256, 0, stream>>>(pl, bstart, bend, chain_off, chain_plane, chain_reverse, nullptr, row_off, n_chains, 0, mw, mask_off, bin_begin, bin_end, values, masked)
-    if (vec_dtype == 0) { if (mw) PB_LAUNCH_FLAT(uint32_t, true); else PB_LAUNCH_FLAT(uint32_t, false); }
-    else { if (mw) PB_LAUNCH_FLAT(double, true); else PB_LAUNCH_FLAT(double, false); }
-#undef PB_LAUNCH_FLAT
+    if (!row_off)
+        pb_window_fill_kernel<<<(unsigned)((n_chains * 32 + 255) / 256), 256, 0, stream>>>(chain_len, row_col, n_chains, width, matrix, maskmat);
+    if (n_blocks > 0) {
+        const unsigned grid = (unsigned)((n_blocks * 32 + 255) / 256);
+#define PB_LAUNCH_WIN(T, M) pb_window_blocks_kernel<T, M><<<grid, 256, 0, stream>>>(pl, bstart, bend, block_chain, block_pos, block_plane, chain_reverse, chain_len, row_col, row_off, n_blocks, width, mw, mask_off, bin_begin, bin_end, matrix, maskmat)
+        if (vec_dtype == 0) { if (mw) PB_LAUNCH_WIN(uint32_t, true); else PB_LAUNCH_WIN(uint32_t, false); }
+        else { if (mw) PB_LAUNCH_WIN(double, true); else PB_LAUNCH_WIN(double, false); }
+#undef PB_LAUNCH_WIN
+    }
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }
@@ -434,22 +540,62 @@ extern "C" int pb_gather_chains_range(const void *const *planes, int vec_dtype,
 extern "C" int pb_gather_windows(const void *const *planes, int vec_dtype,
                                  const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
                                  const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                                 const int32_t *row_col, int64_t n_chains, int32_t width,
+                                 const int32_t *block_chain, const int64_t *block_pos, const uint8_t *block_plane,
+                                 const int64_t *chain_len,
+                                 const int32_t *row_col, int64_t n_chains, int64_t n_blocks, int32_t width,
                                  const uint8_t *mask_bits, const int64_t *mask_off,
+                                 int64_t bin_begin, int64_t bin_end,
                                  double *matrix, uint8_t *maskmat, void *stream_)
 {
-    return pb_gather_windows_range(planes, vec_dtype, bstart, bend, chain_off, chain_plane, chain_reverse, row_col, n_chains,
-                                   width, mask_bits, mask_off, 0, INT64_MAX, matrix, maskmat, stream_);
+    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype, bin_begin, bin_end);
+    if (rc) return rc;
+    if (!chain_reverse || !row_col || !matrix || !maskmat || !block_chain || !block_pos || !block_plane || !chain_len || width <= 0 || n_blocks < 0) {
+        pb_set_error("pb_gather_windows: bad arguments"); return PB_EINVAL;
+    }
+    if (n_chains == 0) return PB_OK;
+    return launch_windows(planes, vec_dtype, bstart, bend, block_chain, block_pos, block_plane, chain_reverse, chain_len, row_col, nullptr,
+                          n_chains, n_blocks, width, mask_bits, mask_off, bin_begin, bin_end, matrix, maskmat, (cudaStream_t)stream_);
+}
+
+extern "C" int pb_gather_chains(const void *const *planes, int vec_dtype,
+                                const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                const int32_t *block_chain, const int64_t *block_pos, const uint8_t *block_plane,
+                                const int64_t *chain_len,
+                                const int64_t *row_off, int64_t n_chains, int64_t n_blocks,
+                                const uint8_t *mask_bits, const int64_t *mask_off,
+                                int64_t bin_begin, int64_t bin_end,
+                                double *values, uint8_t *masked, void *stream_)
+{
+    int rc = check_chains(planes, bstart, bend, chain_off, chain_plane, n_chains, mask_bits, mask_off, vec_dtype, bin_begin, bin_end);
+    if (rc) return rc;
+    if (!chain_reverse || !row_off || !values || !masked || !block_chain || !block_pos || !block_plane || !chain_len || n_blocks < 0) {
+        pb_set_error("pb_gather_chains: bad arguments"); return PB_EINVAL;
+    }
+    if (n_chains == 0) return PB_OK;
+    return launch_windows(planes, vec_dtype, bstart, bend, block_chain, block_pos, block_plane, chain_reverse, chain_len, nullptr, row_off,
+                          n_chains, n_blocks, 0, mask_bits, mask_off, bin_begin, bin_end, values, masked, (cudaStream_t)stream_);
+}
+
+extern "C" size_t pb_chain_counts_workspace_bytes(int64_t total_bins, int64_t n_blocks, int64_t n_chains)
+{
+    if (total_bins < 0 || n_blocks < 0 || n_chains < 0) return 0;
+    const size_t cells = (size_t)(total_bins >> kIndexShift) + 2;
+    return cells * 8 + (size_t)n_blocks * 16 + ((size_t)n_blocks + 1) * 8 + (size_t)pb_scan_part_entries(n_blocks + 1) * 4
+        + (size_t)n_chains * 8 + 256;
 }
 
 extern "C" int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
                                const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                               const uint8_t *chain_plane, int64_t n_chains,
+                               const uint8_t *chain_plane, const int32_t *block_chain, const int64_t *block_pos,
+                               int64_t n_chains, int64_t n_blocks,
                                const uint8_t *mask_bits, const int64_t *mask_off,
                                int64_t bin_begin, int64_t bin_end,
-                               double *sums, int64_t *live_len, uint64_t *stats, void *stream_)
+                               double *sums, int64_t *live_len, uint64_t *stats,
+                               void *workspace, size_t workspace_bytes, void *stream_)
 {
-    if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !sums || !live_len || n_chains < 0) {
+    if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !block_chain || !block_pos || !sums ||
+        !live_len || n_chains < 0 || n_blocks < 0) {
         pb_set_error("pb_chain_counts: null argument"); return PB_EINVAL;
     }
     if (rule->kind != PB_RULE_FIVEPRIME && rule->kind != PB_RULE_THREEPRIME && rule->kind != PB_RULE_VARIABLE) {
@@ -458,14 +604,45 @@ extern "C" int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, c
     if (rule->kind == PB_RULE_VARIABLE && (!rule->lut_fw || !rule->lut_rc)) { pb_set_error("pb_chain_counts: variable rule needs LUTs"); return PB_EINVAL; }
     if (mask_bits && (!mask_off || ((uintptr_t)mask_bits & 3))) { pb_set_error("pb_chain_counts: mask_bits need mask_off and 4-byte alignment"); return PB_EINVAL; }
     if (bin_begin > bin_end) { pb_set_error("pb_chain_counts: inverted bin range"); return PB_EINVAL; }
+    if (((uintptr_t)batch->ref_start & 15) || ((uintptr_t)batch->meta & 15)) {
+        pb_set_error("pb_chain_counts: ref_start and meta must be 16-byte aligned (the reads are loaded four at a time)"); return PB_EINVAL;
+    }
+    if (n_blocks >= ((int64_t)1 << 31) || batch->n_reads / kItemReads + n_blocks >= ((int64_t)1 << 32)) {
+        pb_set_error("pb_chain_counts: too many blocks / work items for one call"); return PB_EINVAL;
+    }
+    if (!workspace || workspace_bytes < pb_chain_counts_workspace_bytes(layout->total_bins, n_blocks, n_chains)) {
+        pb_set_error("pb_chain_counts: workspace too small"); return PB_ENOSPACE;
+    }
     if (n_chains == 0) return PB_OK;
-    if (n_chains > 0x7fffffffll) { pb_set_error("pb_chain_counts: too many chains for one launch"); return PB_EINVAL; }
+    cudaStream_t stream = (cudaStream_t)stream_;
     PbReads b = pb_to_dev(batch);
     PbRuleDev r = pb_to_dev(rule);
     PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
-    pb_chain_counts_kernel<<<(unsigned)n_chains, 128, 0, (cudaStream_t)stream_>>>(
-        b, r, lay, bstart, bend, chain_off, chain_plane, n_chains, reinterpret_cast<const uint32_t *>(mask_bits), mask_off,
-        bin_begin, bin_end, layout->total_bins, sums, live_len, reinterpret_cast<unsigned long long *>(stats));
+    const long long n_cells = layout->total_bins >> kIndexShift;
+    char *w = (char *)workspace;
+    long long *index = (long long *)w;                          w += (size_t)(n_cells + 2) * 8;
+    long long *slices = (long long *)w;                         w += (size_t)n_blocks * 16;
+    uint32_t *items = (uint32_t *)w;                            w += ((size_t)n_blocks + 1) * 4;
+    uint32_t *item_off = (uint32_t *)w;                         w += ((size_t)n_blocks + 1) * 4;
+    uint32_t *part = (uint32_t *)w;                             w += (size_t)pb_scan_part_entries(n_blocks + 1) * 4;
+    w = (char *)(((uintptr_t)w + 15) & ~(uintptr_t)15);
+    unsigned long long *counts = (unsigned long long *)w;
+    const uint32_t *mw = reinterpret_cast<const uint32_t *>(mask_bits);
+    PB_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)n_chains * 8, stream));
+    pb_read_index_kernel<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, stream>>>(b, lay, n_cells, index);
+    if (n_blocks > 0) {
+        pb_chain_slices_kernel<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, stream>>>(
+            b, lay, index, bstart, bend, n_blocks, bin_begin, bin_end, layout->total_bins, slices, items);
+        int rc = pb_launch_exclusive_scan_u32(items, item_off, part, n_blocks, stream);
+        if (rc) return rc;
+        int sms = 148;
+        pb_sm_count(&sms);
+        pb_chain_items_kernel<<<(unsigned)(sms * 6), 256, 0, stream>>>(
+            b, r, lay, bstart, bend, block_chain, block_pos, chain_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
+            slices, item_off, counts, reinterpret_cast<unsigned long long *>(stats));
+    }
+    pb_chain_totals_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, stream>>>(
+        bstart, bend, chain_off, n_chains, mw, mask_off, nullptr, counts, sums, live_len);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

@@ -83,7 +83,7 @@ _workspaces = {}
 
 def _workspace(device, nbytes, slot=0):
     import torch
-    key = (str(device), slot)
+    key = (_lib.device_key(device), slot)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
@@ -330,7 +330,7 @@ _side_streams = {}
 
 def _side_stream(device, j):
     import torch
-    key = (str(device), j)
+    key = (_lib.device_key(device), j)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=device)
     return _side_streams[key]
@@ -347,11 +347,16 @@ def region_sums(planes, table, out=None):
     live = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     ptrs = planes.plane_ptrs()
     # positions outside this rank's bins (position sharding; parts of a region beyond its chromosome) count zero
-    _lib.check(_lib.lib().pb_region_sums_range(ptrs, 1 if planes.dtype == "f64" else 0, _lib.ptr(d["bstart"]),
-                                               _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]),
-                                               n, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
-                                               planes.bin_lo, planes.bin_hi, _lib.ptr(sums), _lib.ptr(live),
-                                               _lib.stream_ptr()))
+    L = _lib.lib()
+    n_blocks = len(table.bstart)
+    ws_bytes = L.pb_region_sums_workspace_bytes(n_blocks)
+    ws = _workspace(dev, ws_bytes, slot="region_sums")
+    _lib.check(L.pb_region_sums(ptrs, 1 if planes.dtype == "f64" else 0, _lib.ptr(d["bstart"]),
+                                _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]),
+                                _lib.ptr(d["block_chain"]), _lib.ptr(d["block_pos"]), _lib.ptr(d["block_plane"]),
+                                n, n_blocks, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
+                                planes.bin_lo, planes.bin_hi, _lib.ptr(sums), _lib.ptr(live), _lib.ptr(ws), ws_bytes,
+                                _lib.stream_ptr()))
     return sums[:n], live[:n]
 
 
@@ -371,10 +376,15 @@ def chain_counts(dbatch, layout, factory, size_filter, table, bin_range=None, st
     live = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     lo, hi = (0, int(layout.total_bins)) if bin_range is None else (int(bin_range[0]), int(bin_range[1]))
     b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
-    _lib.check(_lib.lib().pb_chain_counts(C.byref(b), C.byref(lay), C.byref(rule), _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]),
-                                          _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]), n, _lib.ptr(d["mask_bits"]),
-                                          _lib.ptr(d["mask_off"]), lo, hi, _lib.ptr(sums), _lib.ptr(live), _lib.ptr(stats),
-                                          _lib.stream_ptr()))
+    L = _lib.lib()
+    n_blocks = len(table.bstart)
+    ws_bytes = L.pb_chain_counts_workspace_bytes(int(layout.total_bins), n_blocks, n)
+    ws = _workspace(dev, ws_bytes, slot="chain_counts")
+    _lib.check(L.pb_chain_counts(C.byref(b), C.byref(lay), C.byref(rule), _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]),
+                                 _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]), _lib.ptr(d["block_chain"]),
+                                 _lib.ptr(d["block_pos"]), n, n_blocks, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
+                                 lo, hi, _lib.ptr(sums), _lib.ptr(live), _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
+                                 _lib.stream_ptr()))
     return sums[:n], live[:n]
 
 
@@ -414,13 +424,14 @@ def gather_windows(planes, table, row_col, width):
     n = table.n_chains
     matrix = torch.empty((max(n, 1), width), dtype=torch.float64, device=dev)
     maskmat = torch.empty((max(n, 1), width), dtype=torch.uint8, device=dev)
-    cols = torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
-    _lib.check(_lib.lib().pb_gather_windows_range(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
-                                                  _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
-                                                  _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
-                                                  n, width, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
-                                                  planes.bin_lo, planes.bin_hi,
-                                                  _lib.ptr(matrix), _lib.ptr(maskmat), _lib.stream_ptr()))
+    cols = row_col if hasattr(row_col, "data_ptr") else torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
+    _lib.check(_lib.lib().pb_gather_windows(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
+                                            _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                            _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]),
+                                            _lib.ptr(d["block_chain"]), _lib.ptr(d["block_pos"]), _lib.ptr(d["block_plane"]),
+                                            _lib.ptr(d["chain_len"]), _lib.ptr(cols), n, len(table.bstart), width,
+                                            _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]), planes.bin_lo, planes.bin_hi,
+                                            _lib.ptr(matrix), _lib.ptr(maskmat), _lib.stream_ptr()))
     return matrix[:n], maskmat[:n]
 
 
@@ -438,11 +449,13 @@ def gather_chains(planes, table):
     values = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
     masked = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
     d_off = torch.from_numpy(row_off).to(dev)
-    _lib.check(_lib.lib().pb_gather_chains_range(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
-                                                 _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
-                                                 _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(d_off), n,
-                                                 _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]), planes.bin_lo, planes.bin_hi,
-                                                 _lib.ptr(values), _lib.ptr(masked), _lib.stream_ptr()))
+    _lib.check(_lib.lib().pb_gather_chains(planes.plane_ptrs(), 1 if planes.dtype == "f64" else 0,
+                                           _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                           _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]),
+                                           _lib.ptr(d["block_chain"]), _lib.ptr(d["block_pos"]), _lib.ptr(d["block_plane"]),
+                                           _lib.ptr(d["chain_len"]), _lib.ptr(d_off), n, len(table.bstart),
+                                           _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]), planes.bin_lo, planes.bin_hi,
+                                           _lib.ptr(values), _lib.ptr(masked), _lib.stream_ptr()))
     return values[:total], masked[:total], row_off
 
 
@@ -560,7 +573,7 @@ _scratch_bufs = {}
 def _scratch(device, nbytes):
     """Reusable device scratch (radix-select keys): grown, never shrunk, one per device."""
     import torch
-    key = str(device)
+    key = _lib.device_key(device)
     buf = _scratch_bufs.get(key)
     if buf is None or buf.numel() < nbytes:
         _scratch_bufs[key] = buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
@@ -810,9 +823,6 @@ class BAMGenomeArray(object):
             if hb.transfer is not None and len(hb):
                 self._receiver = self._make_receiver(hb)
                 self._dbatch = self._receiver.receive(hb.transfer_pinned())
-                if self._dbatch.length_hist is None:
-                    from .batch import meta_length_hist
-                    self._dbatch.length_hist = meta_length_hist(hb.meta)
             else:
                 self._dbatch = hb.to_device(self.device)
         return self._dbatch
@@ -882,9 +892,6 @@ class BAMGenomeArray(object):
                     map_wire16_streamed(self._receiver, hb.transfer_pinned(), chunks, self.layout, self.map_fn, sf, need,
                                         self._planes)
                 self._dbatch = self._receiver.batch
-                if self._dbatch.length_hist is None:
-                    from .batch import meta_length_hist
-                    self._dbatch.length_hist = meta_length_hist(hb.meta)
                 self._finish_stats()
                 return self._planes
         dbatch = self._device_batch()

@@ -65,7 +65,7 @@ class _MapFactory(object):
             return None, None
         import torch
         cache = self.__dict__.setdefault("_lut_dev", {})
-        key = str(device)
+        key = _lib.device_key(device)
         if key not in cache:
             cache[key] = (torch.from_numpy(luts[0]).to(device), torch.from_numpy(luts[1]).to(device))
         return cache[key]

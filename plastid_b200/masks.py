@@ -49,7 +49,7 @@ class MaskIndex(object):
 
     def device(self, device):
         import torch
-        key = str(device)
+        key = _lib.device_key(device)
         if key not in self._dev:
             def up(a):
                 return torch.from_numpy(a if len(a) else np.zeros(1, dtype=a.dtype)).to(device)

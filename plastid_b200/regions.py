@@ -102,14 +102,23 @@ class ChainTable(object):
 
     def device(self, device):
         import torch
-        key = str(device)
+        key = _lib.device_key(device)
         if key not in self._dev:
             def up(a):
                 return None if a is None else torch.from_numpy(a).to(device)
             bits = self.mask_bits
             if bits is not None and len(bits) % 4:          # the kernels read the bit array as whole 32-bit words
                 bits = np.concatenate([bits, np.zeros(4 - len(bits) % 4, dtype=np.uint8)])
+            # per block: its chain and the chain position (genomic order) of its first base
+            n_blk = np.diff(self.chain_off)
+            block_chain = np.repeat(np.arange(self.n_chains, dtype=np.int32), n_blk)
+            blen = self.bend - self.bstart
+            before = np.cumsum(blen) - blen
+            first = before[np.minimum(self.chain_off[:-1], max(len(blen) - 1, 0))] if len(blen) else np.zeros(self.n_chains, dtype=np.int64)
+            block_pos = (before - np.repeat(first, n_blk)).astype(np.int64)
             self._dev[key] = dict(bstart=up(self.bstart), bend=up(self.bend), chain_off=up(self.chain_off),
                                   chain_plane=up(self.chain_plane), chain_reverse=up(self.chain_reverse),
+                                  block_chain=up(block_chain), block_pos=up(block_pos), chain_len=up(self.chain_len),
+                                  block_plane=up(np.repeat(self.chain_plane, n_blk)),
                                   mask_bits=up(bits), mask_off=up(self.mask_off))
         return self._dev[key]

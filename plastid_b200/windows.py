@@ -80,7 +80,7 @@ class TranscriptTable(object):
 
     def device(self, device):
         import torch
-        key = str(device)
+        key = _lib.device_key(device)
         if key not in self._dev:
             def up(a):
                 return torch.from_numpy(a if len(a) else np.zeros(1, dtype=a.dtype)).to(device)

@@ -99,3 +99,15 @@ def assert_float_columns_equal(got_rows, want_rows, float_cols, rtol=0.0, label=
                     assert a == b or fa == fb, "%s row %d col %d: %s vs %s" % (label, i, j, a, b)
             else:
                 assert a == b, "%s row %d col %d: %r vs %r" % (label, i, j, a, b)
+
+
+def rules():
+    """tests/golden/ref_rules.json.gz: the reference's own map factories / BAMGenomeArray on seeded reads with every
+    CIGAR op (tests/golden/make_rule_goldens.py)."""
+    import json
+    with gzip.open(os.path.join(HERE, "golden", "ref_rules.json.gz"), "rt") as fh:
+        d = json.load(fh)
+    d["offsets_default"] = {(k if k == "default" else int(k)): v for k, v in d["offsets_default"].items()}
+    d["offsets_plain"] = {int(k): v for k, v in d["offsets_plain"].items()}
+    d["read_tuples"] = [(s, strand == "-", [(_CIGAR_OPS.index(op), int(n)) for n, op in _CIGAR_RE.findall(c)]) for s, strand, c in d["reads"]]
+    return d

@@ -296,6 +296,68 @@ def test_malformed_input_is_reported(tmp_path):
     assert len(hb) == 0 and hb.chroms == ["a"] and hb.mapped == 0
 
 
+def test_corrupt_member_headers_are_errors_not_crashes(tmp_path):
+    """BSIZE was never checked against XLEN — an 18-byte header with BSIZE 5 put the CRC / ISIZE reads before
+    the mapping and crashed the process.  Every damaged header field must come back as an error."""
+    good = tmp_path / "g.bam"
+    bam_io.write_bam(str(good), {"c": 100000}, [(0, 5 + i, 0, [(0, 30)]) for i in range(3000)], block_bytes=8000)
+    data = good.read_bytes()
+    f = tmp_path / "h.bam"
+    # the reported reproducer: a lone 18-byte header whose BSIZE field says 5
+    hdr = bytearray(data[:18])
+    hdr[16:18] = (5).to_bytes(2, "little")
+    f.write_bytes(bytes(hdr))
+    with pytest.raises(_lib.PlastidB200Error, match="corrupt BGZF member header"):
+        bam_io.batch_from_bam(str(f))
+    bsize = int.from_bytes(data[16:18], "little") + 1
+    for name, off, value in (("BSIZE too small", 16, 10), ("BSIZE = header only", 16, 17), ("XLEN larger than BSIZE", 10, 60000),
+                             ("SLEN past XLEN", 14, 40)):
+        bad = bytearray(data)
+        bad[off:off + 2] = value.to_bytes(2, "little")
+        f.write_bytes(bytes(bad))
+        with pytest.raises(_lib.PlastidB200Error):
+            bam_io.batch_from_bam(str(f))
+    bad = bytearray(data)                       # ISIZE beyond the 64 KiB the format allows: no multi-GB allocation
+    bad[bsize - 4:bsize] = (0x7fff0000).to_bytes(4, "little")
+    f.write_bytes(bytes(bad))
+    with pytest.raises(_lib.PlastidB200Error, match="ISIZE"):
+        bam_io.batch_from_bam(str(f))
+    # fuzz: random bytes in the headers of the first members — an error or (when the mutation is harmless) the same
+    # batch, never a crash
+    ref = bam_io.batch_from_bam(str(good), pack=False)
+    rng = np.random.default_rng(7)
+    offs, o = [], 0
+    while o + 18 <= len(data) and len(offs) < 6:
+        offs.append(o)
+        o += int.from_bytes(data[o + 16:o + 18], "little") + 1
+    for _ in range(300):
+        bad = bytearray(data)
+        base = offs[int(rng.integers(len(offs)))]
+        for _k in range(int(rng.integers(1, 4))):
+            bad[base + int(rng.integers(0, 18))] = int(rng.integers(0, 256))
+        f.write_bytes(bytes(bad))
+        try:
+            hb = bam_io.batch_from_bam(str(f), pack=False)
+        except _lib.PlastidB200Error:
+            continue
+        assert len(hb) == len(ref) and (hb.ref_start == ref.ref_start).all()
+
+
+def test_records_the_batch_cannot_hold_are_refused_or_skipped(tmp_path):
+    """a negative position, a reference span beyond int32, or a CIGAR without aligned bases must not turn into
+    garbage rows.  `mapped` is the index statistic (placed records without the unmapped flag), whatever the CIGAR."""
+    f = str(tmp_path / "r.bam")
+    bam_io.write_bam(f, {"c": 1000}, [(0, 5, 0, [(0, 30)]), (0, 7, 0, [(4, 20), (1, 3)]), (0, 9, 16, [(0, 25)]), (0, 11, 0, [])])
+    hb = bam_io.batch_from_bam(f)
+    assert len(hb) == 2 and list(hb.ref_start) == [5, 9] and hb.mapped == 4        # S/I-only and CIGAR-less records: no positions
+    bam_io.write_bam(f, {"c": 1000}, [(0, -3, 0, [(0, 30)])])
+    with pytest.raises(_lib.PlastidB200Error, match="negative position"):
+        bam_io.batch_from_bam(f)
+    bam_io.write_bam(f, {"c": 1000}, [(0, 2_000_000_000, 0, [(0, 30), (3, 200_000_000), (0, 10)])])
+    with pytest.raises(_lib.PlastidB200Error, match="2\\^31"):
+        bam_io.batch_from_bam(f)
+
+
 def test_positions_match_reference_htslib_pileup():
     """SURVEY 8(a) row a1 for EVERY CIGAR op: the reference's vendored htslib pileup engine
     (kent/src/htslib/sam.c bam_plp_auto via oracle/_ref/ref_bam_tool positions; committed output

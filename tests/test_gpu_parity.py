@@ -935,7 +935,11 @@ def test_center_tables_from_batch_metadata_equal_device_histogram(small_world, c
     import torch
     from plastid_b200.batch import DeviceBatch
     w = small_world
-    hb = w["hb"]
+    # the histogram is metadata of the PACKED batch (AlignmentBatch.pack: what the decoder emits); a plain SoA batch
+    # carries none and the Center rule measures it on the device
+    hb = pb.AlignmentBatch(w["hb"].chroms, w["hb"].chrom_len, w["hb"].ref_start, w["hb"].meta, w["hb"].chrom_read_off,
+                           max_span=w["hb"].max_span).pack()
+    assert DeviceBatch.from_host(w["hb"], cuda_device).length_hist is None or w["hb"].transfer is not None
     d_meta = DeviceBatch.from_host(hb, cuda_device)
     assert d_meta.length_hist is not None and d_meta.length_hist.sum() == len(hb)
     for sf in (None, pb.SizeFilterFactory(24, 33), pb.SizeFilterFactory(30, -1)):

@@ -20,10 +20,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def world(cuda_device):
-    chroms, lens = synth.yeast_like_genome(total=1_500_000, n_chrom=5)
-    lens[1] = 16384 * 2 + 5
-    lens[3] = 99_999
-    ann = synth.make_annotation(chroms, lens, 300, seed=11, exons=(1, 4), exon_len=(90, 700), intron_len=(40, 500))
+    chroms, lens = synth.yeast_like_genome(total=2_500_000, n_chrom=5)
+    lens[1] = 16384 * 8 + 5
+    lens[3] = 199_999
+    ann = synth.make_annotation(chroms, lens, 250, seed=11, exons=(1, 4), exon_len=(90, 500), intron_len=(40, 300))
     dbatch = synth.riboseq_reads(ann, 500_000, seed=3, device=cuda_device, lengths=range(20, 40))
     hb = synth.device_batch_to_host(dbatch, chroms, lens)
     layout = pb.GenomeLayout(chroms, lens)
@@ -115,7 +115,7 @@ def test_region_sums_chain_with_many_blocks_and_tiny_blocks(world, cuda_device):
     sums, live = region_sums(planes, table)
     exp_s, exp_l = oracle_table(host_planes(planes, "u32"), table)
     assert (sums.cpu().numpy() == exp_s).all() and (live.cpu().numpy() == exp_l).all()
-    assert live.cpu().numpy()[0] == big.masked_length and exp_s[0] > 0
+    assert live.cpu().numpy()[0] == big.masked_length and exp_s.sum() > 0
 
 
 def test_regions_beyond_the_chromosome_count_zero_there(world, cuda_device):
@@ -197,7 +197,7 @@ def test_plane_free_counts_equal_sums_over_planes(world, cuda_device, rule, spli
     else:
         dbatch, sf = w["dbatch"], pb.SizeFilterFactory(22, 36)
     fac = {"fiveprime": pb.FivePrimeMapFactory(24), "threeprime": pb.ThreePrimeMapFactory(3),
-           "variable": pb.VariableFivePrimeMapFactory({25: 12, 26: 12, 27: 13, 28: 13, 29: 14, 30: 14, 31: 14})}[rule]
+           "variable": pb.VariableFivePrimeMapFactory({25: 12, 26: 12, 27: 13, 28: 13, 29: 14, 30: 14, 31: 14, 100: 47})}[rule]
     chains = masked_chains(w)
     chrom = w["chroms"][2]
     chains.append(pb.SegmentChain(pb.GenomicSegment(chrom, 100, 30_000, "."), pb.GenomicSegment(chrom, 31_000, 45_000, ".")))
@@ -213,7 +213,7 @@ def test_plane_free_counts_equal_sums_over_planes(world, cuda_device, rule, spli
     if rule != "threeprime" and not spliced:          # 20-24 nt reads cannot be placed by these rules: the warning paths
         assert stats.cpu().numpy()[:3].sum() > 0
     # position ranges: sites are counted by the rank owning them, partial tables add up
-    cuts = [0, 16384 * 9, 16384 * 30, int(w["layout"].total_bins)]
+    cuts = [0, 16384 * 9, 16384 * 40, int(w["layout"].total_bins)]
     acc = torch.zeros_like(want_s)
     for lo, hi in zip(cuts[:-1], cuts[1:]):
         s, l = chain_counts(dbatch, w["layout"], fac, sf, table, (lo, hi))

@@ -44,7 +44,7 @@ def test_argument_errors_are_reported_without_a_device():
     L = _lib.lib()
     assert L.pb_map_point(None, None, None, 3, None, None, None, None, None, 0, None) == _lib.PB_EINVAL
     assert b"null" in L.pb_last_error()
-    assert L.pb_region_sums(None, 0, None, None, None, None, 0, None, None, None, None, None) == _lib.PB_EINVAL
+    assert L.pb_region_sums(None, 0, None, None, None, None, None, None, None, 0, 0, None, None, 0, 1, None, None, None, 0, None) == _lib.PB_EINVAL
     assert L.pb_map_workspace_bytes(16384 * 4, 0, 100) > 0
     # the annotation-side entry points validate before touching the device too
     assert L.pb_landmark_windows(None, None, None, None, None, None, 5, 50, 50, None, None, None) == _lib.PB_EINVAL
@@ -1346,3 +1346,29 @@ def test_keep_matrices_follow_numpy_ma_division():
     assert np.array_equal(got_raw, np.ma.getdata(counts), equal_nan=True)
     assert np.array_equal(got_norm, np.ma.getdata(norm_counts), equal_nan=True)
     assert np.array_equal(got_mask, np.ma.getmaskarray(norm_counts))
+
+
+def test_entry_points_declared_in_pyproject_resolve():
+    """the `plastid.mapping_rules` / `plastid.mapping_options` entry points and the console scripts are
+    declared in pyproject.toml; every target imports and honours the contract of docs/source/devinfo/entrypoints.rst
+    (a dict with name / bamfunc / help whose bamfunc(args=...) returns the mapping callable)."""
+    import argparse
+    import importlib
+    import tomllib
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyproject.toml"), "rb") as fh:
+        proj = tomllib.load(fh)["project"]
+
+    def resolve(target):
+        mod, attr = target.split(":")
+        return getattr(importlib.import_module(mod), attr)
+    rules = proj["entry-points"]["plastid.mapping_rules"]
+    assert set(rules) == {"b200_fiveprime", "b200_threeprime", "b200_center", "b200_fiveprime_variable"}
+    for name, target in rules.items():
+        d = resolve(target)
+        assert d["name"] == name and callable(d["bamfunc"]) and isinstance(d["help"], str)
+    ns = argparse.Namespace(offset=7, nibble=3)
+    assert resolve(rules["b200_fiveprime"])["bamfunc"](args=ns).offset == 7
+    assert resolve(rules["b200_center"])["bamfunc"](args=ns).nibble == 3
+    assert resolve(proj["entry-points"]["plastid.mapping_options"]["device"])["name"] == "device"
+    for name, target in proj["scripts"].items():
+        assert callable(resolve(target)), name
