@@ -778,7 +778,7 @@ def main():
         n_blocks = len(table.bstart)
         # compulsory traffic: every read once (8 B) + the chain tables + the result table
         to_alg = 8.0 * sub.n_reads + 16.0 * n_blocks + 8.0 * (ann.n_tx + 1) + ann.n_tx + 16.0 * ann.n_tx
-        table_only = {"kernel": "pb_chain_counts_kernel", "ms_per_step": to_ms, "value": n_total / (to_ms / 1000.0), "unit": UNIT,
+        table_only = {"kernel": "pb_chain_counts (pb_read_index, pb_chain_first_items, scan, pb_chain_items, pb_chain_totals)", "ms_per_step": to_ms, "value": n_total / (to_ms / 1000.0), "unit": UNIT,
                       "region_counts_per_sec": ann.n_tx / (to_ms / 1000.0), "steps": n_to,
                       "identical_to_plane_path": bool(torch.equal(d_sums, ref_sums) and torch.equal(d_live, live)),
                       "algorithmic_bytes_per_launch": to_alg, "plane_bytes_not_written": 4.0 * (hi - lo) * 2,
@@ -895,8 +895,8 @@ def main():
     gpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.exists(gpath) and args.genome_scale == 1.0 and world == 1:
         with open(gpath) as fh:
-            g_traffic = json.load(fh).get("pb_region_sums_kernel:%s" % args.workload)
-    roofline_gather = {"bound": "hbm", "kernel": "pb_region_sums_kernel", "achieved": g_alg / (sums_ms / 1000.0) / 1e9, "peak": peak,
+            g_traffic = json.load(fh).get("pb_region_sums:%s" % args.workload)
+    roofline_gather = {"bound": "hbm", "kernel": "pb_block_sums_kernel + pb_chain_totals_kernel (pb_region_sums)", "achieved": g_alg / (sums_ms / 1000.0) / 1e9, "peak": peak,
                        "unit": "GB/s", "frac": g_alg / (sums_ms / 1000.0) / 1e9 / peak, "traffic": g_traffic,
                        "algorithmic_bytes_per_launch": g_alg, "kernel_ms": sums_ms, "positions": int(own), "chains": ann.n_tx,
                        "note": "CUDA events around the launch inside the timed steps"}
@@ -927,7 +927,7 @@ def main():
         kernels_per_step = ["pb_tile_index_kernel"] + binning + ["pb_center_tiles_kernel"]
     else:
         kernels_per_step = ["pb_tile_index_kernel"] + binning + ["pb_point_tiles_kernel", "pb_point_overflow_kernel"]
-    kernels_per_step += ["pb_stats_finish_kernel", "pb_region_sums_kernel"]
+    kernels_per_step += ["pb_stats_finish_kernel", "pb_block_sums_kernel", "pb_chain_totals_kernel"]
     sharding_text = {"reads": "read-range: every GPU maps its own batch over the whole genome (weak scaling)",
                      "positions": "ONE batch sharded by position range: range-only planes, halo reads, region tables all-reduced "
                                   "(strong scaling, SURVEY 8e)",

@@ -374,7 +374,7 @@ size_t pb_chain_counts_workspace_bytes(int64_t total_bins, int64_t n_blocks, int
 int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
                     const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
                     const uint8_t *chain_plane, const int32_t *block_chain, const int64_t *block_pos,
-                    int64_t n_chains, int64_t n_blocks,
+                    const uint8_t *block_plane, int64_t n_chains, int64_t n_blocks,
                     const uint8_t *mask_bits, const int64_t *mask_off,
                     int64_t bin_begin, int64_t bin_end,
                     double *sums, int64_t *live_len, uint64_t *stats,

@@ -101,7 +101,7 @@ _SIGNATURES = {
     "pb_gather_chains": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64,
                                    _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "pb_chain_counts_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
-    "pb_chain_counts": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), _P, _P, _P, _P, _P, _P, C.c_int64,
+    "pb_chain_counts": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), _P, _P, _P, _P, _P, _P, _P, C.c_int64,
                                   C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
     "pb_stratified_windows_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int, C.c_int,
                                               _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_int32,

@@ -254,12 +254,13 @@ pb_window_fill_kernel(const int64_t *__restrict__ chain_len, const int32_t *__re
 // The reads that can map into a block are a contiguous slice of the coordinate-sorted batch.  Expression is skewed —
 // a few chains hold millions of reads — so the work is cut by READS, not by chains:
 //   1. pb_read_index_kernel   first read at or beyond every 16384-bin boundary of the layout (a few hundred KB, L2)
-//   2. pb_chain_slices_kernel one warp per block: its read slice (two short searches inside the index cell) and the
-//                             number of 2048-read work items it needs
-//   3. exclusive scan of the item counts
-//   4. pb_chain_items_kernel  persistent warps take items round-robin: look the block up (32-ary search of the
-//                             offsets), count the sites of the item's reads that land on unmasked positions of the
-//                             block inside this rank's bins, one 64-bit atomic per item
+//   2. pb_chain_first_items_kernel  one warp per block: its read slice (two short searches inside the index cell), its
+//                             FIRST 2048-read work item counted right away (most blocks need no more), and the number
+//                             of further items
+//   3. exclusive scan of the further-item counts
+//   4. pb_chain_items_kernel  persistent warps take the further items round-robin (the hot blocks): look the block up
+//                             (32-ary search of the offsets), count the sites of the item's reads that land on unmasked
+//                             positions of the block inside this rank's bins, one 64-bit atomic per item
 //   5. pb_chain_totals_kernel one warp per chain: the count as float64, the unmasked length
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kItemReads = 2048;
@@ -289,34 +290,6 @@ __device__ __forceinline__ long long pb_indexed_lower_bound(const PbReads &b, co
     a = a < r0 ? r0 : a;
     e = e > r1 ? r1 : e;
     return pb_lower_bound_warp(b.ref_start, a, e, p);
-}
-
-__global__ void __launch_bounds__(256)
-pb_chain_slices_kernel(PbReads b, PbLayoutDev lay, const long long *__restrict__ index,
-                       const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend, int64_t n_blocks,
-                       long long lo, long long hi, long long total_bins,
-                       long long *__restrict__ slice_first, uint32_t *__restrict__ items)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n_blocks) return;
-    const long long gs = __ldg(bstart + k), ge = __ldg(bend + k);
-    const long long cs = gs > lo ? gs : lo, ce = ge < hi ? ge : hi;
-    long long first = 0, last = 0;
-    if (cs < ce && gs >= 0 && gs < total_bins) {
-        const int ch = pb_chrom_of_bin(lay, gs);
-        const long long base = __ldg(lay.chrom_bin_off + ch), padded_end = __ldg(lay.chrom_bin_off + ch + 1);
-        long long r0 = 0, r1 = 0;
-        if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
-        first = pb_indexed_lower_bound(b, index, base, padded_end, r0, r1, cs - base - b.max_span + 1);
-        last = pb_indexed_lower_bound(b, index, base, padded_end, r0, r1, ce - base);
-        if (last < first) last = first;
-    }
-    if (lane == 0) {
-        slice_first[2 * k] = first;
-        slice_first[2 * k + 1] = last;
-        items[k] = (uint32_t)((last - first + kItemReads - 1) / kItemReads);
-    }
 }
 
 // last k with off[k] <= item (off ascending, off[0] = 0, off[n] = total > item), by a whole warp
@@ -371,10 +344,11 @@ __device__ __forceinline__ unsigned int pb_count_item(const PbReads &b, long lon
             const uint32_t mm[4] = {mq[u].x, mq[u].y, mq[u].z, mq[u].w};
             const int32_t ss[4] = {sq[u].x, sq[u].y, sq[u].z, sq[u].w};
             const int j0 = (q0 + 32 * u) * 4;
+            const bool inner = j0 >= skip && j0 + 4 <= end;          // every read of the quad belongs to the item
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = j0 + e;
-                if (j < skip || j >= end) continue;
+                if (!inner && (j < skip || j >= end)) continue;
                 const uint32_t m = mm[e];
                 const unsigned L = m & 0xFFFFu;
                 // drop bit, size window, strand class in three tests
@@ -398,11 +372,119 @@ __device__ __forceinline__ unsigned int pb_count_item(const PbReads &b, long lon
     return count;
 }
 
+// What one work item fixes: the block's owned positions, its strand class and rule direction, its mask bits.
+struct PbItemCtx {
+    int ps;                      // first owned position (chromosome coordinate)
+    unsigned width;              // owned positions
+    long long mbit;              // + chromosome position = mask bit index
+    int plane;                   // 0 '+', 1 '-', 2 '.'
+    int chain;
+};
+
+__device__ __forceinline__ PbItemCtx pb_item_ctx(const PbLayoutDev &lay, long long gs, long long ge, long long lo, long long hi,
+                                                 int c, int plane, const uint32_t *__restrict__ mask_words,
+                                                 const int64_t *__restrict__ mask_off, long long bpos)
+{
+    const long long cs = gs > lo ? gs : lo, ce = ge < hi ? ge : hi;
+    const int ch = pb_chrom_of_bin(lay, gs);
+    const long long base = __ldg(lay.chrom_bin_off + ch);
+    PbItemCtx x;
+    x.ps = (int)(cs - base);
+    x.width = ce > cs ? (unsigned)(ce - cs) : 0u;
+    x.mbit = mask_words ? __ldg(mask_off + c) + bpos - (gs - base) : 0;
+    x.plane = plane;
+    x.chain = c;
+    return x;
+}
+
+// count the sites of reads [first, first + n) on the item's block (rule / size window / strand class dispatch)
+__device__ __forceinline__ unsigned int pb_count_reads(const PbReads &b, const PbRuleDev &r, const PbItemCtx &x, long long first, int n,
+                                                       int lane, const uint32_t *__restrict__ mask_words, unsigned int &drop_len)
+{
+    // SizeFilterFactory as one unsigned window test: (L - size_lo) <= size_span
+    const unsigned size_lo = r.size_min > 0 ? (unsigned)r.size_min : 0u;
+    const unsigned size_span = r.size_min > 0 && r.size_max != -1 ? (r.size_max >= r.size_min ? (unsigned)(r.size_max - r.size_min) : 0u) : 0xFFFFu;
+    if ((r.size_min > 0 && r.size_max != -1 && r.size_max < r.size_min) || n <= 0 || x.width == 0) return 0;
+    const bool has_blocks = b.blk_off != nullptr;
+    const bool rq = x.plane == 1;                          // rule direction follows the chain's strand
+    const unsigned care = x.plane == 2 ? 0u : 1u, want = x.plane == 1 ? 1u : 0u;
+    if (r.kind == PB_RULE_VARIABLE) {
+        const int32_t *lut = rq ? r.lut_rc : r.lut_fw;
+        return has_blocks ? pb_count_item<2, true>(b, first, n, lane, 0, lut, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len)
+                          : pb_count_item<2, false>(b, first, n, lane, 0, lut, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len);
+    }
+    if ((r.kind == PB_RULE_FIVEPRIME) ? !rq : rq)          // offset counted from the left end
+        return has_blocks ? pb_count_item<0, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len)
+                          : pb_count_item<0, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len);
+    return has_blocks ? pb_count_item<1, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len)
+                      : pb_count_item<1, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len);
+}
+
+__device__ __forceinline__ void pb_flush_drops(unsigned long long *__restrict__ stats, unsigned int drop_len, int drop_plane)
+{
+    if (stats && __any_sync(kFull, drop_len != 0)) {
+        const unsigned int len = __reduce_max_sync(kFull, drop_len);
+        if (drop_len == len) {                                // flags, not counts: which strand class saw a drop
+            const int which = drop_plane == 0 ? PB_STAT_DROPPED_PLUS : (drop_plane == 1 ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_ANY);
+            atomicAdd(stats + which, 1ull);
+            atomicMax(stats + PB_STAT_DROPPED_LEN, (unsigned long long)len);
+        }
+    }
+}
+
+// one warp per block: its read slice through the index, its FIRST work item right away (most blocks have no more),
+// and how many further items it needs
+__global__ void __launch_bounds__(128)
+pb_chain_first_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, const long long *__restrict__ index,
+                            const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                            const int32_t *__restrict__ block_chain, const int64_t *__restrict__ block_pos,
+                            const uint8_t *__restrict__ block_plane, int64_t n_blocks,
+                            const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
+                            long long lo, long long hi, long long total_bins,
+                            long long *__restrict__ slice_first, uint32_t *__restrict__ extra_items,
+                            unsigned long long *__restrict__ counts, unsigned long long *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_blocks) return;
+    const long long gs = __ldg(bstart + k), ge = __ldg(bend + k);
+    const long long cs = gs > lo ? gs : lo, ce = ge < hi ? ge : hi;
+    long long first = 0, last = 0;
+    unsigned int drop_len = 0;
+    int plane = 0;
+    if (cs < ce && gs >= 0 && gs < total_bins) {
+        const int ch = pb_chrom_of_bin(lay, gs);
+        const long long base = __ldg(lay.chrom_bin_off + ch), padded_end = __ldg(lay.chrom_bin_off + ch + 1);
+        long long r0 = 0, r1 = 0;
+        if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
+        first = pb_indexed_lower_bound(b, index, base, padded_end, r0, r1, cs - base - b.max_span + 1);
+        last = pb_indexed_lower_bound(b, index, base, padded_end, r0, r1, ce - base);
+        if (last < first) last = first;
+        if (last > first) {
+            const int c = __ldg(block_chain + k);
+            plane = __ldg(block_plane + k);
+            const PbItemCtx x = pb_item_ctx(lay, gs, ge, lo, hi, c, plane, mask_words, mask_off, __ldg(block_pos + k));
+            const int n = (int)(last - first < kItemReads ? last - first : kItemReads);
+            unsigned int count = pb_count_reads(b, r, x, first, n, lane, mask_words, drop_len);
+            count = __reduce_add_sync(kFull, count);
+            if (lane == 0 && count) atomicAdd(counts + c, (unsigned long long)count);
+        }
+    }
+    if (lane == 0) {
+        slice_first[2 * k] = first;
+        slice_first[2 * k + 1] = last;
+        const long long items = (last - first + kItemReads - 1) / kItemReads;
+        extra_items[k] = items > 1 ? (uint32_t)(items - 1) : 0u;
+    }
+    pb_flush_drops(stats, drop_len, plane);
+}
+
+// persistent warps over the items beyond the first of every block (the hot blocks)
 __global__ void __launch_bounds__(256)
 pb_chain_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
                       const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
                       const int32_t *__restrict__ block_chain, const int64_t *__restrict__ block_pos,
-                      const uint8_t *__restrict__ chain_plane, int64_t n_blocks,
+                      const uint8_t *__restrict__ block_plane, int64_t n_blocks,
                       const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
                       long long lo, long long hi, const long long *__restrict__ slice_first,
                       const uint32_t *__restrict__ item_off, unsigned long long *__restrict__ counts,
@@ -412,55 +494,24 @@ pb_chain_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t total = __ldg(item_off + n_blocks);
-    // SizeFilterFactory as one unsigned window test: (L - size_lo) <= size_span
-    const unsigned size_lo = r.size_min > 0 ? (unsigned)r.size_min : 0u;
-    const unsigned size_span = r.size_min > 0 && r.size_max != -1 ? (r.size_max >= r.size_min ? (unsigned)(r.size_max - r.size_min) : 0u) : 0xFFFFu;
-    const bool size_empty = r.size_min > 0 && r.size_max != -1 && r.size_max < r.size_min;
-    const bool has_blocks = b.blk_off != nullptr;
     unsigned int drop_len = 0;
     int drop_plane = 0;
     for (long long item = warp; item < (long long)total; item += n_warps) {
         const long long k = pb_block_of_item(item_off, n_blocks, (uint32_t)item);
-        const long long gs = __ldg(bstart + k), ge = __ldg(bend + k);
-        const long long cs = gs > lo ? gs : lo, ce = ge < hi ? ge : hi;
         const int c = __ldg(block_chain + k);
-        const int plane = __ldg(chain_plane + c);            // 0 '+', 1 '-', 2 '.'
-        const bool rq = plane == 1;                          // rule direction follows the chain's strand
-        const int ch = pb_chrom_of_bin(lay, gs);
-        const long long base = __ldg(lay.chrom_bin_off + ch);
-        const int ps = (int)(cs - base);
-        const unsigned width = (unsigned)(ce - cs);
-        const long long mbit = mask_words ? __ldg(mask_off + c) + __ldg(block_pos + k) - (gs - base) : 0;   // + p = mask bit
-        const long long first = __ldg(slice_first + 2 * k) + (item - (long long)__ldg(item_off + k)) * kItemReads;
+        const int plane = __ldg(block_plane + k);
+        const PbItemCtx x = pb_item_ctx(lay, __ldg(bstart + k), __ldg(bend + k), lo, hi, c, plane, mask_words, mask_off, __ldg(block_pos + k));
+        // item e of block k is its (e + 1)-th run of kItemReads reads: the first run was counted with the slice
+        const long long first = __ldg(slice_first + 2 * k) + (item - (long long)__ldg(item_off + k) + 1) * kItemReads;
         const long long slice_end = __ldg(slice_first + 2 * k + 1);
         const int n = (int)(slice_end - first < kItemReads ? slice_end - first : kItemReads);
-        const unsigned strand_care = plane == 2 ? 0u : 1u, strand_want = plane == 1 ? 1u : 0u;
-        unsigned int count = 0, dl = 0;
-        if (!size_empty) {
-            if (r.kind == PB_RULE_VARIABLE) {
-                const int32_t *lut = rq ? r.lut_rc : r.lut_fw;
-                count = has_blocks ? pb_count_item<2, true>(b, first, n, lane, 0, lut, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl)
-                                   : pb_count_item<2, false>(b, first, n, lane, 0, lut, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl);
-            } else if (((r.kind == PB_RULE_FIVEPRIME) ? !rq : rq)) {        // offset counted from the left end
-                count = has_blocks ? pb_count_item<0, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl)
-                                   : pb_count_item<0, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl);
-            } else {
-                count = has_blocks ? pb_count_item<1, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl)
-                                   : pb_count_item<1, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, strand_care, strand_want, ps, width, mask_words, mbit, dl);
-            }
-        }
+        unsigned int dl = 0;
+        unsigned int count = pb_count_reads(b, r, x, first, n, lane, mask_words, dl);
         if (dl) { drop_len = dl; drop_plane = plane; }
         count = __reduce_add_sync(kFull, count);
         if (lane == 0 && count) atomicAdd(counts + c, (unsigned long long)count);
     }
-    if (stats && __any_sync(kFull, drop_len != 0)) {
-        const unsigned int len = __reduce_max_sync(kFull, drop_len);
-        if (drop_len == len) {                                // flags, not counts: which strand class saw a drop
-            const int which = drop_plane == 0 ? PB_STAT_DROPPED_PLUS : (drop_plane == 1 ? PB_STAT_DROPPED_MINUS : PB_STAT_DROPPED_ANY);
-            atomicAdd(stats + which, 1ull);
-            atomicMax(stats + PB_STAT_DROPPED_LEN, (unsigned long long)len);
-        }
-    }
+    pb_flush_drops(stats, drop_len, drop_plane);
 }
 
 int check_chains(const void *const *planes, const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
@@ -588,13 +639,13 @@ extern "C" size_t pb_chain_counts_workspace_bytes(int64_t total_bins, int64_t n_
 extern "C" int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
                                const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
                                const uint8_t *chain_plane, const int32_t *block_chain, const int64_t *block_pos,
-                               int64_t n_chains, int64_t n_blocks,
+                               const uint8_t *block_plane, int64_t n_chains, int64_t n_blocks,
                                const uint8_t *mask_bits, const int64_t *mask_off,
                                int64_t bin_begin, int64_t bin_end,
                                double *sums, int64_t *live_len, uint64_t *stats,
                                void *workspace, size_t workspace_bytes, void *stream_)
 {
-    if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !block_chain || !block_pos || !sums ||
+    if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !block_chain || !block_pos || !block_plane || !sums ||
         !live_len || n_chains < 0 || n_blocks < 0) {
         pb_set_error("pb_chain_counts: null argument"); return PB_EINVAL;
     }
@@ -631,14 +682,17 @@ extern "C" int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, c
     PB_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)n_chains * 8, stream));
     pb_read_index_kernel<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, stream>>>(b, lay, n_cells, index);
     if (n_blocks > 0) {
-        pb_chain_slices_kernel<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, stream>>>(
-            b, lay, index, bstart, bend, n_blocks, bin_begin, bin_end, layout->total_bins, slices, items);
+        // 4 warps per CTA: a block's first item is anything from 0 to 2048 reads, and a CTA holds its slot until its
+        // slowest warp is done
+        pb_chain_first_items_kernel<<<(unsigned)((n_blocks * 32 + 127) / 128), 128, 0, stream>>>(
+            b, r, lay, index, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
+            layout->total_bins, slices, items, counts, reinterpret_cast<unsigned long long *>(stats));
         int rc = pb_launch_exclusive_scan_u32(items, item_off, part, n_blocks, stream);
         if (rc) return rc;
         int sms = 148;
         pb_sm_count(&sms);
         pb_chain_items_kernel<<<(unsigned)(sms * 6), 256, 0, stream>>>(
-            b, r, lay, bstart, bend, block_chain, block_pos, chain_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
+            b, r, lay, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
             slices, item_off, counts, reinterpret_cast<unsigned long long *>(stats));
     }
     pb_chain_totals_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, stream>>>(

@@ -382,7 +382,8 @@ def chain_counts(dbatch, layout, factory, size_filter, table, bin_range=None, st
     ws = _workspace(dev, ws_bytes, slot="chain_counts")
     _lib.check(L.pb_chain_counts(C.byref(b), C.byref(lay), C.byref(rule), _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]),
                                  _lib.ptr(d["chain_off"]), _lib.ptr(d["chain_plane"]), _lib.ptr(d["block_chain"]),
-                                 _lib.ptr(d["block_pos"]), n, n_blocks, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
+                                 _lib.ptr(d["block_pos"]), _lib.ptr(d["block_plane"]), n, n_blocks, _lib.ptr(d["mask_bits"]),
+                                 _lib.ptr(d["mask_off"]),
                                  lo, hi, _lib.ptr(sums), _lib.ptr(live), _lib.ptr(stats), _lib.ptr(ws), ws_bytes,
                                  _lib.stream_ptr()))
     return sums[:n], live[:n]

@@ -19,3 +19,7 @@ for wl in $wls; do
   echo "$wl n=$n rc=$?"; tail -2 $out/${tag}_n${n}_$wl.err | cut -c1-300
   head -c 600 $out/${tag}_n${n}_$wl.json; echo
 done
+port=$((port+1))
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
+    profiles/scripts/h2d_ranks.py > $out/${tag}_n${n}_h2d.json 2> $out/${tag}_n${n}_h2d.err
+echo "h2d n=$n rc=$?"; cat $out/${tag}_n${n}_h2d.json

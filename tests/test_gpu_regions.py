@@ -363,3 +363,18 @@ def test_sharded_containers_add_up_to_the_single_gpu_container(world, cuda_devic
         reads_held += len(ga._local)
     assert total_bins == w["layout"].total_bins and reads_held >= len(hb)
     assert np.array_equal(acc_planes, ref_s) and np.array_equal(acc_direct, ref_s) and np.array_equal(acc_vec, ref_vec)
+
+
+def test_genome_array_get_returns_a_copy_documented_divergence(cuda_device):
+    """The reference's ``GenomeArray.get`` returns a VIEW of the chromosome's numpy array (genome_array.py:1526), so
+    writing into the result changes the array.  Here the planes live in HBM and ``get`` returns a fresh host vector
+    (deliberate divergence): writes go through ``__setitem__``, as the reference's own scripts do."""
+    ga = pb.GenomeArray({"chrA": 1000}, strands=("+", "-"), device=cuda_device)
+    seg = pb.GenomicSegment("chrA", 100, 110, "+")
+    ga[seg] = np.arange(10, dtype=float)
+    got = ga.get(seg)
+    assert (got == np.arange(10)).all()
+    got[:] = 99.0                                        # a view would write through
+    assert (ga.get(seg) == np.arange(10)).all()
+    ga[seg] = got                                        # the supported way to write
+    assert (ga[seg] == 99.0).all() and ga.sum() == 990.0
