@@ -222,8 +222,7 @@ def cpu_reference_pass(hb, lens, table, layout, oracle_kw, size_filter, chrom_id
                     bs.append(table.bstart[a:b] - base)
                     be.append(table.bend[a:b] - base)
                     offs.append(offs[-1] + b - a)
-                coracle.region_sums(vec if vec.dtype == np.float64 else vec.astype(np.uint32),
-                                    np.concatenate(bs), np.concatenate(be), offs)
+                coracle.region_sums(vec, np.concatenate(bs), np.concatenate(be), offs)     # int64 / float64 as the rule returned it
             n_reg += len(sel)
         return int(hb.chrom_read_off[c + 1] - hb.chrom_read_off[c]), n_reg
 

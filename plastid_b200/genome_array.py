@@ -798,14 +798,23 @@ class BAMGenomeArray(object):
     def _filtered(self, hb):
         """``hb`` with the verdicts of the generic (non-size) filters in the drop bit.  Filters that are not
         SizeFilterFactory objects are arbitrary python predicates over reads (genome_array.py:819-820): they cannot
-        be lowered and are evaluated once per read on the host."""
+        be lowered and are evaluated once per read on the host — unless they implement ``batch_mask`` (below)."""
         generic = [f for f in self._filters.values() if not isinstance(f, SizeFilterFactory)]
         if not generic:
             return hb
         keep = np.ones(len(hb), dtype=bool)
-        for i in range(len(hb)):
-            read = hb.read_view(i)
-            keep[i] = all(f(read) for f in generic)
+        # a filter may offer `batch_mask(batch) -> bool[n_reads]` (True = keep) and is then asked once for the whole
+        # batch (numpy over ref_start / aligned_len / is_reverse) instead of once per read
+        slow = []
+        for f in generic:
+            if hasattr(f, "batch_mask"):
+                keep &= np.asarray(f.batch_mask(hb), dtype=bool)
+            else:
+                slow.append(f)
+        if slow:
+            for i in np.nonzero(keep)[0]:
+                read = hb.read_view(int(i))
+                keep[i] = all(f(read) for f in slow)
         out = hb.with_drop_mask(~keep)
         if hb.transfer is not None:
             out.pack()

@@ -30,12 +30,15 @@ def rep(path, out, how):
                     fh.write("%s\t%s\t%s\n" % (h, u, v))
 
 
-def launches(path, out, n_steps, how):
+def launches(path, out, n_steps, how, only="pb_"):
+    """`only`: keep the library's own kernels (the bench generates its synthetic reads with torch kernels first)."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     head = rows[0]
     ik, iv = head.index("Kernel Name"), head.index("Metric Value")
     agg = collections.OrderedDict()
     for r in rows[1:]:
+        if only and only not in r[ik]:
+            continue
         k = re.sub(r"\(.*", "", r[ik]).replace("<unnamed>::", "").replace("void ", "")
         agg.setdefault(k, []).append(float(r[iv].replace(",", "")) / 1000.0)
     total = sum(sum(v) for v in agg.values())

@@ -144,6 +144,26 @@ def _worker(rank, world_size, port, results):
         for batch in (hb, spliced):
             sub, lo, hi = pd.shard_positions(batch, lay, rank, world_size)
             assert (pd.global_length_hist(sub, lay, lo, hi) == meta_length_hist(batch.meta)).all()
+        # the container shards itself when a process group exists (round 2): every rank of the group picks its own
+        # position range — by reads or at chromosome boundaries — keeps the reads that can map into it (+ halo) in the
+        # form the decoder emitted, and knows the length histogram of the WHOLE batch (Center tables)
+        import plastid_b200 as pb2
+        for sharding in ("positions", "chromosomes"):
+            ga = pb2.BAMGenomeArray(hb.pack(), mapping=pb2.FivePrimeMapFactory(14), sharding=sharding)
+            assert (ga._rank, ga._world) == (rank, world_size) and ga.is_sharded and ga._collective
+            lo, hi = ga.bin_range
+            spans = [torch.zeros(2, dtype=torch.int64) for _ in range(world_size)]
+            dist.all_gather(spans, torch.tensor([lo, hi], dtype=torch.int64))
+            spans = sorted((int(a), int(b)) for a, b in (x.tolist() for x in spans))
+            assert spans[0][0] == 0 and spans[-1][1] == ga.layout.total_bins
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))          # the ranges tile the genome
+            if sharding == "chromosomes":
+                assert {lo, hi} <= set(int(x) for x in ga.layout.chrom_bin_off)
+            assert ga._local.transfer is not None and ga.sum() == hb.mapped          # sum() is the whole file's
+            held = torch.tensor([len(ga._local)])
+            dist.all_reduce(held)
+            assert int(held) >= len(hb)
+            assert (ga._global_hist == meta_length_hist(hb.meta)).all()
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()

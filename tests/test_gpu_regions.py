@@ -378,3 +378,33 @@ def test_genome_array_get_returns_a_copy_documented_divergence(cuda_device):
     assert (ga.get(seg) == np.arange(10)).all()
     ga[seg] = got                                        # the supported way to write
     assert (ga[seg] == 99.0).all() and ga.sum() == 990.0
+
+
+def test_vectorised_filters_are_asked_once_per_batch(world, cuda_device):
+    """`add_filter` takes any predicate over reads (genome_array.py:697-722); one that also offers
+    `batch_mask(batch)` is evaluated once for the whole batch — same planes as the per-read evaluation."""
+    w = world
+
+    class ForwardOnlyShort(object):
+        calls = 0
+
+        def __call__(self, read):
+            ForwardOnlyShort.calls += 1
+            return (not read.is_reverse) and len(read.positions) < 30
+
+    class Vectorised(ForwardOnlyShort):
+        def batch_mask(self, batch):
+            return (~batch.is_reverse) & (batch.aligned_len < 30)
+
+    small = pdist.shard_chromosomes(w["hb"], [0])                 # per-read python calls: keep it small
+    a = pb.BAMGenomeArray(small, mapping=pb.FivePrimeMapFactory(3), device=cuda_device)
+    a.add_filter("mine", ForwardOnlyShort())
+    b = pb.BAMGenomeArray(small, mapping=pb.FivePrimeMapFactory(3), device=cuda_device)
+    b.add_filter("mine", Vectorised())
+    before = ForwardOnlyShort.calls
+    pa, pbb = a.count_planes(("+", "-", ".")), b.count_planes(("+", "-", "."))
+    import torch
+    for s in "+-.":
+        assert torch.equal(pa.planes[s], pbb.planes[s])
+    assert ForwardOnlyShort.calls - before == len(small)          # only the first container called per read
+    assert int(pa.planes["-"].sum()) == 0 and int(pa.planes["+"].sum()) > 0
