@@ -15,6 +15,7 @@
 // genome_array.py:811-815.  Query strand '.' applies the FORWARD rule to reads of both strands, so it
 // is its own plane, not '+' + '-'.
 #include "pb_tiles.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -32,7 +33,7 @@ __device__ __forceinline__ void pb_smem_inc(uint32_t *smem, unsigned key)
 constexpr int kPThreads = 256;     // threads per persistent CTA
 constexpr int kPTileBins = 4096;   // bins per tile: 16 KB per plane in shared memory
 constexpr int kPUnroll = 4;        // independent read loads in flight per thread
-constexpr int kPSplit = 32768;     // candidate reads one tile job scans; the rest become overflow jobs
+constexpr int kPSplit = 8192;      // candidate reads one tile job scans; the rest become overflow jobs
 
 struct PbCounters {
     unsigned long long drop_p, drop_m, drop_a, map_p, map_m, map_a;
@@ -312,7 +313,9 @@ extern "C" int pb_map_point_range(const pb_batch *batch, const pb_layout *layout
     }
 
     PB_CUDA_CHECK(cudaMemsetAsync(ws.slots, 0, 2 * pb_ws_stat_bytes() + 64, stream));
-    rc = pb_launch_tile_index(b, lay, kPTileBins, tile_begin, n_tiles, read_limit, kPSplit, ws, stream);
+    // PB_POINT_SPLIT=<reads> (A/B aid): candidate reads a tile keeps before the rest become overflow jobs
+    static const int split = [] { const char *e = getenv("PB_POINT_SPLIT"); int v = e ? atoi(e) : kPSplit; return v >= 2048 ? v : kPSplit; }();
+    rc = pb_launch_tile_index(b, lay, kPTileBins, tile_begin, n_tiles, read_limit, split, ws, stream);
     if (rc) return rc;
     // multi-block (spliced) reads: map them once and bin their sites by tile
     rc = pb_launch_binning(b, r, lay, planes, 0, nullptr, kPTileBins, layout->total_bins / kPTileBins, tile_begin, n_tiles,

@@ -92,7 +92,7 @@ template <> __device__ __forceinline__ void add_group<double>(double &acc, const
 // and mask bits), writes ONE partial sum, and a second tiny launch adds the partial sums of every chain in a fixed
 // order (deterministic for float64 planes too).  block_chain / block_pos come from the host table.
 template <typename T, bool MASK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 pb_block_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
                      const int32_t *__restrict__ block_chain, const int64_t *__restrict__ block_pos,
                      const uint8_t *__restrict__ block_plane, int64_t n_blocks,

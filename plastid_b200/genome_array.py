@@ -696,6 +696,7 @@ class BAMGenomeArray(object):
         self._dbatch = None
         self._full_dbatch = None
         self._receiver = None
+        self._host_batch = None           # this rank's reads with the generic filters' verdicts (evaluated once)
         # Center rule on a sharded array: the aligned-length histogram of the WHOLE batch (every rank derives the same
         # slot tables from it); known here when this object shards the sources itself, handed in with pre-sharded ones
         self._global_hist = kwargs.get("length_hist")
@@ -742,13 +743,13 @@ class BAMGenomeArray(object):
         self._filters[name] = func
         self._planes = None
         if not isinstance(func, SizeFilterFactory):      # size filters are lowered into the kernels; others re-flag reads
-            self._dbatch = self._full_dbatch = self._receiver = None
+            self._dbatch = self._full_dbatch = self._receiver = self._host_batch = None
 
     def remove_filter(self, name):
         retval = self._filters.pop(name)
         self._planes = None
         if not isinstance(retval, SizeFilterFactory):
-            self._dbatch = self._full_dbatch = self._receiver = None
+            self._dbatch = self._full_dbatch = self._receiver = self._host_batch = None
         return retval
 
     def chroms(self):
@@ -820,6 +821,11 @@ class BAMGenomeArray(object):
             out.pack()
         return out
 
+    def _local_filtered(self):
+        if self._host_batch is None:
+            self._host_batch = self._filtered(self._local)
+        return self._host_batch
+
     def _make_receiver(self, hb):
         from .batch import Delta3Receiver, Delta3SplicedBatch, Delta3SplicedReceiver
         cls = Delta3SplicedReceiver if isinstance(hb.transfer, Delta3SplicedBatch) else Delta3Receiver
@@ -829,7 +835,7 @@ class BAMGenomeArray(object):
         """This rank's reads on the device (uploaded once): the transfer format when the batch carries it — expanded
         on the device — else the SoA."""
         if self._dbatch is None:
-            hb = self._host_batch = self._filtered(self._local)
+            hb = self._local_filtered()
             if hb.transfer is not None and len(hb):
                 self._receiver = self._make_receiver(hb)
                 self._dbatch = self._receiver.receive(hb.transfer_pinned())
@@ -886,7 +892,7 @@ class BAMGenomeArray(object):
             self._planes.stats = np.zeros(_lib.PB_NSTATS, dtype=np.int64)
             return self._planes
         if self._dbatch is None:
-            hb = self._host_batch = self._filtered(self._local)
+            hb = self._local_filtered()
             spliced = hb.blk is not None
             # point rules stream unspliced batches, the Center rule streams spliced ones (the cases the range kernels
             # can start on before every read has landed); the other two combinations upload whole, then map
