@@ -64,6 +64,8 @@ def parse_args():
                     help="multi-GPU mode: 'positions' (default; strong scaling of ONE batch: every GPU owns a contiguous bin "
                          "range balanced by read count, SURVEY 8e), 'chromosomes' (the same with cuts on chromosome boundaries, "
                          "BASELINE config 5) or 'reads' (weak scaling: every GPU maps its own batch over the whole genome)")
+    ap.add_argument("--pileup", type=int, default=0,
+                    help="c3 only: this many of the reads lie in the last 16.5 kb of the last chromosome (a chrM-like pile-up in the last tiles)")
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5", "peaks"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
@@ -181,7 +183,8 @@ def build_world(args, rank, device):
         elif wl == "c3":
             n_reads = 100_000_000 if args.reads == 200_000_000 else args.reads
             fac, sf, oracle_kw = pb.CenterMapFactory(12), None, dict(nibble=12)
-            name = "C3: CenterMapFactory(nibble=12), 100-nt reads, 30% one N gap, 3% two"
+            name = "C3: CenterMapFactory(nibble=12), 100-nt reads, 30% one N gap, 3% two" + (
+                ", %d of them piled up in the last 16.5 kb of the genome" % args.pileup if getattr(args, "pileup", 0) else "")
         else:
             n_reads = 500_000_000 if args.reads == 200_000_000 else args.reads
             fac, sf, oracle_kw = pb.ThreePrimeMapFactory(0), pb.SizeFilterFactory(25, 100), dict(rule="threeprime", offset=0)
@@ -190,7 +193,7 @@ def build_world(args, rank, device):
     table = synth.annotation_table(ann, layout)
     seed = 100 + rank if getattr(args, "sharding", "positions") == "reads" else 100     # position sharding: ONE batch on all ranks
     if wl == "c3":
-        dbatch = synth.rnaseq_reads(chroms, lens, n_reads, seed=seed, device=device)
+        dbatch = synth.rnaseq_reads(chroms, lens, n_reads, seed=seed, device=device, pileup=getattr(args, "pileup", 0))
     else:
         dbatch = synth.riboseq_reads(ann, n_reads, seed=seed, device=device, frac_in=0.85 if wl != "c1" else 0.9)
     torch.cuda.synchronize()

@@ -86,7 +86,7 @@ class Tx(Chain):
         self.cds_genome_end = attr.get("cds_genome_end", None)
         self.cds_start = self.cds_end = None
         if self.cds_genome_start is not None and self.cds_genome_end is not None:
-            if self.strand != "-":                                  # _update_cds :3883-3913
+            if self.strand == "+":                                  # _update_cds :3883-3913 ('.' takes the minus branch)
                 self.cds_start = get_segmentchain_coordinate(self, self.cds_genome_start)
                 try:
                     self.cds_end = get_segmentchain_coordinate(self, self.cds_genome_end)

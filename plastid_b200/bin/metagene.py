@@ -17,7 +17,7 @@ from ..map_factories import DataWarning
 from ..masks import GenomeHash, apply_mask_index, mask_intervals_of_chains
 from ..regions import ChainTable
 from ..roitools import GenomicSegment, SegmentChain
-from ..windows import TranscriptTable, landmark_windows, layout_for_features, spanning_windows
+from ..windows import STRAND_CODE, TranscriptTable, landmark_windows, layout_for_features, spanning_windows
 
 _NORM_START_DEFAULT, _NORM_END_DEFAULT = 20, 50      # metagene.py:770-771
 
@@ -96,7 +96,7 @@ def _lower_windows(regions, window_func, flank_upstream, flank_downstream, layou
             roi.strand = region.strand
         rois.append(roi)
     table = TranscriptTable.from_transcripts(rois, layout, [None] * len(rois))
-    table.reverse[:] = [1 if r.strand == "-" else 0 for r in rois]
+    table.reverse[:] = [STRAND_CODE.get(r.strand, 0) for r in rois]
     return table, torch.from_numpy(win).to(device), torch.from_numpy(flags).to(device)
 
 

@@ -131,7 +131,8 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
         const PbTile d = cur.d;
         const uint32_t rec_lo = cur.rec_lo, rec_hi = cur.rec_hi;
         const int64_t g0 = tile * T;
-        const bool has_work = d.n > 0 || rec_hi > rec_lo;
+        // pile-up tile (d.pad > 0): left to the overflow jobs and pb_center_finish_hot_kernel, bins included
+        const bool has_work = d.pad == 0 && (d.n > 0 || rec_hi > rec_lo);
         int *diff = diff_all + (size_t)(k & 1) * n_arrays * T;
         int *tot = tot_all + k3 * n_arrays * nChunks;
         int *tot_next2 = tot_all + (k3 == 0 ? 2 : k3 - 1) * n_arrays * nChunks;   // (k + 2) mod 3
@@ -198,7 +199,7 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
             for (uint32_t j = rec_lo + kCThreads + threadIdx.x; j < rec_hi; j += kCThreads) one_rec(recs[j]);
             // this warp's previous bulk copies must have read its staging segment before it is rewritten
             if (!DIRECT && lane == 0) pb_bulk_wait_read0();
-        } else if (threadIdx.x == 0 && !accumulate) {
+        } else if (threadIdx.x == 0 && !accumulate && d.pad == 0) {
             for (int qq = 0; qq < n_planes; ++qq)
                 for (int z = 0; z < T; z += kZeroBins) pb_bulk_store(outs[qq] + g0 + z, zbuf, kZeroBins * 8);
             pb_bulk_commit();
@@ -239,10 +240,10 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
                                      "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
                                      "@p add.s32 %0, %0, t; }" : "+r"(incl) : "r"(dd));
                     const int before = incl - s4 + carry;     // coverage entering this thread's 4 bins
-                    acc0 += pb_u32_to_f64(before + s1) * w;
-                    acc1 += pb_u32_to_f64(before + s2) * w;
-                    acc2 += pb_u32_to_f64(before + s3) * w;
-                    acc3 += pb_u32_to_f64(before + s4) * w;
+                    acc0 = __fma_rn(pb_u32_to_f64(before + s1), w, acc0);    // (explicit: the finish kernel of the pile-up
+                    acc1 = __fma_rn(pb_u32_to_f64(before + s2), w, acc1);    // tiles must round the same way)
+                    acc2 = __fma_rn(pb_u32_to_f64(before + s3), w, acc2);
+                    acc3 = __fma_rn(pb_u32_to_f64(before + s4), w, acc3);
                 }
                 if (DIRECT) {
                     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
@@ -296,22 +297,24 @@ pb_center_tiles_kernel(PbReads b, PbRuleDev r, int planes_rt,
 // coordinate-sorted, so equal targets come in runs) are summed with a segmented warp scan and the last
 // lane of every run issues ONE atomic.  64-bit shared atomics are CAS loops; in a pile-up tile, where
 // hundreds of reads share a start, this removes the same-address contention.  key < 0 = nothing to add.
-__device__ __forceinline__ void pb_run_add_u64(unsigned long long *arr, int key, unsigned long long w)
+template <typename W>
+__device__ __forceinline__ void pb_run_add(W *arr, int key, W w)
 {
     const int lane = threadIdx.x & 31;
     const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
     bool head = (lane == 0) || (key != kprev);
     const int knext = __shfl_down_sync(0xffffffffu, key, 1);
     const bool tail = (lane == 31) || (knext != key);
-    unsigned long long v = w;
+    W v = w;
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) {
-        const unsigned long long up = __shfl_up_sync(0xffffffffu, v, dd);
+        const W up = __shfl_up_sync(0xffffffffu, v, dd);
         const bool hup = __shfl_up_sync(0xffffffffu, (int)head, dd) != 0;
         if (lane >= dd && !head) { v += up; head = hup; }
     }
-    if (tail && key >= 0 && v != 0ull) atomicAdd(arr + key, v);
+    if (tail && key >= 0 && v != (W)0) atomicAdd(arr + key, v);
 }
+__device__ __forceinline__ void pb_run_add_u64(unsigned long long *arr, int key, unsigned long long w) { pb_run_add<unsigned long long>(arr, key, w); }
 
 constexpr int kCDenseReads = 2048;   // candidate reads per tile from which the aggregated path is used
 
@@ -384,7 +387,7 @@ pb_center_fixed_kernel(PbReads b, PbRuleDev r, int planes_rt,
         const PbTile d = cur.d;
         const uint32_t rec_lo = cur.rec_lo, rec_hi = cur.rec_hi;
         const int64_t g0 = tile * T;
-        const bool has_work = d.n > 0 || rec_hi > rec_lo;
+        const bool has_work = d.pad == 0 && (d.n > 0 || rec_hi > rec_lo);      // pile-up tile: see pb_center_tiles_kernel
         u64 *diff = diff_all + (size_t)(k & 1) * n_planes * T;
         u64 *tot = tot_all + k3 * n_planes * nChunks;
         u64 *tot_next2 = tot_all + (k3 == 0 ? 2 : k3 - 1) * n_planes * nChunks;
@@ -486,7 +489,7 @@ pb_center_fixed_kernel(PbReads b, PbRuleDev r, int planes_rt,
                 if (j < rec_hi) rec = recs[j];
                 one_rec(j < rec_hi, rec);
             }
-        } else if (threadIdx.x == 0) {
+        } else if (threadIdx.x == 0 && d.pad == 0) {
             for (int qq = 0; qq < n_planes; ++qq)
                 for (int z = 0; z < T; z += kZeroBins) pb_bulk_store(outs[qq] + g0 + z, zbuf, kZeroBins * 8);
             pb_bulk_commit();
@@ -537,6 +540,322 @@ pb_center_fixed_kernel(PbReads b, PbRuleDev r, int planes_rt,
     if (threadIdx.x == 0) pb_bulk_wait_all();
 }
 
+// ----------------------------------------------------------------------------------------
+// pile-up tiles (highly expressed genes put 10^5-10^6 reads into one tile; one CTA walking them alone would set
+// the kernel's duration)
+// ----------------------------------------------------------------------------------------
+// The difference arrays are integers, so partial arrays add up exactly.  pb_center_jobs_kernel finds the tiles with
+// more than `split` candidate reads or binned records, cuts ALL their candidates and records into jobs of `split`
+// and gives each such tile a scratch index (PbTile.pad = 1 + index: the tiles kernel leaves the tile alone);
+// pb_center_overflow_kernel (persistent CTAs) accumulates every job in shared memory — equal targets of neighbouring
+// lanes summed in the warp first, the reads of a pile-up share their starts — and reduces it into the tile's scratch
+// difference arrays with TMA bulk reductions (cp.reduce.async.bulk .add.u32 / .add.u64, SASS UBLKRED);
+// pb_center_finish_hot_kernel scans the scratch arrays and writes the tile's bins with the arithmetic of the tiles
+// kernel.  The planes are bit-identical to the unsplit run (test_center_pileup_tiles_are_split_bit_identically).
+constexpr int kCSplit = 8192;          // candidate reads / records per job; more than that in a tile = pile-up
+constexpr int kCHotMax = 8192;         // pile-up tiles with a scratch slot (header: their tile numbers)
+constexpr size_t kCHotHeader = (size_t)kCHotMax * sizeof(long long);
+constexpr int kCHotSlots = 64;         // map lengths per pass the finish kernel keeps carries for
+
+__global__ void pb_center_jobs_kernel(PbTile *__restrict__ tiles, const uint32_t *__restrict__ rec_off, int lookback,
+                                      int tile_bins, int64_t tile_begin, int64_t tile_end, int split,
+                                      PbJob *__restrict__ jobs, long long job_capacity,
+                                      unsigned long long *__restrict__ counters, long long hot_cap,
+                                      long long *__restrict__ hot_tiles)
+{
+    const int64_t t = tile_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tile_end) return;
+    PbTile d = tiles[t];
+    long long nrec = 0;
+    uint32_t rl = 0;
+    if (rec_off) {      // the tile's records: its own bucket and those of up to `lookback` earlier tiles of its chromosome
+        const long long first = t - d.p0 / tile_bins;
+        long long from = t - lookback;
+        if (from < first) from = first;
+        rl = __ldg(rec_off + from);
+        nrec = (long long)__ldg(rec_off + t + 1) - rl;
+    }
+    if (d.n <= split && nrec <= split) return;
+    const long long jr = ((long long)d.n + split - 1) / split, jc = (nrec + split - 1) / split;
+    const long long h = (long long)atomicAdd(counters + 3, 1ull);
+    if (h >= hot_cap) return;                                                // out of scratch: the tile is walked whole
+    const long long at = (long long)atomicAdd(counters + 1, (unsigned long long)(jr + jc));
+    const bool fits = at + jr + jc <= job_capacity;                          // else: empty jobs, tile walked whole
+    for (long long j = 0; j < jr + jc && at + j < job_capacity; ++j) {
+        PbJob jb;
+        const bool reads = j < jr;
+        const long long skip = (long long)split * (reads ? j : j - jr);
+        const long long left = (reads ? (long long)d.n : nrec) - skip;
+        jb.lo = (reads ? d.lo : (long long)rl) + skip;
+        jb.tile = t;
+        jb.n = fits ? (int)(left < split ? left : split) : 0;
+        jb.kind = reads ? 0 : 1;
+        jb.hot = (int)h;
+        jb.pad = 0;
+        jobs[at + j] = jb;
+    }
+    hot_tiles[h] = fits ? (long long)t : -1ll;
+    if (fits) {
+        d.pad = (int)h + 1;
+        tiles[t] = d;
+    }
+}
+
+__global__ void pb_center_zero_hot_kernel(uint4 *__restrict__ scratch, const unsigned long long *__restrict__ counters,
+                                          long long hot_cap, size_t stride16)
+{
+    long long nh = (long long)counters[3];
+    if (nh > hot_cap) nh = hot_cap;
+    const size_t n = (size_t)nh * stride16;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+        scratch[j] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+template <bool FIXED> struct PbCenterWord { typedef int type; };
+template <> struct PbCenterWord<true> { typedef unsigned long long type; };
+
+template <bool FIXED>
+__global__ void __launch_bounds__(kCThreads)
+pb_center_overflow_kernel(PbReads b, PbRuleDev r, int planes, const int16_t *__restrict__ slot_of_len,
+                          const long long *__restrict__ w_fix, int slot0, int n_slots, int T, int skip_multi,
+                          const PbTile *__restrict__ tiles, const PbJob *__restrict__ jobs,
+                          const unsigned long long *__restrict__ counters, long long job_capacity,
+                          unsigned long long *__restrict__ job_counter, const PbRec *__restrict__ recs,
+                          void *__restrict__ hot, size_t hot_stride, unsigned long long *__restrict__ stat_slots)
+{
+    typedef typename PbCenterWord<FIXED>::type W;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ long long s_job;
+    long long n_jobs = (long long)counters[1];
+    if (n_jobs > job_capacity) n_jobs = job_capacity;
+    if (n_jobs == 0) return;
+    const bool want_plus = planes & PB_PLANE_PLUS, want_minus = planes & PB_PLANE_MINUS, want_any = planes & PB_PLANE_ANY;
+    const int n_planes = (int)want_plus + (int)want_minus + (int)want_any;
+    const int n_arrays = n_planes * n_slots;
+    int a_plus = 0, a_minus = 0, a_any = 0;
+    {
+        int k = 0;
+        if (want_plus) a_plus = (k++) * n_slots;
+        if (want_minus) a_minus = (k++) * n_slots;
+        if (want_any) a_any = (k++) * n_slots;
+    }
+    W *diff = reinterpret_cast<W *>(smem_raw);            // [n_arrays][T]: the layout of the tile's scratch
+    const uint32_t n_bytes = (uint32_t)((size_t)n_arrays * T * sizeof(W));
+    const int nibble = r.param;
+    unsigned int drop_p = 0, drop_m = 0, drop_a = 0, map_p = 0, map_m = 0, map_a = 0, drop_len = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_job = (long long)atomicAdd(job_counter, 1ull);
+        {
+            uint4 *s4 = reinterpret_cast<uint4 *>(smem_raw);
+            for (uint32_t j = threadIdx.x; j < n_bytes / 16; j += kCThreads) s4[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        const long long job = s_job;
+        if (job >= n_jobs) break;
+        const PbJob jb = jobs[job];
+        const PbTile d = tiles[jb.tile];
+        const int64_t p0 = d.p0, p1 = d.p0 + T, plim = d.p0 + d.live;
+        for (int base = 0; base < jb.n; base += kCThreads) {         // CTA-uniform trip count
+            const int i = base + (int)threadIdx.x;
+            const bool have = i < jb.n;
+            bool valid = false, rev = false;
+            int64_t x = 0, y = 0;
+            int slot = 0;
+            if (jb.kind == 0) {
+                const int32_t s = have ? __ldg(b.ref_start + jb.lo + i) : 0;
+                const uint32_t m = have ? __ldg(b.meta + jb.lo + i) : (1u << 17);
+                if (pb_passes(m, r.size_min, r.size_max) && !(skip_multi && PB_META_NBLK(m) > 1)) {
+                    const int L = PB_META_L(m);
+                    rev = PB_META_REV(m);
+                    const bool own = (s >= p0 && s < p1);
+                    const int map_len = L - 2 * nibble;
+                    if (map_len < 0) {                                 // map_factories.pyx:246-248
+                        if (own) { drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L; }
+                    } else if (map_len > 0) {
+                        if (own) { map_a++; if (rev) map_m++; else map_p++; }      // reads_out semantics (:256)
+                        slot = (int)__ldg(slot_of_len + L) - slot0;
+                        valid = slot >= 0 && slot < (FIXED ? 32768 : n_slots);     // exact kernel: another pass has the rest
+                        x = (int64_t)s + nibble;
+                        y = (int64_t)s + L - nibble;
+                    }
+                }
+            } else if (have) {
+                const PbRec rec = recs[jb.lo + i];
+                slot = (int)(rec.tag & 0xffffu) - slot0;
+                valid = slot >= 0 && slot < (FIXED ? 32768 : n_slots);
+                rev = (rec.tag >> 16) & 1u;
+                x = rec.x; y = rec.y;
+            }
+            const bool in = valid && !(y <= p0 || x >= plim);
+            const bool has_y = in && y < p1;
+            const int ox = in ? (int)((x > p0 ? x : p0) - p0) : 0, oy = has_y ? (int)(y - p0) : 0;
+            const W w = FIXED ? (W)(in ? __ldg(w_fix + slot) : 0ll) : (W)1;
+            const W nw = (W)0 - w;
+            const int sl = FIXED ? 0 : slot;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const bool wanted = q == 0 ? want_plus : (q == 1 ? want_minus : want_any);
+                if (!wanted) continue;                                  // CTA-uniform
+                const bool mine = q == 0 ? !rev : (q == 1 ? rev : true);
+                const int a = (q == 0 ? a_plus : (q == 1 ? a_minus : a_any)) + sl;
+                pb_run_add<W>(diff, in && mine ? a * T + ox : -1, w);
+                pb_run_add<W>(diff, has_y && mine ? a * T + oy : -1, nw);
+            }
+        }
+        pb_fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned char *dst = reinterpret_cast<unsigned char *>(hot) + (size_t)jb.hot * hot_stride * sizeof(W);
+            for (uint32_t o = 0; o < n_bytes; o += 16384u) {
+                const uint32_t n = n_bytes - o < 16384u ? n_bytes - o : 16384u;
+                if (FIXED) pb_bulk_add_u64(dst + o, smem_raw + o, n);
+                else pb_bulk_add_u32(dst + o, smem_raw + o, n);
+            }
+            pb_bulk_commit();
+            pb_bulk_wait_read0();
+        }
+        __syncthreads();
+    }
+    if (stat_slots) pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
+    if (threadIdx.x == 0) pb_bulk_wait_all();
+}
+
+// One CTA per pile-up tile: scan the tile's scratch difference arrays and write its bins exactly as the tiles kernels
+// do — exact: fma over the pass's map lengths in ascending order, stored (first pass) or added to the plane (later
+// passes); fixed point: total * 2^-shift.  1024 bins per round (a thread owns 4 consecutive bins), the running sums
+// carried from round to round per map length.
+template <bool FIXED>
+__global__ void __launch_bounds__(kCThreads)
+pb_center_finish_hot_kernel(const void *__restrict__ hot, const long long *__restrict__ hot_tiles,
+                            const unsigned long long *__restrict__ counters, long long hot_cap, size_t hot_stride,
+                            int planes, int slot0, int n_slots, const double *__restrict__ inv_m, double scale, int T,
+                            int accumulate, double *__restrict__ out_plus, double *__restrict__ out_minus,
+                            double *__restrict__ out_any)
+{
+    typedef typename PbCenterWord<FIXED>::type W;
+    __shared__ long long s_warp[kCWarps];
+    __shared__ long long s_carry[kCHotSlots];
+    long long nh = (long long)counters[3];
+    if (nh > hot_cap) nh = hot_cap;
+    double *outs[3];
+    int n_planes = 0;
+    if (planes & PB_PLANE_PLUS) outs[n_planes++] = out_plus;
+    if (planes & PB_PLANE_MINUS) outs[n_planes++] = out_minus;
+    if (planes & PB_PLANE_ANY) outs[n_planes++] = out_any;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long h = blockIdx.x; h < nh; h += gridDim.x) {
+        const long long tile = hot_tiles[h];
+        if (tile < 0) continue;
+        const W *A = reinterpret_cast<const W *>(hot) + (size_t)h * hot_stride;
+        for (int qq = 0; qq < n_planes; ++qq) {
+            __syncthreads();
+            if ((int)threadIdx.x < n_slots) s_carry[threadIdx.x] = 0;
+            for (int seg = 0; seg < T; seg += 4 * kCThreads) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int sl = 0; sl < n_slots; ++sl) {
+                    const W *src = A + (size_t)(qq * n_slots + sl) * T + seg + threadIdx.x * 4;
+                    const long long s1 = (long long)src[0], s2 = s1 + (long long)src[1], s3 = s2 + (long long)src[2],
+                                    s4 = s3 + (long long)src[3];
+                    long long incl = s4;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const long long up = __shfl_up_sync(0xffffffffu, incl, dd);
+                        if (lane >= dd) incl += up;
+                    }
+                    __syncthreads();                         // s_warp / s_carry of the previous round have been read
+                    if (lane == 31) s_warp[warp] = incl;
+                    __syncthreads();
+                    long long before = incl - s4 + s_carry[sl], total = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < kCWarps; ++w2) { const long long t2 = s_warp[w2]; total += t2; if (w2 < warp) before += t2; }
+                    if (FIXED) {
+                        acc[0] = (double)(before + s1) * scale; acc[1] = (double)(before + s2) * scale;
+                        acc[2] = (double)(before + s3) * scale; acc[3] = (double)(before + s4) * scale;
+                    } else {
+                        const double w = __ldg(inv_m + slot0 + sl);
+                        acc[0] = __fma_rn(pb_u32_to_f64((int)(before + s1)), w, acc[0]);
+                        acc[1] = __fma_rn(pb_u32_to_f64((int)(before + s2)), w, acc[1]);
+                        acc[2] = __fma_rn(pb_u32_to_f64((int)(before + s3)), w, acc[2]);
+                        acc[3] = __fma_rn(pb_u32_to_f64((int)(before + s4)), w, acc[3]);
+                    }
+                    __syncthreads();                         // everyone has read s_carry[sl]
+                    if (threadIdx.x == 0) s_carry[sl] += total;
+                }
+                double *dst = outs[qq] + tile * (long long)T + seg + threadIdx.x * 4;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dst[e] = accumulate ? dst[e] + acc[e] : acc[e];
+            }
+        }
+    }
+}
+
+int pb_center_split()
+{
+    // PB_CENTER_SPLIT=<reads> (tests, A/B): candidates / records per job; 0 = never split
+    if (const char *e = getenv("PB_CENTER_SPLIT")) { const int v = atoi(e); return v <= 0 ? 0x7fffffff : (v < 256 ? 256 : v); }
+    return kCSplit;
+}
+
+// scratch slots that fit behind the header of tile numbers, given the bytes of one tile's arrays
+long long pb_center_hot_cap(const PbWorkspace &ws, size_t tile_bytes, int slots_per_pass)
+{
+    if (ws.hot_bytes <= kCHotHeader || slots_per_pass > kCHotSlots || pb_center_split() == 0x7fffffff) return 0;
+    const long long cap = (long long)((ws.hot_bytes - kCHotHeader) / tile_bytes);
+    return cap < kCHotMax ? cap : kCHotMax;
+}
+
+// after the tile index and the binning: find the pile-up tiles, cut their candidates and records into jobs
+int pb_launch_center_jobs(const PbWorkspace &ws, int lookback, int tile_bins, int64_t tile_lo, int64_t tile_hi,
+                          long long hot_cap, cudaStream_t stream)
+{
+    if (tile_hi <= tile_lo || hot_cap < 1) return PB_OK;
+    pb_center_jobs_kernel<<<(unsigned)((tile_hi - tile_lo + 255) / 256), 256, 0, stream>>>(
+        ws.tiles, ws.rec_off, lookback, tile_bins, tile_lo, tile_hi, pb_center_split(), ws.jobs, (long long)ws.job_capacity,
+        ws.tile_counter, hot_cap, reinterpret_cast<long long *>(ws.hot));
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+// every pass, before the tiles kernel: clear the scratch of the pile-up tiles, run the overflow jobs of the pass
+template <bool FIXED>
+int pb_launch_center_overflow(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const long long *w_fix,
+                              int s0, int ns, int T, const PbWorkspace &ws, long long hot_cap, size_t hot_stride, bool stats,
+                              int sm_count, cudaStream_t stream)
+{
+    typedef typename PbCenterWord<FIXED>::type W;
+    if (hot_cap < 1) return PB_OK;
+    unsigned char *arrays = reinterpret_cast<unsigned char *>(ws.hot) + kCHotHeader;
+    PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter + 2, 0, 8, stream));
+    pb_center_zero_hot_kernel<<<(unsigned)(sm_count * 4), 256, 0, stream>>>(reinterpret_cast<uint4 *>(arrays), ws.tile_counter, hot_cap,
+                                                                           hot_stride * sizeof(W) / 16);
+    const size_t smem = hot_stride * sizeof(W);
+    auto kern = pb_center_overflow_kernel<FIXED>;
+    PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCThreads, smem));
+    if (occ < 1) occ = 1;
+    kern<<<(unsigned)(sm_count * occ), kCThreads, smem, stream>>>(
+        b, r, planes, slot_of_len, w_fix, s0, ns, T, b.n_blk > 0, ws.tiles, ws.jobs, ws.tile_counter, (long long)ws.job_capacity,
+        ws.tile_counter + 2, ws.recs, arrays, hot_stride, stats ? ws.slots : nullptr);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+// every pass, after (or beside) the tiles kernel: the bins of the pile-up tiles
+template <bool FIXED>
+int pb_launch_center_finish(int planes, int s0, int ns, const double *inv_m, double scale, int T, int accumulate,
+                            const PbWorkspace &ws, long long hot_cap, size_t hot_stride, int sm_count,
+                            double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+{
+    if (hot_cap < 1) return PB_OK;
+    const unsigned char *arrays = reinterpret_cast<const unsigned char *>(ws.hot) + kCHotHeader;
+    pb_center_finish_hot_kernel<FIXED><<<(unsigned)(sm_count * 2), kCThreads, 0, stream>>>(
+        arrays, reinterpret_cast<const long long *>(ws.hot), ws.tile_counter, hot_cap, hot_stride, planes, s0, ns, inv_m, scale, T,
+        accumulate, out_plus, out_minus, out_any);
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
 // staging + zero block + double-buffered difference arrays + three rotating copies of the segment sums
 size_t pb_center_smem_bytes(int n_planes, int n_slots, int tile_bins, bool direct)
 {
@@ -547,11 +866,18 @@ size_t pb_center_smem_bytes(int n_planes, int n_slots, int tile_bins, bool direc
 template <int EPT, bool DIRECT, int PLANES, bool ONE_SLOT>
 int launch_center_kernel(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
                          int s0, int ns, int pass, int lookback, int64_t tile_begin, int64_t n_tiles, int sm_count,
-                         const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+                         const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream,
+                         long long hot_cap)
 {
     constexpr int T = EPT * kCThreads;
     const int n_planes = __builtin_popcount(planes);
     const size_t smem = pb_center_smem_bytes(n_planes, ns, T, DIRECT);
+    // pile-up tiles: overflow jobs leave the difference arrays of this pass's map lengths in the scratch
+    const int hns = ns < 1 ? 1 : ns;
+    const size_t hot_stride = (size_t)n_planes * hns * T;
+    int rc = pb_launch_center_overflow<false>(b, r, planes, slot_of_len, nullptr, s0, hns, T, ws, hot_cap, hot_stride,
+                                              pass == 0, sm_count, stream);
+    if (rc) return rc;
     auto kern = pb_center_tiles_kernel<EPT, DIRECT, PLANES, ONE_SLOT>;
     PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -559,13 +885,14 @@ int launch_center_kernel(const PbReads &b, const PbRuleDev &r, int planes, const
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)sm_count * occ;
     if (grid > n_tiles - tile_begin) grid = n_tiles - tile_begin;
-    PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 64, stream));
+    PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 8, stream));
     // statistics are accumulated by the first pass only (later passes see the same reads again)
     kern<<<(unsigned)grid, kCThreads, smem, stream>>>(
         b, r, planes, slot_of_len, inv_m, s0, ns, pass > 0, lookback, ws.tiles, tile_begin, n_tiles, ws.tile_counter,
         ws.rec_off, ws.recs, out_plus, out_minus, out_any, pass == 0 ? ws.slots : nullptr);
     PB_CUDA_CHECK(cudaGetLastError());
-    return PB_OK;
+    return pb_launch_center_finish<false>(planes, s0, ns, inv_m, 0.0, T, pass > 0, ws, ns < 1 ? 0 : hot_cap, hot_stride, sm_count,
+                                          out_plus, out_minus, out_any, stream);
 }
 
 // specialised instantiations exist for the direct-store kernel on 2048-bin tiles with one map length
@@ -573,9 +900,10 @@ int launch_center_kernel(const PbReads &b, const PbRuleDev &r, int planes, const
 template <int EPT, bool DIRECT>
 int launch_center_pass(const PbReads &b, const PbRuleDev &r, int planes, const int16_t *slot_of_len, const double *inv_m,
                        int s0, int ns, int pass, int lookback, int64_t tile_begin, int64_t n_tiles, int sm_count,
-                       const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
+                       const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream,
+                       long long hot_cap)
 {
-#define PB_CENTER_ARGS b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, tile_begin, n_tiles, sm_count, ws, out_plus, out_minus, out_any, stream
+#define PB_CENTER_ARGS b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, tile_begin, n_tiles, sm_count, ws, out_plus, out_minus, out_any, stream, hot_cap
     if (EPT == 8 && DIRECT && ns == 1 && !getenv("PB_CENTER_GENERIC")) {
         if (planes == (PB_PLANE_PLUS | PB_PLANE_MINUS)) return launch_center_kernel<8, true, PB_PLANE_PLUS | PB_PLANE_MINUS, true>(PB_CENTER_ARGS);
         if (planes == PB_PLANE_ANY) return launch_center_kernel<8, true, PB_PLANE_ANY, true>(PB_CENTER_ARGS);
@@ -590,9 +918,15 @@ int launch_center(const PbReads &b, const PbRuleDev &r, int planes, const int16_
                   int n_slots, int per_pass, int lookback, int64_t bin_begin, int64_t bin_end, bool direct_ok,
                   const PbWorkspace &ws, double *out_plus, double *out_minus, double *out_any, cudaStream_t stream)
 {
-    const int64_t tile_begin = bin_begin / (EPT * kCThreads), n_tiles = bin_end / (EPT * kCThreads);   // n_tiles = end
+    constexpr int T = EPT * kCThreads;
+    const int64_t tile_begin = bin_begin / T, n_tiles = bin_end / T;   // n_tiles = end
     int sm_count = 0;
     int rc = pb_sm_count(&sm_count);
+    if (rc) return rc;
+    // pile-up tiles: scratch arrays sized for the widest pass (no map length in the batch: nothing to split)
+    const int pp = per_pass < 1 ? 1 : per_pass;
+    const long long hot_cap = n_slots < 1 ? 0 : pb_center_hot_cap(ws, (size_t)__builtin_popcount(planes) * pp * T * sizeof(int), pp);
+    rc = pb_launch_center_jobs(ws, lookback, T, tile_begin, n_tiles, hot_cap, stream);
     if (rc) return rc;
     for (int s0 = 0, pass = 0; s0 < n_slots || pass == 0; s0 += per_pass, ++pass) {
         int ns = n_slots - s0 < per_pass ? n_slots - s0 : per_pass;
@@ -600,10 +934,10 @@ int launch_center(const PbReads &b, const PbRuleDev &r, int planes, const int16_
         // the first pass stores every bin (direct 256-bit stores when allowed); later passes add to them
         if (pass == 0 && direct_ok)
             rc = launch_center_pass<EPT, true>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, tile_begin, n_tiles,
-                                               sm_count, ws, out_plus, out_minus, out_any, stream);
+                                               sm_count, ws, out_plus, out_minus, out_any, stream, hot_cap);
         else
             rc = launch_center_pass<EPT, false>(b, r, planes, slot_of_len, inv_m, s0, ns, pass, lookback, tile_begin, n_tiles,
-                                                sm_count, ws, out_plus, out_minus, out_any, stream);
+                                                sm_count, ws, out_plus, out_minus, out_any, stream, hot_cap);
         if (rc) return rc;
         if (n_slots == 0) break;
     }
@@ -732,11 +1066,20 @@ int launch_center_fixed(const PbReads &b, const PbRuleDev &r, int planes, const 
     if (rc) return rc;
     int64_t grid = (int64_t)sm_count * occ;
     if (grid > n_tiles - tile_begin) grid = n_tiles - tile_begin;
-    PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 64, stream));
+    // pile-up tiles: jobs, then their partial 64-bit difference arrays, then the tiles
+    constexpr int T = 8 * kCThreads;
+    const size_t hot_stride = (size_t)__builtin_popcount(planes) * T;
+    const long long hot_cap = pb_center_hot_cap(ws, hot_stride * sizeof(unsigned long long), 1);
+    rc = pb_launch_center_jobs(ws, lookback, T, tile_begin, n_tiles, hot_cap, stream);
+    if (rc) return rc;
+    rc = pb_launch_center_overflow<true>(b, r, planes, slot_of_len, w_fix, 0, 1, T, ws, hot_cap, hot_stride, true, sm_count, stream);
+    if (rc) return rc;
+    PB_CUDA_CHECK(cudaMemsetAsync(ws.tile_counter, 0, 8, stream));
     kern<<<(unsigned)grid, kCThreads, smem, stream>>>(b, r, planes, slot_of_len, w_fix, scale, lookback, ws.tiles, tile_begin, n_tiles,
                                                       ws.tile_counter, ws.rec_off, ws.recs, out_plus, out_minus, out_any, ws.slots);
     PB_CUDA_CHECK(cudaGetLastError());
-    return PB_OK;
+    return pb_launch_center_finish<true>(planes, 0, 1, nullptr, scale, T, 0, ws, hot_cap, hot_stride, sm_count, out_plus, out_minus,
+                                         out_any, stream);
 }
 }  // namespace
 

@@ -608,18 +608,50 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
                 if ((plane == 0 && rev) || (plane == 1 && !rev)) continue;    // genome_array.py:811-815
                 const int L = PB_META_L(m);
                 if (L < min_len || L >= min_len + n_len) continue;           // psite.py:187: len(positions) in read_dict
+                // phase mode: the reference does not reset its per-length read lists between the exons of a coding
+                // region (phase_by_size.py:186-194), so a read that the fetch of an EARLIER exon of this chain returned
+                // too — its span reaches back over that exon's end — is mapped once more against this exon per such exon
+                uint32_t mult = 1;
+                if (phase_mode)
+                    for (int64_t j = k - 1; j >= k0 && __ldg(bend + j) - base > (int64_t)sv[u]; --j) ++mult;
+                auto add_site = [&](int64_t p) {
+                    if (base + p < lo_bin || base + p >= hi_bin) return;         // the site belongs to another rank
+                    const int64_t jj = j0 + (p - bs);
+                    int64_t col = col0 + (rev_out ? (len - 1 - jj) : jj);
+                    if (phase_mode) {
+                        const int64_t cod = col / 3;
+                        col = (cod >= cod_lo && cod < cod_hi) ? col - cod * 3 : -1;
+                    }
+                    if (col >= 0 && col < width) atomicAdd(&hist[(L - min_len) * width + (int)col], mult);
+                };
+                if (r.kind == PB_RULE_CENTER) {
+                    // phase mode only: every trimmed aligned position of the read inside this exon counts `mult`
+                    // times 1/(L - 2 nibble); the cell holds the integer, the host applies the weight of its length
+                    const int nib = r.param;
+                    if (L - 2 * nib <= 0) continue;                              // map_factories.pyx:246-248
+                    auto add_range = [&](int64_t x, int64_t y) {
+                        if (x < bs) x = bs;
+                        if (y > be) y = be;
+                        for (int64_t p = x; p < y; ++p) add_site(p);
+                    };
+                    if (PB_META_NBLK(m) <= 1 || b.blk_off == nullptr) {
+                        add_range((int64_t)sv[u] + nib, (int64_t)sv[u] + L - nib);
+                    } else {
+                        int a = 0;
+                        for (uint32_t q = __ldg(b.blk_off + i), q1 = __ldg(b.blk_off + i + 1); q < q1; ++q) {
+                            const int2 bl = __ldg(b.blk + q);
+                            const int ia = a > nib ? a : nib, ib = (a + bl.y) < (L - nib) ? (a + bl.y) : (L - nib);
+                            if (ia < ib) add_range((int64_t)sv[u] + bl.x + (ia - a), (int64_t)sv[u] + bl.x + (ib - a));
+                            a += bl.y;
+                        }
+                    }
+                    continue;
+                }
                 const int idx = pb_rule_index(r, L, rq);
                 if (idx < 0) continue;
                 const int64_t p = pb_position(b, i, sv[u], m, idx);
                 if (p < bs || p >= be) continue;
-                if (base + p < lo_bin || base + p >= hi_bin) continue;        // the site belongs to another rank
-                const int64_t jj = j0 + (p - bs);
-                int64_t col = col0 + (rev_out ? (len - 1 - jj) : jj);
-                if (phase_mode) {
-                    const int64_t cod = col / 3;
-                    col = (cod >= cod_lo && cod < cod_hi) ? col - cod * 3 : -1;
-                }
-                if (col >= 0 && col < width) atomicAdd(&hist[(L - min_len) * width + (int)col], 1u);
+                add_site(p);
             }
         }
         j0 += be - bs;
@@ -658,8 +690,9 @@ extern "C" int pb_stratified_windows_range(const pb_batch *batch, const pb_layou
     if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !chain_reverse || !out ||
         (!phase_mode && (!row_col || !maskmat))) { pb_set_error("pb_stratified_windows: null argument"); return PB_EINVAL; }
     if (phase_mode) width = 3;
-    if (rule->kind != PB_RULE_FIVEPRIME && rule->kind != PB_RULE_THREEPRIME && rule->kind != PB_RULE_VARIABLE) {
-        pb_set_error("pb_stratified_windows: needs a point rule"); return PB_EINVAL;
+    if (rule->kind != PB_RULE_FIVEPRIME && rule->kind != PB_RULE_THREEPRIME && rule->kind != PB_RULE_VARIABLE &&
+        !(rule->kind == PB_RULE_CENTER && phase_mode && rule->param >= 0)) {
+        pb_set_error("pb_stratified_windows: needs a point rule (phase mode: or the center rule)"); return PB_EINVAL;
     }
     if (rule->kind == PB_RULE_VARIABLE && (!rule->lut_fw || !rule->lut_rc)) { pb_set_error("pb_stratified_windows: variable rule needs LUTs"); return PB_EINVAL; }
     if (max_len < min_len || min_len < 0 || width <= 0 || n_chains < 0) { pb_set_error("pb_stratified_windows: bad sizes"); return PB_EINVAL; }

@@ -46,7 +46,7 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
             jb.lo = lo + split + j * split;
             jb.tile = t;
             jb.n = (int)(rest - j * split < split ? rest - j * split : split);
-            jb.pad[0] = jb.pad[1] = jb.pad[2] = 0;
+            jb.kind = jb.hot = jb.pad = 0;
             jobs[at + j] = jb;
         }
         d.n = split;
@@ -335,14 +335,23 @@ static size_t ws_part_bytes(int64_t total_bins) { return (((size_t)(total_bins /
 static size_t ws_idx_bytes(int64_t total_bins) { return (((size_t)(total_bins / 1024 + 2) * sizeof(uint32_t)) + 255) & ~(size_t)255; }
 
 // every candidate read appears in at most two tiles' windows, so sum(n)/split + one per tile bounds
-// the overflow jobs; split is never below 4096 reads
-static int64_t ws_job_capacity(int64_t total_bins, int64_t n_reads) { return 2 * n_reads / 4096 + 1024; }
+// the overflow jobs; split is never below 4096 reads.  The Center rule also cuts the binned records of a tile
+// into jobs (a record is seen by 1 + lookback tiles); a pile-up tile whose jobs do not fit is walked whole.
+static int64_t ws_job_capacity(int64_t total_bins, int64_t n_reads, int64_t n_blk) { return 2 * n_reads / 4096 + 4 * n_blk / 4096 + 1024; }
+// Center rule, pile-up tiles: integer partial difference arrays (16-100 KB per tile); tiles beyond the scratch are
+// walked whole by their CTA
+static size_t ws_hot_bytes(int64_t n_reads, int64_t n_blk)
+{
+    const size_t want = ((size_t)2 << 20) + (size_t)(n_reads + n_blk) * 4;
+    return (want < ((size_t)64 << 20) ? want : ((size_t)64 << 20)) & ~(size_t)255;
+}
 
 extern "C" size_t pb_map_workspace_bytes(int64_t total_bins, int64_t n_blk, int64_t n_reads)
 {
     if (total_bins < 0 || n_blk < 0 || n_reads < 0) return 0;
     size_t bytes = pb_ws_tile_bytes(total_bins) + 2 * pb_ws_stat_bytes() + 256;
-    bytes += (size_t)ws_job_capacity(total_bins, n_reads) * sizeof(PbJob);
+    bytes += (size_t)ws_job_capacity(total_bins, n_reads, n_blk) * sizeof(PbJob);
+    bytes += ws_hot_bytes(n_reads, n_blk) + 256;
     if (n_blk > 0) bytes += 2 * ws_idx_bytes(total_bins) + ws_part_bytes(total_bins) + (size_t)n_blk * sizeof(PbRec);
     return bytes + 256;
 }
@@ -355,8 +364,11 @@ int pb_carve_workspace(void *base, size_t bytes, int64_t total_bins, int64_t n_b
     ws->tiles = (PbTile *)p;                     p += pb_ws_tile_bytes(total_bins);
     ws->slots = (unsigned long long *)p;         p += 2 * pb_ws_stat_bytes();
     ws->tile_counter = (unsigned long long *)p;  p += 256;
-    ws->job_capacity = ws_job_capacity(total_bins, n_reads);
+    ws->job_capacity = ws_job_capacity(total_bins, n_reads, n_blk);
     ws->jobs = (PbJob *)p;                       p += (size_t)ws->job_capacity * sizeof(PbJob);
+    p = (char *)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+    ws->hot = p;                                 ws->hot_bytes = ws_hot_bytes(n_reads, n_blk);
+    p += ws->hot_bytes;
     ws->rec_off = ws->rec_cursor = ws->scan_part = nullptr;
     ws->recs = nullptr;
     if (n_blk > 0) {

@@ -24,24 +24,30 @@ struct __align__(16) PbRec {
     uint32_t pad;
 };
 
-// Overflow job of the point kernel: candidate reads [lo, lo+n) of `tile` beyond the tile job's share.
+// Overflow job: candidate reads [lo, lo+n) of `tile` beyond the tile job's share (point kernel: kind 0 only).
+// Center kernels: kind 0 = candidate reads, kind 1 = binned records [lo, lo+n); hot = index of the tile's scratch
+// arrays (partial difference arrays the jobs reduce into, read back by the tile's own CTA).
 struct __align__(16) PbJob {
     long long lo;
     long long tile;
     int n;
-    int pad[3];
+    int kind;
+    int hot;
+    int pad;
 };
 
 struct PbWorkspace {
     PbTile *tiles;                  // [total_bins/1024 + 1]
     unsigned long long *slots;      // [2][kStatSlots][PB_NSTATS] (second copy: scratch for repeat passes)
-    unsigned long long *tile_counter;  // [0] tile queue, [1] number of overflow jobs, [2] overflow queue
+    unsigned long long *tile_counter;  // [0] tile queue, [1] number of overflow jobs, [2] overflow queue, [3] pile-up tiles
     PbJob *jobs;                    // [job_capacity]
     int64_t job_capacity;
     uint32_t *rec_off;              // [n_tiles + 1] exclusive offsets of the per-tile record buckets
     uint32_t *rec_cursor;           // [n_tiles + 1] counts, then fill cursors
     uint32_t *scan_part;            // per-4096-tile partial sums of the offset scan
     PbRec *recs;                    // [n_blk]
+    void *hot;                      // scratch of the Center rule's pile-up tiles (integer partial difference arrays)
+    size_t hot_bytes;
 };
 
 size_t pb_ws_tile_bytes(int64_t total_bins);
@@ -90,6 +96,12 @@ __device__ __forceinline__ void pb_bulk_add_f64(void *gdst, const void *ssrc, ui
 __device__ __forceinline__ void pb_bulk_add_u32(void *gdst, const void *ssrc, uint32_t bytes)
 {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+// global[dst] += shared[src] elementwise in 64-bit integers (two's complement: serves signed sums too)
+__device__ __forceinline__ void pb_bulk_add_u64(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;"
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void pb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

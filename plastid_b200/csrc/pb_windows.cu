@@ -16,7 +16,7 @@ struct TxTable {
     const int64_t *__restrict__ bend;
     const int64_t *__restrict__ bcum;     // chain coordinate of each block's first base (genomic order)
     const int64_t *__restrict__ tx_off;   // blocks of transcript t: [tx_off[t], tx_off[t+1])
-    const uint8_t *__restrict__ reverse;  // 1 = '-' strand
+    const uint8_t *__restrict__ reverse;  // 0 '+', 1 '-', 2 '.': coordinates run like '+', window columns are laid like '-'
 };
 
 __device__ __forceinline__ int64_t tx_length(const TxTable &tx, int64_t t)
@@ -29,7 +29,7 @@ __device__ __forceinline__ int64_t tx_length(const TxTable &tx, int64_t t)
 // SegmentChain.c_get_genomic_coordinate (roitools.pyx:3055-3119) for 0 <= x < length, stranded
 __device__ __forceinline__ int64_t tx_genomic(const TxTable &tx, int64_t t, int64_t x, int64_t length)
 {
-    if (__ldg(tx.reverse + t)) x = length - 1 - x;
+    if (__ldg(tx.reverse + t) == 1) x = length - 1 - x;
     int64_t lo = __ldg(tx.tx_off + t), hi = __ldg(tx.tx_off + t + 1);   // invariant: bcum[lo] <= x < bcum[hi]
     while (hi - lo > 1) {
         const int64_t mid = (lo + hi) >> 1;
@@ -122,8 +122,9 @@ pb_spanning_windows_kernel(TxTable tx, const int64_t *__restrict__ win, const ui
                     const int64_t t = __ldg(grp_tx + i);
                     const int64_t w_start = __ldg(win + 4 * t + 0), w_end = __ldg(win + 4 * t + 1);
                     const int64_t w_off = __ldg(win + 4 * t + 2);
-                    const int64_t x = w_start + ((int64_t)c - w_off);
-                    if ((int64_t)c < w_off || x >= w_end) { shared = false; break; }
+                    // unstranded rows hold their window's positions back to front (metagene.py:450-455)
+                    const int64_t x = rev0 == 2 ? w_end - 1 - ((int64_t)c - w_off) : w_start + ((int64_t)c - w_off);
+                    if ((int64_t)c < w_off || (int64_t)c - w_off >= w_end - w_start) { shared = false; break; }
                     const int64_t p = tx_genomic(tx, t, x, tx_length(tx, t));
                     if (i == i0) pos = p; else if (p != pos) shared = false;
                 }
@@ -138,8 +139,11 @@ pb_spanning_windows_kernel(TxTable tx, const int64_t *__restrict__ win, const ui
                 const unsigned b_start = __ballot_sync(0xffffffffu, is_start);
                 const unsigned b_end = __ballot_sync(0xffffffffu, is_end);
                 n_pos += __popc(b_shared);
-                zero_before += __popc(__ballot_sync(0xffffffffu, shared && c < up));
-                zero_shared |= __any_sync(0xffffffffu, shared && c == up);
+                // get_segmentchain_coordinate of the landmark in the new window (:498): columns before the zero point
+                // — for an unstranded window its coordinates run left to right while the columns run right to left,
+                // so it is the shared positions LEFT of the landmark that count
+                zero_before += __popc(__ballot_sync(0xffffffffu, shared && (rev0 == 2 ? pos < ref0 : c < up)));
+                zero_shared |= __any_sync(0xffffffffu, shared && (rev0 == 2 ? pos == ref0 : c == up));
                 if (FILL) {
                     // runs come out in column order = 5'->3'; blocks are stored in genomic order
                     if (is_start) {

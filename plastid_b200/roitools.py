@@ -326,7 +326,7 @@ class Transcript(SegmentChain):
     def _update_cds(self):
         gs, ge = int(self.cds_genome_start), int(self.cds_genome_end)
         coord = lambda x: self.get_segmentchain_coordinate(self.chrom, x, self.strand)   # noqa: E731
-        if self.strand != "-":
+        if self.strand == "+":                       # roitools.pyx:3896: an unstranded transcript takes the minus branch
             self.cds_start = coord(gs)
             try:
                 self.cds_end = coord(ge)

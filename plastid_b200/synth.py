@@ -186,8 +186,10 @@ def _finish(chroms, chrom_len, chrom, start, L, rev, device, blocks=None):
 
 
 def rnaseq_reads(chroms, chrom_len, n_reads, seed=0, device="cpu", read_len=100, one_gap=0.30, two_gaps=0.03,
-                 intron=(100, 50000)):
-    """100-nt RNA-seq-like reads, some with one or two ``N`` gaps (BASELINE config 3)."""
+                 intron=(100, 50000), pileup=0):
+    """100-nt RNA-seq-like reads, some with one or two ``N`` gaps (BASELINE config 3).  ``pileup``: that many of
+    the reads lie in the last 16.5 kb of the LAST chromosome — what the mitochondrial genome (chrM, last in hg38 order, 10-30 %
+    of the reads of an RNA-seq library) does to the tiles the mapping kernels reach last."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     clen = torch.tensor(np.asarray(chrom_len), dtype=torch.int64, device=device)
@@ -215,6 +217,12 @@ def rnaseq_reads(chroms, chrom_len, n_reads, seed=0, device="cpu", read_len=100,
     start = (torch.rand(n_reads, generator=gen, device=device, dtype=torch.float64)
              * (clen[chrom] - span - 1).clamp(min=1).double()).long()
     rev = torch.randint(0, 2, (n_reads,), generator=gen, device=device)
+    if pileup:
+        k = min(int(pileup), n_reads)
+        chrom[:k] = len(chroms) - 1
+        nb[:k] = 1
+        last = int(clen[-1].item())
+        start[:k] = last - 16_700 + torch.randint(0, 16_500, (k,), generator=gen, device=device)
     return _finish(chroms, clen, chrom, start, L, rev, device, blocks=(nb, rel, ln))
 
 

@@ -30,6 +30,12 @@ def layout_for_features(*feature_lists):
     return GenomeLayout(chroms, [extent[c] for c in chroms])
 
 
+# per-transcript orientation byte of the window kernels: 0 '+', 1 '-' (coordinates run right to left), 2 '.' —
+# coordinates run left to right like '+', but the reference lays the window's columns right to left like '-'
+# (metagene.py:443-455 tests `strand == "+"`), and so do the kernels
+STRAND_CODE = {"+": 0, "-": 1, ".": 2}
+
+
 class TranscriptTable(object):
     """Flat block table of transcripts in the global-bin coordinates of ``layout``: the input of
     ``pb_landmark_windows`` / ``pb_spanning_windows``."""
@@ -66,14 +72,12 @@ class TranscriptTable(object):
         """``landmarks[i]``: transcript coordinate of transcript i's landmark, or None."""
         bstart, bend, tx_off, reverse, lm, chrom = [], [], [0], [], [], []
         for tx, mark in zip(transcripts, landmarks):
-            if len(tx) and tx.strand not in ("+", "-"):
-                raise ValueError("Transcript %s is unstranded; maximal spanning windows need '+' or '-'" % tx.get_name())
             base = int(layout.chrom_bin_off[layout.index[tx.chrom]]) if len(tx) else 0
             for seg in tx:
                 bstart.append(base + seg.start)
                 bend.append(base + seg.end)
             tx_off.append(len(bstart))
-            reverse.append(1 if tx.strand == "-" else 0)
+            reverse.append(STRAND_CODE.get(tx.strand, 0))
             lm.append(-1 if mark is None else int(mark))
             chrom.append(layout.index[tx.chrom] if len(tx) else -1)
         return cls(layout, bstart, bend, tx_off, reverse, lm, chrom)

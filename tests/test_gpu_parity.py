@@ -687,6 +687,72 @@ def test_center_many_lengths_and_pileup_tiles(cuda_device, monkeypatch, exact):
         assert torch.equal(again.planes[s], first[s])
 
 
+def _pileup_batch(rng, lengths, n_hot=70_000, n_bg=15_000):
+    """Reads piled up on two places of chromosome `a` (one of them across a tile boundary), a third of them spliced
+    with their second block landing in ANOTHER pile (binned records), plus background."""
+    chroms, lens = ["a", "b"], np.array([80_000, 9_000])
+    start = np.concatenate([rng.integers(5000, 5150, n_hot), rng.integers(2040, 2060, n_hot // 2),
+                            rng.integers(0, 69_000, n_bg), rng.integers(0, 8_800, 3000)])
+    cid = np.concatenate([np.zeros(n_hot + n_hot // 2 + n_bg, dtype=int), np.ones(3000, dtype=int)])
+    n = len(start)
+    L = rng.choice(np.asarray(lengths), n)
+    rev = rng.integers(0, 2, n)
+    spliced = rng.random(n) < 0.33
+    cut = np.minimum(rng.integers(5, 30, n), L - 3)
+    gap = np.where(cid == 0, rng.integers(9000, 9040, n), rng.integers(30, 60, n))     # pile -> pile at +9000
+    nb = np.where(spliced, 2, 1)
+    rows = []
+    for i in range(n):
+        if spliced[i]:
+            rows.append((0, cut[i])); rows.append((cut[i] + gap[i], L[i] - cut[i]))
+        else:
+            rows.append((0, L[i]))
+    hb = pb.batch_from_arrays(chroms, lens, cid, start, L, rev, blocks=(nb, np.asarray(rows, dtype=np.int32)))
+    return chroms, lens, hb
+
+
+@pytest.mark.parametrize("mode", ["one_length", "fixed_point", "exact_multi"])
+def test_center_pileup_tiles_are_split_bit_identically(cuda_device, monkeypatch, mode):
+    """Pile-up tiles of the Center rule: candidate reads AND binned records of a tile beyond the split
+    become overflow jobs whose integer partial difference arrays are reduced into a scratch tile.  Planes and
+    statistics are bit-identical to the unsplit run for the exact kernel (one map length / several passes) and the
+    64-bit fixed-point kernel, with small and default splits, whole genome and as bin ranges; and right against the oracle."""
+    import torch
+    rng = np.random.default_rng(17)
+    lengths = [40] if mode == "one_length" else list(range(24, 45))
+    if mode == "exact_multi":
+        monkeypatch.setenv("PB_CENTER_EXACT", "1")
+    chroms, lens, hb = _pileup_batch(rng, lengths)
+    assert hb.blk is not None
+    layout = pb.GenomeLayout(chroms, lens)
+    fac = pb.CenterMapFactory(12)
+    db = hb.to_device(cuda_device)
+    monkeypatch.setenv("PB_CENTER_SPLIT", "0")                     # never split: one CTA walks every pile
+    ref = map_batch(db, layout, fac, None, strands=("+", "-", "."))
+    ref2 = map_batch(db, layout, fac, None, strands=("+", "-"))   # (several passes group the map lengths by plane count)
+    ref_r = map_batch(db, layout, fac, None, strands=("+", "."))
+    exp = coracle.genome_vector(hb, 0, "+", nibble=12)[0]
+    got = plane_chrom(ref, layout, "+", 0)
+    assert ((got == 0) == (exp == 0)).all()
+    np.testing.assert_allclose(got, exp, rtol=CENTER_RTOL, atol=0)
+    for split in ("256", "1000", None):
+        if split is None:
+            monkeypatch.delenv("PB_CENTER_SPLIT")
+        else:
+            monkeypatch.setenv("PB_CENTER_SPLIT", split)
+        out = map_batch(db, layout, fac, None, strands=("+", "-", "."))
+        for s in "+-.":
+            assert torch.equal(out.planes[s], ref.planes[s]), (mode, split, s)
+        assert (np.asarray(out.stats) == np.asarray(ref.stats)).all(), (mode, split)
+        two = map_batch(db, layout, fac, None, strands=("+", "-"))          # the specialised two-plane kernels
+        for s in "+-":
+            assert torch.equal(two.planes[s], ref2.planes[s]), (mode, split, s)
+        total, cut = int(layout.total_bins), 16384                           # bin ranges (position sharding)
+        parts = [map_batch(db, layout, fac, None, strands=("+", "."), bin_range=r) for r in ((0, cut), (cut, total))]
+        for s in "+.":
+            assert torch.equal(torch.cat([q.planes[s] for q in parts]), ref_r.planes[s]), (mode, split, s, "ranges")
+
+
 def test_gpu_reproduces_the_reference_golden_vector_recipe(cuda_device):
     """The CUDA path against count vectors built by the reference's own recipe
     (test_genome_array.py:1832-1866; tests/helpers.py:genome_array_recipe): 5'/3' at offsets 0 and 15 bit

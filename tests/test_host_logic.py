@@ -550,8 +550,8 @@ def test_genome_hash_and_transcript_table_lowering():
         k0, k1 = int(table.tx_off[t]), int(table.tx_off[t + 1])
         lens = table.bend[k0:k1] - table.bstart[k0:k1]
         assert list(table.bcum[k0:k1]) == list(np.cumsum(lens) - lens) and lens.sum() == txs[n].length
-    with pytest.raises(ValueError):
-        TranscriptTable.from_transcripts([pb.SegmentChain(pb.GenomicSegment("2L", 5, 9, "."))], layout, [None])
+    # an unstranded transcript gets orientation code 2: coordinates like '+', window columns like '-' (metagene.py:443-455)
+    assert list(TranscriptTable.from_transcripts([pb.SegmentChain(pb.GenomicSegment("2L", 5, 9, "."))], layout, [None]).reverse) == [2]
     # mask bits -> intervals, in the layout pb_mask_chains writes (bit mask_off[c] + j, genomic order)
     chains = [roi, pb.SegmentChain.from_str("3R:4519776-4519894(-)")]
     ctable = ChainTable.from_chains(chains, layout)
