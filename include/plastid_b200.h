@@ -165,6 +165,23 @@ int pb_bam_copy(const pb_bam *h, int32_t *ref_start, uint32_t *meta, uint32_t *b
                 int64_t *chrom_read_off);
 void pb_bam_close(pb_bam *h);
 
+/* Indexed region access (a .bai beside the file): replaces pysam's AlignmentFile.fetch(reference, start, end) as
+ * BAMGenomeArray.get_reads_and_counts calls it (plastid/genomics/genome_array.py:800-809) and the index statistic
+ * behind `bamfile.mapped` (:690).  pb_bai_open parses the index (SAM/BAM specification 5.2); pb_bai_mapped gives the
+ * mapped-record count of one reference (ref >= 0) or of the file (ref < 0), -1 when the index holds no statistics.
+ * pb_bam_read_header fills the reference names / lengths without touching a record.  pb_bam_fetch makes the records
+ * of reference `tid` whose span overlaps [beg, end) the handle's batch (pb_bam_n_reads / pb_bam_copy as after
+ * pb_bam_decode): only the BGZF members the index points at are read and inflated. */
+typedef struct pb_bai pb_bai;
+int pb_bai_open(const char *path, pb_bai **out);
+void pb_bai_close(pb_bai *idx);
+int pb_bai_n_ref(const pb_bai *idx);
+int64_t pb_bai_mapped(const pb_bai *idx, int ref);
+int pb_bam_read_header(pb_bam *h);
+int pb_bam_fetch(pb_bam *h, const pb_bai *idx, int tid, int64_t beg, int64_t end);
+/* `samtools index` (what pysam needs before the reference can fetch): writes the .bai of a coordinate-sorted BAM. */
+int pb_bam_build_index(const char *bam_path, const char *bai_path);
+
 /* The decoder's own raw-DEFLATE (RFC 1951) inflater, one BGZF member at a time: `in_len` compressed bytes
  * -> exactly `out_len` bytes (the member's ISIZE).  0 on success, -1 on malformed / truncated data or a
  * size mismatch; never writes outside [out, out + out_len).  Stands where htslib's bgzf.c calls zlib's

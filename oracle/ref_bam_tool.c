@@ -6,6 +6,10 @@
  *
  *   ref_bam_tool sam2bam in.sam out.bam
  *   ref_bam_tool dump in.bam          -> "tid pos flag n_cigar op:len,op:len,..." per record
+ *   ref_bam_tool index in.bam         -> in.bam.bai written by htslib's own indexer (sam_index_build)
+ *   ref_bam_tool fetch in.bam tid beg end [tid beg end ...]
+ *                                     -> per region "# tid beg end", one "pos flag op:len,... endpos" line per record
+ *                                        htslib's iterator returns (sam_itr_queryi: pysam's AlignmentFile.fetch), "= n"
  *   ref_bam_tool positions in.bam     -> "qname tid pos" for every reference position a read has an ALIGNED
  *                                        base at, as seen by htslib's own pileup engine (bam_plp_auto:
  *                                        the read is in the column and neither is_del nor is_refskip).
@@ -13,6 +17,7 @@
  *                                        (= get_reference_positions()), the a1 row of SURVEY 8(a).
  */
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "htslib/sam.h"
 
@@ -71,6 +76,34 @@ int main(int argc, char **argv)
         if (n < 0) return 5;
         bam_plp_destroy(it);
         sam_close(src.in);
+        return 0;
+    }
+    if (argc >= 3 && !strcmp(argv[1], "index"))
+        return sam_index_build(argv[2], 0) < 0 ? 6 : 0;
+    if (argc >= 6 && !strcmp(argv[1], "fetch")) {
+        samFile *in = sam_open(argv[2], "r");
+        if (!in) return 2;
+        bam_hdr_t *h = sam_hdr_read(in);
+        hts_idx_t *idx = sam_index_load(in, argv[2]);
+        if (!idx) return 7;
+        bam1_t *b = bam_init1();
+        for (int a = 3; a + 2 < argc; a += 3) {
+            int tid = atoi(argv[a]), beg = atoi(argv[a + 1]), end = atoi(argv[a + 2]);
+            hts_itr_t *it = sam_itr_queryi(idx, tid, beg, end);
+            long n = 0;
+            printf("# %d %d %d\n", tid, beg, end);
+            while (it && sam_itr_next(in, it, b) >= 0) {
+                printf("%d %d ", b->core.pos, b->core.flag);
+                const uint32_t *c = bam_get_cigar(b);
+                for (int k = 0; k < b->core.n_cigar; ++k)
+                    printf("%s%d:%d", k ? "," : "", bam_cigar_op(c[k]), bam_cigar_oplen(c[k]));
+                printf("%s %d\n", b->core.n_cigar ? "" : "*", bam_endpos(b));
+                ++n;
+            }
+            printf("= %ld\n", n);
+            if (it) hts_itr_destroy(it);
+        }
+        sam_close(in);
         return 0;
     }
     fprintf(stderr, "usage: ref_bam_tool sam2bam in.sam out.bam | dump in.bam | positions in.bam\n");

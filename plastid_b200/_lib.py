@@ -61,6 +61,13 @@ _SIGNATURES = {
     "pb_bam_max_span": (C.c_int32, [_P]),
     "pb_bam_copy": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "pb_bam_close": (None, [_P]),
+    "pb_bai_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "pb_bai_close": (None, [_P]),
+    "pb_bai_n_ref": (C.c_int, [_P]),
+    "pb_bai_mapped": (C.c_int64, [_P, C.c_int]),
+    "pb_bam_read_header": (C.c_int, [_P]),
+    "pb_bam_fetch": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64]),
+    "pb_bam_build_index": (C.c_int, [C.c_char_p, C.c_char_p]),
     "pb_inflate_raw": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t]),
     "pb_format_track_bound": (C.c_int64, [C.c_int, C.c_char_p, C.c_int64]),
     "pb_format_track": (C.c_int64, [C.c_int, C.c_char_p, _P, _P, _P, C.c_int, C.c_int64, _P, C.c_int64, C.c_int]),

@@ -58,6 +58,88 @@ def batch_from_bam(source, threads=0, pinned=False, pack=True):
         L.pb_bam_close(handle)
 
 
+def _copy_handle(L, handle, pinned=False):
+    """The batch a decoded / fetched ``pb_bam`` handle holds -> :class:`AlignmentBatch`."""
+    n_ref = L.pb_bam_n_ref(handle)
+    chroms = [L.pb_bam_ref_name(handle, i).decode() for i in range(n_ref)]
+    lens = [L.pb_bam_ref_len(handle, i) for i in range(n_ref)]
+    n, n_blk = L.pb_bam_n_reads(handle), L.pb_bam_n_blk(handle)
+    start, meta = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.uint32)
+    off = np.empty(n_ref + 1, dtype=np.int64)
+    blk_off = blk = None
+    if n_blk:
+        blk_off, blk = np.empty(n + 1, dtype=np.uint32), np.empty(2 * n_blk, dtype=np.int32)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)     # noqa: E731
+    _lib.check(L.pb_bam_copy(handle, p(start), p(meta), p(blk_off), p(blk), p(off)))
+    return AlignmentBatch(chroms, lens, start, meta, off, blk_off, None if blk is None else blk.reshape(-1, 2),
+                          max_span=L.pb_bam_max_span(handle), mapped=L.pb_bam_n_mapped(handle))
+
+
+def index_path(bam_path):
+    """The index beside a BAM file: ``x.bam.bai`` or ``x.bai`` (what ``pysam.AlignmentFile`` looks for), else None."""
+    import os
+    for cand in (bam_path + ".bai", os.path.splitext(bam_path)[0] + ".bai"):
+        if os.path.exists(cand):
+            return cand
+    return None
+
+
+def build_index(bam_path, bai_path=None):
+    """``samtools index``: write the ``.bai`` of a coordinate-sorted BAM (``pb_bam_build_index``).  Returns its path."""
+    bai_path = bam_path + ".bai" if bai_path is None else bai_path
+    _lib.check(_lib.lib().pb_bam_build_index(bam_path.encode(), bai_path.encode()))
+    return bai_path
+
+
+class IndexedBam(object):
+    """A sorted BAM with its ``.bai``: header and index statistics without decoding a record, and
+    ``fetch(chrom, start, end)`` -> :class:`AlignmentBatch` of the reads whose span overlaps the region — what
+    ``pysam.AlignmentFile`` gives the reference (``references`` / ``lengths`` / ``mapped`` / ``fetch``;
+    plastid/genomics/genome_array.py:660-690, 800-809).  Only the BGZF members the index points at are read."""
+
+    def __init__(self, path, index=None):
+        L = _lib.lib()
+        self.path = path
+        self._h, self._idx = C.c_void_p(), C.c_void_p()
+        index = index_path(path) if index is None else index
+        if index is None:
+            raise IOError("no .bai index beside %s (plastid_b200.bam_io.build_index writes one)" % path)
+        _lib.check(L.pb_bam_open(path.encode(), C.byref(self._h)))
+        try:
+            _lib.check(L.pb_bam_read_header(self._h))
+            _lib.check(L.pb_bai_open(index.encode(), C.byref(self._idx)))
+        except Exception:
+            self.close()
+            raise
+        n_ref = L.pb_bam_n_ref(self._h)
+        self.references = tuple(L.pb_bam_ref_name(self._h, i).decode() for i in range(n_ref))
+        self.lengths = tuple(int(L.pb_bam_ref_len(self._h, i)) for i in range(n_ref))
+        self._tid = {c: i for i, c in enumerate(self.references)}
+        m = int(L.pb_bai_mapped(self._idx, -1))
+        self.mapped = None if m < 0 else m          # None: an index written without the statistics pseudo-bin
+
+    def fetch(self, chrom, start, end):
+        L = _lib.lib()
+        if self._h is None:
+            raise ValueError("I/O operation on a closed IndexedBam")
+        _lib.check(L.pb_bam_fetch(self._h, self._idx, self._tid.get(chrom, -1), int(start), int(end)))
+        return _copy_handle(L, self._h)
+
+    def close(self):
+        L = _lib.lib()
+        if getattr(self, "_idx", None):
+            L.pb_bai_close(self._idx)
+        if getattr(self, "_h", None):
+            L.pb_bam_close(self._h)
+        self._h = self._idx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _batch_from_pysam(bam):
     chroms, lengths = list(bam.references), list(bam.lengths)
     per_chrom = [[] for _ in chroms]

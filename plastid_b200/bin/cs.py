@@ -78,12 +78,22 @@ def process_partial_group(transcripts, mask_hash=None, printer=None, device="cud
     for t, tx in zip(txids, txs):
         merged_gene_tx.setdefault(merged_genes[tx.get_gene()], []).append(t)
     gene_ids = list(merged_gene_tx)
+    # A gene whose transcripts lie on several chromosomes or strands: the reference prints "Skipping gene ..." and
+    # then pools the bare position numbers of all of them on the FIRST transcript's chromosome and strand
+    # (cs.py:324-343); every chain of the gene and of its transcripts is written there (:405-406, :444-460), while
+    # 5' / 3' of a transcript's coding region follow the transcript's own strand.  Reproduced: such transcripts are
+    # lowered into the bins of their gene's place.
+    place = {}
     for gene_id, members in merged_gene_tx.items():
-        where = {(transcripts[t].chrom, transcripts[t].strand) for t in members}
-        if len(where) > 1:
-            # the reference notes "Skipping gene ..." but goes on to pool the positions of both places as if
-            # they were one chromosome strand (cs.py:324-343); refuse instead of writing nonsense
-            raise ValueError("gene %s has transcripts on several chromosomes or strands: %s" % (gene_id, sorted(where)))
+        chroms_seen, strands_seen = [], []
+        for t in members:
+            chroms_seen.append(transcripts[t].chrom)
+            strands_seen.append(transcripts[t].strand)
+            if printer is not None and len(set(chroms_seen)) > 1:
+                printer.write("Skipping gene %s which contains multiple chromosomes: %s" % (gene_id, ",".join(chroms_seen)))
+            if printer is not None and len(set(strands_seen)) > 1:
+                printer.write("Skipping gene %s which contains multiple strands: %s" % (gene_id, ",".join(strands_seen)))
+        place[gene_id] = (chroms_seen[0], strands_seen[0])
     gene_index = {g: i for i, g in enumerate(gene_ids)}
     gene_of_tx = np.asarray([gene_index[merged_genes[tx.get_gene()]] for tx in txs], dtype=np.int64)
     n_tx, n_gene = len(txs), len(gene_ids)
@@ -91,13 +101,16 @@ def process_partial_group(transcripts, mask_hash=None, printer=None, device="cud
             "exon_bed", "utr5_bed", "cds_bed", "utr3_bed", "masked_bed"]
     if n_tx == 0:
         return pd.DataFrame({c: [] for c in cols}), pd.DataFrame({c: [] for c in cols}), merged_genes
-    layout = layout_for_features(txs, mask_hash.features)
+    tx_place = [place[merged_genes[tx.get_gene()]] for tx in txs]
+    moved = [SegmentChain(*[GenomicSegment(c, seg.start, seg.end, st) for seg in tx])
+             for tx, (c, st) in zip(txs, tx_place) if (c, st) != (tx.chrom, tx.strand) and len(tx)]
+    layout = layout_for_features(txs, mask_hash.features, moved)
 
     # T: transcripts; R: the three genomic ranges of each transcript (5' of the CDS, CDS, 3' of it)
     bs, be, off, rs, re_, roff = [], [], [0], [], [], [0]
-    for tx in txs:
-        base = int(layout.chrom_bin_off[layout.index[tx.chrom]])
-        top = int(layout.chrom_bin_off[layout.index[tx.chrom] + 1])
+    for tx, (p_chrom, _p_strand) in zip(txs, tx_place):
+        base = int(layout.chrom_bin_off[layout.index[p_chrom]])
+        top = int(layout.chrom_bin_off[layout.index[p_chrom] + 1])
         for seg in tx:
             bs.append(base + seg.start)
             be.append(base + seg.end)
@@ -206,13 +219,14 @@ def process_partial_group(transcripts, mask_hash=None, printer=None, device="cud
             gene_table["%s_bed" % key].append(ch.as_bed())
     for t, txid in enumerate(txids):
         tx, g = txs[t], int(gene_of_tx[t])
-        masked = _chains_from(*h_m, g, layout, tx.chrom, tx.strand, ID=txid)
-        exon = _chains_from(*h_te, t, layout, tx.chrom, tx.strand, ID=txid)
+        t_chrom, t_strand = tx_place[t]
+        masked = _chains_from(*h_m, g, layout, t_chrom, t_strand, ID=txid)
+        exon = _chains_from(*h_te, t, layout, t_chrom, t_strand, ID=txid)
         transcript_table["region"].append(txid)
         transcript_table["exon"].append(str(exon))
         transcript_table["exon_bed"].append(exon.as_bed())
         for k, key in enumerate(CLASSES):
-            ch = _chains_from(*h_tc, 3 * t + k, layout, tx.chrom, tx.strand, ID=txid)
+            ch = _chains_from(*h_tc, 3 * t + k, layout, t_chrom, t_strand, ID=txid)
             transcript_table[key].append(str(ch))
             transcript_table["%s_bed" % key].append(ch.as_bed())
         transcript_table["masked"].append(str(masked))

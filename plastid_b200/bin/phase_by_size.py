@@ -18,11 +18,13 @@ def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
     """Phase sums per read length over the CDS chains: ``{length: float64[3]}``.
 
     ``back_buffer`` is the python slice stop the reference uses (``-1`` with an ROI file,
-    ``-codon_buffer`` with an annotation; note ``-0`` selects nothing there, and here).  Point
-    rules only: with CenterMapFactory the reference re-maps reads of earlier exons against later
-    ones (phase_by_size.py:186-194) — a quirk this path does not reproduce."""
-    if isinstance(ga.map_fn, CenterMapFactory):
-        raise TypeError("phase_by_size on the GPU path supports point mapping rules only")
+    ``-codon_buffer`` with an annotation; note ``-0`` selects nothing there, and here).
+
+    The reference does not reset its per-length read lists between the exons of a coding region
+    (phase_by_size.py:186-194): a read that the fetch of an earlier exon returned too (a read across the exon
+    junction) is mapped once more against the later exon.  The kernel counts such a read with that multiplicity
+    (test_gpu_ref_goldens.py::test_phase_by_size_junction_reads).  Point rules count sites; CenterMapFactory counts
+    every trimmed position as an integer per read length and the weight ``1 / (L - 2 nibble)`` is applied here."""
     back_buffer = -codon_buffer if back_buffer is None else back_buffer
     chains = [c for c in cds_chains if len(c) > 0]
     read_lengths = list(read_lengths)
@@ -35,12 +37,18 @@ def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
                                   lo, hi, phase=(codon_buffer, back_buffer), bin_range=ga.bin_range)
     # multi-GPU: an 11 x 3 table per rank (the sites of its own genome range), completed with one all-reduce
     sums = ga._allreduce(strat.to(torch.float64).sum(dim=1)).cpu().numpy()
+    if isinstance(ga.map_fn, CenterMapFactory):
+        for k in range(lo, hi + 1):
+            m = k - 2 * ga.map_fn.nibble
+            sums[k - lo] = sums[k - lo] * (1.0 / m) if m > 0 else 0.0
     return {k: sums[k - lo] for k in read_lengths}
 
 
 def phase_table(sums):
+    """phase_by_size.py:216-235: ``reads_counted`` is an integer column (the fractional sums of the Center rule are
+    truncated when they are assigned to it), and the fractions are taken from it."""
     lengths = sorted(sums)
-    counted = np.array([sums[k].sum() for k in lengths])
+    counted = np.array([int(sums[k].sum()) for k in lengths], dtype=np.int64)
     with np.errstate(all="ignore"):
         frac = counted.astype(float) / counted.sum()
         phases = np.array([sums[k].astype(float) / sums[k].astype(float).sum() for k in lengths])

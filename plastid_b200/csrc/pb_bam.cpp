@@ -515,3 +515,430 @@ extern "C" int pb_bam_copy(const pb_bam *h, int32_t *ref_start, uint32_t *meta, 
     }
     return PB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Indexed region access: the .bai index and `fetch(reference, start, end)`
+// ---------------------------------------------------------------------------------------------------------------
+// Replaces pysam's `AlignmentFile.fetch(chrom, start, end)` as BAMGenomeArray.get_reads_and_counts calls it
+// (plastid/genomics/genome_array.py:800-809) and `bamfile.mapped` (:690, the index statistic) for a file that has a
+// .bai beside it: only the BGZF members the index points at are read and inflated, so a single-region query does not
+// pay for the whole file.  Format: SAM/BAM specification v1 §5.2 (binning scheme, linear index, metadata pseudo-bin
+// 37450); the same arithmetic as the reference's vendored htslib (kent/src/htslib/hts.c: reg2bins, hts_itr_query).
+#include <unordered_map>
+#include <unistd.h>
+#include <fcntl.h>
+
+struct pb_bai {
+    struct Ref {
+        std::unordered_map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+        std::vector<uint64_t> ioffset;
+        int64_t mapped = -1, unmapped = -1;
+    };
+    std::vector<Ref> refs;
+    int64_t no_coor = -1;
+};
+
+namespace {
+
+inline uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+// One BGZF member at a time, by file offset (pread): inflate + CRC32.
+struct MemberReader {
+    int fd = -1;
+    std::vector<uint8_t> comp, plain;
+    uint64_t coff = 0, next = 0;         // file offset of the member in `plain`, and of the one after it
+    std::string err;
+    ~MemberReader() { if (fd >= 0) close(fd); }
+    bool open(const char *path) { fd = ::open(path, O_RDONLY); return fd >= 0; }
+    // -> 1 member loaded, 0 end of file, -1 error
+    int load(uint64_t at)
+    {
+        uint8_t head[18];
+        const ssize_t got = pread(fd, head, 18, (off_t)at);
+        if (got == 0) return 0;
+        if (got != 18) { err = "truncated BGZF member header"; return -1; }
+        if (head[0] != 31 || head[1] != 139 || head[2] != 8 || !(head[3] & 4)) { err = "not a BGZF member (bad virtual offset in the index?)"; return -1; }
+        const uint32_t xlen = rd16(head + 10);
+        std::vector<uint8_t> extra(xlen);
+        if (xlen && pread(fd, extra.data(), xlen, (off_t)at + 12) != (ssize_t)xlen) { err = "truncated BGZF extra field"; return -1; }
+        uint32_t bsize = 0;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint32_t slen = rd16(extra.data() + x + 2);
+            if (extra[x] == 'B' && extra[x + 1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = rd16(extra.data() + x + 4) + 1u;
+            x += 4 + slen;
+        }
+        if (!bsize || bsize < 12 + xlen + 8) { err = "corrupt BGZF member header"; return -1; }
+        comp.resize(bsize);
+        if (pread(fd, comp.data(), bsize, (off_t)at) != (ssize_t)bsize) { err = "truncated BGZF member"; return -1; }
+        const uint32_t isize = rd32(comp.data() + bsize - 4), crc = rd32(comp.data() + bsize - 8);
+        if (isize > 65536) { err = "corrupt BGZF member header (ISIZE above 64 KiB)"; return -1; }
+        plain.resize(isize);
+        if (isize) {
+            if (pb_inflate_raw(comp.data() + 12 + xlen, bsize - xlen - 20, plain.data(), isize) != 0) { err = "corrupt BGZF member (inflate failed)"; return -1; }
+            if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), plain.data(), (uInt)isize) != crc) { err = "corrupt BGZF member (CRC32 mismatch)"; return -1; }
+        }
+        coff = at;
+        next = at + bsize;
+        return 1;
+    }
+};
+
+// A byte stream over consecutive members that knows the virtual offset of its read position.
+struct VStream {
+    MemberReader mr;
+    size_t upos = 0;
+    bool loaded = false, eof = false;
+    bool seek(uint64_t voff)
+    {
+        const int r = mr.load(voff >> 16);
+        if (r < 0) return false;
+        eof = r == 0;
+        loaded = true;
+        upos = (size_t)(voff & 0xffff);
+        return eof || upos <= mr.plain.size();
+    }
+    uint64_t tell() const { return (mr.coff << 16) | (uint64_t)upos; }
+    // -> bytes read (short only at end of file), -1 on error
+    long read(uint8_t *dst, size_t n)
+    {
+        size_t done = 0;
+        while (done < n && !eof) {
+            if (upos >= mr.plain.size()) {
+                const int r = mr.load(mr.next);
+                if (r < 0) return -1;
+                if (r == 0) { eof = true; break; }
+                upos = 0;
+                continue;
+            }
+            const size_t take = std::min(n - done, mr.plain.size() - upos);
+            memcpy(dst + done, mr.plain.data() + upos, take);
+            upos += take; done += take;
+        }
+        return (long)done;
+    }
+    // a position at the very end of a member is the start of the next one (what htslib's bgzf_tell reports)
+    void normalise()
+    {
+        while (!eof && upos >= mr.plain.size()) {
+            const int r = mr.load(mr.next);
+            if (r <= 0) { eof = true; break; }
+            upos = 0;
+        }
+    }
+};
+
+int read_header_into(pb_bam *h, VStream &vs)
+{
+    if (!vs.seek(0) || vs.eof) { pb_set_error("%s: %s", h->path.c_str(), vs.mr.err.empty() ? "empty BAM file" : vs.mr.err.c_str()); return PB_EINVAL; }
+    uint8_t w[8];
+    if (vs.read(w, 8) != 8 || memcmp(w, "BAM\1", 4) != 0) { pb_set_error("%s: not a BAM file (bad magic)", h->path.c_str()); return PB_EINVAL; }
+    std::vector<uint8_t> text(rd32(w + 4));
+    if (vs.read(text.data(), text.size()) != (long)text.size() || vs.read(w, 4) != 4) { pb_set_error("%s: truncated BAM header", h->path.c_str()); return PB_EINVAL; }
+    const uint32_t n_ref = rd32(w);
+    h->ref_name.clear(); h->ref_len.clear();
+    for (uint32_t i = 0; i < n_ref; ++i) {
+        if (vs.read(w, 4) != 4) { pb_set_error("%s: truncated BAM header", h->path.c_str()); return PB_EINVAL; }
+        const uint32_t l_name = rd32(w);
+        std::vector<uint8_t> nm(l_name + 4);
+        if (l_name > (1u << 20) || vs.read(nm.data(), nm.size()) != (long)nm.size()) { pb_set_error("%s: truncated BAM header", h->path.c_str()); return PB_EINVAL; }
+        h->ref_name.emplace_back((const char *)nm.data(), l_name ? l_name - 1 : 0);
+        h->ref_len.push_back((int32_t)rd32(nm.data() + l_name));
+    }
+    return PB_OK;
+}
+
+}  // namespace
+
+extern "C" int pb_bai_open(const char *path, pb_bai **out)
+{
+    if (!path || !out) { pb_set_error("pb_bai_open: null argument"); return PB_EINVAL; }
+    FILE *fh = fopen(path, "rb");
+    if (!fh) { pb_set_error("pb_bai_open: cannot open %s", path); return PB_EINVAL; }
+    std::vector<uint8_t> buf;
+    {
+        uint8_t tmp[1 << 16];
+        size_t got;
+        while ((got = fread(tmp, 1, sizeof(tmp), fh)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    }
+    fclose(fh);
+    size_t p = 0;
+    auto need = [&](size_t n) { return p + n <= buf.size(); };
+    if (!need(8) || memcmp(buf.data(), "BAI\1", 4) != 0) { pb_set_error("pb_bai_open(%s): not a BAI index (bad magic)", path); return PB_EINVAL; }
+    const int32_t n_ref = (int32_t)rd32(buf.data() + 4);
+    p = 8;
+    if (n_ref < 0) { pb_set_error("pb_bai_open(%s): negative reference count", path); return PB_EINVAL; }
+    pb_bai *idx = new pb_bai();
+    idx->refs.resize((size_t)n_ref);
+    bool ok = true;
+    for (int32_t r = 0; r < n_ref && ok; ++r) {
+        pb_bai::Ref &ref = idx->refs[(size_t)r];
+        if (!need(4)) { ok = false; break; }
+        const int32_t n_bin = (int32_t)rd32(buf.data() + p); p += 4;
+        for (int32_t b = 0; b < n_bin && ok; ++b) {
+            if (!need(8)) { ok = false; break; }
+            const uint32_t bin = rd32(buf.data() + p);
+            const int32_t n_chunk = (int32_t)rd32(buf.data() + p + 4); p += 8;
+            if (n_chunk < 0 || !need((size_t)n_chunk * 16)) { ok = false; break; }
+            if (bin == 37450) {                      // metadata pseudo-bin: (ref_beg, ref_end), (n_mapped, n_unmapped)
+                if (n_chunk >= 2) { ref.mapped = (int64_t)rd64(buf.data() + p + 16); ref.unmapped = (int64_t)rd64(buf.data() + p + 24); }
+            } else {
+                auto &v = ref.bins[bin];
+                for (int32_t c = 0; c < n_chunk; ++c) v.emplace_back(rd64(buf.data() + p + 16 * (size_t)c), rd64(buf.data() + p + 16 * (size_t)c + 8));
+            }
+            p += (size_t)n_chunk * 16;
+        }
+        if (!ok || !need(4)) { ok = false; break; }
+        const int32_t n_intv = (int32_t)rd32(buf.data() + p); p += 4;
+        if (n_intv < 0 || !need((size_t)n_intv * 8)) { ok = false; break; }
+        ref.ioffset.resize((size_t)n_intv);
+        for (int32_t i = 0; i < n_intv; ++i) ref.ioffset[(size_t)i] = rd64(buf.data() + p + 8 * (size_t)i);
+        p += (size_t)n_intv * 8;
+    }
+    if (!ok) { delete idx; pb_set_error("pb_bai_open(%s): truncated index", path); return PB_EINVAL; }
+    if (need(8)) idx->no_coor = (int64_t)rd64(buf.data() + p);
+    *out = idx;
+    return PB_OK;
+}
+
+extern "C" void pb_bai_close(pb_bai *idx) { delete idx; }
+extern "C" int pb_bai_n_ref(const pb_bai *idx) { return idx ? (int)idx->refs.size() : 0; }
+
+// ref >= 0: mapped records of that reference; ref < 0: of the whole file.  -1 where the index carries no statistics.
+extern "C" int64_t pb_bai_mapped(const pb_bai *idx, int ref)
+{
+    if (!idx) return -1;
+    if (ref >= 0) {
+        if ((size_t)ref >= idx->refs.size()) return -1;
+        const pb_bai::Ref &r = idx->refs[(size_t)ref];
+        return r.mapped >= 0 ? r.mapped : (r.bins.empty() ? 0 : -1);      // a reference without records has no pseudo-bin
+    }
+    int64_t total = 0;
+    bool any = false;
+    for (const auto &r : idx->refs) {
+        if (r.mapped >= 0) { total += r.mapped; any = true; }
+        else if (!r.bins.empty()) return -1;                               // records, but no statistics
+    }
+    return any || idx->refs.empty() ? total : -1;
+}
+
+extern "C" int pb_bam_read_header(pb_bam *h)
+{
+    if (!h) { pb_set_error("pb_bam_read_header: null handle"); return PB_EINVAL; }
+    VStream vs;
+    if (!vs.mr.open(h->path.c_str())) { pb_set_error("pb_bam_read_header: cannot open %s", h->path.c_str()); return PB_EINVAL; }
+    return read_header_into(h, vs);
+}
+
+// The records of reference `tid` whose span [pos, end) overlaps [beg, end) — end = pos + reference bases consumed
+// (one base for a record that consumes none), htslib's bam_endpos — become the handle's batch (rows of that
+// reference only).  Replaces whatever the handle held.
+extern "C" int pb_bam_fetch(pb_bam *h, const pb_bai *idx, int tid, int64_t beg, int64_t end)
+{
+    if (!h || !idx) { pb_set_error("pb_bam_fetch: null argument"); return PB_EINVAL; }
+    VStream vs;
+    if (!vs.mr.open(h->path.c_str())) { pb_set_error("pb_bam_fetch: cannot open %s", h->path.c_str()); return PB_EINVAL; }
+    if (h->ref_name.empty()) {
+        const int rc = read_header_into(h, vs);
+        if (rc) return rc;
+    }
+    const size_t n_ref = h->ref_name.size();
+    h->start.clear(); h->meta.clear(); h->blk_off.clear(); h->blk.clear();
+    h->chrom_read_off.assign(n_ref + 1, 0);
+    h->mapped = 0; h->skipped = 0; h->max_span = 1; h->decoded = true;
+    if (tid < 0 || (size_t)tid >= n_ref || (size_t)tid >= idx->refs.size()) return PB_OK;
+    if (beg < 0) beg = 0;
+    if (end > h->ref_len[(size_t)tid]) end = h->ref_len[(size_t)tid];
+    if (end > ((int64_t)1 << 29)) end = (int64_t)1 << 29;          // the binning scheme's reach
+    if (beg >= end) return PB_OK;
+    const pb_bai::Ref &ref = idx->refs[(size_t)tid];
+    // candidate chunks: every bin overlapping the region (SAM spec 5.3, reg2bins), trimmed by the linear index
+    uint64_t min_off = 0;
+    if (!ref.ioffset.empty()) {
+        const size_t w = (size_t)(beg >> 14);
+        min_off = w < ref.ioffset.size() ? ref.ioffset[w] : ref.ioffset.back();
+    }
+    std::vector<std::pair<uint64_t, uint64_t>> chunks;
+    {
+        const int64_t e = end - 1;
+        auto take = [&](uint32_t bin) {
+            auto it = ref.bins.find(bin);
+            if (it == ref.bins.end()) return;
+            for (const auto &c : it->second) if (c.second > min_off) chunks.push_back(c);
+        };
+        take(0);
+        for (int64_t k = 1 + (beg >> 26); k <= 1 + (e >> 26); ++k) take((uint32_t)k);
+        for (int64_t k = 9 + (beg >> 23); k <= 9 + (e >> 23); ++k) take((uint32_t)k);
+        for (int64_t k = 73 + (beg >> 20); k <= 73 + (e >> 20); ++k) take((uint32_t)k);
+        for (int64_t k = 585 + (beg >> 17); k <= 585 + (e >> 17); ++k) take((uint32_t)k);
+        for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (e >> 14); ++k) take((uint32_t)k);
+    }
+    std::sort(chunks.begin(), chunks.end());
+    std::vector<std::pair<uint64_t, uint64_t>> merged;
+    for (const auto &c : chunks) {
+        if (!merged.empty() && c.first <= merged.back().second) merged.back().second = std::max(merged.back().second, c.second);
+        else merged.push_back(c);
+    }
+    Decoded d;
+    std::vector<uint8_t> rec;
+    bool past = false;
+    for (size_t ci = 0; ci < merged.size() && !past; ++ci) {
+        uint64_t from = merged[ci].first;
+        if (from < min_off) from = min_off;
+        if (!vs.seek(from)) { pb_set_error("pb_bam_fetch(%s): %s", h->path.c_str(), vs.mr.err.c_str()); return PB_EINVAL; }
+        for (;;) {
+            vs.normalise();
+            if (vs.eof || vs.tell() >= merged[ci].second) break;
+            uint8_t w[4];
+            const long got = vs.read(w, 4);
+            if (got == 0) break;
+            if (got != 4) { pb_set_error("pb_bam_fetch(%s): truncated BAM record", h->path.c_str()); return PB_EINVAL; }
+            const uint32_t size = rd32(w);
+            if (size < 32 || size > (1u << 29)) { pb_set_error("pb_bam_fetch(%s): implausible BAM record size (bad index?)", h->path.c_str()); return PB_EINVAL; }
+            rec.resize(size);
+            if (vs.read(rec.data(), size) != (long)size) {
+                pb_set_error("pb_bam_fetch(%s): %s", h->path.c_str(), vs.mr.err.empty() ? "truncated BAM record" : vs.mr.err.c_str());
+                return PB_EINVAL;
+            }
+            const int32_t rtid = (int32_t)rd32(rec.data()), pos = (int32_t)rd32(rec.data() + 4);
+            if (rtid != tid) { if (rtid > tid || rtid < 0) { past = true; break; } continue; }
+            if ((int64_t)pos >= end) { past = true; break; }
+            const uint32_t l_read_name = rec[8], n_cigar = rd16(rec.data() + 12);
+            if (32 + l_read_name + 4ull * n_cigar > size) { pb_set_error("pb_bam_fetch(%s): BAM record shorter than its CIGAR", h->path.c_str()); return PB_EINVAL; }
+            int64_t rlen = 0;
+            for (uint32_t k = 0; k < n_cigar; ++k) {
+                const uint32_t c = rd32(rec.data() + 32 + l_read_name + 4 * k), op = c & 0xf;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
+            }
+            if ((int64_t)pos + (rlen ? rlen : 1) <= beg) continue;
+            if (!convert_record(rec.data(), size, d)) { pb_set_error("pb_bam_fetch(%s): %s", h->path.c_str(), d.err.c_str()); return PB_EINVAL; }
+        }
+    }
+    const size_t n = d.start.size();
+    // rows in file order; a leading deletion can shift a start past its successor's: stable sort by start
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = i;
+    bool sorted = true;
+    for (size_t i = 1; i < n; ++i) if (d.start[i] < d.start[i - 1]) { sorted = false; break; }
+    if (!sorted) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return d.start[a] < d.start[b]; });
+    std::vector<uint64_t> blk_start(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) blk_start[i + 1] = blk_start[i] + d.nlisted[i];
+    h->start.resize(n); h->meta.resize(n);
+    const bool any_multi = !d.blk.empty();
+    if (any_multi) h->blk_off.resize(n + 1);
+    uint64_t run = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const size_t j = order[i];
+        h->start[i] = d.start[j]; h->meta[i] = d.meta[j];
+        if (any_multi) {
+            h->blk_off[i] = (uint32_t)run;
+            h->blk.insert(h->blk.end(), d.blk.begin() + 2 * blk_start[j], d.blk.begin() + 2 * blk_start[j + 1]);
+            run += d.nlisted[j];
+        }
+    }
+    if (any_multi) h->blk_off[n] = (uint32_t)run;
+    for (size_t c = (size_t)tid + 1; c <= n_ref; ++c) h->chrom_read_off[c] = (int64_t)n;
+    h->mapped = d.mapped; h->skipped = d.skipped; h->max_span = d.max_span;
+    return PB_OK;
+}
+
+// `samtools index`: writes the .bai of a coordinate-sorted BAM (SAM/BAM specification 5.2: one chunk list per bin of
+// the UCSC binning scheme, a linear index over 16 kb windows, the metadata pseudo-bin with the mapped / unmapped
+// counts that `bamfile.mapped` reads).  Records are walked once, one BGZF member at a time.
+extern "C" int pb_bam_build_index(const char *bam_path, const char *bai_path)
+{
+    if (!bam_path || !bai_path) { pb_set_error("pb_bam_build_index: null argument"); return PB_EINVAL; }
+    pb_bam hdr;
+    hdr.path = bam_path;
+    VStream vs;
+    if (!vs.mr.open(bam_path)) { pb_set_error("pb_bam_build_index: cannot open %s", bam_path); return PB_EINVAL; }
+    int rc = read_header_into(&hdr, vs);
+    if (rc) return rc;
+    const size_t n_ref = hdr.ref_name.size();
+    struct RefIdx {
+        std::vector<std::pair<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>>> bins;   // in order of first use
+        std::unordered_map<uint32_t, size_t> where;
+        std::vector<uint64_t> ioffset;
+        uint64_t off_beg = 0, off_end = 0, mapped = 0, unmapped = 0;
+        bool seen = false;
+    };
+    std::vector<RefIdx> refs(n_ref);
+    uint64_t no_coor = 0;
+    auto reg2bin = [](int64_t beg, int64_t end) -> uint32_t {
+        --end;
+        if (beg >> 14 == end >> 14) return (uint32_t)(((1 << 15) - 1) / 7 + (beg >> 14));
+        if (beg >> 17 == end >> 17) return (uint32_t)(((1 << 12) - 1) / 7 + (beg >> 17));
+        if (beg >> 20 == end >> 20) return (uint32_t)(((1 << 9) - 1) / 7 + (beg >> 20));
+        if (beg >> 23 == end >> 23) return (uint32_t)(((1 << 6) - 1) / 7 + (beg >> 23));
+        if (beg >> 26 == end >> 26) return (uint32_t)(((1 << 3) - 1) / 7 + (beg >> 26));
+        return 0;
+    };
+    std::vector<uint8_t> rec;
+    int32_t last_tid = -1, last_pos = -1;
+    for (;;) {
+        vs.normalise();
+        if (vs.eof) break;
+        const uint64_t v0 = vs.tell();
+        uint8_t w[4];
+        const long got = vs.read(w, 4);
+        if (got == 0) break;
+        if (got < 0) { pb_set_error("pb_bam_build_index(%s): %s", bam_path, vs.mr.err.c_str()); return PB_EINVAL; }
+        const uint32_t size = rd32(w);
+        if (got != 4 || size < 32 || size > (1u << 29)) { pb_set_error("pb_bam_build_index(%s): truncated or implausible BAM record", bam_path); return PB_EINVAL; }
+        rec.resize(size);
+        if (vs.read(rec.data(), size) != (long)size) { pb_set_error("pb_bam_build_index(%s): truncated BAM record", bam_path); return PB_EINVAL; }
+        vs.normalise();
+        const uint64_t v1 = vs.eof ? ((vs.mr.next << 16)) : vs.tell();
+        const int32_t tid = (int32_t)rd32(rec.data()), pos = (int32_t)rd32(rec.data() + 4);
+        const uint32_t flag = rd16(rec.data() + 14);
+        if (tid < 0) { ++no_coor; continue; }
+        if ((size_t)tid >= n_ref) { pb_set_error("pb_bam_build_index(%s): record refers to reference %d of %zu", bam_path, tid, n_ref); return PB_EINVAL; }
+        if (tid < last_tid || (tid == last_tid && pos < last_pos)) { pb_set_error("pb_bam_build_index(%s): file is not coordinate-sorted", bam_path); return PB_EINVAL; }
+        last_tid = tid; last_pos = pos;
+        const uint32_t l_read_name = rec[8], n_cigar = rd16(rec.data() + 12);
+        if (32 + l_read_name + 4ull * n_cigar > size) { pb_set_error("pb_bam_build_index(%s): BAM record shorter than its CIGAR", bam_path); return PB_EINVAL; }
+        int64_t rlen = 0;
+        for (uint32_t k = 0; k < n_cigar; ++k) {
+            const uint32_t c = rd32(rec.data() + 32 + l_read_name + 4 * k), op = c & 0xf;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
+        }
+        const int64_t beg = pos < 0 ? 0 : pos, end = beg + (rlen ? rlen : 1);
+        RefIdx &r = refs[(size_t)tid];
+        if (!r.seen) { r.seen = true; r.off_beg = v0; }
+        r.off_end = v1;
+        if (flag & 0x4) ++r.unmapped; else ++r.mapped;
+        const uint32_t bin = reg2bin(beg, end > ((int64_t)1 << 29) ? ((int64_t)1 << 29) : end);
+        auto it = r.where.find(bin);
+        if (it == r.where.end()) {
+            r.where[bin] = r.bins.size();
+            r.bins.push_back({bin, {{v0, v1}}});
+        } else {
+            auto &chunks = r.bins[it->second].second;
+            if (chunks.back().second == v0) chunks.back().second = v1; else chunks.emplace_back(v0, v1);
+        }
+        const size_t w0 = (size_t)(beg >> 14), w1 = (size_t)((end - 1) >> 14);
+        if (r.ioffset.size() <= w1) r.ioffset.resize(w1 + 1, 0);
+        for (size_t k = w0; k <= w1; ++k) if (r.ioffset[k] == 0) r.ioffset[k] = v0;
+    }
+    FILE *out = fopen(bai_path, "wb");
+    if (!out) { pb_set_error("pb_bam_build_index: cannot write %s", bai_path); return PB_EINVAL; }
+    auto w32 = [&](uint32_t v) { uint8_t b[4] = {(uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24)}; fwrite(b, 1, 4, out); };
+    auto w64 = [&](uint64_t v) { w32((uint32_t)v); w32((uint32_t)(v >> 32)); };
+    fwrite("BAI\1", 1, 4, out);
+    w32((uint32_t)n_ref);
+    for (RefIdx &r : refs) {
+        w32((uint32_t)(r.bins.size() + (r.seen ? 1 : 0)));
+        for (const auto &b : r.bins) {
+            w32(b.first);
+            w32((uint32_t)b.second.size());
+            for (const auto &c : b.second) { w64(c.first); w64(c.second); }
+        }
+        if (r.seen) { w32(37450); w32(2); w64(r.off_beg); w64(r.off_end); w64(r.mapped); w64(r.unmapped); }
+        for (size_t k = 1; k < r.ioffset.size(); ++k) if (r.ioffset[k] == 0) r.ioffset[k] = r.ioffset[k - 1];   // windows no record starts in
+        w32((uint32_t)r.ioffset.size());
+        for (uint64_t v : r.ioffset) w64(v);
+    }
+    w64(no_coor);
+    const bool bad = ferror(out) != 0;
+    if (fclose(out) != 0 || bad) { pb_set_error("pb_bam_build_index: write to %s failed", bai_path); return PB_EINVAL; }
+    return PB_OK;
+}

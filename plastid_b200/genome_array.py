@@ -671,32 +671,75 @@ class BAMGenomeArray(object):
     def __init__(self, *sources, **kwargs):
         if len(sources) == 1 and isinstance(sources[0], (list, tuple)):
             sources = tuple(sources[0])
-        batches = []
-        for src in sources:
-            if isinstance(src, AlignmentBatch):
-                batches.append(src)
-            else:
-                from .bam_io import batch_from_bam
-                batches.append(batch_from_bam(src))
-        if not batches:
+        if not sources:
             raise ValueError("BAMGenomeArray needs at least one alignment source")
-        self.batches = batches
-        self.batch = merge_batches(batches)
-        if len(batches) > 1 and all(b.transfer is not None for b in batches):
-            self.batch.pack()
         self.device = kwargs.get("device", "cuda")
         self.map_fn = kwargs.get("mapping", None) or CenterMapFactory()
         self._strands = _STRANDS
         self._normalize = False
-        self._chr_lengths = {c: int(n) for c, n in zip(self.batch.chroms, self.batch.chrom_len)}
-        self._chroms = sorted(self._chr_lengths)
-        self.layout = GenomeLayout(self.batch.chroms, self.batch.chrom_len)
         self._filters = {}
         self._planes = None
         self._dbatch = None
         self._full_dbatch = None
         self._receiver = None
         self._host_batch = None           # this rank's reads with the generic filters' verdicts (evaluated once)
+        self._kwargs = kwargs
+        self._indexed = None
+        if kwargs.get("indexed"):
+            # header + index only: nothing is decoded until a whole-genome consumer asks (`_attach`)
+            from .bam_io import IndexedBam
+            self._indexed = [IndexedBam(src) for src in sources]
+            self._sources = sources
+            chroms, lens = [], {}
+            for f in self._indexed:                   # lengths take the max over files (genome_array.py:667-672)
+                for c, n in zip(f.references, f.lengths):
+                    if c not in lens:
+                        chroms.append(c)
+                    lens[c] = max(lens.get(c, 0), int(n))
+            self._set_genome(chroms, [lens[c] for c in chroms])
+            self._rank, self._world = _resolve_shard(kwargs.get("shard", "auto"))
+            self._collective = False
+            self._bin_range = (0, int(self.layout.total_bins))
+            if self._world > 1 or any(f.mapped is None for f in self._indexed):
+                self._attach_sources()               # sharded arrays and indexes without statistics: decode now
+            else:
+                self.reset_sum()
+            return
+        self._sources = sources
+        self._attach_sources()
+
+    def _set_genome(self, chroms, chrom_len):
+        self._chr_lengths = {c: int(n) for c, n in zip(chroms, chrom_len)}
+        self._chroms = sorted(self._chr_lengths)
+        self.layout = GenomeLayout(chroms, chrom_len)
+
+    def __getattr__(self, name):
+        # an indexed array decodes its files the first time something needs every read
+        if name in ("batch", "batches", "_local", "_global_hist") and self.__dict__.get("_indexed") is not None \
+                and "batch" not in self.__dict__:
+            self._attach_sources()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    @property
+    def is_lazy(self):
+        """True while an ``indexed=True`` array has not decoded its files (region queries seek through the index)."""
+        return self._indexed is not None and "batch" not in self.__dict__
+
+    def _attach_sources(self):
+        kwargs = self._kwargs
+        batches = []
+        for src in self._sources:
+            if isinstance(src, AlignmentBatch):
+                batches.append(src)
+            else:
+                from .bam_io import batch_from_bam
+                batches.append(batch_from_bam(src))
+        self.batches = batches
+        self.batch = merge_batches(batches)
+        if len(batches) > 1 and all(b.transfer is not None for b in batches):
+            self.batch.pack()
+        self._set_genome(self.batch.chroms, self.batch.chrom_len)
         # Center rule on a sharded array: the aligned-length histogram of the WHOLE batch (every rank derives the same
         # slot tables from it); known here when this object shards the sources itself, handed in with pre-sharded ones
         self._global_hist = kwargs.get("length_hist")
@@ -719,11 +762,17 @@ class BAMGenomeArray(object):
             if self._global_hist is None:
                 from .batch import meta_length_hist
                 self._global_hist = meta_length_hist(self.batch.meta)     # every rank decoded the whole file
+        kept_sum = self.__dict__.get("_sum")          # an indexed array's sum (index statistic or `set_sum`) stays
         self._update()
+        if kept_sum is not None:
+            self._sum = kept_sum
 
     # -- bookkeeping (genome_array.py:681-758, 930-963) ----------------------------------------
     def reset_sum(self):
-        self._sum = sum(b.mapped for b in self.batches)
+        if self.is_lazy:                              # `bamfile.mapped`: the index statistic (genome_array.py:690)
+            self._sum = sum(f.mapped for f in self._indexed)
+        else:
+            self._sum = sum(b.mapped for b in self.batches)
 
     def _update(self):
         self.reset_sum()
@@ -963,9 +1012,16 @@ class BAMGenomeArray(object):
             return [], np.zeros(shape)
         if not isinstance(self.map_fn, _MapFactory):
             raise TypeError("only plastid_b200 map factories can be evaluated on the GPU")
-        dbatch = self._whole_device_batch()
-        hb = self._whole_host if self.is_sharded else self._host_batch
-        lo, hi = self._read_range(hb, chrom, start, end)
+        if self.is_lazy:
+            # the reference's own access pattern (genome_array.py:800-809): seek through the .bai, read the region's
+            # records of every file, map them — nothing else of the files is inflated
+            hb = self._filtered(merge_batches([f.fetch(chrom, start, end) for f in self._indexed]))
+            dbatch = hb.to_device(self.device) if len(hb) else None
+            lo, hi = 0, len(hb)
+        else:
+            dbatch = self._whole_device_batch()
+            hb = self._whole_host if self.is_sharded else self._host_batch
+            lo, hi = self._read_range(hb, chrom, start, end)
         qs = strand if strand in ("+", "-") else "."
         if hi > lo:
             counts, kept = self.map_fn.map_segment(dbatch, lo, hi, start, end, qs, self._size_filter())
@@ -986,7 +1042,7 @@ class BAMGenomeArray(object):
     def get(self, roi, roi_order=True):
         if isinstance(roi, SegmentChain):
             return roi.get_counts(self)
-        if roi.chrom not in self._chr_lengths or not self._is_lowerable():
+        if roi.chrom not in self._chr_lengths or not self._is_lowerable() or (self.is_lazy and self._planes is None):
             return self.get_reads_and_counts(roi, roi_order=roi_order)[1]
         qs = roi.strand if roi.strand in ("+", "-") else "."
         planes = self.count_planes(("+", "-") if qs != "." else (".",))

@@ -46,6 +46,28 @@ def main():
     os.remove(sam)
     print("wrote", bam, os.path.getsize(bam), "bytes")
     write_positions(bam)
+    write_index_and_fetches(bam)
+
+
+def write_index_and_fetches(bam):
+    """htslib_allops.bam.bai: the index htslib's own indexer writes for the golden BAM; htslib_allops.fetch.txt: what
+    htslib's iterator (pysam's ``AlignmentFile.fetch``) returns for 300 seeded regions (and a few whole chromosomes) — the records of every region.  Pins
+    pb_bam_fetch / pb_bam_build_index (plastid_b200/csrc/pb_bam.cpp) against the reference tree's own code."""
+    subprocess.check_call([TOOL, "index", bam])
+    rng = np.random.default_rng(77)
+    lens = [60000, 25000, 500, 9000]
+    args = []
+    for k in range(300):
+        tid = int(rng.integers(0, 4))
+        beg = int(rng.integers(0, lens[tid]))
+        width = int(rng.choice([1, 10, 100, 1000]))
+        args += [str(tid), str(beg), str(min(lens[tid], beg + width))]
+    args += ["0", "0", "60000", "1", "16383", "16385", "3", "8999", "9000", "1", "3000", "25000", "2", "0", "500"]
+    out = subprocess.check_output([TOOL, "fetch", bam] + args)
+    import gzip
+    with open(os.path.join(HERE, "htslib_allops.fetch.txt.gz"), "wb") as raw, gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0) as fh:
+        fh.write(out)
+    print("wrote htslib_allops.bam.bai and htslib_allops.fetch.txt.gz:", out.count(b"#"), "regions")
 
 
 def write_positions(bam):
@@ -75,7 +97,9 @@ def write_positions(bam):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "positions":      # only the pileup-derived positions of the committed BAM
+    if len(sys.argv) > 1 and sys.argv[1] == "index":           # only the index / fetch fixtures of the committed BAM
+        write_index_and_fetches(os.path.join(HERE, "htslib_allops.bam"))
+    elif len(sys.argv) > 1 and sys.argv[1] == "positions":      # only the pileup-derived positions of the committed BAM
         write_positions(os.path.join(HERE, "htslib_allops.bam"))
     else:
         main()

@@ -467,3 +467,154 @@ def test_speculative_walk_holds_on_a_file_written_by_the_reference_htslib(tmp_pa
         assert hb.positions_of(i) == po.positions_from_cigar(pos, cig)
     starts = np.array([int(r[1]) for r in recs])
     assert (hb.ref_start == starts).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# indexed access: pb_bai_open / pb_bam_fetch / pb_bam_build_index against the reference's vendored htslib
+# (tests/golden/htslib_allops.bam.bai written by its indexer, htslib_allops.fetch.txt.gz by its iterator)
+# ------------------------------------------------------------------------------------------------------------------
+def parse_fetches(path):
+    import gzip
+    regions = []
+    with gzip.open(path, "rt") as fh:
+        for line in fh:
+            f = line.split()
+            if f[0] == "#":
+                regions.append([tuple(int(x) for x in f[1:4]), []])
+            elif f[0] == "=":
+                assert int(f[1]) == len(regions[-1][1])
+            else:
+                cigar = [] if f[2] == "*" else [tuple(int(v) for v in c.split(":")) for c in f[2].split(",")]
+                regions[-1][1].append((int(f[0]), int(f[1]), cigar, int(f[3])))
+    return regions
+
+
+def expected_rows(records):
+    """What a batch holds of the records htslib's iterator returned: placed, not flagged unmapped, at least one
+    aligned base; rows by first aligned position (stable)."""
+    rows = []
+    for pos, flag, cigar, _endpos in records:
+        blocks, _span = cigar_to_blocks(cigar) if cigar else ([], 0)
+        if flag & 4 or not blocks:
+            continue
+        rows.append((pos + blocks[0][0], sum(n for _a, n in blocks), (flag >> 4) & 1, len(blocks)))
+    return sorted(rows, key=lambda r: r[0])
+
+
+def batch_rows(hb):
+    return [(int(hb.ref_start[i]), int(hb.meta[i]) & 0xFFFF, (int(hb.meta[i]) >> 16) & 1, int(hb.meta[i]) >> 24) for i in range(len(hb))]
+
+
+def test_index_statistics_and_header_without_decoding():
+    refs, recs = parse_dump(os.path.join(GOLD, "htslib_allops.dump.txt"))
+    f = bam_io.IndexedBam(os.path.join(GOLD, "htslib_allops.bam"))
+    assert list(f.references) == [r[0] for r in refs] and list(f.lengths) == [r[1] for r in refs]
+    # `bamfile.mapped`: placed records without the unmapped flag, from the index's metadata pseudo-bins
+    assert f.mapped == sum(1 for r in recs if r[0] >= 0 and not (r[2] & 4))
+    L = _lib.lib()
+    for t in range(len(refs)):
+        assert L.pb_bai_mapped(f._idx, t) == sum(1 for r in recs if r[0] == t and not (r[2] & 4))
+    f.close()
+    with pytest.raises(ValueError):
+        f.fetch(refs[0][0], 0, 10)
+
+
+def test_fetch_returns_what_the_reference_htslib_iterator_returns():
+    regions = parse_fetches(os.path.join(GOLD, "htslib_allops.fetch.txt.gz"))
+    assert len(regions) >= 300 and sum(len(r) for _k, r in regions) > 4000
+    f = bam_io.IndexedBam(os.path.join(GOLD, "htslib_allops.bam"))
+    whole = bam_io.batch_from_bam(os.path.join(GOLD, "htslib_allops.bam"))
+    for (tid, beg, end), records in regions:
+        hb = f.fetch(f.references[tid], beg, end)
+        assert batch_rows(hb) == expected_rows(records), (tid, beg, end)
+        assert list(np.diff(hb.chrom_read_off)) == [len(hb) if t == tid else 0 for t in range(len(f.references))]
+        for i in range(len(hb)):                      # block rows travel with their reads
+            r0, r1 = int(whole.chrom_read_off[tid]), int(whole.chrom_read_off[tid + 1])
+            cands = [j for j in range(r0, r1) if whole.ref_start[j] == hb.ref_start[i] and whole.meta[j] == hb.meta[i]]
+            assert any(whole.positions_of(j) == hb.positions_of(i) for j in cands)
+    # regions outside the file's references or past a chromosome's end are empty, as pysam's fetch is
+    assert len(f.fetch("nope", 0, 100)) == 0
+    assert len(f.fetch(f.references[2], f.lengths[2], f.lengths[2] + 50)) == 0
+    assert len(f.fetch(f.references[0], 50, 50)) == 0
+
+
+def _parse_bai(path):
+    import struct
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"BAI\1"
+    n_ref, = struct.unpack_from("<i", raw, 4)
+    p, refs = 8, []
+    for _ in range(n_ref):
+        n_bin, = struct.unpack_from("<i", raw, p); p += 4
+        bins = {}
+        for _b in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", raw, p); p += 8
+            bins[b] = [struct.unpack_from("<QQ", raw, p + 16 * k) for k in range(n_chunk)]
+            p += 16 * n_chunk
+        n_intv, = struct.unpack_from("<i", raw, p); p += 4
+        ioff = list(struct.unpack_from("<%dQ" % n_intv, raw, p)); p += 8 * n_intv
+        refs.append((bins, ioff))
+    tail = struct.unpack_from("<Q", raw, p)[0] if p + 8 <= len(raw) else None
+    return refs, tail
+
+
+def test_own_index_serves_the_same_fetches_as_the_reference_htslib_index(tmp_path):
+    bam = os.path.join(GOLD, "htslib_allops.bam")
+    mine = bam_io.build_index(bam, str(tmp_path / "mine.bai"))
+    got, got_tail = _parse_bai(mine)
+    want, want_tail = _parse_bai(bam + ".bai")
+    assert len(got) == len(want) and got_tail == want_tail               # records without coordinates
+    for (gb, gi), (wb, wi) in zip(got, want):
+        assert gb.get(37450) == wb.get(37450)                            # file range + mapped / unmapped counts
+        assert gi == wi                                                   # linear index, window by window
+        # htslib moves the chunks of small bins into their parents; every record offset it lists must still be
+        # covered by a chunk of ours in the same bin or a descendant of it — checked through the fetches below
+    a, b = bam_io.IndexedBam(bam, index=mine), bam_io.IndexedBam(bam)
+    assert a.mapped == b.mapped
+    for (tid, beg, end), records in parse_fetches(os.path.join(GOLD, "htslib_allops.fetch.txt.gz")):
+        assert batch_rows(a.fetch(a.references[tid], beg, end)) == expected_rows(records)
+
+
+def test_build_index_refuses_unsorted_files_and_fetch_reports_bad_indexes(tmp_path):
+    path = str(tmp_path / "u.bam")
+    bam_io.write_bam(path, {"c": 1000}, [(0, 500, 0, [(0, 20)]), (0, 100, 0, [(0, 20)])])
+    with pytest.raises(_lib.PlastidB200Error, match="not coordinate-sorted"):
+        bam_io.build_index(path)
+    open(str(tmp_path / "bad.bai"), "wb").write(b"BAI\1\x01\x00\x00\x00\x05")
+    with pytest.raises(_lib.PlastidB200Error, match="truncated index"):
+        bam_io.IndexedBam(os.path.join(GOLD, "htslib_allops.bam"), index=str(tmp_path / "bad.bai"))
+    with pytest.raises(IOError):
+        bam_io.IndexedBam(path)                                           # no index beside the file
+
+
+@pytest.mark.parametrize("aligned", [False, True])
+def test_fetch_equals_filtering_the_whole_file(tmp_path, aligned):
+    """Many BGZF members, records cut across members (``aligned=False``), spliced reads longer than a 16 kb index
+    window: every fetch equals the rows of the decoded file whose reference span overlaps the region."""
+    rng = np.random.default_rng(21)
+    lens = {"c1": 400000, "c2": 90000}
+    recs, spans = [], []
+    for ci, c in enumerate(lens):
+        reads = sorted(random_cigar_reads(rng, 6000 if ci == 0 else 1500, lens[c], lens[c] - 30000), key=lambda r: r.reference_start)
+        for k, r in enumerate(reads):
+            cig = list(r.cigartuples)
+            if k % 400 == 0:
+                cig = cig + [(3, 20000), (0, 10)]                        # an intron across index windows
+            recs.append((ci, r.reference_start, 16 if r.is_reverse else 0, cig))
+    path = str(tmp_path / "big.bam")
+    bam_io.write_bam(path, lens, recs, block_bytes=3000, record_aligned=aligned)
+    bam_io.build_index(path)
+    f = bam_io.IndexedBam(path)
+    whole = bam_io.batch_from_bam(path)
+    assert f.mapped == whole.mapped == len(recs)
+    per = [[], []]
+    for tid, pos, flag, cig in recs:
+        blocks, span = cigar_to_blocks(cig)
+        per[tid].append((pos, pos + max(span, 1), pos + blocks[0][0], sum(n for _a, n in blocks), (flag >> 4) & 1, len(blocks)))
+    for _ in range(120):
+        tid = int(rng.integers(0, 2))
+        n = lens[f.references[tid]]
+        beg = int(rng.integers(0, n))
+        end = min(n, beg + int(rng.choice([1, 50, 3000, 40000])))
+        want = sorted((r[2:] for r in per[tid] if r[0] < end and r[1] > beg), key=lambda r: r[0])
+        assert batch_rows(f.fetch(f.references[tid], beg, end)) == want, (tid, beg, end)

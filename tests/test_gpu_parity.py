@@ -802,6 +802,60 @@ def test_bam_genome_array_from_bam_file(tmp_path, cuda_device):
             assert (got == exp).all(), (strand, chrom)
 
 
+def test_indexed_bam_genome_array_seeks_and_equals_the_decoded_one(tmp_path, cuda_device):
+    """``BAMGenomeArray(path, indexed=True)``: region queries go through the .bai (the reference's access pattern,
+    genome_array.py:800-809) and give what the whole-file container gives — counts, reads returned, sum from the
+    index statistic, normalisation, generic filters — for point, Center and stratified rules over two files; a
+    whole-genome consumer (``count_chains``) decodes the files on first use."""
+    from plastid_b200 import bam_io
+    rng = np.random.default_rng(18)
+    lens = {"chrA": 60000, "chrB": 20000}
+    paths = []
+    for k in range(2):
+        recs = []
+        for ci, c in enumerate(lens):
+            reads = sorted(random_cigar_reads(rng, 3000 if ci == 0 else 800, lens[c], lens[c] - 2000), key=lambda x: x.reference_start)
+            recs += [(ci, r.reference_start, 16 if r.is_reverse else 0, r.cigartuples) for r in reads]
+        paths.append(str(tmp_path / ("f%d.bam" % k)))
+        bam_io.write_bam(paths[-1], lens, recs, block_bytes=4000)
+        bam_io.build_index(paths[-1])
+    segs = []
+    for _ in range(25):
+        c = "chrA" if rng.random() < 0.7 else "chrB"
+        a = int(rng.integers(0, lens[c] - 10))
+        segs.append(pb.GenomicSegment(c, a, min(lens[c], a + int(rng.choice([1, 30, 700, 9000]))), "+-."[int(rng.integers(0, 3))]))
+    segs.append(pb.GenomicSegment("chrB", 19990, 20040, "+"))               # past the chromosome's end
+    segs.append(pb.GenomicSegment("nope", 0, 10, "+"))
+    for mapping in (pb.FivePrimeMapFactory(3), pb.CenterMapFactory(4), pb.VariableFivePrimeMapFactory({20: 2, 30: 5, "default": 1}),
+                    pb.StratifiedVariableFivePrimeMapFactory({20: 2, 30: 5, "default": 1}, 15, 40)):
+        lazy = pb.BAMGenomeArray(*paths, mapping=mapping, device=cuda_device, indexed=True)
+        eager = pb.BAMGenomeArray(*paths, mapping=mapping, device=cuda_device)
+        assert lazy.is_lazy and lazy.sum() == eager.sum() == 7600
+        assert lazy.chroms() == eager.chroms() and lazy.lengths() == eager.lengths()
+        lazy.add_filter("size", pb.SizeFilterFactory(12, 200)); eager.add_filter("size", pb.SizeFilterFactory(12, 200))
+        lazy.add_filter("fw5", lambda r: r.reference_start % 5 != 0); eager.add_filter("fw5", lambda r: r.reference_start % 5 != 0)
+        lazy.set_normalize(True); eager.set_normalize(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for seg in segs:
+                ra, ca = lazy.get_reads_and_counts(seg)
+                rb, cb = eager.get_reads_and_counts(seg)
+                assert ca.shape == cb.shape and (ca == cb).all(), (type(mapping).__name__, str(seg))
+                key = lambda r: (r.reference_start, r.is_reverse, tuple(r.positions))
+                assert sorted(map(key, ra)) == sorted(map(key, rb))
+                ga, gb = lazy[seg], eager[seg]
+                assert ga.shape == gb.shape and np.allclose(ga, gb, rtol=1e-12, atol=0)
+        assert lazy.is_lazy                                                  # nothing decoded so far
+    lazy = pb.BAMGenomeArray(*paths, mapping=pb.FivePrimeMapFactory(3), device=cuda_device, indexed=True)
+    eager = pb.BAMGenomeArray(*paths, mapping=pb.FivePrimeMapFactory(3), device=cuda_device)
+    lazy.set_sum(123)
+    chains = [pb.SegmentChain(pb.GenomicSegment("chrA", 100, 900, "+"), pb.GenomicSegment("chrA", 2000, 2500, "+")),
+              pb.SegmentChain(pb.GenomicSegment("chrB", 50, 15000, "-"))]
+    sa, la = lazy.count_chains(chains)
+    sb, lb = eager.count_chains(chains)
+    assert not lazy.is_lazy and (sa == sb).all() and (la == lb).all() and sa.sum() > 0 and lazy.sum() == 123
+
+
 def test_golden_bam_count_vectors_from_reference_htslib_positions(cuda_device):
     """End of the chain for non-M CIGARs without the oracle in between: the committed golden BAM (every
     CIGAR op; written and piled up by the reference's vendored htslib, tests/golden/htslib_allops.*) is

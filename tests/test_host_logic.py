@@ -623,14 +623,6 @@ def test_phase_table_reproduces_the_rows_printed_in_the_reference_docs():
         assert ["%.6f" % x for x in phases[i]] == [p0, p1, p2]
 
 
-def test_cs_generate_refuses_genes_on_several_chromosomes():
-    from plastid_b200.bin import cs
-    tx = {"a": pb.Transcript(pb.GenomicSegment("c1", 1, 5, "+"), ID="a", gene_id="g"),
-          "b": pb.Transcript(pb.GenomicSegment("c2", 1, 5, "+"), ID="b", gene_id="g")}
-    with pytest.raises(ValueError):
-        cs.process_partial_group(tx, None, device="cpu")      # raised before any device work
-
-
 def test_merge_and_positions_to_segments_reference_known_answers():
     """test_roitools.py:212-268 and :356-398 for the host objects and the oracle's restatements."""
     from helpers import merge_segments_known_answers, positions_to_segments_known_answers
