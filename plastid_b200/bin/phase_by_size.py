@@ -21,10 +21,12 @@ def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
     ``-codon_buffer`` with an annotation; note ``-0`` selects nothing there, and here).
 
     The reference does not reset its per-length read lists between the exons of a coding region
-    (phase_by_size.py:186-194): a read that the fetch of an earlier exon returned too (a read across the exon
-    junction) is mapped once more against the later exon.  The kernel counts such a read with that multiplicity
-    (test_gpu_ref_goldens.py::test_phase_by_size_junction_reads).  Point rules count sites; CenterMapFactory counts
-    every trimmed position as an integer per read length and the weight ``1 / (L - 2 nibble)`` is applied here."""
+    (phase_by_size.py:186-194).  The lists hold the rule's ``reads_out``: for point rules the reads whose site lies in
+    the exon (they have no site in a later exon — nothing changes), for CenterMapFactory every read the fetch returned,
+    so a read across an exon junction is mapped once more against the later exon.  The kernel counts such a read with
+    that multiplicity under the Center rule (test_gpu_ref_goldens.py::test_phase_by_size_junction_reads).  Point rules
+    count sites; CenterMapFactory counts every trimmed position as an integer per read length and the weight
+    ``1 / (L - 2 nibble)`` is applied here."""
     back_buffer = -codon_buffer if back_buffer is None else back_buffer
     chains = [c for c in cds_chains if len(c) > 0]
     read_lengths = list(read_lengths)
@@ -40,15 +42,17 @@ def do_phase(ga, cds_chains, read_lengths, codon_buffer=5, back_buffer=None):
     if isinstance(ga.map_fn, CenterMapFactory):
         for k in range(lo, hi + 1):
             m = k - 2 * ga.map_fn.nibble
-            sums[k - lo] = sums[k - lo] * (1.0 / m) if m > 0 else 0.0
+            sums[k - lo] = sums[k - lo] / float(m) if m > 0 else 0.0           # integer count / m: correctly rounded
     return {k: sums[k - lo] for k in read_lengths}
 
 
 def phase_table(sums):
     """phase_by_size.py:216-235: ``reads_counted`` is an integer column (the fractional sums of the Center rule are
-    truncated when they are assigned to it), and the fractions are taken from it."""
+    truncated when they are assigned to it), and the fractions are taken from it.  Under the Center rule the reference's
+    float sum of ``1 / m`` weights sits a rounding error above or below an integer whenever whole reads lie inside the
+    region; here the truncation is applied to the exact value (counts / m, a 1e-9 guard against the last bit)."""
     lengths = sorted(sums)
-    counted = np.array([int(sums[k].sum()) for k in lengths], dtype=np.int64)
+    counted = np.array([int(np.floor(sums[k].sum() + 1e-9)) for k in lengths], dtype=np.int64)
     with np.errstate(all="ignore"):
         frac = counted.astype(float) / counted.sum()
         phases = np.array([sums[k].astype(float) / sums[k].astype(float).sum() for k in lengths])

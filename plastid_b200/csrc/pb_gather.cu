@@ -609,10 +609,13 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
                 const int L = PB_META_L(m);
                 if (L < min_len || L >= min_len + n_len) continue;           // psite.py:187: len(positions) in read_dict
                 // phase mode: the reference does not reset its per-length read lists between the exons of a coding
-                // region (phase_by_size.py:186-194), so a read that the fetch of an EARLIER exon of this chain returned
-                // too — its span reaches back over that exon's end — is mapped once more against this exon per such exon
+                // region (phase_by_size.py:186-194); the lists hold what `get_reads` returned, i.e. the rule's
+                // `reads_out`.  CenterMapFactory returns every read it was given (map_factories.pyx:256), so a read
+                // that the fetch of an EARLIER exon of this chain returned too — its span reaches back over that exon's
+                // end — is mapped once more against this exon per such exon.  Point rules return only the reads whose
+                // site lies in the exon (:351-353): a read kept for an earlier exon has no site here, multiplicity 1.
                 uint32_t mult = 1;
-                if (phase_mode)
+                if (phase_mode && r.kind == PB_RULE_CENTER)
                     for (int64_t j = k - 1; j >= k0 && __ldg(bend + j) - base > (int64_t)sv[u]; --j) ++mult;
                 auto add_site = [&](int64_t p) {
                     if (base + p < lo_bin || base + p >= hi_bin) return;         // the site belongs to another rank

@@ -240,27 +240,44 @@ pb_point_overflow_kernel(PbReads b, PbRuleDev r, int planes, const PbTile *__res
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     uint4 *smem4 = reinterpret_cast<uint4 *>(smem);
     PbCounters c = {0, 0, 0, 0, 0, 0, 0};
+    for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
+    // Invariant: the tile buffer is all zero at the top of every iteration.  A job's reads are a run of the sorted
+    // batch, so their sites lie in [first start, last start + longest block): only that stretch of the tile is added to
+    // the planes and re-zeroed.  A pile-up's jobs (hundreds on one tile) then reduce a few hundred bytes each into the
+    // same lines of L2 instead of the whole 16 KB tile per plane.
     for (;;) {
         if (threadIdx.x == 0) s_job = (long long)atomicAdd(job_counter, 1ull);
-        for (int j = threadIdx.x; j < n_planes * kPTileBins / 4; j += kPThreads) smem4[j] = zero4;
         __syncthreads();
         const long long job = s_job;
         if (job >= n_jobs) break;
         const PbJob jb = jobs[job];
         const PbTile d = tiles[jb.tile];
+        long long o_lo = (long long)__ldg(b.ref_start + jb.lo) - d.p0;
+        long long o_hi = (long long)__ldg(b.ref_start + jb.lo + jb.n - 1) + b.max_block_len - d.p0;
+        o_lo = o_lo < 0 ? 0 : (o_lo & ~3ll);                       // bulk copies move 16-byte units
+        o_hi = o_hi > kPTileBins ? kPTileBins : ((o_hi + 3) & ~3ll);
         pb_scan_reads(b, r, skip_multi != 0, jb.lo, jb.lo + jb.n, d.p0, d.p0 + d.live, d.p0 + kPTileBins, smem, pl, c);
-        pb_fence_proxy_async();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int64_t g0 = jb.tile * kPTileBins;
-            int q = 0;
-            if (pl.want_plus) pb_bulk_add_u32(out_plus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
-            if (pl.want_minus) pb_bulk_add_u32(out_minus + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
-            if (pl.want_any) pb_bulk_add_u32(out_any + g0, smem + (q++) * kPTileBins, kPTileBins * 4);
-            pb_bulk_commit();
-            pb_bulk_wait_read0();
+        if (o_lo < o_hi) {
+            pb_fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int64_t g0 = jb.tile * kPTileBins + o_lo;
+                const uint32_t bytes = (uint32_t)(o_hi - o_lo) * 4u;
+                int q = 0;
+                if (pl.want_plus) pb_bulk_add_u32(out_plus + g0, smem + (q++) * kPTileBins + o_lo, bytes);
+                if (pl.want_minus) pb_bulk_add_u32(out_minus + g0, smem + (q++) * kPTileBins + o_lo, bytes);
+                if (pl.want_any) pb_bulk_add_u32(out_any + g0, smem + (q++) * kPTileBins + o_lo, bytes);
+                pb_bulk_commit();
+                pb_bulk_wait_read0();
+            }
+            __syncthreads();
+            const int w4 = (int)((o_hi - o_lo) >> 2);
+            for (int j = threadIdx.x; j < n_planes * w4; j += kPThreads) {
+                const int q = j / w4, k = j - q * w4;
+                smem4[(q * kPTileBins + (int)o_lo) / 4 + k] = zero4;
+            }
         }
-        __syncthreads();
+        __syncthreads();                                           // s_job is rewritten at the top
     }
     pb_flush_cta_stats(c.drop_p, c.drop_m, c.drop_a, c.drop_len, c.map_p, c.map_m, c.map_a, stat_slots);
     if (threadIdx.x == 0) pb_bulk_wait_all();

@@ -64,10 +64,10 @@ def shard_reads(hb, rank, world_size):
     return out
 
 
-def position_cuts(hb, layout, world_size, snap="bins"):
+def position_cuts(hb, layout, world_size, snap="bins", weights=(1.0, 1.0)):
     """Global-bin cut points ``int64[world_size + 1]`` (multiples of PB_LAYOUT_ALIGN, first 0, last
-    ``layout.total_bins``) splitting the reads into ``world_size`` contiguous position ranges of about
-    equal read count.  ``snap="chromosomes"``: cuts fall on chromosome boundaries only (BASELINE config 5,
+    ``layout.total_bins``) splitting the genome into ``world_size`` contiguous position ranges of about
+    equal cost (:func:`balanced_cuts`: reads streamed + plane bins written).  ``snap="chromosomes"``: cuts fall on chromosome boundaries only (BASELINE config 5,
     "sharded by chromosome": every rank owns a run of whole chromosomes) — the boundary whose cumulative read
     count is nearest each target."""
     from . import _lib
@@ -83,16 +83,44 @@ def position_cuts(hb, layout, world_size, snap="bins"):
         return np.asarray(cuts, dtype=np.int64)
     if snap != "bins":
         raise ValueError("snap must be 'bins' or 'chromosomes'")
+    starts, off = hb.ref_start, np.asarray(hb.chrom_read_off, dtype=np.int64)
+
+    def reads_before(c, local):
+        a, b = int(off[c]), int(off[c + 1])
+        return a + int(np.searchsorted(starts[a:b], local, side="left"))
+    return balanced_cuts(layout, n, world_size, reads_before, weights)
+
+
+def balanced_cuts(layout, n_reads, world_size, reads_before, weights=(1.0, 1.0)):
+    """Cut points that give every rank the same COST, ``weights[0] * reads + weights[1] * bins``: a rank's mapping
+    pass streams its reads (8 bytes each) and writes the dense planes of its bins (2 strands x 4 bytes), so equal read
+    counts alone leave the rank with the sparsest stretch of genome the most plane bytes to write (N = 8, C2: 363-401 M
+    bins per rank and tiles-kernel times to match, profiles/NOTES_r02.md section 5).  ``weights=(1, 0)`` is the
+    equal-read-count rule.  ``reads_before(c, local)``: reads of chromosome ``c`` and before that start before
+    chromosome position ``local`` (host: a search in ``ref_start``; device batches search on the device).
+    The cost is monotone in the cut position: one bisection over the PB_LAYOUT_ALIGN grid per cut."""
+    from . import _lib
+    A = _lib.PB_LAYOUT_ALIGN
+    total = int(layout.total_bins)
+    wr, wb = float(weights[0]), float(weights[1])
+    coff = np.asarray(layout.chrom_bin_off, dtype=np.int64)
+
+    def cost(g):
+        c = min(int(np.searchsorted(coff, g, side="right")) - 1, len(layout.chroms) - 1)
+        return wr * reads_before(c, g - int(coff[c])) + wb * g
+    whole = wr * n_reads + wb * total
     cuts = [0]
     for r in range(1, world_size):
-        i = (r * n) // world_size
-        if i >= n:
-            g = int(layout.total_bins)
-        else:
-            c = int(np.searchsorted(hb.chrom_read_off, i, side="right")) - 1
-            g = int(layout.chrom_bin_off[c]) + int(hb.ref_start[i])
-        cuts.append(max((g // A) * A, cuts[-1]))
-    cuts.append(int(layout.total_bins))
+        target = whole * r / world_size
+        lo, hi = cuts[-1] // A, total // A                # smallest grid point whose cost reaches the target
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if cost(mid * A) >= target:
+                hi = mid
+            else:
+                lo = mid + 1
+        cuts.append(lo * A)
+    cuts.append(total)
     return np.asarray(cuts, dtype=np.int64)
 
 
@@ -131,9 +159,9 @@ def shard_positions(hb, layout, rank, world_size, cuts=None, snap="bins"):
     return sub, g_lo, g_hi
 
 
-def shard_positions_device(dbatch, layout, rank, world_size):
+def shard_positions_device(dbatch, layout, rank, world_size, weights=(1.0, 1.0)):
     """:func:`shard_positions` for a batch that already lives on the device (unspliced batches): the
-    same cuts (global bin of read ``r * n // world``, rounded down to the layout granularity), the
+    same cuts (:func:`balanced_cuts`), the
     rank's reads + halo gathered per chromosome with searches on the device.
     Returns ``(sub_batch, bin_lo, bin_hi, cuts)``."""
     import torch
@@ -141,18 +169,18 @@ def shard_positions_device(dbatch, layout, rank, world_size):
     from .batch import DeviceBatch
     if dbatch.blk_off is not None:
         raise ValueError("shard_positions_device handles unspliced batches; shard spliced batches on the host")
-    A, n = _lib.PB_LAYOUT_ALIGN, dbatch.n_reads
+    n = dbatch.n_reads
     off = dbatch.chrom_read_off.cpu().numpy()
-    cuts = [0]
-    for r in range(1, world_size):
-        i = (r * n) // world_size
-        if i >= n:
-            g = int(layout.total_bins)
-        else:
-            c = int(np.searchsorted(off, i, side="right")) - 1
-            g = int(layout.chrom_bin_off[c]) + int(dbatch.ref_start[i].item())
-        cuts.append(max((g // A) * A, cuts[-1]))
-    cuts.append(int(layout.total_bins))
+
+    def reads_before(c, local):
+        a, b = int(off[c]), int(off[c + 1])
+        if b <= a or local <= 0:
+            return a
+        if local >= int(layout.chrom_len[c]):
+            return b
+        key = torch.tensor([local], dtype=dbatch.ref_start.dtype, device=dbatch.ref_start.device)
+        return a + int(torch.searchsorted(dbatch.ref_start[a:b], key, right=False).item())
+    cuts = [int(x) for x in balanced_cuts(layout, n, world_size, reads_before, weights)]
     g_lo, g_hi = cuts[rank], cuts[rank + 1]
     pieces, new_off = [], [0]
     for c in range(dbatch.n_chrom):

@@ -840,11 +840,13 @@ def test_indexed_bam_genome_array_seeks_and_equals_the_decoded_one(tmp_path, cud
             for seg in segs:
                 ra, ca = lazy.get_reads_and_counts(seg)
                 rb, cb = eager.get_reads_and_counts(seg)
-                assert ca.shape == cb.shape and (ca == cb).all(), (type(mapping).__name__, str(seg))
+                # integer rules: bit-exact; Center: float64 atomics in whatever order the reads arrive
+                same = np.allclose(ca, cb, rtol=1e-8, atol=0) if isinstance(mapping, pb.CenterMapFactory) else (ca == cb).all()
+                assert ca.shape == cb.shape and same, (type(mapping).__name__, str(seg))
                 key = lambda r: (r.reference_start, r.is_reverse, tuple(r.positions))
                 assert sorted(map(key, ra)) == sorted(map(key, rb))
                 ga, gb = lazy[seg], eager[seg]
-                assert ga.shape == gb.shape and np.allclose(ga, gb, rtol=1e-12, atol=0)
+                assert ga.shape == gb.shape and np.allclose(ga, gb, rtol=1e-8, atol=0)      # eager Center planes: fixed-point weights
         assert lazy.is_lazy                                                  # nothing decoded so far
     lazy = pb.BAMGenomeArray(*paths, mapping=pb.FivePrimeMapFactory(3), device=cuda_device, indexed=True)
     eager = pb.BAMGenomeArray(*paths, mapping=pb.FivePrimeMapFactory(3), device=cuda_device)

@@ -1291,6 +1291,37 @@ def test_chromosome_cuts_fall_on_chromosome_boundaries():
         assert held == len(hb)          # whole chromosomes: no halo read is needed twice
 
 
+def test_position_cuts_balance_reads_plus_plane_bins():
+    """Cuts give every rank the same cost ``reads + bins`` (bytes streamed + plane bytes written, dist.balanced_cuts):
+    a skewed batch (most reads on one chromosome) no longer leaves one rank with most of the genome to write;
+    ``weights=(1, 0)`` is the equal-read-count rule."""
+    from plastid_b200 import dist as pd, _lib
+    rng = np.random.default_rng(5)
+    lens = [400000, 900000, 250000, 16384, 700000]
+    chroms = ["c%d" % i for i in range(len(lens))]
+    n = 300000
+    cid = np.sort(rng.choice(len(lens), n, p=[0.7, 0.05, 0.1, 0.05, 0.1]))
+    start = np.array([rng.integers(0, lens[c] - 40) for c in cid])
+    hb = pb.batch_from_arrays(chroms, lens, cid, start, np.full(n, 30), np.zeros(n, dtype=bool))
+    layout = pb.GenomeLayout(chroms, lens)
+    g = layout.chrom_bin_off[cid] + hb.ref_start                                       # global bin of every read's start
+    for world in (2, 3, 8):
+        for w in ((1.0, 1.0), (1.0, 0.0), (1.0, 4.0)):
+            cuts = pd.position_cuts(hb, layout, world, weights=w)
+            assert cuts[0] == 0 and cuts[-1] == layout.total_bins and (np.diff(cuts) >= 0).all() and len(cuts) == world + 1
+            assert (cuts % _lib.PB_LAYOUT_ALIGN == 0).all()
+            reads = np.array([np.count_nonzero((g >= cuts[r]) & (g < cuts[r + 1])) for r in range(world)])
+            cost = w[0] * reads + w[1] * np.diff(cuts)
+            assert reads.sum() == n
+            # one grid step of slack: PB_LAYOUT_ALIGN bins and the reads that start in them
+            slack = w[1] * _lib.PB_LAYOUT_ALIGN + w[0] * np.bincount(g // _lib.PB_LAYOUT_ALIGN).max()
+            assert cost.max() - cost.min() <= 2 * slack, (world, w, cost)
+        eq = pd.position_cuts(hb, layout, world, weights=(1.0, 0.0))
+        reads = np.array([np.count_nonzero((g >= eq[r]) & (g < eq[r + 1])) for r in range(world)])
+        bal = pd.position_cuts(hb, layout, world)
+        assert np.diff(bal).max() < np.diff(eq).max()                   # the sparse stretch is shared out
+
+
 def test_mapping_flags_behave_like_the_reference_parser(capsys):
     """argparsers.py:439-470, 656-700: store_const into one destination (last flag wins), no flag -> message + exit 1,
     --fiveprime_variable without an offset file -> message + exit 1; --normalize / --sum handled as in :775-780."""
