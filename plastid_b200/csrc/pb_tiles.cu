@@ -57,10 +57,12 @@ __global__ void pb_tile_index_kernel(PbReads b, PbLayoutDev lay, int tile_bins, 
 // ----------------------------------------------------------------------------------------
 // K1: CIGAR blocks of multi-block reads -> per-tile record buckets (counting sort by tile)
 // ----------------------------------------------------------------------------------------
-template <bool CENTER, int OCC>
+// FILL = 0: count pass (one fire-and-forget RED per record, no record is built); FILL = 1: fill pass.  AGG: lanes that
+// target the same tile share one cursor atomic (match.any) instead of one returning atomic per record.
+template <bool CENTER, int OCC, bool FILL, bool AGG>
 __global__ void __launch_bounds__(256, OCC)   // latency-bound gather chains: resident threads vs registers (OCC CTAs/SM)
 pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t *__restrict__ slot_of_len,
-              int tile_shift, int64_t tile_lo, int64_t tile_hi, int64_t tile_rec_lo, int64_t read_begin, int fill,
+              int tile_shift, int64_t tile_lo, int64_t tile_hi, int64_t tile_rec_lo, int64_t read_begin,
               uint32_t *__restrict__ rec_cursor,
               const uint32_t *__restrict__ rec_off, PbRec *__restrict__ recs, unsigned long long *__restrict__ stat_slots)
 {
@@ -73,45 +75,21 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
                want_any = planes & PB_PLANE_ANY;
     // A warp takes 128 consecutive reads per round.  Only the multi-block ones (a third of the C3 batch)
     // have work to do, so the warp first compacts them into a dense shared-memory list (ballot + prefix
-    // popcount) and then walks that list with all lanes busy: ncu showed the uncompacted loop issue-bound at
-    // 11 of 32 lanes active per instruction.
+    // popcount) and then walks that list 32 at a time with ALL lanes busy; what is left of the list (< 32 entries)
+    // waits at its front for the next round's reads.  ncu history: the uncompacted loop was issue-bound at 11 of 32
+    // lanes active per instruction; the compacted loop without carry-over at 19.8 (a round leaves ~42 entries: one
+    // full pass and one with 10 lanes), 690 M warp instructions per pass at 61 % issue utilisation.
     constexpr int kU = 4;   // 32-read groups per round (independent loads in flight per thread)
-    __shared__ uint4 dense[8][kU * 32];
+    __shared__ uint4 dense[8][kU * 32 + 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t i_base = (read_begin / (kU * 32)) * (kU * 32);       // list entries hold read index - i_base (32 bits)
     // a lane's read indices only grow: the chromosome of the previous read is the place to start from
     int c = 0;
     int64_t c_end = __ldg(b.chrom_read_off + 1);
-    // reads [read_begin, b.n_reads) are looked at (a streamed upload maps a bin range from the reads that can
-    // reach it: those before read_begin end before the range, those from b.n_reads on have not arrived)
-    for (int64_t q = read_begin / (kU * 32) + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-         q * (kU * 32) < b.n_reads; q += n_warps) {
-      const int64_t r0 = q * (kU * 32);
-      uint32_t mv[kU], kv[kU];
-      int32_t sv[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-          const int64_t i = r0 + u * 32 + lane;
-          const bool ok = i >= read_begin && i < b.n_reads;
-          mv[u] = ok ? __ldg(b.meta + i) : 0u;
-          sv[u] = ok ? __ldg(b.ref_start + i) : 0;
-          kv[u] = ok ? __ldg(b.blk_off + i) : 0u;
-      }
-      int n_dense = 0;
-      __syncwarp();                                // the previous round's list has been consumed
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-          // n_blocks 0 is the out-of-range filler
-          const bool work = PB_META_NBLK(mv[u]) > 1 && pb_passes(mv[u], r.size_min, r.size_max);
-          const unsigned bal = __ballot_sync(0xffffffffu, work);
-          if (work) dense[wid][n_dense + __popc(bal & ((1u << lane) - 1u))] =
-              make_uint4(mv[u], (uint32_t)sv[u], kv[u], (uint32_t)(u * 32 + lane));
-          n_dense += __popc(bal);
-      }
-      __syncwarp();
-      for (int j = lane; j < n_dense; j += 32) {
-        const uint4 e = dense[wid][j];
-        const int64_t i = r0 + e.w;
+
+    auto process = [&](const uint4 e) {
+        const int64_t i = i_base + (int64_t)e.w;
         const uint32_t m = e.x;
         const uint32_t k_first = e.z;
         while (i >= c_end && c + 1 < b.n_chrom) { ++c; c_end = __ldg(b.chrom_read_off + c + 1); }
@@ -129,31 +107,35 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
             if (y > clen) y = clen;
             const int64_t tile = (base + x) >> tile_shift;       // tile sizes are powers of two
             if (tile < tile_rec_lo || tile >= tile_hi) return;
-            // reads are coordinate-sorted, so the lanes that are here together mostly target the same
-            // tile: one atomic per group of lanes instead of one per record
-            const unsigned lane = threadIdx.x & 31;
-            const unsigned act = __activemask();
-            const unsigned peers = __match_any_sync(act, (unsigned long long)tile);
-            const int leader = __ffs(peers) - 1;
-            uint32_t k = 0;
-            if ((int)lane == leader) k = atomicAdd(&rec_cursor[tile], (uint32_t)__popc(peers));
-            k = __shfl_sync(peers, k, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            if (fill) {
-                PbRec rec;
-                rec.x = (int32_t)x; rec.y = (int32_t)y; rec.tag = tag; rec.pad = 0;
-                recs[__ldg(rec_off + tile) + k] = rec;
+            if (!FILL) { atomicAdd(&rec_cursor[tile], 1u); return; }        // result unused: a RED, nothing to wait for
+            uint32_t k;
+            if (AGG) {
+                // reads are coordinate-sorted, so the lanes that are here together mostly target the same
+                // tile: one atomic per group of lanes instead of one per record
+                const unsigned ln = threadIdx.x & 31;
+                const unsigned act = __activemask();
+                const unsigned peers = __match_any_sync(act, (unsigned long long)tile);
+                const int leader = __ffs(peers) - 1;
+                k = 0;
+                if ((int)ln == leader) k = atomicAdd(&rec_cursor[tile], (uint32_t)__popc(peers));
+                k = __shfl_sync(peers, k, leader) + (uint32_t)__popc(peers & ((1u << ln) - 1u));
+            } else {
+                k = atomicAdd(&rec_cursor[tile], 1u);
             }
+            PbRec rec;
+            rec.x = (int32_t)x; rec.y = (int32_t)y; rec.tag = tag; rec.pad = 0;
+            recs[__ldg(rec_off + tile) + k] = rec;
         };
         if (CENTER) {
             const int nibble = r.param, map_len = L - 2 * nibble;
             if (map_len < 0) {                                   // map_factories.pyx:246-248
                 if (own) { drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L; }
-                continue;
+                return;
             }
-            if (map_len == 0) continue;
+            if (map_len == 0) return;
             if (own) { map_a++; if (rev) map_m++; else map_p++; }   // reads_out semantics (:256)
             const int slot = (int)__ldg(slot_of_len + L);
-            if (slot < 0) continue;
+            if (slot < 0) return;
             const uint32_t tag = (uint32_t)slot | ((uint32_t)rev << 16);
             const uint32_t k0 = k_first, k1 = k0 + (uint32_t)PB_META_NBLK(m);   // blk lists multi-block reads only
             int a = 0;  // aligned-base index of the block's first base
@@ -168,7 +150,7 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
             const int idx_f = pb_rule_index(r, L, false);
             if (idx_f < 0) {                                     // the reference skips the read and warns
                 if (own) { drop_a++; if (rev) drop_m++; else drop_p++; drop_len = L; }
-                continue;
+                return;
             }
             int64_t p_f = -1, p_r = -1;
             uint32_t tag_f = 0, tag_r = 0;
@@ -187,9 +169,46 @@ pb_bin_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int planes, const int16_t
             if (tag_f) emit(p_f, p_f + 1, tag_f);
             if (tag_r) emit(p_r, p_r + 1, tag_r);
         }
-      }
+    };
+
+    int n_dense = 0;                               // entries waiting in dense[wid][0 .. n_dense): warp-uniform, < 32 between rounds
+    // reads [read_begin, b.n_reads) are looked at (a streamed upload maps a bin range from the reads that can
+    // reach it: those before read_begin end before the range, those from b.n_reads on have not arrived)
+    for (int64_t q = read_begin / (kU * 32) + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+         q * (kU * 32) < b.n_reads; q += n_warps) {
+        const int64_t r0 = q * (kU * 32);
+        uint32_t mv[kU], kv[kU];
+        int32_t sv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int64_t i = r0 + u * 32 + lane;
+            const bool ok = i >= read_begin && i < b.n_reads;
+            mv[u] = ok ? __ldg(b.meta + i) : 0u;
+            sv[u] = ok ? __ldg(b.ref_start + i) : 0;
+            kv[u] = ok ? __ldg(b.blk_off + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            // n_blocks 0 is the out-of-range filler
+            const bool work = PB_META_NBLK(mv[u]) > 1 && pb_passes(mv[u], r.size_min, r.size_max);
+            const unsigned bal = __ballot_sync(0xffffffffu, work);
+            if (work) dense[wid][n_dense + __popc(bal & ((1u << lane) - 1u))] =
+                make_uint4(mv[u], (uint32_t)sv[u], kv[u], (uint32_t)(r0 - i_base) + (uint32_t)(u * 32 + lane));
+            n_dense += __popc(bal);
+        }
+        __syncwarp();
+        int j = 0;
+        for (; j + 32 <= n_dense; j += 32) process(dense[wid][j + lane]);
+        const int left = n_dense - j;
+        uint4 keep = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < left) keep = dense[wid][j + lane];
+        __syncwarp();                              // every lane has read its entry before the front is overwritten
+        if (j > 0 && lane < left) dense[wid][lane] = keep;
+        n_dense = left;
+        __syncwarp();
     }
-    if (!fill) pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
+    if (lane < n_dense) process(dense[wid][lane]);
+    if (!FILL) pb_flush_cta_stats(drop_p, drop_m, drop_a, drop_len, map_p, map_m, map_a, stat_slots);
 }
 
 // exclusive scan of the per-tile record counts in three small launches (4096 counts per CTA, scan
@@ -473,15 +492,22 @@ int pb_launch_binning(const PbReads &b, const PbRuleDev &r, const PbLayoutDev &l
         const int64_t lookback = ((int64_t)b.max_block_len + tile_bins - 1) / tile_bins;
         tile_rec_lo = tile_lo > lookback ? tile_lo - lookback : 0;
     }
-    int occ_sel = 8;
-    if (const char *e = getenv("PB_BIN_OCC")) occ_sel = atoi(e);        // measurement override (profiles/NOTES)
+    if (b.n_reads - (read_begin / 128) * 128 > 0xffffffffll) { pb_set_error("binning: more than 2^32 reads in one launch"); return PB_EINVAL; }
+    // PB_BIN_AGG=1 (A/B aid): the fill pass shares one cursor atomic among the lanes that target the same tile
+    const char *env_agg = getenv("PB_BIN_AGG");
+    const bool agg = env_agg && atoi(env_agg) != 0;
+    // PB_BIN_OCC=8 (A/B aid): 32 registers per thread (a few spills) for eight resident CTAs per SM instead of six
+    const char *env_occ = getenv("PB_BIN_OCC");
+    const int occ_sel = env_occ ? atoi(env_occ) : 6;
     for (int fill = 0; fill < 2; ++fill) {
-#define PB_BIN_LAUNCH(C_, O_) pb_bin_kernel<C_, O_><<<grid, 256, 0, stream>>>(bw, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, tile_rec_lo, read_begin, fill, ws.rec_cursor, ws.rec_off, ws.recs, ws.slots)
+#define PB_BIN_LAUNCH_O(C_, O_, F_, A_) pb_bin_kernel<C_, O_, F_, A_><<<grid, 256, 0, stream>>>(bw, r, lay, planes, slot_of_len, tile_shift, tile_lo, tile_hi, tile_rec_lo, read_begin, ws.rec_cursor, ws.rec_off, ws.recs, ws.slots)
+#define PB_BIN_LAUNCH(C_, F_, A_) do { if (occ_sel == 8) PB_BIN_LAUNCH_O(C_, 8, F_, A_); else PB_BIN_LAUNCH_O(C_, 6, F_, A_); } while (0)
         if (center) {
-            if (occ_sel == 4) PB_BIN_LAUNCH(true, 4); else if (occ_sel == 6) PB_BIN_LAUNCH(true, 6); else PB_BIN_LAUNCH(true, 8);
+            if (!fill) PB_BIN_LAUNCH(true, false, false); else if (agg) PB_BIN_LAUNCH(true, true, true); else PB_BIN_LAUNCH(true, true, false);
         } else {
-            if (occ_sel == 4) PB_BIN_LAUNCH(false, 4); else if (occ_sel == 6) PB_BIN_LAUNCH(false, 6); else PB_BIN_LAUNCH(false, 8);
+            if (!fill) PB_BIN_LAUNCH(false, false, false); else if (agg) PB_BIN_LAUNCH(false, true, true); else PB_BIN_LAUNCH(false, true, false);
         }
+#undef PB_BIN_LAUNCH_O
 #undef PB_BIN_LAUNCH
         if (!fill) {
             const int64_t nb = (n_tiles + kScanChunk - 1) / kScanChunk;
