@@ -6,8 +6,10 @@ Workload (BASELINE.json configs[1], the metric's quoted configuration): Variable
 with per-read-length P-site offsets + size filter 25-100 over 200 M synthetic 25-35 nt ribo-seq reads
 on a human-scale genome (hg38 chromosome lengths, 3.09 Gb) into dense '+' and '-' count vectors,
 followed by masked-free region counts over 60 k CDS-like SegmentChains.  One "step" = that whole
-pass over one batch.  At N > 1 every rank owns one such read shard (read-range sharding, weak
-scaling) and the per-region count tables are summed with one NCCL all-reduce.
+pass over one batch.  At N > 1 (default `--sharding positions`, strong scaling) ONE such batch is cut into
+contiguous position ranges of equal cost (reads streamed + plane bins written): every rank owns the planes of
+its range and the reads that can reach it, and the per-region count tables are completed with one NCCL
+all-reduce.  `--sharding reads` is round 1's weak-scaling mode (every rank its own batch over the whole genome).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 """
@@ -62,7 +64,7 @@ def parse_args():
     ap.add_argument("--regions", type=int, default=60_000)
     ap.add_argument("--sharding", default="positions", choices=["positions", "chromosomes", "reads"],
                     help="multi-GPU mode: 'positions' (default; strong scaling of ONE batch: every GPU owns a contiguous bin "
-                         "range balanced by read count, SURVEY 8e), 'chromosomes' (the same with cuts on chromosome boundaries, "
+                         "range of equal cost = reads + plane bins, SURVEY 8e), 'chromosomes' (the same with cuts on chromosome boundaries, "
                          "BASELINE config 5) or 'reads' (weak scaling: every GPU maps its own batch over the whole genome)")
     ap.add_argument("--pileup", type=int, default=0,
                     help="c3 only: this many of the reads lie in the last 16.5 kb of the last chromosome (a chrM-like pile-up in the last tiles)")
@@ -708,7 +710,8 @@ def main():
     resident_table = sums.cpu().numpy().copy()
 
     # per-rank diagnostics: who holds what, where the step goes (a slow rank or a slow collective shows here)
-    k_ms = kms.value / max(kn.value, 1)
+    # tiles-kernel time per STEP: a spliced Center batch is mapped in several ranges (one tiles launch each, on two streams)
+    k_ms = kms.value / max(args.steps, 1)
     mine = torch.tensor([float(sub.n_reads), float(hi - lo), k_ms, map_ms, sums_ms, coll_ms, float(np.median(step_ms)),
                          float(np.max(step_ms))], dtype=torch.float64, device=device)
     per_rank = [mine]
@@ -889,6 +892,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "launches_timed": kn.value,
+                "launches_per_step": kn.value / max(args.steps, 1),
                 "kernel_share_of_step": k_ms / ms_per_step}
     # region sums: every chain position of this rank's bins read once (4 or 8 B) + tables + results
     own = np.clip(np.minimum(table.bend, hi) - np.maximum(table.bstart, lo), 0, None).sum()

@@ -14,7 +14,7 @@ count-vector collective:
   of all ranks (``gather_matrix``) — a median is not all-reducible.
 
 * **position-range sharding** (``position_cuts`` / ``shard_positions`` / ``clip_table``):
-  the concatenated genome is cut into contiguous bin ranges balanced by read count; a rank holds
+  the concatenated genome is cut into contiguous bin ranges of equal cost (reads + plane bins); a rank holds
   the planes of its range only (1/N of the memory), receives the reads that start inside it plus a
   halo of ``max_span`` before it (those are sent to both neighbours, each counts only sites inside
   its own range), and sums the parts of every region that fall into its range; the partial region
@@ -91,37 +91,62 @@ def position_cuts(hb, layout, world_size, snap="bins", weights=(1.0, 1.0)):
     return balanced_cuts(layout, n, world_size, reads_before, weights)
 
 
-def balanced_cuts(layout, n_reads, world_size, reads_before, weights=(1.0, 1.0)):
+def balanced_cuts(layout, n_reads, world_size, reads_before, weights=(1.0, 1.0), lo=0, hi=None):
     """Cut points that give every rank the same COST, ``weights[0] * reads + weights[1] * bins``: a rank's mapping
     pass streams its reads (8 bytes each) and writes the dense planes of its bins (2 strands x 4 bytes), so equal read
     counts alone leave the rank with the sparsest stretch of genome the most plane bytes to write (N = 8, C2: 363-401 M
     bins per rank and tiles-kernel times to match, profiles/NOTES_r02.md section 5).  ``weights=(1, 0)`` is the
     equal-read-count rule.  ``reads_before(c, local)``: reads of chromosome ``c`` and before that start before
     chromosome position ``local`` (host: a search in ``ref_start``; device batches search on the device).
-    The cost is monotone in the cut position: one bisection over the PB_LAYOUT_ALIGN grid per cut."""
+    ``lo`` / ``hi``: cut the global bins [lo, hi) only (default: the whole layout; ``n_reads`` is ignored then and the
+    reads starting in the range are counted).  The cost is monotone in the cut position: one bisection over the
+    PB_LAYOUT_ALIGN grid per cut."""
     from . import _lib
     A = _lib.PB_LAYOUT_ALIGN
     total = int(layout.total_bins)
+    hi = total if hi is None else int(hi)
+    lo = int(lo)
     wr, wb = float(weights[0]), float(weights[1])
     coff = np.asarray(layout.chrom_bin_off, dtype=np.int64)
 
-    def cost(g):
+    def before(g):
         c = min(int(np.searchsorted(coff, g, side="right")) - 1, len(layout.chroms) - 1)
-        return wr * reads_before(c, g - int(coff[c])) + wb * g
-    whole = wr * n_reads + wb * total
-    cuts = [0]
+        return reads_before(c, g - int(coff[c]))
+    r_lo = before(lo) if lo > 0 else 0
+    r_hi = before(hi) if hi < total else int(n_reads)
+
+    def cost(g):
+        return wr * (before(g) - r_lo) + wb * (g - lo)
+    whole = wr * (r_hi - r_lo) + wb * (hi - lo)
+    cuts = [lo]
     for r in range(1, world_size):
         target = whole * r / world_size
-        lo, hi = cuts[-1] // A, total // A                # smallest grid point whose cost reaches the target
-        while lo < hi:
-            mid = (lo + hi) // 2
+        a, b = cuts[-1] // A, hi // A                     # smallest grid point whose cost reaches the target
+        while a < b:
+            mid = (a + b) // 2
             if cost(mid * A) >= target:
-                hi = mid
+                b = mid
             else:
-                lo = mid + 1
-        cuts.append(lo * A)
-    cuts.append(total)
+                a = mid + 1
+        cuts.append(min(max(a * A, lo), hi))
+    cuts.append(hi)
     return np.asarray(cuts, dtype=np.int64)
+
+
+def device_reads_before(dbatch, layout, off=None):
+    """``reads_before(c, local)`` of :func:`balanced_cuts` for a device batch (one short device search per call)."""
+    import torch
+    off = dbatch.chrom_read_off.cpu().numpy() if off is None else off
+
+    def reads_before(c, local):
+        a, b = int(off[c]), int(off[c + 1])
+        if b <= a or local <= 0:
+            return a
+        if local >= int(layout.chrom_len[c]):
+            return b
+        key = torch.tensor([local], dtype=dbatch.ref_start.dtype, device=dbatch.ref_start.device)
+        return a + int(torch.searchsorted(dbatch.ref_start[a:b], key, right=False).item())
+    return reads_before
 
 
 def shard_positions(hb, layout, rank, world_size, cuts=None, snap="bins"):
@@ -171,15 +196,7 @@ def shard_positions_device(dbatch, layout, rank, world_size, weights=(1.0, 1.0))
         raise ValueError("shard_positions_device handles unspliced batches; shard spliced batches on the host")
     n = dbatch.n_reads
     off = dbatch.chrom_read_off.cpu().numpy()
-
-    def reads_before(c, local):
-        a, b = int(off[c]), int(off[c + 1])
-        if b <= a or local <= 0:
-            return a
-        if local >= int(layout.chrom_len[c]):
-            return b
-        key = torch.tensor([local], dtype=dbatch.ref_start.dtype, device=dbatch.ref_start.device)
-        return a + int(torch.searchsorted(dbatch.ref_start[a:b], key, right=False).item())
+    reads_before = device_reads_before(dbatch, layout, off)
     cuts = [int(x) for x in balanced_cuts(layout, n, world_size, reads_before, weights)]
     g_lo, g_hi = cuts[rank], cuts[rank + 1]
     pieces, new_off = [], [0]

@@ -661,7 +661,7 @@ class BAMGenomeArray(object):
     landing (``map_wire16_streamed`` / ``map_center_streamed``).  A plain SoA batch is uploaded as it is.
 
     More than one GPU (``torch.distributed`` initialised, one process per GPU; or ``shard=(rank, world)``): every
-    rank owns a contiguous range of the concatenated genome (cuts balanced by read count; ``sharding="chromosomes"``
+    rank owns a contiguous range of the concatenated genome (cuts of equal cost: reads + plane bins; ``sharding="chromosomes"``
     puts them on chromosome boundaries), keeps the reads that can map into it (its own plus a halo of ``max_span``)
     and the planes of that range only.  Region tables, window matrices and ``ga[seg]`` vectors are completed with
     one all-reduce (every position is owned by exactly one rank); no count vector ever crosses NVLink.
