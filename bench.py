@@ -68,6 +68,9 @@ def parse_args():
                          "BASELINE config 5) or 'reads' (weak scaling: every GPU maps its own batch over the whole genome)")
     ap.add_argument("--pileup", type=int, default=0,
                     help="c3 only: this many of the reads lie in the last 16.5 kb of the last chromosome (a chrM-like pile-up in the last tiles)")
+    ap.add_argument("--c4-exchange", default="slices", choices=["slices", "matrix"],
+                    help="c4 at N > 1: 'slices' (default) leaves the count matrix on its ranks (rows completed by their owner, "
+                         "medians per column slice after one all-to-all); 'matrix' all-reduces the whole 168 MB matrix (round 2a)")
     ap.add_argument("--cpu-sample-chroms", type=int, default=1, help="chromosomes in the cpu_baseline sample")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2p", "c3", "c4", "c5", "peaks"],
                     help="BASELINE.json config: c2 is the metric's quoted configuration (default); the others "
@@ -379,6 +382,8 @@ def run_c4(args, W, device, rank, world, dist):
     table.device(device)
     cols = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).to(device)       # the ROI table's offsets, resident
     width, n = 350, table.n_chains
+    from plastid_b200 import dist as pdist
+    ranges = pdist.all_ranges(lo, hi, device=device)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     gather_ms = []
 
@@ -388,8 +393,12 @@ def run_c4(args, W, device, rank, world, dist):
         mat, mmask = gather_windows(planes, table, cols, width)
         if timed:
             ev[3].record()
-        if world > 1:
+        if world > 1 and args.c4_exchange == "matrix":
             dist.all_reduce(mat)         # cells of other ranks' positions are 0, cells without a position NaN everywhere
+        elif world > 1:
+            # the matrix stays put: rows completed by their owner, exact medians per column slice after one all-to-all
+            prof, nreg, _d, _s = pdist.window_profile(mat, mmask, table, ranges, 70, 100, 10, "median")
+            return prof, nreg
         denom, sel, norm, nmask = window_normalize(mat, mmask, 70, 100, 10)
         prof, nreg, csum = column_profile(norm, nmask, sel, "median")
         return prof, nreg
@@ -445,6 +454,9 @@ def run_c4(args, W, device, rank, world, dist):
                                    "norm window [20,50) from the landmark, min_counts 10, exact median profile" % (n, width),
                        "reads": n_total, "windows": n, "width": width},
             "sharding": "single GPU" if world == 1 else args.sharding,
+            "exchange": None if world == 1 else {"slices": "matrix stays on its ranks: straddling rows all-reduced, rows normalised by their "
+                                                 "owner, medians per column slice after one all-to-all (dist.window_profile)",
+                                                 "matrix": "whole count matrix all-reduced"}[args.c4_exchange],
             "roofline": {"bound": "hbm", "kernel": "pb_gather_windows_kernel", "achieved": alg / (g_ms / 1000.0) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg / (g_ms / 1000.0) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": g_ms,

@@ -240,7 +240,19 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, use_m
     need = sorted(set("+-."[p] for p in np.unique(table.chain_plane))) or ["+"]
     planes = ga.count_planes(tuple(need))
     mat, mmask = gather_windows(planes, table, cols, window_size)
-    ga._allreduce(mat)           # multi-GPU: every rank filled the cells of its own positions (others 0, NaN where no position)
+    if ga._collective and not keep:
+        # several GPUs: every rank filled the cells of its own positions.  The count matrix stays where it is: rows are
+        # completed and normalised by the rank that owns their first position, means are all-reduced as column sums,
+        # exact medians are taken per column slice after one all-to-all (plastid_b200.dist.window_profile)
+        from .. import dist as pdist
+        ranges = pdist.all_ranges(*ga.bin_range, device=mat.device)
+        profile, n_regions, denom, sel = pdist.window_profile(
+            mat, mmask, table, ranges, norm_start, norm_end, min_counts, "mean" if use_mean else "median",
+            per_million_of=ga.sum() if ga._normalize is True else None)
+        return {"x": np.arange(-flank, window_size - flank), "metagene_average": profile.cpu().numpy(),
+                "regions_counted": n_regions.cpu().numpy(), "row_select": sel.cpu().numpy().astype(bool),
+                "denominator": denom.cpu().numpy()}
+    ga._allreduce(mat)           # --keep wants the whole matrices on the writing rank: cells of other ranks are 0, NaN where no position
     if ga._normalize is True:
         mat = mat / float(ga.sum()) * 1e6
     denom, sel, norm, nmask = window_normalize(mat, mmask, norm_start, norm_end, min_counts)

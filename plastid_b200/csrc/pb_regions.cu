@@ -266,9 +266,34 @@ pb_window_fill_kernel(const int64_t *__restrict__ chain_len, const int32_t *__re
 constexpr int kItemReads = 2048;
 constexpr int kIndexShift = 14;          // PB_LAYOUT_ALIGN = 1 << 14: an index cell never spans two chromosomes
 
-__global__ void pb_read_index_kernel(PbReads b, PbLayoutDev lay, long long n_cells, long long *__restrict__ index)
+// Site table: everything a read's meta word decides — drop bit, size window, strand class of the query strand, rule
+// direction, rule offset — folded into ONE 16-bit look-up per read.  key = aligned length (< 256) | reverse << 8 |
+// drop << 9; entry = index into read.positions of the mapped site, kSiteSkip (the read does not count on this strand
+// class) or kSiteDropped (the rule has no site for this length: the reference skips the read and warns).  One table per
+// strand class (plane 0 '+', 1 '-', 2 '.'), built by the read-index launch, copied to shared memory by every CTA.
+// ncu on the form that evaluated the tests per read (profiles/ncu_regions_r02.txt): ~64 thread instructions per read,
+// a third of them branches and reconvergence barriers around the per-read `continue`s; with the table the per-read
+// path is straight-line and predicated.
+constexpr int kSiteKeys = 1024;
+constexpr int kSiteSkip = -1, kSiteDropped = -2;
+
+__device__ __forceinline__ int pb_site_entry(const PbRuleDev &r, int plane, uint32_t m)
+{
+    const bool rev = PB_META_REV(m);
+    if (!pb_passes(m, r.size_min, r.size_max) || (plane == 0 && rev) || (plane == 1 && !rev)) return kSiteSkip;   // genome_array.py:811-815
+    const int idx = pb_rule_index(r, PB_META_L(m), plane == 1);          // rule direction follows the chain's strand
+    return idx < 0 ? kSiteDropped : idx;
+}
+
+__global__ void pb_read_index_kernel(PbReads b, PbLayoutDev lay, long long n_cells, long long *__restrict__ index,
+                                     PbRuleDev r, int16_t *__restrict__ site_tab)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (site_tab && g < 3 * 1024) {          // the site tables of pb_chain_counts ride along (kSiteKeys entries per plane)
+        const uint32_t key = (uint32_t)g & 1023u;
+        // key bits 8 / 9 are meta bits 16 (reverse) / 17 (drop)
+        site_tab[g] = (int16_t)pb_site_entry(r, (int)(g >> 10), (key & 0xFFu) | ((key & 0x300u) << 8));
+    }
     if (g > n_cells) return;
     if (g == n_cells) { index[g] = b.n_reads; return; }
     const long long bin = g << kIndexShift;
@@ -309,15 +334,13 @@ __device__ __forceinline__ long long pb_block_of_item(const uint32_t *__restrict
     return lo + __popc(__ballot_sync(kFull, p < hi && __ldg(off + p) <= item));
 }
 
-// Sites of the reads [first, first + n) that land on unmasked positions [ps, ps + width) of one block; everything the
-// item fixes (rule direction, strand class, size window, LUT) is resolved before the loop, positions are 32-bit
-// chromosome coordinates, and the range test is one unsigned compare.  A lane takes FOUR consecutive reads per
+// Sites of the reads [first, first + n) that land on unmasked positions [ps, ps + width) of one block.  Positions are
+// 32-bit chromosome coordinates and the range test is one unsigned compare.  A lane takes FOUR consecutive reads per
 // 16-byte load of each array (the item is walked from the 4-aligned read at or before `first`), two such loads of
-// each array in flight.  MODE 0: idx = param, 1: idx = L - 1 - param, 2: LUT.
-template <int MODE, bool BLOCKS>
-__device__ __forceinline__ unsigned int pb_count_item(const PbReads &b, long long first, int n, int lane,
-                                                      int param, const int32_t *__restrict__ lut,
-                                                      unsigned size_lo, unsigned size_span, unsigned strand_care, unsigned strand_want,
+// each array in flight.  `tab`: the plane's site table in shared memory.
+template <bool BLOCKS, bool MASK>
+__device__ __forceinline__ unsigned int pb_count_item(const PbReads &b, const PbRuleDev &r, int plane, const int16_t *tab,
+                                                      long long first, int n, int lane,
                                                       int ps, unsigned width, const uint32_t *__restrict__ mask_words, long long mbit,
                                                       unsigned int &drop_len)
 {
@@ -343,29 +366,33 @@ __device__ __forceinline__ unsigned int pb_count_item(const PbReads &b, long lon
         for (int u = 0; u < kU; ++u) {
             const uint32_t mm[4] = {mq[u].x, mq[u].y, mq[u].z, mq[u].w};
             const int32_t ss[4] = {sq[u].x, sq[u].y, sq[u].z, sq[u].w};
-            const int j0 = (q0 + 32 * u) * 4;
-            const bool inner = j0 >= skip && j0 + 4 <= end;          // every read of the quad belongs to the item
+            const int j0 = (q0 + 32 * u) * 4 - skip;             // index of the quad's first read within the item
+            int idx[4];
+            if (__builtin_expect(((mm[0] | mm[1] | mm[2] | mm[3]) & 0xFF00u) != 0u, 0)) {     // a read of 256 aligned bases or more
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    idx[e] = (mm[e] & 0xFF00u) ? pb_site_entry(r, plane, mm[e]) : tab[(mm[e] & 0xFFu) | ((mm[e] >> 8) & 0x300u)];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) idx[e] = tab[(mm[e] & 0xFFu) | ((mm[e] >> 8) & 0x300u)];
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int j = j0 + e;
-                if (!inner && (j < skip || j >= end)) continue;
-                const uint32_t m = mm[e];
-                const unsigned L = m & 0xFFFFu;
-                // drop bit, size window, strand class in three tests
-                if ((m & (1u << 17)) || (L - size_lo) > size_span || ((((m >> 16) & 1u) ^ strand_want) & strand_care)) continue;
-                int idx;
-                if (MODE == 2) idx = L < (unsigned)PB_LUT_SIZE ? __ldg(lut + L) : -1;
-                else idx = (unsigned)param < L ? (MODE == 0 ? param : (int)L - 1 - param) : -1;
-                if (idx < 0) { drop_len = L; continue; }
-                int p;
-                if (BLOCKS && (m >> 24) > 1) {
-                    const long long pp = pb_block_position(b, a0 + j, ss[e], idx);
-                    if (pp < 0) continue;
-                    p = (int)pp;
-                } else p = ss[e] + idx;
-                if ((unsigned)(p - ps) >= width) continue;
-                if (mask_words && mask_bits_at(mask_words, mbit + p, 1)) continue;
-                count++;
+                const bool mine = (unsigned)(j0 + e) < (unsigned)n;                           // the read belongs to the item
+                int p = ss[e] + idx[e];
+                if (BLOCKS && (mm[e] >> 24) > 1 && idx[e] >= 0 && mine) {
+                    const long long pp = pb_block_position(b, a0 + skip + j0 + e, ss[e], idx[e]);
+                    p = pp < 0 ? ps - 1 : (int)pp;
+                }
+                bool ok = mine && idx[e] >= 0 && (unsigned)(p - ps) < width;
+                if (MASK) { if (ok) ok = !mask_bits_at(mask_words, mbit + p, 1); }
+                count += ok ? 1u : 0u;
+            }
+            const int low = min(min(idx[0], idx[1]), min(idx[2], idx[3]));
+            if (__builtin_expect(low == kSiteDropped, 0)) {                                  // the rule has no site for a length
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (idx[e] == kSiteDropped && (unsigned)(j0 + e) < (unsigned)n) drop_len = mm[e] & 0xFFFFu;
             }
         }
     }
@@ -397,27 +424,27 @@ __device__ __forceinline__ PbItemCtx pb_item_ctx(const PbLayoutDev &lay, long lo
     return x;
 }
 
-// count the sites of reads [first, first + n) on the item's block (rule / size window / strand class dispatch)
-__device__ __forceinline__ unsigned int pb_count_reads(const PbReads &b, const PbRuleDev &r, const PbItemCtx &x, long long first, int n,
-                                                       int lane, const uint32_t *__restrict__ mask_words, unsigned int &drop_len)
+// count the sites of reads [first, first + n) on the item's block; `tabs`: the three site tables in shared memory
+__device__ __forceinline__ unsigned int pb_count_reads(const PbReads &b, const PbRuleDev &r, const PbItemCtx &x, const int16_t *tabs,
+                                                       long long first, int n, int lane, const uint32_t *__restrict__ mask_words,
+                                                       unsigned int &drop_len)
 {
-    // SizeFilterFactory as one unsigned window test: (L - size_lo) <= size_span
-    const unsigned size_lo = r.size_min > 0 ? (unsigned)r.size_min : 0u;
-    const unsigned size_span = r.size_min > 0 && r.size_max != -1 ? (r.size_max >= r.size_min ? (unsigned)(r.size_max - r.size_min) : 0u) : 0xFFFFu;
-    if ((r.size_min > 0 && r.size_max != -1 && r.size_max < r.size_min) || n <= 0 || x.width == 0) return 0;
-    const bool has_blocks = b.blk_off != nullptr;
-    const bool rq = x.plane == 1;                          // rule direction follows the chain's strand
-    const unsigned care = x.plane == 2 ? 0u : 1u, want = x.plane == 1 ? 1u : 0u;
-    if (r.kind == PB_RULE_VARIABLE) {
-        const int32_t *lut = rq ? r.lut_rc : r.lut_fw;
-        return has_blocks ? pb_count_item<2, true>(b, first, n, lane, 0, lut, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len)
-                          : pb_count_item<2, false>(b, first, n, lane, 0, lut, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len);
-    }
-    if ((r.kind == PB_RULE_FIVEPRIME) ? !rq : rq)          // offset counted from the left end
-        return has_blocks ? pb_count_item<0, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len)
-                          : pb_count_item<0, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len);
-    return has_blocks ? pb_count_item<1, true>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len)
-                      : pb_count_item<1, false>(b, first, n, lane, r.param, nullptr, size_lo, size_span, care, want, x.ps, x.width, mask_words, x.mbit, drop_len);
+    if (n <= 0 || x.width == 0) return 0;
+    const int16_t *tab = tabs + x.plane * kSiteKeys;
+    if (mask_words)
+        return b.blk_off != nullptr ? pb_count_item<true, true>(b, r, x.plane, tab, first, n, lane, x.ps, x.width, mask_words, x.mbit, drop_len)
+                                    : pb_count_item<false, true>(b, r, x.plane, tab, first, n, lane, x.ps, x.width, mask_words, x.mbit, drop_len);
+    return b.blk_off != nullptr ? pb_count_item<true, false>(b, r, x.plane, tab, first, n, lane, x.ps, x.width, mask_words, x.mbit, drop_len)
+                                : pb_count_item<false, false>(b, r, x.plane, tab, first, n, lane, x.ps, x.width, mask_words, x.mbit, drop_len);
+}
+
+// the three site tables: global (built once per call) -> shared memory of the CTA
+__device__ __forceinline__ void pb_load_site_tables(int16_t *s_tab, const int16_t *__restrict__ g_tab)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(g_tab);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+    for (int j = threadIdx.x; j < 3 * kSiteKeys * 2 / 16; j += blockDim.x) dst[j] = __ldg(src + j);
+    __syncthreads();
 }
 
 __device__ __forceinline__ void pb_flush_drops(unsigned long long *__restrict__ stats, unsigned int drop_len, int drop_plane)
@@ -442,8 +469,11 @@ pb_chain_first_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, const long 
                             const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
                             long long lo, long long hi, long long total_bins,
                             long long *__restrict__ slice_first, uint32_t *__restrict__ extra_items,
-                            unsigned long long *__restrict__ counts, unsigned long long *__restrict__ stats)
+                            unsigned long long *__restrict__ counts, unsigned long long *__restrict__ stats,
+                            const int16_t *__restrict__ site_tab)
 {
+    __shared__ __align__(16) int16_t s_tab[3 * kSiteKeys];
+    pb_load_site_tables(s_tab, site_tab);
     const int lane = threadIdx.x & 31;
     const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n_blocks) return;
@@ -465,7 +495,7 @@ pb_chain_first_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, const long 
             plane = __ldg(block_plane + k);
             const PbItemCtx x = pb_item_ctx(lay, gs, ge, lo, hi, c, plane, mask_words, mask_off, __ldg(block_pos + k));
             const int n = (int)(last - first < kItemReads ? last - first : kItemReads);
-            unsigned int count = pb_count_reads(b, r, x, first, n, lane, mask_words, drop_len);
+            unsigned int count = pb_count_reads(b, r, x, s_tab, first, n, lane, mask_words, drop_len);
             count = __reduce_add_sync(kFull, count);
             if (lane == 0 && count) atomicAdd(counts + c, (unsigned long long)count);
         }
@@ -488,8 +518,10 @@ pb_chain_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
                       const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
                       long long lo, long long hi, const long long *__restrict__ slice_first,
                       const uint32_t *__restrict__ item_off, unsigned long long *__restrict__ counts,
-                      unsigned long long *__restrict__ stats)
+                      unsigned long long *__restrict__ stats, const int16_t *__restrict__ site_tab)
 {
+    __shared__ __align__(16) int16_t s_tab[3 * kSiteKeys];
+    pb_load_site_tables(s_tab, site_tab);
     const int lane = threadIdx.x & 31;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -506,7 +538,7 @@ pb_chain_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
         const long long slice_end = __ldg(slice_first + 2 * k + 1);
         const int n = (int)(slice_end - first < kItemReads ? slice_end - first : kItemReads);
         unsigned int dl = 0;
-        unsigned int count = pb_count_reads(b, r, x, first, n, lane, mask_words, dl);
+        unsigned int count = pb_count_reads(b, r, x, s_tab, first, n, lane, mask_words, dl);
         if (dl) { drop_len = dl; drop_plane = plane; }
         count = __reduce_add_sync(kFull, count);
         if (lane == 0 && count) atomicAdd(counts + c, (unsigned long long)count);
@@ -633,7 +665,7 @@ extern "C" size_t pb_chain_counts_workspace_bytes(int64_t total_bins, int64_t n_
     if (total_bins < 0 || n_blocks < 0 || n_chains < 0) return 0;
     const size_t cells = (size_t)(total_bins >> kIndexShift) + 2;
     return cells * 8 + (size_t)n_blocks * 16 + ((size_t)n_blocks + 1) * 8 + (size_t)pb_scan_part_entries(n_blocks + 1) * 4
-        + (size_t)n_chains * 8 + 256;
+        + (size_t)n_chains * 8 + 256 + 3 * 1024 * sizeof(int16_t) + 16;
 }
 
 extern "C" int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
@@ -677,23 +709,26 @@ extern "C" int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, c
     uint32_t *item_off = (uint32_t *)w;                         w += ((size_t)n_blocks + 1) * 4;
     uint32_t *part = (uint32_t *)w;                             w += (size_t)pb_scan_part_entries(n_blocks + 1) * 4;
     w = (char *)(((uintptr_t)w + 15) & ~(uintptr_t)15);
-    unsigned long long *counts = (unsigned long long *)w;
+    unsigned long long *counts = (unsigned long long *)w;                     w += (size_t)n_chains * 8;
+    w = (char *)(((uintptr_t)w + 15) & ~(uintptr_t)15);
+    int16_t *site_tab = (int16_t *)w;
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mask_bits);
     PB_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)n_chains * 8, stream));
-    pb_read_index_kernel<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, stream>>>(b, lay, n_cells, index);
+    const long long index_threads = n_cells + 1 > 3 * kSiteKeys ? n_cells + 1 : 3 * kSiteKeys;
+    pb_read_index_kernel<<<(unsigned)((index_threads + 255) / 256), 256, 0, stream>>>(b, lay, n_cells, index, r, site_tab);
     if (n_blocks > 0) {
         // 4 warps per CTA: a block's first item is anything from 0 to 2048 reads, and a CTA holds its slot until its
         // slowest warp is done
         pb_chain_first_items_kernel<<<(unsigned)((n_blocks * 32 + 127) / 128), 128, 0, stream>>>(
             b, r, lay, index, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
-            layout->total_bins, slices, items, counts, reinterpret_cast<unsigned long long *>(stats));
+            layout->total_bins, slices, items, counts, reinterpret_cast<unsigned long long *>(stats), site_tab);
         int rc = pb_launch_exclusive_scan_u32(items, item_off, part, n_blocks, stream);
         if (rc) return rc;
         int sms = 148;
         pb_sm_count(&sms);
         pb_chain_items_kernel<<<(unsigned)(sms * 6), 256, 0, stream>>>(
             b, r, lay, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
-            slices, item_off, counts, reinterpret_cast<unsigned long long *>(stats));
+            slices, item_off, counts, reinterpret_cast<unsigned long long *>(stats), site_tab);
     }
     pb_chain_totals_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, stream>>>(
         bstart, bend, chain_off, n_chains, mw, mask_off, nullptr, counts, sums, live_len);

@@ -378,6 +378,137 @@ def global_length_hist(sub, layout, bin_lo, bin_hi):
     return allreduce_sum(hist).numpy()
 
 
+# ------------------------------------------------------------------------------- window profiles (metagene count)
+def all_ranges(lo, hi, device="cpu"):
+    """The bin range of every rank, ``int64[world, 2]`` (one small all-gather; contiguous in rank order for the
+    partitions this module makes)."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = world()
+    if ws == 1:
+        return np.asarray([[int(lo), int(hi)]], dtype=np.int64)
+    mine = torch.tensor([int(lo), int(hi)], dtype=torch.int64, device=device)
+    parts = [torch.zeros_like(mine) for _ in range(ws)]
+    dist.all_gather(parts, mine)
+    return torch.stack(parts).cpu().numpy()
+
+
+def row_owners(table, ranges):
+    """Which rank completes which row of a window / chain table under position sharding: ``owner[c]`` = the rank whose
+    bins hold the first position of chain ``c`` that lies on the genome (rank 0 for chains without one), and the
+    indices of the chains whose positions lie on more than one rank (a few per cut).  Geometry only."""
+    from .regions import VIRTUAL_BIN
+    n = table.n_chains
+    ranges = np.asarray(ranges, dtype=np.int64)
+    world_size = len(ranges)
+    chain_of = np.repeat(np.arange(n), np.diff(table.chain_off))
+    real = (table.bstart < VIRTUAL_BIN) & (table.bend > table.bstart)
+    his = ranges[:, 1]
+    first = np.minimum(np.searchsorted(his, table.bstart[real], side="right"), world_size - 1)
+    last = np.minimum(np.searchsorted(his, table.bend[real] - 1, side="right"), world_size - 1)
+    lo_r = np.full(n, world_size, dtype=np.int64)
+    hi_r = np.full(n, -1, dtype=np.int64)
+    np.minimum.at(lo_r, chain_of[real], first)
+    np.maximum.at(hi_r, chain_of[real], last)
+    owner = np.where(hi_r >= 0, lo_r, 0)
+    return owner, np.nonzero(hi_r > lo_r)[0]
+
+
+def exchange_column_slices(rows):
+    """``rows`` (float64 ``[k_r, width]``, this rank's rows) -> ``(slice, bounds)``: the columns
+    ``[bounds[rank], bounds[rank + 1])`` of the rows of ALL ranks (rank order), ``[sum(k_r), w_rank]``.  NCCL: one
+    all-to-all (every rank ships ``1 / world`` of its columns to every peer: the exchange an exact per-column median
+    needs, at ``1 / world`` of the bytes of gathering whole rows); other backends: all-gather, then cut."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = world()
+    width = int(rows.shape[1])
+    bounds = [(c * width) // ws for c in range(ws + 1)]
+    if ws == 1:
+        return rows, bounds
+    k = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    ks = [torch.zeros_like(k) for _ in range(ws)]
+    dist.all_gather(ks, k)
+    ks = [int(x.item()) for x in ks]
+    w_mine = bounds[rank + 1] - bounds[rank]
+    if dist.get_backend() == "nccl":
+        ins = [rows[:, bounds[c]:bounds[c + 1]].contiguous() for c in range(ws)]
+        outs = [torch.empty((ks[r], w_mine), dtype=rows.dtype, device=rows.device) for r in range(ws)]
+        dist.all_to_all(outs, ins)
+        return torch.cat(outs, dim=0), bounds
+    return gather_matrix(rows)[:, bounds[rank]:bounds[rank + 1]].contiguous(), bounds
+
+
+def window_profile(mat, mmask, table, ranges, norm_lo, norm_hi, min_counts, mode="median", per_million_of=None):
+    """``metagene count`` on a position-sharded genome without moving the count matrix (60 k x 350 float64 = 168 MB at
+    BASELINE config 4): ``mat`` / ``mmask`` are this rank's ``gather_windows`` output (cells of its own positions,
+    zero elsewhere, NaN where the window has no position).
+
+    * a row is COMPLETED by one rank, the owner of its first position (:func:`row_owners`); the few rows that lie on
+      both sides of a cut are summed over ranks first (one small all-reduce);
+    * every rank normalises and selects its own rows (``pb_window_normalize``; metagene.py:916-924);
+    * mean (``--use_mean``): column sums and counts of the selected rows, all-reduced (2 x width numbers);
+      median (default; not all-reducible): every rank receives ``width / world`` columns of all selected rows
+      (:func:`exchange_column_slices`), takes their exact medians (``pb_column_profile``) and the slices are gathered.
+
+    Returns ``(profile, regions_counted, denominator, row_select)`` complete on every rank; profile and counts equal
+    the single-GPU result (medians bit for bit; means up to the order of the float sums)."""
+    import torch
+    import torch.distributed as dist
+    from .genome_array import window_normalize, column_profile
+    rank, ws = world()
+    dev = mat.device
+    n, width = mat.shape
+    cache = table.__dict__.setdefault("_owners", {})
+    key = tuple(int(x) for x in np.asarray(ranges).reshape(-1))
+    if key not in cache:
+        owner, strad = row_owners(table, ranges)
+        cache[key] = (owner, strad)
+    owner, strad = cache[key]
+    if len(strad) and ws > 1:
+        idx = torch.from_numpy(strad).to(dev)
+        part = mat[idx]
+        allreduce_sum(part)                    # NaN cells are geometry (NaN on every rank); counts have one non-zero summand
+        mat[idx] = part
+    if per_million_of is not None:
+        mat = mat / float(per_million_of) * 1e6
+    denom, sel, norm, nmask = window_normalize(mat, mmask, norm_lo, norm_hi, min_counts)
+    mine = torch.from_numpy(owner == rank).to(dev)
+    sel = sel * mine.to(sel.dtype)
+    denom = torch.where(mine, denom, torch.zeros_like(denom))
+    if mode == "mean":
+        _p, n_regions, col_sum = column_profile(norm, nmask, sel, "mean")
+        allreduce_sum(col_sum)
+        allreduce_sum(n_regions)
+        profile = col_sum / n_regions.to(col_sum.dtype)
+    else:
+        rows = torch.nonzero(sel, as_tuple=False).flatten()
+        x = norm[rows]
+        x = torch.where(nmask[rows] != 0, torch.full_like(x, float("nan")), x)       # masked cells travel as NaN
+        part, bounds = exchange_column_slices(x)
+        w_mine = bounds[rank + 1] - bounds[rank]
+        w_max = max(bounds[c + 1] - bounds[c] for c in range(ws))
+        p_loc = torch.full((w_max,), float("nan"), dtype=torch.float64, device=dev)
+        n_loc = torch.zeros(w_max, dtype=torch.int64, device=dev)
+        if part.shape[0] and w_mine:
+            pmask = torch.isnan(part).to(torch.uint8)
+            every = torch.ones(part.shape[0], dtype=torch.uint8, device=dev)
+            p_c, n_c, _s = column_profile(torch.nan_to_num(part, nan=0.0), pmask, every, "median")
+            p_loc[:w_mine], n_loc[:w_mine] = p_c, n_c
+        if ws > 1:
+            ps, ns = [torch.zeros_like(p_loc) for _ in range(ws)], [torch.zeros_like(n_loc) for _ in range(ws)]
+            dist.all_gather(ps, p_loc)
+            dist.all_gather(ns, n_loc)
+        else:
+            ps, ns = [p_loc], [n_loc]
+        profile = torch.cat([ps[c][:bounds[c + 1] - bounds[c]] for c in range(ws)])
+        n_regions = torch.cat([ns[c][:bounds[c + 1] - bounds[c]] for c in range(ws)])
+    sel_all = sel.to(torch.int32)
+    allreduce_sum(sel_all)
+    allreduce_sum(denom)
+    return profile, n_regions, denom, sel_all.to(torch.uint8)
+
+
 def mean_profile(col_sum, n_regions):
     """Multi-GPU ``--use_mean`` metagene profile: all-reduce numerators and counts, then divide."""
     allreduce_sum(col_sum)

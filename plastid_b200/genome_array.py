@@ -349,6 +349,13 @@ def region_sums(planes, table, out=None):
     # positions outside this rank's bins (position sharding; parts of a region beyond its chromosome) count zero
     L = _lib.lib()
     n_blocks = len(table.bstart)
+    ranged = (planes.bin_lo, planes.bin_hi) != (0, int(planes.layout.total_bins))
+    if ranged and n_blocks:
+        # a rank looks at the blocks that overlap its bins only; unmasked lengths are geometry (the same on every rank)
+        d = table.owned(dev, planes.bin_lo, planes.bin_hi)
+        n_blocks = d["n_blocks"]
+        if n_blocks == 0:                       # no block of the table reaches this rank's bins
+            return sums.zero_()[:n], d["live"][:n]
     ws_bytes = L.pb_region_sums_workspace_bytes(n_blocks)
     ws = _workspace(dev, ws_bytes, slot="region_sums")
     _lib.check(L.pb_region_sums(ptrs, 1 if planes.dtype == "f64" else 0, _lib.ptr(d["bstart"]),
@@ -357,6 +364,8 @@ def region_sums(planes, table, out=None):
                                 n, n_blocks, _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]),
                                 planes.bin_lo, planes.bin_hi, _lib.ptr(sums), _lib.ptr(live), _lib.ptr(ws), ws_bytes,
                                 _lib.stream_ptr()))
+    if ranged and "live" in d:
+        live = d["live"]
     return sums[:n], live[:n]
 
 

@@ -122,3 +122,46 @@ class ChainTable(object):
                                   block_plane=up(np.repeat(self.chain_plane, n_blk)),
                                   mask_bits=up(bits), mask_off=up(self.mask_off))
         return self._dev[key]
+
+    def live_lengths(self):
+        """Unmasked length of every chain (``chain.masked_length``): geometry only — what ``pb_region_sums`` returns in
+        ``live_len`` whatever bin range it is given."""
+        if getattr(self, "_live", None) is None:
+            live = self.chain_len.astype(np.int64).copy()
+            if self.mask_bits is not None and self.n_chains:
+                nbits = int(self.mask_off[-1] + self.chain_len[-1])
+                bits = np.unpackbits(self.mask_bits, bitorder="little")[:nbits].astype(np.int64)
+                run = np.concatenate([[0], np.cumsum(bits)])
+                live -= run[self.mask_off + self.chain_len] - run[self.mask_off]
+            self._live = live
+        return self._live
+
+    def owned_rows(self, lo, hi):
+        """(indices of the blocks that overlap the global bins [lo, hi), chain offsets into that selection)."""
+        idx = np.nonzero((self.bend > lo) & (self.bstart < hi))[0]
+        chain_of = np.repeat(np.arange(self.n_chains), np.diff(self.chain_off))
+        sub_off = np.zeros(self.n_chains + 1, dtype=np.int64)
+        np.cumsum(np.bincount(chain_of[idx], minlength=self.n_chains), out=sub_off[1:])
+        return idx, sub_off
+
+    def owned(self, device, lo, hi):
+        """The rows of the block tables a rank that owns the global bins [lo, hi) has to look at (position sharding):
+        blocks that overlap the range, with the chain offsets that go with them; ``block_pos`` / ``block_chain`` keep
+        their values from the whole table, so mask bits and chain totals are addressed as before.  At N = 8 a rank
+        otherwise walks all blocks of the table to find that 7 / 8 of them lie elsewhere.  Cached per range."""
+        import torch
+        key = (_lib.device_key(device), int(lo), int(hi))
+        cache = self.__dict__.setdefault("_owned", {})
+        if key not in cache:
+            d = self.device(device)
+            idx, sub_off = self.owned_rows(lo, hi)
+            t_idx = torch.from_numpy(idx).to(device)
+            sub = dict(d)
+            for name in ("bstart", "bend", "block_chain", "block_pos", "block_plane"):
+                sub[name] = d[name][t_idx].contiguous()
+            sub["chain_off"] = torch.from_numpy(sub_off).to(device)
+            sub["n_blocks"] = int(len(idx))
+            sub["live"] = torch.from_numpy(self.live_lengths()).to(device)
+            cache[key] = sub
+        return cache[key]
+

@@ -219,3 +219,57 @@ def test_sharding_plans_single_process():
     empty = pd.shard_chromosomes(hb, [])
     assert len(empty) == 0 and empty.chroms == []
     assert pd.world() == (0, 1)
+
+
+def _exchange_worker(rank, world_size, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from plastid_b200 import dist as pd
+        width = 11
+        k = [5, 0, 7][rank % 3]
+        rows = torch.arange(k * width, dtype=torch.float64).reshape(k, width) + 1000.0 * rank
+        part, bounds = pd.exchange_column_slices(rows)
+        every = [torch.arange([5, 0, 7][r % 3] * width, dtype=torch.float64).reshape(-1, width) + 1000.0 * r for r in range(world_size)]
+        want = torch.cat(every, dim=0)[:, bounds[rank]:bounds[rank + 1]]
+        assert bounds[0] == 0 and bounds[-1] == width and torch.equal(part, want)
+        ranges = pd.all_ranges(100 * rank, 100 * (rank + 1))
+        assert ranges.tolist() == [[100 * r, 100 * (r + 1)] for r in range(world_size)]
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size", [2, 3])
+def test_column_slice_exchange_under_gloo(world_size):
+    """The exchange behind multi-GPU exact medians (dist.exchange_column_slices; gloo takes the all-gather route, NCCL
+    an all-to-all): every rank ends with its column slice of the rows of ALL ranks, in rank order, uneven row counts
+    and an empty rank included."""
+    port = _free_port()
+    results = mp.Manager().dict()
+    mp.spawn(_exchange_worker, args=(world_size, port, results), nprocs=world_size, join=True)
+    assert [results[r] for r in range(world_size)] == ["ok"] * world_size
+
+
+def test_row_owners_of_a_window_table():
+    """dist.row_owners: the owner of a row is the rank holding its first position on the genome; rows with positions
+    on both sides of a cut are listed as straddlers; chains without a position on the genome belong to rank 0."""
+    import plastid_b200 as pb
+    from plastid_b200 import dist as pd
+    from plastid_b200.regions import ChainTable
+    layout = pb.GenomeLayout(["c1", "c2"], [40000, 30000])              # c2 starts at global bin 49152
+    S = pb.GenomicSegment
+    chains = [pb.SegmentChain(S("c1", 100, 400, "+")),                              # rank 0
+              pb.SegmentChain(S("c1", 16000, 16300, "+"), S("c1", 16500, 16700, "+")),   # across the cut at 16384: straddler, owner 0
+              pb.SegmentChain(S("c1", 20000, 20100, "-")),                          # rank 1
+              pb.SegmentChain(S("c2", 10, 90, "+")),                                # rank 2 (bins 49162..)
+              pb.SegmentChain(S("c1", -50, 30, "+")),                               # starts before the chromosome: first real position on rank 0
+              pb.SegmentChain(),                                                     # no position
+              pb.SegmentChain(S("nope", 5, 50, "+"))]                               # unknown chromosome
+    t = ChainTable.from_chains(chains, layout)
+    ranges = np.array([[0, 16384], [16384, 49152], [49152, layout.total_bins]])
+    owner, strad = pd.row_owners(t, ranges)
+    assert owner.tolist() == [0, 0, 1, 2, 0, 0, 0] and strad.tolist() == [1]
+    owner1, strad1 = pd.row_owners(t, np.array([[0, layout.total_bins]]))
+    assert not owner1.any() and len(strad1) == 0
+

@@ -65,6 +65,13 @@ def run_all(bam, tmp_path, n, one_device, sharding):
     wh, wr = rg.table(rg.out("mg_start_median_metagene_profile.txt"))
     assert gh == wh
     rg.assert_float_columns_equal(gr, wr, {1}, rtol=1e-14, label="metagene")
+    base = str(tmp_path / "mgm")
+    torchrun(n, "plastid_b200.bin.metagene", ["count", rg.out("mg_start_rois.txt"), base, "--min_counts", "5", "--normalize_over", "20", "80",
+                                                "--use_mean", "--fiveprime_variable", "--offset", rg.inp("p_offsets.txt")] + cnt(bam) + sh, one_device)
+    gh, gr = rg.table(base + "_metagene_profile.txt")
+    wh, wr = rg.table(rg.out("mg_start_mean_metagene_profile.txt"))
+    assert gh == wh
+    rg.assert_float_columns_equal(gr, wr, {1}, rtol=1e-12, label="metagene mean")      # column sums are added rank by rank
     base = str(tmp_path / "mgc")
     torchrun(n, "plastid_b200.bin.metagene", ["count", rg.out("mg_stop_rois.txt"), base, "--min_counts", "5", "--normalize_over", "-80", "-20",
                                                 "--center", "--nibble", "10"] + cnt(bam) + sh, one_device)

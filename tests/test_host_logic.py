@@ -1291,6 +1291,37 @@ def test_chromosome_cuts_fall_on_chromosome_boundaries():
         assert held == len(hb)          # whole chromosomes: no halo read is needed twice
 
 
+def test_chain_table_live_lengths_and_owned_rows():
+    """``ChainTable.live_lengths`` = ``chain.masked_length`` (geometry, host side) and ``owned_rows`` = the blocks that
+    overlap a rank's bins with chain offsets that address them — what a position-sharded rank hands to pb_region_sums."""
+    from plastid_b200.regions import ChainTable
+    layout = pb.GenomeLayout(["c1", "c2"], [50000, 30000])
+    rng = np.random.default_rng(9)
+    chains = []
+    for i in range(60):
+        c = "c1" if i % 3 else "c2"
+        a = int(rng.integers(0, 20000))
+        segs = [pb.GenomicSegment(c, a, a + 300, "+-"[i % 2]), pb.GenomicSegment(c, a + 1000, a + 1400, "+-"[i % 2])]
+        if i % 4 == 0:
+            segs.append(pb.GenomicSegment(c, a + 5000, a + 5100, "+-"[i % 2]))
+        ch = pb.SegmentChain(*segs)
+        if i % 5 == 0:
+            ch.add_masks(pb.GenomicSegment(c, a + 250, a + 1100, "+-"[i % 2]))
+        chains.append(ch)
+    chains.append(pb.SegmentChain())
+    t = ChainTable.from_chains(chains, layout)
+    assert list(t.live_lengths()) == [ch.masked_length for ch in chains]
+    total = 0
+    for lo, hi in ((0, 16384), (16384, 49152), (49152, layout.total_bins)):
+        idx, sub_off = t.owned_rows(lo, hi)
+        total += len(idx)
+        assert ((t.bend[idx] > lo) & (t.bstart[idx] < hi)).all() and len(sub_off) == t.n_chains + 1 and sub_off[-1] == len(idx)
+        chain_of = np.repeat(np.arange(t.n_chains), np.diff(t.chain_off))
+        for c in range(t.n_chains):
+            assert (chain_of[idx[sub_off[c]:sub_off[c + 1]]] == c).all()
+    assert total >= len(t.bstart)                      # a block across a cut belongs to both sides
+
+
 def test_position_cuts_balance_reads_plus_plane_bins():
     """Cuts give every rank the same cost ``reads + bins`` (bytes streamed + plane bytes written, dist.balanced_cuts):
     a skewed batch (most reads on one chromosome) no longer leaves one rank with most of the genome to write;
