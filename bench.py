@@ -390,14 +390,14 @@ def run_c4(args, W, device, rank, world, dist):
     def step(timed=False):
         if timed:
             ev[2].record()
-        mat, mmask = gather_windows(planes, table, cols, width)
+        mat, mmask = gather_windows(planes, table, cols, width, touched_only=world > 1 and args.c4_exchange == "slices")
         if timed:
             ev[3].record()
         if world > 1 and args.c4_exchange == "matrix":
             dist.all_reduce(mat)         # cells of other ranks' positions are 0, cells without a position NaN everywhere
         elif world > 1:
             # the matrix stays put: rows completed by their owner, exact medians per column slice after one all-to-all
-            prof, nreg, _d, _s = pdist.window_profile(mat, mmask, table, ranges, 70, 100, 10, "median")
+            prof, nreg, _d, _s = pdist.window_profile(mat, mmask, table, ranges, 70, 100, 10, "median", want_rows=False)
             return prof, nreg
         denom, sel, norm, nmask = window_normalize(mat, mmask, 70, 100, 10)
         prof, nreg, csum = column_profile(norm, nmask, sel, "median")

@@ -239,7 +239,7 @@ def do_count(ga, roi_table, norm_start=None, norm_end=None, min_counts=10, use_m
     table = ChainTable.from_chains(wins, ga.layout)
     need = sorted(set("+-."[p] for p in np.unique(table.chain_plane))) or ["+"]
     planes = ga.count_planes(tuple(need))
-    mat, mmask = gather_windows(planes, table, cols, window_size)
+    mat, mmask = gather_windows(planes, table, cols, window_size, touched_only=ga._collective and not keep)
     if ga._collective and not keep:
         # several GPUs: every rank filled the cells of its own positions.  The count matrix stays where it is: rows are
         # completed and normalised by the rank that owns their first position, means are all-reduced as column sums,

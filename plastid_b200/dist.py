@@ -414,11 +414,12 @@ def row_owners(table, ranges):
     return owner, np.nonzero(hi_r > lo_r)[0]
 
 
-def exchange_column_slices(rows):
+def exchange_column_slices(rows, row_counts=None):
     """``rows`` (float64 ``[k_r, width]``, this rank's rows) -> ``(slice, bounds)``: the columns
     ``[bounds[rank], bounds[rank + 1])`` of the rows of ALL ranks (rank order), ``[sum(k_r), w_rank]``.  NCCL: one
     all-to-all (every rank ships ``1 / world`` of its columns to every peer: the exchange an exact per-column median
-    needs, at ``1 / world`` of the bytes of gathering whole rows); other backends: all-gather, then cut."""
+    needs, at ``1 / world`` of the bytes of gathering whole rows); other backends: all-gather, then cut.
+    ``row_counts``: ``k_r`` of every rank when the caller knows them (no size exchange, no host synchronisation)."""
     import torch
     import torch.distributed as dist
     rank, ws = world()
@@ -426,33 +427,43 @@ def exchange_column_slices(rows):
     bounds = [(c * width) // ws for c in range(ws + 1)]
     if ws == 1:
         return rows, bounds
-    k = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
-    ks = [torch.zeros_like(k) for _ in range(ws)]
-    dist.all_gather(ks, k)
-    ks = [int(x.item()) for x in ks]
+    if row_counts is None:
+        k = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+        ks = [torch.zeros_like(k) for _ in range(ws)]
+        dist.all_gather(ks, k)
+        row_counts = [int(x.item()) for x in ks]
+    ks = [int(x) for x in row_counts]
     w_mine = bounds[rank + 1] - bounds[rank]
     if dist.get_backend() == "nccl":
         ins = [rows[:, bounds[c]:bounds[c + 1]].contiguous() for c in range(ws)]
         outs = [torch.empty((ks[r], w_mine), dtype=rows.dtype, device=rows.device) for r in range(ws)]
         dist.all_to_all(outs, ins)
         return torch.cat(outs, dim=0), bounds
-    return gather_matrix(rows)[:, bounds[rank]:bounds[rank + 1]].contiguous(), bounds
+    pad = torch.zeros((max(ks), width), dtype=rows.dtype, device=rows.device)
+    pad[:rows.shape[0]] = rows
+    parts = [torch.zeros_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p_[:c, bounds[rank]:bounds[rank + 1]] for p_, c in zip(parts, ks)], dim=0).contiguous(), bounds
 
 
-def window_profile(mat, mmask, table, ranges, norm_lo, norm_hi, min_counts, mode="median", per_million_of=None):
+def window_profile(mat, mmask, table, ranges, norm_lo, norm_hi, min_counts, mode="median", per_million_of=None,
+                   want_rows=True):
     """``metagene count`` on a position-sharded genome without moving the count matrix (60 k x 350 float64 = 168 MB at
     BASELINE config 4): ``mat`` / ``mmask`` are this rank's ``gather_windows`` output (cells of its own positions,
     zero elsewhere, NaN where the window has no position).
 
-    * a row is COMPLETED by one rank, the owner of its first position (:func:`row_owners`); the few rows that lie on
-      both sides of a cut are summed over ranks first (one small all-reduce);
+    * a row is COMPLETED by one rank, the owner of its first position (:func:`row_owners`: geometry, known to every
+      rank without talking); the few rows that lie on both sides of a cut are summed over ranks first (one small
+      all-reduce);
     * every rank normalises and selects its own rows (``pb_window_normalize``; metagene.py:916-924);
     * mean (``--use_mean``): column sums and counts of the selected rows, all-reduced (2 x width numbers);
-      median (default; not all-reducible): every rank receives ``width / world`` columns of all selected rows
-      (:func:`exchange_column_slices`), takes their exact medians (``pb_column_profile``) and the slices are gathered.
+      median (default; not all-reducible): every rank receives ``width / world`` columns of all owned rows (one
+      all-to-all, rows that are not selected travel as NaN), takes their exact medians (``pb_column_profile``) and the
+      slices are gathered.  Three collectives, no host synchronisation.
 
-    Returns ``(profile, regions_counted, denominator, row_select)`` complete on every rank; profile and counts equal
-    the single-GPU result (medians bit for bit; means up to the order of the float sums)."""
+    Returns ``(profile, regions_counted, denominator, row_select)`` complete on every rank (the last two ``None``
+    unless ``want_rows``); profile and counts equal the single-GPU result (medians bit for bit; means up to the order
+    of the float sums)."""
     import torch
     import torch.distributed as dist
     from .genome_array import window_normalize, column_profile
@@ -460,53 +471,64 @@ def window_profile(mat, mmask, table, ranges, norm_lo, norm_hi, min_counts, mode
     dev = mat.device
     n, width = mat.shape
     cache = table.__dict__.setdefault("_owners", {})
-    key = tuple(int(x) for x in np.asarray(ranges).reshape(-1))
+    key = (tuple(int(x) for x in np.asarray(ranges).reshape(-1)), rank, str(dev))
     if key not in cache:
         owner, strad = row_owners(table, ranges)
-        cache[key] = (owner, strad)
-    owner, strad = cache[key]
-    if len(strad) and ws > 1:
-        idx = torch.from_numpy(strad).to(dev)
-        part = mat[idx]
-        allreduce_sum(part)                    # NaN cells are geometry (NaN on every rank); counts have one non-zero summand
-        mat[idx] = part
+        lo, hi = (int(x) for x in np.asarray(ranges)[rank])
+        chain_of = np.repeat(np.arange(table.n_chains), np.diff(table.chain_off))
+        hit = np.zeros(table.n_chains, dtype=bool)
+        hit[chain_of[(table.bend > lo) & (table.bstart < hi)]] = True      # rows this rank wrote (gather_windows touched_only)
+        cache[key] = (np.bincount(owner, minlength=ws)[:ws], torch.from_numpy(np.nonzero(owner == rank)[0]).to(dev),
+                      torch.from_numpy(strad).to(dev), torch.from_numpy(hit[strad]).to(dev))
+    counts, own_idx, strad, strad_mine = cache[key]
+    if strad.numel() and ws > 1:
+        # NaN cells are geometry (NaN on every rank that wrote the row); counts have one non-zero summand; a rank
+        # without a position in the row never wrote it and contributes zeros
+        part = torch.where(strad_mine.unsqueeze(1), mat[strad], torch.zeros((), dtype=mat.dtype, device=dev))
+        allreduce_sum(part)
+        mat[strad] = part
+    k = int(own_idx.numel())
+    x, xm = mat[own_idx], mmask[own_idx]
     if per_million_of is not None:
-        mat = mat / float(per_million_of) * 1e6
-    denom, sel, norm, nmask = window_normalize(mat, mmask, norm_lo, norm_hi, min_counts)
-    mine = torch.from_numpy(owner == rank).to(dev)
-    sel = sel * mine.to(sel.dtype)
-    denom = torch.where(mine, denom, torch.zeros_like(denom))
-    if mode == "mean":
-        _p, n_regions, col_sum = column_profile(norm, nmask, sel, "mean")
-        allreduce_sum(col_sum)
-        allreduce_sum(n_regions)
-        profile = col_sum / n_regions.to(col_sum.dtype)
+        x = x / float(per_million_of) * 1e6
+    if k:
+        denom, sel, norm, nmask = window_normalize(x, xm, norm_lo, norm_hi, min_counts)
     else:
-        rows = torch.nonzero(sel, as_tuple=False).flatten()
-        x = norm[rows]
-        x = torch.where(nmask[rows] != 0, torch.full_like(x, float("nan")), x)       # masked cells travel as NaN
-        part, bounds = exchange_column_slices(x)
+        denom, sel = torch.zeros(0, dtype=torch.float64, device=dev), torch.zeros(0, dtype=torch.uint8, device=dev)
+        norm, nmask = x, xm
+    if mode == "mean":
+        both = torch.zeros(2 * width, dtype=torch.float64, device=dev)
+        if k:
+            _p, n_regions, col_sum = column_profile(norm, nmask, sel, "mean")
+            both[:width], both[width:] = col_sum, n_regions.to(torch.float64)
+        allreduce_sum(both)                    # counts are far below 2^53: exact as float64
+        n_regions = both[width:].to(torch.int64)
+        profile = both[:width] / both[width:]
+    else:
+        y = torch.where((nmask != 0) | (sel == 0).unsqueeze(1), torch.full_like(norm, float("nan")), norm)
+        part, bounds = exchange_column_slices(y, counts)
         w_mine = bounds[rank + 1] - bounds[rank]
         w_max = max(bounds[c + 1] - bounds[c] for c in range(ws))
-        p_loc = torch.full((w_max,), float("nan"), dtype=torch.float64, device=dev)
-        n_loc = torch.zeros(w_max, dtype=torch.int64, device=dev)
+        loc = torch.zeros((2, w_max), dtype=torch.float64, device=dev)
+        loc[0] = float("nan")
         if part.shape[0] and w_mine:
             pmask = torch.isnan(part).to(torch.uint8)
             every = torch.ones(part.shape[0], dtype=torch.uint8, device=dev)
             p_c, n_c, _s = column_profile(torch.nan_to_num(part, nan=0.0), pmask, every, "median")
-            p_loc[:w_mine], n_loc[:w_mine] = p_c, n_c
+            loc[0, :w_mine], loc[1, :w_mine] = p_c, n_c.to(torch.float64)
         if ws > 1:
-            ps, ns = [torch.zeros_like(p_loc) for _ in range(ws)], [torch.zeros_like(n_loc) for _ in range(ws)]
-            dist.all_gather(ps, p_loc)
-            dist.all_gather(ns, n_loc)
+            parts = [torch.zeros_like(loc) for _ in range(ws)]
+            dist.all_gather(parts, loc)
         else:
-            ps, ns = [p_loc], [n_loc]
-        profile = torch.cat([ps[c][:bounds[c + 1] - bounds[c]] for c in range(ws)])
-        n_regions = torch.cat([ns[c][:bounds[c + 1] - bounds[c]] for c in range(ws)])
-    sel_all = sel.to(torch.int32)
-    allreduce_sum(sel_all)
-    allreduce_sum(denom)
-    return profile, n_regions, denom, sel_all.to(torch.uint8)
+            parts = [loc]
+        profile = torch.cat([parts[c][0, :bounds[c + 1] - bounds[c]] for c in range(ws)])
+        n_regions = torch.cat([parts[c][1, :bounds[c + 1] - bounds[c]] for c in range(ws)]).to(torch.int64)
+    if not want_rows:
+        return profile, n_regions, None, None
+    rows = torch.zeros((2, n), dtype=torch.float64, device=dev)
+    rows[0, own_idx], rows[1, own_idx] = denom, sel.to(torch.float64)
+    allreduce_sum(rows)
+    return profile, n_regions, rows[0], rows[1].to(torch.uint8)
 
 
 def mean_profile(col_sum, n_regions):

@@ -425,13 +425,21 @@ class GraphedCount(object):
         return self.sums, self.live
 
 
-def gather_windows(planes, table, row_col, width):
-    """Window matrix (n_chains x width, NaN-filled) + mask matrix, rows laid 5'->3'."""
+def gather_windows(planes, table, row_col, width, touched_only=False):
+    """Window matrix (n_chains x width, NaN-filled) + mask matrix, rows laid 5'->3'.
+    ``touched_only`` (position-sharded planes): only the rows with a position in this rank's bins are produced — whole,
+    positions of other ranks as zeros — and the other rows are left unwritten (``dist.window_profile`` completes rows rank by
+    rank and never looks at them); the rank then walks its own chains' blocks instead of the whole table."""
     import torch
     _lib.require_cuda()
     dev = planes.device
     d = table.device(dev)
     n = table.n_chains
+    n_blocks = len(table.bstart)
+    if touched_only and (planes.bin_lo, planes.bin_hi) != (0, int(planes.layout.total_bins)) and n_blocks:
+        sub = table.owned(dev, planes.bin_lo, planes.bin_hi, whole_chains=True)
+        if sub["n_blocks"]:                     # (a rank that touches no row walks the whole table: nothing is its own)
+            d, n_blocks = sub, sub["n_blocks"]
     matrix = torch.empty((max(n, 1), width), dtype=torch.float64, device=dev)
     maskmat = torch.empty((max(n, 1), width), dtype=torch.uint8, device=dev)
     cols = row_col if hasattr(row_col, "data_ptr") else torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
@@ -439,7 +447,7 @@ def gather_windows(planes, table, row_col, width):
                                             _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
                                             _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]),
                                             _lib.ptr(d["block_chain"]), _lib.ptr(d["block_pos"]), _lib.ptr(d["block_plane"]),
-                                            _lib.ptr(d["chain_len"]), _lib.ptr(cols), n, len(table.bstart), width,
+                                            _lib.ptr(d["chain_len"]), _lib.ptr(cols), n, n_blocks, width,
                                             _lib.ptr(d["mask_bits"]), _lib.ptr(d["mask_off"]), planes.bin_lo, planes.bin_hi,
                                             _lib.ptr(matrix), _lib.ptr(maskmat), _lib.stream_ptr()))
     return matrix[:n], maskmat[:n]

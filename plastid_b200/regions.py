@@ -144,17 +144,28 @@ class ChainTable(object):
         np.cumsum(np.bincount(chain_of[idx], minlength=self.n_chains), out=sub_off[1:])
         return idx, sub_off
 
-    def owned(self, device, lo, hi):
+    def touched_rows(self, lo, hi):
+        """Like :meth:`owned_rows`, but EVERY block of a chain that has a block in [lo, hi): what a rank walks when the
+        rows it touches must come out whole (window matrices whose rows are completed rank by rank)."""
+        chain_of = np.repeat(np.arange(self.n_chains), np.diff(self.chain_off))
+        hit = np.zeros(self.n_chains, dtype=bool)
+        hit[chain_of[(self.bend > lo) & (self.bstart < hi)]] = True
+        idx = np.nonzero(hit[chain_of])[0]
+        sub_off = np.zeros(self.n_chains + 1, dtype=np.int64)
+        np.cumsum(np.bincount(chain_of[idx], minlength=self.n_chains), out=sub_off[1:])
+        return idx, sub_off
+
+    def owned(self, device, lo, hi, whole_chains=False):
         """The rows of the block tables a rank that owns the global bins [lo, hi) has to look at (position sharding):
         blocks that overlap the range, with the chain offsets that go with them; ``block_pos`` / ``block_chain`` keep
         their values from the whole table, so mask bits and chain totals are addressed as before.  At N = 8 a rank
         otherwise walks all blocks of the table to find that 7 / 8 of them lie elsewhere.  Cached per range."""
         import torch
-        key = (_lib.device_key(device), int(lo), int(hi))
+        key = (_lib.device_key(device), int(lo), int(hi), bool(whole_chains))
         cache = self.__dict__.setdefault("_owned", {})
         if key not in cache:
             d = self.device(device)
-            idx, sub_off = self.owned_rows(lo, hi)
+            idx, sub_off = self.touched_rows(lo, hi) if whole_chains else self.owned_rows(lo, hi)
             t_idx = torch.from_numpy(idx).to(device)
             sub = dict(d)
             for name in ("bstart", "bend", "block_chain", "block_pos", "block_plane"):
