@@ -89,6 +89,25 @@ __device__ __forceinline__ int64_t pb_position(const PbReads &b, int64_t i, int3
     return pb_block_position(b, i, start, idx);
 }
 
+// Site table: everything a read's meta word decides — drop bit, size window, strand class of the query strand, rule
+// direction, rule offset — folded into ONE 16-bit look-up per read.  key = aligned length (< 256) | reverse << 8 |
+// drop << 9; entry = index into read.positions of the mapped site, kSiteSkip (the read does not count on this strand
+// class) or kSiteDropped (the rule has no site for this length: the reference skips the read and warns).  One table per
+// strand class (plane 0 '+', 1 '-', 2 '.'), built by the read-index launch, copied to shared memory by every CTA.
+// ncu on the form that evaluated the tests per read (profiles/ncu_regions_r02.txt): ~64 thread instructions per read,
+// a third of them branches and reconvergence barriers around the per-read `continue`s; with the table the per-read
+// path is straight-line and predicated.
+constexpr int kSiteKeys = 1024;
+constexpr int kSiteSkip = -1, kSiteDropped = -2;
+
+__device__ __forceinline__ int pb_site_entry(const PbRuleDev &r, int plane, uint32_t m)
+{
+    const bool rev = PB_META_REV(m);
+    if (!pb_passes(m, r.size_min, r.size_max) || (plane == 0 && rev) || (plane == 1 && !rev)) return kSiteSkip;   // genome_array.py:811-815
+    const int idx = pb_rule_index(r, PB_META_L(m), plane == 1);          // rule direction follows the chain's strand
+    return idx < 0 ? kSiteDropped : idx;
+}
+
 // first index in [lo,hi) with a[i] >= key
 __device__ __forceinline__ int64_t pb_lower_bound(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key)
 {

@@ -7,6 +7,7 @@
 // All of this is HBM/L2-bound gather work: one warp walks one chain with coalesced 128-byte
 // reads of the dense count plane.
 #include "pb_tiles.cuh"
+#include <stdlib.h>
 #include <math.h>
 
 namespace {
@@ -552,7 +553,7 @@ extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,
 // is applied per read and the (length, column) cell is incremented in a shared-memory histogram.
 namespace {
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 10)
 pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_len, int n_len,
                              const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
                              const int64_t *__restrict__ chain_off, const uint8_t *__restrict__ chain_plane,
@@ -560,16 +561,37 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
                              int64_t n_chains, int32_t width, int phase_mode, int32_t codon_front, int32_t codon_back,
                              const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
                              long long lo_bin, long long hi_bin,
-                             uint32_t *__restrict__ out, uint8_t *__restrict__ maskmat)
+                             uint32_t *__restrict__ out, uint8_t *__restrict__ maskmat,
+                             int site_tab)
 {
-    extern __shared__ uint32_t hist[];   // [n_len][width]  (phase mode: width == 3 sub-codon phases)
+    extern __shared__ __align__(16) uint32_t hist[];   // [n_len][width]  (phase mode: width == 3 sub-codon phases)
+    __shared__ __align__(16) int16_t s_tab[kSiteKeys];   // point rules: the site table of this window's strand class
     const int64_t c = blockIdx.x;
-    for (int j = threadIdx.x; j < n_len * width; j += blockDim.x) hist[j] = 0;
+    {
+        const int cells = n_len * width, quads = cells >> 2;
+        for (int j = threadIdx.x; j < quads; j += blockDim.x) reinterpret_cast<uint4 *>(hist)[j] = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = (quads << 2) + threadIdx.x; j < cells; j += blockDim.x) hist[j] = 0;
+    }
+    const int plane = __ldg(chain_plane + c);            // 0 '+', 1 '-', 2 '.'
+    if (site_tab) {
+        // only the lengths of the stratification range count (psite.py:187): everything else is "skip", and the
+        // 2 x n_len live entries (forward / reverse reads) cost one rule look-up each
+        const uint4 skip4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);     // kSiteSkip in every entry
+        for (int j = threadIdx.x; j < kSiteKeys * 2 / 16; j += blockDim.x) reinterpret_cast<uint4 *>(s_tab)[j] = skip4;
+        __syncthreads();
+        for (int j = threadIdx.x; j < 2 * n_len; j += blockDim.x) {
+            const int L = min_len + (j >> 1);
+            const uint32_t rev = (uint32_t)(j & 1);
+            if (L < 256) {
+                const int v = pb_site_entry(r, plane, (uint32_t)L | (rev << 16));
+                s_tab[L | (rev << 8)] = (int16_t)(v < 0 ? kSiteSkip : v);
+            }
+        }
+    }
     __syncthreads();
     const int64_t k0 = __ldg(chain_off + c), k1 = __ldg(chain_off + c + 1);
     int64_t len = 0;
     for (int64_t k = k0; k < k1; ++k) len += __ldg(bend + k) - __ldg(bstart + k);
-    const int plane = __ldg(chain_plane + c);            // 0 '+', 1 '-', 2 '.'
     const bool rev_out = __ldg(chain_reverse + c);
     const bool rq = plane == 1;                          // rule direction follows the window's strand
     const int64_t col0 = phase_mode ? 0 : __ldg(row_col + c);
@@ -590,18 +612,54 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
         const int64_t lo = pb_lower_bound_warp(b.ref_start, r0, r1, bs - b.max_span + 1);
         const int64_t hi = pb_lower_bound_warp(b.ref_start, lo, r1, be);
         constexpr int kU = 4;       // independent reads in flight per thread
-        for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)kU * blockDim.x) {
+        constexpr int kT = 128;     // threads per CTA (the launch below); 32-bit indices relative to the slice: ncu showed
+                                    // ~105 instructions of 64-bit index arithmetic per 4 loads with `i0 + u * blockDim.x`
+        const int n_slice = (int)(hi - lo < 0x7fffffff ? hi - lo : 0x7fffffff);
+        const uint32_t *__restrict__ mp = b.meta + lo;
+        const int32_t *__restrict__ sp = b.ref_start + lo;
+        for (int t0 = threadIdx.x; t0 < n_slice; t0 += kU * kT) {
+            const int64_t i0 = lo + t0;
             uint32_t mv[kU];
             int32_t sv[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                const int64_t i = i0 + (int64_t)u * blockDim.x;
-                mv[u] = i < hi ? __ldg(b.meta + i) : (1u << 17);
-                sv[u] = i < hi ? __ldg(b.ref_start + i) : 0;
+                const int t = t0 + u * kT;
+                mv[u] = t < n_slice ? __ldg(mp + t) : (1u << 17);
+                sv[u] = t < n_slice ? __ldg(sp + t) : 0;
+            }
+            if (site_tab) {
+                // point rules: drop bit, size window, strand class, stratification range and rule offset are ONE look-up
+                // (built per CTA above); the per-read path is straight-line up to the histogram atomic.
+                // ncu on the generic path below: 190 thread instructions per read, issue slots 71 % busy.
+                const int own_lo = (int)max((long long)bs, lo_bin - base), own_w = (int)min((long long)be, hi_bin - base) - own_lo;
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t m = mv[u];
+                    int idx;
+                    if (__builtin_expect((m & 0xFF00u) != 0u, 0)) {
+                        const int L = PB_META_L(m);
+                        idx = (L < min_len || L >= min_len + n_len) ? kSiteSkip : pb_site_entry(r, plane, m);
+                    } else idx = s_tab[(m & 0xFFu) | ((m >> 8) & 0x300u)];
+                    int p = sv[u] + idx;
+                    if (idx >= 0 && PB_META_NBLK(m) > 1 && b.blk_off != nullptr) {
+                        const int64_t pp = pb_block_position(b, i0 + u * kT, sv[u], idx);
+                        p = pp < 0 ? own_lo - 1 : (int)pp;
+                    }
+                    if (idx >= 0 && own_w > 0 && (unsigned)(p - own_lo) < (unsigned)own_w) {      // the site belongs to this block and rank
+                        const int jj = (int)j0 + (p - (int)bs);
+                        int col = (int)col0 + (rev_out ? ((int)len - 1 - jj) : jj);
+                        if (phase_mode) {
+                            const int cod = col / 3;
+                            col = (cod >= cod_lo && cod < cod_hi) ? col - cod * 3 : -1;
+                        }
+                        if ((unsigned)col < (unsigned)width) atomicAdd(&hist[((int)(m & 0xFFFFu) - min_len) * width + col], 1u);
+                    }
+                }
+                continue;
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                const int64_t i = i0 + u * kT;
                 const uint32_t m = mv[u];
                 if (!pb_passes(m, r.size_min, r.size_max)) continue;
                 const bool rev = PB_META_REV(m);
@@ -660,9 +718,11 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
         j0 += be - bs;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < n_len * width; j += blockDim.x) {
-        const int row = j / width, col = j - row * width;
-        out[((int64_t)row * n_chains + c) * width + col] = hist[j];
+    // row by row (ncu: the flat loop's `j / width` made this write-out 37 instructions per cell, a third of the kernel)
+    for (int row = 0; row < n_len; ++row) {
+        uint32_t *__restrict__ dst = out + ((int64_t)row * n_chains + c) * width;
+        const uint32_t *src = hist + row * width;
+        for (int col = threadIdx.x; col < width; col += blockDim.x) dst[col] = src[col];
     }
     // the validity mask every length shares (get_masked_counts(ga).mask, psite.py:166)
     if (phase_mode || !maskmat) return;
@@ -709,10 +769,13 @@ extern "C" int pb_stratified_windows_range(const pb_batch *batch, const pb_layou
     PbRuleDev r = pb_to_dev(rule);
     PbLayoutDev lay{layout->chrom_len, layout->chrom_bin_off, layout->n_chrom};
     PB_CUDA_CHECK(cudaFuncSetAttribute(pb_stratified_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // point rules take the site-table path (the Center form of phase mode walks trimmed intervals); PB_STRAT_GENERIC=1 (A/B aid)
+    const int site_tab = rule->kind != PB_RULE_CENTER && !getenv("PB_STRAT_GENERIC");
     pb_stratified_windows_kernel<<<(unsigned)n_chains, 128, smem, stream>>>(b, r, lay, min_len, n_len, bstart, bend, chain_off,
                                                                            chain_plane, chain_reverse, row_col, n_chains, width,
                                                                            phase_mode, codon_front, codon_back,
-                                                                           mask_bits, mask_off, bin_begin, bin_end, out, maskmat);
+                                                                           mask_bits, mask_off, bin_begin, bin_end, out, maskmat,
+                                                                           site_tab);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
 }

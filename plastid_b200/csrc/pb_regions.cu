@@ -266,25 +266,6 @@ pb_window_fill_kernel(const int64_t *__restrict__ chain_len, const int32_t *__re
 constexpr int kItemReads = 2048;
 constexpr int kIndexShift = 14;          // PB_LAYOUT_ALIGN = 1 << 14: an index cell never spans two chromosomes
 
-// Site table: everything a read's meta word decides — drop bit, size window, strand class of the query strand, rule
-// direction, rule offset — folded into ONE 16-bit look-up per read.  key = aligned length (< 256) | reverse << 8 |
-// drop << 9; entry = index into read.positions of the mapped site, kSiteSkip (the read does not count on this strand
-// class) or kSiteDropped (the rule has no site for this length: the reference skips the read and warns).  One table per
-// strand class (plane 0 '+', 1 '-', 2 '.'), built by the read-index launch, copied to shared memory by every CTA.
-// ncu on the form that evaluated the tests per read (profiles/ncu_regions_r02.txt): ~64 thread instructions per read,
-// a third of them branches and reconvergence barriers around the per-read `continue`s; with the table the per-read
-// path is straight-line and predicated.
-constexpr int kSiteKeys = 1024;
-constexpr int kSiteSkip = -1, kSiteDropped = -2;
-
-__device__ __forceinline__ int pb_site_entry(const PbRuleDev &r, int plane, uint32_t m)
-{
-    const bool rev = PB_META_REV(m);
-    if (!pb_passes(m, r.size_min, r.size_max) || (plane == 0 && rev) || (plane == 1 && !rev)) return kSiteSkip;   // genome_array.py:811-815
-    const int idx = pb_rule_index(r, PB_META_L(m), plane == 1);          // rule direction follows the chain's strand
-    return idx < 0 ? kSiteDropped : idx;
-}
-
 __global__ void pb_read_index_kernel(PbReads b, PbLayoutDev lay, long long n_cells, long long *__restrict__ index,
                                      PbRuleDev r, int16_t *__restrict__ site_tab)
 {
