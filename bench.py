@@ -895,12 +895,13 @@ def main():
     achieved = alg_bytes / (k_ms / 1000.0) / 1e9
     kernel_name = "pb_center_tiles_kernel" if is_center else "pb_point_tiles_kernel"
     traffic = None                    # DRAM bytes per launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath) and args.genome_scale == 1.0 and world == 1:
-        with open(tpath) as fh:
-            traffic = json.load(fh).get("%s:%s" % (kernel_name, args.workload))
-        if traffic is not None and abs(n_batch_reads - {"c2": 200_000_000, "c3": 100_000_000}.get(args.workload, -1)) > 0:
-            traffic = None            # captured at the default size only
+    for tname in ("traffic_r01.json", "traffic_r02.json"):            # the later capture wins
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath) and args.genome_scale == 1.0 and world == 1:
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("%s:%s" % (kernel_name, args.workload), traffic)
+    if traffic is not None and abs(n_batch_reads - {"c2": 200_000_000, "c3": 100_000_000}.get(args.workload, -1)) > 0:
+        traffic = None                # captured at the default size only
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "launches_timed": kn.value,
