@@ -167,7 +167,7 @@ def map_wire16_streamed(receiver, pinned, chunks, layout, factory, size_filter=N
     ws_bytes = L.pb_map_workspace_bytes(layout.total_bins, 0, dbatch.n_reads)
     # Two compute lanes (streams) take the chunks alternately, each with its own workspace and statistics:
     # the tail of one chunk's persistent kernel overlaps the expansion and the first tiles of the next.
-    n_lanes = 2 if len(chunks) > 1 else 1
+    n_lanes = int(os.environ.get("PB_POINT_LANES", "2")) if len(chunks) > 1 else 1       # (env: A/B aid)
     ws = [_workspace(dev, ws_bytes, slot=j) for j in range(n_lanes)]
     stats = [torch.zeros(_lib.PB_NSTATS, dtype=torch.int64, device=dev) for _ in range(n_lanes)]
     copy_stream = copy_stream or torch.cuda.Stream(device=dev)
