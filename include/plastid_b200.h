@@ -507,6 +507,19 @@ int pb_stratified_windows_range(const pb_batch *batch, const pb_layout *layout, 
                                 const uint8_t *mask_bits, const int64_t *mask_off,
                                 int64_t bin_begin, int64_t bin_end,
                                 uint32_t *out, uint8_t *maskmat, void *stream);
+/* The same with a caller-provided workspace (pb_stratified_windows_workspace_bytes(n_blocks), 8-byte aligned; n_blocks =
+ * chain_off[n_chains]): the read slice of every exon block of the table is found by one launch over all blocks before
+ * the windows are counted, instead of two dependent searches per exon inside every window's CTA. */
+size_t pb_stratified_windows_workspace_bytes(int64_t n_blocks);
+int pb_stratified_windows_ws(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                             int min_len, int max_len,
+                             const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                             const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                             const int32_t *row_col, int64_t n_chains, int64_t n_blocks, int32_t width,
+                             int phase_mode, int32_t codon_front, int32_t codon_back,
+                             const uint8_t *mask_bits, const int64_t *mask_off,
+                             int64_t bin_begin, int64_t bin_end,
+                             uint32_t *out, uint8_t *maskmat, void *workspace, size_t workspace_bytes, void *stream);
 
 /* phase_by_size.py:197-214: per chain, counts laid 5'->3' are cut into codons (a trailing partial
  * codon is ignored), the python slice [codon_front:codon_back] of codons is kept, and counts are

@@ -113,6 +113,10 @@ _SIGNATURES = {
     "pb_stratified_windows_range": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int, C.c_int,
                                               _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_int32,
                                               _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "pb_stratified_windows_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "pb_stratified_windows_ws": (C.c_int, [C.POINTER(PbBatch), C.POINTER(PbLayout), C.POINTER(PbRule), C.c_int, C.c_int,
+                                           _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_int32,
+                                           _P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     "pb_phase_sums_range": (C.c_int, [C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_int64, C.c_int64, _P, _P]),
     "pb_window_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,

@@ -553,6 +553,23 @@ extern "C" int pb_phase_sums(const void *const *planes, int vec_dtype,
 // is applied per read and the (length, column) cell is incremented in a shared-memory histogram.
 namespace {
 
+// one warp per exon block: the slice [lo, hi) of the coordinate-sorted batch whose reads can map into it
+__global__ void __launch_bounds__(256)
+pb_stratified_slices_kernel(PbReads b, PbLayoutDev lay, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                            int64_t n_blocks, long long *__restrict__ slices)
+{
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_blocks) return;
+    const int64_t gs = __ldg(bstart + k), ge = __ldg(bend + k);
+    const int ch = pb_chrom_of_bin(lay, gs);
+    const int64_t base = __ldg(lay.chrom_bin_off + ch);
+    int64_t r0 = 0, r1 = 0;
+    if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
+    const int64_t lo = pb_lower_bound_warp(b.ref_start, r0, r1, gs - base - b.max_span + 1);
+    const int64_t hi = pb_lower_bound_warp(b.ref_start, lo, r1, ge - base);
+    if ((threadIdx.x & 31) == 0) { slices[2 * k] = lo; slices[2 * k + 1] = hi; }
+}
+
 __global__ void __launch_bounds__(128, 10)
 pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_len, int n_len,
                              const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
@@ -562,7 +579,7 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
                              const uint8_t *__restrict__ mask_bits, const int64_t *__restrict__ mask_off,
                              long long lo_bin, long long hi_bin,
                              uint32_t *__restrict__ out, uint8_t *__restrict__ maskmat,
-                             int site_tab)
+                             int site_tab, const long long *__restrict__ slices)
 {
     extern __shared__ __align__(16) uint32_t hist[];   // [n_len][width]  (phase mode: width == 3 sub-codon phases)
     __shared__ __align__(16) int16_t s_tab[kSiteKeys];   // point rules: the site table of this window's strand class
@@ -608,9 +625,15 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
         const int64_t bs = gs - base, be = ge - base;    // chromosome coordinates of the block
         int64_t r0 = 0, r1 = 0;
         if (ch < b.n_chrom) { r0 = __ldg(b.chrom_read_off + ch); r1 = __ldg(b.chrom_read_off + ch + 1); }
+        // the block's read slice: looked up when pb_stratified_slices_kernel ran first (all blocks of the table searched
+        // side by side; ncu: a third of this kernel's stall samples sat in the two dependent searches per exon), else
         // every warp runs the same two 32-ary searches (same addresses: L1 hits after the first warp)
-        const int64_t lo = pb_lower_bound_warp(b.ref_start, r0, r1, bs - b.max_span + 1);
-        const int64_t hi = pb_lower_bound_warp(b.ref_start, lo, r1, be);
+        int64_t lo, hi;
+        if (slices) { lo = __ldg(slices + 2 * k); hi = __ldg(slices + 2 * k + 1); }
+        else {
+            lo = pb_lower_bound_warp(b.ref_start, r0, r1, bs - b.max_span + 1);
+            hi = pb_lower_bound_warp(b.ref_start, lo, r1, be);
+        }
         constexpr int kU = 4;       // independent reads in flight per thread
         constexpr int kT = 128;     // threads per CTA (the launch below); 32-bit indices relative to the slice: ncu showed
                                     // ~105 instructions of 64-bit index arithmetic per 4 loads with `i0 + u * blockDim.x`
@@ -740,15 +763,20 @@ pb_stratified_windows_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, int min_le
 
 }  // namespace
 
-extern "C" int pb_stratified_windows_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
-                                           int min_len, int max_len,
-                                           const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
-                                           const uint8_t *chain_plane, const uint8_t *chain_reverse,
-                                           const int32_t *row_col, int64_t n_chains, int32_t width,
-                                           int phase_mode, int32_t codon_front, int32_t codon_back,
-                                           const uint8_t *mask_bits, const int64_t *mask_off,
-                                           int64_t bin_begin, int64_t bin_end,
-                                           uint32_t *out, uint8_t *maskmat, void *stream_)
+extern "C" size_t pb_stratified_windows_workspace_bytes(int64_t n_blocks)
+{
+    return n_blocks < 0 ? 0 : (size_t)n_blocks * 16 + 16;
+}
+
+static int stratified_windows_impl(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                                   int min_len, int max_len,
+                                   const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                   const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                   const int32_t *row_col, int64_t n_chains, int64_t n_blocks, int32_t width,
+                                   int phase_mode, int32_t codon_front, int32_t codon_back,
+                                   const uint8_t *mask_bits, const int64_t *mask_off,
+                                   int64_t bin_begin, int64_t bin_end,
+                                   uint32_t *out, uint8_t *maskmat, void *workspace, size_t workspace_bytes, void *stream_)
 {
     if (!batch || !layout || !rule || !bstart || !bend || !chain_off || !chain_plane || !chain_reverse || !out ||
         (!phase_mode && (!row_col || !maskmat))) { pb_set_error("pb_stratified_windows: null argument"); return PB_EINVAL; }
@@ -771,13 +799,51 @@ extern "C" int pb_stratified_windows_range(const pb_batch *batch, const pb_layou
     PB_CUDA_CHECK(cudaFuncSetAttribute(pb_stratified_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // point rules take the site-table path (the Center form of phase mode walks trimmed intervals); PB_STRAT_GENERIC=1 (A/B aid)
     const int site_tab = rule->kind != PB_RULE_CENTER && !getenv("PB_STRAT_GENERIC");
+    long long *slices = nullptr;
+    if (workspace && n_blocks > 0) {
+        if (workspace_bytes < pb_stratified_windows_workspace_bytes(n_blocks) || ((uintptr_t)workspace & 7)) {
+            pb_set_error("pb_stratified_windows_ws: workspace too small or misaligned"); return PB_ENOSPACE;
+        }
+        slices = (long long *)workspace;
+        pb_stratified_slices_kernel<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, stream>>>(b, lay, bstart, bend, n_blocks, slices);
+    }
     pb_stratified_windows_kernel<<<(unsigned)n_chains, 128, smem, stream>>>(b, r, lay, min_len, n_len, bstart, bend, chain_off,
                                                                            chain_plane, chain_reverse, row_col, n_chains, width,
                                                                            phase_mode, codon_front, codon_back,
                                                                            mask_bits, mask_off, bin_begin, bin_end, out, maskmat,
-                                                                           site_tab);
+                                                                           site_tab, slices);
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
+}
+
+extern "C" int pb_stratified_windows_range(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                                           int min_len, int max_len,
+                                           const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                           const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                           const int32_t *row_col, int64_t n_chains, int32_t width,
+                                           int phase_mode, int32_t codon_front, int32_t codon_back,
+                                           const uint8_t *mask_bits, const int64_t *mask_off,
+                                           int64_t bin_begin, int64_t bin_end,
+                                           uint32_t *out, uint8_t *maskmat, void *stream_)
+{
+    return stratified_windows_impl(batch, layout, rule, min_len, max_len, bstart, bend, chain_off, chain_plane, chain_reverse,
+                                   row_col, n_chains, 0, width, phase_mode, codon_front, codon_back, mask_bits, mask_off,
+                                   bin_begin, bin_end, out, maskmat, nullptr, 0, stream_);
+}
+
+extern "C" int pb_stratified_windows_ws(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,
+                                        int min_len, int max_len,
+                                        const int64_t *bstart, const int64_t *bend, const int64_t *chain_off,
+                                        const uint8_t *chain_plane, const uint8_t *chain_reverse,
+                                        const int32_t *row_col, int64_t n_chains, int64_t n_blocks, int32_t width,
+                                        int phase_mode, int32_t codon_front, int32_t codon_back,
+                                        const uint8_t *mask_bits, const int64_t *mask_off,
+                                        int64_t bin_begin, int64_t bin_end,
+                                        uint32_t *out, uint8_t *maskmat, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    return stratified_windows_impl(batch, layout, rule, min_len, max_len, bstart, bend, chain_off, chain_plane, chain_reverse,
+                                   row_col, n_chains, n_blocks, width, phase_mode, codon_front, codon_back, mask_bits, mask_off,
+                                   bin_begin, bin_end, out, maskmat, workspace, workspace_bytes, stream_);
 }
 
 extern "C" int pb_stratified_windows(const pb_batch *batch, const pb_layout *layout, const pb_rule *rule,

@@ -497,13 +497,17 @@ def stratified_windows(dbatch, layout, factory, size_filter, table, row_col, wid
     cols = torch.from_numpy(np.ascontiguousarray(row_col, dtype=np.int32)).to(dev)
     b, lay, rule = dbatch.c_struct(), layout.c_struct(dev), factory.pb_rule(dev, size_filter)
     lo, hi = (0, int(layout.total_bins)) if bin_range is None else (int(bin_range[0]), int(bin_range[1]))
-    _lib.check(_lib.lib().pb_stratified_windows_range(C.byref(b), C.byref(lay), C.byref(rule), int(min_len), int(max_len),
-                                                      _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
-                                                      _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
-                                                      n, width, int(phase is not None), int(phase[0]) if phase else 0,
-                                                      int(phase[1]) if phase else 0, _lib.ptr(d["mask_bits"]),
-                                                      _lib.ptr(d["mask_off"]), lo, hi, _lib.ptr(out), _lib.ptr(maskmat),
-                                                      _lib.stream_ptr()))
+    L = _lib.lib()
+    n_blocks = len(table.bstart)
+    ws_bytes = L.pb_stratified_windows_workspace_bytes(n_blocks)
+    ws = _workspace(dev, ws_bytes, slot="stratified")            # read slice of every exon block, found by one launch
+    _lib.check(L.pb_stratified_windows_ws(C.byref(b), C.byref(lay), C.byref(rule), int(min_len), int(max_len),
+                                          _lib.ptr(d["bstart"]), _lib.ptr(d["bend"]), _lib.ptr(d["chain_off"]),
+                                          _lib.ptr(d["chain_plane"]), _lib.ptr(d["chain_reverse"]), _lib.ptr(cols),
+                                          n, n_blocks, width, int(phase is not None), int(phase[0]) if phase else 0,
+                                          int(phase[1]) if phase else 0, _lib.ptr(d["mask_bits"]),
+                                          _lib.ptr(d["mask_off"]), lo, hi, _lib.ptr(out), _lib.ptr(maskmat),
+                                          _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
     return out[:, :n], maskmat[:n]
 
 
