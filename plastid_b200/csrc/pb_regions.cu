@@ -8,12 +8,12 @@
 // Shape of the work: tens of thousands of chains, each a few exon blocks of a few hundred positions scattered over a
 // 12-25 GB plane.  Round 1 walked a chain block by block, 32 positions per dependent step, and ran at a quarter of
 // the HBM rate with every warp waiting on one 128-byte row at a time (ncu: 11-15 warps stalled on the long scoreboard
-// per issue, profiles/ncu_gather_r02a.txt).  Here the positions of a chain are FLATTENED over the lanes of its warp:
-// the warp loads the bounds of up to 32 blocks at once (one round trip), a shuffle scan gives every block its first
-// unit, and every lane then owns units u = lane, lane + 32, ... of the whole chain — four independent loads per lane
-// are in flight before the first value is used, whatever the block structure.  Sums read 16-byte aligned groups
-// (uint4 / double2), trimming the group's head and tail against the block; window rows are written column by column
-// from the same flattened index.
+// per issue).  The unit of work is now the exon BLOCK: one warp per block reads 16-byte aligned groups (uint4 /
+// double2, four loads in flight per lane), trims the group's head and tail against the block and its mask bits, and
+// writes one partial sum (region tables) or the block's cells of its window row (window matrices); a second small
+// launch adds the partial sums per chain in block order.  Measured alternatives that were slower — a chain's positions
+// flattened over one warp, several blocks per warp, deeper unrolling — are in profiles/NOTES_r02.md sections 1 and 7.3.
+// The plane-free counts (pb_chain_counts) never touch a plane: reads are counted straight into the chain blocks.
 //
 // Every kernel takes the global-bin range [lo, hi) the calling rank owns (position sharding): positions
 // outside it count zero but keep their place in the chain, so partial tables of all ranks add up to the whole table
@@ -31,11 +31,6 @@ template <typename T> struct VecOf;
 template <> struct VecOf<uint32_t> { static constexpr int V = 4; typedef uint4 L; typedef unsigned long long Acc; };
 template <> struct VecOf<double> { static constexpr int V = 2; typedef double2 L; typedef double Acc; };
 
-__device__ __forceinline__ long long shfl_ll(long long v, int src)
-{
-    return __shfl_sync(kFull, v, src);
-}
-
 __device__ __forceinline__ double warp_sum_f64(double v)
 {
 #pragma unroll
@@ -51,21 +46,6 @@ __device__ __forceinline__ uint32_t mask_bits_at(const uint32_t *__restrict__ wo
     uint32_t bits = __ldg(words + w) >> sh;
     if (sh + n > 32) bits |= __ldg(words + w + 1) << (32 - sh);
     return n == 32 ? bits : (bits & ((1u << n) - 1u));
-}
-
-// number of set bits in [b0, b0 + n) by a whole warp
-__device__ __forceinline__ long long warp_popcount_bits(const uint32_t *__restrict__ words, long long b0, long long n, int lane)
-{
-    if (n <= 0) return 0;
-    const long long wa = b0 >> 5, wb = (b0 + n - 1) >> 5;
-    long long cnt = 0;
-    for (long long w = wa + lane; w <= wb; w += 32) {
-        uint32_t x = __ldg(words + w);
-        if (w == wa) x &= kFull << (b0 & 31);
-        if (w == wb) x &= kFull >> (31 - ((b0 + n - 1) & 31));
-        cnt += __popc(x);
-    }
-    return (long long)pb_warp_sum((unsigned long long)cnt);
 }
 
 template <typename T> __device__ __forceinline__ void add_group(typename VecOf<T>::Acc &acc, const typename VecOf<T>::L &v, uint32_t m);
