@@ -4,23 +4,25 @@ The reference is single-process; counts at a position depend on
 mapped there and region / window values only on their own positions, so the path shards with no
 count-vector collective:
 
-* **read-range sharding** (``shard_reads``): every rank maps a contiguous slice of the
-  coordinate-sorted batch over the whole layout; region sums, phase sums and mean-profile
-  numerators are linear in the reads, so the small result tables are summed with one all-reduce
-  (``allreduce_sum``).  This is the weak-scaling mode ``bench.py`` runs.
-* **chromosome sharding** (``assign_chromosomes`` / ``shard_chromosomes``): every rank owns whole
-  chromosomes (longest-processing-time assignment by read count) and only the regions on them; the
-  per-region tables are gathered (``gather_rows``).  Exact medians need the normalised window rows
-  of all ranks (``gather_matrix``) — a median is not all-reducible.
+* **position-range sharding** (``position_cuts`` / ``balanced_cuts`` / ``shard_positions`` / ``clip_table``, SURVEY §8e;
+  what ``BAMGenomeArray``, the programs and ``bench.py --gpus N`` use): the concatenated genome is cut into contiguous bin
+  ranges of equal cost (reads streamed + plane bins written); a rank holds the planes of its range only (1/N of the
+  memory), receives the reads that start inside it plus a halo of ``max_span`` before it (those go to both neighbours,
+  each counts only sites inside its own range), and sums the parts of every region that fall into its range; the
+  partial region tables are summed with one all-reduce.  ``snap="chromosomes"`` puts the cuts on chromosome boundaries
+  (BASELINE config 5).
+* **window profiles** (``window_profile``: ``metagene count``): the count matrix stays on its ranks — rows are completed
+  and normalised by the rank owning their first position (``row_owners``), means are all-reduced as column sums, exact
+  medians are taken per column slice after one all-to-all (``exchange_column_slices``).
+* **read-range sharding** (``shard_reads``; ``bench.py --sharding reads``, round 1's weak-scaling mode): every rank maps
+  a contiguous slice of the coordinate-sorted batch over the whole layout; region sums, phase sums and mean-profile
+  numerators are linear in the reads, so the small result tables are summed with one all-reduce (``allreduce_sum``).
+* **chromosome assignment** (``assign_chromosomes`` / ``shard_chromosomes`` / ``gather_rows`` / ``gather_matrix``):
+  every rank owns whole chromosomes (longest-processing-time assignment by read count) and only the regions on them;
+  the per-region tables are gathered.
 
-* **position-range sharding** (``position_cuts`` / ``shard_positions`` / ``clip_table``):
-  the concatenated genome is cut into contiguous bin ranges of equal cost (reads + plane bins); a rank holds
-  the planes of its range only (1/N of the memory), receives the reads that start inside it plus a
-  halo of ``max_span`` before it (those are sent to both neighbours, each counts only sites inside
-  its own range), and sums the parts of every region that fall into its range; the partial region
-  tables are summed with one all-reduce.  No count-vector collective here either.
-
-NCCL is used on GPUs, gloo in the CPU tests; all messages are small (<= a few hundred MB).
+NCCL is used on GPUs, gloo in the CPU tests; all messages are small (a few hundred KB for tables, 1/N of a window
+matrix for exact medians).
 """
 import numpy as np
 

@@ -675,6 +675,10 @@ class BAMGenomeArray(object):
 
     ``sources`` are sorted BAM paths (decoded once, whole, by the library's own BGZF/BAM decoder — no index, no
     pysam needed), open ``pysam.AlignmentFile`` handles, or :class:`~plastid_b200.batch.AlignmentBatch` objects.
+    ``indexed=True`` (paths with a ``.bai`` beside them; ``bam_io.build_index`` writes one): nothing is decoded up
+    front — chromosomes and ``sum()`` come from the header and the index statistics, ``ga[seg]`` /
+    ``get_reads_and_counts`` seek through the index like the reference's ``fetch`` (genome_array.py:800-809), and the
+    files are decoded whole only when a whole-genome consumer (``count_planes``, ``count_chains``, track export) asks.
 
     How the alignments reach the device: a batch that carries its transfer format (``AlignmentBatch.pack`` — the
     decoder emits it) is uploaded in that form (1-1.3 bytes per read, 4 per aligned block) chunk by chunk on a copy
