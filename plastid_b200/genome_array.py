@@ -1137,7 +1137,11 @@ class BAMGenomeArray(object):
         4 bytes per genome position), ``None`` (default) takes the planes when they exist already and the
         plane-free path otherwise."""
         table = chains if isinstance(chains, ChainTable) else self.chain_table(chains, use_masks)
-        need = tuple(sorted(set(_STRANDS[p] for p in np.unique(table.chain_plane)), key=_STRANDS.index)) or ("+",)
+        need = table.__dict__.get("_strands_needed")          # geometry of the table: looked at once
+        if need is None:
+            need = tuple(sorted(set(_STRANDS[p] for p in np.unique(table.chain_plane)), key=_STRANDS.index)) or ("+",)
+            table._strands_needed = need
+            table._any_unknown = bool((~table.known).any())
         direct_ok = self._is_lowerable() and not isinstance(self.map_fn, CenterMapFactory)
         have = self._planes is not None and all(s in self._planes.planes for s in need)
         if planes is None:
@@ -1156,7 +1160,8 @@ class BAMGenomeArray(object):
                 self.map_fn._warn_dropped(int(st[:3].sum()), int(st[_lib.PB_STAT_DROPPED_LEN]))
         sums = self._allreduce(sums)
         sums, live = sums.cpu().numpy(), live.cpu().numpy()
-        live[~table.known] = table.unknown_live[~table.known]
+        if table._any_unknown:
+            live[~table.known] = table.unknown_live[~table.known]
         if self._normalize is True:
             sums = sums / float(self.sum()) * 1e6
         return sums, live
