@@ -20,6 +20,7 @@
 // and geometry-only outputs (unmasked lengths, mask matrices, NaN cells) are identical on every rank.
 #include "pb_tiles.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -431,7 +432,7 @@ pb_chain_first_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, const long 
                             long long lo, long long hi, long long total_bins,
                             long long *__restrict__ slice_first, uint32_t *__restrict__ extra_items,
                             unsigned long long *__restrict__ counts, unsigned long long *__restrict__ stats,
-                            const int16_t *__restrict__ site_tab)
+                            const int16_t *__restrict__ site_tab, int first_reads, int item_reads)
 {
     __shared__ __align__(16) int16_t s_tab[3 * kSiteKeys];
     pb_load_site_tables(s_tab, site_tab);
@@ -455,7 +456,7 @@ pb_chain_first_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, const long 
             const int c = __ldg(block_chain + k);
             plane = __ldg(block_plane + k);
             const PbItemCtx x = pb_item_ctx(lay, gs, ge, lo, hi, c, plane, mask_words, mask_off, __ldg(block_pos + k));
-            const int n = (int)(last - first < kItemReads ? last - first : kItemReads);
+            const int n = (int)(last - first < first_reads ? last - first : first_reads);
             unsigned int count = pb_count_reads(b, r, x, s_tab, first, n, lane, mask_words, drop_len);
             count = __reduce_add_sync(kFull, count);
             if (lane == 0 && count) atomicAdd(counts + c, (unsigned long long)count);
@@ -464,8 +465,8 @@ pb_chain_first_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay, const long 
     if (lane == 0) {
         slice_first[2 * k] = first;
         slice_first[2 * k + 1] = last;
-        const long long items = (last - first + kItemReads - 1) / kItemReads;
-        extra_items[k] = items > 1 ? (uint32_t)(items - 1) : 0u;
+        const long long rest = last - first - first_reads;            // reads beyond the first item
+        extra_items[k] = rest > 0 ? (uint32_t)((rest + item_reads - 1) / item_reads) : 0u;
     }
     pb_flush_drops(stats, drop_len, plane);
 }
@@ -479,7 +480,7 @@ pb_chain_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
                       const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
                       long long lo, long long hi, const long long *__restrict__ slice_first,
                       const uint32_t *__restrict__ item_off, unsigned long long *__restrict__ counts,
-                      unsigned long long *__restrict__ stats, const int16_t *__restrict__ site_tab)
+                      unsigned long long *__restrict__ stats, const int16_t *__restrict__ site_tab, int first_reads, int item_reads)
 {
     __shared__ __align__(16) int16_t s_tab[3 * kSiteKeys];
     pb_load_site_tables(s_tab, site_tab);
@@ -494,10 +495,10 @@ pb_chain_items_kernel(PbReads b, PbRuleDev r, PbLayoutDev lay,
         const int c = __ldg(block_chain + k);
         const int plane = __ldg(block_plane + k);
         const PbItemCtx x = pb_item_ctx(lay, __ldg(bstart + k), __ldg(bend + k), lo, hi, c, plane, mask_words, mask_off, __ldg(block_pos + k));
-        // item e of block k is its (e + 1)-th run of kItemReads reads: the first run was counted with the slice
-        const long long first = __ldg(slice_first + 2 * k) + (item - (long long)__ldg(item_off + k) + 1) * kItemReads;
+        // item e of block k is its e-th run of kItemReads reads after the first `first_reads`, which were counted with the slice
+        const long long first = __ldg(slice_first + 2 * k) + first_reads + (item - (long long)__ldg(item_off + k)) * item_reads;
         const long long slice_end = __ldg(slice_first + 2 * k + 1);
-        const int n = (int)(slice_end - first < kItemReads ? slice_end - first : kItemReads);
+        const int n = (int)(slice_end - first < item_reads ? slice_end - first : item_reads);
         unsigned int dl = 0;
         unsigned int count = pb_count_reads(b, r, x, s_tab, first, n, lane, mask_words, dl);
         if (dl) { drop_len = dl; drop_plane = plane; }
@@ -680,16 +681,23 @@ extern "C" int pb_chain_counts(const pb_batch *batch, const pb_layout *layout, c
     if (n_blocks > 0) {
         // 4 warps per CTA: a block's first item is anything from 0 to 2048 reads, and a CTA holds its slot until its
         // slowest warp is done
+        // PB_FIRST_READS (A/B aid): reads of a block counted by the warp that finds its slice; the rest are 2048-read items
+        const char *env_f = getenv("PB_FIRST_READS");
+        const char *env_i = getenv("PB_ITEM_READS");
+        int item_reads = env_i ? atoi(env_i) : kItemReads;
+        if (item_reads < 128 || item_reads > (1 << 20)) item_reads = kItemReads;
+        int first_reads = env_f ? atoi(env_f) : item_reads;
+        if (first_reads < 0 || first_reads > (1 << 20)) first_reads = item_reads;
         pb_chain_first_items_kernel<<<(unsigned)((n_blocks * 32 + 127) / 128), 128, 0, stream>>>(
             b, r, lay, index, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
-            layout->total_bins, slices, items, counts, reinterpret_cast<unsigned long long *>(stats), site_tab);
+            layout->total_bins, slices, items, counts, reinterpret_cast<unsigned long long *>(stats), site_tab, first_reads, item_reads);
         int rc = pb_launch_exclusive_scan_u32(items, item_off, part, n_blocks, stream);
         if (rc) return rc;
         int sms = 148;
         pb_sm_count(&sms);
         pb_chain_items_kernel<<<(unsigned)(sms * 6), 256, 0, stream>>>(
             b, r, lay, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end,
-            slices, item_off, counts, reinterpret_cast<unsigned long long *>(stats), site_tab);
+            slices, item_off, counts, reinterpret_cast<unsigned long long *>(stats), site_tab, first_reads, item_reads);
     }
     pb_chain_totals_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, stream>>>(
         bstart, bend, chain_off, n_chains, mw, mask_off, nullptr, counts, sums, live_len);
