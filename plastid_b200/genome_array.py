@@ -713,6 +713,8 @@ class BAMGenomeArray(object):
         if kwargs.get("indexed"):
             # header + index only: nothing is decoded until a whole-genome consumer asks (`_attach`)
             from .bam_io import IndexedBam
+            if not all(isinstance(src, str) for src in sources):
+                raise TypeError("indexed=True takes paths of sorted, indexed BAM files")
             self._indexed = [IndexedBam(src) for src in sources]
             self._sources = sources
             chroms, lens = [], {}
