@@ -1426,3 +1426,26 @@ def test_entry_points_declared_in_pyproject_resolve():
     assert resolve(proj["entry-points"]["plastid.mapping_options"]["device"])["name"] == "device"
     for name, target in proj["scripts"].items():
         assert callable(resolve(target)), name
+
+
+def test_indexed_container_bookkeeping_without_a_device():
+    """``BAMGenomeArray(path, indexed=True)``: chromosomes, lengths and ``sum()`` come from the header and the ``.bai``
+    statistics (``bamfile.mapped``, genome_array.py:690) without decoding a record; the files are decoded when
+    something asks for every read, and a ``set_sum`` made before that survives it."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden", "htslib_allops.bam")
+    from plastid_b200.bam_io import batch_from_bam
+    whole = batch_from_bam(gold)
+    ga = pb.BAMGenomeArray(gold, indexed=True, device="cpu")
+    assert ga.is_lazy and ga.sum() == whole.mapped
+    assert ga.chroms() == sorted(whole.chroms) and ga.lengths() == dict(zip(whole.chroms, (int(x) for x in whole.chrom_len)))
+    ga.set_mapping(pb.FivePrimeMapFactory(3))
+    ga.add_filter("size", pb.SizeFilterFactory(10, 200))
+    assert ga.is_lazy and ga.sum() == whole.mapped                       # nothing above needs the reads
+    ga.set_sum(1234)
+    assert len(ga.batch) == len(whole) and not ga.is_lazy and ga.sum() == 1234
+    assert (ga.batch.ref_start == whole.ref_start).all() and (ga.batch.meta == whole.meta).all()
+    with pytest.raises(TypeError):
+        pb.BAMGenomeArray(whole, indexed=True, device="cpu")
+    with pytest.raises(IOError):
+        pb.BAMGenomeArray(os.path.join(os.path.dirname(__file__), "golden", "missing.bam"), indexed=True, device="cpu")
