@@ -1000,7 +1000,10 @@ class BAMGenomeArray(object):
         # the point rules' 0.1: fewer, larger chunks there (C3 end to end: 17.4 ms with 8 chunks, 16.3 with 4)
         default = 4 if isinstance(self.map_fn, CenterMapFactory) else 8
         n_chunks = max(1, min(int(os.environ.get("PB_UPLOAD_CHUNKS", default)), len(hb) // 8_000_000))      # (env: A/B aid)
-        chunks = type(self._receiver).plan_chunks(hb.transfer, self.layout, n_chunks)
+        weights = None
+        if os.environ.get("PB_CHUNK_WEIGHTS"):               # (env: A/B aid) relative read counts of the chunks; equal chunks measured best, profiles/NOTES_r02.md 7.13
+            weights = [float(x) for x in os.environ["PB_CHUNK_WEIGHTS"].split(",")]
+        chunks = type(self._receiver).plan_chunks(hb.transfer, self.layout, n_chunks, weights)
         lo, hi = self._bin_range
         out = []
         for a, b, bin_a, bin_b in chunks:
