@@ -119,6 +119,104 @@ pb_block_sums_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const 
     if (lane == 0) block_sum[k] = total;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// the same partial sums with the blocks STAGED by the copy engine (cp.async.bulk global -> shared, completion on an
+// mbarrier): a warp takes kTmaSlots consecutive blocks, one lane per block issues ONE bulk copy of the block's
+// 16-byte-aligned bytes (up to kTmaSlotBytes; longer blocks read the rest with plain loads), and the warp then sums
+// slot after slot out of shared memory.  Bytes in flight cost no registers here (8 x ~1.5 KB per warp).  A/B aid
+// (PB_REGION_TMA=1): see profiles/NOTES_r02.md section 7.14 for what it measured.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTmaSlots = 8, kTmaSlotBytes = 2048, kTmaWarps = 4;
+
+__device__ __forceinline__ uint32_t pb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pb_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" :: "r"(pb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pb_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" :: "r"(pb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pb_bulk_load(void *sdst, const void *gsrc, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(pb_smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(pb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pb_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(pb_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <typename T, bool MASK>
+__global__ void __launch_bounds__(kTmaWarps * 32)
+pb_block_sums_tma_kernel(PbPlanes planes, const int64_t *__restrict__ bstart, const int64_t *__restrict__ bend,
+                         const int32_t *__restrict__ block_chain, const int64_t *__restrict__ block_pos,
+                         const uint8_t *__restrict__ block_plane, int64_t n_blocks,
+                         const uint32_t *__restrict__ mask_words, const int64_t *__restrict__ mask_off,
+                         long long lo, long long hi, double *__restrict__ block_sum)
+{
+    constexpr int V = VecOf<T>::V;
+    typedef typename VecOf<T>::L L;
+    extern __shared__ __align__(128) unsigned char stage[];          // [warp][slot][kTmaSlotBytes]
+    __shared__ __align__(8) uint64_t bars[kTmaWarps][kTmaSlots];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane < kTmaSlots) pb_mbar_init(&bars[wid][lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pb_fence_proxy_async();
+    __syncthreads();
+    const int64_t k0 = (((int64_t)blockIdx.x * kTmaWarps) + wid) * kTmaSlots;
+    if (k0 >= n_blocks) return;
+    // lane j < kTmaSlots owns block k0 + j: its row, its geometry, its bulk copy
+    int head = 0, span = 0, n_groups = 0;
+    long long mbase = 0;
+    const L *src = nullptr;
+    if (lane < kTmaSlots && k0 + lane < n_blocks) {
+        const int64_t k = k0 + lane;
+        const long long bs = __ldg(bstart + k), be = __ldg(bend + k);
+        const long long cs = bs > lo ? bs : lo, ce = be < hi ? be : hi;      // the part this rank owns
+        if (cs < ce) {
+            const T *vec = static_cast<const T *>(planes.p[__ldg(block_plane + k)]);
+            const long long g0 = cs & ~(long long)(V - 1);
+            head = (int)(cs - g0); span = (int)(ce - g0);
+            n_groups = (span + V - 1) / V;
+            src = reinterpret_cast<const L *>(vec + g0);
+            if (MASK) mbase = __ldg(mask_off + __ldg(block_chain + k)) + __ldg(block_pos + k) + (g0 - bs);
+            const unsigned bytes = (unsigned)(n_groups * 16 < kTmaSlotBytes ? n_groups * 16 : kTmaSlotBytes);
+            pb_mbar_expect_tx(&bars[wid][lane], bytes);
+            pb_bulk_load(stage + ((size_t)wid * kTmaSlots + lane) * kTmaSlotBytes, src, bytes, &bars[wid][lane]);
+        }
+    }
+#pragma unroll 1
+    for (int j = 0; j < kTmaSlots; ++j) {
+        if (k0 + j >= n_blocks) break;
+        const int ng = __shfl_sync(kFull, n_groups, j);
+        if (ng == 0) { if (lane == 0) block_sum[k0 + j] = 0.0; continue; }
+        const int hd = __shfl_sync(kFull, head, j), sp = __shfl_sync(kFull, span, j);
+        const long long mb = MASK ? __shfl_sync(kFull, mbase, j) : 0;
+        const L *gsrc = reinterpret_cast<const L *>(__shfl_sync(kFull, (unsigned long long)src, j));
+        const L *ssrc = reinterpret_cast<const L *>(stage + ((size_t)wid * kTmaSlots + j) * kTmaSlotBytes);
+        const int staged = ng < kTmaSlotBytes / 16 ? ng : kTmaSlotBytes / 16;
+        pb_mbar_wait(&bars[wid][j], 0);
+        typename VecOf<T>::Acc acc = 0;
+        for (int u = lane; u < ng; u += 32) {
+            const L v = u < staged ? ssrc[u] : __ldg(gsrc + u);
+            const int rel = u * V;
+            const int e_lo = hd > rel ? hd - rel : 0;
+            const int e_hi = sp - rel < V ? sp - rel : V;
+            uint32_t m = ((1u << e_hi) - 1u) & ~((1u << e_lo) - 1u);
+            if (MASK) m &= ~(mask_bits_at(mask_words, mb + rel + e_lo, e_hi - e_lo) << e_lo);
+            add_group<T>(acc, v, m);
+        }
+        double total;
+        if (sizeof(T) == 4) total = (double)pb_warp_sum((unsigned long long)acc);
+        else total = warp_sum_f64((double)acc);
+        if (lane == 0) block_sum[k0 + j] = total;
+    }
+}
+
 // one THREAD per chain (chains have a handful of blocks): partial sums of its blocks in block order, its length, its
 // masked positions
 __global__ void __launch_bounds__(256)
@@ -547,7 +645,15 @@ extern "C" int pb_region_sums(const void *const *planes, int vec_dtype,
     PbPlanes pl{{planes[0], planes[1], planes[2]}};
     double *block_sum = (double *)workspace;
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mask_bits);
-    if (n_blocks > 0) {
+    if (n_blocks > 0 && getenv("PB_REGION_TMA")) {
+        const unsigned grid = (unsigned)((n_blocks + kTmaWarps * kTmaSlots - 1) / (kTmaWarps * kTmaSlots));
+        const size_t smem = (size_t)kTmaWarps * kTmaSlots * kTmaSlotBytes;
+#define PB_LAUNCH_TMA(T, M) do { PB_CUDA_CHECK(cudaFuncSetAttribute(pb_block_sums_tma_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pb_block_sums_tma_kernel<T, M><<<grid, kTmaWarps * 32, smem, stream>>>(pl, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end, block_sum); } while (0)
+        if (vec_dtype == 0) { if (mw) PB_LAUNCH_TMA(uint32_t, true); else PB_LAUNCH_TMA(uint32_t, false); }
+        else { if (mw) PB_LAUNCH_TMA(double, true); else PB_LAUNCH_TMA(double, false); }
+#undef PB_LAUNCH_TMA
+    } else if (n_blocks > 0) {
         const unsigned grid = (unsigned)((n_blocks * 32 + 255) / 256);
 #define PB_LAUNCH_SUMS(T, M) pb_block_sums_kernel<T, M><<<grid, 256, 0, stream>>>(pl, bstart, bend, block_chain, block_pos, block_plane, n_blocks, mw, mask_off, bin_begin, bin_end, block_sum)
         if (vec_dtype == 0) { if (mw) PB_LAUNCH_SUMS(uint32_t, true); else PB_LAUNCH_SUMS(uint32_t, false); }

@@ -5,6 +5,7 @@ import warnings
 
 import numpy as np
 import pytest
+import torch
 
 import plastid_b200 as pb
 from plastid_b200 import synth, _lib
@@ -116,6 +117,36 @@ def test_region_sums_chain_with_many_blocks_and_tiny_blocks(world, cuda_device):
     exp_s, exp_l = oracle_table(host_planes(planes, "u32"), table)
     assert (sums.cpu().numpy() == exp_s).all() and (live.cpu().numpy() == exp_l).all()
     assert live.cpu().numpy()[0] == big.masked_length and exp_s.sum() > 0
+
+
+def test_region_sums_staged_by_the_copy_engine_give_the_same_table(world, cuda_device, monkeypatch):
+    """``PB_REGION_TMA=1``: the blocks are staged in shared memory by ``cp.async.bulk`` + mbarrier instead of being read
+    with 16-byte loads (the measured-slower variant kept for A/B, profiles/NOTES_r02.md 7.14): same sums and lengths on
+    uint32 and float64 planes, with masks, blocks longer than a staging slot, tiny blocks and an empty chain."""
+    w = world
+    chrom = w["chroms"][0]
+    chains = [pb.SegmentChain(*[pb.GenomicSegment(chrom, 1000 + 37 * k, 1000 + 37 * k + 1 + (k % 9), "+") for k in range(75)]),
+              pb.SegmentChain(pb.GenomicSegment(chrom, 20_001, 23_777, "-"), pb.GenomicSegment(chrom, 30_003, 30_500, "-")),   # > one slot
+              pb.SegmentChain(pb.GenomicSegment(chrom, 5003, 5004, "-")),
+              pb.SegmentChain(pb.GenomicSegment(chrom, 2001, 2777, "."), pb.GenomicSegment(chrom, 9000, 9003, ".")),
+              pb.SegmentChain()]
+    chains[0].add_masks(pb.GenomicSegment(chrom, 1100, 1400, "+"), pb.GenomicSegment(chrom, 3000, 3001, "+"))
+    chains[1].add_masks(pb.GenomicSegment(chrom, 21_000, 22_501, "-"))
+    chains += w["ann"].chains()[:200]
+    table = ChainTable.from_chains(chains, w["layout"])
+    for fac in (pb.FivePrimeMapFactory(0), pb.CenterMapFactory(3)):
+        planes = map_batch(w["dbatch"], w["layout"], fac, None, strands=("+", "-", "."))
+        monkeypatch.delenv("PB_REGION_TMA", raising=False)
+        s0, l0 = region_sums(planes, table)
+        s0, l0 = s0.clone(), l0.clone()
+        monkeypatch.setenv("PB_REGION_TMA", "1")
+        s1, l1 = region_sums(planes, table)
+        assert torch.equal(l0, l1) and float(s0.sum()) > 0
+        if planes.dtype == "u32":
+            assert torch.equal(s0, s1)
+        else:
+            assert torch.allclose(s0, s1, rtol=1e-12, atol=0)          # the lanes meet the groups in another order
+    monkeypatch.delenv("PB_REGION_TMA", raising=False)
 
 
 def test_regions_beyond_the_chromosome_count_zero_there(world, cuda_device):
