@@ -618,3 +618,36 @@ def test_fetch_equals_filtering_the_whole_file(tmp_path, aligned):
         end = min(n, beg + int(rng.choice([1, 50, 3000, 40000])))
         want = sorted((r[2:] for r in per[tid] if r[0] < end and r[1] > beg), key=lambda r: r[0])
         assert batch_rows(f.fetch(f.references[tid], beg, end)) == want, (tid, beg, end)
+
+
+def test_index_without_statistics_falls_back_to_decoding(tmp_path):
+    """An index written without the metadata pseudo-bin (old indexers) has no ``mapped`` statistic: ``IndexedBam.mapped``
+    is None, fetches still work, and ``BAMGenomeArray(indexed=True)`` decodes the file at once to know its sum."""
+    import shutil
+    import struct
+    import plastid_b200 as pb
+    bam = str(tmp_path / "x.bam")
+    shutil.copy(os.path.join(GOLD, "htslib_allops.bam"), bam)
+    raw = open(os.path.join(GOLD, "htslib_allops.bam.bai"), "rb").read()
+    n_ref, = struct.unpack_from("<i", raw, 4)
+    out, p = [raw[:8]], 8
+    for _ in range(n_ref):
+        n_bin, = struct.unpack_from("<i", raw, p); p += 4
+        kept = []
+        for _b in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", raw, p)
+            size = 8 + 16 * n_chunk
+            if b != 37450:
+                kept.append(raw[p:p + size])
+            p += size
+        n_intv, = struct.unpack_from("<i", raw, p)
+        out.append(struct.pack("<i", len(kept)) + b"".join(kept) + raw[p:p + 4 + 8 * n_intv])
+        p += 4 + 8 * n_intv
+    open(bam + ".bai", "wb").write(b"".join(out) + raw[p:])
+    f = bam_io.IndexedBam(bam)
+    assert f.mapped is None
+    regions = parse_fetches(os.path.join(GOLD, "htslib_allops.fetch.txt.gz"))
+    for (tid, beg, end), records in regions[:40]:
+        assert batch_rows(f.fetch(f.references[tid], beg, end)) == expected_rows(records)
+    ga = pb.BAMGenomeArray(bam, indexed=True, device="cpu")
+    assert not ga.is_lazy and ga.sum() == bam_io.batch_from_bam(bam).mapped
