@@ -667,6 +667,10 @@ extern "C" int pb_bai_open(const char *path, pb_bai **out)
     const int32_t n_ref = (int32_t)rd32(buf.data() + 4);
     p = 8;
     if (n_ref < 0) { pb_set_error("pb_bai_open(%s): negative reference count", path); return PB_EINVAL; }
+    if ((size_t)n_ref > (buf.size() - 8) / 8) {       // every reference takes at least its two counts
+        pb_set_error("pb_bai_open(%s): truncated index (%d references do not fit in %zu bytes)", path, n_ref, buf.size());
+        return PB_EINVAL;
+    }
     pb_bai *idx = new pb_bai();
     idx->refs.resize((size_t)n_ref);
     bool ok = true;

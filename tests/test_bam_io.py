@@ -651,3 +651,42 @@ def test_index_without_statistics_falls_back_to_decoding(tmp_path):
         assert batch_rows(f.fetch(f.references[tid], beg, end)) == expected_rows(records)
     ga = pb.BAMGenomeArray(bam, indexed=True, device="cpu")
     assert not ga.is_lazy and ga.sum() == bam_io.batch_from_bam(bam).mapped
+
+
+def test_damaged_indexes_are_errors_or_answers_never_crashes(tmp_path):
+    """Random byte damage in the .bai (bin numbers, chunk counts, virtual offsets, linear index): opening and fetching
+    either raises PlastidB200Error or returns a batch; a damaged offset may lose reads but must not crash or hang."""
+    rng = np.random.default_rng(99)
+    bam = os.path.join(GOLD, "htslib_allops.bam")
+    raw = bytearray(open(bam + ".bai", "rb").read())
+    f_ok = bam_io.IndexedBam(bam)
+    names, lens = f_ok.references, f_ok.lengths
+    outcomes = {"error": 0, "answer": 0}
+    for trial in range(150):
+        bad = bytearray(raw)
+        for _ in range(int(rng.integers(1, 6))):
+            at = int(rng.integers(8, len(bad)))
+            bad[at] = int(rng.integers(0, 256))
+        if trial % 10 == 0:
+            bad = bad[:int(rng.integers(8, len(bad)))]                   # truncated file
+        path = str(tmp_path / ("bad%d.bai" % trial))
+        open(path, "wb").write(bytes(bad))
+        try:
+            f = bam_io.IndexedBam(bam, index=path)
+            for _ in range(4):
+                tid = int(rng.integers(0, len(names)))
+                beg = int(rng.integers(0, max(lens[tid], 1)))
+                hb = f.fetch(names[tid], beg, beg + int(rng.integers(1, 5000)))
+                assert len(hb) >= 0
+            f.close()
+            outcomes["answer"] += 1
+        except _lib.PlastidB200Error:
+            outcomes["error"] += 1
+    assert outcomes["answer"] + outcomes["error"] == 150 and outcomes["error"] > 0
+    for n_ref in (2 ** 31 - 1, 10 ** 6, -5):                             # a reference count the file cannot hold
+        bad = bytearray(raw)
+        bad[4:8] = int(n_ref).to_bytes(4, "little", signed=True)
+        path = str(tmp_path / "nref.bai")
+        open(path, "wb").write(bytes(bad))
+        with pytest.raises(_lib.PlastidB200Error):
+            bam_io.IndexedBam(bam, index=path)
