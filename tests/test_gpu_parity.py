@@ -858,6 +858,28 @@ def test_indexed_bam_genome_array_seeks_and_equals_the_decoded_one(tmp_path, cud
     assert not lazy.is_lazy and (sa == sb).all() and (la == lb).all() and sa.sum() > 0 and lazy.sum() == 123
 
 
+def test_staged_upload_of_large_pageable_arrays(cuda_device, monkeypatch):
+    """Plain SoA batches above 64 MB per array are uploaded through a ring of pinned buffers filled by host threads
+    (batch._staged_upload); with the thresholds turned down, a spliced batch arrives bit for bit — 1-D and 2-D arrays,
+    sizes that are not a multiple of the chunk."""
+    import torch
+    from plastid_b200 import batch as pbatch
+    chroms, lens = synth.yeast_like_genome(total=800_000, n_chrom=3)
+    hb = synth.device_batch_to_host(synth.rnaseq_reads(chroms, lens, 70_001, seed=5, device="cpu", intron=(50, 900)), chroms, lens)
+    monkeypatch.setattr(pbatch, "_STAGED_MIN_BYTES", 1 << 10)
+    monkeypatch.setattr(pbatch, "_STAGED_CHUNK", (1 << 16) + 24)
+    pbatch._staging.clear()
+    try:
+        db = pbatch.DeviceBatch.from_host(hb, cuda_device)
+        torch.cuda.synchronize()
+        assert (db.ref_start.cpu().numpy() == hb.ref_start).all()
+        assert (db.meta.cpu().numpy().view(np.uint32) == hb.meta).all()
+        assert (db.blk_off.cpu().numpy().view(np.uint32) == hb.blk_off).all() and db.blk.shape == hb.blk.shape
+        assert (db.blk.cpu().numpy() == hb.blk).all() and (db.chrom_read_off.cpu().numpy() == hb.chrom_read_off).all()
+    finally:
+        pbatch._staging.clear()
+
+
 def test_golden_bam_count_vectors_from_reference_htslib_positions(cuda_device):
     """End of the chain for non-M CIGARs without the oracle in between: the committed golden BAM (every
     CIGAR op; written and piled up by the reference's vendored htslib, tests/golden/htslib_allops.*) is
