@@ -5,6 +5,8 @@ What pysam hands the reference one ``AlignedSegment`` at a time (``reference_sta
 and ``plastid/genomics/genome_array.py:800-815``) is packed here once into flat arrays the
 kernels stream.  Schema: ``include/plastid_b200.h``.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -873,14 +875,17 @@ def _staged_upload(src, device):
     key = _lib.device_key(device)
     st = _staging.get(key)
     if st is None:
-        bufs = [torch.empty(_STAGED_CHUNK, dtype=torch.uint8).pin_memory() for _ in range(_STAGED_RING)]
-        st = _staging[key] = dict(bufs=bufs, views=[b.numpy() for b in bufs], pool=ThreadPoolExecutor(4),
+        ring = int(os.environ.get("PB_STAGE_RING", _STAGED_RING))
+        bufs = [torch.empty(_STAGED_CHUNK, dtype=torch.uint8).pin_memory() for _ in range(ring)]
+        n_threads = int(os.environ.get("PB_STAGE_THREADS", "4"))          # (env: A/B aid)
+        st = _staging[key] = dict(bufs=bufs, views=[b.numpy() for b in bufs], pool=ThreadPoolExecutor(n_threads),
                                   stream=torch.cuda.Stream(device=device))
     flat = src.reshape(-1).view(np.uint8)
     n = flat.size
     dst = torch.empty(n, dtype=torch.uint8, device=device)
     chunks = [(lo, min(lo + _STAGED_CHUNK, n)) for lo in range(0, n, _STAGED_CHUNK)]
-    events = [None] * _STAGED_RING
+    n_ring = len(st["bufs"])
+    events = [None] * n_ring
     pending = collections.deque()
     state = {"next": 0}
 
@@ -888,9 +893,9 @@ def _staged_upload(src, device):
         np.copyto(st["views"][k][:hi - lo], flat[lo:hi])
 
     def submit():
-        while state["next"] < len(chunks) and len(pending) < _STAGED_RING:
+        while state["next"] < len(chunks) and len(pending) < n_ring:
             i = state["next"]
-            k = i % _STAGED_RING
+            k = i % n_ring
             if events[k] is not None:                # the copy engine has drained this buffer
                 events[k].synchronize()
                 events[k] = None
