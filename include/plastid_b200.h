@@ -264,6 +264,10 @@ int pb_pack_delta3(const int32_t *ref_start, const uint32_t *meta, const int64_t
                    uint8_t *packed, uint8_t *wide, int32_t *blk_base, uint32_t *blk_wide_off,
                    uint32_t *blk_exc_off, int32_t *exc_start, uint32_t *exc_meta, uint32_t *dict32,
                    int64_t *n_wide_out, int64_t *n_exc_out);
+/* Host side (no CUDA): reads per aligned length (int64[65536], meta bits 0-15; reads with the drop bit left out) — the
+ * batch metadata the Center rule derives its map-length tables from (len(read.positions) bucketing, psite.py:187-188;
+ * what pb_length_hist measures on the device).  n_threads < 1: all hardware threads. */
+int pb_meta_length_hist(const uint32_t *meta, int64_t n_reads, int n_threads, int64_t *hist);
 
 /* 5' / 3' / variable-offset mapping of a whole batch into dense uint32 planes.
  * `planes` selects which of out_plus/out_minus/out_any are produced; every bin of a selected

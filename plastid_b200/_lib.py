@@ -68,6 +68,7 @@ _SIGNATURES = {
     "pb_bam_read_header": (C.c_int, [_P]),
     "pb_bam_fetch": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64]),
     "pb_bam_build_index": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "pb_meta_length_hist": (C.c_int, [_P, C.c_int64, C.c_int, _P]),
     "pb_inflate_raw": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t]),
     "pb_format_track_bound": (C.c_int64, [C.c_int, C.c_char_p, C.c_int64]),
     "pb_format_track": (C.c_int64, [C.c_int, C.c_char_p, _P, _P, _P, C.c_int, C.c_int64, _P, C.c_int64, C.c_int]),

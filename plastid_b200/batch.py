@@ -853,9 +853,12 @@ class Delta3SplicedReceiver(object):
 
 def meta_length_hist(meta):
     """Reads per aligned length (int64[65536]) of a host ``meta`` array; reads with the drop bit are left out."""
+    import ctypes as C
     m = np.asarray(meta).view(np.uint32) if np.asarray(meta).dtype != np.uint32 else np.asarray(meta)
-    keep = (m >> 17) & 1 == 0
-    return np.bincount((m[keep] & 0xFFFF).astype(np.int64), minlength=65536).astype(np.int64)
+    m = np.ascontiguousarray(m)
+    hist = np.zeros(65536, dtype=np.int64)
+    _lib.check(_lib.lib().pb_meta_length_hist(C.c_void_p(m.ctypes.data), len(m), _lib.host_threads(0), C.c_void_p(hist.ctypes.data)))
+    return hist
 
 
 # Upload of a large PAGEABLE numpy array (a plain SoA batch built from arrays, nothing precomputed): the driver stages

@@ -163,3 +163,41 @@ extern "C" int pb_pack_delta3(const int32_t *ref_start, const uint32_t *meta, co
     });
     return PB_OK;
 }
+
+// Reads per aligned length (meta bits 0-15) of a host meta array, reads with the drop bit (17) left out: the batch
+// metadata the Center rule derives its tables of map lengths from (len(read.positions) bucketing, psite.py:187-188).
+// One 65536-bin histogram per thread, added up at the end; numpy needed 0.26 s for 20 M reads (mask, gather, astype,
+// bincount), 80 % of packing a batch.
+extern "C" int pb_meta_length_hist(const uint32_t *meta, int64_t n_reads, int n_threads, int64_t *hist)
+{
+    if (n_reads < 0 || !hist || (n_reads > 0 && !meta)) { pb_set_error("pb_meta_length_hist: null argument"); return PB_EINVAL; }
+    if (n_threads < 1) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    constexpr int64_t kPiece = 1 << 20;
+    const int64_t n_piece = (n_reads + kPiece - 1) / kPiece;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n_piece));
+    std::vector<std::vector<int64_t>> part((size_t)nt, std::vector<int64_t>(65536, 0));
+    std::atomic<int64_t> next{0};
+    auto work = [&](int t) {
+        int64_t *h = part[(size_t)t].data();
+        for (int64_t p; (p = next.fetch_add(1)) < n_piece;) {
+            const int64_t a = p * kPiece, e = std::min(n_reads, a + kPiece);
+            for (int64_t i = a; i < e; ++i) {
+                const uint32_t m = meta[i];
+                h[m & 0xFFFFu] += ((m >> 17) & 1u) ^ 1u;
+            }
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    for (int b = 0; b < 65536; ++b) {
+        int64_t v = 0;
+        for (int t = 0; t < nt; ++t) v += part[(size_t)t][(size_t)b];
+        hist[b] = v;
+    }
+    return PB_OK;
+}
+
